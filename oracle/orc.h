@@ -1,0 +1,38 @@
+/* TEST INFRASTRUCTURE ONLY -- shared declarations of the CPU oracle (see orc_seed.c / orc_align.c). */
+#ifndef ORC_H
+#define ORC_H
+#include <stddef.h>
+#include <stdint.h>
+
+typedef struct {
+	/* header of .comp.b (hashmapkma.c:282-289) */
+	int32_t DB_size; uint32_t mlen, prefix_len; uint64_t prefix, size, n, v_index, null_index;
+	uint32_t kmersize, flag;
+	uint64_t kmask, hmask;
+	int mega, exist_wide, values_short, key_wide, vidx_wide;
+	void *exist, *values, *key_index, *value_index;
+	/* .length.b / .seq.b */
+	int32_t *lengths;   /* [DB_size], lengths[0] = k of the alignment index */
+	uint64_t *seq;      /* packed templates, all of .seq.b */
+	int64_t *seq_off;   /* [DB_size] word offset of template t in seq */
+} orc_db;
+
+typedef struct {
+	int32_t M, MM, U, W1, Wl, Mn, PE;
+	int32_t d[25];      /* substitution matrix d[t][q], 5x5 */
+	int32_t exhaustive; /* -ex_mode */
+} orc_params;
+
+typedef struct {
+	int64_t reads, mapped, read_words, lookups, hits, list_fetches, list_ids;
+} orc_stats;
+
+orc_db *orc_db_open(const char *prefix);
+void orc_db_close(orc_db *db);
+int64_t orc_lookup(const orc_db *db, uint64_t key);
+int orc_list(const orc_db *db, int64_t off, int *n_out, const void **ids);
+void orc_revcomp(const uint64_t *seq, int seqlen, const int32_t *N, int nN, uint64_t *rseq, int32_t *rN);
+int64_t orc_seed_stream(const orc_db *db, const orc_params *p, const uint8_t *in, size_t in_bytes,
+                        uint8_t *out, size_t cap, orc_stats *st);
+void orc_default_params(orc_params *p);
+#endif

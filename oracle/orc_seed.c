@@ -1,0 +1,356 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU restatement (oracle) of KMA 1.5.1's stage-2 seeding path.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this. The product (kma_b200/csrc) never links or calls it.
+ *
+ * Parity pin: checked byte-for-byte against the stage-2 stream of the unmodified reference
+ * (`oracle/_ref/kma ... -s2`, built by oracle/Makefile.ref from /root/reference) in
+ * tests/test_oracle_seed.py, and against the committed streams in tests/golden/.
+ *
+ * Restated (not copied) from:
+ *   hashmapkma.c:149-178  hashMap_getGlobal   (flag == 0 path)      -> orc_lookup
+ *   hashmapkma.c:264-273  megaMap_getGlobal                          -> orc_lookup (mega)
+ *   hashmapkma.c:275-455  hashMapKMA_load     (.comp.b layout)      -> orc_db_open
+ *   compdna.c:228-256     rc_comp                                    -> orc_revcomp
+ *   savekmers.c:2442-3065 save_kmers (-1t1)                          -> orc_seed_read
+ *   savekmers.c:273-294   getBestMatch                               -> best_set
+ *   ankers.c:30-50        print_ankers (stage-2 record)              -> emit_record
+ *   savekmers.c:50-92     loadFsa (stage-1 record)                   -> orc_seed_stream
+ *   kmers.c:257           stream terminator  int32 -(#reads)
+ *
+ * Structure differs from the reference on purpose: the k-mer scan is expressed as a stream of
+ * (position, value-list offset) hits feeding one scoring state machine that is shared by both
+ * strands, instead of two unrolled copies.
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "orc.h"
+
+/* ------------------------------------------------------------------ .comp.b ---------- */
+
+static int rd(FILE *f, void *dst, size_t n) { return fread(dst, 1, n, f) == n ? 0 : -1; }
+
+orc_db *orc_db_open(const char *prefix) {
+	char path[4096];
+	orc_db *db = calloc(1, sizeof(orc_db));
+	FILE *f;
+	uint32_t u32[3];
+	uint64_t u64[5];
+
+	snprintf(path, sizeof(path), "%s.comp.b", prefix);
+	if (!(f = fopen(path, "rb"))) { free(db); return 0; }
+	if (rd(f, u32, 12) || rd(f, u64, 40)) { fclose(f); free(db); return 0; }
+	db->DB_size = u32[0]; db->mlen = u32[1]; db->prefix_len = u32[2];
+	db->prefix = u64[0]; db->size = u64[1]; db->n = u64[2]; db->v_index = u64[3]; db->null_index = u64[4];
+	db->kmask = db->mlen >= 32 ? ~0ull : ((1ull << (2 * db->mlen)) - 1);
+	db->mega = (db->size - 1) == db->kmask;
+	db->exist_wide = db->mega ? (db->v_index > 0xFFFFFFFFull) : (db->n > 0xFFFFFFFFull);
+	db->values_short = db->DB_size < 65535;
+	db->key_wide = db->mlen > 16;
+	db->vidx_wide = !(db->v_index < 0xFFFFFFFFull);
+
+	size_t nb = db->size * (db->exist_wide ? 8 : 4);
+	db->exist = malloc(nb);
+	if (rd(f, db->exist, nb)) goto fail;
+	nb = db->v_index * (db->values_short ? 2 : 4);
+	db->values = malloc(nb ? nb : 1);
+	if (rd(f, db->values, nb)) goto fail;
+	if (!db->mega) {
+		nb = (db->n + 1) * (db->key_wide ? 8 : 4);
+		db->key_index = malloc(nb);
+		if (rd(f, db->key_index, nb)) goto fail;
+		nb = db->n * (db->vidx_wide ? 8 : 4);
+		db->value_index = malloc(nb ? nb : 1);
+		if (rd(f, db->value_index, nb)) goto fail;
+	}
+	if (rd(f, u32, 8) == 0) { db->kmersize = u32[0]; db->flag = u32[1]; }
+	else { db->kmersize = db->mlen; db->flag = 0; }
+	fclose(f);
+	db->hmask = db->size - 1; /* "make indexing a masking problem" */
+
+	/* template lengths (optional for -1t1, needed for alignment) */
+	snprintf(path, sizeof(path), "%s.length.b", prefix);
+	if ((f = fopen(path, "rb"))) {
+		int32_t n;
+		if (rd(f, &n, 4) == 0 && n == db->DB_size) {
+			db->lengths = malloc(sizeof(int32_t) * n);
+			if (rd(f, db->lengths, sizeof(int32_t) * n)) { free(db->lengths); db->lengths = 0; }
+		}
+		fclose(f);
+	}
+	return db;
+fail:
+	fclose(f);
+	orc_db_close(db);
+	return 0;
+}
+
+void orc_db_close(orc_db *db) {
+	if (!db) return;
+	free(db->exist); free(db->values); free(db->key_index); free(db->value_index); free(db->lengths);
+	free(db->seq); free(db->seq_off);
+	free(db);
+}
+
+static inline uint64_t get_exist(const orc_db *db, uint64_t i) {
+	return db->exist_wide ? ((uint64_t *)db->exist)[i] : ((uint32_t *)db->exist)[i];
+}
+static inline uint64_t get_key(const orc_db *db, uint64_t i) {
+	return db->key_wide ? ((uint64_t *)db->key_index)[i] : ((uint32_t *)db->key_index)[i];
+}
+static inline uint64_t get_vidx(const orc_db *db, uint64_t i) {
+	return db->vidx_wide ? ((uint64_t *)db->value_index)[i] : ((uint32_t *)db->value_index)[i];
+}
+
+/* k-mer -> offset of its template list inside values[], or -1. Offsets identify lists: the
+ * indexer de-duplicates identical lists (compress.c valuesHash_add), so "same list as the
+ * previous hit" (savekmers.c:2522 pointer compare) == "same offset". */
+int64_t orc_lookup(const orc_db *db, uint64_t key) {
+	if (db->mega) {
+		uint64_t v = get_exist(db, key & db->kmask);
+		return v != 1 ? (int64_t)v : -1;
+	}
+	uint64_t bucket = key & db->hmask;
+	uint64_t pos = get_exist(db, bucket);
+	if (pos == db->null_index) return -1;
+	for (uint64_t k = get_key(db, pos); k != key; k = get_key(db, ++pos)) {
+		if ((k & db->hmask) != bucket) return -1;
+	}
+	return (int64_t)get_vidx(db, pos);
+}
+
+int orc_list(const orc_db *db, int64_t off, int *n_out, const void **ids) {
+	if (db->values_short) {
+		const uint16_t *p = (const uint16_t *)db->values + off;
+		*n_out = p[0]; *ids = p + 1;
+	} else {
+		const uint32_t *p = (const uint32_t *)db->values + off;
+		*n_out = (int)p[0]; *ids = p + 1;
+	}
+	return 0;
+}
+static inline int list_id(const orc_db *db, const void *ids, int i) {
+	return db->values_short ? ((const uint16_t *)ids)[i] : (int)((const uint32_t *)ids)[i];
+}
+
+/* ------------------------------------------------------------------ 2-bit codec ------ */
+
+static uint64_t rev2(uint64_t w) {
+	w = ((w >> 2) & 0x3333333333333333ull) | ((w & 0x3333333333333333ull) << 2);
+	w = ((w >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((w & 0x0F0F0F0F0F0F0F0Full) << 4);
+	return __builtin_bswap64(w);
+}
+
+/* reverse complement of a packed read; N positions mirrored. N bases are stored as A, so they
+ * come out as T in the reverse strand words (compdna.c:236-237 complements blindly). */
+void orc_revcomp(const uint64_t *seq, int seqlen, const int32_t *N, int nN, uint64_t *rseq, int32_t *rN) {
+	int words = (seqlen + 31) >> 5;
+	for (int i = 0; i < words; ++i) rseq[words - 1 - i] = rev2(~seq[i]);
+	int pad = 2 * (32 * words - seqlen);
+	if (pad) {
+		for (int i = 0; i + 1 < words; ++i) rseq[i] = (rseq[i] << pad) | (rseq[i + 1] >> (64 - pad));
+		rseq[words - 1] <<= pad;
+	}
+	for (int i = 0; i < nN; ++i) rN[i] = seqlen - 1 - N[nN - 1 - i];
+}
+
+static inline uint64_t kmer_at(const uint64_t *seq, int pos, int k) {
+	int w = pos >> 5, b = (pos & 31) << 1, sh = 64 - 2 * k;
+	uint64_t x = seq[w] << b;
+	if (b > sh) x |= seq[w + 1] >> (64 - b);
+	return x >> sh;
+}
+
+/* ------------------------------------------------------------------ scoring ---------- */
+
+/* score contribution of one hit that continues a template's run after `gaps` missed k-mers.
+ * `same_list` selects the accumulate-in-run bookkeeping of savekmers.c:2529-2569 (returns the
+ * deltas through acc[4] = {Ms, MMs, Us, W1s}) versus the direct per-template score of
+ * savekmers.c:2592-2625. Only mlen == kmersize is in scope (flag == 0 databases). */
+static void run_deltas(const orc_params *p, int k, int gaps, int acc[4]) {
+	if (gaps == 0) { acc[0] += 1; }
+	else if (gaps == k) { acc[0] += k; acc[1] += 1; }
+	else if (k < gaps) {
+		int g = gaps - (k - 1), mm, m;
+		acc[0] += k;
+		if (g <= 2) { mm = g; m = 0; }
+		else {
+			mm = g / k + (g % k ? 1 : 0); if (mm < 2) mm = 2;
+			m = g - mm; if (k < m) m = k; if (mm < m) m = mm;
+		}
+		if (p->W1 + (g - 1) * p->U <= mm * p->MM + m * p->M) { acc[1] += mm; acc[0] += m; }
+		else { acc[3] += 1; acc[2] += g - 1; }
+	} else { acc[0] += gaps; acc[3] += 1; acc[2] += k - gaps; }
+}
+
+static int resume_score(const orc_params *p, int k, int gaps) {
+	if (gaps == 0) return p->M;
+	if (gaps == k) return k * p->M + p->MM; /* fwd gaps*M+MM == rc k*M+MM when mlen == k */
+	if (k < gaps) {
+		int g = gaps - (k - 1), mm, m, a, b;
+		if (g <= 2) { mm = g; m = 0; }
+		else {
+			mm = g / k + (g % k ? 1 : 0); if (mm < 2) mm = 2;
+			m = g - mm; if (k < m) m = k; if (mm < m) m = mm;
+		}
+		a = p->W1 + (g - 1) * p->U; b = mm * p->MM + m * p->M;
+		return k * p->M + (a <= b ? b : a);
+	}
+	return gaps * p->M + (k - gaps) * p->U + p->W1;
+}
+
+typedef struct {
+	int *score;  /* DB_size, zero between reads */
+	int *ext;    /* DB_size */
+	char *incl;  /* DB_size */
+} scratch_t;
+
+/* One strand. cand[0] = count, cand[1..] = templates in first-seen order. Returns best score and
+ * leaves the arg-max set (first-seen order) in cand. `*lookups` counts hash probes issued. */
+static int scan_strand(const orc_db *db, const orc_params *p, const uint64_t *seq, int seqlen,
+                       const int32_t *N, int nN, scratch_t *S, int *cand, orc_stats *st) {
+	const int k = db->kmersize;
+	int hit = p->exhaustive;
+
+	/* quick check: every k-th k-mer of every N-free stretch, until the first hit */
+	for (int seg = 0, s = 0; seg <= nN && !hit; ++seg) {
+		int e = seg < nN ? N[seg] : seqlen;
+		for (int j = s; j < e - k + 1 && !hit; j += k) {
+			if (st) st->lookups++;
+			hit = orc_lookup(db, kmer_at(seq, j, k)) >= 0;
+		}
+		s = e + 1;
+	}
+	cand[0] = 0;
+	if (!hit) return 0;
+
+	int64_t last = -1;
+	int last_pos = 0, nhits = 0;
+	int acc[4] = {0, 0, 0, 0};
+	for (int seg = 0, s = 0; seg <= nN && s < seqlen - k + 1; ++seg) {
+		int e = seg < nN ? N[seg] : seqlen;
+		for (int j = s; j + k <= e; ++j) {
+			int64_t off = orc_lookup(db, kmer_at(seq, j, k));
+			if (st) st->lookups++;
+			if (off < 0) continue;
+			if (st) st->hits++;
+			int nl; const void *ids;
+			if (off == last) {
+				run_deltas(p, k, j - last_pos - 1, acc);
+			} else if (last >= 0) {
+				int sc = acc[0] * p->M + acc[1] * p->MM + acc[2] * p->U + acc[3] * p->W1;
+				orc_list(db, last, &nl, &ids);
+				for (int i = 0; i < nl; ++i) { int t = list_id(db, ids, i); S->score[t] += sc; S->ext[t] = last_pos; }
+				orc_list(db, off, &nl, &ids);
+				if (st) st->list_fetches++, st->list_ids += nl;
+				for (int i = 0; i < nl; ++i) {
+					int t = list_id(db, ids, i);
+					if (S->incl[t]) S->score[t] += resume_score(p, k, (j - 1) - S->ext[t]);
+					else { S->score[t] = k * p->M; S->incl[t] = 1; cand[++cand[0]] = t; }
+				}
+				acc[0] = acc[1] = acc[2] = acc[3] = 0;
+			} else {
+				orc_list(db, off, &nl, &ids);
+				if (st) st->list_fetches++, st->list_ids += nl;
+				for (int i = 0; i < nl; ++i) {
+					int t = list_id(db, ids, i);
+					S->score[t] = k * p->M; S->incl[t] = 1; cand[i + 1] = t;
+				}
+				cand[0] = nl;
+			}
+			last = off; last_pos = j; ++nhits;
+		}
+		s = e + 1;
+	}
+	if (last >= 0) {
+		int nl; const void *ids;
+		int sc = acc[0] * p->M + acc[1] * p->MM + acc[2] * p->U + acc[3] * p->W1;
+		orc_list(db, last, &nl, &ids);
+		for (int i = 0; i < nl; ++i) S->score[list_id(db, ids, i)] += sc;
+	}
+	/* arg-max set, first-seen order; scratch returned to zero (getBestMatch, savekmers.c:273) */
+	int best = 0, nb = 0;
+	for (int i = 1; i <= cand[0]; ++i) {
+		int t = cand[i], sc = S->score[t] < 0 ? 0 : S->score[t];
+		if (sc > best) { best = sc; nb = 1; cand[1] = t; }
+		else if (sc == best) cand[++nb] = t;
+		S->score[t] = 0; S->ext[t] = 0; S->incl[t] = 0;
+	}
+	cand[0] = nhits ? nb : 0;
+	return nhits ? best : 0;
+}
+
+/* ------------------------------------------------------------------ records ---------- */
+
+static size_t emit_record(uint8_t *out, const uint64_t *seq, int seqlen, const int32_t *N, int nN,
+                          int score, const int *tmpl, int ntmpl, const uint8_t *hdr, int hdrlen, int flag) {
+	int32_t h[7] = {seqlen, (seqlen + 31) >> 5, nN, score, ntmpl, hdrlen, flag};
+	uint8_t *o = out;
+	memcpy(o, h, 28); o += 28;
+	memcpy(o, seq, 8 * (size_t)h[1]); o += 8 * (size_t)h[1];
+	memcpy(o, N, 4 * (size_t)nN); o += 4 * (size_t)nN;
+	memcpy(o, tmpl, 4 * (size_t)ntmpl); o += 4 * (size_t)ntmpl;
+	memcpy(o, hdr, hdrlen); o += hdrlen;
+	return o - out;
+}
+
+/* Whole stage 2 for single-end records under -1t1: stage-1 stream in, stage-2 stream out
+ * (including the terminator). Returns bytes written, or -1 if `cap` is too small. */
+int64_t orc_seed_stream(const orc_db *db, const orc_params *p, const uint8_t *in, size_t in_bytes,
+                        uint8_t *out, size_t cap, orc_stats *st) {
+	const int k = db->kmersize;
+	scratch_t S = {calloc(db->DB_size + 1, sizeof(int)), calloc(db->DB_size + 1, sizeof(int)), calloc(db->DB_size + 1, 1)};
+	int *cf = malloc(sizeof(int) * (2 * (size_t)db->DB_size + 4)), *cr = malloc(sizeof(int) * (db->DB_size + 4));
+	size_t ip = 0, op = 0, rcap = 0;
+	uint64_t *seq = 0, *rseq = 0; int32_t *N = 0, *rN = 0;
+	int32_t nreads = 0;
+	int64_t ret = 0;
+
+	while (ip + 16 <= in_bytes) {
+		int32_t h[4]; memcpy(h, in + ip, 16); ip += 16;
+		int seqlen = h[0], words = h[1], nN = h[2], hdrlen = abs(h[3]);
+		if ((size_t)words + 2 > rcap) {
+			rcap = 2 * (size_t)words + 2;
+			seq = realloc(seq, 8 * rcap); rseq = realloc(rseq, 8 * rcap);
+		}
+		N = realloc(N, 4 * (size_t)(nN + 1)); rN = realloc(rN, 4 * (size_t)(nN + 1));
+		memcpy(seq, in + ip, 8 * (size_t)words); seq[words] = 0; ip += 8 * (size_t)words;
+		memcpy(N, in + ip, 4 * (size_t)nN); ip += 4 * (size_t)nN;
+		const uint8_t *hdr = in + ip; ip += hdrlen;
+		++nreads;
+		if (st) st->reads++, st->read_words += words;
+		if (seqlen < k) continue;
+
+		orc_revcomp(seq, seqlen, N, nN, rseq, rN); rseq[words] = 0;
+		int bf = scan_strand(db, p, seq, seqlen, N, nN, &S, cf, st);
+		int br = scan_strand(db, p, rseq, seqlen, rN, nN, &S, cr, st);
+		if ((bf > 0 || br > 0) && (k <= bf || k <= br)) {
+			size_t need = 28 + 8 * (size_t)words + 4 * (size_t)nN + 4 * (size_t)(cf[0] + cr[0]) + hdrlen;
+			if (op + need + 4 > cap) { ret = -1; goto done; }
+			if (bf > br) op += emit_record(out + op, seq, seqlen, N, nN, bf, cf + 1, cf[0], hdr, hdrlen, 0);
+			else if (bf < br) op += emit_record(out + op, rseq, seqlen, rN, nN, br, cr + 1, cr[0], hdr, hdrlen, 16);
+			else {
+				for (int i = 1; i <= cr[0]; ++i) cf[++cf[0]] = -cr[i];
+				op += emit_record(out + op, seq, seqlen, N, nN, -bf, cf + 1, cf[0], hdr, hdrlen, 0);
+			}
+			if (st) st->mapped++;
+		}
+	}
+	if (op + 4 > cap) { ret = -1; goto done; }
+	nreads = -nreads; memcpy(out + op, &nreads, 4); op += 4;
+	ret = (int64_t)op;
+done:
+	free(S.score); free(S.ext); free(S.incl); free(cf); free(cr); free(seq); free(rseq); free(N); free(rN);
+	return ret;
+}
+
+/* default CLI scoring (kma.c:327-336, 1308-1328): M=1, MM=-2, U=-1, W1=-3, Wl=-6, Mn=0, PE=7 */
+void orc_default_params(orc_params *p) {
+	memset(p, 0, sizeof(*p));
+	p->M = 1; p->MM = -2; p->U = -1; p->W1 = -3; p->Wl = -6; p->Mn = 0; p->PE = 7;
+	for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) p->d[i * 5 + j] = i == j ? 1 : -2;
+	for (int i = 0; i < 5; ++i) p->d[4 * 5 + i] = p->d[i * 5 + 4] = 0;
+}
