@@ -1,0 +1,150 @@
+"""ctypes binding of libkmagpu.so (include/kmagpu.h) -- the host-side mirror of the reference's
+stage drivers. Names follow the reference: `save_kmers_batch` (kmers.c:51) is stage 2.
+
+There is no CPU fallback: if the CUDA library is missing or no device is present every compute
+call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkmagpu.so")
+
+
+class KmaGpuError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("M", C.c_int32), ("MM", C.c_int32), ("U", C.c_int32), ("W1", C.c_int32), ("Wl", C.c_int32),
+                ("Mn", C.c_int32), ("PE", C.c_int32), ("d", C.c_int32 * 25), ("exhaustive", C.c_int32),
+                ("mq", C.c_int32), ("one2one", C.c_int32), ("reserved", C.c_int32 * 5),
+                ("scoreT", C.c_double), ("minFrac", C.c_double)]
+
+
+class DbInfo(C.Structure):
+    _fields_ = [("DB_size", C.c_int32), ("kmersize", C.c_int32), ("kmerindex", C.c_int32), ("mega", C.c_int32),
+                ("size", C.c_uint64), ("n", C.c_uint64), ("v_index", C.c_uint64), ("device_bytes", C.c_uint64),
+                ("seq_bases", C.c_uint64)]
+
+
+class SeedStats(C.Structure):
+    _fields_ = [("reads", C.c_int64), ("mapped", C.c_int64), ("read_words", C.c_int64), ("lookups", C.c_int64),
+                ("hits", C.c_int64), ("list_fetches", C.c_int64), ("list_ids", C.c_int64),
+                ("overflow_reads", C.c_int64), ("ms_seed", C.c_float), ("ms_emit", C.c_float),
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("launches", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+_lib = None
+
+
+def lib():
+    """Load libkmagpu.so (built in-tree by __graft_entry__.build()). Fails loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KmaGpuError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        L.kmagpu_last_error.restype = C.c_char_p
+        L.kmagpu_db_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.kmagpu_db_close.argtypes = [C.c_void_p]
+        L.kmagpu_db_close.restype = None
+        L.kmagpu_db_get_info.argtypes = [C.c_void_p, C.POINTER(DbInfo)]
+        L.kmagpu_default_params.argtypes = [C.POINTER(Params)]
+        L.kmagpu_default_params.restype = None
+        L.kmagpu_seed_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                        C.POINTER(C.c_size_t), C.POINTER(C.c_int64), C.POINTER(SeedStats)]
+        L.kmagpu_seed_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]
+        L.kmagpu_seed_run.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(SeedStats)]
+        L.kmagpu_seed_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.kmagpu_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise KmaGpuError(lib().kmagpu_last_error().decode(errors="replace"))
+
+
+def default_params() -> Params:
+    p = Params()
+    lib().kmagpu_default_params(C.byref(p))
+    return p
+
+
+def _ptr(a):
+    """address of a numpy array or torch tensor's storage"""
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+class TemplateDB:
+    """HBM-resident template database (hashMapKMA_load + .length.b/.seq.b of runKMA)."""
+
+    def __init__(self, prefix: str, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().kmagpu_db_open(os.fsencode(prefix), device, C.byref(self._h)))
+        self.info = DbInfo()
+        _check(lib().kmagpu_db_get_info(self._h, C.byref(self.info)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().kmagpu_db_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- stage 2 -----------------------------------------------------------------------------
+    def save_kmers_batch(self, stage1, params: Params | None = None, out=None):
+        """stage-1 records (uint8 array / pinned tensor) -> (stage-2 bytes incl. no terminator, nreads, stats)"""
+        p = params or default_params()
+        nbytes = int(stage1.numel() if hasattr(stage1, "numel") else stage1.size)
+        if out is None:
+            out = np.empty(2 * nbytes + 4096, dtype=np.uint8)
+        cap = int(out.numel() if hasattr(out, "numel") else out.size)
+        ob, nr, st = C.c_size_t(), C.c_int64(), SeedStats()
+        _check(lib().kmagpu_seed_batch(self._h, C.byref(p), _ptr(stage1), nbytes, _ptr(out), cap,
+                                       C.byref(ob), C.byref(nr), C.byref(st)))
+        return out[: ob.value], nr.value, st
+
+    def seed_upload(self, stage1):
+        nbytes = int(stage1.numel() if hasattr(stage1, "numel") else stage1.size)
+        nr = C.c_int64()
+        _check(lib().kmagpu_seed_upload(self._h, _ptr(stage1), nbytes, C.byref(nr)))
+        return nr.value
+
+    def seed_run(self, params: Params | None = None):
+        p = params or default_params()
+        st = SeedStats()
+        _check(lib().kmagpu_seed_run(self._h, C.byref(p), C.byref(st)))
+        return st
+
+    def seed_download(self, out):
+        cap = int(out.numel() if hasattr(out, "numel") else out.size)
+        ob = C.c_size_t()
+        _check(lib().kmagpu_seed_download(self._h, _ptr(out), cap, C.byref(ob)))
+        return out[: ob.value]
+
+    def lookup(self, kmers: np.ndarray) -> np.ndarray:
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+        out = np.empty(len(kmers), dtype=np.int64)
+        _check(lib().kmagpu_lookup_batch(self._h, kmers.ctypes.data, len(kmers), out.ctypes.data))
+        return out
+
+
+def stream_terminator(nreads: int) -> bytes:
+    """kmers.c:257 -- int32 -(number of reads consumed) ends the stage-2 stream"""
+    return np.array([-nreads], dtype=np.int32).tobytes()

@@ -1,0 +1,74 @@
+// Internal declarations shared by the translation units of libkmagpu.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+#include <vector>
+#include "../../include/kmagpu.h"
+
+void kmagpu_set_error(const char *fmt, ...);
+
+#define KG_CUDA(call)                                                                              \
+	do {                                                                                           \
+		cudaError_t e__ = (call);                                                                  \
+		if (e__ != cudaSuccess) {                                                                  \
+			kmagpu_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+			return -1;                                                                             \
+		}                                                                                          \
+	} while (0)
+
+// Device view of the template k-mer hash (.comp.b re-laid for one-sector lookups).
+struct KgHashView {
+	const uint32_t *exist;   // [size]   bucket -> first slot in kv, or null_index   (mega: value offset, 1 = null)
+	const uint2 *kv;         // [n + 1]  {key, value offset}: key_index and value_index fused (8 B, one sector)
+	const uint16_t *values_s;  // template lists, u16 when DB_size < 65535 ...
+	const uint32_t *values_w;  // ... else u32
+	uint64_t hmask;          // size - 1
+	uint32_t null_index;
+	uint32_t n;
+	int32_t kmersize;
+	int32_t DB_size;
+	int32_t mega;
+};
+
+// growable device / pinned buffers
+struct KgBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	bool pinned = false;
+	int reserve(size_t bytes);
+	void release();
+};
+
+struct SeedBatch {
+	KgBuf d_in, d_off, d_res, d_pool, d_recoff, d_out, d_ctr, d_partial, d_dense;
+	KgBuf h_off;                 // pinned staging of record offsets
+	KgBuf h_in, h_out;           // pinned staging of the streams
+	int64_t nreads = 0;
+	size_t in_bytes = 0;
+	size_t out_bytes = 0;
+	size_t pool_cap = 0;         // ints
+	bool ran = false;
+};
+
+struct kmagpu_db {
+	int device = 0;
+	kmagpu_db_info info{};
+	KgHashView hv{};
+	void *d_exist = nullptr, *d_kv = nullptr, *d_values = nullptr;
+	// alignment side (.length.b / .seq.b)
+	std::vector<int32_t> lengths;      // [DB_size], lengths[0] = kmerindex
+	std::vector<int64_t> seq_off;      // [DB_size] word offset of template t
+	uint64_t *d_seq = nullptr;         // all of .seq.b
+	int32_t *d_lengths = nullptr;
+	int64_t *d_seq_off = nullptr;
+	size_t seq_words = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[8]{};
+	int sm_count = 148;
+	SeedBatch seed;
+};
+
+int kg_seed_free(kmagpu_db *db);

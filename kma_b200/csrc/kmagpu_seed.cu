@@ -1,0 +1,758 @@
+// Stage-2 of KMA on the GPU: k-mer seeding + template candidate scoring (-1t1, single end).
+//
+// What is computed is save_kmers (savekmers.c:2442-3065) for every read of a batch of stage-1
+// records; how it is computed is not the reference's:
+//   * one warp per read, reads pulled from an atomic work counter by a persistent grid;
+//   * phase 1 (gather): the 32 lanes look up 256 consecutive k-mer positions of a strand at once
+//     (8 independent probes in flight per lane) against the HBM/L2-resident fused hash
+//     {exist -> (key, value offset)}; the reverse strand is never materialised -- its k-mers are
+//     the bit-reversed complements of the forward ones;
+//   * phase 2 (score): the warp walks the hit positions found by ballot; hits on the same
+//     template list collapse into a run score, a list change is handled by all lanes at once
+//     (one lane per template of the list) against a per-warp shared-memory hash of the
+//     templates seen by this read (insertion order kept with ballot/popc ranks);
+//   * reads that see more distinct templates than the shared table holds are re-run by the same
+//     code over a dense per-warp scratch in global memory (exactly the reference's Score[] /
+//     extendScore[] / include[] arrays), so the result never depends on the table size;
+//   * record sizes are prefix-summed on the device and a writer kernel emits the stage-2 byte
+//     stream (ankers.c:30-50) in input order, so the host does no per-read work.
+#include "kmagpu_internal.h"
+#include <string.h>
+#include <algorithm>
+
+#define KG_CHUNK 256          // k-mer positions gathered per phase-1 round (8 per lane)
+#define KG_PER_LANE (KG_CHUNK / 32)
+#define KG_CAP 256            // shared hash slots per warp
+#define KG_CAP_LOG 8
+#define KG_FILL 192           // distinct templates a read may see before it goes to the dense path
+#define KG_WARPS 4            // warps per CTA
+#define KG_WORDS 12           // staged u64 words per chunk: (256 + 31 + 31) / 32 + 2
+#define KG_MISS 0xFFFFFFFFu
+
+struct SeedRes { int32_t score, ntmpl, flag; uint32_t pool_off; };
+
+struct SeedParams {
+	int32_t M, MM, U, W1, exhaustive;
+};
+
+// counters living in d_ctr (uint64 slots)
+enum { C_WORK = 0, C_POOL = 1, C_OVF = 2, C_WORK2 = 3, C_POOLFAIL = 4, C_LOOKUPS = 5, C_HITS = 6, C_LISTS = 7,
+       C_LISTIDS = 8, C_MAPPED = 9, C_WORDS = 10, C_TOTAL = 11, C_N = 16 };
+
+// ---------------------------------------------------------------- small device helpers
+
+__device__ __forceinline__ uint32_t ld_u32u(const uint8_t *p) {  // unaligned little-endian load
+	uintptr_t a = (uintptr_t)p;
+	const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+	unsigned sh = (unsigned)(a & 3) * 8;
+	uint32_t lo = __ldg(q);
+	if (sh == 0) return lo;
+	return __funnelshift_r(lo, __ldg(q + 1), sh);
+}
+__device__ __forceinline__ uint64_t ld_u64u(const uint8_t *p) {
+	return (uint64_t)ld_u32u(p) | ((uint64_t)ld_u32u(p + 4) << 32);
+}
+
+// reverse the order of the 32 two-bit symbols of w
+__device__ __forceinline__ uint64_t rev2(uint64_t w) {
+	w = __brevll(w);
+	return ((w >> 1) & 0x5555555555555555ull) | ((w & 0x5555555555555555ull) << 1);
+}
+
+__device__ __forceinline__ uint32_t hash_lookup(const KgHashView &hv, uint64_t key) {
+	if (hv.mega) {
+		uint32_t v = __ldg(hv.exist + key);
+		return v != 1u ? v : KG_MISS;
+	}
+	const uint32_t bucket = (uint32_t)(key & hv.hmask);
+	uint32_t pos = __ldg(hv.exist + bucket);
+	if (pos == hv.null_index) return KG_MISS;
+	uint2 e = __ldg(hv.kv + pos);
+	while (e.x != (uint32_t)key) {
+		if ((e.x & (uint32_t)hv.hmask) != bucket || pos >= hv.n) return KG_MISS;
+		e = __ldg(hv.kv + ++pos);
+	}
+	return e.y;
+}
+
+__device__ __forceinline__ int list_len(const KgHashView &hv, uint32_t off) {
+	return hv.values_s ? (int)__ldg(hv.values_s + off) : (int)__ldg(hv.values_w + off);
+}
+__device__ __forceinline__ int list_id(const KgHashView &hv, uint32_t off, int i) {
+	return hv.values_s ? (int)__ldg(hv.values_s + off + 1 + i) : (int)__ldg(hv.values_w + off + 1 + i);
+}
+
+// score of a hit that resumes template bookkeeping after `gaps` missed k-mer positions.
+// run == true : contribution to the run score of an unchanged template list (savekmers.c:2529-2569)
+// run == false: direct per-template score after a list change            (savekmers.c:2592-2625)
+__device__ __forceinline__ int gap_score(const SeedParams &p, int k, int gaps, bool run) {
+	if (gaps == 0) return p.M;
+	if (gaps == k) return k * p.M + p.MM;
+	if (k < gaps) {
+		int g = gaps - (k - 1), mm, m;
+		if (g <= 2) { mm = g; m = 0; }
+		else {
+			mm = g / k + (g % k ? 1 : 0); mm = max(mm, 2);
+			m = min(min(g - mm, k), mm);
+		}
+		int a = p.W1 + (g - 1) * p.U, b = mm * p.MM + m * p.M;
+		return k * p.M + (a <= b ? b : a);
+	}
+	return gaps * p.M + (k - gaps) * p.U + p.W1;
+}
+
+// ---------------------------------------------------------------- per-read context
+
+struct ReadCtx {
+	const uint8_t *rec;   // stage-1 record
+	const uint8_t *seq;   // packed words (unaligned)
+	const uint8_t *N;     // int32 list (unaligned)
+	int seqlen, words, nN, hdrlen;
+};
+
+// i-th N position in strand coordinates (reverse strand mirrors the list, compdna.c:249-254)
+__device__ __forceinline__ int n_at(const ReadCtx &rc, int i, int strand) {
+	return strand ? rc.seqlen - 1 - (int)ld_u32u(rc.N + 4 * (rc.nN - 1 - i)) : (int)ld_u32u(rc.N + 4 * i);
+}
+
+// validity of k-mer position j (strand coords) and start of its N-free stretch
+__device__ __forceinline__ bool pos_valid(const ReadCtx &rc, int j, int k, int strand, int *segstart) {
+	*segstart = 0;
+	if (j + k > rc.seqlen) return false;
+	if (rc.nN == 0) return true;
+	int lo = 0, hi = rc.nN;   // first N >= j
+	while (lo < hi) {
+		int mid = (lo + hi) >> 1;
+		if (n_at(rc, mid, strand) < j) lo = mid + 1; else hi = mid;
+	}
+	if (lo > 0) *segstart = n_at(rc, lo - 1, strand) + 1;
+	return lo == rc.nN || n_at(rc, lo, strand) > j + k - 1;
+}
+
+// forward-strand k-mer at forward position pos from the staged words (window starts at word w0)
+__device__ __forceinline__ uint64_t kmer_from(const uint64_t *sw, int w0, int pos, int k) {
+	int w = (pos >> 5) - w0, b = (pos & 31) << 1, sh = 64 - 2 * k;
+	uint64_t x = sw[w] << b;
+	if (b > sh) x |= sw[w + 1] >> (64 - b);
+	return x >> sh;
+}
+
+// ---------------------------------------------------------------- template bookkeeping
+
+template <bool DENSE>
+struct Store {
+	// hash mode: shared memory; dense mode: per-warp global scratch indexed by template id
+	int *keys, *score, *ext;   // hash: [KG_CAP]; dense: keys unused, score/ext [DB_size + 1]
+	uint8_t *incl;             // dense only
+	int *cand;                 // first-seen order: hash -> slot, dense -> template id
+	int ncand;
+
+	__device__ __forceinline__ int find(int t) const {
+		if (DENSE) return t;
+		unsigned h = ((unsigned)t * 0x9E3779B1u) >> (32 - KG_CAP_LOG);
+		while (keys[h] != t) h = (h + 1) & (KG_CAP - 1);
+		return (int)h;
+	}
+	__device__ __forceinline__ int find_or_insert(int t, bool *isnew) {
+		if (DENSE) { *isnew = !incl[t]; incl[t] = 1; return t; }
+		unsigned h = ((unsigned)t * 0x9E3779B1u) >> (32 - KG_CAP_LOG);
+		for (;;) {
+			int cur = keys[h];
+			if (cur == t) { *isnew = false; return (int)h; }
+			if (cur == 0) {
+				int old = atomicCAS(&keys[h], 0, t);
+				if (old == 0) { *isnew = true; return (int)h; }
+				if (old == t) { *isnew = false; return (int)h; }
+			}
+			h = (h + 1) & (KG_CAP - 1);
+		}
+	}
+	__device__ __forceinline__ int tmpl_of(int slot) const { return DENSE ? slot : keys[slot]; }
+};
+
+struct WarpStats { unsigned lookups, hits, lists, listids; };
+
+// One strand of one read. Returns best score (>= 0), leaves the arg-max template ids in
+// st.cand[0 .. *nbest) (first-seen order) and the store clean. Returns -1 on table overflow
+// (hash mode only; store is left clean).
+template <bool DENSE>
+__device__ int scan_strand(const KgHashView &hv, const SeedParams &p, const ReadCtx &rc, int strand,
+                           Store<DENSE> &st, uint32_t *hits, uint64_t *sw, int *nbest, WarpStats &ws) {
+	const unsigned lane = threadIdx.x & 31;
+	const int k = hv.kmersize;
+	const int L = rc.seqlen;
+	const int npos = L - k + 1;   // k-mer positions on the strand
+	st.ncand = 0;
+	*nbest = 0;
+
+	// stage the forward words a strand chunk [c0, c0 + KG_CHUNK) needs; returns first staged word
+	auto stage = [&](int c0) -> int {
+		int flo, fhi;   // forward base range touched
+		if (strand == 0) { flo = c0; fhi = min(L, c0 + KG_CHUNK + k - 1) - 1; }
+		else { fhi = L - 1 - c0; flo = max(0, L - k - (c0 + KG_CHUNK - 1)); }
+		int w0 = flo >> 5, w1 = fhi >> 5;
+		__syncwarp();
+		for (int w = w0 + (int)lane; w <= w1 + 1; w += 32)
+			sw[w - w0] = w < rc.words ? ld_u64u(rc.seq + 8 * (size_t)w) : 0ull;
+		__syncwarp();
+		return w0;
+	};
+	auto kmer_of = [&](int w0, int j) -> uint64_t {   // k-mer at strand position j
+		if (strand == 0) return kmer_from(sw, w0, j, k);
+		uint64_t f = kmer_from(sw, w0, L - k - j, k);
+		return rev2(~f) >> (64 - 2 * k);
+	};
+
+	// ---- quick check (savekmers.c:2485-2495): every k-th k-mer of each N-free stretch
+	bool any = p.exhaustive != 0;
+	if (!any) {
+		for (int c0 = 0; c0 < npos && !any; c0 += KG_CHUNK) {
+			int w0 = stage(c0);
+			bool h = false;
+			if (rc.nN == 0) {
+				// probes c0' = multiples of k inside the chunk
+				int first = ((c0 + k - 1) / k) * k;
+				for (int j = first + (int)lane * k; j < min(npos, c0 + KG_CHUNK); j += 32 * k) {
+					h |= hash_lookup(hv, kmer_of(w0, j)) != KG_MISS;
+					ws.lookups++;
+				}
+			} else {
+				for (int j = c0 + (int)lane; j < min(npos, c0 + KG_CHUNK); j += 32) {
+					int ss;
+					if (pos_valid(rc, j, k, strand, &ss) && (j - ss) % k == 0) {
+						h |= hash_lookup(hv, kmer_of(w0, j)) != KG_MISS;
+						ws.lookups++;
+					}
+				}
+			}
+			any = __any_sync(0xffffffffu, h);
+		}
+		if (!any) return 0;
+	}
+
+	// ---- exhaustive scan (savekmers.c:2511-2706)
+	uint32_t last = KG_MISS;
+	int last_pos = 0, run_sc = 0, nhits = 0;
+	bool overflow = false;
+	for (int c0 = 0; c0 < npos && !overflow; c0 += KG_CHUNK) {
+		int w0 = stage(c0);
+		// phase 1: gather. two rounds so that 8 independent probes per lane are in flight.
+		uint32_t e1[KG_PER_LANE];
+		uint64_t km[KG_PER_LANE];
+#pragma unroll
+		for (int u = 0; u < KG_PER_LANE; ++u) {
+			int j = c0 + u * 32 + (int)lane, ss;
+			bool ok = j < npos && (rc.nN == 0 || pos_valid(rc, j, k, strand, &ss));
+			km[u] = ok ? kmer_of(w0, j) : 0ull;
+			e1[u] = KG_MISS;
+			if (ok) {
+				if (hv.mega) { uint32_t v = __ldg(hv.exist + km[u]); e1[u] = v != 1u ? v : KG_MISS; }
+				else { uint32_t q = __ldg(hv.exist + (uint32_t)(km[u] & hv.hmask)); e1[u] = q != hv.null_index ? q : KG_MISS; }
+				ws.lookups++;
+			}
+		}
+		if (!hv.mega) {
+			uint2 e2[KG_PER_LANE];
+#pragma unroll
+			for (int u = 0; u < KG_PER_LANE; ++u)
+				e2[u] = e1[u] != KG_MISS ? __ldg(hv.kv + e1[u]) : make_uint2(0, 0);
+#pragma unroll
+			for (int u = 0; u < KG_PER_LANE; ++u) {
+				if (e1[u] == KG_MISS) continue;
+				uint32_t key = (uint32_t)km[u], bucket = key & (uint32_t)hv.hmask, pos = e1[u];
+				uint2 e = e2[u];
+				uint32_t v = KG_MISS;
+				for (;;) {
+					if (e.x == key) { v = e.y; break; }
+					if ((e.x & (uint32_t)hv.hmask) != bucket || pos >= hv.n) break;
+					e = __ldg(hv.kv + ++pos);
+				}
+				e1[u] = v;
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < KG_PER_LANE; ++u) hits[u * 32 + lane] = e1[u];
+		__syncwarp();
+
+		// phase 2: walk the hits of this chunk in position order
+		for (int u = 0; u < KG_PER_LANE && !overflow; ++u) {
+			unsigned hm = __ballot_sync(0xffffffffu, hits[u * 32 + lane] != KG_MISS);
+			nhits += __popc(hm);
+			while (hm) {
+				int b = __ffs(hm) - 1;
+				hm &= hm - 1;
+				const int j = c0 + u * 32 + b;
+				const uint32_t off = hits[u * 32 + b];
+				if (off == last) {
+					run_sc += gap_score(p, k, j - last_pos - 1, true);
+				} else {
+					int nl = list_len(hv, off);
+					if (!DENSE && st.ncand + nl > KG_FILL) { overflow = true; break; }
+					if (last != KG_MISS) {
+						// flush the run of the previous list (savekmers.c:2575-2582)
+						int pl = list_len(hv, last);
+						for (int i = lane; i < pl; i += 32) {
+							int s = st.find(list_id(hv, last, i));
+							st.score[s] += run_sc;
+							st.ext[s] = last_pos;
+						}
+						__syncwarp();
+					}
+					ws.lists++; ws.listids += lane == 0 ? nl : 0;
+					// score / admit the templates of the new list (savekmers.c:2583-2655, 2682-2688)
+					for (int base = 0; base < nl; base += 32) {
+						int i = base + (int)lane;
+						bool isnew = false;
+						int s = 0;
+						if (i < nl) {
+							s = st.find_or_insert(list_id(hv, off, i), &isnew);
+							if (isnew) st.score[s] = k * p.M;
+							else st.score[s] += gap_score(p, k, (j - 1) - st.ext[s], false);
+						}
+						unsigned nm = __ballot_sync(0xffffffffu, isnew);
+						if (isnew) st.cand[st.ncand + __popc(nm & ((1u << lane) - 1))] = s;
+						st.ncand += __popc(nm);
+					}
+					__syncwarp();
+					run_sc = 0;
+				}
+				last = off;
+				last_pos = j;
+			}
+		}
+		__syncwarp();
+	}
+	ws.hits += lane == 0 ? nhits : 0;
+
+	if (overflow) {   // hash mode only: wipe and report
+		for (int i = lane; i < KG_CAP; i += 32) st.keys[i] = 0;
+		__syncwarp();
+		return -1;
+	}
+
+	if (last != KG_MISS) {   // final flush (savekmers.c:2707-2722)
+		int pl = list_len(hv, last);
+		for (int i = lane; i < pl; i += 32) st.score[st.find(list_id(hv, last, i))] += run_sc;
+		__syncwarp();
+	}
+
+	// arg-max set in first-seen order (getBestMatch, savekmers.c:273-294), negatives clamp to 0
+	int best = 0;
+	for (int i = lane; i < st.ncand; i += 32) best = max(best, st.score[st.cand[i]]);
+#pragma unroll
+	for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+	int nb = 0;
+	for (int base = 0; base < st.ncand; base += 32) {
+		int i = base + (int)lane;
+		bool ok = false;
+		int t = 0;
+		if (i < st.ncand) {
+			int s = st.cand[i];
+			ok = max(st.score[s], 0) == best;
+			t = st.tmpl_of(s);
+			if (DENSE) { st.score[s] = 0; st.ext[s] = 0; st.incl[s] = 0; }
+		}
+		unsigned m = __ballot_sync(0xffffffffu, ok);
+		__syncwarp();
+		if (ok) st.cand[nb + __popc(m & ((1u << lane) - 1))] = t;
+		nb += __popc(m);
+		__syncwarp();
+	}
+	if (!DENSE) {
+		for (int i = lane; i < KG_CAP; i += 32) st.keys[i] = 0;
+		__syncwarp();
+	}
+	*nbest = nhits ? nb : 0;
+	return nhits ? best : 0;
+}
+
+// ---------------------------------------------------------------- the seeding kernel
+
+template <bool DENSE>
+__global__ void __launch_bounds__(KG_WARPS * 32)
+seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, const uint32_t *__restrict__ rec_off,
+               int nreads, SeedRes *__restrict__ res, uint32_t *__restrict__ recsize, int32_t *__restrict__ pool,
+               unsigned long long pool_cap, unsigned long long *ctr, uint32_t *__restrict__ ovf_list,
+               uint8_t *dense_scratch, size_t dense_stride) {
+	__shared__ uint32_t s_hits[KG_WARPS][KG_CHUNK];
+	__shared__ uint64_t s_words[KG_WARPS][KG_WORDS];
+	__shared__ int s_tab[DENSE ? 1 : KG_WARPS][DENSE ? 1 : 3 * KG_CAP];
+	__shared__ int s_cand[DENSE ? 1 : KG_WARPS][DENSE ? 1 : 2 * KG_CAP];
+
+	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint32_t *hits = s_hits[wid];
+	uint64_t *sw = s_words[wid];
+	Store<DENSE> st;
+	int *candF, *candR;
+	if (DENSE) {
+		uint8_t *base = dense_scratch + dense_stride * ((size_t)blockIdx.x * KG_WARPS + wid);
+		const size_t D = (size_t)hv.DB_size + 1;
+		st.score = (int *)base; st.ext = st.score + D; candF = st.ext + D; candR = candF + D;
+		st.incl = (uint8_t *)(candR + D); st.keys = nullptr;
+	} else {
+		st.keys = s_tab[wid]; st.score = st.keys + KG_CAP; st.ext = st.score + KG_CAP; st.incl = nullptr;
+		candF = s_cand[wid]; candR = candF + KG_CAP;
+		for (int i = lane; i < KG_CAP; i += 32) st.keys[i] = 0;
+		__syncwarp();
+	}
+	WarpStats ws = {0, 0, 0, 0};
+	unsigned mapped = 0, words_seen = 0;
+	const int k = hv.kmersize;
+	const int total = DENSE ? (int)ctr[C_OVF] : nreads;
+
+	for (;;) {
+		unsigned long long w = 0;
+		if (lane == 0) w = atomicAdd(&ctr[DENSE ? C_WORK2 : C_WORK], 1ull);
+		w = __shfl_sync(0xffffffffu, w, 0);
+		if (w >= (unsigned long long)total) break;
+		const int r = DENSE ? (int)ovf_list[w] : (int)w;
+
+		ReadCtx rc;
+		rc.rec = in + rec_off[r];
+		rc.seqlen = (int)ld_u32u(rc.rec);
+		rc.words = (int)ld_u32u(rc.rec + 4);
+		rc.nN = (int)ld_u32u(rc.rec + 8);
+		rc.hdrlen = abs((int)ld_u32u(rc.rec + 12));
+		rc.seq = rc.rec + 16;
+		rc.N = rc.seq + 8 * (size_t)rc.words;
+		words_seen += rc.words;
+
+		SeedRes out = {0, 0, 0, 0};
+		uint32_t size = 0;
+		if (rc.seqlen >= k) {
+			int nf = 0, nr = 0;
+			st.cand = candF;
+			int bf = scan_strand<DENSE>(hv, p, rc, 0, st, hits, sw, &nf, ws);
+			int br = -1;
+			if (bf >= 0) { st.cand = candR; br = scan_strand<DENSE>(hv, p, rc, 1, st, hits, sw, &nr, ws); }
+			if (bf < 0 || br < 0) {   // table overflow: hand the read to the dense pass
+				if (lane == 0) ovf_list[atomicAdd(&ctr[C_OVF], 1ull)] = (uint32_t)r;
+				out.flag = -1;
+			} else if ((bf > 0 || br > 0) && (k <= bf || k <= br)) {   // savekmers.c:3039-3061
+				int nt = bf > br ? nf : (bf < br ? nr : nf + nr);
+				unsigned long long po = 0;
+				if (lane == 0) po = atomicAdd(&ctr[C_POOL], (unsigned long long)nt);
+				po = __shfl_sync(0xffffffffu, po, 0);
+				if (po + nt > pool_cap) {
+					if (lane == 0) atomicAdd(&ctr[C_POOLFAIL], 1ull);
+				} else {
+					int32_t *dst = pool + po;
+					if (bf >= br) for (int i = lane; i < nf; i += 32) dst[i] = candF[i];
+					if (bf < br) for (int i = lane; i < nr; i += 32) dst[i] = candR[i];
+					if (bf == br) for (int i = lane; i < nr; i += 32) dst[nf + i] = -candR[i];
+				}
+				out.score = bf > br ? bf : (bf < br ? br : -bf);
+				out.ntmpl = nt;
+				out.flag = bf < br ? 16 : 0;
+				out.pool_off = (uint32_t)po;
+				size = 28u + 8u * rc.words + 4u * rc.nN + 4u * nt + rc.hdrlen;
+				++mapped;
+			}
+		}
+		if (lane == 0) { res[r] = out; recsize[r] = size; }
+		__syncwarp();
+	}
+	// per-warp statistics -> global
+	for (int o = 16; o; o >>= 1) ws.lookups += __shfl_xor_sync(0xffffffffu, ws.lookups, o);
+	if (lane == 0) {
+		atomicAdd(&ctr[C_LOOKUPS], (unsigned long long)ws.lookups);
+		atomicAdd(&ctr[C_HITS], (unsigned long long)ws.hits);
+		atomicAdd(&ctr[C_LISTS], (unsigned long long)ws.lists);
+		atomicAdd(&ctr[C_LISTIDS], (unsigned long long)ws.listids);
+		atomicAdd(&ctr[C_MAPPED], (unsigned long long)mapped);
+		if (!DENSE) atomicAdd(&ctr[C_WORDS], (unsigned long long)words_seen);
+	}
+}
+
+// ---------------------------------------------------------------- exclusive scan of record sizes
+
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t *total) {
+	__shared__ uint32_t wsum[SCAN_THREADS / 32];
+	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint32_t x = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+	if (lane == 31) wsum[wid] = x;
+	__syncthreads();
+	if (wid == 0) {
+		uint32_t s = lane < SCAN_THREADS / 32 ? wsum[lane] : 0;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+		if (lane < SCAN_THREADS / 32) wsum[lane] = s;
+	}
+	__syncthreads();
+	uint32_t prev = wid ? wsum[wid - 1] : 0;
+	*total = wsum[SCAN_THREADS / 32 - 1];
+	__syncthreads();
+	return prev + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const uint32_t *size, int n, uint32_t *off, uint32_t *partial) {
+	const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+	uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = base + i < n ? size[base + i] : 0; s += v[i]; }
+	uint32_t tot, ex = block_exscan(s, &tot);
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) off[base + i] = ex; ex += v[i]; }
+	if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_partials_kernel(uint32_t *partial, int nb, unsigned long long *ctr) {
+	uint32_t carry = 0;
+	for (int base = 0; base < nb; base += SCAN_THREADS) {
+		int i = base + threadIdx.x;
+		uint32_t v = i < nb ? partial[i] : 0, tot;
+		uint32_t ex = block_exscan(v, &tot);
+		if (i < nb) partial[i] = carry + ex;
+		carry += tot;
+	}
+	if (threadIdx.x == 0) ctr[C_TOTAL] = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t *off, int n, const uint32_t *partial) {
+	const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+	const uint32_t add = partial[blockIdx.x];
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) if (base + i < n) off[base + i] += add;
+}
+
+// ---------------------------------------------------------------- stage-2 record writer
+
+__device__ __forceinline__ void st_u32b(uint8_t *p, uint32_t v) {   // unaligned store
+	p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+}
+
+// 32 bases of the forward read starting at base position pos (pos may be negative / past the end)
+__device__ __forceinline__ uint64_t fwd32(const uint8_t *seq, int words, int pos) {
+	if (pos <= -32) return 0;
+	if (pos < 0) return (words > 0 ? ld_u64u(seq) : 0ull) >> (2 * -pos);
+	int w = pos >> 5, b = (pos & 31) << 1;
+	uint64_t x = w < words ? ld_u64u(seq + 8 * (size_t)w) << b : 0ull;
+	if (b && w + 1 < words) x |= ld_u64u(seq + 8 * (size_t)(w + 1)) >> (64 - b);
+	return x;
+}
+
+// one warp per mapped read: header, sequence (forward copy or reverse complement, compdna.c:228),
+// N list, template list, name bytes (ankers.c:30-50)
+__global__ void __launch_bounds__(256) emit_records_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ rec_off,
+		int nreads, const SeedRes *__restrict__ res, const uint32_t *__restrict__ out_off, const int32_t *__restrict__ pool,
+		uint8_t *__restrict__ out) {
+	const unsigned lane = threadIdx.x & 31;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nreads; r += warps) {
+		const SeedRes rs = res[r];
+		if (rs.score == 0) continue;
+		const uint8_t *rec = in + rec_off[r];
+		const int seqlen = (int)ld_u32u(rec), words = (int)ld_u32u(rec + 4), nN = (int)ld_u32u(rec + 8);
+		const int hdrlen = abs((int)ld_u32u(rec + 12));
+		const uint8_t *seq = rec + 16, *N = seq + 8 * (size_t)words, *hdr = N + 4 * (size_t)nN;
+		uint8_t *o = out + out_off[r];
+		const bool rev = rs.flag & 16;
+		if (lane < 7) {
+			int32_t h = lane == 0 ? seqlen : lane == 1 ? words : lane == 2 ? nN : lane == 3 ? rs.score
+			          : lane == 4 ? rs.ntmpl : lane == 5 ? hdrlen : rs.flag;
+			st_u32b(o + 4 * lane, (uint32_t)h);
+		}
+		o += 28;
+		for (int w = lane; w < words; w += 32) {
+			uint64_t x;
+			if (!rev) x = ld_u64u(seq + 8 * (size_t)w);
+			else {
+				x = rev2(~fwd32(seq, words, seqlen - 32 * (w + 1)));
+				int c = seqlen - 32 * w;   // valid bases in this word
+				if (c < 32) x &= ~0ull << (64 - 2 * c);
+			}
+			st_u32b(o + 8 * (size_t)w, (uint32_t)x);
+			st_u32b(o + 8 * (size_t)w + 4, (uint32_t)(x >> 32));
+		}
+		o += 8 * (size_t)words;
+		for (int i = lane; i < nN; i += 32) {
+			uint32_t v = rev ? (uint32_t)(seqlen - 1 - (int)ld_u32u(N + 4 * (size_t)(nN - 1 - i))) : ld_u32u(N + 4 * (size_t)i);
+			st_u32b(o + 4 * (size_t)i, v);
+		}
+		o += 4 * (size_t)nN;
+		for (int i = lane; i < rs.ntmpl; i += 32) st_u32b(o + 4 * (size_t)i, (uint32_t)pool[rs.pool_off + i]);
+		o += 4 * (size_t)rs.ntmpl;
+		for (int i = lane; i < hdrlen; i += 32) o[i] = hdr[i];
+	}
+}
+
+__global__ void lookup_kernel(KgHashView hv, const uint64_t *kmers, size_t n, int64_t *out) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t v = hash_lookup(hv, kmers[i]);
+	out[i] = v == KG_MISS ? -1 : (int64_t)v;
+}
+
+// ---------------------------------------------------------------- host side
+
+int kg_seed_free(kmagpu_db *db) {
+	SeedBatch &b = db->seed;
+	KgBuf *all[] = {&b.d_in, &b.d_off, &b.d_res, &b.d_pool, &b.d_recoff, &b.d_out, &b.d_ctr, &b.d_partial, &b.d_dense,
+	                &b.h_off, &b.h_in, &b.h_out};
+	for (KgBuf *x : all) x->release();
+	return 0;
+}
+
+extern "C" int kmagpu_seed_upload(kmagpu_db *db, const void *stage1, size_t nbytes, int64_t *nreads_out) {
+	if (!db || (!stage1 && nbytes)) { kmagpu_set_error("null argument"); return -1; }
+	if (nbytes >= (1ull << 31)) { kmagpu_set_error("stage-1 batch of %zu bytes exceeds the 2 GiB per-call limit; split it", nbytes); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	SeedBatch &b = db->seed;
+	b.h_off.pinned = true;
+	// record boundaries: the only sequential step (16-byte header walk, loadFsa savekmers.c:50-92)
+	const uint8_t *in = (const uint8_t *)stage1;
+	size_t guess = nbytes / 48 + 16;
+	if (b.h_off.reserve(4 * (guess + 1))) return -1;
+	uint32_t *off = (uint32_t *)b.h_off.p;
+	size_t cap = b.h_off.cap / 4 - 1, n = 0, ip = 0;
+	while (ip + 16 <= nbytes) {
+		int32_t h[4];
+		memcpy(h, in + ip, 16);
+		if (h[0] < 0) break;   // a terminator was included
+		size_t len = 16 + 8 * (size_t)(uint32_t)h[1] + 4 * (size_t)(uint32_t)h[2] + (size_t)abs(h[3]);
+		if (h[1] < 0 || h[2] < 0 || ip + len > nbytes) { kmagpu_set_error("stage-1 stream is truncated or corrupt at byte %zu", ip); return -1; }
+		if (n == cap) {
+			KgBuf bigger; bigger.pinned = true;
+			if (bigger.reserve(8 * (cap + 1))) return -1;
+			memcpy(bigger.p, off, 4 * n);
+			b.h_off.release();
+			b.h_off = bigger;
+			off = (uint32_t *)b.h_off.p; cap = b.h_off.cap / 4 - 1;
+		}
+		off[n++] = (uint32_t)ip;
+		ip += len;
+	}
+	off[n] = (uint32_t)ip;
+	b.nreads = (int64_t)n;
+	b.in_bytes = ip;
+	b.ran = false;
+	if (nreads_out) *nreads_out = (int64_t)n;
+	if (b.d_in.reserve(ip + 64) || b.d_off.reserve(4 * (n + 1))) return -1;
+	KG_CUDA(cudaEventRecord(db->ev[0], db->stream));
+	KG_CUDA(cudaMemcpyAsync(b.d_in.p, in, ip, cudaMemcpyHostToDevice, db->stream));
+	KG_CUDA(cudaMemsetAsync((uint8_t *)b.d_in.p + ip, 0, 64, db->stream));
+	KG_CUDA(cudaMemcpyAsync(b.d_off.p, off, 4 * (n + 1), cudaMemcpyHostToDevice, db->stream));
+	KG_CUDA(cudaEventRecord(db->ev[1], db->stream));
+	KG_CUDA(cudaStreamSynchronize(db->stream));
+	return 0;
+}
+
+extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *stats) {
+	if (!db || !prm) { kmagpu_set_error("null argument"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	SeedBatch &b = db->seed;
+	const int n = (int)b.nreads;
+	if (stats) memset(stats, 0, sizeof(*stats));
+	b.out_bytes = 0;
+	b.ran = true;
+	if (n == 0) return 0;
+	SeedParams sp = {prm->M, prm->MM, prm->U, prm->W1, prm->exhaustive};
+	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+	if (b.pool_cap < (size_t)n * 16 + 1024) b.pool_cap = (size_t)n * 16 + 1024;
+	if (b.d_res.reserve(sizeof(SeedRes) * (size_t)n) || b.d_recoff.reserve(4 * (size_t)(2 * n + 2)) ||
+	    b.d_ctr.reserve(8 * C_N) || b.d_partial.reserve(4 * (size_t)(ntiles + 1) + 4 * (size_t)n)) return -1;
+	const int grid = db->sm_count * 8;
+	// dense fallback scratch: (score, ext, candF, candR: int) + incl (byte) per template, per warp
+	const int dense_grid = db->sm_count * 2;
+	const size_t D = (size_t)db->info.DB_size + 1;
+	const size_t dense_stride = ((16 * D + D) + 255) & ~(size_t)255;
+	const size_t dense_bytes = dense_stride * (size_t)dense_grid * KG_WARPS;
+	if (!b.d_dense.p) {
+		if (b.d_dense.reserve(dense_bytes)) return -1;
+		KG_CUDA(cudaMemsetAsync(b.d_dense.p, 0, b.d_dense.cap, db->stream));
+	}
+	uint32_t *recsize = (uint32_t *)b.d_recoff.p, *recoff = recsize + n + 1;
+	uint32_t *partial = (uint32_t *)b.d_partial.p, *ovf = partial + ntiles + 1;
+	unsigned long long *ctr = (unsigned long long *)b.d_ctr.p;
+	int launches = 0;
+	for (int attempt = 0;; ++attempt) {
+		if (b.d_pool.reserve(4 * b.pool_cap)) return -1;
+		KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * C_N, db->stream));
+		KG_CUDA(cudaEventRecord(db->ev[2], db->stream));
+		seed_se_kernel<false><<<grid, KG_WARPS * 32, 0, db->stream>>>(db->hv, sp, (const uint8_t *)b.d_in.p,
+			(const uint32_t *)b.d_off.p, n, (SeedRes *)b.d_res.p, recsize, (int32_t *)b.d_pool.p,
+			(unsigned long long)b.pool_cap, ctr, ovf, nullptr, 0);
+		seed_se_kernel<true><<<dense_grid, KG_WARPS * 32, 0, db->stream>>>(db->hv, sp, (const uint8_t *)b.d_in.p,
+			(const uint32_t *)b.d_off.p, n, (SeedRes *)b.d_res.p, recsize, (int32_t *)b.d_pool.p,
+			(unsigned long long)b.pool_cap, ctr, ovf, (uint8_t *)b.d_dense.p, dense_stride);
+		KG_CUDA(cudaEventRecord(db->ev[3], db->stream));
+		scan_tiles_kernel<<<ntiles, SCAN_THREADS, 0, db->stream>>>(recsize, n, recoff, partial);
+		scan_partials_kernel<<<1, SCAN_THREADS, 0, db->stream>>>(partial, ntiles, ctr);
+		scan_add_kernel<<<ntiles, SCAN_THREADS, 0, db->stream>>>(recoff, n, partial);
+		launches += 5;
+		unsigned long long h[C_N];
+		KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * C_N, cudaMemcpyDeviceToHost, db->stream));
+		KG_CUDA(cudaStreamSynchronize(db->stream));
+		KG_CUDA(cudaGetLastError());
+		if (h[C_POOLFAIL]) {   // template pool too small: grow and redo (rare)
+			if (attempt > 4) { kmagpu_set_error("template pool overflow persists"); return -1; }
+			b.pool_cap = (size_t)h[C_POOL] + 1024;
+			continue;
+		}
+		b.out_bytes = (size_t)h[C_TOTAL];
+		if (b.d_out.reserve(b.out_bytes + 64)) return -1;
+		emit_records_kernel<<<db->sm_count * 8, 256, 0, db->stream>>>((const uint8_t *)b.d_in.p, (const uint32_t *)b.d_off.p,
+			n, (const SeedRes *)b.d_res.p, recoff, (const int32_t *)b.d_pool.p, (uint8_t *)b.d_out.p);
+		KG_CUDA(cudaEventRecord(db->ev[4], db->stream));
+		KG_CUDA(cudaStreamSynchronize(db->stream));
+		KG_CUDA(cudaGetLastError());
+		++launches;
+		if (stats) {
+			stats->reads = n; stats->mapped = (int64_t)h[C_MAPPED]; stats->read_words = (int64_t)h[C_WORDS];
+			stats->lookups = (int64_t)h[C_LOOKUPS]; stats->hits = (int64_t)h[C_HITS];
+			stats->list_fetches = (int64_t)h[C_LISTS]; stats->list_ids = (int64_t)h[C_LISTIDS];
+			stats->overflow_reads = (int64_t)h[C_OVF];
+			cudaEventElapsedTime(&stats->ms_seed, db->ev[2], db->ev[3]);
+			cudaEventElapsedTime(&stats->ms_emit, db->ev[3], db->ev[4]);
+			stats->launches = launches;
+		}
+		return 0;
+	}
+}
+
+extern "C" int kmagpu_seed_download(kmagpu_db *db, void *stage2_out, size_t out_cap, size_t *out_bytes) {
+	if (!db) { kmagpu_set_error("null argument"); return -1; }
+	SeedBatch &b = db->seed;
+	if (!b.ran) { kmagpu_set_error("kmagpu_seed_download before kmagpu_seed_run"); return -1; }
+	if (out_bytes) *out_bytes = b.out_bytes;
+	if (b.out_bytes > out_cap) { kmagpu_set_error("stage-2 output needs %zu bytes, caller gave %zu", b.out_bytes, out_cap); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	if (b.out_bytes) {
+		KG_CUDA(cudaMemcpyAsync(stage2_out, b.d_out.p, b.out_bytes, cudaMemcpyDeviceToHost, db->stream));
+		KG_CUDA(cudaStreamSynchronize(db->stream));
+	}
+	return 0;
+}
+
+extern "C" int kmagpu_seed_batch(kmagpu_db *db, const kmagpu_params *p, const void *stage1, size_t nbytes,
+                                 void *stage2_out, size_t out_cap, size_t *out_bytes, int64_t *nreads,
+                                 kmagpu_seed_stats *stats) {
+	if (kmagpu_seed_upload(db, stage1, nbytes, nreads)) return -1;
+	if (kmagpu_seed_run(db, p, stats)) return -1;
+	if (kmagpu_seed_download(db, stage2_out, out_cap, out_bytes)) return -1;
+	if (stats) {
+		cudaEventElapsedTime(&stats->ms_h2d, db->ev[0], db->ev[1]);
+	}
+	return 0;
+}
+
+extern "C" int kmagpu_lookup_batch(kmagpu_db *db, const uint64_t *kmers, size_t n, int64_t *out) {
+	if (!db || !kmers || !out) { kmagpu_set_error("null argument"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	uint64_t *dk = nullptr; int64_t *dout = nullptr;
+	KG_CUDA(cudaMalloc(&dk, 8 * n + 8));
+	KG_CUDA(cudaMalloc(&dout, 8 * n + 8));
+	KG_CUDA(cudaMemcpy(dk, kmers, 8 * n, cudaMemcpyHostToDevice));
+	if (n) lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, db->stream>>>(db->hv, dk, n, dout);
+	KG_CUDA(cudaStreamSynchronize(db->stream));
+	KG_CUDA(cudaMemcpy(out, dout, 8 * n, cudaMemcpyDeviceToHost));
+	cudaFree(dk); cudaFree(dout);
+	KG_CUDA(cudaGetLastError());
+	return 0;
+}

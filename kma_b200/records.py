@@ -1,0 +1,70 @@
+"""Stage-1 record stream (runinput.c:765-787 printFsa / printFsa_pair) built with numpy, and parsers for
+the stage-1 / stage-2 (ankers.c:30-50) wire formats. Host-side glue only: no alignment logic here."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def pack_2bit(codes: np.ndarray):
+    """codes: uint8[L] in 0..4 (4 = N) -> (uint64 words MSB-first, int32 N positions). compdna.c:99-127"""
+    L = len(codes)
+    words = (L + 31) >> 5
+    c = np.zeros(words * 32, dtype=np.uint64)
+    npos = np.flatnonzero(codes == 4).astype(np.int32)
+    c[:L] = np.where(codes == 4, 0, codes)
+    sh = (np.uint64(62) - np.uint64(2) * (np.arange(words * 32, dtype=np.uint64) & np.uint64(31)))
+    w = np.bitwise_or.reduce((c << sh).reshape(words, 32), axis=1) if words else np.zeros(0, np.uint64)
+    return w.astype(np.uint64), npos
+
+
+def stage1_records_fixed(reads: np.ndarray, prefix: str = "r", pair_with: np.ndarray | None = None) -> np.ndarray:
+    """Vectorised stage-1 stream for equal-length reads (uint8 [n, L] codes). Header i is b'<prefix><i>\\0'
+    padded... no: real variable-length names, exactly what `kma -s1` would emit for '@<prefix><i>'."""
+    n, L = reads.shape
+    words = (L + 31) >> 5
+    c = np.zeros((n, words * 32), dtype=np.uint64)
+    c[:, :L] = np.where(reads == 4, 0, reads)
+    sh = (np.uint64(62) - np.uint64(2) * (np.arange(words * 32, dtype=np.uint64) & np.uint64(31)))
+    packed = np.bitwise_or.reduce((c << sh).reshape(n, words, 32), axis=2)  # [n, words] uint64
+    out = bytearray()
+    has_n = (reads == 4).any(axis=1)
+    names = [f"{prefix}{i}".encode() + b"\0" for i in range(n)]
+    for i in range(n):
+        npos = np.flatnonzero(reads[i] == 4).astype(np.int32) if has_n[i] else np.zeros(0, np.int32)
+        out += np.array([L, words, len(npos), len(names[i])], dtype=np.int32).tobytes()
+        out += packed[i].tobytes()
+        out += npos.tobytes()
+        out += names[i]
+    return np.frombuffer(bytes(out), dtype=np.uint8)
+
+
+def stage1_records(reads, names=None, prefix="r") -> np.ndarray:
+    """General (ragged) stage-1 stream."""
+    out = bytearray()
+    for i, r in enumerate(reads):
+        r = np.asarray(r, dtype=np.uint8)
+        w, npos = pack_2bit(r)
+        name = (names[i] if names is not None else f"{prefix}{i}").encode() + b"\0"
+        out += np.array([len(r), len(w), len(npos), len(name)], dtype=np.int32).tobytes()
+        out += w.tobytes() + npos.tobytes() + name
+    return np.frombuffer(bytes(out), dtype=np.uint8)
+
+
+def parse_stage2(buf) -> list[dict]:
+    """Split a stage-2 stream into records (dicts); stops at the terminator if present."""
+    b = memoryview(np.ascontiguousarray(buf, dtype=np.uint8)).tobytes()
+    recs, p = [], 0
+    while p + 28 <= len(b):
+        h = np.frombuffer(b, dtype=np.int32, count=7, offset=p)
+        if h[0] < 0:
+            break
+        seqlen, words, nN, score, nt, hl, flag = (int(x) for x in h)
+        p += 28
+        seq = np.frombuffer(b, dtype=np.uint64, count=words, offset=p) if p % 8 == 0 else \
+            np.frombuffer(b[p:p + 8 * words], dtype=np.uint64)
+        p += 8 * words
+        N = np.frombuffer(b[p:p + 4 * nN], dtype=np.int32); p += 4 * nN
+        T = np.frombuffer(b[p:p + 4 * nt], dtype=np.int32); p += 4 * nt
+        name = b[p:p + hl]; p += hl
+        recs.append(dict(seqlen=seqlen, seq=seq, N=N, score=score, templates=T, name=name, flag=flag))
+    return recs

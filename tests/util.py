@@ -1,0 +1,87 @@
+"""Test helpers: oracle bindings (TEST INFRASTRUCTURE), golden fixtures, reference binary wrapper."""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+import gzip
+import os
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF_KMA = os.path.join(ROOT, "oracle", "_ref", "kma")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libkma_ref.so")
+
+_orc = None
+
+
+def orc():
+    global _orc
+    if _orc is None:
+        L = C.CDLL(os.path.join(ROOT, "oracle", "liborc.so"))
+        L.orc_db_open.restype = C.c_void_p
+        L.orc_db_open.argtypes = [C.c_char_p]
+        L.orc_db_close.argtypes = [C.c_void_p]
+        L.orc_lookup.restype = C.c_int64
+        L.orc_lookup.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_seed_stream.restype = C.c_int64
+        L.orc_seed_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        _orc = L
+    return _orc
+
+
+def oracle_params(exhaustive=0):
+    p = (C.c_int32 * 40)()
+    orc().orc_default_params(p)
+    p[32] = exhaustive  # M MM U W1 Wl Mn PE (7) + d[25] -> exhaustive at index 32
+    return p
+
+
+def oracle_seed_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, stats=None) -> np.ndarray:
+    L = orc()
+    db = L.orc_db_open(os.fsencode(db_prefix))
+    assert db, f"oracle cannot open {db_prefix}"
+    out = np.zeros(3 * len(s1) + 4096, dtype=np.uint8)
+    st = (C.c_int64 * 7)()
+    n = L.orc_seed_stream(db, oracle_params(exhaustive), s1.ctypes.data, len(s1), out.ctypes.data, len(out), st)
+    L.orc_db_close(db)
+    assert n >= 0
+    if stats is not None:
+        stats.update(dict(zip(["reads", "mapped", "read_words", "lookups", "hits", "list_fetches", "list_ids"], list(st))))
+    return out[:n].copy()
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_KMA)
+
+
+def ref_kma(args, cwd=None, stdout=None):
+    """Run the unmodified reference binary (oracle/_ref/kma)."""
+    r = subprocess.run([REF_KMA] + list(args), cwd=cwd, stdout=stdout or subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    return r.stdout
+
+
+def ref_index(fasta: str, prefix: str):
+    ref_kma(["index", "-i", fasta, "-o", prefix])
+
+
+@contextlib.contextmanager
+def golden_dir():
+    """tests/golden/*.gz unpacked into a temp dir (the .comp.b is 4 MiB of mostly null slots)."""
+    d = tempfile.mkdtemp(prefix="kma_golden_")
+    try:
+        for f in os.listdir(GOLDEN):
+            src = os.path.join(GOLDEN, f)
+            if f.endswith(".gz"):
+                with gzip.open(src, "rb") as fi, open(os.path.join(d, f[:-3]), "wb") as fo:
+                    shutil.copyfileobj(fi, fo)
+            elif not f.endswith(".py"):
+                shutil.copy(src, os.path.join(d, f))
+        yield d
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
