@@ -52,7 +52,7 @@ typedef struct kmagpu_seed_stats {
 	int64_t lookups, hits, list_fetches, list_ids;
 	int64_t overflow_reads;   /* reads that took the dense-scratch path */
 	float ms_seed, ms_emit;   /* CUDA-event time of the scoring kernels / record writer */
-	float ms_h2d, ms_d2h;
+	float ms_h2d, ms_total;   /* H2D copy; whole device-side step (first kernel start -> writer end) */
 	int32_t launches;         /* kernels launched by the call */
 	int32_t reserved;
 } kmagpu_seed_stats;

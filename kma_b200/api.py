@@ -35,7 +35,7 @@ class SeedStats(C.Structure):
     _fields_ = [("reads", C.c_int64), ("mapped", C.c_int64), ("read_words", C.c_int64), ("lookups", C.c_int64),
                 ("hits", C.c_int64), ("list_fetches", C.c_int64), ("list_ids", C.c_int64),
                 ("overflow_reads", C.c_int64), ("ms_seed", C.c_float), ("ms_emit", C.c_float),
-                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("launches", C.c_int32), ("reserved", C.c_int32)]
+                ("ms_h2d", C.c_float), ("ms_total", C.c_float), ("launches", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -112,13 +112,19 @@ class TemplateDB:
         """stage-1 records (uint8 array / pinned tensor) -> (stage-2 bytes incl. no terminator, nreads, stats)"""
         p = params or default_params()
         nbytes = int(stage1.numel() if hasattr(stage1, "numel") else stage1.size)
-        if out is None:
-            out = np.empty(2 * nbytes + 4096, dtype=np.uint8)
-        cap = int(out.numel() if hasattr(out, "numel") else out.size)
-        ob, nr, st = C.c_size_t(), C.c_int64(), SeedStats()
-        _check(lib().kmagpu_seed_batch(self._h, C.byref(p), _ptr(stage1), nbytes, _ptr(out), cap,
-                                       C.byref(ob), C.byref(nr), C.byref(st)))
-        return out[: ob.value], nr.value, st
+        if out is not None:
+            cap = int(out.numel() if hasattr(out, "numel") else out.size)
+            ob, nr, st = C.c_size_t(), C.c_int64(), SeedStats()
+            _check(lib().kmagpu_seed_batch(self._h, C.byref(p), _ptr(stage1), nbytes, _ptr(out), cap,
+                                           C.byref(ob), C.byref(nr), C.byref(st)))
+            return out[: ob.value], nr.value, st
+        # caller gave no buffer: run, then size the output exactly
+        nr = self.seed_upload(stage1)
+        st = self.seed_run(p)
+        ob = C.c_size_t()
+        lib().kmagpu_seed_download(self._h, None, 0, C.byref(ob))
+        out = np.empty(ob.value + 8, dtype=np.uint8)
+        return self.seed_download(out), nr, st
 
     def seed_upload(self, stage1):
         nbytes = int(stage1.numel() if hasattr(stage1, "numel") else stage1.size)

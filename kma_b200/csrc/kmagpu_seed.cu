@@ -212,9 +212,15 @@ __device__ int scan_strand(const KgHashView &hv, const SeedParams &p, const Read
 			if (rc.nN == 0) {
 				// probes c0' = multiples of k inside the chunk
 				int first = ((c0 + k - 1) / k) * k;
-				for (int j = first + (int)lane * k; j < min(npos, c0 + KG_CHUNK); j += 32 * k) {
-					h |= hash_lookup(hv, kmer_of(w0, j)) != KG_MISS;
-					ws.lookups++;
+				const int lim = min(npos, c0 + KG_CHUNK);
+				for (int jb = first; jb < lim && !h; jb += 32 * k) {
+					const int j = jb + (int)lane * k;
+					const bool act = j < lim;
+					const bool hp = act && hash_lookup(hv, kmer_of(w0, j)) != KG_MISS;
+					const unsigned am = __ballot_sync(0xffffffffu, act), hm = __ballot_sync(0xffffffffu, hp);
+					// algorithmic probe count: the reference stops at the first hit
+					if (lane == 0) ws.lookups += hm ? __ffs(hm) : __popc(am);
+					h = hm != 0;
 				}
 			} else {
 				for (int j = c0 + (int)lane; j < min(npos, c0 + KG_CHUNK); j += 32) {
@@ -710,6 +716,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 			stats->overflow_reads = (int64_t)h[C_OVF];
 			cudaEventElapsedTime(&stats->ms_seed, db->ev[2], db->ev[3]);
 			cudaEventElapsedTime(&stats->ms_emit, db->ev[3], db->ev[4]);
+			cudaEventElapsedTime(&stats->ms_total, db->ev[2], db->ev[4]);
 			stats->launches = launches;
 		}
 		return 0;

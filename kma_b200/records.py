@@ -38,6 +38,29 @@ def stage1_records_fixed(reads: np.ndarray, prefix: str = "r", pair_with: np.nda
     return np.frombuffer(bytes(out), dtype=np.uint8)
 
 
+def stage1_records_fast(reads: np.ndarray, prefix: str = "r", first: int = 0) -> np.ndarray:
+    """Fully vectorised stage-1 stream for N-free equal-length reads with fixed-width names
+    '<prefix><9-digit index>\\0' (what `kma -s1` emits for a FASTQ with those names)."""
+    n, L = reads.shape
+    assert not (reads == 4).any(), "N-free reads only (use stage1_records_fixed)"
+    words = (L + 31) >> 5
+    c = np.zeros((n, words * 32), dtype=np.uint64)
+    c[:, :L] = reads
+    sh = (np.uint64(62) - np.uint64(2) * (np.arange(words * 32, dtype=np.uint64) & np.uint64(31)))
+    packed = np.bitwise_or.reduce((c << sh).reshape(n, words, 32), axis=2)
+    pre = prefix.encode()
+    hl = len(pre) + 10
+    rec = np.zeros((n, 16 + 8 * words + hl), dtype=np.uint8)
+    rec[:, :16] = np.frombuffer(np.array([L, words, 0, hl], dtype=np.int32).tobytes(), dtype=np.uint8)
+    rec[:, 16:16 + 8 * words] = packed.view(np.uint8).reshape(n, 8 * words)
+    o = 16 + 8 * words
+    rec[:, o:o + len(pre)] = np.frombuffer(pre, dtype=np.uint8)
+    idx = np.arange(first, first + n, dtype=np.int64)
+    for d in range(9):
+        rec[:, o + len(pre) + 8 - d] = 48 + (idx // 10 ** d) % 10
+    return rec.reshape(-1)
+
+
 def stage1_records(reads, names=None, prefix="r") -> np.ndarray:
     """General (ragged) stage-1 stream."""
     out = bytearray()

@@ -75,19 +75,22 @@ def write_fasta(path, names, seqs, width=0):
             fh.write(f">{n}\n{decode(s)}\n")
 
 
+def _concat(seqs):
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    offs = np.r_[0, np.cumsum(lens)]
+    return np.concatenate(seqs), lens, offs
+
+
 def short_reads(seed: int, seqs, n: int, L: int = 150, sub: float = 0.005, n_rate: float = 0.0,
                 junk_frac: float = 0.0):
     """Single-end reads: uniform template, uniform start, random strand, substitutions (+ optional N's,
-    + optional fraction of random reads that map nowhere)."""
+    + optional fraction of random reads that map nowhere). Vectorised; uint8 [n, L]."""
     rng = np.random.default_rng(seed)
-    lens = np.array([len(s) for s in seqs])
+    cat, lens, offs = _concat(seqs)
     ok = np.flatnonzero(lens >= L)
-    out = np.empty((n, L), dtype=np.uint8)
     tsel = ok[rng.integers(0, len(ok), size=n)]
-    for i in range(n):
-        s = seqs[tsel[i]]
-        p = int(rng.integers(0, len(s) - L + 1))
-        out[i] = s[p:p + L]
+    start = offs[tsel] + (rng.random(n) * (lens[tsel] - L + 1)).astype(np.int64)
+    out = cat[start[:, None] + np.arange(L)[None, :]]
     hit = rng.random((n, L)) < sub
     out[hit] = (out[hit] + rng.integers(1, 4, size=int(hit.sum())).astype(np.uint8)) & 3
     if junk_frac > 0:
@@ -101,22 +104,18 @@ def short_reads(seed: int, seqs, n: int, L: int = 150, sub: float = 0.005, n_rat
 
 
 def paired_reads(seed: int, seqs, n: int, L: int = 150, sub: float = 0.005, ins_lo: int = 200, ins_hi: int = 450):
-    """FR pairs with insert U[ins_lo, ins_hi] clipped to the template."""
+    """FR pairs with insert U[ins_lo, ins_hi] clipped to the template. Vectorised; two uint8 [n, L]."""
     rng = np.random.default_rng(seed)
-    lens = np.array([len(s) for s in seqs])
+    cat, lens, offs = _concat(seqs)
     ok = np.flatnonzero(lens >= L)
-    r1 = np.empty((n, L), dtype=np.uint8)
-    r2 = np.empty((n, L), dtype=np.uint8)
     tsel = ok[rng.integers(0, len(ok), size=n)]
-    for i in range(n):
-        s = seqs[tsel[i]]
-        ins = int(min(len(s), max(L, rng.integers(ins_lo, ins_hi + 1))))
-        p = int(rng.integers(0, len(s) - ins + 1))
-        frag = s[p:p + ins]
-        if rng.random() < 0.5:
-            frag = revcomp(frag)
-        r1[i] = frag[:L]
-        r2[i] = revcomp(frag)[:L]
+    ins = np.minimum(lens[tsel], np.maximum(L, rng.integers(ins_lo, ins_hi + 1, size=n)))
+    start = offs[tsel] + (rng.random(n) * (lens[tsel] - ins + 1)).astype(np.int64)
+    left = cat[start[:, None] + np.arange(L)[None, :]]                       # fragment 5' end, forward
+    right = _COMP[cat[(start + ins - 1)[:, None] - np.arange(L)[None, :]]]   # fragment 3' end, reverse strand
+    flip = rng.random(n) < 0.5
+    r1 = np.where(flip[:, None], right, left)
+    r2 = np.where(flip[:, None], left, right)
     for r in (r1, r2):
         hit = rng.random((n, L)) < sub
         r[hit] = (r[hit] + rng.integers(1, 4, size=int(hit.sum())).astype(np.uint8)) & 3

@@ -45,9 +45,14 @@ def oracle_seed_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, stats=None)
     L = orc()
     db = L.orc_db_open(os.fsencode(db_prefix))
     assert db, f"oracle cannot open {db_prefix}"
-    out = np.zeros(3 * len(s1) + 4096, dtype=np.uint8)
-    st = (C.c_int64 * 7)()
-    n = L.orc_seed_stream(db, oracle_params(exhaustive), s1.ctypes.data, len(s1), out.ctypes.data, len(out), st)
+    cap = 3 * len(s1) + 4096
+    while True:
+        out = np.zeros(cap, dtype=np.uint8)
+        st = (C.c_int64 * 7)()
+        n = L.orc_seed_stream(db, oracle_params(exhaustive), s1.ctypes.data, len(s1), out.ctypes.data, len(out), st)
+        if n >= 0 or cap > (1 << 32):
+            break
+        cap *= 8
     L.orc_db_close(db)
     assert n >= 0
     if stats is not None:
