@@ -35,4 +35,10 @@ void orc_revcomp(const uint64_t *seq, int seqlen, const int32_t *N, int nN, uint
 int64_t orc_seed_stream(const orc_db *db, const orc_params *p, const uint8_t *in, size_t in_bytes,
                         uint8_t *out, size_t cap, orc_stats *st);
 void orc_default_params(orc_params *p);
+int orc_db_load_seq(orc_db *db, const char *prefix);
+int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const uint8_t *in, size_t in_bytes,
+                     int one2one, double scoreT, int mq, int minlen, double mrc,
+                     uint8_t **frag_out, size_t *frag_bytes, uint64_t *as, uint64_t *uas,
+                     int32_t **cand_out, size_t *cand_rows, int64_t *nw_cells);
+void orc_free(void *p);
 #endif

@@ -1,0 +1,666 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU restatement (oracle) of KMA 1.5.1's alignment pass (stage 3, first half):
+ * stage-2 records in, frag_raw records + ConClave score arrays out.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
+ *
+ * Parity pin: tests/test_oracle_align.py compares (a) every per-candidate AlnScore and (b) the whole frag_raw
+ * stream + alignment_scores/uniq_alignment_scores with the UNMODIFIED reference driven by oracle/ref_harness.c
+ * (oracle/_ref/ref_aln), on fresh seeded data and on the committed golden streams.
+ *
+ * Restated (not copied) from:
+ *   hashmapcci.c:95-199, 409-505  HashMapCCI get/get_bound/getDubPos/getNextDubPos/load  -> tindex_* (sorted
+ *        (k-mer, position) arrays: same answers and the same ascending enumeration order)
+ *   align.c:509-748   KMA_score (seed scan, stitching)          -> kma_score
+ *   align.c:53-212    leadTailAln / trailTailAln                -> lead_tail / trail_tail
+ *   align.c:750-770   preseed                                   -> preseed_hit
+ *   align.c:993-1176  anker_rc_comp                             -> pick_strand
+ *   chain.c:79-260    chainSeeds                                -> chain_mems
+ *   nw.c:642-890      NW_score                                  -> nw_full
+ *   nw.c:892-1188     NW_band_score                             -> nw_band
+ *   alnfrags.c:1052-1218 alnFragsSE, :2150-2294 alnFrags_threaded (SE) -> orc_align_stream
+ *   updatescores.c:203-298 update_Scores (frag_raw record)      -> reduce_and_emit
+ * Out of scope here (asserted): circular templates (t_len < 0), chain-mode q-bounds, paired records.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "orc.h"
+
+#define IMIN(a, b) ((a) < (b) ? (a) : (b))
+#define IMAX(a, b) ((a) < (b) ? (b) : (a))
+
+/* ------------------------------------------------------------------ template side ---- */
+
+int orc_db_load_seq(orc_db *db, const char *prefix) {
+	char path[4096];
+	if (db->seq) return 0;
+	if (!db->lengths) return -1;
+	db->seq_off = calloc(db->DB_size + 1, sizeof(int64_t));
+	for (int t = 1; t < db->DB_size; ++t) db->seq_off[t + 1] = db->seq_off[t] + ((db->lengths[t] >> 5) + 1);
+	size_t words = (size_t)db->seq_off[db->DB_size];
+	db->seq = calloc(words + 2, 8);
+	snprintf(path, sizeof(path), "%s.seq.b", prefix);
+	FILE *f = fopen(path, "rb");
+	if (!f) return -1;
+	size_t got = fread(db->seq, 8, words, f);
+	fclose(f);
+	return got == words ? 0 : -1;
+}
+
+static inline int nuc_at(const uint64_t *seq, int pos) { return (int)((seq[pos >> 5] << ((pos & 31) << 1)) >> 62); }
+
+static inline uint64_t kmer_at(const uint64_t *seq, int pos, int k) {
+	int w = pos >> 5, b = (pos & 31) << 1, sh = 64 - 2 * k;
+	uint64_t x = seq[w] << b;
+	if (b > sh) x |= seq[w + 1] >> (64 - b);
+	return x >> sh;
+}
+
+/* per-template position index: (k-mer, 1-based position) sorted by k-mer then position */
+typedef struct { uint64_t *kmer; int32_t *pos; int n, len, k; const uint64_t *seq; } tindex;
+
+typedef struct { uint64_t k; int32_t p; } kp_t;
+static int kp_cmp(const void *a, const void *b) {
+	const kp_t *x = a, *y = b;
+	if (x->k != y->k) return x->k < y->k ? -1 : 1;
+	return x->p - y->p;
+}
+
+static tindex *tindex_build(const uint64_t *seq, int len, int k) {
+	tindex *ix = calloc(1, sizeof(tindex));
+	int n = len - k + 1;
+	if (n < 0) n = 0;
+	kp_t *v = malloc(sizeof(kp_t) * (n + 1));
+	int m = 0;
+	for (int i = 0; i < n; ++i) {
+		uint64_t key = kmer_at(seq, i, k);
+		if (key == 0) continue; /* hashMapCCI_add skips poly-A (hashmapcci.c:414) */
+		v[m].k = key; v[m].p = i + 1; ++m;
+	}
+	qsort(v, m, sizeof(kp_t), kp_cmp);
+	ix->kmer = malloc(8 * (m + 1)); ix->pos = malloc(4 * (m + 1));
+	for (int i = 0; i < m; ++i) { ix->kmer[i] = v[i].k; ix->pos[i] = v[i].p; }
+	free(v);
+	ix->n = m; ix->len = len; ix->k = k; ix->seq = seq;
+	return ix;
+}
+
+static void tindex_free(tindex *ix) { if (ix) { free(ix->kmer); free(ix->pos); free(ix); } }
+
+/* first slot holding key, or -1; *cnt = occurrences */
+static int tindex_find(const tindex *ix, uint64_t key, int *cnt) {
+	int lo = 0, hi = ix->n;
+	while (lo < hi) { int mid = (lo + hi) >> 1; if (ix->kmer[mid] < key) lo = mid + 1; else hi = mid; }
+	if (lo == ix->n || ix->kmer[lo] != key) { *cnt = 0; return -1; }
+	int e = lo;
+	while (e < ix->n && ix->kmer[e] == key) ++e;
+	*cnt = e - lo;
+	return lo;
+}
+
+/* hashMapCCI_get: 0 = absent, +pos = unique k-mer, -pos(first) = repeated k-mer */
+static int tindex_get(const tindex *ix, uint64_t key, int *slot, int *cnt) {
+	*slot = tindex_find(ix, key, cnt);
+	if (*slot < 0) return 0;
+	return *cnt == 1 ? ix->pos[*slot] : -ix->pos[*slot];
+}
+
+/* hashMapCCI_get_bound used as a boolean by preseed: any occurrence with min < pos < max */
+static int tindex_any_bound(const tindex *ix, uint64_t key, int min, int max) {
+	int cnt, s = tindex_find(ix, key, &cnt);
+	for (int i = 0; i < cnt; ++i) if (min < ix->pos[s + i] && ix->pos[s + i] < max) return 1;
+	return 0;
+}
+
+/* ------------------------------------------------------------------ MEM list --------- */
+
+typedef struct {
+	int cap, len;
+	int *tStart, *tEnd, *qStart, *qEnd, *weight, *score, *next;
+} mems_t;
+
+static void mems_reserve(mems_t *p, int need) {
+	if (need < p->cap) return;
+	int c = p->cap ? p->cap : 1024;
+	while (c <= need) c <<= 1;
+	p->tStart = realloc(p->tStart, 4 * (size_t)c); p->tEnd = realloc(p->tEnd, 4 * (size_t)c);
+	p->qStart = realloc(p->qStart, 4 * (size_t)c); p->qEnd = realloc(p->qEnd, 4 * (size_t)c);
+	p->weight = realloc(p->weight, 4 * (size_t)c); p->score = realloc(p->score, 4 * (size_t)c);
+	p->next = realloc(p->next, 4 * (size_t)c);
+	p->cap = c;
+}
+
+/* extend an exact seed at (query i, template 1-based value) to a maximal exact match.
+ * fwd_lim = exclusive query limit of the forward extension. Returns query end; *tEnd1 = value + 1. */
+static void mem_from_seed(const tindex *ix, const uint8_t *q, int i, int value, int k, int fwd_lim,
+                          int *qs, int *ts, int *qe, int *te) {
+	int prev = value - 2, j;
+	for (j = i - 1; 0 <= j && 0 <= prev && q[j] == nuc_at(ix->seq, prev); --j) --prev;
+	*qs = j + 1; *ts = prev + 2;
+	value += k - 1;
+	int l = i + k;
+	while (l < fwd_lim && value < ix->len && q[l] == nuc_at(ix->seq, value)) { ++l; ++value; }
+	*qe = l; *te = value + 1;
+}
+
+/* ------------------------------------------------------------------ chaining --------- */
+
+static int tail_mm(const orc_params *p, int Ms, int k) { /* mismatch estimate of a gap of Ms bases */
+	int MMs;
+	if (Ms == 2) { MMs = 2; Ms = 0; }
+	else {
+		MMs = Ms / k + (Ms % k ? 1 : 0); MMs = IMAX(2, MMs);
+		Ms = IMIN(Ms - MMs, k); Ms = IMIN(Ms, MMs);
+	}
+	return Ms * p->M + MMs * p->MM;
+}
+
+static int chain_mems(const orc_params *p, mems_t *pt, int q_len, int t_len, int k, unsigned *mapQ) {
+	const int W1 = p->W1, U = p->U, M = p->M;
+	int n = pt->len, bestPos = n - 1, bestScore = 0, secondScore = 0;
+	mems_reserve(pt, n + 1);
+	pt->score[n] = 0; pt->next[n] = 0;
+	for (int i = n - 1; i >= 0; --i) {
+		int weight = pt->weight[i] * M, tEnd = pt->tEnd[i], qEnd = pt->qEnd[i], gap, Ms, score;
+		pt->next[i] = 0;
+		gap = IMIN(t_len - tEnd, q_len - qEnd);
+		Ms = gap;
+		if (--gap) gap = gap * U + W1; else gap = W1;       /* (the reference's third branch is unreachable) */
+		Ms = tail_mm(p, Ms, k);
+		score = weight + (Ms < gap ? gap : Ms);
+		int lim = IMIN(n, i + 128);
+		for (int j = i + 1; j < lim; ++j) {
+			if (qEnd < pt->qStart[j]) {
+				if (tEnd < pt->tStart[j]) {
+					int tGap = pt->tStart[j] - tEnd, qGap = pt->qStart[j] - qEnd;
+					if ((gap = abs(tGap - qGap))) gap = (gap - 1) * U + W1;
+					gap += weight + pt->score[j] + tail_mm(p, IMIN(tGap, qGap), k);
+					if (score <= gap) { score = gap; pt->next[i] = j; }
+				} else if (k <= pt->tEnd[j] - tEnd) {
+					if ((gap = pt->qStart[j] - qEnd)) gap = (gap - 1) * U + W1;
+					gap += weight + pt->score[j] - (pt->tStart[j] - tEnd) * M;
+					if (score < gap) { score = gap; pt->next[i] = j; }
+				}
+			} else if (k <= pt->qEnd[j] - qEnd) {
+				int tStart = pt->tStart[j] + qEnd - pt->qStart[j];
+				if (tEnd < tStart) {
+					if ((gap = tStart - tEnd)) gap = (gap - 1) * U + W1;
+					gap += weight + pt->score[j] - (tStart - tEnd) * M;
+					if (score < gap) { score = gap; pt->next[i] = j; }
+				}
+			}
+		}
+		if (pt->next[i]) pt->weight[i] += pt->weight[pt->next[i]] - k + 1;
+		else pt->weight[i] -= k - 1;
+		pt->score[i] = score;
+		gap = IMIN(pt->tStart[i], pt->qStart[i]);
+		Ms = gap;
+		if (0 < --gap) gap = gap * U + W1; else if (gap == 0) gap = W1; else gap = 0;
+		Ms = tail_mm(p, Ms, k);
+		score += Ms < gap ? gap : Ms;
+		if (bestScore <= score) {
+			if (pt->next[i] != bestPos) secondScore = bestScore;
+			bestScore = score; bestPos = i;
+		} else if (secondScore <= score && pt->next[i] != bestPos) secondScore = bestScore;
+	}
+	*mapQ = 0 < bestScore ? (unsigned)ceil(40 * (1 - 1.0 * secondScore / bestScore) * (pt->weight[bestPos] / 10.0 < 1 ? pt->weight[bestPos] / 10.0 : 1) * log(bestScore)) : 0;
+	pt->score[bestPos] = bestScore;
+	return bestPos;
+}
+
+/* ------------------------------------------------------------------ Needleman-Wunsch - */
+
+typedef struct { int score, len, pos, match, tGaps, qGaps; } aln_t;
+
+static int64_t g_band_calls = 0, g_full_calls = 0;
+int64_t orc_nw_band_calls(void) { return g_band_calls; }
+int64_t orc_nw_full_calls(void) { return g_full_calls; }
+
+typedef struct { int *D[2], *P[2]; size_t cols; uint8_t *E; size_t esize; int64_t cells; } nw_ws;
+
+static void ws_reserve(nw_ws *w, size_t cols, size_t ebytes) {
+	if (w->cols < cols) {
+		w->cols = cols * 2;
+		for (int i = 0; i < 2; ++i) { free(w->D[i]); free(w->P[i]); w->D[i] = calloc(w->cols, 4); w->P[i] = calloc(w->cols, 4); }
+	}
+	if (w->esize < ebytes) { w->esize = ebytes * 2; free(w->E); w->E = calloc(w->esize, 1); }
+}
+
+/* one DP cell; returns the traceback byte (nw.c:166-212): 1 diag, 2/3 Q open/extend, 4/5 P open/extend,
+ * +16 the Q run may open here, +32 the P run may open here */
+static inline uint8_t nw_cell(int Dright, int Qright, int Ddown, int Pdown, int Ddiag, int sub, int W1, int U,
+                              int *Dout, int *Qout, int *Pout) {
+	int Q = Dright + W1, P = Ddown + W1, D, x;
+	uint8_t e, fl = 0;
+	if (Q < P) { D = P; e = 4; } else { D = Q; e = 2; }
+	x = Qright + U;
+	if (Q < x) { Q = x; if (D <= x) { D = x; e = 3; } } else fl |= 16;
+	x = Pdown + U;
+	if (P < x) { P = x; if (D <= x) { D = x; e = 5; } } else fl |= 32;
+	x = Ddiag + sub;
+	if (D <= x) { D = x; e = 1; }
+	*Dout = D; *Qout = Q; *Pout = P;
+	return fl | e;
+}
+
+static aln_t nw_trivial(const orc_params *p, int t_len, int q_len) {
+	aln_t s = {0, 0, 0, 0, 0, 0};
+	if (t_len == q_len) return s;
+	if (t_len == 0) { s.len = q_len; s.tGaps = q_len; s.score = p->W1 + (q_len - 1) * p->U; }
+	else { s.len = t_len; s.qGaps = t_len; s.score = p->W1 + (t_len - 1) * p->U; }
+	return s;
+}
+
+/* walk the traceback bytes from (m, n); `stride` = bytes per row, `dn` = column step of a vertical move
+ * (0 for the full matrix, -1 for the band whose rows are skewed) */
+static void nw_walk(const uint8_t *E, size_t stride, int m, int n, int dn, aln_t *s) {
+	const uint8_t *row = E + (size_t)m * stride;
+	s->len = s->match = s->tGaps = s->qGaps = 0;
+	while (row[n] != 0) {
+		int e = row[n] & 7;
+		if (e == 1) { ++s->match; row += stride; n += 1 + dn; }
+		else if (e >= 4) {
+			while (!(row[n] >> 4)) { row += stride; n += dn; ++s->len; ++s->qGaps; }
+			++s->qGaps; row += stride; n += dn;
+		} else {
+			while (!(row[n] >> 3)) { ++n; ++s->len; ++s->tGaps; }
+			++s->tGaps; ++n;
+		}
+		++s->len;
+	}
+}
+
+static aln_t nw_full(const orc_params *p, nw_ws *w, const uint64_t *tseq, const uint8_t *query, int k,
+                     int t_s, int t_e, int q_s, int q_e) {
+	const int W1 = p->W1, U = p->U, t_len = t_e - t_s, q_len = q_e - q_s;
+	const uint8_t *q = query + q_s;
+	if (t_len == 0 || q_len == 0) return nw_trivial(p, t_len, q_len);
+	const size_t stride = (size_t)q_len + 1;
+	++g_full_calls;
+	ws_reserve(w, (size_t)q_len + 2, ((size_t)q_len + 2) * ((size_t)t_len + 2));
+	w->cells += (int64_t)t_len * q_len;
+	const int NEG = (t_len + q_len) * (p->MM + U + W1);
+	int *Dp = w->D[1], *Pp = w->P[1], *Dc = w->D[0], *Pc = w->P[0];
+	uint8_t *E = w->E, *last = E + (size_t)t_len * stride;
+	aln_t s = {NEG, 0, 0, 0, 0, 0};
+	int best_m = 0, best_n = 0;
+	/* boundary row (all template consumed) and boundary column (all query consumed) */
+	if (k == 2) { for (int n = 0; n <= q_len; ++n) { Dp[n] = 0; Pp[n] = NEG; last[n] = 0; } }
+	else {
+		for (int n = 0; n < q_len; ++n) { Dp[n] = W1 + (q_len - 1 - n) * U; Pp[n] = NEG; last[n] = 3; }
+		last[q_len - 1] = 18; last[q_len] = 0; Dp[q_len] = 0; Pp[q_len] = 0;
+	}
+	for (int m = 0; m < t_len; ++m) E[(size_t)m * stride + q_len] = 0 < k ? 0 : 5;
+	if (!(0 < k)) E[(size_t)(t_len - 1) * stride + q_len] = 36;
+
+	for (int m = t_len - 1; m >= 0; --m) {
+		uint8_t *row = E + (size_t)m * stride;
+		const int tn = nuc_at(tseq, t_s + m);
+		int Qr = NEG;
+		Dc[q_len] = 0 < k ? 0 : W1 + (t_len - 1 - m) * U;
+		for (int n = q_len - 1; n >= 0; --n)
+			row[n] = nw_cell(Dc[n + 1], Qr, Dp[n], Pp[n], Dp[n + 1], p->d[tn * 5 + q[n]], W1, U, &Dc[n], &Qr, &Pc[n]);
+		if (k < 0 && s.score < Dc[0]) { s.score = Dc[0]; best_m = m; }
+		int *t1 = Dc; Dc = Dp; Dp = t1; t1 = Pc; Pc = Pp; Pp = t1;
+	}
+	if (k < 0) {
+		best_n = 0;
+		if (k == -2) for (int n = 0; n < q_len; ++n) if (s.score <= Dp[n]) { s.score = Dp[n]; best_m = 0; best_n = n; }
+	} else { s.score = Dp[0]; best_m = 0; best_n = 0; }
+	int sc = s.score;
+	nw_walk(E, stride, best_m, best_n, 0, &s);
+	s.score = sc; s.pos = 0;
+	return s;
+}
+
+static aln_t nw_band(const orc_params *p, nw_ws *w, const uint64_t *tseq, const uint8_t *query, int k,
+                     int t_s, int t_e, int q_s, int q_e, int band) {
+	const int W1 = p->W1, U = p->U, t_len = t_e - t_s, q_len = q_e - q_s;
+	const uint8_t *q = query + q_s;
+	if (t_len == 0 || q_len == 0) return nw_trivial(p, t_len, q_len);
+	if (band & 1) ++band;
+	++g_band_calls;
+	const int half = band >> 1, bq = band + 1;
+	const size_t stride = (size_t)bq + 1;
+	ws_reserve(w, 2 * (size_t)band + 4, ((size_t)band + 3) * ((size_t)t_len + 2));
+	w->cells += (int64_t)t_len * bq;
+	const int NEG = (t_len + q_len) * (p->MM + U + W1);
+	int *Dp = w->D[1], *Pp = w->P[1], *Dc = w->D[0], *Pc = w->P[0];
+	uint8_t *E = w->E, *last = E + (size_t)t_len * stride;
+	aln_t s = {NEG, 0, 0, 0, 0, 0};
+	int c = (t_len + q_len) >> 1, sn = q_len - 1 - (c - half), en = 0, best_m = 0, best_n = 0, n;
+	if (k != 2) {
+		for (n = sn - 1; n >= 0; --n) { Dp[n] = W1 + (sn - n - 1) * U; Pp[n] = NEG; last[n] = 3; }
+		last[sn - 1] = 18; last[sn] = 0; Dp[sn] = 0; Pp[sn] = 0;
+	} else for (n = sn; n >= 0; --n) { Dp[n] = 0; Pp[n] = NEG; last[n] = 0; }
+
+	for (int m = t_len - 1; m >= 0; --m, --c) {
+		uint8_t *row = E + (size_t)m * stride;
+		int sq = c + half, eq = c - half, qp, Qr = NEG, Dn, Qn, Pn;
+		if (eq < 0) { eq = 0; ++en; } else en = 0;
+		if (sq < q_len - 1) { sn = bq - 1; Dc[bq] = NEG; row[bq] = 37; }
+		else { sq = q_len - 1; sn = en + (q_len - eq); Dc[sn] = 0 < k ? 0 : W1 + (t_len - 1 - m) * U; row[sn] = 0 < k ? 0 : 37; --sn; }
+		const int tn = nuc_at(tseq, t_s + m);
+		for (n = sn, qp = sq; n > en; --qp, --n)
+			row[n] = nw_cell(Dc[n + 1], Qr, Dp[n - 1], Pp[n - 1], Dp[n], p->d[tn * 5 + q[qp]], W1, U, &Dc[n], &Qr, &Pc[n]);
+		/* left edge of the band: no vertical (P) move into this cell (nw.c:1076-1102) */
+		{
+			uint8_t e, fl = 0;
+			Qn = Dc[n + 1] + W1;
+			if (Qn < Qr + U) { Qn = Qr + U; e = 3; } else { e = 2; fl = 16; }
+			Pc[n] = NEG;
+			Dn = Dp[n] + p->d[tn * 5 + q[qp]];
+			if (Qn <= Dn) row[n] = fl | 1; else { Dn = Qn; row[n] = fl | e; }
+			Dc[n] = Dn; (void)Pn;
+		}
+		if (eq == 0 && k < 0 && s.score < Dc[n]) { s.score = Dc[n]; best_m = m; best_n = n; }
+		int *t1 = Dc; Dc = Dp; Dp = t1; t1 = Pc; Pc = Pp; Pp = t1;
+	}
+	if (best_m == 0) { best_n = en; s.score = Dp[en]; }
+	if (k == -2) for (n = en; n < bq; ++n) if (s.score <= Dp[n]) { s.score = Dp[n]; best_m = 0; best_n = n; }
+	int sc = s.score;
+	nw_walk(E, stride, best_m, best_n, -1, &s);
+	s.score = sc; s.pos = 0;
+	return s;
+}
+
+/* ------------------------------------------------------------------ seed-and-extend -- */
+
+#define BANDW 64
+
+static aln_t nw_auto(const orc_params *p, nw_ws *w, const uint64_t *tseq, const uint8_t *q, int k,
+                     int t_s, int t_e, int q_s, int q_e) {
+	int band = abs((t_e - t_s) - (q_e - q_s)) + BANDW;
+	if (q_e - q_s <= band || t_e - t_s <= band) return nw_full(p, w, tseq, q, k, t_s, t_e, q_s, q_e);
+	return nw_band(p, w, tseq, q, k, t_s, t_e, q_s, q_e, band);
+}
+
+static aln_t lead_tail(const orc_params *p, nw_ws *w, const uint64_t *tseq, const uint8_t *q, int t_e, int q_e) {
+	aln_t s = {0, 0, t_e, 0, 0, 0};
+	if (!q_e) return s;
+	int t_s = 0, q_s = 0;
+	if ((q_e << 1) < t_e || (q_e + BANDW) < t_e) t_s = t_e - (q_e + IMIN(q_e, BANDW));
+	else if ((t_e << 1) < q_e || (t_e + BANDW) < q_e) q_s = q_e - (t_e + IMIN(t_e, BANDW));
+	if (t_e - t_s > 0 && q_e - q_s > 0) {
+		aln_t a = nw_auto(p, w, tseq, q, -1 - (t_s == 0), t_s, t_e, q_s, q_e);
+		s.pos -= a.len - a.tGaps;
+		s.score = a.score; s.len = a.len; s.match = a.match; s.tGaps = a.tGaps; s.qGaps = a.qGaps;
+	}
+	return s;
+}
+
+static void trail_tail(const orc_params *p, nw_ws *w, aln_t *s, const uint64_t *tseq, const uint8_t *q,
+                       int t_s, int t_len, int q_s, int q_len) {
+	int q_e = q_len, t_e = t_len;
+	if (((q_len - q_s) << 1) < (t_len - t_s) || (q_len - q_s + BANDW) < (t_len - t_s)) {
+		t_e = q_len - q_s; t_e = t_s + (t_e + IMIN(t_e, BANDW));
+	} else if (((t_len - t_s) << 1) < (q_len - q_s) || (t_len - t_s + BANDW) < (q_len - q_s)) {
+		q_e = t_len - t_s; q_e = q_s + (q_e + IMIN(q_e, BANDW));
+	}
+	if (t_e - t_s > 0 && q_e - q_s > 0) {
+		aln_t a = nw_auto(p, w, tseq, q, 1 + (t_e == t_len), t_s, t_e, q_s, q_e);
+		s->score += a.score; s->len += a.len; s->match += a.match; s->tGaps += a.tGaps; s->qGaps += a.qGaps;
+	}
+}
+
+static aln_t aln_zero(void) { aln_t s = {0, 1, 0, 0, 0, 0}; return s; }
+
+/* KMA_score: MEMs (found here unless pt->len != 0 on entry), chain, stitch with NW. qN[] = N positions with a
+ * q_len sentinel at qN[nN] (the caller's N[0]++ convention). */
+static aln_t kma_score(const orc_params *p, nw_ws *w, const tindex *ix, const uint8_t *q, int q_len,
+                       const uint64_t *qcomp, const int32_t *qN, int nN1, int mq, mems_t *pt) {
+	const int k = ix->k, t_len = ix->len, U = p->U, M = p->M;
+	int n = pt->len;
+	if (!n) {
+		int j = 0;
+		for (int seg = 0; seg < nN1; ++seg) {
+			int end = (seg != nN1 - 1 ? qN[seg] : q_len) - k + 1;
+			while (j < end) {
+				int slot, cnt, value = tindex_get(ix, kmer_at(qcomp, j, k), &slot, &cnt);
+				if (value == 0) { ++j; continue; }
+				mems_reserve(pt, n + cnt + 1);
+				if (0 < value) {
+					mem_from_seed(ix, q, j, value, k, end + k - 1, &pt->qStart[n], &pt->tStart[n], &pt->qEnd[n], &pt->tEnd[n]);
+					pt->weight[n] = pt->qEnd[n] - pt->qStart[n];
+					j = pt->qEnd[n];
+					++n;
+				} else {
+					int bias = j;
+					for (int c = 0; c < cnt; ++c) {   /* every occurrence, ascending template position */
+						mem_from_seed(ix, q, j, ix->pos[slot + c], k, end + k - 1, &pt->qStart[n], &pt->tStart[n], &pt->qEnd[n], &pt->tEnd[n]);
+						pt->weight[n] = pt->qEnd[n] - pt->qStart[n];
+						if (bias < pt->qEnd[n]) bias = pt->qEnd[n];
+						++n;
+					}
+					j = bias + 1;
+				}
+			}
+			j = qN[seg] + 1;
+		}
+	}
+	pt->len = n;
+	if (!n) return aln_zero();
+	unsigned mapQ = 0;
+	int start = chain_mems(p, pt, q_len, t_len, k, &mapQ);
+	if ((int)mapQ < mq || pt->score[start] < k) { pt->len = 0; return aln_zero(); }
+
+	aln_t s = lead_tail(p, w, ix->seq, q, pt->tStart[start] - 1, pt->qStart[start]);
+	for (;;) {
+		int len = pt->qEnd[start] - pt->qStart[start];
+		s.len += len; s.match += len;
+		for (int i = pt->qStart[start]; i < pt->qEnd[start]; ++i) s.score += p->d[q[i] * 5 + q[i]];
+		if (!pt->next[start]) break;
+		int q_s = pt->qEnd[start], t_s = pt->tEnd[start] - 1, t_e, t_l, q_e;
+		start = pt->next[start];
+		if (pt->qStart[start] < q_s) { pt->tStart[start] += q_s - pt->qStart[start]; pt->qStart[start] = q_s; }
+		t_e = pt->tStart[start] - 1;
+		if (t_e < t_s) {
+			if (t_s <= pt->tEnd[start]) { pt->qStart[start] += t_s - t_e; t_e = t_s; t_l = 0; }
+			else t_l = t_len - t_s + t_e;   /* circular joining: never produced by the linear chainer */
+		} else t_l = t_e - t_s;
+		q_e = pt->qStart[start];
+		if (abs(t_l - q_e + q_s) * U > q_len * M || t_l > q_len || q_e - q_s > (q_len >> 1)) { int keep = s.pos; pt->len = 0; s = aln_zero(); s.pos = keep; return s; }
+		if (t_l > 0 || q_e - q_s > 0) {
+			aln_t a;
+			int band = abs(t_l - q_e + q_s) + BANDW;
+			if (q_e - q_s <= band || t_l <= band) a = nw_full(p, w, ix->seq, q, 0, t_s, t_e, q_s, q_e);
+			else a = nw_band(p, w, ix->seq, q, 0, t_s, t_e, q_s, q_e, band);
+			s.score += a.score; s.len += a.len; s.match += a.match; s.tGaps += a.tGaps; s.qGaps += a.qGaps;
+		}
+	}
+	trail_tail(p, w, &s, ix->seq, q, pt->tEnd[start] - 1, t_len, pt->qEnd[start], q_len);
+	pt->len = 0;
+	return s;
+}
+
+/* preseed (align.c:750): does any k-spaced k-mer of the byte read occur in the template? Bytes past the end of
+ * the read are read as 0 (the reference reads whatever its buffer holds there). */
+static int preseed_hit(const tindex *ix, const uint8_t *q, int q_len) {
+	for (int i = 0; i < q_len; i += ix->k) {
+		uint64_t key = 0;
+		for (int b = 0; b < ix->k; ++b) key = (b ? key << 2 : 0) | (i + b < q_len ? q[i + b] : 0);
+		if (tindex_any_bound(ix, key, 0, ix->len)) return 1;
+	}
+	return 0;
+}
+
+/* anker_rc_comp: MEMs of both strands; the strand with the larger MEM mass wins (ties: forward) and its MEMs are
+ * left in pt. Returns +score (forward), -score (reverse) or 0. */
+static int pick_strand(const orc_params *p, const tindex *ix, const uint8_t *qf, const uint8_t *qr,
+                       const uint64_t *cf, const uint64_t *cr, const int32_t *Nf, const int32_t *Nr, int nN1,
+                       int q_len, int one2one, mems_t *pt) {
+	const int k = ix->k, t_len = ix->len;
+	int score_f = 0, best = 0, tot = 0, cnt_strand[2] = {0, 0}, sc[2] = {0, 0};
+	pt->len = 0;
+	for (int rc = 0; rc < 2; ++rc) {
+		const uint8_t *q = rc ? qr : qf;
+		const uint64_t *comp = rc ? cr : cf;
+		const int32_t *Ns = rc ? Nr : Nf;
+		int i = rc ? 0 : (preseed_hit(ix, q, q_len) ? 0 : q_len), seg = 0, s = 0, mc = 0;
+		while (i < q_len) {
+			int end = Ns[seg++] - k + 1;
+			while (i < end) {
+				int slot, cnt, value = tindex_get(ix, kmer_at(comp, i, k), &slot, &cnt);
+				if (value == 0) { ++i; continue; }
+				mems_reserve(pt, tot + cnt + 1);
+				if (0 < value) {
+					mem_from_seed(ix, q, i, value, k, end, &pt->qStart[tot], &pt->tStart[tot], &pt->qEnd[tot], &pt->tEnd[tot]);
+					pt->weight[tot] = pt->tEnd[tot] - pt->tStart[tot];
+					s += pt->qEnd[tot] - pt->qStart[tot];
+					i = pt->qEnd[tot] + 1;
+					++tot; ++mc;
+				} else {
+					int bias = i;
+					s += k;
+					for (int c = 0; c < cnt; ++c) {
+						mem_from_seed(ix, q, i, ix->pos[slot + c], k, end, &pt->qStart[tot], &pt->tStart[tot], &pt->qEnd[tot], &pt->tEnd[tot]);
+						pt->weight[tot] = pt->qEnd[tot] - pt->qStart[tot];
+						if (bias < pt->qEnd[tot]) bias = pt->qEnd[tot];
+						++tot; ++mc;
+					}
+					s += bias - i;
+					i = bias + 1;
+				}
+			}
+			i = end + k;
+		}
+		sc[rc] = s; cnt_strand[rc] = mc;
+		if (best < s) best = s;
+	}
+	score_f = sc[0];
+	if (one2one && best < k && best * k < (q_len - k - best)) { pt->len = 0; return 0; }
+	if (best == score_f) { pt->len = cnt_strand[0]; return best; }
+	int off = cnt_strand[0], mc = cnt_strand[1];
+	if (off) {
+		memmove(pt->tStart, pt->tStart + off, 4 * (size_t)mc); memmove(pt->tEnd, pt->tEnd + off, 4 * (size_t)mc);
+		memmove(pt->qStart, pt->qStart + off, 4 * (size_t)mc); memmove(pt->qEnd, pt->qEnd + off, 4 * (size_t)mc);
+		memmove(pt->weight, pt->weight + off, 4 * (size_t)mc);
+	}
+	pt->len = mc;
+	(void)t_len; (void)p;
+	return -best;
+}
+
+/* ------------------------------------------------------------------ the stream ------- */
+
+typedef struct { uint8_t *p; size_t len, cap; } obuf;
+static void ob_put(obuf *o, const void *src, size_t n) {
+	if (o->len + n > o->cap) { o->cap = (o->len + n) * 2 + 4096; o->p = realloc(o->p, o->cap); }
+	memcpy(o->p + o->len, src, n); o->len += n;
+}
+
+static void unpack(const uint64_t *seq, int len, const int32_t *N, int nN, uint8_t *out) {
+	for (int i = 0; i < len; ++i) out[i] = (uint8_t)nuc_at(seq, i);
+	for (int i = 0; i < nN; ++i) out[N[i]] = 4;
+	out[len] = 0;
+}
+
+/* stage-2 stream (single-end records) -> frag_raw stream (without the final int32 0 of runkma.c:444) and the two
+ * ConClave accumulators. cand (optional): 8 x int32 per (read, candidate), same rows as ref_harness.c writes.
+ * Returned buffers are malloc'ed; free with orc_free. */
+int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const uint8_t *in, size_t in_bytes,
+                     int one2one, double scoreT, int mq, int minlen, double mrc,
+                     uint8_t **frag_out, size_t *frag_bytes, uint64_t *as, uint64_t *uas,
+                     int32_t **cand_out, size_t *cand_rows, int64_t *nw_cells) {
+	if (orc_db_load_seq(db, prefix)) return -1;
+	int k = db->lengths[0];
+	if (k < 4 || 31 < k) k = 16;
+	const int Wl = -p->Wl;
+	(void)Wl;
+	tindex **tix = calloc(db->DB_size, sizeof(tindex *));
+	nw_ws ws; memset(&ws, 0, sizeof(ws));
+	mems_t pt; memset(&pt, 0, sizeof(pt));
+	obuf frag = {0, 0, 0}, cand = {0, 0, 0};
+	size_t ip = 0, cap = 0;
+	uint64_t *seq = 0, *rseq = 0; int32_t *N = 0, *rN = 0; uint8_t *qf = 0, *qr = 0;
+	int *bT = 0, *bS = 0, *bE = 0, *Sc = 0, *Ln = 0; int bcap = 0;
+	int ridx = 0;
+	memset(as, 0, 8 * (size_t)db->DB_size); memset(uas, 0, 8 * (size_t)db->DB_size);
+
+	while (ip + 28 <= in_bytes) {
+		int32_t h[7]; memcpy(h, in + ip, 28);
+		if (h[0] < 0) break;
+		ip += 28;
+		const int q_len = h[0], words = h[1], nN = h[2], rc_flag = h[3], nt = h[4], hl = h[5];
+		int flag = h[6];
+		if ((size_t)words + 2 > cap) {
+			cap = 2 * (size_t)words + 2;
+			seq = realloc(seq, 8 * cap); rseq = realloc(rseq, 8 * cap);
+			qf = realloc(qf, 64 * cap + 64); qr = realloc(qr, 64 * cap + 64);
+		}
+		N = realloc(N, 4 * (size_t)(nN + 2)); rN = realloc(rN, 4 * (size_t)(nN + 2));
+		memcpy(seq, in + ip, 8 * (size_t)words); seq[words] = 0; ip += 8 * (size_t)words;
+		memcpy(N, in + ip, 4 * (size_t)nN); ip += 4 * (size_t)nN;
+		const int32_t *T = (const int32_t *)0; int32_t *Tbuf = malloc(4 * (size_t)(nt + 1));
+		memcpy(Tbuf, in + ip, 4 * (size_t)nt); ip += 4 * (size_t)nt; T = Tbuf;
+		const uint8_t *hdr = in + ip; ip += hl;
+		if (nt == 0) { free(Tbuf); fprintf(stderr, "orc_align_stream: paired records not supported\n"); return -2; }
+		if (q_len < k) { free(Tbuf); ++ridx; continue; }
+
+		if (rc_flag < 0) { orc_revcomp(seq, q_len, N, nN, rseq, rN); rseq[words] = 0; unpack(rseq, q_len, rN, nN, qr); rN[nN] = q_len; }
+		unpack(seq, q_len, N, nN, qf); N[nN] = q_len;
+		if (nt > bcap) { bcap = 2 * nt; bT = realloc(bT, 4 * bcap); bS = realloc(bS, 4 * bcap); bE = realloc(bE, 4 * bcap); Sc = realloc(Sc, 4 * bcap); Ln = realloc(Ln, 4 * bcap); }
+
+		double bestScore = 0; int best_read = 0, hits = 0;
+		const int arc = rc_flag < 0;
+		pt.len = 0;
+		for (int ti = 0; ti < nt; ++ti) {
+			int tmpl = T[ti], at = abs(tmpl);
+			if (!tix[at]) tix[at] = tindex_build(db->seq + db->seq_off[at], db->lengths[at], k);
+			const tindex *ix = tix[at];
+			aln_t a;
+			if (arc) {
+				int rc = pick_strand(p, ix, qf, qr, seq, rseq, N, rN, nN + 1, q_len, one2one, &pt);
+				if (rc < 0) { tmpl = -at; a = kma_score(p, &ws, ix, qr, q_len, rseq, rN, nN + 1, mq, &pt); }
+				else if (rc) { tmpl = at; a = kma_score(p, &ws, ix, qf, q_len, seq, N, nN + 1, mq, &pt); }
+				else { memset(&a, 0, sizeof(a)); pt.len = 0; }
+			} else if (tmpl < 0) a = kma_score(p, &ws, ix, qr, q_len, rseq, rN, nN + 1, mq, &pt);
+			else a = kma_score(p, &ws, ix, qf, q_len, seq, N, nN + 1, mq, &pt);
+			if (cand_out) { int32_t row[8] = {ridx, tmpl, a.score, a.len, a.pos, a.match, a.tGaps, a.qGaps}; ob_put(&cand, row, 32); }
+
+			int aln_len = a.len, start = a.pos, end = start + aln_len - a.tGaps, t_len = db->lengths[at], read_score;
+			double score;
+			if (t_len < end) end -= t_len;
+			if (q_len <= aln_len || t_len <= aln_len) score = aln_len; else score = q_len < t_len ? q_len : t_len;
+			read_score = a.score;
+			if (minlen <= aln_len && ((mrc * q_len <= a.len - a.qGaps) || (mrc * t_len <= a.len - a.tGaps))) score = read_score / score;
+			else { read_score = 0; score = 0; }
+			if (k < read_score && scoreT <= score) {
+				bT[hits] = tmpl; bS[hits] = start; bE[hits] = end; Sc[hits] = read_score; Ln[hits] = aln_len; ++hits;
+				if (bestScore < score) bestScore = score;
+				if (best_read < read_score) best_read = read_score;
+			}
+		}
+		/* note: a reverse-strand record (rc_flag < 0 path absent) aligns the strand stage 2 wrote: qf */
+		if (best_read > k) {   /* update_Scores, minFrac == 1.0 */
+			int kept = 0;
+			for (int i = 0; i < hits; ++i) {
+				double minScore = Sc[i] / Ln[i];
+				if (minScore == bestScore || Sc[i] == best_read) {
+					bT[kept] = bT[i]; bS[kept] = bS[i]; bE[kept] = bE[i]; ++kept;
+					as[abs(bT[kept - 1])] += Sc[i];
+				}
+			}
+			if (kept == 1) uas[abs(bT[0])] += best_read;
+			int32_t b[5] = {q_len, kept, best_read, hl, flag};
+			ob_put(&frag, b, 20); ob_put(&frag, qf, q_len); ob_put(&frag, hdr, hl);
+			ob_put(&frag, bS, 4 * (size_t)kept); ob_put(&frag, bE, 4 * (size_t)kept); ob_put(&frag, bT, 4 * (size_t)kept);
+		}
+		free(Tbuf);
+		++ridx;
+	}
+	for (int t = 0; t < db->DB_size; ++t) tindex_free(tix[t]);
+	free(tix); free(seq); free(rseq); free(N); free(rN); free(qf); free(qr);
+	free(bT); free(bS); free(bE); free(Sc); free(Ln);
+	free(pt.tStart); free(pt.tEnd); free(pt.qStart); free(pt.qEnd); free(pt.weight); free(pt.score); free(pt.next);
+	for (int i = 0; i < 2; ++i) { free(ws.D[i]); free(ws.P[i]); } free(ws.E);
+	*frag_out = frag.p; *frag_bytes = frag.len;
+	if (cand_out) { *cand_out = (int32_t *)cand.p; *cand_rows = cand.len / 32; }
+	if (nw_cells) *nw_cells = ws.cells;
+	return 0;
+}
+
+void orc_free(void *p) { free(p); }

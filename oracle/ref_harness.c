@@ -1,0 +1,155 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- driver around the UNMODIFIED reference (linked from oracle/_ref/libkma.a).
+ * Nothing here restates reference logic: it sets the globals the way kma.c / runkma.c do and calls the
+ * reference's own stage-3 entry point, so tests get ground truth for the alignment pass.
+ *
+ *   ref_aln <db_prefix> <stage2.bin> <frag_raw.out> <scores.out> [cand.out] [-1t1]
+ *
+ * frag_raw.out : what alnFrags_threaded (alnfrags.c:2150) writes to frag_out_raw for the stream
+ * scores.out   : int32 DB_size, uint64 alignment_scores[DB_size], uint64 uniq_alignment_scores[DB_size]
+ * cand.out     : (optional) one 8 x int32 row per (read, candidate template) from a second pass that calls the
+ *                reference's anker_rc_comp / KMA_score exactly as alnFragsSE (alnfrags.c:1080-1128) does:
+ *                {read index, template (signed as aligned), score, len, pos, match, tGaps, qGaps}
+ * Built by Makefile.ref; sources are compiled where they lie under /root/reference.
+ */
+#define _GNU_SOURCE
+#include <fcntl.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include "align.h"
+#include "alnfrags.h"
+#include "ankers.h"
+#include "chain.h"
+#include "compdna.h"
+#include "hashmapcci.h"
+#include "nw.h"
+#include "penalties.h"
+#include "qseqs.h"
+#include "runkma.h"
+
+static Penalties *make_rewards(void) {
+	Penalties *r = calloc(1, sizeof(Penalties));
+	int Ts = -2, Tv = -2, i, j;
+	r->M = 1; r->MM = (Ts + Tv - 1) / 2; r->U = -1; r->W1 = -3; r->Wl = -6; r->Mn = 0; r->PE = 7;
+	int **d = malloc(5 * sizeof(int *) + 25 * sizeof(int));
+	d[0] = (int *)(d + 5);
+	for (i = 0; i < 5; ++i) d[i] = d[0] + 5 * i;
+	for (i = 0; i < 4; ++i) {
+		for (j = 0; j < 4; ++j) d[i][j] = Tv;
+		d[i][4] = r->Mn;
+		d[i][(i - 2) < 0 ? (i + 2) : (i - 2)] = Ts;
+		d[i][i] = r->M;
+	}
+	for (j = 0; j < 5; ++j) d[4][j] = r->Mn;
+	d[4][4] = 0;
+	r->d = d;
+	return r;
+}
+
+int main(int argc, char **argv) {
+	if (argc < 5) { fprintf(stderr, "usage: ref_aln db s2.bin frag_raw.out scores.out [cand.out] [-1t1]\n"); return 2; }
+	int one2one = 0, exhaustive = 0, ts = 0;
+	const char *cand_path = 0;
+	for (int a = 5; a < argc; ++a) { if (!strcmp(argv[a], "-1t1")) one2one = 1; else cand_path = argv[a]; }
+	char path[4096];
+	int *template_lengths; long unsigned *as, *uas;
+	snprintf(path, sizeof(path), "%s", argv[1]);
+	char *p2 = malloc(strlen(path) + 64); strcpy(p2, path);
+	int DB_size = load_DBs_KMA(p2, &as, &uas, &template_lengths, 0);
+	int kmersize = template_lengths[0];
+	if (kmersize < 4 || 31 < kmersize) kmersize = 16;
+	snprintf(path, sizeof(path), "%s.seq.b", argv[1]);
+	int seq_in = open(path, O_RDONLY);
+	if (seq_in < 0) { perror(path); return 1; }
+	long *seq_indexes = malloc((DB_size + 1) * sizeof(long));
+	seq_indexes[0] = 0; seq_indexes[1] = 0;
+	for (int i = 2; i < DB_size; ++i) seq_indexes[i] = seq_indexes[i - 1] + ((template_lengths[i - 1] >> 5) + 1) * sizeof(long unsigned);
+
+	Penalties *rewards = make_rewards();
+	/* the NULL-argument "setter" calls of kma.c:1249-1252, 1428-1429 */
+	preseed(0, 0, exhaustive);
+	trimSeedsPtr(0, ts);
+	anker_rc(0, 0, one2one, 0, 0, 0);
+	anker_rc_comp(0, 0, (unsigned char *)(&one2one), 0, 0, 0, 0, 0);
+	alignLoadPtr = &alignLoad_fly;
+
+	for (int pass = 0; pass < (cand_path ? 2 : 1); ++pass) {
+		FILE *in = fopen(argv[2], "rb");
+		if (!in) { perror(argv[2]); return 1; }
+		HashMapCCI **templates_index = calloc(DB_size, sizeof(HashMapCCI *));
+		CompDNA *qc = malloc(sizeof(CompDNA)), *qrc = malloc(sizeof(CompDNA));
+		allocComp(qc, 1024); allocComp(qrc, 1024);
+		NWmat *NWm = malloc(sizeof(NWmat));
+		NWm->NW_s = 1024 * 1024; NWm->NW_q = 1024; NWm->E = malloc(NWm->NW_s);
+		NWm->D[0] = malloc((NWm->NW_q << 1) * sizeof(int)); NWm->P[0] = malloc((NWm->NW_q << 1) * sizeof(int));
+		NWm->D[1] = NWm->D[0] + NWm->NW_q; NWm->P[1] = NWm->P[0] + NWm->NW_q; NWm->rewards = rewards;
+		AlnPoints *points = seedPoint_init(1024, rewards);
+		int *matched = malloc(((DB_size + 1) << 1) * sizeof(int));
+		if (pass == 0) {
+			Aln_thread *t = calloc(1, sizeof(Aln_thread));
+			t->matched_templates = matched;
+			t->bestTemplates = malloc(((DB_size + 1) << 1) * sizeof(int));
+			t->bestTemplates_r = malloc(((DB_size + 1) << 1) * sizeof(int));
+			t->best_start_pos = malloc((DB_size << 1) * sizeof(int));
+			t->best_end_pos = malloc((DB_size << 1) * sizeof(int));
+			t->Lengths = malloc((DB_size << 1) * sizeof(int));
+			t->alignment_scores = as; t->uniq_alignment_scores = uas;
+			t->seq_indexes = seq_indexes; t->inputfile = in;
+			t->frag_out_raw = fopen(argv[3], "wb"); t->frag_out_all = 0; t->seq_in = seq_in;
+			t->qseq_comp = qc; t->qseq_r_comp = qrc;
+			t->qseq = setQseqs(1024); t->qseq_r = setQseqs(1024); t->header = setQseqs(256); t->header_r = setQseqs(256);
+			t->points = points; t->NWmatrices = NWm; t->kmersize = kmersize; t->minlen = 16; t->mq = 0; t->sam = 0;
+			t->scoreT = 0.5; t->mrc = 0.0; t->minFrac = 1.0;
+			t->template_lengths = template_lengths; t->templates_index = templates_index;
+			alnFrags_threaded(t);
+			fclose(t->frag_out_raw);
+			FILE *so = fopen(argv[4], "wb");
+			fwrite(&DB_size, 4, 1, so); fwrite(as, 8, DB_size, so); fwrite(uas, 8, DB_size, so);
+			fclose(so);
+		} else {
+			/* per-candidate ground truth: the calls alnFragsSE makes, results recorded instead of reduced */
+			FILE *co = fopen(cand_path, "wb");
+			Qseqs *header = setQseqs(256);
+			unsigned char *qseq = malloc(1 << 24), *qseq_r = malloc(1 << 24);
+			int hdr[7], ridx = 0;
+			while (fread(hdr, 4, 7, in) == 7 && hdr[0] >= 0) {
+				qc->seqlen = hdr[0]; qc->complen = hdr[1];
+				if (qc->size <= qc->seqlen) { freeComp(qc); allocComp(qc, qc->seqlen << 1); freeComp(qrc); allocComp(qrc, qc->seqlen << 1); qc->seqlen = hdr[0]; qc->complen = hdr[1]; }
+				qc->N[0] = hdr[2]; matched[0] = hdr[4]; header->len = hdr[5];
+				if (header->size <= header->len) { header->size = header->len << 1; header->seq = realloc(header->seq, header->size); }
+				if (fread(qc->seq, 8, qc->complen, in) != qc->complen) break;
+				if (fread(qc->N + 1, 4, qc->N[0], in) != (size_t)qc->N[0]) break;
+				if (fread(matched + 1, 4, matched[0], in) != (size_t)matched[0]) break;
+				if (fread(header->seq, 1, header->len, in) != (size_t)header->len) break;
+				int rc_flag = hdr[3], q_len = qc->seqlen;
+				if (matched[0] == 0) { fprintf(stderr, "cand pass: paired records not supported\n"); return 3; }
+				if (q_len >= kmersize) {
+					if (rc_flag < 0) { rc_comp(qc, qrc); unCompDNA(qrc, qseq_r); qrc->N[0]++; qrc->N[qrc->N[0]] = q_len; }
+					unCompDNA(qc, qseq); qc->N[0]++; qc->N[qc->N[0]] = q_len;
+					int arc = rc_flag < 0;
+					points->len = 0;
+					for (int t_i = 1; t_i <= matched[0]; ++t_i) {
+						int template = matched[t_i], at = abs(template), rc;
+						AlnScore st;
+						if (!templates_index[at]) templates_index[at] = alignLoadPtr(0, seq_in, template_lengths[at], kmersize, seq_indexes[at]);
+						if (arc) {
+							rc = anker_rc_comp(templates_index[at], qseq, qseq_r, qc, qrc, 0, q_len, points);
+							if (rc < 0) { template = -at; st = KMA_score(templates_index[at], qseq_r, q_len, 0, q_len, qrc, 0, 0.5, points, NWm); }
+							else if (rc) { template = at; st = KMA_score(templates_index[at], qseq, q_len, 0, q_len, qc, 0, 0.5, points, NWm); }
+							else { memset(&st, 0, sizeof(st)); points->len = 0; }
+						} else if (template < 0) st = KMA_score(templates_index[at], qseq_r, q_len, 0, q_len, qrc, 0, 0.5, points, NWm);
+						else st = KMA_score(templates_index[at], qseq, q_len, 0, q_len, qc, 0, 0.5, points, NWm);
+						int row[8] = {ridx, template, st.score, st.len, st.pos, st.match, st.tGaps, st.qGaps};
+						fwrite(row, 4, 8, co);
+					}
+				}
+				++ridx;
+			}
+			fclose(co);
+		}
+		fclose(in);
+	}
+	return 0;
+}

@@ -90,3 +90,64 @@ def golden_dir():
         yield d
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+REF_ALN = os.path.join(ROOT, "oracle", "_ref", "ref_aln")
+
+
+def ref_align(db_prefix: str, s2: bytes, tmp: str, one2one=True, cand=True):
+    """Ground truth of the alignment pass from the unmodified reference (oracle/ref_harness.c):
+    (frag_raw bytes, alignment_scores, uniq_alignment_scores, cand rows [n, 8] or None)."""
+    p = os.path.join(tmp, "s2.bin")
+    with open(p, "wb") as f:
+        f.write(s2)
+    args = [REF_ALN, db_prefix, p, os.path.join(tmp, "fr.out"), os.path.join(tmp, "sc.out")]
+    if cand:
+        args.append(os.path.join(tmp, "cand.out"))
+    if one2one:
+        args.append("-1t1")
+    r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    frag = open(os.path.join(tmp, "fr.out"), "rb").read()
+    sc = np.fromfile(os.path.join(tmp, "sc.out"), dtype=np.uint8)
+    n = int(sc[:4].view(np.int32)[0])
+    arr = sc[4:].view(np.uint64)
+    c = np.fromfile(os.path.join(tmp, "cand.out"), dtype=np.int32).reshape(-1, 8) if cand else None
+    return frag, arr[:n].copy(), arr[n:2 * n].copy(), c
+
+
+def oracle_align_stream(db_prefix: str, s2: np.ndarray, one2one=True, want_cand=True):
+    """(frag_raw bytes, alignment_scores, uniq_alignment_scores, cand rows, nw cells) from the C oracle."""
+    L = orc()
+    L.orc_align_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_int,
+                                   C.c_int, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int64)]
+    L.orc_free.argtypes = [C.c_void_p]
+    db = L.orc_db_open(os.fsencode(db_prefix))
+    assert db
+    DB = int(np.fromfile(db_prefix + ".length.b", dtype=np.int32, count=1)[0])
+    a = np.zeros(DB, dtype=np.uint64)
+    u = np.zeros(DB, dtype=np.uint64)
+    fo, fb, co, cr, cells = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t(), C.c_int64()
+    s2 = np.ascontiguousarray(s2, dtype=np.uint8)
+    rc = L.orc_align_stream(db, os.fsencode(db_prefix), oracle_params(), s2.ctypes.data, len(s2), int(one2one), 0.5, 0, 16, 0.0,
+                            C.byref(fo), C.byref(fb), a.ctypes.data, u.ctypes.data,
+                            C.byref(co) if want_cand else None, C.byref(cr), C.byref(cells))
+    assert rc == 0
+    frag = C.string_at(fo, fb.value) if fb.value else b""
+    cand = None
+    if want_cand:
+        cand = np.frombuffer(C.string_at(co, cr.value * 32), dtype=np.int32).reshape(-1, 8).copy() if cr.value else np.zeros((0, 8), np.int32)
+        L.orc_free(co)
+    L.orc_free(fo)
+    L.orc_db_close(db)
+    return frag, a, u, cand, cells.value
+
+
+def cand_equal(a, b):
+    """candidate rows equal; the reference leaves `match` undefined where nothing aligned"""
+    if a.shape != b.shape:
+        return False
+    ok = a == b
+    ok[:, 5] |= (b[:, 2] == 0)
+    return bool(ok.all())
