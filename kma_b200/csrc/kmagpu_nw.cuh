@@ -1,0 +1,299 @@
+// Warp-level affine-gap Needleman-Wunsch with traceback statistics: the device routine behind the alignment
+// kernel (kmagpu_align.cu) and the stand-alone NW batch entry point.
+//
+// WHAT is computed is NW_score (nw.c:642-890) and NW_band_score (nw.c:892-1188): same int32 recurrences, same tie
+// rules, same traceback byte per cell, same start-cell selection for the k modes, same walk. HOW is ours:
+//
+//   * Coordinates. The reference fills from the END of both sequences (m = t_len-1..0, n = q_len-1..0). We use
+//     i = t_len-1-m, j = q_len-1-n, so cell (i,j) needs (i,j-1) [D,Q], (i-1,j) [D,P] and (i-1,j-1) [D].
+//   * Band as geometry. The reference's skewed band buffer (row m covers query positions c_m-half..c_m+half, c_m
+//     falling by one per row) is the column range [max(0,a+i), min(q_len-1,a+i+band)] of row i; the full matrix is
+//     the same code with the range [0, q_len-1].
+//   * Continuous wavefront. Lane l owns rows l, l+32, l+64, ... Row i = 32r+l computes its cell of in-row offset u
+//     (u = j for the full matrix, u = j-i-a inside the band) at step T = s*l + P*r + u, s = 1 (full) or 2 (band),
+//     P = max(W, 33s-...) the row period, W the row width. Every lane then needs, at every step, exactly the (D,P)
+//     its upper neighbour lane produced one step earlier (one shuffle each) and the D it received the step before
+//     (the diagonal) -- for the full matrix and for the band alike. Lane 0 is fed by lane 31 of the previous round
+//     through a row buffer that it prefetches one step ahead. With W >= 33s the lanes never idle between rounds, so
+//     a band of 65 columns runs at ~97 % lane utilisation instead of the ~50 % of a strip-by-strip wavefront.
+//   * Traceback bytes are stored step-major / lane-minor: one coalesced 32-byte store per warp per step.
+//
+// The per-lane step and the finishing walk are plain functions of (geometry, lane state, neighbour values) so the
+// same source is compiled by g++ into a lock-step emulator (tests/emu/nw_emu.cpp) that is checked against the
+// oracle on the CPU; the CUDA wrapper at the bottom only adds the shuffles.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define NW_HD __host__ __device__ __forceinline__
+#else
+#define NW_HD inline
+#endif
+
+struct NwPen { int W1, U, MM, M; int d[25]; };
+struct NwStat { int score, len, pos, match, tGaps, qGaps; };
+struct NwRow { int D, P; };
+
+struct NwGeo {
+	int t_len, q_len, k, banded, band, a, W, P, s, R, Tmax, NEG, W1, U;
+	NW_HD int off(int i) const { return banded ? a + i : 0; }
+	NW_HD int jlo(int i) const { int v = banded ? a + i : 0; return v < 0 ? 0 : v; }
+	NW_HD int jhi(int i) const { int v = banded ? a + i + band : q_len - 1; return v < q_len - 1 ? v : q_len - 1; }
+	// D of the boundary column (all query consumed) beside row i, and of the boundary row (all template consumed)
+	NW_HD int bcol(int i) const { return i < 0 ? 0 : (0 < k ? 0 : W1 + i * U); }
+	NW_HD int brow(int j) const { return j < 0 ? 0 : (k == 2 ? 0 : W1 + j * U); }
+	NW_HD size_t eaddr(int i, int j) const {
+		const int l = i & 31;
+		return ((size_t)(s * l + P * (i >> 5) + (j - off(i)))) * 32 + (size_t)l;
+	}
+	NW_HD size_t ebytes() const { return (size_t)Tmax * 32; }
+};
+
+// false: geometry the reference itself never produces (band narrower than the length difference)
+NW_HD bool nw_geo_init(NwGeo &g, const NwPen &pen, int t_len, int q_len, int k, int band) {
+	g.t_len = t_len; g.q_len = q_len; g.k = k; g.banded = band != 0;
+	g.W1 = pen.W1; g.U = pen.U;
+	if (band & 1) ++band;   // nw.c:374-376
+	g.band = band;
+	if (g.banded) {
+		const int half = band >> 1, c0 = (t_len + q_len) >> 1;
+		int dlt = t_len - q_len;
+		if (dlt < 0) dlt = -dlt;
+		if (band < dlt + 2 || band < 2) return false;
+		g.a = q_len - 1 - c0 - half;
+		g.W = band + 1; g.s = 2; g.P = g.W < 65 ? 65 : g.W;
+	} else {
+		g.a = 0; g.W = q_len; g.s = 1; g.P = g.W < 33 ? 33 : g.W;
+	}
+	g.R = (t_len + 31) >> 5;
+	g.Tmax = g.s * ((t_len - 1) & 31) + g.P * (g.R - 1) + g.W;
+	g.NEG = (t_len + q_len) * (pen.MM + pen.U + pen.W1);
+	return true;
+}
+
+NW_HD int nw_nuc(const uint64_t *seq, int pos) {
+#if defined(__CUDA_ARCH__)
+	return (int)((__ldg(seq + (pos >> 5)) << ((pos & 31) << 1)) >> 62);
+#else
+	return (int)((seq[pos >> 5] << ((pos & 31) << 1)) >> 62);
+#endif
+}
+
+struct NwLane {
+	int i, u;            // row and in-row offset of the NEXT step
+	int tn;              // template base of row i
+	int myD, myP;        // last cell computed (what the lane below receives)
+	int Dleft, Qleft;    // D, Q of (i, j-1)
+	int Ddiag;           // D of (i-1, j-1)
+	int nxD, nxP;        // lane 0: prefetched (D,P) of (i-1, j) for the next step
+	int colBest, colBestI;   // k < 0: best D over the rows' last column (query start), first maximum in fill order
+};
+
+NW_HD void nw_lane_init(const NwGeo &g, NwLane &L, int lane, const uint64_t *tseq, int t_s) {
+	L.i = lane; L.u = -g.s * lane;
+	L.tn = lane < g.t_len ? nw_nuc(tseq, t_s + g.t_len - 1 - lane) : 0;
+	L.myD = 0; L.myP = g.NEG; L.Dleft = 0; L.Qleft = g.NEG; L.Ddiag = 0; L.nxD = 0; L.nxP = g.NEG;
+	L.colBest = g.NEG; L.colBestI = 0x7fffffff;
+}
+
+// One step of one lane. aD/aP: (D,P) the lane above produced in the previous step (ignored by lane 0).
+// q points at the first query base of the window. Writes E, the row buffer (lane 31) and lastD (last row).
+NW_HD void nw_lane_step(const NwGeo &g, const NwPen &pen, NwLane &L, const int lane, const int T, int aD, int aP,
+                        const uint64_t *tseq, const int t_s, const uint8_t *q, uint8_t *E, NwRow *rowbuf, int *lastD) {
+	const int i = L.i, j = L.u + g.off(i);
+	const bool act = i < g.t_len && L.u >= 0 && L.u < g.W && j >= 0 && j < g.q_len;
+	if (lane == 0 && act) {
+		if (i == 0) { aD = g.brow(j); aP = g.NEG; }
+		else { aD = L.nxD; aP = L.nxP; }
+	}
+	if (act) {
+		const int jl = g.jlo(i);
+		if (j == jl) {   // first cell of the row: what lies to its right and on its diagonal
+			if (jl == 0) { L.Dleft = g.bcol(i); L.Ddiag = g.bcol(i - 1); }
+			else {
+				L.Dleft = g.NEG;   // outside the band (nw.c:1031-1034)
+				if (lane == 0) L.Ddiag = i == 0 ? g.brow(j - 1) : rowbuf[j - 1].D;
+			}
+			L.Qleft = g.NEG;
+		}
+		const int sub = pen.d[L.tn * 5 + q[g.q_len - 1 - j]];
+		const int W1 = g.W1, U = g.U;
+		int D, Q, P, e, fl = 0, x;
+		if (g.banded && j == g.jhi(i)) {   // left edge of the band: no vertical move (nw.c:1076-1102)
+			Q = L.Dleft + W1;
+			x = L.Qleft + U;
+			if (Q < x) { Q = x; e = 3; } else { e = 2; fl = 16; }
+			P = g.NEG;
+			D = L.Ddiag + sub;
+			if (Q <= D) e = 1; else D = Q;
+		} else {                           // nw.c:166-212
+			Q = L.Dleft + W1; P = aD + W1;
+			if (Q < P) { D = P; e = 4; } else { D = Q; e = 2; }
+			x = L.Qleft + U;
+			if (Q < x) { Q = x; if (D <= x) { D = x; e = 3; } } else fl |= 16;
+			x = aP + U;
+			if (P < x) { P = x; if (D <= x) { D = x; e = 5; } } else fl |= 32;
+			x = L.Ddiag + sub;
+			if (D <= x) { D = x; e = 1; }
+		}
+		E[(size_t)T * 32 + lane] = (uint8_t)(fl | e);
+		L.Dleft = D; L.Qleft = Q; L.myD = D; L.myP = P;
+		if (g.k < 0 && j == g.q_len - 1 && L.colBest < D) { L.colBest = D; L.colBestI = i; }
+		if (i == g.t_len - 1) lastD[j] = D;
+		else if (lane == 31) { NwRow o; o.D = D; o.P = P; rowbuf[j] = o; }
+	}
+	L.Ddiag = aD;
+	if (++L.u == g.P) {
+		L.u = 0; L.i += 32;
+		if (L.i < g.t_len) L.tn = nw_nuc(tseq, t_s + g.t_len - 1 - L.i);
+	}
+}
+
+// lane 0, after the step's stores are visible: fetch what the next step needs from the row buffer
+NW_HD void nw_lane0_prefetch(const NwGeo &g, NwLane &L, const NwRow *rowbuf) {
+	if (L.i > 0 && L.i < g.t_len && L.u >= 0 && L.u < g.W) {
+		const int j = L.u + g.off(L.i);
+		if (j >= 0 && j < g.q_len) { NwRow v = rowbuf[j]; L.nxD = v.D; L.nxP = v.P; }
+	}
+}
+
+// traceback byte at (m, qpos) in reference coordinates, including the analytic boundary row / column codes
+NW_HD int nw_e_at(const NwGeo &g, const uint8_t *E, int m, int qpos) {
+	if (m >= g.t_len) {   // row "all template consumed" (nw.c:118-151, 1002-1019)
+		if (g.k == 2 || qpos >= g.q_len) return 0;
+		return qpos == g.q_len - 1 ? 18 : 3;
+	}
+	const int i = g.t_len - 1 - m, j = g.q_len - 1 - qpos, jl = g.jlo(i);
+	if (j < jl) {         // right of the row's last cell
+		if (g.banded) return jl > 0 ? 37 : (0 < g.k ? 0 : 37);
+		return 0 < g.k ? 0 : (m == g.t_len - 1 ? 36 : 5);
+	}
+	if (j > g.jhi(i)) return 0;   // unreachable by construction
+	return E[g.eaddr(i, j)];
+}
+
+// traceback statistics (nw.c:850-887, 1143-1185) from the start cell
+NW_HD void nw_walk(const NwGeo &g, const uint8_t *E, int m, int qp, NwStat &s) {
+	int e;
+	s.len = s.match = s.tGaps = s.qGaps = 0;
+	while ((e = nw_e_at(g, E, m, qp)) != 0) {
+		const int c = e & 7;
+		if (c == 1) { ++s.match; ++m; ++qp; }
+		else if (c >= 4) {
+			while (!(nw_e_at(g, E, m, qp) >> 4)) { ++m; ++s.len; ++s.qGaps; }
+			++s.qGaps; ++m;
+		} else {
+			while (!(nw_e_at(g, E, m, qp) >> 3)) { ++qp; ++s.len; ++s.tGaps; }
+			++s.tGaps; ++qp;
+		}
+		++s.len;
+	}
+}
+
+// start cell (nw.c:831-848, 1127-1141) given the reduced column maximum. rowBest/rowBestQ: k == -2 only, the LAST
+// maximum of D along row m = 0 over the query positions nw_row0_range() names.
+NW_HD void nw_row0_range(const NwGeo &g, int *qlo, int *qhi) {
+	const int last = g.t_len - 1;
+	const int lo0 = g.q_len - 1 - g.jhi(last), hi0 = g.q_len - 1 - g.jlo(last);
+	*qlo = lo0; *qhi = hi0;
+	if (g.banded) {
+		// the reference scans its row buffer n = en..bq-1 (nw.c:1135); en = rows whose band start was clamped
+		int en = 0;
+		if (lo0 == 0) { en = -(g.a + last + g.band - (g.q_len - 1)); if (en < 0) en = 0; }
+		const int qe = lo0 + (g.band - en);
+		if (qe < *qhi) *qhi = qe;
+	}
+}
+
+NW_HD void nw_start_cell(const NwGeo &g, int colBest, int colBestI, const int *lastD, int rowBest, int rowBestQ,
+                         int *best_m, int *best_q, int *score) {
+	const int last = g.t_len - 1;
+	const int lo0 = g.q_len - 1 - g.jhi(last);
+	if (g.k < 0) {
+		if (colBestI == 0x7fffffff) { *best_m = 0; *score = g.NEG; } else { *best_m = g.t_len - 1 - colBestI; *score = colBest; }
+		*best_q = 0;
+		if (g.banded && *best_m == 0) { *best_q = lo0; *score = lastD[g.q_len - 1 - lo0]; }
+		if (g.k == -2 && rowBestQ >= 0 && *score <= rowBest) { *score = rowBest; *best_m = 0; *best_q = rowBestQ; }
+	} else {
+		*best_m = 0; *best_q = g.banded ? lo0 : 0;
+		*score = lastD[g.q_len - 1 - *best_q];
+	}
+}
+
+NW_HD bool nw_trivial(const NwPen &pen, int t_len, int q_len, NwStat &s) {   // nw.c:663-684
+	if (t_len != 0 && q_len != 0) return false;
+	s.score = s.len = s.pos = s.match = s.tGaps = s.qGaps = 0;
+	if (t_len != q_len) {
+		if (t_len == 0) { s.len = q_len; s.tGaps = q_len; s.score = pen.W1 + (q_len - 1) * pen.U; }
+		else { s.len = t_len; s.qGaps = t_len; s.score = pen.W1 + (t_len - 1) * pen.U; }
+	}
+	return true;
+}
+
+#if defined(__CUDACC__)
+// per-warp scratch in global memory
+struct NwScratch {
+	NwRow *rowbuf;    // >= q_cap entries
+	int *lastD;       // >= q_cap entries
+	uint8_t *E;       // e_cap bytes
+	size_t e_cap;
+	int q_cap;
+};
+
+// status of nw_warp
+#define NW_OK 0
+#define NW_TOO_BIG 1      // scratch too small: the caller re-runs the problem on the large-scratch path
+#define NW_BAD_BAND 2
+
+// All 32 lanes call with identical arguments; every lane returns the same result.
+__device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict__ tseq, const uint8_t *query, int k, int t_s,
+                                    int t_e, int q_s, int q_e, int band, const NwScratch &ws, NwStat *out,
+                                    unsigned long long *cells) {
+	const int lane = threadIdx.x & 31;
+	const int t_len = t_e - t_s, q_len = q_e - q_s;
+	NwStat s;
+	if (nw_trivial(pen, t_len, q_len, s)) { *out = s; return NW_OK; }
+	NwGeo g;
+	if (!nw_geo_init(g, pen, t_len, q_len, k, band)) return NW_BAD_BAND;
+	if (g.ebytes() > ws.e_cap || q_len + 1 > ws.q_cap) return NW_TOO_BIG;
+	if (cells) *cells += (unsigned long long)t_len * (unsigned long long)(g.banded ? g.band + 1 : q_len);
+	const uint8_t *q = query + q_s;
+	NwLane L;
+	nw_lane_init(g, L, lane, tseq, t_s);
+	for (int T = 0; T < g.Tmax; ++T) {
+		const int aD = __shfl_up_sync(0xffffffffu, L.myD, 1), aP = __shfl_up_sync(0xffffffffu, L.myP, 1);
+		nw_lane_step(g, pen, L, lane, T, aD, aP, tseq, t_s, q, ws.E, ws.rowbuf, ws.lastD);
+		__syncwarp();
+		if (lane == 0) nw_lane0_prefetch(g, L, ws.rowbuf);
+	}
+	__syncwarp();
+	// column maximum: largest D, ties -> smallest i (first in fill order)
+	int cb = L.colBest, ci = L.colBestI;
+#pragma unroll
+	for (int o = 16; o; o >>= 1) {
+		const int ov = __shfl_xor_sync(0xffffffffu, cb, o), oi = __shfl_xor_sync(0xffffffffu, ci, o);
+		if (ov > cb || (ov == cb && oi < ci)) { cb = ov; ci = oi; }
+	}
+	int rb = g.NEG, rq = -1;
+	if (k == -2) {   // last maximum along row m = 0
+		int qlo, qhi;
+		nw_row0_range(g, &qlo, &qhi);
+		for (int qp = qlo + lane; qp <= qhi; qp += 32) {
+			const int v = ws.lastD[q_len - 1 - qp];
+			if (rq < 0 || v >= rb) { rb = v; rq = qp; }
+		}
+#pragma unroll
+		for (int o = 16; o; o >>= 1) {
+			const int ov = __shfl_xor_sync(0xffffffffu, rb, o), oq = __shfl_xor_sync(0xffffffffu, rq, o);
+			if (oq >= 0 && (rq < 0 || ov > rb || (ov == rb && oq > rq))) { rb = ov; rq = oq; }
+		}
+	}
+	int best_m, best_q, score;
+	nw_start_cell(g, cb, ci, ws.lastD, rb, rq, &best_m, &best_q, &score);
+	nw_walk(g, ws.E, best_m, best_q, s);
+	s.score = score; s.pos = 0;
+	*out = s;
+	return NW_OK;
+}
+#endif

@@ -367,6 +367,15 @@ static aln_t nw_band(const orc_params *p, nw_ws *w, const uint64_t *tseq, const 
 	return s;
 }
 
+/* stand-alone NW entry for the per-call parity tests (band == 0: NW_score, else NW_band_score) */
+void orc_nw(const orc_params *p, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s, int q_e,
+            int band, int *out6) {
+	nw_ws w; memset(&w, 0, sizeof(w));
+	aln_t a = band ? nw_band(p, &w, tseq, query, k, t_s, t_e, q_s, q_e, band) : nw_full(p, &w, tseq, query, k, t_s, t_e, q_s, q_e);
+	out6[0] = a.score; out6[1] = a.len; out6[2] = a.pos; out6[3] = a.match; out6[4] = a.tGaps; out6[5] = a.qGaps;
+	for (int i = 0; i < 2; ++i) { free(w.D[i]); free(w.P[i]); } free(w.E);
+}
+
 /* ------------------------------------------------------------------ seed-and-extend -- */
 
 #define BANDW 64
