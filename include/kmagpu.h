@@ -31,9 +31,12 @@ typedef struct kmagpu_params {
 	int32_t exhaustive;               /* -ex_mode (kma.c:551) */
 	int32_t mq;                       /* -mq  minimum mapQ (align.c:658) */
 	int32_t one2one;                  /* -1t1 */
-	int32_t reserved[5];
+	int32_t minlen;                   /* -ml  minimum alignment length (alnfrags.c:1156), default 16 */
+	int32_t reserved[4];
 	double scoreT;                    /* -mrs (alnfrags.c:1168) */
-	double minFrac;
+	double minFrac;                   /* -mf  (updatescores.c:217-268) */
+	double mrc;                       /* -mrc (alnfrags.h:38 mrcheck) */
+	double reserved_d;
 } kmagpu_params;
 
 typedef struct kmagpu_db_info {
@@ -82,6 +85,53 @@ int kmagpu_seed_batch(kmagpu_db *db, const kmagpu_params *p, const void *stage1,
 int kmagpu_seed_upload(kmagpu_db *db, const void *stage1, size_t nbytes, int64_t *nreads);
 int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *p, kmagpu_seed_stats *stats);
 int kmagpu_seed_download(kmagpu_db *db, void *stage2_out, size_t out_cap, size_t *out_bytes);
+
+/* ------------------------------------------------------------------ alignment pass (stage 3, first half) */
+
+/* one row per (read, candidate template), in stream order: what KMA_score (align.c:509) returned for it */
+typedef struct kmagpu_cand {
+	int32_t read;      /* index of the stage-2 record in the batch */
+	int32_t tmpl;      /* template id, signed as aligned (negative = reverse strand) */
+	int32_t score, len, pos, match, tGaps, qGaps;   /* AlnScore (nw.h:37-44) */
+} kmagpu_cand;
+
+typedef struct kmagpu_align_stats {
+	int64_t reads, tasks, frags;        /* records in, (read, template) pairs aligned, frag_raw records out */
+	int64_t mems;                       /* maximal exact matches found */
+	int64_t nw_full_calls, nw_band_calls;
+	int64_t nw_full_cells, nw_band_cells;  /* DP cells as the reference counts them: t_len*q_len, t_len*(band+1) */
+	int64_t nw_steps;                   /* warp wavefront steps (32 cell slots each) */
+	int64_t overflow_tasks;             /* pairs re-run on the large-scratch path */
+	float ms_prep, ms_align, ms_reduce, ms_h2d, ms_total;
+	int32_t launches, reserved;
+} kmagpu_align_stats;
+
+/* Replaces alnFrags_threaded (alnfrags.c:2150-2294) with alnFragsPE = alnFragsSE (alnfrags.c:1052-1218):
+ * consumes `nbytes` of whole stage-2 records (ankers.c:30-50; a trailing terminator is ignored) and, per read,
+ * runs anker_rc_comp / KMA_score against every candidate template, keeps the best hits (update_Scores,
+ * updatescores.c:203-298), ADDS the ConClave sums into alignment_scores[DB_size] / uniq_alignment_scores[DB_size]
+ * (runkma.c:98-99) and writes the frag_raw records (updatescores.c:284-295) in input order (= `-t 1` order).
+ * cand_out (optional, cand_cap rows) receives the per-candidate AlnScore rows. */
+int kmagpu_align_batch(kmagpu_db *db, const kmagpu_params *p, const void *stage2, size_t nbytes,
+                       void *frag_out, size_t out_cap, size_t *out_bytes,
+                       uint64_t *alignment_scores, uint64_t *uniq_alignment_scores,
+                       kmagpu_cand *cand_out, size_t cand_cap, size_t *cand_rows, kmagpu_align_stats *stats);
+
+/* The same call split so that a caller can keep the batch resident in HBM between the stages and time the kernels
+ * alone: upload = record walk + H2D; from_seed = take the stage-2 stream kmagpu_seed_run left on the device. */
+int kmagpu_align_upload(kmagpu_db *db, const void *stage2, size_t nbytes, int64_t *nreads);
+int kmagpu_align_from_seed(kmagpu_db *db, int64_t *nreads);
+int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *p, int want_cand, kmagpu_align_stats *stats);
+int kmagpu_align_download(kmagpu_db *db, void *frag_out, size_t out_cap, size_t *out_bytes,
+                          uint64_t *alignment_scores, uint64_t *uniq_alignment_scores,
+                          kmagpu_cand *cand_out, size_t cand_cap, size_t *cand_rows);
+
+/* NW_score (nw.c:642) / NW_band_score (nw.c:892) over a batch of independent problems, one warp each.
+ * prob[i] = {template id, t_s, t_e, q_off, q_s, q_e, k, band (0 = full matrix)}; the query bytes (0-4) of problem i
+ * start at qpool + q_off. out[i] = {score, len, pos, match, tGaps, qGaps}; status[i] != 0: not computed
+ * (1 scratch too small, 2 band narrower than the length difference). cells = sum of DP cells, ms = kernel time. */
+int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, const int32_t *prob, const uint8_t *qpool,
+                    size_t qbytes, int32_t *out, int32_t *status, int64_t *cells, int64_t *steps, float *ms);
 
 /* hashMap_get (hashmapkma.h:58; hashMap_getGlobal hashmapkma.c:149 / megaMap_getGlobal :264) over
  * a batch of k-mers: out[i] = offset of the template list inside values[], or -1. Test hook. */

@@ -21,8 +21,8 @@ class KmaGpuError(RuntimeError):
 class Params(C.Structure):
     _fields_ = [("M", C.c_int32), ("MM", C.c_int32), ("U", C.c_int32), ("W1", C.c_int32), ("Wl", C.c_int32),
                 ("Mn", C.c_int32), ("PE", C.c_int32), ("d", C.c_int32 * 25), ("exhaustive", C.c_int32),
-                ("mq", C.c_int32), ("one2one", C.c_int32), ("reserved", C.c_int32 * 5),
-                ("scoreT", C.c_double), ("minFrac", C.c_double)]
+                ("mq", C.c_int32), ("one2one", C.c_int32), ("minlen", C.c_int32), ("reserved", C.c_int32 * 4),
+                ("scoreT", C.c_double), ("minFrac", C.c_double), ("mrc", C.c_double), ("reserved_d", C.c_double)]
 
 
 class DbInfo(C.Structure):
@@ -36,6 +36,17 @@ class SeedStats(C.Structure):
                 ("hits", C.c_int64), ("list_fetches", C.c_int64), ("list_ids", C.c_int64),
                 ("overflow_reads", C.c_int64), ("ms_seed", C.c_float), ("ms_emit", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_total", C.c_float), ("launches", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class AlignStats(C.Structure):
+    _fields_ = [("reads", C.c_int64), ("tasks", C.c_int64), ("frags", C.c_int64), ("mems", C.c_int64),
+                ("nw_full_calls", C.c_int64), ("nw_band_calls", C.c_int64), ("nw_full_cells", C.c_int64),
+                ("nw_band_cells", C.c_int64), ("nw_steps", C.c_int64), ("overflow_tasks", C.c_int64),
+                ("ms_prep", C.c_float), ("ms_align", C.c_float), ("ms_reduce", C.c_float), ("ms_h2d", C.c_float),
+                ("ms_total", C.c_float), ("launches", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -64,6 +75,16 @@ def lib():
         L.kmagpu_seed_run.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(SeedStats)]
         L.kmagpu_seed_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.kmagpu_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.kmagpu_align_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]
+        L.kmagpu_align_from_seed.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        L.kmagpu_align_run.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.POINTER(AlignStats)]
+        L.kmagpu_align_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.kmagpu_align_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                         C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                         C.POINTER(C.c_size_t), C.POINTER(AlignStats)]
+        L.kmagpu_nw_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                      C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -143,6 +164,61 @@ class TemplateDB:
         ob = C.c_size_t()
         _check(lib().kmagpu_seed_download(self._h, _ptr(out), cap, C.byref(ob)))
         return out[: ob.value]
+
+    # --- stage 3, alignment pass ---------------------------------------------------------------
+    def align_upload(self, stage2):
+        nbytes = int(stage2.numel() if hasattr(stage2, "numel") else stage2.size)
+        nr = C.c_int64()
+        _check(lib().kmagpu_align_upload(self._h, _ptr(stage2), nbytes, C.byref(nr)))
+        return nr.value
+
+    def align_from_seed(self):
+        """align the stage-2 stream the last seed_run left in HBM (no host round trip)"""
+        nr = C.c_int64()
+        _check(lib().kmagpu_align_from_seed(self._h, C.byref(nr)))
+        return nr.value
+
+    def align_run(self, params: Params | None = None, want_cand=False):
+        p = params or default_params()
+        st = AlignStats()
+        _check(lib().kmagpu_align_run(self._h, C.byref(p), int(want_cand), C.byref(st)))
+        return st
+
+    def align_download(self, out=None, scores=None, want_cand=False):
+        """-> (frag_raw bytes, alignment_scores, uniq_alignment_scores, cand rows or None); `scores` = a pair of
+        uint64[DB_size] arrays to ADD into (the ConClave accumulators of runkma.c:98-99)"""
+        ob, cr = C.c_size_t(), C.c_size_t()
+        lib().kmagpu_align_download(self._h, None, 0, C.byref(ob), None, None, None, 0, C.byref(cr))
+        if out is None:
+            out = np.empty(ob.value + 8, dtype=np.uint8)
+        cap = int(out.numel() if hasattr(out, "numel") else out.size)
+        a, u = scores if scores is not None else (np.zeros(self.info.DB_size, np.uint64), np.zeros(self.info.DB_size, np.uint64))
+        cand = np.empty((cr.value, 8), dtype=np.int32) if want_cand else None
+        _check(lib().kmagpu_align_download(self._h, _ptr(out), cap, C.byref(ob), a.ctypes.data, u.ctypes.data,
+                                           cand.ctypes.data if want_cand else None, cr.value, C.byref(cr)))
+        return out[: ob.value], a, u, cand
+
+    def alnFrags_batch(self, stage2, params: Params | None = None, want_cand=False, scores=None):
+        """alnFrags_threaded (alnfrags.c:2150) over a batch of stage-2 records ->
+        (frag_raw bytes, alignment_scores, uniq_alignment_scores, cand rows, stats)"""
+        self.align_upload(stage2)
+        st = self.align_run(params, want_cand)
+        frag, a, u, cand = self.align_download(scores=scores, want_cand=want_cand)
+        return frag, a, u, cand, st
+
+    def nw_batch(self, prob: np.ndarray, qpool: np.ndarray, params: Params | None = None):
+        """NW_score / NW_band_score over independent problems; prob[n, 8] int32 =
+        {template, t_s, t_e, q_off, q_s, q_e, k, band}. -> (out[n, 6], status[n], cells, steps, ms)"""
+        p = params or default_params()
+        prob = np.ascontiguousarray(prob, dtype=np.int32)
+        qpool = np.ascontiguousarray(qpool, dtype=np.uint8)
+        n = len(prob)
+        out = np.zeros((n, 6), dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        cells, steps, ms = C.c_int64(), C.c_int64(), C.c_float()
+        _check(lib().kmagpu_nw_batch(self._h, C.byref(p), n, prob.ctypes.data, qpool.ctypes.data, len(qpool), out.ctypes.data,
+                                     status.ctypes.data, C.byref(cells), C.byref(steps), C.byref(ms)))
+        return out, status, cells.value, steps.value, ms.value
 
     def lookup(self, kmers: np.ndarray) -> np.ndarray:
         kmers = np.ascontiguousarray(kmers, dtype=np.uint64)

@@ -1,0 +1,994 @@
+// The alignment pass of KMA on the GPU: stage-2 records in, frag_raw records + ConClave score sums out.
+//
+// WHAT: alnFrags_threaded / alnFragsSE (alnfrags.c:1052-1218, 2150-2294): for every read and every candidate
+// template, (anker_rc_comp when the strand is undecided, align.c:993) -> KMA_score (align.c:509: MEM seeds against
+// the template's position index, chainSeeds chain.c:79, lead/trail tail and gap Needleman-Wunsch nw.c:642/892),
+// then the per-read selection and update_Scores (updatescores.c:203-298).
+//
+// HOW (ours):
+//   * the batch stays in HBM; a prep kernel unpacks every read once into an aligned slab (2-bit words, 0-4 bytes,
+//     N list; reverse complement only for strand-tie reads);
+//   * the unit of work is a (read, template) pair, one warp each, pulled from an atomic counter by a persistent
+//     grid -- candidate counts and NW sizes are irregular, pairs are not;
+//   * MEM discovery: the 32 lanes probe 32 consecutive query positions at once, the first hit (ballot) is extended
+//     on the packed words with XOR + clz/ffs, 32 bases per step; repeated k-mers extend one occurrence per lane;
+//   * chaining: the 128-MEM look-ahead of chainSeeds is evaluated by the lanes in parallel and folded with the
+//     reference's <= / < tie rules (first maximum, last fully-compatible maximum);
+//   * NW: the continuous warp wavefront of kmagpu_nw.cuh;
+//   * pairs whose MEM list or traceback matrix exceeds the per-warp scratch are re-run by the same code on a small
+//     grid with scratch sized from what they asked for -- results never depend on the scratch size;
+//   * selection, the u64 ConClave sums (atomics) and the frag_raw byte stream are produced on the device in input
+//     order (size scan + writer kernel), so the host does no per-read work.
+#include "kmagpu_internal.h"
+#include "kmagpu_dev.cuh"
+#include "kmagpu_nw.cuh"
+#include <string.h>
+#include <algorithm>
+
+#define AL_WARPS 4            // warps per CTA of the pair kernel
+#define AL_BANDW 64           // align.c:511
+#define ST_OK 0
+#define ST_OVERFLOW 1
+
+struct AlnRead {
+	uint32_t rec_off;
+	int32_t q_len, words, nN, rc_flag, nt, hl, flag;
+	uint32_t slab_off;   // 8-byte units
+	uint32_t task0;
+};
+
+struct AlnCand { int32_t tmpl, score, len, pos, match, tGaps, qGaps, status; };
+
+struct AlnParams {
+	NwPen pen;
+	int32_t k, mq, one2one, exhaustive, minlen;
+	double scoreT, mrc, minFrac;
+};
+
+enum { A_WORK = 0, A_OVF = 1, A_NEED_E = 2, A_NEED_MEM = 3, A_NEED_Q = 4, A_MEMS = 5, A_FULL_CALLS = 6, A_BAND_CALLS = 7,
+       A_FULL_CELLS = 8, A_BAND_CELLS = 9, A_STEPS = 10, A_SLAB = 11, A_TASKS = 12, A_OUT = 13, A_FRAGS = 14, A_BAD = 15,
+       A_MAXQ = 16, A_N = 24 };
+
+// ---------------------------------------------------------------- slab layout
+
+struct QView { const uint64_t *w; const uint8_t *b; const int32_t *N; };
+
+__host__ __device__ __forceinline__ uint32_t slab_W(int words) { return (uint32_t)words + 2; }
+__host__ __device__ __forceinline__ uint32_t slab_B(int q_len) { return ((uint32_t)q_len + 8) >> 3; }
+__host__ __device__ __forceinline__ uint32_t slab_N(int nN) { return ((uint32_t)nN + 2) >> 1; }
+__host__ __device__ __forceinline__ uint32_t slab_stride(const AlnRead &R) { return slab_W(R.words) + slab_B(R.q_len) + slab_N(R.nN); }
+
+__device__ __forceinline__ QView read_view(const uint64_t *slab, const AlnRead &R, int strand) {
+	const uint64_t *base = slab + R.slab_off + (strand ? slab_stride(R) : 0);
+	QView v;
+	v.w = base;
+	v.b = (const uint8_t *)(base + slab_W(R.words));
+	v.N = (const int32_t *)(base + slab_W(R.words) + slab_B(R.q_len));
+	return v;
+}
+
+// ---------------------------------------------------------------- pass 1: sizes
+
+__global__ void aln_sizes_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ off, int n, int k,
+                                 AlnRead *reads, uint32_t *slab_sz, uint32_t *task_sz, unsigned long long *ctr) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n) return;
+	AlnRead R;
+	memset(&R, 0, sizeof(R));
+	R.rec_off = off[r];
+	uint32_t ss = 0, ts = 0;
+	if (off[r + 1] - off[r] >= 28) {
+		const uint8_t *rec = in + R.rec_off;
+		R.q_len = (int)ld_u32u(rec); R.words = (int)ld_u32u(rec + 4); R.nN = (int)ld_u32u(rec + 8);
+		R.rc_flag = (int)ld_u32u(rec + 12); R.nt = (int)ld_u32u(rec + 16); R.hl = (int)ld_u32u(rec + 20);
+		R.flag = (int)ld_u32u(rec + 24);
+		if (R.nt == 0) { atomicAdd(&ctr[A_BAD], 1ull); R.q_len = 0; }   // first record of a pair (ankers.c:150)
+		ss = slab_stride(R) * (R.rc_flag < 0 ? 2u : 1u);
+		ts = R.q_len >= k ? (uint32_t)R.nt : 0u;
+		atomicMax(&ctr[A_MAXQ], (unsigned long long)R.q_len);
+	}
+	reads[r] = R;
+	slab_sz[r] = ss; task_sz[r] = ts;
+}
+
+// ---------------------------------------------------------------- pass 2: unpack (one warp per read)
+
+__global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__restrict__ in, int n, AlnRead *reads,
+		const uint32_t *__restrict__ slab_off, const uint32_t *__restrict__ task_off, uint64_t *slab, int32_t *task_read, int k) {
+	const unsigned lane = threadIdx.x & 31;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+		AlnRead R = reads[r];
+		R.slab_off = slab_off[r]; R.task0 = task_off[r];
+		if (lane == 0) { reads[r].slab_off = R.slab_off; reads[r].task0 = R.task0; }
+		if (R.q_len == 0 && R.words == 0) continue;
+		const uint8_t *rec = in + R.rec_off, *seq = rec + 28, *Ns = seq + 8 * (size_t)R.words;
+		const int L = R.q_len, words = R.words, nN = R.nN;
+		for (int strand = 0; strand < (R.rc_flag < 0 ? 2 : 1); ++strand) {
+			uint64_t *base = slab + R.slab_off + (strand ? slab_stride(R) : 0);
+			uint8_t *b = (uint8_t *)(base + slab_W(words));
+			int32_t *N = (int32_t *)(base + slab_W(words) + slab_B(L));
+			for (int w = lane; w < words + 2; w += 32) {
+				uint64_t x = 0;
+				if (w < words) {
+					if (!strand) x = ld_u64u(seq + 8 * (size_t)w);
+					else {   // rc_comp (compdna.c:228)
+						x = rev2(~fwd32(seq, words, L - 32 * (w + 1)));
+						const int c = L - 32 * w;
+						if (c < 32) x = c > 0 ? x & (~0ull << (64 - 2 * c)) : 0ull;
+					}
+				}
+				base[w] = x;
+			}
+			__syncwarp();
+			// bytes 0-3 from the words just written, then N -> 4 (unCompDNA, compdna.c:178)
+			for (int i = lane; i < (int)(slab_B(L) << 3); i += 32)
+				b[i] = i < L ? (uint8_t)((base[i >> 5] << ((i & 31) << 1)) >> 62) : (uint8_t)0;
+			__syncwarp();
+			for (int i = lane; i <= nN; i += 32) {
+				int v = L;   // sentinel N[nN] = q_len (savekmers.c:2483, alnfrags.c:1071)
+				if (i < nN) v = strand ? L - 1 - (int)ld_u32u(Ns + 4 * (size_t)(nN - 1 - i)) : (int)ld_u32u(Ns + 4 * (size_t)i);
+				N[i] = v;
+				if (i < nN) b[v] = 4;
+			}
+		}
+		if (L >= k) for (int i = lane; i < R.nt; i += 32) task_read[R.task0 + i] = r;
+		__syncwarp();
+	}
+}
+
+// ---------------------------------------------------------------- MEMs
+
+struct Mems {
+	int *tS, *tE, *qS, *qE, *W, *sc, *nx;
+	int cap;
+	__device__ __forceinline__ void shift(int o) { tS += o; tE += o; qS += o; qE += o; W += o; sc += o; nx += o; cap -= o; }
+};
+
+struct WarpCtr { unsigned long long full_calls, band_calls, full_cells, band_cells, steps, mems; unsigned need_e, need_mem, need_q; };
+
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+	for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+	for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+	for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// one exact seed at (query p, template 1-based v) extended to a maximal exact match on the packed words
+__device__ __forceinline__ void mem_from_seed(const uint64_t *qw, const uint64_t *tseq, int t_len, int k, int p, int v, int lo,
+                                              int fwd_lim, int *qs, int *ts, int *qe, int *te) {
+	const int t0 = v - 1;
+	const int bw = ext_bwd(qw, p, tseq, t0, min(p - lo, t0));
+	int fmax = min(fwd_lim - (p + k), t_len - (t0 + k));
+	const int fw = fmax > 0 ? ext_fwd(qw, p + k, tseq, t0 + k, fmax) : 0;
+	*qs = p - bw; *ts = v - bw; *qe = p + k + fw; *te = v + k + fw;
+}
+
+// MODE 0: the seed scan of KMA_score (align.c:534-640); MODE 1: one strand of anker_rc_comp (align.c:1044-1143).
+// Appends to M starting at index n; *sscore = strand score of MODE 1. Returns ST_OVERFLOW when M is full.
+template <int MODE>
+__device__ int scan_mems(const KgTIndexView &ix, const KgTMeta &m, const uint64_t *tseq, const QView &q, int nN1, int q_len,
+                         int start, Mems &M, int &n, int &sscore, WarpCtr &wc) {
+	const int lane = threadIdx.x & 31;
+	const int k = ix.k, t_len = m.len;
+	int j = start, s = 0;
+	for (int seg = 0; seg < nN1 && j < q_len; ++seg) {
+		const int segN = q.N[seg], end = segN - k + 1, lo = seg ? q.N[seg - 1] + 1 : 0;
+		const int fwd_lim = MODE == 0 ? segN : end;
+		while (j < end) {
+			const int p0 = j + lane;
+			int val = 0;
+			if (p0 < end) val = tix_get(ix, m, kmer_at(q.w, p0, k));
+			const unsigned hits = __ballot_sync(0xffffffffu, val != 0);
+			if (!hits) { j += 32; continue; }
+			const int f = __ffs(hits) - 1, p = j + f;
+			const int v = __shfl_sync(0xffffffffu, val, f);
+			if (v > 0) {
+				if (n >= M.cap) { wc.need_mem = max(wc.need_mem, (unsigned)n + 1024u); return ST_OVERFLOW; }
+				int qs, ts, qe, te;
+				mem_from_seed(q.w, tseq, t_len, k, p, v, lo, fwd_lim, &qs, &ts, &qe, &te);
+				if (lane == 0) { M.tS[n] = ts; M.tE[n] = te; M.qS[n] = qs; M.qE[n] = qe; M.W[n] = qe - qs; }
+				++n;
+				s += qe - qs;
+				j = MODE == 0 ? qe : qe + 1;
+			} else {
+				int cnt;
+				const int32_t *d = tix_dups(ix, v, &cnt);
+				if (n + cnt > M.cap) { wc.need_mem = max(wc.need_mem, (unsigned)(n + cnt) + 1024u); return ST_OVERFLOW; }
+				int bias = p;
+				for (int c = lane; c < cnt; c += 32) {   // every occurrence, ascending template position
+					int qs, ts, qe, te;
+					mem_from_seed(q.w, tseq, t_len, k, p, __ldg(d + c), lo, fwd_lim, &qs, &ts, &qe, &te);
+					M.tS[n + c] = ts; M.tE[n + c] = te; M.qS[n + c] = qs; M.qE[n + c] = qe; M.W[n + c] = qe - qs;
+					bias = max(bias, qe);
+				}
+				bias = warp_max(bias);
+				n += cnt;
+				s += k + (bias - p);
+				j = bias + 1;
+			}
+		}
+		j = segN + 1;
+	}
+	sscore = s;
+	__syncwarp();
+	return ST_OK;
+}
+
+// ---------------------------------------------------------------- chaining (chainSeeds, chain.c:79-260)
+
+__device__ __forceinline__ int tail_mm(int Ms, int k, int Mv, int MMv) {   // mismatch estimate of Ms unaligned bases
+	int MMs;
+	if (Ms == 2) { MMs = 2; Ms = 0; }
+	else {
+		MMs = Ms / k + (Ms % k ? 1 : 0); MMs = max(2, MMs);
+		Ms = min(Ms - MMs, k); Ms = min(Ms, MMs);
+	}
+	return Ms * Mv + MMs * MMv;
+}
+
+#define NOCAND (-0x7fffffff - 1)
+
+__device__ int chain_warp(const NwPen &pen, Mems &M, int n, int q_len, int t_len, int k, unsigned *mapQ) {
+	const int lane = threadIdx.x & 31;
+	const int W1 = pen.W1, U = pen.U, Mv = pen.M, MMv = pen.MM;
+	int bestPos = n - 1, bestScore = 0, secondScore = 0;
+	if (lane == 0) { M.sc[n] = 0; M.nx[n] = 0; }
+	__syncwarp();
+	for (int i = n - 1; i >= 0; --i) {
+		const int weight = M.W[i] * Mv, tEnd = M.tE[i], qEnd = M.qE[i];
+		int gap = min(t_len - tEnd, q_len - qEnd), Ms = gap;
+		if (--gap) gap = gap * U + W1; else gap = W1;
+		Ms = tail_mm(Ms, k, Mv, MMv);
+		const int score0 = weight + (Ms < gap ? gap : Ms);
+		const int lim = min(n, i + 128);
+		// lane-local fold over j = i+1+lane, +32, ...: best value, first j reaching it, last "<=" j reaching it
+		int lb = NOCAND, lfirst = 0x7fffffff, llast = -1;
+		for (int j = i + 1 + lane; j < lim; j += 32) {
+			const int qSj = M.qS[j], tSj = M.tS[j];
+			int g = 0, type = -1;   // 0: fully compatible (<=), 1: overlap cut (<)
+			if (qEnd < qSj) {
+				if (tEnd < tSj) {
+					const int tGap = tSj - tEnd, qGap = qSj - qEnd;
+					if ((g = abs(tGap - qGap))) g = (g - 1) * U + W1;
+					g += weight + M.sc[j] + tail_mm(min(tGap, qGap), k, Mv, MMv);
+					type = 0;
+				} else if (k <= M.tE[j] - tEnd) {
+					if ((g = qSj - qEnd)) g = (g - 1) * U + W1;
+					g += weight + M.sc[j] - (tSj - tEnd) * Mv;
+					type = 1;
+				}
+			} else if (k <= M.qE[j] - qEnd) {
+				const int tStart = tSj + qEnd - qSj;
+				if (tEnd < tStart) {
+					if ((g = tStart - tEnd)) g = (g - 1) * U + W1;
+					g += weight + M.sc[j] - (tStart - tEnd) * Mv;
+					type = 1;
+				}
+			}
+			if (type >= 0) {
+				if (lb == NOCAND || g > lb) { lb = g; lfirst = j; llast = type == 0 ? j : -1; }
+				else if (g == lb && type == 0) llast = j;
+			}
+		}
+		const int mx = warp_max(lb);
+		int score = score0, next = 0;
+		if (mx != NOCAND && mx >= score0) {
+			const int first = warp_min(lb == mx ? lfirst : 0x7fffffff);
+			const int last = warp_max(lb == mx ? llast : -1);
+			if (mx > score0) { score = mx; next = max(first, last); }
+			else if (last >= 0) next = last;
+		}
+		int w = M.W[i];
+		if (next) w += M.W[next] - k + 1; else w -= k - 1;
+		gap = min(M.tS[i], M.qS[i]); Ms = gap;
+		if (0 < --gap) gap = gap * U + W1; else if (gap == 0) gap = W1; else gap = 0;
+		Ms = tail_mm(Ms, k, Mv, MMv);
+		__syncwarp();
+		if (lane == 0) { M.W[i] = w; M.sc[i] = score; M.nx[i] = next; }
+		__syncwarp();
+		score += Ms < gap ? gap : Ms;
+		if (bestScore <= score) {
+			if (next != bestPos) secondScore = bestScore;
+			bestScore = score; bestPos = i;
+		} else if (secondScore <= score && next != bestPos) secondScore = bestScore;
+	}
+	if (0 < bestScore) {   // chain.c:256 (only compared with -mq, default 0)
+		const double wgt = M.W[bestPos] / 10.0;
+		*mapQ = (unsigned)ceil(40 * (1 - 1.0 * secondScore / bestScore) * (wgt < 1 ? wgt : 1.0) * log((double)bestScore));
+	} else *mapQ = 0;
+	__syncwarp();
+	if (lane == 0) M.sc[bestPos] = bestScore;
+	__syncwarp();
+	return bestPos;
+}
+
+// ---------------------------------------------------------------- stitching (KMA_score, align.c:641-748)
+
+struct TaskCtx {
+	const NwPen *pen;
+	const uint64_t *tseq;
+	const uint8_t *qb;
+	NwScratch nw;
+	WarpCtr *wc;
+};
+
+// NW with the reference's full/banded choice (align.c:92-98, 186-192, 478-484)
+__device__ int nw_auto(const TaskCtx &c, int k, int t_s, int t_e, int q_s, int q_e, NwStat *a) {
+	const int t_l = t_e - t_s, q_l = q_e - q_s;
+	int band = abs(t_l - q_l) + AL_BANDW;
+	if (q_l <= band || t_l <= band) band = 0;
+	unsigned long long cells = 0;
+	const int st = nw_warp(*c.pen, c.tseq, c.qb, k, t_s, t_e, q_s, q_e, band, c.nw, a, &cells);
+	if (st != NW_OK) {
+		NwGeo g;
+		nw_geo_init(g, *c.pen, t_l, q_l, k, band);
+		c.wc->need_e = max(c.wc->need_e, (unsigned)min((size_t)0xF0000000u, g.ebytes() + 4096));
+		c.wc->need_q = max(c.wc->need_q, (unsigned)q_l + 64u);
+		return ST_OVERFLOW;
+	}
+	if (cells) {
+		NwGeo g;
+		nw_geo_init(g, *c.pen, t_l, q_l, k, band);
+		c.wc->steps += (unsigned long long)g.Tmax;
+		if (band) { ++c.wc->band_calls; c.wc->band_cells += cells; } else { ++c.wc->full_calls; c.wc->full_cells += cells; }
+	}
+	return ST_OK;
+}
+
+__device__ int kma_score_warp(const AlnParams &P, const TaskCtx &c, const KgTIndexView &ix, const KgTMeta &m, const QView &q,
+                              int nN1, int q_len, Mems &M, int n, NwStat *out) {
+	const int lane = threadIdx.x & 31;
+	const int k = ix.k, t_len = m.len, U = P.pen.U, Mv = P.pen.M;
+	NwStat s = {0, 1, 0, 0, 0, 0};
+	if (!n) {
+		int dummy;
+		if (scan_mems<0>(ix, m, c.tseq, q, nN1, q_len, 0, M, n, dummy, *c.wc)) return ST_OVERFLOW;
+	}
+	c.wc->mems += (unsigned long long)n;
+	if (!n) { *out = s; return ST_OK; }
+	unsigned mapQ = 0;
+	int start = chain_warp(*c.pen, M, n, q_len, t_len, k, &mapQ);
+	if ((int)mapQ < P.mq || M.sc[start] < k) { *out = s; return ST_OK; }
+
+	// leading tail (leadTailAln, align.c:53-138)
+	{
+		const int t_e = M.tS[start] - 1, q_e = M.qS[start];
+		s.score = 0; s.len = 0; s.pos = t_e; s.match = 0; s.tGaps = 0; s.qGaps = 0;
+		if (q_e) {
+			int t_s = 0, q_s = 0;
+			if ((q_e << 1) < t_e || (q_e + AL_BANDW) < t_e) t_s = t_e - (q_e + min(q_e, AL_BANDW));
+			else if ((t_e << 1) < q_e || (t_e + AL_BANDW) < q_e) q_s = q_e - (t_e + min(t_e, AL_BANDW));
+			if (t_e - t_s > 0 && q_e - q_s > 0) {
+				NwStat a;
+				if (nw_auto(c, -1 - (t_s == 0), t_s, t_e, q_s, q_e, &a)) return ST_OVERFLOW;
+				s.pos -= a.len - a.tGaps;
+				s.score = a.score; s.len = a.len; s.match = a.match; s.tGaps = a.tGaps; s.qGaps = a.qGaps;
+			}
+		}
+	}
+	for (;;) {
+		const int qS = M.qS[start], qE = M.qE[start];
+		const int len = qE - qS;
+		s.len += len; s.match += len;
+		int sc = 0;
+		for (int i = qS + lane; i < qE; i += 32) { const int b = c.qb[i]; sc += P.pen.d[b * 5 + b]; }
+		s.score += warp_sum(sc);
+		const int nxt = M.nx[start];
+		if (!nxt) break;
+		const int q_s = qE, t_s = M.tE[start] - 1;
+		int t_e, t_l, q_e;
+		start = nxt;
+		int qSn = M.qS[start], tSn = M.tS[start];
+		if (qSn < q_s) { tSn += q_s - qSn; qSn = q_s; }
+		t_e = tSn - 1;
+		if (t_e < t_s) {
+			if (t_s <= M.tE[start]) { qSn += t_s - t_e; t_e = t_s; t_l = 0; }
+			else t_l = t_len - t_s + t_e;
+		} else t_l = t_e - t_s;
+		__syncwarp();
+		if (lane == 0) { M.qS[start] = qSn; M.tS[start] = tSn; }
+		__syncwarp();
+		q_e = qSn;
+		if (abs(t_l - q_e + q_s) * U > q_len * Mv || t_l > q_len || q_e - q_s > (q_len >> 1)) {   // align.c:715
+			const int keep = s.pos;
+			s.score = 0; s.len = 1; s.pos = keep; s.match = 0; s.tGaps = 0; s.qGaps = 0;
+			*out = s;
+			return ST_OK;
+		}
+		if (t_l > 0 || q_e - q_s > 0) {
+			NwStat a;
+			if (nw_auto(c, 0, t_s, t_e, q_s, q_e, &a)) return ST_OVERFLOW;
+			s.score += a.score; s.len += a.len; s.match += a.match; s.tGaps += a.tGaps; s.qGaps += a.qGaps;
+		}
+	}
+	// trailing tail (trailTailAln, align.c:140-212)
+	{
+		const int t_s = M.tE[start] - 1, q_s = M.qE[start];
+		int q_e = q_len, t_e = t_len;
+		if (((q_len - q_s) << 1) < (t_len - t_s) || (q_len - q_s + AL_BANDW) < (t_len - t_s)) {
+			t_e = q_len - q_s; t_e = t_s + (t_e + min(t_e, AL_BANDW));
+		} else if (((t_len - t_s) << 1) < (q_len - q_s) || (t_len - t_s + AL_BANDW) < (q_len - q_s)) {
+			q_e = t_len - t_s; q_e = q_s + (q_e + min(q_e, AL_BANDW));
+		}
+		if (t_e - t_s > 0 && q_e - q_s > 0) {
+			NwStat a;
+			if (nw_auto(c, 1 + (t_e == t_len), t_s, t_e, q_s, q_e, &a)) return ST_OVERFLOW;
+			s.score += a.score; s.len += a.len; s.match += a.match; s.tGaps += a.tGaps; s.qGaps += a.qGaps;
+		}
+	}
+	*out = s;
+	return ST_OK;
+}
+
+// preseed (align.c:750-770): does any k-spaced k-mer of the byte read occur in the template? The key is built from
+// bytes exactly as makeKmer (stdnuc.c:424) does, so an N (4) spills into the neighbouring base; bytes past the end
+// of the read count as 0.
+__device__ bool preseed_hit(const KgTIndexView &ix, const KgTMeta &m, const uint8_t *qb, int q_len) {
+	const int lane = threadIdx.x & 31, k = ix.k;
+	for (int i0 = 0; i0 < q_len; i0 += 32 * k) {
+		const int i = i0 + lane * k;
+		int hit = 0;
+		if (i < q_len) {
+			uint64_t key = 0;
+			for (int b = 0; b < k; ++b) key = (b ? key << 2 : 0) | (uint64_t)(i + b < q_len ? qb[i + b] : 0);
+			hit = tix_get(ix, m, key) != 0;
+		}
+		if (__any_sync(0xffffffffu, hit)) return true;
+	}
+	return false;
+}
+
+// ---------------------------------------------------------------- the pair kernel
+
+__device__ int align_pair(const AlnParams &P, const NwPen *pen, const KgTIndexView &ix, const uint64_t *slab, const AlnRead &R,
+                          int tmpl, Mems M, const NwScratch &nws, WarpCtr &wc, AlnCand *out) {
+	const int at = abs(tmpl), q_len = R.q_len, nN1 = R.nN + 1, k = ix.k;
+	const KgTMeta m = ix.meta[at];
+	TaskCtx c;
+	c.pen = pen; c.tseq = ix.seq + m.seq_off; c.nw = nws; c.wc = &wc;
+	NwStat a = {0, 0, 0, 0, 0, 0};
+	int n = 0, strand = 0;
+	if (R.rc_flag < 0) {   // strand undecided: anker_rc_comp (align.c:993-1176)
+		const QView qf = read_view(slab, R, 0), qr = read_view(slab, R, 1);
+		int sf = 0, sr = 0, nf = 0, ntot;
+		const bool pre = P.exhaustive || preseed_hit(ix, m, qf.b, q_len);
+		if (pre && scan_mems<1>(ix, m, c.tseq, qf, nN1, q_len, 0, M, nf, sf, wc)) return ST_OVERFLOW;
+		ntot = nf;
+		if (scan_mems<1>(ix, m, c.tseq, qr, nN1, q_len, 0, M, ntot, sr, wc)) return ST_OVERFLOW;
+		const int best = max(sf, sr);
+		if (P.one2one && best < k && best * k < (q_len - k - best)) { n = 0; strand = -1; }
+		else if (best == sf) {   // forward wins ties; a zero score means nothing seeded on either strand
+			if (best) { n = nf; strand = 0; tmpl = at; } else strand = -1;
+		} else { M.shift(nf); n = ntot - nf; strand = 1; tmpl = -at; }
+		if (strand >= 0) {
+			const QView q = strand ? qr : qf;
+			c.qb = q.b;
+			if (kma_score_warp(P, c, ix, m, q, nN1, q_len, M, n, &a)) return ST_OVERFLOW;
+		}
+	} else {
+		const QView q = read_view(slab, R, 0);   // SE records carry the strand stage 2 chose (ankers.c:30-50)
+		c.qb = q.b;
+		if (kma_score_warp(P, c, ix, m, q, nN1, q_len, M, 0, &a)) return ST_OVERFLOW;
+	}
+	out->tmpl = tmpl; out->score = a.score; out->len = a.len; out->pos = a.pos; out->match = a.match;
+	out->tGaps = a.tGaps; out->qGaps = a.qGaps; out->status = ST_OK;
+	return ST_OK;
+}
+
+struct ScratchLayout { size_t stride; int mem_cap, q_cap; size_t e_cap; };
+
+__global__ void __launch_bounds__(AL_WARPS * 32) aln_pair_kernel(AlnParams P, KgTIndexView ix, const uint8_t *__restrict__ in,
+		const AlnRead *__restrict__ reads, const uint64_t *slab, const int32_t *__restrict__ task_read, int ntasks,
+		const int32_t *__restrict__ task_list, AlnCand *cand, uint8_t *scratch, ScratchLayout lay,
+		unsigned long long *ctr, int32_t *ovf_list) {
+	__shared__ NwPen spen;
+	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&P.pen)[threadIdx.x];
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const size_t wid = (size_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
+	uint8_t *sp = scratch + wid * lay.stride;
+	Mems M;
+	{
+		int *p = (int *)sp;
+		const int c1 = lay.mem_cap + 1;
+		M.tS = p; M.tE = p + c1; M.qS = p + 2 * c1; M.qE = p + 3 * c1; M.W = p + 4 * c1; M.sc = p + 5 * c1; M.nx = p + 6 * c1;
+		M.cap = lay.mem_cap;
+		sp += (((size_t)7 * c1 * 4) + 15) & ~(size_t)15;
+	}
+	NwScratch nws;
+	nws.rowbuf = (NwRow *)sp; sp += (size_t)lay.q_cap * 8;
+	nws.lastD = (int *)sp; sp += (size_t)lay.q_cap * 4;
+	nws.E = sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap;
+	WarpCtr wc;
+	memset(&wc, 0, sizeof(wc));
+	for (;;) {
+		unsigned long long t = 0;
+		if (lane == 0) t = atomicAdd(&ctr[A_WORK], 1ull);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t >= (unsigned long long)ntasks) break;
+		const int task = task_list ? task_list[t] : (int)t;
+		const int r = task_read[task];
+		const AlnRead R = reads[r];
+		const uint8_t *rec = in + R.rec_off;
+		const int ti = task - (int)R.task0;
+		const int tmpl = (int)ld_u32u(rec + 28 + 8 * (size_t)R.words + 4 * (size_t)R.nN + 4 * (size_t)ti);
+		AlnCand res;
+		const int st = align_pair(P, &spen, ix, slab, R, tmpl, M, nws, wc, &res);
+		__syncwarp();
+		if (st != ST_OK) {
+			res.tmpl = tmpl; res.score = res.len = res.pos = res.match = res.tGaps = res.qGaps = 0; res.status = ST_OVERFLOW;
+			if (lane == 0) { const unsigned long long o = atomicAdd(&ctr[A_OVF], 1ull); ovf_list[o] = task; }
+		}
+		if (lane == 0) cand[task] = res;
+	}
+	if (lane == 0) {
+		if (wc.mems) atomicAdd(&ctr[A_MEMS], wc.mems);
+		if (wc.full_calls) { atomicAdd(&ctr[A_FULL_CALLS], wc.full_calls); atomicAdd(&ctr[A_FULL_CELLS], wc.full_cells); }
+		if (wc.band_calls) { atomicAdd(&ctr[A_BAND_CALLS], wc.band_calls); atomicAdd(&ctr[A_BAND_CELLS], wc.band_cells); }
+		if (wc.steps) atomicAdd(&ctr[A_STEPS], wc.steps);
+		if (wc.need_e) atomicMax(&ctr[A_NEED_E], (unsigned long long)wc.need_e);
+		if (wc.need_mem) atomicMax(&ctr[A_NEED_MEM], (unsigned long long)wc.need_mem);
+		if (wc.need_q) atomicMax(&ctr[A_NEED_Q], (unsigned long long)wc.need_q);
+	}
+}
+
+// ---------------------------------------------------------------- selection + ConClave sums (one thread per read)
+
+struct AlnRes { int32_t kept, best; };
+
+__global__ void aln_reduce_kernel(AlnParams P, const AlnRead *__restrict__ reads, int n, AlnCand *cand,
+                                  const KgTMeta *__restrict__ meta, unsigned long long *as, unsigned long long *uas,
+                                  uint32_t *recsize, AlnRes *res, unsigned long long *ctr) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n) return;
+	const AlnRead R = reads[r];
+	const int k = P.k, q_len = R.q_len;
+	const int nt = q_len >= k ? R.nt : 0;
+	AlnCand *c = cand + R.task0;
+	double bestScore = 0;
+	int best_read = 0, hits = 0;
+	for (int ti = 0; ti < nt; ++ti) {   // alnfrags.c:1131-1198
+		const AlnCand a = c[ti];
+		const int t_len = meta[abs(a.tmpl)].len, aln_len = a.len, start = a.pos;
+		int end = start + aln_len - a.tGaps, read_score = a.score;
+		double score;
+		if (t_len < end) end -= t_len;
+		if (q_len <= aln_len || t_len <= aln_len) score = aln_len; else score = q_len < t_len ? q_len : t_len;
+		if (P.minlen <= aln_len && ((P.mrc * q_len <= a.len - a.qGaps) || (P.mrc * t_len <= a.len - a.tGaps))) score = read_score / score;
+		else { read_score = 0; score = 0; }
+		if (k < read_score && P.scoreT <= score) {
+			AlnCand h;
+			h.tmpl = a.tmpl; h.pos = start; h.match = end; h.score = read_score; h.len = aln_len; h.tGaps = h.qGaps = h.status = 0;
+			c[hits++] = h;
+			if (bestScore < score) bestScore = score;
+			if (best_read < read_score) best_read = read_score;
+		}
+	}
+	uint32_t size = 0;
+	AlnRes o = {0, 0};
+	if (best_read > k) {   // update_Scores (updatescores.c:203-298)
+		int kept = 0;
+		double minScore = 0, minFrac = P.minFrac;
+		const int mode = P.minFrac == 1.0 ? 0 : (P.minFrac < 0 ? 1 : 2);
+		if (mode) { minScore = fabs(P.minFrac) * bestScore; minFrac = fabs(P.minFrac) * best_read; }
+		for (int i = 0; i < hits; ++i) {
+			const AlnCand h = c[i];
+			bool keep;
+			if (mode == 0) { const double ms = h.score / h.len; keep = ms == bestScore || h.score == best_read; }
+			else keep = (h.len * minScore <= h.score) || minFrac <= h.score;
+			if (keep) {
+				c[kept++] = h;
+				atomicAdd(&as[abs(h.tmpl)], (unsigned long long)(mode == 2 ? best_read : h.score));
+			}
+		}
+		if (kept == 1) atomicAdd(&uas[abs(c[0].tmpl)], (unsigned long long)best_read);
+		o.kept = kept; o.best = best_read;
+		size = 20u + (uint32_t)q_len + (uint32_t)R.hl + 12u * (uint32_t)kept;
+		atomicAdd(&ctr[A_FRAGS], 1ull);
+	}
+	recsize[r] = size;
+	res[r] = o;
+}
+
+// frag_raw record (updatescores.c:284-295): int32[5]{q_len, hits, score, hdrlen, flag} read(0-4) header start[] end[] template[]
+__global__ void __launch_bounds__(256) aln_emit_kernel(const uint8_t *__restrict__ in, const AlnRead *__restrict__ reads, int n,
+		const uint64_t *__restrict__ slab, const AlnCand *__restrict__ cand, const AlnRes *__restrict__ res,
+		const uint32_t *__restrict__ out_off, uint8_t *__restrict__ out) {
+	const unsigned lane = threadIdx.x & 31;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+		const AlnRes rs = res[r];
+		if (rs.best == 0) continue;
+		const AlnRead R = reads[r];
+		uint8_t *o = out + out_off[r];
+		if (lane < 5) {
+			const int32_t h = lane == 0 ? R.q_len : lane == 1 ? rs.kept : lane == 2 ? rs.best : lane == 3 ? R.hl : R.flag;
+			st_u32b(o + 4 * lane, (uint32_t)h);
+		}
+		o += 20;
+		const QView q = read_view(slab, R, 0);
+		for (int i = lane; i < R.q_len; i += 32) o[i] = q.b[i];
+		o += R.q_len;
+		const uint8_t *hdr = in + R.rec_off + 28 + 8 * (size_t)R.words + 4 * (size_t)R.nN + 4 * (size_t)R.nt;
+		for (int i = lane; i < R.hl; i += 32) o[i] = hdr[i];
+		o += R.hl;
+		const AlnCand *c = cand + R.task0;
+		for (int i = lane; i < rs.kept; i += 32) {
+			st_u32b(o + 4 * (size_t)i, (uint32_t)c[i].pos);
+			st_u32b(o + 4 * (size_t)(rs.kept + i), (uint32_t)c[i].match);
+			st_u32b(o + 4 * (size_t)(2 * rs.kept + i), (uint32_t)c[i].tmpl);
+		}
+	}
+}
+
+// ---------------------------------------------------------------- host side
+
+int kg_align_free(kmagpu_db *db) {
+	AlignBatch &b = db->aln;
+	KgBuf *all[] = {&b.d_in, &b.d_off, &b.d_reads, &b.d_slab, &b.d_sz, &b.d_partial, &b.d_taskread, &b.d_cand, &b.d_recsize,
+	                &b.d_out, &b.d_ctr, &b.d_scores, &b.d_scratch, &b.d_ovf, &b.d_res, &b.h_off};
+	for (KgBuf *x : all) x->release();
+	return 0;
+}
+
+static AlnParams make_params(const kmagpu_db *db, const kmagpu_params *p) {
+	AlnParams P;
+	memset(&P, 0, sizeof(P));
+	P.pen.W1 = p->W1; P.pen.U = p->U; P.pen.MM = p->MM; P.pen.M = p->M;
+	memcpy(P.pen.d, p->d, sizeof(P.pen.d));
+	P.k = db->info.kmerindex; P.mq = p->mq; P.one2one = p->one2one; P.exhaustive = p->exhaustive; P.minlen = p->minlen;
+	P.scoreT = p->scoreT; P.mrc = p->mrc; P.minFrac = p->minFrac;
+	return P;
+}
+
+extern "C" int kmagpu_align_upload(kmagpu_db *db, const void *stage2, size_t nbytes, int64_t *nreads_out) {
+	if (!db || (!stage2 && nbytes)) { kmagpu_set_error("null argument"); return -1; }
+	if (nbytes >= (1ull << 32) - 64) { kmagpu_set_error("stage-2 batch of %zu bytes exceeds the 4 GiB per-call limit; split it", nbytes); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	AlignBatch &b = db->aln;
+	b.h_off.pinned = true;
+	const uint8_t *in = (const uint8_t *)stage2;
+	size_t guess = nbytes / 64 + 16;
+	if (b.h_off.reserve(4 * (guess + 1))) return -1;
+	uint32_t *off = (uint32_t *)b.h_off.p;
+	size_t cap = b.h_off.cap / 4 - 1, n = 0, ip = 0;
+	while (ip + 28 <= nbytes) {   // record walk (get_ankers, ankers.c:163-220)
+		int32_t h[7];
+		memcpy(h, in + ip, 28);
+		if (h[0] < 0) break;   // stream terminator -(number of reads)
+		size_t len = 28 + 8 * (size_t)(uint32_t)h[1] + 4 * (size_t)(uint32_t)h[2] + 4 * (size_t)(uint32_t)h[4] + (size_t)(uint32_t)h[5];
+		if (h[1] < 0 || h[2] < 0 || h[4] < 0 || h[5] < 0 || ip + len > nbytes) { kmagpu_set_error("stage-2 stream is truncated or corrupt at byte %zu", ip); return -1; }
+		if (n == cap) {
+			KgBuf bigger; bigger.pinned = true;
+			if (bigger.reserve(8 * (cap + 1))) return -1;
+			memcpy(bigger.p, off, 4 * n);
+			b.h_off.release();
+			b.h_off = bigger;
+			off = (uint32_t *)b.h_off.p; cap = b.h_off.cap / 4 - 1;
+		}
+		off[n++] = (uint32_t)ip;
+		ip += len;
+	}
+	off[n] = (uint32_t)ip;
+	b.nreads = (int64_t)n; b.in_bytes = ip; b.ran = false;
+	if (nreads_out) *nreads_out = (int64_t)n;
+	if (b.d_in.reserve(ip + 64) || b.d_off.reserve(4 * (n + 2))) return -1;
+	KG_CUDA(cudaEventRecord(db->ev[5], db->stream));
+	KG_CUDA(cudaMemcpyAsync(b.d_in.p, in, ip, cudaMemcpyHostToDevice, db->stream));
+	KG_CUDA(cudaMemsetAsync((uint8_t *)b.d_in.p + ip, 0, 64, db->stream));
+	KG_CUDA(cudaMemcpyAsync(b.d_off.p, off, 4 * (n + 1), cudaMemcpyHostToDevice, db->stream));
+	KG_CUDA(cudaEventRecord(db->ev[6], db->stream));
+	KG_CUDA(cudaStreamSynchronize(db->stream));
+	b.in = (const uint8_t *)b.d_in.p;
+	return 0;
+}
+
+// defined in kmagpu_seed.cu: device view of the last stage-2 stream (all reads; unmapped ones have empty records)
+int kg_seed_device_output(kmagpu_db *db, const uint8_t **out, const uint32_t **rec_off, int64_t *nreads, size_t *bytes);
+
+extern "C" int kmagpu_align_from_seed(kmagpu_db *db, int64_t *nreads_out) {
+	if (!db) { kmagpu_set_error("null argument"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	AlignBatch &b = db->aln;
+	const uint8_t *out; const uint32_t *roff; int64_t n; size_t bytes;
+	if (kg_seed_device_output(db, &out, &roff, &n, &bytes)) return -1;
+	if (b.d_off.reserve(4 * ((size_t)n + 2))) return -1;
+	const uint32_t total = (uint32_t)bytes;
+	KG_CUDA(cudaMemcpyAsync(b.d_off.p, roff, 4 * (size_t)n, cudaMemcpyDeviceToDevice, db->stream));
+	KG_CUDA(cudaMemcpyAsync((uint32_t *)b.d_off.p + n, &total, 4, cudaMemcpyHostToDevice, db->stream));
+	KG_CUDA(cudaStreamSynchronize(db->stream));
+	b.in = out; b.nreads = n; b.in_bytes = bytes; b.ran = false;
+	if (nreads_out) *nreads_out = n;
+	return 0;
+}
+
+static ScratchLayout make_layout(int mem_cap, int q_cap, size_t e_cap) {
+	ScratchLayout l;
+	l.mem_cap = mem_cap; l.q_cap = q_cap; l.e_cap = (e_cap + 255) & ~(size_t)255;
+	size_t s = (((size_t)7 * (mem_cap + 1) * 4) + 15) & ~(size_t)15;
+	s += (size_t)q_cap * 12 + l.e_cap;
+	l.stride = (s + 255) & ~(size_t)255;
+	return l;
+}
+
+extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int want_cand, kmagpu_align_stats *stats) {
+	if (!db || !prm) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->d_tslots) { kmagpu_set_error("database has no alignment index (.seq.b / .length.b missing)"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	AlignBatch &b = db->aln;
+	const int n = (int)b.nreads;
+	const int DB = db->info.DB_size;
+	if (stats) memset(stats, 0, sizeof(*stats));
+	b.out_bytes = 0; b.ntasks = 0; b.ran = true; b.want_cand = want_cand != 0;
+	b.h_cand.clear();
+	b.h_scores.assign(2 * (size_t)DB, 0);
+	if (n == 0) return 0;
+	const AlnParams P = make_params(db, prm);
+	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+	if (b.d_reads.reserve(sizeof(AlnRead) * (size_t)n) || b.d_sz.reserve(4 * (size_t)(4 * n + 8)) ||
+	    b.d_partial.reserve(4 * (size_t)(ntiles + 2)) || b.d_ctr.reserve(8 * A_N) || b.d_scores.reserve(16 * (size_t)DB) ||
+	    b.d_recsize.reserve(4 * (size_t)(2 * n + 4)) || b.d_res.reserve(sizeof(AlnRes) * (size_t)n)) return -1;
+	uint32_t *slab_sz = (uint32_t *)b.d_sz.p, *slab_off = slab_sz + n + 1, *task_sz = slab_off + n + 1, *task_off = task_sz + n + 1;
+	uint32_t *partial = (uint32_t *)b.d_partial.p;
+	unsigned long long *ctr = (unsigned long long *)b.d_ctr.p;
+	unsigned long long *as = (unsigned long long *)b.d_scores.p, *uas = as + DB;
+	AlnRead *reads = (AlnRead *)b.d_reads.p;
+	int launches = 0;
+	unsigned long long h[A_N];
+	cudaStream_t st = db->stream;
+
+	KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * A_N, st));
+	KG_CUDA(cudaMemsetAsync(as, 0, 16 * (size_t)DB, st));
+	KG_CUDA(cudaEventRecord(db->ev[2], st));
+	aln_sizes_kernel<<<(n + 255) / 256, 256, 0, st>>>(b.in, (const uint32_t *)b.d_off.p, n, P.k, reads, slab_sz, task_sz, ctr);
+	kg_exscan(slab_sz, n, slab_off, partial, ctr + A_SLAB, st);
+	kg_exscan(task_sz, n, task_off, partial, ctr + A_TASKS, st);
+	launches += 7;
+	KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	if (h[A_BAD]) { kmagpu_set_error("%llu paired-end records in the stage-2 stream: not supported by kmagpu_align_batch yet", h[A_BAD]); return -1; }
+	const size_t slab_units = (size_t)h[A_SLAB];
+	const int ntasks = (int)h[A_TASKS];
+	const int maxq = (int)h[A_MAXQ];
+	b.ntasks = ntasks;
+	if (b.d_slab.reserve(8 * (slab_units + 4)) || b.d_taskread.reserve(4 * ((size_t)ntasks + 1)) ||
+	    b.d_cand.reserve(sizeof(AlnCand) * ((size_t)ntasks + 1)) || b.d_ovf.reserve(4 * ((size_t)ntasks + 1))) return -1;
+	aln_prep_kernel<<<db->sm_count * 8, 256, 0, st>>>(b.in, n, reads, slab_off, task_off, (uint64_t *)b.d_slab.p, (int32_t *)b.d_taskread.p, P.k);
+	++launches;
+	KG_CUDA(cudaEventRecord(db->ev[3], st));
+
+	if (ntasks) {
+		// per-warp scratch: MEM list, NW row buffers for the longest read, traceback bytes for a tail of that read
+		const int q_cap = std::min(std::max(maxq + 64, 256), 1 << 20);
+		const size_t e_cap = std::min<size_t>(std::max<size_t>(2 * (size_t)maxq * (size_t)maxq + 65536, 65536), 4u << 20);
+		const ScratchLayout lay = make_layout(2048, q_cap, e_cap);
+		int grid = db->sm_count * 4;
+		size_t freeb = 0, totalb = 0;
+		cudaMemGetInfo(&freeb, &totalb);
+		while (grid > db->sm_count && lay.stride * (size_t)grid * AL_WARPS > freeb / 2 + b.d_scratch.cap) grid -= db->sm_count;
+		if (b.d_scratch.reserve(lay.stride * (size_t)grid * AL_WARPS)) return -1;
+		aln_pair_kernel<<<grid, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
+			(const int32_t *)b.d_taskread.p, ntasks, nullptr, (AlnCand *)b.d_cand.p, (uint8_t *)b.d_scratch.p, lay, ctr,
+			(int32_t *)b.d_ovf.p);
+		++launches;
+		KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
+		KG_CUDA(cudaStreamSynchronize(st));
+		KG_CUDA(cudaGetLastError());
+		int novf = (int)h[A_OVF];
+		const unsigned long long first_ovf = h[A_OVF];
+		// large-scratch path: same code, few warps, scratch sized from what the pairs asked for
+		for (int round = 0; novf; ++round) {
+			if (round == 8) { kmagpu_set_error("%d read/template pairs do not fit the alignment scratch", novf); return -1; }
+			const ScratchLayout big = make_layout(std::max<int>(2048, (int)h[A_NEED_MEM]), std::max<int>(q_cap, (int)h[A_NEED_Q]),
+			                                      std::max<size_t>(e_cap, (size_t)h[A_NEED_E]));
+			cudaMemGetInfo(&freeb, &totalb);
+			int g2 = std::min(db->sm_count, (novf + AL_WARPS - 1) / AL_WARPS);
+			while (g2 > 1 && big.stride * (size_t)g2 * AL_WARPS > (freeb + b.d_scratch.cap) / 2) g2 = (g2 + 1) / 2;
+			if (b.d_scratch.reserve(big.stride * (size_t)g2 * AL_WARPS)) return -1;
+			// the overflow list becomes the task list; d_ovf collects what still does not fit
+			KgBuf list2;
+			if (list2.reserve(4 * ((size_t)novf + 1))) return -1;
+			KG_CUDA(cudaMemcpyAsync(list2.p, b.d_ovf.p, 4 * (size_t)novf, cudaMemcpyDeviceToDevice, st));
+			KG_CUDA(cudaMemsetAsync(ctr + A_WORK, 0, 8 * 5, st));   // A_WORK, A_OVF, A_NEED_*
+			aln_pair_kernel<<<g2, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
+				(const int32_t *)b.d_taskread.p, novf, (const int32_t *)list2.p, (AlnCand *)b.d_cand.p,
+				(uint8_t *)b.d_scratch.p, big, ctr, (int32_t *)b.d_ovf.p);
+			++launches;
+			KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
+			KG_CUDA(cudaStreamSynchronize(st));
+			KG_CUDA(cudaGetLastError());
+			list2.release();
+			novf = (int)h[A_OVF];
+		}
+		h[A_OVF] = first_ovf;
+	}
+	KG_CUDA(cudaEventRecord(db->ev[4], st));
+	if (b.want_cand && ntasks) {   // per-candidate rows, before the selection compacts them in place
+		std::vector<AlnCand> hc((size_t)ntasks);
+		std::vector<int32_t> tr((size_t)ntasks);
+		KG_CUDA(cudaMemcpyAsync(hc.data(), b.d_cand.p, sizeof(AlnCand) * (size_t)ntasks, cudaMemcpyDeviceToHost, st));
+		KG_CUDA(cudaMemcpyAsync(tr.data(), b.d_taskread.p, 4 * (size_t)ntasks, cudaMemcpyDeviceToHost, st));
+		KG_CUDA(cudaStreamSynchronize(st));
+		b.h_cand.resize(8 * (size_t)ntasks);
+		for (int i = 0; i < ntasks; ++i) {
+			int32_t *o = &b.h_cand[8 * (size_t)i];
+			o[0] = tr[i]; o[1] = hc[i].tmpl; o[2] = hc[i].score; o[3] = hc[i].len; o[4] = hc[i].pos; o[5] = hc[i].match;
+			o[6] = hc[i].tGaps; o[7] = hc[i].qGaps;
+		}
+	}
+	uint32_t *recsize = (uint32_t *)b.d_recsize.p, *recoff = recsize + n + 1;
+	aln_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(P, reads, n, (AlnCand *)b.d_cand.p, db->tix.meta, as, uas, recsize,
+		(AlnRes *)b.d_res.p, ctr);
+	kg_exscan(recsize, n, recoff, partial, ctr + A_OUT, st);
+	launches += 4;
+	unsigned long long h3[A_N];
+	KG_CUDA(cudaMemcpyAsync(h3, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	b.out_bytes = (size_t)h3[A_OUT];
+	if (b.d_out.reserve(b.out_bytes + 64)) return -1;
+	aln_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>(b.in, reads, n, (const uint64_t *)b.d_slab.p, (const AlnCand *)b.d_cand.p,
+		(const AlnRes *)b.d_res.p, recoff, (uint8_t *)b.d_out.p);
+	++launches;
+	KG_CUDA(cudaEventRecord(db->ev[7], st));
+	KG_CUDA(cudaMemcpyAsync(b.h_scores.data(), as, 16 * (size_t)DB, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	if (stats) {
+		stats->reads = n; stats->tasks = ntasks; stats->frags = (int64_t)h3[A_FRAGS]; stats->mems = (int64_t)h[A_MEMS];
+		stats->nw_full_calls = (int64_t)h[A_FULL_CALLS]; stats->nw_band_calls = (int64_t)h[A_BAND_CALLS];
+		stats->nw_full_cells = (int64_t)h[A_FULL_CELLS]; stats->nw_band_cells = (int64_t)h[A_BAND_CELLS];
+		stats->nw_steps = (int64_t)h[A_STEPS];
+		stats->overflow_tasks = ntasks ? (int64_t)h[A_OVF] : 0;
+		cudaEventElapsedTime(&stats->ms_prep, db->ev[2], db->ev[3]);
+		cudaEventElapsedTime(&stats->ms_align, db->ev[3], db->ev[4]);
+		cudaEventElapsedTime(&stats->ms_reduce, db->ev[4], db->ev[7]);
+		cudaEventElapsedTime(&stats->ms_total, db->ev[2], db->ev[7]);
+		stats->launches = launches;
+	}
+	return 0;
+}
+
+extern "C" int kmagpu_align_download(kmagpu_db *db, void *frag_out, size_t out_cap, size_t *out_bytes,
+                                     uint64_t *alignment_scores, uint64_t *uniq_alignment_scores,
+                                     kmagpu_cand *cand_out, size_t cand_cap, size_t *cand_rows) {
+	if (!db) { kmagpu_set_error("null argument"); return -1; }
+	AlignBatch &b = db->aln;
+	if (!b.ran) { kmagpu_set_error("kmagpu_align_download before kmagpu_align_run"); return -1; }
+	if (out_bytes) *out_bytes = b.out_bytes;
+	if (cand_rows) *cand_rows = b.h_cand.size() / 8;
+	if (b.out_bytes > out_cap) { kmagpu_set_error("frag_raw output needs %zu bytes, caller gave %zu", b.out_bytes, out_cap); return -1; }
+	if (cand_out && b.h_cand.size() / 8 > cand_cap) { kmagpu_set_error("candidate rows need %zu entries, caller gave %zu", b.h_cand.size() / 8, cand_cap); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	if (b.out_bytes) {
+		KG_CUDA(cudaMemcpyAsync(frag_out, b.d_out.p, b.out_bytes, cudaMemcpyDeviceToHost, db->stream));
+		KG_CUDA(cudaStreamSynchronize(db->stream));
+	}
+	const size_t DB = (size_t)db->info.DB_size;
+	if (alignment_scores) for (size_t i = 0; i < DB; ++i) alignment_scores[i] += b.h_scores[i];
+	if (uniq_alignment_scores) for (size_t i = 0; i < DB; ++i) uniq_alignment_scores[i] += b.h_scores[DB + i];
+	if (cand_out && !b.h_cand.empty()) memcpy(cand_out, b.h_cand.data(), 4 * b.h_cand.size());
+	return 0;
+}
+
+extern "C" int kmagpu_align_batch(kmagpu_db *db, const kmagpu_params *p, const void *stage2, size_t nbytes,
+                                  void *frag_out, size_t out_cap, size_t *out_bytes,
+                                  uint64_t *alignment_scores, uint64_t *uniq_alignment_scores,
+                                  kmagpu_cand *cand_out, size_t cand_cap, size_t *cand_rows, kmagpu_align_stats *stats) {
+	int64_t n;
+	if (kmagpu_align_upload(db, stage2, nbytes, &n)) return -1;
+	if (kmagpu_align_run(db, p, cand_out != nullptr, stats)) return -1;
+	if (kmagpu_align_download(db, frag_out, out_cap, out_bytes, alignment_scores, uniq_alignment_scores, cand_out, cand_cap, cand_rows)) return -1;
+	if (stats) cudaEventElapsedTime(&stats->ms_h2d, db->ev[5], db->ev[6]);
+	return 0;
+}
+
+// ---------------------------------------------------------------- stand-alone NW batch
+
+__global__ void __launch_bounds__(AL_WARPS * 32) nw_batch_kernel(NwPen pen, KgTIndexView ix, int n, const int32_t *__restrict__ prob,
+		const uint8_t *qpool, int32_t *out, int32_t *status, uint8_t *scratch, ScratchLayout lay, unsigned long long *ctr) {
+	__shared__ NwPen spen;
+	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&pen)[threadIdx.x];
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const size_t wid = (size_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
+	uint8_t *sp = scratch + wid * lay.stride;
+	NwScratch nws;
+	nws.rowbuf = (NwRow *)sp; sp += (size_t)lay.q_cap * 8;
+	nws.lastD = (int *)sp; sp += (size_t)lay.q_cap * 4;
+	nws.E = sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap;
+	unsigned long long cells = 0, steps = 0;
+	for (;;) {
+		unsigned long long t = 0;
+		if (lane == 0) t = atomicAdd(&ctr[0], 1ull);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t >= (unsigned long long)n) break;
+		const int32_t *pr = prob + 8 * t;
+		const KgTMeta m = ix.meta[pr[0]];
+		NwStat s = {0, 0, 0, 0, 0, 0};
+		const int st = nw_warp(spen, ix.seq + m.seq_off, qpool + pr[3], pr[6], pr[1], pr[2], pr[4], pr[5], pr[7], nws, &s, &cells);
+		if (st == NW_OK && pr[2] > pr[1] && pr[5] > pr[4]) {
+			NwGeo g;
+			nw_geo_init(g, spen, pr[2] - pr[1], pr[5] - pr[4], pr[6], pr[7]);
+			steps += (unsigned long long)g.Tmax;
+		}
+		if (lane == 0) {
+			int32_t *o = out + 6 * t;
+			o[0] = s.score; o[1] = s.len; o[2] = s.pos; o[3] = s.match; o[4] = s.tGaps; o[5] = s.qGaps;
+			status[t] = st;
+		}
+		__syncwarp();
+	}
+	if (lane == 0) { atomicAdd(&ctr[1], cells); atomicAdd(&ctr[2], steps); }
+}
+
+extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, const int32_t *prob, const uint8_t *qpool,
+                               size_t qbytes, int32_t *out, int32_t *status, int64_t *cells, int64_t *steps, float *ms) {
+	if (!db || !p || (n && (!prob || !qpool || !out || !status))) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->d_tmeta) { kmagpu_set_error("database has no template sequences"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	if (cells) *cells = 0;
+	if (steps) *steps = 0;
+	if (ms) *ms = 0;
+	if (!n) return 0;
+	size_t need_e = 65536;
+	int need_q = 256;
+	const AlnParams P = make_params(db, p);
+	for (size_t i = 0; i < n; ++i) {
+		const int32_t *pr = prob + 8 * i;
+		if (pr[0] <= 0 || pr[0] >= db->info.DB_size || pr[1] < 0 || pr[2] < pr[1] || pr[2] > db->lengths[pr[0]] || pr[4] < 0 ||
+		    pr[5] < pr[4] || pr[3] < 0 || (size_t)pr[3] + (size_t)pr[5] > qbytes) {
+			kmagpu_set_error("NW problem %zu is out of range", i);
+			return -1;
+		}
+		NwGeo g;
+		if (pr[2] > pr[1] && pr[5] > pr[4] && nw_geo_init(g, P.pen, pr[2] - pr[1], pr[5] - pr[4], pr[6], pr[7])) {
+			need_e = std::max(need_e, g.ebytes() + 256);
+			need_q = std::max(need_q, pr[5] - pr[4] + 64);
+		}
+	}
+	ScratchLayout lay;
+	lay.mem_cap = 0; lay.q_cap = need_q; lay.e_cap = (need_e + 255) & ~(size_t)255;
+	lay.stride = ((size_t)need_q * 12 + lay.e_cap + 255) & ~(size_t)255;
+	size_t freeb = 0, totalb = 0;
+	cudaMemGetInfo(&freeb, &totalb);
+	int grid = (int)std::min<size_t>((size_t)db->sm_count * 4, (n + AL_WARPS - 1) / AL_WARPS);
+	while (grid > 1 && lay.stride * (size_t)grid * AL_WARPS > freeb / 2) grid = (grid + 1) / 2;
+	uint8_t *scratch = nullptr, *dq = nullptr;
+	int32_t *dprob = nullptr, *dout = nullptr, *dstat = nullptr;
+	unsigned long long *ctr = nullptr;
+	KG_CUDA(cudaMalloc(&scratch, lay.stride * (size_t)grid * AL_WARPS));
+	KG_CUDA(cudaMalloc(&dq, qbytes + 64));
+	KG_CUDA(cudaMalloc(&dprob, 32 * n));
+	KG_CUDA(cudaMalloc(&dout, 24 * n));
+	KG_CUDA(cudaMalloc(&dstat, 4 * n));
+	KG_CUDA(cudaMalloc(&ctr, 64));
+	KG_CUDA(cudaMemcpyAsync(dq, qpool, qbytes, cudaMemcpyHostToDevice, db->stream));
+	KG_CUDA(cudaMemcpyAsync(dprob, prob, 32 * n, cudaMemcpyHostToDevice, db->stream));
+	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, db->stream));
+	KG_CUDA(cudaEventRecord(db->ev[2], db->stream));
+	nw_batch_kernel<<<grid, AL_WARPS * 32, 0, db->stream>>>(P.pen, db->tix, (int)n, dprob, dq, dout, dstat, scratch, lay, ctr);
+	KG_CUDA(cudaEventRecord(db->ev[3], db->stream));
+	unsigned long long hc[8];
+	KG_CUDA(cudaMemcpyAsync(out, dout, 24 * n, cudaMemcpyDeviceToHost, db->stream));
+	KG_CUDA(cudaMemcpyAsync(status, dstat, 4 * n, cudaMemcpyDeviceToHost, db->stream));
+	KG_CUDA(cudaMemcpyAsync(hc, ctr, 64, cudaMemcpyDeviceToHost, db->stream));
+	KG_CUDA(cudaStreamSynchronize(db->stream));
+	KG_CUDA(cudaGetLastError());
+	if (cells) *cells = (int64_t)hc[1];
+	if (steps) *steps = (int64_t)hc[2];
+	if (ms) cudaEventElapsedTime(ms, db->ev[2], db->ev[3]);
+	cudaFree(scratch); cudaFree(dq); cudaFree(dprob); cudaFree(dout); cudaFree(dstat); cudaFree(ctr);
+	return 0;
+}

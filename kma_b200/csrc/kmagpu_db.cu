@@ -33,6 +33,8 @@ extern "C" void kmagpu_default_params(kmagpu_params *p) {
 		for (int j = 0; j < 4; ++j) p->d[i * 5 + j] = i == j ? 1 : -2;
 	p->scoreT = 0.5;
 	p->minFrac = 1.0;
+	p->mrc = 0.0;
+	p->minlen = 16;
 }
 
 int KgBuf::reserve(size_t bytes) {
@@ -169,6 +171,7 @@ extern "C" int kmagpu_db_open(const char *prefix, int device, kmagpu_db **out) {
 	if (cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
 	for (auto &e : db->ev) if (cudaEventCreate(&e) != cudaSuccess) return fail("event");
 	if (cudaGetLastError() != cudaSuccess) return fail("CUDA error while loading the database");
+	if (db->d_seq && kg_tindex_build(db)) return fail(nullptr);
 	*out = db;
 	return 0;
 }
@@ -177,6 +180,8 @@ extern "C" void kmagpu_db_close(kmagpu_db *db) {
 	if (!db) return;
 	cudaSetDevice(db->device);
 	kg_seed_free(db);
+	kg_align_free(db);
+	cudaFree(db->d_tmeta); cudaFree(db->d_tslots); cudaFree(db->d_tdups);
 	cudaFree(db->d_exist); cudaFree(db->d_kv); cudaFree(db->d_values);
 	cudaFree(db->d_seq); cudaFree(db->d_lengths); cudaFree(db->d_seq_off);
 	for (auto &e : db->ev) if (e) cudaEventDestroy(e);

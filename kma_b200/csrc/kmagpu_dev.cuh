@@ -1,0 +1,104 @@
+// Device helpers shared by the translation units of libkmagpu.so: unaligned little-endian access to the
+// reference's record streams, 2-bit sequence windows, and the three-kernel exclusive scan that turns per-read
+// record sizes into output offsets.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+__device__ __forceinline__ uint32_t ld_u32u(const uint8_t *p) {  // unaligned little-endian load
+	uintptr_t a = (uintptr_t)p;
+	const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+	unsigned sh = (unsigned)(a & 3) * 8;
+	uint32_t lo = __ldg(q);
+	if (sh == 0) return lo;
+	return __funnelshift_r(lo, __ldg(q + 1), sh);
+}
+__device__ __forceinline__ uint64_t ld_u64u(const uint8_t *p) {
+	return (uint64_t)ld_u32u(p) | ((uint64_t)ld_u32u(p + 4) << 32);
+}
+__device__ __forceinline__ void st_u32b(uint8_t *p, uint32_t v) {   // unaligned store
+	p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
+}
+
+// reverse the order of the 32 two-bit symbols of w
+__device__ __forceinline__ uint64_t rev2(uint64_t w) {
+	w = __brevll(w);
+	return ((w >> 1) & 0x5555555555555555ull) | ((w & 0x5555555555555555ull) << 1);
+}
+
+// 32 bases of an (unaligned) packed read starting at base position pos (pos may be negative / past the end)
+__device__ __forceinline__ uint64_t fwd32(const uint8_t *seq, int words, int pos) {
+	if (pos <= -32) return 0;
+	if (pos < 0) return (words > 0 ? ld_u64u(seq) : 0ull) >> (2 * -pos);
+	int w = pos >> 5, b = (pos & 31) << 1;
+	uint64_t x = w < words ? ld_u64u(seq + 8 * (size_t)w) << b : 0ull;
+	if (b && w + 1 < words) x |= ld_u64u(seq + 8 * (size_t)(w + 1)) >> (64 - b);
+	return x;
+}
+
+// ---------------------------------------------------------------- exclusive scan (u32 sizes -> u32 offsets)
+
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+static __device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t *total) {
+	__shared__ uint32_t wsum[SCAN_THREADS / 32];
+	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint32_t x = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+	if (lane == 31) wsum[wid] = x;
+	__syncthreads();
+	if (wid == 0) {
+		uint32_t s = lane < SCAN_THREADS / 32 ? wsum[lane] : 0;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+		if (lane < SCAN_THREADS / 32) wsum[lane] = s;
+	}
+	__syncthreads();
+	uint32_t prev = wid ? wsum[wid - 1] : 0;
+	*total = wsum[SCAN_THREADS / 32 - 1];
+	__syncthreads();
+	return prev + x - v;
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const uint32_t *size, int n, uint32_t *off, uint32_t *partial) {
+	const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+	uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = base + i < n ? size[base + i] : 0; s += v[i]; }
+	uint32_t tot, ex = block_exscan(s, &tot);
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) off[base + i] = ex; ex += v[i]; }
+	if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+// *total receives the sum of all sizes
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_partials_kernel(uint32_t *partial, int nb, unsigned long long *total) {
+	uint32_t carry = 0;
+	for (int base = 0; base < nb; base += SCAN_THREADS) {
+		int i = base + threadIdx.x;
+		uint32_t v = i < nb ? partial[i] : 0, tot;
+		uint32_t ex = block_exscan(v, &tot);
+		if (i < nb) partial[i] = carry + ex;
+		carry += tot;
+	}
+	if (threadIdx.x == 0) *total = carry;
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t *off, int n, const uint32_t *partial) {
+	const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+	const uint32_t add = partial[blockIdx.x];
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) if (base + i < n) off[base + i] += add;
+}
+
+// off[i] = sum(size[0..i)), *total = sum(size[0..n)); partial needs (n + SCAN_TILE - 1) / SCAN_TILE + 1 entries
+static inline void kg_exscan(const uint32_t *size, int n, uint32_t *off, uint32_t *partial, unsigned long long *total,
+                             cudaStream_t st) {
+	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+	scan_tiles_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(size, n, off, partial);
+	scan_partials_kernel<<<1, SCAN_THREADS, 0, st>>>(partial, ntiles, total);
+	scan_add_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(off, n, partial);
+}

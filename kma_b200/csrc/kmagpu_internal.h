@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include "../../include/kmagpu.h"
+#include "kmagpu_tindex.cuh"
 
 void kmagpu_set_error(const char *fmt, ...);
 
@@ -53,6 +54,19 @@ struct SeedBatch {
 	bool ran = false;
 };
 
+// one batch of the alignment pass (kmagpu_align.cu)
+struct AlignBatch {
+	KgBuf d_in, d_off, d_reads, d_slab, d_sz, d_partial, d_taskread, d_cand, d_recsize, d_out, d_ctr, d_scores,
+	      d_scratch, d_ovf, d_res;
+	KgBuf h_off;
+	const uint8_t *in = nullptr;   // device pointer of the stage-2 stream (d_in or the seeding output)
+	int64_t nreads = 0, ntasks = 0;
+	size_t in_bytes = 0, out_bytes = 0;
+	bool ran = false, want_cand = false;
+	std::vector<int32_t> h_cand;
+	std::vector<uint64_t> h_scores;
+};
+
 struct kmagpu_db {
 	int device = 0;
 	kmagpu_db_info info{};
@@ -69,6 +83,14 @@ struct kmagpu_db {
 	cudaEvent_t ev[8]{};
 	int sm_count = 148;
 	SeedBatch seed;
+	// per-template alignment index (kmagpu_tindex.cu)
+	void *d_tmeta = nullptr, *d_tslots = nullptr;
+	int32_t *d_tdups = nullptr;
+	KgTIndexView tix{};
+	AlignBatch aln;
 };
+
+int kg_tindex_build(kmagpu_db *db);
+int kg_align_free(kmagpu_db *db);
 
 int kg_seed_free(kmagpu_db *db);

@@ -17,6 +17,7 @@
 //   * record sizes are prefix-summed on the device and a writer kernel emits the stage-2 byte
 //     stream (ankers.c:30-50) in input order, so the host does no per-read work.
 #include "kmagpu_internal.h"
+#include "kmagpu_dev.cuh"
 #include <string.h>
 #include <algorithm>
 
@@ -40,24 +41,6 @@ enum { C_WORK = 0, C_POOL = 1, C_OVF = 2, C_WORK2 = 3, C_POOLFAIL = 4, C_LOOKUPS
        C_LISTIDS = 8, C_MAPPED = 9, C_WORDS = 10, C_TOTAL = 11, C_N = 16 };
 
 // ---------------------------------------------------------------- small device helpers
-
-__device__ __forceinline__ uint32_t ld_u32u(const uint8_t *p) {  // unaligned little-endian load
-	uintptr_t a = (uintptr_t)p;
-	const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
-	unsigned sh = (unsigned)(a & 3) * 8;
-	uint32_t lo = __ldg(q);
-	if (sh == 0) return lo;
-	return __funnelshift_r(lo, __ldg(q + 1), sh);
-}
-__device__ __forceinline__ uint64_t ld_u64u(const uint8_t *p) {
-	return (uint64_t)ld_u32u(p) | ((uint64_t)ld_u32u(p + 4) << 32);
-}
-
-// reverse the order of the 32 two-bit symbols of w
-__device__ __forceinline__ uint64_t rev2(uint64_t w) {
-	w = __brevll(w);
-	return ((w >> 1) & 0x5555555555555555ull) | ((w & 0x5555555555555555ull) << 1);
-}
 
 __device__ __forceinline__ uint32_t hash_lookup(const KgHashView &hv, uint64_t key) {
 	if (hv.mega) {
@@ -470,78 +453,7 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 	}
 }
 
-// ---------------------------------------------------------------- exclusive scan of record sizes
-
-#define SCAN_THREADS 256
-#define SCAN_ITEMS 8
-#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
-
-__device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t *total) {
-	__shared__ uint32_t wsum[SCAN_THREADS / 32];
-	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	uint32_t x = v;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-	if (lane == 31) wsum[wid] = x;
-	__syncthreads();
-	if (wid == 0) {
-		uint32_t s = lane < SCAN_THREADS / 32 ? wsum[lane] : 0;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
-		if (lane < SCAN_THREADS / 32) wsum[lane] = s;
-	}
-	__syncthreads();
-	uint32_t prev = wid ? wsum[wid - 1] : 0;
-	*total = wsum[SCAN_THREADS / 32 - 1];
-	__syncthreads();
-	return prev + x - v;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const uint32_t *size, int n, uint32_t *off, uint32_t *partial) {
-	const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-	uint32_t v[SCAN_ITEMS], s = 0;
-#pragma unroll
-	for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = base + i < n ? size[base + i] : 0; s += v[i]; }
-	uint32_t tot, ex = block_exscan(s, &tot);
-#pragma unroll
-	for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) off[base + i] = ex; ex += v[i]; }
-	if (threadIdx.x == 0) partial[blockIdx.x] = tot;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_partials_kernel(uint32_t *partial, int nb, unsigned long long *ctr) {
-	uint32_t carry = 0;
-	for (int base = 0; base < nb; base += SCAN_THREADS) {
-		int i = base + threadIdx.x;
-		uint32_t v = i < nb ? partial[i] : 0, tot;
-		uint32_t ex = block_exscan(v, &tot);
-		if (i < nb) partial[i] = carry + ex;
-		carry += tot;
-	}
-	if (threadIdx.x == 0) ctr[C_TOTAL] = carry;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t *off, int n, const uint32_t *partial) {
-	const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-	const uint32_t add = partial[blockIdx.x];
-#pragma unroll
-	for (int i = 0; i < SCAN_ITEMS; ++i) if (base + i < n) off[base + i] += add;
-}
-
 // ---------------------------------------------------------------- stage-2 record writer
-
-__device__ __forceinline__ void st_u32b(uint8_t *p, uint32_t v) {   // unaligned store
-	p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
-}
-
-// 32 bases of the forward read starting at base position pos (pos may be negative / past the end)
-__device__ __forceinline__ uint64_t fwd32(const uint8_t *seq, int words, int pos) {
-	if (pos <= -32) return 0;
-	if (pos < 0) return (words > 0 ? ld_u64u(seq) : 0ull) >> (2 * -pos);
-	int w = pos >> 5, b = (pos & 31) << 1;
-	uint64_t x = w < words ? ld_u64u(seq + 8 * (size_t)w) << b : 0ull;
-	if (b && w + 1 < words) x |= ld_u64u(seq + 8 * (size_t)(w + 1)) >> (64 - b);
-	return x;
-}
 
 // one warp per mapped read: header, sequence (forward copy or reverse complement, compdna.c:228),
 // N list, template list, name bytes (ankers.c:30-50)
@@ -688,9 +600,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 			(const uint32_t *)b.d_off.p, n, (SeedRes *)b.d_res.p, recsize, (int32_t *)b.d_pool.p,
 			(unsigned long long)b.pool_cap, ctr, ovf, (uint8_t *)b.d_dense.p, dense_stride);
 		KG_CUDA(cudaEventRecord(db->ev[3], db->stream));
-		scan_tiles_kernel<<<ntiles, SCAN_THREADS, 0, db->stream>>>(recsize, n, recoff, partial);
-		scan_partials_kernel<<<1, SCAN_THREADS, 0, db->stream>>>(partial, ntiles, ctr);
-		scan_add_kernel<<<ntiles, SCAN_THREADS, 0, db->stream>>>(recoff, n, partial);
+		kg_exscan(recsize, n, recoff, partial, ctr + C_TOTAL, db->stream);
 		launches += 5;
 		unsigned long long h[C_N];
 		KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * C_N, cudaMemcpyDeviceToHost, db->stream));
@@ -721,6 +631,17 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 		}
 		return 0;
 	}
+}
+
+// device view of the stage-2 stream of the last run, for kmagpu_align_from_seed (records of unmapped reads are empty)
+int kg_seed_device_output(kmagpu_db *db, const uint8_t **out, const uint32_t **rec_off, int64_t *nreads, size_t *bytes) {
+	SeedBatch &b = db->seed;
+	if (!b.ran) { kmagpu_set_error("kmagpu_align_from_seed before kmagpu_seed_run"); return -1; }
+	*out = (const uint8_t *)b.d_out.p;
+	*rec_off = b.nreads ? (const uint32_t *)b.d_recoff.p + b.nreads + 1 : nullptr;
+	*nreads = b.nreads;
+	*bytes = b.out_bytes;
+	return 0;
 }
 
 extern "C" int kmagpu_seed_download(kmagpu_db *db, void *stage2_out, size_t out_cap, size_t *out_bytes) {

@@ -116,7 +116,7 @@ int main(int argc, char **argv) {
 			int hdr[7], ridx = 0;
 			while (fread(hdr, 4, 7, in) == 7 && hdr[0] >= 0) {
 				qc->seqlen = hdr[0]; qc->complen = hdr[1];
-				if (qc->size <= qc->seqlen) { freeComp(qc); allocComp(qc, qc->seqlen << 1); freeComp(qrc); allocComp(qrc, qc->seqlen << 1); qc->seqlen = hdr[0]; qc->complen = hdr[1]; }
+				if (qc->size <= (unsigned)hdr[0]) { freeComp(qc); allocComp(qc, hdr[0] << 1); freeComp(qrc); allocComp(qrc, hdr[0] << 1); qc->seqlen = hdr[0]; qc->complen = hdr[1]; }
 				qc->N[0] = hdr[2]; matched[0] = hdr[4]; header->len = hdr[5];
 				if (header->size <= header->len) { header->size = header->len << 1; header->seq = realloc(header->seq, header->size); }
 				if (fread(qc->seq, 8, qc->complen, in) != qc->complen) break;

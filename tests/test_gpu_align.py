@@ -1,0 +1,166 @@
+"""GPU parity tests (B200): the CUDA alignment pass (MEM seeding, chaining, warp-wavefront NW, selection,
+update_Scores, frag_raw writer) through the C ABI vs the oracle, which test_oracle_align.py pins to the unmodified
+reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from kma_b200 import api, synth, records
+from tests import util
+from tests.test_nw_emu import problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _first_diff(a, b):
+    n = min(len(a), len(b))
+    d = np.flatnonzero(np.frombuffer(a[:n], np.uint8) != np.frombuffer(b[:n], np.uint8))
+    return int(d[0]) if len(d) else n
+
+
+def _check_align(prefix, s2, params=None):
+    s2 = np.frombuffer(s2, dtype=np.uint8) if isinstance(s2, (bytes, bytearray)) else s2
+    ofrag, oa, ou, ocand, cells = util.oracle_align_stream(prefix, s2)
+    db = api.TemplateDB(prefix, device=0)
+    frag, a, u, cand, st = db.alnFrags_batch(s2, params, want_cand=True)
+    db.close()
+    assert st.launches > 0 and st.tasks == len(ocand)
+    if not util.cand_equal(cand, ocand):
+        bad = np.flatnonzero(((cand != ocand) & ~((np.arange(8) == 5) & (ocand[:, 2:3] == 0))).any(axis=1))
+        raise AssertionError(f"{len(bad)} of {len(cand)} candidate rows differ; first: got {cand[bad[0]]} want {ocand[bad[0]]}")
+    assert np.array_equal(a, oa) and np.array_equal(u, ou)
+    fb = frag.tobytes()
+    assert fb == ofrag, f"frag_raw differs at byte {_first_diff(fb, ofrag)} of {len(ofrag)} (got {len(fb)})"
+    assert st.nw_full_cells + st.nw_band_cells == cells
+    return st, cand
+
+
+def test_golden_alignment_pass():
+    with util.golden_dir() as g:
+        s2 = np.fromfile(f"{g}/s2.bin", dtype=np.uint8)
+        st, cand = _check_align(f"{g}/db", s2)
+    assert st.frags > 1000 and st.mems > 0
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed,L,sub,indel", [(31, 150, 0.01, 0.0), (32, 150, 0.03, 0.01), (33, 400, 0.05, 0.02),
+                                               (34, 1000, 0.04, 0.03), (35, 3000, 0.08, 0.06)])
+def test_fresh_data_vs_oracle(tmp_path, seed, L, sub, indel):
+    """substitutions + indels + N's + strand ties; long reads exercise the banded NW, long tails and the chainer"""
+    names, seqs = synth.gene_db(seed, n_families=12, n_variants=6, len_lo=max(300, L + 50), len_hi=max(1500, 2 * L))
+    synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+    rng = np.random.default_rng(seed)
+    base = synth.short_reads(seed + 1, seqs, 500, L=L, sub=0.0, n_rate=0.0, junk_frac=0.03)
+    reads = [synth.mutate_indel(rng, r, sub, indel / 2, indel / 2) for r in base]
+    for r in reads[::9]:
+        if len(r) > 40:
+            r[rng.integers(0, len(r), size=2)] = 4
+    for i in range(0, 60, 2):
+        r = reads[i]
+        reads[i] = np.concatenate([r[: len(r) // 2], synth.revcomp(r[: len(r) // 2])])
+    synth.write_fastq(tmp_path / "r.fq", reads)
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    s2 = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-1t1", "-s2"], cwd=tmp_path)
+    st, cand = _check_align(str(tmp_path / "db"), s2)
+    assert len(cand) > 300
+    if L >= 400:
+        assert st.nw_band_calls > 0
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+def test_repeats_and_small_scratch_overflow(tmp_path):
+    """templates with internal repeats (repeated k-mers -> one MEM per occurrence) and a read long enough that its
+    tails overflow the per-warp traceback scratch -> large-scratch path"""
+    rng = np.random.default_rng(5)
+    seqs = []
+    for f in range(6):
+        unit = rng.integers(0, 4, size=int(rng.integers(40, 120))).astype(np.uint8)
+        parts = []
+        for _ in range(int(rng.integers(8, 30))):
+            parts.append(synth.mutate_subs(rng, unit, 0.01) if rng.random() < 0.6 else rng.integers(0, 4, size=80).astype(np.uint8))
+        seqs.append(np.concatenate(parts))
+    names = [f"rep{i}" for i in range(len(seqs))]
+    synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+    reads = list(synth.short_reads(6, seqs, 300, L=200, sub=0.02, n_rate=0.0, junk_frac=0.0))
+    reads += [synth.mutate_indel(rng, s[: min(len(s), 2500)].copy(), 0.05, 0.03, 0.03) for s in seqs]
+    synth.write_fastq(tmp_path / "r.fq", reads)
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    s2 = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-1t1", "-s2"], cwd=tmp_path)
+    st, cand = _check_align(str(tmp_path / "db"), s2)
+    assert st.mems > st.tasks
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+def test_seed_then_align_resident(tmp_path):
+    """stage 2 -> stage 3 without leaving HBM gives the same bytes as the two-call path"""
+    names, seqs = synth.gene_db(42, n_families=40, n_variants=8)
+    synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    reads = synth.short_reads(7, seqs, 20000, n_rate=0.0005, junk_frac=0.02)
+    s1 = records.stage1_records_fixed(reads)
+    db = api.TemplateDB(str(tmp_path / "db"))
+    s2, n, _ = db.save_kmers_batch(s1)
+    frag_a, a1, u1, _, st1 = db.alnFrags_batch(s2)
+    db.seed_upload(s1); db.seed_run()
+    assert db.align_from_seed() == n
+    st2 = db.align_run()
+    frag_b, a2, u2, _ = db.align_download()
+    db.close()
+    assert frag_a.tobytes() == frag_b.tobytes() and np.array_equal(a1, a2) and np.array_equal(u1, u2)
+    ofrag, oa, ou, _, _ = util.oracle_align_stream(str(tmp_path / "db"), s2, want_cand=False)
+    assert frag_a.tobytes() == ofrag and np.array_equal(a1, oa) and np.array_equal(u1, ou)
+    # conservation: every kept read adds its score once per kept template
+    assert int(a1.sum()) >= int(u1.sum()) > 0 and st1.frags == st2.frags
+
+
+def test_nw_batch_vs_oracle():
+    """NW_score / NW_band_score as stand-alone problems against golden templates: all k modes, ragged sizes"""
+    L = util.orc()
+    pen = util.oracle_params()
+    rng = np.random.default_rng(11)
+    with util.golden_dir() as g:
+        db = api.TemplateDB(f"{g}/db")
+        lens = np.fromfile(f"{g}/db.length.b", dtype=np.int32)[1:]
+        seqb = np.fromfile(f"{g}/db.seq.b", dtype=np.uint64)
+        off = np.concatenate([[0, 0], np.cumsum((lens[1:] >> 5) + 1)])
+        probs, qs, qoff = [], [], 0
+        for it in range(400):
+            t = int(rng.integers(1, len(lens)))
+            tl = int(lens[t])
+            if it < 250:
+                t_len, q_len, band = int(rng.integers(1, min(tl, 260))), int(rng.integers(1, 260)), 0
+            else:
+                t_len = int(rng.integers(70, min(tl, 900)))
+                q_len = max(66, t_len + int(rng.integers(-50, 50)))
+                band = abs(t_len - q_len) + 64
+                if q_len <= band or t_len <= band:
+                    band = 0
+            t_s = int(rng.integers(0, tl - t_len + 1))
+            # query: the template window with errors, or unrelated
+            tw = seqb[off[t]:off[t] + (tl >> 5) + 1]
+            tb = np.array([(int(tw[i >> 5]) >> (62 - 2 * (i & 31))) & 3 for i in range(t_s, t_s + t_len)], dtype=np.uint8)
+            if rng.random() < 0.85:
+                q = synth.mutate_indel(rng, np.resize(tb, q_len + 20), 0.05, 0.03, 0.03)[:q_len]
+                if len(q) < q_len:
+                    q = np.concatenate([q, rng.integers(0, 4, size=q_len - len(q)).astype(np.uint8)])
+            else:
+                q = rng.integers(0, 4, size=q_len).astype(np.uint8)
+            if rng.random() < 0.2:
+                q[rng.integers(0, q_len)] = 4
+            k = int(rng.choice([0, -1, -2, 1, 2]))
+            probs.append([t, t_s, t_s + t_len, qoff, 0, q_len, k, band])
+            qs.append(q)
+            qoff += q_len
+        probs = np.array(probs, dtype=np.int32)
+        qpool = np.concatenate(qs)
+        out, status, cells, steps, ms = db.nw_batch(probs, qpool)
+        db.close()
+        assert (status == 0).all() and cells > 0 and steps > 0
+        for i, p in enumerate(probs):
+            want = (C.c_int * 6)()
+            tw = np.ascontiguousarray(np.concatenate([seqb[off[p[0]]:off[p[0]] + (int(lens[p[0]]) >> 5) + 1], np.zeros(2, np.uint64)]))
+            q = np.ascontiguousarray(qpool[p[3]:p[3] + p[5]])
+            L.orc_nw(pen, tw.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), int(p[6]), int(p[1]), int(p[2]), 0,
+                     int(p[5]), int(p[7]), want)
+            assert list(out[i]) == list(want), (i, list(p), list(out[i]), list(want))

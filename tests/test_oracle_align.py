@@ -26,7 +26,7 @@ def test_golden_stage2_through_alignment(tmp_path):
 
 
 @pytest.mark.parametrize("seed,L,sub,indel", [(31, 150, 0.01, 0.0), (32, 150, 0.03, 0.01), (33, 400, 0.05, 0.02),
-                                               (34, 1000, 0.04, 0.03)])
+                                               (34, 1000, 0.04, 0.03), (35, 3000, 0.08, 0.06)])
 def test_fresh_data_vs_reference(tmp_path, seed, L, sub, indel):
     """substitutions + indels, reads longer than 64 + band so that the banded NW and long tails are exercised"""
     names, seqs = synth.gene_db(seed, n_families=12, n_variants=6, len_lo=max(300, L + 50), len_hi=max(1500, 2 * L))
