@@ -1,14 +1,17 @@
 #!/usr/bin/env python
-"""bench.py -- KMA mapping-core throughput on B200 (mapped reads/s), one JSON line on stdout.
+"""bench.py -- KMA mapping-core throughput on B200 (mapped reads/s + NW GCUPS), one JSON line on stdout.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path
 
-A "step" is one pass of the hot path over one batch of synthetic stage-1 records per GPU
-(weak scaling: every rank maps its own batch against its own replica of the database).
-`value` is measured with the batch resident in HBM (device events inside libkmagpu); `e2e` is the
-same step through the public C ABI call with pinned HOST buffers, H2D and D2H inside the timed
-region. The roofline object describes the dominant kernel (seed_se_kernel).
+A "step" is one pass of the hot path over one batch of synthetic stage-1 records per GPU: stage 2 (k-mer seeding +
+template scoring, save_kmers) and the stage-3 alignment pass (MEM seeding, chainSeeds, NW, alnFragsSE, update_Scores)
+chained in HBM. Weak scaling: every rank maps its own batch against its own replica of the database; the only
+exchange is the all-reduce of the two ConClave score arrays after the step.
+`value` is measured with the batch resident in HBM (device events inside libkmagpu); `e2e` is the same step through
+the public C ABI with pinned HOST buffers, H2D of the stage-1 records and D2H of the frag_raw stream + score arrays
+inside the timed region. `roofline` describes the dominant kernel (aln_pair_kernel); `roofline_seed` and `nw` carry
+the seeding HBM fraction and the banded-NW GCUPS / integer-roofline fraction BASELINE.json asks for.
 """
 from __future__ import annotations
 
@@ -30,7 +33,10 @@ sys.path.insert(0, ROOT)
 from kma_b200 import synth, records, dbbuild  # noqa: E402
 
 DB_SEED, READ_SEED = 42, 7
-WORKLOAD = "C1/C2 gene DB (300 families x 10 variants, 0.5-3 kb, k=16) + 150 bp single-end reads, -1t1, stage 2 (seeding + template scoring)"
+WORKLOAD = ("C2-shaped: gene DB (300 families x 10 variants, 0.5-3 kb, k=16) + 2M x 150 bp reads per GPU mapped single-end (-1t1): "
+            "stage 2 (k-mer seeding + template scoring) + stage 3 alignment pass (MEM chaining + NW + update_Scores); "
+            "paired-end selection (SURVEY 8 a4) is not built yet")
+METRIC = "mapped reads/sec (seeding + chaining + NW alignment pass)"
 
 
 def peaks():
@@ -97,15 +103,25 @@ def algorithmic_bytes(st, values_width):
 
 
 def cpu_reference(prefix, reads, cores, tmp):
-    """Reference arm: unmodified `kma ... -s2` (stage 1 parse + stage 2) of oracle/_ref on `reads`."""
+    """Reference arm: the unmodified reference on `reads`: `kma -s2` (FASTQ parse + stage 2) piped into
+    alnFrags_threaded on `cores` pthreads (oracle/ref_harness.c drives the reference's own stage-3 entry point the
+    way runKMA does) -- the same span as our step."""
     kma = os.path.join(ROOT, "oracle", "_ref", "kma")
+    aln = os.path.join(ROOT, "oracle", "_ref", "ref_aln")
     fq = os.path.join(tmp, "sample.fq")
     synth.write_fastq(fq, reads, prefix="r")
     t0 = time.perf_counter()
     with open(os.devnull, "wb") as dn:
-        subprocess.run([kma, "-i", fq, "-o", os.path.join(tmp, "o"), "-t_db", prefix, "-1t1", "-s2", "-t", str(cores)],
-                       stdout=dn, stderr=dn, check=True)
+        p1 = subprocess.Popen([kma, "-i", fq, "-o", os.path.join(tmp, "o"), "-t_db", prefix, "-1t1", "-s2", "-t", str(cores)],
+                              stdout=subprocess.PIPE, stderr=dn)
+        p2 = subprocess.Popen([aln, prefix, "-", os.path.join(tmp, "fr.out"), os.path.join(tmp, "sc.out"), "-1t1", "-t", str(cores)],
+                              stdin=p1.stdout, stdout=dn, stderr=dn)
+        p1.stdout.close()
+        rc2 = p2.wait()
+        rc1 = p1.wait()
     dt = time.perf_counter() - t0
+    if rc1 or rc2:
+        raise RuntimeError(f"reference run failed: kma rc={rc1}, ref_aln rc={rc2}")
     return len(reads) / dt, dt
 
 
@@ -120,10 +136,52 @@ def cpu_port(prefix, s1, nreads):
     p = (C.c_int32 * 40)()
     L.orc_default_params(p)
     out = np.zeros(3 * len(s1) + 4096, dtype=np.uint8)
+    L.orc_align_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_int,
+                                   C.c_int, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    DB = int(np.fromfile(prefix + ".length.b", dtype=np.int32, count=1)[0])
+    a, u = np.zeros(DB, np.uint64), np.zeros(DB, np.uint64)
+    fo, fb = C.c_void_p(), C.c_size_t()
     t0 = time.perf_counter()
-    L.orc_seed_stream(db, p, s1.ctypes.data, len(s1), out.ctypes.data, len(out), None)
+    n2 = L.orc_seed_stream(db, p, s1.ctypes.data, len(s1), out.ctypes.data, len(out), None)
+    L.orc_align_stream(db, prefix.encode(), p, out.ctypes.data, n2, 1, 0.5, 0, 16, 0.0, C.byref(fo), C.byref(fb),
+                       a.ctypes.data, u.ctypes.data, None, None, None)
     dt = time.perf_counter() - t0
     return nreads / dt, dt
+
+
+def nw_gcups(db, seqs, peak_iops, n=6000, seed=3):
+    """Banded-NW GCUPS on C3-shaped problems (template windows of 1-3 kb vs a 9 %-error copy, band = |dl| + 64 as
+    KMA_score chooses it), the NW batch kernel timed alone with CUDA events inside the library (burst)."""
+    rng = np.random.default_rng(seed)
+    probs, qs, qoff = [], [], 0
+    while len(probs) < n:
+        t = int(rng.integers(0, len(seqs)))
+        tl = len(seqs[t])
+        if tl < 1000:
+            continue
+        t_len = int(rng.integers(1000, tl + 1))
+        t_s = int(rng.integers(0, tl - t_len + 1))
+        q = synth.mutate_indel(rng, seqs[t][t_s:t_s + t_len], 0.03, 0.03, 0.03)
+        band = abs(t_len - len(q)) + 64
+        if len(q) <= band or t_len <= band:
+            continue
+        probs.append([t + 1, t_s, t_s + t_len, qoff, 0, len(q), 0, band])
+        qs.append(q)
+        qoff += len(q)
+    probs = np.array(probs, dtype=np.int32)
+    qpool = np.concatenate(qs)
+    best = None
+    for _ in range(4):
+        out, status, cells, steps, ms = db.nw_batch(probs, qpool)
+        if best is None or ms < best:
+            best = ms
+    gc = cells / best / 1e6
+    return {"kernel": "nw_batch_kernel (warp wavefront, banded)", "problems": int(n), "cells": int(cells), "ms": best,
+            "gcups": gc, "lane_utilisation": cells / (32.0 * steps), "int_ops_per_cell": 12,
+            "int_roofline": {"achieved_tiops": gc * 12 / 1e3, "peak_tiops": peak_iops / 1e12, "frac": gc * 12e9 / peak_iops,
+                             "peak_kind": "148 SMs x 128 int32 lanes x max SM clock"},
+            "not_ok": int((status != 0).sum())}
 
 
 def main():
@@ -161,14 +219,14 @@ def main():
             if i >= args.warmup:
                 vals.append((v, dt))
         v = sum(sample for _ in vals) / sum(dt for _, dt in vals)
-        line = {"impl": "reference", "metric": "mapped reads/sec (stage 2: k-mer seeding + template scoring)",
+        line = {"impl": "reference", "metric": METRIC,
                 "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * statistics.mean(dt for _, dt in vals), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "reads_per_step": sample},
                 "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores if have_ref else 1,
                                  "kind": "reference" if have_ref else "port",
-                                 "sample": f"{sample} reads of the same workload per step; kma -1t1 -s2 -t {cores} (FASTQ parse + stage 2)"},
+                                 "sample": f"{sample} reads of the same workload per step; unmodified kma -1t1 -s2 -t {cores} | alnFrags_threaded on {cores} pthreads (FASTQ parse + stage 2 + alignment pass)"},
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -195,7 +253,6 @@ def main():
     s1_np = records.stage1_records_fast(reads, first=rank * args.reads)
     s1 = torch.empty(len(s1_np), dtype=torch.uint8, pin_memory=True)
     s1.numpy()[:] = s1_np
-    out = torch.empty(2 * len(s1_np) + 4096, dtype=torch.uint8, pin_memory=True)
 
     db = api.TemplateDB(prefix, device=local_rank)
     params = api.default_params()
@@ -207,71 +264,119 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    frag_out = torch.empty(len(s1_np) * 2 + 4096, dtype=torch.uint8, pin_memory=True)
+    DBn = db.info.DB_size
+    scores = (np.zeros(DBn, np.uint64), np.zeros(DBn, np.uint64))
+
+    def step_resident():
+        st = db.seed_run(params)
+        db.align_from_seed()
+        sa = db.align_run(params)
+        return st, sa
+
     # ---- resident-input timing (value): kernels only, device events inside the library
     db.seed_upload(s1)
     for _ in range(args.warmup):
-        st = db.seed_run(params)
+        st, sa = step_resident()
     sampler = ClockSampler(local_rank)
     sync_all()
     sampler.start()
-    t_dev, t_seed, launches = 0.0, 0.0, 0
+    t_dev, t_seed, t_pair, launches = 0.0, 0.0, 0.0, 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        st = db.seed_run(params)
-        t_dev += st.ms_total
+        st, sa = step_resident()
+        t_dev += st.ms_total + sa.ms_total
         t_seed += st.ms_seed
-        launches += st.launches
+        t_pair += sa.ms_align
+        launches += st.launches + sa.launches
     sync_all()
     t_wall = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop()
-    res = db.seed_download(out)
+    res, _, _, _ = db.align_download(out=frag_out)
     out_bytes = int(res.numel() if hasattr(res, "numel") else len(res))
 
     # ---- end to end through the C ABI: pinned host in, pinned host out, copies inside the timed region
+    def step_e2e():
+        db.seed_upload(s1)
+        db.seed_run(params)
+        db.align_from_seed()
+        db.align_run(params)
+        return db.align_download(out=frag_out, scores=scores)
+
     for _ in range(max(1, args.warmup // 2)):
-        db.save_kmers_batch(s1, params, out=out)
+        step_e2e()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, n_e2e, st_e = db.save_kmers_batch(s1, params, out=out)
+        step_e2e()
     sync_all()
     t_e2e = (time.perf_counter() - t0) * 1e3
 
-    tt = torch.tensor([t_dev, t_e2e, t_wall], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(st.reads), float(st.mapped)], dtype=torch.float64, device="cuda")
+    # ---- the one exchange of the path: ConClave score arrays summed over ranks (runkma.c:98-99, conclave.c:80)
+    t_allreduce = 0.0
+    if world > 1:
+        sc = torch.from_numpy(np.concatenate(scores).astype(np.int64)).cuda()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_reduce(sc, op=dist.ReduceOp.SUM)
+        e1.record()
+        torch.cuda.synchronize()
+        t_allreduce = e0.elapsed_time(e1)
+
+    tt = torch.tensor([t_dev, t_e2e, t_wall, t_allreduce], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(st.reads), float(st.mapped), float(sa.frags)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    t_dev_max, t_e2e_max, t_wall_max = (float(x) for x in tt.cpu())
+    t_dev_max, t_e2e_max, t_wall_max, t_ar_max = (float(x) for x in tt.cpu())
     total_reads = float(cnt[0]) * args.steps
 
     pk, pk_kind = peaks()
-    alg = algorithmic_bytes(st, vw)
+    peak_iops = 148 * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6   # int32 lanes x clock
+    alg_seed = algorithmic_bytes(st, vw)
+    cells = sa.nw_full_cells + sa.nw_band_cells
     ms_seed = t_seed / args.steps
-    achieved = alg / (ms_seed * 1e-3) / 1e9
-
+    ms_pair = t_pair / args.steps
+    # aln_pair_kernel, algorithmic bytes per launch: per pair its read (packed words + 0-4 bytes + N list)
+    # and the 32-byte result row; 8 B per position-index probe the reference's seed scan makes; 2 x 2 bit per base
+    # compared by MEM extension; per NW cell 1 B traceback written + 1 B query base + 2 bit template base
+    alg_pair = (sa.read_bytes + 32 * sa.tasks + 8 * sa.index_probes + sa.mem_bases // 2 + (9 * cells) // 4)
+    ach_pair = alg_pair / (ms_pair * 1e-3) / 1e9
+    ach_seed = alg_seed / (ms_seed * 1e-3) / 1e9
     line = {
-        "metric": "mapped reads/sec (stage 2: k-mer seeding + template scoring)",
+        "metric": METRIC,
         "value": total_reads / (t_dev_max * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_dev_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "reads_per_gpu_per_step": args.reads, "read_len": 150,
                    "db_templates": db.info.DB_size - 1, "db_kmers": int(db.info.n),
                    "db_device_bytes": int(db.info.device_bytes), "mapped_fraction": float(cnt[1]) / float(cnt[0]),
-                   "cache": f"stage-1 batch {len(s1_np) / 1e6:.0f} MB + stage-2 output {out_bytes / 1e6:.0f} MB per step exceed the 126 MB L2; "
-                            "the 18 MB hash table is L2-resident by nature of this config",
-                   "sharding": "reads sharded by rank, database replicated per GPU, no data-path collective"},
+                   "aligned_fraction": float(cnt[2]) / float(cnt[0]),
+                   "pairs_per_read": sa.tasks / max(1, sa.reads),
+                   "cache": f"stage-1 batch {len(s1_np) / 1e6:.0f} MB + stage-2 stream + read slab + frag_raw {out_bytes / 1e6:.0f} MB per step exceed the 126 MB L2; "
+                            "the 150 MB database image (hash table + per-template position index) is mostly L2-resident by nature of this config",
+                   "sharding": "reads sharded by rank, database replicated per GPU; one all-reduce of the ConClave score arrays per step",
+                   "allreduce_ms": t_ar_max},
         "e2e": {"value": total_reads / (t_e2e_max * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(len(s1_np)) + 4 * (args.reads + 1),
-                "d2h_bytes_per_step": out_bytes, "ms_per_step": t_e2e_max / args.steps},
+                "d2h_bytes_per_step": out_bytes + 16 * DBn, "ms_per_step": t_e2e_max / args.steps},
         "gpu_launches": launches,
         "wall_ms_per_step_resident": t_wall_max / args.steps,
-        "roofline": {"kernel": "seed_se_kernel<hash>", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": None,
-                     "algorithmic_bytes_per_launch": alg, "kernel_ms": ms_seed,
-                     "per_read": {"lookups": st.lookups / st.reads, "hits": st.hits / st.reads,
-                                  "list_fetches": st.list_fetches / st.reads, "bytes": alg / st.reads}},
+        "stage_ms": {"seed_total": st.ms_total, "seed_kernel": st.ms_seed, "align_prep": sa.ms_prep, "align_pairs": sa.ms_align,
+                     "align_select_emit": sa.ms_reduce},
+        "roofline": {"kernel": "aln_pair_kernel", "bound": "hbm", "achieved": ach_pair, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": ach_pair / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": None,
+                     "algorithmic_bytes_per_launch": alg_pair, "kernel_ms": ms_pair,
+                     "note": "latency/issue bound (dependent index probes, short DP); see nw for the integer roofline",
+                     "per_read": {"pairs": sa.tasks / sa.reads, "index_probes": sa.index_probes / sa.reads, "mems": sa.mems / sa.reads, "nw_cells": cells / sa.reads, "bytes": alg_pair / sa.reads}},
+        "roofline_seed": {"kernel": "seed_se_kernel<hash>", "bound": "hbm", "achieved": ach_seed, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                          "frac": ach_seed / pk["hbm_gbs"], "algorithmic_bytes_per_launch": alg_seed, "kernel_ms": ms_seed,
+                          "per_read": {"lookups": st.lookups / st.reads, "hits": st.hits / st.reads,
+                                       "list_fetches": st.list_fetches / st.reads, "bytes": alg_seed / st.reads}},
         "clocks": clocks,
     }
+    if rank == 0:
+        line["nw"] = nw_gcups(db, seqs, peak_iops)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = min(args.cpu_sample, args.reads)
@@ -279,11 +384,11 @@ def main():
         if have_ref:
             v, dt = cpu_reference(prefix, reads[:sample], cores, workdir)
             line["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference",
-                                    "sample": f"first {sample} reads of the step; unmodified kma -1t1 -s2 -t {cores} (FASTQ parse + stage 2), {dt:.1f} s"}
+                                    "sample": f"first {sample} reads of the step; unmodified kma -1t1 -s2 -t {cores} | alnFrags_threaded on {cores} pthreads (FASTQ parse + stage 2 + alignment pass), {dt:.1f} s"}
         else:
             v, dt = cpu_port(prefix, records.stage1_records_fast(reads[:sample]), sample)
             line["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": 1, "kind": "port",
-                                    "sample": f"first {sample} reads of the step; oracle/liborc.so stage 2, {dt:.1f} s"}
+                                    "sample": f"first {sample} reads of the step; oracle/liborc.so stage 2 + alignment pass, {dt:.1f} s"}
     db.close()
     if rank == 0:
         print(json.dumps(line))

@@ -102,6 +102,9 @@ typedef struct kmagpu_align_stats {
 	int64_t nw_full_cells, nw_band_cells;  /* DP cells as the reference counts them: t_len*q_len, t_len*(band+1) */
 	int64_t nw_steps;                   /* warp wavefront steps (32 cell slots each) */
 	int64_t overflow_tasks;             /* pairs re-run on the large-scratch path */
+	int64_t index_probes;               /* hashMapCCI_get calls the reference's sequential seed scan makes */
+	int64_t mem_bases;                  /* sum of MEM lengths (bases compared by seed extension) */
+	int64_t read_bytes;                 /* packed words + 0-4 bytes + N list of the reads, once per pair */
 	float ms_prep, ms_align, ms_reduce, ms_h2d, ms_total;
 	int32_t launches, reserved;
 } kmagpu_align_stats;

@@ -45,6 +45,7 @@ class AlignStats(C.Structure):
     _fields_ = [("reads", C.c_int64), ("tasks", C.c_int64), ("frags", C.c_int64), ("mems", C.c_int64),
                 ("nw_full_calls", C.c_int64), ("nw_band_calls", C.c_int64), ("nw_full_cells", C.c_int64),
                 ("nw_band_cells", C.c_int64), ("nw_steps", C.c_int64), ("overflow_tasks", C.c_int64),
+                ("index_probes", C.c_int64), ("mem_bases", C.c_int64), ("read_bytes", C.c_int64),
                 ("ms_prep", C.c_float), ("ms_align", C.c_float), ("ms_reduce", C.c_float), ("ms_h2d", C.c_float),
                 ("ms_total", C.c_float), ("launches", C.c_int32), ("reserved", C.c_int32)]
 

@@ -47,7 +47,7 @@ struct AlnParams {
 
 enum { A_WORK = 0, A_OVF = 1, A_NEED_E = 2, A_NEED_MEM = 3, A_NEED_Q = 4, A_MEMS = 5, A_FULL_CALLS = 6, A_BAND_CALLS = 7,
        A_FULL_CELLS = 8, A_BAND_CELLS = 9, A_STEPS = 10, A_SLAB = 11, A_TASKS = 12, A_OUT = 13, A_FRAGS = 14, A_BAD = 15,
-       A_MAXQ = 16, A_N = 24 };
+       A_MAXQ = 16, A_LOOKUPS = 17, A_MEMBASES = 18, A_READBYTES = 19, A_N = 24 };
 
 // ---------------------------------------------------------------- slab layout
 
@@ -145,7 +145,7 @@ struct Mems {
 	__device__ __forceinline__ void shift(int o) { tS += o; tE += o; qS += o; qE += o; W += o; sc += o; nx += o; cap -= o; }
 };
 
-struct WarpCtr { unsigned long long full_calls, band_calls, full_cells, band_cells, steps, mems; unsigned need_e, need_mem, need_q; };
+struct WarpCtr { unsigned long long full_calls, band_calls, full_cells, band_cells, steps, mems, lookups, mem_bases, read_bytes; unsigned need_e, need_mem, need_q; };
 
 __device__ __forceinline__ int warp_max(int v) {
 #pragma unroll
@@ -189,8 +189,9 @@ __device__ int scan_mems(const KgTIndexView &ix, const KgTMeta &m, const uint64_
 			int val = 0;
 			if (p0 < end) val = tix_get(ix, m, kmer_at(q.w, p0, k));
 			const unsigned hits = __ballot_sync(0xffffffffu, val != 0);
-			if (!hits) { j += 32; continue; }
+			if (!hits) { wc.lookups += (unsigned long long)min(32, end - j); j += 32; continue; }
 			const int f = __ffs(hits) - 1, p = j + f;
+			wc.lookups += (unsigned long long)(f + 1);   // the probes the reference's sequential scan makes
 			const int v = __shfl_sync(0xffffffffu, val, f);
 			if (v > 0) {
 				if (n >= M.cap) { wc.need_mem = max(wc.need_mem, (unsigned)n + 1024u); return ST_OVERFLOW; }
@@ -199,6 +200,7 @@ __device__ int scan_mems(const KgTIndexView &ix, const KgTMeta &m, const uint64_
 				if (lane == 0) { M.tS[n] = ts; M.tE[n] = te; M.qS[n] = qs; M.qE[n] = qe; M.W[n] = qe - qs; }
 				++n;
 				s += qe - qs;
+				wc.mem_bases += (unsigned long long)(qe - qs);
 				j = MODE == 0 ? qe : qe + 1;
 			} else {
 				int cnt;
@@ -213,6 +215,7 @@ __device__ int scan_mems(const KgTIndexView &ix, const KgTMeta &m, const uint64_
 				}
 				bias = warp_max(bias);
 				n += cnt;
+				wc.mem_bases += (unsigned long long)cnt * (unsigned long long)k;
 				s += k + (bias - p);
 				j = bias + 1;
 			}
@@ -522,6 +525,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32) aln_pair_kernel(AlnParams P, Kg
 		const uint8_t *rec = in + R.rec_off;
 		const int ti = task - (int)R.task0;
 		const int tmpl = (int)ld_u32u(rec + 28 + 8 * (size_t)R.words + 4 * (size_t)R.nN + 4 * (size_t)ti);
+		wc.read_bytes += 8ull * (unsigned long long)R.words + (unsigned long long)R.q_len + 4ull * (unsigned long long)R.nN;
 		AlnCand res;
 		const int st = align_pair(P, &spen, ix, slab, R, tmpl, M, nws, wc, &res);
 		__syncwarp();
@@ -533,6 +537,9 @@ __global__ void __launch_bounds__(AL_WARPS * 32) aln_pair_kernel(AlnParams P, Kg
 	}
 	if (lane == 0) {
 		if (wc.mems) atomicAdd(&ctr[A_MEMS], wc.mems);
+		if (wc.lookups) atomicAdd(&ctr[A_LOOKUPS], wc.lookups);
+		if (wc.mem_bases) atomicAdd(&ctr[A_MEMBASES], wc.mem_bases);
+		if (wc.read_bytes) atomicAdd(&ctr[A_READBYTES], wc.read_bytes);
 		if (wc.full_calls) { atomicAdd(&ctr[A_FULL_CALLS], wc.full_calls); atomicAdd(&ctr[A_FULL_CELLS], wc.full_cells); }
 		if (wc.band_calls) { atomicAdd(&ctr[A_BAND_CALLS], wc.band_calls); atomicAdd(&ctr[A_BAND_CELLS], wc.band_cells); }
 		if (wc.steps) atomicAdd(&ctr[A_STEPS], wc.steps);
@@ -850,6 +857,7 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 		stats->nw_full_calls = (int64_t)h[A_FULL_CALLS]; stats->nw_band_calls = (int64_t)h[A_BAND_CALLS];
 		stats->nw_full_cells = (int64_t)h[A_FULL_CELLS]; stats->nw_band_cells = (int64_t)h[A_BAND_CELLS];
 		stats->nw_steps = (int64_t)h[A_STEPS];
+		stats->index_probes = (int64_t)h[A_LOOKUPS]; stats->mem_bases = (int64_t)h[A_MEMBASES]; stats->read_bytes = (int64_t)h[A_READBYTES];
 		stats->overflow_tasks = ntasks ? (int64_t)h[A_OVF] : 0;
 		cudaEventElapsedTime(&stats->ms_prep, db->ev[2], db->ev[3]);
 		cudaEventElapsedTime(&stats->ms_align, db->ev[3], db->ev[4]);

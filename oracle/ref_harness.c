@@ -3,7 +3,11 @@
  * Nothing here restates reference logic: it sets the globals the way kma.c / runkma.c do and calls the
  * reference's own stage-3 entry point, so tests get ground truth for the alignment pass.
  *
- *   ref_aln <db_prefix> <stage2.bin> <frag_raw.out> <scores.out> [cand.out] [-1t1]
+ *   ref_aln <db_prefix> <stage2.bin | -> <frag_raw.out> <scores.out> [cand.out] [-1t1] [-t N]
+ *
+ * "-" reads the stage-2 stream from stdin (`kma ... -s2 | ref_aln db - ...`); -t N runs alnFrags_threaded on N pthreads
+ * the way runKMA does (runkma.c:300-440: one Aln_thread per thread, shared input/output/score arrays, the reference's
+ * own spin locks) -- this is the CPU baseline of the alignment pass in bench.py.
  *
  * frag_raw.out : what alnFrags_threaded (alnfrags.c:2150) writes to frag_out_raw for the stream
  * scores.out   : int32 DB_size, uint64 alignment_scores[DB_size], uint64 uniq_alignment_scores[DB_size]
@@ -18,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <pthread.h>
 #include "align.h"
 #include "alnfrags.h"
 #include "ankers.h"
@@ -52,7 +57,13 @@ int main(int argc, char **argv) {
 	if (argc < 5) { fprintf(stderr, "usage: ref_aln db s2.bin frag_raw.out scores.out [cand.out] [-1t1]\n"); return 2; }
 	int one2one = 0, exhaustive = 0, ts = 0;
 	const char *cand_path = 0;
-	for (int a = 5; a < argc; ++a) { if (!strcmp(argv[a], "-1t1")) one2one = 1; else cand_path = argv[a]; }
+	int nthreads = 1;
+	for (int a = 5; a < argc; ++a) {
+		if (!strcmp(argv[a], "-1t1")) one2one = 1;
+		else if (!strcmp(argv[a], "-t") && a + 1 < argc) nthreads = atoi(argv[++a]);
+		else cand_path = argv[a];
+	}
+	if (nthreads < 1) nthreads = 1;
 	char path[4096];
 	int *template_lengths; long unsigned *as, *uas;
 	snprintf(path, sizeof(path), "%s", argv[1]);
@@ -76,7 +87,7 @@ int main(int argc, char **argv) {
 	alignLoadPtr = &alignLoad_fly;
 
 	for (int pass = 0; pass < (cand_path ? 2 : 1); ++pass) {
-		FILE *in = fopen(argv[2], "rb");
+		FILE *in = strcmp(argv[2], "-") ? fopen(argv[2], "rb") : stdin;
 		if (!in) { perror(argv[2]); return 1; }
 		HashMapCCI **templates_index = calloc(DB_size, sizeof(HashMapCCI *));
 		CompDNA *qc = malloc(sizeof(CompDNA)), *qrc = malloc(sizeof(CompDNA));
@@ -88,22 +99,39 @@ int main(int argc, char **argv) {
 		AlnPoints *points = seedPoint_init(1024, rewards);
 		int *matched = malloc(((DB_size + 1) << 1) * sizeof(int));
 		if (pass == 0) {
-			Aln_thread *t = calloc(1, sizeof(Aln_thread));
-			t->matched_templates = matched;
-			t->bestTemplates = malloc(((DB_size + 1) << 1) * sizeof(int));
-			t->bestTemplates_r = malloc(((DB_size + 1) << 1) * sizeof(int));
-			t->best_start_pos = malloc((DB_size << 1) * sizeof(int));
-			t->best_end_pos = malloc((DB_size << 1) * sizeof(int));
-			t->Lengths = malloc((DB_size << 1) * sizeof(int));
-			t->alignment_scores = as; t->uniq_alignment_scores = uas;
-			t->seq_indexes = seq_indexes; t->inputfile = in;
-			t->frag_out_raw = fopen(argv[3], "wb"); t->frag_out_all = 0; t->seq_in = seq_in;
-			t->qseq_comp = qc; t->qseq_r_comp = qrc;
-			t->qseq = setQseqs(1024); t->qseq_r = setQseqs(1024); t->header = setQseqs(256); t->header_r = setQseqs(256);
-			t->points = points; t->NWmatrices = NWm; t->kmersize = kmersize; t->minlen = 16; t->mq = 0; t->sam = 0;
-			t->scoreT = 0.5; t->mrc = 0.0; t->minFrac = 1.0;
-			t->template_lengths = template_lengths; t->templates_index = templates_index;
-			alnFrags_threaded(t);
+			FILE *fout = fopen(argv[3], "wb");
+			pthread_t *tid = calloc(nthreads, sizeof(pthread_t));
+			Aln_thread *first = 0;
+			for (int ti = 0; ti < nthreads; ++ti) {
+				Aln_thread *t = calloc(1, sizeof(Aln_thread));
+				t->matched_templates = ti ? malloc(((DB_size + 1) << 1) * sizeof(int)) : matched;
+				t->bestTemplates = malloc(((DB_size + 1) << 1) * sizeof(int));
+				t->bestTemplates_r = malloc(((DB_size + 1) << 1) * sizeof(int));
+				t->best_start_pos = malloc((DB_size << 1) * sizeof(int));
+				t->best_end_pos = malloc((DB_size << 1) * sizeof(int));
+				t->Lengths = malloc((DB_size << 1) * sizeof(int));
+				t->alignment_scores = as; t->uniq_alignment_scores = uas;
+				t->seq_indexes = seq_indexes; t->inputfile = in;
+				t->frag_out_raw = fout; t->frag_out_all = 0; t->seq_in = seq_in;
+				if (ti) {
+					t->qseq_comp = malloc(sizeof(CompDNA)); t->qseq_r_comp = malloc(sizeof(CompDNA));
+					allocComp(t->qseq_comp, 1024); allocComp(t->qseq_r_comp, 1024);
+					NWmat *m = malloc(sizeof(NWmat));
+					m->NW_s = 1024 * 1024; m->NW_q = 1024; m->E = malloc(m->NW_s);
+					m->D[0] = malloc((m->NW_q << 1) * sizeof(int)); m->P[0] = malloc((m->NW_q << 1) * sizeof(int));
+					m->D[1] = m->D[0] + m->NW_q; m->P[1] = m->P[0] + m->NW_q; m->rewards = rewards;
+					t->NWmatrices = m;
+					t->points = seedPoint_init(1024, rewards);
+				} else { t->qseq_comp = qc; t->qseq_r_comp = qrc; t->NWmatrices = NWm; t->points = points; }
+				t->qseq = setQseqs(1024); t->qseq_r = setQseqs(1024); t->header = setQseqs(256); t->header_r = setQseqs(256);
+				t->kmersize = kmersize; t->minlen = 16; t->mq = 0; t->sam = 0;
+				t->scoreT = 0.5; t->mrc = 0.0; t->minFrac = 1.0;
+				t->template_lengths = template_lengths; t->templates_index = templates_index;
+				if (ti) pthread_create(&tid[ti], 0, &alnFrags_threaded, t); else first = t;
+			}
+			alnFrags_threaded(first);
+			for (int ti = 1; ti < nthreads; ++ti) pthread_join(tid[ti], 0);
+			Aln_thread *t = first;
 			fclose(t->frag_out_raw);
 			FILE *so = fopen(argv[4], "wb");
 			fwrite(&DB_size, 4, 1, so); fwrite(as, 8, DB_size, so); fwrite(uas, 8, DB_size, so);
@@ -149,7 +177,7 @@ int main(int argc, char **argv) {
 			}
 			fclose(co);
 		}
-		fclose(in);
+		if (in != stdin) fclose(in);
 	}
 	return 0;
 }
