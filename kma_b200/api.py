@@ -185,6 +185,12 @@ class TemplateDB:
         _check(lib().kmagpu_align_run(self._h, C.byref(p), int(want_cand), C.byref(st)))
         return st
 
+    def align_out_bytes(self) -> int:
+        """size of the frag_raw stream of the last align_run"""
+        ob, cr = C.c_size_t(), C.c_size_t()
+        lib().kmagpu_align_download(self._h, None, 0, C.byref(ob), None, None, None, 0, C.byref(cr))
+        return ob.value
+
     def align_download(self, out=None, scores=None, want_cand=False):
         """-> (frag_raw bytes, alignment_scores, uniq_alignment_scores, cand rows or None); `scores` = a pair of
         uint64[DB_size] arrays to ADD into (the ConClave accumulators of runkma.c:98-99)"""

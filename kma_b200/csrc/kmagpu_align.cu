@@ -495,6 +495,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32) aln_pair_kernel(AlnParams P, Kg
 		const int32_t *__restrict__ task_list, AlnCand *cand, uint8_t *scratch, ScratchLayout lay,
 		unsigned long long *ctr, int32_t *ovf_list) {
 	__shared__ NwPen spen;
+	__shared__ NwRow sring[AL_WARPS][NW_RING];
 	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&P.pen)[threadIdx.x];
 	__syncthreads();
 	const int lane = threadIdx.x & 31;
@@ -509,6 +510,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32) aln_pair_kernel(AlnParams P, Kg
 		sp += (((size_t)7 * c1 * 4) + 15) & ~(size_t)15;
 	}
 	NwScratch nws;
+	nws.ring = sring[threadIdx.x >> 5];
 	nws.rowbuf = (NwRow *)sp; sp += (size_t)lay.q_cap * 8;
 	nws.lastD = (int *)sp; sp += (size_t)lay.q_cap * 4;
 	nws.E = sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap;
@@ -653,6 +655,8 @@ static AlnParams make_params(const kmagpu_db *db, const kmagpu_params *p) {
 	memset(&P, 0, sizeof(P));
 	P.pen.W1 = p->W1; P.pen.U = p->U; P.pen.MM = p->MM; P.pen.M = p->M;
 	memcpy(P.pen.d, p->d, sizeof(P.pen.d));
+	P.pen.d8 = 1;
+	for (int i = 0; i < 25; ++i) if (p->d[i] < -128 || p->d[i] > 127) P.pen.d8 = 0;
 	P.k = db->info.kmerindex; P.mq = p->mq; P.one2one = p->one2one; P.exhaustive = p->exhaustive; P.minlen = p->minlen;
 	P.scoreT = p->scoreT; P.mrc = p->mrc; P.minFrac = p->minFrac;
 	return P;
@@ -907,12 +911,14 @@ extern "C" int kmagpu_align_batch(kmagpu_db *db, const kmagpu_params *p, const v
 __global__ void __launch_bounds__(AL_WARPS * 32) nw_batch_kernel(NwPen pen, KgTIndexView ix, int n, const int32_t *__restrict__ prob,
 		const uint8_t *qpool, int32_t *out, int32_t *status, uint8_t *scratch, ScratchLayout lay, unsigned long long *ctr) {
 	__shared__ NwPen spen;
+	__shared__ NwRow sring[AL_WARPS][NW_RING];
 	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&pen)[threadIdx.x];
 	__syncthreads();
 	const int lane = threadIdx.x & 31;
 	const size_t wid = (size_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
 	uint8_t *sp = scratch + wid * lay.stride;
 	NwScratch nws;
+	nws.ring = sring[threadIdx.x >> 5];
 	nws.rowbuf = (NwRow *)sp; sp += (size_t)lay.q_cap * 8;
 	nws.lastD = (int *)sp; sp += (size_t)lay.q_cap * 4;
 	nws.E = sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap;
@@ -971,7 +977,7 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 	lay.stride = ((size_t)need_q * 12 + lay.e_cap + 255) & ~(size_t)255;
 	size_t freeb = 0, totalb = 0;
 	cudaMemGetInfo(&freeb, &totalb);
-	int grid = (int)std::min<size_t>((size_t)db->sm_count * 4, (n + AL_WARPS - 1) / AL_WARPS);
+	int grid = (int)std::min<size_t>((size_t)db->sm_count * 8, (n + AL_WARPS - 1) / AL_WARPS);
 	while (grid > 1 && lay.stride * (size_t)grid * AL_WARPS > freeb / 2) grid = (grid + 1) / 2;
 	uint8_t *scratch = nullptr, *dq = nullptr;
 	int32_t *dprob = nullptr, *dout = nullptr, *dstat = nullptr;

@@ -31,12 +31,14 @@
 #define NW_HD inline
 #endif
 
-struct NwPen { int W1, U, MM, M; int d[25]; };
+#define NW_RING 256
+
+struct NwPen { int W1, U, MM, M; int d[25]; int d8; };   // d8: every d[] fits a signed byte (per-row table in a register)
 struct NwStat { int score, len, pos, match, tGaps, qGaps; };
 struct NwRow { int D, P; };
 
 struct NwGeo {
-	int t_len, q_len, k, banded, band, a, W, P, s, R, Tmax, NEG, W1, U;
+	int t_len, q_len, k, banded, band, a, W, P, s, R, Tmax, NEG, W1, U, rmask, d8;
 	NW_HD int off(int i) const { return banded ? a + i : 0; }
 	NW_HD int jlo(int i) const { int v = banded ? a + i : 0; return v < 0 ? 0 : v; }
 	NW_HD int jhi(int i) const { int v = banded ? a + i + band : q_len - 1; return v < q_len - 1 ? v : q_len - 1; }
@@ -66,6 +68,10 @@ NW_HD bool nw_geo_init(NwGeo &g, const NwPen &pen, int t_len, int q_len, int k, 
 	} else {
 		g.a = 0; g.W = q_len; g.s = 1; g.P = g.W < 33 ? 33 : g.W;
 	}
+	// lane 31 -> lane 0 hand-over: rows of up to NW_RING columns go through a (shared-memory) ring indexed j & rmask,
+	// wider rows through a buffer indexed by j
+	g.rmask = g.W <= NW_RING ? NW_RING - 1 : 0x7fffffff;
+	g.d8 = pen.d8;
 	g.R = (t_len + 31) >> 5;
 	g.Tmax = g.s * ((t_len - 1) & 31) + g.P * (g.R - 1) + g.W;
 	g.NEG = (t_len + q_len) * (pen.MM + pen.U + pen.W1);
@@ -82,7 +88,13 @@ NW_HD int nw_nuc(const uint64_t *seq, int pos) {
 
 struct NwLane {
 	int i, u;            // row and in-row offset of the NEXT step
+	int ua, ub;          // in-row offsets of the first / last cell of row i (ua > ub: no cell)
+	int joff;            // column of the cell at offset u is u + joff
+	int flags;           // per-row facts, NWF_*
+	int Dleft0, Ddiag0;  // what lies right of / diagonal to the first cell when the row starts at the matrix border
 	int tn;              // template base of row i
+	unsigned long long drow;   // d[tn][0..4] packed as signed bytes (when pen.d8)
+	int act, qn;         // the next step computes a cell; its query base
 	int myD, myP;        // last cell computed (what the lane below receives)
 	int Dleft, Qleft;    // D, Q of (i, j-1)
 	int Ddiag;           // D of (i-1, j-1)
@@ -90,44 +102,76 @@ struct NwLane {
 	int colBest, colBestI;   // k < 0: best D over the rows' last column (query start), first maximum in fill order
 };
 
-NW_HD void nw_lane_init(const NwGeo &g, NwLane &L, int lane, const uint64_t *tseq, int t_s) {
+#define NWF_EDGE 1      // banded: the last cell of the row is the band's left edge (no vertical move)
+#define NWF_TRACK 2     // k < 0 and the row reaches the query start: its last cell competes for the start cell
+#define NWF_LAST 4      // last row (m = 0): D goes to lastD
+#define NWF_BORDER 8    // the row's first cell touches the boundary column
+#define NWF_ROW0 16     // first row: the row above is the analytic boundary row
+
+NW_HD unsigned long long nw_pack_row(const NwPen &pen, int tn) {
+	unsigned long long r = 0;
+	for (int b = 0; b < 5; ++b) r |= (unsigned long long)(unsigned char)pen.d[tn * 5 + b] << (8 * b);
+	return r;
+}
+
+// per-row constants of row L.i (called once per row, every P steps)
+NW_HD void nw_row_setup(const NwGeo &g, const NwPen &pen, NwLane &L, const uint64_t *tseq, int t_s) {
+	const int i = L.i;
+	if (i >= g.t_len) { L.ua = 1; L.ub = 0; L.flags = 0; return; }
+	const int jl = g.jlo(i), jh = g.jhi(i);
+	L.joff = g.off(i);
+	L.ua = jl - L.joff; L.ub = jh - L.joff;
+	L.tn = nw_nuc(tseq, t_s + g.t_len - 1 - i);
+	if (g.d8) L.drow = nw_pack_row(pen, L.tn);
+	L.flags = (g.banded ? NWF_EDGE : 0) | ((g.k < 0 && jh == g.q_len - 1) ? NWF_TRACK : 0) | (i == g.t_len - 1 ? NWF_LAST : 0) |
+	          (jl == 0 ? NWF_BORDER : 0) | (i == 0 ? NWF_ROW0 : 0);
+	L.Dleft0 = jl == 0 ? g.bcol(i) : g.NEG;   // outside the band: nw.c:1031-1034
+	L.Ddiag0 = g.bcol(i - 1);
+}
+
+// qlast points at the LAST query base of the window: the cell at column j reads qlast[-j]
+NW_HD void nw_lane_arm(NwLane &L, const uint8_t *qlast) {
+	L.act = L.u >= L.ua && L.u <= L.ub;
+	L.qn = L.act ? qlast[-(L.u + L.joff)] : 0;
+}
+
+NW_HD void nw_lane_init(const NwGeo &g, const NwPen &pen, NwLane &L, int lane, const uint64_t *tseq, int t_s, const uint8_t *q) {
 	L.i = lane; L.u = -g.s * lane;
-	L.tn = lane < g.t_len ? nw_nuc(tseq, t_s + g.t_len - 1 - lane) : 0;
+	L.joff = 0; L.tn = 0; L.drow = 0; L.Dleft0 = 0; L.Ddiag0 = 0;
+	nw_row_setup(g, pen, L, tseq, t_s);
+	nw_lane_arm(L, q + g.q_len - 1);
 	L.myD = 0; L.myP = g.NEG; L.Dleft = 0; L.Qleft = g.NEG; L.Ddiag = 0; L.nxD = 0; L.nxP = g.NEG;
 	L.colBest = g.NEG; L.colBestI = 0x7fffffff;
 }
 
 // One step of one lane. aD/aP: (D,P) the lane above produced in the previous step (ignored by lane 0).
-// q points at the first query base of the window. Writes E, the row buffer (lane 31) and lastD (last row).
-NW_HD void nw_lane_step(const NwGeo &g, const NwPen &pen, NwLane &L, const int lane, const int T, int aD, int aP,
-                        const uint64_t *tseq, const int t_s, const uint8_t *q, uint8_t *E, NwRow *rowbuf, int *lastD) {
-	const int i = L.i, j = L.u + g.off(i);
-	const bool act = i < g.t_len && L.u >= 0 && L.u < g.W && j >= 0 && j < g.q_len;
-	if (lane == 0 && act) {
-		if (i == 0) { aD = g.brow(j); aP = g.NEG; }
-		else { aD = L.nxD; aP = L.nxP; }
-	}
-	if (act) {
-		const int jl = g.jlo(i);
-		if (j == jl) {   // first cell of the row: what lies to its right and on its diagonal
-			if (jl == 0) { L.Dleft = g.bcol(i); L.Ddiag = g.bcol(i - 1); }
-			else {
-				L.Dleft = g.NEG;   // outside the band (nw.c:1031-1034)
-				if (lane == 0) L.Ddiag = i == 0 ? g.brow(j - 1) : rowbuf[j - 1].D;
-			}
-			L.Qleft = g.NEG;
+// qlast points at the last query base of the window; Estep at the 32 traceback bytes of this step. `hand` is the
+// lane 31 -> lane 0 hand-over buffer (ring or row buffer, indexed j & g.rmask); the last row's D goes to lastD.
+NW_HD void nw_lane_step(const NwGeo &g, const NwPen &pen, NwLane &L, const int lane, int aD, int aP,
+                        const uint64_t *tseq, const int t_s, const uint8_t *qlast, uint8_t *Estep, NwRow *hand, int *lastD) {
+	if (L.act) {
+		const int u = L.u, j = u + L.joff;
+		if (lane == 0) {
+			if (L.flags & NWF_ROW0) { aD = g.brow(j); aP = g.NEG; }
+			else { aD = L.nxD; aP = L.nxP; }
 		}
-		const int sub = pen.d[L.tn * 5 + q[g.q_len - 1 - j]];
+		if (u == L.ua) {   // first cell of the row: what lies to its right and on its diagonal
+			L.Dleft = L.Dleft0; L.Qleft = g.NEG;
+			if (L.flags & NWF_BORDER) L.Ddiag = L.Ddiag0;
+			else if (lane == 0) L.Ddiag = (L.flags & NWF_ROW0) ? g.brow(j - 1) : hand[(j - 1) & g.rmask].D;
+		}
+		const int sub = g.d8 ? (int)(signed char)(L.drow >> (L.qn << 3)) : pen.d[L.tn * 5 + L.qn];
 		const int W1 = g.W1, U = g.U;
+		const bool last = u == L.ub;
 		int D, Q, P, e, fl = 0, x;
-		if (g.banded && j == g.jhi(i)) {   // left edge of the band: no vertical move (nw.c:1076-1102)
+		if ((L.flags & NWF_EDGE) && last) {   // left edge of the band: no vertical move (nw.c:1076-1102)
 			Q = L.Dleft + W1;
 			x = L.Qleft + U;
 			if (Q < x) { Q = x; e = 3; } else { e = 2; fl = 16; }
 			P = g.NEG;
 			D = L.Ddiag + sub;
 			if (Q <= D) e = 1; else D = Q;
-		} else {                           // nw.c:166-212
+		} else {                              // nw.c:166-212
 			Q = L.Dleft + W1; P = aD + W1;
 			if (Q < P) { D = P; e = 4; } else { D = Q; e = 2; }
 			x = L.Qleft + U;
@@ -137,25 +181,23 @@ NW_HD void nw_lane_step(const NwGeo &g, const NwPen &pen, NwLane &L, const int l
 			x = L.Ddiag + sub;
 			if (D <= x) { D = x; e = 1; }
 		}
-		E[(size_t)T * 32 + lane] = (uint8_t)(fl | e);
+		Estep[lane] = (uint8_t)(fl | e);
 		L.Dleft = D; L.Qleft = Q; L.myD = D; L.myP = P;
-		if (g.k < 0 && j == g.q_len - 1 && L.colBest < D) { L.colBest = D; L.colBestI = i; }
-		if (i == g.t_len - 1) lastD[j] = D;
-		else if (lane == 31) { NwRow o; o.D = D; o.P = P; rowbuf[j] = o; }
+		if (last && (L.flags & NWF_TRACK) && L.colBest < D) { L.colBest = D; L.colBestI = L.i; }
+		if (L.flags & NWF_LAST) lastD[j] = D;
+		else if (lane == 31) { NwRow o; o.D = D; o.P = P; hand[j & g.rmask] = o; }
 	}
 	L.Ddiag = aD;
 	if (++L.u == g.P) {
 		L.u = 0; L.i += 32;
-		if (L.i < g.t_len) L.tn = nw_nuc(tseq, t_s + g.t_len - 1 - L.i);
+		nw_row_setup(g, pen, L, tseq, t_s);
 	}
+	nw_lane_arm(L, qlast);
 }
 
-// lane 0, after the step's stores are visible: fetch what the next step needs from the row buffer
-NW_HD void nw_lane0_prefetch(const NwGeo &g, NwLane &L, const NwRow *rowbuf) {
-	if (L.i > 0 && L.i < g.t_len && L.u >= 0 && L.u < g.W) {
-		const int j = L.u + g.off(L.i);
-		if (j >= 0 && j < g.q_len) { NwRow v = rowbuf[j]; L.nxD = v.D; L.nxP = v.P; }
-	}
+// lane 0, after the step's stores are visible: fetch what the next step needs from the hand-over buffer
+NW_HD void nw_lane0_prefetch(const NwGeo &g, NwLane &L, const NwRow *hand) {
+	if (L.act && !(L.flags & NWF_ROW0)) { const NwRow v = hand[(L.u + L.joff) & g.rmask]; L.nxD = v.D; L.nxP = v.P; }
 }
 
 // traceback byte at (m, qpos) in reference coordinates, including the analytic boundary row / column codes
@@ -232,11 +274,12 @@ NW_HD bool nw_trivial(const NwPen &pen, int t_len, int q_len, NwStat &s) {   // 
 }
 
 #if defined(__CUDACC__)
-// per-warp scratch in global memory
+// per-warp scratch
 struct NwScratch {
-	NwRow *rowbuf;    // >= q_cap entries
-	int *lastD;       // >= q_cap entries
-	uint8_t *E;       // e_cap bytes
+	NwRow *ring;      // NW_RING entries in shared memory: lane 31 -> lane 0 hand-over of rows up to NW_RING wide
+	NwRow *rowbuf;    // global, >= q_cap entries: the same for wider rows
+	int *lastD;       // global, >= q_cap entries
+	uint8_t *E;       // global, e_cap bytes
 	size_t e_cap;
 	int q_cap;
 };
@@ -245,6 +288,42 @@ struct NwScratch {
 #define NW_OK 0
 #define NW_TOO_BIG 1      // scratch too small: the caller re-runs the problem on the large-scratch path
 #define NW_BAD_BAND 2
+
+// The walk of nw_walk with up to 32 cells examined per memory round trip: the lanes read the traceback bytes along
+// the direction the path is moving (diagonal, down a P run, along a Q run) and a ballot finds where the run ends.
+__device__ __forceinline__ void nw_walk_warp(const NwGeo &g, const uint8_t *E, int m, int qp, NwStat &s) {
+	const int lane = threadIdx.x & 31;
+	s.len = s.match = s.tGaps = s.qGaps = 0;
+	for (;;) {
+		const int e = nw_e_at(g, E, m + lane, qp + lane);
+		const unsigned nd = __ballot_sync(0xffffffffu, (e & 7) != 1);
+		const int r = nd ? __ffs(nd) - 1 : 32;   // leading diagonal steps
+		s.match += r; s.len += r; m += r; qp += r;
+		if (r == 32) continue;
+		const int c = __shfl_sync(0xffffffffu, e, r);
+		if (c == 0) break;
+		if ((c & 7) >= 4) {   // P run: down the column until a cell whose run opens there
+			for (;;) {
+				const int f = nw_e_at(g, E, m + lane, qp);
+				const unsigned stop = __ballot_sync(0xffffffffu, (f >> 4) != 0);
+				const int n = stop ? __ffs(stop) - 1 : 32;
+				m += n; s.len += n; s.qGaps += n;
+				if (stop) break;
+			}
+			++s.qGaps; ++m;
+		} else {              // Q run: along the row
+			for (;;) {
+				const int f = nw_e_at(g, E, m, qp + lane);
+				const unsigned stop = __ballot_sync(0xffffffffu, (f >> 3) != 0);
+				const int n = stop ? __ffs(stop) - 1 : 32;
+				qp += n; s.len += n; s.tGaps += n;
+				if (stop) break;
+			}
+			++s.tGaps; ++qp;
+		}
+		++s.len;
+	}
+}
 
 // All 32 lanes call with identical arguments; every lane returns the same result.
 __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict__ tseq, const uint8_t *query, int k, int t_s,
@@ -259,13 +338,19 @@ __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict
 	if (g.ebytes() > ws.e_cap || q_len + 1 > ws.q_cap) return NW_TOO_BIG;
 	if (cells) *cells += (unsigned long long)t_len * (unsigned long long)(g.banded ? g.band + 1 : q_len);
 	const uint8_t *q = query + q_s;
+	NwRow *hand = g.rmask == NW_RING - 1 ? ws.ring : ws.rowbuf;
 	NwLane L;
-	nw_lane_init(g, L, lane, tseq, t_s);
-	for (int T = 0; T < g.Tmax; ++T) {
-		const int aD = __shfl_up_sync(0xffffffffu, L.myD, 1), aP = __shfl_up_sync(0xffffffffu, L.myP, 1);
-		nw_lane_step(g, pen, L, lane, T, aD, aP, tseq, t_s, q, ws.E, ws.rowbuf, ws.lastD);
-		__syncwarp();
-		if (lane == 0) nw_lane0_prefetch(g, L, ws.rowbuf);
+	nw_lane_init(g, pen, L, lane, tseq, t_s, q);
+	{
+		const uint8_t *qlast = q + q_len - 1;
+		uint8_t *Estep = ws.E;
+		int *lastD = ws.lastD;
+		for (int T = g.Tmax; T > 0; --T, Estep += 32) {
+			const int aD = __shfl_up_sync(0xffffffffu, L.myD, 1), aP = __shfl_up_sync(0xffffffffu, L.myP, 1);
+			nw_lane_step(g, pen, L, lane, aD, aP, tseq, t_s, qlast, Estep, hand, lastD);
+			__syncwarp();
+			if (lane == 0) nw_lane0_prefetch(g, L, hand);
+		}
 	}
 	__syncwarp();
 	// column maximum: largest D, ties -> smallest i (first in fill order)
@@ -291,7 +376,7 @@ __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict
 	}
 	int best_m, best_q, score;
 	nw_start_cell(g, cb, ci, ws.lastD, rb, rq, &best_m, &best_q, &score);
-	nw_walk(g, ws.E, best_m, best_q, s);
+	nw_walk_warp(g, ws.E, best_m, best_q, s);
 	s.score = score; s.pos = 0;
 	*out = s;
 	return NW_OK;

@@ -8,26 +8,27 @@
 #include "../../kma_b200/csrc/kmagpu_nw.cuh"
 
 extern "C" int emu_nw(const int *pen29, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s,
-                      int q_e, int band, int order, int *out6, long long *steps) {
+                      int q_e, int band, int order, int d8, int *out6, long long *steps) {
 	NwPen pen;
 	pen.W1 = pen29[0]; pen.U = pen29[1]; pen.MM = pen29[2]; pen.M = pen29[3];
 	memcpy(pen.d, pen29 + 4, 100);
+	pen.d8 = d8;
 	const int t_len = t_e - t_s, q_len = q_e - q_s;
 	NwStat s;
 	if (nw_trivial(pen, t_len, q_len, s)) { memcpy(out6, &s, 24); return 0; }
 	NwGeo g;
 	if (!nw_geo_init(g, pen, t_len, q_len, k, band)) return 2;
 	std::vector<uint8_t> E(g.ebytes(), 0xEE);
-	std::vector<NwRow> rowbuf(q_len + 1, NwRow{0x3fffffff, 0x3fffffff});
+	std::vector<NwRow> rowbuf(q_len + NW_RING + 1, NwRow{0x3fffffff, 0x3fffffff});
 	std::vector<int> lastD(q_len + 1, 0x3fffffff);
 	NwLane L[32];
-	for (int l = 0; l < 32; ++l) nw_lane_init(g, L[l], l, tseq, t_s);
+	for (int l = 0; l < 32; ++l) nw_lane_init(g, pen, L[l], l, tseq, t_s, query + q_s);
 	for (int T = 0; T < g.Tmax; ++T) {
 		int aD[32], aP[32];
 		for (int l = 0; l < 32; ++l) { aD[l] = L[l ? l - 1 : 0].myD; aP[l] = L[l ? l - 1 : 0].myP; }
 		for (int x = 0; x < 32; ++x) {
 			const int l = order ? 31 - x : x;
-			nw_lane_step(g, pen, L[l], l, T, aD[l], aP[l], tseq, t_s, query + q_s, E.data(), rowbuf.data(), lastD.data());
+			nw_lane_step(g, pen, L[l], l, aD[l], aP[l], tseq, t_s, query + q_s + q_len - 1, E.data() + (size_t)T * 32, rowbuf.data(), lastD.data());
 		}
 		nw_lane0_prefetch(g, L[0], rowbuf.data());
 	}

@@ -65,13 +65,13 @@ def run_both(emu, t, q, k, t_s, t_e, q_s, q_e, band):
     p = list(pen)
     pen29 = (C.c_int * 29)(p[3], p[2], p[1], p[0], *p[7:32])
     res = []
-    for order in (0, 1):
+    for order, d8 in ((0, 1), (1, 1), (0, 0)):
         got = (C.c_int * 6)()
         rc = emu.emu_nw(pen29, tw.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), k, t_s, t_e, q_s, q_e, band,
-                        order, got, None)
+                        order, d8, got, None)
         assert rc == 0
         res.append(list(got))
-    assert res[0] == res[1], "lane order changes the result: same-step hazard"
+    assert res[0] == res[1] == res[2], "lane order / table form changes the result: same-step hazard"
     return list(want), res[0]
 
 
@@ -100,7 +100,7 @@ def test_banded(emu, k):
             continue
         cases.append((t_len, q_len, band))
     cases += [(200, 200, 64), (201, 200, 65), (130, 129, 65), (500, 431, 133), (431, 500, 133), (1000, 1000, 64),
-              (300, 300, 100), (300, 290, 150)]
+              (300, 300, 100), (300, 290, 150), (1200, 900, 364), (700, 700, 300)]
     assert len(cases) > 30
     for t_len, q_len, band in cases:
         t, q = problem(rng, t_len, q_len, err=rng.choice([0.02, 0.1, 0.3]))
