@@ -136,6 +136,12 @@ int kmagpu_align_download(kmagpu_db *db, void *frag_out, size_t out_cap, size_t 
 int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, const int32_t *prob, const uint8_t *qpool,
                     size_t qbytes, int32_t *out, int32_t *status, int64_t *cells, int64_t *steps, float *ms);
 
+/* Host-only helper (no device needed): walk the whole records at the head of a stage-1 (stage = 1, 16-byte headers,
+ * runinput.c:765-787 / loadFsa savekmers.c:50-92) or stage-2 (stage = 2, 28-byte headers, ankers.c:163-220) stream.
+ * Returns the number of whole records (stopping at a terminator or a partial record), stores their byte offsets in
+ * offsets[0..min(count, cap)) when offsets != NULL and the bytes they span in *used. -1 on a corrupt header. */
+int64_t kmagpu_record_walk(int stage, const void *buf, size_t nbytes, uint64_t *offsets, size_t cap, size_t *used);
+
 /* hashMap_get (hashmapkma.h:58; hashMap_getGlobal hashmapkma.c:149 / megaMap_getGlobal :264) over
  * a batch of k-mers: out[i] = offset of the template list inside values[], or -1. Test hook. */
 int kmagpu_lookup_batch(kmagpu_db *db, const uint64_t *kmers, size_t n, int64_t *out);

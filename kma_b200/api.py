@@ -86,6 +86,8 @@ def lib():
                                          C.POINTER(C.c_size_t), C.POINTER(AlignStats)]
         L.kmagpu_nw_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                       C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
+        L.kmagpu_record_walk.restype = C.c_int64
+        L.kmagpu_record_walk.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         _lib = L
     return _lib
 
@@ -232,6 +234,20 @@ class TemplateDB:
         out = np.empty(len(kmers), dtype=np.int64)
         _check(lib().kmagpu_lookup_batch(self._h, kmers.ctypes.data, len(kmers), out.ctypes.data))
         return out
+
+
+def record_offsets(stage: int, buf) -> np.ndarray:
+    """byte offsets of the whole records at the head of a stage-1 / stage-2 stream, plus the end offset (n + 1 values).
+    Host-only: works without a device."""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    used = C.c_size_t()
+    n = lib().kmagpu_record_walk(stage, buf.ctypes.data, len(buf), None, 0, C.byref(used))
+    if n < 0:
+        raise KmaGpuError(lib().kmagpu_last_error().decode(errors="replace"))
+    off = np.empty(n + 1, dtype=np.uint64)
+    lib().kmagpu_record_walk(stage, buf.ctypes.data, len(buf), off.ctypes.data, n, C.byref(used))
+    off[n] = used.value
+    return off
 
 
 def stream_terminator(nreads: int) -> bytes:

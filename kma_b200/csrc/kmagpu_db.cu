@@ -194,3 +194,30 @@ extern "C" int kmagpu_db_get_info(const kmagpu_db *db, kmagpu_db_info *info) {
 	*info = db->info;
 	return 0;
 }
+
+extern "C" int64_t kmagpu_record_walk(int stage, const void *buf, size_t nbytes, uint64_t *offsets, size_t cap, size_t *used) {
+	const uint8_t *in = (const uint8_t *)buf;
+	const size_t hdr = stage == 1 ? 16 : 28;
+	size_t ip = 0;
+	int64_t n = 0;
+	if (stage != 1 && stage != 2) { kmagpu_set_error("kmagpu_record_walk: stage must be 1 or 2"); return -1; }
+	while (ip + hdr <= nbytes) {
+		int32_t h[7];
+		memcpy(h, in + ip, hdr);
+		if (h[0] < 0) break;   // stream terminator
+		size_t len;
+		if (stage == 1) {
+			if (h[1] < 0 || h[2] < 0) { kmagpu_set_error("corrupt stage-1 record at byte %zu", ip); return -1; }
+			len = 16 + 8 * (size_t)h[1] + 4 * (size_t)h[2] + (size_t)abs(h[3]);
+		} else {
+			if (h[1] < 0 || h[2] < 0 || h[4] < 0 || h[5] < 0) { kmagpu_set_error("corrupt stage-2 record at byte %zu", ip); return -1; }
+			len = 28 + 8 * (size_t)h[1] + 4 * (size_t)h[2] + 4 * (size_t)h[4] + (size_t)h[5];
+		}
+		if (ip + len > nbytes) break;   // partial record: the caller refills
+		if (offsets && (size_t)n < cap) offsets[n] = ip;
+		++n;
+		ip += len;
+	}
+	if (used) *used = ip;
+	return n;
+}

@@ -1,0 +1,73 @@
+"""Multi-GPU plumbing of the mapping core: one process per GPU, reads sharded by rank, database
+replicated, no data-path collective. The only exchange of stages 2 + 3a is the sum over ranks of the two ConClave
+accumulators `alignment_scores[DB_size]` / `uniq_alignment_scores[DB_size]` (runkma.c:98-99, updatescores.c:228/276)
+that ConClave's choice pass reads globally (conclave.c:80-123) -- one all-reduce over `torch.distributed` (NCCL over
+NVLink on GPUs, gloo in the CPU tests). frag_raw streams stay per rank; concatenated in rank order they are the
+single-process stream because shards are contiguous slices of the record stream."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import api
+
+
+def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+    """contiguous, balanced split of n records: rank r gets [lo, hi)"""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_stream(stage: int, buf, rank: int, world: int) -> np.ndarray:
+    """the slice of whole records of a stage-1 / stage-2 stream that `rank` maps"""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    off = api.record_offsets(stage, buf)
+    lo, hi = shard_bounds(len(off) - 1, rank, world)
+    return buf[int(off[lo]):int(off[hi])]
+
+
+def allreduce_scores(alignment_scores: np.ndarray, uniq_alignment_scores: np.ndarray, device=None):
+    """sum the ConClave accumulators over all ranks (in place on copies; returns the two reduced uint64 arrays)"""
+    import torch
+    import torch.distributed as dist
+    both = np.concatenate([alignment_scores, uniq_alignment_scores]).astype(np.uint64)
+    t = torch.from_numpy(both.view(np.int64).copy())
+    if device is not None:
+        t = t.to(device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    out = t.cpu().numpy().view(np.uint64)
+    n = len(alignment_scores)
+    return out[:n].copy(), out[n:].copy()
+
+
+def gather_streams(local: bytes, dst: int = 0):
+    """rank-ordered concatenation of the per-rank byte streams on rank `dst` (None elsewhere)"""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    parts = [None] * dist.get_world_size() if dist.get_rank() == dst else None
+    dist.gather_object(local, parts, dst=dst)
+    return b"".join(parts) if parts is not None else None
+
+
+def map_sharded(compute, stage1, rank: int, world: int, device=None):
+    """Map one batch across `world` ranks. `compute(stage1_shard) -> (frag_raw bytes, alignment_scores,
+    uniq_alignment_scores, nreads)` is the per-rank pipeline (TemplateDB stage 2 + alignment pass on the rank's GPU).
+    Returns (this rank's frag_raw bytes, globally reduced alignment_scores, uniq_alignment_scores, local read count)."""
+    shard = shard_stream(1, stage1, rank, world)
+    frag, a, u, n = compute(shard)
+    a, u = allreduce_scores(a, u, device)
+    return frag, a, u, n
+
+
+def gpu_pipeline(db: "api.TemplateDB", params=None):
+    """the per-rank compute of map_sharded on a TemplateDB: stage 2 and the alignment pass chained in HBM"""
+    def run(stage1_shard):
+        n = db.seed_upload(np.ascontiguousarray(stage1_shard))
+        db.seed_run(params)
+        db.align_from_seed()
+        db.align_run(params)
+        frag, a, u, _ = db.align_download()
+        return frag.tobytes(), a, u, n
+    return run
