@@ -20,7 +20,9 @@
  *   nw.c:892-1188     NW_band_score                             -> nw_band
  *   alnfrags.c:1052-1218 alnFragsSE, :2150-2294 alnFrags_threaded (SE) -> orc_align_stream
  *   updatescores.c:203-298 update_Scores (frag_raw record)      -> reduce_and_emit
- * Out of scope here (asserted): circular templates (t_len < 0), chain-mode q-bounds, paired records.
+ *   alnfrags.c:1596-1972 alnFragsPenaltyPE                       -> align_pe
+ *   updatescores.c:300-488 update_Scores_se / update_Scores_pe    -> emit_se / emit_pe
+ * Out of scope here (asserted): circular templates (t_len < 0), chain-mode q-bounds, strand-undecided pairs.
  */
 #include <math.h>
 #include <stdint.h>
@@ -553,7 +555,8 @@ static int pick_strand(const orc_params *p, const tindex *ix, const uint8_t *qf,
 	return -best;
 }
 
-/* ------------------------------------------------------------------ the stream ------- */
+
+/* ------------------------------------------------------------------ output buffer ---- */
 
 typedef struct { uint8_t *p; size_t len, cap; } obuf;
 static void ob_put(obuf *o, const void *src, size_t n) {
@@ -567,7 +570,159 @@ static void unpack(const uint64_t *seq, int len, const int32_t *N, int nN, uint8
 	out[len] = 0;
 }
 
-/* stage-2 stream (single-end records) -> frag_raw stream (without the final int32 0 of runkma.c:444) and the two
+/* ------------------------------------------------------------------ paired end ------- */
+
+typedef struct {
+	int q_len, words, nN, hl, flag;
+	uint64_t *w[2]; int32_t *N[2]; uint8_t *b[2];   /* [0] as recorded, [1] reverse complement */
+	const uint8_t *hdr;
+} pe_mate;
+
+/* update_Scores_se (updatescores.c:300-388): T/S/E/Sc are the candidate arrays (0-based), n candidates */
+static int emit_se(obuf *frag, uint64_t *as, uint64_t *uas, const uint8_t *q, int q_len, const uint8_t *hdr, int hl, int flag,
+                   double minFrac, int n, int best, int *S, int *E, int *T, const int *Sc) {
+	int kept = 0;
+	const int mode = minFrac == 1.0 ? 0 : (minFrac < 0 ? 1 : 2);
+	const double thr = fabs(minFrac) * best;
+	for (int i = 0; i < n; ++i) {
+		int keep = mode == 0 ? Sc[i] == best : thr <= Sc[i];
+		if (keep) {
+			T[kept] = T[i]; S[kept] = S[i]; E[kept] = E[i]; ++kept;
+			as[abs(T[kept - 1])] += mode == 1 ? (uint64_t)Sc[i] : (uint64_t)best;
+		}
+	}
+	if (kept == 1) uas[abs(T[0])] += best;
+	int32_t h[5] = {q_len, kept, best, hl, flag};
+	ob_put(frag, h, 20); ob_put(frag, q, q_len); ob_put(frag, hdr, hl);
+	ob_put(frag, S, 4 * (size_t)kept); ob_put(frag, E, 4 * (size_t)kept); ob_put(frag, T, 4 * (size_t)kept);
+	return kept;
+}
+
+/* update_Scores_pe (updatescores.c:390-488) */
+static void emit_pe(obuf *frag, uint64_t *as, uint64_t *uas, const uint8_t *q, int q_len, const uint8_t *hdr, int hl, int flag,
+                    const uint8_t *q2, int q2_len, const uint8_t *hdr2, int hl2, int flag2,
+                    double minFrac, int n, int best, int *S, int *E, int *T, const int *Sc) {
+	int kept = 0;
+	const int mode = minFrac == 1.0 ? 0 : (minFrac < 0 ? 1 : 2);
+	const double thr = fabs(minFrac) * best;
+	for (int i = 0; i < n; ++i) {
+		int keep = mode == 0 ? Sc[i] == best : thr <= Sc[i];
+		if (keep) {
+			T[kept] = T[i]; S[kept] = S[i]; E[kept] = E[i]; ++kept;
+			as[abs(T[kept - 1])] += mode == 2 ? (uint64_t)best : (uint64_t)Sc[i];
+		}
+	}
+	if (kept == 1) uas[abs(T[0])] += best;
+	int32_t h[5] = {q_len, kept, -best, hl, flag};
+	ob_put(frag, h, 20); ob_put(frag, q, q_len); ob_put(frag, hdr, hl);
+	ob_put(frag, S, 4 * (size_t)kept); ob_put(frag, E, 4 * (size_t)kept); ob_put(frag, T, 4 * (size_t)kept);
+	int32_t h2[3] = {q2_len, hl2, flag2};
+	ob_put(frag, h2, 12); ob_put(frag, q2, q2_len); ob_put(frag, hdr2, hl2);
+}
+
+/* score of one mate against one template the way alnFragsPenaltyPE rates it (alnfrags.c:1683-1718) */
+static int pe_rate(const orc_params *p, const aln_t *a, int q_len, int t_len, int minlen, double mrc, int *start, int *end, double *score) {
+	int read_score = a->score;
+	if (minlen <= a->len && 0 < read_score && ((mrc * q_len <= a->len - a->qGaps) || (mrc * t_len <= a->len - a->tGaps))) {
+		*start = a->pos; *end = a->pos + a->len - a->tGaps;
+		if (*start == 0) read_score += -p->Wl;
+		if (*end == t_len) read_score += -p->Wl;
+		*score = 1.0 * read_score / a->len;
+	} else read_score = 0;
+	return read_score;
+}
+
+/* alnFragsPenaltyPE (alnfrags.c:1596-1972), strands decided by stage 2 (points->len == 0). mt[1..nt] = templates,
+ * arrays bT/bTr/bS/bE have nt + 2 entries. cand rows (optional): two per template (mate 1, mate 2). */
+static void align_pe(const orc_params *p, nw_ws *ws, mems_t *pt, tindex **tix, orc_db *db, int k, pe_mate *m1, pe_mate *m2,
+                     int *mt, int nt, double scoreT, int mq, int minlen, double mrc, double minFrac,
+                     int *bT, int *bTr, int *bS, int *bE, obuf *frag, uint64_t *as, uint64_t *uas, obuf *cand, int ridx) {
+	int flipped = 0, best1 = 0, best2 = 0, comp = 0, start = 0, end = 0, hits = 0;
+	double score = 0;
+	int flag = m1->flag, flag_r = m2->flag;
+	for (int ti = 1; ti <= nt; ++ti) {
+		int at = abs(mt[ti]);
+		if (mt[ti] < 0) flipped = 1;   /* both reads are reverse-complemented once, at the first negative template */
+		if (!tix[at]) tix[at] = tindex_build(db->seq + db->seq_off[at], db->lengths[at], k);
+		const tindex *ix = tix[at];
+		const int t_len = db->lengths[at], o = flipped;
+		pt->len = 0;
+		aln_t a = kma_score(p, ws, ix, m1->b[o], m1->q_len, m1->w[o], m1->N[o], m1->nN + 1, mq, pt);
+		if (cand) { int32_t row[8] = {ridx, mt[ti], a.score, a.len, a.pos, a.match, a.tGaps, a.qGaps}; ob_put(cand, row, 32); }
+		int rs = pe_rate(p, &a, m1->q_len, t_len, minlen, mrc, &start, &end, &score);
+		if (rs > k && score >= scoreT) { bT[ti] = rs; bS[ti] = start; bE[ti] = end; if (best1 < rs) best1 = rs; }
+		else { bT[ti] = 0; bS[ti] = -1; bE[ti] = -1; }
+		pt->len = 0;
+		a = kma_score(p, ws, ix, m2->b[o], m2->q_len, m2->w[o], m2->N[o], m2->nN + 1, mq, pt);
+		if (cand) { int32_t row[8] = {ridx + 1, mt[ti], a.score, a.len, a.pos, a.match, a.tGaps, a.qGaps}; ob_put(cand, row, 32); }
+		rs = pe_rate(p, &a, m2->q_len, t_len, minlen, mrc, &start, &end, &score);
+		if (rs > k && score >= scoreT) {
+			bTr[ti] = rs;
+			if (bT[ti]) { if (start < bS[ti]) bS[ti] = start; else bE[ti] = end; }
+			else { bS[ti] = start; bE[ti] = end; }
+			if (best2 < rs) best2 = rs;
+		} else bTr[ti] = 0;
+		rs += bT[ti];
+		if (comp < rs) comp = rs;
+	}
+	if (!best1 && !best2) return;
+	const int rc = !flipped;
+	const double af = minFrac < 0 ? -minFrac : minFrac;
+	const uint8_t *q1 = m1->b[flipped], *q2 = m2->b[flipped];
+	if (comp && af * (best1 + best2) <= (comp + p->PE)) {   /* proper pair */
+		const int best = comp + p->PE;
+		for (int ti = 1; ti <= nt; ++ti)
+			if (bT[ti] && bTr[ti]) { bTr[hits] = bT[ti] + bTr[ti] + p->PE; bT[hits] = mt[ti]; bS[hits] = bS[ti]; bE[hits] = bE[ti]; ++hits; }
+		if (bT[0] < 0) {
+			for (int i = 0; i < hits; ++i) bT[i] = -bT[i];
+			emit_pe(frag, as, uas, q2, m2->q_len, m2->hdr, m2->hl, flag_r, q1, m1->q_len, m1->hdr, m1->hl, flag, minFrac, hits, best, bS, bE, bT, bTr);
+		} else {
+			if (!rc) { q1 = m1->b[0]; q2 = m2->b[0]; flag ^= 48; flag_r ^= 48; }
+			emit_pe(frag, as, uas, q1, m1->q_len, m1->hdr, m1->hl, flag, q2, m2->q_len, m2->hdr, m2->hl, flag_r, minFrac, hits, best, bS, bE, bT, bTr);
+		}
+	} else if (best1 && best2) {                             /* both map, not as a pair */
+		int hits_r = 0, ti = 1, last = nt, tmp;
+		const double sc = af * best1, sc_r = af * best2;
+		while (ti <= last) {
+			if (sc <= bT[ti]) { mt[hits] = mt[ti]; bT[hits] = bT[ti]; bS[hits] = bS[ti]; bE[hits] = bE[ti]; ++hits; ++ti; }
+			else if (sc_r <= bTr[ti]) {
+				tmp = mt[ti]; mt[ti] = mt[last]; mt[last] = tmp;
+				tmp = bTr[ti]; bTr[ti] = bTr[last]; bTr[last] = tmp;
+				tmp = bS[ti]; bS[ti] = bS[last]; bS[last] = tmp;
+				tmp = bE[ti]; bE[ti] = bE[last]; bE[last] = tmp;
+				++hits_r; --last;
+			} else ++ti;
+		}
+		int *bTr2 = bTr + last;
+		if (bT[0] < 0) { for (int i = 0; i < hits; ++i) bT[i] = -bT[i]; }
+		else if (!rc) { q1 = m1->b[0]; flag ^= 16; flag_r ^= 32; }
+		if (bTr2[0] < 0) { for (int i = 0; i < hits_r; ++i) bTr2[i] = -bTr2[i]; }
+		else if (!rc) { q2 = m2->b[0]; flag ^= 32; flag_r ^= 16; }
+		if (flag & 2) { flag ^= 2; flag_r ^= 2; }
+		mt[0] = emit_se(frag, as, uas, q1, m1->q_len, m1->hdr, m1->hl, flag, minFrac, hits, best1, bS, bE, mt, bT);   /* the count lands in slot 0 */
+		emit_se(frag, as, uas, q2, m2->q_len, m2->hdr, m2->hl, flag_r, minFrac, hits_r, best2, bS + last, bE + last, mt + last, bTr2);
+	} else if (best1) {                                      /* first mate only */
+		for (int ti = 1; ti <= nt; ++ti)
+			if (bT[ti]) { bTr[hits] = bT[ti]; bT[hits] = mt[ti]; bS[hits] = bS[ti]; bE[hits] = bE[ti]; ++hits; }
+		if (bT[0] < 0) { for (int i = 0; i < hits; ++i) bT[i] = -bT[i]; }
+		else if (!rc) { q1 = m1->b[0]; flag ^= 16; flag_r ^= 32; }
+		flag |= 8; flag_r ^= 4;
+		if (flag & 2) { flag ^= 2; flag_r ^= 2; }
+		emit_se(frag, as, uas, q1, m1->q_len, m1->hdr, m1->hl, flag, minFrac, hits, best1, bS, bE, bT, bTr);
+	} else {                                                 /* second mate only */
+		for (int ti = 1; ti <= nt; ++ti)
+			if (bTr[ti]) { bTr[hits] = bTr[ti]; bT[hits] = mt[ti]; bS[hits] = bS[ti]; bE[hits] = bE[ti]; ++hits; }
+		if (bTr[0] < 0) { for (int i = 0; i < hits; ++i) bTr[i] = -bTr[i]; }
+		else if (!rc) { q2 = m2->b[0]; flag ^= 32; flag_r ^= 16; }
+		flag_r |= 8; flag ^= 4;
+		if (flag_r & 2) { flag ^= 2; flag_r ^= 2; }
+		emit_se(frag, as, uas, q2, m2->q_len, m2->hdr, m2->hl, flag_r, minFrac, hits, best2, bS, bE, bT, bTr);
+	}
+}
+
+/* ------------------------------------------------------------------ the stream ------- */
+
+/* stage-2 stream (single-end records and -apm p pairs) -> frag_raw stream (without the final int32 0 of runkma.c:444) and the two
  * ConClave accumulators. cand (optional): 8 x int32 per (read, candidate), same rows as ref_harness.c writes.
  * Returned buffers are malloc'ed; free with orc_free. */
 int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const uint8_t *in, size_t in_bytes,
@@ -606,7 +761,46 @@ int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const 
 		const int32_t *T = (const int32_t *)0; int32_t *Tbuf = malloc(4 * (size_t)(nt + 1));
 		memcpy(Tbuf, in + ip, 4 * (size_t)nt); ip += 4 * (size_t)nt; T = Tbuf;
 		const uint8_t *hdr = in + ip; ip += hl;
-		if (nt == 0) { free(Tbuf); fprintf(stderr, "orc_align_stream: paired records not supported\n"); return -2; }
+		if (nt == 0) {   /* first record of a pair (printPair, ankers.c:150): the mate follows and carries the templates */
+			free(Tbuf);
+			if (ip + 28 > in_bytes) break;
+			int32_t g[7]; memcpy(g, in + ip, 28); ip += 28;
+			pe_mate m1, m2;
+			memset(&m1, 0, sizeof(m1)); memset(&m2, 0, sizeof(m2));
+			m1.q_len = q_len; m1.words = words; m1.nN = nN; m1.hl = hl; m1.flag = flag; m1.hdr = hdr;
+			m2.q_len = g[0]; m2.words = g[1]; m2.nN = g[2]; m2.hl = g[5]; m2.flag = g[6];
+			const int nt2 = g[4];
+			pe_mate *mm[2] = {&m1, &m2};
+			const uint64_t *src[2] = {seq, (const uint64_t *)0};
+			for (int x = 0; x < 2; ++x) {
+				pe_mate *m = mm[x];
+				for (int o = 0; o < 2; ++o) {
+					m->w[o] = calloc((size_t)m->words + 2, 8); m->N[o] = calloc((size_t)m->nN + 2, 4); m->b[o] = calloc((size_t)m->q_len + 64, 1);
+				}
+				if (x == 0) { memcpy(m->w[0], src[0], 8 * (size_t)m->words); memcpy(m->N[0], N, 4 * (size_t)m->nN); }
+				else {
+					memcpy(m->w[0], in + ip, 8 * (size_t)m->words); ip += 8 * (size_t)m->words;
+					memcpy(m->N[0], in + ip, 4 * (size_t)m->nN); ip += 4 * (size_t)m->nN;
+				}
+				orc_revcomp(m->w[0], m->q_len, m->N[0], m->nN, m->w[1], m->N[1]);
+				for (int o = 0; o < 2; ++o) { unpack(m->w[o], m->q_len, m->N[o], m->nN, m->b[o]); m->N[o][m->nN] = m->q_len; }
+			}
+			int *mt = malloc(4 * (size_t)(nt2 + 2));
+			mt[0] = nt2;
+			memcpy(mt + 1, in + ip, 4 * (size_t)nt2); ip += 4 * (size_t)nt2;
+			m2.hdr = in + ip; ip += m2.hl;
+			if (rc_flag < 0) { fprintf(stderr, "orc_align_stream: strand-undecided pairs are not produced by -apm p\n"); return -2; }
+			if (k <= m1.q_len && k <= m2.q_len) {
+				int *bT = calloc((size_t)nt2 + 2, 4), *bTr = calloc((size_t)nt2 + 2, 4), *bS2 = calloc((size_t)nt2 + 2, 4), *bE2 = calloc((size_t)nt2 + 2, 4);
+				align_pe(p, &ws, &pt, tix, db, k, &m1, &m2, mt, nt2, scoreT, mq, minlen, mrc, 1.0, bT, bTr, bS2, bE2, &frag, as, uas,
+				         cand_out ? &cand : 0, ridx);
+				free(bT); free(bTr); free(bS2); free(bE2);
+			}
+			for (int x = 0; x < 2; ++x) for (int o = 0; o < 2; ++o) { free(mm[x]->w[o]); free(mm[x]->N[o]); free(mm[x]->b[o]); }
+			free(mt);
+			ridx += 2;
+			continue;
+		}
 		if (q_len < k) { free(Tbuf); ++ridx; continue; }
 
 		if (rc_flag < 0) { orc_revcomp(seq, q_len, N, nN, rseq, rN); rseq[words] = 0; unpack(rseq, q_len, rN, nN, qr); rN[nN] = q_len; }

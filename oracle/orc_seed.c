@@ -16,7 +16,11 @@
  *   savekmers.c:2442-3065 save_kmers (-1t1)                          -> orc_seed_read
  *   savekmers.c:273-294   getBestMatch                               -> best_set
  *   ankers.c:30-50        print_ankers (stage-2 record)              -> emit_record
- *   savekmers.c:50-92     loadFsa (stage-1 record)                   -> orc_seed_stream
+ *   savekmers.c:50-92     loadFsa (stage-1 record)                   -> load_mate / orc_seed_stream
+ *   savekmers.c:427-688   get_kmers_for_pair                         -> pair_kmers
+ *   savekmers.c:1383-1511, 1648-1680 getFirstPen / getSecondBestPen / getF_Best -> first_pen / second_pen / f_best
+ *   savekmers.c:3572-3777 save_kmers_penaltyPair (-apm p)            -> seed_pair
+ *   ankers.c:150-161      printPair                                  -> seed_pair
  *   kmers.c:257           stream terminator  int32 -(#reads)
  *
  * Structure differs from the reference on purpose: the k-mer scan is expressed as a stream of
@@ -211,7 +215,7 @@ typedef struct {
 /* One strand. cand[0] = count, cand[1..] = templates in first-seen order. Returns best score and
  * leaves the arg-max set (first-seen order) in cand. `*lookups` counts hash probes issued. */
 static int scan_strand(const orc_db *db, const orc_params *p, const uint64_t *seq, int seqlen,
-                       const int32_t *N, int nN, scratch_t *S, int *cand, orc_stats *st) {
+                       const int32_t *N, int nN, scratch_t *S, int *cand, orc_stats *st, int *all_scores) {
 	const int k = db->kmersize;
 	int hit = p->exhaustive;
 
@@ -271,6 +275,14 @@ static int scan_strand(const orc_db *db, const orc_params *p, const uint64_t *se
 		orc_list(db, last, &nl, &ids);
 		for (int i = 0; i < nl; ++i) S->score[list_id(db, ids, i)] += sc;
 	}
+	if (all_scores) {   /* get_kmers_for_pair (savekmers.c:654-686): every template seen keeps its clamped score */
+		for (int i = 1; i <= cand[0]; ++i) {
+			int t = cand[i];
+			all_scores[t] = S->score[t] < 0 ? 0 : S->score[t];
+			S->score[t] = 0; S->ext[t] = 0; S->incl[t] = 0;
+		}
+		return nhits;
+	}
 	/* arg-max set, first-seen order; scratch returned to zero (getBestMatch, savekmers.c:273) */
 	int best = 0, nb = 0;
 	for (int i = 1; i <= cand[0]; ++i) {
@@ -297,44 +309,251 @@ static size_t emit_record(uint8_t *out, const uint64_t *seq, int seqlen, const i
 	return o - out;
 }
 
-/* Whole stage 2 for single-end records under -1t1: stage-1 stream in, stage-2 stream out
- * (including the terminator). Returns bytes written, or -1 if `cap` is too small. */
+
+/* ------------------------------------------------------------------ paired end (-apm p) */
+
+/* One mate as save_kmers_penaltyPair sees it: both strand forms plus which one the in-place comp_rc calls of the
+ * reference currently leave in the buffer (get_kmers_for_pair reverse-complements its read, savekmers.c:471). */
+typedef struct {
+	uint64_t *w[2]; int32_t *N[2];
+	int seqlen, words, nN, cur;
+	const uint8_t *hdr; int hdrlen;
+} mate_t;
+
+typedef struct {
+	scratch_t S;
+	int *Score, *Score_r;        /* per-template scores of the mate scanned last (forward / reverse strand) */
+	int *bt, *bt_r;              /* bestTemplates / bestTemplates_r: templates seen per strand, [0] = count */
+	int *rt, *rs;                /* regionTemplates / regionScores of the first mate */
+} pair_ws;
+
+/* get_kmers_for_pair (savekmers.c:427-688) */
+static int pair_kmers(const orc_db *db, const orc_params *p, mate_t *m, pair_ws *ws, orc_stats *st) {
+	ws->bt[0] = 0; ws->bt_r[0] = 0;
+	if (m->seqlen < (int)db->kmersize) return 0;
+	int hf = scan_strand(db, p, m->w[0], m->seqlen, m->N[0], m->nN, &ws->S, ws->bt, st, ws->Score);
+	int hr = scan_strand(db, p, m->w[1], m->seqlen, m->N[1], m->nN, &ws->S, ws->bt_r, st, ws->Score_r);
+	m->cur = 1;
+	return hf < hr ? hr : hf;
+}
+
+static size_t emit_mate(uint8_t *out, const mate_t *m, int score, const int *tmpl, int ntmpl, int flag) {
+	return emit_record(out, m->w[m->cur], m->seqlen, m->N[m->cur], m->nN, score, tmpl, ntmpl, m->hdr, m->hdrlen, flag);
+}
+
+/* getFirstPen (savekmers.c:1383) */
+static int first_pen(pair_ws *ws) {
+	int best = 0, n = 0;
+	for (int i = 1; i <= ws->bt[0]; ++i) {
+		int t = ws->bt[i], sc = ws->Score[t];
+		if (best < sc) best = sc;
+		++n; ws->rt[n] = t; ws->rs[n] = sc; ws->Score[t] = 0;
+	}
+	for (int i = 1; i <= ws->bt_r[0]; ++i) {
+		int t = ws->bt_r[i], sc = ws->Score_r[t];
+		if (best < sc) best = sc;
+		++n; ws->rt[n] = -t; ws->rs[n] = sc; ws->Score_r[t] = 0;
+	}
+	ws->rt[0] = n;
+	return best;
+}
+
+/* getSecondBestPen (savekmers.c:1415) */
+static int second_pen(pair_ws *ws, int bestScore, int PE) {
+	int best_r = 0, n;
+	for (int i = 1; i <= ws->bt[0]; ++i) if (best_r < ws->Score[ws->bt[i]]) best_r = ws->Score[ws->bt[i]];
+	n = ws->bt[0];
+	for (int i = 1; i <= ws->bt_r[0]; ++i) {
+		if (best_r < ws->Score_r[ws->bt_r[i]]) best_r = ws->Score_r[ws->bt_r[i]];
+		ws->bt[++n] = -ws->bt_r[i];
+	}
+	ws->bt[0] = n;
+	int hits = 0;
+	if (best_r) {
+		int comp = bestScore + best_r - PE;
+		if (comp < 0) comp = 0;
+		for (int i = 1; i <= ws->rt[0]; ++i) {
+			int t = ws->rt[i], sc = 0 < t ? ws->Score_r[t] : ws->Score[-t];   /* the mate must hit the opposite strand */
+			if (0 < sc) {
+				sc += ws->rs[i];
+				if (comp < sc) { comp = sc; hits = 1; ws->rt[hits] = t; }
+				else if (comp == sc) ws->rt[++hits] = t;
+			}
+		}
+	}
+	if (hits) {   /* proper pair */
+		ws->rt[0] = -hits;
+		for (int i = ws->bt[0]; i != 0; --i) { if (0 < ws->bt[i]) ws->Score[ws->bt[i]] = 0; else ws->Score_r[-ws->bt[i]] = 0; }
+	} else {      /* best hits of each mate on its own */
+		for (int i = 1; i <= ws->rt[0]; ++i) if (bestScore == ws->rs[i]) ws->rt[++hits] = ws->rt[i];
+		ws->rt[0] = hits;
+		hits = 0;
+		for (int i = 1; i <= ws->bt[0]; ++i) {
+			int t = ws->bt[i];
+			if (0 < t) { if (best_r == ws->Score[t]) ws->bt[++hits] = t; ws->Score[t] = 0; }
+			else { if (best_r <= ws->Score_r[-t]) ws->bt[++hits] = t; ws->Score_r[-t] = 0; }
+		}
+		ws->bt[0] = hits;
+	}
+	return best_r;
+}
+
+/* getF_Best (savekmers.c:1648) */
+static int f_best(pair_ws *ws) {
+	int best = 0, hits = 0;
+	for (int i = 1; i <= ws->bt[0]; ++i) {
+		int t = ws->bt[i], sc = ws->Score[t];
+		if (best < sc) { best = sc; hits = 1; ws->rt[hits] = t; }
+		else if (best == sc) ws->rt[++hits] = t;
+		ws->Score[t] = 0;
+	}
+	for (int i = 1; i <= ws->bt_r[0]; ++i) {
+		int t = ws->bt_r[i], sc = ws->Score_r[t];
+		if (best < sc) { best = sc; hits = 1; ws->rt[hits] = -t; }
+		else if (best == sc) ws->rt[++hits] = -t;
+		ws->Score_r[t] = 0;
+	}
+	ws->rt[0] = hits;
+	return best;
+}
+
+static int imin(int a, int b) { return a < b ? a : b; }
+
+/* save_kmers_penaltyPair (savekmers.c:3572-3777) with printPtr = print_ankers, printPairPtr = printPair,
+ * deConPrintPtr = printPtr, rev = 1 (no prefix). Appends 0, 1 or 2 stage-2 records to out; returns bytes written. */
+static size_t seed_pair(const orc_db *db, const orc_params *p, mate_t *m1, mate_t *m2, pair_ws *ws, uint8_t *out, orc_stats *st) {
+	const int k = db->kmersize;
+	size_t op = 0;
+	int hc, hc_r, best = 0, best_r = 0, flag = 65, flag_r = 129;
+	if ((hc = pair_kmers(db, p, m1, ws, st))) best = first_pen(ws);
+	if ((hc_r = pair_kmers(db, p, m2, ws, st))) best_r = 0 < best ? second_pen(ws, best, p->PE) : f_best(ws);
+	int *rt = ws->rt, *bt = ws->bt;
+	if (0 < best && 0 < best_r) {
+		if (rt[0] < 0) {   /* proper pair */
+			flag |= 2; flag_r |= 2;
+			int comp = imin(hc + hc_r, best + best_r);
+			if (k <= comp || (m1->seqlen + m2->seqlen - comp - (k << 1)) < comp * k) {
+				rt[0] = -rt[0];
+				if (0 < rt[1]) {
+					flag |= 32; flag_r |= 16;
+					m1->cur ^= 1;
+					op += emit_mate(out + op, m1, best, rt + 1, 0, flag);          /* printPair: first record has no templates */
+					op += emit_mate(out + op, m2, best_r, rt + 1, rt[0], flag_r);
+				} else {
+					flag |= 16; flag_r |= 32;
+					m2->cur ^= 1;
+					for (int i = rt[0]; i != 0; --i) rt[i] = -rt[i];
+					op += emit_mate(out + op, m2, best_r, rt + 1, 0, flag_r);
+					op += emit_mate(out + op, m1, best, rt + 1, rt[0], flag);
+				}
+			}
+		} else {           /* two single mates */
+			int h = imin(hc, best), h_r = imin(hc_r, best_r);
+			h = k <= h || (m1->seqlen - h - k) < h * k;
+			if (h) {
+				if (0 < rt[1]) { m1->cur ^= 1; if (rt[rt[0]] < 0) best = -best; }
+				else { flag |= 16; flag_r |= 32; for (int i = rt[0]; i != 0; --i) rt[i] = -rt[i]; }
+			}
+			h_r = k <= h_r || (m2->seqlen - h_r - k) < h_r * k;
+			if (h_r) {
+				if (0 < bt[1]) { m2->cur ^= 1; if (bt[bt[0]] < 0) best_r = -best_r; }
+				else { flag |= 32; flag_r |= 16; for (int i = bt[0]; i != 0; --i) bt[i] = -bt[i]; }
+			}
+			if (h) op += emit_mate(out + op, m1, best, rt + 1, rt[0], flag);
+			if (h_r) op += emit_mate(out + op, m2, best_r, bt + 1, bt[0], flag_r);
+		}
+	} else if (0 < best) {
+		int h = imin(hc, best);
+		if (k <= h || (m1->seqlen - h - k) < h * k) {
+			flag |= 8 | 32;
+			if (0 < rt[1]) { m1->cur ^= 1; if (rt[rt[0]] < 0) best = -best; }
+			else { flag |= 16; for (int i = rt[0]; i != 0; --i) rt[i] = -rt[i]; }
+			op += emit_mate(out + op, m1, best, rt + 1, rt[0], flag);
+		}
+	} else if (0 < best_r) {
+		int h = imin(hc_r, best_r);
+		if (k <= h || (m2->seqlen - h - k) < h * k) {
+			flag_r |= 8 | 32;
+			if (0 < rt[1]) { m2->cur ^= 1; if (rt[rt[0]] < 0) best_r = -best_r; }
+			else { flag_r |= 16; for (int i = 1; i <= rt[0]; ++i) rt[i] = -rt[i]; }
+			op += emit_mate(out + op, m2, best_r, rt + 1, rt[0], flag_r);
+		}
+	}
+	return op;
+}
+
+/* one stage-1 record (loadFsa, savekmers.c:50-92) -> both strand forms of the read. Returns the signed header
+ * length field (< 0: first mate of a pair), 0 at the end of the stream. */
+typedef struct { uint64_t *w[2]; int32_t *N[2]; size_t wcap, ncap; } mate_buf;
+
+static int load_mate(const uint8_t *in, size_t in_bytes, size_t *ip, mate_buf *b, mate_t *m) {
+	if (*ip + 16 > in_bytes) return 0;
+	int32_t h[4]; memcpy(h, in + *ip, 16);
+	if (h[0] < 0) return 0;
+	*ip += 16;
+	const int seqlen = h[0], words = h[1], nN = h[2];
+	if ((size_t)words + 2 > b->wcap) {
+		b->wcap = 2 * (size_t)words + 2;
+		for (int i = 0; i < 2; ++i) b->w[i] = realloc(b->w[i], 8 * b->wcap);
+	}
+	if ((size_t)nN + 2 > b->ncap) {
+		b->ncap = 2 * (size_t)nN + 2;
+		for (int i = 0; i < 2; ++i) b->N[i] = realloc(b->N[i], 4 * b->ncap);
+	}
+	memcpy(b->w[0], in + *ip, 8 * (size_t)words); b->w[0][words] = 0; *ip += 8 * (size_t)words;
+	memcpy(b->N[0], in + *ip, 4 * (size_t)nN); *ip += 4 * (size_t)nN;
+	m->hdr = in + *ip; m->hdrlen = abs(h[3]); *ip += m->hdrlen;
+	m->seqlen = seqlen; m->words = words; m->nN = nN; m->cur = 0;
+	for (int i = 0; i < 2; ++i) { m->w[i] = b->w[i]; m->N[i] = b->N[i]; }
+	orc_revcomp(b->w[0], seqlen, b->N[0], nN, b->w[1], b->N[1]); b->w[1][words] = 0;
+	return h[3] ? h[3] : 1;
+}
+
+/* Whole stage 2: stage-1 stream in, stage-2 stream out (including the terminator). Single-end records go through
+ * save_kmers (-1t1), pairs (first mate written with a negative header length, runinput.c:789) through
+ * save_kmers_penaltyPair (-apm p). Returns bytes written, or -1 if `cap` is too small. */
 int64_t orc_seed_stream(const orc_db *db, const orc_params *p, const uint8_t *in, size_t in_bytes,
                         uint8_t *out, size_t cap, orc_stats *st) {
 	const int k = db->kmersize;
-	scratch_t S = {calloc(db->DB_size + 1, sizeof(int)), calloc(db->DB_size + 1, sizeof(int)), calloc(db->DB_size + 1, 1)};
-	int *cf = malloc(sizeof(int) * (2 * (size_t)db->DB_size + 4)), *cr = malloc(sizeof(int) * (db->DB_size + 4));
-	size_t ip = 0, op = 0, rcap = 0;
-	uint64_t *seq = 0, *rseq = 0; int32_t *N = 0, *rN = 0;
+	const size_t D = (size_t)db->DB_size + 1;
+	pair_ws ws;
+	ws.S.score = calloc(D, sizeof(int)); ws.S.ext = calloc(D, sizeof(int)); ws.S.incl = calloc(D, 1);
+	ws.Score = calloc(D, sizeof(int)); ws.Score_r = calloc(D, sizeof(int));
+	ws.bt = malloc(sizeof(int) * (2 * D + 4)); ws.bt_r = malloc(sizeof(int) * (2 * D + 4));
+	ws.rt = malloc(sizeof(int) * (2 * D + 4)); ws.rs = malloc(sizeof(int) * (2 * D + 4));
+	int *cf = ws.bt, *cr = ws.bt_r;
+	mate_buf b1, b2; memset(&b1, 0, sizeof(b1)); memset(&b2, 0, sizeof(b2));
+	mate_t m1, m2;
+	size_t ip = 0, op = 0;
 	int32_t nreads = 0;
 	int64_t ret = 0;
+	int go;
 
-	while (ip + 16 <= in_bytes) {
-		int32_t h[4]; memcpy(h, in + ip, 16); ip += 16;
-		int seqlen = h[0], words = h[1], nN = h[2], hdrlen = abs(h[3]);
-		if ((size_t)words + 2 > rcap) {
-			rcap = 2 * (size_t)words + 2;
-			seq = realloc(seq, 8 * rcap); rseq = realloc(rseq, 8 * rcap);
-		}
-		N = realloc(N, 4 * (size_t)(nN + 1)); rN = realloc(rN, 4 * (size_t)(nN + 1));
-		memcpy(seq, in + ip, 8 * (size_t)words); seq[words] = 0; ip += 8 * (size_t)words;
-		memcpy(N, in + ip, 4 * (size_t)nN); ip += 4 * (size_t)nN;
-		const uint8_t *hdr = in + ip; ip += hdrlen;
+	while ((go = load_mate(in, in_bytes, &ip, &b1, &m1)) != 0) {
 		++nreads;
-		if (st) st->reads++, st->read_words += words;
+		if (st) st->reads++, st->read_words += m1.words;
+		if (go < 0) {   /* paired end */
+			if (!load_mate(in, in_bytes, &ip, &b2, &m2)) break;
+			if (st) st->reads++, st->read_words += m2.words;
+			size_t need = 2 * 28 + 8 * (size_t)(m1.words + m2.words) + 4 * (size_t)(m1.nN + m2.nN) + 8 * D + m1.hdrlen + m2.hdrlen;
+			if (op + need + 4 > cap) { ret = -1; goto done; }
+			size_t w = seed_pair(db, p, &m1, &m2, &ws, out + op, st);
+			if (w && st) st->mapped++;
+			op += w;
+			continue;
+		}
+		const int seqlen = m1.seqlen, words = m1.words, nN = m1.nN, hdrlen = m1.hdrlen;
 		if (seqlen < k) continue;
-
-		orc_revcomp(seq, seqlen, N, nN, rseq, rN); rseq[words] = 0;
-		int bf = scan_strand(db, p, seq, seqlen, N, nN, &S, cf, st);
-		int br = scan_strand(db, p, rseq, seqlen, rN, nN, &S, cr, st);
+		int bf = scan_strand(db, p, m1.w[0], seqlen, m1.N[0], nN, &ws.S, cf, st, 0);
+		int br = scan_strand(db, p, m1.w[1], seqlen, m1.N[1], nN, &ws.S, cr, st, 0);
 		if ((bf > 0 || br > 0) && (k <= bf || k <= br)) {
 			size_t need = 28 + 8 * (size_t)words + 4 * (size_t)nN + 4 * (size_t)(cf[0] + cr[0]) + hdrlen;
 			if (op + need + 4 > cap) { ret = -1; goto done; }
-			if (bf > br) op += emit_record(out + op, seq, seqlen, N, nN, bf, cf + 1, cf[0], hdr, hdrlen, 0);
-			else if (bf < br) op += emit_record(out + op, rseq, seqlen, rN, nN, br, cr + 1, cr[0], hdr, hdrlen, 16);
+			if (bf > br) op += emit_record(out + op, m1.w[0], seqlen, m1.N[0], nN, bf, cf + 1, cf[0], m1.hdr, hdrlen, 0);
+			else if (bf < br) op += emit_record(out + op, m1.w[1], seqlen, m1.N[1], nN, br, cr + 1, cr[0], m1.hdr, hdrlen, 16);
 			else {
 				for (int i = 1; i <= cr[0]; ++i) cf[++cf[0]] = -cr[i];
-				op += emit_record(out + op, seq, seqlen, N, nN, -bf, cf + 1, cf[0], hdr, hdrlen, 0);
+				op += emit_record(out + op, m1.w[0], seqlen, m1.N[0], nN, -bf, cf + 1, cf[0], m1.hdr, hdrlen, 0);
 			}
 			if (st) st->mapped++;
 		}
@@ -343,7 +562,9 @@ int64_t orc_seed_stream(const orc_db *db, const orc_params *p, const uint8_t *in
 	nreads = -nreads; memcpy(out + op, &nreads, 4); op += 4;
 	ret = (int64_t)op;
 done:
-	free(S.score); free(S.ext); free(S.incl); free(cf); free(cr); free(seq); free(rseq); free(N); free(rN);
+	free(ws.S.score); free(ws.S.ext); free(ws.S.incl); free(ws.Score); free(ws.Score_r);
+	free(ws.bt); free(ws.bt_r); free(ws.rt); free(ws.rs);
+	for (int i = 0; i < 2; ++i) { free(b1.w[i]); free(b1.N[i]); free(b2.w[i]); free(b2.N[i]); }
 	return ret;
 }
 

@@ -3,7 +3,7 @@
  * Nothing here restates reference logic: it sets the globals the way kma.c / runkma.c do and calls the
  * reference's own stage-3 entry point, so tests get ground truth for the alignment pass.
  *
- *   ref_aln <db_prefix> <stage2.bin | -> <frag_raw.out> <scores.out> [cand.out] [-1t1] [-t N]
+ *   ref_aln <db_prefix> <stage2.bin | -> <frag_raw.out> <scores.out> [cand.out] [-1t1] [-apm-p] [-t N]
  *
  * "-" reads the stage-2 stream from stdin (`kma ... -s2 | ref_aln db - ...`); -t N runs alnFrags_threaded on N pthreads
  * the way runKMA does (runkma.c:300-440: one Aln_thread per thread, shared input/output/score arrays, the reference's
@@ -60,6 +60,7 @@ int main(int argc, char **argv) {
 	int nthreads = 1;
 	for (int a = 5; a < argc; ++a) {
 		if (!strcmp(argv[a], "-1t1")) one2one = 1;
+		else if (!strcmp(argv[a], "-apm-p")) alnFragsPE = &alnFragsPenaltyPE;   /* kma.c:458: -apm p */
 		else if (!strcmp(argv[a], "-t") && a + 1 < argc) nthreads = atoi(argv[++a]);
 		else cand_path = argv[a];
 	}

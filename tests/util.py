@@ -95,7 +95,7 @@ def golden_dir():
 REF_ALN = os.path.join(ROOT, "oracle", "_ref", "ref_aln")
 
 
-def ref_align(db_prefix: str, s2: bytes, tmp: str, one2one=True, cand=True):
+def ref_align(db_prefix: str, s2: bytes, tmp: str, one2one=True, cand=True, pe=False):
     """Ground truth of the alignment pass from the unmodified reference (oracle/ref_harness.c):
     (frag_raw bytes, alignment_scores, uniq_alignment_scores, cand rows [n, 8] or None)."""
     p = os.path.join(tmp, "s2.bin")
@@ -106,6 +106,8 @@ def ref_align(db_prefix: str, s2: bytes, tmp: str, one2one=True, cand=True):
         args.append(os.path.join(tmp, "cand.out"))
     if one2one:
         args.append("-1t1")
+    if pe:
+        args.append("-apm-p")
     r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     frag = open(os.path.join(tmp, "fr.out"), "rb").read()
