@@ -35,13 +35,15 @@ struct AlnRead {
 	int32_t q_len, words, nN, rc_flag, nt, hl, flag;
 	uint32_t slab_off;   // 8-byte units
 	uint32_t task0;
+	int32_t kind;        // 0 single read, 1 first record of a pair (no templates, ankers.c:150), 2 its mate (carries the templates)
+	int32_t fneg;        // kind 2: index of the first negative template (nt when none): both reads flip there (alnfrags.c:1630)
 };
 
 struct AlnCand { int32_t tmpl, score, len, pos, match, tGaps, qGaps, status; };
 
 struct AlnParams {
 	NwPen pen;
-	int32_t k, mq, one2one, exhaustive, minlen;
+	int32_t k, mq, one2one, exhaustive, minlen, Wl, PE;
 	double scoreT, mrc, minFrac;
 };
 
@@ -82,9 +84,18 @@ __global__ void aln_sizes_kernel(const uint8_t *__restrict__ in, const uint32_t 
 		R.q_len = (int)ld_u32u(rec); R.words = (int)ld_u32u(rec + 4); R.nN = (int)ld_u32u(rec + 8);
 		R.rc_flag = (int)ld_u32u(rec + 12); R.nt = (int)ld_u32u(rec + 16); R.hl = (int)ld_u32u(rec + 20);
 		R.flag = (int)ld_u32u(rec + 24);
-		if (R.nt == 0) { atomicAdd(&ctr[A_BAD], 1ull); R.q_len = 0; }   // first record of a pair (ankers.c:150)
-		ss = slab_stride(R) * (R.rc_flag < 0 ? 2u : 1u);
-		ts = R.q_len >= k ? (uint32_t)R.nt : 0u;
+		int prev_nt = 1, prev_len = 0, prev_rc = 0;
+		if (r > 0 && off[r] - off[r - 1] >= 28) {
+			prev_nt = (int)ld_u32u(in + off[r - 1] + 16); prev_len = (int)ld_u32u(in + off[r - 1]); prev_rc = (int)ld_u32u(in + off[r - 1] + 12);
+		}
+		R.kind = R.nt == 0 ? 1 : (prev_nt == 0 ? 2 : 0);
+		R.fneg = R.nt;
+		ss = slab_stride(R) * ((R.rc_flag < 0 || R.kind) ? 2u : 1u);
+		if (R.kind == 2) {
+			// alnFrags_threaded (alnfrags.c:2250): both mates reach k or the pair degenerates to forms stage 2 never writes
+			if (prev_len < k || R.q_len < k || prev_rc < 0) atomicAdd(&ctr[A_BAD], 1ull);
+			else ts = 2u * (uint32_t)R.nt;
+		} else if (R.kind == 0) ts = R.q_len >= k ? (uint32_t)R.nt : 0u;
 		atomicMax(&ctr[A_MAXQ], (unsigned long long)R.q_len);
 	}
 	reads[r] = R;
@@ -92,6 +103,12 @@ __global__ void aln_sizes_kernel(const uint8_t *__restrict__ in, const uint32_t 
 }
 
 // ---------------------------------------------------------------- pass 2: unpack (one warp per read)
+
+__device__ __forceinline__ int warp_min_i(int v) {
+#pragma unroll
+	for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
 
 __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__restrict__ in, int n, AlnRead *reads,
 		const uint32_t *__restrict__ slab_off, const uint32_t *__restrict__ task_off, uint64_t *slab, int32_t *task_read, int k) {
@@ -104,7 +121,7 @@ __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__restrict
 		if (R.q_len == 0 && R.words == 0) continue;
 		const uint8_t *rec = in + R.rec_off, *seq = rec + 28, *Ns = seq + 8 * (size_t)R.words;
 		const int L = R.q_len, words = R.words, nN = R.nN;
-		for (int strand = 0; strand < (R.rc_flag < 0 ? 2 : 1); ++strand) {
+		for (int strand = 0; strand < ((R.rc_flag < 0 || R.kind) ? 2 : 1); ++strand) {
 			uint64_t *base = slab + R.slab_off + (strand ? slab_stride(R) : 0);
 			uint8_t *b = (uint8_t *)(base + slab_W(words));
 			int32_t *N = (int32_t *)(base + slab_W(words) + slab_B(L));
@@ -132,7 +149,15 @@ __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__restrict
 				if (i < nN) b[v] = 4;
 			}
 		}
-		if (L >= k) for (int i = lane; i < R.nt; i += 32) task_read[R.task0 + i] = r;
+		const int ntask = (int)(task_off[r + 1] - task_off[r]);
+		for (int i = lane; i < ntask; i += 32) task_read[R.task0 + i] = r;
+		if (R.kind == 2) {   // first negative template
+			const uint8_t *T = Ns + 4 * (size_t)nN;
+			int f = R.nt;
+			for (int i = lane; i < R.nt; i += 32) if ((int)ld_u32u(T + 4 * (size_t)i) < 0) { f = i; break; }
+			f = warp_min_i(f);
+			if (lane == 0) reads[r].fneg = f;
+		}
 		__syncwarp();
 	}
 }
@@ -488,6 +513,21 @@ __device__ int align_pair(const AlnParams &P, const NwPen *pen, const KgTIndexVi
 	return ST_OK;
 }
 
+// KMA_score of one read in a given orientation against one template
+__device__ int align_fixed(const AlnParams &P, const NwPen *pen, const KgTIndexView &ix, const uint64_t *slab, const AlnRead &R,
+                           int strand, int at, Mems M, const NwScratch &nws, WarpCtr &wc, AlnCand *out) {
+	const KgTMeta m = ix.meta[at];
+	TaskCtx c;
+	c.pen = pen; c.tseq = ix.seq + m.seq_off; c.nw = nws; c.wc = &wc;
+	const QView q = read_view(slab, R, strand);
+	c.qb = q.b;
+	NwStat a = {0, 0, 0, 0, 0, 0};
+	if (kma_score_warp(P, c, ix, m, q, R.nN + 1, R.q_len, M, 0, &a)) return ST_OVERFLOW;
+	out->tmpl = at; out->score = a.score; out->len = a.len; out->pos = a.pos; out->match = a.match;
+	out->tGaps = a.tGaps; out->qGaps = a.qGaps; out->status = ST_OK;
+	return ST_OK;
+}
+
 struct ScratchLayout { size_t stride; int mem_cap, q_cap; size_t e_cap; };
 
 __global__ void __launch_bounds__(AL_WARPS * 32) aln_pair_kernel(AlnParams P, KgTIndexView ix, const uint8_t *__restrict__ in,
@@ -525,11 +565,21 @@ __global__ void __launch_bounds__(AL_WARPS * 32) aln_pair_kernel(AlnParams P, Kg
 		const int r = task_read[task];
 		const AlnRead R = reads[r];
 		const uint8_t *rec = in + R.rec_off;
-		const int ti = task - (int)R.task0;
+		int ti = task - (int)R.task0;
+		const int mate = R.kind == 2 ? ti & 1 : 0;
+		if (R.kind == 2) ti >>= 1;
 		const int tmpl = (int)ld_u32u(rec + 28 + 8 * (size_t)R.words + 4 * (size_t)R.nN + 4 * (size_t)ti);
-		wc.read_bytes += 8ull * (unsigned long long)R.words + (unsigned long long)R.q_len + 4ull * (unsigned long long)R.nN;
 		AlnCand res;
-		const int st = align_pair(P, &spen, ix, slab, R, tmpl, M, nws, wc, &res);
+		int st;
+		if (R.kind == 2) {   // a mate of a pair against one template, strands decided by stage 2 (alnfrags.c:1645-1661, 1712-1731)
+			const AlnRead Rq = mate ? R : reads[r - 1];
+			wc.read_bytes += 8ull * (unsigned long long)Rq.words + (unsigned long long)Rq.q_len + 4ull * (unsigned long long)Rq.nN;
+			st = align_fixed(P, &spen, ix, slab, Rq, ti >= R.fneg, abs(tmpl), M, nws, wc, &res);
+			res.tmpl = tmpl;
+		} else {
+			wc.read_bytes += 8ull * (unsigned long long)R.words + (unsigned long long)R.q_len + 4ull * (unsigned long long)R.nN;
+			st = align_pair(P, &spen, ix, slab, R, tmpl, M, nws, wc, &res);
+		}
 		__syncwarp();
 		if (st != ST_OK) {
 			res.tmpl = tmpl; res.score = res.len = res.pos = res.match = res.tGaps = res.qGaps = 0; res.status = ST_OVERFLOW;
@@ -553,14 +603,184 @@ __global__ void __launch_bounds__(AL_WARPS * 32) aln_pair_kernel(AlnParams P, Kg
 
 // ---------------------------------------------------------------- selection + ConClave sums (one thread per read)
 
-struct AlnRes { int32_t kept, best; };
+// what the writer needs per stage-2 record. Single read: one frag_raw record (kept, best). Pair (stored with the mate
+// that carries the templates): up to two records; rec[x] = {kept, score field, flag, mate (0 = first record of the
+// pair), orientation (1 = reverse complement bytes), offset of its start[]/end[]/template[] arrays in the pair's ints}
+struct AlnRes {
+	int32_t kept, best;
+	int32_t form;        // 0 single read, 1 proper pair (update_Scores_pe), 2 one or two update_Scores_se records
+	int32_t nrec;
+	int32_t rkept[2], rscore[2], rflag[2], rmate[2], rorient[2], roff[2];
+};
 
-__global__ void aln_reduce_kernel(AlnParams P, const AlnRead *__restrict__ reads, int n, AlnCand *cand,
+struct PeEnt { int32_t mt, bT, bTr, bS, bE; };   // the five parallel arrays of alnFragsPenaltyPE, index = template index
+
+// update_Scores_se / update_Scores_pe (updatescores.c:300-488): keep the best templates, add the ConClave sums.
+// T/Sc/S/E are strided views into the PeEnt array (stride 5 ints); kept triples are copied to out[3 * cap].
+__device__ int pe_keep(double minFrac, int pe, int n, int best, const int32_t *S, const int32_t *E, const int32_t *T, const int32_t *Sc,
+                       int32_t *out, int cap, unsigned long long *as, unsigned long long *uas) {
+	int kept = 0;
+	const int mode = minFrac == 1.0 ? 0 : (minFrac < 0 ? 1 : 2);
+	const double thr = fabs(minFrac) * best;
+	for (int i = 0; i < n; ++i) {
+		const int sc = Sc[5 * i];
+		const bool keep = mode == 0 ? sc == best : thr <= sc;
+		if (keep) {
+			out[kept] = S[5 * i]; out[cap + kept] = E[5 * i]; out[2 * cap + kept] = T[5 * i];
+			const int add = pe ? (mode == 2 ? best : sc) : (mode == 1 ? sc : best);
+			atomicAdd(&as[abs(T[5 * i])], (unsigned long long)add);
+			++kept;
+		}
+	}
+	if (kept == 1) atomicAdd(&uas[abs(out[2 * cap])], (unsigned long long)best);
+	return kept;
+}
+
+// alnFragsPenaltyPE (alnfrags.c:1596-1972) for one pair, after its 2 * nt KMA_score results are in cand[task0 ..).
+__device__ void reduce_pair(const AlnParams &P, const AlnRead &RA, const AlnRead &RB, const uint8_t *recB, AlnCand *cand,
+                            const KgTMeta *meta, unsigned long long *as, unsigned long long *uas, AlnRes &o, uint32_t &size) {
+	const int nt = RB.nt, k = P.k, Wl = -P.Wl, PE = P.PE;
+	int32_t *base = (int32_t *)(cand + RB.task0);
+	PeEnt *ent = (PeEnt *)base;
+	int32_t *outA = base + 5 * (nt + 1), *outB = outA + 3 * nt;
+	const uint8_t *T = recB + 28 + 8 * (size_t)RB.words + 4 * (size_t)RB.nN;
+	int best1 = 0, best2 = 0, comp = 0, start = 0, end = 0, hits = 0;
+	double score = 0;
+	for (int ti = 1; ti <= nt; ++ti) {
+		const AlnCand a1 = cand[RB.task0 + 2 * (ti - 1)], a2 = cand[RB.task0 + 2 * (ti - 1) + 1];   // read before the slots are reused
+		const int tmpl = (int)ld_u32u(T + 4 * (size_t)(ti - 1));
+		const int t_len = meta[abs(tmpl)].len;
+		PeEnt e;
+		e.mt = tmpl;
+		int rs = a1.score;
+		if (P.minlen <= a1.len && 0 < rs && ((P.mrc * RA.q_len <= a1.len - a1.qGaps) || (P.mrc * t_len <= a1.len - a1.tGaps))) {
+			start = a1.pos; end = a1.pos + a1.len - a1.tGaps;
+			if (start == 0) rs += Wl;
+			if (end == t_len) rs += Wl;
+			score = 1.0 * rs / a1.len;
+		} else rs = 0;
+		if (rs > k && score >= P.scoreT) { e.bT = rs; e.bS = start; e.bE = end; if (best1 < rs) best1 = rs; }
+		else { e.bT = 0; e.bS = -1; e.bE = -1; }
+		rs = a2.score;
+		if (P.minlen <= a2.len && 0 < rs && ((P.mrc * RB.q_len <= a2.len - a2.qGaps) || (P.mrc * t_len <= a2.len - a2.tGaps))) {
+			start = a2.pos; end = a2.pos + a2.len - a2.tGaps;
+			if (start == 0) rs += Wl;
+			if (end == t_len) rs += Wl;
+			score = 1.0 * rs / a2.len;
+		} else rs = 0;
+		if (rs > k && score >= P.scoreT) {
+			e.bTr = rs;
+			if (e.bT) { if (start < e.bS) e.bS = start; else e.bE = end; }
+			else { e.bS = start; e.bE = end; }
+			if (best2 < rs) best2 = rs;
+		} else e.bTr = 0;
+		rs += e.bT;
+		if (comp < rs) comp = rs;
+		if (ti == 1) { PeEnt z = {nt, 0, 0, 0, 0}; ent[0] = z; }
+		ent[ti] = e;
+	}
+	o.form = 2; o.nrec = 0; size = 0;
+	if (!best1 && !best2) return;
+	const int flipped = RB.fneg < nt, rc = !flipped;
+	const double af = P.minFrac < 0 ? -P.minFrac : P.minFrac;
+	int flag = RA.flag, flag_r = RB.flag, o1 = flipped, o2 = flipped;
+	int32_t *e0 = (int32_t *)ent;
+#define F_MT 0
+#define F_BT 1
+#define F_BTR 2
+#define F_BS 3
+#define F_BE 4
+	auto put = [&](int x, int kept, int sc, int fl, int mate, int orient, int32_t *arr) {
+		o.rkept[x] = kept; o.rscore[x] = sc; o.rflag[x] = fl; o.rmate[x] = mate; o.rorient[x] = orient; o.roff[x] = (int32_t)(arr - base);
+	};
+	const uint32_t szA = (uint32_t)RA.q_len + (uint32_t)RA.hl, szB = (uint32_t)RB.q_len + (uint32_t)RB.hl;
+	if (comp && af * (best1 + best2) <= (comp + PE)) {   // proper pair
+		const int best = comp + PE;
+		for (int ti = 1; ti <= nt; ++ti)
+			if (ent[ti].bT && ent[ti].bTr) {
+				const PeEnt e = ent[ti];
+				ent[hits].bTr = e.bT + e.bTr + PE; ent[hits].bT = e.mt; ent[hits].bS = e.bS; ent[hits].bE = e.bE; ++hits;
+			}
+		o.form = 1; o.nrec = 2;
+		if (ent[0].bT < 0) {
+			for (int i = 0; i < hits; ++i) ent[i].bT = -ent[i].bT;
+			const int kept = pe_keep(P.minFrac, 1, hits, best, e0 + F_BS, e0 + F_BE, e0 + F_BT, e0 + F_BTR, outA, nt, as, uas);
+			put(0, kept, -best, flag_r, 1, o2, outA); put(1, 0, 0, flag, 0, o1, outA);
+			size = 20u + szB + 12u * kept + 12u + szA;
+		} else {
+			if (!rc) { o1 = o2 = 0; flag ^= 48; flag_r ^= 48; }
+			const int kept = pe_keep(P.minFrac, 1, hits, best, e0 + F_BS, e0 + F_BE, e0 + F_BT, e0 + F_BTR, outA, nt, as, uas);
+			put(0, kept, -best, flag, 0, o1, outA); put(1, 0, 0, flag_r, 1, o2, outA);
+			size = 20u + szA + 12u * kept + 12u + szB;
+		}
+	} else if (best1 && best2) {                         // both map, not as a pair
+		int hits_r = 0, ti = 1, last = nt, tmp;
+		const double sc = af * best1, sc_r = af * best2;
+		while (ti <= last) {
+			if (sc <= ent[ti].bT) { ent[hits].mt = ent[ti].mt; ent[hits].bT = ent[ti].bT; ent[hits].bS = ent[ti].bS; ent[hits].bE = ent[ti].bE; ++hits; ++ti; }
+			else if (sc_r <= ent[ti].bTr) {
+				tmp = ent[ti].mt; ent[ti].mt = ent[last].mt; ent[last].mt = tmp;
+				tmp = ent[ti].bTr; ent[ti].bTr = ent[last].bTr; ent[last].bTr = tmp;
+				tmp = ent[ti].bS; ent[ti].bS = ent[last].bS; ent[last].bS = tmp;
+				tmp = ent[ti].bE; ent[ti].bE = ent[last].bE; ent[last].bE = tmp;
+				++hits_r; --last;
+			} else ++ti;
+		}
+		if (ent[0].bT < 0) { for (int i = 0; i < hits; ++i) ent[i].bT = -ent[i].bT; }
+		else if (!rc) { o1 = 0; flag ^= 16; flag_r ^= 32; }
+		if (ent[last].bTr < 0) { for (int i = 0; i < hits_r; ++i) ent[last + i].bTr = -ent[last + i].bTr; }
+		else if (!rc) { o2 = 0; flag ^= 32; flag_r ^= 16; }
+		if (flag & 2) { flag ^= 2; flag_r ^= 2; }
+		const int k1 = pe_keep(P.minFrac, 0, hits, best1, e0 + F_BS, e0 + F_BE, e0 + F_MT, e0 + F_BT, outA, nt, as, uas);
+		ent[0].mt = k1;   // the reference stores the count in slot 0 between the two calls (alnfrags.c:1884)
+		int32_t *eL = e0 + 5 * last;
+		const int k2 = pe_keep(P.minFrac, 0, hits_r, best2, eL + F_BS, eL + F_BE, eL + F_MT, eL + F_BTR, outB, nt, as, uas);
+		o.nrec = 2;
+		put(0, k1, best1, flag, 0, o1, outA); put(1, k2, best2, flag_r, 1, o2, outB);
+		size = 20u + szA + 12u * k1 + 20u + szB + 12u * k2;
+	} else if (best1) {                                  // first mate only
+		for (int ti = 1; ti <= nt; ++ti)
+			if (ent[ti].bT) { const PeEnt e = ent[ti]; ent[hits].bTr = e.bT; ent[hits].bT = e.mt; ent[hits].bS = e.bS; ent[hits].bE = e.bE; ++hits; }
+		if (ent[0].bT < 0) { for (int i = 0; i < hits; ++i) ent[i].bT = -ent[i].bT; }
+		else if (!rc) { o1 = 0; flag ^= 16; flag_r ^= 32; }
+		flag |= 8; flag_r ^= 4;
+		if (flag & 2) { flag ^= 2; flag_r ^= 2; }
+		const int k1 = pe_keep(P.minFrac, 0, hits, best1, e0 + F_BS, e0 + F_BE, e0 + F_BT, e0 + F_BTR, outA, nt, as, uas);
+		o.nrec = 1;
+		put(0, k1, best1, flag, 0, o1, outA);
+		size = 20u + szA + 12u * k1;
+	} else {                                             // second mate only
+		for (int ti = 1; ti <= nt; ++ti)
+			if (ent[ti].bTr) { const PeEnt e = ent[ti]; ent[hits].bTr = e.bTr; ent[hits].bT = e.mt; ent[hits].bS = e.bS; ent[hits].bE = e.bE; ++hits; }
+		if (ent[0].bTr < 0) { for (int i = 0; i < hits; ++i) ent[i].bTr = -ent[i].bTr; }
+		else if (!rc) { o2 = 0; flag ^= 32; flag_r ^= 16; }
+		flag_r |= 8; flag ^= 4;
+		if (flag_r & 2) { flag ^= 2; flag_r ^= 2; }
+		const int k2 = pe_keep(P.minFrac, 0, hits, best2, e0 + F_BS, e0 + F_BE, e0 + F_BT, e0 + F_BTR, outA, nt, as, uas);
+		o.nrec = 1;
+		put(0, k2, best2, flag_r, 1, o2, outA);
+		size = 20u + szB + 12u * k2;
+	}
+}
+
+__global__ void aln_reduce_kernel(AlnParams P, const uint8_t *__restrict__ in, const AlnRead *__restrict__ reads, int n, AlnCand *cand,
                                   const KgTMeta *__restrict__ meta, unsigned long long *as, unsigned long long *uas,
                                   uint32_t *recsize, AlnRes *res, unsigned long long *ctr) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n) return;
 	const AlnRead R = reads[r];
+	if (R.kind) {
+		AlnRes o;
+		memset(&o, 0, sizeof(o));
+		uint32_t size = 0;
+		if (R.kind == 2 && R.nt > 0 && reads[r - 1].q_len >= P.k && R.q_len >= P.k) {
+			reduce_pair(P, reads[r - 1], R, in + R.rec_off, cand, meta, as, uas, o, size);
+			if (o.nrec) atomicAdd(&ctr[A_FRAGS], (unsigned long long)(o.form == 1 ? 1 : o.nrec));
+		}
+		recsize[r] = size;
+		res[r] = o;
+		return;
+	}
 	const int k = P.k, q_len = R.q_len;
 	const int nt = q_len >= k ? R.nt : 0;
 	AlnCand *c = cand + R.task0;
@@ -584,7 +804,8 @@ __global__ void aln_reduce_kernel(AlnParams P, const AlnRead *__restrict__ reads
 		}
 	}
 	uint32_t size = 0;
-	AlnRes o = {0, 0};
+	AlnRes o;
+	memset(&o, 0, sizeof(o));
 	if (best_read > k) {   // update_Scores (updatescores.c:203-298)
 		int kept = 0;
 		double minScore = 0, minFrac = P.minFrac;
@@ -617,6 +838,42 @@ __global__ void __launch_bounds__(256) aln_emit_kernel(const uint8_t *__restrict
 	const int warps = (gridDim.x * blockDim.x) >> 5;
 	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
 		const AlnRes rs = res[r];
+		if (rs.nrec) {   // pair: update_Scores_pe (one record + mate block) or update_Scores_se records (updatescores.c:300-488)
+			const AlnRead RB = reads[r], RA = reads[r - 1];
+			const int32_t *pbase = (const int32_t *)(cand + RB.task0);
+			uint8_t *o = out + out_off[r];
+			for (int x = 0; x < rs.nrec; ++x) {
+				const AlnRead &Rm = rs.rmate[x] ? RB : RA;
+				const QView q = read_view(slab, Rm, rs.rorient[x]);
+				const uint8_t *hdr = in + Rm.rec_off + 28 + 8 * (size_t)Rm.words + 4 * (size_t)Rm.nN + 4 * (size_t)Rm.nt;
+				if (rs.form == 1 && x == 1) {   // mate block: int32[3]{q_len, hdrlen, flag} read header
+					if (lane < 3) st_u32b(o + 4 * lane, (uint32_t)(lane == 0 ? Rm.q_len : lane == 1 ? Rm.hl : rs.rflag[x]));
+					o += 12;
+				} else {
+					if (lane < 5) {
+						const int32_t h = lane == 0 ? Rm.q_len : lane == 1 ? rs.rkept[x] : lane == 2 ? rs.rscore[x] : lane == 3 ? Rm.hl : rs.rflag[x];
+						st_u32b(o + 4 * lane, (uint32_t)h);
+					}
+					o += 20;
+				}
+				for (int i = lane; i < Rm.q_len; i += 32) o[i] = q.b[i];
+				o += Rm.q_len;
+				for (int i = lane; i < Rm.hl; i += 32) o[i] = hdr[i];
+				o += Rm.hl;
+				if (!(rs.form == 1 && x == 1)) {
+					const int32_t *arr = pbase + rs.roff[x];
+					const int kept = rs.rkept[x], cap = RB.nt;
+					for (int i = lane; i < kept; i += 32) {
+						st_u32b(o + 4 * (size_t)i, (uint32_t)arr[i]);
+						st_u32b(o + 4 * (size_t)(kept + i), (uint32_t)arr[cap + i]);
+						st_u32b(o + 4 * (size_t)(2 * kept + i), (uint32_t)arr[2 * cap + i]);
+					}
+					o += 12 * (size_t)kept;
+				}
+				__syncwarp();
+			}
+			continue;
+		}
 		if (rs.best == 0) continue;
 		const AlnRead R = reads[r];
 		uint8_t *o = out + out_off[r];
@@ -657,7 +914,7 @@ static AlnParams make_params(const kmagpu_db *db, const kmagpu_params *p) {
 	memcpy(P.pen.d, p->d, sizeof(P.pen.d));
 	P.pen.d8 = 1;
 	for (int i = 0; i < 25; ++i) if (p->d[i] < -128 || p->d[i] > 127) P.pen.d8 = 0;
-	P.k = db->info.kmerindex; P.mq = p->mq; P.one2one = p->one2one; P.exhaustive = p->exhaustive; P.minlen = p->minlen;
+	P.k = db->info.kmerindex; P.mq = p->mq; P.one2one = p->one2one; P.exhaustive = p->exhaustive; P.minlen = p->minlen; P.Wl = p->Wl; P.PE = p->PE;
 	P.scoreT = p->scoreT; P.mrc = p->mrc; P.minFrac = p->minFrac;
 	return P;
 }
@@ -768,13 +1025,14 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 	KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
 	KG_CUDA(cudaStreamSynchronize(st));
 	KG_CUDA(cudaGetLastError());
-	if (h[A_BAD]) { kmagpu_set_error("%llu paired-end records in the stage-2 stream: not supported by kmagpu_align_batch yet", h[A_BAD]); return -1; }
+	if (h[A_BAD]) { kmagpu_set_error("%llu pair records in the stage-2 stream in a form -apm p never writes (mate shorter than k, or strand-undecided pair)", h[A_BAD]); return -1; }
 	const size_t slab_units = (size_t)h[A_SLAB];
 	const int ntasks = (int)h[A_TASKS];
 	const int maxq = (int)h[A_MAXQ];
 	b.ntasks = ntasks;
 	if (b.d_slab.reserve(8 * (slab_units + 4)) || b.d_taskread.reserve(4 * ((size_t)ntasks + 1)) ||
 	    b.d_cand.reserve(sizeof(AlnCand) * ((size_t)ntasks + 1)) || b.d_ovf.reserve(4 * ((size_t)ntasks + 1))) return -1;
+	KG_CUDA(cudaMemcpyAsync(task_off + n, &ntasks, 4, cudaMemcpyHostToDevice, st));   // the prep kernel reads off[r + 1]
 	aln_prep_kernel<<<db->sm_count * 8, 256, 0, st>>>(b.in, n, reads, slab_off, task_off, (uint64_t *)b.d_slab.p, (int32_t *)b.d_taskread.p, P.k);
 	++launches;
 	KG_CUDA(cudaEventRecord(db->ev[3], st));
@@ -839,7 +1097,7 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 		}
 	}
 	uint32_t *recsize = (uint32_t *)b.d_recsize.p, *recoff = recsize + n + 1;
-	aln_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(P, reads, n, (AlnCand *)b.d_cand.p, db->tix.meta, as, uas, recsize,
+	aln_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(P, b.in, reads, n, (AlnCand *)b.d_cand.p, db->tix.meta, as, uas, recsize,
 		(AlnRes *)b.d_res.p, ctr);
 	kg_exscan(recsize, n, recoff, partial, ctr + A_OUT, st);
 	launches += 4;

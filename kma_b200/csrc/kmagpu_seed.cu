@@ -30,7 +30,11 @@
 #define KG_WORDS 12           // staged u64 words per chunk: (256 + 31 + 31) / 32 + 2
 #define KG_MISS 0xFFFFFFFFu
 
-struct SeedRes { int32_t score, ntmpl, flag; uint32_t pool_off; };
+struct SeedRes { int32_t score, ntmpl, flag; uint32_t pool_off; int32_t src, rev; };   // src: record that supplies read + name, rev: emit its reverse complement
+
+// paired end: what get_kmers_for_pair (savekmers.c:427) leaves behind for one mate -- per strand the templates seen
+// (first-seen order) with their clamped scores, and the larger of the two strands' hit counts
+struct MateRes { uint32_t off_f, off_r; int32_t n_f, n_r, hits, scanned; };
 
 struct SeedParams {
 	int32_t M, MM, U, W1, exhaustive;
@@ -38,7 +42,7 @@ struct SeedParams {
 
 // counters living in d_ctr (uint64 slots)
 enum { C_WORK = 0, C_POOL = 1, C_OVF = 2, C_WORK2 = 3, C_POOLFAIL = 4, C_LOOKUPS = 5, C_HITS = 6, C_LISTS = 7,
-       C_LISTIDS = 8, C_MAPPED = 9, C_WORDS = 10, C_TOTAL = 11, C_N = 16 };
+       C_LISTIDS = 8, C_MAPPED = 9, C_WORDS = 10, C_TOTAL = 11, C_POOL2 = 12, C_N = 16 };
 
 // ---------------------------------------------------------------- small device helpers
 
@@ -160,7 +164,9 @@ struct WarpStats { unsigned lookups, hits, lists, listids; };
 // (hash mode only; store is left clean).
 template <bool DENSE>
 __device__ int scan_strand(const KgHashView &hv, const SeedParams &p, const ReadCtx &rc, int strand,
-                           Store<DENSE> &st, uint32_t *hits, uint64_t *sw, int *nbest, WarpStats &ws) {
+                           Store<DENSE> &st, uint32_t *hits, uint64_t *sw, int *nbest, WarpStats &ws,
+                           int2 *pool2 = nullptr, unsigned long long pool2_cap = 0, unsigned long long *ctr = nullptr,
+                           uint32_t *list_off = nullptr) {
 	const unsigned lane = threadIdx.x & 31;
 	const int k = hv.kmersize;
 	const int L = rc.seqlen;
@@ -325,6 +331,26 @@ __device__ int scan_strand(const KgHashView &hv, const SeedParams &p, const Read
 		__syncwarp();
 	}
 
+	if (pool2) {   // paired end: every template seen keeps its clamped score (savekmers.c:654-686); returns the hit count
+		unsigned long long po = 0;
+		if (lane == 0) po = atomicAdd(&ctr[C_POOL2], (unsigned long long)st.ncand);
+		po = __shfl_sync(0xffffffffu, po, 0);
+		const bool fits = po + st.ncand <= pool2_cap;
+		if (!fits && lane == 0) atomicAdd(&ctr[C_POOLFAIL], 1ull);
+		for (int i = lane; i < st.ncand; i += 32) {
+			const int s = st.cand[i];
+			if (fits) pool2[po + i] = make_int2(st.tmpl_of(s), max(st.score[s], 0));
+			if (DENSE) { st.score[s] = 0; st.ext[s] = 0; st.incl[s] = 0; }
+		}
+		__syncwarp();
+		if (!DENSE) {
+			for (int i = lane; i < KG_CAP; i += 32) st.keys[i] = 0;
+			__syncwarp();
+		}
+		*nbest = st.ncand;
+		*list_off = (uint32_t)po;
+		return nhits;
+	}
 	// arg-max set in first-seen order (getBestMatch, savekmers.c:273-294), negatives clamp to 0
 	int best = 0;
 	for (int i = lane; i < st.ncand; i += 32) best = max(best, st.score[st.cand[i]]);
@@ -362,7 +388,8 @@ __global__ void __launch_bounds__(KG_WARPS * 32)
 seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, const uint32_t *__restrict__ rec_off,
                int nreads, SeedRes *__restrict__ res, uint32_t *__restrict__ recsize, int32_t *__restrict__ pool,
                unsigned long long pool_cap, unsigned long long *ctr, uint32_t *__restrict__ ovf_list,
-               uint8_t *dense_scratch, size_t dense_stride) {
+               uint8_t *dense_scratch, size_t dense_stride, const uint8_t *__restrict__ kinds, MateRes *__restrict__ mates,
+               int2 *pool2, unsigned long long pool2_cap) {
 	__shared__ uint32_t s_hits[KG_WARPS][KG_CHUNK];
 	__shared__ uint64_t s_words[KG_WARPS][KG_WORDS];
 	__shared__ int s_tab[DENSE ? 1 : KG_WARPS][DENSE ? 1 : 3 * KG_CAP];
@@ -406,7 +433,26 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 		rc.N = rc.seq + 8 * (size_t)rc.words;
 		words_seen += rc.words;
 
-		SeedRes out = {0, 0, 0, 0};
+		if (kinds && kinds[r]) {   // a mate of a pair: keep both strands' template scores for pair_select_kernel
+			MateRes m = {0, 0, 0, 0, 0, 0};
+			bool ovf = false;
+			if (rc.seqlen >= k) {
+				int nf = 0, nr = 0;
+				uint32_t of = 0, orr = 0;
+				st.cand = candF;
+				const int hf = scan_strand<DENSE>(hv, p, rc, 0, st, hits, sw, &nf, ws, pool2, pool2_cap, ctr, &of);
+				int hr = -1;
+				if (hf >= 0) { st.cand = candR; hr = scan_strand<DENSE>(hv, p, rc, 1, st, hits, sw, &nr, ws, pool2, pool2_cap, ctr, &orr); }
+				if (hf < 0 || hr < 0) {
+					ovf = true;
+					if (lane == 0) ovf_list[atomicAdd(&ctr[C_OVF], 1ull)] = (uint32_t)r;
+				} else { m.off_f = of; m.off_r = orr; m.n_f = nf; m.n_r = nr; m.hits = max(hf, hr); m.scanned = 1; }
+			}
+			if (lane == 0 && !ovf) mates[r] = m;
+			__syncwarp();
+			continue;
+		}
+		SeedRes out = {0, 0, 0, 0, r, 0};
 		uint32_t size = 0;
 		if (rc.seqlen >= k) {
 			int nf = 0, nr = 0;
@@ -433,6 +479,7 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 				out.score = bf > br ? bf : (bf < br ? br : -bf);
 				out.ntmpl = nt;
 				out.flag = bf < br ? 16 : 0;
+				out.rev = bf < br ? 1 : 0;
 				out.pool_off = (uint32_t)po;
 				size = 28u + 8u * rc.words + 4u * rc.nN + 4u * nt + rc.hdrlen;
 				++mapped;
@@ -453,6 +500,138 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 	}
 }
 
+
+// ---------------------------------------------------------------- paired-end selection (-apm p)
+
+__device__ __forceinline__ int list_score(const int2 *L, int n, int t) {   // Score[t] of a strand (0 when not seen)
+	for (int i = 0; i < n; ++i) if (L[i].x == t) return L[i].y;
+	return 0;
+}
+
+// save_kmers_penaltyPair (savekmers.c:3572-3777) over the per-strand score lists of the two mates, one thread per
+// pair: getFirstPen (:1383), getSecondBestPen (:1415) / getF_Best (:1648), the proper-pair test and flag logic, and
+// printPair's record order (ankers.c:150). Slot r / r+1 of res + recsize describe the first / second record emitted.
+__global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ rec_off, int nrec,
+		const uint8_t *__restrict__ kinds, const MateRes *__restrict__ mates, const int2 *__restrict__ pool2, int32_t *pool,
+		unsigned long long pool_cap, unsigned long long *ctr, SeedRes *res, uint32_t *recsize, int k, int PE) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nrec || kinds[r] != 1) return;
+	const MateRes A = mates[r], B = mates[r + 1];
+	const uint8_t *recA = in + rec_off[r], *recB = in + rec_off[r + 1];
+	const int lenA = (int)ld_u32u(recA), lenB = (int)ld_u32u(recB);
+	const int2 *F1 = pool2 + A.off_f, *R1 = pool2 + A.off_r, *F2 = pool2 + B.off_f, *R2 = pool2 + B.off_r;
+	const int n1 = A.n_f + A.n_r, n2 = B.n_f + B.n_r;
+	SeedRes o1 = {0, 0, 0, 0, r, 0}, o2 = {0, 0, 0, 0, r + 1, 0};
+	uint32_t sz1 = 0, sz2 = 0;
+	unsigned long long po = atomicAdd(&ctr[C_POOL], (unsigned long long)(n1 + n2));
+	if (po + n1 + n2 > pool_cap) { atomicAdd(&ctr[C_POOLFAIL], 1ull); res[r] = o1; res[r + 1] = o2; recsize[r] = recsize[r + 1] = 0; return; }
+	int32_t *rt = pool + po, *bt = rt + n1;
+	int nrt = 0, nbt = 0, best = 0, best_r = 0;
+	const int hc = A.hits, hc_r = B.hits;
+	bool proper = false;
+	if (hc) {   // getFirstPen
+		for (int i = 0; i < A.n_f; ++i) { rt[nrt++] = F1[i].x; best = max(best, F1[i].y); }
+		for (int i = 0; i < A.n_r; ++i) { rt[nrt++] = -R1[i].x; best = max(best, R1[i].y); }
+	}
+	if (hc_r) {
+		if (0 < best) {   // getSecondBestPen
+			for (int i = 0; i < B.n_f; ++i) { bt[nbt++] = F2[i].x; best_r = max(best_r, F2[i].y); }
+			for (int i = 0; i < B.n_r; ++i) { bt[nbt++] = -R2[i].x; best_r = max(best_r, R2[i].y); }
+			int hits = 0;
+			if (best_r) {
+				int comp = max(0, best + best_r - PE);
+				for (int i = 0; i < nrt; ++i) {
+					const int t = rt[i];
+					int sc = 0 < t ? list_score(R2, B.n_r, t) : list_score(F2, B.n_f, -t);   // the mate on the opposite strand
+					if (0 < sc) {
+						sc += i < A.n_f ? F1[i].y : R1[i - A.n_f].y;
+						if (comp < sc) { comp = sc; hits = 1; rt[0] = t; }
+						else if (comp == sc) rt[hits++] = t;
+					}
+				}
+			}
+			if (hits) { proper = true; nrt = hits; }
+			else {
+				for (int i = 0; i < nrt; ++i) if (best == (i < A.n_f ? F1[i].y : R1[i - A.n_f].y)) rt[hits++] = rt[i];
+				nrt = hits;
+				hits = 0;
+				for (int i = 0; i < nbt; ++i) {
+					const int t = bt[i];
+					if (0 < t) { if (best_r == F2[i].y) bt[hits++] = t; }
+					else if (best_r <= R2[i - B.n_f].y) bt[hits++] = t;
+				}
+				nbt = hits;
+			}
+		} else {          // getF_Best: arg-max set of the second mate alone (written where regionTemplates is expected)
+			nrt = 0;
+			for (int i = 0; i < n2; ++i) {
+				const int t = i < B.n_f ? F2[i].x : -R2[i - B.n_f].x, sc = i < B.n_f ? F2[i].y : R2[i - B.n_f].y;
+				if (best_r < sc) { best_r = sc; nrt = 1; rt[0] = t; }
+				else if (best_r == sc) rt[nrt++] = t;
+			}
+		}
+	}
+	// the reads are left reverse-complemented by the scan (savekmers.c:471); cur = 1 means "emit the reverse complement"
+	int curA = A.scanned, curB = B.scanned;
+	int flag = 65, flag_r = 129;
+	const uint32_t baseA = 28u + 8u * ld_u32u(recA + 4) + 4u * ld_u32u(recA + 8) + (uint32_t)abs((int)ld_u32u(recA + 12));
+	const uint32_t baseB = 28u + 8u * ld_u32u(recB + 4) + 4u * ld_u32u(recB + 8) + (uint32_t)abs((int)ld_u32u(recB + 12));
+	const uint32_t rt_off = (uint32_t)po, bt_off = (uint32_t)po + (uint32_t)n1;
+	if (0 < best && 0 < best_r) {
+		if (proper) {
+			flag |= 2; flag_r |= 2;
+			const int comp = min(hc + hc_r, best + best_r);
+			if (k <= comp || (lenA + lenB - comp - (k << 1)) < comp * k) {
+				if (0 < rt[0]) {
+					flag |= 32; flag_r |= 16; curA ^= 1;
+					o1.score = best; o1.ntmpl = 0; o1.flag = flag; o1.src = r; o1.rev = curA; o1.pool_off = rt_off; sz1 = baseA;
+					o2.score = best_r; o2.ntmpl = nrt; o2.flag = flag_r; o2.src = r + 1; o2.rev = curB; o2.pool_off = rt_off; sz2 = baseB + 4u * nrt;
+				} else {
+					flag |= 16; flag_r |= 32; curB ^= 1;
+					for (int i = 0; i < nrt; ++i) rt[i] = -rt[i];
+					o1.score = best_r; o1.ntmpl = 0; o1.flag = flag_r; o1.src = r + 1; o1.rev = curB; o1.pool_off = rt_off; sz1 = baseB;
+					o2.score = best; o2.ntmpl = nrt; o2.flag = flag; o2.src = r; o2.rev = curA; o2.pool_off = rt_off; sz2 = baseA + 4u * nrt;
+				}
+			}
+		} else {
+			int h = min(hc, best), h_r = min(hc_r, best_r), sA = best, sB = best_r;
+			h = k <= h || (lenA - h - k) < h * k;
+			if (h) {
+				if (0 < rt[0]) { curA ^= 1; if (rt[nrt - 1] < 0) sA = -sA; }
+				else { flag |= 16; flag_r |= 32; for (int i = 0; i < nrt; ++i) rt[i] = -rt[i]; }
+			}
+			h_r = k <= h_r || (lenB - h_r - k) < h_r * k;
+			if (h_r) {
+				if (0 < bt[0]) { curB ^= 1; if (bt[nbt - 1] < 0) sB = -sB; }
+				else { flag |= 32; flag_r |= 16; for (int i = 0; i < nbt; ++i) bt[i] = -bt[i]; }
+			}
+			if (h) { o1.score = sA; o1.ntmpl = nrt; o1.flag = flag; o1.src = r; o1.rev = curA; o1.pool_off = rt_off; sz1 = baseA + 4u * nrt; }
+			if (h_r) { o2.score = sB; o2.ntmpl = nbt; o2.flag = flag_r; o2.src = r + 1; o2.rev = curB; o2.pool_off = bt_off; sz2 = baseB + 4u * nbt; }
+		}
+	} else if (0 < best) {
+		const int h = min(hc, best);
+		if (k <= h || (lenA - h - k) < h * k) {
+			int sA = best;
+			flag |= 8 | 32;
+			if (0 < rt[0]) { curA ^= 1; if (rt[nrt - 1] < 0) sA = -sA; }
+			else { flag |= 16; for (int i = 0; i < nrt; ++i) rt[i] = -rt[i]; }
+			o1.score = sA; o1.ntmpl = nrt; o1.flag = flag; o1.src = r; o1.rev = curA; o1.pool_off = rt_off; sz1 = baseA + 4u * nrt;
+		}
+	} else if (0 < best_r) {
+		const int h = min(hc_r, best_r);
+		if (k <= h || (lenB - h - k) < h * k) {
+			int sB = best_r;
+			flag_r |= 8 | 32;
+			if (0 < rt[0]) { curB ^= 1; if (rt[nrt - 1] < 0) sB = -sB; }
+			else { flag_r |= 16; for (int i = 0; i < nrt; ++i) rt[i] = -rt[i]; }
+			o2.score = sB; o2.ntmpl = nrt; o2.flag = flag_r; o2.src = r + 1; o2.rev = curB; o2.pool_off = rt_off; sz2 = baseB + 4u * nrt;
+		}
+	}
+	res[r] = o1; res[r + 1] = o2;
+	recsize[r] = sz1; recsize[r + 1] = sz2;
+	if (sz1 || sz2) atomicAdd(&ctr[C_MAPPED], 1ull);
+}
+
 // ---------------------------------------------------------------- stage-2 record writer
 
 // one warp per mapped read: header, sequence (forward copy or reverse complement, compdna.c:228),
@@ -465,12 +644,12 @@ __global__ void __launch_bounds__(256) emit_records_kernel(const uint8_t *__rest
 	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nreads; r += warps) {
 		const SeedRes rs = res[r];
 		if (rs.score == 0) continue;
-		const uint8_t *rec = in + rec_off[r];
+		const uint8_t *rec = in + rec_off[rs.src];
 		const int seqlen = (int)ld_u32u(rec), words = (int)ld_u32u(rec + 4), nN = (int)ld_u32u(rec + 8);
 		const int hdrlen = abs((int)ld_u32u(rec + 12));
 		const uint8_t *seq = rec + 16, *N = seq + 8 * (size_t)words, *hdr = N + 4 * (size_t)nN;
 		uint8_t *o = out + out_off[r];
-		const bool rev = rs.flag & 16;
+		const bool rev = rs.rev != 0;
 		if (lane < 7) {
 			int32_t h = lane == 0 ? seqlen : lane == 1 ? words : lane == 2 ? nN : lane == 3 ? rs.score
 			          : lane == 4 ? rs.ntmpl : lane == 5 ? hdrlen : rs.flag;
@@ -511,7 +690,7 @@ __global__ void lookup_kernel(KgHashView hv, const uint64_t *kmers, size_t n, in
 
 int kg_seed_free(kmagpu_db *db) {
 	SeedBatch &b = db->seed;
-	KgBuf *all[] = {&b.d_in, &b.d_off, &b.d_res, &b.d_pool, &b.d_recoff, &b.d_out, &b.d_ctr, &b.d_partial, &b.d_dense,
+	KgBuf *all[] = {&b.d_in, &b.d_off, &b.d_res, &b.d_pool, &b.d_recoff, &b.d_out, &b.d_ctr, &b.d_partial, &b.d_dense, &b.d_kinds, &b.d_mates, &b.d_pool2,
 	                &b.h_off, &b.h_in, &b.h_out};
 	for (KgBuf *x : all) x->release();
 	return 0;
@@ -547,11 +726,28 @@ extern "C" int kmagpu_seed_upload(kmagpu_db *db, const void *stage1, size_t nbyt
 		ip += len;
 	}
 	off[n] = (uint32_t)ip;
+	// pairs: the first mate is written with a negative header length (runinput.c:789), its mate follows
+	b.h_kinds.assign(n + 1, 0);
+	size_t npairs = 0;
+	for (size_t i = 0; i < n; ++i) {
+		int32_t hl;
+		memcpy(&hl, in + off[i] + 12, 4);
+		if (hl < 0 && !b.h_kinds[i]) {
+			if (i + 1 >= n) { kmagpu_set_error("stage-1 stream ends inside a pair"); return -1; }
+			b.h_kinds[i] = 1; b.h_kinds[i + 1] = 2; ++npairs;
+		}
+	}
+	b.npairs = (int64_t)npairs;
 	b.nreads = (int64_t)n;
 	b.in_bytes = ip;
 	b.ran = false;
-	if (nreads_out) *nreads_out = (int64_t)n;
+	// what the reference counts (savekmers.c:183): one per single read, one per pair
+	if (nreads_out) *nreads_out = (int64_t)(n - npairs);
 	if (b.d_in.reserve(ip + 64) || b.d_off.reserve(4 * (n + 1))) return -1;
+	if (npairs) {
+		if (b.d_kinds.reserve(n + 1)) return -1;
+		KG_CUDA(cudaMemcpyAsync(b.d_kinds.p, b.h_kinds.data(), n + 1, cudaMemcpyHostToDevice, db->stream));
+	}
 	KG_CUDA(cudaEventRecord(db->ev[0], db->stream));
 	KG_CUDA(cudaMemcpyAsync(b.d_in.p, in, ip, cudaMemcpyHostToDevice, db->stream));
 	KG_CUDA(cudaMemsetAsync((uint8_t *)b.d_in.p + ip, 0, 64, db->stream));
@@ -585,20 +781,36 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 		if (b.d_dense.reserve(dense_bytes)) return -1;
 		KG_CUDA(cudaMemsetAsync(b.d_dense.p, 0, b.d_dense.cap, db->stream));
 	}
+	const bool pe = b.npairs > 0;
+	const uint8_t *kinds = pe ? (const uint8_t *)b.d_kinds.p : nullptr;
+	if (pe) {
+		if (b.pool2_cap < (size_t)n * 24 + 1024) b.pool2_cap = (size_t)n * 24 + 1024;
+		if (b.pool_cap < (size_t)n * 24 + 1024) b.pool_cap = (size_t)n * 24 + 1024;
+		if (b.d_mates.reserve(sizeof(MateRes) * ((size_t)n + 1))) return -1;
+	}
 	uint32_t *recsize = (uint32_t *)b.d_recoff.p, *recoff = recsize + n + 1;
 	uint32_t *partial = (uint32_t *)b.d_partial.p, *ovf = partial + ntiles + 1;
 	unsigned long long *ctr = (unsigned long long *)b.d_ctr.p;
 	int launches = 0;
 	for (int attempt = 0;; ++attempt) {
 		if (b.d_pool.reserve(4 * b.pool_cap)) return -1;
+		if (pe && b.d_pool2.reserve(8 * b.pool2_cap)) return -1;
 		KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * C_N, db->stream));
 		KG_CUDA(cudaEventRecord(db->ev[2], db->stream));
 		seed_se_kernel<false><<<grid, KG_WARPS * 32, 0, db->stream>>>(db->hv, sp, (const uint8_t *)b.d_in.p,
 			(const uint32_t *)b.d_off.p, n, (SeedRes *)b.d_res.p, recsize, (int32_t *)b.d_pool.p,
-			(unsigned long long)b.pool_cap, ctr, ovf, nullptr, 0);
+			(unsigned long long)b.pool_cap, ctr, ovf, nullptr, 0, kinds, (MateRes *)b.d_mates.p, (int2 *)b.d_pool2.p,
+			(unsigned long long)b.pool2_cap);
 		seed_se_kernel<true><<<dense_grid, KG_WARPS * 32, 0, db->stream>>>(db->hv, sp, (const uint8_t *)b.d_in.p,
 			(const uint32_t *)b.d_off.p, n, (SeedRes *)b.d_res.p, recsize, (int32_t *)b.d_pool.p,
-			(unsigned long long)b.pool_cap, ctr, ovf, (uint8_t *)b.d_dense.p, dense_stride);
+			(unsigned long long)b.pool_cap, ctr, ovf, (uint8_t *)b.d_dense.p, dense_stride, kinds, (MateRes *)b.d_mates.p,
+			(int2 *)b.d_pool2.p, (unsigned long long)b.pool2_cap);
+		if (pe) {
+			pair_select_kernel<<<(n + 127) / 128, 128, 0, db->stream>>>((const uint8_t *)b.d_in.p, (const uint32_t *)b.d_off.p, n, kinds,
+				(const MateRes *)b.d_mates.p, (const int2 *)b.d_pool2.p, (int32_t *)b.d_pool.p, (unsigned long long)b.pool_cap, ctr,
+				(SeedRes *)b.d_res.p, recsize, db->hv.kmersize, prm->PE);
+			++launches;
+		}
 		KG_CUDA(cudaEventRecord(db->ev[3], db->stream));
 		kg_exscan(recsize, n, recoff, partial, ctr + C_TOTAL, db->stream);
 		launches += 5;
@@ -608,7 +820,8 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 		KG_CUDA(cudaGetLastError());
 		if (h[C_POOLFAIL]) {   // template pool too small: grow and redo (rare)
 			if (attempt > 4) { kmagpu_set_error("template pool overflow persists"); return -1; }
-			b.pool_cap = (size_t)h[C_POOL] + 1024;
+			b.pool_cap = std::max(b.pool_cap, (size_t)h[C_POOL] + 1024);
+			b.pool2_cap = std::max(b.pool2_cap, (size_t)h[C_POOL2] + 1024);
 			continue;
 		}
 		b.out_bytes = (size_t)h[C_TOTAL];

@@ -61,6 +61,20 @@ def stage1_records_fast(reads: np.ndarray, prefix: str = "r", first: int = 0) ->
     return rec.reshape(-1)
 
 
+def stage1_pairs(r1, r2, prefix="r") -> np.ndarray:
+    """Stage-1 stream of read pairs (printFsa_pair, runinput.c:789): mate records interleaved, the first mate written
+    with a NEGATIVE header length. Names as `kma -ipe a.fq b.fq` emits them for '@<prefix><i>' in both files."""
+    out = bytearray()
+    for i, (a, b) in enumerate(zip(r1, r2)):
+        name = f"{prefix}{i}".encode() + b"\0"
+        for mate, r in enumerate((a, b)):
+            r = np.asarray(r, dtype=np.uint8)
+            w, npos = pack_2bit(r)
+            out += np.array([len(r), len(w), len(npos), -len(name) if mate == 0 else len(name)], dtype=np.int32).tobytes()
+            out += w.tobytes() + npos.tobytes() + name
+    return np.frombuffer(bytes(out), dtype=np.uint8)
+
+
 def stage1_records(reads, names=None, prefix="r") -> np.ndarray:
     """General (ragged) stage-1 stream."""
     out = bytearray()

@@ -164,3 +164,28 @@ def test_nw_batch_vs_oracle():
             L.orc_nw(pen, tw.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), int(p[6]), int(p[1]), int(p[2]), 0,
                      int(p[5]), int(p[7]), want)
             assert list(out[i]) == list(want), (i, list(p), list(out[i]), list(want))
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", [51, 53])
+def test_paired_end_alignment_vs_oracle(tmp_path, seed):
+    """-apm p pairs through alnFragsPenaltyPE + update_Scores_pe/_se on the GPU: frag_raw bytes and ConClave sums"""
+    from tests.test_oracle_pair import make_pairs
+    prefix, s1, s2 = make_pairs(tmp_path, seed, n=3000)
+    s2 = np.frombuffer(s2, dtype=np.uint8)
+    ofrag, oa, ou, ocand, cells = util.oracle_align_stream(prefix, s2, one2one=False)
+    db = api.TemplateDB(prefix)
+    frag, a, u, cand, st = db.alnFrags_batch(s2, want_cand=True)
+    # stage 2 + stage 3 chained in HBM give the same stream
+    db.seed_upload(s1); db.seed_run()
+    db.align_from_seed(); db.align_run()
+    frag2, a2, u2, _ = db.align_download()
+    db.close()
+    assert st.tasks == len(ocand)
+    ok = (cand[:, 1:] == ocand[:, 1:])
+    ok[:, 4] |= (ocand[:, 2] == 0)   # `match` is undefined where nothing aligned
+    assert ok.all(), f"candidate rows differ, first: {cand[~ok.all(axis=1)][:1]} want {ocand[~ok.all(axis=1)][:1]}"
+    assert np.array_equal(a, oa) and np.array_equal(u, ou)
+    fb = frag.tobytes()
+    assert fb == ofrag, f"frag_raw differs at byte {_first_diff(fb, ofrag)} of {len(ofrag)} (got {len(fb)})"
+    assert frag2.tobytes() == ofrag and np.array_equal(a2, oa) and np.array_equal(u2, ou)

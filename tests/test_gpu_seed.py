@@ -108,3 +108,29 @@ def test_full_size_properties(tmp_path):
     recs_rc = records.parse_stage2(np.frombuffer(got_rc, dtype=np.uint8))
     assert [abs(r["score"]) for r in recs] == [abs(r["score"]) for r in recs_rc]
     assert [sorted(abs(t) for t in r["templates"]) for r in recs] == [sorted(abs(t) for t in r["templates"]) for r in recs_rc]
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", [51, 52])
+def test_paired_end_stage2_vs_oracle(tmp_path, seed):
+    """-ipe ... -apm p: get_kmers_for_pair + save_kmers_penaltyPair + printPair on the GPU, byte-exact"""
+    from tests.test_oracle_pair import make_pairs
+    prefix, s1, s2 = make_pairs(tmp_path, seed, n=3000)
+    want = util.oracle_seed_stream(prefix, s1)
+    assert want.tobytes() == s2
+    got, st = _gpu_stream(prefix, s1)
+    assert got == s2
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+def test_paired_end_many_templates_dense_path(tmp_path):
+    """pairs from a 300-variant family: the per-strand template lists overflow the shared table -> dense path"""
+    names, seqs = synth.gene_db(23, n_families=2, n_variants=300, len_lo=500, len_hi=600)
+    synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    r1, r2 = synth.paired_reads(24, seqs, 300, sub=0.01, ins_lo=200, ins_hi=400)
+    s1 = records.stage1_pairs(r1, r2)
+    want = util.oracle_seed_stream(str(tmp_path / "db"), s1)
+    got, st = _gpu_stream(str(tmp_path / "db"), s1)
+    assert st.overflow_reads > 0
+    assert got == want.tobytes()
