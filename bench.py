@@ -33,9 +33,9 @@ sys.path.insert(0, ROOT)
 from kma_b200 import synth, records, dbbuild  # noqa: E402
 
 DB_SEED, READ_SEED = 42, 7
-WORKLOAD = ("C2-shaped: gene DB (300 families x 10 variants, 0.5-3 kb, k=16) + 2M x 150 bp reads per GPU mapped single-end (-1t1): "
-            "stage 2 (k-mer seeding + template scoring) + stage 3 alignment pass (MEM chaining + NW + update_Scores); "
-            "paired-end selection (SURVEY 8 a4) is not built yet")
+WORKLOAD = ("C2: redundant gene DB (300 families x 10 variants, 0.5-3 kb, k=16) + 2M synthetic 2x150 bp read pairs per GPU, "
+            "-ipe -apm p: stage 2 (k-mer seeding + template scoring + pair selection) + stage 3 alignment pass "
+            "(MEM chaining + NW + alnFragsPenaltyPE + update_Scores)")
 METRIC = "mapped reads/sec (seeding + chaining + NW alignment pass)"
 
 
@@ -102,19 +102,20 @@ def algorithmic_bytes(st, values_width):
     return (4 * st.lookups + 8 * st.hits + values_width * (st.list_fetches + st.list_ids) + 8 * st.read_words)
 
 
-def cpu_reference(prefix, reads, cores, tmp):
-    """Reference arm: the unmodified reference on `reads`: `kma -s2` (FASTQ parse + stage 2) piped into
-    alnFrags_threaded on `cores` pthreads (oracle/ref_harness.c drives the reference's own stage-3 entry point the
-    way runKMA does) -- the same span as our step."""
+def cpu_reference(prefix, r1, r2, cores, tmp):
+    """Reference arm: the unmodified reference on the read pairs: `kma -ipe ... -apm p -s2` (FASTQ parse + stage 2)
+    piped into alnFrags_threaded on `cores` pthreads (oracle/ref_harness.c drives the reference's own stage-3 entry
+    point the way runKMA does) -- the same span as our step. Returns reads/s (2 reads per pair)."""
     kma = os.path.join(ROOT, "oracle", "_ref", "kma")
     aln = os.path.join(ROOT, "oracle", "_ref", "ref_aln")
-    fq = os.path.join(tmp, "sample.fq")
-    synth.write_fastq(fq, reads, prefix="r")
+    f1, f2 = os.path.join(tmp, "sample_1.fq"), os.path.join(tmp, "sample_2.fq")
+    synth.write_fastq(f1, r1, prefix="r")
+    synth.write_fastq(f2, r2, prefix="r")
     t0 = time.perf_counter()
     with open(os.devnull, "wb") as dn:
-        p1 = subprocess.Popen([kma, "-i", fq, "-o", os.path.join(tmp, "o"), "-t_db", prefix, "-1t1", "-s2", "-t", str(cores)],
+        p1 = subprocess.Popen([kma, "-ipe", f1, f2, "-o", os.path.join(tmp, "o"), "-t_db", prefix, "-apm", "p", "-s2", "-t", str(cores)],
                               stdout=subprocess.PIPE, stderr=dn)
-        p2 = subprocess.Popen([aln, prefix, "-", os.path.join(tmp, "fr.out"), os.path.join(tmp, "sc.out"), "-1t1", "-t", str(cores)],
+        p2 = subprocess.Popen([aln, prefix, "-", os.path.join(tmp, "fr.out"), os.path.join(tmp, "sc.out"), "-apm-p", "-t", str(cores)],
                               stdin=p1.stdout, stdout=dn, stderr=dn)
         p1.stdout.close()
         rc2 = p2.wait()
@@ -122,7 +123,7 @@ def cpu_reference(prefix, reads, cores, tmp):
     dt = time.perf_counter() - t0
     if rc1 or rc2:
         raise RuntimeError(f"reference run failed: kma rc={rc1}, ref_aln rc={rc2}")
-    return len(reads) / dt, dt
+    return 2 * len(r1) / dt, dt
 
 
 def cpu_port(prefix, s1, nreads):
@@ -144,7 +145,7 @@ def cpu_port(prefix, s1, nreads):
     fo, fb = C.c_void_p(), C.c_size_t()
     t0 = time.perf_counter()
     n2 = L.orc_seed_stream(db, p, s1.ctypes.data, len(s1), out.ctypes.data, len(out), None)
-    L.orc_align_stream(db, prefix.encode(), p, out.ctypes.data, n2, 1, 0.5, 0, 16, 0.0, C.byref(fo), C.byref(fb),
+    L.orc_align_stream(db, prefix.encode(), p, out.ctypes.data, n2, 0, 0.5, 0, 16, 0.0, C.byref(fo), C.byref(fb),
                        a.ctypes.data, u.ctypes.data, None, None, None)
     dt = time.perf_counter() - t0
     return nreads / dt, dt
@@ -190,8 +191,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=2_000_000, help="reads per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=400_000)
+    ap.add_argument("--pairs", type=int, default=2_000_000, help="read pairs per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=200_000, help="read pairs of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -207,26 +208,26 @@ def main():
         if rank != 0:
             return
         prefix, names, seqs = make_db(workdir)
-        sample = min(args.cpu_sample, args.reads)
-        reads = synth.short_reads(READ_SEED, seqs, sample)
+        sample = min(args.cpu_sample, args.pairs)
+        r1, r2 = synth.paired_reads(READ_SEED, seqs, sample)
         have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "kma"))
         vals = []
         for i in range(args.warmup + args.steps):
             if have_ref:
-                v, dt = cpu_reference(prefix, reads, cores, workdir)
+                v, dt = cpu_reference(prefix, r1, r2, cores, workdir)
             else:
-                v, dt = cpu_port(prefix, records.stage1_records_fast(reads), sample)
+                v, dt = cpu_port(prefix, records.stage1_pairs_fast(r1, r2), 2 * sample)
             if i >= args.warmup:
                 vals.append((v, dt))
-        v = sum(sample for _ in vals) / sum(dt for _, dt in vals)
+        v = sum(2 * sample for _ in vals) / sum(dt for _, dt in vals)
         line = {"impl": "reference", "metric": METRIC,
                 "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * statistics.mean(dt for _, dt in vals), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "reads_per_step": sample},
+                "config": {"workload": WORKLOAD, "pairs_per_step": sample, "reads_per_step": 2 * sample},
                 "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores if have_ref else 1,
                                  "kind": "reference" if have_ref else "port",
-                                 "sample": f"{sample} reads of the same workload per step; unmodified kma -1t1 -s2 -t {cores} | alnFrags_threaded on {cores} pthreads (FASTQ parse + stage 2 + alignment pass)"},
+                                 "sample": f"{sample} read pairs of the same workload per step; unmodified kma -ipe -apm p -s2 -t {cores} | alnFrags_threaded on {cores} pthreads (FASTQ parse + stage 2 + alignment pass)"},
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -249,8 +250,8 @@ def main():
     if rank != 0:
         prefix, names, seqs = make_db(workdir)
 
-    reads = synth.short_reads(READ_SEED + 1000 * rank, seqs, args.reads)
-    s1_np = records.stage1_records_fast(reads, first=rank * args.reads)
+    r1, r2 = synth.paired_reads(READ_SEED + 1000 * rank, seqs, args.pairs)
+    s1_np = records.stage1_pairs_fast(r1, r2, first=rank * args.pairs)
     s1 = torch.empty(len(s1_np), dtype=torch.uint8, pin_memory=True)
     s1.numpy()[:] = s1_np
 
@@ -325,7 +326,7 @@ def main():
         t_allreduce = e0.elapsed_time(e1)
 
     tt = torch.tensor([t_dev, t_e2e, t_wall, t_allreduce], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(st.reads), float(st.mapped), float(sa.frags)], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(st.reads), float(st.mapped), float(sa.frags), float(args.pairs)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
@@ -349,16 +350,16 @@ def main():
         "value": total_reads / (t_dev_max * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_dev_max / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reads_per_gpu_per_step": args.reads, "read_len": 150,
+        "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": args.pairs, "reads_per_gpu_per_step": 2 * args.pairs, "read_len": 150,
                    "db_templates": db.info.DB_size - 1, "db_kmers": int(db.info.n),
-                   "db_device_bytes": int(db.info.device_bytes), "mapped_fraction": float(cnt[1]) / float(cnt[0]),
-                   "aligned_fraction": float(cnt[2]) / float(cnt[0]),
-                   "pairs_per_read": sa.tasks / max(1, sa.reads),
+                   "db_device_bytes": int(db.info.device_bytes), "mapped_pair_fraction": float(cnt[1]) / float(cnt[3]),
+                   "frag_records_per_pair": float(cnt[2]) / float(cnt[3]),
+                   "alignments_per_read": sa.tasks / max(1, sa.reads),
                    "cache": f"stage-1 batch {len(s1_np) / 1e6:.0f} MB + stage-2 stream + read slab + frag_raw {out_bytes / 1e6:.0f} MB per step exceed the 126 MB L2; "
                             "the 150 MB database image (hash table + per-template position index) is mostly L2-resident by nature of this config",
                    "sharding": "reads sharded by rank, database replicated per GPU; one all-reduce of the ConClave score arrays per step",
                    "allreduce_ms": t_ar_max},
-        "e2e": {"value": total_reads / (t_e2e_max * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(len(s1_np)) + 4 * (args.reads + 1),
+        "e2e": {"value": total_reads / (t_e2e_max * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(len(s1_np)) + 10 * args.pairs + 4,
                 "d2h_bytes_per_step": out_bytes + 16 * DBn, "ms_per_step": t_e2e_max / args.steps},
         "gpu_launches": launches,
         "wall_ms_per_step_resident": t_wall_max / args.steps,
@@ -368,7 +369,7 @@ def main():
                      "frac": ach_pair / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": None,
                      "algorithmic_bytes_per_launch": alg_pair, "kernel_ms": ms_pair,
                      "note": "latency/issue bound (dependent index probes, short DP); see nw for the integer roofline",
-                     "per_read": {"pairs": sa.tasks / sa.reads, "index_probes": sa.index_probes / sa.reads, "mems": sa.mems / sa.reads, "nw_cells": cells / sa.reads, "bytes": alg_pair / sa.reads}},
+                     "per_read": {"alignments": sa.tasks / sa.reads, "index_probes": sa.index_probes / sa.reads, "mems": sa.mems / sa.reads, "nw_cells": cells / sa.reads, "bytes": alg_pair / sa.reads}},
         "roofline_seed": {"kernel": "seed_se_kernel<hash>", "bound": "hbm", "achieved": ach_seed, "peak": pk["hbm_gbs"], "unit": "GB/s",
                           "frac": ach_seed / pk["hbm_gbs"], "algorithmic_bytes_per_launch": alg_seed, "kernel_ms": ms_seed,
                           "per_read": {"lookups": st.lookups / st.reads, "hits": st.hits / st.reads,
@@ -379,16 +380,16 @@ def main():
         line["nw"] = nw_gcups(db, seqs, peak_iops)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = min(args.cpu_sample, args.reads)
+        sample = min(args.cpu_sample, args.pairs)
         have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "kma"))
         if have_ref:
-            v, dt = cpu_reference(prefix, reads[:sample], cores, workdir)
+            v, dt = cpu_reference(prefix, r1[:sample], r2[:sample], cores, workdir)
             line["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference",
-                                    "sample": f"first {sample} reads of the step; unmodified kma -1t1 -s2 -t {cores} | alnFrags_threaded on {cores} pthreads (FASTQ parse + stage 2 + alignment pass), {dt:.1f} s"}
+                                    "sample": f"first {sample} read pairs of the step; unmodified kma -ipe -apm p -s2 -t {cores} | alnFrags_threaded on {cores} pthreads (FASTQ parse + stage 2 + alignment pass), {dt:.1f} s"}
         else:
-            v, dt = cpu_port(prefix, records.stage1_records_fast(reads[:sample]), sample)
+            v, dt = cpu_port(prefix, records.stage1_pairs_fast(r1[:sample], r2[:sample]), 2 * sample)
             line["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": 1, "kind": "port",
-                                    "sample": f"first {sample} reads of the step; oracle/liborc.so stage 2 + alignment pass, {dt:.1f} s"}
+                                    "sample": f"first {sample} read pairs of the step; oracle/liborc.so stage 2 + alignment pass, {dt:.1f} s"}
     db.close()
     if rank == 0:
         print(json.dumps(line))

@@ -61,6 +61,18 @@ def stage1_records_fast(reads: np.ndarray, prefix: str = "r", first: int = 0) ->
     return rec.reshape(-1)
 
 
+def stage1_pairs_fast(r1: np.ndarray, r2: np.ndarray, prefix: str = "r", first: int = 0) -> np.ndarray:
+    """Fully vectorised stage-1 stream of N-free equal-length read pairs (printFsa_pair, runinput.c:789) with
+    fixed-width names '<prefix><9-digit index>\\0' in both files: mate records interleaved, first mate with a negative
+    header length."""
+    n, L = r1.shape
+    a = stage1_records_fast(r1, prefix, first).reshape(n, -1)
+    b = stage1_records_fast(r2, prefix, first).reshape(n, -1)
+    hl = len(prefix.encode()) + 10
+    a[:, 12:16] = np.frombuffer(np.array([-hl], dtype=np.int32).tobytes(), dtype=np.uint8)
+    return np.concatenate([a, b], axis=1).reshape(-1)
+
+
 def stage1_pairs(r1, r2, prefix="r") -> np.ndarray:
     """Stage-1 stream of read pairs (printFsa_pair, runinput.c:789): mate records interleaved, the first mate written
     with a NEGATIVE header length. Names as `kma -ipe a.fq b.fq` emits them for '@<prefix><i>' in both files."""
