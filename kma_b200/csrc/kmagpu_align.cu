@@ -27,6 +27,9 @@
 
 #define AL_WARPS 4            // warps per CTA of the pair kernel
 #define AL_BANDW 64           // align.c:511
+#ifndef AL_MINB
+#define AL_MINB 6             // resident CTAs per SM the pair kernel is compiled for (register cap 65536 / (128 * AL_MINB))
+#endif
 #define ST_OK 0
 #define ST_OVERFLOW 1
 
@@ -530,7 +533,7 @@ __device__ int align_fixed(const AlnParams &P, const NwPen *pen, const KgTIndexV
 
 struct ScratchLayout { size_t stride; int mem_cap, q_cap; size_t e_cap; };
 
-__global__ void __launch_bounds__(AL_WARPS * 32) aln_pair_kernel(AlnParams P, KgTIndexView ix, const uint8_t *__restrict__ in,
+__global__ void __launch_bounds__(AL_WARPS * 32, AL_MINB) aln_pair_kernel(AlnParams P, KgTIndexView ix, const uint8_t *__restrict__ in,
 		const AlnRead *__restrict__ reads, const uint64_t *slab, const int32_t *__restrict__ task_read, int ntasks,
 		const int32_t *__restrict__ task_list, AlnCand *cand, uint8_t *scratch, ScratchLayout lay,
 		unsigned long long *ctr, int32_t *ovf_list) {
@@ -1036,20 +1039,25 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 	aln_prep_kernel<<<db->sm_count * 8, 256, 0, st>>>(b.in, n, reads, slab_off, task_off, (uint64_t *)b.d_slab.p, (int32_t *)b.d_taskread.p, P.k);
 	++launches;
 	KG_CUDA(cudaEventRecord(db->ev[3], st));
+	KG_CUDA(cudaEventRecord(db->ev[4], st));
 
 	if (ntasks) {
 		// per-warp scratch: MEM list, NW row buffers for the longest read, traceback bytes for a tail of that read
 		const int q_cap = std::min(std::max(maxq + 64, 256), 1 << 20);
 		const size_t e_cap = std::min<size_t>(std::max<size_t>(2 * (size_t)maxq * (size_t)maxq + 65536, 65536), 4u << 20);
 		const ScratchLayout lay = make_layout(2048, q_cap, e_cap);
-		int grid = db->sm_count * 4;
+		int grid = db->sm_count * AL_MINB;
 		size_t freeb = 0, totalb = 0;
-		cudaMemGetInfo(&freeb, &totalb);
-		while (grid > db->sm_count && lay.stride * (size_t)grid * AL_WARPS > freeb / 2 + b.d_scratch.cap) grid -= db->sm_count;
+		if (lay.stride * (size_t)grid * AL_WARPS > b.d_scratch.cap) {   // only when the scratch has to grow
+			cudaMemGetInfo(&freeb, &totalb);
+			while (grid > db->sm_count && lay.stride * (size_t)grid * AL_WARPS > freeb / 2 + b.d_scratch.cap) grid -= db->sm_count;
+		}
 		if (b.d_scratch.reserve(lay.stride * (size_t)grid * AL_WARPS)) return -1;
+		KG_CUDA(cudaEventRecord(db->ev[3], st));   // ms_align = the pair kernel(s) alone; host-side sizing above is in ms_total
 		aln_pair_kernel<<<grid, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
 			(const int32_t *)b.d_taskread.p, ntasks, nullptr, (AlnCand *)b.d_cand.p, (uint8_t *)b.d_scratch.p, lay, ctr,
 			(int32_t *)b.d_ovf.p);
+		KG_CUDA(cudaEventRecord(db->ev[4], st));
 		++launches;
 		KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
 		KG_CUDA(cudaStreamSynchronize(st));
@@ -1081,8 +1089,8 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 			novf = (int)h[A_OVF];
 		}
 		h[A_OVF] = first_ovf;
+		if (first_ovf) KG_CUDA(cudaEventRecord(db->ev[4], st));
 	}
-	KG_CUDA(cudaEventRecord(db->ev[4], st));
 	if (b.want_cand && ntasks) {   // per-candidate rows, before the selection compacts them in place
 		std::vector<AlnCand> hc((size_t)ntasks);
 		std::vector<int32_t> tr((size_t)ntasks);
@@ -1121,9 +1129,9 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 		stats->nw_steps = (int64_t)h[A_STEPS];
 		stats->index_probes = (int64_t)h[A_LOOKUPS]; stats->mem_bases = (int64_t)h[A_MEMBASES]; stats->read_bytes = (int64_t)h[A_READBYTES];
 		stats->overflow_tasks = ntasks ? (int64_t)h[A_OVF] : 0;
-		cudaEventElapsedTime(&stats->ms_prep, db->ev[2], db->ev[3]);
 		cudaEventElapsedTime(&stats->ms_align, db->ev[3], db->ev[4]);
-		cudaEventElapsedTime(&stats->ms_reduce, db->ev[4], db->ev[7]);
+		cudaEventElapsedTime(&stats->ms_total, db->ev[2], db->ev[7]);
+		stats->ms_prep = 0; stats->ms_reduce = stats->ms_total - stats->ms_align;   // everything around the pair kernel
 		cudaEventElapsedTime(&stats->ms_total, db->ev[2], db->ev[7]);
 		stats->launches = launches;
 	}

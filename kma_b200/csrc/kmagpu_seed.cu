@@ -226,7 +226,7 @@ __device__ int scan_strand(const KgHashView &hv, const SeedParams &p, const Read
 	}
 
 	// ---- exhaustive scan (savekmers.c:2511-2706)
-	uint32_t last = KG_MISS;
+	uint32_t last = KG_MISS, carry = KG_MISS;
 	int last_pos = 0, run_sc = 0, nhits = 0;
 	bool overflow = false;
 	for (int c0 = 0; c0 < npos && !overflow; c0 += KG_CHUNK) {
@@ -269,13 +269,27 @@ __device__ int scan_strand(const KgHashView &hv, const SeedParams &p, const Read
 		for (int u = 0; u < KG_PER_LANE; ++u) hits[u * 32 + lane] = e1[u];
 		__syncwarp();
 
-		// phase 2: walk the hits of this chunk in position order
+		// phase 2: walk the hits of this chunk in position order. A hit whose left neighbour position hit the same
+		// list continues the run with gap 0 (+M, savekmers.c:2529): those are counted with popc; only the
+		// remaining hits (first of a run, list changes) are walked one by one.
 		for (int u = 0; u < KG_PER_LANE && !overflow; ++u) {
-			unsigned hm = __ballot_sync(0xffffffffu, hits[u * 32 + lane] != KG_MISS);
-			nhits += __popc(hm);
+			const uint32_t myoff = hits[u * 32 + lane];
+			uint32_t prevoff = __shfl_up_sync(0xffffffffu, myoff, 1);
+			if (lane == 0) prevoff = carry;
+			carry = __shfl_sync(0xffffffffu, myoff, 31);
+			const unsigned hmall = __ballot_sync(0xffffffffu, myoff != KG_MISS);
+			const unsigned sm = __ballot_sync(0xffffffffu, myoff != KG_MISS && prevoff == myoff);
+			unsigned hm = hmall & ~sm, counted = 0;
+			nhits += __popc(hmall);
 			while (hm) {
 				int b = __ffs(hm) - 1;
 				hm &= hm - 1;
+				{
+					const unsigned low = (1u << b) - 1, sb = sm & low & ~counted, hb = hmall & low;
+					run_sc += __popc(sb) * p.M;
+					counted |= sb;
+					if (hb) last_pos = c0 + u * 32 + (31 - __clz(hb));
+				}
 				const int j = c0 + u * 32 + b;
 				const uint32_t off = hits[u * 32 + b];
 				if (off == last) {
@@ -313,6 +327,11 @@ __device__ int scan_strand(const KgHashView &hv, const SeedParams &p, const Read
 				}
 				last = off;
 				last_pos = j;
+			}
+			if (!overflow) {
+				const unsigned sb = sm & ~counted;
+				run_sc += __popc(sb) * p.M;
+				if (hmall) last_pos = c0 + u * 32 + (31 - __clz(hmall));
 			}
 		}
 		__syncwarp();
