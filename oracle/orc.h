@@ -40,6 +40,8 @@ int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const 
                      int one2one, double scoreT, int mq, int minlen, double mrc,
                      uint8_t **frag_out, size_t *frag_bytes, uint64_t *as, uint64_t *uas,
                      int32_t **cand_out, size_t *cand_rows, int64_t *nw_cells);
+int orc_trace_stream(orc_db *db, const char *prefix, const orc_params *p, const uint8_t *in, size_t in_bytes, int one2one,
+                     double scoreT, int mq, int minlen, double mrc, uint8_t **out, size_t *out_bytes);
 void orc_free(void *p);
 void orc_nw(const orc_params *p, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s, int q_e,
             int band, int *out6);

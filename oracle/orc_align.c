@@ -216,6 +216,8 @@ static int chain_mems(const orc_params *p, mems_t *pt, int q_len, int t_len, int
 /* ------------------------------------------------------------------ Needleman-Wunsch - */
 
 typedef struct { int score, len, pos, match, tGaps, qGaps; } aln_t;
+/* aligned strings of one NW call: template / match / query rows (0-3 bases, 4 = N, 5 = gap; '|' or '_') */
+typedef struct { uint8_t *t, *s, *q; } astr;
 
 static int64_t g_band_calls = 0, g_full_calls = 0;
 int64_t orc_nw_band_calls(void) { return g_band_calls; }
@@ -248,38 +250,58 @@ static inline uint8_t nw_cell(int Dright, int Qright, int Ddown, int Pdown, int 
 	return fl | e;
 }
 
-static aln_t nw_trivial(const orc_params *p, int t_len, int q_len) {
+/* one side empty (nw.c:49-85); with `so` the all-gap rows are written too */
+static aln_t nw_trivial(const orc_params *p, int t_len, int q_len, astr *so, const uint64_t *tseq, int t_s, const uint8_t *q) {
 	aln_t s = {0, 0, 0, 0, 0, 0};
 	if (t_len == q_len) return s;
-	if (t_len == 0) { s.len = q_len; s.tGaps = q_len; s.score = p->W1 + (q_len - 1) * p->U; }
-	else { s.len = t_len; s.qGaps = t_len; s.score = p->W1 + (t_len - 1) * p->U; }
+	if (t_len == 0) {
+		s.len = q_len; s.tGaps = q_len; s.score = p->W1 + (q_len - 1) * p->U;
+		if (so) { memset(so->s, '_', q_len); memset(so->t, 5, q_len); memcpy(so->q, q, q_len); }
+	} else {
+		s.len = t_len; s.qGaps = t_len; s.score = p->W1 + (t_len - 1) * p->U;
+		if (so) { memset(so->s, '_', t_len); memset(so->q, 5, t_len); for (int m = 0; m < t_len; ++m) so->t[m] = (uint8_t)nuc_at(tseq, t_s + m); }
+	}
 	return s;
 }
 
 /* walk the traceback bytes from (m, n); `stride` = bytes per row, `dn` = column step of a vertical move
- * (0 for the full matrix, -1 for the band whose rows are skewed) */
-static void nw_walk(const uint8_t *E, size_t stride, int m, int n, int dn, aln_t *s) {
+ * (0 for the full matrix, -1 for the band whose rows are skewed). With `so` the aligned rows are written as
+ * NW / NW_band do (nw.c:250-305, 575-637): tseq/t0 = template and the position of row 0, q/qp = query and the
+ * query position of the start cell. */
+static void nw_walk(const uint8_t *E, size_t stride, int m, int n, int dn, aln_t *s, astr *so, const uint64_t *tseq, int t0,
+                    const uint8_t *q, int qp) {
 	const uint8_t *row = E + (size_t)m * stride;
+	int tp = t0 + m;
 	s->len = s->match = s->tGaps = s->qGaps = 0;
 	while (row[n] != 0) {
 		int e = row[n] & 7;
-		if (e == 1) { ++s->match; row += stride; n += 1 + dn; }
-		else if (e >= 4) {
-			while (!(row[n] >> 4)) { row += stride; n += dn; ++s->len; ++s->qGaps; }
-			++s->qGaps; row += stride; n += dn;
+		if (e == 1) {
+			if (so) { so->t[s->len] = (uint8_t)nuc_at(tseq, tp); so->q[s->len] = q[qp]; so->s[s->len] = so->t[s->len] == so->q[s->len] ? '|' : '_'; }
+			++s->match; row += stride; n += 1 + dn; ++tp; ++qp;
+		} else if (e >= 4) {
+			while (!(row[n] >> 4)) {
+				if (so) { so->t[s->len] = (uint8_t)nuc_at(tseq, tp); so->q[s->len] = 5; so->s[s->len] = '_'; }
+				row += stride; n += dn; ++s->len; ++s->qGaps; ++tp;
+			}
+			if (so) { so->t[s->len] = (uint8_t)nuc_at(tseq, tp); so->q[s->len] = 5; so->s[s->len] = '_'; }
+			++s->qGaps; row += stride; n += dn; ++tp;
 		} else {
-			while (!(row[n] >> 3)) { ++n; ++s->len; ++s->tGaps; }
-			++s->tGaps; ++n;
+			while (!(row[n] >> 3)) {
+				if (so) { so->t[s->len] = 5; so->q[s->len] = q[qp]; so->s[s->len] = '_'; }
+				++n; ++s->len; ++s->tGaps; ++qp;
+			}
+			if (so) { so->t[s->len] = 5; so->q[s->len] = q[qp]; so->s[s->len] = '_'; }
+			++s->tGaps; ++n; ++qp;
 		}
 		++s->len;
 	}
 }
 
 static aln_t nw_full(const orc_params *p, nw_ws *w, const uint64_t *tseq, const uint8_t *query, int k,
-                     int t_s, int t_e, int q_s, int q_e) {
+                     int t_s, int t_e, int q_s, int q_e, astr *so) {
 	const int W1 = p->W1, U = p->U, t_len = t_e - t_s, q_len = q_e - q_s;
 	const uint8_t *q = query + q_s;
-	if (t_len == 0 || q_len == 0) return nw_trivial(p, t_len, q_len);
+	if (t_len == 0 || q_len == 0) return nw_trivial(p, t_len, q_len, so, tseq, t_s, q);
 	const size_t stride = (size_t)q_len + 1;
 	++g_full_calls;
 	ws_reserve(w, (size_t)q_len + 2, ((size_t)q_len + 2) * ((size_t)t_len + 2));
@@ -313,16 +335,16 @@ static aln_t nw_full(const orc_params *p, nw_ws *w, const uint64_t *tseq, const 
 		if (k == -2) for (int n = 0; n < q_len; ++n) if (s.score <= Dp[n]) { s.score = Dp[n]; best_m = 0; best_n = n; }
 	} else { s.score = Dp[0]; best_m = 0; best_n = 0; }
 	int sc = s.score;
-	nw_walk(E, stride, best_m, best_n, 0, &s);
+	nw_walk(E, stride, best_m, best_n, 0, &s, so, tseq, t_s, q, best_n);
 	s.score = sc; s.pos = 0;
 	return s;
 }
 
 static aln_t nw_band(const orc_params *p, nw_ws *w, const uint64_t *tseq, const uint8_t *query, int k,
-                     int t_s, int t_e, int q_s, int q_e, int band) {
+                     int t_s, int t_e, int q_s, int q_e, int band, astr *so) {
 	const int W1 = p->W1, U = p->U, t_len = t_e - t_s, q_len = q_e - q_s;
 	const uint8_t *q = query + q_s;
-	if (t_len == 0 || q_len == 0) return nw_trivial(p, t_len, q_len);
+	if (t_len == 0 || q_len == 0) return nw_trivial(p, t_len, q_len, so, tseq, t_s, q);
 	if (band & 1) ++band;
 	++g_band_calls;
 	const int half = band >> 1, bq = band + 1;
@@ -362,9 +384,10 @@ static aln_t nw_band(const orc_params *p, nw_ws *w, const uint64_t *tseq, const 
 		int *t1 = Dc; Dc = Dp; Dp = t1; t1 = Pc; Pc = Pp; Pp = t1;
 	}
 	if (best_m == 0) { best_n = en; s.score = Dp[en]; }
-	if (k == -2) for (n = en; n < bq; ++n) if (s.score <= Dp[n]) { s.score = Dp[n]; best_m = 0; best_n = n; }
+	int qstart = 0;   /* the reference's q_pos: 0 unless the free-query-prefix scan moves it (nw.c:561-574) */
+	if (k == -2) for (n = en; n < bq; ++n) if (s.score <= Dp[n]) { s.score = Dp[n]; best_m = 0; best_n = n; qstart = n - en; }
 	int sc = s.score;
-	nw_walk(E, stride, best_m, best_n, -1, &s);
+	nw_walk(E, stride, best_m, best_n, -1, &s, so, tseq, t_s, q, qstart);
 	s.score = sc; s.pos = 0;
 	return s;
 }
@@ -373,7 +396,7 @@ static aln_t nw_band(const orc_params *p, nw_ws *w, const uint64_t *tseq, const 
 void orc_nw(const orc_params *p, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s, int q_e,
             int band, int *out6) {
 	nw_ws w; memset(&w, 0, sizeof(w));
-	aln_t a = band ? nw_band(p, &w, tseq, query, k, t_s, t_e, q_s, q_e, band) : nw_full(p, &w, tseq, query, k, t_s, t_e, q_s, q_e);
+	aln_t a = band ? nw_band(p, &w, tseq, query, k, t_s, t_e, q_s, q_e, band, 0) : nw_full(p, &w, tseq, query, k, t_s, t_e, q_s, q_e, 0);
 	out6[0] = a.score; out6[1] = a.len; out6[2] = a.pos; out6[3] = a.match; out6[4] = a.tGaps; out6[5] = a.qGaps;
 	for (int i = 0; i < 2; ++i) { free(w.D[i]); free(w.P[i]); } free(w.E);
 }
@@ -385,8 +408,8 @@ void orc_nw(const orc_params *p, const uint64_t *tseq, const uint8_t *query, int
 static aln_t nw_auto(const orc_params *p, nw_ws *w, const uint64_t *tseq, const uint8_t *q, int k,
                      int t_s, int t_e, int q_s, int q_e) {
 	int band = abs((t_e - t_s) - (q_e - q_s)) + BANDW;
-	if (q_e - q_s <= band || t_e - t_s <= band) return nw_full(p, w, tseq, q, k, t_s, t_e, q_s, q_e);
-	return nw_band(p, w, tseq, q, k, t_s, t_e, q_s, q_e, band);
+	if (q_e - q_s <= band || t_e - t_s <= band) return nw_full(p, w, tseq, q, k, t_s, t_e, q_s, q_e, 0);
+	return nw_band(p, w, tseq, q, k, t_s, t_e, q_s, q_e, band, 0);
 }
 
 static aln_t lead_tail(const orc_params *p, nw_ws *w, const uint64_t *tseq, const uint8_t *q, int t_e, int q_e) {
@@ -477,8 +500,8 @@ static aln_t kma_score(const orc_params *p, nw_ws *w, const tindex *ix, const ui
 		if (t_l > 0 || q_e - q_s > 0) {
 			aln_t a;
 			int band = abs(t_l - q_e + q_s) + BANDW;
-			if (q_e - q_s <= band || t_l <= band) a = nw_full(p, w, ix->seq, q, 0, t_s, t_e, q_s, q_e);
-			else a = nw_band(p, w, ix->seq, q, 0, t_s, t_e, q_s, q_e, band);
+			if (q_e - q_s <= band || t_l <= band) a = nw_full(p, w, ix->seq, q, 0, t_s, t_e, q_s, q_e, 0);
+			else a = nw_band(p, w, ix->seq, q, 0, t_s, t_e, q_s, q_e, band, 0);
 			s.score += a.score; s.len += a.len; s.match += a.match; s.tGaps += a.tGaps; s.qGaps += a.qGaps;
 		}
 	}
@@ -718,6 +741,265 @@ static void align_pe(const orc_params *p, nw_ws *ws, mems_t *pt, tindex **tix, o
 		if (flag_r & 2) { flag ^= 2; flag_r ^= 2; }
 		emit_se(frag, as, uas, q2, m2->q_len, m2->hdr, m2->hl, flag_r, minFrac, hits, best2, bS, bE, bT, bTr);
 	}
+}
+
+
+/* ------------------------------------------------------------------ traceback alignment (assembly pass) */
+
+/* does byte b occur in q[from, len)? position or -1 (charpos, stdnuc.c:436) */
+static int next_n(const uint8_t *q, int from, int len) {
+	for (int i = from; i < len; ++i) if (q[i] == 4) return i;
+	return -1;
+}
+
+static void bytes_rc(uint8_t *q, int len) {   /* strrc, stdnuc.c:450 */
+	static const uint8_t comp[6] = {3, 2, 1, 0, 4, 5};
+	for (int i = 0, j = len - 1; i < j; ++i, --j) { uint8_t c = comp[q[i]]; q[i] = comp[q[j]]; q[j] = c; }
+	if (len & 1) q[len >> 1] = comp[q[len >> 1]];
+}
+
+static uint64_t kmer_bytes(const uint8_t *q, int pos, int k) { uint64_t key = 0; for (int b = 0; b < k; ++b) key = (key << 2) | q[pos + b]; return key; }
+
+/* The byte-read seed scan shared by KMA (align.c:246-377) and anker_rc (align.c:823-957): N-free stretches are found
+ * with charpos, a stretch is only entered (and re-entered after a MEM) while more than k bases remain before its end,
+ * k-mers slide one base at a time. mode 0 = KMA (MEM jumps to its end), mode 1 = anker_rc (also scores the strand).
+ * Appends MEMs at pt[n..]; returns the new count, *score the strand score. */
+static int scan_bytes(const tindex *ix, const uint8_t *q, int q_len, int q_start, int q_end, int mode, mems_t *pt, int n, int first_i, int *score) {
+	const int k = ix->k;
+	int i = first_i, sc = 0;
+	(void)q_start;
+	while (i < q_end) {
+		int end = next_n(q, i, q_len);
+		if (end == -1) end = q_end;
+		int p = i;   /* start of the k-mer under the cursor; the reference's i is p + k - 1 */
+		if (!(p < end - k)) { i = end + 1; continue; }
+		while (p + k - 1 < end) {
+			int slot, cnt, value = tindex_get(ix, kmer_bytes(q, p, k), &slot, &cnt);
+			if (value == 0) { ++p; continue; }
+			mems_reserve(pt, n + cnt + 1);
+			int nextp;
+			if (0 < value) {
+				mem_from_seed(ix, q, p, value, k, end, &pt->qStart[n], &pt->tStart[n], &pt->qEnd[n], &pt->tEnd[n]);
+				pt->weight[n] = mode ? pt->tEnd[n] - pt->tStart[n] : pt->qEnd[n] - pt->qStart[n];
+				sc += pt->qEnd[n] - pt->qStart[n];
+				nextp = pt->qEnd[n];
+				++n;
+			} else {
+				int bias = p;
+				sc += k;
+				for (int c = 0; c < cnt; ++c) {
+					mem_from_seed(ix, q, p, ix->pos[slot + c], k, end, &pt->qStart[n], &pt->tStart[n], &pt->qEnd[n], &pt->tEnd[n]);
+					pt->weight[n] = pt->qEnd[n] - pt->qStart[n];
+					if (bias < pt->qEnd[n]) bias = pt->qEnd[n];
+					++n;
+				}
+				sc += bias - p;
+				nextp = bias + 1;
+			}
+			if (nextp < end - k) p = nextp; else { p = end + 1; break; }   /* "update position" (align.c:309-315) */
+		}
+		i = end + 1;
+	}
+	if (score) *score = sc;
+	return n;
+}
+
+/* anker_rc (align.c:780-991): MEMs of the byte read on both strands, the better strand's MEMs stay in pt and the read
+ * is left in that orientation. Returns the winning strand score (0: nothing). */
+static int pick_strand_bytes(const tindex *ix, uint8_t *q, int q_len, int one2one, int exhaustive, mems_t *pt) {
+	const int k = ix->k;
+	int sf = 0, sr = 0;
+	pt->len = 0;
+	int first = exhaustive || preseed_hit(ix, q, q_len) ? 0 : q_len;   /* preseed returns 0 on a hit, >= q_len otherwise */
+	int nf = scan_bytes(ix, q, q_len, 0, q_len, 1, pt, 0, first, &sf);
+	bytes_rc(q, q_len);
+	int ntot = scan_bytes(ix, q, q_len, 0, q_len, 1, pt, nf, 0, &sr);
+	int best = sf < sr ? sr : sf;
+	if (one2one && best < k && best * k < (q_len - k - best)) { pt->len = 0; return 0; }   /* read stays reverse-complemented */
+	if (best == sf) { bytes_rc(q, q_len); pt->len = nf; return best; }
+	int mc = ntot - nf;
+	if (nf) {
+		memmove(pt->tStart, pt->tStart + nf, 4 * (size_t)mc); memmove(pt->tEnd, pt->tEnd + nf, 4 * (size_t)mc);
+		memmove(pt->qStart, pt->qStart + nf, 4 * (size_t)mc); memmove(pt->qEnd, pt->qEnd + nf, 4 * (size_t)mc);
+		memmove(pt->weight, pt->weight + nf, 4 * (size_t)mc);
+	}
+	pt->len = mc;
+	return best;
+}
+
+typedef struct { astr a; int len; astr frag; int cap; } trace_buf;
+
+static void tb_reserve(trace_buf *b, int need) {
+	if (need <= b->cap) return;
+	b->cap = 2 * need + 64;
+	b->a.t = realloc(b->a.t, b->cap); b->a.s = realloc(b->a.s, b->cap); b->a.q = realloc(b->a.q, b->cap);
+	b->frag.t = realloc(b->frag.t, b->cap); b->frag.s = realloc(b->frag.s, b->cap); b->frag.q = realloc(b->frag.q, b->cap);
+}
+
+static aln_t nw_auto_str(const orc_params *p, nw_ws *w, const uint64_t *tseq, const uint8_t *q, int k,
+                         int t_s, int t_e, int q_s, int q_e, astr *so) {
+	int band = abs((t_e - t_s) - (q_e - q_s)) + BANDW;
+	if (q_e - q_s <= band || t_e - t_s <= band) return nw_full(p, w, tseq, q, k, t_s, t_e, q_s, q_e, so);
+	return nw_band(p, w, tseq, q, k, t_s, t_e, q_s, q_e, band, so);
+}
+
+/* KMA (align.c:214-507): seed, chain, stitch -- with the aligned rows. tb->a receives t/s/q, tb->len columns. */
+static aln_t kma_trace(const orc_params *p, nw_ws *w, const tindex *ix, const uint8_t *q, int q_len, int mq, mems_t *pt, trace_buf *tb) {
+	const int k = ix->k, t_len = ix->len, U = p->U, M = p->M;
+	tb_reserve(tb, 2 * q_len + 2 * BANDW + 64);
+	tb->len = 0;
+	int n = pt->len;
+	if (!n) n = scan_bytes(ix, q, q_len, 0, q_len, 0, pt, 0, 0, 0);
+	pt->len = n;
+	if (!n) return aln_zero();
+	unsigned mapQ = 0;
+	int start = chain_mems(p, pt, q_len, t_len, k, &mapQ);
+	if ((int)mapQ < mq || pt->score[start] < k) { pt->len = 0; return aln_zero(); }
+
+	/* leading tail (leadTailAln with Frag_align, align.c:53-138): leading gap columns are trimmed when the window
+	 * starts at the template start */
+	aln_t s = {0, 0, pt->tStart[start] - 1, 0, 0, 0};
+	{
+		const int t_e = pt->tStart[start] - 1, q_e = pt->qStart[start];
+		if (q_e) {
+			int t_s = 0, q_s = 0;
+			if ((q_e << 1) < t_e || (q_e + BANDW) < t_e) t_s = t_e - (q_e + IMIN(q_e, BANDW));
+			else if ((t_e << 1) < q_e || (t_e + BANDW) < q_e) q_s = q_e - (t_e + IMIN(t_e, BANDW));
+			if (t_e - t_s > 0 && q_e - q_s > 0) {
+				tb_reserve(tb, tb->len + (t_e - t_s) + (q_e - q_s) + 8);
+				aln_t a = nw_auto_str(p, w, ix->seq, q, -1 - (t_s == 0), t_s, t_e, q_s, q_e, &tb->frag);
+				int bias = 0;
+				if (t_s == 0) {
+					while (bias < a.len && (tb->frag.t[bias] == 5 || tb->frag.q[bias] == 5)) {
+						if (tb->frag.t[bias] == 5) --a.tGaps; else --a.qGaps;
+						++bias;
+					}
+					a.len -= bias;
+				}
+				memcpy(tb->a.t, tb->frag.t + bias, a.len); memcpy(tb->a.s, tb->frag.s + bias, a.len); memcpy(tb->a.q, tb->frag.q + bias, a.len);
+				s.pos -= a.len - a.tGaps;
+				s.score = a.score; s.len = a.len; s.match = a.match; s.tGaps = a.tGaps; s.qGaps = a.qGaps;
+			}
+		}
+	}
+	for (;;) {
+		const int q_s0 = pt->qStart[start], len = pt->qEnd[start] - q_s0;
+		tb_reserve(tb, s.len + len + 8);
+		memcpy(tb->a.t + s.len, q + q_s0, len); memset(tb->a.s + s.len, '|', len); memcpy(tb->a.q + s.len, q + q_s0, len);
+		s.len += len; s.match += len;
+		for (int i = q_s0; i < pt->qEnd[start]; ++i) s.score += p->d[q[i] * 5 + q[i]];
+		if (!pt->next[start]) break;
+		int q_s = pt->qEnd[start], t_s = pt->tEnd[start] - 1, t_e, t_l, q_e;
+		start = pt->next[start];
+		if (pt->qStart[start] < q_s) { pt->tStart[start] += q_s - pt->qStart[start]; pt->qStart[start] = q_s; }
+		t_e = pt->tStart[start] - 1;
+		if (t_e < t_s) {
+			if (t_s <= pt->tEnd[start]) { pt->qStart[start] += t_s - t_e; t_e = t_s; t_l = 0; }
+			else t_l = t_len - t_s + t_e;
+		} else t_l = t_e - t_s;
+		q_e = pt->qStart[start];
+		if (abs(t_l - q_e + q_s) * U > q_len * M || t_l > q_len || q_e - q_s > (q_len >> 1)) {
+			int keep = s.pos; pt->len = 0; tb->len = 0; s = aln_zero(); s.pos = keep; return s;
+		}
+		if (t_l > 0 || q_e - q_s > 0) {
+			tb_reserve(tb, s.len + t_l + (q_e - q_s) + 8);
+			aln_t a = nw_auto_str(p, w, ix->seq, q, 0, t_s, t_e, q_s, q_e, &tb->frag);
+			memcpy(tb->a.t + s.len, tb->frag.t, a.len); memcpy(tb->a.s + s.len, tb->frag.s, a.len); memcpy(tb->a.q + s.len, tb->frag.q, a.len);
+			s.score += a.score; s.len += a.len; s.match += a.match; s.tGaps += a.tGaps; s.qGaps += a.qGaps;
+		}
+	}
+	/* trailing tail (trailTailAln with Frag_align, align.c:147-212): trailing gap columns trimmed at the template end */
+	{
+		const int t_s = pt->tEnd[start] - 1, q_s = pt->qEnd[start];
+		int q_e = q_len, t_e = t_len;
+		if (((q_len - q_s) << 1) < (t_len - t_s) || (q_len - q_s + BANDW) < (t_len - t_s)) { t_e = q_len - q_s; t_e = t_s + (t_e + IMIN(t_e, BANDW)); }
+		else if (((t_len - t_s) << 1) < (q_len - q_s) || (t_len - t_s + BANDW) < (q_len - q_s)) { q_e = t_len - t_s; q_e = q_s + (q_e + IMIN(q_e, BANDW)); }
+		if (t_e - t_s > 0 && q_e - q_s > 0) {
+			tb_reserve(tb, s.len + (t_e - t_s) + (q_e - q_s) + 8);
+			aln_t a = nw_auto_str(p, w, ix->seq, q, 1 + (t_e == t_len), t_s, t_e, q_s, q_e, &tb->frag);
+			if (t_e == t_len) {
+				int bias = a.len - 1;
+				while (bias && (tb->frag.t[bias] == 5 || tb->frag.q[bias] == 5)) {
+					if (tb->frag.t[bias] == 5) --a.tGaps; else --a.qGaps;
+					--bias;
+				}
+				++bias;
+				if (bias != a.len) a.len = bias;
+			}
+			memcpy(tb->a.t + s.len, tb->frag.t, a.len); memcpy(tb->a.s + s.len, tb->frag.s, a.len); memcpy(tb->a.q + s.len, tb->frag.q, a.len);
+			s.score += a.score; s.len += a.len; s.match += a.match; s.tGaps += a.tGaps; s.qGaps += a.qGaps;
+		}
+	}
+	tb->len = s.len;
+	pt->len = 0;
+	return s;
+}
+
+/* The alignment part of assemble_KMA's inner loop (assembly.c:1868-1961) over a stream of per-template fragment
+ * records (frags.c:45-48): int32[8]{template, q_len, nHits, score, start, end, hdrlen, flag} + read bytes (0-4) +
+ * header. Per record the output holds int32[12]{accepted, read_score, start, end, score, len, pos, match, tGaps,
+ * qGaps, oriented (1: the read was reverse-complemented by anker_rc), ncol} + t[ncol] s[ncol] q[ncol]. */
+int orc_trace_stream(orc_db *db, const char *prefix, const orc_params *p, const uint8_t *in, size_t in_bytes, int one2one,
+                     double scoreT, int mq, int minlen, double mrc, uint8_t **out, size_t *out_bytes) {
+	if (orc_db_load_seq(db, prefix)) return -1;
+	int k = db->lengths[0];
+	if (k < 4 || 31 < k) k = 16;
+	const int Wl = -p->Wl;
+	tindex **tix = calloc(db->DB_size, sizeof(tindex *));
+	nw_ws ws; memset(&ws, 0, sizeof(ws));
+	mems_t pt; memset(&pt, 0, sizeof(pt));
+	trace_buf tb; memset(&tb, 0, sizeof(tb));
+	obuf o = {0, 0, 0};
+	size_t ip = 0;
+	uint8_t *q = 0; size_t qcap = 0;
+	while (ip + 32 <= in_bytes) {
+		int32_t h[8]; memcpy(h, in + ip, 32);
+		if (h[0] < 0) break;
+		ip += 32;
+		const int tmpl = h[0], q_len = h[1], hl = h[6];
+		int read_score = h[3];
+		if ((size_t)q_len + 64 > qcap) { qcap = 2 * (size_t)q_len + 64; q = realloc(q, qcap); }
+		memcpy(q, in + ip, q_len); memset(q + q_len, 0, 32); ip += (size_t)q_len + hl;
+		if (!tix[tmpl]) tix[tmpl] = tindex_build(db->seq + db->seq_off[tmpl], db->lengths[tmpl], k);
+		const tindex *ix = tix[tmpl];
+		const int t_len = ix->len;
+		int32_t r[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+		tb.len = 0;
+		pt.len = 0;
+		int go = read_score != 0;
+		if (!go) {
+			uint8_t first = q_len ? q[0] : 0, last = q_len ? q[q_len - 1] : 0;
+			go = pick_strand_bytes(ix, q, q_len, one2one, p->exhaustive, &pt) != 0;
+			/* did the read end up reverse-complemented? compare with a fresh copy */
+			r[10] = q_len && memcmp(q, in + ip - hl - q_len, q_len) != 0;
+			(void)first; (void)last;
+		}
+		if (go) {
+			aln_t a = kma_trace(p, &ws, ix, q, q_len, mq, &pt, &tb);
+			int aln_len = a.len, start = a.pos, end = start + aln_len - a.tGaps;
+			if (t_len < end) end -= t_len;
+			read_score = a.score;
+			if (start == 0) read_score += Wl;
+			if (end == t_len) read_score += Wl;
+			double score;
+			if (minlen <= aln_len && ((mrc * q_len <= a.len - a.qGaps) || (mrc * t_len <= a.len - a.tGaps))) score = 1.0 * read_score / aln_len;
+			else { read_score = 0; score = 0; }
+			r[0] = 0 < read_score && scoreT <= score;
+			r[1] = read_score; r[2] = start; r[3] = end;
+			r[4] = a.score; r[5] = a.len; r[6] = a.pos; r[7] = a.match; r[8] = a.tGaps; r[9] = a.qGaps;
+		}
+		pt.len = 0;
+		r[11] = tb.len;   /* columns of the rows that follow (0 when nothing aligned) */
+		ob_put(&o, r, 48);
+		ob_put(&o, tb.a.t, tb.len); ob_put(&o, tb.a.s, tb.len); ob_put(&o, tb.a.q, tb.len);
+	}
+	for (int t = 0; t < db->DB_size; ++t) tindex_free(tix[t]);
+	free(tix); free(q);
+	free(pt.tStart); free(pt.tEnd); free(pt.qStart); free(pt.qEnd); free(pt.weight); free(pt.score); free(pt.next);
+	for (int i = 0; i < 2; ++i) { free(ws.D[i]); free(ws.P[i]); } free(ws.E);
+	free(tb.a.t); free(tb.a.s); free(tb.a.q); free(tb.frag.t); free(tb.frag.s); free(tb.frag.q);
+	*out = o.p; *out_bytes = o.len;
+	return 0;
 }
 
 /* ------------------------------------------------------------------ the stream ------- */

@@ -53,7 +53,89 @@ static Penalties *make_rewards(void) {
 	return r;
 }
 
+/* ref_aln -trace <db> <frags.bin> <out.bin> [-1t1]: the alignment part of assemble_KMA's inner loop
+ * (assembly.c:1868-1961) -- the reference's own anker_rc + KMA per fragment record (frags.c:45-48); per record
+ * int32[12]{accepted, read_score, start, end, score, len, pos, match, tGaps, qGaps, oriented, 0} + t s q rows. */
+static int trace_main(int argc, char **argv) {
+	int one2one = 0, exhaustive = 0, ts = 0;
+	for (int a = 5; a < argc; ++a) if (!strcmp(argv[a], "-1t1")) one2one = 1;
+	char path[4096];
+	int *template_lengths; long unsigned *as, *uas;
+	char *p2 = malloc(strlen(argv[2]) + 64); strcpy(p2, argv[2]);
+	int DB_size = load_DBs_KMA(p2, &as, &uas, &template_lengths, 0);
+	int kmersize = template_lengths[0];
+	if (kmersize < 4 || 31 < kmersize) kmersize = 16;
+	snprintf(path, sizeof(path), "%s.seq.b", argv[2]);
+	int seq_in = open(path, O_RDONLY);
+	if (seq_in < 0) { perror(path); return 1; }
+	long *seq_indexes = malloc((DB_size + 1) * sizeof(long));
+	seq_indexes[0] = 0; seq_indexes[1] = 0;
+	for (int i = 2; i < DB_size; ++i) seq_indexes[i] = seq_indexes[i - 1] + ((template_lengths[i - 1] >> 5) + 1) * sizeof(long unsigned);
+	Penalties *rewards = make_rewards();
+	preseed(0, 0, exhaustive);
+	trimSeedsPtr(0, ts);
+	anker_rc(0, 0, one2one, 0, 0, 0);
+	anker_rc_comp(0, 0, (unsigned char *)(&one2one), 0, 0, 0, 0, 0);
+	alignLoadPtr = &alignLoad_fly;
+	HashMapCCI **templates_index = calloc(DB_size, sizeof(HashMapCCI *));
+	NWmat *NWm = malloc(sizeof(NWmat));
+	NWm->NW_s = 1024 * 1024; NWm->NW_q = 1024; NWm->E = malloc(NWm->NW_s);
+	NWm->D[0] = malloc((NWm->NW_q << 1) * sizeof(int)); NWm->P[0] = malloc((NWm->NW_q << 1) * sizeof(int));
+	NWm->D[1] = NWm->D[0] + NWm->NW_q; NWm->P[1] = NWm->P[0] + NWm->NW_q; NWm->rewards = rewards;
+	AlnPoints *points = seedPoint_init(1024, rewards);
+	FILE *in = fopen(argv[3], "rb"), *out = fopen(argv[4], "wb");
+	if (!in || !out) { perror("open"); return 1; }
+	Aln *aligned = calloc(1, sizeof(Aln)), *gap_align = calloc(1, sizeof(Aln));
+	int delta = 0;
+	unsigned char *qseq = 0, *orig = 0; int qsize = 0;
+	int h[8];
+	const int Wl = -rewards->Wl, minlen = 16, mq = 0;
+	const double scoreT = 0.5, mrc = 0.0;
+	while (fread(h, 4, 8, in) == 8 && h[0] >= 0) {
+		int template = h[0], q_len = h[1], read_score = h[3], st2 = h[4], st3 = h[5], hl = h[6];
+		if (qsize < q_len + 64) { qsize = 2 * q_len + 64; qseq = realloc(qseq, qsize); orig = realloc(orig, qsize); }
+		if (fread(qseq, 1, q_len, in) != (size_t)q_len) break;
+		memcpy(orig, qseq, q_len);
+		fseek(in, hl, SEEK_CUR);
+		if (delta < q_len) {
+			delta = q_len << 1;
+			aligned->t = realloc(aligned->t, (delta + 1) << 1); aligned->s = realloc(aligned->s, (delta + 1) << 1); aligned->q = realloc(aligned->q, (delta + 1) << 1);
+			gap_align->t = realloc(gap_align->t, (delta + 1) << 1); gap_align->s = realloc(gap_align->s, (delta + 1) << 1); gap_align->q = realloc(gap_align->q, (delta + 1) << 1);
+		}
+		if (!templates_index[template]) templates_index[template] = alignLoadPtr(0, seq_in, template_lengths[template], kmersize, seq_indexes[template]);
+		HashMapCCI *ti = templates_index[template];
+		int t_len = template_lengths[template];
+		int r[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, len = 0;
+		points->len = 0;
+		int go = read_score || anker_rc(ti, qseq, q_len, 0, q_len, points);
+		r[10] = memcmp(orig, qseq, q_len) != 0;
+		if (go) {
+			if (st3 <= st2) { st2 = 0; st3 = t_len; }
+			AlnScore a = KMA(ti, qseq, q_len, 0, q_len, aligned, gap_align, st2, t_len < st3 ? t_len : st3, mq, scoreT, points, NWm);
+			int aln_len = a.len, start = a.pos, end = start + aln_len - a.tGaps;
+			double score;
+			if (t_len < end) end -= t_len;
+			read_score = a.score;
+			if (start == 0) read_score += Wl;
+			if (end == t_len) read_score += Wl;
+			if (minlen <= aln_len && ((mrc * q_len <= a.len - a.qGaps) || (mrc * t_len <= a.len - a.tGaps))) score = 1.0 * read_score / aln_len;
+			else { read_score = 0; score = 0; }
+			r[0] = 0 < read_score && scoreT <= score;
+			r[1] = read_score; r[2] = start; r[3] = end;
+			r[4] = a.score; r[5] = a.len; r[6] = a.pos; r[7] = a.match; r[8] = a.tGaps; r[9] = a.qGaps;
+			len = aligned->len;
+		}
+		points->len = 0;
+		r[11] = len;
+		fwrite(r, 4, 12, out);
+		fwrite(aligned->t, 1, len, out); fwrite(aligned->s, 1, len, out); fwrite(aligned->q, 1, len, out);
+	}
+	fclose(in); fclose(out);
+	return 0;
+}
+
 int main(int argc, char **argv) {
+	if (argc >= 5 && !strcmp(argv[1], "-trace")) return trace_main(argc, argv);
 	if (argc < 5) { fprintf(stderr, "usage: ref_aln db s2.bin frag_raw.out scores.out [cand.out] [-1t1]\n"); return 2; }
 	int one2one = 0, exhaustive = 0, ts = 0;
 	const char *cand_path = 0;

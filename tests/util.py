@@ -153,3 +153,79 @@ def cand_equal(a, b):
     ok = a == b
     ok[:, 5] |= (b[:, 2] == 0)
     return bool(ok.all())
+
+
+def parse_frag_raw(buf: bytes):
+    """frag_raw stream (updatescores.c:284-295, single-end records) -> list of dicts"""
+    recs, p = [], 0
+    while p + 20 <= len(buf):
+        q_len, n, score, hl, flag = np.frombuffer(buf, dtype=np.int32, count=5, offset=p)
+        p += 20
+        n = abs(int(n))
+        q = np.frombuffer(buf, dtype=np.uint8, count=int(q_len), offset=p); p += int(q_len)
+        hdr = buf[p:p + int(hl)]; p += int(hl)
+        arr = np.frombuffer(buf[p:p + 12 * n], dtype=np.int32).reshape(3, n); p += 12 * n
+        if score < 0:   # a mate block follows (update_Scores_pe)
+            q2, hl2, fl2 = np.frombuffer(buf, dtype=np.int32, count=3, offset=p)
+            p += 12 + int(q2) + int(hl2)
+        recs.append(dict(q=q, hdr=hdr, score=int(score), flag=int(flag), start=arr[0], end=arr[1], tmpl=arr[2]))
+    return recs
+
+
+def assembly_records(frag_raw: bytes, zero_every=5, max_hits=2) -> np.ndarray:
+    """per-template fragment records as assemble_KMA reads them (frags.c:45-48): int32[8]{template, q_len, nHits,
+    score, start, end, hdrlen, flag} + read bytes + header. Reads chosen on the reverse strand are reverse-complemented
+    (what ConClave does before it files them); every `zero_every`-th record gets score 0 so that anker_rc decides."""
+    comp = np.array([3, 2, 1, 0, 4, 5], dtype=np.uint8)
+    out = bytearray()
+    for i, r in enumerate(parse_frag_raw(frag_raw)):
+        for j in range(min(max_hits, len(r["tmpl"]))):
+            t = int(r["tmpl"][j])
+            q = r["q"] if t > 0 else comp[r["q"][::-1]]
+            score = 0 if (zero_every and i % zero_every == 0) else abs(r["score"])
+            if score == 0 and i % (2 * zero_every) == 0:   # wrong way round: anker_rc has to turn the read
+                q = comp[q[::-1]]
+            out += np.array([abs(t), len(q), len(r["tmpl"]), score, int(r["start"][j]), int(r["end"][j]), len(r["hdr"]), r["flag"]],
+                            dtype=np.int32).tobytes()
+            out += q.tobytes() + r["hdr"]
+    return np.frombuffer(bytes(out), dtype=np.uint8)
+
+
+def ref_trace(db_prefix: str, frags: np.ndarray, tmp: str, one2one=True) -> bytes:
+    """ground truth of the traceback alignment (assemble_KMA's anker_rc + KMA) from the unmodified reference"""
+    p = os.path.join(tmp, "frags.bin")
+    frags.tofile(p)
+    args = [REF_ALN, "-trace", db_prefix, p, os.path.join(tmp, "trace.out")] + (["-1t1"] if one2one else [])
+    r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    return open(os.path.join(tmp, "trace.out"), "rb").read()
+
+
+def oracle_trace(db_prefix: str, frags: np.ndarray, one2one=True) -> bytes:
+    L = orc()
+    L.orc_trace_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_int,
+                                   C.c_int, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.orc_free.argtypes = [C.c_void_p]
+    db = L.orc_db_open(os.fsencode(db_prefix))
+    assert db
+    frags = np.ascontiguousarray(frags, dtype=np.uint8)
+    o, ob = C.c_void_p(), C.c_size_t()
+    rc = L.orc_trace_stream(db, os.fsencode(db_prefix), oracle_params(), frags.ctypes.data, len(frags), int(one2one), 0.5, 0, 16, 0.0,
+                            C.byref(o), C.byref(ob))
+    assert rc == 0
+    out = C.string_at(o, ob.value) if ob.value else b""
+    L.orc_free(o)
+    L.orc_db_close(db)
+    return out
+
+
+def parse_trace(buf: bytes):
+    """trace output -> list of (int32[12] header, t, s, q rows)"""
+    out, p = [], 0
+    while p + 48 <= len(buf):
+        h = np.frombuffer(buf, dtype=np.int32, count=12, offset=p).copy(); p += 48
+        n = int(h[11])
+        rows = [buf[p + i * n:p + (i + 1) * n] for i in range(3)]
+        p += 3 * n
+        out.append((h, rows))
+    return out
