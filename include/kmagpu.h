@@ -129,6 +129,16 @@ int kmagpu_align_download(kmagpu_db *db, void *frag_out, size_t out_cap, size_t 
                           uint64_t *alignment_scores, uint64_t *uniq_alignment_scores,
                           kmagpu_cand *cand_out, size_t cand_cap, size_t *cand_rows);
 
+/* Replaces the alignment part of assemble_KMA's inner loop (assembly.c:1868-1961): per fragment record of the
+ * per-template files ConClave writes (frags.c:45-48: int32[8]{template, q_len, nHits, score, start, end, hdrlen, flag}
+ * + read bytes 0-4 + header; a trailing int32 -1 is ignored) runs anker_rc (align.c:780, when score == 0) and KMA
+ * (align.c:214) with traceback, then the acceptance test. Output per record, input order:
+ * int32[12]{accepted, read_score, start, end, score, len, pos, match, tGaps, qGaps, turned, ncol} + the aligned rows
+ * t[ncol] s[ncol] q[ncol] (Aln, nw.h:46-56: bases 0-3, 4 = N, 5 = gap; '|' match, '_' otherwise) -- what alnToMat
+ * (assembly.c:1317) and updateFrags consume next. `turned` = the read was reverse-complemented by anker_rc. */
+int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *p, const void *frags, size_t nbytes,
+                       void *out, size_t out_cap, size_t *out_bytes, int64_t *nrecords, kmagpu_align_stats *stats);
+
 /* NW_score (nw.c:642) / NW_band_score (nw.c:892) over a batch of independent problems, one warp each.
  * prob[i] = {template id, t_s, t_e, q_off, q_s, q_e, k, band (0 = full matrix)}; the query bytes (0-4) of problem i
  * start at qpool + q_off. out[i] = {score, len, pos, match, tGaps, qGaps}; status[i] != 0: not computed
@@ -137,7 +147,8 @@ int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, const int32
                     size_t qbytes, int32_t *out, int32_t *status, int64_t *cells, int64_t *steps, float *ms);
 
 /* Host-only helper (no device needed): walk the whole records at the head of a stage-1 (stage = 1, 16-byte headers,
- * runinput.c:765-787 / loadFsa savekmers.c:50-92) or stage-2 (stage = 2, 28-byte headers, ankers.c:163-220) stream.
+ * runinput.c:765-787 / loadFsa savekmers.c:50-92), stage-2 (stage = 2, 28-byte headers, ankers.c:163-220) or assembly
+ * fragment (stage = 3, 32-byte headers, frags.c:45-48) stream.
  * Returns the number of whole records (stopping at a terminator or a partial record), stores their byte offsets in
  * offsets[0..min(count, cap)) when offsets != NULL and the bytes they span in *used. -1 on a corrupt header. */
 int64_t kmagpu_record_walk(int stage, const void *buf, size_t nbytes, uint64_t *offsets, size_t cap, size_t *used);

@@ -86,6 +86,8 @@ def lib():
                                          C.POINTER(C.c_size_t), C.POINTER(AlignStats)]
         L.kmagpu_nw_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                       C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
+        L.kmagpu_trace_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                         C.POINTER(C.c_size_t), C.POINTER(C.c_int64), C.POINTER(AlignStats)]
         L.kmagpu_record_walk.restype = C.c_int64
         L.kmagpu_record_walk.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         _lib = L
@@ -214,6 +216,19 @@ class TemplateDB:
         st = self.align_run(params, want_cand)
         frag, a, u, cand = self.align_download(scores=scores, want_cand=want_cand)
         return frag, a, u, cand, st
+
+    def assemble_align_batch(self, frags, params: Params | None = None):
+        """the alignment part of assemble_KMA's inner loop (assembly.c:1868-1961: anker_rc + KMA with traceback +
+        acceptance) over per-template fragment records (frags.c:45-48) -> (output bytes, nrecords, stats); per record
+        int32[12]{accepted, read_score, start, end, score, len, pos, match, tGaps, qGaps, turned, ncol} + t/s/q rows"""
+        p = params or default_params()
+        frags = np.ascontiguousarray(frags, dtype=np.uint8)
+        cap = 64 + 60 * (len(frags) // 32 + 1) + 16 * len(frags)
+        out = np.empty(cap, dtype=np.uint8)
+        ob, nr, st = C.c_size_t(), C.c_int64(), AlignStats()
+        _check(lib().kmagpu_trace_batch(self._h, C.byref(p), frags.ctypes.data, len(frags), out.ctypes.data, cap,
+                                        C.byref(ob), C.byref(nr), C.byref(st)))
+        return out[: ob.value], nr.value, st
 
     def nw_batch(self, prob: np.ndarray, qpool: np.ndarray, params: Params | None = None):
         """NW_score / NW_band_score over independent problems; prob[n, 8] int32 =

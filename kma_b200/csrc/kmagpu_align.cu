@@ -202,8 +202,10 @@ __device__ __forceinline__ void mem_from_seed(const uint64_t *qw, const uint64_t
 }
 
 // MODE 0: the seed scan of KMA_score (align.c:534-640); MODE 1: one strand of anker_rc_comp (align.c:1044-1143).
-// Appends to M starting at index n; *sscore = strand score of MODE 1. Returns ST_OVERFLOW when M is full.
-template <int MODE>
+// BYTES: the byte-read flavour of KMA (align.c:246-377) and anker_rc (align.c:823-957): a stretch between N's is only
+// entered, and re-entered after a MEM, while MORE than k bases remain before its end; MEMs always extend to the
+// stretch end. Appends to M starting at index n; *sscore = strand score of MODE 1. Returns ST_OVERFLOW when M is full.
+template <int MODE, bool BYTES>
 __device__ int scan_mems(const KgTIndexView &ix, const KgTMeta &m, const uint64_t *tseq, const QView &q, int nN1, int q_len,
                          int start, Mems &M, int &n, int &sscore, WarpCtr &wc) {
 	const int lane = threadIdx.x & 31;
@@ -211,7 +213,8 @@ __device__ int scan_mems(const KgTIndexView &ix, const KgTMeta &m, const uint64_
 	int j = start, s = 0;
 	for (int seg = 0; seg < nN1 && j < q_len; ++seg) {
 		const int segN = q.N[seg], end = segN - k + 1, lo = seg ? q.N[seg - 1] + 1 : 0;
-		const int fwd_lim = MODE == 0 ? segN : end;
+		const int fwd_lim = (BYTES || MODE == 0) ? segN : end;
+		if (BYTES && !(j < segN - k)) { j = segN + 1; continue; }
 		while (j < end) {
 			const int p0 = j + lane;
 			int val = 0;
@@ -229,7 +232,7 @@ __device__ int scan_mems(const KgTIndexView &ix, const KgTMeta &m, const uint64_
 				++n;
 				s += qe - qs;
 				wc.mem_bases += (unsigned long long)(qe - qs);
-				j = MODE == 0 ? qe : qe + 1;
+				j = (BYTES || MODE == 0) ? qe : qe + 1;
 			} else {
 				int cnt;
 				const int32_t *d = tix_dups(ix, v, &cnt);
@@ -247,6 +250,7 @@ __device__ int scan_mems(const KgTIndexView &ix, const KgTMeta &m, const uint64_
 				s += k + (bias - p);
 				j = bias + 1;
 			}
+			if (BYTES && !(j < segN - k)) break;   // "update position" (align.c:309-315): the stretch is left
 		}
 		j = segN + 1;
 	}
@@ -383,7 +387,7 @@ __device__ int kma_score_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 	NwStat s = {0, 1, 0, 0, 0, 0};
 	if (!n) {
 		int dummy;
-		if (scan_mems<0>(ix, m, c.tseq, q, nN1, q_len, 0, M, n, dummy, *c.wc)) return ST_OVERFLOW;
+		if (scan_mems<0, false>(ix, m, c.tseq, q, nN1, q_len, 0, M, n, dummy, *c.wc)) return ST_OVERFLOW;
 	}
 	c.wc->mems += (unsigned long long)n;
 	if (!n) { *out = s; return ST_OK; }
@@ -493,9 +497,9 @@ __device__ int align_pair(const AlnParams &P, const NwPen *pen, const KgTIndexVi
 		const QView qf = read_view(slab, R, 0), qr = read_view(slab, R, 1);
 		int sf = 0, sr = 0, nf = 0, ntot;
 		const bool pre = P.exhaustive || preseed_hit(ix, m, qf.b, q_len);
-		if (pre && scan_mems<1>(ix, m, c.tseq, qf, nN1, q_len, 0, M, nf, sf, wc)) return ST_OVERFLOW;
+		if (pre && scan_mems<1, false>(ix, m, c.tseq, qf, nN1, q_len, 0, M, nf, sf, wc)) return ST_OVERFLOW;
 		ntot = nf;
-		if (scan_mems<1>(ix, m, c.tseq, qr, nN1, q_len, 0, M, ntot, sr, wc)) return ST_OVERFLOW;
+		if (scan_mems<1, false>(ix, m, c.tseq, qr, nN1, q_len, 0, M, ntot, sr, wc)) return ST_OVERFLOW;
 		const int best = max(sf, sr);
 		if (P.one2one && best < k && best * k < (q_len - k - best)) { n = 0; strand = -1; }
 		else if (best == sf) {   // forward wins ties; a zero score means nothing seeded on either strand
@@ -900,6 +904,379 @@ __global__ void __launch_bounds__(256) aln_emit_kernel(const uint8_t *__restrict
 	}
 }
 
+
+// ---------------------------------------------------------------- traceback alignment (assemble_KMA's inner loop)
+
+#define ST_ROWS 3   // aligned rows longer than the per-record capacity
+
+struct TrRec {
+	uint32_t rec_off;
+	int32_t tmpl, q_len, score, hl, nN, words;
+	uint32_t slab_off;      // 8-byte units
+	uint32_t row_cap;       // columns reserved per row
+	unsigned long long row_off;   // byte offset of the record's three rows in the row pool
+};
+
+__host__ __device__ __forceinline__ uint32_t tr_stride(const TrRec &R) { return slab_W(R.words) + slab_B(R.q_len) + slab_N(R.nN); }
+
+__device__ __forceinline__ QView tr_view(const uint64_t *slab, const TrRec &R, int strand) {
+	const uint64_t *base = slab + R.slab_off + (strand ? tr_stride(R) : 0);
+	QView v;
+	v.w = base;
+	v.b = (const uint8_t *)(base + slab_W(R.words));
+	v.N = (const int32_t *)(base + slab_W(R.words) + slab_B(R.q_len));
+	return v;
+}
+
+// one warp per record: header fields, number of N's, slab and row-pool sizes
+__global__ void __launch_bounds__(256) tr_sizes_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ off, int n, int DB_size,
+		TrRec *recs, uint32_t *slab_sz, uint32_t *row_sz, unsigned long long *ctr) {
+	const unsigned lane = threadIdx.x & 31;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+		const uint8_t *rec = in + off[r];
+		TrRec R;
+		R.rec_off = off[r];
+		R.tmpl = (int)ld_u32u(rec); R.q_len = (int)ld_u32u(rec + 4); R.score = (int)ld_u32u(rec + 12); R.hl = (int)ld_u32u(rec + 24);
+		const uint8_t *q = rec + 32;
+		int cnt = 0;
+		for (int i = lane; i < R.q_len; i += 32) cnt += q[i] == 4;
+		R.nN = warp_sum(cnt);
+		R.words = (R.q_len + 31) >> 5;
+		R.row_cap = 3u * (uint32_t)R.q_len + 256u;
+		R.slab_off = 0; R.row_off = 0;
+		if (lane == 0) {
+			if (R.tmpl <= 0 || R.tmpl >= DB_size) atomicAdd(&ctr[A_BAD], 1ull);
+			recs[r] = R;
+			slab_sz[r] = tr_stride(R) * (R.score == 0 ? 2u : 1u);
+			row_sz[r] = (3u * R.row_cap + 7u) >> 3;   // 8-byte units
+			atomicMax(&ctr[A_MAXQ], (unsigned long long)R.q_len);
+		}
+	}
+}
+
+// bytes -> slab (packed words, bytes, N list + sentinel), reverse complement too for reads without a strand
+__global__ void __launch_bounds__(256) tr_prep_kernel(const uint8_t *__restrict__ in, int n, TrRec *recs, const uint32_t *__restrict__ slab_off,
+		const uint32_t *__restrict__ row_off, uint64_t *slab) {
+	const unsigned lane = threadIdx.x & 31;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+		TrRec R = recs[r];
+		R.slab_off = slab_off[r]; R.row_off = 8ull * row_off[r];
+		if (lane == 0) { recs[r].slab_off = R.slab_off; recs[r].row_off = R.row_off; }
+		const uint8_t *src = in + R.rec_off + 32;
+		const int L = R.q_len;
+		for (int strand = 0; strand < (R.score == 0 ? 2 : 1); ++strand) {
+			uint64_t *base = slab + R.slab_off + (strand ? tr_stride(R) : 0);
+			uint8_t *b = (uint8_t *)(base + slab_W(R.words));
+			int32_t *N = (int32_t *)(base + slab_W(R.words) + slab_B(L));
+			for (int i = lane; i < (int)(slab_B(L) << 3); i += 32) {
+				uint8_t v = 0;
+				if (i < L) { v = strand ? src[L - 1 - i] : src[i]; if (strand && v < 4) v = 3 - v; }
+				b[i] = v;
+			}
+			__syncwarp();
+			for (int w = lane; w < R.words + 2; w += 32) {
+				uint64_t x = 0;
+				if (w < R.words) for (int i = 0; i < 32 && 32 * w + i < L; ++i) x |= (uint64_t)(b[32 * w + i] & 3 & (b[32 * w + i] < 4 ? 3 : 0)) << (62 - 2 * i);
+				base[w] = x;
+			}
+			// N positions in ascending order: ranks by ballot
+			int cnt = 0;
+			for (int i0 = 0; i0 < L; i0 += 32) {
+				const int i = i0 + (int)lane;
+				const bool isn = i < L && b[i] == 4;
+				const unsigned mk = __ballot_sync(0xffffffffu, isn);
+				if (isn) N[cnt + __popc(mk & ((1u << lane) - 1))] = i;
+				cnt += __popc(mk);
+			}
+			if (lane == 0) N[cnt] = L;   // sentinel
+			__syncwarp();
+		}
+	}
+}
+
+// KMA (align.c:214-507): MEMs (found here with the byte-read scan unless n != 0), chain, stitch with NW -- writing the
+// aligned rows. *ncol = columns written (0 when nothing aligned).
+__device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTIndexView &ix, const KgTMeta &m, const QView &q,
+                              int nN1, int q_len, Mems &M, int n, NwStat *out, const NwRows &rows, int row_cap, int *ncol) {
+	const int lane = threadIdx.x & 31;
+	const int k = ix.k, t_len = m.len, U = P.pen.U, Mv = P.pen.M;
+	NwStat s = {0, 1, 0, 0, 0, 0};
+	*ncol = 0;
+	if (!n) {
+		int dummy;
+		if (scan_mems<0, true>(ix, m, c.tseq, q, nN1, q_len, 0, M, n, dummy, *c.wc)) return ST_OVERFLOW;
+	}
+	c.wc->mems += (unsigned long long)n;
+	if (!n) { *out = s; return ST_OK; }
+	unsigned mapQ = 0;
+	int start = chain_warp(*c.pen, M, n, q_len, t_len, k, &mapQ);
+	if ((int)mapQ < P.mq || M.sc[start] < k) { *out = s; return ST_OK; }
+	auto nw_rows = [&](int kk, int t_s, int t_e, int q_s, int q_e, int at, NwStat *a) -> int {
+		if (at + (t_e - t_s) + (q_e - q_s) + 8 > row_cap) return ST_ROWS;
+		const int t_l = t_e - t_s, q_l = q_e - q_s;
+		int band = abs(t_l - q_l) + AL_BANDW;
+		if (q_l <= band || t_l <= band) band = 0;
+		NwRows r = {rows.t + at, rows.s + at, rows.q + at};
+		unsigned long long cells = 0;
+		const int st = nw_warp(*c.pen, c.tseq, c.qb, kk, t_s, t_e, q_s, q_e, band, c.nw, a, &cells, &r);
+		if (st != NW_OK) {
+			NwGeo g;
+			nw_geo_init(g, *c.pen, t_l, q_l, kk, band);
+			c.wc->need_e = max(c.wc->need_e, (unsigned)min((size_t)0xF0000000u, g.ebytes() + 4096));
+			c.wc->need_q = max(c.wc->need_q, (unsigned)q_l + 64u);
+			return ST_OVERFLOW;
+		}
+		if (cells) { if (band) { ++c.wc->band_calls; c.wc->band_cells += cells; } else { ++c.wc->full_calls; c.wc->full_cells += cells; } }
+		return ST_OK;
+	};
+	// leading tail (leadTailAln with Frag_align, align.c:53-138)
+	{
+		const int t_e = M.tS[start] - 1, q_e = M.qS[start];
+		s.score = 0; s.len = 0; s.pos = t_e; s.match = 0; s.tGaps = 0; s.qGaps = 0;
+		if (q_e) {
+			int t_s = 0, q_s = 0;
+			if ((q_e << 1) < t_e || (q_e + AL_BANDW) < t_e) t_s = t_e - (q_e + min(q_e, AL_BANDW));
+			else if ((t_e << 1) < q_e || (t_e + AL_BANDW) < q_e) q_s = q_e - (t_e + min(t_e, AL_BANDW));
+			if (t_e - t_s > 0 && q_e - q_s > 0) {
+				NwStat a;
+				const int st = nw_rows(-1 - (t_s == 0), t_s, t_e, q_s, q_e, 0, &a);
+				if (st) return st;
+				if (t_s == 0) {   // trim leading gap columns (align.c:99-113)
+					int bias = 0;
+					while (bias < a.len) {
+						const int i = bias + lane;
+						const int gt = i < a.len && rows.t[i] == 5, gq = i < a.len && rows.q[i] == 5;
+						const unsigned gm = __ballot_sync(0xffffffffu, gt || gq), tm = __ballot_sync(0xffffffffu, gt);
+						const int run = ~gm ? __ffs(~gm) - 1 : 32;
+						const unsigned low = run == 32 ? 0xffffffffu : ((1u << run) - 1);
+						a.tGaps -= __popc(tm & low); a.qGaps -= __popc(gm & ~tm & low);
+						bias += run;
+						if (run < 32) break;
+					}
+					if (bias > a.len) bias = a.len;
+					if (bias) {   // shift the rows left by `bias`, 32 columns at a time
+						for (int i0 = 0; i0 < a.len - bias; i0 += 32) {
+							const int i = i0 + lane;
+							uint8_t vt = 0, vs = 0, vq = 0;
+							if (i < a.len - bias) { vt = rows.t[i + bias]; vs = rows.s[i + bias]; vq = rows.q[i + bias]; }
+							__syncwarp();
+							if (i < a.len - bias) { rows.t[i] = vt; rows.s[i] = vs; rows.q[i] = vq; }
+							__syncwarp();
+						}
+						a.len -= bias;
+					}
+				}
+				s.pos -= a.len - a.tGaps;
+				s.score = a.score; s.len = a.len; s.match = a.match; s.tGaps = a.tGaps; s.qGaps = a.qGaps;
+			}
+		}
+	}
+	for (;;) {
+		const int qS = M.qS[start], qE = M.qE[start];
+		const int len = qE - qS;
+		if (s.len + len + 8 > row_cap) return ST_ROWS;
+		int sc = 0;
+		for (int i = qS + lane; i < qE; i += 32) {
+			const int b = c.qb[i];
+			rows.t[s.len + i - qS] = (uint8_t)b; rows.s[s.len + i - qS] = '|'; rows.q[s.len + i - qS] = (uint8_t)b;
+			sc += P.pen.d[b * 5 + b];
+		}
+		s.len += len; s.match += len;
+		s.score += warp_sum(sc);
+		const int nxt = M.nx[start];
+		if (!nxt) break;
+		const int q_s = qE, t_s = M.tE[start] - 1;
+		int t_e, t_l, q_e;
+		start = nxt;
+		int qSn = M.qS[start], tSn = M.tS[start];
+		if (qSn < q_s) { tSn += q_s - qSn; qSn = q_s; }
+		t_e = tSn - 1;
+		if (t_e < t_s) {
+			if (t_s <= M.tE[start]) { qSn += t_s - t_e; t_e = t_s; t_l = 0; }
+			else t_l = t_len - t_s + t_e;
+		} else t_l = t_e - t_s;
+		__syncwarp();
+		if (lane == 0) { M.qS[start] = qSn; M.tS[start] = tSn; }
+		__syncwarp();
+		q_e = qSn;
+		if (abs(t_l - q_e + q_s) * U > q_len * Mv || t_l > q_len || q_e - q_s > (q_len >> 1)) {   // align.c:465
+			const int keep = s.pos;
+			s.score = 0; s.len = 1; s.pos = keep; s.match = 0; s.tGaps = 0; s.qGaps = 0;
+			*out = s;
+			return ST_OK;
+		}
+		if (t_l > 0 || q_e - q_s > 0) {
+			NwStat a;
+			const int st = nw_rows(0, t_s, t_e, q_s, q_e, s.len, &a);
+			if (st) return st;
+			s.score += a.score; s.len += a.len; s.match += a.match; s.tGaps += a.tGaps; s.qGaps += a.qGaps;
+		}
+	}
+	// trailing tail (trailTailAln with Frag_align, align.c:147-212)
+	{
+		const int t_s = M.tE[start] - 1, q_s = M.qE[start];
+		int q_e = q_len, t_e = t_len;
+		if (((q_len - q_s) << 1) < (t_len - t_s) || (q_len - q_s + AL_BANDW) < (t_len - t_s)) {
+			t_e = q_len - q_s; t_e = t_s + (t_e + min(t_e, AL_BANDW));
+		} else if (((t_len - t_s) << 1) < (q_len - q_s) || (t_len - t_s + AL_BANDW) < (q_len - q_s)) {
+			q_e = t_len - t_s; q_e = q_s + (q_e + min(q_e, AL_BANDW));
+		}
+		if (t_e - t_s > 0 && q_e - q_s > 0) {
+			NwStat a;
+			const int st = nw_rows(1 + (t_e == t_len), t_s, t_e, q_s, q_e, s.len, &a);
+			if (st) return st;
+			if (t_e == t_len) {   // trim trailing gap columns (align.c:183-199); column 0 is never trimmed
+				int bias = a.len - 1;
+				const uint8_t *rt = rows.t + s.len, *rq = rows.q + s.len;
+				while (bias > 0) {
+					const int i = bias - lane;
+					const int gt = i > 0 && rt[i] == 5, gq = i > 0 && rq[i] == 5;
+					const unsigned gm = __ballot_sync(0xffffffffu, gt || gq), tm = __ballot_sync(0xffffffffu, gt);
+					const int run = ~gm ? __ffs(~gm) - 1 : 32;
+					const unsigned low = run == 32 ? 0xffffffffu : ((1u << run) - 1);
+					a.tGaps -= __popc(tm & low); a.qGaps -= __popc(gm & ~tm & low);
+					bias -= run;
+					if (run < 32) break;
+				}
+				if (bias < 0) bias = 0;
+				a.len = bias + 1;
+			}
+			s.score += a.score; s.len += a.len; s.match += a.match; s.tGaps += a.tGaps; s.qGaps += a.qGaps;
+		}
+	}
+	*ncol = s.len;
+	*out = s;
+	return ST_OK;
+}
+
+struct TrOut { int32_t h[12]; int32_t status; };
+
+// one warp per fragment record: (anker_rc when the strand is open) -> KMA -> acceptance (assembly.c:1925-1961)
+__global__ void __launch_bounds__(AL_WARPS * 32, AL_MINB) tr_task_kernel(AlnParams P, KgTIndexView ix, const TrRec *__restrict__ recs,
+		const uint64_t *slab, int n, const int32_t *__restrict__ task_list, TrOut *outs, uint8_t *rowpool, uint8_t *scratch,
+		ScratchLayout lay, unsigned long long *ctr, int32_t *ovf_list) {
+	__shared__ NwPen spen;
+	__shared__ NwRow sring[AL_WARPS][NW_RING];
+	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&P.pen)[threadIdx.x];
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const size_t wid = (size_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
+	uint8_t *sp = scratch + wid * lay.stride;
+	Mems M0;
+	{
+		int *p = (int *)sp;
+		const int c1 = lay.mem_cap + 1;
+		M0.tS = p; M0.tE = p + c1; M0.qS = p + 2 * c1; M0.qE = p + 3 * c1; M0.W = p + 4 * c1; M0.sc = p + 5 * c1; M0.nx = p + 6 * c1;
+		M0.cap = lay.mem_cap;
+		sp += (((size_t)7 * c1 * 4) + 15) & ~(size_t)15;
+	}
+	NwScratch nws;
+	nws.ring = sring[threadIdx.x >> 5];
+	nws.rowbuf = (NwRow *)sp; sp += (size_t)lay.q_cap * 8;
+	nws.lastD = (int *)sp; sp += (size_t)lay.q_cap * 4;
+	nws.E = sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap;
+	WarpCtr wc;
+	memset(&wc, 0, sizeof(wc));
+	for (;;) {
+		unsigned long long t = 0;
+		if (lane == 0) t = atomicAdd(&ctr[A_WORK], 1ull);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t >= (unsigned long long)n) break;
+		const int r = task_list ? task_list[t] : (int)t;
+		const TrRec R = recs[r];
+		const KgTMeta m = ix.meta[R.tmpl];
+		const int k = ix.k, q_len = R.q_len, nN1 = R.nN + 1, t_len = m.len;
+		Mems M = M0;
+		TaskCtx c;
+		c.pen = &spen; c.tseq = ix.seq + m.seq_off; c.nw = nws; c.wc = &wc;
+		TrOut o;
+		memset(&o, 0, sizeof(o));
+		int strand = 0, nmem = 0, st = ST_OK;
+		bool go = R.score != 0;
+		if (!go) {   // anker_rc (align.c:780-991)
+			const QView qf = tr_view(slab, R, 0), qr = tr_view(slab, R, 1);
+			int sf = 0, sr = 0, nf = 0, ntot;
+			const bool pre = P.exhaustive || preseed_hit(ix, m, qf.b, q_len);
+			if (pre) st = scan_mems<1, true>(ix, m, c.tseq, qf, nN1, q_len, 0, M, nf, sf, wc);
+			ntot = nf;
+			if (!st) st = scan_mems<1, true>(ix, m, c.tseq, qr, nN1, q_len, 0, M, ntot, sr, wc);
+			const int best = max(sf, sr);
+			if (!st) {
+				int turned = 0;
+				if (P.one2one && best < k && best * k < (q_len - k - best)) turned = 1;   // rejected; the read stays turned
+				else if (best == sf) { nmem = nf; go = best != 0; }
+				else { strand = 1; M.shift(nf); nmem = ntot - nf; go = true; turned = 1; }
+				if (turned) {   // "oriented": do the bytes differ from what came in? (a palindrome does not)
+					int diff = 0;
+					for (int i = lane; i < q_len; i += 32) diff |= qf.b[i] != qr.b[i];
+					o.h[10] = __any_sync(0xffffffffu, diff) ? 1 : 0;
+				}
+			}
+		}
+		if (go && !st) {
+			const QView q = tr_view(slab, R, strand);
+			c.qb = q.b;
+			NwRows rows;
+			rows.t = rowpool + R.row_off; rows.s = rows.t + R.row_cap; rows.q = rows.s + R.row_cap;
+			NwStat a = {0, 0, 0, 0, 0, 0};
+			int ncol = 0;
+			st = kma_trace_warp(P, c, ix, m, q, nN1, q_len, M, nmem, &a, rows, (int)R.row_cap, &ncol);
+			if (!st) {
+				const int aln_len = a.len, start = a.pos;
+				int end = start + aln_len - a.tGaps, read_score = a.score;
+				double score;
+				if (t_len < end) end -= t_len;
+				if (start == 0) read_score += -P.Wl;
+				if (end == t_len) read_score += -P.Wl;
+				if (P.minlen <= aln_len && ((P.mrc * q_len <= a.len - a.qGaps) || (P.mrc * t_len <= a.len - a.tGaps))) score = 1.0 * read_score / aln_len;
+				else { read_score = 0; score = 0; }
+				o.h[0] = 0 < read_score && P.scoreT <= score;
+				o.h[1] = read_score; o.h[2] = start; o.h[3] = end;
+				o.h[4] = a.score; o.h[5] = a.len; o.h[6] = a.pos; o.h[7] = a.match; o.h[8] = a.tGaps; o.h[9] = a.qGaps;
+				o.h[11] = ncol;
+			}
+		}
+		__syncwarp();
+		o.status = st;
+		if (st == ST_OVERFLOW && lane == 0) { const unsigned long long x = atomicAdd(&ctr[A_OVF], 1ull); ovf_list[x] = r; }
+		if (st == ST_ROWS && lane == 0) atomicAdd(&ctr[A_BAD], 1ull);
+		if (lane == 0) outs[r] = o;
+	}
+	if (lane == 0) {
+		if (wc.mems) atomicAdd(&ctr[A_MEMS], wc.mems);
+		if (wc.full_calls) { atomicAdd(&ctr[A_FULL_CALLS], wc.full_calls); atomicAdd(&ctr[A_FULL_CELLS], wc.full_cells); }
+		if (wc.band_calls) { atomicAdd(&ctr[A_BAND_CALLS], wc.band_calls); atomicAdd(&ctr[A_BAND_CELLS], wc.band_cells); }
+		if (wc.need_e) atomicMax(&ctr[A_NEED_E], (unsigned long long)wc.need_e);
+		if (wc.need_mem) atomicMax(&ctr[A_NEED_MEM], (unsigned long long)wc.need_mem);
+		if (wc.need_q) atomicMax(&ctr[A_NEED_Q], (unsigned long long)wc.need_q);
+	}
+}
+
+__global__ void tr_outsize_kernel(const TrOut *__restrict__ outs, int n, uint32_t *size) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < n) size[r] = 48u + 3u * (uint32_t)outs[r].h[11];
+}
+
+// per record: int32[12] header + t, s, q rows (ncol bytes each), input order
+__global__ void __launch_bounds__(256) tr_emit_kernel(const TrRec *__restrict__ recs, const TrOut *__restrict__ outs, int n,
+		const uint8_t *__restrict__ rowpool, const uint32_t *__restrict__ out_off, uint8_t *__restrict__ out) {
+	const unsigned lane = threadIdx.x & 31;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+		const TrOut o = outs[r];
+		const TrRec R = recs[r];
+		uint8_t *dst = out + out_off[r];
+		if (lane < 12) st_u32b(dst + 4 * lane, (uint32_t)o.h[lane]);
+		dst += 48;
+		const int ncol = o.h[11];
+		const uint8_t *src = rowpool + R.row_off;
+		for (int row = 0; row < 3; ++row)
+			for (int i = lane; i < ncol; i += 32) dst[(size_t)row * ncol + i] = src[(size_t)row * R.row_cap + i];
+	}
+}
+
 // ---------------------------------------------------------------- host side
 
 int kg_align_free(kmagpu_db *db) {
@@ -1169,6 +1546,134 @@ extern "C" int kmagpu_align_batch(kmagpu_db *db, const kmagpu_params *p, const v
 	if (kmagpu_align_run(db, p, cand_out != nullptr, stats)) return -1;
 	if (kmagpu_align_download(db, frag_out, out_cap, out_bytes, alignment_scores, uniq_alignment_scores, cand_out, cand_cap, cand_rows)) return -1;
 	if (stats) cudaEventElapsedTime(&stats->ms_h2d, db->ev[5], db->ev[6]);
+	return 0;
+}
+
+
+// ---------------------------------------------------------------- traceback batch (host)
+
+extern "C" int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *prm, const void *frags, size_t nbytes,
+                                  void *out, size_t out_cap, size_t *out_bytes, int64_t *nrecords, kmagpu_align_stats *stats) {
+	if (!db || !prm || (!frags && nbytes)) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->d_tslots) { kmagpu_set_error("database has no alignment index (.seq.b / .length.b missing)"); return -1; }
+	if (nbytes >= (1ull << 32) - 64) { kmagpu_set_error("fragment batch of %zu bytes exceeds the 4 GiB per-call limit; split it", nbytes); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	if (stats) memset(stats, 0, sizeof(*stats));
+	if (out_bytes) *out_bytes = 0;
+	if (nrecords) *nrecords = 0;
+	size_t used = 0;
+	const int64_t n64 = kmagpu_record_walk(3, frags, nbytes, nullptr, 0, &used);
+	if (n64 < 0) return -1;
+	const int n = (int)n64;
+	if (nrecords) *nrecords = n64;
+	if (n == 0) return 0;
+	std::vector<uint64_t> off64((size_t)n);
+	kmagpu_record_walk(3, frags, nbytes, off64.data(), (size_t)n, &used);
+	std::vector<uint32_t> off((size_t)n + 1);
+	for (int i = 0; i < n; ++i) off[i] = (uint32_t)off64[i];
+	off[n] = (uint32_t)used;
+
+	const AlnParams P = make_params(db, prm);
+	cudaStream_t st = db->stream;
+	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+	KgBuf d_in, d_off, d_recs, d_sz, d_partial, d_ctr, d_slab, d_rows, d_outs, d_ovf, d_out;
+	struct Guard { std::vector<KgBuf *> v; ~Guard() { for (KgBuf *b : v) b->release(); } } guard;
+	guard.v = {&d_in, &d_off, &d_recs, &d_sz, &d_partial, &d_ctr, &d_slab, &d_rows, &d_outs, &d_ovf, &d_out};
+	if (d_in.reserve(used + 64) || d_off.reserve(4 * ((size_t)n + 2)) || d_recs.reserve(sizeof(TrRec) * (size_t)n) ||
+	    d_sz.reserve(4 * (size_t)(6 * n + 12)) || d_partial.reserve(4 * (size_t)(ntiles + 2)) || d_ctr.reserve(8 * A_N) ||
+	    d_outs.reserve(sizeof(TrOut) * (size_t)n) || d_ovf.reserve(4 * ((size_t)n + 1))) return -1;
+	uint32_t *slab_sz = (uint32_t *)d_sz.p, *slab_off = slab_sz + n + 1, *row_sz = slab_off + n + 1, *row_off = row_sz + n + 1,
+	         *osz = row_off + n + 1, *ooff = osz + n + 1;
+	unsigned long long *ctr = (unsigned long long *)d_ctr.p;
+	unsigned long long h[A_N];
+	int launches = 0;
+	KG_CUDA(cudaMemcpyAsync(d_in.p, frags, used, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemsetAsync((uint8_t *)d_in.p + used, 0, 64, st));
+	KG_CUDA(cudaMemcpyAsync(d_off.p, off.data(), 4 * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * A_N, st));
+	KG_CUDA(cudaEventRecord(db->ev[2], st));
+	tr_sizes_kernel<<<db->sm_count * 8, 256, 0, st>>>((const uint8_t *)d_in.p, (const uint32_t *)d_off.p, n, db->info.DB_size,
+		(TrRec *)d_recs.p, slab_sz, row_sz, ctr);
+	kg_exscan(slab_sz, n, slab_off, (uint32_t *)d_partial.p, ctr + A_SLAB, st);
+	kg_exscan(row_sz, n, row_off, (uint32_t *)d_partial.p, ctr + A_TASKS, st);
+	launches += 7;
+	KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	if (h[A_BAD]) { kmagpu_set_error("%llu fragment records name a template outside the database", h[A_BAD]); return -1; }
+	const int maxq = (int)h[A_MAXQ];
+	if (d_slab.reserve(8 * ((size_t)h[A_SLAB] + 4)) || d_rows.reserve(8 * ((size_t)h[A_TASKS] + 4))) return -1;
+	tr_prep_kernel<<<db->sm_count * 8, 256, 0, st>>>((const uint8_t *)d_in.p, n, (TrRec *)d_recs.p, slab_off, row_off, (uint64_t *)d_slab.p);
+	++launches;
+	const int q_cap = std::min(std::max(maxq + 64, 256), 1 << 20);
+	const size_t e_cap = std::min<size_t>(std::max<size_t>(2 * (size_t)maxq * (size_t)maxq + 65536, 65536), 4u << 20);
+	ScratchLayout lay = make_layout(2048, q_cap, e_cap);
+	AlignBatch &b = db->aln;   // the per-warp scratch is shared with the alignment pass
+	int grid = db->sm_count * AL_MINB;
+	size_t freeb = 0, totalb = 0;
+	if (lay.stride * (size_t)grid * AL_WARPS > b.d_scratch.cap) {
+		cudaMemGetInfo(&freeb, &totalb);
+		while (grid > db->sm_count && lay.stride * (size_t)grid * AL_WARPS > freeb / 2 + b.d_scratch.cap) grid -= db->sm_count;
+	}
+	if (b.d_scratch.reserve(lay.stride * (size_t)grid * AL_WARPS)) return -1;
+	KG_CUDA(cudaEventRecord(db->ev[3], st));
+	tr_task_kernel<<<grid, AL_WARPS * 32, 0, st>>>(P, db->tix, (const TrRec *)d_recs.p, (const uint64_t *)d_slab.p, n, nullptr,
+		(TrOut *)d_outs.p, (uint8_t *)d_rows.p, (uint8_t *)b.d_scratch.p, lay, ctr, (int32_t *)d_ovf.p);
+	KG_CUDA(cudaEventRecord(db->ev[4], st));
+	++launches;
+	KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	int novf = (int)h[A_OVF];
+	const unsigned long long first_ovf = h[A_OVF];
+	for (int round = 0; novf; ++round) {   // large-scratch path, as in the alignment pass
+		if (round == 8) { kmagpu_set_error("%d fragment records do not fit the alignment scratch", novf); return -1; }
+		const ScratchLayout big = make_layout(std::max<int>(2048, (int)h[A_NEED_MEM]), std::max<int>(q_cap, (int)h[A_NEED_Q]),
+		                                      std::max<size_t>(e_cap, (size_t)h[A_NEED_E]));
+		cudaMemGetInfo(&freeb, &totalb);
+		int g2 = std::min(db->sm_count, (novf + AL_WARPS - 1) / AL_WARPS);
+		while (g2 > 1 && big.stride * (size_t)g2 * AL_WARPS > (freeb + b.d_scratch.cap) / 2) g2 = (g2 + 1) / 2;
+		if (b.d_scratch.reserve(big.stride * (size_t)g2 * AL_WARPS)) return -1;
+		KgBuf list2;
+		if (list2.reserve(4 * ((size_t)novf + 1))) return -1;
+		KG_CUDA(cudaMemcpyAsync(list2.p, d_ovf.p, 4 * (size_t)novf, cudaMemcpyDeviceToDevice, st));
+		KG_CUDA(cudaMemsetAsync(ctr + A_WORK, 0, 8 * 5, st));
+		tr_task_kernel<<<g2, AL_WARPS * 32, 0, st>>>(P, db->tix, (const TrRec *)d_recs.p, (const uint64_t *)d_slab.p, novf,
+			(const int32_t *)list2.p, (TrOut *)d_outs.p, (uint8_t *)d_rows.p, (uint8_t *)b.d_scratch.p, big, ctr, (int32_t *)d_ovf.p);
+		++launches;
+		KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
+		KG_CUDA(cudaStreamSynchronize(st));
+		KG_CUDA(cudaGetLastError());
+		list2.release();
+		novf = (int)h[A_OVF];
+	}
+	if (h[A_BAD]) { kmagpu_set_error("%llu alignments are longer than 3 * read length + 256 columns", h[A_BAD]); return -1; }
+	tr_outsize_kernel<<<(n + 255) / 256, 256, 0, st>>>((const TrOut *)d_outs.p, n, osz);
+	kg_exscan(osz, n, ooff, (uint32_t *)d_partial.p, ctr + A_OUT, st);
+	launches += 4;
+	unsigned long long h2[A_N];
+	KG_CUDA(cudaMemcpyAsync(h2, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	const size_t ob = (size_t)h2[A_OUT];
+	if (out_bytes) *out_bytes = ob;
+	if (ob > out_cap) { kmagpu_set_error("trace output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
+	if (d_out.reserve(ob + 64)) return -1;
+	tr_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>((const TrRec *)d_recs.p, (const TrOut *)d_outs.p, n, (const uint8_t *)d_rows.p, ooff,
+		(uint8_t *)d_out.p);
+	++launches;
+	KG_CUDA(cudaEventRecord(db->ev[7], st));
+	KG_CUDA(cudaMemcpyAsync(out, d_out.p, ob, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	if (stats) {
+		stats->reads = n; stats->tasks = n; stats->mems = (int64_t)h[A_MEMS];
+		stats->nw_full_calls = (int64_t)h[A_FULL_CALLS]; stats->nw_band_calls = (int64_t)h[A_BAND_CALLS];
+		stats->nw_full_cells = (int64_t)h[A_FULL_CELLS]; stats->nw_band_cells = (int64_t)h[A_BAND_CELLS];
+		stats->overflow_tasks = (int64_t)first_ovf;
+		cudaEventElapsedTime(&stats->ms_align, db->ev[3], db->ev[4]);
+		cudaEventElapsedTime(&stats->ms_total, db->ev[2], db->ev[7]);
+		stats->launches = launches;
+	}
 	return 0;
 }
 

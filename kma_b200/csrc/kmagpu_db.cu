@@ -197,21 +197,24 @@ extern "C" int kmagpu_db_get_info(const kmagpu_db *db, kmagpu_db_info *info) {
 
 extern "C" int64_t kmagpu_record_walk(int stage, const void *buf, size_t nbytes, uint64_t *offsets, size_t cap, size_t *used) {
 	const uint8_t *in = (const uint8_t *)buf;
-	const size_t hdr = stage == 1 ? 16 : 28;
+	const size_t hdr = stage == 1 ? 16 : (stage == 2 ? 28 : 32);
 	size_t ip = 0;
 	int64_t n = 0;
-	if (stage != 1 && stage != 2) { kmagpu_set_error("kmagpu_record_walk: stage must be 1 or 2"); return -1; }
+	if (stage < 1 || stage > 3) { kmagpu_set_error("kmagpu_record_walk: stage must be 1, 2 or 3"); return -1; }
 	while (ip + hdr <= nbytes) {
-		int32_t h[7];
+		int32_t h[8];
 		memcpy(h, in + ip, hdr);
 		if (h[0] < 0) break;   // stream terminator
 		size_t len;
 		if (stage == 1) {
 			if (h[1] < 0 || h[2] < 0) { kmagpu_set_error("corrupt stage-1 record at byte %zu", ip); return -1; }
 			len = 16 + 8 * (size_t)h[1] + 4 * (size_t)h[2] + (size_t)abs(h[3]);
-		} else {
+		} else if (stage == 2) {
 			if (h[1] < 0 || h[2] < 0 || h[4] < 0 || h[5] < 0) { kmagpu_set_error("corrupt stage-2 record at byte %zu", ip); return -1; }
 			len = 28 + 8 * (size_t)h[1] + 4 * (size_t)h[2] + 4 * (size_t)h[4] + (size_t)h[5];
+		} else {   // per-template fragment record of the assembly pass (frags.c:45-48)
+			if (h[1] < 0 || h[6] < 0) { kmagpu_set_error("corrupt fragment record at byte %zu", ip); return -1; }
+			len = 32 + (size_t)h[1] + (size_t)h[6];
 		}
 		if (ip + len > nbytes) break;   // partial record: the caller refills
 		if (offsets && (size_t)n < cap) offsets[n] = ip;

@@ -289,15 +289,24 @@ struct NwScratch {
 #define NW_TOO_BIG 1      // scratch too small: the caller re-runs the problem on the large-scratch path
 #define NW_BAD_BAND 2
 
+// aligned rows of one call (NW / NW_band, nw.c:250-305): template, match and query row, written from column 0.
+// tseq/t_s/q give the bases; all null for the score-only calls.
+struct NwRows { uint8_t *t, *s, *q; };
+
 // The walk of nw_walk with up to 32 cells examined per memory round trip: the lanes read the traceback bytes along
 // the direction the path is moving (diagonal, down a P run, along a Q run) and a ballot finds where the run ends.
-__device__ __forceinline__ void nw_walk_warp(const NwGeo &g, const uint8_t *E, int m, int qp, NwStat &s) {
+__device__ __forceinline__ void nw_walk_warp(const NwGeo &g, const uint8_t *E, int m, int qp, NwStat &s, const NwRows *rows,
+                                             const uint64_t *tseq, int t_s, const uint8_t *q) {
 	const int lane = threadIdx.x & 31;
 	s.len = s.match = s.tGaps = s.qGaps = 0;
 	for (;;) {
 		const int e = nw_e_at(g, E, m + lane, qp + lane);
 		const unsigned nd = __ballot_sync(0xffffffffu, (e & 7) != 1);
 		const int r = nd ? __ffs(nd) - 1 : 32;   // leading diagonal steps
+		if (rows && lane < r) {
+			const uint8_t tb = (uint8_t)nw_nuc(tseq, t_s + m + lane), qb = q[qp + lane];
+			rows->t[s.len + lane] = tb; rows->q[s.len + lane] = qb; rows->s[s.len + lane] = tb == qb ? '|' : '_';
+		}
 		s.match += r; s.len += r; m += r; qp += r;
 		if (r == 32) continue;
 		const int c = __shfl_sync(0xffffffffu, e, r);
@@ -307,6 +316,8 @@ __device__ __forceinline__ void nw_walk_warp(const NwGeo &g, const uint8_t *E, i
 				const int f = nw_e_at(g, E, m + lane, qp);
 				const unsigned stop = __ballot_sync(0xffffffffu, (f >> 4) != 0);
 				const int n = stop ? __ffs(stop) - 1 : 32;
+				const int w = stop ? n + 1 : 32;   // columns written: the run so far and, at its end, the closing cell
+				if (rows && lane < w) { rows->t[s.len + lane] = (uint8_t)nw_nuc(tseq, t_s + m + lane); rows->q[s.len + lane] = 5; rows->s[s.len + lane] = '_'; }
 				m += n; s.len += n; s.qGaps += n;
 				if (stop) break;
 			}
@@ -316,6 +327,8 @@ __device__ __forceinline__ void nw_walk_warp(const NwGeo &g, const uint8_t *E, i
 				const int f = nw_e_at(g, E, m, qp + lane);
 				const unsigned stop = __ballot_sync(0xffffffffu, (f >> 3) != 0);
 				const int n = stop ? __ffs(stop) - 1 : 32;
+				const int w = stop ? n + 1 : 32;
+				if (rows && lane < w) { rows->t[s.len + lane] = 5; rows->q[s.len + lane] = q[qp + lane]; rows->s[s.len + lane] = '_'; }
 				qp += n; s.len += n; s.tGaps += n;
 				if (stop) break;
 			}
@@ -328,11 +341,19 @@ __device__ __forceinline__ void nw_walk_warp(const NwGeo &g, const uint8_t *E, i
 // All 32 lanes call with identical arguments; every lane returns the same result.
 __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict__ tseq, const uint8_t *query, int k, int t_s,
                                     int t_e, int q_s, int q_e, int band, const NwScratch &ws, NwStat *out,
-                                    unsigned long long *cells) {
+                                    unsigned long long *cells, const NwRows *rows = nullptr) {
 	const int lane = threadIdx.x & 31;
 	const int t_len = t_e - t_s, q_len = q_e - q_s;
 	NwStat s;
-	if (nw_trivial(pen, t_len, q_len, s)) { *out = s; return NW_OK; }
+	if (nw_trivial(pen, t_len, q_len, s)) {   // nw.c:49-85: one side empty -> all-gap rows
+		if (rows) {
+			if (t_len == 0) for (int i = lane; i < q_len; i += 32) { rows->t[i] = 5; rows->s[i] = '_'; rows->q[i] = query[q_s + i]; }
+			else for (int i = lane; i < t_len; i += 32) { rows->t[i] = (uint8_t)nw_nuc(tseq, t_s + i); rows->s[i] = '_'; rows->q[i] = 5; }
+			__syncwarp();
+		}
+		*out = s;
+		return NW_OK;
+	}
 	NwGeo g;
 	if (!nw_geo_init(g, pen, t_len, q_len, k, band)) return NW_BAD_BAND;
 	if (g.ebytes() > ws.e_cap || q_len + 1 > ws.q_cap) return NW_TOO_BIG;
@@ -376,7 +397,8 @@ __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict
 	}
 	int best_m, best_q, score;
 	nw_start_cell(g, cb, ci, ws.lastD, rb, rq, &best_m, &best_q, &score);
-	nw_walk_warp(g, ws.E, best_m, best_q, s);
+	nw_walk_warp(g, ws.E, best_m, best_q, s, rows, tseq, t_s, q);
+	__syncwarp();
 	s.score = score; s.pos = 0;
 	*out = s;
 	return NW_OK;

@@ -189,3 +189,23 @@ def test_paired_end_alignment_vs_oracle(tmp_path, seed):
     fb = frag.tobytes()
     assert fb == ofrag, f"frag_raw differs at byte {_first_diff(fb, ofrag)} of {len(ofrag)} (got {len(fb)})"
     assert frag2.tobytes() == ofrag and np.array_equal(a2, oa) and np.array_equal(u2, ou)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed,L,sub,indel", [(31, 150, 0.01, 0.0), (32, 150, 0.03, 0.01), (33, 400, 0.05, 0.02),
+                                               (34, 1000, 0.04, 0.03), (35, 3000, 0.08, 0.06)])
+def test_traceback_alignment_vs_oracle(tmp_path, seed, L, sub, indel):
+    """assemble_KMA's anker_rc + KMA with aligned rows on the GPU: headers and t/s/q rows byte-exact"""
+    from tests.test_oracle_trace import make_frags
+    prefix, frags = make_frags(tmp_path, seed, L, sub, indel)
+    want = util.oracle_trace(prefix, frags)
+    db = api.TemplateDB(prefix)
+    got, n, st = db.assemble_align_batch(frags)
+    db.close()
+    W, G = util.parse_trace(want), util.parse_trace(got.tobytes())
+    assert n == len(W) == len(G)
+    for i, ((hw, rw), (hg, rg)) in enumerate(zip(W, G)):
+        assert np.array_equal(hw, hg), (i, hw, hg)
+        assert rw == rg, (i, hw)
+    assert got.tobytes() == want
+    assert st.nw_full_cells + st.nw_band_cells > 0
