@@ -194,6 +194,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=2_000_000, help="read pairs per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="read pairs of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-workers", type=int, default=2, help="host threads / library handles of the end-to-end pipeline")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks the batch is cut into for the end-to-end pipeline")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -296,22 +298,30 @@ def main():
     res, _, _, _ = db.align_download(out=frag_out)
     out_bytes = int(res.numel() if hasattr(res, "numel") else len(res))
 
-    # ---- end to end through the C ABI: pinned host in, pinned host out, copies inside the timed region
+    # ---- end to end through the public API: pinned host in, pinned host out, copies inside the timed region.
+    # The batch goes through kma_b200.pipeline.MapPipeline: `--e2e-workers` host threads, each with its own library
+    # handle and stream, take the `--e2e-chunks` chunks of the record stream in turn so that one chunk's PCIe copies
+    # hide behind another chunk's kernels. Every byte still crosses PCIe inside the timed region.
+    from kma_b200 import pipeline
+    pipe = pipeline.MapPipeline(prefix, device=local_rank, workers=args.e2e_workers, params=params)
+    bounds = pipe.chunk_bounds(s1.numpy(), args.e2e_chunks)
+    per_chunk = (out_bytes // max(1, len(bounds))) * 5 // 4 + (1 << 20)
+    outs = [torch.empty(per_chunk, dtype=torch.uint8, pin_memory=True) for _ in bounds]
+
     def step_e2e():
-        db.seed_upload(s1)
-        db.seed_run(params)
-        db.align_from_seed()
-        db.align_run(params)
-        return db.align_download(out=frag_out, scores=scores)
+        return pipe.map(s1, bounds, outs, scores)
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step_e2e()
+        r_e2e = step_e2e()
     sync_all()
     t_e2e = (time.perf_counter() - t0) * 1e3
+    e2e_out_bytes = sum(int(f.numel() if hasattr(f, "numel") else len(f)) for f, _ in r_e2e)
+    assert e2e_out_bytes == out_bytes, "chunked end-to-end run produced a different frag_raw size"
+    pipe.close()
 
     # ---- the one exchange of the path: ConClave score arrays summed over ranks (runkma.c:98-99, conclave.c:80)
     t_allreduce = 0.0
@@ -360,7 +370,8 @@ def main():
                    "sharding": "reads sharded by rank, database replicated per GPU; one all-reduce of the ConClave score arrays per step",
                    "allreduce_ms": t_ar_max},
         "e2e": {"value": total_reads / (t_e2e_max * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(len(s1_np)) + 10 * args.pairs + 4,
-                "d2h_bytes_per_step": out_bytes + 16 * DBn, "ms_per_step": t_e2e_max / args.steps},
+                "d2h_bytes_per_step": out_bytes + 16 * DBn * len(bounds), "ms_per_step": t_e2e_max / args.steps,
+                "pipeline": {"workers": args.e2e_workers, "chunks": len(bounds)}},
         "gpu_launches": launches,
         "wall_ms_per_step_resident": t_wall_max / args.steps,
         "stage_ms": {"seed_total": st.ms_total, "seed_kernel": st.ms_seed, "align_prep": sa.ms_prep, "align_pairs": sa.ms_align,

@@ -46,7 +46,7 @@ struct KgBuf {
 struct SeedBatch {
 	KgBuf d_in, d_off, d_res, d_pool, d_recoff, d_out, d_ctr, d_partial, d_dense;
 	KgBuf d_kinds, d_mates, d_pool2;   // paired end: record kinds (0 single, 1/2 mates), per-mate strand lists
-	std::vector<uint8_t> h_kinds;
+	KgBuf h_kinds;                     // pinned staging of the record kinds
 	int64_t npairs = 0;
 	size_t pool2_cap = 0;
 	KgBuf h_off;                 // pinned staging of record offsets

@@ -710,7 +710,7 @@ __global__ void lookup_kernel(KgHashView hv, const uint64_t *kmers, size_t n, in
 int kg_seed_free(kmagpu_db *db) {
 	SeedBatch &b = db->seed;
 	KgBuf *all[] = {&b.d_in, &b.d_off, &b.d_res, &b.d_pool, &b.d_recoff, &b.d_out, &b.d_ctr, &b.d_partial, &b.d_dense, &b.d_kinds, &b.d_mates, &b.d_pool2,
-	                &b.h_off, &b.h_in, &b.h_out};
+	                &b.h_off, &b.h_in, &b.h_out, &b.h_kinds};
 	for (KgBuf *x : all) x->release();
 	return 0;
 }
@@ -720,13 +720,21 @@ extern "C" int kmagpu_seed_upload(kmagpu_db *db, const void *stage1, size_t nbyt
 	if (nbytes >= (1ull << 31)) { kmagpu_set_error("stage-1 batch of %zu bytes exceeds the 2 GiB per-call limit; split it", nbytes); return -1; }
 	KG_CUDA(cudaSetDevice(db->device));
 	SeedBatch &b = db->seed;
-	b.h_off.pinned = true;
-	// record boundaries: the only sequential step (16-byte header walk, loadFsa savekmers.c:50-92)
+	b.h_off.pinned = true; b.h_kinds.pinned = true;
 	const uint8_t *in = (const uint8_t *)stage1;
+	// the bytes go first: the copy engine moves them while the host walks the record headers below
+	if (b.d_in.reserve(nbytes + 64)) return -1;
+	KG_CUDA(cudaEventRecord(db->ev[0], db->stream));
+	if (nbytes) KG_CUDA(cudaMemcpyAsync(b.d_in.p, in, nbytes, cudaMemcpyHostToDevice, db->stream));
+	KG_CUDA(cudaMemsetAsync((uint8_t *)b.d_in.p + nbytes, 0, 64, db->stream));
+	// record boundaries: the only sequential step (16-byte header walk, loadFsa savekmers.c:50-92). Pairs: the first
+	// mate is written with a negative header length (runinput.c:789), its mate follows.
 	size_t guess = nbytes / 48 + 16;
-	if (b.h_off.reserve(4 * (guess + 1))) return -1;
+	if (b.h_off.reserve(4 * (guess + 1)) || b.h_kinds.reserve(guess + 2)) return -1;
 	uint32_t *off = (uint32_t *)b.h_off.p;
-	size_t cap = b.h_off.cap / 4 - 1, n = 0, ip = 0;
+	uint8_t *kinds = (uint8_t *)b.h_kinds.p;
+	size_t cap = std::min(b.h_off.cap / 4 - 1, b.h_kinds.cap - 2), n = 0, ip = 0, npairs = 0;
+	bool mate = false;
 	while (ip + 16 <= nbytes) {
 		int32_t h[4];
 		memcpy(h, in + ip, 16);
@@ -734,42 +742,34 @@ extern "C" int kmagpu_seed_upload(kmagpu_db *db, const void *stage1, size_t nbyt
 		size_t len = 16 + 8 * (size_t)(uint32_t)h[1] + 4 * (size_t)(uint32_t)h[2] + (size_t)abs(h[3]);
 		if (h[1] < 0 || h[2] < 0 || ip + len > nbytes) { kmagpu_set_error("stage-1 stream is truncated or corrupt at byte %zu", ip); return -1; }
 		if (n == cap) {
-			KgBuf bigger; bigger.pinned = true;
-			if (bigger.reserve(8 * (cap + 1))) return -1;
-			memcpy(bigger.p, off, 4 * n);
-			b.h_off.release();
-			b.h_off = bigger;
-			off = (uint32_t *)b.h_off.p; cap = b.h_off.cap / 4 - 1;
+			KgBuf bigger, bigk; bigger.pinned = true; bigk.pinned = true;
+			if (bigger.reserve(8 * (cap + 1)) || bigk.reserve(2 * (cap + 2))) return -1;
+			memcpy(bigger.p, off, 4 * n); memcpy(bigk.p, kinds, n);
+			b.h_off.release(); b.h_kinds.release();
+			b.h_off = bigger; b.h_kinds = bigk;
+			off = (uint32_t *)b.h_off.p; kinds = (uint8_t *)b.h_kinds.p;
+			cap = std::min(b.h_off.cap / 4 - 1, b.h_kinds.cap - 2);
 		}
+		if (mate) { kinds[n] = 2; mate = false; }
+		else if (h[3] < 0) { kinds[n] = 1; mate = true; ++npairs; }
+		else kinds[n] = 0;
 		off[n++] = (uint32_t)ip;
 		ip += len;
 	}
+	if (mate) { kmagpu_set_error("stage-1 stream ends inside a pair"); return -1; }
 	off[n] = (uint32_t)ip;
-	// pairs: the first mate is written with a negative header length (runinput.c:789), its mate follows
-	b.h_kinds.assign(n + 1, 0);
-	size_t npairs = 0;
-	for (size_t i = 0; i < n; ++i) {
-		int32_t hl;
-		memcpy(&hl, in + off[i] + 12, 4);
-		if (hl < 0 && !b.h_kinds[i]) {
-			if (i + 1 >= n) { kmagpu_set_error("stage-1 stream ends inside a pair"); return -1; }
-			b.h_kinds[i] = 1; b.h_kinds[i + 1] = 2; ++npairs;
-		}
-	}
+	kinds[n] = 0;
 	b.npairs = (int64_t)npairs;
 	b.nreads = (int64_t)n;
 	b.in_bytes = ip;
 	b.ran = false;
 	// what the reference counts (savekmers.c:183): one per single read, one per pair
 	if (nreads_out) *nreads_out = (int64_t)(n - npairs);
-	if (b.d_in.reserve(ip + 64) || b.d_off.reserve(4 * (n + 1))) return -1;
+	if (b.d_off.reserve(4 * (n + 1))) return -1;
 	if (npairs) {
 		if (b.d_kinds.reserve(n + 1)) return -1;
-		KG_CUDA(cudaMemcpyAsync(b.d_kinds.p, b.h_kinds.data(), n + 1, cudaMemcpyHostToDevice, db->stream));
+		KG_CUDA(cudaMemcpyAsync(b.d_kinds.p, kinds, n + 1, cudaMemcpyHostToDevice, db->stream));
 	}
-	KG_CUDA(cudaEventRecord(db->ev[0], db->stream));
-	KG_CUDA(cudaMemcpyAsync(b.d_in.p, in, ip, cudaMemcpyHostToDevice, db->stream));
-	KG_CUDA(cudaMemsetAsync((uint8_t *)b.d_in.p + ip, 0, 64, db->stream));
 	KG_CUDA(cudaMemcpyAsync(b.d_off.p, off, 4 * (n + 1), cudaMemcpyHostToDevice, db->stream));
 	KG_CUDA(cudaEventRecord(db->ev[1], db->stream));
 	KG_CUDA(cudaStreamSynchronize(db->stream));

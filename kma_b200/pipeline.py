@@ -1,0 +1,72 @@
+"""Host-side driver of the mapping core for one GPU: what the reference's stage drivers (save_kmers_batch kmers.c:51,
+runKMA's alignment loop runkma.c:291-445) do with T pthreads over a shared FILE*, done here with a few host threads
+that each own one TemplateDB handle (own CUDA stream and batch buffers, database image shared read-only semantics but
+replicated per handle) and take the chunks of a record stream in turn. While one chunk's frag_raw stream is on its way
+back over PCIe, the next chunk's records are being walked / uploaded and a third is in the kernels -- the copies hide
+behind the compute instead of adding to it. Output order is chunk order = input order."""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+from . import api
+
+
+class MapPipeline:
+    def __init__(self, prefix: str, device: int = 0, workers: int = 2, params=None):
+        self.dbs = [api.TemplateDB(prefix, device) for _ in range(workers)]
+        self.params = params or api.default_params()
+        self.info = self.dbs[0].info
+
+    def close(self):
+        for d in self.dbs:
+            d.close()
+
+    def chunk_bounds(self, stage1, n_chunks: int):
+        """byte ranges of n_chunks contiguous groups of whole records; pairs are never split"""
+        off = api.record_offsets(1, stage1)
+        n = len(off) - 1
+        cuts = [0]
+        for c in range(1, n_chunks):
+            i = (n * c) // n_chunks
+            # a second mate (positive header length right after a negative one) must stay with its first mate
+            if 0 < i < n and int(np.frombuffer(stage1[int(off[i - 1]) + 12:int(off[i - 1]) + 16].tobytes(), dtype=np.int32)[0]) < 0:
+                i += 1
+            cuts.append(int(off[min(i, n)]))
+        cuts.append(int(off[n]))
+        return [(cuts[i], cuts[i + 1]) for i in range(n_chunks) if cuts[i + 1] > cuts[i]]
+
+    def map(self, stage1, bounds, outs, scores):
+        """stage 2 + alignment pass over the chunks `bounds` of the stage-1 stream (a pinned uint8 tensor / array).
+        outs[i]: buffer for chunk i's frag_raw bytes; scores: (alignment_scores, uniq_alignment_scores) uint64 arrays
+        that receive the sums. Returns per-chunk (frag bytes, groups read)."""
+        res = [None] * len(bounds)
+        part = [(np.zeros_like(scores[0]), np.zeros_like(scores[1])) for _ in self.dbs]
+        err = []
+
+        def work(w):
+            db = self.dbs[w]
+            try:
+                for i in range(w, len(bounds), len(self.dbs)):
+                    lo, hi = bounds[i]
+                    n = db.seed_upload(stage1[lo:hi])
+                    db.seed_run(self.params)
+                    db.align_from_seed()
+                    db.align_run(self.params)
+                    frag, _, _, _ = db.align_download(out=outs[i], scores=part[w])
+                    res[i] = (frag, n)
+            except Exception as e:   # surfaced to the caller below
+                err.append(e)
+
+        ts = [threading.Thread(target=work, args=(w,)) for w in range(len(self.dbs))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if err:
+            raise err[0]
+        for a, u in part:
+            scores[0][:] += a
+            scores[1][:] += u
+        return res

@@ -209,3 +209,27 @@ def test_traceback_alignment_vs_oracle(tmp_path, seed, L, sub, indel):
         assert rw == rg, (i, hw)
     assert got.tobytes() == want
     assert st.nw_full_cells + st.nw_band_cells > 0
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+def test_chunked_pipeline_equals_single_call(tmp_path):
+    """MapPipeline (host threads, one library handle + stream each, chunks in turn) == one resident call; pairs are
+    never split across chunks"""
+    from kma_b200 import pipeline
+    from tests.test_oracle_pair import make_pairs
+    prefix, s1, s2 = make_pairs(tmp_path, 52, n=3000)
+    db = api.TemplateDB(prefix)
+    db.seed_upload(s1); db.seed_run(); db.align_from_seed(); db.align_run()
+    frag, a, u, _ = db.align_download()
+    db.close()
+    pipe = pipeline.MapPipeline(prefix, workers=2)
+    bounds = pipe.chunk_bounds(s1, 5)
+    assert len(bounds) == 5 and bounds[0][0] == 0
+    outs = [np.empty(len(frag) + 4096, dtype=np.uint8) for _ in bounds]
+    scores = (np.zeros_like(a), np.zeros_like(u))
+    res = pipe.map(np.ascontiguousarray(s1), bounds, outs, scores)
+    pipe.close()
+    got = b"".join(f.tobytes() for f, _ in res)
+    assert got == frag.tobytes()
+    assert np.array_equal(scores[0], a) and np.array_equal(scores[1], u)
+    assert sum(n for _, n in res) == 3000
