@@ -194,8 +194,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=2_000_000, help="read pairs per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="read pairs of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-workers", type=int, default=2, help="host threads / library handles of the end-to-end pipeline")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks the batch is cut into for the end-to-end pipeline")
+    ap.add_argument("--e2e-workers", type=int, default=4, help="host threads / library handles of the end-to-end pipeline")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks the batch is cut into for the end-to-end pipeline")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
