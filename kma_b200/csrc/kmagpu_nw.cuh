@@ -354,6 +354,30 @@ __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict
 		*out = s;
 		return NW_OK;
 	}
+#ifndef KG_NO_FAST11
+	if (t_len == 1 && q_len == 1 && k == 0 && !rows) {   // the single mismatch between two MEMs: one cell, closed form
+		const int W1 = pen.W1, U = pen.U, NEG = 2 * (pen.MM + U + W1);
+		const int sub = pen.d[nw_nuc(tseq, t_s) * 5 + query[q_s]];
+		// the cell of nw.c:166-212 with Dleft = D(0,-1) = W1, aD = D(-1,0) = W1, Qleft = aP = NEG, Ddiag = D(-1,-1) = 0
+		int Q = W1 + W1, P = W1 + W1, D, e, fl = 0, x;
+		if (Q < P) { D = P; e = 4; } else { D = Q; e = 2; }
+		x = NEG + U;
+		if (Q < x) { Q = x; if (D <= x) { D = x; e = 3; } } else fl |= 16;
+		if (P < x) { P = x; if (D <= x) { D = x; e = 5; } } else fl |= 32;
+		x = sub;
+		if (D <= x) { D = x; e = 1; }
+		if (e == 1 || fl) {
+			// diagonal: one column. Otherwise the run closes in this cell (flag set) and the walk crosses one gap of
+			// each kind through the boundary codes (36 / 18): two columns
+			s.score = D; s.pos = 0;
+			if (e == 1) { s.len = 1; s.match = 1; s.tGaps = 0; s.qGaps = 0; }
+			else { s.len = 2; s.match = 0; s.tGaps = 1; s.qGaps = 1; }
+			if (cells) *cells += 1;
+			*out = s;
+			return NW_OK;
+		}
+	}
+#endif
 	NwGeo g;
 	if (!nw_geo_init(g, pen, t_len, q_len, k, band)) return NW_BAD_BAND;
 	if (g.ebytes() > ws.e_cap || q_len + 1 > ws.q_cap) return NW_TOO_BIG;
