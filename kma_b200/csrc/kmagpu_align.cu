@@ -40,6 +40,7 @@ struct AlnRead {
 	uint32_t task0;
 	int32_t kind;        // 0 single read, 1 first record of a pair (no templates, ankers.c:150), 2 its mate (carries the templates)
 	int32_t fneg;        // kind 2: index of the first negative template (nt when none): both reads flip there (alnfrags.c:1630)
+	int32_t two;         // the slab also holds the reverse complement (strand-tie reads, pairs with a negative template)
 };
 
 struct AlnCand { int32_t tmpl, score, len, pos, match, tGaps, qGaps, status; };
@@ -93,7 +94,19 @@ __global__ void aln_sizes_kernel(const uint8_t *__restrict__ in, const uint32_t 
 		}
 		R.kind = R.nt == 0 ? 1 : (prev_nt == 0 ? 2 : 0);
 		R.fneg = R.nt;
-		ss = slab_stride(R) * ((R.rc_flag < 0 || R.kind) ? 2u : 1u);
+		R.two = R.rc_flag < 0;
+		if (R.kind) {   // a pair is reverse-complemented from its first negative template on: look for one
+			const bool mate_ok = R.kind == 2 || (r + 1 < n && off[r + 2] - off[r + 1] >= 28);
+			const uint8_t *trec = R.kind == 2 ? rec : in + off[mate_ok ? r + 1 : r];
+			int nt2 = R.nt;
+			if (R.kind == 1) nt2 = mate_ok ? (int)ld_u32u(trec + 16) : 0;
+			const uint8_t *T = trec + 28 + 8 * (size_t)ld_u32u(trec + 4) + 4 * (size_t)ld_u32u(trec + 8);
+			int f = nt2;
+			for (int i = 0; i < nt2; ++i) if ((int)ld_u32u(T + 4 * (size_t)i) < 0) { f = i; break; }
+			if (R.kind == 2) R.fneg = f;
+			R.two |= f < nt2;
+		}
+		ss = slab_stride(R) * (R.two ? 2u : 1u);
 		if (R.kind == 2) {
 			// alnFrags_threaded (alnfrags.c:2250): both mates reach k or the pair degenerates to forms stage 2 never writes
 			if (prev_len < k || R.q_len < k || prev_rc < 0) atomicAdd(&ctr[A_BAD], 1ull);
@@ -124,7 +137,7 @@ __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__restrict
 		if (R.q_len == 0 && R.words == 0) continue;
 		const uint8_t *rec = in + R.rec_off, *seq = rec + 28, *Ns = seq + 8 * (size_t)R.words;
 		const int L = R.q_len, words = R.words, nN = R.nN;
-		for (int strand = 0; strand < ((R.rc_flag < 0 || R.kind) ? 2 : 1); ++strand) {
+		for (int strand = 0; strand < (R.two ? 2 : 1); ++strand) {
 			uint64_t *base = slab + R.slab_off + (strand ? slab_stride(R) : 0);
 			uint8_t *b = (uint8_t *)(base + slab_W(words));
 			int32_t *N = (int32_t *)(base + slab_W(words) + slab_B(L));
@@ -154,13 +167,6 @@ __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__restrict
 		}
 		const int ntask = (int)(task_off[r + 1] - task_off[r]);
 		for (int i = lane; i < ntask; i += 32) task_read[R.task0 + i] = r;
-		if (R.kind == 2) {   // first negative template
-			const uint8_t *T = Ns + 4 * (size_t)nN;
-			int f = R.nt;
-			for (int i = lane; i < R.nt; i += 32) if ((int)ld_u32u(T + 4 * (size_t)i) < 0) { f = i; break; }
-			f = warp_min_i(f);
-			if (lane == 0) reads[r].fneg = f;
-		}
 		__syncwarp();
 	}
 }
