@@ -26,6 +26,9 @@
 #include <algorithm>
 
 #define AL_WARPS 4            // warps per CTA of the pair kernel
+#ifndef KG_STAGE_INL
+#define KG_STAGE_INL                // inlined per call site: 50 ms vs 71 ms out of line (arguments by reference go through the stack)
+#endif
 #define AL_BANDW 64           // align.c:511
 #ifndef AL_MINB
 #define AL_MINB 6             // resident CTAs per SM the pair kernel is compiled for (register cap 65536 / (128 * AL_MINB))
@@ -212,7 +215,7 @@ __device__ __forceinline__ void mem_from_seed(const uint64_t *qw, const uint64_t
 // entered, and re-entered after a MEM, while MORE than k bases remain before its end; MEMs always extend to the
 // stretch end. Appends to M starting at index n; *sscore = strand score of MODE 1. Returns ST_OVERFLOW when M is full.
 template <int MODE, bool BYTES>
-__device__ int scan_mems(const KgTIndexView &ix, const KgTMeta &m, const uint64_t *tseq, const QView &q, int nN1, int q_len,
+__device__ KG_STAGE_INL int scan_mems(const KgTIndexView &ix, const KgTMeta &m, const uint64_t *tseq, const QView &q, int nN1, int q_len,
                          int start, Mems &M, int &n, int &sscore, WarpCtr &wc) {
 	const int lane = threadIdx.x & 31;
 	const int k = ix.k, t_len = m.len;
@@ -386,7 +389,7 @@ __device__ int nw_auto(const TaskCtx &c, int k, int t_s, int t_e, int q_s, int q
 	return ST_OK;
 }
 
-__device__ int kma_score_warp(const AlnParams &P, const TaskCtx &c, const KgTIndexView &ix, const KgTMeta &m, const QView &q,
+__device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c, const KgTIndexView &ix, const KgTMeta &m, const QView &q,
                               int nN1, int q_len, Mems &M, int n, NwStat *out) {
 	const int lane = threadIdx.x & 31;
 	const int k = ix.k, t_len = m.len, U = P.pen.U, Mv = P.pen.M;

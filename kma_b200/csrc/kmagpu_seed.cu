@@ -162,8 +162,11 @@ struct WarpStats { unsigned lookups, hits, lists, listids; };
 // One strand of one read. Returns best score (>= 0), leaves the arg-max template ids in
 // st.cand[0 .. *nbest) (first-seen order) and the store clean. Returns -1 on table overflow
 // (hash mode only; store is left clean).
+#ifndef KG_SCAN_INL
+#define KG_SCAN_INL                // inlined per call site: measured 40 ms vs 61 ms out of line (by-reference arguments go through
+#endif                             // the stack), although the four copies make 200 KB of code
 template <bool DENSE>
-__device__ int scan_strand(const KgHashView &hv, const SeedParams &p, const ReadCtx &rc, int strand,
+__device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p, const ReadCtx &rc, int strand,
                            Store<DENSE> &st, uint32_t *hits, uint64_t *sw, int *nbest, WarpStats &ws,
                            int2 *pool2 = nullptr, unsigned long long pool2_cap = 0, unsigned long long *ctr = nullptr,
                            uint32_t *list_off = nullptr) {
