@@ -233,3 +233,27 @@ def test_chunked_pipeline_equals_single_call(tmp_path):
     assert got == frag.tobytes()
     assert np.array_equal(scores[0], a) and np.array_equal(scores[1], u)
     assert sum(n for _, n in res) == 3000
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+def test_nanopore_like_long_reads(tmp_path):
+    """C3-shaped input: 5-20 kb reads with 10 % errors (1/3 sub, del, ins) built from templates and spacers, mapped with
+    -1t1 records: hundreds of MEMs per pair, wide banded NW, large traceback matrices (large-scratch path) -- alignment
+    pass and traceback alignment byte-exact vs the oracle"""
+    names, seqs = synth.gene_db(61, n_families=15, n_variants=6, len_lo=800, len_hi=3000)
+    synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+    reads = synth.long_reads(62, seqs, 120, len_lo=5000, len_hi=20000)
+    synth.write_fastq(tmp_path / "r.fq", reads, qual="5")
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    s2 = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-1t1", "-s2"], cwd=tmp_path)
+    prefix = str(tmp_path / "db")
+    st, cand = _check_align(prefix, s2)
+    assert st.nw_band_calls > 0 and st.mems > 10 * st.tasks
+    ofrag, _, _, _, _ = util.oracle_align_stream(prefix, np.frombuffer(s2, dtype=np.uint8), want_cand=False)
+    frags = util.assembly_records(ofrag, zero_every=4, max_hits=1)
+    want = util.oracle_trace(prefix, frags)
+    db = api.TemplateDB(prefix)
+    got, n, st2 = db.assemble_align_batch(frags)
+    db.close()
+    assert got.tobytes() == want
+    assert st2.nw_band_cells > 0
