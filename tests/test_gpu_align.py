@@ -257,3 +257,50 @@ def test_nanopore_like_long_reads(tmp_path):
     db.close()
     assert got.tobytes() == want
     assert st2.nw_band_cells > 0
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("k", [10, 12, 14])
+def test_small_k_databases(tmp_path, k):
+    """`kma index -k K`: K = 10 gives the direct-addressed table (megaMap_getGlobal), every K a different k for the
+    per-template position index; stage 2, alignment pass and traceback alignment vs the oracle"""
+    names, seqs = synth.gene_db(71, n_families=10, n_variants=5, len_lo=400, len_hi=1200)
+    synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+    reads = synth.short_reads(72, seqs, 600, L=150, sub=0.02, n_rate=0.002, junk_frac=0.05)
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db", "-k", str(k)], cwd=tmp_path)
+    prefix = str(tmp_path / "db")
+    s1 = records.stage1_records_fixed(reads)
+    want2 = util.oracle_seed_stream(prefix, s1)
+    db = api.TemplateDB(prefix)
+    assert db.info.kmersize == k and db.info.kmerindex == k and db.info.mega == (1 if k == 10 else 0)
+    s2, n, _ = db.save_kmers_batch(s1)
+    db.close()
+    assert s2.tobytes() + api.stream_terminator(n) == want2.tobytes()
+    _check_align(prefix, want2)
+    ofrag, _, _, _, _ = util.oracle_align_stream(prefix, want2, want_cand=False)
+    frags = util.assembly_records(ofrag)
+    db = api.TemplateDB(prefix)
+    got, _, _ = db.assemble_align_batch(frags)
+    db.close()
+    assert got.tobytes() == util.oracle_trace(prefix, frags)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+def test_single_genome_template(tmp_path):
+    """C4-shaped database: one 400 kb random genome (one big position-index table, long tails clipped to read + 64)"""
+    rng = np.random.default_rng(81)
+    genome = rng.integers(0, 4, size=400_000).astype(np.uint8)
+    genome[100_000:100_300] = genome[250_000:250_300]          # a repeat: k-mers with two positions
+    synth.write_fasta(tmp_path / "db.fsa", ["genome"], [genome])
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    reads = synth.short_reads(82, [genome], 3000, L=150, sub=0.01, n_rate=0.001, junk_frac=0.02)
+    reads = list(reads) + [synth.mutate_subs(rng, genome[99_900:100_500].copy(), 0.01), synth.revcomp(genome[249_950:250_400])]
+    prefix = str(tmp_path / "db")
+    s1 = records.stage1_records(reads)
+    want2 = util.oracle_seed_stream(prefix, s1)
+    db = api.TemplateDB(prefix)
+    s2, n, _ = db.save_kmers_batch(s1)
+    db.close()
+    assert s2.tobytes() + api.stream_terminator(n) == want2.tobytes()
+    st, cand = _check_align(prefix, want2)
+    assert st.frags > 2800
