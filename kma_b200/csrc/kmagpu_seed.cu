@@ -455,20 +455,25 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 		rc.N = rc.seq + 8 * (size_t)rc.words;
 		words_seen += rc.words;
 
-		if (kinds && kinds[r]) {   // a mate of a pair: keep both strands' template scores for pair_select_kernel
+		// both strands through ONE call site (one inlined copy of the scan: four copies made 200 KB of code). A mate of
+		// a pair keeps every template's score for pair_select_kernel, a single read only its arg-max sets.
+		const bool mate = kinds && kinds[r];
+		int sres[2] = {0, 0}, scnt[2] = {0, 0};
+		uint32_t soff[2] = {0, 0};
+		bool ovf = false;
+		if (rc.seqlen >= k) {
+			for (int strand = 0; strand < 2 && !ovf; ++strand) {
+				st.cand = strand ? candR : candF;
+				sres[strand] = scan_strand<DENSE>(hv, p, rc, strand, st, hits, sw, &scnt[strand], ws, mate ? pool2 : nullptr,
+				                                  pool2_cap, ctr, &soff[strand]);
+				ovf = sres[strand] < 0;
+			}
+			if (ovf && lane == 0) ovf_list[atomicAdd(&ctr[C_OVF], 1ull)] = (uint32_t)r;   // table overflow: dense pass
+		}
+		if (mate) {
 			MateRes m = {0, 0, 0, 0, 0, 0};
-			bool ovf = false;
-			if (rc.seqlen >= k) {
-				int nf = 0, nr = 0;
-				uint32_t of = 0, orr = 0;
-				st.cand = candF;
-				const int hf = scan_strand<DENSE>(hv, p, rc, 0, st, hits, sw, &nf, ws, pool2, pool2_cap, ctr, &of);
-				int hr = -1;
-				if (hf >= 0) { st.cand = candR; hr = scan_strand<DENSE>(hv, p, rc, 1, st, hits, sw, &nr, ws, pool2, pool2_cap, ctr, &orr); }
-				if (hf < 0 || hr < 0) {
-					ovf = true;
-					if (lane == 0) ovf_list[atomicAdd(&ctr[C_OVF], 1ull)] = (uint32_t)r;
-				} else { m.off_f = of; m.off_r = orr; m.n_f = nf; m.n_r = nr; m.hits = max(hf, hr); m.scanned = 1; }
+			if (rc.seqlen >= k && !ovf) {
+				m.off_f = soff[0]; m.off_r = soff[1]; m.n_f = scnt[0]; m.n_r = scnt[1]; m.hits = max(sres[0], sres[1]); m.scanned = 1;
 			}
 			if (lane == 0 && !ovf) mates[r] = m;
 			__syncwarp();
@@ -477,15 +482,9 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 		SeedRes out = {0, 0, 0, 0, r, 0};
 		uint32_t size = 0;
 		if (rc.seqlen >= k) {
-			int nf = 0, nr = 0;
-			st.cand = candF;
-			int bf = scan_strand<DENSE>(hv, p, rc, 0, st, hits, sw, &nf, ws);
-			int br = -1;
-			if (bf >= 0) { st.cand = candR; br = scan_strand<DENSE>(hv, p, rc, 1, st, hits, sw, &nr, ws); }
-			if (bf < 0 || br < 0) {   // table overflow: hand the read to the dense pass
-				if (lane == 0) ovf_list[atomicAdd(&ctr[C_OVF], 1ull)] = (uint32_t)r;
-				out.flag = -1;
-			} else if ((bf > 0 || br > 0) && (k <= bf || k <= br)) {   // savekmers.c:3039-3061
+			const int nf = scnt[0], nr = scnt[1], bf = sres[0], br = sres[1];
+			if (ovf) out.flag = -1;
+			else if ((bf > 0 || br > 0) && (k <= bf || k <= br)) {   // savekmers.c:3039-3061
 				int nt = bf > br ? nf : (bf < br ? nr : nf + nr);
 				unsigned long long po = 0;
 				if (lane == 0) po = atomicAdd(&ctr[C_POOL], (unsigned long long)nt);
