@@ -142,6 +142,27 @@ def long_reads(seed: int, seqs, n: int, len_lo: int = 5000, len_hi: int = 20000,
 
 
 def write_fastq(path, reads, prefix="r", qual="I"):
+    if isinstance(reads, np.ndarray) and reads.ndim == 2:      # fixed-length reads: one byte matrix per id width
+        n, L = reads.shape
+        head = np.frombuffer(f"@{prefix}".encode(), dtype=np.uint8)
+        c = len(head)
+        with open(path, "wb") as fh:
+            lo, w = 0, 1
+            while lo < n:
+                hi = min(n, 10 ** w)
+                m = hi - lo
+                ids = np.arange(lo, hi).astype(f"S{w}").view(np.uint8).reshape(m, w)
+                rec = np.empty((m, c + w + 1 + L + 3 + L + 1), dtype=np.uint8)
+                rec[:, :c] = head
+                rec[:, c:c + w] = ids
+                rec[:, c + w] = 10
+                rec[:, c + w + 1:c + w + 1 + L] = _BASES[reads[lo:hi]]
+                rec[:, c + w + 1 + L:c + w + 4 + L] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+                rec[:, c + w + 4 + L:c + w + 4 + 2 * L] = ord(qual)
+                rec[:, -1] = 10
+                fh.write(rec.tobytes())
+                lo, w = hi, w + 1
+        return
     with open(path, "w") as fh:
         for i, r in enumerate(reads):
             s = decode(np.asarray(r))

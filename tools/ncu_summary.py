@@ -1,0 +1,53 @@
+"""Summarise an `ncu --set full` report into a small text file for profiles/ and record per-launch DRAM traffic.
+usage: ncu_summary.py <report.ncu-rep> <out.txt> [traffic.json]
+The traffic file maps kernel base names to {"dram_bytes": read+write per launch, "units": ..., "report": ...};
+bench.py scales it to its own launch by the recorded unit count (bytes per pair / per read)."""
+import csv, json, os, subprocess, sys
+
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sectors.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    tj = sys.argv[3] if len(sys.argv) > 3 else None
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, units = rows[0], rows[1]
+    traffic = json.load(open(tj)) if tj and os.path.exists(tj) else {}
+    with open(out, "w") as f:
+        f.write(f"# ncu --set full --clock-control none, report {os.path.basename(rep)} (per launch, cold cache, serialised)\n")
+        for r in rows[2:]:
+            name = r[h.index("Kernel Name")]
+            base = name.split("(")[0].replace("void ", "").strip()
+            f.write(f"\n== {base}\n")
+            for k in KEYS:
+                if k in h:
+                    f.write(f"{k:88s} {r[h.index(k)]:>18s} {units[h.index(k)]}\n")
+            rd = float(r[h.index("dram__bytes_read.sum")]) * SCALE[units[h.index("dram__bytes_read.sum")]]
+            wr = float(r[h.index("dram__bytes_write.sum")]) * SCALE[units[h.index("dram__bytes_write.sum")]]
+            f.write(f"{'dram traffic (read+write)':88s} {rd + wr:18.0f} byte\n")
+            traffic[base.split("<")[0]] = {"dram_bytes": rd + wr, "report": os.path.basename(rep),
+                                           "grid": r[h.index("launch__grid_size")]}
+    if tj:
+        json.dump(traffic, open(tj, "w"), indent=1)
+
+
+main()
