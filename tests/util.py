@@ -30,6 +30,9 @@ def orc():
         L.orc_lookup.argtypes = [C.c_void_p, C.c_uint64]
         L.orc_seed_stream.restype = C.c_int64
         L.orc_seed_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.orc_chain_stream.restype = C.c_int64
+        L.orc_chain_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_double,
+                                       C.c_double, C.c_void_p, C.c_size_t, C.c_void_p]
         _orc = L
     return _orc
 
@@ -55,6 +58,27 @@ def oracle_seed_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, stats=None)
         cap *= 8
     L.orc_db_close(db)
     assert n >= 0
+    if stats is not None:
+        stats.update(dict(zip(["reads", "mapped", "read_words", "lookups", "hits", "list_fetches", "list_ids"], list(st))))
+    return out[:n].copy()
+
+
+def oracle_chain_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, minlen=16, mrs=0.5, coverT=0.1, mrc=0.0, stats=None) -> np.ndarray:
+    """Stage 2 in chain mode (save_kmers_chain, the default without -1t1); CLI defaults kma.c:309-320."""
+    L = orc()
+    db = L.orc_db_open(os.fsencode(db_prefix))
+    assert db, f"oracle cannot open {db_prefix}"
+    cap = 8 * len(s1) + 4096
+    while True:
+        out = np.zeros(cap, dtype=np.uint8)
+        st = (C.c_int64 * 7)()
+        n = L.orc_chain_stream(db, oracle_params(exhaustive), s1.ctypes.data, len(s1), minlen, mrs, coverT, mrc,
+                               out.ctypes.data, len(out), st)
+        if n != -1 or cap > (1 << 32):
+            break
+        cap *= 8
+    L.orc_db_close(db)
+    assert n >= 0, f"oracle chain error {n}"
     if stats is not None:
         stats.update(dict(zip(["reads", "mapped", "read_words", "lookups", "hits", "list_fetches", "list_ids"], list(st))))
     return out[:n].copy()
