@@ -18,6 +18,7 @@
 //     stream (ankers.c:30-50) in input order, so the host does no per-read work.
 #include "kmagpu_internal.h"
 #include "kmagpu_dev.cuh"
+#include "kmagpu_seed.cuh"
 #include <string.h>
 #include <algorithm>
 
@@ -28,7 +29,6 @@
 #define KG_FILL 192           // distinct templates a read may see before it goes to the dense path
 #define KG_WARPS 4            // warps per CTA
 #define KG_WORDS 12           // staged u64 words per chunk: (256 + 31 + 31) / 32 + 2
-#define KG_MISS 0xFFFFFFFFu
 
 struct SeedRes { int32_t score, ntmpl, flag; uint32_t pool_off; int32_t src, rev; };   // src: record that supplies read + name, rev: emit its reverse complement
 
@@ -39,35 +39,6 @@ struct MateRes { uint32_t off_f, off_r; int32_t n_f, n_r, hits, scanned; };
 struct SeedParams {
 	int32_t M, MM, U, W1, exhaustive;
 };
-
-// counters living in d_ctr (uint64 slots)
-enum { C_WORK = 0, C_POOL = 1, C_OVF = 2, C_WORK2 = 3, C_POOLFAIL = 4, C_LOOKUPS = 5, C_HITS = 6, C_LISTS = 7,
-       C_LISTIDS = 8, C_MAPPED = 9, C_WORDS = 10, C_TOTAL = 11, C_POOL2 = 12, C_N = 16 };
-
-// ---------------------------------------------------------------- small device helpers
-
-__device__ __forceinline__ uint32_t hash_lookup(const KgHashView &hv, uint64_t key) {
-	if (hv.mega) {
-		uint32_t v = __ldg(hv.exist + key);
-		return v != 1u ? v : KG_MISS;
-	}
-	const uint32_t bucket = (uint32_t)(key & hv.hmask);
-	uint32_t pos = __ldg(hv.exist + bucket);
-	if (pos == hv.null_index) return KG_MISS;
-	uint2 e = __ldg(hv.kv + pos);
-	while (e.x != (uint32_t)key) {
-		if ((e.x & (uint32_t)hv.hmask) != bucket || pos >= hv.n) return KG_MISS;
-		e = __ldg(hv.kv + ++pos);
-	}
-	return e.y;
-}
-
-__device__ __forceinline__ int list_len(const KgHashView &hv, uint32_t off) {
-	return hv.values_s ? (int)__ldg(hv.values_s + off) : (int)__ldg(hv.values_w + off);
-}
-__device__ __forceinline__ int list_id(const KgHashView &hv, uint32_t off, int i) {
-	return hv.values_s ? (int)__ldg(hv.values_s + off + 1 + i) : (int)__ldg(hv.values_w + off + 1 + i);
-}
 
 // score of a hit that resumes template bookkeeping after `gaps` missed k-mer positions.
 // run == true : contribution to the run score of an unchanged template list (savekmers.c:2529-2569)
@@ -86,42 +57,6 @@ __device__ __forceinline__ int gap_score(const SeedParams &p, int k, int gaps, b
 		return k * p.M + (a <= b ? b : a);
 	}
 	return gaps * p.M + (k - gaps) * p.U + p.W1;
-}
-
-// ---------------------------------------------------------------- per-read context
-
-struct ReadCtx {
-	const uint8_t *rec;   // stage-1 record
-	const uint8_t *seq;   // packed words (unaligned)
-	const uint8_t *N;     // int32 list (unaligned)
-	int seqlen, words, nN, hdrlen;
-};
-
-// i-th N position in strand coordinates (reverse strand mirrors the list, compdna.c:249-254)
-__device__ __forceinline__ int n_at(const ReadCtx &rc, int i, int strand) {
-	return strand ? rc.seqlen - 1 - (int)ld_u32u(rc.N + 4 * (rc.nN - 1 - i)) : (int)ld_u32u(rc.N + 4 * i);
-}
-
-// validity of k-mer position j (strand coords) and start of its N-free stretch
-__device__ __forceinline__ bool pos_valid(const ReadCtx &rc, int j, int k, int strand, int *segstart) {
-	*segstart = 0;
-	if (j + k > rc.seqlen) return false;
-	if (rc.nN == 0) return true;
-	int lo = 0, hi = rc.nN;   // first N >= j
-	while (lo < hi) {
-		int mid = (lo + hi) >> 1;
-		if (n_at(rc, mid, strand) < j) lo = mid + 1; else hi = mid;
-	}
-	if (lo > 0) *segstart = n_at(rc, lo - 1, strand) + 1;
-	return lo == rc.nN || n_at(rc, lo, strand) > j + k - 1;
-}
-
-// forward-strand k-mer at forward position pos from the staged words (window starts at word w0)
-__device__ __forceinline__ uint64_t kmer_from(const uint64_t *sw, int w0, int pos, int k) {
-	int w = (pos >> 5) - w0, b = (pos & 31) << 1, sh = 64 - 2 * k;
-	uint64_t x = sw[w] << b;
-	if (b > sh) x |= sw[w + 1] >> (64 - b);
-	return x >> sh;
 }
 
 // ---------------------------------------------------------------- template bookkeeping
