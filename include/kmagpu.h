@@ -32,11 +32,13 @@ typedef struct kmagpu_params {
 	int32_t mq;                       /* -mq  minimum mapQ (align.c:658) */
 	int32_t one2one;                  /* -1t1 */
 	int32_t minlen;                   /* -ml  minimum alignment length (alnfrags.c:1156), default 16 */
-	int32_t reserved[4];
-	double scoreT;                    /* -mrs (alnfrags.c:1168) */
+	int32_t kmerscan;                 /* which kmerScan (savekmers.h:50): 0 = save_kmers (-1t1, savekmers.c:2442),
+	                                     1 = save_kmers_chain (the default without -1t1, savekmers.c:5127) */
+	int32_t reserved[3];
+	double scoreT;                    /* -mrs (alnfrags.c:1168; also `mrs` of save_kmers_chain, kmers.c:51) */
 	double minFrac;                   /* -mf  (updatescores.c:217-268) */
 	double mrc;                       /* -mrc (alnfrags.h:38 mrcheck) */
-	double reserved_d;
+	double coverT;                    /* -cov  maximum overlap of two regions of one read (save_kmers_chain), default 0.1 */
 } kmagpu_params;
 
 typedef struct kmagpu_db_info {

@@ -35,6 +35,7 @@ extern "C" void kmagpu_default_params(kmagpu_params *p) {
 	p->minFrac = 1.0;
 	p->mrc = 0.0;
 	p->minlen = 16;
+	p->coverT = 0.1;
 }
 
 int KgBuf::reserve(size_t bytes) {

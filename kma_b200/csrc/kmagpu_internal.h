@@ -47,6 +47,12 @@ struct SeedBatch {
 	KgBuf d_in, d_off, d_res, d_pool, d_recoff, d_out, d_ctr, d_partial, d_dense;
 	KgBuf d_kinds, d_mates, d_pool2;   // paired end: record kinds (0 single, 1/2 mates), per-mate strand lists
 	KgBuf h_kinds;                     // pinned staging of the record kinds
+	KgBuf d_chain, d_regpool, d_regs, d_rsize, d_partial2;   // chain mode: per-warp scratch, regions (as found / in read order), sizes
+	size_t chain_stride = 0, reg_cap = 0;
+	int chain_grid = 0;
+	int32_t max_seqlen = 0;            // longest read of the batch
+	int64_t out_nrec = 0;              // records in the device output stream (chain mode: regions, else reads)
+	const uint32_t *out_recoff = nullptr;   // their offsets (device)
 	int64_t npairs = 0;
 	size_t pool2_cap = 0;
 	KgBuf h_off;                 // pinned staging of record offsets
@@ -98,3 +104,4 @@ int kg_tindex_build(kmagpu_db *db);
 int kg_align_free(kmagpu_db *db);
 
 int kg_seed_free(kmagpu_db *db);
+int kg_chain_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *stats);

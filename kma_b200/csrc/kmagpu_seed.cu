@@ -647,7 +647,7 @@ __global__ void lookup_kernel(KgHashView hv, const uint64_t *kmers, size_t n, in
 int kg_seed_free(kmagpu_db *db) {
 	SeedBatch &b = db->seed;
 	KgBuf *all[] = {&b.d_in, &b.d_off, &b.d_res, &b.d_pool, &b.d_recoff, &b.d_out, &b.d_ctr, &b.d_partial, &b.d_dense, &b.d_kinds, &b.d_mates, &b.d_pool2,
-	                &b.h_off, &b.h_in, &b.h_out, &b.h_kinds};
+	                &b.h_off, &b.h_in, &b.h_out, &b.h_kinds, &b.d_chain, &b.d_regpool, &b.d_regs, &b.d_rsize, &b.d_partial2};
 	for (KgBuf *x : all) x->release();
 	return 0;
 }
@@ -672,6 +672,7 @@ extern "C" int kmagpu_seed_upload(kmagpu_db *db, const void *stage1, size_t nbyt
 	uint8_t *kinds = (uint8_t *)b.h_kinds.p;
 	size_t cap = std::min(b.h_off.cap / 4 - 1, b.h_kinds.cap - 2), n = 0, ip = 0, npairs = 0;
 	bool mate = false;
+	int32_t maxlen = 0;
 	while (ip + 16 <= nbytes) {
 		int32_t h[4];
 		memcpy(h, in + ip, 16);
@@ -691,12 +692,14 @@ extern "C" int kmagpu_seed_upload(kmagpu_db *db, const void *stage1, size_t nbyt
 		else if (h[3] < 0) { kinds[n] = 1; mate = true; ++npairs; }
 		else kinds[n] = 0;
 		off[n++] = (uint32_t)ip;
+		maxlen = std::max(maxlen, h[0]);
 		ip += len;
 	}
 	if (mate) { kmagpu_set_error("stage-1 stream ends inside a pair"); return -1; }
 	off[n] = (uint32_t)ip;
 	kinds[n] = 0;
 	b.npairs = (int64_t)npairs;
+	b.max_seqlen = maxlen;
 	b.nreads = (int64_t)n;
 	b.in_bytes = ip;
 	b.ran = false;
@@ -721,7 +724,10 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 	if (stats) memset(stats, 0, sizeof(*stats));
 	b.out_bytes = 0;
 	b.ran = true;
+	b.out_nrec = 0; b.out_recoff = nullptr;
 	if (n == 0) return 0;
+	if (prm->kmerscan == 1) return kg_chain_run(db, prm, stats);
+	if (prm->kmerscan != 0) { kmagpu_set_error("kmerscan %d: only save_kmers (0) and save_kmers_chain (1) are built", prm->kmerscan); return -1; }
 	SeedParams sp = {prm->M, prm->MM, prm->U, prm->W1, prm->exhaustive};
 	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	if (b.pool_cap < (size_t)n * 16 + 1024) b.pool_cap = (size_t)n * 16 + 1024;
@@ -781,6 +787,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 			continue;
 		}
 		b.out_bytes = (size_t)h[C_TOTAL];
+		b.out_nrec = n; b.out_recoff = recoff;
 		if (b.d_out.reserve(b.out_bytes + 64)) return -1;
 		emit_records_kernel<<<db->sm_count * 8, 256, 0, db->stream>>>((const uint8_t *)b.d_in.p, (const uint32_t *)b.d_off.p,
 			n, (const SeedRes *)b.d_res.p, recoff, (const int32_t *)b.d_pool.p, (uint8_t *)b.d_out.p);
@@ -807,8 +814,8 @@ int kg_seed_device_output(kmagpu_db *db, const uint8_t **out, const uint32_t **r
 	SeedBatch &b = db->seed;
 	if (!b.ran) { kmagpu_set_error("kmagpu_align_from_seed before kmagpu_seed_run"); return -1; }
 	*out = (const uint8_t *)b.d_out.p;
-	*rec_off = b.nreads ? (const uint32_t *)b.d_recoff.p + b.nreads + 1 : nullptr;
-	*nreads = b.nreads;
+	*rec_off = b.out_recoff;
+	*nreads = b.out_nrec;
 	*bytes = b.out_bytes;
 	return 0;
 }
