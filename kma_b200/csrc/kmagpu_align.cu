@@ -44,6 +44,7 @@ struct AlnRead {
 	int32_t kind;        // 0 single read, 1 first record of a pair (no templates, ankers.c:150), 2 its mate (carries the templates)
 	int32_t fneg;        // kind 2: index of the first negative template (nt when none): both reads flip there (alnfrags.c:1630)
 	int32_t two;         // the slab also holds the reverse complement (strand-tie reads, pairs with a negative template)
+	int32_t q_start, q_end;   // query bounds of a chain-mode record (qseqs.c:41, alnfrags.c:1091-1099); else 0, q_len
 };
 
 struct AlnCand { int32_t tmpl, score, len, pos, match, tGaps, qGaps, status; };
@@ -97,6 +98,11 @@ __global__ void aln_sizes_kernel(const uint8_t *__restrict__ in, const uint32_t 
 		}
 		R.kind = R.nt == 0 ? 1 : (prev_nt == 0 ? 2 : 0);
 		R.fneg = R.nt;
+		R.q_start = 0; R.q_end = R.q_len;
+		if (9 < R.hl) {
+			const uint8_t *he = rec + 28 + 8 * (size_t)R.words + 4 * (size_t)R.nN + 4 * (size_t)R.nt + (size_t)R.hl;
+			if (he[-9] == 0) { R.q_start = (int)ld_u32u(he - 8); R.q_end = (int)ld_u32u(he - 4); }
+		}
 		R.two = R.rc_flag < 0;
 		if (R.kind) {   // a pair is reverse-complemented from its first negative template on: look for one
 			const bool mate_ok = R.kind == 2 || (r + 1 < n && off[r + 2] - off[r + 1] >= 28);
@@ -215,13 +221,16 @@ __device__ __forceinline__ void mem_from_seed(const uint64_t *qw, const uint64_t
 // entered, and re-entered after a MEM, while MORE than k bases remain before its end; MEMs always extend to the
 // stretch end. Appends to M starting at index n; *sscore = strand score of MODE 1. Returns ST_OVERFLOW when M is full.
 template <int MODE, bool BYTES>
+// Query bounds [start, q_end) (chain-mode records): KMA_score starts its first stretch at `start` and clips only the
+// last stretch to q_end (align.c:535-541); anker_rc_comp stops entering stretches at q_end (align.c:1044).
 __device__ KG_STAGE_INL int scan_mems(const KgTIndexView &ix, const KgTMeta &m, const uint64_t *tseq, const QView &q, int nN1, int q_len,
-                         int start, Mems &M, int &n, int &sscore, WarpCtr &wc) {
+                         int start, int q_end, Mems &M, int &n, int &sscore, WarpCtr &wc) {
 	const int lane = threadIdx.x & 31;
 	const int k = ix.k, t_len = m.len;
 	int j = start, s = 0;
-	for (int seg = 0; seg < nN1 && j < q_len; ++seg) {
-		const int segN = q.N[seg], end = segN - k + 1, lo = seg ? q.N[seg - 1] + 1 : 0;
+	for (int seg = 0; seg < nN1 && j < ((MODE == 1 && !BYTES) ? q_end : q_len); ++seg) {
+		const int realN = q.N[seg];
+		const int segN = (MODE == 0 && !BYTES && seg == nN1 - 1) ? q_end : realN, end = segN - k + 1, lo = seg ? q.N[seg - 1] + 1 : 0;
 		const int fwd_lim = (BYTES || MODE == 0) ? segN : end;
 		if (BYTES && !(j < segN - k)) { j = segN + 1; continue; }
 		while (j < end) {
@@ -261,7 +270,7 @@ __device__ KG_STAGE_INL int scan_mems(const KgTIndexView &ix, const KgTMeta &m, 
 			}
 			if (BYTES && !(j < segN - k)) break;   // "update position" (align.c:309-315): the stretch is left
 		}
-		j = segN + 1;
+		j = realN + 1;
 	}
 	sscore = s;
 	__syncwarp();
@@ -390,13 +399,13 @@ __device__ int nw_auto(const TaskCtx &c, int k, int t_s, int t_e, int q_s, int q
 }
 
 __device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c, const KgTIndexView &ix, const KgTMeta &m, const QView &q,
-                              int nN1, int q_len, Mems &M, int n, NwStat *out) {
+                              int nN1, int q_len, int q_start, int q_end, Mems &M, int n, NwStat *out) {
 	const int lane = threadIdx.x & 31;
 	const int k = ix.k, t_len = m.len, U = P.pen.U, Mv = P.pen.M;
 	NwStat s = {0, 1, 0, 0, 0, 0};
 	if (!n) {
 		int dummy;
-		if (scan_mems<0, false>(ix, m, c.tseq, q, nN1, q_len, 0, M, n, dummy, *c.wc)) return ST_OVERFLOW;
+		if (scan_mems<0, false>(ix, m, c.tseq, q, nN1, q_len, q_start, q_end, M, n, dummy, *c.wc)) return ST_OVERFLOW;
 	}
 	c.wc->mems += (unsigned long long)n;
 	if (!n) { *out = s; return ST_OK; }
@@ -477,12 +486,12 @@ __device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c,
 // preseed (align.c:750-770): does any k-spaced k-mer of the byte read occur in the template? The key is built from
 // bytes exactly as makeKmer (stdnuc.c:424) does, so an N (4) spills into the neighbouring base; bytes past the end
 // of the read count as 0.
-__device__ bool preseed_hit(const KgTIndexView &ix, const KgTMeta &m, const uint8_t *qb, int q_len) {
+__device__ bool preseed_hit(const KgTIndexView &ix, const KgTMeta &m, const uint8_t *qb, int q_len, int lim) {
 	const int lane = threadIdx.x & 31, k = ix.k;
-	for (int i0 = 0; i0 < q_len; i0 += 32 * k) {
+	for (int i0 = 0; i0 < lim; i0 += 32 * k) {
 		const int i = i0 + lane * k;
 		int hit = 0;
-		if (i < q_len) {
+		if (i < lim) {
 			uint64_t key = 0;
 			for (int b = 0; b < k; ++b) key = (b ? key << 2 : 0) | (uint64_t)(i + b < q_len ? qb[i + b] : 0);
 			hit = tix_get(ix, m, key) != 0;
@@ -505,10 +514,11 @@ __device__ int align_pair(const AlnParams &P, const NwPen *pen, const KgTIndexVi
 	if (R.rc_flag < 0) {   // strand undecided: anker_rc_comp (align.c:993-1176)
 		const QView qf = read_view(slab, R, 0), qr = read_view(slab, R, 1);
 		int sf = 0, sr = 0, nf = 0, ntot;
-		const bool pre = P.exhaustive || preseed_hit(ix, m, qf.b, q_len);
-		if (pre && scan_mems<1, false>(ix, m, c.tseq, qf, nN1, q_len, 0, M, nf, sf, wc)) return ST_OVERFLOW;
+		// query bounds are mirrored for the reverse strand; preseed only runs without a lower bound (align.c:1031-1041)
+		const bool pre = R.q_start || P.exhaustive || preseed_hit(ix, m, qf.b, q_len, R.q_end);
+		if (pre && scan_mems<1, false>(ix, m, c.tseq, qf, nN1, q_len, R.q_start, R.q_end, M, nf, sf, wc)) return ST_OVERFLOW;
 		ntot = nf;
-		if (scan_mems<1, false>(ix, m, c.tseq, qr, nN1, q_len, 0, M, ntot, sr, wc)) return ST_OVERFLOW;
+		if (scan_mems<1, false>(ix, m, c.tseq, qr, nN1, q_len, q_len - R.q_end, q_len - R.q_start, M, ntot, sr, wc)) return ST_OVERFLOW;
 		const int best = max(sf, sr);
 		if (P.one2one && best < k && best * k < (q_len - k - best)) { n = 0; strand = -1; }
 		else if (best == sf) {   // forward wins ties; a zero score means nothing seeded on either strand
@@ -517,12 +527,12 @@ __device__ int align_pair(const AlnParams &P, const NwPen *pen, const KgTIndexVi
 		if (strand >= 0) {
 			const QView q = strand ? qr : qf;
 			c.qb = q.b;
-			if (kma_score_warp(P, c, ix, m, q, nN1, q_len, M, n, &a)) return ST_OVERFLOW;
+			if (kma_score_warp(P, c, ix, m, q, nN1, q_len, 0, q_len, M, n, &a)) return ST_OVERFLOW;   // MEMs are in place: no scan
 		}
 	} else {
 		const QView q = read_view(slab, R, 0);   // SE records carry the strand stage 2 chose (ankers.c:30-50)
 		c.qb = q.b;
-		if (kma_score_warp(P, c, ix, m, q, nN1, q_len, M, 0, &a)) return ST_OVERFLOW;
+		if (kma_score_warp(P, c, ix, m, q, nN1, q_len, R.q_start, R.q_end, M, 0, &a)) return ST_OVERFLOW;
 	}
 	out->tmpl = tmpl; out->score = a.score; out->len = a.len; out->pos = a.pos; out->match = a.match;
 	out->tGaps = a.tGaps; out->qGaps = a.qGaps; out->status = ST_OK;
@@ -538,7 +548,7 @@ __device__ int align_fixed(const AlnParams &P, const NwPen *pen, const KgTIndexV
 	const QView q = read_view(slab, R, strand);
 	c.qb = q.b;
 	NwStat a = {0, 0, 0, 0, 0, 0};
-	if (kma_score_warp(P, c, ix, m, q, R.nN + 1, R.q_len, M, 0, &a)) return ST_OVERFLOW;
+	if (kma_score_warp(P, c, ix, m, q, R.nN + 1, R.q_len, 0, R.q_len, M, 0, &a)) return ST_OVERFLOW;
 	out->tmpl = at; out->score = a.score; out->len = a.len; out->pos = a.pos; out->match = a.match;
 	out->tGaps = a.tGaps; out->qGaps = a.qGaps; out->status = ST_OK;
 	return ST_OK;
@@ -1015,7 +1025,7 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 	*ncol = 0;
 	if (!n) {
 		int dummy;
-		if (scan_mems<0, true>(ix, m, c.tseq, q, nN1, q_len, 0, M, n, dummy, *c.wc)) return ST_OVERFLOW;
+		if (scan_mems<0, true>(ix, m, c.tseq, q, nN1, q_len, 0, q_len, M, n, dummy, *c.wc)) return ST_OVERFLOW;
 	}
 	c.wc->mems += (unsigned long long)n;
 	if (!n) { *out = s; return ST_OK; }
@@ -1207,10 +1217,10 @@ __global__ void __launch_bounds__(AL_WARPS * 32, AL_MINB) tr_task_kernel(AlnPara
 		if (!go) {   // anker_rc (align.c:780-991)
 			const QView qf = tr_view(slab, R, 0), qr = tr_view(slab, R, 1);
 			int sf = 0, sr = 0, nf = 0, ntot;
-			const bool pre = P.exhaustive || preseed_hit(ix, m, qf.b, q_len);
-			if (pre) st = scan_mems<1, true>(ix, m, c.tseq, qf, nN1, q_len, 0, M, nf, sf, wc);
+			const bool pre = P.exhaustive || preseed_hit(ix, m, qf.b, q_len, q_len);
+			if (pre) st = scan_mems<1, true>(ix, m, c.tseq, qf, nN1, q_len, 0, q_len, M, nf, sf, wc);
 			ntot = nf;
-			if (!st) st = scan_mems<1, true>(ix, m, c.tseq, qr, nN1, q_len, 0, M, ntot, sr, wc);
+			if (!st) st = scan_mems<1, true>(ix, m, c.tseq, qr, nN1, q_len, 0, q_len, M, ntot, sr, wc);
 			const int best = max(sf, sr);
 			if (!st) {
 				int turned = 0;

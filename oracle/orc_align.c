@@ -444,14 +444,16 @@ static aln_t aln_zero(void) { aln_t s = {0, 1, 0, 0, 0, 0}; return s; }
 
 /* KMA_score: MEMs (found here unless pt->len != 0 on entry), chain, stitch with NW. qN[] = N positions with a
  * q_len sentinel at qN[nN] (the caller's N[0]++ convention). */
-static aln_t kma_score(const orc_params *p, nw_ws *w, const tindex *ix, const uint8_t *q, int q_len,
+static aln_t kma_score(const orc_params *p, nw_ws *w, const tindex *ix, const uint8_t *q, int q_len, int q_start, int q_end,
                        const uint64_t *qcomp, const int32_t *qN, int nN1, int mq, mems_t *pt) {
 	const int k = ix->k, t_len = ix->len, U = p->U, M = p->M;
 	int n = pt->len;
 	if (!n) {
-		int j = 0;
+		/* q_start / q_end: the query bounds a chain-mode record carries (alnfrags.c:1091-1099). Only the first stretch
+		 * starts at q_start and only the last one stops at q_end (align.c:535-541, 638). */
+		int j = q_start;
 		for (int seg = 0; seg < nN1; ++seg) {
-			int end = (seg != nN1 - 1 ? qN[seg] : q_len) - k + 1;
+			int end = (seg != nN1 - 1 ? qN[seg] : q_end) - k + 1;
 			while (j < end) {
 				int slot, cnt, value = tindex_get(ix, kmer_at(qcomp, j, k), &slot, &cnt);
 				if (value == 0) { ++j; continue; }
@@ -512,8 +514,8 @@ static aln_t kma_score(const orc_params *p, nw_ws *w, const tindex *ix, const ui
 
 /* preseed (align.c:750): does any k-spaced k-mer of the byte read occur in the template? Bytes past the end of
  * the read are read as 0 (the reference reads whatever its buffer holds there). */
-static int preseed_hit(const tindex *ix, const uint8_t *q, int q_len) {
-	for (int i = 0; i < q_len; i += ix->k) {
+static int preseed_hit(const tindex *ix, const uint8_t *q, int q_len, int lim) {
+	for (int i = 0; i < lim; i += ix->k) {
 		uint64_t key = 0;
 		for (int b = 0; b < ix->k; ++b) key = (b ? key << 2 : 0) | (i + b < q_len ? q[i + b] : 0);
 		if (tindex_any_bound(ix, key, 0, ix->len)) return 1;
@@ -525,7 +527,7 @@ static int preseed_hit(const tindex *ix, const uint8_t *q, int q_len) {
  * left in pt. Returns +score (forward), -score (reverse) or 0. */
 static int pick_strand(const orc_params *p, const tindex *ix, const uint8_t *qf, const uint8_t *qr,
                        const uint64_t *cf, const uint64_t *cr, const int32_t *Nf, const int32_t *Nr, int nN1,
-                       int q_len, int one2one, mems_t *pt) {
+                       int q_len, int q_start, int q_end, int one2one, mems_t *pt) {
 	const int k = ix->k, t_len = ix->len;
 	int score_f = 0, best = 0, tot = 0, cnt_strand[2] = {0, 0}, sc[2] = {0, 0};
 	pt->len = 0;
@@ -533,8 +535,10 @@ static int pick_strand(const orc_params *p, const tindex *ix, const uint8_t *qf,
 		const uint8_t *q = rc ? qr : qf;
 		const uint64_t *comp = rc ? cr : cf;
 		const int32_t *Ns = rc ? Nr : Nf;
-		int i = rc ? 0 : (preseed_hit(ix, q, q_len) ? 0 : q_len), seg = 0, s = 0, mc = 0;
-		while (i < q_len) {
+		/* query bounds (align.c:1031-1041): mirrored for the reverse strand; preseed only without a lower bound */
+		const int qs = rc ? q_len - q_end : q_start, qe = rc ? q_len - q_start : q_end;
+		int i = (rc || qs) ? qs : (preseed_hit(ix, q, q_len, qe) ? 0 : q_len), seg = 0, s = 0, mc = 0;
+		while (i < qe) {
 			int end = Ns[seg++] - k + 1;
 			while (i < end) {
 				int slot, cnt, value = tindex_get(ix, kmer_at(comp, i, k), &slot, &cnt);
@@ -670,13 +674,13 @@ static void align_pe(const orc_params *p, nw_ws *ws, mems_t *pt, tindex **tix, o
 		const tindex *ix = tix[at];
 		const int t_len = db->lengths[at], o = flipped;
 		pt->len = 0;
-		aln_t a = kma_score(p, ws, ix, m1->b[o], m1->q_len, m1->w[o], m1->N[o], m1->nN + 1, mq, pt);
+		aln_t a = kma_score(p, ws, ix, m1->b[o], m1->q_len, 0, m1->q_len, m1->w[o], m1->N[o], m1->nN + 1, mq, pt);
 		if (cand) { int32_t row[8] = {ridx, mt[ti], a.score, a.len, a.pos, a.match, a.tGaps, a.qGaps}; ob_put(cand, row, 32); }
 		int rs = pe_rate(p, &a, m1->q_len, t_len, minlen, mrc, &start, &end, &score);
 		if (rs > k && score >= scoreT) { bT[ti] = rs; bS[ti] = start; bE[ti] = end; if (best1 < rs) best1 = rs; }
 		else { bT[ti] = 0; bS[ti] = -1; bE[ti] = -1; }
 		pt->len = 0;
-		a = kma_score(p, ws, ix, m2->b[o], m2->q_len, m2->w[o], m2->N[o], m2->nN + 1, mq, pt);
+		a = kma_score(p, ws, ix, m2->b[o], m2->q_len, 0, m2->q_len, m2->w[o], m2->N[o], m2->nN + 1, mq, pt);
 		if (cand) { int32_t row[8] = {ridx + 1, mt[ti], a.score, a.len, a.pos, a.match, a.tGaps, a.qGaps}; ob_put(cand, row, 32); }
 		rs = pe_rate(p, &a, m2->q_len, t_len, minlen, mrc, &start, &end, &score);
 		if (rs > k && score >= scoreT) {
@@ -810,7 +814,7 @@ static int pick_strand_bytes(const tindex *ix, uint8_t *q, int q_len, int one2on
 	const int k = ix->k;
 	int sf = 0, sr = 0;
 	pt->len = 0;
-	int first = exhaustive || preseed_hit(ix, q, q_len) ? 0 : q_len;   /* preseed returns 0 on a hit, >= q_len otherwise */
+	int first = exhaustive || preseed_hit(ix, q, q_len, q_len) ? 0 : q_len;   /* preseed returns 0 on a hit, >= q_len otherwise */
 	int nf = scan_bytes(ix, q, q_len, 0, q_len, 1, pt, 0, first, &sf);
 	bytes_rc(q, q_len);
 	int ntot = scan_bytes(ix, q, q_len, 0, q_len, 1, pt, nf, 0, &sr);
@@ -1092,18 +1096,20 @@ int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const 
 		double bestScore = 0; int best_read = 0, hits = 0;
 		const int arc = rc_flag < 0;
 		pt.len = 0;
+		int q_start = 0, q_end = q_len;   /* q-bound of a chain-mode record (alnfrags.c:1091-1099, qseqs.c:41) */
+		if (9 < hl && hdr[hl - 9] == 0) { memcpy(&q_start, hdr + hl - 8, 4); memcpy(&q_end, hdr + hl - 4, 4); }
 		for (int ti = 0; ti < nt; ++ti) {
 			int tmpl = T[ti], at = abs(tmpl);
 			if (!tix[at]) tix[at] = tindex_build(db->seq + db->seq_off[at], db->lengths[at], k);
 			const tindex *ix = tix[at];
 			aln_t a;
 			if (arc) {
-				int rc = pick_strand(p, ix, qf, qr, seq, rseq, N, rN, nN + 1, q_len, one2one, &pt);
-				if (rc < 0) { tmpl = -at; a = kma_score(p, &ws, ix, qr, q_len, rseq, rN, nN + 1, mq, &pt); }
-				else if (rc) { tmpl = at; a = kma_score(p, &ws, ix, qf, q_len, seq, N, nN + 1, mq, &pt); }
+				int rc = pick_strand(p, ix, qf, qr, seq, rseq, N, rN, nN + 1, q_len, q_start, q_end, one2one, &pt);
+				if (rc < 0) { tmpl = -at; a = kma_score(p, &ws, ix, qr, q_len, q_len - q_end, q_len - q_start, rseq, rN, nN + 1, mq, &pt); }
+				else if (rc) { tmpl = at; a = kma_score(p, &ws, ix, qf, q_len, q_start, q_end, seq, N, nN + 1, mq, &pt); }
 				else { memset(&a, 0, sizeof(a)); pt.len = 0; }
-			} else if (tmpl < 0) a = kma_score(p, &ws, ix, qr, q_len, rseq, rN, nN + 1, mq, &pt);
-			else a = kma_score(p, &ws, ix, qf, q_len, seq, N, nN + 1, mq, &pt);
+			} else if (tmpl < 0) a = kma_score(p, &ws, ix, qr, q_len, q_len - q_end, q_len - q_start, rseq, rN, nN + 1, mq, &pt);
+			else a = kma_score(p, &ws, ix, qf, q_len, q_start, q_end, seq, N, nN + 1, mq, &pt);
 			if (cand_out) { int32_t row[8] = {ridx, tmpl, a.score, a.len, a.pos, a.match, a.tGaps, a.qGaps}; ob_put(&cand, row, 32); }
 
 			int aln_len = a.len, start = a.pos, end = start + aln_len - a.tGaps, t_len = db->lengths[at], read_score;

@@ -245,13 +245,18 @@ int main(int argc, char **argv) {
 						int template = matched[t_i], at = abs(template), rc;
 						AlnScore st;
 						if (!templates_index[at]) templates_index[at] = alignLoadPtr(0, seq_in, template_lengths[at], kmersize, seq_indexes[at]);
+						int q_start = 0, q_end = q_len;   /* q-bound exactly as alnFragsSE takes it (alnfrags.c:1091-1099) */
+						if (2 * sizeof(int) + 1 < (size_t)header->len && header->seq[header->len - 2 * sizeof(int) - 1] == 0) {
+							int *qb = (int *)(header->seq + (header->len - 2 * sizeof(int)));
+							q_start = qb[0]; q_end = qb[1];
+						}
 						if (arc) {
-							rc = anker_rc_comp(templates_index[at], qseq, qseq_r, qc, qrc, 0, q_len, points);
-							if (rc < 0) { template = -at; st = KMA_score(templates_index[at], qseq_r, q_len, 0, q_len, qrc, 0, 0.5, points, NWm); }
-							else if (rc) { template = at; st = KMA_score(templates_index[at], qseq, q_len, 0, q_len, qc, 0, 0.5, points, NWm); }
+							rc = anker_rc_comp(templates_index[at], qseq, qseq_r, qc, qrc, q_start, q_end, points);
+							if (rc < 0) { template = -at; st = KMA_score(templates_index[at], qseq_r, q_len, q_len - q_end, q_len - q_start, qrc, 0, 0.5, points, NWm); }
+							else if (rc) { template = at; st = KMA_score(templates_index[at], qseq, q_len, q_start, q_end, qc, 0, 0.5, points, NWm); }
 							else { memset(&st, 0, sizeof(st)); points->len = 0; }
-						} else if (template < 0) st = KMA_score(templates_index[at], qseq_r, q_len, 0, q_len, qrc, 0, 0.5, points, NWm);
-						else st = KMA_score(templates_index[at], qseq, q_len, 0, q_len, qc, 0, 0.5, points, NWm);
+						} else if (template < 0) st = KMA_score(templates_index[at], qseq_r, q_len, q_len - q_end, q_len - q_start, qrc, 0, 0.5, points, NWm);
+						else st = KMA_score(templates_index[at], qseq, q_len, q_start, q_end, qc, 0, 0.5, points, NWm);
 						int row[8] = {ridx, template, st.score, st.len, st.pos, st.match, st.tGaps, st.qGaps};
 						fwrite(row, 4, 8, co);
 					}

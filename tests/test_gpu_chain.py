@@ -97,3 +97,44 @@ def test_chain_long_reads_vs_oracle(tmp_path):
     got, st = _gpu_chain(prefix, s1)
     assert st.mapped > 200
     assert got == want, _first_diff(got, want)
+
+
+def _chain_params():
+    p = api.default_params()
+    p.kmerscan = 1
+    return p
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case,seed,err,n_rate", [("chain", 51, 0.10, 0.0), ("chain", 52, 0.04, 0.002), ("tie", 53, 0, 0)])
+def test_chain_records_through_alignment(tmp_path, case, seed, err, n_rate):
+    """Stage-2 records of chain mode carry query bounds (qseqs.c:41); the alignment pass restricts its seed scans with
+    them (alnfrags.c:1091-1099). CUDA vs oracle (pinned to alnFrags_threaded in tests/test_oracle_align.py), from the
+    reference's stream and chained in HBM behind the CUDA chain kernel."""
+    if case == "chain":
+        prefix, s1, s2 = chain_case(tmp_path, seed, 80, 1000, 5000, err, n_rate)
+    else:
+        prefix, s1, s2 = tie_case(tmp_path, seed)
+    s2 = np.frombuffer(s2, dtype=np.uint8)
+    ofrag, oa, ou, ocand, cells = util.oracle_align_stream(prefix, s2, one2one=False)
+    db = api.TemplateDB(prefix, device=0)
+    p = _chain_params()
+    frag, a, u, cand, st = db.alnFrags_batch(s2, p, want_cand=True)
+    assert st.tasks == len(ocand)
+    if not util.cand_equal(cand, ocand):
+        bad = np.flatnonzero(((cand != ocand) & ~((np.arange(8) == 5) & (ocand[:, 2:3] == 0))).any(axis=1))
+        raise AssertionError(f"{len(bad)} of {len(cand)} candidate rows differ; first: got {cand[bad[0]]} want {ocand[bad[0]]}")
+    assert np.array_equal(a, oa) and np.array_equal(u, ou)
+    assert frag.tobytes() == ofrag
+    # the same, stage 2 and the alignment pass chained in HBM
+    db.seed_upload(s1)
+    sst = db.seed_run(p)
+    assert sst.mapped > 0
+    db.align_from_seed()
+    st2 = db.align_run(p, want_cand=True)
+    frag2, a2, u2, cand2 = db.align_download(want_cand=True)
+    db.close()
+    assert st2.tasks == len(ocand)
+    assert util.cand_equal(cand2, ocand)
+    assert np.array_equal(a2, oa) and np.array_equal(u2, ou)
+    assert frag2.tobytes() == ofrag

@@ -53,3 +53,27 @@ def test_fresh_data_vs_reference(tmp_path, seed, L, sub, indel):
     print('banded NW calls:', nband)
     if L >= 400:
         assert nband > 0
+
+
+@pytest.mark.parametrize("seed,err,n_rate", [(51, 0.10, 0.0), (52, 0.04, 0.002)])
+def test_chain_mode_records_with_query_bounds(tmp_path, seed, err, n_rate):
+    """stage-2 records of save_kmers_chain carry query bounds behind the name (qseqs.c:41); alnFragsSE hands them to
+    anker_rc_comp / KMA_score (alnfrags.c:1091-1099), which restrict the seed scan of the first / last stretch."""
+    from tests.test_oracle_chain import chain_case, tie_case
+    prefix, s1, s2 = chain_case(tmp_path, seed, 80, 1000, 5000, err, n_rate)
+    nb = sum(1 for r in __import__("kma_b200.records", fromlist=["x"]).parse_stage2(np.frombuffer(s2, np.uint8))
+             if len(r["name"]) > 9 and r["name"][-9] == 0)
+    assert nb > 50
+    frag, a, u, cand = util.ref_align(prefix, s2, str(tmp_path), one2one=False)
+    ofrag, oa, ou, ocand, cells = util.oracle_align_stream(prefix, np.frombuffer(s2, dtype=np.uint8), one2one=False)
+    assert util.cand_equal(ocand, cand)
+    assert ofrag == frag
+    assert np.array_equal(oa, a) and np.array_equal(ou, u)
+    d2 = tmp_path / "t"
+    d2.mkdir()
+    prefix, s1, s2 = tie_case(d2, seed)     # strand ties: anker_rc_comp with mirrored bounds
+    frag, a, u, cand = util.ref_align(prefix, s2, str(d2), one2one=False)
+    ofrag, oa, ou, ocand, cells = util.oracle_align_stream(prefix, np.frombuffer(s2, dtype=np.uint8), one2one=False)
+    assert util.cand_equal(ocand, cand)
+    assert ofrag == frag
+    assert np.array_equal(oa, a) and np.array_equal(ou, u)
