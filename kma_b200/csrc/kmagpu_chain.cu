@@ -77,7 +77,7 @@ __device__ __forceinline__ int link_score(const ChainParams &p, int k, int gaps,
 // ---------------------------------------------------------------- segment tree (lane 0 only)
 
 // addSeqmentTrees (seqmenttree.c:107-181), the recursion unrolled over an explicit stack
-__device__ unsigned st_add(STree &T, SFrame *fs, int root0, int node) {
+__device__ __noinline__ unsigned st_add(STree &T, SFrame *fs, int root0, int node) {
 	int sp = 0;
 	unsigned ret = 0;
 	fs[0].root = root0; fs[0].state = 0;
@@ -142,7 +142,7 @@ __device__ unsigned st_add(STree &T, SFrame *fs, int root0, int node) {
 }
 
 // growSeqmentTree (seqmenttree.c:183); the reference's resize is undefined behaviour: refuse (returns -1)
-__device__ int st_grow(STree &T, SFrame *fs, unsigned start, unsigned end) {
+__device__ __noinline__ int st_grow(STree &T, SFrame *fs, unsigned start, unsigned end) {
 	if (KC_ST <= T.n + 2) return -1;
 	if (T.n == 0) {
 		T.n = 1; T.start[0] = start; T.end[0] = end; T.cov[0] = end - start; T.b0[0] = T.b1[0] = -1;
@@ -156,7 +156,7 @@ __device__ int st_grow(STree &T, SFrame *fs, unsigned start, unsigned end) {
 }
 
 // queSeqmentTree (seqmenttree.c:211)
-__device__ unsigned st_query(const STree &T, SFrame *fs, unsigned start, unsigned end) {
+__device__ __noinline__ unsigned st_query(const STree &T, SFrame *fs, unsigned start, unsigned end) {
 	int sp = 0;
 	unsigned sum = 0;
 	fs[0].root = 0;
@@ -182,7 +182,7 @@ __device__ unsigned st_query(const STree &T, SFrame *fs, unsigned start, unsigne
 struct ChainStats { unsigned lookups, hits, lists, listids; };
 
 __device__ int find_ankers(const KgHashView &hv, const ChainParams &p, const ReadCtx &rc, const int strand, const Ank &A,
-                           uint64_t *sw, ChainStats &ws) {
+                           uint64_t *sw, uint32_t *hits, ChainStats &ws) {
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1;
 	const int k = hv.kmersize, L = rc.seqlen, npos = L - k + 1, sh = 64 - 2 * k;
@@ -217,34 +217,74 @@ __device__ int find_ankers(const KgHashView &hv, const ChainParams &p, const Rea
 		__syncwarp();
 		for (int w = w0 + (int)lane; w <= w1 + 1; w += 32) sw[w - w0] = w < rc.words ? ld_u64u(rc.seq + 8 * (size_t)w) : 0ull;
 		__syncwarp();
-		uint32_t off[KC_PER_LANE];
+		// phase 1: gather, in three rounds so that 8 independent probes per lane are in flight (exist -> kv -> chain)
+		uint32_t e1[KC_PER_LANE];
+		if (rc.nN) {   // reads with N's (rare): validity per position, one probe at a time
+#pragma unroll 1
+			for (int u = 0; u < KC_PER_LANE; ++u) {
+				const int j = c0 + u * 32 + (int)lane;
+				int ss = 0;
+				uint32_t v = KG_MISS;
+				if (j < npos && pos_valid(rc, j, k, 0, &ss)) {
+					uint64_t km;
+					if (strand == 0) km = kmer_from(sw, w0, j, k);
+					else km = rev2(~kmer_from(sw, w0, ss ? j - k : j, k)) >> sh;
+					v = hash_lookup(hv, km);
+					ws.lookups++;
+				}
+				hits[u * 32 + lane] = v;
+			}
+		} else {
+		uint64_t km[KC_PER_LANE];
 #pragma unroll
 		for (int u = 0; u < KC_PER_LANE; ++u) {
 			const int j = c0 + u * 32 + (int)lane;
-			int ss = 0;
-			const bool ok = j < npos && (rc.nN == 0 || pos_valid(rc, j, k, 0, &ss));
-			off[u] = KG_MISS;
-			if (ok) {
-				uint64_t km;
-				if (strand == 0) km = kmer_from(sw, w0, j, k);
-				else km = rev2(~kmer_from(sw, w0, ss ? j - k : j, k)) >> sh;
-				off[u] = hash_lookup(hv, km);
+			e1[u] = KG_MISS; km[u] = 0;
+			if (j < npos) {
+				km[u] = kmer_from(sw, w0, j, k);
+				if (strand) km[u] = rev2(~km[u]) >> sh;
+				if (hv.mega) { const uint32_t v = __ldg(hv.exist + km[u]); e1[u] = v != 1u ? v : KG_MISS; }
+				else { const uint32_t q = __ldg(hv.exist + (uint32_t)(km[u] & hv.hmask)); e1[u] = q != hv.null_index ? q : KG_MISS; }
 				ws.lookups++;
 			}
 		}
+		if (!hv.mega) {
+			uint2 e2[KC_PER_LANE];
 #pragma unroll
+			for (int u = 0; u < KC_PER_LANE; ++u) e2[u] = e1[u] != KG_MISS ? __ldg(hv.kv + e1[u]) : make_uint2(0, 0);
+#pragma unroll
+			for (int u = 0; u < KC_PER_LANE; ++u) {
+				if (e1[u] == KG_MISS) continue;
+				const uint32_t key = (uint32_t)km[u], bucket = key & (uint32_t)hv.hmask;
+				uint32_t pos = e1[u], v = KG_MISS;
+				uint2 e = e2[u];
+				for (;;) {
+					if (e.x == key) { v = e.y; break; }
+					if ((e.x & (uint32_t)hv.hmask) != bucket || pos >= hv.n) break;
+					e = __ldg(hv.kv + ++pos);
+				}
+				e1[u] = v;
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < KC_PER_LANE; ++u) hits[u * 32 + lane] = e1[u];
+		}
+		__syncwarp();
+		// phase 2: ankers of the chunk, 32 positions at a time
+#pragma unroll 1
 		for (int u = 0; u < KC_PER_LANE; ++u) {
-			const unsigned hm = __ballot_sync(FULL, off[u] != KG_MISS);
+			const uint32_t myoff = hits[u * 32 + lane];
+			const unsigned hm = __ballot_sync(FULL, myoff != KG_MISS);
 			if (!hm) continue;
 			const int j = c0 + u * 32 + (int)lane;
-			const bool h = off[u] != KG_MISS;
+			const bool h = myoff != KG_MISS;
 			const unsigned below = hm & lt;
 			const int pl = below ? 31 - __clz(below) : -1;
-			uint32_t pOff = __shfl_sync(FULL, off[u], pl < 0 ? 0 : pl);
+			uint32_t pOff = __shfl_sync(FULL, myoff, pl < 0 ? 0 : pl);
 			int pPos = j - ((int)lane - pl);
 			if (pl < 0) { pOff = prevOff; pPos = prevPos; }
 			const int gap = j - pPos - 1;
-			const bool cont = h && pPos >= 0 && off[u] == pOff && (gap == 0 || gap == k);
+			const bool cont = h && pPos >= 0 && myoff == pOff && (gap == 0 || gap == k);
 			const bool isstart = h && !cont;
 			int w = cont ? (gap == 0 ? p.M : k * p.M + p.MM) : 0;
 #pragma unroll
@@ -257,14 +297,14 @@ __device__ int find_ankers(const KgHashView &hv, const ChainParams &p, const Rea
 			if (!sbelow) Wst = startW;
 			if (isstart) {
 				const int idx = nank + __popc(sbelow);
-				A.start[idx] = j; A.vals[idx] = off[u];
+				A.start[idx] = j; A.vals[idx] = myoff;
 				if (idx > 0) { A.weight[idx - 1] = k * p.M + w - Wst; A.end[idx - 1] = pPos + 1 + k; }
-				if (pPos < 0 || off[u] != pOff) { ws.lists++; ws.listids += (unsigned)list_len(hv, off[u]); }
+				if (pPos < 0 || myoff != pOff) { ws.lists++; ws.listids += (unsigned)list_len(hv, myoff); }
 			}
 			ws.hits += h ? 1u : 0u;
 			const int hl = 31 - __clz(hm);
 			prevPos = c0 + u * 32 + hl;
-			prevOff = __shfl_sync(FULL, off[u], hl);
+			prevOff = __shfl_sync(FULL, myoff, hl);
 			Wcarry = __shfl_sync(FULL, w, 31);
 			if (smask) { startW = __shfl_sync(FULL, w, 31 - __clz(smask)); nank += __popc(smask); }
 		}
@@ -293,7 +333,7 @@ struct WarpCtx {
 // Walk back from anker `src` of strand s, re-scoring its templates anker by anker until one of them reproduces src's
 // score at a chain start. dst[1 .. *count] receives the templates that reach it. Marks walked ankers as used.
 // Returns the anker the chain starts at, -1 if no template is left. *err is set when the walk leaves the array.
-__device__ int chain_templates(const KgHashView &hv, const ChainParams &p, WarpCtx &W, const int s, const int src, int *dst,
+__device__ __noinline__ int chain_templates(const KgHashView &hv, const ChainParams &p, WarpCtx &W, const int s, const int src, int *dst,
                                int *count, int *err) {
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1;
@@ -365,7 +405,7 @@ __device__ int chain_templates(const KgHashView &hv, const ChainParams &p, WarpC
 
 // getBestAnkerScore (kmeranker.c:398) as an array reduction: the LAST anker with the largest non-zero score,
 // ties = how many others share it. Returns -1 when every anker is used up.
-__device__ int best_anker(const Ank &V, int cnt, unsigned *ties) {
+__device__ __noinline__ int best_anker(const Ank &V, int cnt, unsigned *ties) {
 	const unsigned lane = threadIdx.x & 31;
 	int best = 0, idx = -1, n = 0;
 	for (int a = lane; a < cnt; a += 32) {
@@ -387,7 +427,7 @@ __device__ int best_anker(const Ank &V, int cnt, unsigned *ties) {
 }
 
 // getTieAnkerScore (kmeranker.c:480): nearest anker before src that starts behind `stop` and scores like best
-__device__ int tie_anker(const Ank &V, int stop, int src, int bestScore) {
+__device__ __noinline__ int tie_anker(const Ank &V, int stop, int src, int bestScore) {
 	const unsigned lane = threadIdx.x & 31;
 	if (src < 0 || V.start[src] <= stop) return -1;
 	for (int hi = src - 1; hi >= 0; hi -= 32) {
@@ -405,7 +445,7 @@ __device__ int tie_anker(const Ank &V, int stop, int src, int bestScore) {
 }
 
 // chooseChain (kmeranker.c:512-592), proxi == 1.0
-__device__ int choose_chain(int fscore, int fend, int rscore, int rend, int cs, int cs_r, double coverT, int *Start, int *Len) {
+__device__ __noinline__ int choose_chain(int fscore, int fend, int rscore, int rend, int cs, int cs_r, double coverT, int *Start, int *Len) {
 	int rc = rscore < fscore ? 1 : fscore < rscore ? 2 : 3, start, end;
 	if (rc == 1) { start = cs; end = fend; }
 	else if (rc == 2) { start = cs_r; end = rend; }
@@ -436,6 +476,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
              int32_t *__restrict__ pool, unsigned long long pool_cap, Region *__restrict__ regpool, unsigned long long reg_cap,
              unsigned long long *ctr, uint8_t *scratch, ChainScratch lay) {
 	__shared__ uint64_t s_words[KC_WARPS][KC_WORDS];
+	__shared__ uint32_t s_hits[KC_WARPS][KC_CHUNK];
 	__shared__ STree s_tree[KC_WARPS];
 	__shared__ SFrame s_frames[KC_WARPS][KC_ST + 2];
 
@@ -487,10 +528,11 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 		do {
 			if (seqlen < k) break;
 			// ---- ankers
+#pragma unroll 1
 			for (int s = 0; s < 2; ++s) {
 				if (lane == 0) { W.V[s].start[0] = 0; W.V[s].end[0] = 0; W.V[s].score[0] = 0; W.V[s].vals[0] = KG_MISS; }
 				__syncwarp();
-				W.cnt[s] = find_ankers(hv, p, rc, s, W.V[s], sw, ws);
+				W.cnt[s] = find_ankers(hv, p, rc, s, W.V[s], sw, s_hits[wid], ws);
 			}
 			if (!W.cnt[0] && !W.cnt[1]) break;
 
@@ -498,6 +540,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 			unsigned ties = 0;
 			int bIdx[2] = {0, 0};
 			int btN[2] = {0, 0};
+#pragma unroll 1
 			for (int s = 0; s < 2; ++s) {
 				const Ank &V = W.V[s];
 				int *bests = W.bt[s];
@@ -539,6 +582,11 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 #pragma unroll
 						for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
 						if (nscore < mx) nscore = mx;
+						// every template of the chunk as long as the current pick (or nothing picked yet): the fold is a maximum
+						const int ll0 = __shfl_sync(FULL, ll, 0);
+						if (__all_sync(FULL, !act || ll == ll0) && (nll == ll0 || nll == 1)) {
+							if (nsl < mx) { nsl = mx; nll = ll0; }
+						} else
 						for (int l = 0; l < cntl; ++l) {
 							const int sc = __shfl_sync(FULL, score, l), tl = __shfl_sync(FULL, ll, l);
 							bool upd;
@@ -596,6 +644,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 			__syncwarp();
 			while (bIdx[0] >= 0 || bIdx[1] >= 0) {
 				if (ties) {   // equal ankers further up the read join when they overlap enough (savekmers.c:5701-5781)
+#pragma unroll 1
 					for (int s = 0; s < 2; ++s) {
 						if (!(rcm & (s + 1))) continue;
 						int *bl = W.bt[s];
@@ -619,6 +668,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 					if (err) break;
 				}
 				if (p.mrc != 0.0) {   // mrchain (kmeranker.c:57)
+#pragma unroll 1
 					for (int s = 0; s < 2; ++s) {
 						if (!(rcm & (s + 1))) continue;
 						const double thr = __dmul_rn(p.mrc, (double)len);
@@ -675,6 +725,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 
 				// next chain of either strand (savekmers.c:5838-5924)
 				ties = 0; rcm = 0;
+#pragma unroll 1
 				for (int s = 0; s < 2 && !err; ++s) {
 					if (bIdx[s] < 0) continue;
 					const Ank &V = W.V[s];
@@ -834,7 +885,7 @@ int kg_chain_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *sta
 	lay.cap = (((size_t)std::max(b.max_seqlen, 64) + 8) + 3) & ~(size_t)3;
 	lay.regcap = lay.cap / 8 + 64;
 	lay.stride = (16 * lay.D + 2 * 4 * (2 * lay.D + 4) + sizeof(Region) * lay.regcap + 2 * 20 * lay.cap + 255) & ~(size_t)255;
-	int grid = db->sm_count * 4;
+	int grid = db->sm_count * 5;
 	const size_t budget = (size_t)12 << 30;
 	while (grid > db->sm_count && lay.stride * (size_t)grid * KC_WARPS > budget) grid -= db->sm_count;
 	grid = (int)std::min<size_t>((size_t)grid, ((size_t)n + KC_WARPS - 1) / KC_WARPS);
