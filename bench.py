@@ -200,6 +200,65 @@ def nw_gcups(db, seqs, peak_iops, n=24000, seed=3):
             "not_ok": int((status != 0).sum())}
 
 
+def c3_chain(db, api, seqs, prefix, workdir, cores, n=20000, ref_n=2000, seed=22):
+    """BASELINE.json configs[2] (C3) beside the headline: Nanopore-like reads (5-20 kb, 10 % errors) through stage 2 in
+    chain mode (save_kmers_chain, the reference's default without -1t1: `chain_kernel`) and the alignment pass with
+    the records' query bounds, chained in HBM; kernels timed by CUDA events inside the library, `e2e` from pinned-free
+    host buffers (H2D of the stage-1 records, D2H of frag_raw + score arrays inside the timed region). The unmodified
+    reference runs `kma -s2 -t cores | alnFrags_threaded` on the first `ref_n` reads."""
+    reads = synth.long_reads(seed, seqs, n)
+    s1 = records.stage1_records(reads)
+    bases = int(sum(len(r) for r in reads))
+    p = api.default_params()
+    p.kmerscan = 1
+    db.seed_upload(s1)
+    best = None
+    for _ in range(4):
+        st = db.seed_run(p)
+        nrec = db.align_from_seed()
+        sa = db.align_run(p)
+        if best is None or st.ms_total + sa.ms_total < best[0]:
+            best = (st.ms_total + sa.ms_total, st, sa, nrec)
+    ms, st, sa, nrec = best
+    import torch
+    s1p = torch.empty(len(s1), dtype=torch.uint8, pin_memory=True)
+    s1p.numpy()[:] = s1
+    fragp = torch.empty(db.align_out_bytes() + 4096, dtype=torch.uint8, pin_memory=True)
+    t0 = time.perf_counter()
+    db.seed_upload(s1p)
+    db.seed_run(p)
+    db.align_from_seed()
+    db.align_run(p)
+    frag, _, _, _ = db.align_download(out=fragp)
+    t_e2e = time.perf_counter() - t0
+    cells = sa.nw_full_cells + sa.nw_band_cells
+    out = {"workload": f"C3: {n} synthetic Nanopore-like reads (5-20 kb, 10 % errors, {bases / 1e6:.0f} Mb) vs the redundant gene DB, chain mode (no -1t1)",
+           "reads_per_s": n / (ms * 1e-3), "bases_per_s": bases / (ms * 1e-3), "ms": ms,
+           "e2e_reads_per_s": n / t_e2e, "h2d_bytes": int(len(s1)), "d2h_bytes": int(len(frag)),
+           "stage2_records": int(nrec), "alignments": int(sa.tasks), "frag_records": int(sa.frags),
+           "chain_kernel_ms": st.ms_seed, "lookups_per_read": st.lookups / n, "ankers_per_read": st.list_fetches / n,
+           "aln_pair_kernel_ms": sa.ms_align, "nw_cells": int(cells), "nw_cells_banded_fraction": sa.nw_band_cells / max(1, cells),
+           "align_gcups": cells / max(sa.ms_align, 1e-9) / 1e6}
+    kma = os.path.join(ROOT, "oracle", "_ref", "kma")
+    aln = os.path.join(ROOT, "oracle", "_ref", "ref_aln")
+    if os.path.exists(kma) and os.path.exists(aln):
+        fq = os.path.join(workdir, f"c3_{ref_n}.fq")
+        synth.write_fastq(fq, reads[:ref_n], qual="5")
+        t0 = time.perf_counter()
+        with open(os.devnull, "wb") as dn:
+            p1 = subprocess.Popen([kma, "-i", fq, "-o", os.path.join(workdir, "o3"), "-t_db", prefix, "-s2", "-t", str(cores)],
+                                  stdout=subprocess.PIPE, stderr=dn)
+            p2 = subprocess.Popen([aln, prefix, "-", os.path.join(workdir, "fr3.out"), os.path.join(workdir, "sc3.out"), "-t", str(cores)],
+                                  stdin=p1.stdout, stdout=dn, stderr=dn)
+            p1.stdout.close()
+            rc2, rc1 = p2.wait(), p1.wait()
+        dt = time.perf_counter() - t0
+        if not (rc1 or rc2):
+            out["cpu_reference"] = {"reads_per_s": ref_n / dt, "cores": cores, "seconds": dt,
+                                    "sample": f"first {ref_n} reads; unmodified kma -s2 -t {cores} | alnFrags_threaded on {cores} pthreads"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,6 +268,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=2_000_000, help="read pairs per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="read pairs of the CPU legs (default: the whole step, ~7 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c3", action="store_true", help="skip the C3 (long reads, chain mode) side measurement")
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads / library handles of the end-to-end pipeline")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks the batch is cut into for the end-to-end pipeline")
     args = ap.parse_args()
@@ -404,6 +464,8 @@ def main():
     }
     if rank == 0:
         line["nw"] = nw_gcups(db, seqs, peak_iops)
+        if not args.no_c3:
+            line["c3"] = c3_chain(db, api, seqs, prefix, workdir, cores)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = min(args.cpu_sample, args.pairs)

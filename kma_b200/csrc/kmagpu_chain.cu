@@ -228,7 +228,13 @@ __device__ int find_ankers(const KgHashView &hv, const ChainParams &p, const Rea
 				if (j < npos && pos_valid(rc, j, k, 0, &ss)) {
 					uint64_t km;
 					if (strand == 0) km = kmer_from(sw, w0, j, k);
-					else km = rev2(~kmer_from(sw, w0, ss ? j - k : j, k)) >> sh;
+					else if (ss && j < k) {
+						// the reference's shifted reverse cursor (savekmers.c:5443) starts past the end of the read when an
+						// N sits in the first k bases: undefined there, zero bits here (oracle/orc_chain.c header), i.e.
+						// the complement of T in front of the read
+						const uint64_t head = kmer_from(sw, w0, 0, k) >> (2 * (k - j));
+						km = rev2(~(head | (~0ull << (2 * j)))) >> sh;
+					} else km = rev2(~kmer_from(sw, w0, ss ? j - k : j, k)) >> sh;
 					v = hash_lookup(hv, km);
 					ws.lookups++;
 				}

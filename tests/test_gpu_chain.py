@@ -138,3 +138,14 @@ def test_chain_records_through_alignment(tmp_path, case, seed, err, n_rate):
     assert util.cand_equal(cand2, ocand)
     assert np.array_equal(a2, oa) and np.array_equal(u2, ou)
     assert frag2.tobytes() == ofrag
+
+
+def test_chain_golden_reads_with_early_n():
+    """the golden 150 bp reads through chain mode; 98 of them carry an N in their first k bases, where the reference
+    reads past its reverse-complement buffer (undefined): the CUDA path follows the oracle's zero-bits convention"""
+    with util.golden_dir() as g:
+        s1 = np.fromfile(f"{g}/s1.bin", dtype=np.uint8)
+        want = util.oracle_chain_stream(f"{g}/db", s1).tobytes()
+        got, st = _gpu_chain(f"{g}/db", s1)
+    assert st.mapped > 2000
+    assert got == want, _first_diff(got, want)
