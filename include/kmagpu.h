@@ -34,7 +34,9 @@ typedef struct kmagpu_params {
 	int32_t minlen;                   /* -ml  minimum alignment length (alnfrags.c:1156), default 16 */
 	int32_t kmerscan;                 /* which kmerScan (savekmers.h:50): 0 = save_kmers (-1t1, savekmers.c:2442),
 	                                     1 = save_kmers_chain (the default without -1t1, savekmers.c:5127) */
-	int32_t reserved[3];
+	int32_t matrix;                   /* kmagpu_trace_batch: add every accepted alignment to the base-count matrix as alnToMatPtr does
+	                                     (assembly.c:1968): 0 = no, 1 = alnToMat (template nodes, assembly.c:1317), 2 = alnToMatDense (-dense, :1446) */
+	int32_t reserved[2];
 	double scoreT;                    /* -mrs (alnfrags.c:1168; also `mrs` of save_kmers_chain, kmers.c:51) */
 	double minFrac;                   /* -mf  (updatescores.c:217-268) */
 	double mrc;                       /* -mrc (alnfrags.h:38 mrcheck) */
@@ -140,6 +142,18 @@ int kmagpu_align_download(kmagpu_db *db, void *frag_out, size_t out_cap, size_t 
  * (assembly.c:1317) and updateFrags consume next. `turned` = the read was reverse-complemented by anker_rc. */
 int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *p, const void *frags, size_t nbytes,
                        void *out, size_t out_cap, size_t *out_bytes, int64_t *nrecords, kmagpu_align_stats *stats);
+
+/* The per-position base counts of the assembly pass (Assembly.counts[6] = {A, C, G, T, N, gap}, assembly.h:55-58) for
+ * the template nodes of every template, HBM resident: uint32 [sum of template lengths][6], template t starting at
+ * position sum(len[1..t-1]). kmagpu_trace_batch with params->matrix != 0 adds the accepted alignments of a batch
+ * (alnToMat, assembly.c:1317-1444, restricted to the template nodes -- insertion nodes are order dependent and stay
+ * on the host -- or alnToMatDense, assembly.c:1446-1497). Counts are kept unsaturated on the device so that ranks can
+ * be summed (kmagpu_matrix_device gives the device pointer for the NCCL all-reduce); kmagpu_matrix_download clamps
+ * to the reference's uint16 saturation (assembly.c:1436). tmpl = 0 downloads every template, else one template's
+ * len * 6 entries; counts = NULL only reports the entry count. */
+int kmagpu_matrix_reset(kmagpu_db *db);
+int kmagpu_matrix_device(kmagpu_db *db, void **device_ptr, uint64_t *entries);
+int kmagpu_matrix_download(kmagpu_db *db, int32_t tmpl, uint16_t *counts, size_t cap_entries, size_t *entries);
 
 /* NW_score (nw.c:642) / NW_band_score (nw.c:892) over a batch of independent problems, one warp each.
  * prob[i] = {template id, t_s, t_e, q_off, q_s, q_e, k, band (0 = full matrix)}; the query bytes (0-4) of problem i

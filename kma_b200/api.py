@@ -21,7 +21,7 @@ class KmaGpuError(RuntimeError):
 class Params(C.Structure):
     _fields_ = [("M", C.c_int32), ("MM", C.c_int32), ("U", C.c_int32), ("W1", C.c_int32), ("Wl", C.c_int32),
                 ("Mn", C.c_int32), ("PE", C.c_int32), ("d", C.c_int32 * 25), ("exhaustive", C.c_int32),
-                ("mq", C.c_int32), ("one2one", C.c_int32), ("minlen", C.c_int32), ("kmerscan", C.c_int32), ("reserved", C.c_int32 * 3),
+                ("mq", C.c_int32), ("one2one", C.c_int32), ("minlen", C.c_int32), ("kmerscan", C.c_int32), ("matrix", C.c_int32), ("reserved", C.c_int32 * 2),
                 ("scoreT", C.c_double), ("minFrac", C.c_double), ("mrc", C.c_double), ("coverT", C.c_double)]
 
 
@@ -75,6 +75,9 @@ def lib():
         L.kmagpu_seed_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]
         L.kmagpu_seed_run.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(SeedStats)]
         L.kmagpu_seed_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.kmagpu_matrix_reset.argtypes = [C.c_void_p]
+        L.kmagpu_matrix_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.kmagpu_matrix_download.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.kmagpu_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.kmagpu_align_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]
         L.kmagpu_align_from_seed.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
@@ -229,6 +232,28 @@ class TemplateDB:
         _check(lib().kmagpu_trace_batch(self._h, C.byref(p), frags.ctypes.data, len(frags), out.ctypes.data, cap,
                                         C.byref(ob), C.byref(nr), C.byref(st)))
         return out[: ob.value], nr.value, st
+
+    # --- base-count matrix of the assembly pass (alnToMat / alnToMatDense) ----------------------
+    def matrix_reset(self):
+        _check(lib().kmagpu_matrix_reset(self._h))
+
+    def matrix_download(self, template: int = 0) -> np.ndarray:
+        """uint16 [positions, 6] counts {A, C, G, T, N, gap} of one template (template > 0) or of the whole database"""
+        n = C.c_size_t()
+        _check(lib().kmagpu_matrix_download(self._h, int(template), None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.uint16)
+        _check(lib().kmagpu_matrix_download(self._h, int(template), out.ctypes.data, n.value, C.byref(n)))
+        return out.reshape(-1, 6)
+
+    def matrix_tensor(self):
+        """the unsaturated device matrix as a torch int32 tensor (zero copy) for the NCCL all-reduce over ranks"""
+        import torch
+        ptr, n = C.c_void_p(), C.c_uint64()
+        _check(lib().kmagpu_matrix_device(self._h, C.byref(ptr), C.byref(n)))
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<i4", "data": (int(ptr.value), False), "version": 2}
+        return torch.as_tensor(_View(), device=torch.device("cuda", self.device))
 
     def nw_batch(self, prob: np.ndarray, qpool: np.ndarray, params: Params | None = None):
         """NW_score / NW_band_score over independent problems; prob[n, 8] int32 =

@@ -1296,6 +1296,76 @@ __global__ void __launch_bounds__(256) tr_emit_kernel(const TrRec *__restrict__ 
 	}
 }
 
+
+// ---------------------------------------------------------------- base-count matrix (alnToMat / alnToMatDense)
+
+// One warp per accepted alignment: +1 on counts[template position][query code] for every aligned column that has a
+// template base (assembly.c:1317-1444 restricted to the template nodes; assembly.c:1446-1497 when dense). The
+// reference serialises these updates under a lock and saturates its uint16 counters; +1 increments commute, so the
+// device adds atomically into uint32 and the read-out clamps to 65535 (= the saturated sum). Gap-column trimming
+// follows the reference: alnToMat drops gap columns at both ends (its trailing loop stops at column 0) and moves
+// the start past leading deletions, alnToMatDense only drops trailing ones.
+__global__ void __launch_bounds__(256) tr_matrix_kernel(const TrRec *__restrict__ recs, const TrOut *__restrict__ outs, int n,
+		const uint8_t *__restrict__ rowpool, const KgTMeta *__restrict__ meta, const int64_t *__restrict__ mat_off, int dense,
+		unsigned int *mat, unsigned long long *ctr) {
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	unsigned long long added = 0;
+	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+		const TrOut o = outs[r];
+		if (!o.h[0]) continue;
+		const TrRec R = recs[r];
+		const uint8_t *t = rowpool + R.row_off, *q = t + 2 * (size_t)R.row_cap;
+		const int t_len = meta[R.tmpl].len;
+		unsigned int *C = mat + 6 * (size_t)mat_off[R.tmpl];
+		int aln_len = o.h[5], start = o.h[6], i0 = 0;
+		// trailing gap columns
+		{
+			int i = aln_len - 1;
+			for (;;) {
+				const int c = i - (int)lane;
+				const bool gap = c >= (dense ? 0 : 1) && (t[c] == 5 || q[c] == 5);
+				const unsigned stop = __ballot_sync(0xffffffffu, !gap);
+				if (stop) { i -= __ffs(stop) - 1; break; }
+				i -= 32;
+			}
+			aln_len = i + 1;
+		}
+		if (!dense) {   // leading gap columns; deletions move the start
+			for (;;) {
+				const int c = i0 + (int)lane;
+				const bool gap = c < aln_len && (t[c] == 5 || q[c] == 5);
+				const unsigned stop = __ballot_sync(0xffffffffu, !gap);
+				const int take = stop ? __ffs(stop) - 1 : 32;
+				start += __popc(__ballot_sync(0xffffffffu, gap && q[c] == 5) & (take == 32 ? 0xffffffffu : (1u << take) - 1));
+				i0 += take;
+				if (stop) break;
+			}
+		}
+		int pos = start % t_len;
+		for (int base = i0; base < aln_len; base += 32) {
+			const int c = base + (int)lane;
+			const bool has = c < aln_len && t[c] != 5;
+			const unsigned m = __ballot_sync(0xffffffffu, has);
+			if (has) {
+				int p = pos + __popc(m & lt);
+				if (p >= t_len) p %= t_len;
+				atomicAdd(&C[6 * (size_t)p + q[c]], 1u);
+			}
+			pos += __popc(m);
+			if (pos >= t_len) pos %= t_len;
+			added += lane == 0 ? __popc(m) : 0;
+		}
+	}
+	if (lane == 0 && added) atomicAdd(&ctr[A_MEMBASES], added);
+}
+
+__global__ void __launch_bounds__(256) mat_clamp_kernel(const unsigned int *__restrict__ mat, size_t n, uint16_t *__restrict__ out) {
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+		out[i] = (uint16_t)min(mat[i], 65535u);
+}
+
 // ---------------------------------------------------------------- host side
 
 int kg_align_free(kmagpu_db *db) {
@@ -1667,6 +1737,13 @@ extern "C" int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *prm, const
 		novf = (int)h[A_OVF];
 	}
 	if (h[A_BAD]) { kmagpu_set_error("%llu alignments are longer than 3 * read length + 256 columns", h[A_BAD]); return -1; }
+	if (prm->matrix) {   // alnToMatPtr (assembly.c:1968) on every accepted alignment
+		if (prm->matrix != 1 && prm->matrix != 2) { kmagpu_set_error("matrix mode %d: 1 = alnToMat (template nodes), 2 = alnToMatDense", prm->matrix); return -1; }
+		if (!db->d_mat && kmagpu_matrix_reset(db)) return -1;
+		tr_matrix_kernel<<<db->sm_count * 8, 256, 0, st>>>((const TrRec *)d_recs.p, (const TrOut *)d_outs.p, n, (const uint8_t *)d_rows.p,
+			db->tix.meta, db->d_mat_off, prm->matrix == 2, db->d_mat, ctr);
+		++launches;
+	}
 	tr_outsize_kernel<<<(n + 255) / 256, 256, 0, st>>>((const TrOut *)d_outs.p, n, osz);
 	kg_exscan(osz, n, ooff, (uint32_t *)d_partial.p, ctr + A_OUT, st);
 	launches += 4;
@@ -1693,6 +1770,58 @@ extern "C" int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *prm, const
 		cudaEventElapsedTime(&stats->ms_total, db->ev[2], db->ev[7]);
 		stats->launches = launches;
 	}
+	return 0;
+}
+
+// ---------------------------------------------------------------- base-count matrix: host side
+
+extern "C" int kmagpu_matrix_reset(kmagpu_db *db) {
+	if (!db) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->d_tmeta) { kmagpu_set_error("database has no template sequences"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	const int DB = db->info.DB_size;
+	if (!db->d_mat) {
+		std::vector<int64_t> off((size_t)DB + 1, 0);
+		for (int t = 2; t <= DB; ++t) off[t] = off[t - 1] + db->lengths[t - 1];
+		db->mat_entries = 6 * (size_t)off[DB];
+		KG_CUDA(cudaMalloc(&db->d_mat_off, 8 * ((size_t)DB + 1)));
+		KG_CUDA(cudaMemcpy(db->d_mat_off, off.data(), 8 * ((size_t)DB + 1), cudaMemcpyHostToDevice));
+		KG_CUDA(cudaMalloc(&db->d_mat, 4 * db->mat_entries + 64));
+		db->info.device_bytes += 4 * db->mat_entries;
+	}
+	KG_CUDA(cudaMemsetAsync(db->d_mat, 0, 4 * db->mat_entries, db->stream));
+	KG_CUDA(cudaStreamSynchronize(db->stream));
+	return 0;
+}
+
+extern "C" int kmagpu_matrix_device(kmagpu_db *db, void **ptr, uint64_t *entries) {
+	if (!db || !ptr || !entries) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->d_mat && kmagpu_matrix_reset(db)) return -1;
+	*ptr = db->d_mat; *entries = db->mat_entries;
+	return 0;
+}
+
+extern "C" int kmagpu_matrix_download(kmagpu_db *db, int32_t tmpl, uint16_t *counts, size_t cap_entries, size_t *entries) {
+	if (!db) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->d_mat) { kmagpu_set_error("kmagpu_matrix_download before any alignment was added"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	const int DB = db->info.DB_size;
+	if (tmpl < 0 || tmpl >= DB) { kmagpu_set_error("template %d outside the database", tmpl); return -1; }
+	size_t first = 0, cnt = db->mat_entries;   // template 0 = the whole database
+	if (tmpl) {
+		for (int t = 1; t < tmpl; ++t) first += 6 * (size_t)db->lengths[t];
+		cnt = 6 * (size_t)db->lengths[tmpl];
+	}
+	if (entries) *entries = cnt;
+	if (!counts) return 0;
+	if (cnt > cap_entries) { kmagpu_set_error("matrix needs %zu entries, caller gave %zu", cnt, cap_entries); return -1; }
+	KgBuf tmp;
+	if (tmp.reserve(2 * cnt + 64)) return -1;
+	mat_clamp_kernel<<<db->sm_count * 4, 256, 0, db->stream>>>(db->d_mat + first, cnt, (uint16_t *)tmp.p);
+	cudaError_t e = cudaMemcpyAsync(counts, tmp.p, 2 * cnt, cudaMemcpyDeviceToHost, db->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
+	tmp.release();
+	if (e != cudaSuccess) { kmagpu_set_error("matrix download: %s", cudaGetErrorString(e)); return -1; }
 	return 0;
 }
 

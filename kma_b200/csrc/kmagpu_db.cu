@@ -185,6 +185,7 @@ extern "C" void kmagpu_db_close(kmagpu_db *db) {
 	cudaFree(db->d_tmeta); cudaFree(db->d_tslots); cudaFree(db->d_tdups);
 	cudaFree(db->d_exist); cudaFree(db->d_kv); cudaFree(db->d_values);
 	cudaFree(db->d_seq); cudaFree(db->d_lengths); cudaFree(db->d_seq_off);
+	cudaFree(db->d_mat); cudaFree(db->d_mat_off);
 	for (auto &e : db->ev) if (e) cudaEventDestroy(e);
 	if (db->stream) cudaStreamDestroy(db->stream);
 	delete db;

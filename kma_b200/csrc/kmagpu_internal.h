@@ -98,6 +98,10 @@ struct kmagpu_db {
 	int32_t *d_tdups = nullptr;
 	KgTIndexView tix{};
 	AlignBatch aln;
+	// base-count matrix of the assembly pass: uint32 [sum of template lengths][6], template t at d_mat_off[t] positions
+	unsigned int *d_mat = nullptr;
+	int64_t *d_mat_off = nullptr;
+	size_t mat_entries = 0;
 };
 
 int kg_tindex_build(kmagpu_db *db);

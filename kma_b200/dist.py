@@ -41,6 +41,27 @@ def allreduce_scores(alignment_scores: np.ndarray, uniq_alignment_scores: np.nda
     return out[:n].copy(), out[n:].copy()
 
 
+def allreduce_matrix(counts):
+    """Second exchange of the path: the per-position base counts of the assembly pass summed over ranks.
+    `counts` is the UNSATURATED matrix -- TemplateDB.matrix_tensor() (device, int32, reduced in place over NCCL) or a
+    numpy integer array (CPU tests, gloo). +1 increments commute and the reference saturates at 65535
+    (assembly.c:1436), so min(sum over ranks, 65535) is what one process would have produced. Exact for the template
+    nodes of alnToMat and for all of alnToMatDense; alnToMat's insertion nodes depend on the read order and are not
+    part of the matrix. Returns the clamped uint16 counts as a numpy array [positions, 6]."""
+    import torch
+    import torch.distributed as dist
+    t = counts if isinstance(counts, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(counts).astype(np.int32).reshape(-1))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.clamp(max=65535).cpu().numpy().astype(np.uint16).reshape(-1, 6)
+
+
+def shard_records(off: np.ndarray, rank: int, world: int) -> tuple[int, int]:
+    """byte range of the whole records rank `rank` takes, given record offsets with the end offset appended"""
+    lo, hi = shard_bounds(len(off) - 1, rank, world)
+    return int(off[lo]), int(off[hi])
+
+
 def gather_streams(local: bytes, dst: int = 0):
     """rank-ordered concatenation of the per-rank byte streams on rank `dst` (None elsewhere)"""
     import torch.distributed as dist

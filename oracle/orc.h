@@ -44,6 +44,8 @@ int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const 
                      int32_t **cand_out, size_t *cand_rows, int64_t *nw_cells);
 int orc_trace_stream(orc_db *db, const char *prefix, const orc_params *p, const uint8_t *in, size_t in_bytes, int one2one,
                      double scoreT, int mq, int minlen, double mrc, uint8_t **out, size_t *out_bytes);
+int orc_matrix_stream(const int32_t *lengths, int DB_size, const uint8_t *frags, size_t fb, const uint8_t *trace, size_t tb,
+                      int dense, uint16_t *counts);
 void orc_free(void *p);
 void orc_nw(const orc_params *p, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s, int q_e,
             int band, int *out6);

@@ -1154,4 +1154,60 @@ int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const 
 	return 0;
 }
 
+
+/* ------------------------------------------------------------------ base-count matrix - */
+
+/* alnToMat (assembly.c:1317-1444) restricted to the template nodes, and alnToMatDense (assembly.c:1446-1497): the
+ * per-position counts counts[6] = {A, C, G, T, N, gap} every accepted alignment of the traceback pass adds to its
+ * template. Insertion nodes (alnToMat's linked nodes behind position t_len; order dependent) are not
+ * restated: an insertion column leaves the template position where it is. Inputs are the fragment records and the
+ * trace output they produced (orc_trace_stream layout). counts = uint16 [sum of template lengths][6], template t at
+ * offset sum(len[1..t-1]); increments saturate at 65535 (assembly.c:1436). The reference's quirks are kept: alnToMat
+ * trims gap columns at both ends (its trailing loop stops at column 0), alnToMatDense only at the end. */
+int orc_matrix_stream(const int32_t *lengths, int DB_size, const uint8_t *frags, size_t fb, const uint8_t *trace, size_t tb,
+                      int dense, uint16_t *counts) {
+	int64_t *off = malloc(8 * (size_t)(DB_size + 1));
+	off[0] = off[1] = 0;
+	for (int t = 2; t <= DB_size; ++t) off[t] = off[t - 1] + lengths[t - 1];
+	size_t ip = 0, tp = 0;
+	int n = 0;
+	while (ip + 32 <= fb && tp + 48 <= tb) {
+		int32_t h[8], r[12];
+		memcpy(h, frags + ip, 32);
+		if (h[0] < 0) break;
+		ip += 32 + (size_t)h[1] + (size_t)h[6];
+		memcpy(r, trace + tp, 48); tp += 48;
+		const int ncol = r[11];
+		const uint8_t *t = trace + tp, *q = t + 2 * (size_t)ncol;
+		tp += 3 * (size_t)ncol;
+		if (!r[0]) continue;
+		const int tmpl = h[0], t_len = lengths[tmpl];
+		uint16_t *C = counts + 6 * off[tmpl];
+		int aln_len = r[5], start = r[6], i;
+		if (dense) {
+			i = aln_len - 1;
+			while (i >= 0 && (t[i] == 5 || q[i] == 5)) --i;   /* the reference has no lower bound here */
+			aln_len = i + 1;
+			i = 0;
+		} else {
+			i = aln_len - 1;
+			while (i && (t[i] == 5 || q[i] == 5)) --i;
+			aln_len = i + 1;
+			i = 0;
+			while (i < aln_len && (t[i] == 5 || q[i] == 5)) { if (q[i] == 5) ++start; ++i; }
+		}
+		int pos = start;
+		for (; i < aln_len; ++i) {
+			if (t[i] == 5) continue;
+			if (pos >= t_len) pos -= t_len;   /* next of the last template node is node 0 */
+			uint16_t *c = C + 6 * (size_t)pos + q[i];
+			if (!++*c) *c = 65535;
+			++pos;
+		}
+		++n;
+	}
+	free(off);
+	return n;
+}
+
 void orc_free(void *p) { free(p); }

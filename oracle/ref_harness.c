@@ -24,6 +24,7 @@
 #include <unistd.h>
 #include <pthread.h>
 #include "align.h"
+#include "assembly.h"
 #include "alnfrags.h"
 #include "ankers.h"
 #include "chain.h"
@@ -57,8 +58,13 @@ static Penalties *make_rewards(void) {
  * (assembly.c:1868-1961) -- the reference's own anker_rc + KMA per fragment record (frags.c:45-48); per record
  * int32[12]{accepted, read_score, start, end, score, len, pos, match, tGaps, qGaps, oriented, 0} + t s q rows. */
 static int trace_main(int argc, char **argv) {
-	int one2one = 0, exhaustive = 0, ts = 0;
-	for (int a = 5; a < argc; ++a) if (!strcmp(argv[a], "-1t1")) one2one = 1;
+	int one2one = 0, exhaustive = 0, ts = 0, dense = 0;
+	const char *mat_path = 0;   /* -mat <file> [-dense]: the reference's alnToMat / alnToMatDense on every accepted alignment */
+	for (int a = 5; a < argc; ++a) {
+		if (!strcmp(argv[a], "-1t1")) one2one = 1;
+		else if (!strcmp(argv[a], "-dense")) dense = 1;
+		else if (!strcmp(argv[a], "-mat") && a + 1 < argc) mat_path = argv[++a];
+	}
 	char path[4096];
 	int *template_lengths; long unsigned *as, *uas;
 	char *p2 = malloc(strlen(argv[2]) + 64); strcpy(p2, argv[2]);
@@ -85,6 +91,8 @@ static int trace_main(int argc, char **argv) {
 	AlnPoints *points = seedPoint_init(1024, rewards);
 	FILE *in = fopen(argv[3], "rb"), *out = fopen(argv[4], "wb");
 	if (!in || !out) { perror("open"); return 1; }
+	AssemInfo **mats = calloc(DB_size, sizeof(AssemInfo *));
+	Assem *aa = calloc(1, sizeof(Assem));
 	Aln *aligned = calloc(1, sizeof(Aln)), *gap_align = calloc(1, sizeof(Aln));
 	int delta = 0;
 	unsigned char *qseq = 0, *orig = 0; int qsize = 0;
@@ -124,6 +132,17 @@ static int trace_main(int argc, char **argv) {
 			r[1] = read_score; r[2] = start; r[3] = end;
 			r[4] = a.score; r[5] = a.len; r[6] = a.pos; r[7] = a.match; r[8] = a.tGaps; r[9] = a.qGaps;
 			len = aligned->len;
+			if (mat_path && r[0]) {   /* assembly.c:1968: the matrix as assemble_KMA initialises it (assembly.c:1811-1856) */
+				if (!mats[template]) {
+					AssemInfo *m = mats[template] = malloc(sizeof(AssemInfo));
+					m->len = t_len; m->size = t_len << 1;
+					m->assmb = malloc(m->size * sizeof(Assembly));
+					for (int i = 0; i < t_len; ++i) { memset(m->assmb[i].counts, 0, 12); m->assmb[i].next = i + 1; }
+					m->assmb[t_len - 1].next = 0;
+				}
+				if (dense) alnToMatDense(mats[template], aa, aligned, a, t_len, h[7]);
+				else alnToMat(mats[template], aa, aligned, a, t_len, h[7]);
+			}
 		}
 		points->len = 0;
 		r[11] = len;
@@ -131,6 +150,15 @@ static int trace_main(int argc, char **argv) {
 		fwrite(aligned->t, 1, len, out); fwrite(aligned->s, 1, len, out); fwrite(aligned->q, 1, len, out);
 	}
 	fclose(in); fclose(out);
+	if (mat_path) {   /* per template that saw an alignment: int32 {template, t_len, nodes}, then counts[6] of the t_len template nodes */
+		FILE *mo = fopen(mat_path, "wb");
+		for (int t = 1; t < DB_size; ++t) if (mats[t]) {
+			int hd[3] = {t, template_lengths[t], mats[t]->len};
+			fwrite(hd, 4, 3, mo);
+			for (int i = 0; i < template_lengths[t]; ++i) fwrite(mats[t]->assmb[i].counts, 2, 6, mo);
+		}
+		fclose(mo);
+	}
 	return 0;
 }
 

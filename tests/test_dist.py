@@ -74,3 +74,36 @@ def test_world_size_2_gloo(tmp_path):
     assert got == want_frag
     assert np.array_equal(np.load(tmp_path / "a.npy"), want_a) and np.array_equal(np.load(tmp_path / "u.npy"), want_u)
     assert int(np.load(tmp_path / "n0.npy")[0]) + int(np.load(tmp_path / "n1.npy")[0]) == n_all
+
+
+def _matrix_worker(rank, world, port, prefix, frags_path, out_dir):
+    import torch.distributed as td
+    td.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    frags = np.fromfile(frags_path, dtype=np.uint8)
+    off = api.record_offsets(3, frags)
+    lo, hi = dist.shard_records(off, rank, world)
+    mine = frags[lo:hi]
+    trace = util.oracle_trace(prefix, mine)
+    counts = util.oracle_matrix(prefix, mine, trace, dense=True, saturate=False)
+    total = dist.allreduce_matrix(counts)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "mat.npy"), total)
+    td.barrier()
+    td.destroy_process_group()
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+def test_matrix_allreduce_world_size_2_gloo(tmp_path):
+    """fragment records sharded over two ranks, per-rank base counts summed and clamped = the single-process matrix"""
+    import torch.multiprocessing as mp
+    from tests.test_oracle_trace import make_frags
+    prefix, frags = make_frags(tmp_path, 61, 150, 0.02, 0.02, n=600)
+    frags_path = str(tmp_path / "frags.bin")
+    frags.tofile(frags_path)
+    want = util.oracle_matrix(prefix, frags, util.oracle_trace(prefix, frags), dense=True)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_matrix_worker, args=(2, port, prefix, frags_path, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "mat.npy")
+    assert want.sum() > 1000 and np.array_equal(got, want)

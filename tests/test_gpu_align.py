@@ -304,3 +304,40 @@ def test_single_genome_template(tmp_path):
     assert s2.tobytes() + api.stream_terminator(n) == want2.tobytes()
     st, cand = _check_align(prefix, want2)
     assert st.frags > 2800
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed,L,sub,indel,mode", [(41, 150, 0.02, 0.02, 1), (42, 150, 0.02, 0.02, 2), (43, 1000, 0.04, 0.04, 1),
+                                                    (44, 1000, 0.04, 0.04, 2)])
+def test_base_count_matrix_vs_oracle(tmp_path, seed, L, sub, indel, mode):
+    """alnToMat (template nodes) / alnToMatDense counts accumulated on the device by the traceback pass, in two
+    batches (the matrix is HBM resident between calls), against the oracle that tests/test_oracle_trace.py pins to
+    the reference's own functions; per-template and whole-database downloads; the zero-copy device view for NCCL"""
+    from tests.test_oracle_trace import make_frags
+    prefix, frags = make_frags(tmp_path, seed, L, sub, indel, n=900)
+    trace = util.oracle_trace(prefix, frags)
+    want = util.oracle_matrix(prefix, frags, trace, dense=mode == 2)
+    db = api.TemplateDB(prefix, device=0)
+    p = api.default_params()
+    p.one2one = 1
+    p.matrix = mode
+    db.matrix_reset()
+    off = api.record_offsets(3, frags)
+    cut = int(off[len(off) // 2])
+    got1, n1, _ = db.assemble_align_batch(frags[:cut], p)
+    got2, n2, _ = db.assemble_align_batch(frags[cut:], p)
+    assert got1.tobytes() + got2.tobytes() == trace
+    got = db.matrix_download()
+    assert got.shape == want.shape and want.sum() > 1000
+    assert np.array_equal(got, want)
+    moff = util.matrix_offsets(prefix)
+    t = next(t for t in range(1, len(moff) - 1) if want[moff[t]:moff[t + 1]].any())
+    one = db.matrix_download(t)
+    assert np.array_equal(one, want[moff[t]:moff[t + 1]])
+    dev = db.matrix_tensor()
+    assert int(dev.sum().item()) == int(want.astype(np.int64).sum())
+    from kma_b200 import dist
+    assert np.array_equal(dist.allreduce_matrix(dev), want)    # world size 1: clamp only
+    db.matrix_reset()
+    assert int(db.matrix_download().sum()) == 0
+    db.close()

@@ -38,3 +38,24 @@ def test_trace_vs_reference(tmp_path, seed, L, sub, indel):
     assert sum(int(h[10]) for h, _ in recs) > 10                          # reads anker_rc had to turn around
     if indel:
         assert any(b"_" in rows[1] for _, rows in recs)
+
+
+@pytest.mark.parametrize("seed,L,sub,indel,mode", [(41, 150, 0.02, 0.02, "sparse"), (42, 150, 0.02, 0.02, "dense"),
+                                                    (43, 1000, 0.04, 0.04, "sparse"), (44, 1000, 0.04, 0.04, "dense")])
+def test_matrix_counts_vs_reference(tmp_path, seed, L, sub, indel, mode):
+    """the per-position base counts alnToMat (template nodes) / alnToMatDense add for every accepted alignment: oracle
+    restatement vs the reference's own functions run by ref_harness -trace -mat"""
+    prefix, frags = make_frags(tmp_path, seed, L, sub, indel, n=900)
+    trace, mats, nodes = util.ref_trace(prefix, frags, str(tmp_path), matrix=mode)
+    assert util.oracle_trace(prefix, frags) == trace
+    got = util.oracle_matrix(prefix, frags, trace, dense=mode == "dense")
+    off = util.matrix_offsets(prefix)
+    assert len(mats) > 20
+    seen = np.zeros(len(got), dtype=bool)
+    for t, m in mats.items():
+        assert np.array_equal(got[off[t]:off[t] + len(m)], m), f"template {t}"
+        seen[off[t]:off[t] + len(m)] = True
+    assert not got[~seen].any()
+    assert int(got[:, 5].sum()) > 0                     # deletions were counted
+    if mode == "sparse":
+        assert any(nodes[t] > len(m) for t, m in mats.items())   # reads with insertions grew the reference's node list

@@ -215,14 +215,54 @@ def assembly_records(frag_raw: bytes, zero_every=5, max_hits=2) -> np.ndarray:
     return np.frombuffer(bytes(out), dtype=np.uint8)
 
 
-def ref_trace(db_prefix: str, frags: np.ndarray, tmp: str, one2one=True) -> bytes:
-    """ground truth of the traceback alignment (assemble_KMA's anker_rc + KMA) from the unmodified reference"""
+def ref_trace(db_prefix: str, frags: np.ndarray, tmp: str, one2one=True, matrix=None):
+    """ground truth of the traceback alignment (assemble_KMA's anker_rc + KMA) from the unmodified reference.
+    matrix = "sparse" | "dense": also run the reference's alnToMat / alnToMatDense on every accepted alignment and
+    return (trace bytes, {template: uint16 counts[t_len, 6] of the template nodes}, {template: total nodes})."""
     p = os.path.join(tmp, "frags.bin")
     frags.tofile(p)
     args = [REF_ALN, "-trace", db_prefix, p, os.path.join(tmp, "trace.out")] + (["-1t1"] if one2one else [])
+    if matrix:
+        args += ["-mat", os.path.join(tmp, "mat.out")] + (["-dense"] if matrix == "dense" else [])
     r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
-    return open(os.path.join(tmp, "trace.out"), "rb").read()
+    trace = open(os.path.join(tmp, "trace.out"), "rb").read()
+    if not matrix:
+        return trace
+    buf = open(os.path.join(tmp, "mat.out"), "rb").read()
+    mats, nodes, o = {}, {}, 0
+    while o + 12 <= len(buf):
+        t, tl, nn = np.frombuffer(buf, dtype=np.int32, count=3, offset=o)
+        o += 12
+        mats[int(t)] = np.frombuffer(buf, dtype=np.uint16, count=6 * int(tl), offset=o).reshape(int(tl), 6).copy()
+        nodes[int(t)] = int(nn)
+        o += 12 * int(tl)
+    return trace, mats, nodes
+
+
+def matrix_offsets(db_prefix: str) -> np.ndarray:
+    """offset (in template positions) of template t in the all-template count matrix: sum(len[1..t-1]); entry DB_size = total"""
+    lengths = np.fromfile(db_prefix + ".length.b", dtype=np.int32)[1:].astype(np.int64)
+    off = np.zeros(len(lengths) + 1, dtype=np.int64)
+    off[2:] = np.cumsum(lengths[1:])
+    return off
+
+
+def oracle_matrix(db_prefix: str, frags: np.ndarray, trace: bytes, dense=False, saturate=True) -> np.ndarray:
+    """uint16 [total template positions, 6] from the oracle's restatement of alnToMat (template nodes) / alnToMatDense"""
+    L = orc()
+    raw = np.fromfile(db_prefix + ".length.b", dtype=np.int32)
+    DB, lengths = int(raw[0]), np.ascontiguousarray(raw[1:])
+    off = matrix_offsets(db_prefix)
+    counts = np.zeros((int(off[DB]), 6), dtype=np.uint16)
+    frags = np.ascontiguousarray(frags, dtype=np.uint8)
+    tr = np.frombuffer(trace, dtype=np.uint8)
+    L.orc_matrix_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    n = L.orc_matrix_stream(lengths.ctypes.data, DB, frags.ctypes.data, len(frags), tr.ctypes.data, len(tr), int(dense), counts.ctypes.data)
+    assert n >= 0
+    if not saturate:
+        assert counts.max() < 65535, "per-rank counts for the all-reduce must not have saturated"
+    return counts
 
 
 def oracle_trace(db_prefix: str, frags: np.ndarray, one2one=True) -> bytes:
