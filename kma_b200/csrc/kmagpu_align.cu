@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__restrict
 			uint64_t *base = slab + R.slab_off + (strand ? slab_stride(R) : 0);
 			uint8_t *b = (uint8_t *)(base + slab_W(words));
 			int32_t *N = (int32_t *)(base + slab_W(words) + slab_B(L));
+#pragma unroll 1
 			for (int w = lane; w < words + 2; w += 32) {
 				uint64_t x = 0;
 				if (w < words) {
@@ -164,9 +165,11 @@ __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__restrict
 			}
 			__syncwarp();
 			// bytes 0-3 from the words just written, then N -> 4 (unCompDNA, compdna.c:178)
+#pragma unroll 1
 			for (int i = lane; i < (int)(slab_B(L) << 3); i += 32)
 				b[i] = i < L ? (uint8_t)((base[i >> 5] << ((i & 31) << 1)) >> 62) : (uint8_t)0;
 			__syncwarp();
+#pragma unroll 1
 			for (int i = lane; i <= nN; i += 32) {
 				int v = L;   // sentinel N[nN] = q_len (savekmers.c:2483, alnfrags.c:1071)
 				if (i < nN) v = strand ? L - 1 - (int)ld_u32u(Ns + 4 * (size_t)(nN - 1 - i)) : (int)ld_u32u(Ns + 4 * (size_t)i);
@@ -175,6 +178,7 @@ __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__restrict
 			}
 		}
 		const int ntask = (int)(task_off[r + 1] - task_off[r]);
+#pragma unroll 1
 		for (int i = lane; i < ntask; i += 32) task_read[R.task0 + i] = r;
 		__syncwarp();
 	}
@@ -256,6 +260,7 @@ __device__ KG_STAGE_INL int scan_mems(const KgTIndexView &ix, const KgTMeta &m, 
 				const int32_t *d = tix_dups(ix, v, &cnt);
 				if (n + cnt > M.cap) { wc.need_mem = max(wc.need_mem, (unsigned)(n + cnt) + 1024u); return ST_OVERFLOW; }
 				int bias = p;
+#pragma unroll 1
 				for (int c = lane; c < cnt; c += 32) {   // every occurrence, ascending template position
 					int qs, ts, qe, te;
 					mem_from_seed(q.w, tseq, t_len, k, p, __ldg(d + c), lo, fwd_lim, &qs, &ts, &qe, &te);
@@ -306,6 +311,7 @@ __device__ int chain_warp(const NwPen &pen, Mems &M, int n, int q_len, int t_len
 		const int lim = min(n, i + 128);
 		// lane-local fold over j = i+1+lane, +32, ...: best value, first j reaching it, last "<=" j reaching it
 		int lb = NOCAND, lfirst = 0x7fffffff, llast = -1;
+#pragma unroll 1
 		for (int j = i + 1 + lane; j < lim; j += 32) {
 			const int qSj = M.qS[j], tSj = M.tS[j];
 			int g = 0, type = -1;   // 0: fully compatible (<=), 1: overlap cut (<)
@@ -434,6 +440,7 @@ __device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c,
 		const int len = qE - qS;
 		s.len += len; s.match += len;
 		int sc = 0;
+#pragma unroll 1
 		for (int i = qS + lane; i < qE; i += 32) { const int b = c.qb[i]; sc += P.pen.d[b * 5 + b]; }
 		s.score += warp_sum(sc);
 		const int nxt = M.nx[start];
@@ -882,13 +889,16 @@ __global__ void __launch_bounds__(256) aln_emit_kernel(const uint8_t *__restrict
 					}
 					o += 20;
 				}
+#pragma unroll 1
 				for (int i = lane; i < Rm.q_len; i += 32) o[i] = q.b[i];
 				o += Rm.q_len;
+#pragma unroll 1
 				for (int i = lane; i < Rm.hl; i += 32) o[i] = hdr[i];
 				o += Rm.hl;
 				if (!(rs.form == 1 && x == 1)) {
 					const int32_t *arr = pbase + rs.roff[x];
 					const int kept = rs.rkept[x], cap = RB.nt;
+#pragma unroll 1
 					for (int i = lane; i < kept; i += 32) {
 						st_u32b(o + 4 * (size_t)i, (uint32_t)arr[i]);
 						st_u32b(o + 4 * (size_t)(kept + i), (uint32_t)arr[cap + i]);
@@ -909,12 +919,15 @@ __global__ void __launch_bounds__(256) aln_emit_kernel(const uint8_t *__restrict
 		}
 		o += 20;
 		const QView q = read_view(slab, R, 0);
+#pragma unroll 1
 		for (int i = lane; i < R.q_len; i += 32) o[i] = q.b[i];
 		o += R.q_len;
 		const uint8_t *hdr = in + R.rec_off + 28 + 8 * (size_t)R.words + 4 * (size_t)R.nN + 4 * (size_t)R.nt;
+#pragma unroll 1
 		for (int i = lane; i < R.hl; i += 32) o[i] = hdr[i];
 		o += R.hl;
 		const AlnCand *c = cand + R.task0;
+#pragma unroll 1
 		for (int i = lane; i < rs.kept; i += 32) {
 			st_u32b(o + 4 * (size_t)i, (uint32_t)c[i].pos);
 			st_u32b(o + 4 * (size_t)(rs.kept + i), (uint32_t)c[i].match);
@@ -959,6 +972,7 @@ __global__ void __launch_bounds__(256) tr_sizes_kernel(const uint8_t *__restrict
 		R.tmpl = (int)ld_u32u(rec); R.q_len = (int)ld_u32u(rec + 4); R.score = (int)ld_u32u(rec + 12); R.hl = (int)ld_u32u(rec + 24);
 		const uint8_t *q = rec + 32;
 		int cnt = 0;
+#pragma unroll 1
 		for (int i = lane; i < R.q_len; i += 32) cnt += q[i] == 4;
 		R.nN = warp_sum(cnt);
 		R.words = (R.q_len + 31) >> 5;
@@ -989,12 +1003,14 @@ __global__ void __launch_bounds__(256) tr_prep_kernel(const uint8_t *__restrict_
 			uint64_t *base = slab + R.slab_off + (strand ? tr_stride(R) : 0);
 			uint8_t *b = (uint8_t *)(base + slab_W(R.words));
 			int32_t *N = (int32_t *)(base + slab_W(R.words) + slab_B(L));
+#pragma unroll 1
 			for (int i = lane; i < (int)(slab_B(L) << 3); i += 32) {
 				uint8_t v = 0;
 				if (i < L) { v = strand ? src[L - 1 - i] : src[i]; if (strand && v < 4) v = 3 - v; }
 				b[i] = v;
 			}
 			__syncwarp();
+#pragma unroll 1
 			for (int w = lane; w < R.words + 2; w += 32) {
 				uint64_t x = 0;
 				if (w < R.words) for (int i = 0; i < 32 && 32 * w + i < L; ++i) x |= (uint64_t)(b[32 * w + i] & 3 & (b[32 * w + i] < 4 ? 3 : 0)) << (62 - 2 * i);
@@ -1097,6 +1113,7 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 		const int len = qE - qS;
 		if (s.len + len + 8 > row_cap) return ST_ROWS;
 		int sc = 0;
+#pragma unroll 1
 		for (int i = qS + lane; i < qE; i += 32) {
 			const int b = c.qb[i];
 			rows.t[s.len + i - qS] = (uint8_t)b; rows.s[s.len + i - qS] = '|'; rows.q[s.len + i - qS] = (uint8_t)b;
@@ -1229,6 +1246,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, AL_MINB) tr_task_kernel(AlnPara
 				else { strand = 1; M.shift(nf); nmem = ntot - nf; go = true; turned = 1; }
 				if (turned) {   // "oriented": do the bytes differ from what came in? (a palindrome does not)
 					int diff = 0;
+#pragma unroll 1
 					for (int i = lane; i < q_len; i += 32) diff |= qf.b[i] != qr.b[i];
 					o.h[10] = __any_sync(0xffffffffu, diff) ? 1 : 0;
 				}
@@ -1292,6 +1310,7 @@ __global__ void __launch_bounds__(256) tr_emit_kernel(const TrRec *__restrict__ 
 		const int ncol = o.h[11];
 		const uint8_t *src = rowpool + R.row_off;
 		for (int row = 0; row < 3; ++row)
+#pragma unroll 1
 			for (int i = lane; i < ncol; i += 32) dst[(size_t)row * ncol + i] = src[(size_t)row * R.row_cap + i];
 	}
 }

@@ -215,6 +215,7 @@ __device__ int find_ankers(const KgHashView &hv, const ChainParams &p, const Rea
 		const int flo = max(0, c0 - k), fhi = min(L, c0 + KC_CHUNK + k - 1) - 1;
 		const int w0 = flo >> 5, w1 = fhi >> 5;
 		__syncwarp();
+#pragma unroll 1
 		for (int w = w0 + (int)lane; w <= w1 + 1; w += 32) sw[w - w0] = w < rc.words ? ld_u64u(rc.seq + 8 * (size_t)w) : 0ull;
 		__syncwarp();
 		// phase 1: gather, in three rounds so that 8 independent probes per lane are in flight (exist -> kv -> chain)
@@ -349,6 +350,7 @@ __device__ __noinline__ int chain_templates(const KgHashView &hv, const ChainPar
 	const uint32_t soff = V.vals[src];
 	const int nl0 = list_len(hv, soff);
 	bool more = false;
+#pragma unroll 1
 	for (int i = lane; i < nl0; i += 32) {
 		const int t = list_id(hv, soff, i);
 		dst[1 + i] = t;
@@ -367,6 +369,7 @@ __device__ __noinline__ int chain_templates(const KgHashView &hv, const ChainPar
 		const int nl = list_len(hv, off);
 		const int start = V.start[node], end = V.end[node], weight = V.weight[node];
 		bool used = false, done = false;
+#pragma unroll 1
 		for (int i = lane; i < nl; i += 32) {
 			const int t = list_id(hv, off, i);
 			int4 x = W.st[t];
@@ -414,6 +417,7 @@ __device__ __noinline__ int chain_templates(const KgHashView &hv, const ChainPar
 __device__ __noinline__ int best_anker(const Ank &V, int cnt, unsigned *ties) {
 	const unsigned lane = threadIdx.x & 31;
 	int best = 0, idx = -1, n = 0;
+#pragma unroll 1
 	for (int a = lane; a < cnt; a += 32) {
 		const int sc = V.score[a];
 		if (sc == 0) continue;
@@ -614,6 +618,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 					}
 					__syncwarp();
 				}
+#pragma unroll 1
 				for (int i = lane; i < nb; i += 32) W.st[bests[1 + i]] = make_int4(0, 0, 0, 0);
 				__syncwarp();
 				bIdx[s] = bi;
@@ -625,6 +630,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 			// pruneAnkers (kmeranker.c:372): ankers scoring below k leave the list for good
 			__syncwarp();
 			for (int s = 0; s < 2; ++s)
+#pragma unroll 1
 				for (int a = lane; a < max(W.cnt[s], 1); a += 32) if (W.V[s].score[a] < k) W.V[s].score[a] = 0;
 			__syncwarp();
 			if (scF < k) scF = 0;
@@ -660,6 +666,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 						int v = bIdx[s];
 						while ((v = tie_anker(V, stop, v, bsScore)) >= 0) {
 							if ((double)((unsigned)V.end[v] - (unsigned)start) < __dmul_rn(p.coverT, (double)len)) break;
+#pragma unroll 1
 							for (int i = lane; i < btN[s]; i += 32) W.st[bl[1 + i]] = make_int4(0, 0, 1, 0);
 							__syncwarp();
 							int add = 0;
@@ -668,6 +675,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 							btN[s] += add;
 						}
 						if (err) break;
+#pragma unroll 1
 						for (int i = lane; i < btN[s]; i += 32) W.st[bl[1 + i]] = make_int4(0, 0, 0, 0);
 						__syncwarp();
 					}
@@ -712,6 +720,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 					po = __shfl_sync(FULL, po, 0);
 					if (po + nt <= pool_cap) {
 						int32_t *dstp = pool + po;
+#pragma unroll 1
 						for (int i = lane; i < btN[side]; i += 32) dstp[i] = W.bt[side][1 + i];
 						if (rcm == 3) for (int i = lane; i < btN[1]; i += 32) dstp[btN[0] + i] = -W.bt[1][1 + i];
 					} else if (lane == 0) atomicAdd(&ctr[C_POOLFAIL], 1ull);
@@ -774,6 +783,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 
 		if (err) {
 			// the per-template rows may be dirty: wipe them before the next read
+#pragma unroll 1
 			for (size_t i = lane; i < lay.D; i += 32) W.st[i] = make_int4(0, 0, 0, 0);
 			if (err == 1) ++e_walk; else ++e_tree;
 			nreg = 0;
@@ -843,6 +853,7 @@ __global__ void __launch_bounds__(256) chain_emit_kernel(const uint8_t *__restri
 			st_u32b(o + 4 * lane, (uint32_t)h);
 		}
 		o += 28;
+#pragma unroll 1
 		for (int w = lane; w < words; w += 32) {
 			uint64_t x;
 			if (!rev) x = ld_u64u(seq + 8 * (size_t)w);
@@ -855,13 +866,16 @@ __global__ void __launch_bounds__(256) chain_emit_kernel(const uint8_t *__restri
 			st_u32b(o + 8 * (size_t)w + 4, (uint32_t)(x >> 32));
 		}
 		o += 8 * (size_t)words;
+#pragma unroll 1
 		for (int i = lane; i < nN; i += 32) {
 			const uint32_t v = rev ? (uint32_t)(seqlen - 1 - (int)ld_u32u(N + 4 * (size_t)(nN - 1 - i))) : ld_u32u(N + 4 * (size_t)i);
 			st_u32b(o + 4 * (size_t)i, v);
 		}
 		o += 4 * (size_t)nN;
+#pragma unroll 1
 		for (int i = lane; i < rg.ntmpl; i += 32) st_u32b(o + 4 * (size_t)i, (uint32_t)pool[rg.pool_off + i]);
 		o += 4 * (size_t)rg.ntmpl;
+#pragma unroll 1
 		for (int i = lane; i < hdrlen; i += 32) o[i] = hdr[i];
 		o += hdrlen;
 		if (lane == 0) { o[0] = 0; st_u32b(o + 1, (uint32_t)rg.b0); st_u32b(o + 5, (uint32_t)rg.b1); }

@@ -119,6 +119,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 		else { fhi = L - 1 - c0; flo = max(0, L - k - (c0 + KG_CHUNK - 1)); }
 		int w0 = flo >> 5, w1 = fhi >> 5;
 		__syncwarp();
+#pragma unroll 1
 		for (int w = w0 + (int)lane; w <= w1 + 1; w += 32)
 			sw[w - w0] = w < rc.words ? ld_u64u(rc.seq + 8 * (size_t)w) : 0ull;
 		__syncwarp();
@@ -150,6 +151,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 					h = hm != 0;
 				}
 			} else {
+#pragma unroll 1
 				for (int j = c0 + (int)lane; j < min(npos, c0 + KG_CHUNK); j += 32) {
 					int ss;
 					if (pos_valid(rc, j, k, strand, &ss) && (j - ss) % k == 0) {
@@ -170,12 +172,22 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 	for (int c0 = 0; c0 < npos && !overflow; c0 += KG_CHUNK) {
 		int w0 = stage(c0);
 		// phase 1: gather. two rounds so that 8 independent probes per lane are in flight.
+		if (rc.nN) {   // reads with N's (rare): validity per position, one probe at a time; kept off the hot path
+#pragma unroll 1
+			for (int u = 0; u < KG_PER_LANE; ++u) {
+				const int j = c0 + u * 32 + (int)lane;
+				int ss;
+				uint32_t v = KG_MISS;
+				if (j < npos && pos_valid(rc, j, k, strand, &ss)) { v = hash_lookup(hv, kmer_of(w0, j)); ws.lookups++; }
+				hits[u * 32 + lane] = v;
+			}
+		} else {
 		uint32_t e1[KG_PER_LANE];
 		uint64_t km[KG_PER_LANE];
 #pragma unroll
 		for (int u = 0; u < KG_PER_LANE; ++u) {
-			int j = c0 + u * 32 + (int)lane, ss;
-			bool ok = j < npos && (rc.nN == 0 || pos_valid(rc, j, k, strand, &ss));
+			int j = c0 + u * 32 + (int)lane;
+			bool ok = j < npos;
 			km[u] = ok ? kmer_of(w0, j) : 0ull;
 			e1[u] = KG_MISS;
 			if (ok) {
@@ -205,6 +217,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 		}
 #pragma unroll
 		for (int u = 0; u < KG_PER_LANE; ++u) hits[u * 32 + lane] = e1[u];
+		}
 		__syncwarp();
 
 		// phase 2: walk the hits of this chunk in position order. A hit whose left neighbour position hit the same
@@ -238,6 +251,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 					if (last != KG_MISS) {
 						// flush the run of the previous list (savekmers.c:2575-2582)
 						int pl = list_len(hv, last);
+#pragma unroll 1
 						for (int i = lane; i < pl; i += 32) {
 							int s = st.find(list_id(hv, last, i));
 							st.score[s] += run_sc;
@@ -277,6 +291,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 	ws.hits += lane == 0 ? nhits : 0;
 
 	if (overflow) {   // hash mode only: wipe and report
+#pragma unroll 1
 		for (int i = lane; i < KG_CAP; i += 32) st.keys[i] = 0;
 		__syncwarp();
 		return -1;
@@ -284,6 +299,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 
 	if (last != KG_MISS) {   // final flush (savekmers.c:2707-2722)
 		int pl = list_len(hv, last);
+#pragma unroll 1
 		for (int i = lane; i < pl; i += 32) st.score[st.find(list_id(hv, last, i))] += run_sc;
 		__syncwarp();
 	}
@@ -294,6 +310,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 		po = __shfl_sync(0xffffffffu, po, 0);
 		const bool fits = po + st.ncand <= pool2_cap;
 		if (!fits && lane == 0) atomicAdd(&ctr[C_POOLFAIL], 1ull);
+#pragma unroll 1
 		for (int i = lane; i < st.ncand; i += 32) {
 			const int s = st.cand[i];
 			if (fits) pool2[po + i] = make_int2(st.tmpl_of(s), max(st.score[s], 0));
@@ -301,6 +318,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 		}
 		__syncwarp();
 		if (!DENSE) {
+#pragma unroll 1
 			for (int i = lane; i < KG_CAP; i += 32) st.keys[i] = 0;
 			__syncwarp();
 		}
@@ -310,6 +328,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 	}
 	// arg-max set in first-seen order (getBestMatch, savekmers.c:273-294), negatives clamp to 0
 	int best = 0;
+#pragma unroll 1
 	for (int i = lane; i < st.ncand; i += 32) best = max(best, st.score[st.cand[i]]);
 #pragma unroll
 	for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -331,6 +350,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 		__syncwarp();
 	}
 	if (!DENSE) {
+#pragma unroll 1
 		for (int i = lane; i < KG_CAP; i += 32) st.keys[i] = 0;
 		__syncwarp();
 	}
@@ -365,6 +385,7 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 	} else {
 		st.keys = s_tab[wid]; st.score = st.keys + KG_CAP; st.ext = st.score + KG_CAP; st.incl = nullptr;
 		candF = s_cand[wid]; candR = candF + KG_CAP;
+#pragma unroll 1
 		for (int i = lane; i < KG_CAP; i += 32) st.keys[i] = 0;
 		__syncwarp();
 	}
@@ -472,6 +493,9 @@ __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_
 		unsigned long long pool_cap, unsigned long long *ctr, SeedRes *res, uint32_t *recsize, int k, int PE) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= nrec || kinds[r] != 1) return;
+	// a strand list that did not fit the pool was never written and its offset points past the allocation: the host
+	// grows the pools and redoes the batch, nothing of this attempt is used
+	if (ctr[C_POOLFAIL]) { recsize[r] = recsize[r + 1] = 0; return; }
 	const MateRes A = mates[r], B = mates[r + 1];
 	const uint8_t *recA = in + rec_off[r], *recB = in + rec_off[r + 1];
 	const int lenA = (int)ld_u32u(recA), lenB = (int)ld_u32u(recB);
@@ -612,6 +636,7 @@ __global__ void __launch_bounds__(256) emit_records_kernel(const uint8_t *__rest
 			st_u32b(o + 4 * lane, (uint32_t)h);
 		}
 		o += 28;
+#pragma unroll 1
 		for (int w = lane; w < words; w += 32) {
 			uint64_t x;
 			if (!rev) x = ld_u64u(seq + 8 * (size_t)w);
@@ -624,13 +649,16 @@ __global__ void __launch_bounds__(256) emit_records_kernel(const uint8_t *__rest
 			st_u32b(o + 8 * (size_t)w + 4, (uint32_t)(x >> 32));
 		}
 		o += 8 * (size_t)words;
+#pragma unroll 1
 		for (int i = lane; i < nN; i += 32) {
 			uint32_t v = rev ? (uint32_t)(seqlen - 1 - (int)ld_u32u(N + 4 * (size_t)(nN - 1 - i))) : ld_u32u(N + 4 * (size_t)i);
 			st_u32b(o + 4 * (size_t)i, v);
 		}
 		o += 4 * (size_t)nN;
+#pragma unroll 1
 		for (int i = lane; i < rs.ntmpl; i += 32) st_u32b(o + 4 * (size_t)i, (uint32_t)pool[rs.pool_off + i]);
 		o += 4 * (size_t)rs.ntmpl;
+#pragma unroll 1
 		for (int i = lane; i < hdrlen; i += 32) o[i] = hdr[i];
 	}
 }
