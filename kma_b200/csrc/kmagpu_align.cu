@@ -194,17 +194,17 @@ struct Mems {
 
 struct WarpCtr { unsigned long long full_calls, band_calls, full_cells, band_cells, steps, mems, lookups, mem_bases, read_bytes; unsigned need_e, need_mem, need_q; };
 
-__device__ __forceinline__ int warp_max(int v) {
+__device__ __noinline__ int warp_max(int v) {
 #pragma unroll
 	for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
 	return v;
 }
-__device__ __forceinline__ int warp_min(int v) {
+__device__ __noinline__ int warp_min(int v) {
 #pragma unroll
 	for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
 	return v;
 }
-__device__ __forceinline__ int warp_sum(int v) {
+__device__ __noinline__ int warp_sum(int v) {
 #pragma unroll
 	for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	return v;
