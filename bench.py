@@ -200,7 +200,7 @@ def nw_gcups(db, seqs, peak_iops, n=24000, seed=3):
             "not_ok": int((status != 0).sum())}
 
 
-def c3_chain(db, api, seqs, prefix, workdir, cores, n=20000, ref_n=2000, seed=22):
+def c3_chain(db, api, seqs, prefix, workdir, cores, peak_gbs, n=20000, ref_n=2000, seed=22):
     """BASELINE.json configs[2] (C3) beside the headline: Nanopore-like reads (5-20 kb, 10 % errors) through stage 2 in
     chain mode (save_kmers_chain, the reference's default without -1t1: `chain_kernel`) and the alignment pass with
     the records' query bounds, chained in HBM; kernels timed by CUDA events inside the library, `e2e` from pinned-free
@@ -239,6 +239,15 @@ def c3_chain(db, api, seqs, prefix, workdir, cores, n=20000, ref_n=2000, seed=22
            "chain_kernel_ms": st.ms_seed, "lookups_per_read": st.lookups / n, "ankers_per_read": st.list_fetches / n,
            "aln_pair_kernel_ms": sa.ms_align, "nw_cells": int(cells), "nw_cells_banded_fraction": sa.nw_band_cells / max(1, cells),
            "align_gcups": cells / max(sa.ms_align, 1e-9) / 1e6}
+    # chain_kernel, algorithmic bytes: the seeding figure of SURVEY 8d + 40 B per anker (written once,
+    # read once) + 32 B per (anker, template) visit of the chaining DP (one 16-byte row read and written)
+    vw = 2 if db.info.DB_size < 65535 else 4
+    alg = algorithmic_bytes(st, vw) + 40 * st.list_fetches + 32 * st.list_ids
+    ach = alg / (st.ms_seed * 1e-3) / 1e9
+    out["chain_roofline"] = {"kernel": "chain_kernel", "bound": "hbm", "achieved": ach, "peak": peak_gbs, "unit": "GB/s",
+                             "frac": ach / peak_gbs, "algorithmic_bytes_per_launch": int(alg), "bytes_per_read": alg / n,
+                             "kernel_ms": st.ms_seed, "traffic": None,
+                             "note": "table and per-warp rows are L2 resident; bound by dependent L2 round trips (ncu: long_scoreboard)"}
     kma = os.path.join(ROOT, "oracle", "_ref", "kma")
     aln = os.path.join(ROOT, "oracle", "_ref", "ref_aln")
     if os.path.exists(kma) and os.path.exists(aln):
@@ -465,7 +474,7 @@ def main():
     if rank == 0:
         line["nw"] = nw_gcups(db, seqs, peak_iops)
         if not args.no_c3:
-            line["c3"] = c3_chain(db, api, seqs, prefix, workdir, cores)
+            line["c3"] = c3_chain(db, api, seqs, prefix, workdir, cores, pk["hbm_gbs"])
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = min(args.cpu_sample, args.pairs)
