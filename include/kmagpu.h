@@ -164,7 +164,8 @@ int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, const int32
 
 /* Host-only helper (no device needed): walk the whole records at the head of a stage-1 (stage = 1, 16-byte headers,
  * runinput.c:765-787 / loadFsa savekmers.c:50-92), stage-2 (stage = 2, 28-byte headers, ankers.c:163-220) or assembly
- * fragment (stage = 3, 32-byte headers, frags.c:45-48) stream.
+ * fragment (stage = 3, 32-byte headers, frags.c:45-48) or frag_raw (stage = 4, 20-byte headers, updatescores.c:284-295;
+ * a record with a negative score includes the mate block that follows it) stream.
  * Returns the number of whole records (stopping at a terminator or a partial record), stores their byte offsets in
  * offsets[0..min(count, cap)) when offsets != NULL and the bytes they span in *used. -1 on a corrupt header. */
 int64_t kmagpu_record_walk(int stage, const void *buf, size_t nbytes, uint64_t *offsets, size_t cap, size_t *used);

@@ -199,16 +199,26 @@ extern "C" int kmagpu_db_get_info(const kmagpu_db *db, kmagpu_db_info *info) {
 
 extern "C" int64_t kmagpu_record_walk(int stage, const void *buf, size_t nbytes, uint64_t *offsets, size_t cap, size_t *used) {
 	const uint8_t *in = (const uint8_t *)buf;
-	const size_t hdr = stage == 1 ? 16 : (stage == 2 ? 28 : 32);
+	const size_t hdr = stage == 1 ? 16 : (stage == 2 ? 28 : (stage == 3 ? 32 : 20));
 	size_t ip = 0;
 	int64_t n = 0;
-	if (stage < 1 || stage > 3) { kmagpu_set_error("kmagpu_record_walk: stage must be 1, 2 or 3"); return -1; }
+	if (stage < 1 || stage > 4) { kmagpu_set_error("kmagpu_record_walk: stage must be 1, 2, 3 or 4"); return -1; }
 	while (ip + hdr <= nbytes) {
 		int32_t h[8];
 		memcpy(h, in + ip, hdr);
-		if (h[0] < 0) break;   // stream terminator
+		if (h[0] < 0 || (stage == 4 && h[0] == 0)) break;   // stream terminator
 		size_t len;
-		if (stage == 1) {
+		if (stage == 4) {   // frag_raw record (updatescores.c:284-295); a negative score means the mate block follows
+			if (h[3] < 0) { kmagpu_set_error("corrupt frag_raw record at byte %zu", ip); return -1; }
+			len = 20 + (size_t)h[0] + (size_t)h[3] + 12 * (size_t)abs(h[1]);
+			if (h[2] < 0) {
+				if (ip + len + 12 > nbytes) break;
+				int32_t m[3];
+				memcpy(m, in + ip + len, 12);
+				if (m[0] < 0 || m[1] < 0) { kmagpu_set_error("corrupt frag_raw mate block at byte %zu", ip + len); return -1; }
+				len += 12 + (size_t)m[0] + (size_t)m[1];
+			}
+		} else if (stage == 1) {
 			if (h[1] < 0 || h[2] < 0) { kmagpu_set_error("corrupt stage-1 record at byte %zu", ip); return -1; }
 			len = 16 + 8 * (size_t)h[1] + 4 * (size_t)h[2] + (size_t)abs(h[3]);
 		} else if (stage == 2) {

@@ -46,6 +46,9 @@ int orc_trace_stream(orc_db *db, const char *prefix, const orc_params *p, const 
                      double scoreT, int mq, int minlen, double mrc, uint8_t **out, size_t *out_bytes);
 int orc_matrix_stream(const int32_t *lengths, int DB_size, const uint8_t *frags, size_t fb, const uint8_t *trace, size_t tb,
                       int dense, uint16_t *counts);
+int64_t orc_conclave_stream(const int32_t *template_lengths, int DB_size, const uint8_t *frag, size_t fb,
+                            const uint64_t *alignment_scores, const uint64_t *uniq_alignment_scores,
+                            uint8_t *out, size_t cap, uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts);
 void orc_free(void *p);
 void orc_nw(const orc_params *p, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s, int q_e,
             int band, int *out6);

@@ -25,6 +25,8 @@
 #include <pthread.h>
 #include "align.h"
 #include "assembly.h"
+#include "conclave.h"
+#include "frags.h"
 #include "alnfrags.h"
 #include "ankers.h"
 #include "chain.h"
@@ -162,7 +164,56 @@ static int trace_main(int argc, char **argv) {
 	return 0;
 }
 
+/* -conclave db frag_raw.bin scores.bin out.bin: the reference's runConClave (conclave.c:43-213) + printFrags
+ * (frags.c:30-61) on a frag_raw stream with the given ConClave accumulators (scores.bin: int32 DB_size, u64
+ * alignment_scores[DB_size], u64 uniq_alignment_scores[DB_size] -- the file the alignment pass of this harness writes).
+ * out.bin: int32 nfiles, then per file int64 bytes + the bytes printFrags wrote; then u64 w_scores[DB_size],
+ * u32 fragmentCounts[DB_size], u32 readCounts[DB_size]. maxFrag as argv[6] (default 1048576, kma.c:340). */
+static int conclave_main(int argc, char **argv) {
+	if (argc < 6) { fprintf(stderr, "usage: ref_aln -conclave db frag_raw.bin scores.bin out.bin [maxFrag]\n"); return 2; }
+	int *template_lengths; long unsigned *as, *uas;
+	char *p2 = malloc(strlen(argv[2]) + 64); strcpy(p2, argv[2]);
+	int DB_size = load_DBs_KMA(p2, &as, &uas, &template_lengths, 0);
+	int maxFrag = argc > 6 ? atoi(argv[6]) : 1048576;
+	FILE *sc = fopen(argv[4], "rb");
+	int n = 0;
+	if (!sc || fread(&n, 4, 1, sc) != 1 || n != DB_size) { fprintf(stderr, "scores file does not match the database\n"); return 1; }
+	if (fread(as, 8, DB_size, sc) != (size_t)DB_size || fread(uas, 8, DB_size, sc) != (size_t)DB_size) return 1;
+	fclose(sc);
+	/* frag_raw as runKMA leaves it: the records followed by an int 0 (runkma.c:444) */
+	FILE *in = fopen(argv[3], "rb");
+	if (!in) { perror(argv[3]); return 1; }
+	FILE *tmp = tmpfile();
+	char buf[1 << 16]; size_t got; long maxq = 1024;
+	while ((got = fread(buf, 1, sizeof(buf), in))) fwrite(buf, 1, got, tmp);
+	int zero = 0; fwrite(&zero, 4, 1, tmp);
+	fseek(in, 0, SEEK_END); maxq = ftell(in) + 64; fclose(in);
+	rewind(tmp);
+	Qseqs *header = setQseqs(maxq), *qseq = setQseqs(maxq);
+	int *bestTemplates = malloc(((DB_size + 1) << 1) * sizeof(int)), *bs = malloc(((DB_size + 1) << 1) * sizeof(int)), *be = malloc(((DB_size + 1) << 1) * sizeof(int));
+	FILE **template_fragments = calloc(DB_size + 1, sizeof(FILE *));
+	Frag **alignFrags = calloc(DB_size, sizeof(Frag *));
+	long unsigned *w_scores = calloc(DB_size, sizeof(long unsigned));
+	unsigned *fragmentCounts = calloc(DB_size, sizeof(unsigned)), *readCounts = calloc(DB_size, sizeof(unsigned));
+	int files = runConClave(tmp, &template_fragments, DB_size, maxFrag, w_scores, fragmentCounts, readCounts, as, uas, template_lengths,
+	                        header, qseq, bestTemplates, bs, be, alignFrags);
+	FILE *out = fopen(argv[5], "wb");
+	fwrite(&files, 4, 1, out);
+	for (int f = 0; f < files; ++f) {
+		FILE *tf = template_fragments[f];
+		fseek(tf, 0, SEEK_END);
+		long long bytes = ftell(tf);
+		rewind(tf);
+		fwrite(&bytes, 8, 1, out);
+		while ((got = fread(buf, 1, sizeof(buf), tf))) fwrite(buf, 1, got, out);
+	}
+	fwrite(w_scores, 8, DB_size, out); fwrite(fragmentCounts, 4, DB_size, out); fwrite(readCounts, 4, DB_size, out);
+	fclose(out);
+	return 0;
+}
+
 int main(int argc, char **argv) {
+	if (argc >= 5 && !strcmp(argv[1], "-conclave")) return conclave_main(argc, argv);
 	if (argc >= 5 && !strcmp(argv[1], "-trace")) return trace_main(argc, argv);
 	if (argc < 5) { fprintf(stderr, "usage: ref_aln db s2.bin frag_raw.out scores.out [cand.out] [-1t1]\n"); return 2; }
 	int one2one = 0, exhaustive = 0, ts = 0;

@@ -1,0 +1,74 @@
+"""CPU tests: the oracle restatement of ConClave's choice pass + per-template bucketing (runConClave, conclave.c:43;
+printFrags, frags.c:30) is pinned byte for byte to the reference's own functions run by oracle/ref_harness.c -conclave."""
+import numpy as np
+import pytest
+
+from kma_b200 import synth
+from tests import util
+
+pytestmark = pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+
+
+def se_case(tmp_path, seed, n=1500, L=150, chain=False):
+    names, seqs = synth.gene_db(seed, n_families=10, n_variants=8, len_lo=300, len_hi=1200)
+    # a few templates stored on the other strand so that reads are chosen reverse-complemented
+    for i in range(0, len(seqs), 7):
+        names.append(names[i] + "_rc")
+        seqs.append(synth.revcomp(seqs[i]))
+    synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    rng = np.random.default_rng(seed)
+    reads = list(synth.short_reads(seed + 1, seqs, n, L=L, sub=0.01, junk_frac=0.02))
+    if chain:
+        reads += synth.long_reads(seed + 2, seqs, 60, len_lo=1000, len_hi=4000, err=0.06)
+    synth.write_fastq(tmp_path / "r.fq", reads)
+    flags = [] if chain else ["-1t1"]
+    s2 = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-s2"] + flags, cwd=tmp_path)
+    frag, a, u, _ = util.ref_align(str(tmp_path / "db"), s2, str(tmp_path), one2one=not chain, cand=False)
+    return str(tmp_path / "db"), frag, a, u
+
+
+@pytest.mark.parametrize("seed,chain", [(71, False), (72, True)])
+def test_conclave_single_end(tmp_path, seed, chain):
+    prefix, frag, a, u = se_case(tmp_path, seed, chain=chain)
+    files, w, fc, rc = util.ref_conclave(prefix, frag, a, u, str(tmp_path))
+    got, ow, ofc, orc_ = util.oracle_conclave(prefix, frag, a, u)
+    assert len(files) == 1 and len(files[0]) > 10000
+    assert got == files[0]
+    assert np.array_equal(ow, w) and np.array_equal(ofc, fc) and np.array_equal(orc_, rc)
+    assert (w > 0).sum() > 5
+    recs = np.frombuffer(got[:32], dtype=np.int32)
+    assert recs[0] > 0
+
+
+def test_conclave_paired_end(tmp_path):
+    names, seqs = synth.gene_db(73, n_families=10, n_variants=8, len_lo=500, len_hi=1500)
+    synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    r1, r2 = synth.paired_reads(74, seqs, 1200, sub=0.01)
+    synth.write_fastq(tmp_path / "a.fq", r1)
+    synth.write_fastq(tmp_path / "b.fq", r2)
+    s2 = util.ref_kma(["-ipe", "a.fq", "b.fq", "-o", "o", "-t_db", "db", "-apm", "p", "-s2"], cwd=tmp_path)
+    prefix = str(tmp_path / "db")
+    frag, a, u, _ = util.ref_align(prefix, s2, str(tmp_path), one2one=False, cand=False, pe=True)
+    files, w, fc, rc = util.ref_conclave(prefix, frag, a, u, str(tmp_path))
+    got, ow, ofc, orc_ = util.oracle_conclave(prefix, frag, a, u)
+    assert got == files[0]
+    assert np.array_equal(ow, w) and np.array_equal(ofc, fc) and np.array_equal(orc_, rc)
+    assert int(rc.sum()) > int(fc.sum())          # pairs count two reads per fragment
+
+
+def test_conclave_chunks_of_maxfrag(tmp_path):
+    """the reference cuts a new file every maxFrag fragments: each file is one oracle call on that slice of records"""
+    from kma_b200 import api
+    prefix, frag, a, u = se_case(tmp_path, 75, n=900)
+    files, w, fc, rc = util.ref_conclave(prefix, frag, a, u, str(tmp_path), max_frag=400)
+    assert len(files) == 3
+    off = api.record_offsets(4, np.frombuffer(frag, dtype=np.uint8))
+    tot_w = np.zeros_like(w)
+    for i, f in enumerate(files):
+        lo, hi = int(off[min(400 * i, len(off) - 1)]), int(off[min(400 * (i + 1), len(off) - 1)])
+        got, ow, _, _ = util.oracle_conclave(prefix, frag[lo:hi], a, u)
+        assert got == f
+        tot_w += ow
+    assert np.array_equal(tot_w, w)

@@ -293,3 +293,45 @@ def parse_trace(buf: bytes):
         p += 3 * n
         out.append((h, rows))
     return out
+
+
+def ref_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarray, tmp: str, max_frag=None):
+    """ground truth of ConClave's choice pass + printFrags from the unmodified reference (ref_harness -conclave):
+    (list of per-file byte strings, w_scores u64[DB], fragmentCounts u32[DB], readCounts u32[DB])"""
+    fp, sp, op = os.path.join(tmp, "cc_frag.bin"), os.path.join(tmp, "cc_sc.bin"), os.path.join(tmp, "cc_out.bin")
+    open(fp, "wb").write(frag_raw)
+    with open(sp, "wb") as f:
+        f.write(np.array([len(a)], dtype=np.int32).tobytes() + a.astype(np.uint64).tobytes() + u.astype(np.uint64).tobytes())
+    args = [REF_ALN, "-conclave", db_prefix, fp, sp, op] + ([str(max_frag)] if max_frag else [])
+    r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    buf = open(op, "rb").read()
+    nf = int(np.frombuffer(buf, dtype=np.int32, count=1)[0])
+    o, files = 4, []
+    for _ in range(nf):
+        nb = int(np.frombuffer(buf, dtype=np.int64, count=1, offset=o)[0])
+        files.append(buf[o + 8:o + 8 + nb])
+        o += 8 + nb
+    DB = len(a)
+    w = np.frombuffer(buf, dtype=np.uint64, count=DB, offset=o).copy(); o += 8 * DB
+    fc = np.frombuffer(buf, dtype=np.uint32, count=DB, offset=o).copy(); o += 4 * DB
+    rc = np.frombuffer(buf, dtype=np.uint32, count=DB, offset=o).copy()
+    return files, w, fc, rc
+
+
+def oracle_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarray):
+    """(per-template fragment records of one file, w_scores, fragmentCounts, readCounts) from the C oracle"""
+    L = orc()
+    raw = np.fromfile(db_prefix + ".length.b", dtype=np.int32)
+    DB, lengths = int(raw[0]), np.ascontiguousarray(raw[1:])
+    fr = np.frombuffer(frag_raw, dtype=np.uint8)
+    out = np.zeros(2 * len(fr) + 4096, dtype=np.uint8)
+    w, fc, rc = np.zeros(DB, np.uint64), np.zeros(DB, np.uint32), np.zeros(DB, np.uint32)
+    a, u = np.ascontiguousarray(a, dtype=np.uint64), np.ascontiguousarray(u, dtype=np.uint64)
+    L.orc_conclave_stream.restype = C.c_int64
+    L.orc_conclave_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
+    n = L.orc_conclave_stream(lengths.ctypes.data, DB, fr.ctypes.data, len(fr), a.ctypes.data, u.ctypes.data, out.ctypes.data, len(out),
+                              w.ctypes.data, fc.ctypes.data, rc.ctypes.data)
+    assert n >= 0, f"oracle conclave error {n}"
+    return out[:n].tobytes(), w, fc, rc
