@@ -143,6 +143,18 @@ int kmagpu_align_download(kmagpu_db *db, void *frag_out, size_t out_cap, size_t 
 int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *p, const void *frags, size_t nbytes,
                        void *out, size_t out_cap, size_t *out_bytes, int64_t *nrecords, kmagpu_align_stats *stats);
 
+/* Replaces runConClave (conclave.c:43-213, -ConClave 1) + printFrags (frags.c:30-61) for one chunk of frag_raw records
+ * (the reference cuts a new chunk every maxFrag fragments, conclave.c:196-207): per record the template with the
+ * largest GLOBAL alignment score wins (ties: score per template base, unique score, smaller id) -- so
+ * alignment_scores / uniq_alignment_scores [DB_size] must be the sums over the whole run and over all GPUs -- reads
+ * chosen on the reverse strand are reverse-complemented and their query bounds mirrored; w_scores[DB_size],
+ * fragmentCounts[DB_size], readCounts[DB_size] are ADDED into (NULL = not wanted). frags_out receives the
+ * per-template fragment stream of frags.c:45-48 (template order, reverse arrival order inside a template, int32 -1
+ * at the end): the input of kmagpu_trace_batch. */
+int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t nbytes, const uint64_t *alignment_scores,
+                          const uint64_t *uniq_alignment_scores, void *frags_out, size_t out_cap, size_t *out_bytes,
+                          uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts, int64_t *nrecords);
+
 /* The per-position base counts of the assembly pass (Assembly.counts[6] = {A, C, G, T, N, gap}, assembly.h:55-58) for
  * the template nodes of every template, HBM resident: uint32 [sum of template lengths][6], template t starting at
  * position sum(len[1..t-1]). kmagpu_trace_batch with params->matrix != 0 adds the accepted alignments of a batch

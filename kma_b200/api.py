@@ -75,6 +75,8 @@ def lib():
         L.kmagpu_seed_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]
         L.kmagpu_seed_run.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(SeedStats)]
         L.kmagpu_seed_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.kmagpu_conclave_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.kmagpu_matrix_reset.argtypes = [C.c_void_p]
         L.kmagpu_matrix_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.kmagpu_matrix_download.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
@@ -232,6 +234,22 @@ class TemplateDB:
         _check(lib().kmagpu_trace_batch(self._h, C.byref(p), frags.ctypes.data, len(frags), out.ctypes.data, cap,
                                         C.byref(ob), C.byref(nr), C.byref(st)))
         return out[: ob.value], nr.value, st
+
+    # --- ConClave choice pass + per-template bucketing --------------------------------------------
+    def conclave_batch(self, frag_raw, alignment_scores, uniq_alignment_scores, totals=None):
+        """runConClave (conclave.c:43) + printFrags (frags.c:30) over one chunk of frag_raw records with the GLOBAL score
+        arrays -> (per-template fragment records incl. the -1 terminator, w_scores, fragmentCounts, readCounts, nrecords);
+        `totals` = (w_scores u64, fragmentCounts u32, readCounts u32) arrays to add into"""
+        fr = np.ascontiguousarray(np.frombuffer(frag_raw, dtype=np.uint8) if isinstance(frag_raw, (bytes, bytearray)) else frag_raw, dtype=np.uint8)
+        a = np.ascontiguousarray(alignment_scores, dtype=np.uint64)
+        u = np.ascontiguousarray(uniq_alignment_scores, dtype=np.uint64)
+        DB = self.info.DB_size
+        w, fc, rc = totals if totals is not None else (np.zeros(DB, np.uint64), np.zeros(DB, np.uint32), np.zeros(DB, np.uint32))
+        out = np.empty(2 * len(fr) + 64, dtype=np.uint8)
+        ob, nr = C.c_size_t(), C.c_int64()
+        _check(lib().kmagpu_conclave_batch(self._h, fr.ctypes.data, len(fr), a.ctypes.data, u.ctypes.data, out.ctypes.data, len(out),
+                                           C.byref(ob), w.ctypes.data, fc.ctypes.data, rc.ctypes.data, C.byref(nr)))
+        return out[: ob.value], w, fc, rc, nr.value
 
     # --- base-count matrix of the assembly pass (alnToMat / alnToMatDense) ----------------------
     def matrix_reset(self):

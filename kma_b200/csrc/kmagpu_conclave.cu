@@ -1,0 +1,226 @@
+// ConClave's choice pass and the per-template bucketing that follows it, on the GPU.
+//
+// What is computed is runConClave (conclave.c:43-213, the default -ConClave 1) + printFrags (frags.c:30-61) for one
+// chunk of frag_raw records (updatescores.c:284-295): per read the template with the largest GLOBAL alignment score
+// wins (ties: score per template base as a double, then unique score, then the smaller template id), reads chosen on
+// the reverse strand are reverse-complemented (strrc, stdnuc.c:450) with their query bounds mirrored, the weighted
+// scores and read / fragment counts are summed per template, and the fragments leave grouped by template -- inside a
+// template in REVERSE arrival order (the reference prepends to a linked list), the mate of a pair before its first
+// read. The output is the per-template fragment stream kmagpu_trace_batch consumes (frags.c:45-48).
+// How it is computed is not the reference's serial re-read with a malloc per read:
+//   * one thread per record walks its candidate list against the score arrays (HBM/L2 resident) and makes the choice
+//     with the reference's int truncations (best_read_score / bestNum are ints compared with the 64-bit sums);
+//   * the order "template ascending, arrival descending" is one 64-bit radix sort (CUB) of (template, ~arrival) keys;
+//   * a scan turns record sizes into offsets and one warp per fragment writes its record.
+#include "kmagpu_internal.h"
+#include "kmagpu_dev.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <string.h>
+#include <vector>
+
+struct CcItem {
+	uint32_t q_off, hdr_off;     // byte offsets of the read bytes / name in the frag_raw stream
+	int32_t q_len, hl, tmpl, bestHits, score, start, end, flag, rc, has_bound, b0, b1;
+};
+
+__global__ void __launch_bounds__(256) cc_choose_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ off, int n,
+		const unsigned long long *__restrict__ as, const unsigned long long *__restrict__ uas, const int32_t *__restrict__ lengths,
+		int DB_size, CcItem *items, unsigned long long *keys, uint32_t *vals, unsigned long long *w, unsigned int *fc, unsigned int *rcn,
+		unsigned long long *ctr) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n) return;
+	const uint8_t *rec = in + off[r];
+	const int q_len = (int)ld_u32u(rec), sparse = (int)ld_u32u(rec + 4), sc = (int)ld_u32u(rec + 8), hl = (int)ld_u32u(rec + 12);
+	int flag = (int)ld_u32u(rec + 16);
+	const int bestHits = abs(sparse), read_score = abs(sc);
+	const uint8_t *S = rec + 20 + (size_t)q_len + (size_t)hl, *E = S + 4 * (size_t)bestHits, *T = E + 4 * (size_t)bestHits;
+	int bestTemplate, start, end;
+	if (bestHits > 1) {
+		double bestScore = 0;
+		int best_read_score = 0, bestNum = 0;
+		bestTemplate = -1; start = 0; end = 0;
+		for (int i = 0; i < bestHits; ++i) {
+			const int tt = (int)ld_u32u(T + 4 * (size_t)i);
+			const int t = tt < 0 ? -tt : tt;
+			if (t <= 0 || t >= DB_size) { atomicAdd(&ctr[1], 1ull); continue; }
+			const unsigned long long a = as[t], u = uas[t];
+			const double tmp_score = __ddiv_rn(1.0 * (double)a, (double)__ldg(lengths + t));
+			// the reference compares the 64-bit sums with ints: the ints are converted (sign-extended) to unsigned long
+			const unsigned long long brs = (unsigned long long)(long long)best_read_score, bn = (unsigned long long)(long long)bestNum;
+			bool take = false;
+			if (a > brs) take = true;
+			else if (a == brs) {
+				if (tmp_score > bestScore) take = true;
+				else if (tmp_score == bestScore) {
+					if (u > bn) take = true;
+					else if (u == bn && t < abs(bestTemplate)) take = true;
+				}
+			}
+			if (take) {
+				bestTemplate = tt; best_read_score = (int)a; bestScore = tmp_score; bestNum = (int)u;
+				start = (int)ld_u32u(S + 4 * (size_t)i); end = (int)ld_u32u(E + 4 * (size_t)i);
+			}
+		}
+	} else { bestTemplate = (int)ld_u32u(T); start = (int)ld_u32u(S); end = (int)ld_u32u(E); }
+	CcItem a;
+	a.q_off = off[r] + 20u; a.hdr_off = a.q_off + (uint32_t)q_len; a.q_len = q_len; a.hl = hl;
+	a.rc = 0; a.has_bound = 0; a.b0 = a.b1 = 0;
+	if (bestTemplate < 0) {
+		bestTemplate = -bestTemplate; a.rc = 1; flag |= 16;
+		const uint8_t *hdr = rec + 20 + q_len;
+		if (9 < hl && hdr[hl - 9] == 0) {   // mirrored query bounds (conclave.c:131-140)
+			a.has_bound = 1;
+			a.b0 = q_len - (int)ld_u32u(hdr + hl - 4);
+			a.b1 = q_len - (int)ld_u32u(hdr + hl - 8);
+		}
+	}
+	const bool ok = bestTemplate > 0 && bestTemplate < DB_size;
+	if (!ok) atomicAdd(&ctr[1], 1ull);
+	a.tmpl = bestTemplate; a.bestHits = bestHits; a.score = sparse < 0 ? 0 : read_score; a.start = start; a.end = end; a.flag = flag;
+	const bool mate = sc < 0;
+	if (ok) {
+		atomicAdd(&w[bestTemplate], (unsigned long long)read_score);
+		atomicAdd(&fc[bestTemplate], 1u);
+		atomicAdd(&rcn[bestTemplate], mate ? 2u : 1u);
+	}
+	items[2 * r] = a;
+	keys[2 * r] = ok ? ((unsigned long long)(unsigned)bestTemplate << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(2 * r)) : ~0ull;
+	vals[2 * r] = 2u * (unsigned)r;
+	unsigned long long k2 = ~0ull;
+	if (mate) {   // the mate block: int32[3]{q_len, hdrlen, flag} + bytes; same template and span, never turned
+		const uint8_t *m = T + 4 * (size_t)bestHits;
+		CcItem b = a;
+		b.q_len = (int)ld_u32u(m); b.hl = (int)ld_u32u(m + 4); b.flag = (int)ld_u32u(m + 8);
+		b.q_off = (uint32_t)(m + 12 - in); b.hdr_off = b.q_off + (uint32_t)b.q_len;
+		b.rc = 0; b.has_bound = 0;
+		items[2 * r + 1] = b;
+		if (ok) k2 = ((unsigned long long)(unsigned)bestTemplate << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(2 * r + 1));
+	}
+	keys[2 * r + 1] = k2;
+	vals[2 * r + 1] = 2u * (unsigned)r + 1u;
+	atomicAdd(&ctr[0], (ok ? 1ull : 0ull) + (ok && mate ? 1ull : 0ull));
+}
+
+__global__ void __launch_bounds__(256) cc_sizes_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals,
+		const CcItem *__restrict__ items, int nitems, uint32_t *size) {
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= nitems) return;
+	uint32_t s = 0;
+	if (keys[k] != ~0ull) { const CcItem it = items[vals[k]]; s = 32u + (uint32_t)it.q_len + (uint32_t)it.hl; }
+	size[k] = s;
+}
+
+// one warp per fragment, in output order: int32 template, int32[7] {q_len, bestHits, score, start, end, hdrlen, flag},
+// read bytes (0-5 codes), name (frags.c:45-48)
+__global__ void __launch_bounds__(256) cc_emit_kernel(const uint8_t *__restrict__ in, const unsigned long long *__restrict__ keys,
+		const uint32_t *__restrict__ vals, const CcItem *__restrict__ items, int nitems, const uint32_t *__restrict__ out_off,
+		uint8_t *__restrict__ out) {
+	const unsigned lane = threadIdx.x & 31;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < nitems; k += warps) {
+		if (keys[k] == ~0ull) continue;
+		const CcItem it = items[vals[k]];
+		uint8_t *o = out + out_off[k];
+		if (lane < 8) {
+			const int32_t h = lane == 0 ? it.tmpl : lane == 1 ? it.q_len : lane == 2 ? it.bestHits : lane == 3 ? it.score
+			                : lane == 4 ? it.start : lane == 5 ? it.end : lane == 6 ? it.hl : it.flag;
+			st_u32b(o + 4 * lane, (uint32_t)h);
+		}
+		o += 32;
+		const uint8_t *q = in + it.q_off, *hdr = in + it.hdr_off;
+		if (it.rc) {
+			for (int i = lane; i < it.q_len; i += 32) { const uint8_t c = q[it.q_len - 1 - i]; o[i] = c < 4 ? (uint8_t)(3 - c) : c; }
+		} else for (int i = lane; i < it.q_len; i += 32) o[i] = q[i];
+		o += it.q_len;
+		for (int i = lane; i < it.hl; i += 32) o[i] = hdr[i];
+		__syncwarp();
+		if (it.has_bound && lane == 0) { st_u32b(o + it.hl - 8, (uint32_t)it.b0); st_u32b(o + it.hl - 4, (uint32_t)it.b1); }
+	}
+}
+
+__global__ void cc_tail_kernel(uint8_t *out, const unsigned long long *total) { st_u32b(out + *total, 0xFFFFFFFFu); }
+
+extern "C" int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t nbytes, const uint64_t *alignment_scores,
+                                     const uint64_t *uniq_alignment_scores, void *frags_out, size_t out_cap, size_t *out_bytes,
+                                     uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts, int64_t *nrecords) {
+	if (!db || (!frag_raw && nbytes) || !alignment_scores || !uniq_alignment_scores) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->d_lengths) { kmagpu_set_error("database has no template lengths (.length.b missing)"); return -1; }
+	if (nbytes >= (1ull << 32) - 64) { kmagpu_set_error("frag_raw batch of %zu bytes exceeds the 4 GiB per-call limit; split it", nbytes); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	if (out_bytes) *out_bytes = 0;
+	if (nrecords) *nrecords = 0;
+	size_t used = 0;
+	const int64_t n64 = kmagpu_record_walk(4, frag_raw, nbytes, nullptr, 0, &used);
+	if (n64 < 0) return -1;
+	const int n = (int)n64;
+	if (nrecords) *nrecords = n64;
+	const int DB = db->info.DB_size;
+	cudaStream_t st = db->stream;
+	if (n == 0) {   // printFrags of an empty chunk: the terminator alone
+		if (out_cap < 4) { kmagpu_set_error("fragment output needs 4 bytes"); return -1; }
+		const int32_t m1 = -1;
+		memcpy(frags_out, &m1, 4);
+		if (out_bytes) *out_bytes = 4;
+		return 0;
+	}
+	std::vector<uint64_t> off64((size_t)n);
+	kmagpu_record_walk(4, frag_raw, nbytes, off64.data(), (size_t)n, &used);
+	std::vector<uint32_t> off((size_t)n + 1);
+	for (int i = 0; i < n; ++i) off[i] = (uint32_t)off64[i];
+	off[n] = (uint32_t)used;
+	const int ni = 2 * n, ntiles = (ni + SCAN_TILE - 1) / SCAN_TILE;
+	KgBuf d_in, d_off, d_sc, d_items, d_keys, d_vals, d_sz, d_partial, d_ctr, d_acc, d_tmp, d_out;
+	struct Guard { std::vector<KgBuf *> v; ~Guard() { for (KgBuf *b : v) b->release(); } } guard;
+	guard.v = {&d_in, &d_off, &d_sc, &d_items, &d_keys, &d_vals, &d_sz, &d_partial, &d_ctr, &d_acc, &d_tmp, &d_out};
+	if (d_in.reserve(used + 64) || d_off.reserve(4 * ((size_t)n + 2)) || d_sc.reserve(16 * (size_t)DB) ||
+	    d_items.reserve(sizeof(CcItem) * (size_t)ni) || d_keys.reserve(16 * (size_t)ni) || d_vals.reserve(8 * (size_t)ni) ||
+	    d_sz.reserve(4 * (size_t)(2 * ni + 4)) || d_partial.reserve(4 * (size_t)(ntiles + 2)) || d_ctr.reserve(64) ||
+	    d_acc.reserve(16 * (size_t)DB)) return -1;
+	unsigned long long *as = (unsigned long long *)d_sc.p, *uas = as + DB;
+	unsigned long long *keys = (unsigned long long *)d_keys.p, *keys2 = keys + ni;
+	uint32_t *vals = (uint32_t *)d_vals.p, *vals2 = vals + ni;
+	uint32_t *size = (uint32_t *)d_sz.p, *ooff = size + ni + 1;
+	unsigned long long *ctr = (unsigned long long *)d_ctr.p;
+	unsigned long long *w = (unsigned long long *)d_acc.p;
+	unsigned int *fc = (unsigned int *)(w + DB), *rcn = fc + DB;
+	KG_CUDA(cudaMemcpyAsync(d_in.p, frag_raw, used, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemsetAsync((uint8_t *)d_in.p + used, 0, 64, st));
+	KG_CUDA(cudaMemcpyAsync(d_off.p, off.data(), 4 * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemcpyAsync(as, alignment_scores, 8 * (size_t)DB, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemcpyAsync(uas, uniq_alignment_scores, 8 * (size_t)DB, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
+	KG_CUDA(cudaMemsetAsync(d_acc.p, 0, 16 * (size_t)DB, st));
+	cc_choose_kernel<<<(n + 255) / 256, 256, 0, st>>>((const uint8_t *)d_in.p, (const uint32_t *)d_off.p, n, as, uas, db->d_lengths, DB,
+		(CcItem *)d_items.p, keys, vals, w, fc, rcn, ctr);
+	size_t tmp_bytes = 0;
+	cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, ni, 0, 64, st);
+	if (d_tmp.reserve(tmp_bytes + 64)) return -1;
+	cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, keys, keys2, vals, vals2, ni, 0, 64, st);
+	cc_sizes_kernel<<<(ni + 255) / 256, 256, 0, st>>>(keys2, vals2, (const CcItem *)d_items.p, ni, size);
+	kg_exscan(size, ni, ooff, (uint32_t *)d_partial.p, ctr + 2, st);
+	unsigned long long h[8];
+	KG_CUDA(cudaMemcpyAsync(h, ctr, 64, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	if (h[1]) { kmagpu_set_error("%llu frag_raw candidates name a template outside the database", h[1]); return -1; }
+	const size_t ob = (size_t)h[2] + 4;
+	if (out_bytes) *out_bytes = ob;
+	if (ob > out_cap) { kmagpu_set_error("fragment output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
+	if (d_out.reserve(ob + 64)) return -1;
+	cc_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>((const uint8_t *)d_in.p, keys2, vals2, (const CcItem *)d_items.p, ni, ooff,
+		(uint8_t *)d_out.p);
+	cc_tail_kernel<<<1, 1, 0, st>>>((uint8_t *)d_out.p, ctr + 2);
+	KG_CUDA(cudaMemcpyAsync(frags_out, d_out.p, ob, cudaMemcpyDeviceToHost, st));
+	std::vector<uint8_t> acc(16 * (size_t)DB);
+	KG_CUDA(cudaMemcpyAsync(acc.data(), d_acc.p, 16 * (size_t)DB, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	const uint64_t *hw = (const uint64_t *)acc.data();
+	const uint32_t *hfc = (const uint32_t *)(hw + DB), *hrc = hfc + DB;
+	for (int t = 0; t < DB; ++t) {
+		if (w_scores) w_scores[t] += hw[t];
+		if (fragmentCounts) fragmentCounts[t] += hfc[t];
+		if (readCounts) readCounts[t] += hrc[t];
+	}
+	return 0;
+}

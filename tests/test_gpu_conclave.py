@@ -1,0 +1,73 @@
+"""GPU parity tests (B200): ConClave's choice pass + per-template bucketing through the C ABI vs the oracle that
+tests/test_oracle_conclave.py pins to the reference's own runConClave / printFrags; and the whole of stage 3 on the
+device: alignment pass -> ConClave -> traceback alignment + base counts."""
+import numpy as np
+import pytest
+
+from kma_b200 import api, synth
+from tests import util
+from tests.test_oracle_conclave import se_case
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")]
+
+
+@pytest.mark.parametrize("seed,chain", [(71, False), (72, True)])
+def test_conclave_single_end(tmp_path, seed, chain):
+    prefix, frag, a, u = se_case(tmp_path, seed, chain=chain)
+    want, ow, ofc, orc_ = util.oracle_conclave(prefix, frag, a, u)
+    db = api.TemplateDB(prefix, device=0)
+    got, w, fc, rc, n = db.conclave_batch(frag, a, u)
+    db.close()
+    assert n > 1000
+    assert got.tobytes() == want
+    assert np.array_equal(w, ow) and np.array_equal(fc, ofc) and np.array_equal(rc, orc_)
+
+
+def test_conclave_paired_end_and_empty(tmp_path):
+    names, seqs = synth.gene_db(73, n_families=10, n_variants=8, len_lo=500, len_hi=1500)
+    synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    r1, r2 = synth.paired_reads(74, seqs, 1200, sub=0.01)
+    synth.write_fastq(tmp_path / "a.fq", r1)
+    synth.write_fastq(tmp_path / "b.fq", r2)
+    s2 = util.ref_kma(["-ipe", "a.fq", "b.fq", "-o", "o", "-t_db", "db", "-apm", "p", "-s2"], cwd=tmp_path)
+    prefix = str(tmp_path / "db")
+    frag, a, u, _ = util.ref_align(prefix, s2, str(tmp_path), one2one=False, cand=False, pe=True)
+    want, ow, ofc, orc_ = util.oracle_conclave(prefix, frag, a, u)
+    db = api.TemplateDB(prefix, device=0)
+    got, w, fc, rc, n = db.conclave_batch(frag, a, u)
+    assert got.tobytes() == want
+    assert np.array_equal(w, ow) and np.array_equal(fc, ofc) and np.array_equal(rc, orc_)
+    empty, w0, _, _, n0 = db.conclave_batch(b"", a, u)
+    db.close()
+    assert n0 == 0 and empty.tobytes() == np.array([-1], dtype=np.int32).tobytes() and not w0.any()
+
+
+def test_stage3_on_the_device(tmp_path):
+    """alignment pass -> (score arrays) -> ConClave -> traceback alignment + base counts, every step on the GPU, equal to
+    the oracle chain (each link of which is pinned to the reference)"""
+    names, seqs = synth.gene_db(81, n_families=10, n_variants=8, len_lo=300, len_hi=1200)
+    synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    rng = np.random.default_rng(81)
+    reads = [synth.mutate_indel(rng, r, 0.02, 0.01, 0.01) for r in synth.short_reads(82, seqs, 1500, L=150, sub=0.0, junk_frac=0.02)]
+    synth.write_fastq(tmp_path / "r.fq", reads)
+    s2 = np.frombuffer(util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-1t1", "-s2"], cwd=tmp_path), dtype=np.uint8)
+    prefix = str(tmp_path / "db")
+    ofrag, oa, ou, _, _ = util.oracle_align_stream(prefix, s2, want_cand=False)
+    ofrags, ow, _, _ = util.oracle_conclave(prefix, ofrag, oa, ou)
+    otrace = util.oracle_trace(prefix, np.frombuffer(ofrags, dtype=np.uint8))
+    omat = util.oracle_matrix(prefix, np.frombuffer(ofrags, dtype=np.uint8), otrace)
+    db = api.TemplateDB(prefix, device=0)
+    p = api.default_params()
+    p.one2one = 1
+    p.matrix = 1
+    frag, a, u, _, _ = db.alnFrags_batch(s2, p)
+    frags, w, _, _, _ = db.conclave_batch(frag, a, u)
+    db.matrix_reset()
+    trace, n, _ = db.assemble_align_batch(frags, p)
+    mat = db.matrix_download()
+    db.close()
+    assert frags.tobytes() == ofrags and np.array_equal(w, ow)
+    assert trace.tobytes() == otrace
+    assert np.array_equal(mat, omat) and int(mat.sum()) > 100000
