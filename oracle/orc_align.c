@@ -1155,6 +1155,76 @@ int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const 
 }
 
 
+/* ------------------------------------------------------------------ -mem_mode -------- */
+
+/* The "Collecting k-mer scores" loop of runKMA_MEM (runkma.c:1088-1140) with update_Scores_MEM (updatescores.c:26) and
+ * update_Scores_pe_MEM (:64): in -mem_mode the alignment pass is skipped, every stage-2 record becomes a frag_raw record
+ * whose hits are its candidate templates spanning the whole template (start 0, end = template length), scored with
+ * the k-mer score of stage 2; a record with one candidate also adds to the unique scores. lengths[0] = k of the
+ * alignment index. Returns 0; *frag_out is malloc'ed. */
+int orc_memscore_stream(const int32_t *lengths, int DB_size, const uint8_t *in, size_t in_bytes, uint8_t **frag_out, size_t *frag_bytes,
+                        uint64_t *as, uint64_t *uas) {
+	int k = lengths[0];
+	if (k < 4 || 31 < k) k = 16;
+	obuf o = {0, 0, 0};
+	size_t ip = 0;
+	uint8_t *q = 0, *q2 = 0; size_t qcap = 0;
+	memset(as, 0, 8 * (size_t)DB_size); memset(uas, 0, 8 * (size_t)DB_size);
+	while (ip + 28 <= in_bytes) {
+		int32_t h[7], g[7];
+		memcpy(h, in + ip, 28);
+		if (h[0] < 0) break;
+		const uint8_t *rec1 = in + ip;
+		ip += 28 + 8 * (size_t)h[1] + 4 * (size_t)h[2] + 4 * (size_t)h[4] + (size_t)h[5];
+		const uint8_t *recT = rec1;   /* the record that carries the templates */
+		int read_score = 0, pe = 0;
+		if (h[4] == 0) {              /* first record of a pair: the mate follows (ankers.c:150) */
+			if (ip + 28 > in_bytes) break;
+			memcpy(g, in + ip, 28);
+			recT = in + ip;
+			ip += 28 + 8 * (size_t)g[1] + 4 * (size_t)g[2] + 4 * (size_t)g[4] + (size_t)g[5];
+			read_score = abs(g[3]);
+			pe = 1;
+		} else memcpy(g, h, 28);
+		const int q_len = h[0];
+		if (q_len < k) continue;
+		if ((size_t)(q_len > g[0] ? q_len : g[0]) + 64 > qcap) { qcap = 2 * (size_t)(q_len > g[0] ? q_len : g[0]) + 64; q = realloc(q, qcap); q2 = realloc(q2, qcap); }
+		{   /* unCompDNA of the first record */
+			uint64_t *w = malloc(8 * ((size_t)h[1] + 1)); int32_t *N = malloc(4 * ((size_t)h[2] + 1));
+			memcpy(w, rec1 + 28, 8 * (size_t)h[1]); memcpy(N, rec1 + 28 + 8 * (size_t)h[1], 4 * (size_t)h[2]);
+			unpack(w, q_len, N, h[2], q);
+			free(w); free(N);
+		}
+		const int nt = g[4];
+		const uint8_t *T = recT + 28 + 8 * (size_t)g[1] + 4 * (size_t)g[2];
+		int32_t last;
+		memcpy(&last, T + 4 * (size_t)(nt - 1), 4);
+		int bestHits = nt;
+		if (h[3] < 0 && 0 < last) bestHits = -bestHits;
+		const int two = pe && read_score && k <= g[0];
+		const int score = abs(h[3]) + (two ? read_score : 0);
+		int32_t b[5] = {q_len, bestHits, two ? -score : score, h[5], h[6]};
+		const uint8_t *hdr1 = rec1 + 28 + 8 * (size_t)h[1] + 4 * (size_t)h[2] + 4 * (size_t)h[4];
+		ob_put(&o, b, 20); ob_put(&o, q, q_len); ob_put(&o, hdr1, h[5]);
+		for (int i = 0; i < nt; ++i) { int32_t z = 0; ob_put(&o, &z, 4); }
+		for (int i = 0; i < nt; ++i) { int32_t t; memcpy(&t, T + 4 * (size_t)i, 4); int32_t e = lengths[abs(t)]; ob_put(&o, &e, 4); }
+		ob_put(&o, T, 4 * (size_t)nt);
+		if (two) {
+			uint64_t *w = malloc(8 * ((size_t)g[1] + 1)); int32_t *N = malloc(4 * ((size_t)g[2] + 1));
+			memcpy(w, recT + 28, 8 * (size_t)g[1]); memcpy(N, recT + 28 + 8 * (size_t)g[1], 4 * (size_t)g[2]);
+			unpack(w, g[0], N, g[2], q2);
+			free(w); free(N);
+			int32_t m[3] = {g[0], g[5], g[6]};
+			ob_put(&o, m, 12); ob_put(&o, q2, g[0]); ob_put(&o, T + 4 * (size_t)nt, g[5]);
+		}
+		if (nt == 1) { as[abs(last)] += score; uas[abs(last)] += score; }
+		else for (int i = 0; i < nt; ++i) { int32_t t; memcpy(&t, T + 4 * (size_t)i, 4); as[abs(t)] += score; }
+	}
+	free(q); free(q2);
+	*frag_out = o.p; *frag_bytes = o.len;
+	return 0;
+}
+
 /* ------------------------------------------------------------------ base-count matrix - */
 
 /* alnToMat (assembly.c:1317-1444) restricted to the template nodes, and alnToMatDense (assembly.c:1446-1497): the

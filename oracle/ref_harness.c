@@ -26,6 +26,7 @@
 #include "align.h"
 #include "assembly.h"
 #include "conclave.h"
+#include "updatescores.h"
 #include "frags.h"
 #include "alnfrags.h"
 #include "ankers.h"
@@ -36,6 +37,9 @@
 #include "penalties.h"
 #include "qseqs.h"
 #include "runkma.h"
+#ifndef MAX
+#define MAX(X, Y) ((X) < (Y) ? (Y) : (X))
+#endif
 
 static Penalties *make_rewards(void) {
 	Penalties *r = calloc(1, sizeof(Penalties));
@@ -212,7 +216,61 @@ static int conclave_main(int argc, char **argv) {
 	return 0;
 }
 
+/* -memscore db s2.bin frag_raw.out scores.out: the "Collecting k-mer scores" loop of runKMA_MEM (runkma.c:1088-1140,
+ * -mem_mode) around the reference's own get_ankers, unCompDNA, update_Scores_MEM and update_Scores_pe_MEM. */
+static int memscore_main(int argc, char **argv) {
+	if (argc < 6) { fprintf(stderr, "usage: ref_aln -memscore db s2.bin frag_raw.out scores.out\n"); return 2; }
+	int *template_lengths; long unsigned *alignment_scores, *uniq_alignment_scores;
+	char *p2 = malloc(strlen(argv[2]) + 64); strcpy(p2, argv[2]);
+	int DB_size = load_DBs_KMA(p2, &alignment_scores, &uniq_alignment_scores, &template_lengths, 0);
+	int kmersize = template_lengths[0];
+	if (kmersize < 4 || 31 < kmersize) kmersize = 16;
+	FILE *inputfile = fopen(argv[3], "rb"), *frag_out_raw = fopen(argv[4], "wb");
+	if (!inputfile || !frag_out_raw) { perror("open"); return 1; }
+	CompDNA *qseq_comp = malloc(sizeof(CompDNA)), *qseq_r_comp = malloc(sizeof(CompDNA));
+	allocComp(qseq_comp, 1024); allocComp(qseq_r_comp, 1024);
+	Qseqs *qseq = setQseqs(1024), *qseq_r = setQseqs(1024), *header = setQseqs(256), *header_r = setQseqs(256);
+	int *matched_templates = malloc(((DB_size + 1) << 1) * sizeof(int));
+	int *best_start_pos = calloc((DB_size << 1), sizeof(int)), *best_end_pos = malloc((DB_size << 1) * sizeof(int));
+	int *bestTemplates = matched_templates + 1;
+	int rc_flag, flag, flag_r, read_score = 0, best_read_score, bestHits, i, delta = 1024;
+	qseq_r->len = 0;
+	while ((rc_flag = get_ankers(matched_templates, qseq_comp, header, &flag, inputfile)) != 0) {
+		if (*matched_templates) read_score = 0;
+		else {
+			read_score = get_ankers(matched_templates, qseq_r_comp, header_r, &flag_r, inputfile);
+			read_score = labs(read_score);
+			qseq_r->len = qseq_r_comp->seqlen;
+		}
+		qseq->len = qseq_comp->seqlen;
+		if (kmersize <= qseq->len) {
+			if (delta <= MAX(qseq->len, qseq_r->len)) {
+				delta = MAX(qseq->len, qseq_r->len); delta <<= 1;
+				qseq->size = delta; qseq_r->size = delta;
+				free(qseq->seq); free(qseq_r->seq);
+				qseq->seq = malloc(delta); qseq_r->seq = malloc(delta);
+			}
+			unCompDNA(qseq_comp, qseq->seq);
+			best_read_score = abs(rc_flag);
+			for (i = 1, bestHits = 0; i <= *matched_templates; ++i, ++bestHits) best_end_pos[bestHits] = template_lengths[abs(matched_templates[i])];
+			if (rc_flag < 0 && 0 < matched_templates[*matched_templates]) bestHits = -bestHits;
+			if (read_score && kmersize <= qseq_r->len) {
+				unCompDNA(qseq_r_comp, qseq_r->seq);
+				update_Scores_pe_MEM(qseq->seq, qseq->len, qseq_r->seq, qseq_r->len, bestHits, best_read_score + read_score, best_start_pos, best_end_pos,
+				                     bestTemplates, header, header_r, flag, flag_r, alignment_scores, uniq_alignment_scores, frag_out_raw);
+			} else update_Scores_MEM(qseq->seq, qseq->len, bestHits, best_read_score, best_start_pos, best_end_pos, bestTemplates, header, flag,
+			                         alignment_scores, uniq_alignment_scores, frag_out_raw);
+		}
+	}
+	fclose(frag_out_raw);
+	FILE *so = fopen(argv[5], "wb");
+	fwrite(&DB_size, 4, 1, so); fwrite(alignment_scores, 8, DB_size, so); fwrite(uniq_alignment_scores, 8, DB_size, so);
+	fclose(so);
+	return 0;
+}
+
 int main(int argc, char **argv) {
+	if (argc >= 5 && !strcmp(argv[1], "-memscore")) return memscore_main(argc, argv);
 	if (argc >= 5 && !strcmp(argv[1], "-conclave")) return conclave_main(argc, argv);
 	if (argc >= 5 && !strcmp(argv[1], "-trace")) return trace_main(argc, argv);
 	if (argc < 5) { fprintf(stderr, "usage: ref_aln db s2.bin frag_raw.out scores.out [cand.out] [-1t1]\n"); return 2; }

@@ -335,3 +335,34 @@ def oracle_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarra
                               w.ctypes.data, fc.ctypes.data, rc.ctypes.data)
     assert n >= 0, f"oracle conclave error {n}"
     return out[:n].tobytes(), w, fc, rc
+
+
+def ref_memscore(db_prefix: str, s2: bytes, tmp: str):
+    """-mem_mode: the k-mer score collection of runKMA_MEM from the unmodified reference (ref_harness -memscore):
+    (frag_raw bytes, alignment_scores, uniq_alignment_scores)"""
+    p = os.path.join(tmp, "ms_s2.bin")
+    open(p, "wb").write(s2)
+    args = [REF_ALN, "-memscore", db_prefix, p, os.path.join(tmp, "ms_fr.out"), os.path.join(tmp, "ms_sc.out")]
+    r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    frag = open(os.path.join(tmp, "ms_fr.out"), "rb").read()
+    sc = np.fromfile(os.path.join(tmp, "ms_sc.out"), dtype=np.uint8)
+    n = int(sc[:4].view(np.int32)[0])
+    arr = sc[4:].view(np.uint64)
+    return frag, arr[:n].copy(), arr[n:2 * n].copy()
+
+
+def oracle_memscore(db_prefix: str, s2) -> tuple:
+    L = orc()
+    raw = np.fromfile(db_prefix + ".length.b", dtype=np.int32)
+    DB, lengths = int(raw[0]), np.ascontiguousarray(raw[1:])
+    s2 = np.ascontiguousarray(np.frombuffer(s2, dtype=np.uint8) if isinstance(s2, (bytes, bytearray)) else s2, dtype=np.uint8)
+    a, u = np.zeros(DB, np.uint64), np.zeros(DB, np.uint64)
+    fo, fb = C.c_void_p(), C.c_size_t()
+    L.orc_memscore_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
+    L.orc_free.argtypes = [C.c_void_p]
+    rc = L.orc_memscore_stream(lengths.ctypes.data, DB, s2.ctypes.data, len(s2), C.byref(fo), C.byref(fb), a.ctypes.data, u.ctypes.data)
+    assert rc == 0
+    frag = C.string_at(fo, fb.value) if fb.value else b""
+    L.orc_free(fo)
+    return frag, a, u
