@@ -143,6 +143,13 @@ int kmagpu_align_download(kmagpu_db *db, void *frag_out, size_t out_cap, size_t 
 int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *p, const void *frags, size_t nbytes,
                        void *out, size_t out_cap, size_t *out_bytes, int64_t *nrecords, kmagpu_align_stats *stats);
 
+/* -mem_mode: replaces the "Collecting k-mer scores" loop of runKMA_MEM (runkma.c:1088-1140) with update_Scores_MEM
+ * (updatescores.c:26) / update_Scores_pe_MEM (:64): every stage-2 record (pairs included) becomes a frag_raw record
+ * whose hits are its candidate templates over their whole length, scored with stage 2's k-mer score, written in input
+ * order; the scores are ADDED into alignment_scores / uniq_alignment_scores [DB_size] (NULL = not wanted). */
+int kmagpu_memscore_batch(kmagpu_db *db, const void *stage2, size_t nbytes, void *frag_out, size_t out_cap, size_t *out_bytes,
+                          uint64_t *alignment_scores, uint64_t *uniq_alignment_scores, int64_t *nrecords);
+
 /* Replaces runConClave (conclave.c:43-213, -ConClave 1) + printFrags (frags.c:30-61) for one chunk of frag_raw records
  * (the reference cuts a new chunk every maxFrag fragments, conclave.c:196-207): per record the template with the
  * largest GLOBAL alignment score wins (ties: score per template base, unique score, smaller id) -- so

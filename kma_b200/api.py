@@ -75,6 +75,8 @@ def lib():
         L.kmagpu_seed_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]
         L.kmagpu_seed_run.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(SeedStats)]
         L.kmagpu_seed_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.kmagpu_memscore_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p,
+                                            C.c_void_p, C.POINTER(C.c_int64)]
         L.kmagpu_conclave_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                             C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.kmagpu_matrix_reset.argtypes = [C.c_void_p]
@@ -234,6 +236,18 @@ class TemplateDB:
         _check(lib().kmagpu_trace_batch(self._h, C.byref(p), frags.ctypes.data, len(frags), out.ctypes.data, cap,
                                         C.byref(ob), C.byref(nr), C.byref(st)))
         return out[: ob.value], nr.value, st
+
+    # --- -mem_mode: k-mer score collection of runKMA_MEM ------------------------------------------
+    def memscore_batch(self, stage2, scores=None):
+        """update_Scores_MEM / _pe_MEM over a batch of stage-2 records -> (frag_raw bytes, alignment_scores, uniq_alignment_scores, nrecords)"""
+        s2 = np.ascontiguousarray(np.frombuffer(stage2, dtype=np.uint8) if isinstance(stage2, (bytes, bytearray)) else stage2, dtype=np.uint8)
+        DB = self.info.DB_size
+        a, u = scores if scores is not None else (np.zeros(DB, np.uint64), np.zeros(DB, np.uint64))
+        out = np.empty(8 * len(s2) + 4096, dtype=np.uint8)
+        ob, nr = C.c_size_t(), C.c_int64()
+        _check(lib().kmagpu_memscore_batch(self._h, s2.ctypes.data, len(s2), out.ctypes.data, len(out), C.byref(ob), a.ctypes.data,
+                                           u.ctypes.data, C.byref(nr)))
+        return out[: ob.value], a, u, nr.value
 
     # --- ConClave choice pass + per-template bucketing --------------------------------------------
     def conclave_batch(self, frag_raw, alignment_scores, uniq_alignment_scores, totals=None):

@@ -71,3 +71,63 @@ def test_stage3_on_the_device(tmp_path):
     assert frags.tobytes() == ofrags and np.array_equal(w, ow)
     assert trace.tobytes() == otrace
     assert np.array_equal(mat, omat) and int(mat.sum()) > 100000
+
+
+def test_memscore_vs_oracle(tmp_path):
+    """-mem_mode score collection (update_Scores_MEM / _pe_MEM): single reads with N's and strand ties, then pairs"""
+    from tests.test_oracle_memscore import _db
+    prefix, seqs = _db(tmp_path, 91)
+    reads = list(synth.short_reads(92, seqs, 1200, L=150, sub=0.01, junk_frac=0.03, n_rate=0.002))
+    reads += [np.zeros(12, dtype=np.uint8)]
+    for i in range(0, 40, 2):
+        r = reads[i]
+        reads[i] = np.concatenate([r[:75], synth.revcomp(r[:75])])
+    synth.write_fastq(tmp_path / "r.fq", reads)
+    s2 = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-1t1", "-s2"], cwd=tmp_path)
+    r1, r2 = synth.paired_reads(94, seqs, 800, sub=0.01)
+    synth.write_fastq(tmp_path / "a.fq", r1)
+    synth.write_fastq(tmp_path / "b.fq", r2)
+    s2pe = util.ref_kma(["-ipe", "a.fq", "b.fq", "-o", "o", "-t_db", "db", "-apm", "p", "-s2"], cwd=tmp_path)
+    db = api.TemplateDB(prefix, device=0)
+    for stream in (s2, s2pe):
+        ofrag, oa, ou = util.oracle_memscore(prefix, stream)
+        frag, a, u, n = db.memscore_batch(stream)
+        assert n > 500 and frag.tobytes() == ofrag
+        assert np.array_equal(a, oa) and np.array_equal(u, ou)
+    db.close()
+
+
+def test_mem_mode_flow_on_one_genome(tmp_path):
+    """C4-shaped: one genome as the only template, reads through stage 2 (-1t1), -mem_mode score collection, ConClave,
+    traceback alignment and base counts -- every step on the GPU, equal to the oracle chain"""
+    from kma_b200 import records
+    rng = np.random.default_rng(5)
+    genome = rng.integers(0, 4, size=200_000).astype(np.uint8)
+    synth.write_fasta(tmp_path / "db.fsa", ["genome"], [genome])
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    prefix = str(tmp_path / "db")
+    reads = [synth.mutate_indel(rng, r, 0.01, 0.003, 0.003) for r in synth.short_reads(6, [genome], 3000, L=150, sub=0.0)]
+    s1 = records.stage1_records(reads)
+    os2 = util.oracle_seed_stream(prefix, s1)
+    ofrag, oa, ou = util.oracle_memscore(prefix, os2)
+    ofrags, ow, _, _ = util.oracle_conclave(prefix, ofrag, oa, ou)
+    otrace = util.oracle_trace(prefix, np.frombuffer(ofrags, dtype=np.uint8))
+    omat = util.oracle_matrix(prefix, np.frombuffer(ofrags, dtype=np.uint8), otrace)
+    db = api.TemplateDB(prefix, device=0)
+    p = api.default_params()
+    p.one2one = 1
+    p.matrix = 1
+    s2, nreads, _ = db.save_kmers_batch(s1, p)
+    s2 = s2.tobytes() + api.stream_terminator(nreads)
+    assert s2 == os2.tobytes()
+    frag, a, u, _ = db.memscore_batch(s2)
+    frags, w, _, _, _ = db.conclave_batch(frag, a, u)
+    db.matrix_reset()
+    trace, n, _ = db.assemble_align_batch(frags, p)
+    mat = db.matrix_download(1)
+    db.close()
+    assert frag.tobytes() == ofrag and frags.tobytes() == ofrags and int(w[1]) == int(ow[1]) > 0
+    assert trace.tobytes() == otrace
+    assert np.array_equal(mat, omat) and mat.shape == (200_000, 6)
+    depth = mat[:, :4].sum(axis=1)
+    assert depth.mean() > 1.5     # 3000 x 150 bp over 200 kb
