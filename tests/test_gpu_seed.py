@@ -134,3 +134,37 @@ def test_paired_end_many_templates_dense_path(tmp_path):
     got, st = _gpu_stream(str(tmp_path / "db"), s1)
     assert st.overflow_reads > 0
     assert got == want.tobytes()
+
+
+def test_database_with_more_than_65535_templates(tmp_path):
+    """DB_size >= 65535 switches the template lists of .comp.b from uint16 to uint32 (hashmapkma.c:339-348): stage 2,
+    the alignment pass and chain mode against the oracle on a database of 66 000 short templates"""
+    from kma_b200 import dbbuild
+    rng = np.random.default_rng(77)
+    base = [rng.integers(0, 4, size=120).astype(np.uint8) for _ in range(6600)]
+    seqs, names = [], []
+    for f, b in enumerate(base):
+        for v in range(10):
+            s = b.copy()
+            if v:
+                s[rng.integers(0, 120, size=2)] = rng.integers(0, 4, size=2)
+            seqs.append(s)
+            names.append(f"t{f}_{v}")
+    prefix = str(tmp_path / "db")
+    dbbuild.build_db(prefix, names, seqs)
+    reads = synth.short_reads(78, seqs, 3000, L=100, sub=0.01)
+    s1 = records.stage1_records_fast(reads)
+    want = util.oracle_seed_stream(prefix, s1)
+    db = api.TemplateDB(prefix, device=0)
+    assert db.info.DB_size > 65535
+    got, n, st = db.save_kmers_batch(s1)
+    assert got.tobytes() + api.stream_terminator(n) == want.tobytes()
+    ofrag, oa, ou, _, _ = util.oracle_align_stream(prefix, want, want_cand=False)
+    frag, a, u, _, _ = db.alnFrags_batch(want)
+    assert frag.tobytes() == ofrag and np.array_equal(a, oa) and np.array_equal(u, ou)
+    p = api.default_params()
+    p.kmerscan = 1
+    cwant = util.oracle_chain_stream(prefix, s1)
+    cgot, cn, _ = db.save_kmers_batch(s1, p)
+    db.close()
+    assert cgot.tobytes() + api.stream_terminator(cn) == cwant.tobytes()
