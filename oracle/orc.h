@@ -21,6 +21,8 @@ typedef struct {
 	int32_t M, MM, U, W1, Wl, Mn, PE;
 	int32_t d[25];      /* substitution matrix d[t][q], 5x5 */
 	int32_t exhaustive; /* -ex_mode */
+	int32_t apm;        /* pairing of read pairs: 0 = -apm p (save_kmers_penaltyPair / alnFragsPenaltyPE), 1 = -apm u, the default
+	                       (save_kmers_unionPair / alnFragsUnionPE) */
 } orc_params;
 
 typedef struct {

@@ -417,6 +417,94 @@ static int f_best(pair_ws *ws) {
 	return best;
 }
 
+/* getR_Best (savekmers.c:1682-1762): the second mate's arg-max set goes to bt (reverse-strand ids negated); the
+ * templates of the first mate's set that the second mate also has among ITS best on the opposite strand are swapped to
+ * the front of rt, and rt[0] goes negative to mark the pair (union). Only the best templates still carry a score when
+ * the union is checked: the others were zeroed while the maximum was searched. */
+static int r_best(pair_ws *ws) {
+	int best_r = 0, hits = 0, sc;
+	for (int i = 1; i <= ws->bt[0]; ++i) {
+		if (best_r < (sc = ws->Score[ws->bt[i]])) {
+			for (int j = hits; j != 0; --j) ws->Score[ws->bt[j]] = 0;
+			best_r = sc; hits = 1; ws->bt[hits] = ws->bt[i];
+		} else if (best_r == sc) ws->bt[++hits] = ws->bt[i];
+		else ws->Score[ws->bt[i]] = 0;
+	}
+	for (int i = 1; i <= ws->bt_r[0]; ++i) {
+		if (best_r < (sc = ws->Score_r[ws->bt_r[i]])) {
+			for (int j = hits; j != 0; --j) { if (0 < ws->bt[j]) ws->Score[ws->bt[j]] = 0; else ws->Score_r[-ws->bt[j]] = 0; }
+			best_r = sc; hits = 1; ws->bt[hits] = -ws->bt_r[i];
+		} else if (best_r == sc) ws->bt[++hits] = -ws->bt_r[i];
+		else ws->Score_r[ws->bt_r[i]] = 0;
+	}
+	ws->bt[0] = hits;
+	hits = 0;
+	for (int i = 1; i <= ws->rt[0]; ++i) {
+		const int t = ws->rt[i];
+		if (0 < t ? ws->Score_r[t] : ws->Score[-t]) {
+			++hits;
+			const int tmp = ws->rt[hits]; ws->rt[hits] = ws->rt[i]; ws->rt[i] = tmp;
+		}
+	}
+	if (hits) ws->rt[0] = -hits;
+	for (int i = ws->bt[0]; i != 0; --i) { if (0 < ws->bt[i]) ws->Score[ws->bt[i]] = 0; else ws->Score_r[-ws->bt[i]] = 0; }
+	return best_r;
+}
+
+/* save_kmers_unionPair (savekmers.c:3367-3570, the default pairing) with getF = getF_Best, getR = getR_Best, rev = 1 */
+static size_t seed_pair_union(const orc_db *db, const orc_params *p, mate_t *m1, mate_t *m2, pair_ws *ws, uint8_t *out, orc_stats *st) {
+	const int k = db->kmersize;
+	size_t op = 0;
+	int best = 0, best_r = 0, flag = 65, flag_r = 129;
+	int *rt = ws->rt, *bt = ws->bt;
+	if (pair_kmers(db, p, m1, ws, st)) {
+		best = f_best(ws);
+		if (k < best && best * k < (m1->seqlen - best)) best = 0;
+	}
+	if (pair_kmers(db, p, m2, ws, st)) {
+		best_r = best ? r_best(ws) : f_best(ws);
+		if (k < best_r && best_r * k < (m2->seqlen - best_r)) { best_r = 0; rt[0] = abs(rt[0]); }
+	} else {   /* the lists are emptied: a first mate that kept its score still has its set in rt */
+		bt[0] = 0; ws->bt_r[0] = 0;
+	}
+	if (0 < best && 0 < best_r) {
+		if (rt[0] < 0) {   /* union found: a pair */
+			flag |= 2; flag_r |= 2;
+			rt[0] = -rt[0];
+			if (0 < rt[1]) {
+				flag |= 32; flag_r |= 16;
+				m1->cur ^= 1;
+				op += emit_mate(out + op, m1, best, rt + 1, 0, flag);
+				op += emit_mate(out + op, m2, best_r, rt + 1, rt[0], flag_r);
+			} else {
+				flag |= 16; flag_r |= 32;
+				m2->cur ^= 1;
+				for (int i = rt[0]; i != 0; --i) rt[i] = -rt[i];
+				op += emit_mate(out + op, m2, best_r, rt + 1, 0, flag_r);
+				op += emit_mate(out + op, m1, best, rt + 1, rt[0], flag);
+			}
+		} else {           /* two single mates */
+			if (0 < rt[1]) { m1->cur ^= 1; if (rt[rt[0]] < 0) best = -best; }
+			else { flag |= 16; flag_r |= 32; for (int i = 1; i <= rt[0]; ++i) rt[i] = -rt[i]; }
+			if (0 < bt[1]) { m2->cur ^= 1; if (bt[bt[0]] < 0) best_r = -best_r; }
+			else { flag |= 32; flag_r |= 16; for (int i = 1; i <= bt[0]; ++i) bt[i] = -bt[i]; }
+			op += emit_mate(out + op, m1, best, rt + 1, rt[0], flag);
+			op += emit_mate(out + op, m2, best_r, bt + 1, bt[0], flag_r);
+		}
+	} else if (best) {
+		flag |= 8 | 32;
+		if (0 < rt[1]) { m1->cur ^= 1; if (rt[rt[0]] < 0) best = -best; }
+		else { flag |= 16; for (int i = 1; i <= rt[0]; ++i) rt[i] = -rt[i]; }
+		op += emit_mate(out + op, m1, best, rt + 1, rt[0], flag);
+	} else if (best_r) {
+		flag_r |= 8 | 32;
+		if (0 < rt[1]) { m2->cur ^= 1; if (rt[rt[0]] < 0) best_r = -best_r; }
+		else { flag_r |= 16; for (int i = 1; i <= rt[0]; ++i) rt[i] = -rt[i]; }
+		op += emit_mate(out + op, m2, best_r, rt + 1, rt[0], flag_r);
+	}
+	return op;
+}
+
 static int imin(int a, int b) { return a < b ? a : b; }
 
 /* save_kmers_penaltyPair (savekmers.c:3572-3777) with printPtr = print_ankers, printPairPtr = printPair,
@@ -537,7 +625,7 @@ int64_t orc_seed_stream(const orc_db *db, const orc_params *p, const uint8_t *in
 			if (st) st->reads++, st->read_words += m2.words;
 			size_t need = 2 * 28 + 8 * (size_t)(m1.words + m2.words) + 4 * (size_t)(m1.nN + m2.nN) + 8 * D + m1.hdrlen + m2.hdrlen;
 			if (op + need + 4 > cap) { ret = -1; goto done; }
-			size_t w = seed_pair(db, p, &m1, &m2, &ws, out + op, st);
+			size_t w = p->apm == 1 ? seed_pair_union(db, p, &m1, &m2, &ws, out + op, st) : seed_pair(db, p, &m1, &m2, &ws, out + op, st);
 			if (w && st) st->mapped++;
 			op += w;
 			continue;

@@ -12,7 +12,7 @@ from tests import util
 pytestmark = pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
 
 
-def make_pairs(tmp_path, seed, n=1500):
+def make_pairs(tmp_path, seed, n=1500, apm="p"):
     """pairs with junk mates, N's, mates from different templates, same-strand mates"""
     names, seqs = synth.gene_db(seed, n_families=20, n_variants=6, len_lo=400, len_hi=1500)
     synth.write_fasta(tmp_path / "db.fsa", names, seqs)
@@ -34,7 +34,7 @@ def make_pairs(tmp_path, seed, n=1500):
     synth.write_fastq(tmp_path / "r1.fq", r1)
     synth.write_fastq(tmp_path / "r2.fq", r2)
     util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
-    args = ["-ipe", "r1.fq", "r2.fq", "-o", "o", "-t_db", "db", "-apm", "p"]
+    args = ["-ipe", "r1.fq", "r2.fq", "-o", "o", "-t_db", "db", "-apm", apm]
     s1 = util.ref_kma(args + ["-s1"], cwd=tmp_path)
     s2 = util.ref_kma(args + ["-s2"], cwd=tmp_path)
     return str(tmp_path / "db"), np.frombuffer(s1, dtype=np.uint8), s2
@@ -53,3 +53,14 @@ def test_pair_seeding_and_alignment_vs_reference(tmp_path, seed):
     assert ofrag == frag
     assert np.array_equal(oa, a) and np.array_equal(ou, u)
     assert cells > 0 and len(ocand) > 1000
+
+
+@pytest.mark.parametrize("seed", [61, 62, 63])
+def test_union_pairing_stage2_vs_reference(tmp_path, seed):
+    """-apm u, the reference's default pairing: save_kmers_unionPair with getF_Best / getR_Best (savekmers.c:3367, 1648, 1682)"""
+    prefix, s1, s2 = make_pairs(tmp_path, seed, apm="u")
+    got = util.oracle_seed_stream(prefix, s1, apm=1)
+    assert got.tobytes() == s2
+    recs = records.parse_stage2(np.frombuffer(s2, dtype=np.uint8))
+    kinds = collections.Counter((r["flag"], len(r["templates"]) == 0) for r in recs)
+    assert sum(1 for (f, first) in kinds if first) >= 2 and len(kinds) >= 8

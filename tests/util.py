@@ -37,14 +37,15 @@ def orc():
     return _orc
 
 
-def oracle_params(exhaustive=0):
+def oracle_params(exhaustive=0, apm=0):
     p = (C.c_int32 * 40)()
     orc().orc_default_params(p)
     p[32] = exhaustive  # M MM U W1 Wl Mn PE (7) + d[25] -> exhaustive at index 32
+    p[33] = apm         # 0 = -apm p, 1 = -apm u (the default pairing)
     return p
 
 
-def oracle_seed_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, stats=None) -> np.ndarray:
+def oracle_seed_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, stats=None, apm=0) -> np.ndarray:
     L = orc()
     db = L.orc_db_open(os.fsencode(db_prefix))
     assert db, f"oracle cannot open {db_prefix}"
@@ -52,7 +53,7 @@ def oracle_seed_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, stats=None)
     while True:
         out = np.zeros(cap, dtype=np.uint8)
         st = (C.c_int64 * 7)()
-        n = L.orc_seed_stream(db, oracle_params(exhaustive), s1.ctypes.data, len(s1), out.ctypes.data, len(out), st)
+        n = L.orc_seed_stream(db, oracle_params(exhaustive, apm), s1.ctypes.data, len(s1), out.ctypes.data, len(out), st)
         if n >= 0 or cap > (1 << 32):
             break
         cap *= 8
