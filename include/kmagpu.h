@@ -36,7 +36,9 @@ typedef struct kmagpu_params {
 	                                     1 = save_kmers_chain (the default without -1t1, savekmers.c:5127) */
 	int32_t matrix;                   /* kmagpu_trace_batch: add every accepted alignment to the base-count matrix as alnToMatPtr does
 	                                     (assembly.c:1968): 0 = no, 1 = alnToMat (template nodes, assembly.c:1317), 2 = alnToMatDense (-dense, :1446) */
-	int32_t reserved[2];
+	int32_t apm;                      /* pairing of read pairs (-apm): 0 = p (save_kmers_penaltyPair savekmers.c:3572 / alnFragsPenaltyPE
+	                                     alnfrags.c:1596), 1 = u, the reference's default (save_kmers_unionPair :3367 / alnFragsUnionPE :1220) */
+	int32_t reserved[1];
 	double scoreT;                    /* -mrs (alnfrags.c:1168; also `mrs` of save_kmers_chain, kmers.c:51) */
 	double minFrac;                   /* -mf  (updatescores.c:217-268) */
 	double mrc;                       /* -mrc (alnfrags.h:38 mrcheck) */

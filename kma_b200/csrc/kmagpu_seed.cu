@@ -490,7 +490,7 @@ __device__ __forceinline__ int list_score(const int2 *L, int n, int t) {   // Sc
 // printPair's record order (ankers.c:150). Slot r / r+1 of res + recsize describe the first / second record emitted.
 __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ rec_off, int nrec,
 		const uint8_t *__restrict__ kinds, const MateRes *__restrict__ mates, const int2 *__restrict__ pool2, int32_t *pool,
-		unsigned long long pool_cap, unsigned long long *ctr, SeedRes *res, uint32_t *recsize, int k, int PE) {
+		unsigned long long pool_cap, unsigned long long *ctr, SeedRes *res, uint32_t *recsize, int k, int PE, int apm) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= nrec || kinds[r] != 1) return;
 	// a strand list that did not fit the pool was never written and its offset points past the allocation: the host
@@ -509,6 +509,86 @@ __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_
 	int nrt = 0, nbt = 0, best = 0, best_r = 0;
 	const int hc = A.hits, hc_r = B.hits;
 	bool proper = false;
+	if (apm == 1) {
+		// save_kmers_unionPair (savekmers.c:3367-3570, the default pairing) with getF_Best (:1648) / getR_Best (:1682):
+		// each mate keeps its arg-max set; the pair is proper when a template of the first mate's set is also among
+		// the second mate's best on the opposite strand
+		auto argmax = [&](const int2 *F, int nf, const int2 *R, int nr, int32_t *dst, int *cnt) {
+			int b = 0, h = 0;
+			for (int i = 0; i < nf + nr; ++i) {
+				const int t = i < nf ? F[i].x : -R[i - nf].x, sc = i < nf ? F[i].y : R[i - nf].y;
+				if (b < sc) { b = sc; h = 1; dst[0] = t; }
+				else if (b == sc) dst[h++] = t;
+			}
+			*cnt = h;
+			return b;
+		};
+		if (hc) {
+			best = argmax(F1, A.n_f, R1, A.n_r, rt, &nrt);
+			if (k < best && best * k < (lenA - best)) best = 0;
+		}
+		if (hc_r) {
+			if (best) {
+				best_r = argmax(F2, B.n_f, R2, B.n_r, bt, &nbt);
+				int hits = 0;
+				if (best_r) {
+					for (int i = 0; i < nrt; ++i) {
+						const int t = rt[i];
+						if ((0 < t ? list_score(R2, B.n_r, t) : list_score(F2, B.n_f, -t)) == best_r) {
+							const int tmp = rt[hits]; rt[hits] = rt[i]; rt[i] = tmp;
+							++hits;
+						}
+					}
+				}
+				if (hits) { proper = true; nrt = hits; }
+			} else best_r = argmax(F2, B.n_f, R2, B.n_r, rt, &nrt);
+			if (k < best_r && best_r * k < (lenB - best_r)) { best_r = 0; proper = false; }
+		}
+		int curA = A.scanned, curB = B.scanned;
+		int flag = 65, flag_r = 129;
+		const uint32_t baseA = 28u + 8u * ld_u32u(recA + 4) + 4u * ld_u32u(recA + 8) + (uint32_t)abs((int)ld_u32u(recA + 12));
+		const uint32_t baseB = 28u + 8u * ld_u32u(recB + 4) + 4u * ld_u32u(recB + 8) + (uint32_t)abs((int)ld_u32u(recB + 12));
+		const uint32_t rt_off = (uint32_t)po, bt_off = (uint32_t)po + (uint32_t)n1;
+		if (0 < best && 0 < best_r) {
+			if (proper) {
+				flag |= 2; flag_r |= 2;
+				if (0 < rt[0]) {
+					flag |= 32; flag_r |= 16; curA ^= 1;
+					o1.score = best; o1.ntmpl = 0; o1.flag = flag; o1.src = r; o1.rev = curA; o1.pool_off = rt_off; sz1 = baseA;
+					o2.score = best_r; o2.ntmpl = nrt; o2.flag = flag_r; o2.src = r + 1; o2.rev = curB; o2.pool_off = rt_off; sz2 = baseB + 4u * nrt;
+				} else {
+					flag |= 16; flag_r |= 32; curB ^= 1;
+					for (int i = 0; i < nrt; ++i) rt[i] = -rt[i];
+					o1.score = best_r; o1.ntmpl = 0; o1.flag = flag_r; o1.src = r + 1; o1.rev = curB; o1.pool_off = rt_off; sz1 = baseB;
+					o2.score = best; o2.ntmpl = nrt; o2.flag = flag; o2.src = r; o2.rev = curA; o2.pool_off = rt_off; sz2 = baseA + 4u * nrt;
+				}
+			} else {
+				int sA = best, sB = best_r;
+				if (0 < rt[0]) { curA ^= 1; if (rt[nrt - 1] < 0) sA = -sA; }
+				else { flag |= 16; flag_r |= 32; for (int i = 0; i < nrt; ++i) rt[i] = -rt[i]; }
+				if (0 < bt[0]) { curB ^= 1; if (bt[nbt - 1] < 0) sB = -sB; }
+				else { flag |= 32; flag_r |= 16; for (int i = 0; i < nbt; ++i) bt[i] = -bt[i]; }
+				o1.score = sA; o1.ntmpl = nrt; o1.flag = flag; o1.src = r; o1.rev = curA; o1.pool_off = rt_off; sz1 = baseA + 4u * nrt;
+				o2.score = sB; o2.ntmpl = nbt; o2.flag = flag_r; o2.src = r + 1; o2.rev = curB; o2.pool_off = bt_off; sz2 = baseB + 4u * nbt;
+			}
+		} else if (0 < best) {
+			int sA = best;
+			flag |= 8 | 32;
+			if (0 < rt[0]) { curA ^= 1; if (rt[nrt - 1] < 0) sA = -sA; }
+			else { flag |= 16; for (int i = 0; i < nrt; ++i) rt[i] = -rt[i]; }
+			o1.score = sA; o1.ntmpl = nrt; o1.flag = flag; o1.src = r; o1.rev = curA; o1.pool_off = rt_off; sz1 = baseA + 4u * nrt;
+		} else if (0 < best_r) {
+			int sB = best_r;
+			flag_r |= 8 | 32;
+			if (0 < rt[0]) { curB ^= 1; if (rt[nrt - 1] < 0) sB = -sB; }
+			else { flag_r |= 16; for (int i = 0; i < nrt; ++i) rt[i] = -rt[i]; }
+			o2.score = sB; o2.ntmpl = nrt; o2.flag = flag_r; o2.src = r + 1; o2.rev = curB; o2.pool_off = rt_off; sz2 = baseB + 4u * nrt;
+		}
+		res[r] = o1; res[r + 1] = o2;
+		recsize[r] = sz1; recsize[r + 1] = sz2;
+		if (sz1 || sz2) atomicAdd(&ctr[C_MAPPED], 1ull);
+		return;
+	}
 	if (hc) {   // getFirstPen
 		for (int i = 0; i < A.n_f; ++i) { rt[nrt++] = F1[i].x; best = max(best, F1[i].y); }
 		for (int i = 0; i < A.n_r; ++i) { rt[nrt++] = -R1[i].x; best = max(best, R1[i].y); }
@@ -798,7 +878,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 		if (pe) {
 			pair_select_kernel<<<(n + 127) / 128, 128, 0, db->stream>>>((const uint8_t *)b.d_in.p, (const uint32_t *)b.d_off.p, n, kinds,
 				(const MateRes *)b.d_mates.p, (const int2 *)b.d_pool2.p, (int32_t *)b.d_pool.p, (unsigned long long)b.pool_cap, ctr,
-				(SeedRes *)b.d_res.p, recsize, db->hv.kmersize, prm->PE);
+				(SeedRes *)b.d_res.p, recsize, db->hv.kmersize, prm->PE, prm->apm);
 			++launches;
 		}
 		KG_CUDA(cudaEventRecord(db->ev[3], db->stream));

@@ -696,10 +696,24 @@ static void align_pe(const orc_params *p, nw_ws *ws, mems_t *pt, tindex **tix, o
 	const int rc = !flipped;
 	const double af = minFrac < 0 ? -minFrac : minFrac;
 	const uint8_t *q1 = m1->b[flipped], *q2 = m2->b[flipped];
-	if (comp && af * (best1 + best2) <= (comp + p->PE)) {   /* proper pair */
-		const int best = comp + p->PE;
-		for (int ti = 1; ti <= nt; ++ti)
-			if (bT[ti] && bTr[ti]) { bTr[hits] = bT[ti] + bTr[ti] + p->PE; bT[hits] = mt[ti]; bS[hits] = bS[ti]; bE[hits] = bE[ti]; ++hits; }
+	int proper, best = 0;
+	if (p->apm == 1) {   /* alnFragsUnionPE (alnfrags.c:1408-1422): templates both mates reach within minFrac of their own best */
+		if (best1 && best2) {
+			const double sc = af * best1, sc_r = af * best2;
+			for (int ti = 1; ti <= nt; ++ti)
+				if (sc <= bT[ti] && sc_r <= bTr[ti]) { bTr[hits] = bT[ti] + bTr[ti]; bT[hits] = mt[ti]; bS[hits] = bS[ti]; bE[hits] = bE[ti]; ++hits; }
+		}
+		proper = hits != 0;
+		best = best1 + best2;
+	} else {             /* alnFragsPenaltyPE (alnfrags.c:1787-1808) */
+		proper = comp && af * (best1 + best2) <= (comp + p->PE);
+		if (proper) {
+			best = comp + p->PE;
+			for (int ti = 1; ti <= nt; ++ti)
+				if (bT[ti] && bTr[ti]) { bTr[hits] = bT[ti] + bTr[ti] + p->PE; bT[hits] = mt[ti]; bS[hits] = bS[ti]; bE[hits] = bE[ti]; ++hits; }
+		}
+	}
+	if (proper) {   /* proper pair */
 		if (bT[0] < 0) {
 			for (int i = 0; i < hits; ++i) bT[i] = -bT[i];
 			emit_pe(frag, as, uas, q2, m2->q_len, m2->hdr, m2->hl, flag_r, q1, m1->q_len, m1->hdr, m1->hl, flag, minFrac, hits, best, bS, bE, bT, bTr);

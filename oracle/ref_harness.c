@@ -280,6 +280,7 @@ int main(int argc, char **argv) {
 	for (int a = 5; a < argc; ++a) {
 		if (!strcmp(argv[a], "-1t1")) one2one = 1;
 		else if (!strcmp(argv[a], "-apm-p")) alnFragsPE = &alnFragsPenaltyPE;   /* kma.c:458: -apm p */
+		else if (!strcmp(argv[a], "-apm-u")) alnFragsPE = &alnFragsUnionPE;     /* kma.c:460: -apm u (the default) */
 		else if (!strcmp(argv[a], "-t") && a + 1 < argc) nthreads = atoi(argv[++a]);
 		else cand_path = argv[a];
 	}

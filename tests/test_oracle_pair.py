@@ -64,3 +64,10 @@ def test_union_pairing_stage2_vs_reference(tmp_path, seed):
     recs = records.parse_stage2(np.frombuffer(s2, dtype=np.uint8))
     kinds = collections.Counter((r["flag"], len(r["templates"]) == 0) for r in recs)
     assert sum(1 for (f, first) in kinds if first) >= 2 and len(kinds) >= 8
+    # stage 3: alnFragsUnionPE (alnfrags.c:1220) + update_Scores_pe / _se
+    frag, a, u, _ = util.ref_align(prefix, s2, str(tmp_path), one2one=False, cand=False, pe="u")
+    ofrag, oa, ou, ocand, cells = util.oracle_align_stream(prefix, np.frombuffer(s2, dtype=np.uint8), one2one=False, apm=1)
+    assert ofrag == frag
+    assert np.array_equal(oa, a) and np.array_equal(ou, u)
+    pfrag, _, _, _, _ = util.oracle_align_stream(prefix, np.frombuffer(s2, dtype=np.uint8), one2one=False, apm=0)
+    assert pfrag != ofrag, "the case is meant to tell the two pairings apart"
