@@ -51,7 +51,7 @@ struct AlnCand { int32_t tmpl, score, len, pos, match, tGaps, qGaps, status; };
 
 struct AlnParams {
 	NwPen pen;
-	int32_t k, mq, one2one, exhaustive, minlen, Wl, PE;
+	int32_t k, mq, one2one, exhaustive, minlen, Wl, PE, apm;
 	double scoreT, mrc, minFrac;
 };
 
@@ -727,13 +727,31 @@ __device__ void reduce_pair(const AlnParams &P, const AlnRead &RA, const AlnRead
 		o.rkept[x] = kept; o.rscore[x] = sc; o.rflag[x] = fl; o.rmate[x] = mate; o.rorient[x] = orient; o.roff[x] = (int32_t)(arr - base);
 	};
 	const uint32_t szA = (uint32_t)RA.q_len + (uint32_t)RA.hl, szB = (uint32_t)RB.q_len + (uint32_t)RB.hl;
-	if (comp && af * (best1 + best2) <= (comp + PE)) {   // proper pair
-		const int best = comp + PE;
-		for (int ti = 1; ti <= nt; ++ti)
-			if (ent[ti].bT && ent[ti].bTr) {
-				const PeEnt e = ent[ti];
-				ent[hits].bTr = e.bT + e.bTr + PE; ent[hits].bT = e.mt; ent[hits].bS = e.bS; ent[hits].bE = e.bE; ++hits;
-			}
+	bool proper;
+	int best = 0;
+	if (P.apm == 1) {   // alnFragsUnionPE (alnfrags.c:1408-1422): templates both mates reach within minFrac of their own best
+		if (best1 && best2) {
+			const double sc = af * best1, sc_r = af * best2;
+			for (int ti = 1; ti <= nt; ++ti)
+				if (sc <= ent[ti].bT && sc_r <= ent[ti].bTr) {
+					const PeEnt e = ent[ti];
+					ent[hits].bTr = e.bT + e.bTr; ent[hits].bT = e.mt; ent[hits].bS = e.bS; ent[hits].bE = e.bE; ++hits;
+				}
+		}
+		proper = hits != 0;
+		best = best1 + best2;
+	} else {            // alnFragsPenaltyPE (alnfrags.c:1787-1808)
+		proper = comp && af * (best1 + best2) <= (comp + PE);
+		if (proper) {
+			best = comp + PE;
+			for (int ti = 1; ti <= nt; ++ti)
+				if (ent[ti].bT && ent[ti].bTr) {
+					const PeEnt e = ent[ti];
+					ent[hits].bTr = e.bT + e.bTr + PE; ent[hits].bT = e.mt; ent[hits].bS = e.bS; ent[hits].bE = e.bE; ++hits;
+				}
+		}
+	}
+	if (proper) {   // proper pair
 		o.form = 1; o.nrec = 2;
 		if (ent[0].bT < 0) {
 			for (int i = 0; i < hits; ++i) ent[i].bT = -ent[i].bT;
@@ -1402,7 +1420,7 @@ static AlnParams make_params(const kmagpu_db *db, const kmagpu_params *p) {
 	memcpy(P.pen.d, p->d, sizeof(P.pen.d));
 	P.pen.d8 = 1;
 	for (int i = 0; i < 25; ++i) if (p->d[i] < -128 || p->d[i] > 127) P.pen.d8 = 0;
-	P.k = db->info.kmerindex; P.mq = p->mq; P.one2one = p->one2one; P.exhaustive = p->exhaustive; P.minlen = p->minlen; P.Wl = p->Wl; P.PE = p->PE;
+	P.k = db->info.kmerindex; P.mq = p->mq; P.one2one = p->one2one; P.exhaustive = p->exhaustive; P.minlen = p->minlen; P.Wl = p->Wl; P.PE = p->PE; P.apm = p->apm;
 	P.scoreT = p->scoreT; P.mrc = p->mrc; P.minFrac = p->minFrac;
 	return P;
 }

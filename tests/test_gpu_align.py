@@ -341,3 +341,29 @@ def test_base_count_matrix_vs_oracle(tmp_path, seed, L, sub, indel, mode):
     db.matrix_reset()
     assert int(db.matrix_download().sum()) == 0
     db.close()
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", [61, 63])
+def test_union_pairing_vs_reference(tmp_path, seed):
+    """-apm u, the reference's default pairing: save_kmers_unionPair (stage 2, byte-exact vs `kma -ipe -apm u -s2`) and
+    alnFragsUnionPE (alignment pass, vs the oracle pinned to alnFrags_threaded), from the stream and chained in HBM"""
+    from tests.test_oracle_pair import make_pairs
+    prefix, s1, s2 = make_pairs(tmp_path, seed, n=3000, apm="u")
+    db = api.TemplateDB(prefix)
+    p = api.default_params()
+    p.apm = 1
+    got, n, st = db.save_kmers_batch(s1, p)
+    assert got.tobytes() + api.stream_terminator(n) == s2
+    s2a = np.frombuffer(s2, dtype=np.uint8)
+    ofrag, oa, ou, ocand, cells = util.oracle_align_stream(prefix, s2a, one2one=False, apm=1)
+    frag, a, u, cand, sta = db.alnFrags_batch(s2a, p, want_cand=True)
+    db.seed_upload(s1); db.seed_run(p)
+    db.align_from_seed(); db.align_run(p)
+    frag2, a2, u2, _ = db.align_download()
+    db.close()
+    assert sta.tasks == len(ocand)
+    assert np.array_equal(a, oa) and np.array_equal(u, ou)
+    fb = frag.tobytes()
+    assert fb == ofrag, f"frag_raw differs at byte {_first_diff(fb, ofrag)} of {len(ofrag)} (got {len(fb)})"
+    assert frag2.tobytes() == ofrag and np.array_equal(a2, oa) and np.array_equal(u2, ou)
