@@ -387,17 +387,17 @@ __device__ int nw_auto(const TaskCtx &c, int k, int t_s, int t_e, int q_s, int q
 	int band = abs(t_l - q_l) + AL_BANDW;
 	if (q_l <= band || t_l <= band) band = 0;
 	unsigned long long cells = 0;
-	const int st = nw_warp(*c.pen, c.tseq, c.qb, k, t_s, t_e, q_s, q_e, band, c.nw, a, &cells);
+	const int st = nw_warp<false>(*c.pen, c.tseq, c.qb, k, t_s, t_e, q_s, q_e, band, c.nw, a, &cells);
 	if (st != NW_OK) {
 		NwGeo g;
-		nw_geo_init(g, *c.pen, t_l, q_l, k, band);
+		nw_geo_init(g, *c.pen, t_l, q_l, k, band, false);
 		c.wc->need_e = max(c.wc->need_e, (unsigned)min((size_t)0xF0000000u, g.ebytes() + 4096));
 		c.wc->need_q = max(c.wc->need_q, (unsigned)q_l + 64u);
 		return ST_OVERFLOW;
 	}
 	if (cells) {
 		NwGeo g;
-		nw_geo_init(g, *c.pen, t_l, q_l, k, band);
+		nw_geo_init(g, *c.pen, t_l, q_l, k, band, false);
 		c.wc->steps += (unsigned long long)g.Tmax;
 		if (band) { ++c.wc->band_calls; c.wc->band_cells += cells; } else { ++c.wc->full_calls; c.wc->full_cells += cells; }
 	}
@@ -1073,10 +1073,10 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 		if (q_l <= band || t_l <= band) band = 0;
 		NwRows r = {rows.t + at, rows.s + at, rows.q + at};
 		unsigned long long cells = 0;
-		const int st = nw_warp(*c.pen, c.tseq, c.qb, kk, t_s, t_e, q_s, q_e, band, c.nw, a, &cells, &r);
+		const int st = nw_warp<false>(*c.pen, c.tseq, c.qb, kk, t_s, t_e, q_s, q_e, band, c.nw, a, &cells, &r);
 		if (st != NW_OK) {
 			NwGeo g;
-			nw_geo_init(g, *c.pen, t_l, q_l, kk, band);
+			nw_geo_init(g, *c.pen, t_l, q_l, kk, band, false);
 			c.wc->need_e = max(c.wc->need_e, (unsigned)min((size_t)0xF0000000u, g.ebytes() + 4096));
 			c.wc->need_q = max(c.wc->need_q, (unsigned)q_l + 64u);
 			return ST_OVERFLOW;
@@ -1887,11 +1887,11 @@ __global__ void __launch_bounds__(AL_WARPS * 32) nw_batch_kernel(NwPen pen, KgTI
 		const int32_t *pr = prob + 8 * t;
 		const KgTMeta m = ix.meta[pr[0]];
 		NwStat s = {0, 0, 0, 0, 0, 0};
-		const int st = nw_warp(spen, ix.seq + m.seq_off, qpool + pr[3], pr[6], pr[1], pr[2], pr[4], pr[5], pr[7], nws, &s, &cells);
+		const int st = nw_warp<true>(spen, ix.seq + m.seq_off, qpool + pr[3], pr[6], pr[1], pr[2], pr[4], pr[5], pr[7], nws, &s, &cells);
 		if (st == NW_OK && pr[2] > pr[1] && pr[5] > pr[4]) {
 			NwGeo g;
-			nw_geo_init(g, spen, pr[2] - pr[1], pr[5] - pr[4], pr[6], pr[7]);
-			steps += (unsigned long long)g.Tmax;
+			nw_geo_init(g, spen, pr[2] - pr[1], pr[5] - pr[4], pr[6], pr[7], true);
+			steps += g.C ? (unsigned long long)g.t_len * g.C : (unsigned long long)g.Tmax;
 		}
 		if (lane == 0) {
 			int32_t *o = out + 6 * t;
@@ -1923,7 +1923,7 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 			return -1;
 		}
 		NwGeo g;
-		if (pr[2] > pr[1] && pr[5] > pr[4] && nw_geo_init(g, P.pen, pr[2] - pr[1], pr[5] - pr[4], pr[6], pr[7])) {
+		if (pr[2] > pr[1] && pr[5] > pr[4] && nw_geo_init(g, P.pen, pr[2] - pr[1], pr[5] - pr[4], pr[6], pr[7], true)) {
 			need_e = std::max(need_e, g.ebytes() + 256);
 			need_q = std::max(need_q, pr[5] - pr[4] + 64);
 		}

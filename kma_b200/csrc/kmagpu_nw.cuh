@@ -35,10 +35,11 @@
 
 struct NwPen { int W1, U, MM, M; int d[25]; int d8; };   // d8: every d[] fits a signed byte (per-row table in a register)
 struct NwStat { int score, len, pos, match, tGaps, qGaps; };
-struct NwRow { int D, P; };
+struct alignas(8) NwRow { int D, P; };
 
 struct NwGeo {
 	int t_len, q_len, k, banded, band, a, W, P, s, R, Tmax, NEG, W1, U, rmask, d8;
+	int C;   // row sweep: cells per lane (0: the continuous wavefront)
 	NW_HD int off(int i) const { return banded ? a + i : 0; }
 	NW_HD int jlo(int i) const { int v = banded ? a + i : 0; return v < 0 ? 0 : v; }
 	NW_HD int jhi(int i) const { int v = banded ? a + i + band : q_len - 1; return v < q_len - 1 ? v : q_len - 1; }
@@ -46,14 +47,27 @@ struct NwGeo {
 	NW_HD int bcol(int i) const { return i < 0 ? 0 : (0 < k ? 0 : W1 + i * U); }
 	NW_HD int brow(int j) const { return j < 0 ? 0 : (k == 2 ? 0 : W1 + j * U); }
 	NW_HD size_t eaddr(int i, int j) const {
+		if (C) return (size_t)i * (size_t)(32 * C) + (size_t)(j - off(i));   // row sweep: row-major, 32*C bytes per row
 		const int l = i & 31;
 		return ((size_t)(s * l + P * (i >> 5) + (j - off(i)))) * 32 + (size_t)l;
 	}
-	NW_HD size_t ebytes() const { return (size_t)Tmax * 32; }
+	NW_HD size_t ebytes() const { return C ? (size_t)t_len * (size_t)(32 * C) + 8 : (size_t)Tmax * 32; }
 };
 
 // false: geometry the reference itself never produces (band narrower than the length difference)
-NW_HD bool nw_geo_init(NwGeo &g, const NwPen &pen, int t_len, int q_len, int k, int band) {
+#ifndef NW_RS_MAXC
+#define NW_RS_MAXC 8
+#endif
+#ifndef NW_RS_FULL
+#define NW_RS_FULL 1   // row sweep for full matrices
+#endif
+#ifndef NW_RS_BAND
+#define NW_RS_BAND 1   // row sweep for bands
+#endif
+// rs: the caller's kernel sweeps narrow rows (the stand-alone NW batch kernel). Inside the alignment kernels every
+// variant of the row sweep measured slower than the wavefront (profiles/r01_ab_rowsweep.log: those kernels stall on
+// instruction fetch, and the sweep adds a dozen more loops to them), so they pass false.
+NW_HD bool nw_geo_init(NwGeo &g, const NwPen &pen, int t_len, int q_len, int k, int band, bool rs) {
 	g.t_len = t_len; g.q_len = q_len; g.k = k; g.banded = band != 0;
 	g.W1 = pen.W1; g.U = pen.U;
 	if (band & 1) ++band;   // nw.c:374-376
@@ -75,6 +89,14 @@ NW_HD bool nw_geo_init(NwGeo &g, const NwPen &pen, int t_len, int q_len, int k, 
 	g.R = (t_len + 31) >> 5;
 	g.Tmax = g.s * ((t_len - 1) & 31) + g.P * (g.R - 1) + g.W;
 	g.NEG = (t_len + q_len) * (pen.MM + pen.U + pen.W1);
+	// rows of up to 32 * NW_RS_MAXC cells are swept row by row (nw_rs_*), wider ones run as the wavefront
+	g.C = 0;
+	if (rs && pen.d8 && g.W <= 32 * NW_RS_MAXC && (g.banded ? NW_RS_BAND : NW_RS_FULL)) {
+		int c = (g.W + 31) >> 5;
+		if (c == 5) c = 6;
+		if (c == 7) c = 8;
+		g.C = c;
+	}
 	return true;
 }
 
@@ -198,6 +220,180 @@ NW_HD void nw_lane_step(const NwGeo &g, const NwPen &pen, NwLane &L, const int l
 // lane 0, after the step's stores are visible: fetch what the next step needs from the hand-over buffer
 NW_HD void nw_lane0_prefetch(const NwGeo &g, NwLane &L, const NwRow *hand) {
 	if (L.act && !(L.flags & NWF_ROW0)) { const NwRow v = hand[(L.u + L.joff) & g.rmask]; L.nxD = v.D; L.nxP = v.P; }
+}
+
+// ------------------------------------------------------------------------------------------------ row sweep
+// Rows of up to 32 * NW_RS_MAXC cells (every default band, every short gap between two MEMs) are filled row by row:
+// lane l owns the C consecutive in-row offsets u = l*C .. l*C+C-1 of every row and keeps (D, P) of the previous row's
+// own cells in registers. The vertical and diagonal inputs are then the lane's own registers (one neighbour value
+// per row comes by shuffle); the horizontal run Q(u) = max(D(u-1) + W1, Q(u-1) + U) is a max-plus prefix:
+//   pass 1  per cell: P (open / extend, flag 32), diag + substitution; H = max(P, diag) is what the cell is worth
+//           without its horizontal run; the lane folds its cells into A = the run leaving the chunk;
+//   scan    5 shuffle rounds of a prefix maximum over the lanes give every lane the exact Q of its first cell,
+//           because D(u-1) = max(H(u-1), Q(u-1)) makes Q(u) = max(H(u-1) + W1, Q(u-1) + max(W1, U));
+//   pass 2  per cell, sequentially inside the lane: Q open / extend (flag 16), the reference's tie order among
+//           Q, P and the diagonal, the traceback byte. The first cell's open / extend flag needs (D, Q) of the left
+//           lane's last cell: two shuffles after the pass and a fix of that byte.
+// The tie order of nw.c:166-212 in closed form: the vertical run wins against the horizontal one iff
+// P >= Q + [P opened here]; the winner's code is 5 - [P opened] or 3 - [Q opened]; the diagonal wins iff it is >=.
+#define NW_NINF (-0x3f000000)   // below every value a valid cell can hold, far from overflow
+
+template <int C> struct NwRsLane {
+	int pD[C], pP[C];          // previous row's own cells; between the passes: diag + substitution and P of this row
+	int qs[C];                 // 8 * query base of the own cells' columns
+	int colBest, colBestI;     // as NwLane
+};
+
+struct NwRsRow {
+	int ua, ub, border, track, gen, Dleft0, Ddiag0, Qstart;
+	unsigned lo, hi;           // d[tn][0..3] as signed bytes, d[tn][4]
+};
+
+NW_HD unsigned nw_fsr(unsigned lo, unsigned hi, unsigned sh) {   // (hi:lo) >> sh, sh <= 32
+#if defined(__CUDA_ARCH__)
+	return __funnelshift_rc(lo, hi, sh);
+#else
+	return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (sh > 32 ? 32 : sh));
+#endif
+}
+
+NW_HD int nw_max(int a, int b) { return a < b ? b : a; }
+
+// the per-template-base substitution rows, 8 bytes each (5 entries), written once per call
+NW_HD unsigned long long nw_rs_tab(const NwPen &pen, int tn) {
+	unsigned long long r = 0;
+	for (int b = 0; b < 4; ++b) r |= (unsigned long long)(unsigned char)pen.d[tn * 5 + b] << (8 * b);
+	return r | (unsigned long long)(unsigned char)pen.d[tn * 5 + 4] << 32;
+}
+
+// query base (times 8) under in-row offset u of row i; 0 outside the query
+template <bool BANDED> NW_HD int nw_rs_q8(const NwGeo &g, int i, int u, const uint8_t *qlast) {
+	const int j = BANDED ? u + g.a + i : u;
+	return (j >= 0 && j < g.q_len) ? (int)qlast[-j] << 3 : 0;
+}
+
+template <int C, bool BANDED> NW_HD void nw_rs_init(const NwGeo &g, NwRsLane<C> &L, int lane, const uint8_t *qlast) {
+	for (int c = 0; c < C; ++c) {
+		const int u = lane * C + c;
+		const int j = BANDED ? u + g.a - 1 : u;   // column the cell of row -1 (the analytic boundary row) stands for
+		L.pD[c] = g.brow(j); L.pP[c] = g.NEG;
+		L.qs[c] = nw_rs_q8<BANDED>(g, 0, u, qlast);
+	}
+	L.colBest = g.NEG; L.colBestI = 0x7fffffff;
+}
+
+NW_HD void nw_rs_row(const NwGeo &g, NwRsRow &R, int i, unsigned long long tabrow) {
+	const int jl = g.jlo(i), jh = g.jhi(i), off = g.off(i);
+	R.ua = jl - off; R.ub = jh - off;
+	R.border = jl == 0;
+	R.gen = R.ua > 0;   // the row starts inside the lanes' range (first rows of a band): the general per-cell tests run
+	R.track = g.k < 0 && jh == g.q_len - 1;
+	R.Dleft0 = jl == 0 ? g.bcol(i) : g.NEG;
+	R.Ddiag0 = g.bcol(i - 1);
+	R.Qstart = nw_max(R.Dleft0 + g.W1, g.NEG + g.U);
+	R.lo = (unsigned)tabrow; R.hi = (unsigned)(tabrow >> 32);
+}
+
+// nbD / nbP: banded -- (D, P) of the right lane's first cell; full -- D of the left lane's last cell (previous row).
+// Returns A, the horizontal run leaving the chunk as far as the lane's own cells decide it. Cells right of the row's
+// last one compute on whatever they hold: nothing flows from them into a valid cell.
+template <int C, bool BANDED>
+NW_HD int nw_rs_pass1(const NwGeo &g, NwRsLane<C> &L, int lane, const NwRsRow &R, int nbD, int nbP, int Ue, int *fP) {
+	const int u0 = lane * C;
+	int dprev = nbD, r = NW_NINF;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int c = 0; c < C; ++c) {
+		const int u = u0 + c;
+		int upD, upP, dg;
+		if (BANDED) {
+			dg = L.pD[c];
+			upD = c + 1 < C ? L.pD[c + 1 < C ? c + 1 : c] : nbD;
+			upP = c + 1 < C ? L.pP[c + 1 < C ? c + 1 : c] : nbP;
+		} else {
+			dg = dprev; upD = L.pD[c]; upP = L.pP[c]; dprev = upD;
+		}
+		if ((c == 0 || (BANDED && R.gen)) && u == R.ua) {   // the row's first cell
+			if (R.border) dg = R.Ddiag0;
+			r = R.Qstart;
+		}
+		dg += (int)(signed char)nw_fsr(R.lo, R.hi, (unsigned)L.qs[c]);
+		const int Po = upD + g.W1, Pe = upP + g.U;
+		const bool edge = BANDED && u == R.ub;   // the row's last cell has no vertical move (nw.c:1076-1102)
+		fP[c] = (!edge && Po >= Pe) ? 1 : 0;
+		const int P = edge ? g.NEG : nw_max(Po, Pe);
+		L.pD[c] = dg; L.pP[c] = P;
+		int H = nw_max(P, dg);
+		if (BANDED && R.gen && u < R.ua) H = NW_NINF;
+		r = nw_max(H + g.W1, r + Ue);
+	}
+	return r;
+}
+
+// Qfirst: the exact Q of the lane's first cell. e[]: traceback bytes (e[0] lacks the first cell's Q-opened flag).
+template <int C, bool BANDED>
+NW_HD void nw_rs_pass2(const NwGeo &g, NwRsLane<C> &L, int lane, const NwRsRow &R, int Qfirst, const int *fP, int *e, int *Dlast,
+                       int *Qlast) {
+	const int u0 = lane * C;
+	int Dl = 0, Ql = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int c = 0; c < C; ++c) {
+		const int u = u0 + c;
+		int Q, cq, fq;
+		if (c == 0) { Q = u == R.ua ? R.Qstart : Qfirst; cq = 3; fq = 0; }
+		else {
+			int Qo = Dl + g.W1, Qe = Ql + g.U;
+			if (BANDED && R.gen && u == R.ua) { Qo = R.Dleft0 + g.W1; Qe = g.NEG + g.U; }
+			const bool o = Qo >= Qe;
+			Q = o ? Qo : Qe; cq = o ? 2 : 3; fq = o ? 16 : 0;
+		}
+		const int P = L.pP[c], dg = L.pD[c];
+		const bool edge = BANDED && u == R.ub;
+		const bool pw = !edge && P >= Q + fP[c];
+		const int D1 = pw ? P : Q;
+		int ec = pw ? 5 - fP[c] : cq;
+		if (D1 <= dg) ec = 1;
+		e[c] = ec + fq + (fP[c] << 5);
+		const int D = nw_max(D1, dg);
+		L.pD[c] = D;
+		Dl = D; Ql = Q;
+	}
+	*Dlast = Dl; *Qlast = Ql;
+}
+
+// the first cell's Q-opened flag once (D, Q) of the cell left of it are known
+template <int C> NW_HD int nw_rs_fix0(const NwGeo &g, int lane, const NwRsRow &R, int e0, int Dl, int Ql) {
+	if (lane * C == R.ua) { Dl = R.Dleft0; Ql = g.NEG; }
+	if (Dl + g.W1 >= Ql + g.U) {
+		if ((e0 & 7) == 3) e0 = (e0 & ~7) | 2;
+		e0 |= 16;
+	}
+	return e0;
+}
+
+// after the row: the row's last cell competes for the start cell (k < 0); next row's query bases
+template <int C, bool BANDED>
+NW_HD void nw_rs_rowend(const NwGeo &g, NwRsLane<C> &L, int lane, const NwRsRow &R, int i, int q8next) {
+	if (R.track) {
+		for (int c = 0; c < C; ++c)
+			if (lane * C + c == R.ub && L.colBest < L.pD[c]) { L.colBest = L.pD[c]; L.colBestI = i; }
+	}
+	if (BANDED) {
+		for (int c = 0; c + 1 < C; ++c) L.qs[c] = L.qs[c + 1];
+		L.qs[C - 1] = q8next;
+	}
+}
+
+// the last row's D by query column (what nw_start_cell reads)
+template <int C, bool BANDED> NW_HD void nw_rs_lastrow(const NwGeo &g, const NwRsLane<C> &L, int lane, int *lastD) {
+	const int i = g.t_len - 1, off = g.off(i), ua = g.jlo(i) - off, ub = g.jhi(i) - off;
+	for (int c = 0; c < C; ++c) {
+		const int u = lane * C + c;
+		if (u >= ua && u <= ub) lastD[u + off] = L.pD[c];
+	}
 }
 
 // traceback byte at (m, qpos) in reference coordinates, including the analytic boundary row / column codes
@@ -338,7 +534,84 @@ __device__ __forceinline__ void nw_walk_warp(const NwGeo &g, const uint8_t *E, i
 	}
 }
 
-// All 32 lanes call with identical arguments; every lane returns the same result.
+// Row sweep of one problem: fills E (row-major, 32*C bytes per row) and lastD, leaves the lane's column maximum.
+template <int C, bool BANDED>
+__device__ __noinline__ void nw_rs_fill(const NwGeo &gin, const uint64_t *__restrict__ tseq, int t_s, const uint8_t *q,
+                                        const unsigned long long *tab, uint8_t *E, int *lastD, int *cbo, int *cio) {
+	const NwGeo g = gin;   // by value: the traceback stores below must not force reloads of the geometry
+	const int lane = threadIdx.x & 31;
+	const unsigned full = 0xffffffffu;
+	const uint8_t *qlast = q + g.q_len - 1;
+	NwRsLane<C> L;
+	nw_rs_init<C, BANDED>(g, L, lane, qlast);
+	const int Ue = g.W1 > g.U ? g.W1 : g.U, lstep = lane * C * Ue;
+	uint8_t *Erow = E + lane * C;
+	int tpos = t_s + g.t_len - 1;
+	for (int i = 0; i < g.t_len; ++i, Erow += 32 * C, --tpos) {
+		NwRsRow R;
+		nw_rs_row(g, R, i, tab[nw_nuc(tseq, tpos)]);
+		int q8n = 0;
+		if (BANDED) q8n = nw_rs_q8<true>(g, i + 1, lane * C + C - 1, qlast);   // next row's new column, used at the row's end
+		int nbD, nbP = 0;
+		if (BANDED) { nbD = __shfl_down_sync(full, L.pD[0], 1); nbP = __shfl_down_sync(full, L.pP[0], 1); }
+		else nbD = __shfl_up_sync(full, L.pD[C - 1], 1);
+		int fP[C];
+		int B = nw_rs_pass1<C, BANDED>(g, L, lane, R, nbD, nbP, Ue, fP) - lstep;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) B = max(B, __shfl_up_sync(full, B, o));   // lanes below o get their own value back
+		int Qf = __shfl_up_sync(full, B + lstep, 1);
+		if (lane == 0) Qf = NW_NINF;
+		int e[C], Dlast, Qlast;
+		nw_rs_pass2<C, BANDED>(g, L, lane, R, Qf, fP, e, &Dlast, &Qlast);
+		const int Dl = __shfl_up_sync(full, Dlast, 1), Ql = __shfl_up_sync(full, Qlast, 1);
+		e[0] = nw_rs_fix0<C>(g, lane, R, e[0], Dl, Ql);
+		if (C == 1) Erow[0] = (uint8_t)e[0];
+		else if (C == 2) *(uint16_t *)Erow = (uint16_t)(e[0] | e[1] << 8);
+		else if (C == 3) { Erow[0] = (uint8_t)e[0]; Erow[1] = (uint8_t)e[1]; Erow[2] = (uint8_t)e[2]; }
+		else if (C == 4) *(uint32_t *)Erow = (uint32_t)(e[0] | e[1] << 8 | e[2] << 16 | e[3] << 24);
+		else if (C == 6) {
+			((uint16_t *)Erow)[0] = (uint16_t)(e[0] | e[1] << 8);
+			((uint16_t *)Erow)[1] = (uint16_t)(e[2 % C] | e[3 % C] << 8);
+			((uint16_t *)Erow)[2] = (uint16_t)(e[4 % C] | e[5 % C] << 8);
+		} else {
+			uint2 w;
+			w.x = (uint32_t)(e[0] | e[1 % C] << 8 | e[2 % C] << 16 | e[3 % C] << 24);
+			w.y = (uint32_t)(e[4 % C] | e[5 % C] << 8 | e[6 % C] << 16 | e[7 % C] << 24);
+			*(uint2 *)Erow = w;
+		}
+		nw_rs_rowend<C, BANDED>(g, L, lane, R, i, q8n);
+	}
+	nw_rs_lastrow<C, BANDED>(g, L, lane, lastD);
+	*cbo = L.colBest; *cio = L.colBestI;
+}
+
+template <bool BANDED>
+__device__ __forceinline__ void nw_rs_dispatch(const NwGeo &g, const uint64_t *__restrict__ tseq, int t_s, const uint8_t *q,
+                                               const unsigned long long *tab, uint8_t *E, int *lastD, int *cb, int *ci) {
+	if (BANDED ? !NW_RS_BAND : !NW_RS_FULL) return;
+	switch (g.C) {
+	case 1: nw_rs_fill<1, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci); break;
+#if NW_RS_MAXC >= 2
+	case 2: nw_rs_fill<2, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci); break;
+#endif
+#if NW_RS_MAXC >= 3
+	case 3: nw_rs_fill<3, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci); break;
+#endif
+#if NW_RS_MAXC >= 4
+	case 4: nw_rs_fill<4, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci); break;
+#endif
+#if NW_RS_MAXC >= 6
+	case 6: nw_rs_fill<6, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci); break;
+#endif
+#if NW_RS_MAXC >= 8
+	default: nw_rs_fill<8, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci); break;
+#endif
+	}
+}
+
+// All 32 lanes call with identical arguments; every lane returns the same result. RS: rows of up to 32 * NW_RS_MAXC
+// cells run as the row sweep.
+template <bool RS>
 __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict__ tseq, const uint8_t *query, int k, int t_s,
                                     int t_e, int q_s, int q_e, int band, const NwScratch &ws, NwStat *out,
                                     unsigned long long *cells, const NwRows *rows = nullptr) {
@@ -379,14 +652,25 @@ __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict
 	}
 #endif
 	NwGeo g;
-	if (!nw_geo_init(g, pen, t_len, q_len, k, band)) return NW_BAD_BAND;
+	if (!nw_geo_init(g, pen, t_len, q_len, k, band, RS)) return NW_BAD_BAND;
 	if (g.ebytes() > ws.e_cap || q_len + 1 > ws.q_cap) return NW_TOO_BIG;
 	if (cells) *cells += (unsigned long long)t_len * (unsigned long long)(g.banded ? g.band + 1 : q_len);
 	const uint8_t *q = query + q_s;
-	NwRow *hand = g.rmask == NW_RING - 1 ? ws.ring : ws.rowbuf;
-	NwLane L;
-	nw_lane_init(g, pen, L, lane, tseq, t_s, q);
-	{
+	const uint8_t *E = ws.E;
+	int cb, ci;
+	if (RS && g.C) {   // row sweep; the substitution rows go to the (otherwise unused) shared-memory ring
+		unsigned long long *tab = (unsigned long long *)ws.ring;
+		__syncwarp();
+		if (lane < 5) tab[lane] = nw_rs_tab(pen, lane);
+		__syncwarp();
+		uint8_t *E8 = (uint8_t *)(((uintptr_t)ws.E + 7) & ~(uintptr_t)7);
+		if (g.banded) nw_rs_dispatch<true>(g, tseq, t_s, q, tab, E8, ws.lastD, &cb, &ci);
+		else nw_rs_dispatch<false>(g, tseq, t_s, q, tab, E8, ws.lastD, &cb, &ci);
+		E = E8;
+	} else {
+		NwRow *hand = g.rmask == NW_RING - 1 ? ws.ring : ws.rowbuf;
+		NwLane L;
+		nw_lane_init(g, pen, L, lane, tseq, t_s, q);
 		const uint8_t *qlast = q + q_len - 1;
 		uint8_t *Estep = ws.E;
 		int *lastD = ws.lastD;
@@ -396,10 +680,10 @@ __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict
 			__syncwarp();
 			if (lane == 0) nw_lane0_prefetch(g, L, hand);
 		}
+		cb = L.colBest; ci = L.colBestI;
 	}
 	__syncwarp();
 	// column maximum: largest D, ties -> smallest i (first in fill order)
-	int cb = L.colBest, ci = L.colBestI;
 #pragma unroll
 	for (int o = 16; o; o >>= 1) {
 		const int ov = __shfl_xor_sync(0xffffffffu, cb, o), oi = __shfl_xor_sync(0xffffffffu, ci, o);
@@ -421,7 +705,7 @@ __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict
 	}
 	int best_m, best_q, score;
 	nw_start_cell(g, cb, ci, ws.lastD, rb, rq, &best_m, &best_q, &score);
-	nw_walk_warp(g, ws.E, best_m, best_q, s, rows, tseq, t_s, q);
+	nw_walk_warp(g, E, best_m, best_q, s, rows, tseq, t_s, q);
 	__syncwarp();
 	s.score = score; s.pos = 0;
 	*out = s;

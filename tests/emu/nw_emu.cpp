@@ -7,8 +7,71 @@
 #include <vector>
 #include "../../kma_b200/csrc/kmagpu_nw.cuh"
 
-extern "C" int emu_nw(const int *pen29, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s,
-                      int q_e, int band, int order, int d8, int *out6, long long *steps) {
+// Row sweep (nw_rs_*): the phases of one row run for all 32 lanes in turn, the shuffles between them are array reads.
+template <int C, bool BANDED>
+static int emu_rs_fill(const NwGeo &g, const NwPen &pen, const uint64_t *tseq, int t_s, const uint8_t *q, uint8_t *E, int *lastD,
+                       int *cbo, int *cio) {
+	NwRsLane<C> L[32];
+	unsigned long long tab[5];
+	for (int tn = 0; tn < 5; ++tn) tab[tn] = nw_rs_tab(pen, tn);
+	const uint8_t *qlast = q + g.q_len - 1;
+	for (int l = 0; l < 32; ++l) nw_rs_init<C, BANDED>(g, L[l], l, qlast);
+	const int Ue = g.W1 > g.U ? g.W1 : g.U, step = C * Ue;
+	int bad = 0;
+	for (int i = 0; i < g.t_len; ++i) {
+		NwRsRow R;
+		nw_rs_row(g, R, i, tab[nw_nuc(tseq, t_s + g.t_len - 1 - i)]);
+		int nbD[32], nbP[32], B[32], old[32], Qf[32], e[32][C], Dlast[32], Qlast[32], fP[32][C];
+		for (int l = 0; l < 32; ++l) {
+			if (BANDED) { const int s = l < 31 ? l + 1 : 31; nbD[l] = L[s].pD[0]; nbP[l] = L[s].pP[0]; }
+			else { const int s = l ? l - 1 : 0; nbD[l] = L[s].pD[C - 1]; nbP[l] = 0; }
+		}
+		for (int l = 0; l < 32; ++l) B[l] = nw_rs_pass1<C, BANDED>(g, L[l], l, R, nbD[l], nbP[l], Ue, fP[l]) - l * step;
+		for (int o = 1; o < 32; o <<= 1) {
+			memcpy(old, B, sizeof(B));
+			for (int l = o; l < 32; ++l) if (old[l - o] > B[l]) B[l] = old[l - o];
+		}
+		for (int l = 0; l < 32; ++l) Qf[l] = l ? B[l - 1] + (l - 1) * step : NW_NINF;
+		for (int l = 0; l < 32; ++l) nw_rs_pass2<C, BANDED>(g, L[l], l, R, Qf[l], fP[l], e[l], &Dlast[l], &Qlast[l]);
+		for (int l = 0; l < 32; ++l) {
+			const int s = l ? l - 1 : 0;
+			const int u = l * C;
+			if (u > R.ua && u <= R.ub) {   // the scan must reproduce the sequential recurrence
+				const int a = Dlast[s] + g.W1, b = Qlast[s] + g.U;
+				if (Qf[l] != (a < b ? b : a)) ++bad;
+			}
+			e[l][0] = nw_rs_fix0<C>(g, l, R, e[l][0], Dlast[s], Qlast[s]);
+		}
+		for (int l = 0; l < 32; ++l)
+			for (int c = 0; c < C; ++c) E[(size_t)i * (32 * C) + l * C + c] = (uint8_t)e[l][c];
+		for (int l = 0; l < 32; ++l) nw_rs_rowend<C, BANDED>(g, L[l], l, R, i, nw_rs_q8<BANDED>(g, i + 1, l * C + C - 1, qlast));
+	}
+	for (int l = 0; l < 32; ++l) nw_rs_lastrow<C, BANDED>(g, L[l], l, lastD);
+	int cb = g.NEG, ci = 0x7fffffff;
+	for (int l = 0; l < 32; ++l)
+		if (L[l].colBest > cb || (L[l].colBest == cb && L[l].colBestI < ci)) { cb = L[l].colBest; ci = L[l].colBestI; }
+	*cbo = cb; *cio = ci;
+	return bad;
+}
+
+template <bool BANDED>
+static int emu_rs_dispatch(const NwGeo &g, const NwPen &pen, const uint64_t *tseq, int t_s, const uint8_t *q, uint8_t *E, int *lastD,
+                           int *cb, int *ci) {
+	switch (g.C) {
+	case 1: return emu_rs_fill<1, BANDED>(g, pen, tseq, t_s, q, E, lastD, cb, ci);
+	case 2: return emu_rs_fill<2, BANDED>(g, pen, tseq, t_s, q, E, lastD, cb, ci);
+	case 3: return emu_rs_fill<3, BANDED>(g, pen, tseq, t_s, q, E, lastD, cb, ci);
+	case 4: return emu_rs_fill<4, BANDED>(g, pen, tseq, t_s, q, E, lastD, cb, ci);
+	case 6: return emu_rs_fill<6, BANDED>(g, pen, tseq, t_s, q, E, lastD, cb, ci);
+	case 8: return emu_rs_fill<8, BANDED>(g, pen, tseq, t_s, q, E, lastD, cb, ci);
+	}
+	return -1;
+}
+
+// rs = 1: rows of up to 256 cells run as the row sweep (what the kernel does), rs = 0: the wavefront for every size.
+// emap (optional, t_len * q_len bytes): the traceback byte of every cell inside the matrix / band, 0xFF outside.
+extern "C" int emu_nw2(const int *pen29, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s,
+                       int q_e, int band, int order, int d8, int rs, int *out6, long long *steps, uint8_t *emap) {
 	NwPen pen;
 	pen.W1 = pen29[0]; pen.U = pen29[1]; pen.MM = pen29[2]; pen.M = pen29[3];
 	memcpy(pen.d, pen29 + 4, 100);
@@ -17,11 +80,18 @@ extern "C" int emu_nw(const int *pen29, const uint64_t *tseq, const uint8_t *que
 	NwStat s;
 	if (nw_trivial(pen, t_len, q_len, s)) { memcpy(out6, &s, 24); return 0; }
 	NwGeo g;
-	if (!nw_geo_init(g, pen, t_len, q_len, k, band)) return 2;
+	if (!nw_geo_init(g, pen, t_len, q_len, k, band, rs != 0)) return 2;
 	std::vector<uint8_t> E(g.ebytes(), 0xEE);
 	std::vector<NwRow> rowbuf(q_len + NW_RING + 1, NwRow{0x3fffffff, 0x3fffffff});
 	std::vector<int> lastD(q_len + 1, 0x3fffffff);
 	NwLane L[32];
+	int cb = g.NEG, ci = 0x7fffffff;
+	if (g.C) {
+		const int bad = g.banded ? emu_rs_dispatch<true>(g, pen, tseq, t_s, query + q_s, E.data(), lastD.data(), &cb, &ci)
+		                         : emu_rs_dispatch<false>(g, pen, tseq, t_s, query + q_s, E.data(), lastD.data(), &cb, &ci);
+		if (bad) return 3;
+		if (steps) *steps += (long long)g.t_len * g.C;
+	} else {
 	for (int l = 0; l < 32; ++l) nw_lane_init(g, pen, L[l], l, tseq, t_s, query + q_s);
 	for (int T = 0; T < g.Tmax; ++T) {
 		int aD[32], aP[32];
@@ -33,9 +103,13 @@ extern "C" int emu_nw(const int *pen29, const uint64_t *tseq, const uint8_t *que
 		nw_lane0_prefetch(g, L[0], rowbuf.data());
 	}
 	if (steps) *steps += g.Tmax;
-	int cb = g.NEG, ci = 0x7fffffff;
 	for (int l = 0; l < 32; ++l)
 		if (L[l].colBest > cb || (L[l].colBest == cb && L[l].colBestI < ci)) { cb = L[l].colBest; ci = L[l].colBestI; }
+	}
+	if (emap)
+		for (int i = 0; i < t_len; ++i)
+			for (int j = 0; j < q_len; ++j)
+				emap[(size_t)i * q_len + j] = (j >= g.jlo(i) && j <= g.jhi(i)) ? E[g.eaddr(i, j)] : 0xFF;
 	int rb = g.NEG, rq = -1;
 	if (k == -2) {
 		int qlo, qhi;
@@ -48,4 +122,9 @@ extern "C" int emu_nw(const int *pen29, const uint64_t *tseq, const uint8_t *que
 	s.score = sc; s.pos = 0;
 	memcpy(out6, &s, 24);
 	return 0;
+}
+
+extern "C" int emu_nw(const int *pen29, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s,
+                      int q_e, int band, int order, int d8, int *out6, long long *steps) {
+	return emu_nw2(pen29, tseq, query, k, t_s, t_e, q_s, q_e, band, order, d8, 1, out6, steps, nullptr);
 }

@@ -65,13 +65,22 @@ def run_both(emu, t, q, k, t_s, t_e, q_s, q_e, band):
     p = list(pen)
     pen29 = (C.c_int * 29)(p[3], p[2], p[1], p[0], *p[7:32])
     res = []
-    for order, d8 in ((0, 1), (1, 1), (0, 0)):
+    t_len, q_len = t_e - t_s, q_e - q_s
+    maps = []
+    # rs = 1: the row sweep for rows of up to 256 cells (what the kernel runs); rs = 0: the wavefront for every size
+    for order, d8, rs in ((0, 1, 1), (0, 1, 0), (1, 1, 0), (0, 0, 0)):
         got = (C.c_int * 6)()
-        rc = emu.emu_nw(pen29, tw.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), k, t_s, t_e, q_s, q_e, band,
-                        order, d8, got, None)
-        assert rc == 0
+        emap = np.zeros(max(1, t_len * q_len), dtype=np.uint8)
+        rc = emu.emu_nw2(pen29, tw.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), k, t_s, t_e, q_s, q_e, band,
+                         order, d8, rs, got, None, emap.ctypes.data_as(C.c_void_p))
+        assert rc == 0, (rc, k, t_len, q_len, band, rs)
         res.append(list(got))
-    assert res[0] == res[1] == res[2], "lane order / table form changes the result: same-step hazard"
+        maps.append(emap)
+    assert res[1] == res[2] == res[3], "lane order / table form changes the result: same-step hazard"
+    assert res[0] == res[1], ("row sweep != wavefront", k, t_len, q_len, band, res[0], res[1])
+    if t_len and q_len:
+        assert np.array_equal(maps[0], maps[1]), ("traceback bytes of the row sweep differ", k, t_len, q_len, band,
+                                                  np.argwhere(maps[0] != maps[1])[:5])
     return list(want), res[0]
 
 
