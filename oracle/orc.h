@@ -53,6 +53,9 @@ int64_t orc_conclave_stream(const int32_t *template_lengths, int DB_size, const 
                             uint8_t *out, size_t cap, uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts);
 int orc_memscore_stream(const int32_t *lengths, int DB_size, const uint8_t *in, size_t in_bytes, uint8_t **frag_out, size_t *frag_bytes,
                         uint64_t *as, uint64_t *uas);
+int orc_consensus(const uint16_t *counts, const uint64_t *seq, int t_len, int bcd, int caller, int sig, double support, double evalue,
+                  uint8_t *t, uint8_t *s, uint8_t *q, uint64_t *stats);
+double orc_chi2_min(double evalue);
 void orc_free(void *p);
 void orc_nw(const orc_params *p, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s, int q_e,
             int band, int *out6);

@@ -269,10 +269,73 @@ static int memscore_main(int argc, char **argv) {
 	return 0;
 }
 
+/* -consensus db mat.bin out.bin [-bcd N] [-evalue X] [-caller 0..4] [-sig 0..2] [-support X]: the reference's own
+ * callConsensus (assembly.c:1499-1631) on base-count matrices holding template nodes only. mat.bin: per template
+ * int32 {template, t_len, nodes} + uint16 counts[t_len][6] (what -trace -mat writes); out.bin: per template
+ * int32 {template, t_len}, u64 {depth, depthVar, len, aln_len, cover}, then the t, s, q rows (t_len bytes each). */
+static int consensus_main(int argc, char **argv) {
+	if (argc < 5) { fprintf(stderr, "usage: ref_aln -consensus db mat.bin out.bin [options]\n"); return 2; }
+	int bcd = 1, caller = 0, sig = 0;
+	double evalue = 0.05, support = 0.0;
+	for (int a = 5; a + 1 < argc; a += 2) {
+		if (!strcmp(argv[a], "-bcd")) bcd = atoi(argv[a + 1]);
+		else if (!strcmp(argv[a], "-evalue")) evalue = strtod(argv[a + 1], 0);
+		else if (!strcmp(argv[a], "-caller")) caller = atoi(argv[a + 1]);
+		else if (!strcmp(argv[a], "-sig")) sig = atoi(argv[a + 1]);
+		else if (!strcmp(argv[a], "-support")) support = strtod(argv[a + 1], 0);
+	}
+	/* the bindings kma.c:743-766 makes for -bc / -bc90 / -bcg / -bcNano (and the two ref callers) */
+	baseCall = caller == 0 ? &baseCaller : caller == 1 ? &orgBaseCaller : caller == 2 ? &refCaller : caller == 3 ? &nanoCaller : &refNanoCaller;
+	significantBase = sig == 0 ? &significantNuc : sig == 1 ? &significantAnd90Nuc : &significantAndSupport;
+	if (sig == 2) significantAndSupport(0, 0, support);
+	int *template_lengths; long unsigned *as, *uas;
+	char *p2 = malloc(strlen(argv[2]) + 64); strcpy(p2, argv[2]);
+	int DB_size = load_DBs_KMA(p2, &as, &uas, &template_lengths, 0);
+	char path[4096];
+	snprintf(path, sizeof(path), "%s.seq.b", argv[2]);
+	FILE *sf = fopen(path, "rb");
+	if (!sf) { perror(path); return 1; }
+	long *seq_indexes = malloc((DB_size + 1) * sizeof(long));
+	seq_indexes[0] = 0; seq_indexes[1] = 0;
+	for (int i = 2; i < DB_size; ++i) seq_indexes[i] = seq_indexes[i - 1] + ((template_lengths[i - 1] >> 5) + 1) * sizeof(long unsigned);
+	FILE *in = fopen(argv[3], "rb"), *out = fopen(argv[4], "wb");
+	if (!in || !out) { perror("open"); return 1; }
+	int hd[3];
+	while (fread(hd, 4, 3, in) == 3) {
+		const int t = hd[0], t_len = hd[1];
+		if (t <= 0 || t >= DB_size || t_len != template_lengths[t]) { fprintf(stderr, "matrix does not match the database\n"); return 1; }
+		AssemInfo m;
+		m.len = t_len; m.size = t_len << 1;
+		m.assmb = malloc(m.size * sizeof(Assembly));
+		for (int i = 0; i < t_len; ++i) {
+			if (fread(m.assmb[i].counts, 2, 6, in) != 6) return 1;
+			m.assmb[i].next = i + 1;
+		}
+		m.assmb[t_len - 1].next = 0;
+		const int words = (t_len >> 5) + 1;
+		long unsigned *seq = calloc(words + 1, sizeof(long unsigned));
+		fseek(sf, seq_indexes[t], SEEK_SET);
+		if (fread(seq, sizeof(long unsigned), words, sf) != (size_t)words) { fprintf(stderr, "short read of %s\n", path); return 1; }
+		Assem aa;
+		memset(&aa, 0, sizeof(aa));
+		aa.size = (t_len + 1) << 1;
+		aa.t = malloc(aa.size); aa.s = malloc(aa.size); aa.q = malloc(aa.size);
+		callConsensus(&m, &aa, seq, t_len, bcd, evalue, 1);
+		int oh[2] = {t, t_len};
+		unsigned long long st[5] = {aa.depth, aa.depthVar, aa.len, aa.aln_len, aa.cover};
+		fwrite(oh, 4, 2, out); fwrite(st, 8, 5, out);
+		fwrite(aa.t, 1, t_len, out); fwrite(aa.s, 1, t_len, out); fwrite(aa.q, 1, t_len, out);
+		free(aa.t); free(aa.s); free(aa.q); free(seq); free(m.assmb);
+	}
+	fclose(in); fclose(out);
+	return 0;
+}
+
 int main(int argc, char **argv) {
 	if (argc >= 5 && !strcmp(argv[1], "-memscore")) return memscore_main(argc, argv);
 	if (argc >= 5 && !strcmp(argv[1], "-conclave")) return conclave_main(argc, argv);
 	if (argc >= 5 && !strcmp(argv[1], "-trace")) return trace_main(argc, argv);
+	if (argc >= 5 && !strcmp(argv[1], "-consensus")) return consensus_main(argc, argv);
 	if (argc < 5) { fprintf(stderr, "usage: ref_aln db s2.bin frag_raw.out scores.out [cand.out] [-1t1]\n"); return 2; }
 	int one2one = 0, exhaustive = 0, ts = 0;
 	const char *cand_path = 0;

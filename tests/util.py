@@ -367,3 +367,96 @@ def oracle_memscore(db_prefix: str, s2) -> tuple:
     frag = C.string_at(fo, fb.value) if fb.value else b""
     L.orc_free(fo)
     return frag, a, u
+
+
+# ---------------------------------------------------------------- consensus call of the assembly pass
+
+def template_bases(db_prefix: str, t: int) -> np.ndarray:
+    """bases 0-3 of template t from .seq.b / .length.b"""
+    raw = np.fromfile(db_prefix + ".length.b", dtype=np.int32)
+    lengths = raw[1:]
+    off = 0
+    for i in range(1, t):
+        off += (int(lengths[i]) >> 5) + 1
+    words = np.fromfile(db_prefix + ".seq.b", dtype=np.uint64, count=(int(lengths[t]) >> 5) + 1, offset=8 * off)
+    pos = np.arange(int(lengths[t]))
+    return ((words[pos >> 5] << ((pos & 31).astype(np.uint64) << np.uint64(1))) >> np.uint64(62)).astype(np.uint8)
+
+
+def random_count_matrix(rng, tb: np.ndarray) -> np.ndarray:
+    """uint16 [t_len, 6] base counts around template bases tb with every regime callConsensus distinguishes: no depth,
+    depth below -bcd, ties, a best base short of half the depth, gap majorities, borderline significance, saturation."""
+    n = len(tb)
+    m = np.zeros((n, 6), dtype=np.int64)
+    regime = rng.integers(0, 10, size=n)
+    depth = np.select([regime == 0, regime <= 2, regime <= 6, regime <= 8], [0, rng.integers(1, 6, size=n), rng.integers(4, 80, size=n),
+                      rng.integers(80, 6000, size=n)], default=rng.integers(60000, 70000, size=n))
+    for i in range(n):
+        d = int(depth[i])
+        if d == 0:
+            continue
+        kind = rng.integers(0, 8)
+        if kind <= 2:      # clean majority for the template base
+            p = np.full(6, 0.01); p[tb[i]] = 1.0
+        elif kind == 3:    # a variant base with errors
+            p = np.full(6, 0.03); p[(tb[i] + 1 + rng.integers(0, 3)) % 4] = 1.0
+        elif kind == 4:    # two competing bases
+            p = np.full(6, 0.02); a, b = rng.choice(6, size=2, replace=False); p[a] = 1.0; p[b] = rng.choice([1.0, 0.8, 0.5])
+        elif kind == 5:    # deletion majority
+            p = np.full(6, 0.05); p[5] = 1.0; p[tb[i]] = rng.choice([0.0, 0.3, 0.9])
+        elif kind == 6:    # flat
+            p = np.ones(6)
+        else:              # N-rich
+            p = np.full(6, 0.1); p[4] = 1.0
+        m[i] = rng.multinomial(d, p / p.sum())
+        if kind == 4 and rng.integers(0, 2):
+            m[i, b] = m[i, a]   # exact tie
+    return np.minimum(m, 65535).astype(np.uint16)
+
+
+def ref_consensus(db_prefix: str, mats: dict, tmp: str, bcd=1, evalue=0.05, caller=0, sig=0, support=0.0):
+    """ground truth: the reference's own callConsensus (ref_harness -consensus). mats: {template: uint16 [t_len, 6]}.
+    Returns {template: (t, s, q bytes, uint64 stats[5] = depth, depthVar, len, aln_len, cover)}."""
+    p = os.path.join(tmp, "cmat.bin")
+    with open(p, "wb") as f:
+        for t, m in mats.items():
+            f.write(np.array([t, len(m), len(m)], dtype=np.int32).tobytes())
+            f.write(np.ascontiguousarray(m, dtype=np.uint16).tobytes())
+    o = os.path.join(tmp, "cons.out")
+    r = subprocess.run([REF_ALN, "-consensus", db_prefix, p, o, "-bcd", str(bcd), "-evalue", repr(evalue), "-caller", str(caller),
+                        "-sig", str(sig), "-support", repr(support)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    buf, out, q = open(o, "rb").read(), {}, 0
+    while q + 48 <= len(buf):
+        t, tl = (int(x) for x in np.frombuffer(buf, dtype=np.int32, count=2, offset=q))
+        st = np.frombuffer(buf, dtype=np.uint64, count=5, offset=q + 8).copy()
+        q += 48
+        out[t] = (buf[q:q + tl], buf[q + tl:q + 2 * tl], buf[q + 2 * tl:q + 3 * tl], st)
+        q += 3 * tl
+    return out
+
+
+def oracle_consensus(db_prefix: str, t: int, counts: np.ndarray, bcd=1, evalue=0.05, caller=0, sig=0, support=0.0):
+    L = orc()
+    L.orc_consensus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p]
+    raw = np.fromfile(db_prefix + ".length.b", dtype=np.int32)
+    lengths = raw[1:]
+    off = sum((int(lengths[i]) >> 5) + 1 for i in range(1, t))
+    tl = int(lengths[t])
+    assert counts.shape == (tl, 6)
+    words = np.fromfile(db_prefix + ".seq.b", dtype=np.uint64, count=(tl >> 5) + 1, offset=8 * off)
+    counts = np.ascontiguousarray(counts, dtype=np.uint16)
+    ts, ss, qs = (np.zeros(tl, dtype=np.uint8) for _ in range(3))
+    st = np.zeros(5, dtype=np.uint64)
+    rc = L.orc_consensus(counts.ctypes.data, words.ctypes.data, tl, bcd, caller, sig, support, evalue, ts.ctypes.data, ss.ctypes.data,
+                         qs.ctypes.data, st.ctypes.data)
+    assert rc == 0
+    return ts.tobytes(), ss.tobytes(), qs.tobytes(), st
+
+
+def oracle_chi2_min(evalue: float) -> float:
+    L = orc()
+    L.orc_chi2_min.restype = C.c_double
+    L.orc_chi2_min.argtypes = [C.c_double]
+    return float(L.orc_chi2_min(evalue))
