@@ -176,6 +176,36 @@ int kmagpu_matrix_reset(kmagpu_db *db);
 int kmagpu_matrix_device(kmagpu_db *db, void **device_ptr, uint64_t *entries);
 int kmagpu_matrix_download(kmagpu_db *db, int32_t tmpl, uint16_t *counts, size_t cap_entries, size_t *entries);
 
+/* Replaces callConsensus (assembly.c:1499-1631; called from assemble_KMA, assembly.c:2065) over the template nodes of
+ * the HBM-resident base-count matrix: per template position the template base, the called base and the match mark
+ * (the t / q / s rows of `Assem`, assembly.h:34-53) and per template the sums callConsensus leaves in aligned_assem.
+ * Insertion nodes (order dependent) stay with the host, which splices their calls between the rows. */
+typedef struct kmagpu_consensus_params {
+	int32_t bcd;          /* -bcd: minimum depth of an upper-case call (kma.c:318, default 1) */
+	int32_t caller;       /* baseCall (assembly.c:46): 0 baseCaller (:162), 1 orgBaseCaller (-bcg, :181), 2 refCaller (:193),
+	                         3 nanoCaller (-bcNano, :205), 4 refNanoCaller (:238) */
+	int32_t significance; /* significantBase (assembly.c:45): 0 significantNuc (:141), 1 significantAnd90Nuc (-bc90, :145),
+	                         2 significantAndSupport (-bc x, :149) */
+	int32_t reserved;
+	double support;       /* the x of -bc x */
+	double chi2_min;      /* kmagpu_chi2_threshold(evalue, p_chisqr): a call is significant from this statistic on */
+} kmagpu_consensus_params;
+
+typedef struct kmagpu_consensus_stats {   /* what callConsensus adds to aligned_assem (assembly.c:1621-1627) */
+	uint64_t depth, depthVar;
+	uint32_t len, aln_len, cover, reserved;
+} kmagpu_consensus_stats;
+
+/* Host only: the smallest statistic x with p_chisqr(x) <= evalue, found by bisection over p_chisqr (stdstat.c:136; the
+ * reference passes its own function, NULL uses the closed form of stdstat.c:146 with the host libm, which covers
+ * evalue >= 1e-11). Negative on error. */
+double kmagpu_chi2_threshold(double evalue, double (*p_chisqr)(long double));
+
+/* tmpl != 0: rows of that template (len bytes each, cap = capacity of each row buffer), stats[1]. tmpl = 0: every
+ * template, rows concatenated in template order, stats[DB_size] indexed by template id. Row pointers may be NULL. */
+int kmagpu_consensus(kmagpu_db *db, int32_t tmpl, const kmagpu_consensus_params *cp, uint8_t *t, uint8_t *s, uint8_t *q,
+                     size_t cap, kmagpu_consensus_stats *stats, float *ms);
+
 /* NW_score (nw.c:642) / NW_band_score (nw.c:892) over a batch of independent problems, one warp each.
  * prob[i] = {template id, t_s, t_e, q_off, q_s, q_e, k, band (0 = full matrix)}; the query bytes (0-4) of problem i
  * start at qpool + q_off. out[i] = {score, len, pos, match, tGaps, qGaps}; status[i] != 0: not computed

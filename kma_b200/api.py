@@ -53,6 +53,14 @@ class AlignStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class ConsensusParams(C.Structure):
+    _fields_ = [("bcd", C.c_int32), ("caller", C.c_int32), ("significance", C.c_int32), ("reserved", C.c_int32),
+                ("support", C.c_double), ("chi2_min", C.c_double)]
+
+
+CONSENSUS_STATS = np.dtype([("depth", "<u8"), ("depthVar", "<u8"), ("len", "<u4"), ("aln_len", "<u4"), ("cover", "<u4"),
+                            ("reserved", "<u4")])
+
 _lib = None
 
 
@@ -83,6 +91,10 @@ def lib():
         L.kmagpu_matrix_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.kmagpu_matrix_download.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.kmagpu_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.kmagpu_chi2_threshold.restype = C.c_double
+        L.kmagpu_chi2_threshold.argtypes = [C.c_double, C.c_void_p]
+        L.kmagpu_consensus.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ConsensusParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.c_void_p, C.POINTER(C.c_float)]
         L.kmagpu_align_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int64)]
         L.kmagpu_align_from_seed.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.kmagpu_align_run.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.POINTER(AlignStats)]
@@ -128,6 +140,15 @@ class TemplateDB:
         self.info = DbInfo()
         _check(lib().kmagpu_db_get_info(self._h, C.byref(self.info)))
         self.device = device
+        self.prefix = prefix
+        self._lengths = None
+
+    @property
+    def lengths(self) -> np.ndarray:
+        """.length.b: lengths[t] of template t >= 1 (lengths[0] = k of the alignment index)"""
+        if self._lengths is None:
+            self._lengths = np.fromfile(self.prefix + ".length.b", dtype=np.int32)[1:]
+        return self._lengths
 
     def close(self):
         if self._h:
@@ -276,6 +297,26 @@ class TemplateDB:
         out = np.empty(n.value, dtype=np.uint16)
         _check(lib().kmagpu_matrix_download(self._h, int(template), out.ctypes.data, n.value, C.byref(n)))
         return out.reshape(-1, 6)
+
+    def consensus(self, template: int = 0, bcd: int = 1, evalue: float = 0.05, caller: int = 0, significance: int = 0,
+                  support: float = 0.0, p_chisqr=None):
+        """callConsensus (assembly.c:1499) over the template nodes of the device matrix. caller: 0 baseCaller, 1 orgBaseCaller
+        (-bcg), 2 refCaller, 3 nanoCaller (-bcNano), 4 refNanoCaller; significance: 0 significantNuc, 1 significantAnd90Nuc
+        (-bc90), 2 significantAndSupport (-bc support). p_chisqr: C function pointer of the reference's p_chisqr (None: the
+        closed form with the host libm). -> (t, s, q uint8 rows, stats structured array, kernel ms); template = 0: all
+        templates concatenated, stats indexed by template id."""
+        x0 = lib().kmagpu_chi2_threshold(float(evalue), p_chisqr)
+        if x0 < 0:
+            raise KmaGpuError(lib().kmagpu_last_error().decode())
+        cp = ConsensusParams(int(bcd), int(caller), int(significance), 0, float(support), x0)
+        info = self.info
+        n = int(self.lengths[template]) if template else int(np.sum(self.lengths[1:], dtype=np.int64))
+        t, s, q = (np.empty(n, dtype=np.uint8) for _ in range(3))
+        st = np.zeros(1 if template else info.DB_size, dtype=CONSENSUS_STATS)
+        ms = C.c_float()
+        _check(lib().kmagpu_consensus(self._h, int(template), C.byref(cp), t.ctypes.data, s.ctypes.data, q.ctypes.data, n,
+                                      st.ctypes.data, C.byref(ms)))
+        return t, s, q, st, ms.value
 
     def matrix_tensor(self):
         """the unsaturated device matrix as a torch int32 tensor (zero copy) for the NCCL all-reduce over ranks"""

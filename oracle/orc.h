@@ -56,6 +56,9 @@ int orc_memscore_stream(const int32_t *lengths, int DB_size, const uint8_t *in, 
 int orc_consensus(const uint16_t *counts, const uint64_t *seq, int t_len, int bcd, int caller, int sig, double support, double evalue,
                   uint8_t *t, uint8_t *s, uint8_t *q, uint64_t *stats);
 double orc_chi2_min(double evalue);
+void orc_to2bit(uint8_t *trans);
+size_t orc_stage1(const uint8_t *text1, size_t n1, const uint8_t *text2, size_t n2, int fastq, int min_phred, int phred_scale,
+                  int minlen, int maxlen, uint8_t *out, size_t cap, int64_t *count);
 void orc_free(void *p);
 void orc_nw(const orc_params *p, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s, int q_e,
             int band, int *out6);

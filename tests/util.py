@@ -460,3 +460,51 @@ def oracle_chi2_min(evalue: float) -> float:
     L.orc_chi2_min.restype = C.c_double
     L.orc_chi2_min.argtypes = [C.c_double]
     return float(L.orc_chi2_min(evalue))
+
+
+# ---------------------------------------------------------------- stage 1 (FASTQ / FASTA text -> stage-1 records)
+
+def fastq_text(reads, quals=None, prefix="r", fasta=False, crlf=False) -> bytes:
+    """4-line FASTQ (or 2-line FASTA) text of reads given as codes 0-4; quals: list of uint8 phred+offset arrays"""
+    nl = b"\r\n" if crlf else b"\n"
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    out = bytearray()
+    for i, r in enumerate(reads):
+        seq = lut[np.asarray(r, dtype=np.uint8)].tobytes()
+        if fasta:
+            out += b">" + f"{prefix}{i} some description".encode() + nl + seq + nl
+        else:
+            q = np.asarray(quals[i], dtype=np.uint8).tobytes() if quals is not None else b"I" * len(seq)
+            out += b"@" + f"{prefix}{i}".encode() + (b" 1:N:0" if i % 3 == 0 else b"") + nl + seq + nl + b"+" + nl + q + nl
+    return bytes(out)
+
+
+def random_quals(rng, reads, scale=33):
+    """phred qualities with decaying ends, so that the -mp end trim cuts something off most reads"""
+    out = []
+    for r in reads:
+        n = len(r)
+        q = rng.integers(22, 41, size=n)
+        a, b = int(rng.integers(0, 12)), int(rng.integers(0, 25))
+        if a and a < n:
+            q[:a] = rng.integers(2, 24, size=a)
+        if b and b < n:
+            q[n - b:] = rng.integers(2, 24, size=b)
+        if rng.integers(0, 25) == 0:
+            q[:] = rng.integers(2, 19, size=n)   # nothing survives
+        out.append((q + scale).astype(np.uint8))
+    return out
+
+
+def oracle_stage1(text1: bytes, text2: bytes | None = None, fastq=True, min_phred=20, phred_scale=33, minlen=16, maxlen=2147483647):
+    L = orc()
+    L.orc_stage1.restype = C.c_size_t
+    L.orc_stage1.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                             C.c_size_t, C.POINTER(C.c_int64)]
+    cap = len(text1) + (len(text2) if text2 else 0) + 4096
+    out = np.zeros(cap, dtype=np.uint8)
+    cnt = C.c_int64()
+    n = L.orc_stage1(text1, len(text1), text2, len(text2) if text2 else 0, int(fastq), min_phred, phred_scale, minlen, maxlen,
+                     out.ctypes.data, cap, C.byref(cnt))
+    assert n <= cap
+    return out[:n].tobytes(), cnt.value
