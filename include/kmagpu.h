@@ -206,6 +206,36 @@ double kmagpu_chi2_threshold(double evalue, double (*p_chisqr)(long double));
 int kmagpu_consensus(kmagpu_db *db, int32_t tmpl, const kmagpu_consensus_params *cp, uint8_t *t, uint8_t *s, uint8_t *q,
                      size_t cap, kmagpu_consensus_stats *stats, float *ms);
 
+/* Stage 1 on the device: replaces, per read, what run_input / run_input_PE (runinput.c:370-560) do between the record
+ * splitter (FileBuffgetFq seqparse.c:241 / FileBuffgetFsa) and the stage-1 pipe: base translation through `trans`
+ * (the reference passes its to2Bit, kma.c:1439-1482), phredStat's end trim (runinput.c:127-167; the default branch:
+ * -mp only -- -eq, the hard mask and the QC report are not built) or fsastat's N trim (runinput.c:315-368), the -ml /
+ * -xl filters, the pairing rule of run_input_PE (runinput.c:528-539), compDNA (compdna.c:99-127) and the records of
+ * printFsa / printFsa_pair (runinput.c:765-825). */
+typedef struct kmagpu_ingest_params {
+	int32_t fastq;        /* 1: qualities present (phredStat), 0: FASTA (fsastat) */
+	int32_t paired;       /* reads 2i and 2i + 1 are mates (run_input_PE / run_input_INT) */
+	int32_t min_phred;    /* -mp (kma.c:293, default 20) */
+	int32_t phred_scale;  /* what getPhredFileBuff (seqparse.c:551) found: 33 or 64 */
+	int32_t minlen;       /* -ml (kma.c:309, default 16) */
+	int32_t maxlen;       /* -xl (kma.c:310, default 2147483647) */
+	int32_t reserved[2];
+	uint8_t trans[256];   /* byte -> 0-3 base, 4 N, 8 other, 16 newline */
+} kmagpu_ingest_params;
+
+/* Host only: the line structure of a chunk of 4-line FASTQ (fastq != 0) or 2-line FASTA text. fields[i][5] = {header
+ * offset (past '@' / '>'), header length without trailing white space, sequence offset, sequence length without
+ * trailing bytes `trans` maps to 8, quality offset}. Returns the number of whole records, *used = the bytes they span
+ * (fields = NULL only counts); -1 on malformed input. */
+int64_t kmagpu_fastx_split(const void *text, size_t nbytes, int fastq, const uint8_t *trans, uint32_t *fields, size_t cap, size_t *used);
+
+/* text (host) -> stage-1 records in input order. The stream always stays in HBM as the input of the next
+ * kmagpu_seed_run (as if kmagpu_seed_upload had been called with it); stage1_out != NULL also downloads it.
+ * count = what run_input returns (one per printed read or pair), ms = the three kernels and their scans. For paired
+ * input put both files' text into one buffer and interleave their fields. */
+int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip, const void *text, size_t text_bytes, const uint32_t *fields,
+                        size_t nreads, void *stage1_out, size_t cap, size_t *out_bytes, int64_t *count, float *ms);
+
 /* NW_score (nw.c:642) / NW_band_score (nw.c:892) over a batch of independent problems, one warp each.
  * prob[i] = {template id, t_s, t_e, q_off, q_s, q_e, k, band (0 = full matrix)}; the query bytes (0-4) of problem i
  * start at qpool + q_off. out[i] = {score, len, pos, match, tGaps, qGaps}; status[i] != 0: not computed

@@ -53,6 +53,35 @@ class AlignStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class IngestParams(C.Structure):
+    _fields_ = [("fastq", C.c_int32), ("paired", C.c_int32), ("min_phred", C.c_int32), ("phred_scale", C.c_int32),
+                ("minlen", C.c_int32), ("maxlen", C.c_int32), ("reserved", C.c_int32 * 2), ("trans", C.c_uint8 * 256)]
+
+
+def to2bit() -> np.ndarray:
+    """the byte -> code table the CLI builds (kma.c:1439-1482): 0-3 bases (IUPAC codes fold onto one of their bases),
+    4 = N / X, 16 = newline, 8 = everything else. Host glue: the reference passes its own table."""
+    t = np.full(256, 8, dtype=np.uint8)
+    t[ord("\n")] = 16
+    for v, chars in enumerate(("AaRrMmDd", "CcYyBb", "GgSsKkVv", "TtWwHhUu", "NnXx")):
+        for ch in chars:
+            t[ord(ch)] = v
+    return t
+
+
+def fastx_split(text, fastq: bool = True, trans: np.ndarray | None = None):
+    """host only: line structure of a FASTQ / FASTA chunk -> (uint32 fields[n, 5], bytes used)"""
+    trans = to2bit() if trans is None else trans
+    buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
+    used = C.c_size_t()
+    n = lib().kmagpu_fastx_split(buf.ctypes.data, len(buf), int(fastq), trans.ctypes.data, None, 0, C.byref(used))
+    if n < 0:
+        raise KmaGpuError(lib().kmagpu_last_error().decode())
+    fields = np.zeros((n, 5), dtype=np.uint32)
+    lib().kmagpu_fastx_split(buf.ctypes.data, len(buf), int(fastq), trans.ctypes.data, fields.ctypes.data, n, C.byref(used))
+    return fields, used.value
+
+
 class ConsensusParams(C.Structure):
     _fields_ = [("bcd", C.c_int32), ("caller", C.c_int32), ("significance", C.c_int32), ("reserved", C.c_int32),
                 ("support", C.c_double), ("chi2_min", C.c_double)]
@@ -91,6 +120,10 @@ def lib():
         L.kmagpu_matrix_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.kmagpu_matrix_download.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         L.kmagpu_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.kmagpu_fastx_split.restype = C.c_int64
+        L.kmagpu_fastx_split.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.kmagpu_stage1_batch.argtypes = [C.c_void_p, C.POINTER(IngestParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                          C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
         L.kmagpu_chi2_threshold.restype = C.c_double
         L.kmagpu_chi2_threshold.argtypes = [C.c_double, C.c_void_p]
         L.kmagpu_consensus.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ConsensusParams), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -160,6 +193,24 @@ class TemplateDB:
             self.close()
         except Exception:
             pass
+
+    # --- stage 1 -----------------------------------------------------------------------------
+    def run_input_batch(self, text, fields: np.ndarray, fastq=True, paired=False, min_phred=20, phred_scale=33, minlen=16,
+                        maxlen=2147483647, trans: np.ndarray | None = None, download=True):
+        """FASTQ / FASTA text + its line structure (fastx_split) -> stage-1 records (run_input / run_input_PE per read:
+        translation, end trim, -ml / -xl, pairing rule, compDNA, printFsa). The stream stays on the device as the input
+        of seed_run(); download=False skips the copy back. -> (stage-1 bytes | None, count, kernel ms)"""
+        ip = IngestParams()
+        ip.fastq, ip.paired, ip.min_phred, ip.phred_scale, ip.minlen, ip.maxlen = int(fastq), int(paired), min_phred, phred_scale, minlen, maxlen
+        C.memmove(ip.trans, (to2bit() if trans is None else trans).ctypes.data, 256)
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
+        fields = np.ascontiguousarray(fields, dtype=np.uint32)
+        nbytes = int(buf.numel() if hasattr(buf, "numel") else buf.size)
+        out = np.empty(nbytes + 64 if download else 0, dtype=np.uint8)
+        ob, cnt, ms = C.c_size_t(), C.c_int64(), C.c_float()
+        _check(lib().kmagpu_stage1_batch(self._h, C.byref(ip), _ptr(buf), nbytes, fields.ctypes.data, len(fields),
+                                         out.ctypes.data if download else None, len(out), C.byref(ob), C.byref(cnt), C.byref(ms)))
+        return (out[: ob.value] if download else None), cnt.value, ms.value
 
     # --- stage 2 -----------------------------------------------------------------------------
     def save_kmers_batch(self, stage1, params: Params | None = None, out=None):

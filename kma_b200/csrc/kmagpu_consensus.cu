@@ -23,16 +23,21 @@
 struct CsParams { int bcd, caller, sig; double support, chi2_min; };
 struct CsStat { unsigned long long depth, depthVar; unsigned int len, aln_len, cover, reserved; };
 
-__device__ __forceinline__ int cs_base(int i) { return (int)((0x2d4e54474341ull >> (8 * i)) & 0xff); }   // "ACGTN-"[i]
+__device__ __forceinline__ int cs_base(int i) { return (int)(__byte_perm(0x54474341u, 0x00002d4eu, (unsigned)i) & 0xffu); }   // "ACGTN-"[i]
 __device__ __forceinline__ int cs_lower(int c) { return (c >= 'A' && c <= 'Z') ? c + 32 : c; }
 
-// significantNuc / significantAnd90Nuc / significantAndSupport (assembly.c:141-160)
-__device__ __forceinline__ bool cs_significant(const CsParams &P, int X, int Y) {
+// significantNuc / significantAnd90Nuc / significantAndSupport (assembly.c:141-160). The statistic (X-Y)^2 / (X+Y)
+// is compared with chi2_min as the reference's double quotient; the division itself only runs when the product form
+// cannot decide with a margin (1e-13 relative) far above the rounding of either side.
+template <int SIG> __device__ __forceinline__ bool cs_significant(const CsParams &P, int X, int Y) {
 	if (!(Y < X)) return false;
-	if (P.sig == 1 && !(9 * (X + Y) <= 10 * X)) return false;
-	if (P.sig == 2 && !(P.support * (double)(X + Y) <= (double)X)) return false;
+	if (SIG == 1 && !(9 * (X + Y) <= 10 * X)) return false;
+	if (SIG == 2 && !(P.support * (double)(X + Y) <= (double)X)) return false;
 	const long long d = (long long)X - Y;
-	return (double)(d * d) / (double)(X + Y) >= P.chi2_min;
+	const double dd = (double)(d * d), n = (double)(X + Y), lim = P.chi2_min * n;
+	if (dd > lim * (1.0 + 1e-13)) return true;
+	if (dd < lim * (1.0 - 1e-13)) return false;
+	return dd / n >= P.chi2_min;
 }
 
 __device__ __forceinline__ int cs_best_base(const unsigned *c, int *best) {   // first maximum over A C G T N, 0 when all are 0
@@ -44,10 +49,11 @@ __device__ __forceinline__ int cs_best_base(const unsigned *c, int *best) {   //
 }
 
 // baseCaller / orgBaseCaller / refCaller / nanoCaller / refNanoCaller (assembly.c:162-271)
+template <int CALLER, int SIG>
 __device__ __forceinline__ int cs_base_call(const CsParams &P, int bestNuc, int bestScore, int depthUpdate, const unsigned *c) {
-	const bool sigf = depthUpdate != 0 && cs_significant(P, bestScore, depthUpdate - bestScore);
+	const bool sigf = depthUpdate != 0 && cs_significant<SIG>(P, bestScore, depthUpdate - bestScore);
 	int bn;
-	switch (P.caller) {
+	switch (CALLER) {
 	case 0:
 		if (depthUpdate == 0) return '-';
 		if (!sigf) return (bestNuc == '-' && bestScore != depthUpdate) ? 'n' : cs_lower(bestNuc);   // tNuc is never '-' on a template node
@@ -87,6 +93,17 @@ __device__ __forceinline__ void cs_flush(CsStat *stats, int t, unsigned long lon
 	atomicAdd(&stats[t].aln_len, aln); atomicAdd(&stats[t].cover, cover);
 }
 
+// the warp's running sums into the per-template totals: one reduction when every lane ran inside the same template
+__device__ __forceinline__ void cs_fold(CsStat *stats, int t, unsigned long long depth, unsigned long long var, unsigned aln, unsigned cover,
+                                        unsigned lane) {
+	const int t0 = __shfl_sync(0xffffffffu, t, 0);
+	if (__all_sync(0xffffffffu, t == t0)) {
+		depth = cs_warp_sum64(depth); var = cs_warp_sum64(var);
+		aln = __reduce_add_sync(0xffffffffu, aln); cover = __reduce_add_sync(0xffffffffu, cover);
+		if (lane == 0) cs_flush(stats, t0, depth, var, aln, cover);
+	} else cs_flush(stats, t, depth, var, aln, cover);
+}
+
 // ---- TMA bulk copies (cp.async.bulk, 1-D) completing on an mbarrier
 __device__ __forceinline__ unsigned cs_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cs_mbar_init(unsigned long long *bar, unsigned count) {
@@ -109,6 +126,7 @@ __device__ __forceinline__ void cs_mbar_wait(unsigned long long *bar, unsigned p
 // positions of that space so that every tile starts on a 16-byte boundary. A block owns tiles_per_block consecutive
 // tiles and keeps CS_STAGES - 1 of them in flight: thread 0 posts one 6 KB bulk copy per tile into a ring of shared-
 // memory stages, everybody waits on the stage's mbarrier. rows: t at out_t[pos - p0], likewise s and q.
+template <int CALLER, int SIG>
 __global__ void __launch_bounds__(CS_TILE) consensus_kernel(CsParams P, const unsigned int *__restrict__ mat, unsigned long long mat_bytes,
 		const int64_t *__restrict__ mat_off, int DB_size, const KgTMeta *__restrict__ meta, const uint64_t *__restrict__ seq, long long p0,
 		long long p1, long long tiles_per_block, uint8_t *__restrict__ out_t, uint8_t *__restrict__ out_s, uint8_t *__restrict__ out_q,
@@ -132,7 +150,7 @@ __global__ void __launch_bounds__(CS_TILE) consensus_kernel(CsParams P, const un
 		cs_bulk_load(stage[k % CS_STAGES], (const uint8_t *)mat + at, bytes, &bar[k % CS_STAGES]);
 	};
 	if (threadIdx.x == 0) for (int k = 0; k < CS_STAGES - 1 && k < ntiles; ++k) post(k);
-	int run_t = 0;                                            // lane 0: the template the running sums belong to
+	int run_t = 0;                                            // the template this thread's running sums belong to
 	unsigned long long run_depth = 0, run_var = 0;
 	unsigned run_aln = 0, run_cover = 0;
 	int cur = 0;                                              // template of this thread's previous position and its range
@@ -153,8 +171,11 @@ __global__ void __launch_bounds__(CS_TILE) consensus_kernel(CsParams P, const un
 			tn = (int)((__ldg(seq + cur_seq + (tp >> 5)) << ((tp & 31) << 1)) >> 62);
 		}
 		cs_mbar_wait(&bar[k % CS_STAGES], (unsigned)(k / CS_STAGES) & 1u);
-		unsigned long long depth = 0, var = 0;
-		unsigned aln = 0, cover = 0;
+		// per-template sums run in registers; a warp folds them (shuffles, four atomics) when it leaves a template
+		if (__any_sync(0xffffffffu, in && t != run_t)) {
+			cs_fold(stats, run_t, run_depth, run_var, run_aln, run_cover, lane);
+			run_t = t; run_depth = run_var = 0; run_aln = run_cover = 0;
+		}
 		if (in) {
 			const unsigned *tile = stage[k % CS_STAGES];
 			unsigned c[6];
@@ -182,29 +203,17 @@ __global__ void __launch_bounds__(CS_TILE) consensus_kernel(CsParams P, const un
 				} else call = cs_lower(call);
 				bestScore = depthUpdate - (int)c[5];
 			} else if (depthUpdate < P.bcd) call = cs_lower(call);
-			call = cs_base_call(P, call, bestScore, depthUpdate, c);
+			call = cs_base_call<CALLER, SIG>(P, call, bestScore, depthUpdate, c);
 			int sc = '_';
 			if (call != '-') {
-				depth = (unsigned long long)depthUpdate; var = depth * depth; aln = 1;
-				if (cs_base(tn) == (call >= 'a' ? call - 32 : call)) { cover = 1; sc = '|'; }
+				run_depth += (unsigned long long)depthUpdate; run_var += (unsigned long long)depthUpdate * (unsigned long long)depthUpdate; ++run_aln;
+				if (cs_base(tn) == (call >= 'a' ? call - 32 : call)) { ++run_cover; sc = '|'; }
 			}
 			out_t[pos - p0] = (uint8_t)cs_base(tn); out_s[pos - p0] = (uint8_t)sc; out_q[pos - p0] = (uint8_t)call;
 		}
 		__syncthreads();   // every thread has read its counts: the stage may be refilled
-		// per-template sums: one template per warp in the common case
-		const int t0 = __shfl_sync(0xffffffffu, t, 0);
-		if (__all_sync(0xffffffffu, t == t0)) {
-			if (t0) {
-				depth = cs_warp_sum64(depth); var = cs_warp_sum64(var);
-				aln = __reduce_add_sync(0xffffffffu, aln); cover = __reduce_add_sync(0xffffffffu, cover);
-				if (lane == 0) {
-					if (t0 != run_t) { cs_flush(stats, run_t, run_depth, run_var, run_aln, run_cover); run_t = t0; run_depth = run_var = 0; run_aln = run_cover = 0; }
-					run_depth += depth; run_var += var; run_aln += aln; run_cover += cover;
-				}
-			}
-		} else cs_flush(stats, t, depth, var, aln, cover);   // a template boundary (or the range's edge) inside the warp
 	}
-	if (lane == 0) cs_flush(stats, run_t, run_depth, run_var, run_aln, run_cover);
+	cs_fold(stats, run_t, run_depth, run_var, run_aln, run_cover, lane);
 }
 
 // ---------------------------------------------------------------- host side
@@ -255,13 +264,22 @@ extern "C" int kmagpu_consensus(kmagpu_db *db, int32_t tmpl, const kmagpu_consen
 	KG_CUDA(cudaMemsetAsync(dstat.p, 0, sizeof(CsStat) * (size_t)DB, st));
 	CsParams P = {cp->bcd, cp->caller, cp->significance, cp->support, cp->chi2_min};
 	const long long tiles = (p1 + CS_TILE - 1) / CS_TILE - p0 / CS_TILE;
-	long long grid = (long long)db->sm_count * 8;
+	typedef void (*kern_t)(CsParams, const unsigned int *, unsigned long long, const int64_t *, int, const KgTMeta *, const uint64_t *, long long,
+	                       long long, long long, uint8_t *, uint8_t *, uint8_t *, CsStat *);
+	static const kern_t kerns[5][3] = {
+		{consensus_kernel<0, 0>, consensus_kernel<0, 1>, consensus_kernel<0, 2>}, {consensus_kernel<1, 0>, consensus_kernel<1, 1>, consensus_kernel<1, 2>},
+		{consensus_kernel<2, 0>, consensus_kernel<2, 1>, consensus_kernel<2, 2>}, {consensus_kernel<3, 0>, consensus_kernel<3, 1>, consensus_kernel<3, 2>},
+		{consensus_kernel<4, 0>, consensus_kernel<4, 1>, consensus_kernel<4, 2>}};
+	const kern_t kern = kerns[cp->caller][cp->significance];
+	int per_sm = 0;   // one wave of resident blocks, each with a contiguous run of tiles
+	KG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CS_TILE, 0));
+	long long grid = (long long)db->sm_count * (per_sm > 0 ? per_sm : 1);
 	if (grid > tiles) grid = tiles > 0 ? tiles : 1;
 	const long long per = (tiles + grid - 1) / grid;
 	grid = per ? (tiles + per - 1) / per : 1;
 	if (grid < 1) grid = 1;
 	KG_CUDA(cudaEventRecord(db->ev[2], st));
-	if (n) consensus_kernel<<<(unsigned)grid, CS_TILE, 0, st>>>(P, db->d_mat, 4ull * db->mat_entries, db->d_mat_off, DB, db->tix.meta, db->tix.seq, p0, p1, per,
+	if (n) kern<<<(unsigned)grid, CS_TILE, 0, st>>>(P, db->d_mat, 4ull * db->mat_entries, db->d_mat_off, DB, db->tix.meta, db->tix.seq, p0, p1, per,
 		(uint8_t *)rows.p, (uint8_t *)rows.p + n, (uint8_t *)rows.p + 2 * n, (CsStat *)dstat.p);
 	KG_CUDA(cudaEventRecord(db->ev[3], st));
 	if (t) KG_CUDA(cudaMemcpyAsync(t, rows.p, n, cudaMemcpyDeviceToHost, st));

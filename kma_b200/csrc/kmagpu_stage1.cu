@@ -1,0 +1,247 @@
+// Stage 1 on the device: what run_input / run_input_PE (runinput.c:370-560) do per read between the record splitter
+// (FileBuffgetFq seqparse.c:241 / FileBuffgetFsa) and the stage-1 pipe -- base translation through the caller's `trans`
+// table (to2Bit, kma.c:1439-1482), phredStat's end trim in its default branch (runinput.c:127-167, -mp) or fsastat's
+// N trim (runinput.c:315-368), the -ml / -xl filters, the pairing rule of run_input_PE (runinput.c:528-539), compDNA
+// (compdna.c:99-127) and the records of printFsa / printFsa_pair (runinput.c:765-825).
+//
+// The host keeps the one sequential step, finding the line ends (kmagpu_fastx_split, memchr speed); the raw text goes
+// to HBM once and three small kernels turn it into the stage-1 stream in input order: a warp per read finds the kept
+// window and counts its N's, a thread per read (or pair) applies the filters and sizes the records, two scans place
+// them, a warp per kept read packs 32 bases per step into a 2-bit word with two warp-wide OR reductions and writes the
+// N positions by ballot rank. The stream and its record offsets stay in HBM as the input of kmagpu_seed_run, so reads
+// never come back to the host between the file and stage 2.
+#include "kmagpu_internal.h"
+#include "kmagpu_dev.cuh"
+#include <string.h>
+#include <vector>
+
+struct S1Win { int32_t start, end, nN, klen; };   // kept window, its N count, the length the -ml filter sees
+
+struct S1Tab { uint8_t t[256]; };
+
+// fields[r] = {header offset, header length, sequence offset, sequence length, quality offset}
+__global__ void __launch_bounds__(256) s1_window_kernel(const uint8_t *__restrict__ text, const uint32_t *__restrict__ fields, int n, S1Tab tab,
+		int fastq, int thr, int maxlen, S1Win *win) {
+	__shared__ uint8_t tr[256];
+	tr[threadIdx.x] = tab.t[threadIdx.x];
+	__syncthreads();
+	const unsigned lane = threadIdx.x & 31;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+		const uint32_t *f = fields + 5 * (size_t)r;
+		const uint8_t *seq = text + f[2], *qual = text + f[4];
+		const int len = (int)f[3];
+		int start = 0, end = 0, nN = 0;
+		if (len <= maxlen) {
+			// first / last position that stays: quality >= threshold (phredStat) or not an N (fsastat)
+			start = len;
+			for (int base = 0; base < len; base += 32) {
+				const int i = base + (int)lane;
+				const bool ok = i < len && (fastq ? (int)qual[i] >= thr : tr[seq[i]] != 4);
+				const unsigned m = __ballot_sync(0xffffffffu, ok);
+				if (m) { start = base + __ffs(m) - 1; break; }
+			}
+			end = start;
+			for (int base = len - 1; base >= start; base -= 32) {
+				const int i = base - (int)lane;
+				const bool ok = i >= start && (fastq ? (int)qual[i] >= thr : tr[seq[i]] != 4);
+				const unsigned m = __ballot_sync(0xffffffffu, ok);
+				if (m) { end = base - (__ffs(m) - 1) + 1; break; }
+			}
+			for (int base = start; base < end; base += 32) {
+				const int i = base + (int)lane;
+				nN += __popc(__ballot_sync(0xffffffffu, i < end && tr[seq[i]] == 4));
+			}
+		}
+		if (lane == 0) { S1Win w = {start, end, nN, fastq ? end - start : end - start - nN}; win[r] = w; }
+	}
+}
+
+// one thread per read (single) or per pair: -ml filter, pairing rule, record sizes and kinds (0 single, 1 / 2 mates)
+__global__ void __launch_bounds__(256) s1_decide_kernel(const uint32_t *__restrict__ fields, const S1Win *__restrict__ win, int n, int paired,
+		int minlen, uint32_t *size, uint32_t *keep, uint8_t *kind, unsigned long long *ctr) {
+	const int u = blockIdx.x * blockDim.x + threadIdx.x;
+	const int units = paired ? n >> 1 : n;
+	if (u >= units) return;
+	const int r0 = paired ? 2 * u : u, cnt = paired ? 2 : 1;
+	bool k[2] = {false, false};
+	for (int j = 0; j < cnt; ++j) k[j] = minlen <= win[r0 + j].klen;
+	const bool both = paired && k[0] && k[1];
+	int maxL = 0;
+	for (int j = 0; j < cnt; ++j) {
+		const int r = r0 + j;
+		uint32_t sz = 0;
+		if (k[j]) {
+			const S1Win w = win[r];
+			const int L = w.end - w.start;
+			sz = 16u + 8u * (uint32_t)((L + 31) >> 5) + 4u * (uint32_t)w.nN + fields[5 * (size_t)r + 1] + 1u;
+			maxL = max(maxL, L);
+		}
+		size[r] = sz; keep[r] = k[j] ? 1u : 0u;
+		kind[r] = both ? (uint8_t)(1 + j) : 0;
+	}
+	if (k[0] || k[1]) atomicAdd(&ctr[0], 1ull);           // what run_input counts: one per printed read or pair
+	if (both) atomicAdd(&ctr[1], 1ull);
+	if (maxL) atomicMax(&ctr[2], (unsigned long long)maxL);
+}
+
+__device__ __forceinline__ void s1_store_u64(uint8_t *p, unsigned long long v) {   // records are not aligned
+	if (((uintptr_t)p & 3) == 0) { ((uint32_t *)p)[0] = (uint32_t)v; ((uint32_t *)p)[1] = (uint32_t)(v >> 32); }
+	else { st_u32b(p, (uint32_t)v); st_u32b(p + 4, (uint32_t)(v >> 32)); }
+}
+
+// one warp per kept read: compDNA + printFsa
+__global__ void __launch_bounds__(256) s1_emit_kernel(const uint8_t *__restrict__ text, const uint32_t *__restrict__ fields, const S1Win *__restrict__ win,
+		int n, S1Tab tab, const uint32_t *__restrict__ size, const uint32_t *__restrict__ boff, const uint32_t *__restrict__ ridx,
+		const uint8_t *__restrict__ kind, uint8_t *out, uint32_t *rec_off, uint8_t *rec_kind) {
+	__shared__ uint8_t tr[256];
+	tr[threadIdx.x] = tab.t[threadIdx.x];
+	__syncthreads();
+	const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+		if (!size[r]) continue;
+		const uint32_t *f = fields + 5 * (size_t)r;
+		const S1Win w = win[r];
+		const uint8_t *seq = text + f[2] + w.start, *hdr = text + f[0];
+		const int L = w.end - w.start, words = (L + 31) >> 5, hl = (int)f[1] + 1;
+		uint8_t *o = out + boff[r];
+		if (lane == 0) {
+			rec_off[ridx[r]] = boff[r]; rec_kind[ridx[r]] = kind[r];
+			st_u32b(o, (uint32_t)L); st_u32b(o + 4, (uint32_t)words); st_u32b(o + 8, (uint32_t)w.nN);
+			st_u32b(o + 12, (uint32_t)(kind[r] == 1 ? -hl : hl));
+		}
+		uint8_t *ow = o + 16, *oN = ow + 8 * (size_t)words, *oh = oN + 4 * (size_t)w.nN;
+		int nbase = 0;
+		for (int wd = 0; wd < words; ++wd) {
+			const int i = 32 * wd + (int)lane;
+			const unsigned c = i < L ? tr[seq[i]] : 0u;
+			const bool isN = c == 4u;
+			// (word << 2) | base for 32 bases = the OR of base << (62 - 2 * lane); an N shifts in zero (compdna.c:113-121)
+			const unsigned long long x = isN ? 0ull : (unsigned long long)c << (62 - 2 * (int)lane);
+			const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(x >> 32)), lo = __reduce_or_sync(0xffffffffu, (unsigned)x);
+			if (lane == 0) s1_store_u64(ow + 8 * (size_t)wd, ((unsigned long long)hi << 32) | lo);
+			const unsigned m = __ballot_sync(0xffffffffu, isN);
+			if (isN) st_u32b(oN + 4 * (size_t)(nbase + __popc(m & lt)), (uint32_t)i);
+			nbase += __popc(m);
+		}
+		for (int i = lane; i < hl; i += 32) oh[i] = i < hl - 1 ? hdr[i] : (uint8_t)0;
+	}
+}
+
+// ---------------------------------------------------------------- host side
+
+static inline bool s1_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
+
+// Host only: the line structure of a chunk of 4-line FASTQ (fastq != 0) or 2-line FASTA text. fields[i] = {header
+// offset (past '@' / '>'), header length without trailing white space, sequence offset, sequence length without
+// trailing bytes that `trans` maps to 8 (a '\r'), quality offset}. Returns the number of whole records (stops at a
+// partial one), *used = the bytes they span; -1 when a record does not start with '@' / '>'.
+extern "C" int64_t kmagpu_fastx_split(const void *text_, size_t nbytes, int fastq, const uint8_t *trans, uint32_t *fields, size_t cap,
+                                      size_t *used) {
+	const uint8_t *text = (const uint8_t *)text_;
+	if (!text || !trans) { kmagpu_set_error("null argument"); return -1; }
+	if (nbytes >= (1ull << 32)) { kmagpu_set_error("text chunk of %zu bytes exceeds the 4 GiB per-call limit; split it", nbytes); return -1; }
+	size_t p = 0, n = 0;
+	while (p < nbytes) {
+		if (text[p] != (fastq ? '@' : '>')) { kmagpu_set_error("malformed input at byte %zu", p); return -1; }
+		const uint8_t *e = (const uint8_t *)memchr(text + p, '\n', nbytes - p);
+		if (!e) break;
+		size_t ho = p + 1, hl = (size_t)(e - text) - ho;
+		while (hl > 0 && s1_space(text[ho + hl - 1])) --hl;
+		size_t so = (size_t)(e - text) + 1;
+		if (so >= nbytes) break;
+		e = (const uint8_t *)memchr(text + so, '\n', nbytes - so);
+		if (!e && fastq) break;
+		size_t send = e ? (size_t)(e - text) : nbytes, sl = send - so, next = e ? send + 1 : nbytes, qo = 0;
+		while (sl > 0 && trans[text[so + sl - 1]] == 8) --sl;
+		if (fastq) {
+			if (next >= nbytes) break;
+			e = (const uint8_t *)memchr(text + next, '\n', nbytes - next);
+			if (!e) break;
+			qo = (size_t)(e - text) + 1;
+			if (qo + sl > nbytes) break;
+			e = (const uint8_t *)memchr(text + qo + sl, '\n', nbytes - qo - sl);
+			next = e ? (size_t)(e - text) + 1 : nbytes;
+		}
+		if (fields && n < cap) {
+			uint32_t *f = fields + 5 * n;
+			f[0] = (uint32_t)ho; f[1] = (uint32_t)hl; f[2] = (uint32_t)so; f[3] = (uint32_t)sl; f[4] = (uint32_t)qo;
+		}
+		++n;
+		p = next;
+	}
+	if (used) *used = p;
+	return (int64_t)n;
+}
+
+extern "C" int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip, const void *text, size_t text_bytes, const uint32_t *fields,
+                                   size_t nreads, void *stage1_out, size_t cap, size_t *out_bytes, int64_t *count, float *ms) {
+	if (!db || !ip || (!text && text_bytes) || (!fields && nreads)) { kmagpu_set_error("null argument"); return -1; }
+	if (text_bytes >= (1ull << 32) - 64) { kmagpu_set_error("text chunk of %zu bytes exceeds the 4 GiB per-call limit; split it", text_bytes); return -1; }
+	if (nreads >= (1ull << 31)) { kmagpu_set_error("too many reads in one call"); return -1; }
+	if (ip->paired && (nreads & 1)) { kmagpu_set_error("paired input needs an even number of reads (mates at 2i, 2i + 1)"); return -1; }
+	for (size_t i = 0; i < nreads; ++i) {
+		const uint32_t *f = fields + 5 * i;
+		if ((size_t)f[0] + f[1] > text_bytes || (size_t)f[2] + f[3] > text_bytes || (ip->fastq && (size_t)f[4] + f[3] > text_bytes)) {
+			kmagpu_set_error("read %zu points outside the text", i); return -1;
+		}
+	}
+	KG_CUDA(cudaSetDevice(db->device));
+	if (out_bytes) *out_bytes = 0;
+	if (count) *count = 0;
+	if (ms) *ms = 0.f;
+	const int n = (int)nreads;
+	SeedBatch &b = db->seed;
+	b.nreads = 0; b.npairs = 0; b.in_bytes = 0; b.max_seqlen = 0; b.ran = false;
+	if (n == 0) return 0;
+	cudaStream_t st = db->stream;
+	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+	KgBuf d_text, d_fields, d_win, d_u32, d_kind, d_partial, d_ctr;
+	struct Guard { std::vector<KgBuf *> v; ~Guard() { for (KgBuf *x : v) x->release(); } } guard;
+	guard.v = {&d_text, &d_fields, &d_win, &d_u32, &d_kind, &d_partial, &d_ctr};
+	if (d_text.reserve(text_bytes + 64) || d_fields.reserve(20 * (size_t)n) || d_win.reserve(sizeof(S1Win) * (size_t)n) ||
+	    d_u32.reserve(16 * ((size_t)n + 2)) || d_kind.reserve((size_t)n + 8) || d_partial.reserve(4 * (size_t)(ntiles + 2)) || d_ctr.reserve(64)) return -1;
+	uint32_t *size = (uint32_t *)d_u32.p, *keep = size + n + 1, *boff = keep + n + 1, *ridx = boff + n + 1;
+	unsigned long long *ctr = (unsigned long long *)d_ctr.p;
+	S1Tab tab;
+	memcpy(tab.t, ip->trans, 256);
+	KG_CUDA(cudaMemcpyAsync(d_text.p, text, text_bytes, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemcpyAsync(d_fields.p, fields, 20 * (size_t)n, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
+	KG_CUDA(cudaEventRecord(db->ev[0], st));
+	const int grid = db->sm_count * 8;
+	s1_window_kernel<<<grid, 256, 0, st>>>((const uint8_t *)d_text.p, (const uint32_t *)d_fields.p, n, tab, ip->fastq, ip->phred_scale + ip->min_phred,
+		ip->maxlen, (S1Win *)d_win.p);
+	const int units = ip->paired ? n / 2 : n;
+	s1_decide_kernel<<<(units + 255) / 256, 256, 0, st>>>((const uint32_t *)d_fields.p, (const S1Win *)d_win.p, n, ip->paired, ip->minlen, size, keep,
+		(uint8_t *)d_kind.p, ctr);
+	kg_exscan(size, n, boff, (uint32_t *)d_partial.p, ctr + 3, st);
+	kg_exscan(keep, n, ridx, (uint32_t *)d_partial.p, ctr + 4, st);
+	unsigned long long h[8];
+	KG_CUDA(cudaMemcpyAsync(h, ctr, 64, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	const size_t ob = (size_t)h[3], nrec = (size_t)h[4];
+	if (ob >= (1ull << 31)) { kmagpu_set_error("stage-1 stream of %zu bytes exceeds the 2 GiB per-call limit of stage 2; split the text", ob); return -1; }
+	if (b.d_in.reserve(ob + 64) || b.d_off.reserve(4 * (nrec + 1)) || b.d_kinds.reserve(nrec + 1)) return -1;
+	s1_emit_kernel<<<grid, 256, 0, st>>>((const uint8_t *)d_text.p, (const uint32_t *)d_fields.p, (const S1Win *)d_win.p, n, tab, size, boff, ridx,
+		(const uint8_t *)d_kind.p, (uint8_t *)b.d_in.p, (uint32_t *)b.d_off.p, (uint8_t *)b.d_kinds.p);
+	const uint32_t last = (uint32_t)ob;
+	KG_CUDA(cudaMemcpyAsync((uint32_t *)b.d_off.p + nrec, &last, 4, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemsetAsync((uint8_t *)b.d_kinds.p + nrec, 0, 1, st));
+	KG_CUDA(cudaMemsetAsync((uint8_t *)b.d_in.p + ob, 0, 64, st));
+	KG_CUDA(cudaEventRecord(db->ev[1], st));
+	if (stage1_out) {
+		if (ob > cap) { kmagpu_set_error("stage-1 output needs %zu bytes, caller gave %zu", ob, cap); cudaStreamSynchronize(st); return -1; }
+		if (ob) KG_CUDA(cudaMemcpyAsync(stage1_out, b.d_in.p, ob, cudaMemcpyDeviceToHost, st));
+	}
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	// the batch now looks as kmagpu_seed_upload would have left it
+	b.nreads = (int64_t)nrec; b.npairs = (int64_t)h[1]; b.max_seqlen = (int32_t)h[2]; b.in_bytes = ob;
+	if (out_bytes) *out_bytes = ob;
+	if (count) *count = (int64_t)h[0];
+	if (ms) cudaEventElapsedTime(ms, db->ev[0], db->ev[1]);
+	return 0;
+}

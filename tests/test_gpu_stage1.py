@@ -1,0 +1,130 @@
+"""Stage 1 through the C ABI. CPU part: the host record splitter (kmagpu_fastx_split). GPU part (B200): the device path
+(kmagpu_stage1_batch: translation, end trim, filters, pairing rule, compDNA, printFsa) vs the oracle that
+tests/test_oracle_stage1.py pins to `kma -s1`, and text -> stage 1 -> stage 2 chained in HBM."""
+import numpy as np
+import pytest
+
+from kma_b200 import api, synth
+from tests import util
+
+
+def _reads(seed, n=700, L=150, n_rate=0.01):
+    names, seqs = synth.gene_db(seed, n_families=4, n_variants=3, len_lo=400, len_hi=1200)
+    rng = np.random.default_rng(seed)
+    reads = [np.array(r) for r in synth.short_reads(seed + 1, seqs, n, L=L, sub=0.01, n_rate=n_rate)]
+    for i in range(0, n, 7):
+        reads[i] = reads[i][: int(rng.integers(5, L))]
+    for i in range(3, n, 11):
+        reads[i][: int(rng.integers(1, 6))] = 4
+        reads[i][-int(rng.integers(1, 6)):] = 4
+    reads[5] = reads[5][:0]           # an empty sequence line
+    reads[9] = np.full(40, 4, dtype=np.uint8)   # nothing but N
+    return rng, names, seqs, reads
+
+
+def test_fastx_split_host():
+    rng, _, _, reads = _reads(3, n=120)
+    for crlf in (False, True):
+        text = util.fastq_text(reads, util.random_quals(rng, reads), crlf=crlf)
+        f, used = api.fastx_split(text)
+        assert len(f) == len(reads) and used == len(text)
+        lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+        for i, r in enumerate(reads):
+            ho, hl, so, sl, qo = (int(x) for x in f[i])
+            assert text[ho:ho + hl] == f"r{i}".encode() + (b" 1:N:0" if i % 3 == 0 else b"")
+            assert text[so:so + sl] == lut[r].tobytes() and text[ho - 1:ho] == b"@"
+            assert qo > so and (sl == 0 or 33 <= text[qo] < 127)
+        # a chunk cut inside a record: the whole records before it, nothing more
+        cut = int(f[50][2]) + 3
+        f2, used2 = api.fastx_split(text[:cut])
+        assert len(f2) == 50 and used2 == int(f[50][0]) - 1 and np.array_equal(f2, f[:50])
+    fa = util.fastq_text(reads[:30], fasta=True)
+    f3, used3 = api.fastx_split(fa, fastq=False)
+    assert len(f3) == 30 and used3 == len(fa) and fa[int(f3[7][0]):int(f3[7][0]) + int(f3[7][1])] == b"r7 some description"
+    with pytest.raises(api.KmaGpuError):
+        api.fastx_split(b"ACGT\nACGT\n")
+
+
+gpu = pytest.mark.gpu
+
+
+@gpu
+@pytest.mark.parametrize("seed,kw", [(11, {}), (12, {"min_phred": 30}), (13, {"minlen": 60}), (14, {"maxlen": 120}), (15, {"min_phred": 0}),
+                                     (16, {"min_phred": 33, "phred_scale": 64})])
+def test_single_end_vs_oracle(tmp_path, seed, kw):
+    rng, names, seqs, reads = _reads(seed)
+    scale = kw.get("phred_scale", 33)
+    text = util.fastq_text(reads, util.random_quals(rng, reads, scale=scale), crlf=seed == 13)
+    want, wcnt = util.oracle_stage1(text, **kw)
+    prefix = util.build_db(tmp_path, names, seqs)
+    db = api.TemplateDB(prefix, device=0)
+    f, _ = api.fastx_split(text)
+    got, cnt, ms = db.run_input_batch(text, f, **kw)
+    db.close()
+    assert got.tobytes() == want and cnt == wcnt and ms > 0
+
+
+@gpu
+def test_fasta_and_long_reads(tmp_path):
+    rng, names, seqs, reads = _reads(17, n_rate=0.03)
+    reads += [np.array(r) for r in synth.long_reads(18, seqs, 6, len_lo=800, len_hi=5000)]
+    prefix = util.build_db(tmp_path, names, seqs)
+    db = api.TemplateDB(prefix, device=0)
+    text = util.fastq_text(reads, fasta=True)
+    f, _ = api.fastx_split(text, fastq=False)
+    got, cnt, _ = db.run_input_batch(text, f, fastq=False, minlen=40)
+    want, wcnt = util.oracle_stage1(text, fastq=False, minlen=40)
+    assert got.tobytes() == want and cnt == wcnt
+    empty, c0, _ = db.run_input_batch(b"", np.zeros((0, 5), dtype=np.uint32))
+    db.close()
+    assert len(empty) == 0 and c0 == 0
+
+
+@gpu
+@pytest.mark.parametrize("seed,kw", [(21, {}), (22, {"min_phred": 28, "minlen": 50})])
+def test_paired_end_vs_oracle(tmp_path, seed, kw):
+    rng, names, seqs, r1 = _reads(seed, n=500)
+    _, _, _, r2 = _reads(seed + 100, n=500)
+    t1 = util.fastq_text(r1, util.random_quals(rng, r1))
+    t2 = util.fastq_text(r2, util.random_quals(rng, r2))
+    want, wcnt = util.oracle_stage1(t1, t2, **kw)
+    f1, _ = api.fastx_split(t1)
+    f2, _ = api.fastx_split(t2)
+    f2 = f2.copy()
+    f2[:, [0, 2, 4]] += len(t1)                      # both files in one buffer, mates interleaved
+    fields = np.stack([f1, f2], axis=1).reshape(-1, 5)
+    prefix = util.build_db(tmp_path, names, seqs)
+    db = api.TemplateDB(prefix, device=0)
+    got, cnt, _ = db.run_input_batch(t1 + t2, fields, paired=True, **kw)
+    db.close()
+    assert got.tobytes() == want and cnt == wcnt
+
+
+@gpu
+def test_text_to_stage2_in_hbm(tmp_path):
+    """FASTQ text -> stage 1 on the device -> stage 2 without the records leaving HBM, single and paired"""
+    rng, names, seqs, reads = _reads(31, n=900)
+    prefix = util.build_db(tmp_path, names, seqs)
+    db = api.TemplateDB(prefix, device=0)
+    text = util.fastq_text(reads, util.random_quals(rng, reads))
+    s1, _ = util.oracle_stage1(text)
+    want = util.oracle_seed_stream(prefix, np.frombuffer(s1, dtype=np.uint8))
+    f, _ = api.fastx_split(text)
+    _, cnt, _ = db.run_input_batch(text, f, download=False)
+    st = db.seed_run(api.default_params())
+    out = np.empty(len(want) + 64, dtype=np.uint8)
+    got = db.seed_download(out)
+    assert got.tobytes() + api.stream_terminator(cnt) == want.tobytes() and st.mapped > 300
+    r1, r2 = synth.paired_reads(33, seqs, 400, sub=0.01)
+    t1, t2 = util.fastq_text(r1), util.fastq_text(r2)
+    s1pe, _ = util.oracle_stage1(t1, t2)
+    wantpe = util.oracle_seed_stream(prefix, np.frombuffer(s1pe, dtype=np.uint8))
+    f1, _ = api.fastx_split(t1)
+    f2, _ = api.fastx_split(t2)
+    f2 = f2.copy(); f2[:, [0, 2, 4]] += len(t1)
+    _, cntpe, _ = db.run_input_batch(t1 + t2, np.stack([f1, f2], axis=1).reshape(-1, 5), paired=True, download=False)
+    db.seed_run(api.default_params())
+    out = np.empty(len(wantpe) + 64, dtype=np.uint8)
+    gotpe = db.seed_download(out)
+    db.close()
+    assert gotpe.tobytes() + api.stream_terminator(cntpe) == wantpe.tobytes()

@@ -508,3 +508,11 @@ def oracle_stage1(text1: bytes, text2: bytes | None = None, fastq=True, min_phre
                      out.ctypes.data, cap, C.byref(cnt))
     assert n <= cap
     return out[:n].tobytes(), cnt.value
+
+
+def build_db(tmp_path, names, seqs) -> str:
+    """a database in the reference's format made by kma_b200.dbbuild (no reference binary needed)"""
+    from kma_b200 import dbbuild
+    prefix = os.path.join(str(tmp_path), "db")
+    dbbuild.build_db(prefix, names, seqs)
+    return prefix
