@@ -286,6 +286,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c3", action="store_true", help="skip the C3 (long reads, chain mode) side measurement")
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads / library handles of the end-to-end pipeline")
+    ap.add_argument("--no-text", action="store_true", help="skip the FASTQ-text end-to-end leg (stage 1 on the device)")
+    ap.add_argument("--split-threads", type=int, default=8, help="host threads of the FASTQ record splitter in the text leg")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks the batch is cut into for the end-to-end pipeline")
     args = ap.parse_args()
 
@@ -416,6 +418,49 @@ def main():
     t_e2e = (time.perf_counter() - t0) * 1e3
     e2e_out_bytes = sum(int(f.numel() if hasattr(f, "numel") else len(f)) for f, _ in r_e2e)
     assert e2e_out_bytes == out_bytes, "chunked end-to-end run produced a different frag_raw size"
+
+    # ---- the same from FASTQ text: the two files' text in pinned memory, the record splitter on
+    # `--split-threads` host threads, then per chunk text -> HBM -> stage 1 on the device -> stage 2 -> alignment pass.
+    # Same reads, same names: the frag_raw stream must come out byte for byte as long as the one from the records.
+    t_text, t_split = 0.0, 0.0
+    text_bytes = 0
+    if not args.no_text:
+        txt = []
+        for r in (r1, r2):
+            a = synth.fastq_fixed(r, first=rank * args.pairs)
+            t = torch.empty(len(a), dtype=torch.uint8, pin_memory=True)
+            t.numpy()[:] = a
+            txt.append(t)
+            text_bytes += len(a)
+        del a
+
+        def step_text():
+            ts0 = time.perf_counter()
+            f1 = api.fastx_split_parallel(txt[0], threads=args.split_threads)
+            f2 = api.fastx_split_parallel(txt[1], threads=args.split_threads)
+            ts1 = time.perf_counter()
+            return pipe.map_text(txt[0], f1, txt[1], f2, args.e2e_chunks, outs, scores), (ts1 - ts0) * 1e3
+
+        step_text()
+        # the stage-1 kernels alone on the whole batch (window scan, filters + sizes, two scans, packing), CUDA events
+        # inside the library; algorithmic bytes: sequence + header read once, the stage-1 records written once
+        f1 = api.fastx_split_parallel(txt[0], threads=args.split_threads)
+        f2 = api.fastx_split_parallel(txt[1], threads=args.split_threads)
+        f2[:, [0, 2, 4]] += np.uint32(len(txt[0]))
+        fboth = np.stack([f1, f2], axis=1).reshape(-1, 5)
+        s1_ms = min(db.run_input_batch(txt[0], fboth, paired=True, download=False, text2=txt[1])[2] for _ in range(3))
+        s1_alg = int(fboth[:, 1].sum(dtype=np.int64) + fboth[:, 3].sum(dtype=np.int64)) + len(s1_np)
+        del f1, f2, fboth
+        db.seed_upload(s1)   # the resident batch again (the c3 / nw legs below do not need it, later legs might)
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r_text, sp = step_text()
+            t_split += sp
+        sync_all()
+        t_text = (time.perf_counter() - t0) * 1e3
+        assert sum(int(f.numel() if hasattr(f, "numel") else len(f)) for f, _ in r_text) == out_bytes, "text path produced a different frag_raw size"
+        assert sum(c for _, c in r_text) == args.pairs
     pipe.close()
 
     # ---- the one exchange of the path: ConClave score arrays summed over ranks (runkma.c:98-99, conclave.c:80)
@@ -430,12 +475,12 @@ def main():
         torch.cuda.synchronize()
         t_allreduce = e0.elapsed_time(e1)
 
-    tt = torch.tensor([t_dev, t_e2e, t_wall, t_allreduce], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([t_dev, t_e2e, t_wall, t_allreduce, t_text], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([float(st.reads), float(st.mapped), float(sa.frags), float(args.pairs)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    t_dev_max, t_e2e_max, t_wall_max, t_ar_max = (float(x) for x in tt.cpu())
+    t_dev_max, t_e2e_max, t_wall_max, t_ar_max, t_text_max = (float(x) for x in tt.cpu())
     total_reads = float(cnt[0]) * args.steps
 
     pk, pk_kind = peaks()
@@ -467,6 +512,13 @@ def main():
         "e2e": {"value": total_reads / (t_e2e_max * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(len(s1_np)) + 10 * args.pairs + 4,
                 "d2h_bytes_per_step": out_bytes + 16 * DBn * len(bounds), "ms_per_step": t_e2e_max / args.steps,
                 "pipeline": {"workers": args.e2e_workers, "chunks": len(bounds)}},
+        "e2e_text": None if args.no_text else {
+            "what": "the same step from FASTQ text in pinned host memory: record splitter on host threads, stage 1 (translation, end trim, "
+                    "filters, 2-bit packing) on the device, then as e2e",
+            "value": total_reads / (t_text_max * 1e-3), "unit": "reads/s", "ms_per_step": t_text_max / args.steps,
+            "split_ms_per_step": t_split / args.steps, "split_threads": args.split_threads, "h2d_bytes_per_step": text_bytes + 40 * args.pairs,
+            "stage1_kernels": {"ms": s1_ms, "alg_bytes": s1_alg, "achieved_GBs": s1_alg / (s1_ms * 1e-3) / 1e9,
+                               "reads_per_s": 2 * args.pairs / (s1_ms * 1e-3)}},
         "gpu_launches": launches,
         "wall_ms_per_step_resident": t_wall_max / args.steps,
         "stage_ms": {"seed_total": st.ms_total, "seed_kernel": st.ms_seed, "align_prep": sa.ms_prep, "align_pairs": sa.ms_align,

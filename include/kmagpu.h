@@ -229,12 +229,19 @@ typedef struct kmagpu_ingest_params {
  * (fields = NULL only counts); -1 on malformed input. */
 int64_t kmagpu_fastx_split(const void *text, size_t nbytes, int fastq, const uint8_t *trans, uint32_t *fields, size_t cap, size_t *used);
 
+/* Host only: the start of the first record at or after byte `from` (FASTQ: a line starting with '@' whose second-next
+ * line starts with '+'), so that several host threads can run kmagpu_fastx_split on byte ranges of one chunk.
+ * Returns nbytes when there is none. */
+size_t kmagpu_fastx_sync(const void *text, size_t nbytes, int fastq, size_t from);
+
 /* text (host) -> stage-1 records in input order. The stream always stays in HBM as the input of the next
  * kmagpu_seed_run (as if kmagpu_seed_upload had been called with it); stage1_out != NULL also downloads it.
- * count = what run_input returns (one per printed read or pair), ms = the three kernels and their scans. For paired
- * input put both files' text into one buffer and interleave their fields. */
-int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip, const void *text, size_t text_bytes, const uint32_t *fields,
-                        size_t nreads, void *stage1_out, size_t cap, size_t *out_bytes, int64_t *count, float *ms);
+ * count = what run_input returns (one per printed read or pair), ms = the three kernels and their scans. Paired
+ * input: interleave the two files' fields (mates at 2i, 2i + 1); text2 (may be NULL) is the second file's chunk, its
+ * fields count their offsets from text_bytes on (the two chunks sit back to back in one device buffer). */
+int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip, const void *text, size_t text_bytes, const void *text2,
+                        size_t text2_bytes, const uint32_t *fields, size_t nreads, void *stage1_out, size_t cap, size_t *out_bytes,
+                        int64_t *count, float *ms);
 
 /* NW_score (nw.c:642) / NW_band_score (nw.c:892) over a batch of independent problems, one warp each.
  * prob[i] = {template id, t_s, t_e, q_off, q_s, q_e, k, band (0 = full matrix)}; the query bytes (0-4) of problem i

@@ -82,6 +82,30 @@ def fastx_split(text, fastq: bool = True, trans: np.ndarray | None = None):
     return fields, used.value
 
 
+def fastx_split_parallel(text, threads: int = 8, fastq: bool = True, trans: np.ndarray | None = None) -> np.ndarray:
+    """fastx_split by `threads` host threads over byte ranges of the chunk (cut at record starts found by
+    kmagpu_fastx_sync; the C calls run without the GIL). -> uint32 fields[n, 5] with offsets into the whole chunk"""
+    from concurrent.futures import ThreadPoolExecutor
+    trans = to2bit() if trans is None else trans
+    buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
+    buf = buf.numpy() if hasattr(buf, "numpy") else buf
+    nb = len(buf)
+    L = lib()
+    cuts = sorted({L.kmagpu_fastx_sync(buf.ctypes.data, nb, int(fastq), (nb * i) // threads) for i in range(threads)} | {nb})
+
+    def part(i):
+        lo, hi = cuts[i], cuts[i + 1]
+        f, used = fastx_split(buf[lo:hi], fastq, trans)
+        if used != hi - lo:
+            raise KmaGpuError(f"text range {lo}..{hi} does not end at a record boundary")
+        f[:, [0, 2, 4]] += np.uint32(lo)
+        return f
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        parts = list(ex.map(part, range(len(cuts) - 1)))
+    return np.concatenate(parts) if parts else np.zeros((0, 5), dtype=np.uint32)
+
+
 class ConsensusParams(C.Structure):
     _fields_ = [("bcd", C.c_int32), ("caller", C.c_int32), ("significance", C.c_int32), ("reserved", C.c_int32),
                 ("support", C.c_double), ("chi2_min", C.c_double)]
@@ -122,8 +146,10 @@ def lib():
         L.kmagpu_lookup_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.kmagpu_fastx_split.restype = C.c_int64
         L.kmagpu_fastx_split.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.kmagpu_fastx_sync.restype = C.c_size_t
+        L.kmagpu_fastx_sync.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_size_t]
         L.kmagpu_stage1_batch.argtypes = [C.c_void_p, C.POINTER(IngestParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
-                                          C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
+                                          C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
         L.kmagpu_chi2_threshold.restype = C.c_double
         L.kmagpu_chi2_threshold.argtypes = [C.c_double, C.c_void_p]
         L.kmagpu_consensus.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ConsensusParams), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -196,19 +222,23 @@ class TemplateDB:
 
     # --- stage 1 -----------------------------------------------------------------------------
     def run_input_batch(self, text, fields: np.ndarray, fastq=True, paired=False, min_phred=20, phred_scale=33, minlen=16,
-                        maxlen=2147483647, trans: np.ndarray | None = None, download=True):
+                        maxlen=2147483647, trans: np.ndarray | None = None, download=True, text2=None):
         """FASTQ / FASTA text + its line structure (fastx_split) -> stage-1 records (run_input / run_input_PE per read:
         translation, end trim, -ml / -xl, pairing rule, compDNA, printFsa). The stream stays on the device as the input
-        of seed_run(); download=False skips the copy back. -> (stage-1 bytes | None, count, kernel ms)"""
+        of seed_run(); download=False skips the copy back. text2: the second file's chunk of a pair of files (its fields
+        count their offsets from len(text) on). -> (stage-1 bytes | None, count, kernel ms)"""
         ip = IngestParams()
         ip.fastq, ip.paired, ip.min_phred, ip.phred_scale, ip.minlen, ip.maxlen = int(fastq), int(paired), min_phred, phred_scale, minlen, maxlen
         C.memmove(ip.trans, (to2bit() if trans is None else trans).ctypes.data, 256)
         buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
         fields = np.ascontiguousarray(fields, dtype=np.uint32)
         nbytes = int(buf.numel() if hasattr(buf, "numel") else buf.size)
-        out = np.empty(nbytes + 64 if download else 0, dtype=np.uint8)
+        buf2 = np.frombuffer(text2, dtype=np.uint8) if isinstance(text2, (bytes, bytearray)) else text2
+        nbytes2 = 0 if buf2 is None else int(buf2.numel() if hasattr(buf2, "numel") else buf2.size)
+        out = np.empty(nbytes + nbytes2 + 64 if download else 0, dtype=np.uint8)
         ob, cnt, ms = C.c_size_t(), C.c_int64(), C.c_float()
-        _check(lib().kmagpu_stage1_batch(self._h, C.byref(ip), _ptr(buf), nbytes, fields.ctypes.data, len(fields),
+        _check(lib().kmagpu_stage1_batch(self._h, C.byref(ip), _ptr(buf), nbytes, _ptr(buf2) if nbytes2 else None, nbytes2,
+                                         fields.ctypes.data, len(fields),
                                          out.ctypes.data if download else None, len(out), C.byref(ob), C.byref(cnt), C.byref(ms)))
         return (out[: ob.value] if download else None), cnt.value, ms.value
 

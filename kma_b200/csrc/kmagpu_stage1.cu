@@ -175,9 +175,43 @@ extern "C" int64_t kmagpu_fastx_split(const void *text_, size_t nbytes, int fast
 	return (int64_t)n;
 }
 
-extern "C" int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip, const void *text, size_t text_bytes, const uint32_t *fields,
-                                   size_t nreads, void *stage1_out, size_t cap, size_t *out_bytes, int64_t *count, float *ms) {
-	if (!db || !ip || (!text && text_bytes) || (!fields && nreads)) { kmagpu_set_error("null argument"); return -1; }
+// Host only: the start of the first record at or after byte `from` of a FASTQ / FASTA chunk, so that several threads
+// can split byte ranges of one chunk independently. FASTQ: a line that starts with '@' whose second-next line starts
+// with '+' (a quality line may start with '@', a sequence line cannot start with '+'). Returns nbytes when none.
+extern "C" size_t kmagpu_fastx_sync(const void *text_, size_t nbytes, int fastq, size_t from) {
+	const uint8_t *text = (const uint8_t *)text_;
+	if (!text) return nbytes;
+	size_t p = from;
+	if (p > 0) {   // move to the start of the next line unless `from` already is one
+		if (p >= nbytes) return nbytes;
+		if (text[p - 1] != '\n') {
+			const uint8_t *e = (const uint8_t *)memchr(text + p, '\n', nbytes - p);
+			if (!e) return nbytes;
+			p = (size_t)(e - text) + 1;
+		}
+	}
+	while (p < nbytes) {
+		const uint8_t *e1 = (const uint8_t *)memchr(text + p, '\n', nbytes - p);
+		if (text[p] == (fastq ? '@' : '>')) {
+			if (!fastq) return p;
+			if (!e1) return nbytes;
+			const size_t l2 = (size_t)(e1 - text) + 1;
+			const uint8_t *e2 = l2 < nbytes ? (const uint8_t *)memchr(text + l2, '\n', nbytes - l2) : nullptr;
+			if (!e2) return nbytes;
+			const size_t l3 = (size_t)(e2 - text) + 1;
+			if (l3 < nbytes && text[l3] == '+') return p;
+		}
+		if (!e1) return nbytes;
+		p = (size_t)(e1 - text) + 1;
+	}
+	return nbytes;
+}
+
+extern "C" int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip, const void *text, size_t text1_bytes, const void *text2,
+                                   size_t text2_bytes, const uint32_t *fields, size_t nreads, void *stage1_out, size_t cap, size_t *out_bytes,
+                                   int64_t *count, float *ms) {
+	if (!db || !ip || (!text && text1_bytes) || (!text2 && text2_bytes) || (!fields && nreads)) { kmagpu_set_error("null argument"); return -1; }
+	const size_t text_bytes = text1_bytes + text2_bytes;   // the second file's text follows the first in one device buffer
 	if (text_bytes >= (1ull << 32) - 64) { kmagpu_set_error("text chunk of %zu bytes exceeds the 4 GiB per-call limit; split it", text_bytes); return -1; }
 	if (nreads >= (1ull << 31)) { kmagpu_set_error("too many reads in one call"); return -1; }
 	if (ip->paired && (nreads & 1)) { kmagpu_set_error("paired input needs an even number of reads (mates at 2i, 2i + 1)"); return -1; }
@@ -206,7 +240,8 @@ extern "C" int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip
 	unsigned long long *ctr = (unsigned long long *)d_ctr.p;
 	S1Tab tab;
 	memcpy(tab.t, ip->trans, 256);
-	KG_CUDA(cudaMemcpyAsync(d_text.p, text, text_bytes, cudaMemcpyHostToDevice, st));
+	if (text1_bytes) KG_CUDA(cudaMemcpyAsync(d_text.p, text, text1_bytes, cudaMemcpyHostToDevice, st));
+	if (text2_bytes) KG_CUDA(cudaMemcpyAsync((uint8_t *)d_text.p + text1_bytes, text2, text2_bytes, cudaMemcpyHostToDevice, st));
 	KG_CUDA(cudaMemcpyAsync(d_fields.p, fields, 20 * (size_t)n, cudaMemcpyHostToDevice, st));
 	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
 	KG_CUDA(cudaEventRecord(db->ev[0], st));

@@ -37,6 +37,58 @@ class MapPipeline:
         cuts.append(int(off[n]))
         return [(cuts[i], cuts[i + 1]) for i in range(n_chunks) if cuts[i + 1] > cuts[i]]
 
+    def map_text(self, text1, fields1, text2, fields2, n_chunks, outs, scores, **ingest):
+        """The same from FASTQ text (pinned uint8 arrays / tensors): stage 1 runs on the device too (run_input_batch), so a
+        chunk's reads go text -> HBM -> stage-1 records -> stage 2 -> alignment pass without coming back. fields1 / fields2:
+        api.fastx_split of the two files (fields2 = None: single end). Chunks are ranges of reads (pairs)."""
+        n = len(fields1)
+        cuts = [(n * c) // n_chunks for c in range(n_chunks + 1)]
+        chunks = [(cuts[i], cuts[i + 1]) for i in range(n_chunks) if cuts[i + 1] > cuts[i]]
+        res = [None] * len(chunks)
+        part = [(np.zeros_like(scores[0]), np.zeros_like(scores[1])) for _ in self.dbs]
+        err = []
+        end1 = int(text1.numel() if hasattr(text1, "numel") else text1.size)
+        end2 = 0 if text2 is None else int(text2.numel() if hasattr(text2, "numel") else text2.size)
+
+        def span(fields, a, b, end):   # bytes of reads a..b-1: from the '@' of a to the '@' of b
+            return int(fields[a][0]) - 1, (int(fields[b][0]) - 1 if b < len(fields) else end)
+
+        def work(w):
+            db = self.dbs[w]
+            try:
+                for i in range(w, len(chunks), len(self.dbs)):
+                    a, b = chunks[i]
+                    lo1, hi1 = span(fields1, a, b, end1)
+                    f = fields1[a:b].copy()
+                    f[:, [0, 2, 4]] -= np.uint32(lo1)
+                    t2 = None
+                    if fields2 is not None:
+                        lo2, hi2 = span(fields2, a, b, end2)
+                        g = fields2[a:b].copy()
+                        g[:, [0, 2, 4]] += np.uint32(hi1 - lo1) - np.uint32(lo2)
+                        f = np.stack([f, g], axis=1).reshape(-1, 5)
+                        t2 = text2[lo2:hi2]
+                    _, cnt, _ = db.run_input_batch(text1[lo1:hi1], f, paired=fields2 is not None, download=False, text2=t2, **ingest)
+                    db.seed_run(self.params)
+                    db.align_from_seed()
+                    db.align_run(self.params)
+                    frag, _, _, _ = db.align_download(out=outs[i], scores=part[w])
+                    res[i] = (frag, cnt)
+            except Exception as e:
+                err.append(e)
+
+        ts = [threading.Thread(target=work, args=(w,)) for w in range(len(self.dbs))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if err:
+            raise err[0]
+        for a, u in part:
+            scores[0][:] += a
+            scores[1][:] += u
+        return res
+
     def map(self, stage1, bounds, outs, scores):
         """stage 2 + alignment pass over the chunks `bounds` of the stage-1 stream (a pinned uint8 tensor / array).
         outs[i]: buffer for chunk i's frag_raw bytes; scores: (alignment_scores, uniq_alignment_scores) uint64 arrays

@@ -167,3 +167,23 @@ def write_fastq(path, reads, prefix="r", qual="I"):
         for i, r in enumerate(reads):
             s = decode(np.asarray(r))
             fh.write(f"@{prefix}{i}\n{s}\n+\n{qual * len(s)}\n")
+
+
+def fastq_fixed(reads: np.ndarray, prefix: str = "r", first: int = 0, qual: int = 73) -> np.ndarray:
+    """Vectorised 4-line FASTQ text (uint8 array) of equal-length reads (codes 0-4) with fixed-width names
+    '@<prefix><9-digit index>' -- the text whose stage-1 stream is records.stage1_records_fast(reads, prefix, first)."""
+    n, L = reads.shape
+    pre = prefix.encode()
+    hl = 1 + len(pre) + 9
+    rec = np.empty((n, hl + 1 + L + 3 + L + 1), dtype=np.uint8)
+    rec[:, 0] = ord("@")
+    rec[:, 1:1 + len(pre)] = np.frombuffer(pre, dtype=np.uint8)
+    idx = np.arange(first, first + n, dtype=np.int64)
+    for d in range(9):
+        rec[:, hl - 1 - d] = 48 + (idx // 10 ** d) % 10
+    rec[:, hl] = 10
+    rec[:, hl + 1:hl + 1 + L] = np.frombuffer(b"ACGTN", dtype=np.uint8)[reads]
+    rec[:, hl + 1 + L:hl + 4 + L] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+    rec[:, hl + 4 + L:hl + 4 + 2 * L] = qual
+    rec[:, -1] = 10
+    return rec.reshape(-1)

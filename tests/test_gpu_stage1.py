@@ -38,6 +38,9 @@ def test_fastx_split_host():
         cut = int(f[50][2]) + 3
         f2, used2 = api.fastx_split(text[:cut])
         assert len(f2) == 50 and used2 == int(f[50][0]) - 1 and np.array_equal(f2, f[:50])
+        # byte ranges split by several threads give the same table (quality lines that start with '@' included)
+        for th in (2, 3, 7):
+            assert np.array_equal(api.fastx_split_parallel(text, threads=th), f)
     fa = util.fastq_text(reads[:30], fasta=True)
     f3, used3 = api.fastx_split(fa, fastq=False)
     assert len(f3) == 30 and used3 == len(fa) and fa[int(f3[7][0]):int(f3[7][0]) + int(f3[7][1])] == b"r7 some description"
@@ -96,7 +99,9 @@ def test_paired_end_vs_oracle(tmp_path, seed, kw):
     prefix = util.build_db(tmp_path, names, seqs)
     db = api.TemplateDB(prefix, device=0)
     got, cnt, _ = db.run_input_batch(t1 + t2, fields, paired=True, **kw)
+    got2, cnt2, _ = db.run_input_batch(t1, fields, paired=True, text2=t2, **kw)   # the two files as separate host buffers
     db.close()
+    assert got2.tobytes() == want and cnt2 == wcnt
     assert got.tobytes() == want and cnt == wcnt
 
 

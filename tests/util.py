@@ -492,6 +492,8 @@ def random_quals(rng, reads, scale=33):
             q[n - b:] = rng.integers(2, 24, size=b)
         if rng.integers(0, 25) == 0:
             q[:] = rng.integers(2, 19, size=n)   # nothing survives
+        if n and rng.integers(0, 6) == 0:
+            q[0] = 31                            # '@' as the first quality character (phred 33)
         out.append((q + scale).astype(np.uint8))
     return out
 
