@@ -425,6 +425,7 @@ def main():
     t_text, t_split = 0.0, 0.0
     text_bytes = 0
     if not args.no_text:
+        from concurrent.futures import ThreadPoolExecutor
         txt = []
         for r in (r1, r2):
             a = synth.fastq_fixed(r, first=rank * args.pairs)
@@ -436,8 +437,8 @@ def main():
 
         def step_text():
             ts0 = time.perf_counter()
-            f1 = api.fastx_split_parallel(txt[0], threads=args.split_threads)
-            f2 = api.fastx_split_parallel(txt[1], threads=args.split_threads)
+            with ThreadPoolExecutor(max_workers=2) as ex:   # the two files side by side, `--split-threads` threads each
+                f1, f2 = ex.map(lambda t: api.fastx_split_parallel(t, threads=args.split_threads), txt)
             ts1 = time.perf_counter()
             return pipe.map_text(txt[0], f1, txt[1], f2, args.e2e_chunks, outs, scores), (ts1 - ts0) * 1e3
 

@@ -64,6 +64,11 @@ struct SeedBatch {
 	bool ran = false;
 };
 
+// working buffers of stage 1 (kmagpu_stage1.cu): kept across calls, a pipeline calls it once per chunk
+struct Stage1Batch {
+	KgBuf d_text, d_fields, d_win, d_u32, d_kind, d_partial, d_ctr, h_ctr;
+};
+
 // one batch of the alignment pass (kmagpu_align.cu)
 struct AlignBatch {
 	KgBuf d_in, d_off, d_reads, d_slab, d_sz, d_partial, d_taskread, d_cand, d_recsize, d_out, d_ctr, d_scores,
@@ -93,6 +98,7 @@ struct kmagpu_db {
 	cudaEvent_t ev[8]{};
 	int sm_count = 148;
 	SeedBatch seed;
+	Stage1Batch s1;
 	// per-template alignment index (kmagpu_tindex.cu)
 	void *d_tmeta = nullptr, *d_tslots = nullptr;
 	int32_t *d_tdups = nullptr;
@@ -108,4 +114,5 @@ int kg_tindex_build(kmagpu_db *db);
 int kg_align_free(kmagpu_db *db);
 
 int kg_seed_free(kmagpu_db *db);
+int kg_stage1_free(kmagpu_db *db);
 int kg_chain_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *stats);

@@ -207,6 +207,13 @@ extern "C" size_t kmagpu_fastx_sync(const void *text_, size_t nbytes, int fastq,
 	return nbytes;
 }
 
+int kg_stage1_free(kmagpu_db *db) {
+	Stage1Batch &w = db->s1;
+	KgBuf *all[] = {&w.d_text, &w.d_fields, &w.d_win, &w.d_u32, &w.d_kind, &w.d_partial, &w.d_ctr, &w.h_ctr};
+	for (KgBuf *x : all) x->release();
+	return 0;
+}
+
 extern "C" int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip, const void *text, size_t text1_bytes, const void *text2,
                                    size_t text2_bytes, const uint32_t *fields, size_t nreads, void *stage1_out, size_t cap, size_t *out_bytes,
                                    int64_t *count, float *ms) {
@@ -231,9 +238,11 @@ extern "C" int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip
 	if (n == 0) return 0;
 	cudaStream_t st = db->stream;
 	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-	KgBuf d_text, d_fields, d_win, d_u32, d_kind, d_partial, d_ctr;
-	struct Guard { std::vector<KgBuf *> v; ~Guard() { for (KgBuf *x : v) x->release(); } } guard;
-	guard.v = {&d_text, &d_fields, &d_win, &d_u32, &d_kind, &d_partial, &d_ctr};
+	Stage1Batch &w = db->s1;   // buffers persist: no allocation (and no implicit device synchronisation) in the steady state
+	KgBuf &d_text = w.d_text, &d_fields = w.d_fields, &d_win = w.d_win, &d_u32 = w.d_u32, &d_kind = w.d_kind, &d_partial = w.d_partial,
+	      &d_ctr = w.d_ctr;
+	w.h_ctr.pinned = true;
+	if (w.h_ctr.reserve(64)) return -1;
 	if (d_text.reserve(text_bytes + 64) || d_fields.reserve(20 * (size_t)n) || d_win.reserve(sizeof(S1Win) * (size_t)n) ||
 	    d_u32.reserve(16 * ((size_t)n + 2)) || d_kind.reserve((size_t)n + 8) || d_partial.reserve(4 * (size_t)(ntiles + 2)) || d_ctr.reserve(64)) return -1;
 	uint32_t *size = (uint32_t *)d_u32.p, *keep = size + n + 1, *boff = keep + n + 1, *ridx = boff + n + 1;
@@ -253,7 +262,7 @@ extern "C" int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip
 		(uint8_t *)d_kind.p, ctr);
 	kg_exscan(size, n, boff, (uint32_t *)d_partial.p, ctr + 3, st);
 	kg_exscan(keep, n, ridx, (uint32_t *)d_partial.p, ctr + 4, st);
-	unsigned long long h[8];
+	unsigned long long *h = (unsigned long long *)w.h_ctr.p;
 	KG_CUDA(cudaMemcpyAsync(h, ctr, 64, cudaMemcpyDeviceToHost, st));
 	KG_CUDA(cudaStreamSynchronize(st));
 	KG_CUDA(cudaGetLastError());
@@ -262,8 +271,8 @@ extern "C" int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip
 	if (b.d_in.reserve(ob + 64) || b.d_off.reserve(4 * (nrec + 1)) || b.d_kinds.reserve(nrec + 1)) return -1;
 	s1_emit_kernel<<<grid, 256, 0, st>>>((const uint8_t *)d_text.p, (const uint32_t *)d_fields.p, (const S1Win *)d_win.p, n, tab, size, boff, ridx,
 		(const uint8_t *)d_kind.p, (uint8_t *)b.d_in.p, (uint32_t *)b.d_off.p, (uint8_t *)b.d_kinds.p);
-	const uint32_t last = (uint32_t)ob;
-	KG_CUDA(cudaMemcpyAsync((uint32_t *)b.d_off.p + nrec, &last, 4, cudaMemcpyHostToDevice, st));
+	h[7] = (unsigned long long)ob;   // the closing offset, from pinned memory
+	KG_CUDA(cudaMemcpyAsync((uint32_t *)b.d_off.p + nrec, &h[7], 4, cudaMemcpyHostToDevice, st));
 	KG_CUDA(cudaMemsetAsync((uint8_t *)b.d_kinds.p + nrec, 0, 1, st));
 	KG_CUDA(cudaMemsetAsync((uint8_t *)b.d_in.p + ob, 0, 64, st));
 	KG_CUDA(cudaEventRecord(db->ev[1], st));

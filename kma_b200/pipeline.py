@@ -65,7 +65,7 @@ class MapPipeline:
                     if fields2 is not None:
                         lo2, hi2 = span(fields2, a, b, end2)
                         g = fields2[a:b].copy()
-                        g[:, [0, 2, 4]] += np.uint32(hi1 - lo1) - np.uint32(lo2)
+                        g[:, [0, 2, 4]] = (g[:, [0, 2, 4]].astype(np.int64) + (hi1 - lo1 - lo2)).astype(np.uint32)
                         f = np.stack([f, g], axis=1).reshape(-1, 5)
                         t2 = text2[lo2:hi2]
                     _, cnt, _ = db.run_input_batch(text1[lo1:hi1], f, paired=fields2 is not None, download=False, text2=t2, **ingest)
