@@ -125,7 +125,11 @@ def test_mem_mode_flow_on_one_genome(tmp_path):
     db.matrix_reset()
     trace, n, _ = db.assemble_align_batch(frags, p)
     mat = db.matrix_download(1)
+    ct, cs, cq, cst, _ = db.consensus(1)   # the consensus of the genome from the device's own counts
     db.close()
+    wt, ws, wq, wst = util.oracle_consensus(prefix, 1, omat)
+    assert ct.tobytes() == wt and cs.tobytes() == ws and cq.tobytes() == wq
+    assert [int(cst[0][k]) for k in ("depth", "depthVar", "len", "aln_len", "cover")] == [int(x) for x in wst] and int(wst[4]) > 150_000
     assert frag.tobytes() == ofrag and frags.tobytes() == ofrags and int(w[1]) == int(ow[1]) > 0
     assert trace.tobytes() == otrace
     assert np.array_equal(mat, omat) and mat.shape == (200_000, 6)

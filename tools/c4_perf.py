@@ -1,0 +1,75 @@
+"""C4-shaped flow (BASELINE.json configs[3]: one bacterial genome as the only template, 150 bp reads, -mem_mode -1t1,
+base counts and consensus) through the C ABI, stage by stage with wall-clock per call (host buffers, copies included):
+FASTQ text -> stage 1 -> stage 2 (-1t1) -> -mem_mode score collection -> ConClave -> traceback alignment + base counts
+-> consensus. usage: c4_perf.py [genome_bases=5000000] [reads=1000000] [check=1]
+check: compares the consensus / matrix of the first 3000 reads' flow with the oracle chain first."""
+import os, sys, time, json, tempfile
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from kma_b200 import api, synth, records, dbbuild
+from tests import util
+
+
+def flow(db, text, p, tag):
+    t = {}
+    def lap(name, t0):
+        t[name] = round((time.perf_counter() - t0) * 1e3, 2)
+    t0 = time.perf_counter(); f = api.fastx_split_parallel(text, threads=8); lap("split_host", t0)
+    t0 = time.perf_counter(); _, cnt, ms1 = db.run_input_batch(text, f, download=False); lap("stage1", t0)
+    t0 = time.perf_counter(); st = db.seed_run(p); lap("stage2", t0)
+    out = np.empty(int(len(text) * 0.6) + 4096, dtype=np.uint8)
+    t0 = time.perf_counter(); s2 = db.seed_download(out); lap("stage2_download", t0)
+    s2 = s2.tobytes() + api.stream_terminator(cnt)
+    t0 = time.perf_counter(); frag, a, u, n = db.memscore_batch(s2); lap("memscore", t0)
+    t0 = time.perf_counter(); frags, w, fc, rc, _ = db.conclave_batch(frag, a, u); lap("conclave", t0)
+    db.matrix_reset()
+    t0 = time.perf_counter(); trace, nrec, sa = db.assemble_align_batch(frags, p); lap("trace+matrix", t0)
+    t0 = time.perf_counter(); ct, cs, cq, cst, msc = db.consensus(1); lap("consensus", t0)
+    t["stage1_kernels_ms"] = round(ms1, 3); t["stage2_kernels_ms"] = round(st.ms_total, 3); t["trace_kernel_ms"] = round(sa.ms_align, 3)
+    t["consensus_kernel_ms"] = round(msc, 4)
+    return t, (frags, trace, ct, cs, cq, cst, cnt, nrec, sa)
+
+
+def main():
+    G = int(sys.argv[1]) if len(sys.argv) > 1 else 5_000_000
+    nreads = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+    check = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+    wd = os.path.join(tempfile.gettempdir(), f"kma_b200_c4_{G}"); os.makedirs(wd, exist_ok=True)
+    prefix = os.path.join(wd, "db")
+    rng = np.random.default_rng(4)
+    genome = rng.integers(0, 4, size=G).astype(np.uint8)
+    if not os.path.exists(prefix + ".comp.b"):
+        dbbuild.build_db(prefix, ["genome"], [genome])
+    db = api.TemplateDB(prefix)
+    p = api.default_params(); p.one2one = 1; p.matrix = 1
+    reads = synth.short_reads(6, [genome], nreads, L=150, sub=0.01)
+    if check:
+        small = np.asarray(reads[:3000])
+        text = synth.fastq_fixed(small)
+        _, (frags, trace, ct, cs, cq, cst, cnt, nrec, sa) = flow(db, text, p, "check")
+        s1 = records.stage1_records_fast(small)
+        os2 = util.oracle_seed_stream(prefix, s1)
+        ofrag, oa, ou = util.oracle_memscore(prefix, os2)
+        ofrags, _, _, _ = util.oracle_conclave(prefix, ofrag, oa, ou)
+        otrace = util.oracle_trace(prefix, np.frombuffer(ofrags, dtype=np.uint8))
+        omat = util.oracle_matrix(prefix, np.frombuffer(ofrags, dtype=np.uint8), otrace)
+        wt, ws, wq, wst = util.oracle_consensus(prefix, 1, omat)
+        assert frags.tobytes() == ofrags and trace.tobytes() == otrace, "fragment stream / traceback differ from the oracle"
+        assert ct.tobytes() == wt and cq.tobytes() == wq and cs.tobytes() == ws and int(cst[0]["depth"]) == int(wst[0]), "consensus differs"
+        print("parity ok on 3000 reads", flush=True)
+    text = synth.fastq_fixed(np.asarray(reads))
+    best = None
+    for _ in range(3):
+        t, r = flow(db, text, p, "full")
+        tot = sum(v for k, v in t.items() if not k.endswith("_ms"))
+        if best is None or tot < best[0]:
+            best = (tot, t, r)
+    tot, t, r = best
+    cst = r[5]
+    print(json.dumps({"genome_bases": G, "reads": nreads, "stage_wall_ms": t, "total_wall_ms": round(tot, 1), "reads_per_s": nreads / (tot * 1e-3),
+                      "fragments": int(r[7]), "mean_depth": float(cst[0]["depth"]) / G, "consensus_identity_positions": int(cst[0]["cover"])}))
+    db.close()
+
+
+main()
