@@ -287,6 +287,7 @@ def main():
     ap.add_argument("--no-c3", action="store_true", help="skip the C3 (long reads, chain mode) side measurement")
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads / library handles of the end-to-end pipeline")
     ap.add_argument("--no-text", action="store_true", help="skip the FASTQ-text end-to-end leg (stage 1 on the device)")
+    ap.add_argument("--host-split", action="store_true", help="text leg: always split records on the host (default: on the device when the files line up)")
     ap.add_argument("--split-threads", type=int, default=8, help="host threads of the FASTQ record splitter in the text leg")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks the batch is cut into for the end-to-end pipeline")
     args = ap.parse_args()
@@ -436,6 +437,11 @@ def main():
         del a
 
         def step_text():
+            # record splitter on the device when the two files' records line up chunk by chunk (checked per chunk) ...
+            r = pipe.map_text_device_split(txt[0], txt[1], args.e2e_chunks, outs, scores) if not args.host_split else None
+            if r is not None:
+                return r, 0.0
+            # ... else on host threads, pairs by record index
             ts0 = time.perf_counter()
             with ThreadPoolExecutor(max_workers=2) as ex:   # the two files side by side, `--split-threads` threads each
                 f1, f2 = ex.map(lambda t: api.fastx_split_parallel(t, threads=args.split_threads), txt)
@@ -514,10 +520,10 @@ def main():
                 "d2h_bytes_per_step": out_bytes + 16 * DBn * len(bounds), "ms_per_step": t_e2e_max / args.steps,
                 "pipeline": {"workers": args.e2e_workers, "chunks": len(bounds)}},
         "e2e_text": None if args.no_text else {
-            "what": "the same step from FASTQ text in pinned host memory: record splitter on host threads, stage 1 (translation, end trim, "
-                    "filters, 2-bit packing) on the device, then as e2e",
+            "what": "the same step from FASTQ text in pinned host memory: record splitter (device, or host threads when the two files do not line "
+                    "up) + stage 1 (translation, end trim, filters, 2-bit packing) on the device, then as e2e",
             "value": total_reads / (t_text_max * 1e-3), "unit": "reads/s", "ms_per_step": t_text_max / args.steps,
-            "split_ms_per_step": t_split / args.steps, "split_threads": args.split_threads, "h2d_bytes_per_step": text_bytes + 40 * args.pairs,
+            "split": "host" if (args.host_split or t_split > 0) else "device", "split_ms_per_step": t_split / args.steps, "split_threads": args.split_threads, "h2d_bytes_per_step": text_bytes + 40 * args.pairs,
             "stage1_kernels": {"ms": s1_ms, "alg_bytes": s1_alg, "achieved_GBs": s1_alg / (s1_ms * 1e-3) / 1e9,
                                "reads_per_s": 2 * args.pairs / (s1_ms * 1e-3)}},
         "gpu_launches": launches,

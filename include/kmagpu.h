@@ -243,6 +243,14 @@ int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip, const voi
                         size_t text2_bytes, const uint32_t *fields, size_t nreads, void *stage1_out, size_t cap, size_t *out_bytes,
                         int64_t *count, float *ms);
 
+/* The same with the record splitter on the device too: the chunk(s) of file text go to HBM as they are, newline
+ * positions are counted / scanned / scattered by 64-byte blocks and a thread per record builds the field row
+ * kmagpu_fastx_split would have produced. text2 != NULL with ip->paired: the chunk of the second file; records are
+ * paired by index, min(records1, records2) pairs are taken. eof != 0: a last line without its newline counts.
+ * used1 / used2 = the bytes the taken records span (the caller carries the rest over to its next chunk). */
+int kmagpu_stage1_text(kmagpu_db *db, const kmagpu_ingest_params *ip, const void *text1, size_t bytes1, const void *text2, size_t bytes2,
+                       int eof, size_t *used1, size_t *used2, void *stage1_out, size_t cap, size_t *out_bytes, int64_t *count, float *ms);
+
 /* NW_score (nw.c:642) / NW_band_score (nw.c:892) over a batch of independent problems, one warp each.
  * prob[i] = {template id, t_s, t_e, q_off, q_s, q_e, k, band (0 = full matrix)}; the query bytes (0-4) of problem i
  * start at qpool + q_off. out[i] = {score, len, pos, match, tGaps, qGaps}; status[i] != 0: not computed

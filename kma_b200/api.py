@@ -150,6 +150,9 @@ def lib():
         L.kmagpu_fastx_sync.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_size_t]
         L.kmagpu_stage1_batch.argtypes = [C.c_void_p, C.POINTER(IngestParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
                                           C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
+        L.kmagpu_stage1_text.argtypes = [C.c_void_p, C.POINTER(IngestParams), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int,
+                                         C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                         C.POINTER(C.c_int64), C.POINTER(C.c_float)]
         L.kmagpu_chi2_threshold.restype = C.c_double
         L.kmagpu_chi2_threshold.argtypes = [C.c_double, C.c_void_p]
         L.kmagpu_consensus.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ConsensusParams), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -241,6 +244,25 @@ class TemplateDB:
                                          fields.ctypes.data, len(fields),
                                          out.ctypes.data if download else None, len(out), C.byref(ob), C.byref(cnt), C.byref(ms)))
         return (out[: ob.value] if download else None), cnt.value, ms.value
+
+    def run_input_text(self, text, text2=None, fastq=True, min_phred=20, phred_scale=33, minlen=16, maxlen=2147483647,
+                       trans: np.ndarray | None = None, download=True, eof=True):
+        """run_input / run_input_PE on chunks of file text with the record splitter on the device as well
+        (kmagpu_stage1_text). text2: the second file's chunk (pairs by record index). -> (stage-1 bytes | None, count,
+        kernel ms, bytes used of text, bytes used of text2)"""
+        ip = IngestParams()
+        ip.fastq, ip.paired, ip.min_phred, ip.phred_scale, ip.minlen, ip.maxlen = int(fastq), int(text2 is not None), min_phred, phred_scale, minlen, maxlen
+        C.memmove(ip.trans, (to2bit() if trans is None else trans).ctypes.data, 256)
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
+        buf2 = np.frombuffer(text2, dtype=np.uint8) if isinstance(text2, (bytes, bytearray)) else text2
+        nb = int(buf.numel() if hasattr(buf, "numel") else buf.size)
+        nb2 = 0 if buf2 is None else int(buf2.numel() if hasattr(buf2, "numel") else buf2.size)
+        out = np.empty(nb + nb2 + 64 if download else 0, dtype=np.uint8)
+        ob, cnt, ms, u1, u2 = C.c_size_t(), C.c_int64(), C.c_float(), C.c_size_t(), C.c_size_t()
+        _check(lib().kmagpu_stage1_text(self._h, C.byref(ip), _ptr(buf) if nb else None, nb, _ptr(buf2) if buf2 is not None else None, nb2,
+                                        int(eof), C.byref(u1), C.byref(u2), out.ctypes.data if download else None, len(out), C.byref(ob),
+                                        C.byref(cnt), C.byref(ms)))
+        return (out[: ob.value] if download else None), cnt.value, ms.value, u1.value, u2.value
 
     # --- stage 2 -----------------------------------------------------------------------------
     def save_kmers_batch(self, stage1, params: Params | None = None, out=None):

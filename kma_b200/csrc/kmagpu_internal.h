@@ -67,6 +67,7 @@ struct SeedBatch {
 // working buffers of stage 1 (kmagpu_stage1.cu): kept across calls, a pipeline calls it once per chunk
 struct Stage1Batch {
 	KgBuf d_text, d_fields, d_win, d_u32, d_kind, d_partial, d_ctr, h_ctr;
+	KgBuf d_cnt1, d_cnt2, d_lines1, d_lines2;   // device record splitter: newline counts + offsets per 64-byte block, line ends
 };
 
 // one batch of the alignment pass (kmagpu_align.cu)

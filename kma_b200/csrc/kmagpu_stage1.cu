@@ -13,6 +13,7 @@
 #include "kmagpu_internal.h"
 #include "kmagpu_dev.cuh"
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 struct S1Win { int32_t start, end, nN, klen; };   // kept window, its N count, the length the -ml filter sees
@@ -209,59 +210,33 @@ extern "C" size_t kmagpu_fastx_sync(const void *text_, size_t nbytes, int fastq,
 
 int kg_stage1_free(kmagpu_db *db) {
 	Stage1Batch &w = db->s1;
-	KgBuf *all[] = {&w.d_text, &w.d_fields, &w.d_win, &w.d_u32, &w.d_kind, &w.d_partial, &w.d_ctr, &w.h_ctr};
+	KgBuf *all[] = {&w.d_text, &w.d_fields, &w.d_win, &w.d_u32, &w.d_kind, &w.d_partial, &w.d_ctr, &w.h_ctr, &w.d_cnt1, &w.d_cnt2, &w.d_lines1,
+	                &w.d_lines2};
 	for (KgBuf *x : all) x->release();
 	return 0;
 }
 
-extern "C" int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip, const void *text, size_t text1_bytes, const void *text2,
-                                   size_t text2_bytes, const uint32_t *fields, size_t nreads, void *stage1_out, size_t cap, size_t *out_bytes,
-                                   int64_t *count, float *ms) {
-	if (!db || !ip || (!text && text1_bytes) || (!text2 && text2_bytes) || (!fields && nreads)) { kmagpu_set_error("null argument"); return -1; }
-	const size_t text_bytes = text1_bytes + text2_bytes;   // the second file's text follows the first in one device buffer
-	if (text_bytes >= (1ull << 32) - 64) { kmagpu_set_error("text chunk of %zu bytes exceeds the 4 GiB per-call limit; split it", text_bytes); return -1; }
-	if (nreads >= (1ull << 31)) { kmagpu_set_error("too many reads in one call"); return -1; }
-	if (ip->paired && (nreads & 1)) { kmagpu_set_error("paired input needs an even number of reads (mates at 2i, 2i + 1)"); return -1; }
-	for (size_t i = 0; i < nreads; ++i) {
-		const uint32_t *f = fields + 5 * i;
-		if ((size_t)f[0] + f[1] > text_bytes || (size_t)f[2] + f[3] > text_bytes || (ip->fastq && (size_t)f[4] + f[3] > text_bytes)) {
-			kmagpu_set_error("read %zu points outside the text", i); return -1;
-		}
-	}
-	KG_CUDA(cudaSetDevice(db->device));
-	if (out_bytes) *out_bytes = 0;
-	if (count) *count = 0;
-	if (ms) *ms = 0.f;
-	const int n = (int)nreads;
+// the part both entry points share: d_text and d_fields hold the chunk and its n field rows; window scan -> filters ->
+// scans -> records into the seed batch
+static int s1_core(kmagpu_db *db, const kmagpu_ingest_params *ip, int n, void *stage1_out, size_t cap, size_t *out_bytes, int64_t *count) {
 	SeedBatch &b = db->seed;
-	b.nreads = 0; b.npairs = 0; b.in_bytes = 0; b.max_seqlen = 0; b.ran = false;
-	if (n == 0) return 0;
+	Stage1Batch &w = db->s1;
 	cudaStream_t st = db->stream;
 	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-	Stage1Batch &w = db->s1;   // buffers persist: no allocation (and no implicit device synchronisation) in the steady state
-	KgBuf &d_text = w.d_text, &d_fields = w.d_fields, &d_win = w.d_win, &d_u32 = w.d_u32, &d_kind = w.d_kind, &d_partial = w.d_partial,
-	      &d_ctr = w.d_ctr;
-	w.h_ctr.pinned = true;
-	if (w.h_ctr.reserve(64)) return -1;
-	if (d_text.reserve(text_bytes + 64) || d_fields.reserve(20 * (size_t)n) || d_win.reserve(sizeof(S1Win) * (size_t)n) ||
-	    d_u32.reserve(16 * ((size_t)n + 2)) || d_kind.reserve((size_t)n + 8) || d_partial.reserve(4 * (size_t)(ntiles + 2)) || d_ctr.reserve(64)) return -1;
-	uint32_t *size = (uint32_t *)d_u32.p, *keep = size + n + 1, *boff = keep + n + 1, *ridx = boff + n + 1;
-	unsigned long long *ctr = (unsigned long long *)d_ctr.p;
+	if (w.d_win.reserve(sizeof(S1Win) * (size_t)n) || w.d_u32.reserve(16 * ((size_t)n + 2)) || w.d_kind.reserve((size_t)n + 8) ||
+	    w.d_partial.reserve(4 * (size_t)(ntiles + 2))) return -1;
+	uint32_t *size = (uint32_t *)w.d_u32.p, *keep = size + n + 1, *boff = keep + n + 1, *ridx = boff + n + 1;
+	unsigned long long *ctr = (unsigned long long *)w.d_ctr.p;
 	S1Tab tab;
 	memcpy(tab.t, ip->trans, 256);
-	if (text1_bytes) KG_CUDA(cudaMemcpyAsync(d_text.p, text, text1_bytes, cudaMemcpyHostToDevice, st));
-	if (text2_bytes) KG_CUDA(cudaMemcpyAsync((uint8_t *)d_text.p + text1_bytes, text2, text2_bytes, cudaMemcpyHostToDevice, st));
-	KG_CUDA(cudaMemcpyAsync(d_fields.p, fields, 20 * (size_t)n, cudaMemcpyHostToDevice, st));
-	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
-	KG_CUDA(cudaEventRecord(db->ev[0], st));
 	const int grid = db->sm_count * 8;
-	s1_window_kernel<<<grid, 256, 0, st>>>((const uint8_t *)d_text.p, (const uint32_t *)d_fields.p, n, tab, ip->fastq, ip->phred_scale + ip->min_phred,
-		ip->maxlen, (S1Win *)d_win.p);
+	s1_window_kernel<<<grid, 256, 0, st>>>((const uint8_t *)w.d_text.p, (const uint32_t *)w.d_fields.p, n, tab, ip->fastq, ip->phred_scale + ip->min_phred,
+		ip->maxlen, (S1Win *)w.d_win.p);
 	const int units = ip->paired ? n / 2 : n;
-	s1_decide_kernel<<<(units + 255) / 256, 256, 0, st>>>((const uint32_t *)d_fields.p, (const S1Win *)d_win.p, n, ip->paired, ip->minlen, size, keep,
-		(uint8_t *)d_kind.p, ctr);
-	kg_exscan(size, n, boff, (uint32_t *)d_partial.p, ctr + 3, st);
-	kg_exscan(keep, n, ridx, (uint32_t *)d_partial.p, ctr + 4, st);
+	s1_decide_kernel<<<(units + 255) / 256, 256, 0, st>>>((const uint32_t *)w.d_fields.p, (const S1Win *)w.d_win.p, n, ip->paired, ip->minlen, size, keep,
+		(uint8_t *)w.d_kind.p, ctr);
+	kg_exscan(size, n, boff, (uint32_t *)w.d_partial.p, ctr + 3, st);
+	kg_exscan(keep, n, ridx, (uint32_t *)w.d_partial.p, ctr + 4, st);
 	unsigned long long *h = (unsigned long long *)w.h_ctr.p;
 	KG_CUDA(cudaMemcpyAsync(h, ctr, 64, cudaMemcpyDeviceToHost, st));
 	KG_CUDA(cudaStreamSynchronize(st));
@@ -269,8 +244,8 @@ extern "C" int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip
 	const size_t ob = (size_t)h[3], nrec = (size_t)h[4];
 	if (ob >= (1ull << 31)) { kmagpu_set_error("stage-1 stream of %zu bytes exceeds the 2 GiB per-call limit of stage 2; split the text", ob); return -1; }
 	if (b.d_in.reserve(ob + 64) || b.d_off.reserve(4 * (nrec + 1)) || b.d_kinds.reserve(nrec + 1)) return -1;
-	s1_emit_kernel<<<grid, 256, 0, st>>>((const uint8_t *)d_text.p, (const uint32_t *)d_fields.p, (const S1Win *)d_win.p, n, tab, size, boff, ridx,
-		(const uint8_t *)d_kind.p, (uint8_t *)b.d_in.p, (uint32_t *)b.d_off.p, (uint8_t *)b.d_kinds.p);
+	s1_emit_kernel<<<grid, 256, 0, st>>>((const uint8_t *)w.d_text.p, (const uint32_t *)w.d_fields.p, (const S1Win *)w.d_win.p, n, tab, size, boff, ridx,
+		(const uint8_t *)w.d_kind.p, (uint8_t *)b.d_in.p, (uint32_t *)b.d_off.p, (uint8_t *)b.d_kinds.p);
 	h[7] = (unsigned long long)ob;   // the closing offset, from pinned memory
 	KG_CUDA(cudaMemcpyAsync((uint32_t *)b.d_off.p + nrec, &h[7], 4, cudaMemcpyHostToDevice, st));
 	KG_CUDA(cudaMemsetAsync((uint8_t *)b.d_kinds.p + nrec, 0, 1, st));
@@ -286,6 +261,186 @@ extern "C" int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip
 	b.nreads = (int64_t)nrec; b.npairs = (int64_t)h[1]; b.max_seqlen = (int32_t)h[2]; b.in_bytes = ob;
 	if (out_bytes) *out_bytes = ob;
 	if (count) *count = (int64_t)h[0];
+	return 0;
+}
+
+static int s1_begin(kmagpu_db *db, const void *text, size_t text1_bytes, const void *text2, size_t text2_bytes, size_t *out_bytes, int64_t *count, float *ms) {
+	KG_CUDA(cudaSetDevice(db->device));
+	if (out_bytes) *out_bytes = 0;
+	if (count) *count = 0;
+	if (ms) *ms = 0.f;
+	SeedBatch &b = db->seed;
+	b.nreads = 0; b.npairs = 0; b.in_bytes = 0; b.max_seqlen = 0; b.ran = false;
+	Stage1Batch &w = db->s1;   // buffers persist: no allocation (and no implicit device synchronisation) in the steady state
+	w.h_ctr.pinned = true;
+	if (w.h_ctr.reserve(128) || w.d_ctr.reserve(64) || w.d_text.reserve(text1_bytes + text2_bytes + 128)) return -1;
+	cudaStream_t st = db->stream;
+	if (text1_bytes) KG_CUDA(cudaMemcpyAsync(w.d_text.p, text, text1_bytes, cudaMemcpyHostToDevice, st));
+	if (text2_bytes) KG_CUDA(cudaMemcpyAsync((uint8_t *)w.d_text.p + text1_bytes, text2, text2_bytes, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemsetAsync((uint8_t *)w.d_text.p + text1_bytes + text2_bytes, 0, 64, st));
+	KG_CUDA(cudaMemsetAsync(w.d_ctr.p, 0, 64, st));
+	return 0;
+}
+
+extern "C" int kmagpu_stage1_batch(kmagpu_db *db, const kmagpu_ingest_params *ip, const void *text, size_t text1_bytes, const void *text2,
+                                   size_t text2_bytes, const uint32_t *fields, size_t nreads, void *stage1_out, size_t cap, size_t *out_bytes,
+                                   int64_t *count, float *ms) {
+	if (!db || !ip || (!text && text1_bytes) || (!text2 && text2_bytes) || (!fields && nreads)) { kmagpu_set_error("null argument"); return -1; }
+	const size_t text_bytes = text1_bytes + text2_bytes;   // the second file's text follows the first in one device buffer
+	if (text_bytes >= (1ull << 32) - 128) { kmagpu_set_error("text chunk of %zu bytes exceeds the 4 GiB per-call limit; split it", text_bytes); return -1; }
+	if (nreads >= (1ull << 31)) { kmagpu_set_error("too many reads in one call"); return -1; }
+	if (ip->paired && (nreads & 1)) { kmagpu_set_error("paired input needs an even number of reads (mates at 2i, 2i + 1)"); return -1; }
+	for (size_t i = 0; i < nreads; ++i) {
+		const uint32_t *f = fields + 5 * i;
+		if ((size_t)f[0] + f[1] > text_bytes || (size_t)f[2] + f[3] > text_bytes || (ip->fastq && (size_t)f[4] + f[3] > text_bytes)) {
+			kmagpu_set_error("read %zu points outside the text", i); return -1;
+		}
+	}
+	if (s1_begin(db, text, text1_bytes, text2, text2_bytes, out_bytes, count, ms)) return -1;
+	const int n = (int)nreads;
+	if (n == 0) return 0;
+	Stage1Batch &w = db->s1;
+	if (w.d_fields.reserve(20 * (size_t)n)) return -1;
+	KG_CUDA(cudaMemcpyAsync(w.d_fields.p, fields, 20 * (size_t)n, cudaMemcpyHostToDevice, db->stream));
+	KG_CUDA(cudaEventRecord(db->ev[0], db->stream));
+	if (s1_core(db, ip, n, stage1_out, cap, out_bytes, count)) return -1;
+	if (ms) cudaEventElapsedTime(ms, db->ev[0], db->ev[1]);
+	return 0;
+}
+
+// ---------------------------------------------------------------- the record splitter on the device
+// Line ends of a text: one thread per 64-byte block counts its newlines (byte-wise SIMD compare), a scan places them,
+// the same threads write the positions; a thread per record then turns four (FASTQ) or two (FASTA) consecutive lines
+// into the field row the host splitter would have produced.
+
+#define S1_BLK 64
+
+__device__ __forceinline__ unsigned s1_nl_mask(unsigned w) { return __vcmpeq4(w, 0x0a0a0a0au); }   // 0xff per newline byte
+
+__global__ void __launch_bounds__(256) s1_nl_count_kernel(const uint4 *__restrict__ text, uint32_t nblk, uint32_t nbytes, int eof, uint32_t *cnt) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nblk) return;
+	uint32_t c = 0;
+#pragma unroll
+	for (int j = 0; j < S1_BLK / 16; ++j) {   // the buffer is zero padded past nbytes: no newline there
+		const uint4 v = __ldg(text + (size_t)i * (S1_BLK / 16) + j);
+		c += (__popc(s1_nl_mask(v.x)) + __popc(s1_nl_mask(v.y)) + __popc(s1_nl_mask(v.z)) + __popc(s1_nl_mask(v.w))) >> 3;
+	}
+	// a last line without its newline counts as a line at the end of the file
+	if (eof && i == nblk - 1 && nbytes && ((const uint8_t *)text)[nbytes - 1] != '\n') ++c;
+	cnt[i] = c;
+}
+
+__global__ void __launch_bounds__(256) s1_nl_scatter_kernel(const uint8_t *__restrict__ text, uint32_t nblk, uint32_t nbytes, int eof,
+		const uint32_t *__restrict__ off, uint32_t *line_end) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nblk) return;
+	uint32_t o = off[i];
+	const uint32_t base = i * S1_BLK;
+#pragma unroll 4
+	for (int j = 0; j < S1_BLK / 4; ++j) {
+		unsigned m = s1_nl_mask(__ldg((const unsigned *)(text + base) + j)) & 0x01010101u;
+		while (m) { const int b = (__ffs(m) - 1) >> 3; line_end[o++] = base + 4 * j + b; m &= m - 1; }
+	}
+	if (eof && i == nblk - 1 && nbytes && text[nbytes - 1] != '\n') line_end[o] = nbytes;
+}
+
+// record r of a file whose text starts at byte `base` of the chunk buffer: lines lpr*r .. lpr*r + lpr - 1
+__global__ void __launch_bounds__(256) s1_fields_kernel(const uint8_t *__restrict__ text, const uint32_t *__restrict__ line_end, int nrec, uint32_t base,
+		int fastq, S1Tab tab, int stride, int which, uint32_t *fields, unsigned long long *ctr) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nrec) return;
+	const int lpr = fastq ? 4 : 2, l0 = lpr * r;
+	const uint32_t s0 = l0 ? line_end[l0 - 1] + 1 : 0, e0 = line_end[l0], e1 = line_end[l0 + 1];
+	const uint8_t *t = text + base;
+	if (t[s0] != (fastq ? '@' : '>')) atomicAdd(&ctr[5], 1ull);
+	uint32_t ho = s0 + 1, hl = e0 > ho ? e0 - ho : 0;
+	while (hl > 0) { const uint8_t c = t[ho + hl - 1]; if (c == ' ' || (c >= 9 && c <= 13)) --hl; else break; }
+	uint32_t so = e0 + 1, sl = e1 > so ? e1 - so : 0, qo = 0;
+	while (sl > 0 && tab.t[t[so + sl - 1]] == 8) --sl;
+	if (fastq) {
+		qo = line_end[l0 + 2] + 1;
+		if (line_end[l0 + 3] < qo + sl) atomicAdd(&ctr[5], 1ull);   // quality line shorter than the sequence
+	}
+	uint32_t *f = fields + 5 * ((size_t)stride * r + which);
+	f[0] = base + ho; f[1] = hl; f[2] = base + so; f[3] = sl; f[4] = base + qo;
+}
+
+static int s1_lines(kmagpu_db *db, const uint8_t *d_text, size_t nbytes, int eof, KgBuf &d_cnt, unsigned long long *total_ctr) {
+	const uint32_t nblk = (uint32_t)((nbytes + S1_BLK - 1) / S1_BLK);
+	Stage1Batch &w = db->s1;
+	const int ntiles = (int)((nblk + SCAN_TILE - 1) / SCAN_TILE);
+	if (d_cnt.reserve(8 * ((size_t)nblk + 2)) || w.d_partial.reserve(4 * (size_t)(ntiles + 2))) return -1;
+	uint32_t *cnt = (uint32_t *)d_cnt.p, *off = cnt + nblk + 1;
+	cudaStream_t st = db->stream;
+	s1_nl_count_kernel<<<(nblk + 255) / 256, 256, 0, st>>>((const uint4 *)d_text, nblk, (uint32_t)nbytes, eof, cnt);
+	kg_exscan(cnt, (int)nblk, off, (uint32_t *)w.d_partial.p, total_ctr, st);
+	return 0;
+}
+
+extern "C" int kmagpu_stage1_text(kmagpu_db *db, const kmagpu_ingest_params *ip, const void *text1, size_t bytes1, const void *text2, size_t bytes2,
+                                  int eof, size_t *used1, size_t *used2, void *stage1_out, size_t cap, size_t *out_bytes, int64_t *count, float *ms) {
+	if (!db || !ip || (!text1 && bytes1) || (!text2 && bytes2)) { kmagpu_set_error("null argument"); return -1; }
+	if (used1) *used1 = 0;
+	if (used2) *used2 = 0;
+	if (ip->paired && !text2) { kmagpu_set_error("paired text input needs the second file's chunk"); return -1; }
+	if (!ip->paired && bytes2) { kmagpu_set_error("a second chunk needs paired = 1"); return -1; }
+	// the second chunk starts on a 64-byte boundary of the device buffer so that both are scanned in aligned blocks
+	const size_t base2 = (bytes1 + S1_BLK - 1) / S1_BLK * S1_BLK;
+	if (base2 + bytes2 >= (1ull << 32) - 256) { kmagpu_set_error("text chunks of %zu bytes exceed the 4 GiB per-call limit; split them", bytes1 + bytes2); return -1; }
+	if (s1_begin(db, nullptr, 0, nullptr, 0, out_bytes, count, ms)) return -1;
+	if (bytes1 == 0) return 0;
+	Stage1Batch &w = db->s1;
+	cudaStream_t st = db->stream;
+	if (w.d_text.reserve(base2 + bytes2 + 256)) return -1;
+	uint8_t *dt = (uint8_t *)w.d_text.p;
+	KG_CUDA(cudaMemsetAsync(w.d_ctr.p, 0, 64, st));
+	KG_CUDA(cudaMemcpyAsync(dt, text1, bytes1, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemsetAsync(dt + bytes1, 0, base2 - bytes1 + 64, st));
+	if (bytes2) {
+		KG_CUDA(cudaMemcpyAsync(dt + base2, text2, bytes2, cudaMemcpyHostToDevice, st));
+		KG_CUDA(cudaMemsetAsync(dt + base2 + bytes2, 0, 128, st));
+	}
+	KG_CUDA(cudaEventRecord(db->ev[0], st));
+	unsigned long long *ctr = (unsigned long long *)w.d_ctr.p, *h = (unsigned long long *)w.h_ctr.p;
+	// pass 1: newline counts per block + scan, for both chunks (ctr[6], ctr[7] = their line counts)
+	if (s1_lines(db, dt, bytes1, eof, w.d_cnt1, ctr + 6)) return -1;
+	if (bytes2 && s1_lines(db, dt + base2, bytes2, eof, w.d_cnt2, ctr + 7)) return -1;
+	KG_CUDA(cudaMemcpyAsync(h, ctr, 64, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	const int lpr = ip->fastq ? 4 : 2;
+	const size_t lines1 = (size_t)h[6], lines2 = (size_t)h[7];
+	size_t nrec = lines1 / lpr;
+	if (ip->paired && lines2 / lpr < nrec) nrec = lines2 / lpr;
+	if (nrec >= (1ull << 30)) { kmagpu_set_error("too many reads in one call"); return -1; }
+	if (nrec == 0) return 0;
+	// pass 2: line ends, then the field rows (mates interleaved)
+	if (w.d_lines1.reserve(4 * (lines1 + 2)) || (bytes2 && w.d_lines2.reserve(4 * (lines2 + 2)))) return -1;
+	const int stride = ip->paired ? 2 : 1, n = (int)nrec * stride;
+	if (w.d_fields.reserve(20 * (size_t)n)) return -1;
+	S1Tab tab;
+	memcpy(tab.t, ip->trans, 256);
+	{
+		const uint32_t nblk = (uint32_t)((bytes1 + S1_BLK - 1) / S1_BLK);
+		s1_nl_scatter_kernel<<<(nblk + 255) / 256, 256, 0, st>>>(dt, nblk, (uint32_t)bytes1, eof, (const uint32_t *)w.d_cnt1.p + nblk + 1, (uint32_t *)w.d_lines1.p);
+		s1_fields_kernel<<<((int)nrec + 255) / 256, 256, 0, st>>>(dt, (const uint32_t *)w.d_lines1.p, (int)nrec, 0u, ip->fastq, tab, stride, 0,
+			(uint32_t *)w.d_fields.p, ctr);
+	}
+	if (bytes2) {
+		const uint32_t nblk = (uint32_t)((bytes2 + S1_BLK - 1) / S1_BLK);
+		s1_nl_scatter_kernel<<<(nblk + 255) / 256, 256, 0, st>>>(dt + base2, nblk, (uint32_t)bytes2, eof, (const uint32_t *)w.d_cnt2.p + nblk + 1, (uint32_t *)w.d_lines2.p);
+		s1_fields_kernel<<<((int)nrec + 255) / 256, 256, 0, st>>>(dt, (const uint32_t *)w.d_lines2.p, (int)nrec, (uint32_t)base2, ip->fastq, tab, stride, 1,
+			(uint32_t *)w.d_fields.p, ctr);
+	}
+	// bytes the whole records span (what the host carries over is the rest)
+	uint32_t *hu = (uint32_t *)(h + 8);   // past the eight counters s1_core reads back
+	KG_CUDA(cudaMemcpyAsync(hu, (const uint32_t *)w.d_lines1.p + nrec * lpr - 1, 4, cudaMemcpyDeviceToHost, st));
+	if (bytes2) KG_CUDA(cudaMemcpyAsync(hu + 2, (const uint32_t *)w.d_lines2.p + nrec * lpr - 1, 4, cudaMemcpyDeviceToHost, st));
+	if (s1_core(db, ip, n, stage1_out, cap, out_bytes, count)) return -1;   // synchronises the stream
+	if (h[5]) { kmagpu_set_error("%llu records are malformed (no '@' / '>' at the start, or a quality line shorter than its sequence)", h[5]); return -1; }
+	if (used1) *used1 = std::min<size_t>((size_t)hu[0] + 1, bytes1);
+	if (used2 && bytes2) *used2 = std::min<size_t>((size_t)hu[2] + 1, bytes2);
 	if (ms) cudaEventElapsedTime(ms, db->ev[0], db->ev[1]);
 	return 0;
 }

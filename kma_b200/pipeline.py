@@ -89,6 +89,58 @@ class MapPipeline:
             scores[1][:] += u
         return res
 
+    def map_text_device_split(self, text1, text2, n_chunks, outs, scores, fastq=True, **ingest):
+        """map_text with the record splitter on the device as well (run_input_text): the host only looks for n_chunks
+        record starts at even byte fractions of each file (kmagpu_fastx_sync). That pairs the right mates only when the
+        two files' records line up chunk by chunk (equal-length reads and names, the usual shape of an Illumina pair of
+        files); every chunk checks that both of its texts were consumed to the last byte, and the caller falls back to
+        map_text (host splitter, pairs by index) when one was not. Returns None in that case."""
+        L = api.lib()
+        def cuts(t):
+            if t is None:
+                return None
+            a = t.numpy() if hasattr(t, "numpy") else t
+            nb = len(a)
+            return sorted({L.kmagpu_fastx_sync(a.ctypes.data, nb, int(fastq), (nb * i) // n_chunks) for i in range(n_chunks)} | {nb})
+        c1, c2 = cuts(text1), cuts(text2)
+        if c2 is not None and len(c2) != len(c1):
+            return None
+        nch = len(c1) - 1
+        res = [None] * nch
+        part = [(np.zeros_like(scores[0]), np.zeros_like(scores[1])) for _ in self.dbs]
+        err, bad = [], []
+
+        def work(w):
+            db = self.dbs[w]
+            try:
+                for i in range(w, nch, len(self.dbs)):
+                    t2 = None if c2 is None else text2[c2[i]:c2[i + 1]]
+                    _, cnt, _, u1, u2 = db.run_input_text(text1[c1[i]:c1[i + 1]], text2=t2, fastq=fastq, download=False, **ingest)
+                    if u1 != c1[i + 1] - c1[i] or (c2 is not None and u2 != c2[i + 1] - c2[i]):
+                        bad.append(i)
+                        return
+                    db.seed_run(self.params)
+                    db.align_from_seed()
+                    db.align_run(self.params)
+                    frag, _, _, _ = db.align_download(out=outs[i], scores=part[w])
+                    res[i] = (frag, cnt)
+            except Exception as e:
+                err.append(e)
+
+        ts = [threading.Thread(target=work, args=(w,)) for w in range(len(self.dbs))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if err:
+            raise err[0]
+        if bad:
+            return None
+        for a, u in part:
+            scores[0][:] += a
+            scores[1][:] += u
+        return res
+
     def map(self, stage1, bounds, outs, scores):
         """stage 2 + alignment pass over the chunks `bounds` of the stage-1 stream (a pinned uint8 tensor / array).
         outs[i]: buffer for chunk i's frag_raw bytes; scores: (alignment_scores, uniq_alignment_scores) uint64 arrays

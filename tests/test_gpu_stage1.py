@@ -133,3 +133,72 @@ def test_text_to_stage2_in_hbm(tmp_path):
     gotpe = db.seed_download(out)
     db.close()
     assert gotpe.tobytes() + api.stream_terminator(cntpe) == wantpe.tobytes()
+
+
+@gpu
+@pytest.mark.parametrize("crlf", [False, True])
+def test_device_splitter_vs_oracle(tmp_path, crlf):
+    """kmagpu_stage1_text: the record splitter on the device too -- single end, FASTA, pairs, a chunk cut inside a record,
+    a file without its last newline"""
+    rng, names, seqs, reads = _reads(41, n=900)
+    prefix = util.build_db(tmp_path, names, seqs)
+    db = api.TemplateDB(prefix, device=0)
+    text = util.fastq_text(reads, util.random_quals(rng, reads), crlf=crlf)
+    want, wcnt = util.oracle_stage1(text)
+    got, cnt, ms, used, _ = db.run_input_text(text)
+    assert got.tobytes() == want and cnt == wcnt and used == len(text) and ms > 0
+    got, cnt, _, used, _ = db.run_input_text(text[:-1])               # no newline at the end of the file
+    assert got.tobytes() == want and cnt == wcnt and used == len(text) - 1
+    f, _ = api.fastx_split(text)
+    cut = int(f[500][2]) + 7                                          # a chunk that ends inside record 500
+    part, pcnt, _, used, _ = db.run_input_text(text[:cut], eof=False)
+    w2, c2 = util.oracle_stage1(text[:int(f[500][0]) - 1])
+    assert part.tobytes() == w2 and pcnt == c2 and used == int(f[500][0]) - 1
+    rest, rcnt, _, used2, _ = db.run_input_text(text[used:])          # the carried-over rest gives the other records
+    assert part.tobytes() + rest.tobytes() == want and pcnt + rcnt == wcnt
+    fa = util.fastq_text(reads, fasta=True, crlf=crlf)
+    wfa, cfa = util.oracle_stage1(fa, fastq=False, minlen=40)
+    gfa, gc, _, _, _ = db.run_input_text(fa, fastq=False, minlen=40)
+    assert gfa.tobytes() == wfa and gc == cfa
+    _, _, _, r2 = _reads(141, n=820)                                  # the second file is shorter: 820 pairs are taken
+    t2 = util.fastq_text(r2, util.random_quals(rng, r2), crlf=crlf)
+    f1, _ = api.fastx_split(text)
+    wpe, cpe = util.oracle_stage1(text[:int(f1[820][0]) - 1], t2)
+    gpe, gcpe, _, u1, u2 = db.run_input_text(text, text2=t2)
+    assert gpe.tobytes() == wpe and gcpe == cpe and u1 == int(f1[820][0]) - 1 and u2 == len(t2)
+    with pytest.raises(api.KmaGpuError):
+        db.run_input_text(b"@r0\nACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIII\nr1\nACGT\n+\nIIII\n")   # second record without '@'
+    empty, c0, _, _, _ = db.run_input_text(b"")
+    db.close()
+    assert len(empty) == 0 and c0 == 0
+
+
+@gpu
+def test_text_pipelines_equal_record_pipeline(tmp_path):
+    """MapPipeline.map_text (host splitter) and map_text_device_split == the resident call on the stage-1 records of the
+    same reads; files whose records do not line up make the device-split path step aside"""
+    from kma_b200 import pipeline, records
+    names, seqs = synth.gene_db(51, n_families=10, n_variants=6, len_lo=500, len_hi=1500)
+    prefix = util.build_db(tmp_path, names, seqs)
+    r1, r2 = synth.paired_reads(52, seqs, 3000, sub=0.01)
+    r1, r2 = np.asarray(r1), np.asarray(r2)
+    s1 = records.stage1_pairs_fast(r1, r2)
+    p = api.default_params()
+    db = api.TemplateDB(prefix)
+    db.seed_upload(s1); db.seed_run(p); db.align_from_seed(); db.align_run(p)
+    frag, a, u, _ = db.align_download()
+    db.close()
+    t1, t2 = synth.fastq_fixed(r1), synth.fastq_fixed(r2)
+    pipe = pipeline.MapPipeline(prefix, workers=2, params=p)
+    outs = [np.empty(len(frag) + 4096, dtype=np.uint8) for _ in range(5)]
+    f1, f2 = api.fastx_split_parallel(t1, threads=3), api.fastx_split_parallel(t2, threads=2)
+    for mode in ("host", "device"):
+        scores = (np.zeros_like(a), np.zeros_like(u))
+        res = pipe.map_text(t1, f1, t2, f2, 5, outs, scores) if mode == "host" else pipe.map_text_device_split(t1, t2, 5, outs, scores)
+        assert res is not None and b"".join(f.tobytes() for f, _ in res) == frag.tobytes(), mode
+        assert np.array_equal(scores[0], a) and np.array_equal(scores[1], u) and sum(c for _, c in res) == 3000
+    # second file with longer names: same records, different byte positions -> chunks do not line up
+    t2b = np.frombuffer(util.fastq_text(list(r2), prefix="a_longer_name_"), dtype=np.uint8)
+    scores = (np.zeros_like(a), np.zeros_like(u))
+    assert pipe.map_text_device_split(t1, t2b, 5, outs, scores) is None
+    pipe.close()
