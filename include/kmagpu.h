@@ -164,6 +164,12 @@ int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t nbytes, co
                           const uint64_t *uniq_alignment_scores, void *frags_out, size_t out_cap, size_t *out_bytes,
                           uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts, int64_t *nrecords);
 
+/* kmagpu_trace_batch on the fragment stream the last kmagpu_conclave_batch of this handle left in HBM (that call may
+ * pass frags_out = NULL when the host does not need the fragments). out = NULL in either trace call: no row output,
+ * only the base counts (params->matrix) and the statistics -- what -dense / -matrix runs need. */
+int kmagpu_trace_from_conclave(kmagpu_db *db, const kmagpu_params *params, void *out, size_t out_cap, size_t *out_bytes,
+                               int64_t *nrecords, kmagpu_align_stats *stats);
+
 /* The per-position base counts of the assembly pass (Assembly.counts[6] = {A, C, G, T, N, gap}, assembly.h:55-58) for
  * the template nodes of every template, HBM resident: uint32 [sum of template lengths][6], template t starting at
  * position sum(len[1..t-1]). kmagpu_trace_batch with params->matrix != 0 adds the accepted alignments of a batch

@@ -169,6 +169,8 @@ def lib():
                                       C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
         L.kmagpu_trace_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                          C.POINTER(C.c_size_t), C.POINTER(C.c_int64), C.POINTER(AlignStats)]
+        L.kmagpu_trace_from_conclave.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64),
+                                                 C.POINTER(AlignStats)]
         L.kmagpu_record_walk.restype = C.c_int64
         L.kmagpu_record_walk.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         _lib = L
@@ -348,18 +350,18 @@ class TemplateDB:
         frag, a, u, cand = self.align_download(scores=scores, want_cand=want_cand)
         return frag, a, u, cand, st
 
-    def assemble_align_batch(self, frags, params: Params | None = None):
+    def assemble_align_batch(self, frags, params: Params | None = None, download=True):
         """the alignment part of assemble_KMA's inner loop (assembly.c:1868-1961: anker_rc + KMA with traceback +
         acceptance) over per-template fragment records (frags.c:45-48) -> (output bytes, nrecords, stats); per record
         int32[12]{accepted, read_score, start, end, score, len, pos, match, tGaps, qGaps, turned, ncol} + t/s/q rows"""
         p = params or default_params()
         frags = np.ascontiguousarray(frags, dtype=np.uint8)
-        cap = 64 + 60 * (len(frags) // 32 + 1) + 16 * len(frags)
+        cap = 64 + 60 * (len(frags) // 32 + 1) + 16 * len(frags) if download else 0
         out = np.empty(cap, dtype=np.uint8)
         ob, nr, st = C.c_size_t(), C.c_int64(), AlignStats()
-        _check(lib().kmagpu_trace_batch(self._h, C.byref(p), frags.ctypes.data, len(frags), out.ctypes.data, cap,
+        _check(lib().kmagpu_trace_batch(self._h, C.byref(p), frags.ctypes.data, len(frags), out.ctypes.data if download else None, cap,
                                         C.byref(ob), C.byref(nr), C.byref(st)))
-        return out[: ob.value], nr.value, st
+        return (out[: ob.value] if download else None), nr.value, st
 
     # --- -mem_mode: k-mer score collection of runKMA_MEM ------------------------------------------
     def memscore_batch(self, stage2, scores=None):
@@ -374,7 +376,7 @@ class TemplateDB:
         return out[: ob.value], a, u, nr.value
 
     # --- ConClave choice pass + per-template bucketing --------------------------------------------
-    def conclave_batch(self, frag_raw, alignment_scores, uniq_alignment_scores, totals=None):
+    def conclave_batch(self, frag_raw, alignment_scores, uniq_alignment_scores, totals=None, download=True):
         """runConClave (conclave.c:43) + printFrags (frags.c:30) over one chunk of frag_raw records with the GLOBAL score
         arrays -> (per-template fragment records incl. the -1 terminator, w_scores, fragmentCounts, readCounts, nrecords);
         `totals` = (w_scores u64, fragmentCounts u32, readCounts u32) arrays to add into"""
@@ -383,11 +385,26 @@ class TemplateDB:
         u = np.ascontiguousarray(uniq_alignment_scores, dtype=np.uint64)
         DB = self.info.DB_size
         w, fc, rc = totals if totals is not None else (np.zeros(DB, np.uint64), np.zeros(DB, np.uint32), np.zeros(DB, np.uint32))
-        out = np.empty(2 * len(fr) + 64, dtype=np.uint8)
+        out = np.empty(2 * len(fr) + 64 if download else 0, dtype=np.uint8)   # download=False: fragments stay in HBM for trace_from_conclave
         ob, nr = C.c_size_t(), C.c_int64()
-        _check(lib().kmagpu_conclave_batch(self._h, fr.ctypes.data, len(fr), a.ctypes.data, u.ctypes.data, out.ctypes.data, len(out),
+        _check(lib().kmagpu_conclave_batch(self._h, fr.ctypes.data, len(fr), a.ctypes.data, u.ctypes.data,
+                                           out.ctypes.data if download else None, len(out),
                                            C.byref(ob), w.ctypes.data, fc.ctypes.data, rc.ctypes.data, C.byref(nr)))
-        return out[: ob.value], w, fc, rc, nr.value
+        self._frag_bytes = ob.value
+        return (out[: ob.value] if download else None), w, fc, rc, nr.value
+
+    def trace_from_conclave(self, params: Params | None = None, download=True):
+        """assemble_align_batch on the fragment stream the last conclave_batch of this handle left in HBM; download=False:
+        no row output, only the base counts (params.matrix) and the statistics -> (output bytes | None, nrecords, stats)"""
+        p = params or default_params()
+        cap = 0
+        if download:
+            cap = 64 + 16 * int(self._frag_bytes) + 60 * (int(self._frag_bytes) // 32 + 1)
+        out = np.empty(cap, dtype=np.uint8)
+        ob, nr, st = C.c_size_t(), C.c_int64(), AlignStats()
+        _check(lib().kmagpu_trace_from_conclave(self._h, C.byref(p), out.ctypes.data if download else None, cap, C.byref(ob), C.byref(nr),
+                                                C.byref(st)))
+        return (out[: ob.value] if download else None), nr.value, st
 
     # --- base-count matrix of the assembly pass (alnToMat / alnToMatDense) ----------------------
     def matrix_reset(self):

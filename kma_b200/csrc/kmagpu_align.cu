@@ -1406,6 +1406,13 @@ __global__ void __launch_bounds__(256) mat_clamp_kernel(const unsigned int *__re
 // ---------------------------------------------------------------- host side
 
 int kg_align_free(kmagpu_db *db) {
+	{
+		TraceBatch &t = db->trc;
+		KgBuf *tr[] = {&t.d_in, &t.d_off, &t.d_recs, &t.d_sz, &t.d_partial, &t.d_ctr, &t.d_slab, &t.d_rows, &t.d_outs, &t.d_ovf, &t.d_out,
+		               &db->frg.d_out, &db->frg.d_sz};
+		for (KgBuf *x : tr) x->release();
+		db->frg.valid = false;
+	}
 	AlignBatch &b = db->aln;
 	KgBuf *all[] = {&b.d_in, &b.d_off, &b.d_reads, &b.d_slab, &b.d_sz, &b.d_partial, &b.d_taskread, &b.d_cand, &b.d_recsize,
 	                &b.d_out, &b.d_ctr, &b.d_scores, &b.d_scratch, &b.d_ovf, &b.d_res, &b.h_off};
@@ -1678,34 +1685,17 @@ extern "C" int kmagpu_align_batch(kmagpu_db *db, const kmagpu_params *p, const v
 
 // ---------------------------------------------------------------- traceback batch (host)
 
-extern "C" int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *prm, const void *frags, size_t nbytes,
-                                  void *out, size_t out_cap, size_t *out_bytes, int64_t *nrecords, kmagpu_align_stats *stats) {
-	if (!db || !prm || (!frags && nbytes)) { kmagpu_set_error("null argument"); return -1; }
-	if (!db->d_tslots) { kmagpu_set_error("database has no alignment index (.seq.b / .length.b missing)"); return -1; }
-	if (nbytes >= (1ull << 32) - 64) { kmagpu_set_error("fragment batch of %zu bytes exceeds the 4 GiB per-call limit; split it", nbytes); return -1; }
-	KG_CUDA(cudaSetDevice(db->device));
-	if (stats) memset(stats, 0, sizeof(*stats));
-	if (out_bytes) *out_bytes = 0;
-	if (nrecords) *nrecords = 0;
-	size_t used = 0;
-	const int64_t n64 = kmagpu_record_walk(3, frags, nbytes, nullptr, 0, &used);
-	if (n64 < 0) return -1;
-	const int n = (int)n64;
-	if (nrecords) *nrecords = n64;
-	if (n == 0) return 0;
-	std::vector<uint64_t> off64((size_t)n);
-	kmagpu_record_walk(3, frags, nbytes, off64.data(), (size_t)n, &used);
-	std::vector<uint32_t> off((size_t)n + 1);
-	for (int i = 0; i < n; ++i) off[i] = (uint32_t)off64[i];
-	off[n] = (uint32_t)used;
-
+// the alignment part of assemble_KMA's inner loop over n fragment records that sit in HBM (din, record offsets doff[n + 1]);
+// out == NULL: no row output (base counts / statistics only)
+static int trace_core(kmagpu_db *db, const kmagpu_params *prm, const uint8_t *din, const uint32_t *doff, int n, void *out, size_t out_cap,
+                      size_t *out_bytes, kmagpu_align_stats *stats) {
 	const AlnParams P = make_params(db, prm);
 	cudaStream_t st = db->stream;
 	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-	KgBuf d_in, d_off, d_recs, d_sz, d_partial, d_ctr, d_slab, d_rows, d_outs, d_ovf, d_out;
-	struct Guard { std::vector<KgBuf *> v; ~Guard() { for (KgBuf *b : v) b->release(); } } guard;
-	guard.v = {&d_in, &d_off, &d_recs, &d_sz, &d_partial, &d_ctr, &d_slab, &d_rows, &d_outs, &d_ovf, &d_out};
-	if (d_in.reserve(used + 64) || d_off.reserve(4 * ((size_t)n + 2)) || d_recs.reserve(sizeof(TrRec) * (size_t)n) ||
+	TraceBatch &tb = db->trc;   // working buffers persist across calls
+	KgBuf &d_recs = tb.d_recs, &d_sz = tb.d_sz, &d_partial = tb.d_partial, &d_ctr = tb.d_ctr, &d_slab = tb.d_slab, &d_rows = tb.d_rows,
+	      &d_outs = tb.d_outs, &d_ovf = tb.d_ovf, &d_out = tb.d_out;
+	if (d_recs.reserve(sizeof(TrRec) * (size_t)n) ||
 	    d_sz.reserve(4 * (size_t)(6 * n + 12)) || d_partial.reserve(4 * (size_t)(ntiles + 2)) || d_ctr.reserve(8 * A_N) ||
 	    d_outs.reserve(sizeof(TrOut) * (size_t)n) || d_ovf.reserve(4 * ((size_t)n + 1))) return -1;
 	uint32_t *slab_sz = (uint32_t *)d_sz.p, *slab_off = slab_sz + n + 1, *row_sz = slab_off + n + 1, *row_off = row_sz + n + 1,
@@ -1713,12 +1703,9 @@ extern "C" int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *prm, const
 	unsigned long long *ctr = (unsigned long long *)d_ctr.p;
 	unsigned long long h[A_N];
 	int launches = 0;
-	KG_CUDA(cudaMemcpyAsync(d_in.p, frags, used, cudaMemcpyHostToDevice, st));
-	KG_CUDA(cudaMemsetAsync((uint8_t *)d_in.p + used, 0, 64, st));
-	KG_CUDA(cudaMemcpyAsync(d_off.p, off.data(), 4 * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
 	KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * A_N, st));
 	KG_CUDA(cudaEventRecord(db->ev[2], st));
-	tr_sizes_kernel<<<db->sm_count * 8, 256, 0, st>>>((const uint8_t *)d_in.p, (const uint32_t *)d_off.p, n, db->info.DB_size,
+	tr_sizes_kernel<<<db->sm_count * 8, 256, 0, st>>>(din, doff, n, db->info.DB_size,
 		(TrRec *)d_recs.p, slab_sz, row_sz, ctr);
 	kg_exscan(slab_sz, n, slab_off, (uint32_t *)d_partial.p, ctr + A_SLAB, st);
 	kg_exscan(row_sz, n, row_off, (uint32_t *)d_partial.p, ctr + A_TASKS, st);
@@ -1729,7 +1716,7 @@ extern "C" int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *prm, const
 	if (h[A_BAD]) { kmagpu_set_error("%llu fragment records name a template outside the database", h[A_BAD]); return -1; }
 	const int maxq = (int)h[A_MAXQ];
 	if (d_slab.reserve(8 * ((size_t)h[A_SLAB] + 4)) || d_rows.reserve(8 * ((size_t)h[A_TASKS] + 4))) return -1;
-	tr_prep_kernel<<<db->sm_count * 8, 256, 0, st>>>((const uint8_t *)d_in.p, n, (TrRec *)d_recs.p, slab_off, row_off, (uint64_t *)d_slab.p);
+	tr_prep_kernel<<<db->sm_count * 8, 256, 0, st>>>(din, n, (TrRec *)d_recs.p, slab_off, row_off, (uint64_t *)d_slab.p);
 	++launches;
 	const int q_cap = std::min(std::max(maxq + 64, 256), 1 << 20);
 	const size_t e_cap = std::min<size_t>(std::max<size_t>(2 * (size_t)maxq * (size_t)maxq + 65536, 65536), 4u << 20);
@@ -1781,21 +1768,24 @@ extern "C" int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *prm, const
 			db->tix.meta, db->d_mat_off, prm->matrix == 2, db->d_mat, ctr);
 		++launches;
 	}
-	tr_outsize_kernel<<<(n + 255) / 256, 256, 0, st>>>((const TrOut *)d_outs.p, n, osz);
-	kg_exscan(osz, n, ooff, (uint32_t *)d_partial.p, ctr + A_OUT, st);
-	launches += 4;
-	unsigned long long h2[A_N];
-	KG_CUDA(cudaMemcpyAsync(h2, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
-	KG_CUDA(cudaStreamSynchronize(st));
-	const size_t ob = (size_t)h2[A_OUT];
-	if (out_bytes) *out_bytes = ob;
-	if (ob > out_cap) { kmagpu_set_error("trace output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
-	if (d_out.reserve(ob + 64)) return -1;
-	tr_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>((const TrRec *)d_recs.p, (const TrOut *)d_outs.p, n, (const uint8_t *)d_rows.p, ooff,
-		(uint8_t *)d_out.p);
-	++launches;
-	KG_CUDA(cudaEventRecord(db->ev[7], st));
-	KG_CUDA(cudaMemcpyAsync(out, d_out.p, ob, cudaMemcpyDeviceToHost, st));
+	if (out) {
+		tr_outsize_kernel<<<(n + 255) / 256, 256, 0, st>>>((const TrOut *)d_outs.p, n, osz);
+		kg_exscan(osz, n, ooff, (uint32_t *)d_partial.p, ctr + A_OUT, st);
+		launches += 4;
+		unsigned long long h2[A_N];
+		KG_CUDA(cudaMemcpyAsync(h2, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
+		KG_CUDA(cudaStreamSynchronize(st));
+		const size_t ob = (size_t)h2[A_OUT];
+		if (out_bytes) *out_bytes = ob;
+		if (ob > out_cap) { kmagpu_set_error("trace output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
+		if (d_out.reserve(ob + 64)) return -1;
+		tr_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>((const TrRec *)d_recs.p, (const TrOut *)d_outs.p, n, (const uint8_t *)d_rows.p, ooff,
+			(uint8_t *)d_out.p);
+		++launches;
+		KG_CUDA(cudaEventRecord(db->ev[7], st));
+		KG_CUDA(cudaMemcpyAsync(out, d_out.p, ob, cudaMemcpyDeviceToHost, st));
+	} else KG_CUDA(cudaEventRecord(db->ev[7], st));
+	KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));   // counters incl. the matrix kernel's
 	KG_CUDA(cudaStreamSynchronize(st));
 	KG_CUDA(cudaGetLastError());
 	if (stats) {
@@ -1808,6 +1798,51 @@ extern "C" int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *prm, const
 		stats->launches = launches;
 	}
 	return 0;
+}
+
+extern "C" int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *prm, const void *frags, size_t nbytes,
+                                  void *out, size_t out_cap, size_t *out_bytes, int64_t *nrecords, kmagpu_align_stats *stats) {
+	if (!db || !prm || (!frags && nbytes)) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->d_tslots) { kmagpu_set_error("database has no alignment index (.seq.b / .length.b missing)"); return -1; }
+	if (nbytes >= (1ull << 32) - 64) { kmagpu_set_error("fragment batch of %zu bytes exceeds the 4 GiB per-call limit; split it", nbytes); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	if (stats) memset(stats, 0, sizeof(*stats));
+	if (out_bytes) *out_bytes = 0;
+	if (nrecords) *nrecords = 0;
+	size_t used = 0;
+	const int64_t n64 = kmagpu_record_walk(3, frags, nbytes, nullptr, 0, &used);
+	if (n64 < 0) return -1;
+	const int n = (int)n64;
+	if (nrecords) *nrecords = n64;
+	if (n == 0) return 0;
+	std::vector<uint64_t> off64((size_t)n);
+	kmagpu_record_walk(3, frags, nbytes, off64.data(), (size_t)n, &used);
+	std::vector<uint32_t> off((size_t)n + 1);
+	for (int i = 0; i < n; ++i) off[i] = (uint32_t)off64[i];
+	off[n] = (uint32_t)used;
+	TraceBatch &t = db->trc;
+	if (t.d_in.reserve(used + 64) || t.d_off.reserve(4 * ((size_t)n + 2))) return -1;
+	cudaStream_t st = db->stream;
+	KG_CUDA(cudaMemcpyAsync(t.d_in.p, frags, used, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemsetAsync((uint8_t *)t.d_in.p + used, 0, 64, st));
+	KG_CUDA(cudaMemcpyAsync(t.d_off.p, off.data(), 4 * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaStreamSynchronize(st));   // `off` lives on this stack frame
+	return trace_core(db, prm, (const uint8_t *)t.d_in.p, (const uint32_t *)t.d_off.p, n, out, out_cap, out_bytes, stats);
+}
+
+// The same on the fragment stream the last kmagpu_conclave_batch left in HBM (no host round trip of the fragments).
+extern "C" int kmagpu_trace_from_conclave(kmagpu_db *db, const kmagpu_params *prm, void *out, size_t out_cap, size_t *out_bytes,
+                                          int64_t *nrecords, kmagpu_align_stats *stats) {
+	if (!db || !prm) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->d_tslots) { kmagpu_set_error("database has no alignment index (.seq.b / .length.b missing)"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	if (stats) memset(stats, 0, sizeof(*stats));
+	if (out_bytes) *out_bytes = 0;
+	const FragBatch &f = db->frg;
+	if (!f.valid) { kmagpu_set_error("kmagpu_trace_from_conclave without a preceding kmagpu_conclave_batch on this handle"); return -1; }
+	if (nrecords) *nrecords = f.n;
+	if (f.n == 0) return 0;
+	return trace_core(db, prm, (const uint8_t *)f.d_out.p, f.off, (int)f.n, out, out_cap, out_bytes, stats);
 }
 
 // ---------------------------------------------------------------- base-count matrix: host side

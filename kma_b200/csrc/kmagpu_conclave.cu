@@ -144,6 +144,7 @@ extern "C" int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t
                                      const uint64_t *uniq_alignment_scores, void *frags_out, size_t out_cap, size_t *out_bytes,
                                      uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts, int64_t *nrecords) {
 	if (!db || (!frag_raw && nbytes) || !alignment_scores || !uniq_alignment_scores) { kmagpu_set_error("null argument"); return -1; }
+	db->frg.valid = false; db->frg.n = 0; db->frg.bytes = 0;
 	if (!db->d_lengths) { kmagpu_set_error("database has no template lengths (.length.b missing)"); return -1; }
 	if (nbytes >= (1ull << 32) - 64) { kmagpu_set_error("frag_raw batch of %zu bytes exceeds the 4 GiB per-call limit; split it", nbytes); return -1; }
 	KG_CUDA(cudaSetDevice(db->device));
@@ -157,10 +158,12 @@ extern "C" int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t
 	const int DB = db->info.DB_size;
 	cudaStream_t st = db->stream;
 	if (n == 0) {   // printFrags of an empty chunk: the terminator alone
+		if (out_bytes) *out_bytes = 4;
+		db->frg.valid = true;
+		if (!frags_out) return 0;
 		if (out_cap < 4) { kmagpu_set_error("fragment output needs 4 bytes"); return -1; }
 		const int32_t m1 = -1;
 		memcpy(frags_out, &m1, 4);
-		if (out_bytes) *out_bytes = 4;
 		return 0;
 	}
 	std::vector<uint64_t> off64((size_t)n);
@@ -169,9 +172,10 @@ extern "C" int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t
 	for (int i = 0; i < n; ++i) off[i] = (uint32_t)off64[i];
 	off[n] = (uint32_t)used;
 	const int ni = 2 * n, ntiles = (ni + SCAN_TILE - 1) / SCAN_TILE;
-	KgBuf d_in, d_off, d_sc, d_items, d_keys, d_vals, d_sz, d_partial, d_ctr, d_acc, d_tmp, d_out;
+	KgBuf d_in, d_off, d_sc, d_items, d_keys, d_vals, d_partial, d_ctr, d_acc, d_tmp;
+	KgBuf &d_sz = db->frg.d_sz, &d_out = db->frg.d_out;   // the fragment stream and its offsets stay for kmagpu_trace_from_conclave
 	struct Guard { std::vector<KgBuf *> v; ~Guard() { for (KgBuf *b : v) b->release(); } } guard;
-	guard.v = {&d_in, &d_off, &d_sc, &d_items, &d_keys, &d_vals, &d_sz, &d_partial, &d_ctr, &d_acc, &d_tmp, &d_out};
+	guard.v = {&d_in, &d_off, &d_sc, &d_items, &d_keys, &d_vals, &d_partial, &d_ctr, &d_acc, &d_tmp};
 	if (d_in.reserve(used + 64) || d_off.reserve(4 * ((size_t)n + 2)) || d_sc.reserve(16 * (size_t)DB) ||
 	    d_items.reserve(sizeof(CcItem) * (size_t)ni) || d_keys.reserve(16 * (size_t)ni) || d_vals.reserve(8 * (size_t)ni) ||
 	    d_sz.reserve(4 * (size_t)(2 * ni + 4)) || d_partial.reserve(4 * (size_t)(ntiles + 2)) || d_ctr.reserve(64) ||
@@ -205,16 +209,18 @@ extern "C" int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t
 	if (h[1]) { kmagpu_set_error("%llu frag_raw candidates name a template outside the database", h[1]); return -1; }
 	const size_t ob = (size_t)h[2] + 4;
 	if (out_bytes) *out_bytes = ob;
-	if (ob > out_cap) { kmagpu_set_error("fragment output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
+	if (frags_out && ob > out_cap) { kmagpu_set_error("fragment output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
 	if (d_out.reserve(ob + 64)) return -1;
 	cc_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>((const uint8_t *)d_in.p, keys2, vals2, (const CcItem *)d_items.p, ni, ooff,
 		(uint8_t *)d_out.p);
 	cc_tail_kernel<<<1, 1, 0, st>>>((uint8_t *)d_out.p, ctr + 2);
-	KG_CUDA(cudaMemcpyAsync(frags_out, d_out.p, ob, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaMemsetAsync((uint8_t *)d_out.p + ob, 0, 64, st));
+	if (frags_out) KG_CUDA(cudaMemcpyAsync(frags_out, d_out.p, ob, cudaMemcpyDeviceToHost, st));
 	std::vector<uint8_t> acc(16 * (size_t)DB);
 	KG_CUDA(cudaMemcpyAsync(acc.data(), d_acc.p, 16 * (size_t)DB, cudaMemcpyDeviceToHost, st));
 	KG_CUDA(cudaStreamSynchronize(st));
 	KG_CUDA(cudaGetLastError());
+	db->frg.off = ooff; db->frg.n = (int64_t)h[0]; db->frg.bytes = ob; db->frg.valid = true;   // valid items sort first
 	const uint64_t *hw = (const uint64_t *)acc.data();
 	const uint32_t *hfc = (const uint32_t *)(hw + DB), *hrc = hfc + DB;
 	for (int t = 0; t < DB; ++t) {

@@ -70,6 +70,20 @@ struct Stage1Batch {
 	KgBuf d_cnt1, d_cnt2, d_lines1, d_lines2;   // device record splitter: newline counts + offsets per 64-byte block, line ends
 };
 
+// working buffers of the traceback pass (kmagpu_trace_batch / kmagpu_trace_from_conclave), kept across calls
+struct TraceBatch {
+	KgBuf d_in, d_off, d_recs, d_sz, d_partial, d_ctr, d_slab, d_rows, d_outs, d_ovf, d_out;
+};
+
+// the per-template fragment stream the last kmagpu_conclave_batch wrote, resident for kmagpu_trace_from_conclave
+struct FragBatch {
+	KgBuf d_out, d_sz;
+	const uint32_t *off = nullptr;   // record offsets (inside d_sz)
+	int64_t n = 0;
+	size_t bytes = 0;
+	bool valid = false;
+};
+
 // one batch of the alignment pass (kmagpu_align.cu)
 struct AlignBatch {
 	KgBuf d_in, d_off, d_reads, d_slab, d_sz, d_partial, d_taskread, d_cand, d_recsize, d_out, d_ctr, d_scores,
@@ -100,6 +114,8 @@ struct kmagpu_db {
 	int sm_count = 148;
 	SeedBatch seed;
 	Stage1Batch s1;
+	TraceBatch trc;
+	FragBatch frg;
 	// per-template alignment index (kmagpu_tindex.cu)
 	void *d_tmeta = nullptr, *d_tslots = nullptr;
 	int32_t *d_tdups = nullptr;

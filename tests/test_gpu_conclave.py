@@ -67,7 +67,20 @@ def test_stage3_on_the_device(tmp_path):
     db.matrix_reset()
     trace, n, _ = db.assemble_align_batch(frags, p)
     mat = db.matrix_download()
+    # the same with the fragments staying in HBM between ConClave and the traceback pass, with and without row output
+    none, w2, _, _, _ = db.conclave_batch(frag, a, u, download=False)
+    db.matrix_reset()
+    trace2, n2, _ = db.trace_from_conclave(p)
+    mat2 = db.matrix_download()
+    db.matrix_reset()
+    none2, n3, st3 = db.trace_from_conclave(p, download=False)
+    mat3 = db.matrix_download()
+    db.matrix_reset()
+    none3, n4, _ = db.assemble_align_batch(frags, p, download=False)
+    mat4 = db.matrix_download()
     db.close()
+    assert none is None and none2 is None and none3 is None and n2 == n3 == n4 == n and np.array_equal(w2, w)
+    assert trace2.tobytes() == trace.tobytes() and np.array_equal(mat2, mat) and np.array_equal(mat3, mat) and np.array_equal(mat4, mat)
     assert frags.tobytes() == ofrags and np.array_equal(w, ow)
     assert trace.tobytes() == otrace
     assert np.array_equal(mat, omat) and int(mat.sum()) > 100000
