@@ -152,6 +152,11 @@ int kmagpu_trace_batch(kmagpu_db *db, const kmagpu_params *p, const void *frags,
 int kmagpu_memscore_batch(kmagpu_db *db, const void *stage2, size_t nbytes, void *frag_out, size_t out_cap, size_t *out_bytes,
                           uint64_t *alignment_scores, uint64_t *uniq_alignment_scores, int64_t *nrecords);
 
+/* kmagpu_memscore_batch on the stage-2 stream the last kmagpu_seed_run of this handle left in HBM. Either call keeps its
+ * frag_raw stream resident for kmagpu_conclave_resident; frag_out = NULL skips the download. */
+int kmagpu_memscore_from_seed(kmagpu_db *db, void *frag_out, size_t out_cap, size_t *out_bytes, uint64_t *alignment_scores,
+                              uint64_t *uniq_alignment_scores, int64_t *nrecords);
+
 /* Replaces runConClave (conclave.c:43-213, -ConClave 1) + printFrags (frags.c:30-61) for one chunk of frag_raw records
  * (the reference cuts a new chunk every maxFrag fragments, conclave.c:196-207): per record the template with the
  * largest GLOBAL alignment score wins (ties: score per template base, unique score, smaller id) -- so
@@ -164,7 +169,14 @@ int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t nbytes, co
                           const uint64_t *uniq_alignment_scores, void *frags_out, size_t out_cap, size_t *out_bytes,
                           uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts, int64_t *nrecords);
 
-/* kmagpu_trace_batch on the fragment stream the last kmagpu_conclave_batch of this handle left in HBM (that call may
+/* kmagpu_conclave_batch on the frag_raw stream the last score collection (kmagpu_memscore_batch / _from_seed) of this
+ * handle left in HBM; with kmagpu_trace_from_conclave the whole -mem_mode flow (stage 1 text -> stage 2 -> score
+ * collection -> ConClave -> traceback + base counts -> consensus) runs without a record leaving the device. */
+int kmagpu_conclave_resident(kmagpu_db *db, const uint64_t *alignment_scores, const uint64_t *uniq_alignment_scores, void *frags_out,
+                             size_t out_cap, size_t *out_bytes, uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts,
+                             int64_t *nrecords);
+
+/* kmagpu_trace_batch on the fragment stream the last kmagpu_conclave_batch / _resident of this handle left in HBM (that call may
  * pass frags_out = NULL when the host does not need the fragments). out = NULL in either trace call: no row output,
  * only the base counts (params->matrix) and the statistics -- what -dense / -matrix runs need. */
 int kmagpu_trace_from_conclave(kmagpu_db *db, const kmagpu_params *params, void *out, size_t out_cap, size_t *out_bytes,

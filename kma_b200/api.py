@@ -169,6 +169,9 @@ def lib():
                                       C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
         L.kmagpu_trace_batch.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                          C.POINTER(C.c_size_t), C.POINTER(C.c_int64), C.POINTER(AlignStats)]
+        L.kmagpu_memscore_from_seed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+        L.kmagpu_conclave_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.kmagpu_trace_from_conclave.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64),
                                                  C.POINTER(AlignStats)]
         L.kmagpu_record_walk.restype = C.c_int64
@@ -374,6 +377,34 @@ class TemplateDB:
         _check(lib().kmagpu_memscore_batch(self._h, s2.ctypes.data, len(s2), out.ctypes.data, len(out), C.byref(ob), a.ctypes.data,
                                            u.ctypes.data, C.byref(nr)))
         return out[: ob.value], a, u, nr.value
+
+    def memscore_from_seed(self, scores=None, download=True, cap=None):
+        """memscore_batch on the stage-2 stream the last seed_run left in HBM; the frag_raw stream stays resident for
+        conclave_resident. -> (frag_raw bytes | None, alignment_scores, uniq_alignment_scores, nrecords)"""
+        DB = self.info.DB_size
+        a, u = scores if scores is not None else (np.zeros(DB, np.uint64), np.zeros(DB, np.uint64))
+        ob, nr = C.c_size_t(), C.c_int64()
+        out = np.empty(int(cap) if (download and cap) else 0, dtype=np.uint8)
+        if download and not cap:   # size it: run once without output, then fetch
+            raise KmaGpuError("memscore_from_seed(download=True) needs cap (bytes of the output buffer)")
+        _check(lib().kmagpu_memscore_from_seed(self._h, out.ctypes.data if download else None, len(out), C.byref(ob), a.ctypes.data,
+                                               u.ctypes.data, C.byref(nr)))
+        return (out[: ob.value] if download else None), a, u, nr.value
+
+    def conclave_resident(self, alignment_scores, uniq_alignment_scores, totals=None, download=True, cap=None):
+        """conclave_batch on the frag_raw stream the last score collection left in HBM"""
+        a = np.ascontiguousarray(alignment_scores, dtype=np.uint64)
+        u = np.ascontiguousarray(uniq_alignment_scores, dtype=np.uint64)
+        DB = self.info.DB_size
+        w, fc, rc = totals if totals is not None else (np.zeros(DB, np.uint64), np.zeros(DB, np.uint32), np.zeros(DB, np.uint32))
+        if download and not cap:
+            raise KmaGpuError("conclave_resident(download=True) needs cap (bytes of the output buffer)")
+        out = np.empty(int(cap) if download else 0, dtype=np.uint8)
+        ob, nr = C.c_size_t(), C.c_int64()
+        _check(lib().kmagpu_conclave_resident(self._h, a.ctypes.data, u.ctypes.data, out.ctypes.data if download else None, len(out),
+                                              C.byref(ob), w.ctypes.data, fc.ctypes.data, rc.ctypes.data, C.byref(nr)))
+        self._frag_bytes = ob.value
+        return (out[: ob.value] if download else None), w, fc, rc, nr.value
 
     # --- ConClave choice pass + per-template bucketing --------------------------------------------
     def conclave_batch(self, frag_raw, alignment_scores, uniq_alignment_scores, totals=None, download=True):

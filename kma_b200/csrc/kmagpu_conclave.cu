@@ -29,6 +29,10 @@ __global__ void __launch_bounds__(256) cc_choose_kernel(const uint8_t *__restric
 		unsigned long long *ctr) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n) return;
+	if (off[r + 1] - off[r] < 20) {   // an empty slot of a resident frag_raw stream: no record
+		keys[2 * r] = ~0ull; keys[2 * r + 1] = ~0ull; vals[2 * r] = 2u * (unsigned)r; vals[2 * r + 1] = 2u * (unsigned)r + 1u;
+		return;
+	}
 	const uint8_t *rec = in + off[r];
 	const int q_len = (int)ld_u32u(rec), sparse = (int)ld_u32u(rec + 4), sc = (int)ld_u32u(rec + 8), hl = (int)ld_u32u(rec + 12);
 	int flag = (int)ld_u32u(rec + 16);
@@ -140,43 +144,18 @@ __global__ void __launch_bounds__(256) cc_emit_kernel(const uint8_t *__restrict_
 
 __global__ void cc_tail_kernel(uint8_t *out, const unsigned long long *total) { st_u32b(out + *total, 0xFFFFFFFFu); }
 
-extern "C" int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t nbytes, const uint64_t *alignment_scores,
-                                     const uint64_t *uniq_alignment_scores, void *frags_out, size_t out_cap, size_t *out_bytes,
-                                     uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts, int64_t *nrecords) {
-	if (!db || (!frag_raw && nbytes) || !alignment_scores || !uniq_alignment_scores) { kmagpu_set_error("null argument"); return -1; }
-	db->frg.valid = false; db->frg.n = 0; db->frg.bytes = 0;
-	if (!db->d_lengths) { kmagpu_set_error("database has no template lengths (.length.b missing)"); return -1; }
-	if (nbytes >= (1ull << 32) - 64) { kmagpu_set_error("frag_raw batch of %zu bytes exceeds the 4 GiB per-call limit; split it", nbytes); return -1; }
-	KG_CUDA(cudaSetDevice(db->device));
-	if (out_bytes) *out_bytes = 0;
-	if (nrecords) *nrecords = 0;
-	size_t used = 0;
-	const int64_t n64 = kmagpu_record_walk(4, frag_raw, nbytes, nullptr, 0, &used);
-	if (n64 < 0) return -1;
-	const int n = (int)n64;
-	if (nrecords) *nrecords = n64;
+// ConClave over n frag_raw slots in HBM (din, offsets doff[n + 1]; empty slots allowed)
+static int conclave_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff, int n, const uint64_t *alignment_scores,
+                         const uint64_t *uniq_alignment_scores, void *frags_out, size_t out_cap, size_t *out_bytes, uint64_t *w_scores,
+                         uint32_t *fragmentCounts, uint32_t *readCounts) {
 	const int DB = db->info.DB_size;
 	cudaStream_t st = db->stream;
-	if (n == 0) {   // printFrags of an empty chunk: the terminator alone
-		if (out_bytes) *out_bytes = 4;
-		db->frg.valid = true;
-		if (!frags_out) return 0;
-		if (out_cap < 4) { kmagpu_set_error("fragment output needs 4 bytes"); return -1; }
-		const int32_t m1 = -1;
-		memcpy(frags_out, &m1, 4);
-		return 0;
-	}
-	std::vector<uint64_t> off64((size_t)n);
-	kmagpu_record_walk(4, frag_raw, nbytes, off64.data(), (size_t)n, &used);
-	std::vector<uint32_t> off((size_t)n + 1);
-	for (int i = 0; i < n; ++i) off[i] = (uint32_t)off64[i];
-	off[n] = (uint32_t)used;
 	const int ni = 2 * n, ntiles = (ni + SCAN_TILE - 1) / SCAN_TILE;
-	KgBuf d_in, d_off, d_sc, d_items, d_keys, d_vals, d_partial, d_ctr, d_acc, d_tmp;
+	KgBuf d_sc, d_items, d_keys, d_vals, d_partial, d_ctr, d_acc, d_tmp;
 	KgBuf &d_sz = db->frg.d_sz, &d_out = db->frg.d_out;   // the fragment stream and its offsets stay for kmagpu_trace_from_conclave
 	struct Guard { std::vector<KgBuf *> v; ~Guard() { for (KgBuf *b : v) b->release(); } } guard;
-	guard.v = {&d_in, &d_off, &d_sc, &d_items, &d_keys, &d_vals, &d_partial, &d_ctr, &d_acc, &d_tmp};
-	if (d_in.reserve(used + 64) || d_off.reserve(4 * ((size_t)n + 2)) || d_sc.reserve(16 * (size_t)DB) ||
+	guard.v = {&d_sc, &d_items, &d_keys, &d_vals, &d_partial, &d_ctr, &d_acc, &d_tmp};
+	if (d_sc.reserve(16 * (size_t)DB) ||
 	    d_items.reserve(sizeof(CcItem) * (size_t)ni) || d_keys.reserve(16 * (size_t)ni) || d_vals.reserve(8 * (size_t)ni) ||
 	    d_sz.reserve(4 * (size_t)(2 * ni + 4)) || d_partial.reserve(4 * (size_t)(ntiles + 2)) || d_ctr.reserve(64) ||
 	    d_acc.reserve(16 * (size_t)DB)) return -1;
@@ -187,14 +166,11 @@ extern "C" int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t
 	unsigned long long *ctr = (unsigned long long *)d_ctr.p;
 	unsigned long long *w = (unsigned long long *)d_acc.p;
 	unsigned int *fc = (unsigned int *)(w + DB), *rcn = fc + DB;
-	KG_CUDA(cudaMemcpyAsync(d_in.p, frag_raw, used, cudaMemcpyHostToDevice, st));
-	KG_CUDA(cudaMemsetAsync((uint8_t *)d_in.p + used, 0, 64, st));
-	KG_CUDA(cudaMemcpyAsync(d_off.p, off.data(), 4 * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
 	KG_CUDA(cudaMemcpyAsync(as, alignment_scores, 8 * (size_t)DB, cudaMemcpyHostToDevice, st));
 	KG_CUDA(cudaMemcpyAsync(uas, uniq_alignment_scores, 8 * (size_t)DB, cudaMemcpyHostToDevice, st));
 	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
 	KG_CUDA(cudaMemsetAsync(d_acc.p, 0, 16 * (size_t)DB, st));
-	cc_choose_kernel<<<(n + 255) / 256, 256, 0, st>>>((const uint8_t *)d_in.p, (const uint32_t *)d_off.p, n, as, uas, db->d_lengths, DB,
+	cc_choose_kernel<<<(n + 255) / 256, 256, 0, st>>>(din, doff, n, as, uas, db->d_lengths, DB,
 		(CcItem *)d_items.p, keys, vals, w, fc, rcn, ctr);
 	size_t tmp_bytes = 0;
 	cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, ni, 0, 64, st);
@@ -211,7 +187,7 @@ extern "C" int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t
 	if (out_bytes) *out_bytes = ob;
 	if (frags_out && ob > out_cap) { kmagpu_set_error("fragment output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
 	if (d_out.reserve(ob + 64)) return -1;
-	cc_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>((const uint8_t *)d_in.p, keys2, vals2, (const CcItem *)d_items.p, ni, ooff,
+	cc_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>(din, keys2, vals2, (const CcItem *)d_items.p, ni, ooff,
 		(uint8_t *)d_out.p);
 	cc_tail_kernel<<<1, 1, 0, st>>>((uint8_t *)d_out.p, ctr + 2);
 	KG_CUDA(cudaMemsetAsync((uint8_t *)d_out.p + ob, 0, 64, st));
@@ -229,4 +205,61 @@ extern "C" int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t
 		if (readCounts) readCounts[t] += hrc[t];
 	}
 	return 0;
+}
+extern "C" int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t nbytes, const uint64_t *alignment_scores,
+                                     const uint64_t *uniq_alignment_scores, void *frags_out, size_t out_cap, size_t *out_bytes,
+                                     uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts, int64_t *nrecords) {
+	if (!db || (!frag_raw && nbytes) || !alignment_scores || !uniq_alignment_scores) { kmagpu_set_error("null argument"); return -1; }
+	db->frg.valid = false; db->frg.n = 0; db->frg.bytes = 0;
+	if (!db->d_lengths) { kmagpu_set_error("database has no template lengths (.length.b missing)"); return -1; }
+	if (nbytes >= (1ull << 32) - 64) { kmagpu_set_error("frag_raw batch of %zu bytes exceeds the 4 GiB per-call limit; split it", nbytes); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	if (out_bytes) *out_bytes = 0;
+	if (nrecords) *nrecords = 0;
+	size_t used = 0;
+	const int64_t n64 = kmagpu_record_walk(4, frag_raw, nbytes, nullptr, 0, &used);
+	if (n64 < 0) return -1;
+	const int n = (int)n64;
+	if (nrecords) *nrecords = n64;
+	cudaStream_t st = db->stream;
+	if (n == 0) {   // printFrags of an empty chunk: the terminator alone
+		if (out_bytes) *out_bytes = 4;
+		db->frg.valid = true;
+		if (!frags_out) return 0;
+		if (out_cap < 4) { kmagpu_set_error("fragment output needs 4 bytes"); return -1; }
+		const int32_t m1 = -1;
+		memcpy(frags_out, &m1, 4);
+		return 0;
+	}
+	std::vector<uint64_t> off64((size_t)n);
+	kmagpu_record_walk(4, frag_raw, nbytes, off64.data(), (size_t)n, &used);
+	std::vector<uint32_t> off((size_t)n + 1);
+	for (int i = 0; i < n; ++i) off[i] = (uint32_t)off64[i];
+	off[n] = (uint32_t)used;
+	KgBuf d_in, d_off;
+	struct G2 { KgBuf *a, *b; ~G2() { a->release(); b->release(); } } g2 = {&d_in, &d_off};
+	if (d_in.reserve(used + 64) || d_off.reserve(4 * ((size_t)n + 2))) return -1;
+	KG_CUDA(cudaMemcpyAsync(d_in.p, frag_raw, used, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemsetAsync((uint8_t *)d_in.p + used, 0, 64, st));
+	KG_CUDA(cudaMemcpyAsync(d_off.p, off.data(), 4 * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	return conclave_core(db, (const uint8_t *)d_in.p, (const uint32_t *)d_off.p, n, alignment_scores, uniq_alignment_scores, frags_out, out_cap,
+	                     out_bytes, w_scores, fragmentCounts, readCounts);
+}
+
+// The same on the frag_raw stream the last -mem_mode score collection (kmagpu_memscore_batch / _from_seed) left in HBM.
+extern "C" int kmagpu_conclave_resident(kmagpu_db *db, const uint64_t *alignment_scores, const uint64_t *uniq_alignment_scores, void *frags_out,
+                                        size_t out_cap, size_t *out_bytes, uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts,
+                                        int64_t *nrecords) {
+	if (!db || !alignment_scores || !uniq_alignment_scores) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->d_lengths) { kmagpu_set_error("database has no template lengths (.length.b missing)"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	if (out_bytes) *out_bytes = 0;
+	db->frg.valid = false; db->frg.n = 0; db->frg.bytes = 0;
+	const RawBatch &r = db->raw;
+	if (!r.valid) { kmagpu_set_error("kmagpu_conclave_resident without a preceding score collection on this handle"); return -1; }
+	if (nrecords) *nrecords = r.n;
+	if (r.n == 0) { kmagpu_set_error("empty batch"); return -1; }
+	return conclave_core(db, (const uint8_t *)r.d_out.p, r.off, (int)r.n, alignment_scores, uniq_alignment_scores, frags_out, out_cap, out_bytes,
+	                     w_scores, fragmentCounts, readCounts);
 }

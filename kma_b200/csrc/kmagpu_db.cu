@@ -182,6 +182,7 @@ extern "C" void kmagpu_db_close(kmagpu_db *db) {
 	cudaSetDevice(db->device);
 	kg_seed_free(db);
 	kg_stage1_free(db);
+	kg_memscore_free(db);
 	kg_align_free(db);
 	cudaFree(db->d_tmeta); cudaFree(db->d_tslots); cudaFree(db->d_tdups);
 	cudaFree(db->d_exist); cudaFree(db->d_kv); cudaFree(db->d_values);

@@ -84,6 +84,16 @@ struct FragBatch {
 	bool valid = false;
 };
 
+// the frag_raw stream of the last -mem_mode score collection, resident for kmagpu_conclave_resident: one slot per
+// stage-2 record (empty slots: mates consumed with their first read, reads shorter than k)
+struct RawBatch {
+	KgBuf d_in, d_off, d_recs, d_sz, d_partial, d_ctr, d_acc, d_out;
+	const uint32_t *off = nullptr;   // slot offsets (inside d_sz), n + 1 entries
+	int64_t n = 0;
+	size_t bytes = 0;
+	bool valid = false;
+};
+
 // one batch of the alignment pass (kmagpu_align.cu)
 struct AlignBatch {
 	KgBuf d_in, d_off, d_reads, d_slab, d_sz, d_partial, d_taskread, d_cand, d_recsize, d_out, d_ctr, d_scores,
@@ -116,6 +126,7 @@ struct kmagpu_db {
 	Stage1Batch s1;
 	TraceBatch trc;
 	FragBatch frg;
+	RawBatch raw;
 	// per-template alignment index (kmagpu_tindex.cu)
 	void *d_tmeta = nullptr, *d_tslots = nullptr;
 	int32_t *d_tdups = nullptr;
@@ -132,4 +143,6 @@ int kg_align_free(kmagpu_db *db);
 
 int kg_seed_free(kmagpu_db *db);
 int kg_stage1_free(kmagpu_db *db);
+int kg_memscore_free(kmagpu_db *db);
+int kg_seed_device_output(kmagpu_db *db, const uint8_t **out, const uint32_t **rec_off, int64_t *nreads, size_t *bytes);
 int kg_chain_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *stats);

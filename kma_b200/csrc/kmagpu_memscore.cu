@@ -17,12 +17,13 @@ __global__ void __launch_bounds__(256) ms_sizes_kernel(const uint8_t *__restrict
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n) return;
 	const uint8_t *rec = in + off[r];
-	const int q_len = (int)ld_u32u(rec), sc1 = (int)ld_u32u(rec + 12), nt1 = (int)ld_u32u(rec + 16);
 	MsRec R = {off[r], off[r], 0, 0, 0};
 	uint32_t sz = 0;
+	const bool empty = off[r + 1] - off[r] < 28;   // a slot of the resident stage-2 stream that holds no record
+	const int q_len = empty ? 0 : (int)ld_u32u(rec), sc1 = empty ? 0 : (int)ld_u32u(rec + 12), nt1 = empty ? 1 : (int)ld_u32u(rec + 16);
 	// the mate of a pair is consumed together with the record before it (printPair, ankers.c:150)
-	const bool is_mate = r > 0 && (int)ld_u32u(in + off[r - 1] + 16) == 0;
-	if (!is_mate) {
+	const bool is_mate = r > 0 && off[r] - off[r - 1] >= 28 && (int)ld_u32u(in + off[r - 1] + 16) == 0;
+	if (!is_mate && !empty) {
 		const uint8_t *recT = rec;
 		int read_score = 0, q2 = 0, hl2 = 0;
 		bool pe = false, ok = true;
@@ -102,6 +103,55 @@ __global__ void __launch_bounds__(256) ms_emit_kernel(const uint8_t *__restrict_
 	}
 }
 
+int kg_memscore_free(kmagpu_db *db) {
+	RawBatch &w = db->raw;
+	KgBuf *all[] = {&w.d_in, &w.d_off, &w.d_recs, &w.d_sz, &w.d_partial, &w.d_ctr, &w.d_acc, &w.d_out};
+	for (KgBuf *x : all) x->release();
+	w.valid = false;
+	return 0;
+}
+
+// n stage-2 slots in HBM (din, offsets doff[n + 1]) -> frag_raw stream in db->raw (+ optional download) and the score sums
+static int memscore_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff, int n, void *frag_out, size_t out_cap, size_t *out_bytes,
+                         uint64_t *alignment_scores, uint64_t *uniq_alignment_scores) {
+	const int DB = db->info.DB_size, ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+	cudaStream_t st = db->stream;
+	RawBatch &w = db->raw;
+	w.valid = false;
+	if (w.d_recs.reserve(sizeof(MsRec) * (size_t)n) || w.d_sz.reserve(4 * (size_t)(2 * n + 4)) || w.d_partial.reserve(4 * (size_t)(ntiles + 2)) ||
+	    w.d_ctr.reserve(64) || w.d_acc.reserve(16 * (size_t)DB)) return -1;
+	uint32_t *size = (uint32_t *)w.d_sz.p, *ooff = size + n + 1;
+	unsigned long long *ctr = (unsigned long long *)w.d_ctr.p, *as = (unsigned long long *)w.d_acc.p, *uas = as + DB;
+	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
+	KG_CUDA(cudaMemsetAsync(w.d_acc.p, 0, 16 * (size_t)DB, st));
+	ms_sizes_kernel<<<(n + 255) / 256, 256, 0, st>>>(din, doff, n, db->info.kmerindex, DB, (MsRec *)w.d_recs.p, size, as, uas, ctr);
+	kg_exscan(size, n, ooff, (uint32_t *)w.d_partial.p, ctr + 2, st);
+	unsigned long long h[8];
+	KG_CUDA(cudaMemcpyAsync(h, ctr, 64, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	if (h[1]) { kmagpu_set_error("%llu stage-2 records are truncated pairs or name a template outside the database", h[1]); return -1; }
+	const size_t ob = (size_t)h[2];
+	if (out_bytes) *out_bytes = ob;
+	if (frag_out && ob > out_cap) { kmagpu_set_error("frag_raw output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
+	if (w.d_out.reserve(ob + 64)) return -1;
+	ms_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>(din, (const MsRec *)w.d_recs.p, n, size, ooff, db->d_lengths, (uint8_t *)w.d_out.p);
+	const uint32_t total = (uint32_t)ob;
+	KG_CUDA(cudaMemcpyAsync(ooff + n, &total, 4, cudaMemcpyHostToDevice, st));   // closing offset for the next stage
+	KG_CUDA(cudaMemsetAsync((uint8_t *)w.d_out.p + ob, 0, 64, st));
+	if (frag_out && ob) KG_CUDA(cudaMemcpyAsync(frag_out, w.d_out.p, ob, cudaMemcpyDeviceToHost, st));
+	std::vector<uint64_t> acc(2 * (size_t)DB);
+	KG_CUDA(cudaMemcpyAsync(acc.data(), w.d_acc.p, 16 * (size_t)DB, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaStreamSynchronize(st));
+	KG_CUDA(cudaGetLastError());
+	for (int t = 0; t < DB; ++t) {
+		if (alignment_scores) alignment_scores[t] += acc[t];
+		if (uniq_alignment_scores) uniq_alignment_scores[t] += acc[(size_t)DB + t];
+	}
+	w.off = ooff; w.n = n; w.bytes = ob; w.valid = true;
+	return 0;
+}
+
 extern "C" int kmagpu_memscore_batch(kmagpu_db *db, const void *stage2, size_t nbytes, void *frag_out, size_t out_cap, size_t *out_bytes,
                                      uint64_t *alignment_scores, uint64_t *uniq_alignment_scores, int64_t *nrecords) {
 	if (!db || (!stage2 && nbytes)) { kmagpu_set_error("null argument"); return -1; }
@@ -110,6 +160,7 @@ extern "C" int kmagpu_memscore_batch(kmagpu_db *db, const void *stage2, size_t n
 	KG_CUDA(cudaSetDevice(db->device));
 	if (out_bytes) *out_bytes = 0;
 	if (nrecords) *nrecords = 0;
+	db->raw.valid = false;
 	size_t used = 0;
 	const int64_t n64 = kmagpu_record_walk(2, stage2, nbytes, nullptr, 0, &used);
 	if (n64 < 0) return -1;
@@ -121,41 +172,35 @@ extern "C" int kmagpu_memscore_batch(kmagpu_db *db, const void *stage2, size_t n
 	std::vector<uint32_t> off((size_t)n + 1);
 	for (int i = 0; i < n; ++i) off[i] = (uint32_t)off64[i];
 	off[n] = (uint32_t)used;
-	const int DB = db->info.DB_size, ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+	RawBatch &w = db->raw;
+	if (w.d_in.reserve(used + 64) || w.d_off.reserve(4 * ((size_t)n + 2))) return -1;
 	cudaStream_t st = db->stream;
-	KgBuf d_in, d_off, d_recs, d_sz, d_partial, d_ctr, d_acc, d_out;
-	struct Guard { std::vector<KgBuf *> v; ~Guard() { for (KgBuf *b : v) b->release(); } } guard;
-	guard.v = {&d_in, &d_off, &d_recs, &d_sz, &d_partial, &d_ctr, &d_acc, &d_out};
-	if (d_in.reserve(used + 64) || d_off.reserve(4 * ((size_t)n + 2)) || d_recs.reserve(sizeof(MsRec) * (size_t)n) ||
-	    d_sz.reserve(4 * (size_t)(2 * n + 4)) || d_partial.reserve(4 * (size_t)(ntiles + 2)) || d_ctr.reserve(64) || d_acc.reserve(16 * (size_t)DB)) return -1;
-	uint32_t *size = (uint32_t *)d_sz.p, *ooff = size + n + 1;
-	unsigned long long *ctr = (unsigned long long *)d_ctr.p, *as = (unsigned long long *)d_acc.p, *uas = as + DB;
-	KG_CUDA(cudaMemcpyAsync(d_in.p, stage2, used, cudaMemcpyHostToDevice, st));
-	KG_CUDA(cudaMemsetAsync((uint8_t *)d_in.p + used, 0, 64, st));
-	KG_CUDA(cudaMemcpyAsync(d_off.p, off.data(), 4 * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
-	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
-	KG_CUDA(cudaMemsetAsync(d_acc.p, 0, 16 * (size_t)DB, st));
-	ms_sizes_kernel<<<(n + 255) / 256, 256, 0, st>>>((const uint8_t *)d_in.p, (const uint32_t *)d_off.p, n, db->info.kmerindex, DB,
-		(MsRec *)d_recs.p, size, as, uas, ctr);
-	kg_exscan(size, n, ooff, (uint32_t *)d_partial.p, ctr + 2, st);
-	unsigned long long h[8];
-	KG_CUDA(cudaMemcpyAsync(h, ctr, 64, cudaMemcpyDeviceToHost, st));
+	KG_CUDA(cudaMemcpyAsync(w.d_in.p, stage2, used, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemsetAsync((uint8_t *)w.d_in.p + used, 0, 64, st));
+	KG_CUDA(cudaMemcpyAsync(w.d_off.p, off.data(), 4 * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
 	KG_CUDA(cudaStreamSynchronize(st));
-	KG_CUDA(cudaGetLastError());
-	if (h[1]) { kmagpu_set_error("%llu stage-2 records are truncated pairs or name a template outside the database", h[1]); return -1; }
-	const size_t ob = (size_t)h[2];
-	if (out_bytes) *out_bytes = ob;
-	if (ob > out_cap) { kmagpu_set_error("frag_raw output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
-	if (d_out.reserve(ob + 64)) return -1;
-	ms_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>((const uint8_t *)d_in.p, (const MsRec *)d_recs.p, n, size, ooff, db->d_lengths, (uint8_t *)d_out.p);
-	if (ob) KG_CUDA(cudaMemcpyAsync(frag_out, d_out.p, ob, cudaMemcpyDeviceToHost, st));
-	std::vector<uint64_t> acc(2 * (size_t)DB);
-	KG_CUDA(cudaMemcpyAsync(acc.data(), d_acc.p, 16 * (size_t)DB, cudaMemcpyDeviceToHost, st));
-	KG_CUDA(cudaStreamSynchronize(st));
-	KG_CUDA(cudaGetLastError());
-	for (int t = 0; t < DB; ++t) {
-		if (alignment_scores) alignment_scores[t] += acc[t];
-		if (uniq_alignment_scores) uniq_alignment_scores[t] += acc[(size_t)DB + t];
-	}
-	return 0;
+	return memscore_core(db, (const uint8_t *)w.d_in.p, (const uint32_t *)w.d_off.p, n, frag_out, out_cap, out_bytes, alignment_scores,
+	                     uniq_alignment_scores);
+}
+
+// The same on the stage-2 stream the last kmagpu_seed_run left in HBM.
+extern "C" int kmagpu_memscore_from_seed(kmagpu_db *db, void *frag_out, size_t out_cap, size_t *out_bytes, uint64_t *alignment_scores,
+                                         uint64_t *uniq_alignment_scores, int64_t *nrecords) {
+	if (!db) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->d_lengths) { kmagpu_set_error("database has no template lengths (.length.b missing)"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	if (out_bytes) *out_bytes = 0;
+	if (nrecords) *nrecords = 0;
+	db->raw.valid = false;
+	const uint8_t *out; const uint32_t *roff; int64_t n; size_t bytes;
+	if (kg_seed_device_output(db, &out, &roff, &n, &bytes)) return -1;
+	if (nrecords) *nrecords = n;
+	if (n == 0) return 0;
+	RawBatch &w = db->raw;   // the slot offsets with their closing entry
+	if (w.d_off.reserve(4 * ((size_t)n + 2))) return -1;
+	const uint32_t total = (uint32_t)bytes;
+	KG_CUDA(cudaMemcpyAsync(w.d_off.p, roff, 4 * (size_t)n, cudaMemcpyDeviceToDevice, db->stream));
+	KG_CUDA(cudaMemcpyAsync((uint32_t *)w.d_off.p + n, &total, 4, cudaMemcpyHostToDevice, db->stream));
+	KG_CUDA(cudaStreamSynchronize(db->stream));
+	return memscore_core(db, out, (const uint32_t *)w.d_off.p, (int)n, frag_out, out_cap, out_bytes, alignment_scores, uniq_alignment_scores);
 }

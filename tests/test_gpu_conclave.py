@@ -139,6 +139,19 @@ def test_mem_mode_flow_on_one_genome(tmp_path):
     trace, n, _ = db.assemble_align_batch(frags, p)
     mat = db.matrix_download(1)
     ct, cs, cq, cst, _ = db.consensus(1)   # the consensus of the genome from the device's own counts
+    # the whole flow again without a record leaving HBM: FASTQ text -> stage 1 -> stage 2 -> score collection -> ConClave
+    # -> traceback + base counts -> consensus
+    text = util.fastq_text(reads, desc=False)
+    _, cnt, _, _, _ = db.run_input_text(text, download=False)
+    db.seed_run(p)
+    f2, a2, u2, _ = db.memscore_from_seed(download=True, cap=len(frag) + 4096)
+    g2, w2, _, _, _ = db.conclave_resident(a2, u2, download=True, cap=len(frags) + 4096)
+    db.matrix_reset()
+    none, n2, _ = db.trace_from_conclave(p, download=False)
+    mat_r = db.matrix_download(1)
+    ct2 = db.consensus(1)
+    assert cnt == nreads and f2.tobytes() == ofrag and np.array_equal(a2, a) and g2.tobytes() == ofrags and np.array_equal(w2, w)
+    assert none is None and n2 == n and np.array_equal(mat_r, mat) and ct2[2].tobytes() == cq.tobytes()
     db.close()
     wt, ws, wq, wst = util.oracle_consensus(prefix, 1, omat)
     assert ct.tobytes() == wt and cs.tobytes() == ws and cq.tobytes() == wq

@@ -464,7 +464,7 @@ def oracle_chi2_min(evalue: float) -> float:
 
 # ---------------------------------------------------------------- stage 1 (FASTQ / FASTA text -> stage-1 records)
 
-def fastq_text(reads, quals=None, prefix="r", fasta=False, crlf=False) -> bytes:
+def fastq_text(reads, quals=None, prefix="r", fasta=False, crlf=False, desc=True) -> bytes:
     """4-line FASTQ (or 2-line FASTA) text of reads given as codes 0-4; quals: list of uint8 phred+offset arrays"""
     nl = b"\r\n" if crlf else b"\n"
     lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
@@ -475,7 +475,7 @@ def fastq_text(reads, quals=None, prefix="r", fasta=False, crlf=False) -> bytes:
             out += b">" + f"{prefix}{i} some description".encode() + nl + seq + nl
         else:
             q = np.asarray(quals[i], dtype=np.uint8).tobytes() if quals is not None else b"I" * len(seq)
-            out += b"@" + f"{prefix}{i}".encode() + (b" 1:N:0" if i % 3 == 0 else b"") + nl + seq + nl + b"+" + nl + q + nl
+            out += b"@" + f"{prefix}{i}".encode() + (b" 1:N:0" if desc and i % 3 == 0 else b"") + nl + seq + nl + b"+" + nl + q + nl
     return bytes(out)
 
 
