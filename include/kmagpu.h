@@ -176,6 +176,12 @@ int kmagpu_conclave_resident(kmagpu_db *db, const uint64_t *alignment_scores, co
                              size_t out_cap, size_t *out_bytes, uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts,
                              int64_t *nrecords);
 
+/* ... and on the frag_raw stream the last kmagpu_align_run of this handle left in HBM. (ConClave needs the score sums
+ * of the WHOLE run: a multi-batch run keeps one handle per resident batch, or takes the host path for the others.) */
+int kmagpu_conclave_from_align(kmagpu_db *db, const uint64_t *alignment_scores, const uint64_t *uniq_alignment_scores, void *frags_out,
+                               size_t out_cap, size_t *out_bytes, uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts,
+                               int64_t *nrecords);
+
 /* kmagpu_trace_batch on the fragment stream the last kmagpu_conclave_batch / _resident of this handle left in HBM (that call may
  * pass frags_out = NULL when the host does not need the fragments). out = NULL in either trace call: no row output,
  * only the base counts (params->matrix) and the statistics -- what -dense / -matrix runs need. */

@@ -172,6 +172,7 @@ def lib():
         L.kmagpu_memscore_from_seed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.kmagpu_conclave_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+        L.kmagpu_conclave_from_align.argtypes = L.kmagpu_conclave_resident.argtypes
         L.kmagpu_trace_from_conclave.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64),
                                                  C.POINTER(AlignStats)]
         L.kmagpu_record_walk.restype = C.c_int64
@@ -391,8 +392,9 @@ class TemplateDB:
                                                u.ctypes.data, C.byref(nr)))
         return (out[: ob.value] if download else None), a, u, nr.value
 
-    def conclave_resident(self, alignment_scores, uniq_alignment_scores, totals=None, download=True, cap=None):
-        """conclave_batch on the frag_raw stream the last score collection left in HBM"""
+    def conclave_resident(self, alignment_scores, uniq_alignment_scores, totals=None, download=True, cap=None, source="memscore"):
+        """conclave_batch on the frag_raw stream the last score collection (source="memscore") or the last align_run
+        (source="align") left in HBM"""
         a = np.ascontiguousarray(alignment_scores, dtype=np.uint64)
         u = np.ascontiguousarray(uniq_alignment_scores, dtype=np.uint64)
         DB = self.info.DB_size
@@ -401,7 +403,8 @@ class TemplateDB:
             raise KmaGpuError("conclave_resident(download=True) needs cap (bytes of the output buffer)")
         out = np.empty(int(cap) if download else 0, dtype=np.uint8)
         ob, nr = C.c_size_t(), C.c_int64()
-        _check(lib().kmagpu_conclave_resident(self._h, a.ctypes.data, u.ctypes.data, out.ctypes.data if download else None, len(out),
+        fn = lib().kmagpu_conclave_from_align if source == "align" else lib().kmagpu_conclave_resident
+        _check(fn(self._h, a.ctypes.data, u.ctypes.data, out.ctypes.data if download else None, len(out),
                                               C.byref(ob), w.ctypes.data, fc.ctypes.data, rc.ctypes.data, C.byref(nr)))
         self._frag_bytes = ob.value
         return (out[: ob.value] if download else None), w, fc, rc, nr.value

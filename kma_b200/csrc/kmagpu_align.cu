@@ -1656,10 +1656,10 @@ extern "C" int kmagpu_align_download(kmagpu_db *db, void *frag_out, size_t out_c
 	if (!b.ran) { kmagpu_set_error("kmagpu_align_download before kmagpu_align_run"); return -1; }
 	if (out_bytes) *out_bytes = b.out_bytes;
 	if (cand_rows) *cand_rows = b.h_cand.size() / 8;
-	if (b.out_bytes > out_cap) { kmagpu_set_error("frag_raw output needs %zu bytes, caller gave %zu", b.out_bytes, out_cap); return -1; }
+	if (frag_out && b.out_bytes > out_cap) { kmagpu_set_error("frag_raw output needs %zu bytes, caller gave %zu", b.out_bytes, out_cap); return -1; }
 	if (cand_out && b.h_cand.size() / 8 > cand_cap) { kmagpu_set_error("candidate rows need %zu entries, caller gave %zu", b.h_cand.size() / 8, cand_cap); return -1; }
 	KG_CUDA(cudaSetDevice(db->device));
-	if (b.out_bytes) {
+	if (b.out_bytes && frag_out) {   // frag_out = NULL: the stream stays in HBM (kmagpu_conclave_from_align), only the score arrays come back
 		KG_CUDA(cudaMemcpyAsync(frag_out, b.d_out.p, b.out_bytes, cudaMemcpyDeviceToHost, db->stream));
 		KG_CUDA(cudaStreamSynchronize(db->stream));
 	}

@@ -23,17 +23,12 @@ struct CcItem {
 	int32_t q_len, hl, tmpl, bestHits, score, start, end, flag, rc, has_bound, b0, b1;
 };
 
-__global__ void __launch_bounds__(256) cc_choose_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ off, int n,
-		const unsigned long long *__restrict__ as, const unsigned long long *__restrict__ uas, const int32_t *__restrict__ lengths,
-		int DB_size, CcItem *items, unsigned long long *keys, uint32_t *vals, unsigned long long *w, unsigned int *fc, unsigned int *rcn,
-		unsigned long long *ctr) {
-	const int r = blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= n) return;
-	if (off[r + 1] - off[r] < 20) {   // an empty slot of a resident frag_raw stream: no record
-		keys[2 * r] = ~0ull; keys[2 * r + 1] = ~0ull; vals[2 * r] = 2u * (unsigned)r; vals[2 * r + 1] = 2u * (unsigned)r + 1u;
-		return;
-	}
-	const uint8_t *rec = in + off[r];
+// one frag_raw record at byte `pos`: the choice among its candidates, the item(s) it contributes (idx, and idx + 1 for
+// the mate block of a pair record); returns the bytes the record spans
+__device__ uint32_t cc_record(const uint8_t *__restrict__ in, uint32_t pos, int idx, const unsigned long long *__restrict__ as,
+		const unsigned long long *__restrict__ uas, const int32_t *__restrict__ lengths, int DB_size, CcItem *items, unsigned long long *keys,
+		unsigned long long *w, unsigned int *fc, unsigned int *rcn, unsigned long long *ctr, bool *has_mate) {
+	const uint8_t *rec = in + pos;
 	const int q_len = (int)ld_u32u(rec), sparse = (int)ld_u32u(rec + 4), sc = (int)ld_u32u(rec + 8), hl = (int)ld_u32u(rec + 12);
 	int flag = (int)ld_u32u(rec + 16);
 	const int bestHits = abs(sparse), read_score = abs(sc);
@@ -67,7 +62,7 @@ __global__ void __launch_bounds__(256) cc_choose_kernel(const uint8_t *__restric
 		}
 	} else { bestTemplate = (int)ld_u32u(T); start = (int)ld_u32u(S); end = (int)ld_u32u(E); }
 	CcItem a;
-	a.q_off = off[r] + 20u; a.hdr_off = a.q_off + (uint32_t)q_len; a.q_len = q_len; a.hl = hl;
+	a.q_off = pos + 20u; a.hdr_off = a.q_off + (uint32_t)q_len; a.q_len = q_len; a.hl = hl;
 	a.rc = 0; a.has_bound = 0; a.b0 = a.b1 = 0;
 	if (bestTemplate < 0) {
 		bestTemplate = -bestTemplate; a.rc = 1; flag |= 16;
@@ -87,22 +82,42 @@ __global__ void __launch_bounds__(256) cc_choose_kernel(const uint8_t *__restric
 		atomicAdd(&fc[bestTemplate], 1u);
 		atomicAdd(&rcn[bestTemplate], mate ? 2u : 1u);
 	}
-	items[2 * r] = a;
-	keys[2 * r] = ok ? ((unsigned long long)(unsigned)bestTemplate << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(2 * r)) : ~0ull;
-	vals[2 * r] = 2u * (unsigned)r;
-	unsigned long long k2 = ~0ull;
+	items[idx] = a;
+	keys[idx] = ok ? ((unsigned long long)(unsigned)bestTemplate << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx) : ~0ull;
+	uint32_t bytes = 20u + (uint32_t)q_len + (uint32_t)hl + 12u * (uint32_t)bestHits;
 	if (mate) {   // the mate block: int32[3]{q_len, hdrlen, flag} + bytes; same template and span, never turned
 		const uint8_t *m = T + 4 * (size_t)bestHits;
 		CcItem b = a;
 		b.q_len = (int)ld_u32u(m); b.hl = (int)ld_u32u(m + 4); b.flag = (int)ld_u32u(m + 8);
 		b.q_off = (uint32_t)(m + 12 - in); b.hdr_off = b.q_off + (uint32_t)b.q_len;
 		b.rc = 0; b.has_bound = 0;
-		items[2 * r + 1] = b;
-		if (ok) k2 = ((unsigned long long)(unsigned)bestTemplate << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(2 * r + 1));
+		items[idx + 1] = b;
+		if (ok) keys[idx + 1] = ((unsigned long long)(unsigned)bestTemplate << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(idx + 1));
+		bytes += 12u + (uint32_t)b.q_len + (uint32_t)b.hl;
 	}
-	keys[2 * r + 1] = k2;
-	vals[2 * r + 1] = 2u * (unsigned)r + 1u;
 	atomicAdd(&ctr[0], (ok ? 1ull : 0ull) + (ok && mate ? 1ull : 0ull));
+	*has_mate = mate;
+	return bytes;
+}
+
+
+// one thread per slot of the frag_raw stream: a slot holds one record (host streams: every record is its own slot), none
+// (resident -mem_mode stream) or up to two (resident alignment-pass stream: a pair resolved as two single reads)
+__global__ void __launch_bounds__(256) cc_choose_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ off, int n,
+		const unsigned long long *__restrict__ as, const unsigned long long *__restrict__ uas, const int32_t *__restrict__ lengths,
+		int DB_size, CcItem *items, unsigned long long *keys, uint32_t *vals, unsigned long long *w, unsigned int *fc, unsigned int *rcn,
+		unsigned long long *ctr) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n) return;
+	keys[2 * r] = ~0ull; keys[2 * r + 1] = ~0ull; vals[2 * r] = 2u * (unsigned)r; vals[2 * r + 1] = 2u * (unsigned)r + 1u;
+	uint32_t pos = off[r];
+	const uint32_t end = off[r + 1];
+	for (int idx = 2 * r; idx < 2 * r + 2 && end - pos >= 20u && pos < end;) {
+		bool mate = false;
+		pos += cc_record(in, pos, idx, as, uas, lengths, DB_size, items, keys, w, fc, rcn, ctr, &mate);
+		idx += mate ? 2 : 1;
+	}
+	if (pos != end && end - off[r] >= 20u) atomicAdd(&ctr[3], 1ull);   // the slot's bytes are not a whole number of records
 }
 
 __global__ void __launch_bounds__(256) cc_sizes_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals,
@@ -183,6 +198,7 @@ static int conclave_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff
 	KG_CUDA(cudaStreamSynchronize(st));
 	KG_CUDA(cudaGetLastError());
 	if (h[1]) { kmagpu_set_error("%llu frag_raw candidates name a template outside the database", h[1]); return -1; }
+	if (h[3]) { kmagpu_set_error("%llu slots of the frag_raw stream do not hold whole records", h[3]); return -1; }
 	const size_t ob = (size_t)h[2] + 4;
 	if (out_bytes) *out_bytes = ob;
 	if (frags_out && ob > out_cap) { kmagpu_set_error("fragment output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
@@ -261,5 +277,28 @@ extern "C" int kmagpu_conclave_resident(kmagpu_db *db, const uint64_t *alignment
 	if (nrecords) *nrecords = r.n;
 	if (r.n == 0) { kmagpu_set_error("empty batch"); return -1; }
 	return conclave_core(db, (const uint8_t *)r.d_out.p, r.off, (int)r.n, alignment_scores, uniq_alignment_scores, frags_out, out_cap, out_bytes,
+	                     w_scores, fragmentCounts, readCounts);
+}
+
+// The same on the frag_raw stream the last kmagpu_align_run left in HBM (one slot per stage-2 record: empty, one record,
+// or two for a pair that was resolved as two single reads).
+extern "C" int kmagpu_conclave_from_align(kmagpu_db *db, const uint64_t *alignment_scores, const uint64_t *uniq_alignment_scores, void *frags_out,
+                                          size_t out_cap, size_t *out_bytes, uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts,
+                                          int64_t *nrecords) {
+	if (!db || !alignment_scores || !uniq_alignment_scores) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->d_lengths) { kmagpu_set_error("database has no template lengths (.length.b missing)"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	if (out_bytes) *out_bytes = 0;
+	db->frg.valid = false; db->frg.n = 0; db->frg.bytes = 0;
+	AlignBatch &b = db->aln;
+	if (!b.ran) { kmagpu_set_error("kmagpu_conclave_from_align without a preceding kmagpu_align_run on this handle"); return -1; }
+	const int n = (int)b.nreads;
+	if (nrecords) *nrecords = n;
+	if (n == 0 || b.out_bytes == 0) { kmagpu_set_error("empty batch"); return -1; }
+	uint32_t *recoff = (uint32_t *)b.d_recsize.p + n + 1;
+	const uint32_t total = (uint32_t)b.out_bytes;
+	KG_CUDA(cudaMemcpyAsync(recoff + n, &total, 4, cudaMemcpyHostToDevice, db->stream));
+	KG_CUDA(cudaStreamSynchronize(db->stream));
+	return conclave_core(db, (const uint8_t *)b.d_out.p, recoff, n, alignment_scores, uniq_alignment_scores, frags_out, out_cap, out_bytes,
 	                     w_scores, fragmentCounts, readCounts);
 }

@@ -43,6 +43,34 @@ def test_conclave_paired_end_and_empty(tmp_path):
     assert n0 == 0 and empty.tobytes() == np.array([-1], dtype=np.int32).tobytes() and not w0.any()
 
 
+def test_resident_pair_stream_through_conclave(tmp_path):
+    """paired reads: the alignment pass leaves pair records with mate blocks and pairs resolved as two single records
+    in one slot; ConClave on that resident stream == ConClave on the downloaded one == the oracle"""
+    names, seqs = synth.gene_db(75, n_families=10, n_variants=8, len_lo=500, len_hi=1500)
+    synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    r1, r2 = synth.paired_reads(76, seqs, 1500, sub=0.02)
+    r2 = [r if i % 5 else synth.revcomp(np.asarray(r)) for i, r in enumerate(r2)]   # some pairs that are not proper pairs
+    synth.write_fastq(tmp_path / "a.fq", r1)
+    synth.write_fastq(tmp_path / "b.fq", r2)
+    prefix = str(tmp_path / "db")
+    for apm in ("p", "u"):
+        s2 = np.frombuffer(util.ref_kma(["-ipe", "a.fq", "b.fq", "-o", "o", "-t_db", "db", "-apm", apm, "-s2"], cwd=tmp_path), dtype=np.uint8)
+        db = api.TemplateDB(prefix, device=0)
+        p = api.default_params()
+        p.apm = 1 if apm == "u" else 0
+        frag, a, u, _, _ = db.alnFrags_batch(s2, p)
+        want, ow, ofc, orc_ = util.oracle_conclave(prefix, frag.tobytes(), a, u)
+        got, w, fc, rc, _ = db.conclave_batch(frag, a, u)
+        assert got.tobytes() == want
+        db.align_upload(s2); db.align_run(p)
+        g2, w2, fc2, rc2, _ = db.conclave_resident(a, u, cap=len(want) + 4096, source="align")
+        db.close()
+        assert g2.tobytes() == want and np.array_equal(w2, ow) and np.array_equal(fc2, ofc) and np.array_equal(rc2, orc_), apm
+        rec = api.record_offsets(4, np.frombuffer(frag.tobytes(), dtype=np.uint8))
+        assert len(rec) - 1 > 1200
+
+
 def test_stage3_on_the_device(tmp_path):
     """alignment pass -> (score arrays) -> ConClave -> traceback alignment + base counts, every step on the GPU, equal to
     the oracle chain (each link of which is pinned to the reference)"""
@@ -78,6 +106,10 @@ def test_stage3_on_the_device(tmp_path):
     db.matrix_reset()
     none3, n4, _ = db.assemble_align_batch(frags, p, download=False)
     mat4 = db.matrix_download()
+    # ... and with the frag_raw stream staying in HBM between the alignment pass and ConClave as well
+    db.align_upload(s2); db.align_run(p)
+    g5, w5, fc5, rc5, _ = db.conclave_resident(a, u, cap=len(frags) + 4096, source="align")
+    assert g5.tobytes() == ofrags and np.array_equal(w5, ow)
     db.close()
     assert none is None and none2 is None and none3 is None and n2 == n3 == n4 == n and np.array_equal(w2, w)
     assert trace2.tobytes() == trace.tobytes() and np.array_equal(mat2, mat) and np.array_equal(mat3, mat) and np.array_equal(mat4, mat)
