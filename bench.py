@@ -200,6 +200,49 @@ def nw_gcups(db, seqs, peak_iops, n=24000, seed=3):
             "not_ok": int((status != 0).sum())}
 
 
+def c4_flow(api, workdir, device, genome_bases=5_000_000, n=1_000_000):
+    """BASELINE.json configs[3] (C4) beside the headline: one synthetic genome as the only template, 150 bp reads,
+    -mem_mode -1t1, base counts and consensus, every stream resident in HBM between the stages: FASTQ text (pinned) ->
+    record splitter + stage 1 -> stage 2 -> k-mer score collection -> ConClave -> traceback alignment + base counts ->
+    consensus; wall clock per call, the text upload and the consensus download included. The stage outputs of this
+    chain are compared with the oracle chain in tests/test_gpu_conclave.py and tools/c4_perf.py."""
+    import torch
+    from kma_b200 import dbbuild
+    wd = os.path.join(workdir, f"c4_{genome_bases}")
+    os.makedirs(wd, exist_ok=True)
+    prefix = os.path.join(wd, "db")
+    genome = np.random.default_rng(4).integers(0, 4, size=genome_bases).astype(np.uint8)
+    if not os.path.exists(prefix + ".comp.b"):
+        dbbuild.build_db(prefix, ["genome"], [genome])
+    db = api.TemplateDB(prefix, device=device)
+    p = api.default_params()
+    p.one2one = 1
+    p.matrix = 1
+    a = synth.fastq_fixed(np.asarray(synth.short_reads(6, [genome], n, L=150, sub=0.01)))
+    text = torch.empty(len(a), dtype=torch.uint8, pin_memory=True)
+    text.numpy()[:] = a
+    best = None
+    for _ in range(4):
+        t = {}
+        t0 = time.perf_counter(); _, cnt, ms1, _, _ = db.run_input_text(text, download=False); t["split+stage1"] = time.perf_counter() - t0
+        t0 = time.perf_counter(); st = db.seed_run(p); t["stage2"] = time.perf_counter() - t0
+        t0 = time.perf_counter(); _, sa_, su_, _ = db.memscore_from_seed(download=False); t["score_collection"] = time.perf_counter() - t0
+        t0 = time.perf_counter(); db.conclave_resident(sa_, su_, download=False); t["conclave"] = time.perf_counter() - t0
+        db.matrix_reset()
+        t0 = time.perf_counter(); _, nrec, sa = db.trace_from_conclave(p, download=False); t["traceback+counts"] = time.perf_counter() - t0
+        t0 = time.perf_counter(); ct, cs, cq, cst, msc = db.consensus(1); t["consensus"] = time.perf_counter() - t0
+        tot = sum(t.values())
+        if best is None or tot < best[0]:
+            best = (tot, t, cnt, nrec, sa, cst, st, ms1, msc)
+    tot, t, cnt, nrec, sa, cst, st, ms1, msc = best
+    db.close()
+    return {"workload": f"C4: {n} synthetic 150 bp reads vs one {genome_bases / 1e6:.0f} Mb genome, -mem_mode -1t1, base counts + consensus, resident in HBM",
+            "reads_per_s": n / tot, "ms": tot * 1e3, "stage_wall_ms": {k: round(v * 1e3, 2) for k, v in t.items()},
+            "kernel_ms": {"stage1": ms1, "stage2": st.ms_total, "traceback": sa.ms_align, "consensus": msc},
+            "reads_kept": int(cnt), "fragments": int(nrec), "h2d_bytes": int(len(a)), "d2h_bytes": 3 * genome_bases,
+            "mean_depth": float(cst[0]["depth"]) / genome_bases, "consensus_matches_template": int(cst[0]["cover"])}
+
+
 def c3_chain(db, api, seqs, prefix, workdir, cores, peak_gbs, n=20000, ref_n=2000, seed=22):
     """BASELINE.json configs[2] (C3) beside the headline: Nanopore-like reads (5-20 kb, 10 % errors) through stage 2 in
     chain mode (save_kmers_chain, the reference's default without -1t1: `chain_kernel`) and the alignment pass with
@@ -284,6 +327,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=2_000_000, help="read pairs per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="read pairs of the CPU legs (default: the whole step, ~7 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (one genome, -mem_mode, consensus; resident flow) side measurement")
     ap.add_argument("--no-c3", action="store_true", help="skip the C3 (long reads, chain mode) side measurement")
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads / library handles of the end-to-end pipeline")
     ap.add_argument("--no-text", action="store_true", help="skip the FASTQ-text end-to-end leg (stage 1 on the device)")
@@ -545,6 +589,11 @@ def main():
         line["nw"] = nw_gcups(db, seqs, peak_iops)
         if not args.no_c3:
             line["c3"] = c3_chain(db, api, seqs, prefix, workdir, cores, pk["hbm_gbs"])
+        if not args.no_c4:
+            try:
+                line["c4"] = c4_flow(api, workdir, local_rank)
+            except Exception as e:   # a side measurement must not cost the headline line
+                line["c4"] = {"error": repr(e)[:300]}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = min(args.cpu_sample, args.pairs)

@@ -10,7 +10,7 @@ python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 tail -c 600 gpurun_out/bench_$tag.err
 cut -c1-400 gpurun_out/bench_$tag.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-c3 > gpurun_out/ncu_launch_$tag.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-c3 --no-c4 --no-text > gpurun_out/ncu_launch_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"aln_pair_kernel|seed_se_kernel" --launch-skip 2 -c 2 \
     -f -o gpurun_out/prof_$tag python tools/pe_perf.py 2000000 2 > gpurun_out/ncu_full_$tag.log 2>&1
 tail -3 gpurun_out/ncu_full_$tag.log
