@@ -33,6 +33,12 @@
 #ifndef AL_MINB
 #define AL_MINB 6             // resident CTAs per SM the pair kernel is compiled for (register cap 65536 / (128 * AL_MINB))
 #endif
+// The pair kernel exists twice: short reads (little state per task) run faster with more, register-poorer warps, long
+// reads (C3) with fewer, register-richer ones (profiles/r01_ab_minb.log: 10 CTAs/SM -8.6 % on C2, +39 % on C3).
+#ifndef AL_MINB_SHORT
+#define AL_MINB_SHORT 10
+#endif
+#define AL_SHORT_MAXQ 512     // batches whose longest read is at most this use the short-read variant
 #define ST_OK 0
 #define ST_OVERFLOW 1
 
@@ -563,7 +569,8 @@ __device__ int align_fixed(const AlnParams &P, const NwPen *pen, const KgTIndexV
 
 struct ScratchLayout { size_t stride; int mem_cap, q_cap; size_t e_cap; };
 
-__global__ void __launch_bounds__(AL_WARPS * 32, AL_MINB) aln_pair_kernel(AlnParams P, KgTIndexView ix, const uint8_t *__restrict__ in,
+template <int MINB>
+__global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(AlnParams P, KgTIndexView ix, const uint8_t *__restrict__ in,
 		const AlnRead *__restrict__ reads, const uint64_t *slab, const int32_t *__restrict__ task_read, int ntasks,
 		const int32_t *__restrict__ task_list, AlnCand *cand, uint8_t *scratch, ScratchLayout lay,
 		unsigned long long *ctr, int32_t *ovf_list) {
@@ -1556,7 +1563,8 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 		const int q_cap = std::min(std::max(maxq + 64, 256), 1 << 20);
 		const size_t e_cap = std::min<size_t>(std::max<size_t>(2 * (size_t)maxq * (size_t)maxq + 65536, 65536), 4u << 20);
 		const ScratchLayout lay = make_layout(2048, q_cap, e_cap);
-		int grid = db->sm_count * AL_MINB;
+		const bool short_reads = maxq <= AL_SHORT_MAXQ;
+		int grid = db->sm_count * (short_reads ? AL_MINB_SHORT : AL_MINB);
 		size_t freeb = 0, totalb = 0;
 		if (lay.stride * (size_t)grid * AL_WARPS > b.d_scratch.cap) {   // only when the scratch has to grow
 			cudaMemGetInfo(&freeb, &totalb);
@@ -1564,9 +1572,14 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 		}
 		if (b.d_scratch.reserve(lay.stride * (size_t)grid * AL_WARPS)) return -1;
 		KG_CUDA(cudaEventRecord(db->ev[3], st));   // ms_align = the pair kernel(s) alone; host-side sizing above is in ms_total
-		aln_pair_kernel<<<grid, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
-			(const int32_t *)b.d_taskread.p, ntasks, nullptr, (AlnCand *)b.d_cand.p, (uint8_t *)b.d_scratch.p, lay, ctr,
-			(int32_t *)b.d_ovf.p);
+		if (short_reads)
+			aln_pair_kernel<AL_MINB_SHORT><<<grid, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
+				(const int32_t *)b.d_taskread.p, ntasks, nullptr, (AlnCand *)b.d_cand.p, (uint8_t *)b.d_scratch.p, lay, ctr,
+				(int32_t *)b.d_ovf.p);
+		else
+			aln_pair_kernel<AL_MINB><<<grid, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
+				(const int32_t *)b.d_taskread.p, ntasks, nullptr, (AlnCand *)b.d_cand.p, (uint8_t *)b.d_scratch.p, lay, ctr,
+				(int32_t *)b.d_ovf.p);
 		KG_CUDA(cudaEventRecord(db->ev[4], st));
 		++launches;
 		KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
@@ -1588,7 +1601,7 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 			if (list2.reserve(4 * ((size_t)novf + 1))) return -1;
 			KG_CUDA(cudaMemcpyAsync(list2.p, b.d_ovf.p, 4 * (size_t)novf, cudaMemcpyDeviceToDevice, st));
 			KG_CUDA(cudaMemsetAsync(ctr + A_WORK, 0, 8 * 5, st));   // A_WORK, A_OVF, A_NEED_*
-			aln_pair_kernel<<<g2, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
+			aln_pair_kernel<AL_MINB><<<g2, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
 				(const int32_t *)b.d_taskread.p, novf, (const int32_t *)list2.p, (AlnCand *)b.d_cand.p,
 				(uint8_t *)b.d_scratch.p, big, ctr, (int32_t *)b.d_ovf.p);
 			++launches;
