@@ -28,6 +28,9 @@
 #define KG_CAP_LOG 8
 #define KG_FILL 192           // distinct templates a read may see before it goes to the dense path
 #define KG_WARPS 4            // warps per CTA
+#ifndef KG_MINB
+#define KG_MINB 8             // CTAs per SM the seeding grid is sized for (24.9 KB of shared memory each: at most 9). The kernel carries no
+#endif                        // minimum-blocks bound: forcing 6 / 8 / 9 measured 41.8 / 38.8 / 41.9 ms against 37.7 ms without (profiles/r01_ab_seed.log)
 #define KG_WORDS 12           // staged u64 words per chunk: (256 + 31 + 31) / 32 + 2
 
 struct SeedRes { int32_t score, ntmpl, flag; uint32_t pool_off; int32_t src, rev; };   // src: record that supplies read + name, rev: emit its reverse complement
@@ -841,7 +844,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 	if (b.pool_cap < (size_t)n * 16 + 1024) b.pool_cap = (size_t)n * 16 + 1024;
 	if (b.d_res.reserve(sizeof(SeedRes) * (size_t)n) || b.d_recoff.reserve(4 * (size_t)(2 * n + 2)) ||
 	    b.d_ctr.reserve(8 * C_N) || b.d_partial.reserve(4 * (size_t)(ntiles + 1) + 4 * (size_t)n)) return -1;
-	const int grid = db->sm_count * 8;
+	const int grid = db->sm_count * KG_MINB;
 	// dense fallback scratch: (score, ext, candF, candR: int) + incl (byte) per template, per warp
 	const int dense_grid = db->sm_count * 2;
 	const size_t D = (size_t)db->info.DB_size + 1;
