@@ -346,6 +346,14 @@ class TemplateDB:
                                            cand.ctypes.data if want_cand else None, cr.value, C.byref(cr)))
         return out[: ob.value], a, u, cand
 
+    def align_scores(self, scores=None):
+        """only the two ConClave score arrays of the last align_run; the frag_raw stream stays in HBM
+        (conclave_resident(..., source="align"))"""
+        a, u = scores if scores is not None else (np.zeros(self.info.DB_size, np.uint64), np.zeros(self.info.DB_size, np.uint64))
+        ob, cr = C.c_size_t(), C.c_size_t()
+        _check(lib().kmagpu_align_download(self._h, None, 0, C.byref(ob), a.ctypes.data, u.ctypes.data, None, 0, C.byref(cr)))
+        return a, u
+
     def alnFrags_batch(self, stage2, params: Params | None = None, want_cand=False, scores=None):
         """alnFrags_threaded (alnfrags.c:2150) over a batch of stage-2 records ->
         (frag_raw bytes, alignment_scores, uniq_alignment_scores, cand rows, stats)"""

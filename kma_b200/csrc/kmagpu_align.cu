@@ -1416,7 +1416,8 @@ int kg_align_free(kmagpu_db *db) {
 	{
 		TraceBatch &t = db->trc;
 		KgBuf *tr[] = {&t.d_in, &t.d_off, &t.d_recs, &t.d_sz, &t.d_partial, &t.d_ctr, &t.d_slab, &t.d_rows, &t.d_outs, &t.d_ovf, &t.d_out,
-		               &db->frg.d_out, &db->frg.d_sz};
+		               &db->frg.d_out, &db->frg.d_sz, &db->frg.d_sc, &db->frg.d_items, &db->frg.d_keys, &db->frg.d_vals, &db->frg.d_partial,
+		               &db->frg.d_ctr, &db->frg.d_acc, &db->frg.d_tmp};
 		for (KgBuf *x : tr) x->release();
 		db->frg.valid = false;
 	}

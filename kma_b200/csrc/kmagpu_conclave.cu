@@ -166,10 +166,10 @@ static int conclave_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff
 	const int DB = db->info.DB_size;
 	cudaStream_t st = db->stream;
 	const int ni = 2 * n, ntiles = (ni + SCAN_TILE - 1) / SCAN_TILE;
-	KgBuf d_sc, d_items, d_keys, d_vals, d_partial, d_ctr, d_acc, d_tmp;
-	KgBuf &d_sz = db->frg.d_sz, &d_out = db->frg.d_out;   // the fragment stream and its offsets stay for kmagpu_trace_from_conclave
-	struct Guard { std::vector<KgBuf *> v; ~Guard() { for (KgBuf *b : v) b->release(); } } guard;
-	guard.v = {&d_sc, &d_items, &d_keys, &d_vals, &d_partial, &d_ctr, &d_acc, &d_tmp};
+	FragBatch &fb = db->frg;   // working buffers persist; the fragment stream and its offsets stay for kmagpu_trace_from_conclave
+	KgBuf &d_sc = fb.d_sc, &d_items = fb.d_items, &d_keys = fb.d_keys, &d_vals = fb.d_vals, &d_partial = fb.d_partial, &d_ctr = fb.d_ctr,
+	      &d_acc = fb.d_acc, &d_tmp = fb.d_tmp;
+	KgBuf &d_sz = fb.d_sz, &d_out = fb.d_out;
 	if (d_sc.reserve(16 * (size_t)DB) ||
 	    d_items.reserve(sizeof(CcItem) * (size_t)ni) || d_keys.reserve(16 * (size_t)ni) || d_vals.reserve(8 * (size_t)ni) ||
 	    d_sz.reserve(4 * (size_t)(2 * ni + 4)) || d_partial.reserve(4 * (size_t)(ntiles + 2)) || d_ctr.reserve(64) ||

@@ -78,6 +78,7 @@ struct TraceBatch {
 // the per-template fragment stream the last kmagpu_conclave_batch wrote, resident for kmagpu_trace_from_conclave
 struct FragBatch {
 	KgBuf d_out, d_sz;
+	KgBuf d_sc, d_items, d_keys, d_vals, d_partial, d_ctr, d_acc, d_tmp;   // ConClave's working buffers, kept across calls
 	const uint32_t *off = nullptr;   // record offsets (inside d_sz)
 	int64_t n = 0;
 	size_t bytes = 0;
