@@ -38,7 +38,8 @@ typedef struct kmagpu_params {
 	                                     (assembly.c:1968): 0 = no, 1 = alnToMat (template nodes, assembly.c:1317), 2 = alnToMatDense (-dense, :1446) */
 	int32_t apm;                      /* pairing of read pairs (-apm): 0 = p (save_kmers_penaltyPair savekmers.c:3572 / alnFragsPenaltyPE
 	                                     alnfrags.c:1596), 1 = u, the reference's default (save_kmers_unionPair :3367 / alnFragsUnionPE :1220) */
-	int32_t reserved[1];
+	int32_t counters;                 /* alignment pass: collect the in-kernel statistic counters (kmagpu_align_stats mems, index_probes,
+	                                     mem_bases, read_bytes, nw_*): measurement only, ~10 % of the pair kernel; kmagpu_default_params sets 1 */
 	double scoreT;                    /* -mrs (alnfrags.c:1168; also `mrs` of save_kmers_chain, kmers.c:51) */
 	double minFrac;                   /* -mf  (updatescores.c:217-268) */
 	double mrc;                       /* -mrc (alnfrags.h:38 mrcheck) */
@@ -168,6 +169,10 @@ int kmagpu_memscore_from_seed(kmagpu_db *db, void *frag_out, size_t out_cap, siz
 int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t nbytes, const uint64_t *alignment_scores,
                           const uint64_t *uniq_alignment_scores, void *frags_out, size_t out_cap, size_t *out_bytes,
                           uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts, int64_t *nrecords);
+
+/* Which ConClavePtr (conclave.c:30) kmagpu_conclave_batch / _resident / _from_align stand for: 0 = runConClave (the
+ * default), 1 = runConClave_lc (conclave.c:215-384, bound by -lc: score per template base before the total). */
+int kmagpu_conclave_mode(kmagpu_db *db, int length_corrected);
 
 /* kmagpu_conclave_batch on the frag_raw stream the last score collection (kmagpu_memscore_batch / _from_seed) of this
  * handle left in HBM; with kmagpu_trace_from_conclave the whole -mem_mode flow (stage 1 text -> stage 2 -> score

@@ -21,7 +21,7 @@ class KmaGpuError(RuntimeError):
 class Params(C.Structure):
     _fields_ = [("M", C.c_int32), ("MM", C.c_int32), ("U", C.c_int32), ("W1", C.c_int32), ("Wl", C.c_int32),
                 ("Mn", C.c_int32), ("PE", C.c_int32), ("d", C.c_int32 * 25), ("exhaustive", C.c_int32),
-                ("mq", C.c_int32), ("one2one", C.c_int32), ("minlen", C.c_int32), ("kmerscan", C.c_int32), ("matrix", C.c_int32), ("apm", C.c_int32), ("reserved", C.c_int32 * 1),
+                ("mq", C.c_int32), ("one2one", C.c_int32), ("minlen", C.c_int32), ("kmerscan", C.c_int32), ("matrix", C.c_int32), ("apm", C.c_int32), ("counters", C.c_int32),
                 ("scoreT", C.c_double), ("minFrac", C.c_double), ("mrc", C.c_double), ("coverT", C.c_double)]
 
 
@@ -172,6 +172,7 @@ def lib():
         L.kmagpu_memscore_from_seed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.kmagpu_conclave_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+        L.kmagpu_conclave_mode.argtypes = [C.c_void_p, C.c_int]
         L.kmagpu_conclave_from_align.argtypes = L.kmagpu_conclave_resident.argtypes
         L.kmagpu_trace_from_conclave.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64),
                                                  C.POINTER(AlignStats)]
@@ -386,6 +387,10 @@ class TemplateDB:
         _check(lib().kmagpu_memscore_batch(self._h, s2.ctypes.data, len(s2), out.ctypes.data, len(out), C.byref(ob), a.ctypes.data,
                                            u.ctypes.data, C.byref(nr)))
         return out[: ob.value], a, u, nr.value
+
+    def conclave_mode(self, length_corrected: bool):
+        """ConClavePtr: False = runConClave, True = runConClave_lc (-lc)"""
+        _check(lib().kmagpu_conclave_mode(self._h, int(length_corrected)))
 
     def memscore_from_seed(self, scores=None, download=True, cap=None):
         """memscore_batch on the stage-2 stream the last seed_run left in HBM; the frag_raw stream stays resident for

@@ -85,7 +85,7 @@ __device__ __forceinline__ QView read_view(const uint64_t *slab, const AlnRead &
 
 // ---------------------------------------------------------------- pass 1: sizes
 
-__global__ void aln_sizes_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ off, int n, int k,
+static __global__ void aln_sizes_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ off, int n, int k,
                                  AlnRead *reads, uint32_t *slab_sz, uint32_t *task_sz, unsigned long long *ctr) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n) return;
@@ -141,7 +141,7 @@ __device__ __forceinline__ int warp_min_i(int v) {
 	return v;
 }
 
-__global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__restrict__ in, int n, AlnRead *reads,
+static __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__restrict__ in, int n, AlnRead *reads,
 		const uint32_t *__restrict__ slab_off, const uint32_t *__restrict__ task_off, uint64_t *slab, int32_t *task_read, int k) {
 	const unsigned lane = threadIdx.x & 31;
 	const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -198,6 +198,12 @@ struct Mems {
 	__device__ __forceinline__ void shift(int o) { tS += o; tE += o; qS += o; qE += o; W += o; sc += o; nx += o; cap -= o; }
 };
 
+// KG_STAT: the statistic counters of the alignment kernels (algorithmic-byte inputs of the bench); -DKG_NO_STATS compiles them out
+#ifdef KG_NO_STATS
+#define KG_STAT(x)
+#else
+#define KG_STAT(x) x
+#endif
 struct WarpCtr { unsigned long long full_calls, band_calls, full_cells, band_cells, steps, mems, lookups, mem_bases, read_bytes; unsigned need_e, need_mem, need_q; };
 
 __device__ __noinline__ int warp_max(int v) {
@@ -248,9 +254,9 @@ __device__ KG_STAGE_INL int scan_mems(const KgTIndexView &ix, const KgTMeta &m, 
 			int val = 0;
 			if (p0 < end) val = tix_get(ix, m, kmer_at(q.w, p0, k));
 			const unsigned hits = __ballot_sync(0xffffffffu, val != 0);
-			if (!hits) { wc.lookups += (unsigned long long)min(32, end - j); j += 32; continue; }
+			if (!hits) { KG_STAT(wc.lookups += (unsigned long long)min(32, end - j);) j += 32; continue; }
 			const int f = __ffs(hits) - 1, p = j + f;
-			wc.lookups += (unsigned long long)(f + 1);   // the probes the reference's sequential scan makes
+			KG_STAT(wc.lookups += (unsigned long long)(f + 1);)   // the probes the reference's sequential scan makes
 			const int v = __shfl_sync(0xffffffffu, val, f);
 			if (v > 0) {
 				if (n >= M.cap) { wc.need_mem = max(wc.need_mem, (unsigned)n + 1024u); return ST_OVERFLOW; }
@@ -259,7 +265,7 @@ __device__ KG_STAGE_INL int scan_mems(const KgTIndexView &ix, const KgTMeta &m, 
 				if (lane == 0) { M.tS[n] = ts; M.tE[n] = te; M.qS[n] = qs; M.qE[n] = qe; M.W[n] = qe - qs; }
 				++n;
 				s += qe - qs;
-				wc.mem_bases += (unsigned long long)(qe - qs);
+				KG_STAT(wc.mem_bases += (unsigned long long)(qe - qs);)
 				j = (BYTES || MODE == 0) ? qe : qe + 1;
 			} else {
 				int cnt;
@@ -275,7 +281,7 @@ __device__ KG_STAGE_INL int scan_mems(const KgTIndexView &ix, const KgTMeta &m, 
 				}
 				bias = warp_max(bias);
 				n += cnt;
-				wc.mem_bases += (unsigned long long)cnt * (unsigned long long)k;
+				KG_STAT(wc.mem_bases += (unsigned long long)cnt * (unsigned long long)k;)
 				s += k + (bias - p);
 				j = bias + 1;
 			}
@@ -392,8 +398,12 @@ __device__ int nw_auto(const TaskCtx &c, int k, int t_s, int t_e, int q_s, int q
 	const int t_l = t_e - t_s, q_l = q_e - q_s;
 	int band = abs(t_l - q_l) + AL_BANDW;
 	if (q_l <= band || t_l <= band) band = 0;
+#ifndef KG_NO_STATS
 	unsigned long long cells = 0;
 	const int st = nw_warp<false>(*c.pen, c.tseq, c.qb, k, t_s, t_e, q_s, q_e, band, c.nw, a, &cells);
+#else
+	const int st = nw_warp<false>(*c.pen, c.tseq, c.qb, k, t_s, t_e, q_s, q_e, band, c.nw, a, nullptr);
+#endif
 	if (st != NW_OK) {
 		NwGeo g;
 		nw_geo_init(g, *c.pen, t_l, q_l, k, band, false);
@@ -401,12 +411,14 @@ __device__ int nw_auto(const TaskCtx &c, int k, int t_s, int t_e, int q_s, int q
 		c.wc->need_q = max(c.wc->need_q, (unsigned)q_l + 64u);
 		return ST_OVERFLOW;
 	}
+#ifndef KG_NO_STATS
 	if (cells) {
 		NwGeo g;
 		nw_geo_init(g, *c.pen, t_l, q_l, k, band, false);
 		c.wc->steps += (unsigned long long)g.Tmax;
 		if (band) { ++c.wc->band_calls; c.wc->band_cells += cells; } else { ++c.wc->full_calls; c.wc->full_cells += cells; }
 	}
+#endif
 	return ST_OK;
 }
 
@@ -419,7 +431,7 @@ __device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c,
 		int dummy;
 		if (scan_mems<0, false>(ix, m, c.tseq, q, nN1, q_len, q_start, q_end, M, n, dummy, *c.wc)) return ST_OVERFLOW;
 	}
-	c.wc->mems += (unsigned long long)n;
+	KG_STAT(c.wc->mems += (unsigned long long)n;)
 	if (!n) { *out = s; return ST_OK; }
 	unsigned mapQ = 0;
 	int start = chain_warp(*c.pen, M, n, q_len, t_len, k, &mapQ);
@@ -613,11 +625,11 @@ __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(AlnParams
 		int st;
 		if (R.kind == 2) {   // a mate of a pair against one template, strands decided by stage 2 (alnfrags.c:1645-1661, 1712-1731)
 			const AlnRead Rq = mate ? R : reads[r - 1];
-			wc.read_bytes += 8ull * (unsigned long long)Rq.words + (unsigned long long)Rq.q_len + 4ull * (unsigned long long)Rq.nN;
+			KG_STAT(wc.read_bytes += 8ull * (unsigned long long)Rq.words + (unsigned long long)Rq.q_len + 4ull * (unsigned long long)Rq.nN;)
 			st = align_fixed(P, &spen, ix, slab, Rq, ti >= R.fneg, abs(tmpl), M, nws, wc, &res);
 			res.tmpl = tmpl;
 		} else {
-			wc.read_bytes += 8ull * (unsigned long long)R.words + (unsigned long long)R.q_len + 4ull * (unsigned long long)R.nN;
+			KG_STAT(wc.read_bytes += 8ull * (unsigned long long)R.words + (unsigned long long)R.q_len + 4ull * (unsigned long long)R.nN;)
 			st = align_pair(P, &spen, ix, slab, R, tmpl, M, nws, wc, &res);
 		}
 		__syncwarp();
@@ -640,6 +652,25 @@ __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(AlnParams
 		if (wc.need_q) atomicMax(&ctr[A_NEED_Q], (unsigned long long)wc.need_q);
 	}
 }
+
+// The pair kernel without the statistic counters is compiled in a translation unit of its own (kmagpu_align_fast.cu
+// includes this file inside a namespace with KG_NO_STATS and KG_PAIR_VARIANT_ONLY): the counters cost it 21 registers
+// and ~10 % of its time. The launcher has C linkage and takes the structs by address because the two translation units
+// define them in different namespaces (same source, same layout).
+#ifdef KG_PAIR_VARIANT_ONLY
+extern "C" void kg_launch_pair_nostats(int short_reads, int grid, cudaStream_t st, const void *P, const void *ix, const uint8_t *in,
+                                       const void *reads, const uint64_t *slab, const int32_t *task_read, int ntasks, const int32_t *task_list,
+                                       void *cand, uint8_t *scratch, const void *lay, unsigned long long *ctr, int32_t *ovf_list) {
+	const AlnParams &p = *(const AlnParams *)P;
+	const KgTIndexView &x = *(const KgTIndexView *)ix;
+	const ScratchLayout &l = *(const ScratchLayout *)lay;
+	if (short_reads) aln_pair_kernel<AL_MINB_SHORT><<<grid, AL_WARPS * 32, 0, st>>>(p, x, in, (const AlnRead *)reads, slab, task_read, ntasks, task_list, (AlnCand *)cand, scratch, l, ctr, ovf_list);
+	else aln_pair_kernel<AL_MINB><<<grid, AL_WARPS * 32, 0, st>>>(p, x, in, (const AlnRead *)reads, slab, task_read, ntasks, task_list, (AlnCand *)cand, scratch, l, ctr, ovf_list);
+}
+#else
+extern "C" void kg_launch_pair_nostats(int short_reads, int grid, cudaStream_t st, const void *P, const void *ix, const uint8_t *in,
+                                       const void *reads, const uint64_t *slab, const int32_t *task_read, int ntasks, const int32_t *task_list,
+                                       void *cand, uint8_t *scratch, const void *lay, unsigned long long *ctr, int32_t *ovf_list);
 
 // ---------------------------------------------------------------- selection + ConClave sums (one thread per read)
 
@@ -1068,7 +1099,7 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 		int dummy;
 		if (scan_mems<0, true>(ix, m, c.tseq, q, nN1, q_len, 0, q_len, M, n, dummy, *c.wc)) return ST_OVERFLOW;
 	}
-	c.wc->mems += (unsigned long long)n;
+	KG_STAT(c.wc->mems += (unsigned long long)n;)
 	if (!n) { *out = s; return ST_OK; }
 	unsigned mapQ = 0;
 	int start = chain_warp(*c.pen, M, n, q_len, t_len, k, &mapQ);
@@ -1573,7 +1604,10 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 		}
 		if (b.d_scratch.reserve(lay.stride * (size_t)grid * AL_WARPS)) return -1;
 		KG_CUDA(cudaEventRecord(db->ev[3], st));   // ms_align = the pair kernel(s) alone; host-side sizing above is in ms_total
-		if (short_reads)
+		if (!prm->counters)   // production: no statistic counters (stats->mems, index_probes, mem_bases, read_bytes, nw_* stay 0)
+			kg_launch_pair_nostats(short_reads, grid, st, &P, &db->tix, b.in, reads, (const uint64_t *)b.d_slab.p, (const int32_t *)b.d_taskread.p,
+				ntasks, nullptr, b.d_cand.p, (uint8_t *)b.d_scratch.p, &lay, ctr, (int32_t *)b.d_ovf.p);
+		else if (short_reads)
 			aln_pair_kernel<AL_MINB_SHORT><<<grid, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
 				(const int32_t *)b.d_taskread.p, ntasks, nullptr, (AlnCand *)b.d_cand.p, (uint8_t *)b.d_scratch.p, lay, ctr,
 				(int32_t *)b.d_ovf.p);
@@ -2011,3 +2045,4 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 	cudaFree(scratch); cudaFree(dq); cudaFree(dprob); cudaFree(dout); cudaFree(dstat); cudaFree(ctr);
 	return 0;
 }
+#endif   // KG_PAIR_VARIANT_ONLY

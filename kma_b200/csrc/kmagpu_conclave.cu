@@ -27,7 +27,7 @@ struct CcItem {
 // the mate block of a pair record); returns the bytes the record spans
 __device__ uint32_t cc_record(const uint8_t *__restrict__ in, uint32_t pos, int idx, const unsigned long long *__restrict__ as,
 		const unsigned long long *__restrict__ uas, const int32_t *__restrict__ lengths, int DB_size, CcItem *items, unsigned long long *keys,
-		unsigned long long *w, unsigned int *fc, unsigned int *rcn, unsigned long long *ctr, bool *has_mate) {
+		unsigned long long *w, unsigned int *fc, unsigned int *rcn, unsigned long long *ctr, bool *has_mate, int lc) {
 	const uint8_t *rec = in + pos;
 	const int q_len = (int)ld_u32u(rec), sparse = (int)ld_u32u(rec + 4), sc = (int)ld_u32u(rec + 8), hl = (int)ld_u32u(rec + 12);
 	int flag = (int)ld_u32u(rec + 16);
@@ -47,7 +47,16 @@ __device__ uint32_t cc_record(const uint8_t *__restrict__ in, uint32_t pos, int 
 			// the reference compares the 64-bit sums with ints: the ints are converted (sign-extended) to unsigned long
 			const unsigned long long brs = (unsigned long long)(long long)best_read_score, bn = (unsigned long long)(long long)bestNum;
 			bool take = false;
-			if (a > brs) take = true;
+			if (lc) {   // runConClave_lc (conclave.c:215-384, -lc): score per template base first, then the total
+				if (tmp_score > bestScore) take = true;
+				else if (tmp_score == bestScore) {
+					if (a > brs) take = true;
+					else if (a == brs) {
+						if (u > bn) take = true;
+						else if (u == bn && t < abs(bestTemplate)) take = true;
+					}
+				}
+			} else if (a > brs) take = true;
 			else if (a == brs) {
 				if (tmp_score > bestScore) take = true;
 				else if (tmp_score == bestScore) {
@@ -106,7 +115,7 @@ __device__ uint32_t cc_record(const uint8_t *__restrict__ in, uint32_t pos, int 
 __global__ void __launch_bounds__(256) cc_choose_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ off, int n,
 		const unsigned long long *__restrict__ as, const unsigned long long *__restrict__ uas, const int32_t *__restrict__ lengths,
 		int DB_size, CcItem *items, unsigned long long *keys, uint32_t *vals, unsigned long long *w, unsigned int *fc, unsigned int *rcn,
-		unsigned long long *ctr) {
+		unsigned long long *ctr, int lc) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n) return;
 	keys[2 * r] = ~0ull; keys[2 * r + 1] = ~0ull; vals[2 * r] = 2u * (unsigned)r; vals[2 * r + 1] = 2u * (unsigned)r + 1u;
@@ -114,7 +123,7 @@ __global__ void __launch_bounds__(256) cc_choose_kernel(const uint8_t *__restric
 	const uint32_t end = off[r + 1];
 	for (int idx = 2 * r; idx < 2 * r + 2 && end - pos >= 20u && pos < end;) {
 		bool mate = false;
-		pos += cc_record(in, pos, idx, as, uas, lengths, DB_size, items, keys, w, fc, rcn, ctr, &mate);
+		pos += cc_record(in, pos, idx, as, uas, lengths, DB_size, items, keys, w, fc, rcn, ctr, &mate, lc);
 		idx += mate ? 2 : 1;
 	}
 	if (pos != end && end - off[r] >= 20u) atomicAdd(&ctr[3], 1ull);   // the slot's bytes are not a whole number of records
@@ -186,7 +195,7 @@ static int conclave_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff
 	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
 	KG_CUDA(cudaMemsetAsync(d_acc.p, 0, 16 * (size_t)DB, st));
 	cc_choose_kernel<<<(n + 255) / 256, 256, 0, st>>>(din, doff, n, as, uas, db->d_lengths, DB,
-		(CcItem *)d_items.p, keys, vals, w, fc, rcn, ctr);
+		(CcItem *)d_items.p, keys, vals, w, fc, rcn, ctr, db->conclave_lc);
 	size_t tmp_bytes = 0;
 	cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, ni, 0, 64, st);
 	if (d_tmp.reserve(tmp_bytes + 64)) return -1;
@@ -301,4 +310,11 @@ extern "C" int kmagpu_conclave_from_align(kmagpu_db *db, const uint64_t *alignme
 	KG_CUDA(cudaStreamSynchronize(db->stream));
 	return conclave_core(db, (const uint8_t *)b.d_out.p, recoff, n, alignment_scores, uniq_alignment_scores, frags_out, out_cap, out_bytes,
 	                     w_scores, fragmentCounts, readCounts);
+}
+
+// which ConClavePtr the three ConClave entry points stand for: 0 = runConClave (conclave.c:43), 1 = runConClave_lc (:215, -lc)
+extern "C" int kmagpu_conclave_mode(kmagpu_db *db, int length_corrected) {
+	if (!db) { kmagpu_set_error("null argument"); return -1; }
+	db->conclave_lc = length_corrected != 0;
+	return 0;
 }

@@ -36,6 +36,7 @@ extern "C" void kmagpu_default_params(kmagpu_params *p) {
 	p->mrc = 0.0;
 	p->minlen = 16;
 	p->coverT = 0.1;
+	p->counters = 1;
 }
 
 int KgBuf::reserve(size_t bytes) {

@@ -128,6 +128,7 @@ struct kmagpu_db {
 	TraceBatch trc;
 	FragBatch frg;
 	RawBatch raw;
+	int conclave_lc = 0;   // 1: runConClave_lc
 	// per-template alignment index (kmagpu_tindex.cu)
 	void *d_tmeta = nullptr, *d_tslots = nullptr;
 	int32_t *d_tdups = nullptr;

@@ -59,6 +59,7 @@ double orc_chi2_min(double evalue);
 void orc_to2bit(uint8_t *trans);
 size_t orc_stage1(const uint8_t *text1, size_t n1, const uint8_t *text2, size_t n2, int fastq, int min_phred, int phred_scale,
                   int minlen, int maxlen, uint8_t *out, size_t cap, int64_t *count);
+void orc_conclave_set_lc(int lc);
 void orc_free(void *p);
 void orc_nw(const orc_params *p, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s, int q_e,
             int band, int *out6);

@@ -16,6 +16,9 @@
 
 typedef struct { int tmpl, buf[7]; const uint8_t *q, *hdr; int rc; int b0, b1, has_bound; } cfrag;
 
+static int orc_lc = 0;
+void orc_conclave_set_lc(int lc) { orc_lc = lc; }   /* 1: runConClave_lc */
+
 int64_t orc_conclave_stream(const int32_t *template_lengths, int DB_size, const uint8_t *frag, size_t fb,
                             const uint64_t *alignment_scores, const uint64_t *uniq_alignment_scores,
                             uint8_t *out, size_t cap, uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts) {
@@ -45,7 +48,16 @@ int64_t orc_conclave_stream(const int32_t *template_lengths, int DB_size, const 
 				const int t = tt < 0 ? -tt : tt;
 				tmp_score = 1.0 * alignment_scores[t] / template_lengths[t];
 				int take = 0;
-				if (alignment_scores[t] > best_read_score) take = 1;
+				if (orc_lc) {   /* runConClave_lc (conclave.c:215-384, -lc): score per template base first, then the total */
+					if (tmp_score > bestScore) take = 1;
+					else if (tmp_score == bestScore) {
+						if (alignment_scores[t] > best_read_score) take = 1;
+						else if (alignment_scores[t] == best_read_score) {
+							if (uniq_alignment_scores[t] > bestNum) take = 1;
+							else if (uniq_alignment_scores[t] == bestNum && t < abs(bestTemplate)) take = 1;
+						}
+					}
+				} else if (alignment_scores[t] > best_read_score) take = 1;
 				else if (alignment_scores[t] == best_read_score) {
 					if (tmp_score > bestScore) take = 1;
 					else if (tmp_score == bestScore) {

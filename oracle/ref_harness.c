@@ -178,7 +178,8 @@ static int conclave_main(int argc, char **argv) {
 	int *template_lengths; long unsigned *as, *uas;
 	char *p2 = malloc(strlen(argv[2]) + 64); strcpy(p2, argv[2]);
 	int DB_size = load_DBs_KMA(p2, &as, &uas, &template_lengths, 0);
-	int maxFrag = argc > 6 ? atoi(argv[6]) : 1048576;
+	int maxFrag = argc > 6 && strcmp(argv[6], "-lc") ? atoi(argv[6]) : 1048576;
+	const int lc = !strcmp(argv[argc - 1], "-lc");   /* runConClave_lc (kma.c:700: -lc) */
 	FILE *sc = fopen(argv[4], "rb");
 	int n = 0;
 	if (!sc || fread(&n, 4, 1, sc) != 1 || n != DB_size) { fprintf(stderr, "scores file does not match the database\n"); return 1; }
@@ -199,7 +200,7 @@ static int conclave_main(int argc, char **argv) {
 	Frag **alignFrags = calloc(DB_size, sizeof(Frag *));
 	long unsigned *w_scores = calloc(DB_size, sizeof(long unsigned));
 	unsigned *fragmentCounts = calloc(DB_size, sizeof(unsigned)), *readCounts = calloc(DB_size, sizeof(unsigned));
-	int files = runConClave(tmp, &template_fragments, DB_size, maxFrag, w_scores, fragmentCounts, readCounts, as, uas, template_lengths,
+	int files = (lc ? runConClave_lc : runConClave)(tmp, &template_fragments, DB_size, maxFrag, w_scores, fragmentCounts, readCounts, as, uas, template_lengths,
 	                        header, qseq, bestTemplates, bs, be, alignFrags);
 	FILE *out = fopen(argv[5], "wb");
 	fwrite(&files, 4, 1, out);

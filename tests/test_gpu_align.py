@@ -367,3 +367,39 @@ def test_union_pairing_vs_reference(tmp_path, seed):
     fb = frag.tobytes()
     assert fb == ofrag, f"frag_raw differs at byte {_first_diff(fb, ofrag)} of {len(ofrag)} (got {len(fb)})"
     assert frag2.tobytes() == ofrag and np.array_equal(a2, oa) and np.array_equal(u2, ou)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+def test_pair_kernel_without_counters_is_the_same(tmp_path):
+    """params.counters = 0 runs the pair kernel built without its statistic counters (kmagpu_align_fast.cu): same
+    frag_raw bytes, score arrays and candidate rows; only the counters of the statistics stay zero. Short reads (the
+    10-CTA variant) and long reads (the 6-CTA variant)."""
+    from tests.test_oracle_pair import make_pairs
+    prefix, s1, s2 = make_pairs(tmp_path, 53, n=2500)
+    names, seqs = synth.gene_db(61, n_families=15, n_variants=6, len_lo=800, len_hi=3000)
+    db = api.TemplateDB(prefix)
+    for stream in (np.frombuffer(s2, dtype=np.uint8) if isinstance(s2, (bytes, bytearray)) else np.ascontiguousarray(s2),):
+        p = api.default_params()
+        frag1, a1, u1, c1, st1 = db.alnFrags_batch(stream, p, want_cand=True)
+        p.counters = 0
+        frag0, a0, u0, c0, st0 = db.alnFrags_batch(stream, p, want_cand=True)
+        assert len(frag1) > 100000 and frag0.tobytes() == frag1.tobytes() and np.array_equal(a0, a1) and np.array_equal(u0, u1) and np.array_equal(c0, c1)
+        assert st1.mems > 0 and st1.index_probes > 0 and st0.tasks == st1.tasks
+        assert st0.mems * 4 < st1.mems and st0.index_probes * 4 < st1.index_probes   # only the large-scratch retries still count
+    db.close()
+    # long reads
+    lp = tmp_path / "long"
+    lp.mkdir()
+    synth.write_fasta(lp / "db.fsa", names, seqs)
+    reads = synth.long_reads(62, seqs, 60, len_lo=3000, len_hi=9000)
+    synth.write_fastq(lp / "r.fq", reads, qual="5")
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=lp)
+    s2l = np.frombuffer(util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-1t1", "-s2"], cwd=lp), dtype=np.uint8)
+    db = api.TemplateDB(str(lp / "db"))
+    p = api.default_params()
+    p.one2one = 1
+    frag1, a1, u1, c1, st1 = db.alnFrags_batch(s2l, p, want_cand=True)
+    p.counters = 0
+    frag0, a0, u0, c0, st0 = db.alnFrags_batch(s2l, p, want_cand=True)
+    db.close()
+    assert frag0.tobytes() == frag1.tobytes() and np.array_equal(a0, a1) and np.array_equal(c0, c1) and st1.nw_band_calls > 0 and st0.nw_band_calls * 4 < st1.nw_band_calls

@@ -23,6 +23,25 @@ def test_conclave_single_end(tmp_path, seed, chain):
     assert np.array_equal(w, ow) and np.array_equal(fc, ofc) and np.array_equal(rc, orc_)
 
 
+def test_conclave_length_corrected(tmp_path):
+    """-lc (runConClave_lc): per-base score before the total, real and arbitrary score arrays"""
+    prefix, frag, a, u = se_case(tmp_path, 77, chain=True)
+    rng = np.random.default_rng(77)
+    a2 = rng.integers(1, 50000, size=len(a)).astype(np.uint64)
+    u2 = rng.integers(0, 3, size=len(u)).astype(np.uint64)
+    db = api.TemplateDB(prefix, device=0)
+    db.conclave_mode(True)
+    for aa, uu in ((a, u), (a2, u2)):
+        want, ow, ofc, orc_ = util.oracle_conclave(prefix, frag, aa, uu, lc=True)
+        got, w, fc, rc, _ = db.conclave_batch(frag, aa, uu)
+        assert got.tobytes() == want and np.array_equal(w, ow) and np.array_equal(fc, ofc) and np.array_equal(rc, orc_)
+    db.conclave_mode(False)
+    want, ow, _, _ = util.oracle_conclave(prefix, frag, a2, u2)
+    got, w, _, _, _ = db.conclave_batch(frag, a2, u2)
+    db.close()
+    assert got.tobytes() == want and np.array_equal(w, ow)
+
+
 def test_conclave_paired_end_and_empty(tmp_path):
     names, seqs = synth.gene_db(73, n_families=10, n_variants=8, len_lo=500, len_hi=1500)
     synth.write_fasta(tmp_path / "db.fsa", names, seqs)

@@ -72,3 +72,34 @@ def test_conclave_chunks_of_maxfrag(tmp_path):
         assert got == f
         tot_w += ow
     assert np.array_equal(tot_w, w)
+
+
+@pytest.mark.parametrize("seed,chain", [(75, False), (76, True)])
+def test_conclave_length_corrected(tmp_path, seed, chain):
+    """-lc: runConClave_lc (conclave.c:215-384) orders the candidates by score per template base before the total"""
+    prefix, frag, a, u = se_case(tmp_path, seed, chain=chain)
+    files, w, fc, rc = util.ref_conclave(prefix, frag, a, u, str(tmp_path), lc=True)
+    got, ow, ofc, orc_ = util.oracle_conclave(prefix, frag, a, u, lc=True)
+    assert got == files[0] and np.array_equal(ow, w) and np.array_equal(ofc, fc) and np.array_equal(orc_, rc)
+    # arbitrary global score arrays (any values are valid input) make the two key orders disagree
+    rng = np.random.default_rng(seed)
+    a2 = rng.integers(1, 50000, size=len(a)).astype(np.uint64)
+    u2 = rng.integers(0, 3, size=len(u)).astype(np.uint64)
+    files2, w2, fc2, rc2 = util.ref_conclave(prefix, frag, a2, u2, str(tmp_path), lc=True)
+    got2, ow2, ofc2, orc2 = util.oracle_conclave(prefix, frag, a2, u2, lc=True)
+    assert got2 == files2[0] and np.array_equal(ow2, w2) and np.array_equal(ofc2, fc2) and np.array_equal(orc2, rc2)
+    # a hand-made record with two candidates whose total and per-base orders disagree: the short template wins under -lc
+    lengths = np.fromfile(prefix + ".length.b", dtype=np.int32)[1:]
+    t_short, t_long = int(np.argmin(lengths[1:])) + 1, int(np.argmax(lengths[1:])) + 1
+    a3 = np.zeros(len(a), dtype=np.uint64)
+    a3[t_short], a3[t_long] = 1000, 1001
+    assert 1000 / lengths[t_short] > 1001 / lengths[t_long]
+    read = np.arange(40, dtype=np.uint8) % 4
+    rec = (np.array([40, 2, 30, 3, 0], dtype=np.int32).tobytes() + read.tobytes() + b"x1\0" +
+           np.array([0, 0, 40, 40, t_short, t_long], dtype=np.int32).tobytes())
+    u3 = np.zeros(len(a), dtype=np.uint64)
+    for lc, want_t in ((False, t_long), (True, t_short)):
+        files3, w3, _, _ = util.ref_conclave(prefix, rec, a3, u3, str(tmp_path), lc=lc)
+        got3, ow3, _, _ = util.oracle_conclave(prefix, rec, a3, u3, lc=lc)
+        assert got3 == files3[0] and np.array_equal(ow3, w3)
+        assert int(np.frombuffer(got3[:4], dtype=np.int32)[0]) == want_t

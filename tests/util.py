@@ -296,14 +296,14 @@ def parse_trace(buf: bytes):
     return out
 
 
-def ref_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarray, tmp: str, max_frag=None):
+def ref_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarray, tmp: str, max_frag=None, lc=False):
     """ground truth of ConClave's choice pass + printFrags from the unmodified reference (ref_harness -conclave):
     (list of per-file byte strings, w_scores u64[DB], fragmentCounts u32[DB], readCounts u32[DB])"""
     fp, sp, op = os.path.join(tmp, "cc_frag.bin"), os.path.join(tmp, "cc_sc.bin"), os.path.join(tmp, "cc_out.bin")
     open(fp, "wb").write(frag_raw)
     with open(sp, "wb") as f:
         f.write(np.array([len(a)], dtype=np.int32).tobytes() + a.astype(np.uint64).tobytes() + u.astype(np.uint64).tobytes())
-    args = [REF_ALN, "-conclave", db_prefix, fp, sp, op] + ([str(max_frag)] if max_frag else [])
+    args = [REF_ALN, "-conclave", db_prefix, fp, sp, op] + ([str(max_frag)] if max_frag else []) + (["-lc"] if lc else [])
     r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     buf = open(op, "rb").read()
@@ -320,7 +320,7 @@ def ref_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarray, 
     return files, w, fc, rc
 
 
-def oracle_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarray):
+def oracle_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarray, lc=False):
     """(per-template fragment records of one file, w_scores, fragmentCounts, readCounts) from the C oracle"""
     L = orc()
     raw = np.fromfile(db_prefix + ".length.b", dtype=np.int32)
@@ -332,8 +332,10 @@ def oracle_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarra
     L.orc_conclave_stream.restype = C.c_int64
     L.orc_conclave_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_conclave_set_lc(int(lc))
     n = L.orc_conclave_stream(lengths.ctypes.data, DB, fr.ctypes.data, len(fr), a.ctypes.data, u.ctypes.data, out.ctypes.data, len(out),
                               w.ctypes.data, fc.ctypes.data, rc.ctypes.data)
+    L.orc_conclave_set_lc(0)
     assert n >= 0, f"oracle conclave error {n}"
     return out[:n].tobytes(), w, fc, rc
 
