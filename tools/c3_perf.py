@@ -22,7 +22,7 @@ def main():
     s1 = records.stage1_records(reads)
     bases = sum(len(r) for r in reads)
     print("reads", nreads, "bases", bases, "gen s", round(time.time() - t0, 1), flush=True)
-    p = api.default_params(); p.kmerscan = 1
+    p = api.default_params(); p.kmerscan = 1; p.counters = int(os.environ.get("KG_COUNTERS", "1"))
     for mode in ("chain", "1t1"):
         p.kmerscan = 1 if mode == "chain" else 0
         p.one2one = 0 if mode == "chain" else 1

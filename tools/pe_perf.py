@@ -12,13 +12,15 @@ def main():
     wd = os.path.join(tempfile.gettempdir(), "kma_b200_bench"); os.makedirs(wd, exist_ok=True)
     prefix, names, seqs = bench.make_db(wd)
     db = api.TemplateDB(prefix)
+    p = api.default_params()
+    p.counters = int(os.environ.get("KG_COUNTERS", "0"))   # 0: the production pair kernel (no statistic counters)
     for n in sizes:
         r1, r2 = synth.paired_reads(7, seqs, n)
         s1 = records.stage1_pairs_fast(r1, r2)
         db.seed_upload(s1)
         rows = []
         for it in range(steps):
-            st = db.seed_run(); db.align_from_seed(); sa = db.align_run()
+            st = db.seed_run(p); db.align_from_seed(); sa = db.align_run(p)
             rows.append((round(st.ms_seed, 2), round(sa.ms_prep, 2), round(sa.ms_align, 2), round(sa.ms_reduce, 2)))
         per = [round(1e3 * (a + b + c + d) / (2 * n), 4) for a, b, c, d in rows]
         print(json.dumps({"pairs": n, "seed/prep/pairs/reduce ms": rows, "us_per_read": per, "tasks": sa.tasks}))
