@@ -1,5 +1,5 @@
 """Summarise an `ncu --set full` report into a small text file for profiles/ and record per-launch DRAM traffic.
-usage: ncu_summary.py <report.ncu-rep> <out.txt> [traffic.json]
+usage: ncu_summary.py <report.ncu-rep> <out.txt> [traffic.json [pairs]]   (pairs: batch size of the profiled run, default 2000000)
 The traffic file maps kernel base names to {"dram_bytes": read+write per launch, "units": ..., "report": ...};
 bench.py scales it to its own launch by the recorded unit count (bytes per pair / per read)."""
 import csv, json, os, subprocess, sys
@@ -28,6 +28,7 @@ SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     tj = sys.argv[3] if len(sys.argv) > 3 else None
+    pairs = int(sys.argv[4]) if len(sys.argv) > 4 else 2000000
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     h, units = rows[0], rows[1]
@@ -44,8 +45,9 @@ def main():
             rd = float(r[h.index("dram__bytes_read.sum")]) * SCALE[units[h.index("dram__bytes_read.sum")]]
             wr = float(r[h.index("dram__bytes_write.sum")]) * SCALE[units[h.index("dram__bytes_write.sum")]]
             f.write(f"{'dram traffic (read+write)':88s} {rd + wr:18.0f} byte\n")
-            traffic[base.split("<")[0]] = {"dram_bytes": rd + wr, "report": os.path.basename(rep),
-                                           "grid": r[h.index("launch__grid_size")]}
+            if rd + wr == rd + wr:   # a capture whose DRAM counters came back as NaN keeps the older entry
+                traffic[base.split("<")[0].split("::")[-1]] = {"dram_bytes": rd + wr, "report": os.path.basename(rep),
+                                                               "grid": r[h.index("launch__grid_size")], "pairs": pairs}
     if tj:
         json.dump(traffic, open(tj, "w"), indent=1)
 
