@@ -653,24 +653,25 @@ __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(AlnParams
 	}
 }
 
-// The pair kernel without the statistic counters is compiled in a translation unit of its own (kmagpu_align_fast.cu
-// includes this file inside a namespace with KG_NO_STATS and KG_PAIR_VARIANT_ONLY): the counters cost it 21 registers
-// and ~10 % of its time. The launcher has C linkage and takes the structs by address because the two translation units
-// define them in different namespaces (same source, same layout).
+// The pair kernel without the statistic counters is compiled in translation units of its own (kmagpu_align_fast.cu for
+// long reads, kmagpu_align_fast_short.cu for short ones include this file inside a namespace with KG_NO_STATS and
+// KG_PAIR_VARIANT_ONLY): the counters cost it 21 registers and ~10 % of its time, and the short-read build also takes
+// the NW scratch descriptor by value (NW_SCRATCH_BYVAL). The launchers have C linkage and take the structs by address
+// because the translation units define them in different namespaces (same source, same layout).
 #ifdef KG_PAIR_VARIANT_ONLY
-extern "C" void kg_launch_pair_nostats(int short_reads, int grid, cudaStream_t st, const void *P, const void *ix, const uint8_t *in,
-                                       const void *reads, const uint64_t *slab, const int32_t *task_read, int ntasks, const int32_t *task_list,
-                                       void *cand, uint8_t *scratch, const void *lay, unsigned long long *ctr, int32_t *ovf_list) {
-	const AlnParams &p = *(const AlnParams *)P;
-	const KgTIndexView &x = *(const KgTIndexView *)ix;
-	const ScratchLayout &l = *(const ScratchLayout *)lay;
-	if (short_reads) aln_pair_kernel<AL_MINB_SHORT><<<grid, AL_WARPS * 32, 0, st>>>(p, x, in, (const AlnRead *)reads, slab, task_read, ntasks, task_list, (AlnCand *)cand, scratch, l, ctr, ovf_list);
-	else aln_pair_kernel<AL_MINB><<<grid, AL_WARPS * 32, 0, st>>>(p, x, in, (const AlnRead *)reads, slab, task_read, ntasks, task_list, (AlnCand *)cand, scratch, l, ctr, ovf_list);
+extern "C" void KG_VARIANT_LAUNCHER(int grid, cudaStream_t st, const void *P, const void *ix, const uint8_t *in,
+                                    const void *reads, const uint64_t *slab, const int32_t *task_read, int ntasks, const int32_t *task_list,
+                                    void *cand, uint8_t *scratch, const void *lay, unsigned long long *ctr, int32_t *ovf_list) {
+	aln_pair_kernel<KG_VARIANT_MINB><<<grid, AL_WARPS * 32, 0, st>>>(*(const AlnParams *)P, *(const KgTIndexView *)ix, in, (const AlnRead *)reads, slab,
+		task_read, ntasks, task_list, (AlnCand *)cand, scratch, *(const ScratchLayout *)lay, ctr, ovf_list);
 }
 #else
-extern "C" void kg_launch_pair_nostats(int short_reads, int grid, cudaStream_t st, const void *P, const void *ix, const uint8_t *in,
-                                       const void *reads, const uint64_t *slab, const int32_t *task_read, int ntasks, const int32_t *task_list,
-                                       void *cand, uint8_t *scratch, const void *lay, unsigned long long *ctr, int32_t *ovf_list);
+#define KG_DECL_LAUNCHER(name)                                                                                                              \
+	extern "C" void name(int grid, cudaStream_t st, const void *P, const void *ix, const uint8_t *in, const void *reads, const uint64_t *slab, \
+	                     const int32_t *task_read, int ntasks, const int32_t *task_list, void *cand, uint8_t *scratch, const void *lay,      \
+	                     unsigned long long *ctr, int32_t *ovf_list)
+KG_DECL_LAUNCHER(kg_launch_pair_fast_long);
+KG_DECL_LAUNCHER(kg_launch_pair_fast_short);
 
 // ---------------------------------------------------------------- selection + ConClave sums (one thread per read)
 
@@ -1605,8 +1606,8 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 		if (b.d_scratch.reserve(lay.stride * (size_t)grid * AL_WARPS)) return -1;
 		KG_CUDA(cudaEventRecord(db->ev[3], st));   // ms_align = the pair kernel(s) alone; host-side sizing above is in ms_total
 		if (!prm->counters)   // production: no statistic counters (stats->mems, index_probes, mem_bases, read_bytes, nw_* stay 0)
-			kg_launch_pair_nostats(short_reads, grid, st, &P, &db->tix, b.in, reads, (const uint64_t *)b.d_slab.p, (const int32_t *)b.d_taskread.p,
-				ntasks, nullptr, b.d_cand.p, (uint8_t *)b.d_scratch.p, &lay, ctr, (int32_t *)b.d_ovf.p);
+			(short_reads ? kg_launch_pair_fast_short : kg_launch_pair_fast_long)(grid, st, &P, &db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
+				(const int32_t *)b.d_taskread.p, ntasks, nullptr, b.d_cand.p, (uint8_t *)b.d_scratch.p, &lay, ctr, (int32_t *)b.d_ovf.p);
 		else if (short_reads)
 			aln_pair_kernel<AL_MINB_SHORT><<<grid, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
 				(const int32_t *)b.d_taskread.p, ntasks, nullptr, (AlnCand *)b.d_cand.p, (uint8_t *)b.d_scratch.p, lay, ctr,

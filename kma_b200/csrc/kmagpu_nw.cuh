@@ -609,11 +609,20 @@ __device__ __forceinline__ void nw_rs_dispatch(const NwGeo &g, const uint64_t *_
 	}
 }
 
+// How the out-of-line nw_warp takes the scratch descriptor: by reference it lives in the caller's local memory, by value
+// in registers across the call. The short-read build of the pair kernel gains 6 % by value, the long-read build loses
+// 4-6 % (profiles/r01_ab_nwscratch_byvalue.log), so the translation unit chooses.
+#ifdef NW_SCRATCH_BYVAL
+typedef const NwScratch NwScratchArg;
+#else
+typedef const NwScratch &NwScratchArg;
+#endif
+
 // All 32 lanes call with identical arguments; every lane returns the same result. RS: rows of up to 32 * NW_RS_MAXC
 // cells run as the row sweep.
 template <bool RS>
 __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict__ tseq, const uint8_t *query, int k, int t_s,
-                                    int t_e, int q_s, int q_e, int band, const NwScratch &ws, NwStat *out,
+                                    int t_e, int q_s, int q_e, int band, NwScratchArg ws, NwStat *out,
                                     unsigned long long *cells, const NwRows *rows = nullptr) {
 	const int lane = threadIdx.x & 31;
 	const int t_len = t_e - t_s, q_len = q_e - q_s;
