@@ -192,10 +192,24 @@ static __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__r
 
 // ---------------------------------------------------------------- MEMs
 
+// One 32-byte record per MEM (tS, tE, qS, qE, W, sc, nx, pad): a MEM is one sector, and the table is one pointer in
+// registers instead of seven (the pair kernel runs under a 48-register cap).
 struct Mems {
-	int *tS, *tE, *qS, *qE, *W, *sc, *nx;
+	int *base;
 	int cap;
-	__device__ __forceinline__ void shift(int o) { tS += o; tE += o; qS += o; qE += o; W += o; sc += o; nx += o; cap -= o; }
+	__device__ __forceinline__ int &tS(int i) const { return base[8 * i]; }
+	__device__ __forceinline__ int &tE(int i) const { return base[8 * i + 1]; }
+	__device__ __forceinline__ int &qS(int i) const { return base[8 * i + 2]; }
+	__device__ __forceinline__ int &qE(int i) const { return base[8 * i + 3]; }
+	__device__ __forceinline__ int &W(int i) const { return base[8 * i + 4]; }
+	__device__ __forceinline__ int &sc(int i) const { return base[8 * i + 5]; }
+	__device__ __forceinline__ int &nx(int i) const { return base[8 * i + 6]; }
+	__device__ __forceinline__ int4 pos(int i) const { return *(const int4 *)(base + 8 * i); }   // tS, tE, qS, qE
+	__device__ __forceinline__ void set(int i, int ts, int te, int qs, int qe) const {
+		*(int4 *)(base + 8 * i) = make_int4(ts, te, qs, qe);
+		base[8 * i + 4] = qe - qs;
+	}
+	__device__ __forceinline__ void shift(int o) { base += 8 * o; cap -= o; }
 };
 
 // KG_STAT: the statistic counters of the alignment kernels (algorithmic-byte inputs of the bench); -DKG_NO_STATS compiles them out
@@ -262,7 +276,7 @@ __device__ KG_STAGE_INL int scan_mems(const KgTIndexView &ix, const KgTMeta &m, 
 				if (n >= M.cap) { wc.need_mem = max(wc.need_mem, (unsigned)n + 1024u); return ST_OVERFLOW; }
 				int qs, ts, qe, te;
 				mem_from_seed(q.w, tseq, t_len, k, p, v, lo, fwd_lim, &qs, &ts, &qe, &te);
-				if (lane == 0) { M.tS[n] = ts; M.tE[n] = te; M.qS[n] = qs; M.qE[n] = qe; M.W[n] = qe - qs; }
+				if (lane == 0) M.set(n, ts, te, qs, qe);
 				++n;
 				s += qe - qs;
 				KG_STAT(wc.mem_bases += (unsigned long long)(qe - qs);)
@@ -276,7 +290,7 @@ __device__ KG_STAGE_INL int scan_mems(const KgTIndexView &ix, const KgTMeta &m, 
 				for (int c = lane; c < cnt; c += 32) {   // every occurrence, ascending template position
 					int qs, ts, qe, te;
 					mem_from_seed(q.w, tseq, t_len, k, p, __ldg(d + c), lo, fwd_lim, &qs, &ts, &qe, &te);
-					M.tS[n + c] = ts; M.tE[n + c] = te; M.qS[n + c] = qs; M.qE[n + c] = qe; M.W[n + c] = qe - qs;
+					M.set(n + c, ts, te, qs, qe);
 					bias = max(bias, qe);
 				}
 				bias = warp_max(bias);
@@ -296,11 +310,20 @@ __device__ KG_STAGE_INL int scan_mems(const KgTIndexView &ix, const KgTMeta &m, 
 
 // ---------------------------------------------------------------- chaining (chainSeeds, chain.c:79-260)
 
-__device__ __forceinline__ int tail_mm(int Ms, int k, int Mv, int MMv) {   // mismatch estimate of Ms unaligned bases
+// cold paths kept out of line so that the chaining loop stays short in the instruction cache
+__device__ __noinline__ int cold_div(int a, int b) { return a / b; }
+__device__ __noinline__ unsigned chain_mapq(int bestScore, int secondScore, int w) {   // chain.c:256
+	const double wgt = w / 10.0;
+	return (unsigned)ceil(40 * (1 - 1.0 * secondScore / bestScore) * (wgt < 1 ? wgt : 1.0) * log((double)bestScore));
+}
+
+// kr = 0xFFFFFFFF / k + 1: __umulhi(Ms, kr) == Ms / k exactly for Ms < 2^32 / k (gaps are bounded by the read length)
+__device__ __forceinline__ int tail_mm(int Ms, int k, unsigned kr, int Mv, int MMv) {   // mismatch estimate of Ms unaligned bases
 	int MMs;
 	if (Ms == 2) { MMs = 2; Ms = 0; }
 	else {
-		MMs = Ms / k + (Ms % k ? 1 : 0); MMs = max(2, MMs);
+		const int q = (unsigned)Ms < (1u << 26) ? (int)__umulhi((unsigned)Ms, kr) : cold_div(Ms, k);
+		MMs = q + (Ms != q * k ? 1 : 0); MMs = max(2, MMs);
 		Ms = min(Ms - MMs, k); Ms = min(Ms, MMs);
 	}
 	return Ms * Mv + MMs * MMv;
@@ -308,41 +331,44 @@ __device__ __forceinline__ int tail_mm(int Ms, int k, int Mv, int MMv) {   // mi
 
 #define NOCAND (-0x7fffffff - 1)
 
-__device__ int chain_warp(const NwPen &pen, Mems &M, int n, int q_len, int t_len, int k, unsigned *mapQ) {
+// mapQ is only computed when the caller compares it (-mq != 0): its double-precision log is ~120 warp instructions per chain
+__device__ int chain_warp(const NwPen &pen, Mems &M, int n, int q_len, int t_len, int k, unsigned *mapQ, bool want_mapq) {
 	const int lane = threadIdx.x & 31;
+	const unsigned kr = 0xFFFFFFFFu / (unsigned)k + 1u;
 	const int W1 = pen.W1, U = pen.U, Mv = pen.M, MMv = pen.MM;
 	int bestPos = n - 1, bestScore = 0, secondScore = 0;
-	if (lane == 0) { M.sc[n] = 0; M.nx[n] = 0; }
+	if (lane == 0) { M.sc(n) = 0; M.nx(n) = 0; }
 	__syncwarp();
 	for (int i = n - 1; i >= 0; --i) {
-		const int weight = M.W[i] * Mv, tEnd = M.tE[i], qEnd = M.qE[i];
+		const int weight = M.W(i) * Mv, tEnd = M.tE(i), qEnd = M.qE(i);
 		int gap = min(t_len - tEnd, q_len - qEnd), Ms = gap;
 		if (--gap) gap = gap * U + W1; else gap = W1;
-		Ms = tail_mm(Ms, k, Mv, MMv);
+		Ms = tail_mm(Ms, k, kr, Mv, MMv);
 		const int score0 = weight + (Ms < gap ? gap : Ms);
 		const int lim = min(n, i + 128);
 		// lane-local fold over j = i+1+lane, +32, ...: best value, first j reaching it, last "<=" j reaching it
 		int lb = NOCAND, lfirst = 0x7fffffff, llast = -1;
 #pragma unroll 1
 		for (int j = i + 1 + lane; j < lim; j += 32) {
-			const int qSj = M.qS[j], tSj = M.tS[j];
+			const int4 pj = M.pos(j);
+			const int qSj = pj.z, tSj = pj.x;
 			int g = 0, type = -1;   // 0: fully compatible (<=), 1: overlap cut (<)
 			if (qEnd < qSj) {
 				if (tEnd < tSj) {
 					const int tGap = tSj - tEnd, qGap = qSj - qEnd;
 					if ((g = abs(tGap - qGap))) g = (g - 1) * U + W1;
-					g += weight + M.sc[j] + tail_mm(min(tGap, qGap), k, Mv, MMv);
+					g += weight + M.sc(j) + tail_mm(min(tGap, qGap), k, kr, Mv, MMv);
 					type = 0;
-				} else if (k <= M.tE[j] - tEnd) {
+				} else if (k <= pj.y - tEnd) {
 					if ((g = qSj - qEnd)) g = (g - 1) * U + W1;
-					g += weight + M.sc[j] - (tSj - tEnd) * Mv;
+					g += weight + M.sc(j) - (tSj - tEnd) * Mv;
 					type = 1;
 				}
-			} else if (k <= M.qE[j] - qEnd) {
+			} else if (k <= pj.w - qEnd) {
 				const int tStart = tSj + qEnd - qSj;
 				if (tEnd < tStart) {
 					if ((g = tStart - tEnd)) g = (g - 1) * U + W1;
-					g += weight + M.sc[j] - (tStart - tEnd) * Mv;
+					g += weight + M.sc(j) - (tStart - tEnd) * Mv;
 					type = 1;
 				}
 			}
@@ -359,13 +385,13 @@ __device__ int chain_warp(const NwPen &pen, Mems &M, int n, int q_len, int t_len
 			if (mx > score0) { score = mx; next = max(first, last); }
 			else if (last >= 0) next = last;
 		}
-		int w = M.W[i];
-		if (next) w += M.W[next] - k + 1; else w -= k - 1;
-		gap = min(M.tS[i], M.qS[i]); Ms = gap;
+		int w = M.W(i);
+		if (next) w += M.W(next) - k + 1; else w -= k - 1;
+		gap = min(M.tS(i), M.qS(i)); Ms = gap;
 		if (0 < --gap) gap = gap * U + W1; else if (gap == 0) gap = W1; else gap = 0;
-		Ms = tail_mm(Ms, k, Mv, MMv);
+		Ms = tail_mm(Ms, k, kr, Mv, MMv);
 		__syncwarp();
-		if (lane == 0) { M.W[i] = w; M.sc[i] = score; M.nx[i] = next; }
+		if (lane == 0) { M.W(i) = w; M.sc(i) = score; M.nx(i) = next; }
 		__syncwarp();
 		score += Ms < gap ? gap : Ms;
 		if (bestScore <= score) {
@@ -373,12 +399,10 @@ __device__ int chain_warp(const NwPen &pen, Mems &M, int n, int q_len, int t_len
 			bestScore = score; bestPos = i;
 		} else if (secondScore <= score && next != bestPos) secondScore = bestScore;
 	}
-	if (0 < bestScore) {   // chain.c:256 (only compared with -mq, default 0)
-		const double wgt = M.W[bestPos] / 10.0;
-		*mapQ = (unsigned)ceil(40 * (1 - 1.0 * secondScore / bestScore) * (wgt < 1 ? wgt : 1.0) * log((double)bestScore));
-	} else *mapQ = 0;
+	if (want_mapq && 0 < bestScore) *mapQ = chain_mapq(bestScore, secondScore, M.W(bestPos));   // only compared with -mq, default 0
+	else *mapQ = 0;
 	__syncwarp();
-	if (lane == 0) M.sc[bestPos] = bestScore;
+	if (lane == 0) M.sc(bestPos) = bestScore;
 	__syncwarp();
 	return bestPos;
 }
@@ -434,12 +458,12 @@ __device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c,
 	KG_STAT(c.wc->mems += (unsigned long long)n;)
 	if (!n) { *out = s; return ST_OK; }
 	unsigned mapQ = 0;
-	int start = chain_warp(*c.pen, M, n, q_len, t_len, k, &mapQ);
-	if ((int)mapQ < P.mq || M.sc[start] < k) { *out = s; return ST_OK; }
+	int start = chain_warp(*c.pen, M, n, q_len, t_len, k, &mapQ, P.mq != 0);
+	if ((P.mq != 0 && mapQ < (unsigned)P.mq) || M.sc(start) < k) { *out = s; return ST_OK; }
 
 	// leading tail (leadTailAln, align.c:53-138)
 	{
-		const int t_e = M.tS[start] - 1, q_e = M.qS[start];
+		const int t_e = M.tS(start) - 1, q_e = M.qS(start);
 		s.score = 0; s.len = 0; s.pos = t_e; s.match = 0; s.tGaps = 0; s.qGaps = 0;
 		if (q_e) {
 			int t_s = 0, q_s = 0;
@@ -454,27 +478,27 @@ __device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c,
 		}
 	}
 	for (;;) {
-		const int qS = M.qS[start], qE = M.qE[start];
+		const int qS = M.qS(start), qE = M.qE(start);
 		const int len = qE - qS;
 		s.len += len; s.match += len;
 		int sc = 0;
 #pragma unroll 1
-		for (int i = qS + lane; i < qE; i += 32) { const int b = c.qb[i]; sc += P.pen.d[b * 5 + b]; }
+		for (int i = qS + lane; i < qE; i += 32) { const int b = c.qb[i]; sc += c.pen->d[b * 5 + b]; }
 		s.score += warp_sum(sc);
-		const int nxt = M.nx[start];
+		const int nxt = M.nx(start);
 		if (!nxt) break;
-		const int q_s = qE, t_s = M.tE[start] - 1;
+		const int q_s = qE, t_s = M.tE(start) - 1;
 		int t_e, t_l, q_e;
 		start = nxt;
-		int qSn = M.qS[start], tSn = M.tS[start];
+		int qSn = M.qS(start), tSn = M.tS(start);
 		if (qSn < q_s) { tSn += q_s - qSn; qSn = q_s; }
 		t_e = tSn - 1;
 		if (t_e < t_s) {
-			if (t_s <= M.tE[start]) { qSn += t_s - t_e; t_e = t_s; t_l = 0; }
+			if (t_s <= M.tE(start)) { qSn += t_s - t_e; t_e = t_s; t_l = 0; }
 			else t_l = t_len - t_s + t_e;
 		} else t_l = t_e - t_s;
 		__syncwarp();
-		if (lane == 0) { M.qS[start] = qSn; M.tS[start] = tSn; }
+		if (lane == 0) { M.qS(start) = qSn; M.tS(start) = tSn; }
 		__syncwarp();
 		q_e = qSn;
 		if (abs(t_l - q_e + q_s) * U > q_len * Mv || t_l > q_len || q_e - q_s > (q_len >> 1)) {   // align.c:715
@@ -491,7 +515,7 @@ __device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c,
 	}
 	// trailing tail (trailTailAln, align.c:140-212)
 	{
-		const int t_s = M.tE[start] - 1, q_s = M.qE[start];
+		const int t_s = M.tE(start) - 1, q_s = M.qE(start);
 		int q_e = q_len, t_e = t_len;
 		if (((q_len - q_s) << 1) < (t_len - t_s) || (q_len - q_s + AL_BANDW) < (t_len - t_s)) {
 			t_e = q_len - q_s; t_e = t_s + (t_e + min(t_e, AL_BANDW));
@@ -597,9 +621,9 @@ __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(AlnParams
 	{
 		int *p = (int *)sp;
 		const int c1 = lay.mem_cap + 1;
-		M.tS = p; M.tE = p + c1; M.qS = p + 2 * c1; M.qE = p + 3 * c1; M.W = p + 4 * c1; M.sc = p + 5 * c1; M.nx = p + 6 * c1;
+		M.base = p;
 		M.cap = lay.mem_cap;
-		sp += (((size_t)7 * c1 * 4) + 15) & ~(size_t)15;
+		sp += (size_t)c1 * 32;
 	}
 	NwScratch nws;
 	nws.ring = sring[threadIdx.x >> 5];
@@ -1103,8 +1127,8 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 	KG_STAT(c.wc->mems += (unsigned long long)n;)
 	if (!n) { *out = s; return ST_OK; }
 	unsigned mapQ = 0;
-	int start = chain_warp(*c.pen, M, n, q_len, t_len, k, &mapQ);
-	if ((int)mapQ < P.mq || M.sc[start] < k) { *out = s; return ST_OK; }
+	int start = chain_warp(*c.pen, M, n, q_len, t_len, k, &mapQ, P.mq != 0);
+	if ((P.mq != 0 && mapQ < (unsigned)P.mq) || M.sc(start) < k) { *out = s; return ST_OK; }
 	auto nw_rows = [&](int kk, int t_s, int t_e, int q_s, int q_e, int at, NwStat *a) -> int {
 		if (at + (t_e - t_s) + (q_e - q_s) + 8 > row_cap) return ST_ROWS;
 		const int t_l = t_e - t_s, q_l = q_e - q_s;
@@ -1125,7 +1149,7 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 	};
 	// leading tail (leadTailAln with Frag_align, align.c:53-138)
 	{
-		const int t_e = M.tS[start] - 1, q_e = M.qS[start];
+		const int t_e = M.tS(start) - 1, q_e = M.qS(start);
 		s.score = 0; s.len = 0; s.pos = t_e; s.match = 0; s.tGaps = 0; s.qGaps = 0;
 		if (q_e) {
 			int t_s = 0, q_s = 0;
@@ -1166,7 +1190,7 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 		}
 	}
 	for (;;) {
-		const int qS = M.qS[start], qE = M.qE[start];
+		const int qS = M.qS(start), qE = M.qE(start);
 		const int len = qE - qS;
 		if (s.len + len + 8 > row_cap) return ST_ROWS;
 		int sc = 0;
@@ -1178,20 +1202,20 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 		}
 		s.len += len; s.match += len;
 		s.score += warp_sum(sc);
-		const int nxt = M.nx[start];
+		const int nxt = M.nx(start);
 		if (!nxt) break;
-		const int q_s = qE, t_s = M.tE[start] - 1;
+		const int q_s = qE, t_s = M.tE(start) - 1;
 		int t_e, t_l, q_e;
 		start = nxt;
-		int qSn = M.qS[start], tSn = M.tS[start];
+		int qSn = M.qS(start), tSn = M.tS(start);
 		if (qSn < q_s) { tSn += q_s - qSn; qSn = q_s; }
 		t_e = tSn - 1;
 		if (t_e < t_s) {
-			if (t_s <= M.tE[start]) { qSn += t_s - t_e; t_e = t_s; t_l = 0; }
+			if (t_s <= M.tE(start)) { qSn += t_s - t_e; t_e = t_s; t_l = 0; }
 			else t_l = t_len - t_s + t_e;
 		} else t_l = t_e - t_s;
 		__syncwarp();
-		if (lane == 0) { M.qS[start] = qSn; M.tS[start] = tSn; }
+		if (lane == 0) { M.qS(start) = qSn; M.tS(start) = tSn; }
 		__syncwarp();
 		q_e = qSn;
 		if (abs(t_l - q_e + q_s) * U > q_len * Mv || t_l > q_len || q_e - q_s > (q_len >> 1)) {   // align.c:465
@@ -1209,7 +1233,7 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 	}
 	// trailing tail (trailTailAln with Frag_align, align.c:147-212)
 	{
-		const int t_s = M.tE[start] - 1, q_s = M.qE[start];
+		const int t_s = M.tE(start) - 1, q_s = M.qE(start);
 		int q_e = q_len, t_e = t_len;
 		if (((q_len - q_s) << 1) < (t_len - t_s) || (q_len - q_s + AL_BANDW) < (t_len - t_s)) {
 			t_e = q_len - q_s; t_e = t_s + (t_e + min(t_e, AL_BANDW));
@@ -1261,9 +1285,9 @@ __global__ void __launch_bounds__(AL_WARPS * 32, AL_MINB) tr_task_kernel(AlnPara
 	{
 		int *p = (int *)sp;
 		const int c1 = lay.mem_cap + 1;
-		M0.tS = p; M0.tE = p + c1; M0.qS = p + 2 * c1; M0.qE = p + 3 * c1; M0.W = p + 4 * c1; M0.sc = p + 5 * c1; M0.nx = p + 6 * c1;
+		M0.base = p;
 		M0.cap = lay.mem_cap;
-		sp += (((size_t)7 * c1 * 4) + 15) & ~(size_t)15;
+		sp += (size_t)c1 * 32;
 	}
 	NwScratch nws;
 	nws.ring = sring[threadIdx.x >> 5];
@@ -1536,7 +1560,7 @@ extern "C" int kmagpu_align_from_seed(kmagpu_db *db, int64_t *nreads_out) {
 static ScratchLayout make_layout(int mem_cap, int q_cap, size_t e_cap) {
 	ScratchLayout l;
 	l.mem_cap = mem_cap; l.q_cap = q_cap; l.e_cap = (e_cap + 255) & ~(size_t)255;
-	size_t s = (((size_t)7 * (mem_cap + 1) * 4) + 15) & ~(size_t)15;
+	size_t s = (size_t)(mem_cap + 1) * 32;
 	s += (size_t)q_cap * 12 + l.e_cap;
 	l.stride = (s + 255) & ~(size_t)255;
 	return l;

@@ -481,7 +481,7 @@ static aln_t kma_score(const orc_params *p, nw_ws *w, const tindex *ix, const ui
 	if (!n) return aln_zero();
 	unsigned mapQ = 0;
 	int start = chain_mems(p, pt, q_len, t_len, k, &mapQ);
-	if ((int)mapQ < mq || pt->score[start] < k) { pt->len = 0; return aln_zero(); }
+	if (mapQ < (unsigned)mq || pt->score[start] < k) { pt->len = 0; return aln_zero(); }
 
 	aln_t s = lead_tail(p, w, ix->seq, q, pt->tStart[start] - 1, pt->qStart[start]);
 	for (;;) {
@@ -872,7 +872,7 @@ static aln_t kma_trace(const orc_params *p, nw_ws *w, const tindex *ix, const ui
 	if (!n) return aln_zero();
 	unsigned mapQ = 0;
 	int start = chain_mems(p, pt, q_len, t_len, k, &mapQ);
-	if ((int)mapQ < mq || pt->score[start] < k) { pt->len = 0; return aln_zero(); }
+	if (mapQ < (unsigned)mq || pt->score[start] < k) { pt->len = 0; return aln_zero(); }
 
 	/* leading tail (leadTailAln with Frag_align, align.c:53-138): leading gap columns are trimmed when the window
 	 * starts at the template start */
