@@ -606,14 +606,30 @@ __device__ int align_fixed(const AlnParams &P, const NwPen *pen, const KgTIndexV
 struct ScratchLayout { size_t stride; int mem_cap, q_cap; size_t e_cap; };
 
 template <int MINB>
-__global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(AlnParams P, KgTIndexView ix, const uint8_t *__restrict__ in,
+__global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(const AlnParams P_, const KgTIndexView ix_, const uint8_t *__restrict__ in,
 		const AlnRead *__restrict__ reads, const uint64_t *slab, const int32_t *__restrict__ task_read, int ntasks,
 		const int32_t *__restrict__ task_list, AlnCand *cand, uint8_t *scratch, ScratchLayout lay,
 		unsigned long long *ctr, int32_t *ovf_list) {
+#ifdef KG_LOCAL_PARAMS
 	__shared__ NwPen spen;
 	__shared__ NwRow sring[AL_WARPS][NW_RING];
+	const AlnParams &P = P_;
+	const KgTIndexView &ix = ix_;
 	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&P.pen)[threadIdx.x];
 	__syncthreads();
+#else
+	// the out-of-line stages take the parameters and the index view by reference: one copy per CTA in shared memory
+	// instead of one per thread in local memory
+	__shared__ AlnParams sP;
+	__shared__ KgTIndexView six;
+	__shared__ NwRow sring[AL_WARPS][NW_RING];
+	for (int i = threadIdx.x; i < (int)(sizeof(AlnParams) / 4); i += blockDim.x) ((int *)&sP)[i] = ((const int *)&P_)[i];
+	for (int i = threadIdx.x; i < (int)(sizeof(KgTIndexView) / 4); i += blockDim.x) ((int *)&six)[i] = ((const int *)&ix_)[i];
+	__syncthreads();
+	const AlnParams &P = sP;
+	const KgTIndexView &ix = six;
+	NwPen &spen = sP.pen;
+#endif
 	const int lane = threadIdx.x & 31;
 	const size_t wid = (size_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
 	uint8_t *sp = scratch + wid * lay.stride;
@@ -627,9 +643,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(AlnParams
 	}
 	NwScratch nws;
 	nws.ring = sring[threadIdx.x >> 5];
-	nws.rowbuf = (NwRow *)sp; sp += (size_t)lay.q_cap * 8;
-	nws.lastD = (int *)sp; sp += (size_t)lay.q_cap * 4;
-	nws.E = sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap;
+	nws.rowbuf = (NwRow *)sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap; nws.finish();
 	WarpCtr wc;
 	memset(&wc, 0, sizeof(wc));
 	for (;;) {
@@ -1291,9 +1305,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, AL_MINB) tr_task_kernel(AlnPara
 	}
 	NwScratch nws;
 	nws.ring = sring[threadIdx.x >> 5];
-	nws.rowbuf = (NwRow *)sp; sp += (size_t)lay.q_cap * 8;
-	nws.lastD = (int *)sp; sp += (size_t)lay.q_cap * 4;
-	nws.E = sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap;
+	nws.rowbuf = (NwRow *)sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap; nws.finish();
 	WarpCtr wc;
 	memset(&wc, 0, sizeof(wc));
 	for (;;) {
@@ -1983,9 +1995,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32) nw_batch_kernel(NwPen pen, KgTI
 	uint8_t *sp = scratch + wid * lay.stride;
 	NwScratch nws;
 	nws.ring = sring[threadIdx.x >> 5];
-	nws.rowbuf = (NwRow *)sp; sp += (size_t)lay.q_cap * 8;
-	nws.lastD = (int *)sp; sp += (size_t)lay.q_cap * 4;
-	nws.E = sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap;
+	nws.rowbuf = (NwRow *)sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap; nws.finish();
 	unsigned long long cells = 0, steps = 0;
 	for (;;) {
 		unsigned long long t = 0;

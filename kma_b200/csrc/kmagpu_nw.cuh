@@ -473,11 +473,19 @@ NW_HD bool nw_trivial(const NwPen &pen, int t_len, int q_len, NwStat &s) {   // 
 // per-warp scratch
 struct NwScratch {
 	NwRow *ring;      // NW_RING entries in shared memory: lane 31 -> lane 0 hand-over of rows up to NW_RING wide
-	NwRow *rowbuf;    // global, >= q_cap entries: the same for wider rows
-	int *lastD;       // global, >= q_cap entries
-	uint8_t *E;       // global, e_cap bytes
+	NwRow *rowbuf;    // global, q_cap entries: the same for wider rows; lastD (q_cap ints) and E (e_cap bytes) follow it
 	size_t e_cap;
 	int q_cap;
+#ifdef NW_SCRATCH_WIDE
+	int *lastD_; uint8_t *E_;
+	__device__ __forceinline__ int *lastD() const { return lastD_; }
+	__device__ __forceinline__ uint8_t *E() const { return E_; }
+	__device__ __forceinline__ void finish() { lastD_ = (int *)(rowbuf + q_cap); E_ = (uint8_t *)(rowbuf + q_cap) + 4 * (size_t)q_cap; }
+#else
+	__device__ __forceinline__ int *lastD() const { return (int *)(rowbuf + q_cap); }
+	__device__ __forceinline__ uint8_t *E() const { return (uint8_t *)(rowbuf + q_cap) + 4 * (size_t)q_cap; }
+	__device__ __forceinline__ void finish() {}
+#endif
 };
 
 // status of nw_warp
@@ -665,24 +673,24 @@ __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict
 	if (g.ebytes() > ws.e_cap || q_len + 1 > ws.q_cap) return NW_TOO_BIG;
 	if (cells) *cells += (unsigned long long)t_len * (unsigned long long)(g.banded ? g.band + 1 : q_len);
 	const uint8_t *q = query + q_s;
-	const uint8_t *E = ws.E;
+	const uint8_t *E = ws.E();
 	int cb, ci;
 	if (RS && g.C) {   // row sweep; the substitution rows go to the (otherwise unused) shared-memory ring
 		unsigned long long *tab = (unsigned long long *)ws.ring;
 		__syncwarp();
 		if (lane < 5) tab[lane] = nw_rs_tab(pen, lane);
 		__syncwarp();
-		uint8_t *E8 = (uint8_t *)(((uintptr_t)ws.E + 7) & ~(uintptr_t)7);
-		if (g.banded) nw_rs_dispatch<true>(g, tseq, t_s, q, tab, E8, ws.lastD, &cb, &ci);
-		else nw_rs_dispatch<false>(g, tseq, t_s, q, tab, E8, ws.lastD, &cb, &ci);
+		uint8_t *E8 = (uint8_t *)(((uintptr_t)ws.E() + 7) & ~(uintptr_t)7);
+		if (g.banded) nw_rs_dispatch<true>(g, tseq, t_s, q, tab, E8, ws.lastD(), &cb, &ci);
+		else nw_rs_dispatch<false>(g, tseq, t_s, q, tab, E8, ws.lastD(), &cb, &ci);
 		E = E8;
 	} else {
 		NwRow *hand = g.rmask == NW_RING - 1 ? ws.ring : ws.rowbuf;
 		NwLane L;
 		nw_lane_init(g, pen, L, lane, tseq, t_s, q);
 		const uint8_t *qlast = q + q_len - 1;
-		uint8_t *Estep = ws.E;
-		int *lastD = ws.lastD;
+		uint8_t *Estep = ws.E();
+		int *lastD = ws.lastD();
 		for (int T = g.Tmax; T > 0; --T, Estep += 32) {
 			const int aD = __shfl_up_sync(0xffffffffu, L.myD, 1), aP = __shfl_up_sync(0xffffffffu, L.myP, 1);
 			nw_lane_step(g, pen, L, lane, aD, aP, tseq, t_s, qlast, Estep, hand, lastD);
@@ -703,7 +711,7 @@ __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict
 		int qlo, qhi;
 		nw_row0_range(g, &qlo, &qhi);
 		for (int qp = qlo + lane; qp <= qhi; qp += 32) {
-			const int v = ws.lastD[q_len - 1 - qp];
+			const int v = ws.lastD()[q_len - 1 - qp];
 			if (rq < 0 || v >= rb) { rb = v; rq = qp; }
 		}
 #pragma unroll
@@ -713,7 +721,7 @@ __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict
 		}
 	}
 	int best_m, best_q, score;
-	nw_start_cell(g, cb, ci, ws.lastD, rb, rq, &best_m, &best_q, &score);
+	nw_start_cell(g, cb, ci, ws.lastD(), rb, rq, &best_m, &best_q, &score);
 	nw_walk_warp(g, E, best_m, best_q, s, rows, tseq, t_s, q);
 	__syncwarp();
 	s.score = score; s.pos = 0;
