@@ -36,6 +36,29 @@ def _check_align(prefix, s2, params=None):
     return st, cand
 
 
+@pytest.mark.parametrize("mq", [200, 300, -1])
+def test_golden_alignment_pass_with_min_mapq(mq):
+    """-mq: chainSeeds' mapQ (chain.c:256) is only evaluated when it is compared; the comparison is unsigned < int
+    as in align.c:658, so a negative -mq rejects every chain"""
+    with util.golden_dir() as g:
+        s2 = np.fromfile(f"{g}/s2.bin", dtype=np.uint8)
+        prefix = f"{g}/db"
+        ofrag, oa, ou, ocand, _ = util.oracle_align_stream(prefix, s2, mq=mq)
+        ofrag0, _, _, ocand0, _ = util.oracle_align_stream(prefix, s2)
+        db = api.TemplateDB(prefix, device=0)
+        p = api.default_params()
+        p.mq = mq
+        frag, a, u, cand, st = db.alnFrags_batch(s2, p, want_cand=True)
+        db.close()
+    assert st.launches > 0 and util.cand_equal(cand, ocand)
+    assert np.array_equal(a, oa) and np.array_equal(u, ou) and frag.tobytes() == ofrag
+    assert not np.array_equal(ocand, ocand0)   # the threshold does reject chains of the golden batch
+    if mq != 200:
+        assert len(ofrag) == 0
+    else:
+        assert 0 < len(ofrag) < len(ofrag0)
+
+
 def test_golden_alignment_pass():
     with util.golden_dir() as g:
         s2 = np.fromfile(f"{g}/s2.bin", dtype=np.uint8)

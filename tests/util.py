@@ -143,7 +143,7 @@ def ref_align(db_prefix: str, s2: bytes, tmp: str, one2one=True, cand=True, pe=F
     return frag, arr[:n].copy(), arr[n:2 * n].copy(), c
 
 
-def oracle_align_stream(db_prefix: str, s2: np.ndarray, one2one=True, want_cand=True, apm=0):
+def oracle_align_stream(db_prefix: str, s2: np.ndarray, one2one=True, want_cand=True, apm=0, mq=0):
     """(frag_raw bytes, alignment_scores, uniq_alignment_scores, cand rows, nw cells) from the C oracle."""
     L = orc()
     L.orc_align_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_int,
@@ -157,7 +157,7 @@ def oracle_align_stream(db_prefix: str, s2: np.ndarray, one2one=True, want_cand=
     u = np.zeros(DB, dtype=np.uint64)
     fo, fb, co, cr, cells = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t(), C.c_int64()
     s2 = np.ascontiguousarray(s2, dtype=np.uint8)
-    rc = L.orc_align_stream(db, os.fsencode(db_prefix), oracle_params(apm=apm), s2.ctypes.data, len(s2), int(one2one), 0.5, 0, 16, 0.0,
+    rc = L.orc_align_stream(db, os.fsencode(db_prefix), oracle_params(apm=apm), s2.ctypes.data, len(s2), int(one2one), 0.5, int(mq), 16, 0.0,
                             C.byref(fo), C.byref(fb), a.ctypes.data, u.ctypes.data,
                             C.byref(co) if want_cand else None, C.byref(cr), C.byref(cells))
     assert rc == 0
