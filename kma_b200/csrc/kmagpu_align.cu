@@ -41,6 +41,7 @@
 #define AL_SHORT_MAXQ 512     // batches whose longest read is at most this use the short-read variant
 #define ST_OK 0
 #define ST_OVERFLOW 1
+#define ST_GIVEUP 4           // KMA_score gave the chain up (align.c:715): queued gap / trail problems of the task are void
 
 struct AlnRead {
 	uint32_t rec_off;
@@ -63,7 +64,7 @@ struct AlnParams {
 
 enum { A_WORK = 0, A_OVF = 1, A_NEED_E = 2, A_NEED_MEM = 3, A_NEED_Q = 4, A_MEMS = 5, A_FULL_CALLS = 6, A_BAND_CALLS = 7,
        A_FULL_CELLS = 8, A_BAND_CELLS = 9, A_STEPS = 10, A_SLAB = 11, A_TASKS = 12, A_OUT = 13, A_FRAGS = 14, A_BAD = 15,
-       A_MAXQ = 16, A_LOOKUPS = 17, A_MEMBASES = 18, A_READBYTES = 19, A_N = 24 };
+       A_MAXQ = 16, A_LOOKUPS = 17, A_MEMBASES = 18, A_READBYTES = 19, A_NPROB = 20, A_PCLS = 21 /* .. 25 */, A_N = 32 };
 
 // ---------------------------------------------------------------- slab layout
 
@@ -409,41 +410,89 @@ __device__ int chain_warp(const NwPen &pen, Mems &M, int n, int q_len, int t_len
 
 // ---------------------------------------------------------------- stitching (KMA_score, align.c:641-748)
 
+// ---- NW problem queue. The alignment pass is split in phases: the pair kernel finds MEMs, chains them and, instead of
+// running Needleman-Wunsch itself, appends every tail / gap problem KMA_score would hand to NW_score / NW_band_score
+// (align.c:92-98, 186-192, 478-484) to a queue; queue kernels then solve the problems -- one THREAD per problem for the
+// small ones (classes 0-3 by size, so that a warp's 32 problems are alike), one WARP per problem for the rest -- and add
+// their AlnScore fields into the task's candidate row (all of them are sums; the lead tail also moves `pos`).
+#define NWQ_CLASSES 5
+struct NwProb { int32_t task, tmpl, t_s, t_e, q_s, q_e, kband; uint32_t qoff; };   // kband = (k + 2) | band << 8; query bytes at qbase + (qoff << qshift)
+struct NwQueue { NwProb *probs; uint32_t *order; unsigned cap; unsigned long long *ctr; };
+
+__host__ __device__ __forceinline__ int nwq_class(int t_l, int q_l, int band) {
+	if (band || q_l > 64 || t_l > 128 || t_l <= 0 || q_l <= 0) return 4;
+	if (q_l > 32 || t_l > 64) return 3;
+	const int cells = t_l * q_l;
+	return cells <= 96 ? 0 : (cells <= 384 ? 1 : 2);
+}
+static const int nwq_qmax[4] = {32, 32, 32, 64};          // query columns the thread kernel of a class holds in shared memory
+static const int nwq_cells[4] = {96, 384, 2048, 8192};    // traceback bytes per problem
+
 struct TaskCtx {
 	const NwPen *pen;
 	const uint64_t *tseq;
 	const uint8_t *qb;
 	NwScratch nw;
 	WarpCtr *wc;
+	const NwQueue *queue;   // pair kernel: where the NW problems go
+	const uint64_t *slab;
+	int task, tmpl;
 };
 
-// NW with the reference's full/banded choice (align.c:92-98, 186-192, 478-484)
-__device__ int nw_auto(const TaskCtx &c, int k, int t_s, int t_e, int q_s, int q_e, NwStat *a) {
+// The NW calls that need no matrix, solved where they arise: one side empty (nw.c:663-684) and the single mismatch
+// between two MEMs (73 % of the calls of short reads, SURVEY 6: one cell of nw.c:166-212 in closed form).
+__device__ __forceinline__ bool nw_closed_form(const NwPen &pen, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e,
+                                               int q_s, int q_e, NwStat &s) {
+	const int t_len = t_e - t_s, q_len = q_e - q_s;
+	if (nw_trivial(pen, t_len, q_len, s)) return true;
+	if (t_len == 1 && q_len == 1 && k == 0) {
+		const int W1 = pen.W1, U = pen.U, NEG = 2 * (pen.MM + U + W1);
+		const int sub = pen.d[nw_nuc(tseq, t_s) * 5 + query[q_s]];
+		// Dleft = D(0,-1) = W1, aD = D(-1,0) = W1, Qleft = aP = NEG, Ddiag = D(-1,-1) = 0
+		int Q = W1 + W1, P = W1 + W1, D, e, fl = 0, x;
+		if (Q < P) { D = P; e = 4; } else { D = Q; e = 2; }
+		x = NEG + U;
+		if (Q < x) { Q = x; if (D <= x) { D = x; e = 3; } } else fl |= 16;
+		if (P < x) { P = x; if (D <= x) { D = x; e = 5; } } else fl |= 32;
+		x = sub;
+		if (D <= x) { D = x; e = 1; }
+		if (e == 1 || fl) {   // diagonal: one column; else the run closes here and the walk crosses one gap of each kind (codes 36 / 18)
+			s.score = D; s.pos = 0;
+			if (e == 1) { s.len = 1; s.match = 1; s.tGaps = 0; s.qGaps = 0; }
+			else { s.len = 2; s.match = 0; s.tGaps = 1; s.qGaps = 1; }
+			return true;
+		}
+	}
+	return false;
+}
+
+// append one NW problem of the task to the queue (all lanes call with the same arguments)
+__device__ __forceinline__ void nw_enqueue(const TaskCtx &c, int k, int t_s, int t_e, int q_s, int q_e) {
 	const int t_l = t_e - t_s, q_l = q_e - q_s;
 	int band = abs(t_l - q_l) + AL_BANDW;
 	if (q_l <= band || t_l <= band) band = 0;
-#ifndef KG_NO_STATS
-	unsigned long long cells = 0;
-	const int st = nw_warp<false>(*c.pen, c.tseq, c.qb, k, t_s, t_e, q_s, q_e, band, c.nw, a, &cells);
-#else
-	const int st = nw_warp<false>(*c.pen, c.tseq, c.qb, k, t_s, t_e, q_s, q_e, band, c.nw, a, nullptr);
-#endif
-	if (st != NW_OK) {
-		NwGeo g;
-		nw_geo_init(g, *c.pen, t_l, q_l, k, band, false);
-		c.wc->need_e = max(c.wc->need_e, (unsigned)min((size_t)0xF0000000u, g.ebytes() + 4096));
-		c.wc->need_q = max(c.wc->need_q, (unsigned)q_l + 64u);
-		return ST_OVERFLOW;
+	const int cls = nwq_class(t_l, q_l, band);
+	if ((threadIdx.x & 31) == 0) {
+		const NwQueue &Q = *c.queue;
+		const unsigned long long slot = atomicAdd(&Q.ctr[A_NPROB], 1ull);
+		const unsigned long long ci = atomicAdd(&Q.ctr[A_PCLS + cls], 1ull);
+		if (slot < Q.cap && ci < Q.cap) {
+			NwProb p;
+			p.task = c.task; p.tmpl = c.tmpl; p.t_s = t_s; p.t_e = t_e; p.q_s = q_s; p.q_e = q_e;
+			p.kband = (k + 2) | (band << 8);
+			p.qoff = (uint32_t)((c.qb - (const uint8_t *)c.slab) >> 3);
+			*(int4 *)&Q.probs[slot] = *(const int4 *)&p;
+			*((int4 *)&Q.probs[slot] + 1) = *((const int4 *)&p + 1);
+			Q.order[(size_t)cls * Q.cap + ci] = (uint32_t)slot;
+		}
 	}
-#ifndef KG_NO_STATS
-	if (cells) {
+	if (cls == 4) {   // the warp-per-problem kernel sizes its scratch from the largest problem
 		NwGeo g;
-		nw_geo_init(g, *c.pen, t_l, q_l, k, band, false);
-		c.wc->steps += (unsigned long long)g.Tmax;
-		if (band) { ++c.wc->band_calls; c.wc->band_cells += cells; } else { ++c.wc->full_calls; c.wc->full_cells += cells; }
+		if (nw_geo_init(g, *c.pen, t_l, q_l, k, band, true)) {
+			c.wc->need_e = max(c.wc->need_e, (unsigned)min((size_t)0xF0000000u, g.ebytes() + 4096));
+			c.wc->need_q = max(c.wc->need_q, (unsigned)q_l + 64u);
+		}
 	}
-#endif
-	return ST_OK;
 }
 
 __device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c, const KgTIndexView &ix, const KgTMeta &m, const QView &q,
@@ -469,12 +518,7 @@ __device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c,
 			int t_s = 0, q_s = 0;
 			if ((q_e << 1) < t_e || (q_e + AL_BANDW) < t_e) t_s = t_e - (q_e + min(q_e, AL_BANDW));
 			else if ((t_e << 1) < q_e || (t_e + AL_BANDW) < q_e) q_s = q_e - (t_e + min(t_e, AL_BANDW));
-			if (t_e - t_s > 0 && q_e - q_s > 0) {
-				NwStat a;
-				if (nw_auto(c, -1 - (t_s == 0), t_s, t_e, q_s, q_e, &a)) return ST_OVERFLOW;
-				s.pos -= a.len - a.tGaps;
-				s.score = a.score; s.len = a.len; s.match = a.match; s.tGaps = a.tGaps; s.qGaps = a.qGaps;
-			}
+			if (t_e - t_s > 0 && q_e - q_s > 0) nw_enqueue(c, -1 - (t_s == 0), t_s, t_e, q_s, q_e);   // adds its fields and moves pos by len - tGaps
 		}
 	}
 	for (;;) {
@@ -505,12 +549,13 @@ __device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c,
 			const int keep = s.pos;
 			s.score = 0; s.len = 1; s.pos = keep; s.match = 0; s.tGaps = 0; s.qGaps = 0;
 			*out = s;
-			return ST_OK;
+			return ST_GIVEUP;   // queued problems of the task are void, but for the lead tail's move of pos
 		}
 		if (t_l > 0 || q_e - q_s > 0) {
 			NwStat a;
-			if (nw_auto(c, 0, t_s, t_e, q_s, q_e, &a)) return ST_OVERFLOW;
-			s.score += a.score; s.len += a.len; s.match += a.match; s.tGaps += a.tGaps; s.qGaps += a.qGaps;
+			if (nw_closed_form(*c.pen, c.tseq, c.qb, 0, t_s, t_e, q_s, q_e, a)) {
+				s.score += a.score; s.len += a.len; s.match += a.match; s.tGaps += a.tGaps; s.qGaps += a.qGaps;
+			} else nw_enqueue(c, 0, t_s, t_e, q_s, q_e);
 		}
 	}
 	// trailing tail (trailTailAln, align.c:140-212)
@@ -522,11 +567,7 @@ __device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c,
 		} else if (((t_len - t_s) << 1) < (q_len - q_s) || (t_len - t_s + AL_BANDW) < (q_len - q_s)) {
 			q_e = t_len - t_s; q_e = q_s + (q_e + min(q_e, AL_BANDW));
 		}
-		if (t_e - t_s > 0 && q_e - q_s > 0) {
-			NwStat a;
-			if (nw_auto(c, 1 + (t_e == t_len), t_s, t_e, q_s, q_e, &a)) return ST_OVERFLOW;
-			s.score += a.score; s.len += a.len; s.match += a.match; s.tGaps += a.tGaps; s.qGaps += a.qGaps;
-		}
+		if (t_e - t_s > 0 && q_e - q_s > 0) nw_enqueue(c, 1 + (t_e == t_len), t_s, t_e, q_s, q_e);
 	}
 	*out = s;
 	return ST_OK;
@@ -553,13 +594,13 @@ __device__ bool preseed_hit(const KgTIndexView &ix, const KgTMeta &m, const uint
 // ---------------------------------------------------------------- the pair kernel
 
 __device__ int align_pair(const AlnParams &P, const NwPen *pen, const KgTIndexView &ix, const uint64_t *slab, const AlnRead &R,
-                          int tmpl, Mems M, const NwScratch &nws, WarpCtr &wc, AlnCand *out) {
+                          int tmpl, Mems M, const NwQueue *queue, int task, WarpCtr &wc, AlnCand *out) {
 	const int at = abs(tmpl), q_len = R.q_len, nN1 = R.nN + 1, k = ix.k;
 	const KgTMeta m = ix.meta[at];
 	TaskCtx c;
-	c.pen = pen; c.tseq = ix.seq + m.seq_off; c.nw = nws; c.wc = &wc;
+	c.pen = pen; c.tseq = ix.seq + m.seq_off; c.wc = &wc; c.queue = queue; c.slab = slab; c.task = task; c.tmpl = at;
 	NwStat a = {0, 0, 0, 0, 0, 0};
-	int n = 0, strand = 0;
+	int n = 0, strand = 0, st = ST_OK;
 	if (R.rc_flag < 0) {   // strand undecided: anker_rc_comp (align.c:993-1176)
 		const QView qf = read_view(slab, R, 0), qr = read_view(slab, R, 1);
 		int sf = 0, sr = 0, nf = 0, ntot;
@@ -576,30 +617,31 @@ __device__ int align_pair(const AlnParams &P, const NwPen *pen, const KgTIndexVi
 		if (strand >= 0) {
 			const QView q = strand ? qr : qf;
 			c.qb = q.b;
-			if (kma_score_warp(P, c, ix, m, q, nN1, q_len, 0, q_len, M, n, &a)) return ST_OVERFLOW;   // MEMs are in place: no scan
+			if ((st = kma_score_warp(P, c, ix, m, q, nN1, q_len, 0, q_len, M, n, &a)) == ST_OVERFLOW) return ST_OVERFLOW;   // MEMs are in place: no scan
 		}
 	} else {
 		const QView q = read_view(slab, R, 0);   // SE records carry the strand stage 2 chose (ankers.c:30-50)
 		c.qb = q.b;
-		if (kma_score_warp(P, c, ix, m, q, nN1, q_len, R.q_start, R.q_end, M, 0, &a)) return ST_OVERFLOW;
+		if ((st = kma_score_warp(P, c, ix, m, q, nN1, q_len, R.q_start, R.q_end, M, 0, &a)) == ST_OVERFLOW) return ST_OVERFLOW;
 	}
 	out->tmpl = tmpl; out->score = a.score; out->len = a.len; out->pos = a.pos; out->match = a.match;
-	out->tGaps = a.tGaps; out->qGaps = a.qGaps; out->status = ST_OK;
+	out->tGaps = a.tGaps; out->qGaps = a.qGaps; out->status = st;
 	return ST_OK;
 }
 
 // KMA_score of one read in a given orientation against one template
 __device__ int align_fixed(const AlnParams &P, const NwPen *pen, const KgTIndexView &ix, const uint64_t *slab, const AlnRead &R,
-                           int strand, int at, Mems M, const NwScratch &nws, WarpCtr &wc, AlnCand *out) {
+                           int strand, int at, Mems M, const NwQueue *queue, int task, WarpCtr &wc, AlnCand *out) {
 	const KgTMeta m = ix.meta[at];
 	TaskCtx c;
-	c.pen = pen; c.tseq = ix.seq + m.seq_off; c.nw = nws; c.wc = &wc;
+	c.pen = pen; c.tseq = ix.seq + m.seq_off; c.wc = &wc; c.queue = queue; c.slab = slab; c.task = task; c.tmpl = at;
 	const QView q = read_view(slab, R, strand);
 	c.qb = q.b;
 	NwStat a = {0, 0, 0, 0, 0, 0};
-	if (kma_score_warp(P, c, ix, m, q, R.nN + 1, R.q_len, 0, R.q_len, M, 0, &a)) return ST_OVERFLOW;
+	const int st = kma_score_warp(P, c, ix, m, q, R.nN + 1, R.q_len, 0, R.q_len, M, 0, &a);
+	if (st == ST_OVERFLOW) return ST_OVERFLOW;
 	out->tmpl = at; out->score = a.score; out->len = a.len; out->pos = a.pos; out->match = a.match;
-	out->tGaps = a.tGaps; out->qGaps = a.qGaps; out->status = ST_OK;
+	out->tGaps = a.tGaps; out->qGaps = a.qGaps; out->status = st;
 	return ST_OK;
 }
 
@@ -609,41 +651,24 @@ template <int MINB>
 __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(const AlnParams P_, const KgTIndexView ix_, const uint8_t *__restrict__ in,
 		const AlnRead *__restrict__ reads, const uint64_t *slab, const int32_t *__restrict__ task_read, int ntasks,
 		const int32_t *__restrict__ task_list, AlnCand *cand, uint8_t *scratch, ScratchLayout lay,
-		unsigned long long *ctr, int32_t *ovf_list) {
-#ifdef KG_LOCAL_PARAMS
-	__shared__ NwPen spen;
-	__shared__ NwRow sring[AL_WARPS][NW_RING];
-	const AlnParams &P = P_;
-	const KgTIndexView &ix = ix_;
-	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&P.pen)[threadIdx.x];
-	__syncthreads();
-#else
-	// the out-of-line stages take the parameters and the index view by reference: one copy per CTA in shared memory
-	// instead of one per thread in local memory
+		unsigned long long *ctr, int32_t *ovf_list, const NwQueue queue_) {
+	// the out-of-line stages take the parameters, the index view and the queue by reference: one copy per CTA in shared
+	// memory instead of one per thread in local memory
 	__shared__ AlnParams sP;
 	__shared__ KgTIndexView six;
-	__shared__ NwRow sring[AL_WARPS][NW_RING];
+	__shared__ NwQueue squeue;
 	for (int i = threadIdx.x; i < (int)(sizeof(AlnParams) / 4); i += blockDim.x) ((int *)&sP)[i] = ((const int *)&P_)[i];
 	for (int i = threadIdx.x; i < (int)(sizeof(KgTIndexView) / 4); i += blockDim.x) ((int *)&six)[i] = ((const int *)&ix_)[i];
+	for (int i = threadIdx.x; i < (int)(sizeof(NwQueue) / 4); i += blockDim.x) ((int *)&squeue)[i] = ((const int *)&queue_)[i];
 	__syncthreads();
 	const AlnParams &P = sP;
 	const KgTIndexView &ix = six;
 	NwPen &spen = sP.pen;
-#endif
 	const int lane = threadIdx.x & 31;
 	const size_t wid = (size_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
-	uint8_t *sp = scratch + wid * lay.stride;
 	Mems M;
-	{
-		int *p = (int *)sp;
-		const int c1 = lay.mem_cap + 1;
-		M.base = p;
-		M.cap = lay.mem_cap;
-		sp += (size_t)c1 * 32;
-	}
-	NwScratch nws;
-	nws.ring = sring[threadIdx.x >> 5];
-	nws.rowbuf = (NwRow *)sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap; nws.finish();
+	M.base = (int *)(scratch + wid * lay.stride);
+	M.cap = lay.mem_cap;
 	WarpCtr wc;
 	memset(&wc, 0, sizeof(wc));
 	for (;;) {
@@ -664,11 +689,11 @@ __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(const Aln
 		if (R.kind == 2) {   // a mate of a pair against one template, strands decided by stage 2 (alnfrags.c:1645-1661, 1712-1731)
 			const AlnRead Rq = mate ? R : reads[r - 1];
 			KG_STAT(wc.read_bytes += 8ull * (unsigned long long)Rq.words + (unsigned long long)Rq.q_len + 4ull * (unsigned long long)Rq.nN;)
-			st = align_fixed(P, &spen, ix, slab, Rq, ti >= R.fneg, abs(tmpl), M, nws, wc, &res);
+			st = align_fixed(P, &spen, ix, slab, Rq, ti >= R.fneg, abs(tmpl), M, &squeue, task, wc, &res);
 			res.tmpl = tmpl;
 		} else {
 			KG_STAT(wc.read_bytes += 8ull * (unsigned long long)R.words + (unsigned long long)R.q_len + 4ull * (unsigned long long)R.nN;)
-			st = align_pair(P, &spen, ix, slab, R, tmpl, M, nws, wc, &res);
+			st = align_pair(P, &spen, ix, slab, R, tmpl, M, &squeue, task, wc, &res);
 		}
 		__syncwarp();
 		if (st != ST_OK) {
@@ -682,9 +707,6 @@ __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(const Aln
 		if (wc.lookups) atomicAdd(&ctr[A_LOOKUPS], wc.lookups);
 		if (wc.mem_bases) atomicAdd(&ctr[A_MEMBASES], wc.mem_bases);
 		if (wc.read_bytes) atomicAdd(&ctr[A_READBYTES], wc.read_bytes);
-		if (wc.full_calls) { atomicAdd(&ctr[A_FULL_CALLS], wc.full_calls); atomicAdd(&ctr[A_FULL_CELLS], wc.full_cells); }
-		if (wc.band_calls) { atomicAdd(&ctr[A_BAND_CALLS], wc.band_calls); atomicAdd(&ctr[A_BAND_CELLS], wc.band_cells); }
-		if (wc.steps) atomicAdd(&ctr[A_STEPS], wc.steps);
 		if (wc.need_e) atomicMax(&ctr[A_NEED_E], (unsigned long long)wc.need_e);
 		if (wc.need_mem) atomicMax(&ctr[A_NEED_MEM], (unsigned long long)wc.need_mem);
 		if (wc.need_q) atomicMax(&ctr[A_NEED_Q], (unsigned long long)wc.need_q);
@@ -693,21 +715,20 @@ __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(const Aln
 
 // The pair kernel without the statistic counters is compiled in translation units of its own (kmagpu_align_fast.cu for
 // long reads, kmagpu_align_fast_short.cu for short ones include this file inside a namespace with KG_NO_STATS and
-// KG_PAIR_VARIANT_ONLY): the counters cost it 21 registers and ~10 % of its time, and the short-read build also takes
-// the NW scratch descriptor by value (NW_SCRATCH_BYVAL). The launchers have C linkage and take the structs by address
-// because the translation units define them in different namespaces (same source, same layout).
+// KG_PAIR_VARIANT_ONLY): the counters cost it registers and time. The launchers have C linkage and take the structs by
+// address because the translation units define them in different namespaces (same source, same layout).
 #ifdef KG_PAIR_VARIANT_ONLY
 extern "C" void KG_VARIANT_LAUNCHER(int grid, cudaStream_t st, const void *P, const void *ix, const uint8_t *in,
                                     const void *reads, const uint64_t *slab, const int32_t *task_read, int ntasks, const int32_t *task_list,
-                                    void *cand, uint8_t *scratch, const void *lay, unsigned long long *ctr, int32_t *ovf_list) {
+                                    void *cand, uint8_t *scratch, const void *lay, unsigned long long *ctr, int32_t *ovf_list, const void *queue) {
 	aln_pair_kernel<KG_VARIANT_MINB><<<grid, AL_WARPS * 32, 0, st>>>(*(const AlnParams *)P, *(const KgTIndexView *)ix, in, (const AlnRead *)reads, slab,
-		task_read, ntasks, task_list, (AlnCand *)cand, scratch, *(const ScratchLayout *)lay, ctr, ovf_list);
+		task_read, ntasks, task_list, (AlnCand *)cand, scratch, *(const ScratchLayout *)lay, ctr, ovf_list, *(const NwQueue *)queue);
 }
 #else
 #define KG_DECL_LAUNCHER(name)                                                                                                              \
 	extern "C" void name(int grid, cudaStream_t st, const void *P, const void *ix, const uint8_t *in, const void *reads, const uint64_t *slab, \
 	                     const int32_t *task_read, int ntasks, const int32_t *task_list, void *cand, uint8_t *scratch, const void *lay,      \
-	                     unsigned long long *ctr, int32_t *ovf_list)
+	                     unsigned long long *ctr, int32_t *ovf_list, const void *queue)
 KG_DECL_LAUNCHER(kg_launch_pair_fast_long);
 KG_DECL_LAUNCHER(kg_launch_pair_fast_short);
 
@@ -1491,7 +1512,7 @@ int kg_align_free(kmagpu_db *db) {
 	}
 	AlignBatch &b = db->aln;
 	KgBuf *all[] = {&b.d_in, &b.d_off, &b.d_reads, &b.d_slab, &b.d_sz, &b.d_partial, &b.d_taskread, &b.d_cand, &b.d_recsize,
-	                &b.d_out, &b.d_ctr, &b.d_scores, &b.d_scratch, &b.d_ovf, &b.d_res, &b.h_off};
+	                &b.d_out, &b.d_ctr, &b.d_scores, &b.d_scratch, &b.d_ovf, &b.d_res, &b.h_off, &b.d_probs, &b.d_order};
 	for (KgBuf *x : all) x->release();
 	return 0;
 }
@@ -1578,6 +1599,131 @@ static ScratchLayout make_layout(int mem_cap, int q_cap, size_t e_cap) {
 	return l;
 }
 
+// ---------------------------------------------------------------- NW queue kernels (phase 2 of the alignment pass)
+
+// add a problem's AlnScore into the candidate row of its task (AlnCand as int32[8]: tmpl score len pos match tGaps qGaps status)
+__device__ __forceinline__ void nwq_apply(int32_t *row, const NwStat &a, int k, int status) {
+	if (k < 0) atomicSub(&row[3], a.len - a.tGaps);   // leadTailAln: pos -= len - tGaps (align.c:119)
+	if (status == ST_GIVEUP) return;
+	atomicAdd(&row[1], a.score); atomicAdd(&row[2], a.len); atomicAdd(&row[4], a.match); atomicAdd(&row[5], a.tGaps); atomicAdd(&row[6], a.qGaps);
+}
+
+// classes 0-3: one thread per problem (nw_thread); the previous DP row of the CTA's 128 problems in shared memory
+// [column][thread], traceback bytes in a per-warp scratch [cell][lane]
+__global__ void __launch_bounds__(128) nw_thread_kernel(const NwPen pen, const KgTIndexView ix, const NwProb *__restrict__ probs,
+		const uint32_t *__restrict__ order, int n, const uint8_t *qbase, int qshift, int32_t *res, uint8_t *escratch, int ecells,
+		unsigned long long *ctr) {
+	extern __shared__ NwRow srows[];
+	__shared__ NwPen spen;
+	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&pen)[threadIdx.x];
+	__syncthreads();
+	const int tid = blockIdx.x * 128 + threadIdx.x, nthreads = gridDim.x * 128;
+	uint8_t *E = escratch + (size_t)(tid >> 5) * (size_t)ecells * 32 + (tid & 31);
+	NwRow *rows = srows + threadIdx.x;
+	unsigned long long cells = 0;
+	unsigned calls = 0;
+	for (int idx = tid; idx < n; idx += nthreads) {
+		const NwProb p = probs[order[idx]];
+		int32_t *row = res + 8 * (size_t)p.task;
+		const int status = row[7], k = (p.kband & 255) - 2;
+		if (status == ST_GIVEUP && k >= 0) continue;
+		const KgTMeta m = ix.meta[p.tmpl];
+		const int t_len = p.t_e - p.t_s, q_len = p.q_e - p.q_s;
+		NwStat a;
+		nw_thread(spen, ix.seq + m.seq_off, p.t_s, t_len, qbase + ((size_t)p.qoff << qshift) + p.q_s, q_len, k, rows, 128, E, 32, &a);
+		nwq_apply(row, a, k, status);
+		cells += (unsigned long long)(t_len * q_len); ++calls;
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) { cells += __shfl_xor_sync(0xffffffffu, cells, o); calls += __shfl_xor_sync(0xffffffffu, calls, o); }
+	if ((threadIdx.x & 31) == 0 && calls) { atomicAdd(&ctr[A_FULL_CELLS], cells); atomicAdd(&ctr[A_FULL_CALLS], (unsigned long long)calls); }
+}
+
+// class 4: one warp per problem (nw_warp: row sweep for rows of up to 256 cells, the continuous wavefront beyond)
+__global__ void __launch_bounds__(AL_WARPS * 32) nw_warp_kernel(const NwPen pen, const KgTIndexView ix, const NwProb *__restrict__ probs,
+		const uint32_t *__restrict__ order, int n, const uint8_t *qbase, int qshift, int32_t *res, int32_t *status_out,
+		uint8_t *scratch, ScratchLayout lay, unsigned long long *ctr) {
+	__shared__ NwPen spen;
+	__shared__ NwRow sring[AL_WARPS][NW_RING];
+	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&pen)[threadIdx.x];
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const size_t wid = (size_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
+	NwScratch nws;
+	nws.ring = sring[threadIdx.x >> 5];
+	nws.rowbuf = (NwRow *)(scratch + wid * lay.stride); nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap; nws.finish();
+	unsigned long long fcells = 0, bcells = 0, fcalls = 0, bcalls = 0, steps = 0;
+	for (;;) {
+		unsigned long long t = 0;
+		if (lane == 0) t = atomicAdd(&ctr[A_WORK], 1ull);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t >= (unsigned long long)n) break;
+		const NwProb p = probs[order[t]];
+		int32_t *row = res + 8 * (size_t)p.task;
+		const int status = row[7], k = (p.kband & 255) - 2, band = p.kband >> 8;
+		if (status == ST_GIVEUP && k >= 0) continue;
+		const KgTMeta m = ix.meta[p.tmpl];
+		NwStat a = {0, 0, 0, 0, 0, 0};
+		unsigned long long cells = 0;
+		const int st = nw_warp<true>(spen, ix.seq + m.seq_off, qbase + ((size_t)p.qoff << qshift), k, p.t_s, p.t_e, p.q_s, p.q_e, band, nws, &a, &cells);
+		if (st == NW_OK) {
+			if (lane == 0) nwq_apply(row, a, k, status);
+			if (cells) {
+				NwGeo g;
+				nw_geo_init(g, spen, p.t_e - p.t_s, p.q_e - p.q_s, k, band, true);
+				steps += g.C ? (unsigned long long)g.t_len * g.C : (unsigned long long)g.Tmax;
+				if (band) { bcells += cells; ++bcalls; } else { fcells += cells; ++fcalls; }
+			}
+		} else if (lane == 0 && !status_out) atomicAdd(&ctr[A_BAD], 1ull);
+		if (lane == 0 && status_out) status_out[p.task] = st;
+		__syncwarp();
+	}
+	if (lane == 0) {
+		if (fcalls) { atomicAdd(&ctr[A_FULL_CALLS], fcalls); atomicAdd(&ctr[A_FULL_CELLS], fcells); }
+		if (bcalls) { atomicAdd(&ctr[A_BAND_CALLS], bcalls); atomicAdd(&ctr[A_BAND_CELLS], bcells); }
+		if (steps) atomicAdd(&ctr[A_STEPS], steps);
+	}
+}
+
+// Solve the queued problems. counts[c] = problems of class c (their queue slots in order[c * cap ..)); need_e / need_q:
+// scratch the largest class-4 problem asked for. Uses (and may grow) the batch's per-warp scratch buffer.
+static int nw_queue_run(kmagpu_db *db, const AlnParams &P, const NwProb *probs, const uint32_t *order, size_t cap, const unsigned long long *counts,
+                        size_t need_e, int need_q, const uint8_t *qbase, int qshift, int32_t *res, int32_t *status_out, unsigned long long *ctr,
+                        int *launches) {
+	cudaStream_t st = db->stream;
+	KgBuf &scr = db->aln.d_scratch;
+	KG_CUDA(cudaFuncSetAttribute(nw_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * (int)sizeof(NwRow)));
+	for (int c = 0; c < 4; ++c) {
+		const int n = (int)counts[c];
+		if (!n) continue;
+		const size_t smem = (size_t)nwq_qmax[c] * 128 * sizeof(NwRow);
+		int per_sm = 0;
+		KG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_thread_kernel, 128, smem));
+		const int grid = std::max(1, std::min((n + 127) / 128, db->sm_count * std::max(per_sm, 1)));
+		if (scr.reserve((size_t)grid * 4 * (size_t)nwq_cells[c] * 32)) return -1;
+		nw_thread_kernel<<<grid, 128, smem, st>>>(P.pen, db->tix, probs, order + (size_t)c * cap, n, qbase, qshift, res, (uint8_t *)scr.p,
+			nwq_cells[c], ctr);
+		++*launches;
+	}
+	if (counts[4]) {
+		const int n = (int)counts[4];
+		ScratchLayout lay;
+		lay.mem_cap = 0; lay.q_cap = std::max(need_q, 256); lay.e_cap = (std::max<size_t>(need_e, 65536) + 255) & ~(size_t)255;
+		lay.stride = ((size_t)lay.q_cap * 12 + lay.e_cap + 255) & ~(size_t)255;
+		int grid = (int)std::min<size_t>((size_t)db->sm_count * 8, ((size_t)n + AL_WARPS - 1) / AL_WARPS);
+		if (lay.stride * (size_t)grid * AL_WARPS > scr.cap) {
+			size_t freeb = 0, totalb = 0;
+			cudaMemGetInfo(&freeb, &totalb);
+			while (grid > 1 && lay.stride * (size_t)grid * AL_WARPS > freeb / 2 + scr.cap) grid = (grid + 1) / 2;
+		}
+		if (scr.reserve(lay.stride * (size_t)grid * AL_WARPS)) return -1;
+		KG_CUDA(cudaMemsetAsync(ctr + A_WORK, 0, 8, st));
+		nw_warp_kernel<<<grid, AL_WARPS * 32, 0, st>>>(P.pen, db->tix, probs, order + 4 * cap, n, qbase, qshift, res, status_out, (uint8_t *)scr.p, lay, ctr);
+		++*launches;
+	}
+	return 0;
+}
+
 extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int want_cand, kmagpu_align_stats *stats) {
 	if (!db || !prm) { kmagpu_set_error("null argument"); return -1; }
 	if (!db->d_tslots) { kmagpu_set_error("database has no alignment index (.seq.b / .length.b missing)"); return -1; }
@@ -1628,10 +1774,8 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 	KG_CUDA(cudaEventRecord(db->ev[4], st));
 
 	if (ntasks) {
-		// per-warp scratch: MEM list, NW row buffers for the longest read, traceback bytes for a tail of that read
-		const int q_cap = std::min(std::max(maxq + 64, 256), 1 << 20);
-		const size_t e_cap = std::min<size_t>(std::max<size_t>(2 * (size_t)maxq * (size_t)maxq + 65536, 65536), 4u << 20);
-		const ScratchLayout lay = make_layout(2048, q_cap, e_cap);
+		// phase 1: MEMs + chaining per (read, template) pair; per-warp scratch = the MEM table. NW problems go to the queue.
+		const ScratchLayout lay = make_layout(2048, 0, 0);
 		const bool short_reads = maxq <= AL_SHORT_MAXQ;
 		int grid = db->sm_count * (short_reads ? AL_MINB_SHORT : AL_MINB);
 		size_t freeb = 0, totalb = 0;
@@ -1640,51 +1784,74 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 			while (grid > db->sm_count && lay.stride * (size_t)grid * AL_WARPS > freeb / 2 + b.d_scratch.cap) grid -= db->sm_count;
 		}
 		if (b.d_scratch.reserve(lay.stride * (size_t)grid * AL_WARPS)) return -1;
-		KG_CUDA(cudaEventRecord(db->ev[3], st));   // ms_align = the pair kernel(s) alone; host-side sizing above is in ms_total
-		if (!prm->counters)   // production: no statistic counters (stats->mems, index_probes, mem_bases, read_bytes, nw_* stay 0)
-			(short_reads ? kg_launch_pair_fast_short : kg_launch_pair_fast_long)(grid, st, &P, &db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
-				(const int32_t *)b.d_taskread.p, ntasks, nullptr, b.d_cand.p, (uint8_t *)b.d_scratch.p, &lay, ctr, (int32_t *)b.d_ovf.p);
-		else if (short_reads)
-			aln_pair_kernel<AL_MINB_SHORT><<<grid, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
-				(const int32_t *)b.d_taskread.p, ntasks, nullptr, (AlnCand *)b.d_cand.p, (uint8_t *)b.d_scratch.p, lay, ctr,
-				(int32_t *)b.d_ovf.p);
-		else
-			aln_pair_kernel<AL_MINB><<<grid, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
-				(const int32_t *)b.d_taskread.p, ntasks, nullptr, (AlnCand *)b.d_cand.p, (uint8_t *)b.d_scratch.p, lay, ctr,
-				(int32_t *)b.d_ovf.p);
-		KG_CUDA(cudaEventRecord(db->ev[4], st));
-		++launches;
-		KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
-		KG_CUDA(cudaStreamSynchronize(st));
-		KG_CUDA(cudaGetLastError());
-		int novf = (int)h[A_OVF];
-		const unsigned long long first_ovf = h[A_OVF];
-		// large-scratch path: same code, few warps, scratch sized from what the pairs asked for
-		for (int round = 0; novf; ++round) {
-			if (round == 8) { kmagpu_set_error("%d read/template pairs do not fit the alignment scratch", novf); return -1; }
-			const ScratchLayout big = make_layout(std::max<int>(2048, (int)h[A_NEED_MEM]), std::max<int>(q_cap, (int)h[A_NEED_Q]),
-			                                      std::max<size_t>(e_cap, (size_t)h[A_NEED_E]));
-			cudaMemGetInfo(&freeb, &totalb);
-			int g2 = std::min(db->sm_count, (novf + AL_WARPS - 1) / AL_WARPS);
-			while (g2 > 1 && big.stride * (size_t)g2 * AL_WARPS > (freeb + b.d_scratch.cap) / 2) g2 = (g2 + 1) / 2;
-			if (b.d_scratch.reserve(big.stride * (size_t)g2 * AL_WARPS)) return -1;
-			// the overflow list becomes the task list; d_ovf collects what still does not fit
-			KgBuf list2;
-			if (list2.reserve(4 * ((size_t)novf + 1))) return -1;
-			KG_CUDA(cudaMemcpyAsync(list2.p, b.d_ovf.p, 4 * (size_t)novf, cudaMemcpyDeviceToDevice, st));
-			KG_CUDA(cudaMemsetAsync(ctr + A_WORK, 0, 8 * 5, st));   // A_WORK, A_OVF, A_NEED_*
-			aln_pair_kernel<AL_MINB><<<g2, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
-				(const int32_t *)b.d_taskread.p, novf, (const int32_t *)list2.p, (AlnCand *)b.d_cand.p,
-				(uint8_t *)b.d_scratch.p, big, ctr, (int32_t *)b.d_ovf.p);
+		if (b.prob_cap < (size_t)ntasks + 65536) b.prob_cap = (size_t)ntasks + 65536;
+		unsigned long long first_ovf = 0;
+		KG_CUDA(cudaEventRecord(db->ev[3], st));   // ms_align = the pair kernel(s) + the NW queue kernels; host-side sizing above is in ms_total
+		for (int attempt = 0;; ++attempt) {
+			if (b.prob_cap >= (1ull << 32)) { kmagpu_set_error("NW problem queue exceeds 2^32 entries; split the batch"); return -1; }
+			if (b.d_probs.reserve(sizeof(NwProb) * b.prob_cap) || b.d_order.reserve(4 * NWQ_CLASSES * b.prob_cap)) return -1;
+			NwQueue queue;
+			queue.probs = (NwProb *)b.d_probs.p; queue.order = (uint32_t *)b.d_order.p; queue.cap = (unsigned)b.prob_cap; queue.ctr = ctr;
+			if (!prm->counters)   // production: no statistic counters (stats->mems, index_probes, mem_bases, read_bytes stay 0)
+				(short_reads ? kg_launch_pair_fast_short : kg_launch_pair_fast_long)(grid, st, &P, &db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
+					(const int32_t *)b.d_taskread.p, ntasks, nullptr, b.d_cand.p, (uint8_t *)b.d_scratch.p, &lay, ctr, (int32_t *)b.d_ovf.p, &queue);
+			else if (short_reads)
+				aln_pair_kernel<AL_MINB_SHORT><<<grid, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
+					(const int32_t *)b.d_taskread.p, ntasks, nullptr, (AlnCand *)b.d_cand.p, (uint8_t *)b.d_scratch.p, lay, ctr,
+					(int32_t *)b.d_ovf.p, queue);
+			else
+				aln_pair_kernel<AL_MINB><<<grid, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
+					(const int32_t *)b.d_taskread.p, ntasks, nullptr, (AlnCand *)b.d_cand.p, (uint8_t *)b.d_scratch.p, lay, ctr,
+					(int32_t *)b.d_ovf.p, queue);
 			++launches;
 			KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
 			KG_CUDA(cudaStreamSynchronize(st));
 			KG_CUDA(cudaGetLastError());
-			list2.release();
-			novf = (int)h[A_OVF];
+			int novf = (int)h[A_OVF];
+			first_ovf = h[A_OVF];
+			// large MEM tables: the same code on few warps, table sized from what the pairs asked for
+			for (int round = 0; novf; ++round) {
+				if (round == 8) { kmagpu_set_error("%d read/template pairs do not fit the alignment scratch", novf); return -1; }
+				const ScratchLayout big = make_layout(std::max<int>(2048, (int)h[A_NEED_MEM]), 0, 0);
+				cudaMemGetInfo(&freeb, &totalb);
+				int g2 = std::min(db->sm_count, (novf + AL_WARPS - 1) / AL_WARPS);
+				while (g2 > 1 && big.stride * (size_t)g2 * AL_WARPS > (freeb + b.d_scratch.cap) / 2) g2 = (g2 + 1) / 2;
+				if (b.d_scratch.reserve(big.stride * (size_t)g2 * AL_WARPS)) return -1;
+				// the overflow list becomes the task list; d_ovf collects what still does not fit
+				KgBuf list2;
+				if (list2.reserve(4 * ((size_t)novf + 1))) return -1;
+				KG_CUDA(cudaMemcpyAsync(list2.p, b.d_ovf.p, 4 * (size_t)novf, cudaMemcpyDeviceToDevice, st));
+				KG_CUDA(cudaMemsetAsync(ctr + A_WORK, 0, 8 * 2, st));   // A_WORK, A_OVF
+				KG_CUDA(cudaMemsetAsync(ctr + A_NEED_MEM, 0, 8, st));
+				aln_pair_kernel<AL_MINB><<<g2, AL_WARPS * 32, 0, st>>>(P, db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
+					(const int32_t *)b.d_taskread.p, novf, (const int32_t *)list2.p, (AlnCand *)b.d_cand.p,
+					(uint8_t *)b.d_scratch.p, big, ctr, (int32_t *)b.d_ovf.p, queue);
+				++launches;
+				KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
+				KG_CUDA(cudaStreamSynchronize(st));
+				KG_CUDA(cudaGetLastError());
+				list2.release();
+				novf = (int)h[A_OVF];
+			}
+			if (h[A_NPROB] <= b.prob_cap) break;
+			// the queue was too small: the count is exact now, redo phase 1 (the capacity persists with the handle)
+			if (attempt) { kmagpu_set_error("NW problem queue overflow persists (%llu problems)", h[A_NPROB]); return -1; }
+			b.prob_cap = (size_t)h[A_NPROB] + (size_t)h[A_NPROB] / 8 + 65536;
+			KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * A_N, st));
 		}
 		h[A_OVF] = first_ovf;
-		if (first_ovf) KG_CUDA(cudaEventRecord(db->ev[4], st));
+		// phase 2: the queued NW problems add their scores into the candidate rows
+		if (h[A_NPROB]) {
+			if (nw_queue_run(db, P, (const NwProb *)b.d_probs.p, (const uint32_t *)b.d_order.p, b.prob_cap, &h[A_PCLS], (size_t)h[A_NEED_E], (int)h[A_NEED_Q],
+			                 (const uint8_t *)b.d_slab.p, 3, (int32_t *)b.d_cand.p, nullptr, ctr, &launches)) return -1;
+		}
+		KG_CUDA(cudaEventRecord(db->ev[4], st));
+		unsigned long long h2[A_N];
+		KG_CUDA(cudaMemcpyAsync(h2, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
+		KG_CUDA(cudaStreamSynchronize(st));
+		KG_CUDA(cudaGetLastError());
+		if (h2[A_BAD]) { kmagpu_set_error("%llu NW problems did not fit the scratch sized for them", h2[A_BAD]); return -1; }
+		for (int i : {A_FULL_CALLS, A_BAND_CALLS, A_FULL_CELLS, A_BAND_CELLS, A_STEPS}) h[i] = h2[i];
 	}
 	if (b.want_cand && ntasks) {   // per-candidate rows, before the selection compacts them in place
 		std::vector<AlnCand> hc((size_t)ntasks);
@@ -1984,47 +2151,13 @@ extern "C" int kmagpu_matrix_download(kmagpu_db *db, int32_t tmpl, uint16_t *cou
 
 // ---------------------------------------------------------------- stand-alone NW batch
 
-__global__ void __launch_bounds__(AL_WARPS * 32) nw_batch_kernel(NwPen pen, KgTIndexView ix, int n, const int32_t *__restrict__ prob,
-		const uint8_t *qpool, int32_t *out, int32_t *status, uint8_t *scratch, ScratchLayout lay, unsigned long long *ctr) {
-	__shared__ NwPen spen;
-	__shared__ NwRow sring[AL_WARPS][NW_RING];
-	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&pen)[threadIdx.x];
-	__syncthreads();
-	const int lane = threadIdx.x & 31;
-	const size_t wid = (size_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
-	uint8_t *sp = scratch + wid * lay.stride;
-	NwScratch nws;
-	nws.ring = sring[threadIdx.x >> 5];
-	nws.rowbuf = (NwRow *)sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap; nws.finish();
-	unsigned long long cells = 0, steps = 0;
-	for (;;) {
-		unsigned long long t = 0;
-		if (lane == 0) t = atomicAdd(&ctr[0], 1ull);
-		t = __shfl_sync(0xffffffffu, t, 0);
-		if (t >= (unsigned long long)n) break;
-		const int32_t *pr = prob + 8 * t;
-		const KgTMeta m = ix.meta[pr[0]];
-		NwStat s = {0, 0, 0, 0, 0, 0};
-		const int st = nw_warp<true>(spen, ix.seq + m.seq_off, qpool + pr[3], pr[6], pr[1], pr[2], pr[4], pr[5], pr[7], nws, &s, &cells);
-		if (st == NW_OK && pr[2] > pr[1] && pr[5] > pr[4]) {
-			NwGeo g;
-			nw_geo_init(g, spen, pr[2] - pr[1], pr[5] - pr[4], pr[6], pr[7], true);
-			steps += g.C ? (unsigned long long)g.t_len * g.C : (unsigned long long)g.Tmax;
-		}
-		if (lane == 0) {
-			int32_t *o = out + 6 * t;
-			o[0] = s.score; o[1] = s.len; o[2] = s.pos; o[3] = s.match; o[4] = s.tGaps; o[5] = s.qGaps;
-			status[t] = st;
-		}
-		__syncwarp();
-	}
-	if (lane == 0) { atomicAdd(&ctr[1], cells); atomicAdd(&ctr[2], steps); }
-}
-
+// The problems go through the same queue kernels as the alignment pass's (nw_queue_run): what this entry point times is
+// the NW the mapping path runs.
 extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, const int32_t *prob, const uint8_t *qpool,
                                size_t qbytes, int32_t *out, int32_t *status, int64_t *cells, int64_t *steps, float *ms) {
 	if (!db || !p || (n && (!prob || !qpool || !out || !status))) { kmagpu_set_error("null argument"); return -1; }
 	if (!db->d_tmeta) { kmagpu_set_error("database has no template sequences"); return -1; }
+	if (n >= (1ull << 31)) { kmagpu_set_error("too many NW problems in one call"); return -1; }
 	KG_CUDA(cudaSetDevice(db->device));
 	if (cells) *cells = 0;
 	if (steps) *steps = 0;
@@ -2033,51 +2166,69 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 	size_t need_e = 65536;
 	int need_q = 256;
 	const AlnParams P = make_params(db, p);
+	std::vector<NwProb> hp(n);
+	std::vector<uint32_t> horder(NWQ_CLASSES * n);
+	unsigned long long counts[NWQ_CLASSES] = {0, 0, 0, 0, 0};
 	for (size_t i = 0; i < n; ++i) {
 		const int32_t *pr = prob + 8 * i;
 		if (pr[0] <= 0 || pr[0] >= db->info.DB_size || pr[1] < 0 || pr[2] < pr[1] || pr[2] > db->lengths[pr[0]] || pr[4] < 0 ||
-		    pr[5] < pr[4] || pr[3] < 0 || (size_t)pr[3] + (size_t)pr[5] > qbytes) {
+		    pr[5] < pr[4] || pr[3] < 0 || (size_t)pr[3] + (size_t)pr[5] > qbytes || pr[6] < -2 || pr[6] > 2 || pr[7] < 0 || pr[7] >= (1 << 23)) {
 			kmagpu_set_error("NW problem %zu is out of range", i);
 			return -1;
 		}
+		const int t_l = pr[2] - pr[1], q_l = pr[5] - pr[4];
+		const int cls = nwq_class(t_l, q_l, pr[7]);
 		NwGeo g;
-		if (pr[2] > pr[1] && pr[5] > pr[4] && nw_geo_init(g, P.pen, pr[2] - pr[1], pr[5] - pr[4], pr[6], pr[7], true)) {
+		if (cls == 4 && t_l > 0 && q_l > 0 && nw_geo_init(g, P.pen, t_l, q_l, pr[6], pr[7], true)) {
 			need_e = std::max(need_e, g.ebytes() + 256);
-			need_q = std::max(need_q, pr[5] - pr[4] + 64);
+			need_q = std::max(need_q, q_l + 64);
 		}
+		NwProb &q = hp[i];
+		q.task = (int32_t)i; q.tmpl = pr[0]; q.t_s = pr[1]; q.t_e = pr[2]; q.q_s = pr[4]; q.q_e = pr[5]; q.kband = (pr[6] + 2) | (pr[7] << 8);
+		q.qoff = (uint32_t)pr[3];
+		horder[(size_t)cls * n + counts[cls]++] = (uint32_t)i;
 	}
-	ScratchLayout lay;
-	lay.mem_cap = 0; lay.q_cap = need_q; lay.e_cap = (need_e + 255) & ~(size_t)255;
-	lay.stride = ((size_t)need_q * 12 + lay.e_cap + 255) & ~(size_t)255;
-	size_t freeb = 0, totalb = 0;
-	cudaMemGetInfo(&freeb, &totalb);
-	int grid = (int)std::min<size_t>((size_t)db->sm_count * 8, (n + AL_WARPS - 1) / AL_WARPS);
-	while (grid > 1 && lay.stride * (size_t)grid * AL_WARPS > freeb / 2) grid = (grid + 1) / 2;
-	uint8_t *scratch = nullptr, *dq = nullptr;
-	int32_t *dprob = nullptr, *dout = nullptr, *dstat = nullptr;
+	uint8_t *dq = nullptr;
+	NwProb *dprob = nullptr;
+	uint32_t *dorder = nullptr;
+	int32_t *dres = nullptr, *dstat = nullptr;
 	unsigned long long *ctr = nullptr;
-	KG_CUDA(cudaMalloc(&scratch, lay.stride * (size_t)grid * AL_WARPS));
 	KG_CUDA(cudaMalloc(&dq, qbytes + 64));
-	KG_CUDA(cudaMalloc(&dprob, 32 * n));
-	KG_CUDA(cudaMalloc(&dout, 24 * n));
+	KG_CUDA(cudaMalloc(&dprob, sizeof(NwProb) * n));
+	KG_CUDA(cudaMalloc(&dorder, 4 * NWQ_CLASSES * n));
+	KG_CUDA(cudaMalloc(&dres, 32 * n));
 	KG_CUDA(cudaMalloc(&dstat, 4 * n));
-	KG_CUDA(cudaMalloc(&ctr, 64));
-	KG_CUDA(cudaMemcpyAsync(dq, qpool, qbytes, cudaMemcpyHostToDevice, db->stream));
-	KG_CUDA(cudaMemcpyAsync(dprob, prob, 32 * n, cudaMemcpyHostToDevice, db->stream));
-	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, db->stream));
-	KG_CUDA(cudaEventRecord(db->ev[2], db->stream));
-	nw_batch_kernel<<<grid, AL_WARPS * 32, 0, db->stream>>>(P.pen, db->tix, (int)n, dprob, dq, dout, dstat, scratch, lay, ctr);
-	KG_CUDA(cudaEventRecord(db->ev[3], db->stream));
-	unsigned long long hc[8];
-	KG_CUDA(cudaMemcpyAsync(out, dout, 24 * n, cudaMemcpyDeviceToHost, db->stream));
-	KG_CUDA(cudaMemcpyAsync(status, dstat, 4 * n, cudaMemcpyDeviceToHost, db->stream));
-	KG_CUDA(cudaMemcpyAsync(hc, ctr, 64, cudaMemcpyDeviceToHost, db->stream));
-	KG_CUDA(cudaStreamSynchronize(db->stream));
+	KG_CUDA(cudaMalloc(&ctr, 8 * A_N));
+	cudaStream_t st = db->stream;
+	KG_CUDA(cudaMemcpyAsync(dq, qpool, qbytes, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemcpyAsync(dprob, hp.data(), sizeof(NwProb) * n, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemcpyAsync(dorder, horder.data(), 4 * NWQ_CLASSES * n, cudaMemcpyHostToDevice, st));
+	KG_CUDA(cudaMemsetAsync(dres, 0, 32 * n, st));
+	KG_CUDA(cudaMemsetAsync(dstat, 0, 4 * n, st));
+	KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * A_N, st));
+	KG_CUDA(cudaEventRecord(db->ev[2], st));
+	int launches = 0;
+	const int rc = nw_queue_run(db, P, dprob, dorder, n, counts, need_e, need_q, dq, 0, dres, dstat, ctr, &launches);
+	KG_CUDA(cudaEventRecord(db->ev[3], st));
+	std::vector<int32_t> hres(8 * n);
+	unsigned long long hc[A_N];
+	if (!rc) {
+		KG_CUDA(cudaMemcpyAsync(hres.data(), dres, 32 * n, cudaMemcpyDeviceToHost, st));
+		KG_CUDA(cudaMemcpyAsync(status, dstat, 4 * n, cudaMemcpyDeviceToHost, st));
+		KG_CUDA(cudaMemcpyAsync(hc, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
+	}
+	KG_CUDA(cudaStreamSynchronize(st));
+	cudaFree(dq); cudaFree(dprob); cudaFree(dorder); cudaFree(dres); cudaFree(dstat); cudaFree(ctr);
+	if (rc) return -1;
 	KG_CUDA(cudaGetLastError());
-	if (cells) *cells = (int64_t)hc[1];
-	if (steps) *steps = (int64_t)hc[2];
+	for (size_t i = 0; i < n; ++i) {
+		const int32_t *r = &hres[8 * i];
+		int32_t *o = out + 6 * i;
+		o[0] = r[1]; o[1] = r[2]; o[2] = 0; o[3] = r[4]; o[4] = r[5]; o[5] = r[6];   // AlnScore.pos of NW_score itself is 0
+	}
+	if (cells) *cells = (int64_t)(hc[A_FULL_CELLS] + hc[A_BAND_CELLS]);
+	if (steps) *steps = (int64_t)hc[A_STEPS];
 	if (ms) cudaEventElapsedTime(ms, db->ev[2], db->ev[3]);
-	cudaFree(scratch); cudaFree(dq); cudaFree(dprob); cudaFree(dout); cudaFree(dstat); cudaFree(ctr);
 	return 0;
 }
 #endif   // KG_PAIR_VARIANT_ONLY

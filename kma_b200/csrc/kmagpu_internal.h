@@ -99,6 +99,8 @@ struct RawBatch {
 struct AlignBatch {
 	KgBuf d_in, d_off, d_reads, d_slab, d_sz, d_partial, d_taskread, d_cand, d_recsize, d_out, d_ctr, d_scores,
 	      d_scratch, d_ovf, d_res;
+	KgBuf d_probs, d_order;        // NW problem queue of the phase-split alignment pass + its per-class order lists
+	size_t prob_cap = 0;           // queue capacity (grows to what a batch asked for, kept across calls)
 	KgBuf h_off;
 	const uint8_t *in = nullptr;   // device pointer of the stage-2 stream (d_in or the seeding output)
 	int64_t nreads = 0, ntasks = 0;

@@ -469,6 +469,92 @@ NW_HD bool nw_trivial(const NwPen &pen, int t_len, int q_len, NwStat &s) {   // 
 	return true;
 }
 
+// ------------------------------------------------------------------------------------------------ one thread per problem
+// The short tails and gaps of short reads (C1/C2: ~130 cells per read, a few bases by a few bases) are far too small
+// for a warp: NW_score (nw.c:642-890) of a FULL matrix filled by ONE thread, row by row, 32 independent problems per
+// warp. The previous row (D, P) lives in `rows` (q_len entries, element x at rows[x * rstride]: shared memory,
+// transposed so that the lanes of a warp never conflict), the traceback bytes in `E` (cell c at E[c * estride]: the
+// warp's lanes write neighbouring bytes of one sector as long as they are at the same cell). Same recurrence, tie
+// rules, start cell and walk as nw_lane_step / nw_start_cell / nw_walk; checked against the oracle by the emulator.
+NW_HD int nw_thread_e_at(const uint8_t *E, size_t estride, int t_len, int q_len, int k, int m, int qpos) {
+	if (m >= t_len) {
+		if (k == 2 || qpos >= q_len) return 0;
+		return qpos == q_len - 1 ? 18 : 3;
+	}
+	if (qpos >= q_len) return 0 < k ? 0 : (m == t_len - 1 ? 36 : 5);
+	return E[((size_t)(t_len - 1 - m) * (size_t)q_len + (size_t)(q_len - 1 - qpos)) * estride];
+}
+
+NW_HD void nw_thread(const NwPen &pen, const uint64_t *tseq, int t_s, int t_len, const uint8_t *q, int q_len, int k,
+                     NwRow *rows, int rstride, uint8_t *E, size_t estride, NwStat *out) {
+	const int W1 = pen.W1, U = pen.U;
+	const int NEG = (t_len + q_len) * (pen.MM + U + W1);
+	const uint8_t *qlast = q + q_len - 1;
+	for (int j = 0; j < q_len; ++j) { NwRow r; r.D = k == 2 ? 0 : W1 + j * U; r.P = NEG; rows[(size_t)j * rstride] = r; }
+	int colBest = NEG, colBestI = 0x7fffffff;
+	// ONE loop over the cells in fill order (row by row): the 32 problems of a warp stay in lock step however their
+	// shapes differ, and the warp takes max(cells) iterations instead of max(t_len) * max(q_len)
+	uint8_t *e = E;
+	NwRow *rp = rows;
+	int i = 0, j = 0, tn = 0, Dleft = 0, Qleft = 0, Ddiag = 0;
+	unsigned long long drow = 0;
+	for (int c = t_len * q_len; c > 0; --c, e += estride) {
+		if (j == 0) {   // a new row: template base, what lies beside and diagonal to its first cell
+			tn = nw_nuc(tseq, t_s + t_len - 1 - i);
+			drow = nw_pack_row(pen, tn);
+			Dleft = 0 < k ? 0 : W1 + i * U; Qleft = NEG;
+			Ddiag = i == 0 ? 0 : (0 < k ? 0 : W1 + (i - 1) * U);
+			rp = rows;
+		}
+		const int qn = qlast[-j];
+		const NwRow a = *rp;
+		const int sub = pen.d8 ? (int)(signed char)(drow >> (qn << 3)) : pen.d[tn * 5 + qn];
+		int Q = Dleft + W1, P = a.D + W1, D, ec, fl = 0, x;
+		if (Q < P) { D = P; ec = 4; } else { D = Q; ec = 2; }
+		x = Qleft + U;
+		if (Q < x) { Q = x; if (D <= x) { D = x; ec = 3; } } else fl |= 16;
+		x = a.P + U;
+		if (P < x) { P = x; if (D <= x) { D = x; ec = 5; } } else fl |= 32;
+		x = Ddiag + sub;
+		if (D <= x) { D = x; ec = 1; }
+		*e = (uint8_t)(fl | ec);
+		NwRow o; o.D = D; o.P = P;
+		*rp = o;
+		rp += rstride;
+		Ddiag = a.D; Dleft = D; Qleft = Q;
+		if (++j == q_len) {
+			if (k < 0 && colBest < D) { colBest = D; colBestI = i; }   // the row's cell at the query start competes (nw.c:217-220)
+			j = 0; ++i;
+		}
+	}
+	int best_m = 0, best_q = 0, score;
+	if (k < 0) {
+		if (colBestI == 0x7fffffff) score = NEG; else { best_m = t_len - 1 - colBestI; score = colBest; }
+		if (k == -2) {   // last maximum along row m = 0 (nw.c:235-243)
+			int rb = NEG, rq = -1;
+			for (int qp = 0; qp < q_len; ++qp) { const int v = rows[(size_t)(q_len - 1 - qp) * rstride].D; if (rq < 0 || v >= rb) { rb = v; rq = qp; } }
+			if (rq >= 0 && score <= rb) { score = rb; best_m = 0; best_q = rq; }
+		}
+	} else score = rows[(size_t)(q_len - 1) * rstride].D;
+	NwStat s;
+	s.len = s.match = s.tGaps = s.qGaps = 0;
+	int m = best_m, qp = best_q, c;
+	while ((c = nw_thread_e_at(E, estride, t_len, q_len, k, m, qp)) != 0) {   // nw.c:850-887
+		const int d = c & 7;
+		if (d == 1) { ++s.match; ++m; ++qp; }
+		else if (d >= 4) {
+			while (!(nw_thread_e_at(E, estride, t_len, q_len, k, m, qp) >> 4)) { ++m; ++s.len; ++s.qGaps; }
+			++s.qGaps; ++m;
+		} else {
+			while (!(nw_thread_e_at(E, estride, t_len, q_len, k, m, qp) >> 3)) { ++qp; ++s.len; ++s.tGaps; }
+			++s.tGaps; ++qp;
+		}
+		++s.len;
+	}
+	s.score = score; s.pos = 0;
+	*out = s;
+}
+
 #if defined(__CUDACC__)
 // per-warp scratch
 struct NwScratch {

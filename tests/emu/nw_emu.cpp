@@ -128,3 +128,22 @@ extern "C" int emu_nw(const int *pen29, const uint64_t *tseq, const uint8_t *que
                       int q_e, int band, int order, int d8, int *out6, long long *steps) {
 	return emu_nw2(pen29, tseq, query, k, t_s, t_e, q_s, q_e, band, order, d8, 1, out6, steps, nullptr);
 }
+
+// nw_thread (one thread per problem): estride / rstride > 1 emulate the interleaved device layouts
+extern "C" int emu_nw_thread(const int *pen29, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s,
+                             int q_e, int d8, int stride, int *out6, uint8_t *emap) {
+	NwPen pen;
+	pen.W1 = pen29[0]; pen.U = pen29[1]; pen.MM = pen29[2]; pen.M = pen29[3];
+	memcpy(pen.d, pen29 + 4, 100);
+	pen.d8 = d8;
+	const int t_len = t_e - t_s, q_len = q_e - q_s;
+	NwStat s;
+	if (nw_trivial(pen, t_len, q_len, s)) { memcpy(out6, &s, 24); return 0; }
+	std::vector<NwRow> rows((size_t)q_len * stride + 1, NwRow{0x3fffffff, 0x3fffffff});
+	std::vector<uint8_t> E((size_t)t_len * q_len * stride + 1, 0xEE);
+	nw_thread(pen, tseq, t_s, t_len, query + q_s, q_len, k, rows.data(), stride, E.data(), (size_t)stride, &s);
+	if (emap)
+		for (int c = 0; c < t_len * q_len; ++c) emap[c] = E[(size_t)c * stride];
+	memcpy(out6, &s, 24);
+	return 0;
+}

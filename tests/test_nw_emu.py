@@ -140,3 +140,40 @@ def test_trivial_and_unrelated(emu):
         t_len, q_len, k = int(rng.integers(1, 150)), int(rng.integers(1, 150)), int(rng.choice([0, -1, -2, 1, 2]))
         want, got = run_both(emu, t, q, k, 0, t_len, 0, q_len, 0)
         assert want == got, (k, t_len, q_len)
+
+
+@pytest.mark.parametrize("k", [0, -1, -2, 1, 2])
+def test_thread_per_problem(emu, k):
+    """nw_thread (the one-thread-per-problem NW of the queue kernels) against the oracle and, byte for byte of the
+    traceback matrix, against the wavefront"""
+    rng = np.random.default_rng(300 + k)
+    L = util.orc()
+    pen = util.oracle_params()
+    p = list(pen)
+    pen29 = (C.c_int * 29)(p[3], p[2], p[1], p[0], *p[7:32])
+    sizes = [(1, 1), (1, 2), (2, 1), (3, 7), (8, 16), (16, 8), (31, 31), (64, 32), (128, 64), (5, 64), (100, 3), (1, 64)]
+    sizes += [(int(rng.integers(1, 129)), int(rng.integers(1, 65))) for _ in range(120)]
+    for t_len, q_len in sizes:
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            t, q = problem(rng, t_len, q_len + 8, err=rng.choice([0.0, 0.05, 0.2, 0.6]))
+        elif kind == 1:
+            t = rng.integers(0, 4, size=t_len + 64).astype(np.uint8); q = rng.integers(0, 4, size=q_len + 8).astype(np.uint8)
+        else:
+            t = np.zeros(t_len + 64, dtype=np.uint8); q = np.zeros(q_len + 8, dtype=np.uint8)
+            t[rng.integers(0, t_len + 64, size=6)] = 1; q[rng.integers(0, q_len + 8, size=4)] = 1
+        t_s, q_s = int(rng.integers(0, 40)), int(rng.integers(0, 8))
+        tw = pack(t)
+        want = (C.c_int * 6)()
+        L.orc_nw(pen, tw.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), k, t_s, t_s + t_len, q_s, q_s + q_len, 0, want)
+        ref_map = np.zeros(t_len * q_len, dtype=np.uint8)
+        got0 = (C.c_int * 6)()
+        assert emu.emu_nw2(pen29, tw.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), k, t_s, t_s + t_len, q_s, q_s + q_len, 0,
+                           0, 1, 0, got0, None, ref_map.ctypes.data_as(C.c_void_p)) == 0
+        for d8, stride in ((1, 1), (0, 1), (1, 32)):
+            got = (C.c_int * 6)()
+            emap = np.zeros(t_len * q_len, dtype=np.uint8)
+            assert emu.emu_nw_thread(pen29, tw.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), k, t_s, t_s + t_len, q_s,
+                                     q_s + q_len, d8, stride, got, emap.ctypes.data_as(C.c_void_p)) == 0
+            assert list(got) == list(want), (k, t_len, q_len, d8, stride, list(want), list(got))
+            assert np.array_equal(emap, ref_map), (k, t_len, q_len)
