@@ -555,6 +555,7 @@ __device__ KG_STAGE_INL int kma_score_warp(const AlnParams &P, const TaskCtx &c,
 			NwStat a;
 			if (nw_closed_form(*c.pen, c.tseq, c.qb, 0, t_s, t_e, q_s, q_e, a)) {
 				s.score += a.score; s.len += a.len; s.match += a.match; s.tGaps += a.tGaps; s.qGaps += a.qGaps;
+				KG_STAT(if (t_l == 1 && q_e - q_s == 1) { ++c.wc->full_calls; ++c.wc->full_cells; })   // the one-cell matrix, as the reference counts it
 			} else nw_enqueue(c, 0, t_s, t_e, q_s, q_e);
 		}
 	}
@@ -707,6 +708,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(const Aln
 		if (wc.lookups) atomicAdd(&ctr[A_LOOKUPS], wc.lookups);
 		if (wc.mem_bases) atomicAdd(&ctr[A_MEMBASES], wc.mem_bases);
 		if (wc.read_bytes) atomicAdd(&ctr[A_READBYTES], wc.read_bytes);
+		if (wc.full_calls) { atomicAdd(&ctr[A_FULL_CALLS], wc.full_calls); atomicAdd(&ctr[A_FULL_CELLS], wc.full_cells); }
 		if (wc.need_e) atomicMax(&ctr[A_NEED_E], (unsigned long long)wc.need_e);
 		if (wc.need_mem) atomicMax(&ctr[A_NEED_MEM], (unsigned long long)wc.need_mem);
 		if (wc.need_q) atomicMax(&ctr[A_NEED_Q], (unsigned long long)wc.need_q);
@@ -1005,21 +1007,14 @@ __global__ void __launch_bounds__(256) aln_emit_kernel(const uint8_t *__restrict
 					}
 					o += 20;
 				}
-#pragma unroll 1
-				for (int i = lane; i < Rm.q_len; i += 32) o[i] = q.b[i];
+				warp_copy(o, q.b, Rm.q_len, lane);
 				o += Rm.q_len;
-#pragma unroll 1
-				for (int i = lane; i < Rm.hl; i += 32) o[i] = hdr[i];
+				warp_copy(o, hdr, Rm.hl, lane);
 				o += Rm.hl;
 				if (!(rs.form == 1 && x == 1)) {
 					const int32_t *arr = pbase + rs.roff[x];
 					const int kept = rs.rkept[x], cap = RB.nt;
-#pragma unroll 1
-					for (int i = lane; i < kept; i += 32) {
-						st_u32b(o + 4 * (size_t)i, (uint32_t)arr[i]);
-						st_u32b(o + 4 * (size_t)(kept + i), (uint32_t)arr[cap + i]);
-						st_u32b(o + 4 * (size_t)(2 * kept + i), (uint32_t)arr[2 * cap + i]);
-					}
+					warp_store_u32(o, 3 * kept, lane, [&](int i) { const int a = i / kept; return arr[a * cap + (i - a * kept)]; });
 					o += 12 * (size_t)kept;
 				}
 				__syncwarp();
@@ -1035,20 +1030,14 @@ __global__ void __launch_bounds__(256) aln_emit_kernel(const uint8_t *__restrict
 		}
 		o += 20;
 		const QView q = read_view(slab, R, 0);
-#pragma unroll 1
-		for (int i = lane; i < R.q_len; i += 32) o[i] = q.b[i];
+		warp_copy(o, q.b, R.q_len, lane);
 		o += R.q_len;
 		const uint8_t *hdr = in + R.rec_off + 28 + 8 * (size_t)R.words + 4 * (size_t)R.nN + 4 * (size_t)R.nt;
-#pragma unroll 1
-		for (int i = lane; i < R.hl; i += 32) o[i] = hdr[i];
+		warp_copy(o, hdr, R.hl, lane);
 		o += R.hl;
 		const AlnCand *c = cand + R.task0;
-#pragma unroll 1
-		for (int i = lane; i < rs.kept; i += 32) {
-			st_u32b(o + 4 * (size_t)i, (uint32_t)c[i].pos);
-			st_u32b(o + 4 * (size_t)(rs.kept + i), (uint32_t)c[i].match);
-			st_u32b(o + 4 * (size_t)(2 * rs.kept + i), (uint32_t)c[i].tmpl);
-		}
+		const int kept = rs.kept;
+		warp_store_u32(o, 3 * kept, lane, [&](int i) { const int a = i / kept, x = i - a * kept; return a == 0 ? c[x].pos : (a == 1 ? c[x].match : c[x].tmpl); });
 	}
 }
 

@@ -20,6 +20,32 @@ __device__ __forceinline__ void st_u32b(uint8_t *p, uint32_t v) {   // unaligned
 	p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24);
 }
 
+// n bytes from src to dst by one warp, any alignment on either side: the destination is written in aligned 4-byte
+// words (one 128-byte store per warp instruction; each word = two aligned loads + a funnel shift), at most 3 bytes at
+// either end go byte-wise. src must be read-only for the kernel (__ldg).
+__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, int n, unsigned lane) {
+	int head = (int)((4u - (unsigned)((uintptr_t)dst & 3)) & 3u);
+	if (head > n) head = n;
+	if ((int)lane < head) dst[lane] = __ldg(src + lane);
+	const int nw = (n - head) >> 2;
+	uint32_t *d4 = (uint32_t *)(dst + head);
+	const uint8_t *s = src + head;
+#pragma unroll 1
+	for (int w = (int)lane; w < nw; w += 32) d4[w] = ld_u32u(s + 4 * (size_t)w);
+	const int done = head + 4 * nw;
+	if ((int)lane < n - done) dst[done + lane] = __ldg(src + done + lane);
+}
+// n 32-bit values val(i) to dst (any alignment) by one warp: aligned destinations take whole-word stores
+template <typename F> __device__ __forceinline__ void warp_store_u32(uint8_t *dst, int n, unsigned lane, F val) {
+	if (((uintptr_t)dst & 3) == 0) {
+#pragma unroll 1
+		for (int i = (int)lane; i < n; i += 32) ((uint32_t *)dst)[i] = (uint32_t)val(i);
+	} else {
+#pragma unroll 1
+		for (int i = (int)lane; i < n; i += 32) st_u32b(dst + 4 * (size_t)i, (uint32_t)val(i));
+	}
+}
+
 // reverse the order of the 32 two-bit symbols of w
 __device__ __forceinline__ uint64_t rev2(uint64_t w) {
 	w = __brevll(w);
