@@ -40,6 +40,8 @@ typedef struct kmagpu_params {
 	                                     alnfrags.c:1596), 1 = u, the reference's default (save_kmers_unionPair :3367 / alnFragsUnionPE :1220) */
 	int32_t counters;                 /* alignment pass: collect the in-kernel statistic counters (kmagpu_align_stats mems, index_probes,
 	                                     mem_bases, read_bytes, nw_*): measurement only, ~10 % of the pair kernel; kmagpu_default_params sets 1 */
+	int32_t ts;                       /* -ts  seed trim of the traceback alignment (trimSeeds chain.c:496, called by KMA align.c:413); default 0 */
+	int32_t reserved0;
 	double scoreT;                    /* -mrs (alnfrags.c:1168; also `mrs` of save_kmers_chain, kmers.c:51) */
 	double minFrac;                   /* -mf  (updatescores.c:217-268) */
 	double mrc;                       /* -mrc (alnfrags.h:38 mrcheck) */
@@ -76,6 +78,11 @@ int kmagpu_device_count(void);
  * `device`. */
 int kmagpu_db_open(const char *prefix, int device, kmagpu_db **out);
 void kmagpu_db_close(kmagpu_db *db);
+/* A further handle on the SAME HBM image (hash table, template sequences, position index: read-only, shared, freed by
+ * the last handle to close) with its own CUDA stream and batch buffers: what the reference's T worker threads share when
+ * they all read one HashMapKMA / HashMapCCI (savekmers.c:94, alnfrags.c:2150). One handle per host thread; handles may
+ * run concurrently. The base-count matrix (kmagpu_matrix_*) is per handle. */
+int kmagpu_db_clone(kmagpu_db *db, kmagpu_db **out);
 int kmagpu_db_get_info(const kmagpu_db *db, kmagpu_db_info *info);
 
 /* Replaces the per-read loop of save_kmers_threaded (savekmers.c:94-271) with kmerScan =

@@ -22,7 +22,7 @@ class Params(C.Structure):
     _fields_ = [("M", C.c_int32), ("MM", C.c_int32), ("U", C.c_int32), ("W1", C.c_int32), ("Wl", C.c_int32),
                 ("Mn", C.c_int32), ("PE", C.c_int32), ("d", C.c_int32 * 25), ("exhaustive", C.c_int32),
                 ("mq", C.c_int32), ("one2one", C.c_int32), ("minlen", C.c_int32), ("kmerscan", C.c_int32), ("matrix", C.c_int32), ("apm", C.c_int32), ("counters", C.c_int32),
-                ("scoreT", C.c_double), ("minFrac", C.c_double), ("mrc", C.c_double), ("coverT", C.c_double)]
+                ("ts", C.c_int32), ("reserved0", C.c_int32), ("scoreT", C.c_double), ("minFrac", C.c_double), ("mrc", C.c_double), ("coverT", C.c_double)]
 
 
 class DbInfo(C.Structure):
@@ -128,6 +128,7 @@ def lib():
         L.kmagpu_db_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         L.kmagpu_db_close.argtypes = [C.c_void_p]
         L.kmagpu_db_close.restype = None
+        L.kmagpu_db_clone.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.kmagpu_db_get_info.argtypes = [C.c_void_p, C.POINTER(DbInfo)]
         L.kmagpu_default_params.argtypes = [C.POINTER(Params)]
         L.kmagpu_default_params.restype = None
@@ -203,9 +204,12 @@ def _ptr(a):
 class TemplateDB:
     """HBM-resident template database (hashMapKMA_load + .length.b/.seq.b of runKMA)."""
 
-    def __init__(self, prefix: str, device: int = 0):
+    def __init__(self, prefix: str, device: int = 0, _clone_of: "TemplateDB | None" = None):
         self._h = C.c_void_p()
-        _check(lib().kmagpu_db_open(os.fsencode(prefix), device, C.byref(self._h)))
+        if _clone_of is not None:
+            _check(lib().kmagpu_db_clone(_clone_of._h, C.byref(self._h)))
+        else:
+            _check(lib().kmagpu_db_open(os.fsencode(prefix), device, C.byref(self._h)))
         self.info = DbInfo()
         _check(lib().kmagpu_db_get_info(self._h, C.byref(self.info)))
         self.device = device
@@ -218,6 +222,10 @@ class TemplateDB:
         if self._lengths is None:
             self._lengths = np.fromfile(self.prefix + ".length.b", dtype=np.int32)[1:]
         return self._lengths
+
+    def clone(self) -> "TemplateDB":
+        """a further handle on the same HBM image (kmagpu_db_clone): own stream and batch buffers, for another host thread"""
+        return TemplateDB(self.prefix, self.device, _clone_of=self)
 
     def close(self):
         if self._h:

@@ -24,6 +24,9 @@
 #include "kmagpu_nw.cuh"
 #include <string.h>
 #include <algorithm>
+#ifndef KG_PAIR_VARIANT_ONLY
+#include <cub/device/device_radix_sort.cuh>
+#endif
 
 #define AL_WARPS 4            // warps per CTA of the pair kernel
 #ifndef KG_STAGE_INL
@@ -58,13 +61,13 @@ struct AlnCand { int32_t tmpl, score, len, pos, match, tGaps, qGaps, status; };
 
 struct AlnParams {
 	NwPen pen;
-	int32_t k, mq, one2one, exhaustive, minlen, Wl, PE, apm;
+	int32_t k, mq, one2one, exhaustive, minlen, Wl, PE, apm, ts, pad0;
 	double scoreT, mrc, minFrac;
 };
 
 enum { A_WORK = 0, A_OVF = 1, A_NEED_E = 2, A_NEED_MEM = 3, A_NEED_Q = 4, A_MEMS = 5, A_FULL_CALLS = 6, A_BAND_CALLS = 7,
        A_FULL_CELLS = 8, A_BAND_CELLS = 9, A_STEPS = 10, A_SLAB = 11, A_TASKS = 12, A_OUT = 13, A_FRAGS = 14, A_BAD = 15,
-       A_MAXQ = 16, A_LOOKUPS = 17, A_MEMBASES = 18, A_READBYTES = 19, A_NPROB = 20, A_PCLS = 21 /* .. 25 */, A_N = 32 };
+       A_MAXQ = 16, A_LOOKUPS = 17, A_MEMBASES = 18, A_READBYTES = 19, A_NPROB = 20, A_PCLS = 21 /* .. 23 */, A_N = 32 };
 
 // ---------------------------------------------------------------- slab layout
 
@@ -259,9 +262,12 @@ __device__ KG_STAGE_INL int scan_mems(const KgTIndexView &ix, const KgTMeta &m, 
 	const int lane = threadIdx.x & 31;
 	const int k = ix.k, t_len = m.len;
 	int j = start, s = 0;
-	for (int seg = 0; seg < nN1 && j < ((MODE == 1 && !BYTES) ? q_end : q_len); ++seg) {
+	for (int seg = 0; seg < nN1 && j < ((MODE == 1 || BYTES) ? q_end : q_len); ++seg) {
 		const int realN = q.N[seg];
-		const int segN = (MODE == 0 && !BYTES && seg == nN1 - 1) ? q_end : realN, end = segN - k + 1, lo = seg ? q.N[seg - 1] + 1 : 0;
+		// byte flavour (align.c:250-254, 823-827): a stretch runs from the cursor to the next N at or after it (N's before
+		// the cursor are never looked at), or to q_end when there is none
+		if (BYTES && realN < j) continue;
+		const int segN = ((MODE == 0 || BYTES) && seg == nN1 - 1) ? q_end : realN, end = segN - k + 1, lo = seg ? q.N[seg - 1] + 1 : 0;
 		const int fwd_lim = (BYTES || MODE == 0) ? segN : end;
 		if (BYTES && !(j < segN - k)) { j = segN + 1; continue; }
 		while (j < end) {
@@ -415,18 +421,18 @@ __device__ int chain_warp(const NwPen &pen, Mems &M, int n, int q_len, int t_len
 // (align.c:92-98, 186-192, 478-484) to a queue; queue kernels then solve the problems -- one THREAD per problem for the
 // small ones (classes 0-3 by size, so that a warp's 32 problems are alike), one WARP per problem for the rest -- and add
 // their AlnScore fields into the task's candidate row (all of them are sums; the lead tail also moves `pos`).
-#define NWQ_CLASSES 5
+#define NWQ_CLASSES 3
 struct NwProb { int32_t task, tmpl, t_s, t_e, q_s, q_e, kband; uint32_t qoff; };   // kband = (k + 2) | band << 8; query bytes at qbase + (qoff << qshift)
-struct NwQueue { NwProb *probs; uint32_t *order; unsigned cap; unsigned long long *ctr; };
+// order / cells: per class `cap` queue slots and their cell counts in arrival order; the thread classes are then sorted by
+// cells so that the 32 problems of a warp are alike
+struct NwQueue { NwProb *probs; uint32_t *order, *cells; unsigned cap; unsigned long long *ctr; };
 
 __host__ __device__ __forceinline__ int nwq_class(int t_l, int q_l, int band) {
-	if (band || q_l > 64 || t_l > 128 || t_l <= 0 || q_l <= 0) return 4;
-	if (q_l > 32 || t_l > 64) return 3;
-	const int cells = t_l * q_l;
-	return cells <= 96 ? 0 : (cells <= 384 ? 1 : 2);
+	if (band || q_l > 64 || t_l > 128 || t_l <= 0 || q_l <= 0) return 2;   // one warp per problem
+	return (q_l > 32 || t_l > 64) ? 1 : 0;                                  // one thread per problem
 }
-static const int nwq_qmax[4] = {32, 32, 32, 64};          // query columns the thread kernel of a class holds in shared memory
-static const int nwq_cells[4] = {96, 384, 2048, 8192};    // traceback bytes per problem
+static const int nwq_qmax[2] = {32, 64};        // query columns the thread kernel of a class holds in shared memory
+static const int nwq_cells[2] = {2048, 8192};   // traceback bytes per problem
 
 struct TaskCtx {
 	const NwPen *pen;
@@ -484,9 +490,10 @@ __device__ __forceinline__ void nw_enqueue(const TaskCtx &c, int k, int t_s, int
 			*(int4 *)&Q.probs[slot] = *(const int4 *)&p;
 			*((int4 *)&Q.probs[slot] + 1) = *((const int4 *)&p + 1);
 			Q.order[(size_t)cls * Q.cap + ci] = (uint32_t)slot;
+			if (cls < 2) Q.cells[(size_t)cls * Q.cap + ci] = (uint32_t)(t_l * q_l);
 		}
 	}
-	if (cls == 4) {   // the warp-per-problem kernel sizes its scratch from the largest problem
+	if (cls == 2) {   // the warp-per-problem kernel sizes its scratch from the largest problem
 		NwGeo g;
 		if (nw_geo_init(g, *c.pen, t_l, q_l, k, band, true)) {
 			c.wc->need_e = max(c.wc->need_e, (unsigned)min((size_t)0xF0000000u, g.ebytes() + 4096));
@@ -1052,6 +1059,7 @@ struct TrRec {
 	uint32_t slab_off;      // 8-byte units
 	uint32_t row_cap;       // columns reserved per row
 	unsigned long long row_off;   // byte offset of the record's three rows in the row pool
+	int32_t q_start, q_end; // query bounds of a chain-mode fragment (name ends in \0, start, end: assembly.c:1916-1923); else 0, q_len
 };
 
 __host__ __device__ __forceinline__ uint32_t tr_stride(const TrRec &R) { return slab_W(R.words) + slab_B(R.q_len) + slab_N(R.nN); }
@@ -1083,6 +1091,11 @@ __global__ void __launch_bounds__(256) tr_sizes_kernel(const uint8_t *__restrict
 		R.words = (R.q_len + 31) >> 5;
 		R.row_cap = 3u * (uint32_t)R.q_len + 256u;
 		R.slab_off = 0; R.row_off = 0;
+		R.q_start = 0; R.q_end = R.q_len;
+		if (9 < R.hl) {
+			const uint8_t *he = q + R.q_len + R.hl;
+			if (he[-9] == 0) { R.q_start = (int)ld_u32u(he - 8); R.q_end = (int)ld_u32u(he - 4); }
+		}
 		if (lane == 0) {
 			if (R.tmpl <= 0 || R.tmpl >= DB_size) atomicAdd(&ctr[A_BAD], 1ull);
 			recs[r] = R;
@@ -1139,20 +1152,32 @@ __global__ void __launch_bounds__(256) tr_prep_kernel(const uint8_t *__restrict_
 // KMA (align.c:214-507): MEMs (found here with the byte-read scan unless n != 0), chain, stitch with NW -- writing the
 // aligned rows. *ncol = columns written (0 when nothing aligned).
 __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTIndexView &ix, const KgTMeta &m, const QView &q,
-                              int nN1, int q_len, Mems &M, int n, NwStat *out, const NwRows &rows, int row_cap, int *ncol) {
+                              int nN1, int q_len, int q_start, int q_end, Mems &M, int n, NwStat *out, const NwRows &rows, int row_cap, int *ncol) {
 	const int lane = threadIdx.x & 31;
 	const int k = ix.k, t_len = m.len, U = P.pen.U, Mv = P.pen.M;
 	NwStat s = {0, 1, 0, 0, 0, 0};
 	*ncol = 0;
 	if (!n) {
 		int dummy;
-		if (scan_mems<0, true>(ix, m, c.tseq, q, nN1, q_len, 0, q_len, M, n, dummy, *c.wc)) return ST_OVERFLOW;
+		if (scan_mems<0, true>(ix, m, c.tseq, q, nN1, q_len, q_start, q_end, M, n, dummy, *c.wc)) return ST_OVERFLOW;
 	}
 	KG_STAT(c.wc->mems += (unsigned long long)n;)
 	if (!n) { *out = s; return ST_OK; }
 	unsigned mapQ = 0;
 	int start = chain_warp(*c.pen, M, n, q_len, t_len, k, &mapQ, P.mq != 0);
 	if ((P.mq != 0 && mapQ < (unsigned)P.mq) || M.sc(start) < k) { *out = s; return ST_OK; }
+	if (P.ts) {   // trimSeeds (chain.c:496-538): the first ts bases of every seed of the chain go back to the DP
+		__syncwarp();
+		if (lane == 0) {
+			int cidx = start;
+			if (!M.qS(cidx)) cidx = M.nx(cidx);
+			for (; cidx; cidx = M.nx(cidx)) {
+				const int len = M.qE(cidx) - M.qS(cidx), cut = len < P.ts ? len - 1 : P.ts;
+				M.tS(cidx) += cut; M.qS(cidx) += cut;
+			}
+		}
+		__syncwarp();
+	}
 	auto nw_rows = [&](int kk, int t_s, int t_e, int q_s, int q_e, int at, NwStat *a) -> int {
 		if (at + (t_e - t_s) + (q_e - q_s) + 8 > row_cap) return ST_ROWS;
 		const int t_l = t_e - t_s, q_l = q_e - q_s;
@@ -1337,10 +1362,11 @@ __global__ void __launch_bounds__(AL_WARPS * 32, AL_MINB) tr_task_kernel(AlnPara
 		if (!go) {   // anker_rc (align.c:780-991)
 			const QView qf = tr_view(slab, R, 0), qr = tr_view(slab, R, 1);
 			int sf = 0, sr = 0, nf = 0, ntot;
-			const bool pre = P.exhaustive || preseed_hit(ix, m, qf.b, q_len, q_len);
-			if (pre) st = scan_mems<1, true>(ix, m, c.tseq, qf, nN1, q_len, 0, q_len, M, nf, sf, wc);
+			// query bounds (chain-mode fragments): a lower bound skips preseed, the reverse strand sees them mirrored (align.c:806-817)
+			const bool pre = R.q_start || P.exhaustive || preseed_hit(ix, m, qf.b, q_len, R.q_end - R.q_start);
+			if (pre) st = scan_mems<1, true>(ix, m, c.tseq, qf, nN1, q_len, R.q_start, R.q_end, M, nf, sf, wc);
 			ntot = nf;
-			if (!st) st = scan_mems<1, true>(ix, m, c.tseq, qr, nN1, q_len, 0, q_len, M, ntot, sr, wc);
+			if (!st) st = scan_mems<1, true>(ix, m, c.tseq, qr, nN1, q_len, q_len - R.q_end, q_len - R.q_start, M, ntot, sr, wc);
 			const int best = max(sf, sr);
 			if (!st) {
 				int turned = 0;
@@ -1362,7 +1388,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, AL_MINB) tr_task_kernel(AlnPara
 			rows.t = rowpool + R.row_off; rows.s = rows.t + R.row_cap; rows.q = rows.s + R.row_cap;
 			NwStat a = {0, 0, 0, 0, 0, 0};
 			int ncol = 0;
-			st = kma_trace_warp(P, c, ix, m, q, nN1, q_len, M, nmem, &a, rows, (int)R.row_cap, &ncol);
+			st = kma_trace_warp(P, c, ix, m, q, nN1, q_len, R.q_start, R.q_end, M, nmem, &a, rows, (int)R.row_cap, &ncol);
 			if (!st) {
 				const int aln_len = a.len, start = a.pos;
 				int end = start + aln_len - a.tGaps, read_score = a.score;
@@ -1501,7 +1527,7 @@ int kg_align_free(kmagpu_db *db) {
 	}
 	AlignBatch &b = db->aln;
 	KgBuf *all[] = {&b.d_in, &b.d_off, &b.d_reads, &b.d_slab, &b.d_sz, &b.d_partial, &b.d_taskread, &b.d_cand, &b.d_recsize,
-	                &b.d_out, &b.d_ctr, &b.d_scores, &b.d_scratch, &b.d_ovf, &b.d_res, &b.h_off, &b.d_probs, &b.d_order};
+	                &b.d_out, &b.d_ctr, &b.d_scores, &b.d_scratch, &b.d_ovf, &b.d_res, &b.h_off, &b.d_probs, &b.d_order, &b.d_sorttmp};
 	for (KgBuf *x : all) x->release();
 	return 0;
 }
@@ -1513,7 +1539,7 @@ static AlnParams make_params(const kmagpu_db *db, const kmagpu_params *p) {
 	memcpy(P.pen.d, p->d, sizeof(P.pen.d));
 	P.pen.d8 = 1;
 	for (int i = 0; i < 25; ++i) if (p->d[i] < -128 || p->d[i] > 127) P.pen.d8 = 0;
-	P.k = db->info.kmerindex; P.mq = p->mq; P.one2one = p->one2one; P.exhaustive = p->exhaustive; P.minlen = p->minlen; P.Wl = p->Wl; P.PE = p->PE; P.apm = p->apm;
+	P.k = db->info.kmerindex; P.mq = p->mq; P.one2one = p->one2one; P.exhaustive = p->exhaustive; P.minlen = p->minlen; P.Wl = p->Wl; P.PE = p->PE; P.apm = p->apm; P.ts = p->ts;
 	P.scoreT = p->scoreT; P.mrc = p->mrc; P.minFrac = p->minFrac;
 	return P;
 }
@@ -1597,18 +1623,23 @@ __device__ __forceinline__ void nwq_apply(int32_t *row, const NwStat &a, int k, 
 	atomicAdd(&row[1], a.score); atomicAdd(&row[2], a.len); atomicAdd(&row[4], a.match); atomicAdd(&row[5], a.tGaps); atomicAdd(&row[6], a.qGaps);
 }
 
-// classes 0-3: one thread per problem (nw_thread); the previous DP row of the CTA's 128 problems in shared memory
-// [column][thread], traceback bytes in a per-warp scratch [cell][lane]
+// classes 0-1: one thread per problem (nw_thread); the previous DP row and the query bases of the CTA's 128 problems in
+// shared memory [column][thread], traceback bytes in a per-warp scratch [cell][lane]
+template <int QMAX, bool D8>
 __global__ void __launch_bounds__(128) nw_thread_kernel(const NwPen pen, const KgTIndexView ix, const NwProb *__restrict__ probs,
 		const uint32_t *__restrict__ order, int n, const uint8_t *qbase, int qshift, int32_t *res, uint8_t *escratch, int ecells,
 		unsigned long long *ctr) {
-	extern __shared__ NwRow srows[];
+	extern __shared__ NwRow srows[];   // [QMAX][128] rows, then [QMAX][128] query bytes
 	__shared__ NwPen spen;
+	__shared__ unsigned long long stab[5];
 	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&pen)[threadIdx.x];
+	__syncthreads();
+	if (threadIdx.x < 5) stab[threadIdx.x] = nw_pack_row(spen, threadIdx.x);
 	__syncthreads();
 	const int tid = blockIdx.x * 128 + threadIdx.x, nthreads = gridDim.x * 128;
 	uint8_t *E = escratch + (size_t)(tid >> 5) * (size_t)ecells * 32 + (tid & 31);
 	NwRow *rows = srows + threadIdx.x;
+	uint8_t *qs = (uint8_t *)(srows + QMAX * 128) + threadIdx.x;
 	unsigned long long cells = 0;
 	unsigned calls = 0;
 	for (int idx = tid; idx < n; idx += nthreads) {
@@ -1618,8 +1649,10 @@ __global__ void __launch_bounds__(128) nw_thread_kernel(const NwPen pen, const K
 		if (status == ST_GIVEUP && k >= 0) continue;
 		const KgTMeta m = ix.meta[p.tmpl];
 		const int t_len = p.t_e - p.t_s, q_len = p.q_e - p.q_s;
+		const uint8_t *qlast = qbase + ((size_t)p.qoff << qshift) + p.q_e - 1;
+		for (int j = 0; j < q_len; ++j) qs[j * 128] = (uint8_t)(qlast[-j] << 3);
 		NwStat a;
-		nw_thread(spen, ix.seq + m.seq_off, p.t_s, t_len, qbase + ((size_t)p.qoff << qshift) + p.q_s, q_len, k, rows, 128, E, 32, &a);
+		nw_thread<D8>(spen, stab, ix.seq + m.seq_off, p.t_s, t_len, qs, 128, q_len, k, rows, 128, E, 32, &a);
 		nwq_apply(row, a, k, status);
 		cells += (unsigned long long)(t_len * q_len); ++calls;
 	}
@@ -1628,7 +1661,7 @@ __global__ void __launch_bounds__(128) nw_thread_kernel(const NwPen pen, const K
 	if ((threadIdx.x & 31) == 0 && calls) { atomicAdd(&ctr[A_FULL_CELLS], cells); atomicAdd(&ctr[A_FULL_CALLS], (unsigned long long)calls); }
 }
 
-// class 4: one warp per problem (nw_warp: row sweep for rows of up to 256 cells, the continuous wavefront beyond)
+// class 2: one warp per problem (nw_warp: row sweep for rows of up to 256 cells, the continuous wavefront beyond)
 __global__ void __launch_bounds__(AL_WARPS * 32) nw_warp_kernel(const NwPen pen, const KgTIndexView ix, const NwProb *__restrict__ probs,
 		const uint32_t *__restrict__ order, int n, const uint8_t *qbase, int qshift, int32_t *res, int32_t *status_out,
 		uint8_t *scratch, ScratchLayout lay, unsigned long long *ctr) {
@@ -1674,28 +1707,52 @@ __global__ void __launch_bounds__(AL_WARPS * 32) nw_warp_kernel(const NwPen pen,
 	}
 }
 
-// Solve the queued problems. counts[c] = problems of class c (their queue slots in order[c * cap ..)); need_e / need_q:
-// scratch the largest class-4 problem asked for. Uses (and may grow) the batch's per-warp scratch buffer.
-static int nw_queue_run(kmagpu_db *db, const AlnParams &P, const NwProb *probs, const uint32_t *order, size_t cap, const unsigned long long *counts,
-                        size_t need_e, int need_q, const uint8_t *qbase, int qshift, int32_t *res, int32_t *status_out, unsigned long long *ctr,
-                        int *launches) {
+// Solve the queued problems. counts[c] = problems of class c (their queue slots in order[c * cap ..), their cell counts
+// in cells[c * cap ..) for the thread classes; cells == NULL: the caller's order is sorted already). need_e / need_q:
+// scratch the largest class-2 problem asked for. sorted: 4 * cap uint32 of working space for the sort. Uses (and may
+// grow) the batch's per-warp scratch buffer.
+template <int QMAX, bool D8>
+static int nw_thread_launch(kmagpu_db *db, const AlnParams &P, const NwProb *probs, const uint32_t *order, int n, const uint8_t *qbase, int qshift,
+                            int32_t *res, int ecells, unsigned long long *ctr) {
+	const size_t smem = (size_t)QMAX * 128 * (sizeof(NwRow) + 1);
+	KG_CUDA(cudaFuncSetAttribute(nw_thread_kernel<QMAX, D8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int per_sm = 0;
+	KG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_thread_kernel<QMAX, D8>, 128, smem));
+	const int grid = std::max(1, std::min((n + 127) / 128, db->sm_count * std::max(per_sm, 1)));
+	KgBuf &scr = db->aln.d_scratch;
+	if (scr.reserve((size_t)grid * 4 * (size_t)ecells * 32)) return -1;
+	nw_thread_kernel<QMAX, D8><<<grid, 128, smem, db->stream>>>(P.pen, db->tix, probs, order, n, qbase, qshift, res, (uint8_t *)scr.p, ecells, ctr);
+	return 0;
+}
+
+static int nw_queue_run(kmagpu_db *db, const AlnParams &P, const NwProb *probs, const uint32_t *order, const uint32_t *cells, uint32_t *sorted,
+                        size_t cap, const unsigned long long *counts, size_t need_e, int need_q, const uint8_t *qbase, int qshift, int32_t *res,
+                        int32_t *status_out, unsigned long long *ctr, int *launches) {
 	cudaStream_t st = db->stream;
 	KgBuf &scr = db->aln.d_scratch;
-	KG_CUDA(cudaFuncSetAttribute(nw_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 128 * (int)sizeof(NwRow)));
-	for (int c = 0; c < 4; ++c) {
+	for (int c = 0; c < 2; ++c) {
 		const int n = (int)counts[c];
 		if (!n) continue;
-		const size_t smem = (size_t)nwq_qmax[c] * 128 * sizeof(NwRow);
-		int per_sm = 0;
-		KG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_thread_kernel, 128, smem));
-		const int grid = std::max(1, std::min((n + 127) / 128, db->sm_count * std::max(per_sm, 1)));
-		if (scr.reserve((size_t)grid * 4 * (size_t)nwq_cells[c] * 32)) return -1;
-		nw_thread_kernel<<<grid, 128, smem, st>>>(P.pen, db->tix, probs, order + (size_t)c * cap, n, qbase, qshift, res, (uint8_t *)scr.p,
-			nwq_cells[c], ctr);
+		const uint32_t *ord = order + (size_t)c * cap;
+		if (cells) {   // largest problems first, neighbours alike: a warp's lanes then finish together
+			uint32_t *ks = sorted + (size_t)(2 * c) * cap, *vs = ks + cap;
+			size_t tmp_bytes = 0;
+			cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, cells + (size_t)c * cap, ks, ord, vs, n, 0, 14, st);
+			if (db->aln.d_sorttmp.reserve(tmp_bytes + 256)) return -1;
+			cub::DeviceRadixSort::SortPairsDescending(db->aln.d_sorttmp.p, tmp_bytes, cells + (size_t)c * cap, ks, ord, vs, n, 0, 14, st);
+			ord = vs;
+			*launches += 3;
+		}
+		int rc;
+		if (c == 0) rc = P.pen.d8 ? nw_thread_launch<32, true>(db, P, probs, ord, n, qbase, qshift, res, nwq_cells[0], ctr)
+		                          : nw_thread_launch<32, false>(db, P, probs, ord, n, qbase, qshift, res, nwq_cells[0], ctr);
+		else rc = P.pen.d8 ? nw_thread_launch<64, true>(db, P, probs, ord, n, qbase, qshift, res, nwq_cells[1], ctr)
+		                   : nw_thread_launch<64, false>(db, P, probs, ord, n, qbase, qshift, res, nwq_cells[1], ctr);
+		if (rc) return -1;
 		++*launches;
 	}
-	if (counts[4]) {
-		const int n = (int)counts[4];
+	if (counts[2]) {
+		const int n = (int)counts[2];
 		ScratchLayout lay;
 		lay.mem_cap = 0; lay.q_cap = std::max(need_q, 256); lay.e_cap = (std::max<size_t>(need_e, 65536) + 255) & ~(size_t)255;
 		lay.stride = ((size_t)lay.q_cap * 12 + lay.e_cap + 255) & ~(size_t)255;
@@ -1707,7 +1764,7 @@ static int nw_queue_run(kmagpu_db *db, const AlnParams &P, const NwProb *probs, 
 		}
 		if (scr.reserve(lay.stride * (size_t)grid * AL_WARPS)) return -1;
 		KG_CUDA(cudaMemsetAsync(ctr + A_WORK, 0, 8, st));
-		nw_warp_kernel<<<grid, AL_WARPS * 32, 0, st>>>(P.pen, db->tix, probs, order + 4 * cap, n, qbase, qshift, res, status_out, (uint8_t *)scr.p, lay, ctr);
+		nw_warp_kernel<<<grid, AL_WARPS * 32, 0, st>>>(P.pen, db->tix, probs, order + 2 * cap, n, qbase, qshift, res, status_out, (uint8_t *)scr.p, lay, ctr);
 		++*launches;
 	}
 	return 0;
@@ -1778,9 +1835,11 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 		KG_CUDA(cudaEventRecord(db->ev[3], st));   // ms_align = the pair kernel(s) + the NW queue kernels; host-side sizing above is in ms_total
 		for (int attempt = 0;; ++attempt) {
 			if (b.prob_cap >= (1ull << 32)) { kmagpu_set_error("NW problem queue exceeds 2^32 entries; split the batch"); return -1; }
-			if (b.d_probs.reserve(sizeof(NwProb) * b.prob_cap) || b.d_order.reserve(4 * NWQ_CLASSES * b.prob_cap)) return -1;
+			// order[3][cap], cells[2][cap], 4 * cap of sorted keys / slots
+			if (b.d_probs.reserve(sizeof(NwProb) * b.prob_cap) || b.d_order.reserve(4 * 9 * b.prob_cap)) return -1;
 			NwQueue queue;
-			queue.probs = (NwProb *)b.d_probs.p; queue.order = (uint32_t *)b.d_order.p; queue.cap = (unsigned)b.prob_cap; queue.ctr = ctr;
+			queue.probs = (NwProb *)b.d_probs.p; queue.order = (uint32_t *)b.d_order.p; queue.cells = queue.order + 3 * b.prob_cap;
+			queue.cap = (unsigned)b.prob_cap; queue.ctr = ctr;
 			if (!prm->counters)   // production: no statistic counters (stats->mems, index_probes, mem_bases, read_bytes stay 0)
 				(short_reads ? kg_launch_pair_fast_short : kg_launch_pair_fast_long)(grid, st, &P, &db->tix, b.in, reads, (const uint64_t *)b.d_slab.p,
 					(const int32_t *)b.d_taskread.p, ntasks, nullptr, b.d_cand.p, (uint8_t *)b.d_scratch.p, &lay, ctr, (int32_t *)b.d_ovf.p, &queue);
@@ -1831,8 +1890,9 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 		h[A_OVF] = first_ovf;
 		// phase 2: the queued NW problems add their scores into the candidate rows
 		if (h[A_NPROB]) {
-			if (nw_queue_run(db, P, (const NwProb *)b.d_probs.p, (const uint32_t *)b.d_order.p, b.prob_cap, &h[A_PCLS], (size_t)h[A_NEED_E], (int)h[A_NEED_Q],
-			                 (const uint8_t *)b.d_slab.p, 3, (int32_t *)b.d_cand.p, nullptr, ctr, &launches)) return -1;
+			uint32_t *ord = (uint32_t *)b.d_order.p;
+			if (nw_queue_run(db, P, (const NwProb *)b.d_probs.p, ord, ord + 3 * b.prob_cap, ord + 5 * b.prob_cap, b.prob_cap, &h[A_PCLS],
+			                 (size_t)h[A_NEED_E], (int)h[A_NEED_Q], (const uint8_t *)b.d_slab.p, 3, (int32_t *)b.d_cand.p, nullptr, ctr, &launches)) return -1;
 		}
 		KG_CUDA(cudaEventRecord(db->ev[4], st));
 		unsigned long long h2[A_N];
@@ -2157,7 +2217,7 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 	const AlnParams P = make_params(db, p);
 	std::vector<NwProb> hp(n);
 	std::vector<uint32_t> horder(NWQ_CLASSES * n);
-	unsigned long long counts[NWQ_CLASSES] = {0, 0, 0, 0, 0};
+	unsigned long long counts[NWQ_CLASSES] = {0, 0, 0};
 	for (size_t i = 0; i < n; ++i) {
 		const int32_t *pr = prob + 8 * i;
 		if (pr[0] <= 0 || pr[0] >= db->info.DB_size || pr[1] < 0 || pr[2] < pr[1] || pr[2] > db->lengths[pr[0]] || pr[4] < 0 ||
@@ -2168,7 +2228,7 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 		const int t_l = pr[2] - pr[1], q_l = pr[5] - pr[4];
 		const int cls = nwq_class(t_l, q_l, pr[7]);
 		NwGeo g;
-		if (cls == 4 && t_l > 0 && q_l > 0 && nw_geo_init(g, P.pen, t_l, q_l, pr[6], pr[7], true)) {
+		if (cls == 2 && t_l > 0 && q_l > 0 && nw_geo_init(g, P.pen, t_l, q_l, pr[6], pr[7], true)) {
 			need_e = std::max(need_e, g.ebytes() + 256);
 			need_q = std::max(need_q, q_l + 64);
 		}
@@ -2177,6 +2237,9 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 		q.qoff = (uint32_t)pr[3];
 		horder[(size_t)cls * n + counts[cls]++] = (uint32_t)i;
 	}
+	for (int c = 0; c < 2; ++c)   // the thread classes sorted by cells, largest first (the alignment pass sorts on the device)
+		std::stable_sort(horder.begin() + (size_t)c * n, horder.begin() + (size_t)c * n + counts[c], [&](uint32_t x, uint32_t y) {
+			return (hp[x].t_e - hp[x].t_s) * (hp[x].q_e - hp[x].q_s) > (hp[y].t_e - hp[y].t_s) * (hp[y].q_e - hp[y].q_s); });
 	uint8_t *dq = nullptr;
 	NwProb *dprob = nullptr;
 	uint32_t *dorder = nullptr;
@@ -2197,7 +2260,7 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 	KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * A_N, st));
 	KG_CUDA(cudaEventRecord(db->ev[2], st));
 	int launches = 0;
-	const int rc = nw_queue_run(db, P, dprob, dorder, n, counts, need_e, need_q, dq, 0, dres, dstat, ctr, &launches);
+	const int rc = nw_queue_run(db, P, dprob, dorder, nullptr, nullptr, n, counts, need_e, need_q, dq, 0, dres, dstat, ctr, &launches);
 	KG_CUDA(cudaEventRecord(db->ev[3], st));
 	std::vector<int32_t> hres(8 * n);
 	unsigned long long hc[A_N];

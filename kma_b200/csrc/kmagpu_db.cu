@@ -8,6 +8,9 @@
 #include <errno.h>
 #include <string.h>
 #include <stdlib.h>
+#include <mutex>
+
+static std::mutex g_image_mutex;
 
 static thread_local char g_err[1024] = "";
 
@@ -84,6 +87,7 @@ extern "C" int kmagpu_db_open(const char *prefix, int device, kmagpu_db **out) {
 
 	kmagpu_db *db = new kmagpu_db();
 	db->device = device;
+	db->image = new KgImageRef();
 	std::vector<uint32_t> exist(size), keys, vidx;
 	std::vector<uint8_t> values(v_index * (vshort ? 2 : 4));
 	int bad = read_all(f, exist.data(), size * 4) || read_all(f, values.data(), values.size());
@@ -178,6 +182,27 @@ extern "C" int kmagpu_db_open(const char *prefix, int device, kmagpu_db **out) {
 	return 0;
 }
 
+// A second handle on the same HBM image: own stream, events and batch buffers (so that it can run concurrently with
+// the first from another host thread), no second copy of the hash table, the sequences or the position index.
+extern "C" int kmagpu_db_clone(kmagpu_db *src, kmagpu_db **out) {
+	if (!src || !out) { kmagpu_set_error("null argument"); return -1; }
+	*out = nullptr;
+	KG_CUDA(cudaSetDevice(src->device));
+	kmagpu_db *db = new kmagpu_db();
+	db->device = src->device; db->image = src->image; db->info = src->info; db->hv = src->hv;
+	db->d_exist = src->d_exist; db->d_kv = src->d_kv; db->d_values = src->d_values;
+	db->lengths = src->lengths; db->seq_off = src->seq_off;
+	db->d_seq = src->d_seq; db->d_lengths = src->d_lengths; db->d_seq_off = src->d_seq_off; db->seq_words = src->seq_words;
+	db->sm_count = src->sm_count; db->conclave_lc = src->conclave_lc;
+	db->d_tmeta = src->d_tmeta; db->d_tslots = src->d_tslots; db->d_tdups = src->d_tdups; db->tix = src->tix;
+	{ std::lock_guard<std::mutex> g(g_image_mutex); ++db->image->refs; }
+	bool ok = cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking) == cudaSuccess;
+	for (auto &e : db->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+	if (!ok) { kmagpu_db_close(db); kmagpu_set_error("stream / event creation failed"); return -1; }
+	*out = db;
+	return 0;
+}
+
 extern "C" void kmagpu_db_close(kmagpu_db *db) {
 	if (!db) return;
 	cudaSetDevice(db->device);
@@ -185,9 +210,17 @@ extern "C" void kmagpu_db_close(kmagpu_db *db) {
 	kg_stage1_free(db);
 	kg_memscore_free(db);
 	kg_align_free(db);
-	cudaFree(db->d_tmeta); cudaFree(db->d_tslots); cudaFree(db->d_tdups);
-	cudaFree(db->d_exist); cudaFree(db->d_kv); cudaFree(db->d_values);
-	cudaFree(db->d_seq); cudaFree(db->d_lengths); cudaFree(db->d_seq_off);
+	bool last = true;
+	if (db->image) {
+		std::lock_guard<std::mutex> g(g_image_mutex);
+		last = --db->image->refs == 0;
+		if (last) delete db->image;
+	}
+	if (last) {
+		cudaFree(db->d_tmeta); cudaFree(db->d_tslots); cudaFree(db->d_tdups);
+		cudaFree(db->d_exist); cudaFree(db->d_kv); cudaFree(db->d_values);
+		cudaFree(db->d_seq); cudaFree(db->d_lengths); cudaFree(db->d_seq_off);
+	}
 	cudaFree(db->d_mat); cudaFree(db->d_mat_off);
 	for (auto &e : db->ev) if (e) cudaEventDestroy(e);
 	if (db->stream) cudaStreamDestroy(db->stream);

@@ -99,6 +99,7 @@ struct RawBatch {
 struct AlignBatch {
 	KgBuf d_in, d_off, d_reads, d_slab, d_sz, d_partial, d_taskread, d_cand, d_recsize, d_out, d_ctr, d_scores,
 	      d_scratch, d_ovf, d_res;
+	KgBuf d_sorttmp;
 	KgBuf d_probs, d_order;        // NW problem queue of the phase-split alignment pass + its per-class order lists
 	size_t prob_cap = 0;           // queue capacity (grows to what a batch asked for, kept across calls)
 	KgBuf h_off;
@@ -110,8 +111,13 @@ struct AlignBatch {
 	std::vector<uint64_t> h_scores;
 };
 
+// The read-only database image in HBM is shared by every handle made from it with kmagpu_db_clone: the handles differ
+// in their stream, events and batch buffers only. The last handle to close frees the image.
+struct KgImageRef { int refs = 1; };
+
 struct kmagpu_db {
 	int device = 0;
+	KgImageRef *image = nullptr;
 	kmagpu_db_info info{};
 	KgHashView hv{};
 	void *d_exist = nullptr, *d_kv = nullptr, *d_values = nullptr;

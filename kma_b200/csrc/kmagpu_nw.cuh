@@ -485,42 +485,49 @@ NW_HD int nw_thread_e_at(const uint8_t *E, size_t estride, int t_len, int q_len,
 	return E[((size_t)(t_len - 1 - m) * (size_t)q_len + (size_t)(q_len - 1 - qpos)) * estride];
 }
 
-NW_HD void nw_thread(const NwPen &pen, const uint64_t *tseq, int t_s, int t_len, const uint8_t *q, int q_len, int k,
-                     NwRow *rows, int rstride, uint8_t *E, size_t estride, NwStat *out) {
+// qs: the window's query bases in FILL order (qs[j * qstride] = 8 * q[q_len - 1 - j]: the shift that selects the
+// substitution byte), staged by the caller next to `rows`. D8: the substitution rows fit signed bytes (pen.d8) and
+// tab[tn] = nw_pack_row(pen, tn).
+template <bool D8>
+NW_HD void nw_thread(const NwPen &pen, const unsigned long long *tab, const uint64_t *tseq, int t_s, int t_len, const uint8_t *qs,
+                     int qstride, int q_len, int k, NwRow *rows, int rstride, uint8_t *E, size_t estride, NwStat *out) {
 	const int W1 = pen.W1, U = pen.U;
 	const int NEG = (t_len + q_len) * (pen.MM + U + W1);
-	const uint8_t *qlast = q + q_len - 1;
 	for (int j = 0; j < q_len; ++j) { NwRow r; r.D = k == 2 ? 0 : W1 + j * U; r.P = NEG; rows[(size_t)j * rstride] = r; }
 	int colBest = NEG, colBestI = 0x7fffffff;
 	// ONE loop over the cells in fill order (row by row): the 32 problems of a warp stay in lock step however their
-	// shapes differ, and the warp takes max(cells) iterations instead of max(t_len) * max(q_len)
+	// shapes differ, and the warp takes max(cells) iterations instead of max(t_len) * max(q_len). The cell is the
+	// recurrence of nw.c:166-212 in closed form (see the row sweep above): the vertical run wins against the horizontal
+	// one iff P >= Q + [P opened here]; the winner's code is 5 - [P opened] or 3 - [Q opened]; the diagonal wins ties.
 	uint8_t *e = E;
 	NwRow *rp = rows;
+	const uint8_t *qp = qs;
 	int i = 0, j = 0, tn = 0, Dleft = 0, Qleft = 0, Ddiag = 0;
 	unsigned long long drow = 0;
 	for (int c = t_len * q_len; c > 0; --c, e += estride) {
 		if (j == 0) {   // a new row: template base, what lies beside and diagonal to its first cell
 			tn = nw_nuc(tseq, t_s + t_len - 1 - i);
-			drow = nw_pack_row(pen, tn);
+			if (D8) drow = tab[tn];
 			Dleft = 0 < k ? 0 : W1 + i * U; Qleft = NEG;
 			Ddiag = i == 0 ? 0 : (0 < k ? 0 : W1 + (i - 1) * U);
-			rp = rows;
+			rp = rows; qp = qs;
 		}
-		const int qn = qlast[-j];
+		const int q8 = *qp;
 		const NwRow a = *rp;
-		const int sub = pen.d8 ? (int)(signed char)(drow >> (qn << 3)) : pen.d[tn * 5 + qn];
-		int Q = Dleft + W1, P = a.D + W1, D, ec, fl = 0, x;
-		if (Q < P) { D = P; ec = 4; } else { D = Q; ec = 2; }
-		x = Qleft + U;
-		if (Q < x) { Q = x; if (D <= x) { D = x; ec = 3; } } else fl |= 16;
-		x = a.P + U;
-		if (P < x) { P = x; if (D <= x) { D = x; ec = 5; } } else fl |= 32;
-		x = Ddiag + sub;
-		if (D <= x) { D = x; ec = 1; }
-		*e = (uint8_t)(fl | ec);
+		const int sub = D8 ? (int)(signed char)(drow >> q8) : pen.d[tn * 5 + (q8 >> 3)];
+		const int Qo = Dleft + W1, Qe = Qleft + U, Po = a.D + W1, Pe = a.P + U, dg = Ddiag + sub;
+		const bool qo = Qo >= Qe, po = Po >= Pe;
+		const int Q = qo ? Qo : Qe, P = po ? Po : Pe;
+		const bool pw = P - (po ? 1 : 0) >= Q;
+		const int D1 = pw ? P : Q;
+		int ec = pw ? (po ? 4 : 5) : (qo ? 2 : 3);
+		const bool dw = D1 <= dg;
+		const int D = dw ? dg : D1;
+		if (dw) ec = 1;
+		*e = (uint8_t)(ec | (qo ? 16 : 0) | (po ? 32 : 0));
 		NwRow o; o.D = D; o.P = P;
 		*rp = o;
-		rp += rstride;
+		rp += rstride; qp += qstride;
 		Ddiag = a.D; Dleft = D; Qleft = Q;
 		if (++j == q_len) {
 			if (k < 0 && colBest < D) { colBest = D; colBestI = i; }   // the row's cell at the query start competes (nw.c:217-220)
@@ -532,22 +539,22 @@ NW_HD void nw_thread(const NwPen &pen, const uint64_t *tseq, int t_s, int t_len,
 		if (colBestI == 0x7fffffff) score = NEG; else { best_m = t_len - 1 - colBestI; score = colBest; }
 		if (k == -2) {   // last maximum along row m = 0 (nw.c:235-243)
 			int rb = NEG, rq = -1;
-			for (int qp = 0; qp < q_len; ++qp) { const int v = rows[(size_t)(q_len - 1 - qp) * rstride].D; if (rq < 0 || v >= rb) { rb = v; rq = qp; } }
+			for (int qp2 = 0; qp2 < q_len; ++qp2) { const int v = rows[(size_t)(q_len - 1 - qp2) * rstride].D; if (rq < 0 || v >= rb) { rb = v; rq = qp2; } }
 			if (rq >= 0 && score <= rb) { score = rb; best_m = 0; best_q = rq; }
 		}
 	} else score = rows[(size_t)(q_len - 1) * rstride].D;
 	NwStat s;
 	s.len = s.match = s.tGaps = s.qGaps = 0;
-	int m = best_m, qp = best_q, c;
-	while ((c = nw_thread_e_at(E, estride, t_len, q_len, k, m, qp)) != 0) {   // nw.c:850-887
+	int m = best_m, qpos = best_q, c;
+	while ((c = nw_thread_e_at(E, estride, t_len, q_len, k, m, qpos)) != 0) {   // nw.c:850-887
 		const int d = c & 7;
-		if (d == 1) { ++s.match; ++m; ++qp; }
+		if (d == 1) { ++s.match; ++m; ++qpos; }
 		else if (d >= 4) {
-			while (!(nw_thread_e_at(E, estride, t_len, q_len, k, m, qp) >> 4)) { ++m; ++s.len; ++s.qGaps; }
+			while (!(nw_thread_e_at(E, estride, t_len, q_len, k, m, qpos) >> 4)) { ++m; ++s.len; ++s.qGaps; }
 			++s.qGaps; ++m;
 		} else {
-			while (!(nw_thread_e_at(E, estride, t_len, q_len, k, m, qp) >> 3)) { ++qp; ++s.len; ++s.tGaps; }
-			++s.tGaps; ++qp;
+			while (!(nw_thread_e_at(E, estride, t_len, q_len, k, m, qpos) >> 3)) { ++qpos; ++s.len; ++s.tGaps; }
+			++s.tGaps; ++qpos;
 		}
 		++s.len;
 	}

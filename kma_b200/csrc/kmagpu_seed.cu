@@ -837,7 +837,13 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 	b.ran = true;
 	b.out_nrec = 0; b.out_recoff = nullptr;
 	if (n == 0) return 0;
-	if (prm->kmerscan == 1) return kg_chain_run(db, prm, stats);
+	// kmerScan (save_kmers_chain) only sees single reads; read pairs always go through save_kmers_pair (savekmers.c:196-199)
+	const bool all_pairs = b.npairs > 0 && 2 * b.npairs == b.nreads;
+	if (prm->kmerscan == 1 && b.npairs > 0 && !all_pairs) {
+		kmagpu_set_error("chain mode: a batch mixes single reads and read pairs; hand them over in runs of one kind");
+		return -1;
+	}
+	if (prm->kmerscan == 1 && !all_pairs) return kg_chain_run(db, prm, stats);
 	if (prm->kmerscan != 0) { kmagpu_set_error("kmerscan %d: only save_kmers (0) and save_kmers_chain (1) are built", prm->kmerscan); return -1; }
 	SeedParams sp = {prm->M, prm->MM, prm->U, prm->W1, prm->exhaustive};
 	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;

@@ -1,7 +1,7 @@
 """Host-side driver of the mapping core for one GPU: what the reference's stage drivers (save_kmers_batch kmers.c:51,
 runKMA's alignment loop runkma.c:291-445) do with T pthreads over a shared FILE*, done here with a few host threads
-that each own one TemplateDB handle (own CUDA stream and batch buffers, database image shared read-only semantics but
-replicated per handle) and take the chunks of a record stream in turn. While one chunk's frag_raw stream is on its way
+that each own one TemplateDB handle (own CUDA stream and batch buffers; the handles are clones of one another and share
+ONE read-only database image in HBM, kmagpu_db_clone) and take the chunks of a record stream in turn. While one chunk's frag_raw stream is on its way
 back over PCIe, the next chunk's records are being walked / uploaded and a third is in the kernels -- the copies hide
 behind the compute instead of adding to it. Output order is chunk order = input order."""
 from __future__ import annotations
@@ -15,7 +15,8 @@ from . import api
 
 class MapPipeline:
     def __init__(self, prefix: str, device: int = 0, workers: int = 2, params=None):
-        self.dbs = [api.TemplateDB(prefix, device) for _ in range(workers)]
+        first = api.TemplateDB(prefix, device)
+        self.dbs = [first] + [first.clone() for _ in range(workers - 1)]   # one image per GPU however many workers
         self.params = params or api.default_params()
         self.info = self.dbs[0].info
 

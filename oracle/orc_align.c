@@ -824,14 +824,16 @@ static int scan_bytes(const tindex *ix, const uint8_t *q, int q_len, int q_start
 
 /* anker_rc (align.c:780-991): MEMs of the byte read on both strands, the better strand's MEMs stay in pt and the read
  * is left in that orientation. Returns the winning strand score (0: nothing). */
-static int pick_strand_bytes(const tindex *ix, uint8_t *q, int q_len, int one2one, int exhaustive, mems_t *pt) {
+static int pick_strand_bytes(const tindex *ix, uint8_t *q, int q_len, int q_start, int q_end, int one2one, int exhaustive, mems_t *pt) {
 	const int k = ix->k;
 	int sf = 0, sr = 0;
 	pt->len = 0;
-	int first = exhaustive || preseed_hit(ix, q, q_len, q_len) ? 0 : q_len;   /* preseed returns 0 on a hit, >= q_len otherwise */
-	int nf = scan_bytes(ix, q, q_len, 0, q_len, 1, pt, 0, first, &sf);
+	/* align.c:813-817: a lower query bound skips preseed; preseed returns 0 on a hit, >= q_len otherwise */
+	int first = q_start ? q_start : (exhaustive || preseed_hit(ix, q, q_len, q_end - q_start) ? 0 : q_len);
+	int nf = scan_bytes(ix, q, q_len, q_start, q_end, 1, pt, 0, first, &sf);
 	bytes_rc(q, q_len);
-	int ntot = scan_bytes(ix, q, q_len, 0, q_len, 1, pt, nf, 0, &sr);
+	/* the bounds mirrored (align.c:808-812) */
+	int ntot = scan_bytes(ix, q, q_len, q_len - q_end, q_len - q_start, 1, pt, nf, q_len - q_end, &sr);
 	int best = sf < sr ? sr : sf;
 	if (one2one && best < k && best * k < (q_len - k - best)) { pt->len = 0; return 0; }   /* read stays reverse-complemented */
 	if (best == sf) { bytes_rc(q, q_len); pt->len = nf; return best; }
@@ -862,17 +864,34 @@ static aln_t nw_auto_str(const orc_params *p, nw_ws *w, const uint64_t *tseq, co
 }
 
 /* KMA (align.c:214-507): seed, chain, stitch -- with the aligned rows. tb->a receives t/s/q, tb->len columns. */
-static aln_t kma_trace(const orc_params *p, nw_ws *w, const tindex *ix, const uint8_t *q, int q_len, int mq, mems_t *pt, trace_buf *tb) {
+/* -ts (trimSeeds, chain.c:496-538; called by KMA only, align.c:413) */
+static int g_trim_seeds = 0;
+void orc_trace_set_ts(int ts) { g_trim_seeds = ts; }
+
+static aln_t kma_trace(const orc_params *p, nw_ws *w, const tindex *ix, const uint8_t *q, int q_len, int q_start, int q_end, int mq, mems_t *pt, trace_buf *tb) {
 	const int k = ix->k, t_len = ix->len, U = p->U, M = p->M;
 	tb_reserve(tb, 2 * q_len + 2 * BANDW + 64);
 	tb->len = 0;
 	int n = pt->len;
-	if (!n) n = scan_bytes(ix, q, q_len, 0, q_len, 0, pt, 0, 0, 0);
+	if (!n) n = scan_bytes(ix, q, q_len, q_start, q_end, 0, pt, 0, q_start, 0);
 	pt->len = n;
 	if (!n) return aln_zero();
 	unsigned mapQ = 0;
 	int start = chain_mems(p, pt, q_len, t_len, k, &mapQ);
 	if (mapQ < (unsigned)mq || pt->score[start] < k) { pt->len = 0; return aln_zero(); }
+
+	/* trimSeeds (chain.c:496-538): the first ts bases of every seed of the chain go back to the DP (all but one base of a
+	 * seed shorter than ts); the first seed keeps its start when it begins at the query start */
+	if (g_trim_seeds) {
+		int c = start;
+		if (!pt->qStart[c]) c = pt->next[c];
+		for (; c; c = pt->next[c]) {
+			int len = pt->qEnd[c] - pt->qStart[c];
+			const int cut = len < g_trim_seeds ? len - 1 : g_trim_seeds;
+			pt->tStart[c] += cut; pt->qStart[c] += cut;
+			if (!pt->next[c]) break;
+		}
+	}
 
 	/* leading tail (leadTailAln with Frag_align, align.c:53-138): leading gap columns are trimmed when the window
 	 * starts at the template start */
@@ -985,15 +1004,18 @@ int orc_trace_stream(orc_db *db, const char *prefix, const orc_params *p, const 
 		tb.len = 0;
 		pt.len = 0;
 		int go = read_score != 0;
+		/* q-bound of chain-mode records (assembly.c:1916-1923) */
+		int q_start = 0, q_end = q_len;
+		if (9 < hl && in[ip - 9] == 0) { memcpy(&q_start, in + ip - 8, 4); memcpy(&q_end, in + ip - 4, 4); }
 		if (!go) {
 			uint8_t first = q_len ? q[0] : 0, last = q_len ? q[q_len - 1] : 0;
-			go = pick_strand_bytes(ix, q, q_len, one2one, p->exhaustive, &pt) != 0;
+			go = pick_strand_bytes(ix, q, q_len, q_start, q_end, one2one, p->exhaustive, &pt) != 0;
 			/* did the read end up reverse-complemented? compare with a fresh copy */
 			r[10] = q_len && memcmp(q, in + ip - hl - q_len, q_len) != 0;
 			(void)first; (void)last;
 		}
 		if (go) {
-			aln_t a = kma_trace(p, &ws, ix, q, q_len, mq, &pt, &tb);
+			aln_t a = kma_trace(p, &ws, ix, q, q_len, q_start, q_end, mq, &pt, &tb);
 			int aln_len = a.len, start = a.pos, end = start + aln_len - a.tGaps;
 			if (t_len < end) end -= t_len;
 			read_score = a.score;

@@ -70,6 +70,7 @@ static int trace_main(int argc, char **argv) {
 		if (!strcmp(argv[a], "-1t1")) one2one = 1;
 		else if (!strcmp(argv[a], "-dense")) dense = 1;
 		else if (!strcmp(argv[a], "-mat") && a + 1 < argc) mat_path = argv[++a];
+		else if (!strcmp(argv[a], "-ts") && a + 1 < argc) ts = atoi(argv[++a]);   /* kma.c:571 */
 	}
 	char path[4096];
 	int *template_lengths; long unsigned *as, *uas;
@@ -110,7 +111,14 @@ static int trace_main(int argc, char **argv) {
 		if (qsize < q_len + 64) { qsize = 2 * q_len + 64; qseq = realloc(qseq, qsize); orig = realloc(orig, qsize); }
 		if (fread(qseq, 1, q_len, in) != (size_t)q_len) break;
 		memcpy(orig, qseq, q_len);
-		fseek(in, hl, SEEK_CUR);
+		/* q-bound of chain-mode records, as assemble_KMA reads it (assembly.c:1916-1923) */
+		int q_start = 0, q_end = q_len;
+		{
+			unsigned char *hb = malloc(hl + 1);
+			if (fread(hb, 1, hl, in) != (size_t)hl) break;
+			if (2 * sizeof(int) + 1 < (size_t)hl && hb[hl - 2 * sizeof(int) - 1] == 0) { memcpy(&q_start, hb + hl - 8, 4); memcpy(&q_end, hb + hl - 4, 4); }
+			free(hb);
+		}
 		if (delta < q_len) {
 			delta = q_len << 1;
 			aligned->t = realloc(aligned->t, (delta + 1) << 1); aligned->s = realloc(aligned->s, (delta + 1) << 1); aligned->q = realloc(aligned->q, (delta + 1) << 1);
@@ -121,11 +129,11 @@ static int trace_main(int argc, char **argv) {
 		int t_len = template_lengths[template];
 		int r[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, len = 0;
 		points->len = 0;
-		int go = read_score || anker_rc(ti, qseq, q_len, 0, q_len, points);
+		int go = read_score || anker_rc(ti, qseq, q_len, q_start, q_end, points);
 		r[10] = memcmp(orig, qseq, q_len) != 0;
 		if (go) {
 			if (st3 <= st2) { st2 = 0; st3 = t_len; }
-			AlnScore a = KMA(ti, qseq, q_len, 0, q_len, aligned, gap_align, st2, t_len < st3 ? t_len : st3, mq, scoreT, points, NWm);
+			AlnScore a = KMA(ti, qseq, q_len, q_start, q_end, aligned, gap_align, st2, t_len < st3 ? t_len : st3, mq, scoreT, points, NWm);
 			int aln_len = a.len, start = a.pos, end = start + aln_len - a.tGaps;
 			double score;
 			if (t_len < end) end -= t_len;

@@ -140,8 +140,12 @@ extern "C" int emu_nw_thread(const int *pen29, const uint64_t *tseq, const uint8
 	NwStat s;
 	if (nw_trivial(pen, t_len, q_len, s)) { memcpy(out6, &s, 24); return 0; }
 	std::vector<NwRow> rows((size_t)q_len * stride + 1, NwRow{0x3fffffff, 0x3fffffff});
-	std::vector<uint8_t> E((size_t)t_len * q_len * stride + 1, 0xEE);
-	nw_thread(pen, tseq, t_s, t_len, query + q_s, q_len, k, rows.data(), stride, E.data(), (size_t)stride, &s);
+	std::vector<uint8_t> E((size_t)t_len * q_len * stride + 1, 0xEE), qs((size_t)q_len * stride + 1, 0xEE);
+	for (int j = 0; j < q_len; ++j) qs[(size_t)j * stride] = (uint8_t)(query[q_s + q_len - 1 - j] << 3);   // what the kernel stages
+	unsigned long long tab[5];
+	for (int tn = 0; tn < 5; ++tn) tab[tn] = nw_pack_row(pen, tn);
+	if (d8) nw_thread<true>(pen, tab, tseq, t_s, t_len, qs.data(), stride, q_len, k, rows.data(), stride, E.data(), (size_t)stride, &s);
+	else nw_thread<false>(pen, tab, tseq, t_s, t_len, qs.data(), stride, q_len, k, rows.data(), stride, E.data(), (size_t)stride, &s);
 	if (emap)
 		for (int c = 0; c < t_len * q_len; ++c) emap[c] = E[(size_t)c * stride];
 	memcpy(out6, &s, 24);
