@@ -182,7 +182,9 @@ int __wrap_save_kmers_batch(char *templatefilename, char *exePrev, unsigned shm,
 		/* a stage-2 record is its stage-1 record + 12 header bytes + 4 bytes per template; chain mode may emit several
 		   per read */
 		obuf = shim_grow(obuf, &ocap, 4 * fill + (64u << 20));
+		SHIM_TRACE("stage 2: %zu bytes of records -> device", fill);
 		if (kmagpu_seed_batch(db, &prm, buf, fill, obuf, ocap, &obytes, &n, 0)) shim_die("kmagpu_seed_batch");
+		SHIM_TRACE("stage 2: %lld reads, %zu bytes of stage-2 records", (long long)n, obytes);
 		sfwrite(obuf, 1, obytes, out);
 		total += n;
 		fill = 0;
@@ -245,8 +247,10 @@ void *__wrap_alnFrags_threaded(void *arg) {
 		}
 		if (!fill) break;
 		obuf = shim_grow(obuf, &ocap, 5 * fill + (16u << 20));
+		SHIM_TRACE("alignment pass: %zu bytes of stage-2 records -> device", fill);
 		if (kmagpu_align_batch(db, &prm, buf, fill, obuf, ocap, &obytes, (uint64_t *)thr->alignment_scores, (uint64_t *)thr->uniq_alignment_scores,
 		                       0, 0, 0, 0)) shim_die("kmagpu_align_batch");
+		SHIM_TRACE("alignment pass: %zu bytes of frag_raw", obytes);
 		sfwrite(obuf, 1, obytes, thr->frag_out_raw);
 		fill = 0;
 	}
@@ -332,6 +336,7 @@ static int shim_next_chunk(void) {
 	if (!n) return 0;
 	/* per fragment 48 bytes + three rows of at most 3 * q_len + 256 columns (the library's row capacity) */
 	g_tr.out[c] = shim_grow(g_tr.out[c], &g_tr.out_cap[c], 9 * fill + 1024 * n + 4096);
+	SHIM_TRACE("assembly: template %d, %zu fragments (%zu bytes) -> device", g_tr.template, n, fill);
 	if (kmagpu_trace_batch(g_db_aln, &g_tr.prm, g_tr.in[c], fill, g_tr.out[c], g_tr.out_cap[c], &obytes, &nrec, 0)) shim_die("kmagpu_trace_batch");
 	if ((size_t)nrec != n) { fprintf(stderr, "kma (GPU host): fragment count mismatch\n"); exit(1); }
 	if (g_tr.frag_cap[c] < n) {

@@ -302,6 +302,29 @@ int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, const int32
  * offsets[0..min(count, cap)) when offsets != NULL and the bytes they span in *used. -1 on a corrupt header. */
 int64_t kmagpu_record_walk(int stage, const void *buf, size_t nbytes, uint64_t *offsets, size_t cap, size_t *used);
 
+/* ------------------------------------------------------------------ multi-GPU exchange
+ * One process per GPU, reads sharded by rank, database replicated. The only exchanges of the path are sums over ranks,
+ * done with ncclAllReduce INSIDE the library, in place in HBM, on the handle's stream (NCCL is bound at run time with
+ * dlopen; a single-GPU host never loads it):
+ *   - alignment_scores / uniq_alignment_scores [DB_size] (runkma.c:98-99), which update_Scores adds to per read
+ *     (updatescores.c:228/276) and ConClave's choice pass reads as GLOBAL sums (conclave.c:80-123);
+ *   - the base-count matrix of the assembly pass (assembly.c:1436: +1 per aligned base; unsaturated uint32 sums commute).
+ * kmagpu_comm_unique_id: rank 0 makes the 128-byte NCCL id, the host hands it to the other ranks (file, MPI, TCP store ...);
+ * kmagpu_comm_init: every rank, once per handle (world = 1: no communicator, the reductions below are no-ops).
+ * kmagpu_scores_reset: start the run-wide device accumulators of this handle; every kmagpu_align_run / kmagpu_memscore_*
+ *   then also adds its batch sums to them. kmagpu_allreduce_scores sums them over ranks (ms = device time of the
+ *   all-reduce) and optionally copies them out; kmagpu_conclave_* with alignment_scores = uniq_alignment_scores = NULL
+ *   reads them on the device -- the score arrays never leave HBM between the alignment pass and ConClave.
+ * kmagpu_allreduce_matrix: the handle's base-count matrix, in place. kmagpu_allreduce_u64: any host array of counters
+ *   (w_scores ...), the generic export of SURVEY 8b(5). */
+int kmagpu_comm_unique_id(void *id128, size_t cap);
+int kmagpu_comm_init(kmagpu_db *db, const void *id128, int rank, int world);
+void kmagpu_comm_destroy(kmagpu_db *db);
+int kmagpu_scores_reset(kmagpu_db *db);
+int kmagpu_allreduce_scores(kmagpu_db *db, uint64_t *alignment_scores, uint64_t *uniq_alignment_scores, float *ms);
+int kmagpu_allreduce_matrix(kmagpu_db *db, float *ms);
+int kmagpu_allreduce_u64(kmagpu_db *db, uint64_t *buf, size_t n);
+
 /* hashMap_get (hashmapkma.h:58; hashMap_getGlobal hashmapkma.c:149 / megaMap_getGlobal :264) over
  * a batch of k-mers: out[i] = offset of the template list inside values[], or -1. Test hook. */
 int kmagpu_lookup_batch(kmagpu_db *db, const uint64_t *kmers, size_t n, int64_t *out);

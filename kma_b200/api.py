@@ -129,6 +129,14 @@ def lib():
         L.kmagpu_db_close.argtypes = [C.c_void_p]
         L.kmagpu_db_close.restype = None
         L.kmagpu_db_clone.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.kmagpu_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+        L.kmagpu_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.kmagpu_comm_destroy.argtypes = [C.c_void_p]
+        L.kmagpu_comm_destroy.restype = None
+        L.kmagpu_scores_reset.argtypes = [C.c_void_p]
+        L.kmagpu_allreduce_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        L.kmagpu_allreduce_matrix.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.kmagpu_allreduce_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.kmagpu_db_get_info.argtypes = [C.c_void_p, C.POINTER(DbInfo)]
         L.kmagpu_default_params.argtypes = [C.POINTER(Params)]
         L.kmagpu_default_params.restype = None
@@ -222,6 +230,47 @@ class TemplateDB:
         if self._lengths is None:
             self._lengths = np.fromfile(self.prefix + ".length.b", dtype=np.int32)[1:]
         return self._lengths
+
+    # ---- multi-GPU exchange inside the library (kmagpu_comm.cu): NCCL all-reduces in place in HBM
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """rank 0: the 128-byte NCCL id every rank passes to comm_init"""
+        buf = C.create_string_buffer(128)
+        _check(lib().kmagpu_comm_unique_id(buf, 128))
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        _check(lib().kmagpu_comm_init(self._h, uid, rank, world))
+
+    def comm_init_torch(self):
+        """comm_init with the id broadcast over an initialised torch.distributed process group (host plumbing only)"""
+        import torch.distributed as td
+        rank, world = td.get_rank(), td.get_world_size()
+        box = [self.comm_unique_id() if rank == 0 else None]
+        td.broadcast_object_list(box, src=0)
+        self.comm_init(box[0], rank, world)
+
+    def scores_reset(self):
+        """start the run-wide ConClave accumulators of this handle on the device"""
+        _check(lib().kmagpu_scores_reset(self._h))
+
+    def allreduce_scores(self, download=True):
+        """sum the device-resident accumulators over ranks, in place -> (alignment_scores, uniq_alignment_scores, all-reduce ms)"""
+        ms = C.c_float()
+        a = np.zeros(self.info.DB_size, np.uint64) if download else None
+        u = np.zeros(self.info.DB_size, np.uint64) if download else None
+        _check(lib().kmagpu_allreduce_scores(self._h, a.ctypes.data if download else None, u.ctypes.data if download else None, C.byref(ms)))
+        return a, u, ms.value
+
+    def allreduce_matrix(self) -> float:
+        ms = C.c_float()
+        _check(lib().kmagpu_allreduce_matrix(self._h, C.byref(ms)))
+        return ms.value
+
+    def allreduce_u64(self, arr: np.ndarray):
+        assert arr.dtype == np.uint64 and arr.flags.c_contiguous
+        _check(lib().kmagpu_allreduce_u64(self._h, arr.ctypes.data, arr.size))
+        return arr
 
     def clone(self) -> "TemplateDB":
         """a further handle on the same HBM image (kmagpu_db_clone): own stream and batch buffers, for another host thread"""

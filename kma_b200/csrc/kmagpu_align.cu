@@ -1930,6 +1930,7 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 		(const AlnRes *)b.d_res.p, recoff, (uint8_t *)b.d_out.p);
 	++launches;
 	KG_CUDA(cudaEventRecord(db->ev[7], st));
+	kg_scores_accumulate(db, as);   // the run-wide sums on the device, for kmagpu_allreduce_scores / ConClave (kmagpu_scores_reset)
 	KG_CUDA(cudaMemcpyAsync(b.h_scores.data(), as, 16 * (size_t)DB, cudaMemcpyDeviceToHost, st));
 	KG_CUDA(cudaStreamSynchronize(st));
 	KG_CUDA(cudaGetLastError());

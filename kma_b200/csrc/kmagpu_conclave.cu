@@ -190,8 +190,13 @@ static int conclave_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff
 	unsigned long long *ctr = (unsigned long long *)d_ctr.p;
 	unsigned long long *w = (unsigned long long *)d_acc.p;
 	unsigned int *fc = (unsigned int *)(w + DB), *rcn = fc + DB;
-	KG_CUDA(cudaMemcpyAsync(as, alignment_scores, 8 * (size_t)DB, cudaMemcpyHostToDevice, st));
-	KG_CUDA(cudaMemcpyAsync(uas, uniq_alignment_scores, 8 * (size_t)DB, cudaMemcpyHostToDevice, st));
+	if (alignment_scores) {
+		KG_CUDA(cudaMemcpyAsync(as, alignment_scores, 8 * (size_t)DB, cudaMemcpyHostToDevice, st));
+		KG_CUDA(cudaMemcpyAsync(uas, uniq_alignment_scores, 8 * (size_t)DB, cudaMemcpyHostToDevice, st));
+	} else {   // the run-wide sums this handle holds on the device (kmagpu_scores_reset ... kmagpu_allreduce_scores): they never left HBM
+		if (!db->run_scores) { kmagpu_set_error("ConClave without score arrays needs the device-resident sums (kmagpu_scores_reset)"); return -1; }
+		KG_CUDA(cudaMemcpyAsync(as, db->d_run_scores.p, 16 * (size_t)DB, cudaMemcpyDeviceToDevice, st));
+	}
 	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
 	KG_CUDA(cudaMemsetAsync(d_acc.p, 0, 16 * (size_t)DB, st));
 	cc_choose_kernel<<<(n + 255) / 256, 256, 0, st>>>(din, doff, n, as, uas, db->d_lengths, DB,
@@ -231,10 +236,21 @@ static int conclave_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff
 	}
 	return 0;
 }
+// printFrags of a chunk without fragments: the terminator alone (what kmagpu_conclave_batch does for n == 0)
+static int conclave_empty(kmagpu_db *db, void *frags_out, size_t out_cap, size_t *out_bytes) {
+	if (out_bytes) *out_bytes = 4;
+	db->frg.valid = true; db->frg.n = 0; db->frg.bytes = 4;
+	if (!frags_out) return 0;
+	if (out_cap < 4) { kmagpu_set_error("fragment output needs 4 bytes"); return -1; }
+	const int32_t m1 = -1;
+	memcpy(frags_out, &m1, 4);
+	return 0;
+}
+
 extern "C" int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t nbytes, const uint64_t *alignment_scores,
                                      const uint64_t *uniq_alignment_scores, void *frags_out, size_t out_cap, size_t *out_bytes,
                                      uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts, int64_t *nrecords) {
-	if (!db || (!frag_raw && nbytes) || !alignment_scores || !uniq_alignment_scores) { kmagpu_set_error("null argument"); return -1; }
+	if (!db || (!frag_raw && nbytes) || (!alignment_scores != !uniq_alignment_scores)) { kmagpu_set_error("null argument"); return -1; }
 	db->frg.valid = false; db->frg.n = 0; db->frg.bytes = 0;
 	if (!db->d_lengths) { kmagpu_set_error("database has no template lengths (.length.b missing)"); return -1; }
 	if (nbytes >= (1ull << 32) - 64) { kmagpu_set_error("frag_raw batch of %zu bytes exceeds the 4 GiB per-call limit; split it", nbytes); return -1; }
@@ -276,7 +292,7 @@ extern "C" int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t
 extern "C" int kmagpu_conclave_resident(kmagpu_db *db, const uint64_t *alignment_scores, const uint64_t *uniq_alignment_scores, void *frags_out,
                                         size_t out_cap, size_t *out_bytes, uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts,
                                         int64_t *nrecords) {
-	if (!db || !alignment_scores || !uniq_alignment_scores) { kmagpu_set_error("null argument"); return -1; }
+	if (!db || (!alignment_scores != !uniq_alignment_scores)) { kmagpu_set_error("null argument"); return -1; }
 	if (!db->d_lengths) { kmagpu_set_error("database has no template lengths (.length.b missing)"); return -1; }
 	KG_CUDA(cudaSetDevice(db->device));
 	if (out_bytes) *out_bytes = 0;
@@ -284,7 +300,7 @@ extern "C" int kmagpu_conclave_resident(kmagpu_db *db, const uint64_t *alignment
 	const RawBatch &r = db->raw;
 	if (!r.valid) { kmagpu_set_error("kmagpu_conclave_resident without a preceding score collection on this handle"); return -1; }
 	if (nrecords) *nrecords = r.n;
-	if (r.n == 0) { kmagpu_set_error("empty batch"); return -1; }
+	if (r.n == 0) return conclave_empty(db, frags_out, out_cap, out_bytes);
 	return conclave_core(db, (const uint8_t *)r.d_out.p, r.off, (int)r.n, alignment_scores, uniq_alignment_scores, frags_out, out_cap, out_bytes,
 	                     w_scores, fragmentCounts, readCounts);
 }
@@ -294,7 +310,7 @@ extern "C" int kmagpu_conclave_resident(kmagpu_db *db, const uint64_t *alignment
 extern "C" int kmagpu_conclave_from_align(kmagpu_db *db, const uint64_t *alignment_scores, const uint64_t *uniq_alignment_scores, void *frags_out,
                                           size_t out_cap, size_t *out_bytes, uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts,
                                           int64_t *nrecords) {
-	if (!db || !alignment_scores || !uniq_alignment_scores) { kmagpu_set_error("null argument"); return -1; }
+	if (!db || (!alignment_scores != !uniq_alignment_scores)) { kmagpu_set_error("null argument"); return -1; }
 	if (!db->d_lengths) { kmagpu_set_error("database has no template lengths (.length.b missing)"); return -1; }
 	KG_CUDA(cudaSetDevice(db->device));
 	if (out_bytes) *out_bytes = 0;
@@ -303,7 +319,7 @@ extern "C" int kmagpu_conclave_from_align(kmagpu_db *db, const uint64_t *alignme
 	if (!b.ran) { kmagpu_set_error("kmagpu_conclave_from_align without a preceding kmagpu_align_run on this handle"); return -1; }
 	const int n = (int)b.nreads;
 	if (nrecords) *nrecords = n;
-	if (n == 0 || b.out_bytes == 0) { kmagpu_set_error("empty batch"); return -1; }
+	if (n == 0 || b.out_bytes == 0) return conclave_empty(db, frags_out, out_cap, out_bytes);
 	uint32_t *recoff = (uint32_t *)b.d_recsize.p + n + 1;
 	const uint32_t total = (uint32_t)b.out_bytes;
 	KG_CUDA(cudaMemcpyAsync(recoff + n, &total, 4, cudaMemcpyHostToDevice, db->stream));

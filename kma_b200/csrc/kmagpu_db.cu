@@ -222,6 +222,8 @@ extern "C" void kmagpu_db_close(kmagpu_db *db) {
 		cudaFree(db->d_seq); cudaFree(db->d_lengths); cudaFree(db->d_seq_off);
 	}
 	cudaFree(db->d_mat); cudaFree(db->d_mat_off);
+	kmagpu_comm_destroy(db);
+	db->d_run_scores.release();
 	for (auto &e : db->ev) if (e) cudaEventDestroy(e);
 	if (db->stream) cudaStreamDestroy(db->stream);
 	delete db;

@@ -146,7 +146,13 @@ struct kmagpu_db {
 	unsigned int *d_mat = nullptr;
 	int64_t *d_mat_off = nullptr;
 	size_t mat_entries = 0;
+	// multi-GPU exchange (kmagpu_comm.cu): NCCL communicator of this handle, the run-wide ConClave accumulators on the device
+	void *comm = nullptr;
+	int comm_rank = 0, comm_world = 1;
+	KgBuf d_run_scores;
+	bool run_scores = false;
 };
+int kg_scores_accumulate(kmagpu_db *db, const unsigned long long *batch_scores);
 
 int kg_tindex_build(kmagpu_db *db);
 int kg_align_free(kmagpu_db *db);

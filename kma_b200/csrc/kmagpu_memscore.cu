@@ -141,6 +141,7 @@ static int memscore_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff
 	KG_CUDA(cudaMemsetAsync((uint8_t *)w.d_out.p + ob, 0, 64, st));
 	if (frag_out && ob) KG_CUDA(cudaMemcpyAsync(frag_out, w.d_out.p, ob, cudaMemcpyDeviceToHost, st));
 	std::vector<uint64_t> acc(2 * (size_t)DB);
+	kg_scores_accumulate(db, as);   // the run-wide sums on the device (kmagpu_scores_reset)
 	KG_CUDA(cudaMemcpyAsync(acc.data(), w.d_acc.p, 16 * (size_t)DB, cudaMemcpyDeviceToHost, st));
 	KG_CUDA(cudaStreamSynchronize(st));
 	KG_CUDA(cudaGetLastError());

@@ -169,15 +169,50 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 	}
 
 	// ---- exhaustive scan (savekmers.c:2511-2706)
-	uint32_t last = KG_MISS, carry = KG_MISS;
-	int last_pos = 0, run_sc = 0, nhits = 0;
+	// The reference walks the hits in order: a hit on the list of the hit before it adds a gap-class score to the run of
+	// that list (gap 0: +M), a hit on another list flushes the run into the templates of the old list and scores the
+	// templates of the new one by their own gap since they were last seen. Restated per SEGMENT = maximal series of hits
+	// on one list (gaps included): every hit's contribution to its segment's run score depends only on the hit before
+	// it, so the lanes compute them in parallel and a prefix sum folds them; a segment then touches every template of
+	// its list ONCE (first-seen score or gap score, + the whole run score, + the position it was last seen at) -- the
+	// sums and the last-seen positions are the reference's, without its flush pass.
+	const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+	int nhits = 0;
 	bool overflow = false;
+	int prev_pos = -1;                 // position / list of the last hit so far
+	uint32_t prev_off = KG_MISS;
+	uint32_t seg_off = KG_MISS;        // the open segment: list, first and last hit position, run score
+	int seg_first = 0, seg_last = 0, seg_run = 0;
+
+	auto apply_segment = [&](uint32_t off, int first, int last, int run) -> bool {
+		const int nl = list_len(hv, off);
+		if (!DENSE && st.ncand + nl > KG_FILL) return false;
+		ws.lists++; ws.listids += lane == 0 ? nl : 0;
+		for (int base = 0; base < nl; base += 32) {
+			const int i = base + (int)lane;
+			bool isnew = false;
+			int sl = 0;
+			if (i < nl) {
+				sl = st.find_or_insert(list_id(hv, off, i), &isnew);
+				if (isnew) st.score[sl] = k * p.M + run;                                              // savekmers.c:2682-2688
+				else st.score[sl] += gap_score(p, k, (first - 1) - st.ext[sl], false) + run;      // savekmers.c:2583-2655, 2575-2582
+				st.ext[sl] = last;
+			}
+			const unsigned nm = __ballot_sync(full, isnew);
+			if (isnew) st.cand[st.ncand + __popc(nm & lt)] = sl;
+			st.ncand += __popc(nm);
+		}
+		__syncwarp();
+		return true;
+	};
+
 	for (int c0 = 0; c0 < npos && !overflow; c0 += KG_CHUNK) {
-		int w0 = stage(c0);
-		// phase 1: gather. two rounds so that 8 independent probes per lane are in flight.
+		const int w0 = stage(c0);
+		const int lim = min(npos, c0 + KG_CHUNK), nround = (lim - c0 + 31) >> 5;
+		// phase 1: gather, four rounds of 32 positions at a time so that 4 independent probes per lane are in flight
 		if (rc.nN) {   // reads with N's (rare): validity per position, one probe at a time; kept off the hot path
 #pragma unroll 1
-			for (int u = 0; u < KG_PER_LANE; ++u) {
+			for (int u = 0; u < nround; ++u) {
 				const int j = c0 + u * 32 + (int)lane;
 				int ss;
 				uint32_t v = KG_MISS;
@@ -185,112 +220,93 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 				hits[u * 32 + lane] = v;
 			}
 		} else {
-		uint32_t e1[KG_PER_LANE];
-		uint64_t km[KG_PER_LANE];
+#pragma unroll 1
+			for (int ug = 0; ug < nround; ug += 4) {
+				uint32_t e1[4];
+				uint64_t km[4];
 #pragma unroll
-		for (int u = 0; u < KG_PER_LANE; ++u) {
-			int j = c0 + u * 32 + (int)lane;
-			bool ok = j < npos;
-			km[u] = ok ? kmer_of(w0, j) : 0ull;
-			e1[u] = KG_MISS;
-			if (ok) {
-				if (hv.mega) { uint32_t v = __ldg(hv.exist + km[u]); e1[u] = v != 1u ? v : KG_MISS; }
-				else { uint32_t q = __ldg(hv.exist + (uint32_t)(km[u] & hv.hmask)); e1[u] = q != hv.null_index ? q : KG_MISS; }
-				ws.lookups++;
-			}
-		}
-		if (!hv.mega) {
-			uint2 e2[KG_PER_LANE];
-#pragma unroll
-			for (int u = 0; u < KG_PER_LANE; ++u)
-				e2[u] = e1[u] != KG_MISS ? __ldg(hv.kv + e1[u]) : make_uint2(0, 0);
-#pragma unroll
-			for (int u = 0; u < KG_PER_LANE; ++u) {
-				if (e1[u] == KG_MISS) continue;
-				uint32_t key = (uint32_t)km[u], bucket = key & (uint32_t)hv.hmask, pos = e1[u];
-				uint2 e = e2[u];
-				uint32_t v = KG_MISS;
-				for (;;) {
-					if (e.x == key) { v = e.y; break; }
-					if ((e.x & (uint32_t)hv.hmask) != bucket || pos >= hv.n) break;
-					e = __ldg(hv.kv + ++pos);
+				for (int u = 0; u < 4; ++u) {
+					const int j = c0 + (ug + u) * 32 + (int)lane;
+					const bool ok = j < lim;
+					km[u] = ok ? kmer_of(w0, j) : 0ull;
+					e1[u] = KG_MISS;
+					if (ok) {
+						if (hv.mega) { uint32_t v = __ldg(hv.exist + km[u]); e1[u] = v != 1u ? v : KG_MISS; }
+						else { uint32_t q = __ldg(hv.exist + (uint32_t)(km[u] & hv.hmask)); e1[u] = q != hv.null_index ? q : KG_MISS; }
+						ws.lookups++;
+					}
 				}
-				e1[u] = v;
-			}
-		}
+				if (!hv.mega) {
+					uint2 e2[4];
 #pragma unroll
-		for (int u = 0; u < KG_PER_LANE; ++u) hits[u * 32 + lane] = e1[u];
+					for (int u = 0; u < 4; ++u) e2[u] = e1[u] != KG_MISS ? __ldg(hv.kv + e1[u]) : make_uint2(0, 0);
+#pragma unroll
+					for (int u = 0; u < 4; ++u) {
+						if (e1[u] == KG_MISS) continue;
+						const uint32_t key = (uint32_t)km[u], bucket = key & (uint32_t)hv.hmask;
+						uint32_t pos = e1[u];
+						uint2 e = e2[u];
+						uint32_t v = KG_MISS;
+						for (;;) {
+							if (e.x == key) { v = e.y; break; }
+							if ((e.x & (uint32_t)hv.hmask) != bucket || pos >= hv.n) break;
+							e = __ldg(hv.kv + ++pos);
+						}
+						e1[u] = v;
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < 4; ++u) hits[(ug + u) * 32 + lane] = e1[u];
+			}
 		}
 		__syncwarp();
 
-		// phase 2: walk the hits of this chunk in position order. A hit whose left neighbour position hit the same
-		// list continues the run with gap 0 (+M, savekmers.c:2529): those are counted with popc; only the
-		// remaining hits (first of a run, list changes) are walked one by one.
-		for (int u = 0; u < KG_PER_LANE && !overflow; ++u) {
-			const uint32_t myoff = hits[u * 32 + lane];
-			uint32_t prevoff = __shfl_up_sync(0xffffffffu, myoff, 1);
-			if (lane == 0) prevoff = carry;
-			carry = __shfl_sync(0xffffffffu, myoff, 31);
-			const unsigned hmall = __ballot_sync(0xffffffffu, myoff != KG_MISS);
-			const unsigned sm = __ballot_sync(0xffffffffu, myoff != KG_MISS && prevoff == myoff);
-			unsigned hm = hmall & ~sm, counted = 0;
-			nhits += __popc(hmall);
-			while (hm) {
-				int b = __ffs(hm) - 1;
-				hm &= hm - 1;
-				{
-					const unsigned low = (1u << b) - 1, sb = sm & low & ~counted, hb = hmall & low;
-					run_sc += __popc(sb) * p.M;
-					counted |= sb;
-					if (hb) last_pos = c0 + u * 32 + (31 - __clz(hb));
-				}
-				const int j = c0 + u * 32 + b;
-				const uint32_t off = hits[u * 32 + b];
-				if (off == last) {
-					run_sc += gap_score(p, k, j - last_pos - 1, true);
-				} else {
-					int nl = list_len(hv, off);
-					if (!DENSE && st.ncand + nl > KG_FILL) { overflow = true; break; }
-					if (last != KG_MISS) {
-						// flush the run of the previous list (savekmers.c:2575-2582)
-						int pl = list_len(hv, last);
+		// phase 2: segments of this chunk, 32 positions per round
 #pragma unroll 1
-						for (int i = lane; i < pl; i += 32) {
-							int s = st.find(list_id(hv, last, i));
-							st.score[s] += run_sc;
-							st.ext[s] = last_pos;
-						}
-						__syncwarp();
-					}
-					ws.lists++; ws.listids += lane == 0 ? nl : 0;
-					// score / admit the templates of the new list (savekmers.c:2583-2655, 2682-2688)
-					for (int base = 0; base < nl; base += 32) {
-						int i = base + (int)lane;
-						bool isnew = false;
-						int s = 0;
-						if (i < nl) {
-							s = st.find_or_insert(list_id(hv, off, i), &isnew);
-							if (isnew) st.score[s] = k * p.M;
-							else st.score[s] += gap_score(p, k, (j - 1) - st.ext[s], false);
-						}
-						unsigned nm = __ballot_sync(0xffffffffu, isnew);
-						if (isnew) st.cand[st.ncand + __popc(nm & ((1u << lane) - 1))] = s;
-						st.ncand += __popc(nm);
-					}
-					__syncwarp();
-					run_sc = 0;
-				}
-				last = off;
-				last_pos = j;
+		for (int u = 0; u < nround && !overflow; ++u) {
+			const uint32_t myoff = hits[u * 32 + lane];
+			const bool hit = myoff != KG_MISS;
+			const unsigned hm = __ballot_sync(full, hit);
+			if (!hm) continue;
+			nhits += __popc(hm);
+			const int base = c0 + u * 32;
+			// the hit before this position: in this round, or the one carried over
+			const unsigned below = hm & lt;
+			const int pl = below ? 31 - __clz(below) : -1;
+			uint32_t poff = __shfl_sync(full, myoff, pl < 0 ? 0 : pl);
+			int ppos = base + pl;
+			if (pl < 0) { poff = prev_off; ppos = prev_pos; }
+			const bool same = hit && poff == myoff;   // continues (gap 0) or resumes the list of the hit before it
+			int ps = same ? gap_score(p, k, base + (int)lane - ppos - 1, true) : 0;   // what this hit adds to its segment's run score
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, ps, o); if ((int)lane >= o) ps += y; }
+			const unsigned sm = __ballot_sync(full, hit && !same);   // list changes: a new segment starts
+			const int fs = sm ? __ffs(sm) - 1 : 32;
+			const unsigned head = hm & (fs == 32 ? full : ((1u << fs) - 1u));   // hits that still belong to the open segment
+			if (head) {
+				const int hl = 31 - __clz(head);
+				seg_run += __shfl_sync(full, ps, hl);
+				seg_last = base + hl;
 			}
-			if (!overflow) {
-				const unsigned sb = sm & ~counted;
-				run_sc += __popc(sb) * p.M;
-				if (hmall) last_pos = c0 + u * 32 + (31 - __clz(hmall));
+			unsigned rest = sm;
+			while (rest) {
+				const int b = __ffs(rest) - 1;
+				rest &= rest - 1;
+				if (seg_off != KG_MISS && !apply_segment(seg_off, seg_first, seg_last, seg_run)) { overflow = true; break; }
+				const int e = rest ? __ffs(rest) - 1 : 32;
+				const unsigned body = hm & (e == 32 ? full : ((1u << e) - 1u)) & ~((1u << b) - 1u);   // this segment's hits in the round
+				const int ll = 31 - __clz(body);
+				seg_off = __shfl_sync(full, myoff, b);
+				seg_first = base + b; seg_last = base + ll;
+				seg_run = __shfl_sync(full, ps, ll) - __shfl_sync(full, ps, b);
 			}
+			const int lh = 31 - __clz(hm);
+			prev_pos = base + lh;
+			prev_off = __shfl_sync(full, myoff, lh);
 		}
 		__syncwarp();
 	}
+	if (!overflow && seg_off != KG_MISS && !apply_segment(seg_off, seg_first, seg_last, seg_run)) overflow = true;   // savekmers.c:2707-2722
 	ws.hits += lane == 0 ? nhits : 0;
 
 	if (overflow) {   // hash mode only: wipe and report
@@ -298,13 +314,6 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 		for (int i = lane; i < KG_CAP; i += 32) st.keys[i] = 0;
 		__syncwarp();
 		return -1;
-	}
-
-	if (last != KG_MISS) {   // final flush (savekmers.c:2707-2722)
-		int pl = list_len(hv, last);
-#pragma unroll 1
-		for (int i = lane; i < pl; i += 32) st.score[st.find(list_id(hv, last, i))] += run_sc;
-		__syncwarp();
 	}
 
 	if (pool2) {   // paired end: every template seen keeps its clamped score (savekmers.c:654-686); returns the hit count

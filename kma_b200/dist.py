@@ -18,12 +18,28 @@ def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def group_starts(stage: int, buf, off: np.ndarray) -> np.ndarray:
+    """indices of the records a shard may start at: never the second mate of a pair. Stage 1 marks the first mate with a
+    negative header length (runinput.c:789), stage 2 writes it without templates (printPair, ankers.c:150)."""
+    n = len(off) - 1
+    if n == 0 or stage not in (1, 2):
+        return np.arange(n + 1)
+    field = 12 if stage == 1 else 16
+    v = np.ndarray(n, dtype="<i4", buffer=np.ascontiguousarray(
+        np.stack([buf[off[:-1].astype(np.int64) + field + b] for b in range(4)], axis=1)).tobytes())
+    first_mate = v < 0 if stage == 1 else v == 0
+    second = np.zeros(n + 1, dtype=bool)
+    second[1:n] = first_mate[: n - 1]       # the record after a first mate is its mate
+    return np.flatnonzero(~second)
+
+
 def shard_stream(stage: int, buf, rank: int, world: int) -> np.ndarray:
-    """the slice of whole records of a stage-1 / stage-2 stream that `rank` maps"""
+    """the slice of whole records of a stage-1 / stage-2 stream that `rank` maps; pairs are never split"""
     buf = np.ascontiguousarray(buf, dtype=np.uint8)
     off = api.record_offsets(stage, buf)
-    lo, hi = shard_bounds(len(off) - 1, rank, world)
-    return buf[int(off[lo]):int(off[hi])]
+    starts = group_starts(stage, buf, off)   # groups = single reads and pairs; the last entry is the end of the stream
+    lo, hi = shard_bounds(len(starts) - 1, rank, world)
+    return buf[int(off[starts[lo]]):int(off[starts[hi]])]
 
 
 def allreduce_scores(alignment_scores: np.ndarray, uniq_alignment_scores: np.ndarray, device=None):
@@ -92,3 +108,18 @@ def gpu_pipeline(db: "api.TemplateDB", params=None):
         frag, a, u, _ = db.align_download()
         return frag.tobytes(), a, u, n
     return run
+
+
+def map_sharded_device(db: "api.TemplateDB", stage1, rank: int, world: int, params=None):
+    """map_sharded with the exchange inside the library: the ConClave sums stay in HBM, are all-reduced in place by NCCL on
+    the library's stream (kmagpu_allreduce_scores) and are what a following db.conclave_from_align(None, None) reads.
+    The handle needs db.comm_init(...) first. Returns (frag_raw bytes, alignment_scores, uniq_alignment_scores, reads, all-reduce ms)."""
+    shard = shard_stream(1, stage1, rank, world)
+    db.scores_reset()
+    n = db.seed_upload(np.ascontiguousarray(shard))
+    db.seed_run(params)
+    db.align_from_seed()
+    db.align_run(params)
+    frag, _, _, _ = db.align_download()
+    a, u, ms = db.allreduce_scores()
+    return frag.tobytes(), a, u, n, ms
