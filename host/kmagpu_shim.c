@@ -53,14 +53,18 @@ static void shim_atexit(void) { void *bt[32]; int n = backtrace(bt, 32); fprintf
 static int shim_debug(void) { static int d = -1; if (d < 0) { d = getenv("KMAGPU_DEBUG") != 0; if (d) atexit(shim_atexit); } return d; }
 #define SHIM_TRACE(...) do { if (shim_debug()) { fprintf(stderr, "[shim] " __VA_ARGS__); fputc('\n', stderr); } } while (0)
 
+/* _exit, not exit: the stages are threads of one process (kmaPipeThread), and exit() would wait for the stdio locks of the
+   pipes another stage is blocked on */
 static void shim_die(const char *what) {
 	fprintf(stderr, "kma (GPU host): %s: %s\n", what, kmagpu_last_error());
-	exit(1);
+	fflush(stderr);
+	_exit(1);
 }
 
 static void shim_unsupported(const char *what) {
 	fprintf(stderr, "kma (GPU host): %s is not covered by the GPU mapping core; there is no CPU fallback.\n", what);
-	exit(1);
+	fflush(stderr);
+	_exit(1);
 }
 
 static int shim_device(void) {
@@ -174,7 +178,7 @@ int __wrap_save_kmers_batch(char *templatefilename, char *exePrev, unsigned shm,
 			len = 8 * (size_t)hdr[1] + 4 * (size_t)hdr[2] + (size_t)abs(hdr[3]);
 			buf = shim_grow(buf, &cap, fill + 16 + len);
 			memcpy(buf + fill, hdr, 16);
-			if (len && !shim_read(buf + fill + 16, len, in)) { fprintf(stderr, "kma (GPU host): truncated stage-1 stream\n"); exit(1); }
+			if (len && !shim_read(buf + fill + 16, len, in)) { fprintf(stderr, "kma (GPU host): truncated stage-1 stream\n"); _exit(1); }
 			fill += 16 + len;
 			pending_mate = !pending_mate && hdr[3] < 0;
 		}
@@ -226,7 +230,7 @@ void *__wrap_alnFrags_threaded(void *arg) {
 	else shim_unsupported("-apm f");
 	/* the database prefix: stage 2 opened it already (same process, kmaPipeThread); if not, it is not known here */
 	db = g_db_aln ? g_db_aln : (g_db_seed ? shim_db(0, 3) : 0);
-	if (!db) { fprintf(stderr, "kma (GPU host): the alignment pass needs the database stage 2 opened (forked stages are not supported)\n"); exit(1); }
+	if (!db) { fprintf(stderr, "kma (GPU host): the alignment pass needs the database stage 2 opened (forked stages are not supported)\n"); _exit(1); }
 	kmagpu_db_get_info(db, &info);
 	if (info.kmerindex != thr->kmersize) shim_unsupported("-k different from the index' k");
 
@@ -235,11 +239,11 @@ void *__wrap_alnFrags_threaded(void *arg) {
 			size_t len;
 			if (!shim_read(hdr, 4, in)) { eof = 1; break; }
 			if (hdr[0] < 0) { nfrags = -hdr[0]; eof = 1; break; }
-			if (!shim_read(hdr + 1, 24, in)) { fprintf(stderr, "kma (GPU host): truncated stage-2 stream\n"); exit(1); }
+			if (!shim_read(hdr + 1, 24, in)) { fprintf(stderr, "kma (GPU host): truncated stage-2 stream\n"); _exit(1); }
 			len = 8 * (size_t)hdr[1] + 4 * (size_t)hdr[2] + 4 * (size_t)hdr[4] + (size_t)hdr[5];
 			buf = shim_grow(buf, &cap, fill + 28 + len);
 			memcpy(buf + fill, hdr, 28);
-			if (len && !shim_read(buf + fill + 28, len, in)) { fprintf(stderr, "kma (GPU host): truncated stage-2 stream\n"); exit(1); }
+			if (len && !shim_read(buf + fill + 28, len, in)) { fprintf(stderr, "kma (GPU host): truncated stage-2 stream\n"); _exit(1); }
 			fill += 28 + len;
 			pending_mate = hdr[4] == 0;   /* the first record of a pair has no templates (ankers.c:150) */
 			if (maxq < hdr[0]) maxq = hdr[0];
@@ -277,7 +281,7 @@ void *__wrap_alnFrags_threaded(void *arg) {
 			if (!ix || !(ix->seq = malloc(bytes))) { ERROR(); }
 			ix->len = thr->template_lengths[t];
 			ix->kmerindex = thr->kmersize;
-			if (pread(thr->seq_in, ix->seq, bytes, thr->seq_indexes[t]) != (ssize_t)bytes) { fprintf(stderr, "Corrupted *.seq.b\n"); exit(1); }
+			if (pread(thr->seq_in, ix->seq, bytes, thr->seq_indexes[t]) != (ssize_t)bytes) { fprintf(stderr, "Corrupted *.seq.b\n"); _exit(1); }
 			thr->templates_index[t] = ix;
 		}
 	}
@@ -328,7 +332,7 @@ static int shim_next_chunk(void) {
 		if (h[0] == g_tr.template) {
 			const size_t len = 32 + (size_t)h[1] + (size_t)h[6];
 			g_tr.in[c] = shim_grow(g_tr.in[c], &g_tr.in_cap[c], fill + len);
-			if (pread(fd, g_tr.in[c] + fill, len, g_tr.pos[f]) != (ssize_t)len) { fprintf(stderr, "kma (GPU host): truncated fragment file\n"); exit(1); }
+			if (pread(fd, g_tr.in[c] + fill, len, g_tr.pos[f]) != (ssize_t)len) { fprintf(stderr, "kma (GPU host): truncated fragment file\n"); _exit(1); }
 			fill += len; ++n;
 		}
 		g_tr.pos[f] += 32 + (off_t)h[1] + (off_t)h[6];
@@ -338,7 +342,7 @@ static int shim_next_chunk(void) {
 	g_tr.out[c] = shim_grow(g_tr.out[c], &g_tr.out_cap[c], 9 * fill + 1024 * n + 4096);
 	SHIM_TRACE("assembly: template %d, %zu fragments (%zu bytes) -> device", g_tr.template, n, fill);
 	if (kmagpu_trace_batch(g_db_aln, &g_tr.prm, g_tr.in[c], fill, g_tr.out[c], g_tr.out_cap[c], &obytes, &nrec, 0)) shim_die("kmagpu_trace_batch");
-	if ((size_t)nrec != n) { fprintf(stderr, "kma (GPU host): fragment count mismatch\n"); exit(1); }
+	if ((size_t)nrec != n) { fprintf(stderr, "kma (GPU host): fragment count mismatch\n"); _exit(1); }
 	if (g_tr.frag_cap[c] < n) {
 		g_tr.frag_cap[c] = n + n / 2 + 64;
 		g_tr.frag[c] = realloc(g_tr.frag[c], g_tr.frag_cap[c] * sizeof(ShimFrag));
@@ -376,7 +380,7 @@ static const ShimFrag *shim_lookup(const unsigned char *qseq, int q_len) {
 		if (!hit && !shim_next_chunk()) break;
 	}
 	pthread_mutex_unlock(&g_lock);
-	if (!hit) { fprintf(stderr, "kma (GPU host): a fragment of template %d reached KMA without a device result\n", g_tr.template); exit(1); }
+	if (!hit) { fprintf(stderr, "kma (GPU host): a fragment of template %d reached KMA without a device result\n", g_tr.template); _exit(1); }
 	return hit;
 }
 
@@ -453,7 +457,7 @@ static void *shim_assemble(void *arg) {
 		shim_params(&g_tr.prm, thr->NWmatrices->rewards);
 		g_tr.prm.minlen = thr->minlen; g_tr.prm.mq = thr->mq; g_tr.prm.scoreT = thr->scoreT; g_tr.prm.mrc = thr->mrc;
 		g_tr.prm.ts = shim_trim();
-		if (!g_db_aln) { fprintf(stderr, "kma (GPU host): the assembly needs the database of the alignment pass\n"); exit(1); }
+		if (!g_db_aln) { fprintf(stderr, "kma (GPU host): the assembly needs the database of the alignment pass\n"); _exit(1); }
 		g_tr.ready = 1;
 		pthread_mutex_unlock(&g_lock);
 	}
@@ -513,7 +517,7 @@ HashMapCCI *__wrap_hashMapCCI_load_thread(HashMapCCI *src, int seq, int len, int
 	if (src->len == 0) {
 		const long check = (((long)len >> 5) + 1) * (long)sizeof(long unsigned);
 		hashMapCCI_initialize(src, len, kmersize);
-		if (read(seq, src->seq, check) != check) { fprintf(stderr, "Corrupted *.seq.b\n"); exit(1); }
+		if (read(seq, src->seq, check) != check) { fprintf(stderr, "Corrupted *.seq.b\n"); _exit(1); }
 	}
 	pthread_mutex_unlock(&g_lock);
 	return src;

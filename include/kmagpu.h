@@ -81,7 +81,8 @@ void kmagpu_db_close(kmagpu_db *db);
 /* A further handle on the SAME HBM image (hash table, template sequences, position index: read-only, shared, freed by
  * the last handle to close) with its own CUDA stream and batch buffers: what the reference's T worker threads share when
  * they all read one HashMapKMA / HashMapCCI (savekmers.c:94, alnfrags.c:2150). One handle per host thread; handles may
- * run concurrently. The base-count matrix (kmagpu_matrix_*) is per handle. */
+ * run concurrently. The base-count matrix (kmagpu_matrix_*), the run-wide score accumulators (kmagpu_scores_reset) and the NCCL
+ * communicator belong to the image: the handles of one GPU add to ONE set of sums (atomics). */
 int kmagpu_db_clone(kmagpu_db *db, kmagpu_db **out);
 int kmagpu_db_get_info(const kmagpu_db *db, kmagpu_db_info *info);
 

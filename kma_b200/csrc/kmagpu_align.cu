@@ -2065,9 +2065,9 @@ static int trace_core(kmagpu_db *db, const kmagpu_params *prm, const uint8_t *di
 	if (h[A_BAD]) { kmagpu_set_error("%llu alignments are longer than 3 * read length + 256 columns", h[A_BAD]); return -1; }
 	if (prm->matrix) {   // alnToMatPtr (assembly.c:1968) on every accepted alignment
 		if (prm->matrix != 1 && prm->matrix != 2) { kmagpu_set_error("matrix mode %d: 1 = alnToMat (template nodes), 2 = alnToMatDense", prm->matrix); return -1; }
-		if (!db->d_mat && kmagpu_matrix_reset(db)) return -1;
+		if (!db->image->d_mat && kmagpu_matrix_reset(db)) return -1;
 		tr_matrix_kernel<<<db->sm_count * 8, 256, 0, st>>>((const TrRec *)d_recs.p, (const TrOut *)d_outs.p, n, (const uint8_t *)d_rows.p,
-			db->tix.meta, db->d_mat_off, prm->matrix == 2, db->d_mat, ctr);
+			db->tix.meta, db->image->d_mat_off, prm->matrix == 2, db->image->d_mat, ctr);
 		++launches;
 	}
 	if (out) {
@@ -2149,39 +2149,44 @@ extern "C" int kmagpu_trace_from_conclave(kmagpu_db *db, const kmagpu_params *pr
 
 // ---------------------------------------------------------------- base-count matrix: host side
 
+// The matrix belongs to the database image: every handle (kmagpu_db_clone) adds to the same counts with atomics.
 extern "C" int kmagpu_matrix_reset(kmagpu_db *db) {
 	if (!db) { kmagpu_set_error("null argument"); return -1; }
 	if (!db->d_tmeta) { kmagpu_set_error("database has no template sequences"); return -1; }
 	KG_CUDA(cudaSetDevice(db->device));
 	const int DB = db->info.DB_size;
-	if (!db->d_mat) {
+	KgImageRef *img = db->image;
+	if (!img->d_mat) {
 		std::vector<int64_t> off((size_t)DB + 1, 0);
 		for (int t = 2; t <= DB; ++t) off[t] = off[t - 1] + db->lengths[t - 1];
-		db->mat_entries = 6 * (size_t)off[DB];
-		KG_CUDA(cudaMalloc(&db->d_mat_off, 8 * ((size_t)DB + 1)));
-		KG_CUDA(cudaMemcpy(db->d_mat_off, off.data(), 8 * ((size_t)DB + 1), cudaMemcpyHostToDevice));
-		KG_CUDA(cudaMalloc(&db->d_mat, 4 * db->mat_entries + 64));
-		db->info.device_bytes += 4 * db->mat_entries;
+		const size_t entries = 6 * (size_t)off[DB];
+		int64_t *d_off = nullptr;
+		unsigned int *d_mat = nullptr;
+		KG_CUDA(cudaMalloc(&d_off, 8 * ((size_t)DB + 1)));
+		KG_CUDA(cudaMemcpy(d_off, off.data(), 8 * ((size_t)DB + 1), cudaMemcpyHostToDevice));
+		KG_CUDA(cudaMalloc(&d_mat, 4 * entries + 64));
+		img->d_mat_off = d_off; img->mat_entries = entries; img->d_mat = d_mat;
+		db->info.device_bytes += 4 * entries;
 	}
-	KG_CUDA(cudaMemsetAsync(db->d_mat, 0, 4 * db->mat_entries, db->stream));
+	KG_CUDA(cudaMemsetAsync(img->d_mat, 0, 4 * img->mat_entries, db->stream));
 	KG_CUDA(cudaStreamSynchronize(db->stream));
 	return 0;
 }
 
 extern "C" int kmagpu_matrix_device(kmagpu_db *db, void **ptr, uint64_t *entries) {
 	if (!db || !ptr || !entries) { kmagpu_set_error("null argument"); return -1; }
-	if (!db->d_mat && kmagpu_matrix_reset(db)) return -1;
-	*ptr = db->d_mat; *entries = db->mat_entries;
+	if (!db->image->d_mat && kmagpu_matrix_reset(db)) return -1;
+	*ptr = db->image->d_mat; *entries = db->image->mat_entries;
 	return 0;
 }
 
 extern "C" int kmagpu_matrix_download(kmagpu_db *db, int32_t tmpl, uint16_t *counts, size_t cap_entries, size_t *entries) {
 	if (!db) { kmagpu_set_error("null argument"); return -1; }
-	if (!db->d_mat) { kmagpu_set_error("kmagpu_matrix_download before any alignment was added"); return -1; }
+	if (!db->image->d_mat) { kmagpu_set_error("kmagpu_matrix_download before any alignment was added"); return -1; }
 	KG_CUDA(cudaSetDevice(db->device));
 	const int DB = db->info.DB_size;
 	if (tmpl < 0 || tmpl >= DB) { kmagpu_set_error("template %d outside the database", tmpl); return -1; }
-	size_t first = 0, cnt = db->mat_entries;   // template 0 = the whole database
+	size_t first = 0, cnt = db->image->mat_entries;   // template 0 = the whole database
 	if (tmpl) {
 		for (int t = 1; t < tmpl; ++t) first += 6 * (size_t)db->lengths[t];
 		cnt = 6 * (size_t)db->lengths[tmpl];
@@ -2191,7 +2196,7 @@ extern "C" int kmagpu_matrix_download(kmagpu_db *db, int32_t tmpl, uint16_t *cou
 	if (cnt > cap_entries) { kmagpu_set_error("matrix needs %zu entries, caller gave %zu", cnt, cap_entries); return -1; }
 	KgBuf tmp;
 	if (tmp.reserve(2 * cnt + 64)) return -1;
-	mat_clamp_kernel<<<db->sm_count * 4, 256, 0, db->stream>>>(db->d_mat + first, cnt, (uint16_t *)tmp.p);
+	mat_clamp_kernel<<<db->sm_count * 4, 256, 0, db->stream>>>(db->image->d_mat + first, cnt, (uint16_t *)tmp.p);
 	cudaError_t e = cudaMemcpyAsync(counts, tmp.p, 2 * cnt, cudaMemcpyDeviceToHost, db->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
 	tmp.release();

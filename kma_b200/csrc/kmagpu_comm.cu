@@ -61,55 +61,66 @@ extern "C" int kmagpu_comm_unique_id(void *id, size_t cap) {
 
 extern "C" int kmagpu_comm_init(kmagpu_db *db, const void *id, int rank, int world) {
 	if (!db || !id || world < 1 || rank < 0 || rank >= world) { kmagpu_set_error("bad argument"); return -1; }
-	if (db->comm) { kmagpu_set_error("this handle already has a communicator"); return -1; }
-	db->comm_rank = rank; db->comm_world = world;
+	KgImageRef *img = db->image;
+	if (img->comm) { kmagpu_set_error("this database image already has a communicator"); return -1; }
+	img->comm_rank = rank; img->comm_world = world;
 	if (world == 1) return 0;
 	if (nccl_load()) return -1;
 	KG_CUDA(cudaSetDevice(db->device));
 	kgNcclUniqueId uid;
 	memcpy(&uid, id, sizeof(uid));
-	KG_NCCL(g_nccl.CommInitRank((kgNcclComm *)&db->comm, world, uid, rank));
+	KG_NCCL(g_nccl.CommInitRank((kgNcclComm *)&img->comm, world, uid, rank));
 	return 0;
 }
 
 extern "C" void kmagpu_comm_destroy(kmagpu_db *db) {
-	if (db && db->comm && g_nccl.CommDestroy) { cudaSetDevice(db->device); g_nccl.CommDestroy((kgNcclComm)db->comm); }
-	if (db) { db->comm = nullptr; db->comm_world = 1; db->comm_rank = 0; }
+	if (!db || !db->image) return;
+	KgImageRef *img = db->image;
+	if (img->comm && g_nccl.CommDestroy) { cudaSetDevice(db->device); g_nccl.CommDestroy((kgNcclComm)img->comm); }
+	img->comm = nullptr; img->comm_world = 1; img->comm_rank = 0;
 }
 
-// the run-wide ConClave accumulators of this handle on the device: [alignment_scores[DB], uniq_alignment_scores[DB]]
+// the run-wide ConClave accumulators on the device: [alignment_scores[DB], uniq_alignment_scores[DB]], one set per database
+// image -- every handle of the image (kmagpu_db_clone) adds its batches to them
 extern "C" int kmagpu_scores_reset(kmagpu_db *db) {
 	if (!db) { kmagpu_set_error("null argument"); return -1; }
 	KG_CUDA(cudaSetDevice(db->device));
-	if (db->d_run_scores.reserve(16 * (size_t)db->info.DB_size)) return -1;
-	KG_CUDA(cudaMemsetAsync(db->d_run_scores.p, 0, 16 * (size_t)db->info.DB_size, db->stream));
-	db->run_scores = true;
+	KgImageRef *img = db->image;
+	const size_t bytes = 16 * (size_t)db->info.DB_size;
+	if (!img->d_run_scores) {
+		unsigned long long *p = nullptr;
+		KG_CUDA(cudaMalloc(&p, bytes));
+		img->d_run_scores = p;
+	}
+	KG_CUDA(cudaMemsetAsync(img->d_run_scores, 0, bytes, db->stream));
+	KG_CUDA(cudaStreamSynchronize(db->stream));
 	return 0;
 }
 
 static __global__ void add_u64_kernel(unsigned long long *dst, const unsigned long long *src, size_t n) {
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) dst[i] += src[i];
+	if (i < n && src[i]) atomicAdd(&dst[i], src[i]);   // handles of one image add from their own streams
 }
 
 // called by kmagpu_align_run / the -mem_mode score collection: this batch's sums join the run's (stream-ordered)
 int kg_scores_accumulate(kmagpu_db *db, const unsigned long long *batch_scores) {
-	if (!db->run_scores) return 0;
+	if (!db->image->d_run_scores) return 0;
 	const size_t n = 2 * (size_t)db->info.DB_size;
-	add_u64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, db->stream>>>((unsigned long long *)db->d_run_scores.p, batch_scores, n);
+	add_u64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, db->stream>>>(db->image->d_run_scores, batch_scores, n);
 	return 0;
 }
 
 extern "C" int kmagpu_allreduce_scores(kmagpu_db *db, uint64_t *alignment_scores, uint64_t *uniq_alignment_scores, float *ms) {
 	if (!db) { kmagpu_set_error("null argument"); return -1; }
-	if (!db->run_scores) { kmagpu_set_error("kmagpu_allreduce_scores before kmagpu_scores_reset"); return -1; }
+	KgImageRef *img = db->image;
+	if (!img->d_run_scores) { kmagpu_set_error("kmagpu_allreduce_scores before kmagpu_scores_reset"); return -1; }
 	KG_CUDA(cudaSetDevice(db->device));
 	const size_t DB = (size_t)db->info.DB_size;
 	if (ms) KG_CUDA(cudaEventRecord(db->ev[5], db->stream));
-	if (db->comm) KG_NCCL(g_nccl.AllReduce(db->d_run_scores.p, db->d_run_scores.p, 2 * DB, KG_NCCL_UINT64, KG_NCCL_SUM, (kgNcclComm)db->comm, db->stream));
+	if (img->comm) KG_NCCL(g_nccl.AllReduce(img->d_run_scores, img->d_run_scores, 2 * DB, KG_NCCL_UINT64, KG_NCCL_SUM, (kgNcclComm)img->comm, db->stream));
 	if (ms) KG_CUDA(cudaEventRecord(db->ev[6], db->stream));
-	if (alignment_scores) KG_CUDA(cudaMemcpyAsync(alignment_scores, db->d_run_scores.p, 8 * DB, cudaMemcpyDeviceToHost, db->stream));
-	if (uniq_alignment_scores) KG_CUDA(cudaMemcpyAsync(uniq_alignment_scores, (const uint64_t *)db->d_run_scores.p + DB, 8 * DB, cudaMemcpyDeviceToHost, db->stream));
+	if (alignment_scores) KG_CUDA(cudaMemcpyAsync(alignment_scores, img->d_run_scores, 8 * DB, cudaMemcpyDeviceToHost, db->stream));
+	if (uniq_alignment_scores) KG_CUDA(cudaMemcpyAsync(uniq_alignment_scores, img->d_run_scores + DB, 8 * DB, cudaMemcpyDeviceToHost, db->stream));
 	KG_CUDA(cudaStreamSynchronize(db->stream));
 	if (ms) cudaEventElapsedTime(ms, db->ev[5], db->ev[6]);
 	return 0;
@@ -117,10 +128,11 @@ extern "C" int kmagpu_allreduce_scores(kmagpu_db *db, uint64_t *alignment_scores
 
 extern "C" int kmagpu_allreduce_matrix(kmagpu_db *db, float *ms) {
 	if (!db) { kmagpu_set_error("null argument"); return -1; }
-	if (!db->d_mat) { kmagpu_set_error("kmagpu_allreduce_matrix before any alignment was added to the matrix"); return -1; }
+	KgImageRef *img = db->image;
+	if (!img->d_mat) { kmagpu_set_error("kmagpu_allreduce_matrix before any alignment was added to the matrix"); return -1; }
 	KG_CUDA(cudaSetDevice(db->device));
 	if (ms) KG_CUDA(cudaEventRecord(db->ev[5], db->stream));
-	if (db->comm) KG_NCCL(g_nccl.AllReduce(db->d_mat, db->d_mat, db->mat_entries, KG_NCCL_UINT32, KG_NCCL_SUM, (kgNcclComm)db->comm, db->stream));
+	if (img->comm) KG_NCCL(g_nccl.AllReduce(img->d_mat, img->d_mat, img->mat_entries, KG_NCCL_UINT32, KG_NCCL_SUM, (kgNcclComm)img->comm, db->stream));
 	if (ms) KG_CUDA(cudaEventRecord(db->ev[6], db->stream));
 	KG_CUDA(cudaStreamSynchronize(db->stream));
 	if (ms) cudaEventElapsedTime(ms, db->ev[5], db->ev[6]);
@@ -130,13 +142,13 @@ extern "C" int kmagpu_allreduce_matrix(kmagpu_db *db, float *ms) {
 // any host array of u64 counters (w_scores, read counts widened by the caller ...): up, summed over ranks, down
 extern "C" int kmagpu_allreduce_u64(kmagpu_db *db, uint64_t *buf, size_t n) {
 	if (!db || (!buf && n)) { kmagpu_set_error("null argument"); return -1; }
-	if (!db->comm || !n) return 0;
+	if (!db->image->comm || !n) return 0;
 	KG_CUDA(cudaSetDevice(db->device));
 	KgBuf tmp;
 	if (tmp.reserve(8 * n)) return -1;
 	cudaError_t e = cudaMemcpyAsync(tmp.p, buf, 8 * n, cudaMemcpyHostToDevice, db->stream);
 	int r = 0;
-	if (e == cudaSuccess) r = g_nccl.AllReduce(tmp.p, tmp.p, n, KG_NCCL_UINT64, KG_NCCL_SUM, (kgNcclComm)db->comm, db->stream);
+	if (e == cudaSuccess) r = g_nccl.AllReduce(tmp.p, tmp.p, n, KG_NCCL_UINT64, KG_NCCL_SUM, (kgNcclComm)db->image->comm, db->stream);
 	if (e == cudaSuccess && !r) e = cudaMemcpyAsync(buf, tmp.p, 8 * n, cudaMemcpyDeviceToHost, db->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
 	tmp.release();

@@ -194,8 +194,8 @@ static int conclave_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff
 		KG_CUDA(cudaMemcpyAsync(as, alignment_scores, 8 * (size_t)DB, cudaMemcpyHostToDevice, st));
 		KG_CUDA(cudaMemcpyAsync(uas, uniq_alignment_scores, 8 * (size_t)DB, cudaMemcpyHostToDevice, st));
 	} else {   // the run-wide sums this handle holds on the device (kmagpu_scores_reset ... kmagpu_allreduce_scores): they never left HBM
-		if (!db->run_scores) { kmagpu_set_error("ConClave without score arrays needs the device-resident sums (kmagpu_scores_reset)"); return -1; }
-		KG_CUDA(cudaMemcpyAsync(as, db->d_run_scores.p, 16 * (size_t)DB, cudaMemcpyDeviceToDevice, st));
+		if (!db->image->d_run_scores) { kmagpu_set_error("ConClave without score arrays needs the device-resident sums (kmagpu_scores_reset)"); return -1; }
+		KG_CUDA(cudaMemcpyAsync(as, db->image->d_run_scores, 16 * (size_t)DB, cudaMemcpyDeviceToDevice, st));
 	}
 	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
 	KG_CUDA(cudaMemsetAsync(d_acc.p, 0, 16 * (size_t)DB, st));

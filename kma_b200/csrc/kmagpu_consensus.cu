@@ -244,14 +244,14 @@ extern "C" double kmagpu_chi2_threshold(double evalue, double (*p_chisqr)(long d
 extern "C" int kmagpu_consensus(kmagpu_db *db, int32_t tmpl, const kmagpu_consensus_params *cp, uint8_t *t, uint8_t *s, uint8_t *q,
                                 size_t cap, kmagpu_consensus_stats *stats, float *ms) {
 	if (!db || !cp) { kmagpu_set_error("null argument"); return -1; }
-	if (!db->d_mat) { kmagpu_set_error("kmagpu_consensus before any alignment was added to the matrix"); return -1; }
+	if (!db->image->d_mat) { kmagpu_set_error("kmagpu_consensus before any alignment was added to the matrix"); return -1; }
 	if (cp->caller < 0 || cp->caller > 4 || cp->significance < 0 || cp->significance > 2) { kmagpu_set_error("unknown base caller / significance test"); return -1; }
 	if (!(cp->chi2_min >= 0.0)) { kmagpu_set_error("chi2_min must come from kmagpu_chi2_threshold"); return -1; }
 	static_assert(sizeof(CsStat) == sizeof(kmagpu_consensus_stats), "stats layout");
 	KG_CUDA(cudaSetDevice(db->device));
 	const int DB = db->info.DB_size;
 	if (tmpl < 0 || tmpl >= DB) { kmagpu_set_error("template %d outside the database", tmpl); return -1; }
-	long long p0 = 0, p1 = (long long)(db->mat_entries / 6);
+	long long p0 = 0, p1 = (long long)(db->image->mat_entries / 6);
 	if (tmpl) {
 		for (int i = 1; i < tmpl; ++i) p0 += db->lengths[i];
 		p1 = p0 + db->lengths[tmpl];
@@ -279,7 +279,7 @@ extern "C" int kmagpu_consensus(kmagpu_db *db, int32_t tmpl, const kmagpu_consen
 	grid = per ? (tiles + per - 1) / per : 1;
 	if (grid < 1) grid = 1;
 	KG_CUDA(cudaEventRecord(db->ev[2], st));
-	if (n) kern<<<(unsigned)grid, CS_TILE, 0, st>>>(P, db->d_mat, 4ull * db->mat_entries, db->d_mat_off, DB, db->tix.meta, db->tix.seq, p0, p1, per,
+	if (n) kern<<<(unsigned)grid, CS_TILE, 0, st>>>(P, db->image->d_mat, 4ull * db->image->mat_entries, db->image->d_mat_off, DB, db->tix.meta, db->tix.seq, p0, p1, per,
 		(uint8_t *)rows.p, (uint8_t *)rows.p + n, (uint8_t *)rows.p + 2 * n, (CsStat *)dstat.p);
 	KG_CUDA(cudaEventRecord(db->ev[3], st));
 	if (t) KG_CUDA(cudaMemcpyAsync(t, rows.p, n, cudaMemcpyDeviceToHost, st));

@@ -211,19 +211,21 @@ extern "C" void kmagpu_db_close(kmagpu_db *db) {
 	kg_memscore_free(db);
 	kg_align_free(db);
 	bool last = true;
-	if (db->image) {
+	KgImageRef *img = db->image;
+	if (img) {
 		std::lock_guard<std::mutex> g(g_image_mutex);
-		last = --db->image->refs == 0;
-		if (last) delete db->image;
+		last = --img->refs == 0;
 	}
 	if (last) {
 		cudaFree(db->d_tmeta); cudaFree(db->d_tslots); cudaFree(db->d_tdups);
 		cudaFree(db->d_exist); cudaFree(db->d_kv); cudaFree(db->d_values);
 		cudaFree(db->d_seq); cudaFree(db->d_lengths); cudaFree(db->d_seq_off);
+		if (img) {
+			kmagpu_comm_destroy(db);
+			cudaFree(img->d_mat); cudaFree(img->d_mat_off); cudaFree(img->d_run_scores);
+			delete img;
+		}
 	}
-	cudaFree(db->d_mat); cudaFree(db->d_mat_off);
-	kmagpu_comm_destroy(db);
-	db->d_run_scores.release();
 	for (auto &e : db->ev) if (e) cudaEventDestroy(e);
 	if (db->stream) cudaStreamDestroy(db->stream);
 	delete db;

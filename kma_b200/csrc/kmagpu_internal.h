@@ -113,7 +113,17 @@ struct AlignBatch {
 
 // The read-only database image in HBM is shared by every handle made from it with kmagpu_db_clone: the handles differ
 // in their stream, events and batch buffers only. The last handle to close frees the image.
-struct KgImageRef { int refs = 1; };
+struct KgImageRef {
+	int refs = 1;
+	// state every handle of the image adds to with atomics, so that worker handles of one GPU feed ONE set of sums:
+	// the base-count matrix of the assembly pass, the run-wide ConClave accumulators, and the GPU's NCCL communicator
+	unsigned int *d_mat = nullptr;     // uint32 [sum of template lengths][6], template t at d_mat_off[t] positions
+	int64_t *d_mat_off = nullptr;
+	size_t mat_entries = 0;
+	unsigned long long *d_run_scores = nullptr;   // [alignment_scores[DB_size], uniq_alignment_scores[DB_size]]
+	void *comm = nullptr;
+	int comm_rank = 0, comm_world = 1;
+};
 
 struct kmagpu_db {
 	int device = 0;
@@ -142,15 +152,6 @@ struct kmagpu_db {
 	int32_t *d_tdups = nullptr;
 	KgTIndexView tix{};
 	AlignBatch aln;
-	// base-count matrix of the assembly pass: uint32 [sum of template lengths][6], template t at d_mat_off[t] positions
-	unsigned int *d_mat = nullptr;
-	int64_t *d_mat_off = nullptr;
-	size_t mat_entries = 0;
-	// multi-GPU exchange (kmagpu_comm.cu): NCCL communicator of this handle, the run-wide ConClave accumulators on the device
-	void *comm = nullptr;
-	int comm_rank = 0, comm_world = 1;
-	KgBuf d_run_scores;
-	bool run_scores = false;
 };
 int kg_scores_accumulate(kmagpu_db *db, const unsigned long long *batch_scores);
 

@@ -46,19 +46,22 @@ struct SeedParams {
 // score of a hit that resumes template bookkeeping after `gaps` missed k-mer positions.
 // run == true : contribution to the run score of an unchanged template list (savekmers.c:2529-2569)
 // run == false: direct per-template score after a list change            (savekmers.c:2592-2625)
+// more than k missed positions (an indel or several mismatches): rare, and its division is long -- kept out of the scan loops
+__device__ __noinline__ int gap_score_far(const SeedParams &p, int k, int gaps) {
+	int g = gaps - (k - 1), mm, m;
+	if (g <= 2) { mm = g; m = 0; }
+	else {
+		mm = g / k + (g % k ? 1 : 0); mm = max(mm, 2);
+		m = min(min(g - mm, k), mm);
+	}
+	const int a = p.W1 + (g - 1) * p.U, b = mm * p.MM + m * p.M;
+	return k * p.M + (a <= b ? b : a);
+}
+
 __device__ __forceinline__ int gap_score(const SeedParams &p, int k, int gaps, bool run) {
 	if (gaps == 0) return p.M;
 	if (gaps == k) return k * p.M + p.MM;
-	if (k < gaps) {
-		int g = gaps - (k - 1), mm, m;
-		if (g <= 2) { mm = g; m = 0; }
-		else {
-			mm = g / k + (g % k ? 1 : 0); mm = max(mm, 2);
-			m = min(min(g - mm, k), mm);
-		}
-		int a = p.W1 + (g - 1) * p.U, b = mm * p.MM + m * p.M;
-		return k * p.M + (a <= b ? b : a);
-	}
+	if (k < gaps) return gap_score_far(p, k, gaps);
 	return gaps * p.M + (k - gaps) * p.U + p.W1;
 }
 
@@ -103,7 +106,9 @@ struct WarpStats { unsigned lookups, hits, lists, listids; };
 #ifndef KG_SCAN_INL
 #define KG_SCAN_INL                // inlined per call site: measured 40 ms vs 61 ms out of line (by-reference arguments go through
 #endif                             // the stack), although the four copies make 200 KB of code
-template <bool DENSE>
+// GENERIC = false: the kernel for the common shape -- hashed table (not direct addressed), 16-bit template lists, read
+// without N's -- compiled without the other branches, which keeps its loops short in the instruction cache.
+template <bool DENSE, bool GENERIC>
 __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p, const ReadCtx &rc, int strand,
                            Store<DENSE> &st, uint32_t *hits, uint64_t *sw, int *nbest, WarpStats &ws,
                            int2 *pool2 = nullptr, unsigned long long pool2_cap = 0, unsigned long long *ctr = nullptr,
@@ -140,7 +145,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 		for (int c0 = 0; c0 < npos && !any; c0 += KG_CHUNK) {
 			int w0 = stage(c0);
 			bool h = false;
-			if (rc.nN == 0) {
+			if (!GENERIC || rc.nN == 0) {
 				// probes c0' = multiples of k inside the chunk
 				int first = ((c0 + k - 1) / k) * k;
 				const int lim = min(npos, c0 + KG_CHUNK);
@@ -185,15 +190,16 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 	int seg_first = 0, seg_last = 0, seg_run = 0;
 
 	auto apply_segment = [&](uint32_t off, int first, int last, int run) -> bool {
-		const int nl = list_len(hv, off);
+		const int nl = GENERIC ? list_len(hv, off) : (int)__ldg(hv.values_s + off);
 		if (!DENSE && st.ncand + nl > KG_FILL) return false;
 		ws.lists++; ws.listids += lane == 0 ? nl : 0;
+#pragma unroll 1
 		for (int base = 0; base < nl; base += 32) {
 			const int i = base + (int)lane;
 			bool isnew = false;
 			int sl = 0;
 			if (i < nl) {
-				sl = st.find_or_insert(list_id(hv, off, i), &isnew);
+				sl = st.find_or_insert(GENERIC ? list_id(hv, off, i) : (int)__ldg(hv.values_s + off + 1 + i), &isnew);
 				if (isnew) st.score[sl] = k * p.M + run;                                              // savekmers.c:2682-2688
 				else st.score[sl] += gap_score(p, k, (first - 1) - st.ext[sl], false) + run;      // savekmers.c:2583-2655, 2575-2582
 				st.ext[sl] = last;
@@ -210,7 +216,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 		const int w0 = stage(c0);
 		const int lim = min(npos, c0 + KG_CHUNK), nround = (lim - c0 + 31) >> 5;
 		// phase 1: gather, four rounds of 32 positions at a time so that 4 independent probes per lane are in flight
-		if (rc.nN) {   // reads with N's (rare): validity per position, one probe at a time; kept off the hot path
+		if (GENERIC && rc.nN) {   // reads with N's (rare): validity per position, one probe at a time; kept off the hot path
 #pragma unroll 1
 			for (int u = 0; u < nround; ++u) {
 				const int j = c0 + u * 32 + (int)lane;
@@ -231,12 +237,12 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 					km[u] = ok ? kmer_of(w0, j) : 0ull;
 					e1[u] = KG_MISS;
 					if (ok) {
-						if (hv.mega) { uint32_t v = __ldg(hv.exist + km[u]); e1[u] = v != 1u ? v : KG_MISS; }
+						if (GENERIC && hv.mega) { uint32_t v = __ldg(hv.exist + km[u]); e1[u] = v != 1u ? v : KG_MISS; }
 						else { uint32_t q = __ldg(hv.exist + (uint32_t)(km[u] & hv.hmask)); e1[u] = q != hv.null_index ? q : KG_MISS; }
 						ws.lookups++;
 					}
 				}
-				if (!hv.mega) {
+				if (!GENERIC || !hv.mega) {
 					uint2 e2[4];
 #pragma unroll
 					for (int u = 0; u < 4; ++u) e2[u] = e1[u] != KG_MISS ? __ldg(hv.kv + e1[u]) : make_uint2(0, 0);
@@ -345,6 +351,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 #pragma unroll
 	for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
 	int nb = 0;
+#pragma unroll 1
 	for (int base = 0; base < st.ncand; base += 32) {
 		int i = base + (int)lane;
 		bool ok = false;
@@ -372,13 +379,13 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 
 // ---------------------------------------------------------------- the seeding kernel
 
-template <bool DENSE>
+template <bool DENSE, bool GENERIC>
 __global__ void __launch_bounds__(KG_WARPS * 32)
 seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, const uint32_t *__restrict__ rec_off,
                int nreads, SeedRes *__restrict__ res, uint32_t *__restrict__ recsize, int32_t *__restrict__ pool,
                unsigned long long pool_cap, unsigned long long *ctr, uint32_t *__restrict__ ovf_list,
                uint8_t *dense_scratch, size_t dense_stride, const uint8_t *__restrict__ kinds, MateRes *__restrict__ mates,
-               int2 *pool2, unsigned long long pool2_cap) {
+               int2 *pool2, unsigned long long pool2_cap, uint32_t *__restrict__ nlist, int from_nlist) {
 	__shared__ uint32_t s_hits[KG_WARPS][KG_CHUNK];
 	__shared__ uint64_t s_words[KG_WARPS][KG_WORDS];
 	__shared__ int s_tab[DENSE ? 1 : KG_WARPS][DENSE ? 1 : 3 * KG_CAP];
@@ -404,14 +411,16 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 	WarpStats ws = {0, 0, 0, 0};
 	unsigned mapped = 0, words_seen = 0;
 	const int k = hv.kmersize;
-	const int total = DENSE ? (int)ctr[C_OVF] : nreads;
+	// work: every read (the first pass), the reads with N's the first pass set aside (GENERIC, from_nlist), or the reads
+	// whose template table overflowed (DENSE)
+	const int total = DENSE ? (int)ctr[C_OVF] : (from_nlist ? (int)ctr[C_NLIST] : nreads);
 
 	for (;;) {
 		unsigned long long w = 0;
-		if (lane == 0) w = atomicAdd(&ctr[DENSE ? C_WORK2 : C_WORK], 1ull);
+		if (lane == 0) w = atomicAdd(&ctr[DENSE ? C_WORK2 : (from_nlist ? C_WORK3 : C_WORK)], 1ull);
 		w = __shfl_sync(0xffffffffu, w, 0);
 		if (w >= (unsigned long long)total) break;
-		const int r = DENSE ? (int)ovf_list[w] : (int)w;
+		const int r = DENSE ? (int)ovf_list[w] : (from_nlist ? (int)nlist[w] : (int)w);
 
 		ReadCtx rc;
 		rc.rec = in + rec_off[r];
@@ -421,6 +430,10 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 		rc.hdrlen = abs((int)ld_u32u(rc.rec + 12));
 		rc.seq = rc.rec + 16;
 		rc.N = rc.seq + 8 * (size_t)rc.words;
+		if (!GENERIC && rc.nN) {   // not this kernel's shape: the generic pass takes it
+			if (lane == 0) nlist[atomicAdd(&ctr[C_NLIST], 1ull)] = (uint32_t)r;
+			continue;
+		}
 		words_seen += rc.words;
 
 		// both strands through ONE call site (one inlined copy of the scan: four copies made 200 KB of code). A mate of
@@ -432,7 +445,7 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 		if (rc.seqlen >= k) {
 			for (int strand = 0; strand < 2 && !ovf; ++strand) {
 				st.cand = strand ? candR : candF;
-				sres[strand] = scan_strand<DENSE>(hv, p, rc, strand, st, hits, sw, &scnt[strand], ws, mate ? pool2 : nullptr,
+				sres[strand] = scan_strand<DENSE, GENERIC>(hv, p, rc, strand, st, hits, sw, &scnt[strand], ws, mate ? pool2 : nullptr,
 				                                  pool2_cap, ctr, &soff[strand]);
 				ovf = sres[strand] < 0;
 			}
@@ -461,9 +474,14 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 					if (lane == 0) atomicAdd(&ctr[C_POOLFAIL], 1ull);
 				} else {
 					int32_t *dst = pool + po;
-					if (bf >= br) for (int i = lane; i < nf; i += 32) dst[i] = candF[i];
-					if (bf < br) for (int i = lane; i < nr; i += 32) dst[i] = candR[i];
-					if (bf == br) for (int i = lane; i < nr; i += 32) dst[nf + i] = -candR[i];
+#pragma unroll 1
+					for (int i = lane; i < nt; i += 32) {   // forward set, reverse set, or both with the reverse ids negated
+						int v;
+						if (bf > br) v = candF[i];
+						else if (bf < br) v = candR[i];
+						else v = i < nf ? candF[i] : -candR[i - nf];
+						dst[i] = v;
+					}
 				}
 				out.score = bf > br ? bf : (bf < br ? br : -bf);
 				out.ntmpl = nt;
@@ -853,12 +871,12 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 		return -1;
 	}
 	if (prm->kmerscan == 1 && !all_pairs) return kg_chain_run(db, prm, stats);
-	if (prm->kmerscan != 0) { kmagpu_set_error("kmerscan %d: only save_kmers (0) and save_kmers_chain (1) are built", prm->kmerscan); return -1; }
+	if (prm->kmerscan != 0 && prm->kmerscan != 1) { kmagpu_set_error("kmerscan %d: only save_kmers (0) and save_kmers_chain (1) are built", prm->kmerscan); return -1; }
 	SeedParams sp = {prm->M, prm->MM, prm->U, prm->W1, prm->exhaustive};
 	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	if (b.pool_cap < (size_t)n * 16 + 1024) b.pool_cap = (size_t)n * 16 + 1024;
 	if (b.d_res.reserve(sizeof(SeedRes) * (size_t)n) || b.d_recoff.reserve(4 * (size_t)(2 * n + 2)) ||
-	    b.d_ctr.reserve(8 * C_N) || b.d_partial.reserve(4 * (size_t)(ntiles + 1) + 4 * (size_t)n)) return -1;
+	    b.d_ctr.reserve(8 * C_N) || b.d_partial.reserve(4 * (size_t)(ntiles + 1) + 8 * (size_t)n)) return -1;
 	const int grid = db->sm_count * KG_MINB;
 	// dense fallback scratch: (score, ext, candF, candR: int) + incl (byte) per template, per warp
 	const int dense_grid = db->sm_count * 2;
@@ -877,7 +895,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 		if (b.d_mates.reserve(sizeof(MateRes) * ((size_t)n + 1))) return -1;
 	}
 	uint32_t *recsize = (uint32_t *)b.d_recoff.p, *recoff = recsize + n + 1;
-	uint32_t *partial = (uint32_t *)b.d_partial.p, *ovf = partial + ntiles + 1;
+	uint32_t *partial = (uint32_t *)b.d_partial.p, *ovf = partial + ntiles + 1, *nlist = ovf + n;
 	unsigned long long *ctr = (unsigned long long *)b.d_ctr.p;
 	int launches = 0;
 	for (int attempt = 0;; ++attempt) {
@@ -885,14 +903,22 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 		if (pe && b.d_pool2.reserve(8 * b.pool2_cap)) return -1;
 		KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * C_N, db->stream));
 		KG_CUDA(cudaEventRecord(db->ev[2], db->stream));
-		seed_se_kernel<false><<<grid, KG_WARPS * 32, 0, db->stream>>>(db->hv, sp, (const uint8_t *)b.d_in.p,
+		// the common shape (hashed table, 16-bit lists) runs the specialised kernel and sets reads with N's aside for the
+		// generic one; any other database runs the generic kernel on every read
+		const bool common = !db->hv.mega && db->hv.values_s;
+		if (common)
+			seed_se_kernel<false, false><<<grid, KG_WARPS * 32, 0, db->stream>>>(db->hv, sp, (const uint8_t *)b.d_in.p,
+				(const uint32_t *)b.d_off.p, n, (SeedRes *)b.d_res.p, recsize, (int32_t *)b.d_pool.p,
+				(unsigned long long)b.pool_cap, ctr, ovf, nullptr, 0, kinds, (MateRes *)b.d_mates.p, (int2 *)b.d_pool2.p,
+				(unsigned long long)b.pool2_cap, nlist, 0);
+		seed_se_kernel<false, true><<<common ? db->sm_count * 2 : grid, KG_WARPS * 32, 0, db->stream>>>(db->hv, sp, (const uint8_t *)b.d_in.p,
 			(const uint32_t *)b.d_off.p, n, (SeedRes *)b.d_res.p, recsize, (int32_t *)b.d_pool.p,
 			(unsigned long long)b.pool_cap, ctr, ovf, nullptr, 0, kinds, (MateRes *)b.d_mates.p, (int2 *)b.d_pool2.p,
-			(unsigned long long)b.pool2_cap);
-		seed_se_kernel<true><<<dense_grid, KG_WARPS * 32, 0, db->stream>>>(db->hv, sp, (const uint8_t *)b.d_in.p,
+			(unsigned long long)b.pool2_cap, nlist, common ? 1 : 0);
+		seed_se_kernel<true, true><<<dense_grid, KG_WARPS * 32, 0, db->stream>>>(db->hv, sp, (const uint8_t *)b.d_in.p,
 			(const uint32_t *)b.d_off.p, n, (SeedRes *)b.d_res.p, recsize, (int32_t *)b.d_pool.p,
 			(unsigned long long)b.pool_cap, ctr, ovf, (uint8_t *)b.d_dense.p, dense_stride, kinds, (MateRes *)b.d_mates.p,
-			(int2 *)b.d_pool2.p, (unsigned long long)b.pool2_cap);
+			(int2 *)b.d_pool2.p, (unsigned long long)b.pool2_cap, nlist, 0);
 		if (pe) {
 			pair_select_kernel<<<(n + 127) / 128, 128, 0, db->stream>>>((const uint8_t *)b.d_in.p, (const uint32_t *)b.d_off.p, n, kinds,
 				(const MateRes *)b.d_mates.p, (const int2 *)b.d_pool2.p, (int32_t *)b.d_pool.p, (unsigned long long)b.pool_cap, ctr,
@@ -901,7 +927,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 		}
 		KG_CUDA(cudaEventRecord(db->ev[3], db->stream));
 		kg_exscan(recsize, n, recoff, partial, ctr + C_TOTAL, db->stream);
-		launches += 5;
+		launches += 6;
 		unsigned long long h[C_N];
 		KG_CUDA(cudaMemcpyAsync(h, ctr, 8 * C_N, cudaMemcpyDeviceToHost, db->stream));
 		KG_CUDA(cudaStreamSynchronize(db->stream));

@@ -8,7 +8,7 @@
 
 // counters living in d_ctr (uint64 slots)
 enum { C_WORK = 0, C_POOL = 1, C_OVF = 2, C_WORK2 = 3, C_POOLFAIL = 4, C_LOOKUPS = 5, C_HITS = 6, C_LISTS = 7,
-       C_LISTIDS = 8, C_MAPPED = 9, C_WORDS = 10, C_TOTAL = 11, C_POOL2 = 12, C_N = 16 };
+       C_LISTIDS = 8, C_MAPPED = 9, C_WORDS = 10, C_TOTAL = 11, C_POOL2 = 12, C_NLIST = 13, C_WORK3 = 14, C_N = 16 };
 
 // ---------------------------------------------------------------- small device helpers
 
