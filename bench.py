@@ -2,16 +2,24 @@
 """bench.py -- KMA mapping-core throughput on B200 (mapped reads/s + NW GCUPS), one JSON line on stdout.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU program
 
-A "step" is one pass of the hot path over one batch of synthetic stage-1 records per GPU: stage 2 (k-mer seeding +
-template scoring, save_kmers) and the stage-3 alignment pass (MEM seeding, chainSeeds, NW, alnFragsSE, update_Scores)
-chained in HBM. Weak scaling: every rank maps its own batch against its own replica of the database; the only
-exchange is the all-reduce of the two ConClave score arrays after the step.
-`value` is measured with the batch resident in HBM (device events inside libkmagpu); `e2e` is the same step through
-the public C ABI with pinned HOST buffers, H2D of the stage-1 records and D2H of the frag_raw stream + score arrays
-inside the timed region. `roofline` describes the kernel with the larger share of the step (seed_se_kernel or aln_pair_kernel; the other
-one is `roofline_pair` / `roofline_seed`); `nw` carries the banded-NW GCUPS / integer-roofline fraction BASELINE.json asks for.
+A "step" is one pass of the hot path over one batch of synthetic reads per GPU (BASELINE.json configs[1], C2: read pairs
+against the redundant gene DB, -ipe -apm p). Weak scaling: every rank maps its own batch against its own replica of the
+database; the exchanges are the all-reduce of the two ConClave score arrays and of the base-count matrix (NCCL inside the
+library).
+  value  stage 2 (k-mer seeding + template scoring + pair selection) + stage 3a (MEM chaining + NW + alnFragsPE +
+         update_Scores) with the batch resident in HBM (device events inside libkmagpu).
+  e2e    the WHOLE program span from host buffers: FASTQ text of the two files in pinned host memory -> record splitter +
+         stage 1 -> stage 2 -> alignment pass -> ConClave (global sums) -> traceback alignment + base counts -> consensus;
+         the per-template fragment stream and the consensus rows come back to the host (what the reference's writers turn
+         into .frag.gz / .res / .fsa / .aln). Every copy is inside the timed region. The reference arm runs plain
+         `kma -ipe ... -o out -t <cores>` on the same reads: the same span.
+  parity the numbers are only worth something if the results are the reference's: the ConClave arrays and the frag_raw
+         multiset of the step's own reads against the unmodified reference, and the output files of the reference host
+         running on libkmagpu.so (oracle/_ref/kma_gpu) against `kma` on a sample.
+`roofline` describes the kernel with the largest share of the step; `nw` the NW kernels of the mapping path on banded
+C3-shaped problems; c3 / c4 / c5 the other BASELINE configs beside the headline (c5: the k-mer table no longer fits L2).
 """
 from __future__ import annotations
 
@@ -114,31 +122,154 @@ def algorithmic_bytes(st, values_width):
     return (4 * st.lookups + 8 * st.hits + values_width * (st.list_fetches + st.list_ids) + 8 * st.read_words)
 
 
-def cpu_reference(prefix, r1, r2, cores, tmp):
-    """Reference arm: the unmodified reference on the read pairs: `kma -ipe ... -apm p -s2` (FASTQ parse + stage 2)
-    piped into alnFrags_threaded on `cores` pthreads (oracle/ref_harness.c drives the reference's own stage-3 entry
-    point the way runKMA does) -- the same span as our step. Returns reads/s (2 reads per pair)."""
-    kma = os.path.join(ROOT, "oracle", "_ref", "kma")
-    aln = os.path.join(ROOT, "oracle", "_ref", "ref_aln")
-    f1, f2 = os.path.join(tmp, f"sample_{len(r1)}_1.fq"), os.path.join(tmp, f"sample_{len(r1)}_2.fq")
-    if not (os.path.exists(f1) and os.path.exists(f2)):          # written once, outside the timed region
-        synth.write_fastq(f1 + ".tmp", r1, prefix="r")
-        synth.write_fastq(f2 + ".tmp", r2, prefix="r")
-        os.replace(f1 + ".tmp", f1)
-        os.replace(f2 + ".tmp", f2)
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def pair_fastq(tmp, r1, r2, tag, first=0):
+    """the two FASTQ files of a set of read pairs, written once (outside every timed region)"""
+    f1, f2 = os.path.join(tmp, f"{tag}_{len(r1)}_1.fq"), os.path.join(tmp, f"{tag}_{len(r1)}_2.fq")
+    if not (os.path.exists(f1) and os.path.exists(f2)):
+        for f, r in ((f1, r1), (f2, r2)):
+            open(f + ".tmp", "wb").write(synth.fastq_fixed(np.asarray(r), first=first).tobytes())
+            os.replace(f + ".tmp", f)
+    return f1, f2
+
+
+def ref_hotpath(prefix, inputs, cores, tmp, tag, flags=(), aln_flags=()):
+    """The unmodified reference over the hot path alone: `kma ... -s2` (FASTQ parse + stage 2) piped into alnFrags_threaded
+    on `cores` pthreads (oracle/ref_harness.c drives the reference's own stage-3a entry point the way runKMA does). Leaves
+    the frag_raw stream and the two ConClave arrays in <tmp>/fr_<tag>.out / sc_<tag>.out. Returns seconds."""
+    kma, aln = os.path.join(REF, "kma"), os.path.join(REF, "ref_aln")
+    fr, sc = os.path.join(tmp, f"fr_{tag}.out"), os.path.join(tmp, f"sc_{tag}.out")
     t0 = time.perf_counter()
     with open(os.devnull, "wb") as dn:
-        p1 = subprocess.Popen([kma, "-ipe", f1, f2, "-o", os.path.join(tmp, "o"), "-t_db", prefix, "-apm", "p", "-s2", "-t", str(cores)],
+        p1 = subprocess.Popen([kma] + list(inputs) + ["-o", os.path.join(tmp, "o_" + tag), "-t_db", prefix, "-s2", "-t", str(cores)] + list(flags),
                               stdout=subprocess.PIPE, stderr=dn)
-        p2 = subprocess.Popen([aln, prefix, "-", os.path.join(tmp, "fr.out"), os.path.join(tmp, "sc.out"), "-apm-p", "-t", str(cores)],
-                              stdin=p1.stdout, stdout=dn, stderr=dn)
+        p2 = subprocess.Popen([aln, prefix, "-", fr, sc, "-t", str(cores)] + list(aln_flags), stdin=p1.stdout, stdout=dn, stderr=dn)
         p1.stdout.close()
         rc2 = p2.wait()
         rc1 = p1.wait()
     dt = time.perf_counter() - t0
     if rc1 or rc2:
         raise RuntimeError(f"reference run failed: kma rc={rc1}, ref_aln rc={rc2}")
+    return dt, fr, sc
+
+
+def ref_program(binary, prefix, inputs, cores, cwd, out, flags=(), env=None):
+    """the whole reference program (or the same host on libkmagpu.so): input files -> .res / .fsa / .aln / .frag.gz. Seconds."""
+    t0 = time.perf_counter()
+    r = subprocess.run([os.path.join(REF, binary)] + list(inputs) + ["-o", out, "-t_db", prefix, "-t", str(cores)] + list(flags),
+                       cwd=cwd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
+    if r.returncode:
+        raise RuntimeError(f"{binary} failed ({r.returncode}): {r.stderr.decode()[-500:]}")
+    return time.perf_counter() - t0
+
+
+def cpu_reference(prefix, r1, r2, cores, tmp):
+    """Reference arm: the unmodified program on the read pairs, `kma -ipe f1 f2 -apm p -t cores -o out` -- FASTQ parse,
+    stage 2, alignment pass, ConClave, assembly, consensus, writers: the span of our `e2e`. Returns reads/s (2 per pair)."""
+    f1, f2 = pair_fastq(tmp, r1, r2, "sample")
+    dt = ref_program("kma", prefix, ["-ipe", f1, f2], cores, tmp, os.path.join(tmp, "ref_out"), ["-apm", "p"])
     return 2 * len(r1) / dt, dt
+
+
+def read_scores(path, DB):
+    raw = np.fromfile(path, dtype=np.uint8)
+    n = int(np.frombuffer(raw[:4].tobytes(), dtype=np.int32)[0])
+    assert n == DB, "score file does not match the database"
+    v = np.frombuffer(raw[4:4 + 16 * DB].tobytes(), dtype=np.uint64)
+    return v[:DB].copy(), v[DB:].copy()
+
+
+def frag_multiset(api, buf):
+    """the frag_raw records of a stream (updatescores.c:284-295; a pair's record includes its mate block), sorted: thread
+    scheduling permutes the reference's output order, the multiset is what must be equal"""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    off = api.record_offsets(4, buf)
+    mv = memoryview(buf)
+    recs = [bytes(mv[int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
+    recs.sort()
+    return recs
+
+
+def compare_hotpath(api, got_frag, got_a, got_u, fr_path, sc_path, DB):
+    ref_a, ref_u = read_scores(sc_path, DB)
+    ref_frag = np.fromfile(fr_path, dtype=np.uint8)
+    t0 = time.perf_counter()
+    mine, theirs = frag_multiset(api, got_frag), frag_multiset(api, ref_frag)
+    return {"scores_equal": bool(np.array_equal(got_a, ref_a) and np.array_equal(got_u, ref_u)),
+            "frag_sorted_equal": mine == theirs, "frag_records": len(mine), "frag_records_reference": len(theirs),
+            "frag_bytes": int(len(got_frag)), "score_sum": int(ref_a.sum()), "compare_s": round(time.perf_counter() - t0, 1)}
+
+
+def compare_files(cwd, want, got, exts=("res", "fsa", "aln", "frag.gz", "mat.gz")):
+    """the output files of two runs: .res numbers within 1e-9 relative, everything else byte-equal after gunzip
+    (.frag.gz as a sorted set of lines: the reference's threads permute them)"""
+    import gzip
+    out = {}
+    for e in exts:
+        pw, pg = os.path.join(cwd, f"{want}.{e}"), os.path.join(cwd, f"{got}.{e}")
+        if not os.path.exists(pw) and not os.path.exists(pg):
+            continue
+        if not (os.path.exists(pw) and os.path.exists(pg)):
+            out[e] = False
+            continue
+        rd = (lambda p: gzip.open(p, "rb").read()) if e.endswith(".gz") else (lambda p: open(p, "rb").read())
+        a, b = rd(pw), rd(pg)
+        if e == "res":
+            ok = True
+            la, lb = a.decode().splitlines(), b.decode().splitlines()
+            ok = len(la) == len(lb)
+            for x, y in zip(la, lb):
+                fx, fy = x.split("\t"), y.split("\t")
+                ok = ok and len(fx) == len(fy)
+                for u, v in zip(fx, fy):
+                    u, v = u.strip(), v.strip()
+                    if u == v:
+                        continue
+                    try:
+                        ok = ok and abs(float(u) - float(v)) <= 1e-9 * max(abs(float(u)), abs(float(v)))
+                    except ValueError:
+                        ok = False
+            out[e] = ok
+        elif e == "frag.gz":
+            out[e] = sorted(a.splitlines()) == sorted(b.splitlines())
+        else:
+            out[e] = a == b
+        out[e + "_bytes"] = len(a)
+    return out
+
+
+def parity_c2(api, prefix, r1, r2, cores, tmp, device, file_pairs):
+    """Parity where the numbers are taken. (1) The step's own read pairs through the unmodified reference's hot path
+    (`kma -ipe ... -apm p -s2 -t cores | alnFrags_threaded`): both ConClave arrays equal, frag_raw multiset equal.
+    (2) The first `file_pairs` pairs through the whole program twice -- `kma` and the same host linked over libkmagpu.so
+    (oracle/_ref/kma_gpu) -- and the output files compared."""
+    from kma_b200 import records
+    n = len(r1)
+    out = {"config": "C2", "n": n}
+    f1, f2 = pair_fastq(tmp, r1, r2, "step")
+    dt, fr, sc = ref_hotpath(prefix, ["-ipe", f1, f2], cores, tmp, "c2", ["-apm", "p"], ["-apm-p"])
+    db = api.TemplateDB(prefix, device=device)
+    p = api.default_params()
+    p.counters = 0
+    db.seed_upload(records.stage1_pairs_fast(r1, r2))
+    db.seed_run(p)
+    db.align_from_seed()
+    db.align_run(p)
+    frag, a, u, _ = db.align_download()
+    out.update(compare_hotpath(api, frag, a, u, fr, sc, db.info.DB_size))
+    out["reference_s"] = round(dt, 1)
+    db.close()
+    if os.path.exists(os.path.join(REF, "kma_gpu")) and file_pairs:
+        m = min(file_pairs, n)
+        g1, g2 = pair_fastq(tmp, r1[:m], r2[:m], "files")
+        env = dict(os.environ, KMAGPU_DEVICE=str(device))
+        t_ref = ref_program("kma", prefix, ["-ipe", g1, g2], cores, tmp, "pf_ref", ["-apm", "p", "-matrix"])
+        t_gpu = ref_program("kma_gpu", prefix, ["-ipe", g1, g2], 1, tmp, "pf_gpu", ["-apm", "p", "-matrix"], env=env)
+        out["files"] = dict(compare_files(tmp, "pf_ref", "pf_gpu"), pairs=m, reference_s=round(t_ref, 1), gpu_host_s=round(t_gpu, 1),
+                            what="kma -ipe -apm p -matrix vs the same host on libkmagpu.so (oracle/_ref/kma_gpu)")
+    return out
 
 
 def cpu_port(prefix, s1, nreads):

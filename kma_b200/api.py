@@ -479,6 +479,23 @@ class TemplateDB:
         self._frag_bytes = ob.value
         return (out[: ob.value] if download else None), w, fc, rc, nr.value
 
+    def conclave_from_align(self, alignment_scores=None, uniq_alignment_scores=None, out=None, totals=None):
+        """ConClave on the frag_raw stream the last align_run of this handle left in HBM. Scores None: the run-wide sums the
+        database image holds on the device (scores_reset ... allreduce_scores) -- they never left HBM. out: a (pinned)
+        uint8 buffer for the per-template fragment stream, None: the fragments stay in HBM for trace_from_conclave.
+        -> (fragment bytes | None, w_scores, fragmentCounts, readCounts, nrecords)"""
+        DB = self.info.DB_size
+        a = None if alignment_scores is None else np.ascontiguousarray(alignment_scores, dtype=np.uint64)
+        u = None if uniq_alignment_scores is None else np.ascontiguousarray(uniq_alignment_scores, dtype=np.uint64)
+        w, fc, rc = totals if totals is not None else (np.zeros(DB, np.uint64), np.zeros(DB, np.uint32), np.zeros(DB, np.uint32))
+        cap = 0 if out is None else int(out.numel() if hasattr(out, "numel") else out.size)
+        ob, nr = C.c_size_t(), C.c_int64()
+        _check(lib().kmagpu_conclave_from_align(self._h, None if a is None else a.ctypes.data, None if u is None else u.ctypes.data,
+                                                None if out is None else _ptr(out), cap, C.byref(ob), w.ctypes.data, fc.ctypes.data,
+                                                rc.ctypes.data, C.byref(nr)))
+        self._frag_bytes = ob.value
+        return (None if out is None else out[: ob.value]), w, fc, rc, nr.value
+
     # --- ConClave choice pass + per-template bucketing --------------------------------------------
     def conclave_batch(self, frag_raw, alignment_scores, uniq_alignment_scores, totals=None, download=True):
         """runConClave (conclave.c:43) + printFrags (frags.c:30) over one chunk of frag_raw records with the GLOBAL score

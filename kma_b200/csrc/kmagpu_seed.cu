@@ -24,9 +24,11 @@
 
 #define KG_CHUNK 256          // k-mer positions gathered per phase-1 round (8 per lane)
 #define KG_PER_LANE (KG_CHUNK / 32)
-#define KG_CAP 256            // shared hash slots per warp
+#ifndef KG_CAP_LOG
 #define KG_CAP_LOG 8
-#define KG_FILL 192           // distinct templates a read may see before it goes to the dense path
+#endif
+#define KG_CAP (1 << KG_CAP_LOG)          // shared hash slots per warp
+#define KG_FILL (3 * KG_CAP / 4)          // distinct templates a read may see before it goes to the dense path
 #define KG_WARPS 4            // warps per CTA
 #ifndef KG_MINB
 #define KG_MINB 8             // CTAs per SM the seeding grid is sized for (24.9 KB of shared memory each: at most 9). The kernel carries no
@@ -190,6 +192,10 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 	int seg_first = 0, seg_last = 0, seg_run = 0;
 
 	auto apply_segment = [&](uint32_t off, int first, int last, int run) -> bool {
+		// the list's length and its first 32 ids in one round trip (the id load does not wait for the length: the value
+		// array is padded, ids past the list are never looked at)
+		int id0 = 0;
+		if (!GENERIC) id0 = (int)__ldg(hv.values_s + off + 1 + lane);
 		const int nl = GENERIC ? list_len(hv, off) : (int)__ldg(hv.values_s + off);
 		if (!DENSE && st.ncand + nl > KG_FILL) return false;
 		ws.lists++; ws.listids += lane == 0 ? nl : 0;
@@ -199,7 +205,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 			bool isnew = false;
 			int sl = 0;
 			if (i < nl) {
-				sl = st.find_or_insert(GENERIC ? list_id(hv, off, i) : (int)__ldg(hv.values_s + off + 1 + i), &isnew);
+				sl = st.find_or_insert(GENERIC ? list_id(hv, off, i) : (base ? (int)__ldg(hv.values_s + off + 1 + i) : id0), &isnew);
 				if (isnew) st.score[sl] = k * p.M + run;                                              // savekmers.c:2682-2688
 				else st.score[sl] += gap_score(p, k, (first - 1) - st.ext[sl], false) + run;      // savekmers.c:2583-2655, 2575-2582
 				st.ext[sl] = last;
@@ -379,8 +385,11 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 
 // ---------------------------------------------------------------- the seeding kernel
 
+#ifndef KG_LB
+#define KG_LB 1               // minimum resident CTAs per SM the kernels are compiled for (register cap 65536 / (128 * KG_LB))
+#endif
 template <bool DENSE, bool GENERIC>
-__global__ void __launch_bounds__(KG_WARPS * 32)
+__global__ void __launch_bounds__(KG_WARPS * 32, KG_LB)
 seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, const uint32_t *__restrict__ rec_off,
                int nreads, SeedRes *__restrict__ res, uint32_t *__restrict__ recsize, int32_t *__restrict__ pool,
                unsigned long long pool_cap, unsigned long long *ctr, uint32_t *__restrict__ ovf_list,
@@ -877,7 +886,10 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 	if (b.pool_cap < (size_t)n * 16 + 1024) b.pool_cap = (size_t)n * 16 + 1024;
 	if (b.d_res.reserve(sizeof(SeedRes) * (size_t)n) || b.d_recoff.reserve(4 * (size_t)(2 * n + 2)) ||
 	    b.d_ctr.reserve(8 * C_N) || b.d_partial.reserve(4 * (size_t)(ntiles + 1) + 8 * (size_t)n)) return -1;
-	const int grid = db->sm_count * KG_MINB;
+	// persistent grid: as many CTAs as are resident at once (registers and shared memory decide)
+	int per_sm = KG_MINB;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, seed_se_kernel<false, false>, KG_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = KG_MINB;
+	const int grid = db->sm_count * per_sm;
 	// dense fallback scratch: (score, ext, candF, candR: int) + incl (byte) per template, per warp
 	const int dense_grid = db->sm_count * 2;
 	const size_t D = (size_t)db->info.DB_size + 1;

@@ -175,3 +175,90 @@ class MapPipeline:
             scores[0][:] += a
             scores[1][:] += u
         return res
+
+    def map_to_consensus(self, text1, text2, frag_outs, params, fastq=True, consensus_args=None, **ingest):
+        """The whole mapping core on one batch of FASTQ text (pinned uint8 tensors; text2 = the second file of a pair of
+        files or None), every stream resident in HBM, what `kma -i / -ipe ... -o out` computes between its input files and
+        its writers: record splitter + stage 1 -> stage 2 -> alignment pass | ConClave sums all-reduced over ranks (NCCL
+        inside the library, in place) | ConClave choice -> traceback alignment + base counts | matrix all-reduced over
+        ranks | consensus of every template. Each worker handle (clones of one database image: one set of sums) takes one
+        slice of the batch, so one slice's PCIe copies hide behind another's kernels; the two exchanges are the only
+        points where the workers meet. Down come: per worker its per-template fragment stream into frag_outs[w] (what the
+        .frag.gz writer needs), then the consensus rows and per-template sums (what .res / .fsa / .aln are written from).
+        Paired files must line up slice by slice (equal-length records), as map_text_device_split requires.
+        Returns dict(reads, fragments, consensus=(t, s, q, stats), totals=(w_scores, fragmentCounts, readCounts), frag_bytes)."""
+        import torch  # noqa: F401  (pinned tensors come from the caller)
+        L = api.lib()
+        W = len(self.dbs)
+
+        def cuts(t):
+            a = t.numpy() if hasattr(t, "numpy") else t
+            nb = len(a)
+            return sorted({L.kmagpu_fastx_sync(a.ctypes.data, nb, int(fastq), (nb * i) // W) for i in range(W)} | {nb})
+        c1 = cuts(text1)
+        c2 = cuts(text2) if text2 is not None else None
+        if c2 is not None and len(c2) != len(c1):
+            raise api.KmaGpuError("the two files do not split into the same number of slices")
+        nsl = len(c1) - 1
+        DB = self.info.DB_size
+        totals = [(np.zeros(DB, np.uint64), np.zeros(DB, np.uint32), np.zeros(DB, np.uint32)) for _ in range(W)]
+        res = {"reads": [0] * W, "fragments": [0] * W, "frag": [None] * W}
+        err = []
+        lead = self.dbs[0]
+        p_trace = api.Params.from_buffer_copy(bytes(params))
+        p_trace.matrix = 1
+        lead.scores_reset()
+        lead.matrix_reset()
+
+        def exchange_scores():
+            try:
+                lead.allreduce_scores(download=False)
+            except Exception as e:
+                err.append(e)
+
+        def exchange_matrix():
+            try:
+                lead.allreduce_matrix()
+            except Exception as e:
+                err.append(e)
+        b1 = threading.Barrier(W, action=exchange_scores)
+        b2 = threading.Barrier(W, action=exchange_matrix)
+
+        def work(w):
+            db = self.dbs[w]
+            try:
+                if w < nsl:
+                    t2 = None if c2 is None else text2[c2[w]:c2[w + 1]]
+                    _, cnt, _, u1, u2 = db.run_input_text(text1[c1[w]:c1[w + 1]], text2=t2, fastq=fastq, download=False, **ingest)
+                    if u1 != c1[w + 1] - c1[w] or (c2 is not None and u2 != c2[w + 1] - c2[w]):
+                        raise api.KmaGpuError("the two files' records do not line up slice by slice")
+                    res["reads"][w] = cnt
+                    db.seed_run(params)
+                    db.align_from_seed()
+                    db.align_run(params)
+            except Exception as e:
+                err.append(e)
+            b1.wait()
+            try:
+                if w < nsl and not err:
+                    frag, _, _, _, _ = db.conclave_from_align(None, None, out=frag_outs[w], totals=totals[w])
+                    res["frag"][w] = frag
+                    _, nfr, _ = db.trace_from_conclave(p_trace, download=False)
+                    res["fragments"][w] = nfr
+            except Exception as e:
+                err.append(e)
+            b2.wait()
+
+        ts = [threading.Thread(target=work, args=(w,)) for w in range(W)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if err:
+            raise err[0]
+        wsc = sum(t[0] for t in totals)
+        lead.allreduce_u64(wsc)
+        cons = lead.consensus(0, **(consensus_args or {}))
+        return {"reads": sum(res["reads"]), "fragments": sum(res["fragments"]), "consensus": cons[:4],
+                "totals": (wsc, sum(t[1] for t in totals), sum(t[2] for t in totals)),
+                "frag_bytes": sum(int(f.numel() if hasattr(f, "numel") else len(f)) for f in res["frag"] if f is not None)}
