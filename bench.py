@@ -299,7 +299,8 @@ def cpu_port(prefix, s1, nreads):
 
 def nw_gcups(db, seqs, peak_iops, n=24000, seed=3):
     """Banded-NW GCUPS on C3-shaped problems (template windows of 1-3 kb vs a 9 %-error copy, band = |dl| + 64 as
-    KMA_score chooses it), the NW batch kernel timed alone with CUDA events inside the library (burst)."""
+    KMA_score chooses it) through the NW queue kernels the alignment pass runs, timed alone with CUDA events inside the
+    library (burst)."""
     rng = np.random.default_rng(seed)
     probs, qs, qoff = [], [], 0
     while len(probs) < n:
@@ -324,7 +325,7 @@ def nw_gcups(db, seqs, peak_iops, n=24000, seed=3):
         if best is None or ms < best:
             best = ms
     gc = cells / best / 1e6
-    return {"kernel": "nw_batch_kernel (warp wavefront, banded)", "problems": int(n), "cells": int(cells), "ms": best,
+    return {"kernel": "nw_warp_kernel / nw_thread_kernel: the NW queue kernels of the alignment pass (kmagpu_nw_batch feeds the same queue)", "problems": int(n), "cells": int(cells), "ms": best,
             "gcups": gc, "lane_utilisation": cells / (32.0 * steps), "int_ops_per_cell": 12,
             "int_roofline": {"achieved_tiops": gc * 12 / 1e3, "peak_tiops": peak_iops / 1e12, "frac": gc * 12e9 / peak_iops,
                              "peak_kind": "148 SMs x 128 int32 lanes x max SM clock"},
@@ -444,23 +445,138 @@ def c3_chain(db, api, seqs, prefix, workdir, cores, peak_gbs, n=20000, ref_n=200
                              "frac": ach / peak_gbs, "algorithmic_bytes_per_launch": int(alg), "bytes_per_read": alg / n,
                              "kernel_ms": st.ms_seed, "traffic": None,
                              "note": "table and per-warp rows are L2 resident; bound by dependent L2 round trips (ncu: long_scoreboard)"}
-    kma = os.path.join(ROOT, "oracle", "_ref", "kma")
-    aln = os.path.join(ROOT, "oracle", "_ref", "ref_aln")
-    if os.path.exists(kma) and os.path.exists(aln):
+    # ncu DRAM traffic of chain_kernel per launch (profiles/traffic.json, scaled by reads)
+    tr = ncu_traffic("chain_kernel", n)
+    out["chain_roofline"]["traffic"] = tr
+    if os.path.exists(os.path.join(REF, "kma")) and os.path.exists(os.path.join(REF, "ref_aln")):
         fq = os.path.join(workdir, f"c3_{ref_n}.fq")
         synth.write_fastq(fq, reads[:ref_n], qual="5")
+        dt, fr, sc = ref_hotpath(prefix, ["-i", fq], cores, workdir, "c3")
+        out["cpu_reference"] = {"reads_per_s": ref_n / dt, "cores": cores, "seconds": dt,
+                                "sample": f"first {ref_n} reads; unmodified kma -s2 -t {cores} | alnFrags_threaded on {cores} pthreads"}
+        # parity on the reference's sample: the same reads through the device path
+        db.seed_upload(records.stage1_records(reads[:ref_n]))
+        db.seed_run(p)
+        db.align_from_seed()
+        db.align_run(p)
+        frag, a, u, _ = db.align_download()
+        out["parity"] = dict(compare_hotpath(api, frag, a, u, fr, sc, db.info.DB_size), config="C3", n=ref_n)
+    return out
+
+
+def c4_files(api, workdir, device, cores, genome_bases, n):
+    """C4 at file level: `kma -mem_mode -1t1 -matrix` and the same host on libkmagpu.so on a sample of the reads"""
+    if not os.path.exists(os.path.join(REF, "kma_gpu")):
+        return None
+    wd = os.path.join(workdir, f"c4_{genome_bases}")
+    genome = np.random.default_rng(4).integers(0, 4, size=genome_bases).astype(np.uint8)
+    fq = os.path.join(wd, f"c4_{n}.fq")
+    if not os.path.exists(fq):
+        open(fq + ".tmp", "wb").write(synth.fastq_fixed(np.asarray(synth.short_reads(6, [genome], n, L=150, sub=0.01))).tobytes())
+        os.replace(fq + ".tmp", fq)
+    env = dict(os.environ, KMAGPU_DEVICE=str(device))
+    flags = ["-mem_mode", "-1t1", "-matrix"]
+    t_ref = ref_program("kma", "db", ["-i", fq], cores, wd, "pf_ref", flags)
+    t_gpu = ref_program("kma_gpu", "db", ["-i", fq], 1, wd, "pf_gpu", flags, env=env)
+    return dict(compare_files(wd, "pf_ref", "pf_gpu"), config="C4", n=n, reference_s=round(t_ref, 1), gpu_host_s=round(t_gpu, 1),
+                what="kma -mem_mode -1t1 -matrix vs the same host on libkmagpu.so")
+
+
+C5_FAMILIES, C5_TLEN = 1250, 10000
+
+
+def c5_db(workdir):
+    """BASELINE.json configs[4] at a quarter of its size (12.5k templates in 1250 families, ~125 Mb, ~29 M distinct 16-mers):
+    the largest database `kma index` builds in about a minute, and already one whose k-mer table (128 MB of buckets +
+    230 MB of keys) and position index (GBs) cannot sit in the 126 MB L2 -- the HBM-resident gather. Built once per box with
+    the reference's own indexer, cached in the work directory."""
+    wd = os.path.join(workdir, f"c5_{C5_FAMILIES}_{C5_TLEN}")
+    os.makedirs(wd, exist_ok=True)
+    prefix = os.path.join(wd, "db")
+    names, seqs = synth.gene_db(55, n_families=C5_FAMILIES, n_variants=10, len_lo=C5_TLEN * 3 // 4, len_hi=C5_TLEN * 5 // 4)
+    how = "cached"
+    if not os.path.exists(prefix + ".comp.b"):
         t0 = time.perf_counter()
-        with open(os.devnull, "wb") as dn:
-            p1 = subprocess.Popen([kma, "-i", fq, "-o", os.path.join(workdir, "o3"), "-t_db", prefix, "-s2", "-t", str(cores)],
-                                  stdout=subprocess.PIPE, stderr=dn)
-            p2 = subprocess.Popen([aln, prefix, "-", os.path.join(workdir, "fr3.out"), os.path.join(workdir, "sc3.out"), "-t", str(cores)],
-                                  stdin=p1.stdout, stdout=dn, stderr=dn)
-            p1.stdout.close()
-            rc2, rc1 = p2.wait(), p1.wait()
-        dt = time.perf_counter() - t0
-        if not (rc1 or rc2):
-            out["cpu_reference"] = {"reads_per_s": ref_n / dt, "cores": cores, "seconds": dt,
-                                    "sample": f"first {ref_n} reads; unmodified kma -s2 -t {cores} | alnFrags_threaded on {cores} pthreads"}
+        if os.path.exists(os.path.join(REF, "kma")):
+            synth.write_fasta(os.path.join(wd, "db.fsa"), names, seqs)
+            r = subprocess.run([os.path.join(REF, "kma"), "index", "-i", "db.fsa", "-o", "dbtmp"], cwd=wd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+            if r.returncode:
+                raise RuntimeError("kma index failed: " + r.stderr.decode()[-300:])
+            os.remove(os.path.join(wd, "db.fsa"))
+            how = "kma index"
+        else:
+            dbbuild.build_db(os.path.join(wd, "dbtmp"), names, seqs)
+            how = "kma_b200.dbbuild"
+        for ext in (".length.b", ".seq.b", ".name", ".comp.b"):
+            os.replace(os.path.join(wd, "dbtmp" + ext), prefix + ext)
+        how += f" {time.perf_counter() - t0:.0f} s"
+    return prefix, seqs, how
+
+
+def c5_leg(api, workdir, rank, world, device, cores, pk, dist, n=4_000_000, ref_n=2000):
+    """C5 beside the headline: short single-end reads against the large redundant database, -1t1, stage 2 + alignment pass
+    resident in HBM, every rank its own reads against its own replica (the scaling-sweep config). Seeding here is the
+    random-sector gather of SURVEY 8d: `roofline` is seed_se_kernel against the measured HBM peak, in algorithmic bytes
+    and in 32-byte sectors."""
+    import torch
+    if rank == 0:
+        prefix, seqs, how = c5_db(workdir)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        prefix, seqs, how = c5_db(workdir)
+    t0 = time.perf_counter()
+    db = api.TemplateDB(prefix, device=device)
+    t_open = time.perf_counter() - t0
+    reads = synth.short_reads(56 + 1000 * rank, seqs, n)
+    s1 = records.stage1_records_fast(reads, first=rank * n)
+    p = api.default_params()
+    p.one2one = 1
+    p.counters = 0
+    db.seed_upload(s1)
+    best = None
+    for _ in range(4):
+        st = db.seed_run(p)
+        db.align_from_seed()
+        sa = db.align_run(p)
+        if best is None or st.ms_total + sa.ms_total < best[0]:
+            best = (st.ms_total + sa.ms_total, st, sa)
+    ms, st, sa = best
+    tt = torch.tensor([ms, st.ms_seed, sa.ms_align], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_max, seed_max, aln_max = (float(x) for x in tt.cpu())
+    info = db.info
+    vw = 2 if info.DB_size < 65535 else 4
+    alg = algorithmic_bytes(st, vw)
+    # 32-byte sectors the gather needs at the least: one per bucket probe, one per key / value-offset pair, the lists
+    sectors = st.lookups + st.hits + st.list_fetches + (vw * st.list_ids + 31) // 32 + (8 * st.read_words + 31) // 32
+    ach = alg / (st.ms_seed * 1e-3) / 1e9
+    out = {"workload": f"C5 (quarter scale): {info.DB_size - 1} templates / {info.seq_bases / 1e6:.0f} Mb redundant DB ({C5_FAMILIES} families x 10), "
+                       f"{n} synthetic 150 bp single-end reads per GPU, -1t1: stage 2 + alignment pass resident in HBM",
+           "db": {"templates": info.DB_size - 1, "bases": int(info.seq_bases), "kmers": int(info.n), "hash_slots": int(info.size),
+                  "device_bytes": int(info.device_bytes), "built": how, "open_s": round(t_open, 1)},
+           "reads_per_s": world * n / (ms_max * 1e-3), "ms": ms_max, "seed_kernel_ms": seed_max, "align_ms": aln_max,
+           "lookups_per_read": st.lookups / n, "lookups_per_s": st.lookups / (st.ms_seed * 1e-3), "alignments_per_read": sa.tasks / max(1, sa.reads),
+           "overflow_reads": int(st.overflow_reads),
+           "roofline": {"kernel": "seed_se_kernel", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                        "algorithmic_bytes_per_launch": int(alg), "kernel_ms": st.ms_seed, "traffic": ncu_traffic("c5:seed_se_kernel", n),
+                        "sector_bytes_per_launch": int(32 * sectors), "sector_GBs": 32 * sectors / (st.ms_seed * 1e-3) / 1e9,
+                        "sector_frac": 32 * sectors / (st.ms_seed * 1e-3) / 1e9 / pk["hbm_gbs"],
+                        "note": "k-mer table out of L2: every bucket / key probe is a 32-byte HBM sector"}}
+    if rank == 0 and os.path.exists(os.path.join(REF, "kma")) and os.path.exists(os.path.join(REF, "ref_aln")):
+        fq = os.path.join(workdir, f"c5_{ref_n}.fq")
+        open(fq, "wb").write(synth.fastq_fixed(np.asarray(reads[:ref_n])).tobytes())
+        dt, fr, sc = ref_hotpath(prefix, ["-i", fq], cores, workdir, "c5", ["-1t1"], ["-1t1"])
+        db.seed_upload(records.stage1_records_fast(reads[:ref_n]))
+        db.seed_run(p)
+        db.align_from_seed()
+        db.align_run(p)
+        frag, a, u, _ = db.align_download()
+        out["parity"] = dict(compare_hotpath(api, frag, a, u, fr, sc, info.DB_size), config="C5", n=ref_n)
+        out["cpu_reference"] = {"reads_per_s": ref_n / dt, "cores": cores, "seconds": round(dt, 2),
+                                "sample": f"first {ref_n} reads; unmodified kma -1t1 -s2 -t {cores} | alnFrags_threaded (incl. loading the {info.device_bytes / 1e9:.1f} GB-class DB)"}
+    db.close()
     return out
 
 
@@ -471,15 +587,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=2_000_000, help="read pairs per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="read pairs of the CPU legs (default: the whole step, ~7 s on 16 cores)")
+    ap.add_argument("--cpu-sample", type=int, default=500_000, help="read pairs per step of the reference program (a step of the reference arm / the cpu_baseline leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (one genome, -mem_mode, consensus; resident flow) side measurement")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity legs (reference hot path on the step's own reads, output files on a sample)")
+    ap.add_argument("--file-pairs", type=int, default=100_000, help="read pairs of the file-level parity sample")
     ap.add_argument("--no-c3", action="store_true", help="skip the C3 (long reads, chain mode) side measurement")
-    ap.add_argument("--e2e-workers", type=int, default=4, help="host threads / library handles of the end-to-end pipeline")
-    ap.add_argument("--no-text", action="store_true", help="skip the FASTQ-text end-to-end leg (stage 1 on the device)")
-    ap.add_argument("--host-split", action="store_true", help="text leg: always split records on the host (default: on the device when the files line up)")
-    ap.add_argument("--split-threads", type=int, default=8, help="host threads of the FASTQ record splitter in the text leg")
-    ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks the batch is cut into for the end-to-end pipeline")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (one genome, -mem_mode, consensus; resident flow) side measurement")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 (large redundant DB: k-mer table out of L2) side measurement")
+    ap.add_argument("--c5-reads", type=int, default=4_000_000)
+    ap.add_argument("--e2e-workers", type=int, default=4, help="host threads / library handles (clones of one database image) of the end-to-end pipelines")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks the batch is cut into for the hot-path-only end-to-end pipeline")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -488,6 +605,7 @@ def main():
     cores = os.cpu_count() or 1
     workdir = os.path.join(tempfile.gettempdir(), "kma_b200_bench")
     os.makedirs(workdir, exist_ok=True)
+    have_ref = os.path.exists(os.path.join(REF, "kma"))
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -496,7 +614,6 @@ def main():
         prefix, names, seqs = make_db(workdir)
         sample = min(args.cpu_sample, args.pairs)
         r1, r2 = synth.paired_reads(READ_SEED, seqs, sample)
-        have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "kma"))
         vals = []
         for i in range(args.warmup + args.steps):
             if have_ref:
@@ -506,14 +623,15 @@ def main():
             if i >= args.warmup:
                 vals.append((v, dt))
         v = sum(2 * sample for _ in vals) / sum(dt for _, dt in vals)
+        what = (f"{sample} read pairs of the same workload per step; the unmodified program, kma -ipe f1 f2 -apm p -t {cores} -o out: FASTQ parse, stage 2, "
+                "alignment pass, ConClave, assembly + consensus, .res/.fsa/.aln/.frag.gz writers") if have_ref else \
+               f"{sample} read pairs per step; oracle/liborc.so stage 2 + alignment pass (the reference is not built here)"
         line = {"impl": "reference", "metric": METRIC,
                 "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * statistics.mean(dt for _, dt in vals), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "pairs_per_step": sample, "reads_per_step": 2 * sample},
-                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores if have_ref else 1,
-                                 "kind": "reference" if have_ref else "port",
-                                 "sample": f"{sample} read pairs of the same workload per step; unmodified kma -ipe -apm p -s2 -t {cores} | alnFrags_threaded on {cores} pthreads (FASTQ parse + stage 2 + alignment pass)"},
+                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores if have_ref else 1, "kind": "reference" if have_ref else "port", "sample": what},
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -521,7 +639,7 @@ def main():
     # ------------------------------------------------------------------ our arm (GPU)
     import torch
     import torch.distributed as dist
-    from kma_b200 import api
+    from kma_b200 import api, pipeline
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
@@ -541,6 +659,7 @@ def main():
         prefix, names, seqs = make_db(workdir)
 
     r1, r2 = synth.paired_reads(READ_SEED + 1000 * rank, seqs, args.pairs)
+    r1, r2 = np.asarray(r1), np.asarray(r2)
     s1_np = records.stage1_pairs_fast(r1, r2, first=rank * args.pairs)
     s1 = torch.empty(len(s1_np), dtype=torch.uint8, pin_memory=True)
     s1.numpy()[:] = s1_np
@@ -549,15 +668,14 @@ def main():
     params = api.default_params()
     params.counters = 0
     vw = 2 if db.info.DB_size < 65535 else 4
+    DBn = db.info.DB_size
+    total_bases = int(db.info.seq_bases)
 
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
-
-    DBn = db.info.DB_size
-    scores = (np.zeros(DBn, np.uint64), np.zeros(DBn, np.uint64))
 
     def step_resident():
         st = db.seed_run(params)
@@ -569,7 +687,6 @@ def main():
     db.seed_upload(s1)
     for _ in range(args.warmup):
         st, sa = step_resident()
-    frag_out = torch.empty(db.align_out_bytes() + 4096, dtype=torch.uint8, pin_memory=True)
     sampler = ClockSampler(local_rank)
     sync_all()
     sampler.start()
@@ -584,107 +701,71 @@ def main():
     sync_all()
     t_wall = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop()
-    res, _, _, _ = db.align_download(out=frag_out)
-    out_bytes = int(res.numel() if hasattr(res, "numel") else len(res))
-    # the timed steps run without the alignment kernel's statistic counters (params.counters = 0: they are measurement
-    # instrumentation and cost the pair kernel ~10 %); one untimed step with them gives the algorithmic-byte inputs
+    out_bytes = db.align_out_bytes()
+    # the timed steps run without the pair kernel's statistic counters (measurement instrumentation); one untimed step with
+    # them gives the algorithmic-byte inputs
     params.counters = 1
     _, sa_counted = step_resident()
     params.counters = 0
     copy_counters(sa_counted, sa)
 
-    # ---- end to end through the public API: pinned host in, pinned host out, copies inside the timed region.
-    # The batch goes through kma_b200.pipeline.MapPipeline: `--e2e-workers` host threads, each with its own library
-    # handle and stream, take the `--e2e-chunks` chunks of the record stream in turn so that one chunk's PCIe copies
-    # hide behind another chunk's kernels. Every byte still crosses PCIe inside the timed region.
-    from kma_b200 import pipeline
+    # ---- hot path only, end to end (extra): stage-1 records in pinned host memory -> frag_raw + score arrays on the host
     pipe = pipeline.MapPipeline(prefix, device=local_rank, workers=args.e2e_workers, params=params)
+    scores = (np.zeros(DBn, np.uint64), np.zeros(DBn, np.uint64))
     bounds = pipe.chunk_bounds(s1.numpy(), args.e2e_chunks)
     per_chunk = (out_bytes // max(1, len(bounds))) * 5 // 4 + (1 << 20)
     outs = [torch.empty(per_chunk, dtype=torch.uint8, pin_memory=True) for _ in bounds]
-
-    def step_e2e():
-        return pipe.map(s1, bounds, outs, scores)
-
     for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+        pipe.map(s1, bounds, outs, scores)
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r_e2e = step_e2e()
+        r_hot = pipe.map(s1, bounds, outs, scores)
+    sync_all()
+    t_hot = (time.perf_counter() - t0) * 1e3
+    hot_bytes = sum(int(f.numel() if hasattr(f, "numel") else len(f)) for f, _ in r_hot)
+    assert hot_bytes == out_bytes, "chunked end-to-end run produced a different frag_raw size"
+    del outs
+
+    # ---- e2e: the whole program span. FASTQ text of both files in pinned host memory -> ... -> consensus rows + the
+    # per-template fragment stream on the host; both exchanges (ConClave sums, base-count matrix) through NCCL inside the
+    # library. Every byte crosses PCIe inside the timed region.
+    if world > 1:
+        pipe.dbs[0].comm_init_torch()
+    txt, text_bytes = [], 0
+    for r in (r1, r2):
+        a = synth.fastq_fixed(r, first=rank * args.pairs)
+        t = torch.empty(len(a), dtype=torch.uint8, pin_memory=True)
+        t.numpy()[:] = a
+        txt.append(t)
+        text_bytes += len(a)
+    del a
+    W = args.e2e_workers
+    frag_cap = (2 * args.pairs * 260) // W * 5 // 4 + (1 << 20)
+    frag_outs = [torch.empty(frag_cap, dtype=torch.uint8, pin_memory=True) for _ in range(W)]
+    for _ in range(max(2, args.warmup // 2)):
+        full = pipe.map_to_consensus(txt[0], txt[1], frag_outs, params)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        full = pipe.map_to_consensus(txt[0], txt[1], frag_outs, params)
     sync_all()
     t_e2e = (time.perf_counter() - t0) * 1e3
-    e2e_out_bytes = sum(int(f.numel() if hasattr(f, "numel") else len(f)) for f, _ in r_e2e)
-    assert e2e_out_bytes == out_bytes, "chunked end-to-end run produced a different frag_raw size"
-
-    # ---- the same from FASTQ text: the two files' text in pinned memory, the record splitter on
-    # `--split-threads` host threads, then per chunk text -> HBM -> stage 1 on the device -> stage 2 -> alignment pass.
-    # Same reads, same names: the frag_raw stream must come out byte for byte as long as the one from the records.
-    t_text, t_split = 0.0, 0.0
-    text_bytes = 0
-    if not args.no_text:
-        from concurrent.futures import ThreadPoolExecutor
-        txt = []
-        for r in (r1, r2):
-            a = synth.fastq_fixed(r, first=rank * args.pairs)
-            t = torch.empty(len(a), dtype=torch.uint8, pin_memory=True)
-            t.numpy()[:] = a
-            txt.append(t)
-            text_bytes += len(a)
-        del a
-
-        def step_text():
-            # record splitter on the device when the two files' records line up chunk by chunk (checked per chunk) ...
-            r = pipe.map_text_device_split(txt[0], txt[1], args.e2e_chunks, outs, scores) if not args.host_split else None
-            if r is not None:
-                return r, 0.0
-            # ... else on host threads, pairs by record index
-            ts0 = time.perf_counter()
-            with ThreadPoolExecutor(max_workers=2) as ex:   # the two files side by side, `--split-threads` threads each
-                f1, f2 = ex.map(lambda t: api.fastx_split_parallel(t, threads=args.split_threads), txt)
-            ts1 = time.perf_counter()
-            return pipe.map_text(txt[0], f1, txt[1], f2, args.e2e_chunks, outs, scores), (ts1 - ts0) * 1e3
-
-        step_text()
-        # the stage-1 kernels alone on the whole batch (window scan, filters + sizes, two scans, packing), CUDA events
-        # inside the library; algorithmic bytes: sequence + header read once, the stage-1 records written once
-        f1 = api.fastx_split_parallel(txt[0], threads=args.split_threads)
-        f2 = api.fastx_split_parallel(txt[1], threads=args.split_threads)
-        f2[:, [0, 2, 4]] += np.uint32(len(txt[0]))
-        fboth = np.stack([f1, f2], axis=1).reshape(-1, 5)
-        s1_ms = min(db.run_input_batch(txt[0], fboth, paired=True, download=False, text2=txt[1])[2] for _ in range(3))
-        s1_alg = int(fboth[:, 1].sum(dtype=np.int64) + fboth[:, 3].sum(dtype=np.int64)) + len(s1_np)
-        del f1, f2, fboth
-        db.seed_upload(s1)   # the resident batch again (the c3 / nw legs below do not need it, later legs might)
-        sync_all()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            r_text, sp = step_text()
-            t_split += sp
-        sync_all()
-        t_text = (time.perf_counter() - t0) * 1e3
-        assert sum(int(f.numel() if hasattr(f, "numel") else len(f)) for f, _ in r_text) == out_bytes, "text path produced a different frag_raw size"
-        assert sum(c for _, c in r_text) == args.pairs
+    assert full["reads"] == args.pairs, "the text path kept a different number of pairs"
+    cons_stats = full["consensus"][3]
+    e2e_d2h = int(full["frag_bytes"]) + 3 * total_bases + int(cons_stats.nbytes) + 16 * DBn
+    # warm, repeated timing of the two exchanges alone (device events inside the library)
+    ar_scores = min(pipe.dbs[0].allreduce_scores(download=False)[2] for _ in range(20))
+    ar_matrix = min(pipe.dbs[0].allreduce_matrix() for _ in range(5))
     pipe.close()
+    del frag_outs, txt
 
-    # ---- the one exchange of the path: ConClave score arrays summed over ranks (runkma.c:98-99, conclave.c:80)
-    t_allreduce = 0.0
-    if world > 1:
-        sc = torch.from_numpy(np.concatenate(scores).astype(np.int64)).cuda()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.all_reduce(sc, op=dist.ReduceOp.SUM)
-        e1.record()
-        torch.cuda.synchronize()
-        t_allreduce = e0.elapsed_time(e1)
-
-    tt = torch.tensor([t_dev, t_e2e, t_wall, t_allreduce, t_text], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(st.reads), float(st.mapped), float(sa.frags), float(args.pairs)], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([t_dev, t_e2e, t_wall, t_hot, ar_scores, ar_matrix], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(st.reads), float(st.mapped), float(sa.frags), float(args.pairs), float(full["fragments"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    t_dev_max, t_e2e_max, t_wall_max, t_ar_max, t_text_max = (float(x) for x in tt.cpu())
+    t_dev_max, t_e2e_max, t_wall_max, t_hot_max, ar_scores_max, ar_matrix_max = (float(x) for x in tt.cpu())
     total_reads = float(cnt[0]) * args.steps
 
     pk, pk_kind = peaks()
@@ -693,22 +774,22 @@ def main():
     cells = sa.nw_full_cells + sa.nw_band_cells
     ms_seed = t_seed / args.steps
     ms_pair = t_pair / args.steps
-    # aln_pair_kernel, algorithmic bytes per launch: per pair its read (packed words + 0-4 bytes + N list)
-    # and the 32-byte result row; 8 B per position-index probe the reference's seed scan makes; 2 x 2 bit per base
-    # compared by MEM extension; per NW cell 1 B traceback written + 1 B query base + 2 bit template base
+    # alignment pass (pair kernel + NW queue kernels), algorithmic bytes per launch: per pair its read (packed
+    # words + 0-4 bytes + N list) and the 32-byte result row; 8 B per position-index probe the reference's seed scan makes;
+    # 2 x 2 bit per base compared by MEM extension; per NW cell 1 B traceback written + 1 B query base + 2 bit template base
     alg_pair = (sa.read_bytes + 32 * sa.tasks + 8 * sa.index_probes + sa.mem_bases // 2 + (9 * cells) // 4)
     ach_pair = alg_pair / (ms_pair * 1e-3) / 1e9
     ach_seed = alg_seed / (ms_seed * 1e-3) / 1e9
-    rf_pair = {"kernel": "aln_pair_kernel", "bound": "hbm", "achieved": ach_pair, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach_pair / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": ncu_traffic("aln_pair_kernel", args.pairs),
-                     "algorithmic_bytes_per_launch": alg_pair, "kernel_ms": ms_pair,
-                     "note": "latency/issue bound (dependent index probes, short DP); see nw for the integer roofline",
-                     "per_read": {"alignments": sa.tasks / sa.reads, "index_probes": sa.index_probes / sa.reads, "mems": sa.mems / sa.reads, "nw_cells": cells / sa.reads, "bytes": alg_pair / sa.reads}}
-    rf_seed = {"kernel": "seed_se_kernel<hash>", "bound": "hbm", "achieved": ach_seed, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                          "frac": ach_seed / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": ncu_traffic("seed_se_kernel", args.pairs), "algorithmic_bytes_per_launch": alg_seed, "kernel_ms": ms_seed,
-                          "per_read": {"lookups": st.lookups / st.reads, "hits": st.hits / st.reads,
-                                       "list_fetches": st.list_fetches / st.reads, "bytes": alg_seed / st.reads}}
-    # `roofline` is the kernel with the larger share of the step; the other one keeps its own key
+    rf_pair = {"kernel": "aln_pair_kernel + nw_thread_kernel / nw_warp_kernel", "bound": "hbm", "achieved": ach_pair, "peak": pk["hbm_gbs"], "unit": "GB/s",
+               "frac": ach_pair / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": ncu_traffic("aln_pair_kernel", args.pairs),
+               "algorithmic_bytes_per_launch": alg_pair, "kernel_ms": ms_pair,
+               "note": "latency/issue bound (dependent index probes, short DP); see nw for the integer roofline",
+               "per_read": {"alignments": sa.tasks / sa.reads, "index_probes": sa.index_probes / sa.reads, "mems": sa.mems / sa.reads, "nw_cells": cells / sa.reads, "bytes": alg_pair / sa.reads}}
+    rf_seed = {"kernel": "seed_se_kernel<hash, common shape>", "bound": "hbm", "achieved": ach_seed, "peak": pk["hbm_gbs"], "unit": "GB/s",
+               "frac": ach_seed / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": ncu_traffic("seed_se_kernel", args.pairs), "algorithmic_bytes_per_launch": alg_seed, "kernel_ms": ms_seed,
+               "note": "the C2 database image (20 MB table) is L2 resident: the gather never reaches HBM here; c5.roofline is the same kernel with the table out of L2",
+               "per_read": {"lookups": st.lookups / st.reads, "hits": st.hits / st.reads,
+                            "list_fetches": st.list_fetches / st.reads, "bytes": alg_seed / st.reads}}
     line = {
         "metric": METRIC,
         "value": total_reads / (t_dev_max * 1e-3), "unit": "reads/s", "n_gpus": world, "steps": args.steps,
@@ -721,22 +802,24 @@ def main():
                    "alignments_per_read": sa.tasks / max(1, sa.reads),
                    "cache": f"stage-1 batch {len(s1_np) / 1e6:.0f} MB + stage-2 stream + read slab + frag_raw {out_bytes / 1e6:.0f} MB per step exceed the 126 MB L2; "
                             "the 150 MB database image (hash table + per-template position index) is mostly L2-resident by nature of this config",
-                   "sharding": "reads sharded by rank, database replicated per GPU; one all-reduce of the ConClave score arrays per step",
-                   "allreduce_ms": t_ar_max},
-        "e2e": {"value": total_reads / (t_e2e_max * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(len(s1_np)) + 10 * args.pairs + 4,
-                "d2h_bytes_per_step": out_bytes + 16 * DBn * len(bounds), "ms_per_step": t_e2e_max / args.steps,
-                "pipeline": {"workers": args.e2e_workers, "chunks": len(bounds)}},
-        "e2e_text": None if args.no_text else {
-            "what": "the same step from FASTQ text in pinned host memory: record splitter (device, or host threads when the two files do not line "
-                    "up) + stage 1 (translation, end trim, filters, 2-bit packing) on the device, then as e2e",
-            "value": total_reads / (t_text_max * 1e-3), "unit": "reads/s", "ms_per_step": t_text_max / args.steps,
-            "split": "host" if (args.host_split or t_split > 0) else "device", "split_ms_per_step": t_split / args.steps, "split_threads": args.split_threads, "h2d_bytes_per_step": text_bytes + 40 * args.pairs,
-            "stage1_kernels": {"ms": s1_ms, "alg_bytes": s1_alg, "achieved_GBs": s1_alg / (s1_ms * 1e-3) / 1e9,
-                               "reads_per_s": 2 * args.pairs / (s1_ms * 1e-3)}},
+                   "sharding": "reads sharded by rank, database replicated per GPU; per step one NCCL all-reduce of the ConClave score arrays and one of the base-count matrix, inside libkmagpu",
+                   "allreduce_scores_ms": ar_scores_max, "allreduce_matrix_ms": ar_matrix_max},
+        "e2e": {"value": total_reads / (t_e2e_max * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": int(text_bytes),
+                "d2h_bytes_per_step": e2e_d2h, "ms_per_step": t_e2e_max / args.steps,
+                "span": "FASTQ text of both files (pinned host) -> record splitter + stage 1 -> stage 2 -> alignment pass -> [all-reduce of the ConClave sums] -> "
+                        "ConClave -> traceback alignment + base counts -> [all-reduce of the matrix] -> consensus; down: per-template fragment stream + consensus "
+                        "rows + per-template sums (what .frag.gz / .res / .fsa / .aln are written from). The reference arm runs the same span: kma -ipe ... -o out",
+                "pipeline": {"workers": W, "slices": W, "handles": "clones of one database image per GPU"},
+                "fragments_per_step": float(cnt[4]), "templates_with_consensus": int((cons_stats["cover"] > 0).sum()),
+                "host_link_GBs": (text_bytes + e2e_d2h) / (t_e2e_max / args.steps * 1e-3) / 1e9},
+        "e2e_hotpath": {"what": "stage 2 + alignment pass only, from stage-1 records in pinned host memory to frag_raw + score arrays on the host (the boundary of "
+                                "kmagpu_seed_batch / kmagpu_align_batch), chunked over the worker handles",
+                        "value": total_reads / (t_hot_max * 1e-3), "unit": "reads/s", "ms_per_step": t_hot_max / args.steps,
+                        "h2d_bytes_per_step": int(len(s1_np)), "d2h_bytes_per_step": out_bytes + 16 * DBn * len(bounds), "chunks": len(bounds)},
         "gpu_launches": launches,
         "wall_ms_per_step_resident": t_wall_max / args.steps,
-        "stage_ms": {"seed_total": st.ms_total, "seed_kernel": st.ms_seed, "align_prep": sa.ms_prep, "align_pairs": sa.ms_align,
-                     "align_select_emit": sa.ms_reduce},
+        "stage_ms": {"seed_total": st.ms_total, "seed_kernel": st.ms_seed, "align_pairs_and_nw": sa.ms_align,
+                     "align_sizes_prep_select_emit": sa.ms_reduce},
         "clocks": clocks,
     }
     if ms_seed > ms_pair:
@@ -745,21 +828,43 @@ def main():
         line["roofline"], line["roofline_seed"] = rf_pair, rf_seed
     if rank == 0:
         line["nw"] = nw_gcups(db, seqs, peak_iops)
-        if not args.no_c3:
+    side_err = {}
+    if not args.no_c3 and rank == 0:
+        try:
             line["c3"] = c3_chain(db, api, seqs, prefix, workdir, cores, pk["hbm_gbs"])
-        if not args.no_c4:
-            try:
-                line["c4"] = c4_flow(api, workdir, local_rank)
-            except Exception as e:   # a side measurement must not cost the headline line
-                line["c4"] = {"error": repr(e)[:300]}
+        except Exception as e:   # a side measurement must not cost the headline line
+            side_err["c3"] = repr(e)[:300]
+    if not args.no_c4 and rank == 0:
+        try:
+            line["c4"] = c4_flow(api, workdir, local_rank)
+            if have_ref and not args.no_parity:
+                line["c4"]["parity"] = c4_files(api, workdir, local_rank, cores, 5_000_000, 100_000)
+        except Exception as e:
+            side_err["c4"] = repr(e)[:300]
+    if not args.no_c5:   # every rank: the scaling-sweep config
+        try:
+            c5 = c5_leg(api, workdir, rank, world, local_rank, cores, pk, dist, n=args.c5_reads)
+            if rank == 0:
+                line["c5"] = c5
+        except Exception as e:
+            side_err["c5"] = repr(e)[:300]
+            if world > 1:
+                raise
+    if side_err:
+        line["side_errors"] = side_err
 
+    if rank == 0 and world == 1 and have_ref and not args.no_parity:
+        try:
+            line["parity"] = parity_c2(api, prefix, r1, r2, cores, workdir, local_rank, args.file_pairs)
+        except Exception as e:
+            line["parity"] = {"config": "C2", "error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = min(args.cpu_sample, args.pairs)
-        have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "kma"))
         if have_ref:
             v, dt = cpu_reference(prefix, r1[:sample], r2[:sample], cores, workdir)
             line["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference",
-                                    "sample": f"first {sample} read pairs of the step; unmodified kma -ipe -apm p -s2 -t {cores} | alnFrags_threaded on {cores} pthreads (FASTQ parse + stage 2 + alignment pass), {dt:.1f} s"}
+                                    "sample": f"first {sample} read pairs of the step; the unmodified program, kma -ipe f1 f2 -apm p -t {cores} -o out (FASTQ parse ... "
+                                              f"consensus + writers: the span of e2e), {dt:.1f} s"}
         else:
             v, dt = cpu_port(prefix, records.stage1_pairs_fast(r1[:sample], r2[:sample]), 2 * sample)
             line["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": 1, "kind": "port",

@@ -1807,6 +1807,8 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 	KG_CUDA(cudaStreamSynchronize(st));
 	KG_CUDA(cudaGetLastError());
 	if (h[A_BAD]) { kmagpu_set_error("%llu pair records in the stage-2 stream in a form -apm p never writes (mate shorter than k, or strand-undecided pair)", h[A_BAD]); return -1; }
+	KG_SCAN_FITS(h[A_SLAB], "the unpacked reads");
+	if (h[A_TASKS] >= (1ull << 31)) { kmagpu_set_error("%llu (read, template) pairs in one batch: split it", h[A_TASKS]); return -1; }
 	const size_t slab_units = (size_t)h[A_SLAB];
 	const int ntasks = (int)h[A_TASKS];
 	const int maxq = (int)h[A_MAXQ];
@@ -1924,6 +1926,7 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 	KG_CUDA(cudaMemcpyAsync(h3, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
 	KG_CUDA(cudaStreamSynchronize(st));
 	KG_CUDA(cudaGetLastError());
+	KG_SCAN_FITS(h3[A_OUT], "the frag_raw stream");   // reads travel at 1 byte per base here, 4x their stage-2 size
 	b.out_bytes = (size_t)h3[A_OUT];
 	if (b.d_out.reserve(b.out_bytes + 64)) return -1;
 	aln_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>(b.in, reads, n, (const uint64_t *)b.d_slab.p, (const AlnCand *)b.d_cand.p,
@@ -2017,6 +2020,8 @@ static int trace_core(kmagpu_db *db, const kmagpu_params *prm, const uint8_t *di
 	KG_CUDA(cudaGetLastError());
 	if (h[A_BAD]) { kmagpu_set_error("%llu fragment records name a template outside the database", h[A_BAD]); return -1; }
 	const int maxq = (int)h[A_MAXQ];
+	KG_SCAN_FITS(h[A_SLAB], "the unpacked fragments");
+	KG_SCAN_FITS(h[A_TASKS], "the alignment row pool");
 	if (d_slab.reserve(8 * ((size_t)h[A_SLAB] + 4)) || d_rows.reserve(8 * ((size_t)h[A_TASKS] + 4))) return -1;
 	tr_prep_kernel<<<db->sm_count * 8, 256, 0, st>>>(din, n, (TrRec *)d_recs.p, slab_off, row_off, (uint64_t *)d_slab.p);
 	++launches;
@@ -2077,6 +2082,7 @@ static int trace_core(kmagpu_db *db, const kmagpu_params *prm, const uint8_t *di
 		unsigned long long h2[A_N];
 		KG_CUDA(cudaMemcpyAsync(h2, ctr, 8 * A_N, cudaMemcpyDeviceToHost, st));
 		KG_CUDA(cudaStreamSynchronize(st));
+		KG_SCAN_FITS(h2[A_OUT], "the traceback output");
 		const size_t ob = (size_t)h2[A_OUT];
 		if (out_bytes) *out_bytes = ob;
 		if (ob > out_cap) { kmagpu_set_error("trace output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }

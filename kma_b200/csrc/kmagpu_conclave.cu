@@ -213,6 +213,7 @@ static int conclave_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff
 	KG_CUDA(cudaGetLastError());
 	if (h[1]) { kmagpu_set_error("%llu frag_raw candidates name a template outside the database", h[1]); return -1; }
 	if (h[3]) { kmagpu_set_error("%llu slots of the frag_raw stream do not hold whole records", h[3]); return -1; }
+	KG_SCAN_FITS(h[2] + 4, "the fragment stream");
 	const size_t ob = (size_t)h[2] + 4;
 	if (out_bytes) *out_bytes = ob;
 	if (frags_out && ob > out_cap) { kmagpu_set_error("fragment output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }

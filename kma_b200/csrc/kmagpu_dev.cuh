@@ -100,18 +100,26 @@ static __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const u
 	if (threadIdx.x == 0) partial[blockIdx.x] = tot;
 }
 
-// *total receives the sum of all sizes
+// *total receives the sum of all sizes as a 64-bit number: offsets are 32-bit, so a caller whose total reaches 2^32 must
+// refuse the batch (KG_SCAN_FITS) before any kernel writes through the wrapped offsets
 static __global__ void __launch_bounds__(SCAN_THREADS) scan_partials_kernel(uint32_t *partial, int nb, unsigned long long *total) {
-	uint32_t carry = 0;
+	unsigned long long carry = 0;
 	for (int base = 0; base < nb; base += SCAN_THREADS) {
 		int i = base + threadIdx.x;
 		uint32_t v = i < nb ? partial[i] : 0, tot;
-		uint32_t ex = block_exscan(v, &tot);
-		if (i < nb) partial[i] = carry + ex;
+		uint32_t ex = block_exscan(v, &tot);   // a group of 256 tiles of 2048 sizes: the callers' sizes keep this below 2^32
+		if (i < nb) partial[i] = (uint32_t)(carry + ex);
 		carry += tot;
 	}
 	if (threadIdx.x == 0) *total = carry;
 }
+#define KG_SCAN_FITS(total, what)                                                                                         \
+	do {                                                                                                                  \
+		if ((unsigned long long)(total) >= (1ull << 32)) {                                                                \
+			kmagpu_set_error("%s of this batch needs %llu bytes / entries, more than 32-bit offsets address: split the batch", what, (unsigned long long)(total)); \
+			return -1;                                                                                                    \
+		}                                                                                                                 \
+	} while (0)
 
 static __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(uint32_t *off, int n, const uint32_t *partial) {
 	const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;

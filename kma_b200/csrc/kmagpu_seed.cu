@@ -386,8 +386,8 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 // ---------------------------------------------------------------- the seeding kernel
 
 #ifndef KG_LB
-#define KG_LB 1               // minimum resident CTAs per SM the kernels are compiled for (register cap 65536 / (128 * KG_LB))
-#endif
+#define KG_LB 8               // resident CTAs per SM the kernels are compiled for (register cap 65536 / (128 * KG_LB) = 64). Measured on C2
+#endif                        // (profiles/r02_seed_occupancy.log): 8 -> 28.9 ms, 10 (48 registers, spills) 29.3, 12 (40) 31.1, no cap (6 resident) 35.4
 template <bool DENSE, bool GENERIC>
 __global__ void __launch_bounds__(KG_WARPS * 32, KG_LB)
 seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, const uint32_t *__restrict__ rec_off,
@@ -950,6 +950,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 			b.pool2_cap = std::max(b.pool2_cap, (size_t)h[C_POOL2] + 1024);
 			continue;
 		}
+		KG_SCAN_FITS(h[C_TOTAL], "the stage-2 stream");
 		b.out_bytes = (size_t)h[C_TOTAL];
 		b.out_nrec = n; b.out_recoff = recoff;
 		if (b.d_out.reserve(b.out_bytes + 64)) return -1;
