@@ -1561,6 +1561,7 @@ extern "C" int kmagpu_align_upload(kmagpu_db *db, const void *stage2, size_t nby
 		if (h[0] < 0) break;   // stream terminator -(number of reads)
 		size_t len = 28 + 8 * (size_t)(uint32_t)h[1] + 4 * (size_t)(uint32_t)h[2] + 4 * (size_t)(uint32_t)h[4] + (size_t)(uint32_t)h[5];
 		if (h[1] < 0 || h[2] < 0 || h[4] < 0 || h[5] < 0 || ip + len > nbytes) { kmagpu_set_error("stage-2 stream is truncated or corrupt at byte %zu", ip); return -1; }
+		if (kg_check_record(in + ip, 2, db->info.DB_size, ip)) return -1;
 		if (n == cap) {
 			KgBuf bigger; bigger.pinned = true;
 			if (bigger.reserve(8 * (cap + 1))) return -1;

@@ -231,6 +231,36 @@ extern "C" void kmagpu_db_close(kmagpu_db *db) {
 	delete db;
 }
 
+// Host-side validation of one record of a caller-supplied stream, so that the kernels can trust its fields: the sequence
+// fits its packed words, the N positions are ascending and inside the read, the template ids name templates of this
+// database. (Streams that a previous stage left in HBM are the library's own output and are not re-checked.)
+int kg_check_record(const uint8_t *rec, int stage, int DB_size, size_t at) {
+	int32_t h[7];
+	memcpy(h, rec, stage == 1 ? 16 : 28);
+	const int64_t seqlen = h[0], words = h[1], nN = h[2];
+	if (seqlen < 0 || seqlen > 32 * words) {
+		kmagpu_set_error("record at byte %zu: %lld bases do not fit %lld packed words", at, (long long)seqlen, (long long)words);
+		return -1;
+	}
+	const uint8_t *N = rec + (stage == 1 ? 16 : 28) + 8 * (size_t)words;
+	int32_t prev = -1;
+	for (int64_t i = 0; i < nN; ++i) {
+		int32_t v;
+		memcpy(&v, N + 4 * (size_t)i, 4);
+		if (v <= prev || v >= seqlen) { kmagpu_set_error("record at byte %zu: N position %d outside the read or out of order", at, v); return -1; }
+		prev = v;
+	}
+	if (stage == 2) {
+		const uint8_t *T = N + 4 * (size_t)nN;
+		for (int32_t i = 0; i < h[4]; ++i) {
+			int32_t t;
+			memcpy(&t, T + 4 * (size_t)i, 4);
+			if (t == 0 || t <= -DB_size || t >= DB_size) { kmagpu_set_error("record at byte %zu names template %d outside the database", at, t); return -1; }
+		}
+	}
+	return 0;
+}
+
 extern "C" int kmagpu_db_get_info(const kmagpu_db *db, kmagpu_db_info *info) {
 	if (!db || !info) { kmagpu_set_error("null argument"); return -1; }
 	*info = db->info;

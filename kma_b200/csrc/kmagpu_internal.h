@@ -156,6 +156,7 @@ struct kmagpu_db {
 int kg_scores_accumulate(kmagpu_db *db, const unsigned long long *batch_scores);
 
 int kg_tindex_build(kmagpu_db *db);
+int kg_check_record(const uint8_t *rec, int stage, int DB_size, size_t at);
 int kg_align_free(kmagpu_db *db);
 
 int kg_seed_free(kmagpu_db *db);

@@ -131,6 +131,7 @@ static int memscore_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff
 	KG_CUDA(cudaStreamSynchronize(st));
 	KG_CUDA(cudaGetLastError());
 	if (h[1]) { kmagpu_set_error("%llu stage-2 records are truncated pairs or name a template outside the database", h[1]); return -1; }
+	KG_SCAN_FITS(h[2], "the frag_raw stream");
 	const size_t ob = (size_t)h[2];
 	if (out_bytes) *out_bytes = ob;
 	if (frag_out && ob > out_cap) { kmagpu_set_error("frag_raw output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
@@ -171,7 +172,10 @@ extern "C" int kmagpu_memscore_batch(kmagpu_db *db, const void *stage2, size_t n
 	std::vector<uint64_t> off64((size_t)n);
 	kmagpu_record_walk(2, stage2, nbytes, off64.data(), (size_t)n, &used);
 	std::vector<uint32_t> off((size_t)n + 1);
-	for (int i = 0; i < n; ++i) off[i] = (uint32_t)off64[i];
+	for (int i = 0; i < n; ++i) {
+		off[i] = (uint32_t)off64[i];
+		if (kg_check_record((const uint8_t *)stage2 + off64[i], 2, db->info.DB_size, (size_t)off64[i])) return -1;
+	}
 	off[n] = (uint32_t)used;
 	RawBatch &w = db->raw;
 	if (w.d_in.reserve(used + 64) || w.d_off.reserve(4 * ((size_t)n + 2))) return -1;

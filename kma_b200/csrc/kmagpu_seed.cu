@@ -826,6 +826,7 @@ extern "C" int kmagpu_seed_upload(kmagpu_db *db, const void *stage1, size_t nbyt
 		if (h[0] < 0) break;   // a terminator was included
 		size_t len = 16 + 8 * (size_t)(uint32_t)h[1] + 4 * (size_t)(uint32_t)h[2] + (size_t)abs(h[3]);
 		if (h[1] < 0 || h[2] < 0 || ip + len > nbytes) { kmagpu_set_error("stage-1 stream is truncated or corrupt at byte %zu", ip); return -1; }
+		if (kg_check_record(in + ip, 1, db->info.DB_size, ip)) return -1;
 		if (n == cap) {
 			KgBuf bigger, bigk; bigger.pinned = true; bigk.pinned = true;
 			if (bigger.reserve(8 * (cap + 1)) || bigk.reserve(2 * (cap + 2))) return -1;
