@@ -1731,7 +1731,6 @@ __global__ void __launch_bounds__(AL_WARPS * 32) nw_cb_kernel(const NwPen pen, c
 	if (threadIdx.x < 5) stab[threadIdx.x] = nw_pack_row(spen, threadIdx.x);
 	__syncthreads();
 	const int lane = threadIdx.x & 31, grp = lane / NW_CB_LANES, h = lane % NW_CB_LANES;
-	const unsigned gmask = ((1u << NW_CB_LANES) - 1u) << (grp * NW_CB_LANES);
 	const size_t wid = (size_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
 	uint8_t *wbase = scratch + wid * stride;   // per warp, per group: [lastD (q_cap ints) | E (e_cap bytes)]
 	const size_t pstride = 4 * (size_t)q_cap + e_cap;
@@ -1754,30 +1753,45 @@ __global__ void __launch_bounds__(AL_WARPS * 32) nw_cb_kernel(const NwPen pen, c
 				go = !(status == ST_GIVEUP && k >= 0) && nw_cb_geo(g, spen, p.t_e - p.t_s, p.q_e - p.q_s, k, p.kband >> 8) && g.cb == C &&
 				     g.ebytes() <= e_cap && g.q_len + 2 <= q_cap;
 			}
+			// the whole warp runs ONE step loop (the longest of its problems decides the count, a finished or absent problem's
+			// lanes idle): the lane groups must not drift apart, or the warp would issue every step once per group
+			int *lastD = (int *)(wbase + grp * pstride);
+			uint8_t *E = (uint8_t *)(lastD + q_cap);
+			const uint64_t *tseq = ix.seq;
+			const uint8_t *qlast = qbase;
+			NwCbLane<C> L;
+			int t_s = 0, nsteps = 0;
 			if (go) {
-				int *lastD = (int *)(wbase + grp * pstride);
-				uint8_t *E = (uint8_t *)(lastD + q_cap);
 				const KgTMeta m = ix.meta[p.tmpl];
-				const uint64_t *tseq = ix.seq + m.seq_off;
-				const uint8_t *qlast = qbase + ((size_t)p.qoff << qshift) + p.q_e - 1;
-				NwCbLane<C> L;
+				tseq = ix.seq + m.seq_off;
+				qlast = qbase + ((size_t)p.qoff << qshift) + p.q_e - 1;
+				t_s = p.t_s;
 				nw_cb_init<C>(g, L, h, qlast);
-				const int nsteps = nw_cb_steps(g);
-				const int src = grp * NW_CB_LANES + ((h + NW_CB_LANES - 1) % NW_CB_LANES);
-#pragma unroll 1
-				for (int s = 0; s < nsteps; ++s) {
-					const int nD = __shfl_sync(gmask, L.eD, src), nQ = __shfl_sync(gmask, L.eQ, src), nO = __shfl_sync(gmask, L.eOld, src);
-					nw_cb_step<C>(g, L, h, s, nD, nQ, nO, stab, tseq, p.t_s, qlast, E, lastD);
-				}
-				// the one lane that owns the column at the query start holds the column maximum (k < 0): the group agrees on it
-				int cb = L.colBest, ci = L.colBestI;
+				nsteps = nw_cb_steps(g);
+			} else {
+				memset(&g, 0, sizeof(g));
+				L.b = h; L.ifirst = 0x7fffffff; L.ilast = -0x7fffffff; L.trackc = -1;
+				L.eD = L.eQ = L.eOld = 0; L.colBest = 0; L.colBestI = 0x7fffffff;
 #pragma unroll
-				for (int o = NW_CB_LANES / 2; o; o >>= 1) {
-					const int ov = __shfl_xor_sync(gmask, cb, o), oi = __shfl_xor_sync(gmask, ci, o);
-					if (ov > cb || (ov == cb && oi < ci)) { cb = ov; ci = oi; }
-				}
-				if (h == 0) { lastD[g.q_len] = cb; lastD[g.q_len + 1] = ci; }
+				for (int c = 0; c < C; ++c) { L.pD[c] = 0; L.pP[c] = 0; L.q8[c] = 0; }
 			}
+			int nmax = nsteps;
+#pragma unroll
+			for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+			const int src = grp * NW_CB_LANES + ((h + NW_CB_LANES - 1) % NW_CB_LANES);
+#pragma unroll 1
+			for (int s = 0; s < nmax; ++s) {
+				const int nD = __shfl_sync(0xffffffffu, L.eD, src), nQ = __shfl_sync(0xffffffffu, L.eQ, src), nO = __shfl_sync(0xffffffffu, L.eOld, src);
+				nw_cb_step<C>(g, L, h, s, nD, nQ, nO, stab, tseq, t_s, qlast, E, lastD);
+			}
+			// the one lane that owns the column at the query start holds the column maximum (k < 0): the group agrees on it
+			int cb = L.colBest, ci = L.colBestI;
+#pragma unroll
+			for (int o = NW_CB_LANES / 2; o; o >>= 1) {
+				const int ov = __shfl_xor_sync(0xffffffffu, cb, o), oi = __shfl_xor_sync(0xffffffffu, ci, o);
+				if (ov > cb || (ov == cb && oi < ci)) { cb = ov; ci = oi; }
+			}
+			if (go && h == 0) { lastD[g.q_len] = cb; lastD[g.q_len + 1] = ci; }
 		}
 		__syncwarp();
 		// ---- walks: the whole warp, one problem after the other
