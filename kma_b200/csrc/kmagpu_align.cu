@@ -67,7 +67,7 @@ struct AlnParams {
 
 enum { A_WORK = 0, A_OVF = 1, A_NEED_E = 2, A_NEED_MEM = 3, A_NEED_Q = 4, A_MEMS = 5, A_FULL_CALLS = 6, A_BAND_CALLS = 7,
        A_FULL_CELLS = 8, A_BAND_CELLS = 9, A_STEPS = 10, A_SLAB = 11, A_TASKS = 12, A_OUT = 13, A_FRAGS = 14, A_BAD = 15,
-       A_MAXQ = 16, A_LOOKUPS = 17, A_MEMBASES = 18, A_READBYTES = 19, A_NPROB = 20, A_PCLS = 21 /* .. 26 */, A_NEED_E2 = 27, A_N = 32 };
+       A_MAXQ = 16, A_LOOKUPS = 17, A_MEMBASES = 18, A_READBYTES = 19, A_NPROB = 20, A_PCLS = 21 /* .. 23 */, A_N = 32 };
 
 // ---------------------------------------------------------------- slab layout
 
@@ -222,7 +222,7 @@ struct Mems {
 #else
 #define KG_STAT(x) x
 #endif
-struct WarpCtr { unsigned long long full_calls, band_calls, full_cells, band_cells, steps, mems, lookups, mem_bases, read_bytes; unsigned need_e, need_mem, need_q, need_e2; };
+struct WarpCtr { unsigned long long full_calls, band_calls, full_cells, band_cells, steps, mems, lookups, mem_bases, read_bytes; unsigned need_e, need_mem, need_q; };
 
 __device__ __noinline__ int warp_max(int v) {
 #pragma unroll
@@ -421,21 +421,20 @@ __device__ int chain_warp(const NwPen &pen, Mems &M, int n, int q_len, int t_len
 // (align.c:92-98, 186-192, 478-484) to a queue; queue kernels then solve the problems -- one THREAD per problem for the
 // small ones (classes 0-3 by size, so that a warp's 32 problems are alike), one WARP per problem for the rest -- and add
 // their AlnScore fields into the task's candidate row (all of them are sums; the lead tail also moves `pos`).
-#define NWQ_CLASSES 6
+#define NWQ_CLASSES 3
 struct NwProb { int32_t task, tmpl, t_s, t_e, q_s, q_e, kband; uint32_t qoff; };   // kband = (k + 2) | band << 8; query bytes at qbase + (qoff << qshift)
-// order / cells: per class `cap` queue slots and their cell counts in arrival order; all classes but 2 are then sorted by
-// cells so that the problems a warp works on together are alike
+// order / cells: per class `cap` queue slots and their cell counts in arrival order; the thread classes are then sorted by
+// cells so that the 32 problems of a warp are alike
 struct NwQueue { NwProb *probs; uint32_t *order, *cells; unsigned cap; unsigned long long *ctr; int d8; };
 
-// 0, 1: one thread per problem (small full matrices); 3, 4, 5: banded, column blocks of 10 / 12 / 16 columns, a quarter of a
-// warp per problem (nw_cb_*); 2: everything else, one warp per problem (nw_warp)
+// 0, 1: one thread per problem (small full matrices); 2: everything else -- bands, wide matrices -- one warp per problem
+// (nw_warp: row sweep for rows of up to 256 cells, the continuous wavefront beyond). A third scheme for the bands --
+// column blocks in registers, 8 lanes per problem, three shuffles per step -- was built, verified byte for byte and
+// measured at 143 GCUPS against the row sweep's 213 (profiles/r02_ab_column_blocks.log: ~77 instructions per cell as
+// compiled, 168 registers), so the row sweep stays.
 __host__ __device__ __forceinline__ int nwq_class(int t_l, int q_l, int band, int d8) {
-	if (t_l <= 0 || q_l <= 0) return 2;
-	if (band) {
-		const int c = d8 ? nw_cb_columns((band + 1) & ~1) : 0;
-		return c == 10 ? 3 : (c == 12 ? 4 : (c == 16 ? 5 : 2));
-	}
-	if (q_l > 64 || t_l > 128) return 2;
+	(void)d8;
+	if (band || q_l > 64 || t_l > 128 || t_l <= 0 || q_l <= 0) return 2;
 	return (q_l > 32 || t_l > 64) ? 1 : 0;
 }
 static const int nwq_qmax[2] = {32, 64};        // query columns the thread kernel of a class holds in shared memory
@@ -497,14 +496,13 @@ __device__ __forceinline__ void nw_enqueue(const TaskCtx &c, int k, int t_s, int
 			*(int4 *)&Q.probs[slot] = *(const int4 *)&p;
 			*((int4 *)&Q.probs[slot] + 1) = *((const int4 *)&p + 1);
 			Q.order[(size_t)cls * Q.cap + ci] = (uint32_t)slot;
-			if (cls != 2) Q.cells[(size_t)cls * Q.cap + ci] = (uint32_t)min(t_l * (band ? band + 2 : q_l), (1 << 27) - 1);
+			if (cls != 2) Q.cells[(size_t)cls * Q.cap + ci] = (uint32_t)(t_l * q_l);
 		}
 	}
-	if (cls >= 2) {   // the warp / half-warp kernels size their scratch from the largest problem of their kind
+	if (cls == 2) {   // the warp-per-problem kernel sizes its scratch from the largest problem
 		NwGeo g;
-		if (cls == 2 ? nw_geo_init(g, *c.pen, t_l, q_l, k, band, true) : nw_cb_geo(g, *c.pen, t_l, q_l, k, band)) {
-			const unsigned need = (unsigned)min((size_t)0xF0000000u, g.ebytes() + 4096);
-			if (cls == 2) c.wc->need_e = max(c.wc->need_e, need); else c.wc->need_e2 = max(c.wc->need_e2, need);
+		if (nw_geo_init(g, *c.pen, t_l, q_l, k, band, true)) {
+			c.wc->need_e = max(c.wc->need_e, (unsigned)min((size_t)0xF0000000u, g.ebytes() + 4096));
 			c.wc->need_q = max(c.wc->need_q, (unsigned)q_l + 64u);
 		}
 	}
@@ -725,7 +723,6 @@ __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(const Aln
 		if (wc.read_bytes) atomicAdd(&ctr[A_READBYTES], wc.read_bytes);
 		if (wc.full_calls) { atomicAdd(&ctr[A_FULL_CALLS], wc.full_calls); atomicAdd(&ctr[A_FULL_CELLS], wc.full_cells); }
 		if (wc.need_e) atomicMax(&ctr[A_NEED_E], (unsigned long long)wc.need_e);
-		if (wc.need_e2) atomicMax(&ctr[A_NEED_E2], (unsigned long long)wc.need_e2);
 		if (wc.need_mem) atomicMax(&ctr[A_NEED_MEM], (unsigned long long)wc.need_mem);
 		if (wc.need_q) atomicMax(&ctr[A_NEED_Q], (unsigned long long)wc.need_q);
 	}
@@ -1717,156 +1714,6 @@ __global__ void __launch_bounds__(AL_WARPS * 32) nw_warp_kernel(const NwPen pen,
 	}
 }
 
-// classes 3-5: banded problems, NW_CB_LANES lanes each (nw_cb_*: column blocks). A warp takes neighbouring problems of
-// the size-sorted list; its lane groups fill their matrices side by side, then the whole warp walks the tracebacks in turn.
-#define NW_CB_GROUPS (32 / NW_CB_LANES)
-template <int C>
-__global__ void __launch_bounds__(AL_WARPS * 32) nw_cb_kernel(const NwPen pen, const KgTIndexView ix, const NwProb *__restrict__ probs,
-		const uint32_t *__restrict__ order, int n, const uint8_t *qbase, int qshift, int32_t *res, int32_t *status_out,
-		uint8_t *scratch, size_t stride, size_t e_cap, int q_cap, unsigned long long *ctr) {
-	__shared__ NwPen spen;
-	__shared__ unsigned long long stab[5];
-	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&pen)[threadIdx.x];
-	__syncthreads();
-	if (threadIdx.x < 5) stab[threadIdx.x] = nw_pack_row(spen, threadIdx.x);
-	__syncthreads();
-	const int lane = threadIdx.x & 31, grp = lane / NW_CB_LANES, h = lane % NW_CB_LANES;
-	const size_t wid = (size_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
-	uint8_t *wbase = scratch + wid * stride;   // per warp, per group: [lastD (q_cap ints) | E (e_cap bytes)]
-	const size_t pstride = 4 * (size_t)q_cap + e_cap;
-	unsigned long long bcells = 0, bcalls = 0, steps = 0;
-	for (;;) {
-		unsigned long long t = 0;
-		if (lane == 0) t = atomicAdd(&ctr[A_WORK], 1ull);
-		t = __shfl_sync(0xffffffffu, t, 0);
-		if (NW_CB_GROUPS * t >= (unsigned long long)n) break;
-		// ---- fill: each lane group its own problem
-		{
-			const long long idx = (long long)(NW_CB_GROUPS * t) + grp;
-			bool go = idx < n;
-			NwProb p;
-			NwGeo g;
-			int status = 0, k = 0;
-			if (go) {
-				p = probs[order[idx]];
-				status = res[8 * (size_t)p.task + 7]; k = (p.kband & 255) - 2;
-				go = !(status == ST_GIVEUP && k >= 0) && nw_cb_geo(g, spen, p.t_e - p.t_s, p.q_e - p.q_s, k, p.kband >> 8) && g.cb == C &&
-				     g.ebytes() <= e_cap && g.q_len + 2 <= q_cap;
-			}
-			// the whole warp runs ONE step loop (the longest of its problems decides the count, a finished or absent problem's
-			// lanes idle): the lane groups must not drift apart, or the warp would issue every step once per group
-			int *lastD = (int *)(wbase + grp * pstride);
-			uint8_t *E = (uint8_t *)(lastD + q_cap);
-			const uint64_t *tseq = ix.seq;
-			const uint8_t *qlast = qbase;
-			NwCbLane<C> L;
-			int t_s = 0, nsteps = 0;
-			if (go) {
-				const KgTMeta m = ix.meta[p.tmpl];
-				tseq = ix.seq + m.seq_off;
-				qlast = qbase + ((size_t)p.qoff << qshift) + p.q_e - 1;
-				t_s = p.t_s;
-				nw_cb_init<C>(g, L, h, qlast);
-				nsteps = nw_cb_steps(g);
-			} else {
-				memset(&g, 0, sizeof(g));
-				L.b = h; L.ifirst = 0x7fffffff; L.ilast = -0x7fffffff; L.trackc = -1;
-				L.eD = L.eQ = L.eOld = 0; L.colBest = 0; L.colBestI = 0x7fffffff;
-#pragma unroll
-				for (int c = 0; c < C; ++c) { L.pD[c] = 0; L.pP[c] = 0; L.q8[c] = 0; }
-			}
-			int nmax = nsteps;
-#pragma unroll
-			for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-			const int src = grp * NW_CB_LANES + ((h + NW_CB_LANES - 1) % NW_CB_LANES);
-#pragma unroll 1
-			for (int s = 0; s < nmax; ++s) {
-				const int nD = __shfl_sync(0xffffffffu, L.eD, src), nQ = __shfl_sync(0xffffffffu, L.eQ, src), nO = __shfl_sync(0xffffffffu, L.eOld, src);
-				nw_cb_step<C>(g, L, h, s, nD, nQ, nO, stab, tseq, t_s, qlast, E, lastD);
-			}
-			// the one lane that owns the column at the query start holds the column maximum (k < 0): the group agrees on it
-			int cb = L.colBest, ci = L.colBestI;
-#pragma unroll
-			for (int o = NW_CB_LANES / 2; o; o >>= 1) {
-				const int ov = __shfl_xor_sync(0xffffffffu, cb, o), oi = __shfl_xor_sync(0xffffffffu, ci, o);
-				if (ov > cb || (ov == cb && oi < ci)) { cb = ov; ci = oi; }
-			}
-			if (go && h == 0) { lastD[g.q_len] = cb; lastD[g.q_len + 1] = ci; }
-		}
-		__syncwarp();
-		// ---- walks: the whole warp, one problem after the other
-#pragma unroll 1
-		for (int x = 0; x < NW_CB_GROUPS; ++x) {
-			const long long idx = (long long)(NW_CB_GROUPS * t) + x;
-			if (idx >= n) break;
-			const NwProb p = probs[order[idx]];
-			int32_t *row = res + 8 * (size_t)p.task;
-			const int status = row[7], k = (p.kband & 255) - 2, band = p.kband >> 8;
-			if (status == ST_GIVEUP && k >= 0) continue;
-			NwGeo g;
-			const bool ok = nw_cb_geo(g, spen, p.t_e - p.t_s, p.q_e - p.q_s, k, band) && g.cb == C && g.ebytes() <= e_cap && g.q_len + 2 <= q_cap;
-			if (!ok) {
-				if (lane == 0) { if (status_out) status_out[p.task] = NW_TOO_BIG; else atomicAdd(&ctr[A_BAD], 1ull); }
-				continue;
-			}
-			const int *lastD = (const int *)(wbase + x * pstride);
-			const uint8_t *E = (const uint8_t *)(lastD + q_cap);
-			const int cb = lastD[g.q_len], ci = lastD[g.q_len + 1];
-			int rb = g.NEG, rq = -1;
-			if (k == -2) {   // last maximum along row m = 0
-				int qlo, qhi;
-				nw_row0_range(g, &qlo, &qhi);
-				for (int qp = qlo + lane; qp <= qhi; qp += 32) {
-					const int v = lastD[g.q_len - 1 - qp];
-					if (rq < 0 || v >= rb) { rb = v; rq = qp; }
-				}
-#pragma unroll
-				for (int o = 16; o; o >>= 1) {
-					const int ov = __shfl_xor_sync(0xffffffffu, rb, o), oq = __shfl_xor_sync(0xffffffffu, rq, o);
-					if (oq >= 0 && (rq < 0 || ov > rb || (ov == rb && oq > rq))) { rb = ov; rq = oq; }
-				}
-			}
-			int best_m, best_q, score;
-			nw_start_cell(g, cb, ci, lastD, rb, rq, &best_m, &best_q, &score);
-			NwStat a;
-			const KgTMeta m = ix.meta[p.tmpl];
-			nw_walk_warp(g, E, best_m, best_q, a, nullptr, ix.seq + m.seq_off, p.t_s, qbase + ((size_t)p.qoff << qshift) + p.q_s);
-			a.score = score; a.pos = 0;
-			if (lane == 0) {
-				nwq_apply(row, a, k, status);
-				if (status_out) status_out[p.task] = NW_OK;
-			}
-			bcells += (unsigned long long)g.t_len * (unsigned long long)(g.band + 1); ++bcalls;
-			steps += (unsigned long long)nw_cb_steps(g);
-			__syncwarp();
-		}
-	}
-	if (lane == 0 && bcalls) { atomicAdd(&ctr[A_BAND_CALLS], bcalls); atomicAdd(&ctr[A_BAND_CELLS], bcells); atomicAdd(&ctr[A_STEPS], steps); }
-}
-
-template <int C>
-static int nw_cb_launch(kmagpu_db *db, const AlnParams &P, const NwProb *probs, const uint32_t *order, int n, size_t need_e, int need_q,
-                        const uint8_t *qbase, int qshift, int32_t *res, int32_t *status_out, unsigned long long *ctr) {
-	cudaStream_t st = db->stream;
-	KgBuf &scr = db->aln.d_scratch;
-	const int q_cap = (std::max(need_q, 256) + 3) & ~3;
-	const size_t e_cap = (std::max<size_t>(need_e, 65536) + 255) & ~(size_t)255;
-	const size_t stride = NW_CB_GROUPS * (4 * (size_t)q_cap + e_cap);
-	const int pairs = (n + NW_CB_GROUPS - 1) / NW_CB_GROUPS;
-	int per_sm = 0;
-	KG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_cb_kernel<C>, AL_WARPS * 32, 0));
-	int grid = (int)std::min<size_t>((size_t)db->sm_count * std::max(per_sm, 1), ((size_t)pairs + AL_WARPS - 1) / AL_WARPS);
-	if (stride * (size_t)grid * AL_WARPS > scr.cap) {
-		size_t freeb = 0, totalb = 0;
-		cudaMemGetInfo(&freeb, &totalb);
-		while (grid > 1 && stride * (size_t)grid * AL_WARPS > freeb / 2 + scr.cap) grid = (grid + 1) / 2;
-	}
-	if (scr.reserve(stride * (size_t)grid * AL_WARPS)) return -1;
-	KG_CUDA(cudaMemsetAsync(ctr + A_WORK, 0, 8, st));
-	nw_cb_kernel<C><<<grid, AL_WARPS * 32, 0, st>>>(P.pen, db->tix, probs, order, n, qbase, qshift, res, status_out, (uint8_t *)scr.p, stride, e_cap, q_cap, ctr);
-	return 0;
-}
-
 // Solve the queued problems. counts[c] = problems of class c (their queue slots in order[c * cap ..), their cell counts
 // in cells[c * cap ..) for the thread classes; cells == NULL: the caller's order is sorted already). need_e / need_q:
 // scratch the largest class-2 problem asked for. sorted: 4 * cap uint32 of working space for the sort. Uses (and may
@@ -1886,7 +1733,7 @@ static int nw_thread_launch(kmagpu_db *db, const AlnParams &P, const NwProb *pro
 }
 
 static int nw_queue_run(kmagpu_db *db, const AlnParams &P, const NwProb *probs, const uint32_t *order, const uint32_t *cells, uint32_t *sorted,
-                        size_t cap, const unsigned long long *counts, size_t need_e, size_t need_e2, int need_q, const uint8_t *qbase, int qshift,
+                        size_t cap, const unsigned long long *counts, size_t need_e, int need_q, const uint8_t *qbase, int qshift,
                         int32_t *res, int32_t *status_out, unsigned long long *ctr, int *launches) {
 	cudaStream_t st = db->stream;
 	KgBuf &scr = db->aln.d_scratch;
@@ -1897,7 +1744,7 @@ static int nw_queue_run(kmagpu_db *db, const AlnParams &P, const NwProb *probs, 
 		if (cells && c != 2) {   // largest problems first, neighbours alike: what a warp works on together finishes together
 			uint32_t *ks = sorted, *vs = ks + cap;
 			size_t tmp_bytes = 0;
-			const int bits = c < 2 ? 14 : 27;
+			const int bits = 14;   // at most 128 x 64 cells
 			cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, cells + (size_t)c * cap, ks, ord, vs, n, 0, bits, st);
 			if (db->aln.d_sorttmp.reserve(tmp_bytes + 256)) return -1;
 			cub::DeviceRadixSort::SortPairsDescending(db->aln.d_sorttmp.p, tmp_bytes, cells + (size_t)c * cap, ks, ord, vs, n, 0, bits, st);
@@ -1909,9 +1756,6 @@ static int nw_queue_run(kmagpu_db *db, const AlnParams &P, const NwProb *probs, 
 		                          : nw_thread_launch<32, false>(db, P, probs, ord, n, qbase, qshift, res, nwq_cells[0], ctr);
 		else if (c == 1) rc = P.pen.d8 ? nw_thread_launch<64, true>(db, P, probs, ord, n, qbase, qshift, res, nwq_cells[1], ctr)
 		                               : nw_thread_launch<64, false>(db, P, probs, ord, n, qbase, qshift, res, nwq_cells[1], ctr);
-		else if (c == 3) rc = nw_cb_launch<10>(db, P, probs, ord, n, need_e2, need_q, qbase, qshift, res, status_out, ctr);
-		else if (c == 4) rc = nw_cb_launch<12>(db, P, probs, ord, n, need_e2, need_q, qbase, qshift, res, status_out, ctr);
-		else if (c == 5) rc = nw_cb_launch<16>(db, P, probs, ord, n, need_e2, need_q, qbase, qshift, res, status_out, ctr);
 		else {
 			ScratchLayout lay;
 			lay.mem_cap = 0; lay.q_cap = std::max(need_q, 256); lay.e_cap = (std::max<size_t>(need_e, 65536) + 255) & ~(size_t)255;
@@ -2056,7 +1900,7 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 		if (h[A_NPROB]) {
 			uint32_t *ord = (uint32_t *)b.d_order.p;
 			if (nw_queue_run(db, P, (const NwProb *)b.d_probs.p, ord, ord + NWQ_CLASSES * b.prob_cap, ord + 2 * NWQ_CLASSES * b.prob_cap, b.prob_cap,
-			                 &h[A_PCLS], (size_t)h[A_NEED_E], (size_t)h[A_NEED_E2], (int)h[A_NEED_Q], (const uint8_t *)b.d_slab.p, 3,
+			                 &h[A_PCLS], (size_t)h[A_NEED_E], (int)h[A_NEED_Q], (const uint8_t *)b.d_slab.p, 3,
 			                 (int32_t *)b.d_cand.p, nullptr, ctr, &launches)) return -1;
 		}
 		KG_CUDA(cudaEventRecord(db->ev[4], st));
@@ -2392,8 +2236,7 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 	const AlnParams P = make_params(db, p);
 	std::vector<NwProb> hp(n);
 	std::vector<uint32_t> horder(NWQ_CLASSES * n);
-	unsigned long long counts[NWQ_CLASSES] = {0, 0, 0, 0, 0, 0};
-	size_t need_e2 = 65536;
+	unsigned long long counts[NWQ_CLASSES] = {0, 0, 0};
 	for (size_t i = 0; i < n; ++i) {
 		const int32_t *pr = prob + 8 * i;
 		if (pr[0] <= 0 || pr[0] >= db->info.DB_size || pr[1] < 0 || pr[2] < pr[1] || pr[2] > db->lengths[pr[0]] || pr[4] < 0 ||
@@ -2403,13 +2246,9 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 		}
 		const int t_l = pr[2] - pr[1], q_l = pr[5] - pr[4];
 		NwGeo g;
-		int cls = nwq_class(t_l, q_l, pr[7], P.pen.d8);
-		if (cls >= 3 && !nw_cb_geo(g, P.pen, t_l, q_l, pr[6], pr[7])) cls = 2;   // a band the reference would not make: the generic kernel reports it
+		const int cls = nwq_class(t_l, q_l, pr[7], P.pen.d8);
 		if (cls == 2 && t_l > 0 && q_l > 0 && nw_geo_init(g, P.pen, t_l, q_l, pr[6], pr[7], true)) {
 			need_e = std::max(need_e, g.ebytes() + 256);
-			need_q = std::max(need_q, q_l + 64);
-		} else if (cls >= 3) {
-			need_e2 = std::max(need_e2, g.ebytes() + 256);
 			need_q = std::max(need_q, q_l + 64);
 		}
 		NwProb &q = hp[i];
@@ -2441,7 +2280,7 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 	KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * A_N, st));
 	KG_CUDA(cudaEventRecord(db->ev[2], st));
 	int launches = 0;
-	const int rc = nw_queue_run(db, P, dprob, dorder, nullptr, nullptr, n, counts, need_e, need_e2, need_q, dq, 0, dres, dstat, ctr, &launches);
+	const int rc = nw_queue_run(db, P, dprob, dorder, nullptr, nullptr, n, counts, need_e, need_q, dq, 0, dres, dstat, ctr, &launches);
 	KG_CUDA(cudaEventRecord(db->ev[3], st));
 	std::vector<int32_t> hres(8 * n);
 	unsigned long long hc[A_N];

@@ -32,7 +32,6 @@
 #endif
 
 #define NW_RING 256
-#define NW_CB_LANES 8    // lanes per problem of the column-block fill (four problems per warp)
 
 struct NwPen { int W1, U, MM, M; int d[25]; int d8; };   // d8: every d[] fits a signed byte (per-row table in a register)
 struct NwStat { int score, len, pos, match, tGaps, qGaps; };
@@ -41,7 +40,6 @@ struct alignas(8) NwRow { int D, P; };
 struct NwGeo {
 	int t_len, q_len, k, banded, band, a, W, P, s, R, Tmax, NEG, W1, U, rmask, d8;
 	int C;   // row sweep: cells per lane (0: the continuous wavefront)
-	int cb;  // column blocks (nw_cb_*): columns per block (0: off)
 	NW_HD int off(int i) const { return banded ? a + i : 0; }
 	NW_HD int jlo(int i) const { int v = banded ? a + i : 0; return v < 0 ? 0 : v; }
 	NW_HD int jhi(int i) const { int v = banded ? a + i + band : q_len - 1; return v < q_len - 1 ? v : q_len - 1; }
@@ -49,15 +47,11 @@ struct NwGeo {
 	NW_HD int bcol(int i) const { return i < 0 ? 0 : (0 < k ? 0 : W1 + i * U); }
 	NW_HD int brow(int j) const { return j < 0 ? 0 : (k == 2 ? 0 : W1 + j * U); }
 	NW_HD size_t eaddr(int i, int j) const {
-		if (cb) { const int b = j / cb; return ((size_t)(i + b) * NW_CB_LANES + (size_t)(b & (NW_CB_LANES - 1))) * (size_t)cb + (size_t)(j - b * cb); }
 		if (C) return (size_t)i * (size_t)(32 * C) + (size_t)(j - off(i));   // row sweep: row-major, 32*C bytes per row
 		const int l = i & 31;
 		return ((size_t)(s * l + P * (i >> 5) + (j - off(i)))) * 32 + (size_t)l;
 	}
-	NW_HD size_t ebytes() const {
-		if (cb) return ((size_t)t_len + (size_t)((q_len + cb - 1) / cb) + 2) * NW_CB_LANES * (size_t)cb;
-		return C ? (size_t)t_len * (size_t)(32 * C) + 8 : (size_t)Tmax * 32;
-	}
+	NW_HD size_t ebytes() const { return C ? (size_t)t_len * (size_t)(32 * C) + 8 : (size_t)Tmax * 32; }
 };
 
 // false: geometry the reference itself never produces (band narrower than the length difference)
@@ -96,7 +90,7 @@ NW_HD bool nw_geo_init(NwGeo &g, const NwPen &pen, int t_len, int q_len, int k, 
 	g.Tmax = g.s * ((t_len - 1) & 31) + g.P * (g.R - 1) + g.W;
 	g.NEG = (t_len + q_len) * (pen.MM + pen.U + pen.W1);
 	// rows of up to 32 * NW_RS_MAXC cells are swept row by row (nw_rs_*), wider ones run as the wavefront
-	g.C = 0; g.cb = 0;
+	g.C = 0;
 	if (rs && pen.d8 && g.W <= 32 * NW_RS_MAXC && (g.banded ? NW_RS_BAND : NW_RS_FULL)) {
 		int c = (g.W + 31) >> 5;
 		if (c == 5) c = 6;
@@ -474,133 +468,6 @@ NW_HD bool nw_trivial(const NwPen &pen, int t_len, int q_len, NwStat &s) {   // 
 	}
 	return true;
 }
-
-// ------------------------------------------------------------------------------------------------ column blocks
-// Banded problems (NW_band_score, nw.c:892-1188) filled by NW_CB_LANES lanes: the query columns are cut into blocks of C
-// columns, block b belongs to lane b mod NW_CB_LANES, and a lane computes the C cells of its block in row i at step
-// s = i + b. In TRUE column coordinates every dependency of a cell points at its own column (vertical), at the column
-// left of it in the same row (horizontal) or in the row above (diagonal): own registers, or what the lane of the block
-// to the left produced one step earlier (three shuffles per step, whatever C is). The band (a block is inside it for
-// band + C rows, then the lane moves to block b + NW_CB_LANES) only decides which cells exist: a cell outside holds NEG,
-// which is exactly how the reference treats what lies beyond the band edges (nw.c:1031-1034, 1076-1102). The previous
-// row's (D, P) of the own columns and the query bases stay in registers for the life of a block; the traceback bytes of
-// a step are one C-byte store per lane. C is chosen so that a lane's consecutive blocks never overlap in time
-// (nw_cb_columns): with 8 lanes and the reference's usual band of 64 + |length difference|, 10 columns keep 84 % of the
-// lane-steps busy.
-template <int C> struct NwCbLane {
-	int b;                 // current block: columns b*C .. b*C + C-1
-	int ifirst, ilast;     // rows in which the block meets the band (ifirst > ilast: no block left)
-	int pD[C], pP[C];      // the row above, own columns (NEG outside the band; the boundary row before row 0)
-	int q8[C];             // 8 * query base of the own columns
-	int eD, eQ, eOld;      // for the lane to the right: D, Q of the last own column in the row just computed (NEG: none), D one row earlier
-	int trackc;            // the block's column at the query start (q_len - 1), -1: not in this block
-	int colBest, colBestI; // k < 0: best D over the rows of that column (first maximum in fill order)
-};
-
-// columns per block: a lane's consecutive blocks (b, b + NW_CB_LANES) must not overlap in time, nor may the next block's
-// exports start while the right neighbour still reads the old block's: (NW_CB_LANES - 2) C + NW_CB_LANES - 1 >= band
-NW_HD int nw_cb_columns(int band) { return band <= 67 ? 10 : (band <= 79 ? 12 : (band <= 103 ? 16 : 0)); }
-
-// geometry of a banded problem for the column-block fill; false: not a shape this fill takes
-NW_HD bool nw_cb_geo(NwGeo &g, const NwPen &pen, int t_len, int q_len, int k, int band) {
-	if (!band || !pen.d8 || !nw_geo_init(g, pen, t_len, q_len, k, band, false)) return false;
-	g.cb = nw_cb_columns(g.band);
-	return g.cb != 0;
-}
-
-template <int C> NW_HD void nw_cb_block(const NwGeo &g, NwCbLane<C> &L, int b, const uint8_t *qlast) {
-	L.b = b;
-	L.trackc = -1;
-	if (b * C >= g.q_len) { L.ifirst = 0x7fffffff; L.ilast = -0x7fffffff; return; }
-	const int f = b * C - g.a - g.band, l = b * C + C - 1 - g.a;
-	L.ifirst = f < 0 ? 0 : f;
-	L.ilast = l > g.t_len - 1 ? g.t_len - 1 : l;
-	if (g.k < 0 && g.q_len - 1 - b * C < C) L.trackc = g.q_len - 1 - b * C;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-	for (int c = 0; c < C; ++c) {
-		const int j = b * C + c;
-		L.pD[c] = L.ifirst == 0 ? g.brow(j) : g.NEG;
-		L.pP[c] = g.NEG;
-		L.q8[c] = j < g.q_len ? (int)qlast[-j] << 3 : 0;
-	}
-}
-
-template <int C> NW_HD void nw_cb_init(const NwGeo &g, NwCbLane<C> &L, int h, const uint8_t *qlast) {
-	nw_cb_block<C>(g, L, h, qlast);
-	L.eD = L.eQ = L.eOld = g.NEG;
-	L.colBest = g.NEG; L.colBestI = 0x7fffffff;
-}
-
-// One step of one lane. (nD, nQ, nOld): the exports of the lane to the left as they stood BEFORE this step.
-// E: the problem's traceback bytes (layout NwGeo::eaddr with cb = C); lastD: D of the last row by query column.
-template <int C>
-NW_HD void nw_cb_step(const NwGeo &g, NwCbLane<C> &L, int h, int s, int nD, int nQ, int nOld, const unsigned long long *tab,
-                      const uint64_t *tseq, int t_s, const uint8_t *qlast, uint8_t *E, int *lastD) {
-	const int i = s - L.b, NEG = g.NEG, W1 = g.W1, U = g.U;
-	const int oldLast = L.pD[C - 1];
-	int outD = NEG, outQ = NEG;
-	if (i >= L.ifirst && i <= L.ilast) {
-		int jl = g.a + i, jh = jl + g.band;
-		if (jl < 0) jl = 0;
-		if (jh > g.q_len - 1) jh = g.q_len - 1;
-		const unsigned long long drow = tab[nw_nuc(tseq, t_s + g.t_len - 1 - i)];
-		const int j0 = L.b * C;
-		int Dl, Ql, dg;
-		if (j0 == 0) { Dl = g.bcol(i); Ql = NEG; dg = g.bcol(i - 1); }                 // the boundary column
-		else { Dl = nD; Ql = nQ; dg = i == 0 ? g.brow(j0 - 1) : nOld; }              // (row 0: the boundary row is analytic)
-		unsigned ew[(C + 3) / 4];
-		for (int x = 0; x < (C + 3) / 4; ++x) ew[x] = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-		for (int c = 0; c < C; ++c) {
-			const int j = j0 + c;
-			const bool valid = j >= jl && j <= jh, edge = j == jh;   // the row's last cell has no vertical move (nw.c:1076-1102)
-			const int upD = L.pD[c], upP = L.pP[c];
-			const int sub = (int)(signed char)(drow >> L.q8[c]);
-			// the cell of nw.c:166-212 / 1040-1102 in closed form (see nw_thread): the vertical run wins against the horizontal
-			// one iff P >= Q + [P opened here]; the diagonal wins ties
-			const int Qo = Dl + W1, Qe = Ql + U, Po = upD + W1, Pe = upP + U, dgs = dg + sub;
-			const bool qo = Qo >= Qe, po = Po >= Pe && !edge;
-			const int Q = qo ? Qo : Qe;
-			int P = edge ? NEG : (po ? Po : Pe);
-			const bool pw = !edge && P - (po ? 1 : 0) >= Q;
-			const int D1 = pw ? P : Q;
-			int ec = pw ? (po ? 4 : 5) : (qo ? 2 : 3);
-			const bool dw = D1 <= dgs;
-			int D = dw ? dgs : D1;
-			if (dw) ec = 1;
-			int Qn = Q;
-			if (!valid) { D = NEG; P = NEG; Qn = NEG; }
-			ew[c >> 2] |= (valid ? (unsigned)(ec | (qo ? 16 : 0) | (po ? 32 : 0)) : 0u) << (8 * (c & 3));
-			dg = upD;
-			L.pD[c] = D; L.pP[c] = P;
-			Dl = D; Ql = Qn;
-		}
-		outD = Dl; outQ = Ql;
-		if (L.trackc >= 0 && jh == g.q_len - 1 && jl <= jh) {   // the row reaches the query start: its cell there competes (nw.c:1106-1109)
-			int D = L.pD[0];
-			for (int c = 1; c < C; ++c) if (c == L.trackc) D = L.pD[c];
-			if (L.colBest < D) { L.colBest = D; L.colBestI = i; }
-		}
-		if (i == g.t_len - 1)
-			for (int c = 0; c < C; ++c) if (j0 + c >= jl && j0 + c <= jh) lastD[j0 + c] = L.pD[c];
-		uint8_t *e = E + ((size_t)s * NW_CB_LANES + (size_t)h) * C;
-#if defined(__CUDA_ARCH__)
-		// C bytes per lane and step, in the widest stores the alignment of e (2 for C = 10, 4 for C = 12, 16) allows
-		if (C % 4 == 0) { for (int x = 0; x < C / 4; ++x) ((uint32_t *)e)[x] = ew[x]; }
-		else for (int x = 0; x < C / 2; ++x) ((uint16_t *)e)[x] = (uint16_t)(ew[x >> 1] >> (16 * (x & 1)));
-#else
-		for (int c = 0; c < C; ++c) e[c] = (uint8_t)(ew[c >> 2] >> (8 * (c & 3)));
-#endif
-	}
-	L.eOld = oldLast; L.eD = outD; L.eQ = outQ;
-	if (i == L.ilast + 1 || (L.ifirst > L.ilast && L.ifirst != 0x7fffffff)) nw_cb_block<C>(g, L, L.b + NW_CB_LANES, qlast);
-}
-
-NW_HD int nw_cb_steps(const NwGeo &g) { return g.t_len + (g.q_len + g.cb - 1) / g.cb + 1; }
 
 // ------------------------------------------------------------------------------------------------ one thread per problem
 // The short tails and gaps of short reads (C1/C2: ~130 cells per read, a few bases by a few bases) are far too small

@@ -151,61 +151,3 @@ extern "C" int emu_nw_thread(const int *pen29, const uint64_t *tseq, const uint8
 	memcpy(out6, &s, 24);
 	return 0;
 }
-
-// nw_cb_* (column blocks, NW_CB_LANES lanes per banded problem): the lanes of a step run in turn on a snapshot of their
-// left neighbours' exports, as the shuffles deliver them
-template <int C>
-static void emu_cb_fill(const NwGeo &g, const NwPen &pen, const uint64_t *tseq, int t_s, const uint8_t *q, uint8_t *E, int *lastD, int *cb, int *ci) {
-	NwCbLane<C> L[NW_CB_LANES];
-	unsigned long long tab[5];
-	for (int tn = 0; tn < 5; ++tn) tab[tn] = nw_pack_row(pen, tn);
-	const uint8_t *qlast = q + g.q_len - 1;
-	for (int h = 0; h < NW_CB_LANES; ++h) nw_cb_init<C>(g, L[h], h, qlast);
-	const int steps = nw_cb_steps(g);
-	for (int s = 0; s < steps; ++s) {
-		int nD[NW_CB_LANES], nQ[NW_CB_LANES], nO[NW_CB_LANES];
-		for (int h = 0; h < NW_CB_LANES; ++h) { const int l = (h + NW_CB_LANES - 1) % NW_CB_LANES; nD[h] = L[l].eD; nQ[h] = L[l].eQ; nO[h] = L[l].eOld; }
-		for (int h = 0; h < NW_CB_LANES; ++h) nw_cb_step<C>(g, L[h], h, s, nD[h], nQ[h], nO[h], tab, tseq, t_s, qlast, E, lastD);
-	}
-	*cb = g.NEG; *ci = 0x7fffffff;
-	for (int h = 0; h < NW_CB_LANES; ++h)
-		if (L[h].colBest > *cb || (L[h].colBest == *cb && L[h].colBestI < *ci)) { *cb = L[h].colBest; *ci = L[h].colBestI; }
-}
-
-extern "C" int emu_nw_cb(const int *pen29, const uint64_t *tseq, const uint8_t *query, int k, int t_s, int t_e, int q_s, int q_e, int band,
-                         int *out6, uint8_t *emap) {
-	NwPen pen;
-	pen.W1 = pen29[0]; pen.U = pen29[1]; pen.MM = pen29[2]; pen.M = pen29[3];
-	memcpy(pen.d, pen29 + 4, 100);
-	pen.d8 = 1;
-	const int t_len = t_e - t_s, q_len = q_e - q_s;
-	NwStat s;
-	if (nw_trivial(pen, t_len, q_len, s)) { memcpy(out6, &s, 24); return 0; }
-	NwGeo g;
-	if (!nw_cb_geo(g, pen, t_len, q_len, k, band)) return 2;
-	std::vector<uint8_t> E(g.ebytes(), 0xEE);
-	std::vector<int> lastD(q_len + 1, 0x3fffffff);
-	int cb, ci;
-	const uint8_t *q = query + q_s;
-	switch (g.cb) {
-	case 10: emu_cb_fill<10>(g, pen, tseq, t_s, q, E.data(), lastD.data(), &cb, &ci); break;
-	case 12: emu_cb_fill<12>(g, pen, tseq, t_s, q, E.data(), lastD.data(), &cb, &ci); break;
-	default: emu_cb_fill<16>(g, pen, tseq, t_s, q, E.data(), lastD.data(), &cb, &ci); break;
-	}
-	if (emap)
-		for (int i = 0; i < t_len; ++i)
-			for (int j = 0; j < q_len; ++j)
-				emap[(size_t)i * q_len + j] = (j >= g.jlo(i) && j <= g.jhi(i)) ? E[g.eaddr(i, j)] : 0xFF;
-	int rb = g.NEG, rq = -1;
-	if (k == -2) {
-		int qlo, qhi;
-		nw_row0_range(g, &qlo, &qhi);
-		for (int qp = qlo; qp <= qhi; ++qp) { int v = lastD[q_len - 1 - qp]; if (rq < 0 || v >= rb) { rb = v; rq = qp; } }
-	}
-	int bm, bq, sc;
-	nw_start_cell(g, cb, ci, lastD.data(), rb, rq, &bm, &bq, &sc);
-	nw_walk(g, E.data(), bm, bq, s);
-	s.score = sc; s.pos = 0;
-	memcpy(out6, &s, 24);
-	return 0;
-}

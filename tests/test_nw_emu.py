@@ -177,44 +177,3 @@ def test_thread_per_problem(emu, k):
                                      q_s + q_len, d8, stride, got, emap.ctypes.data_as(C.c_void_p)) == 0
             assert list(got) == list(want), (k, t_len, q_len, d8, stride, list(want), list(got))
             assert np.array_equal(emap, ref_map), (k, t_len, q_len)
-
-
-@pytest.mark.parametrize("k", [0, -1, -2, 1, 2])
-def test_column_blocks_banded(emu, k):
-    """nw_cb_* (banded fill by column blocks, 16 lanes per problem) against the oracle and, byte for byte of the traceback
-    matrix, against the wavefront"""
-    rng = np.random.default_rng(400 + k)
-    L = util.orc()
-    pen = util.oracle_params()
-    p = list(pen)
-    pen29 = (C.c_int * 29)(p[3], p[2], p[1], p[0], *p[7:32])
-    cases = []
-    for _ in range(60):
-        t_len = int(rng.integers(70, 900))
-        q_len = max(66, t_len + int(rng.integers(-38, 38)))
-        band = abs(t_len - q_len) + 64
-        if q_len <= band or t_len <= band:
-            continue
-        cases.append((t_len, q_len, band))
-    cases += [(200, 200, 64), (201, 200, 65), (130, 129, 65), (500, 470, 94), (470, 500, 94), (1000, 1000, 64), (300, 300, 100),
-              (300, 290, 102), (900, 862, 102), (700, 700, 70), (150, 149, 72), (400, 380, 84), (333, 340, 68), (340, 333, 78)]
-    assert len(cases) > 40
-    for t_len, q_len, band in cases:
-        t, q = problem(rng, t_len, q_len, err=rng.choice([0.02, 0.1, 0.3]))
-        t_s = int(rng.integers(0, 40))
-        tw = pack(t)
-        want = (C.c_int * 6)()
-        L.orc_nw(pen, tw.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), k, t_s, t_s + t_len, 0, q_len, band, want)
-        ref_map = np.zeros(t_len * q_len, dtype=np.uint8)
-        got0 = (C.c_int * 6)()
-        assert emu.emu_nw2(pen29, tw.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), k, t_s, t_s + t_len, 0, q_len, band,
-                           0, 1, 0, got0, None, ref_map.ctypes.data_as(C.c_void_p)) == 0
-        got = (C.c_int * 6)()
-        emap = np.zeros(t_len * q_len, dtype=np.uint8)
-        rc = emu.emu_nw_cb(pen29, tw.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), k, t_s, t_s + t_len, 0, q_len, band, got,
-                           emap.ctypes.data_as(C.c_void_p))
-        assert rc == 0, (rc, t_len, q_len, band)
-        if not np.array_equal(emap, ref_map):
-            bad = np.argwhere(emap != ref_map)[:5].ravel()
-            raise AssertionError(f"traceback bytes differ k={k} {t_len}x{q_len} band {band}: cells {[(int(c) // q_len, int(c) % q_len, int(emap[c]), int(ref_map[c])) for c in bad]}")
-        assert list(got) == list(want), (k, t_len, q_len, band, list(want), list(got))
