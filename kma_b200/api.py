@@ -540,20 +540,30 @@ class TemplateDB:
         return out.reshape(-1, 6)
 
     def consensus(self, template: int = 0, bcd: int = 1, evalue: float = 0.05, caller: int = 0, significance: int = 0,
-                  support: float = 0.0, p_chisqr=None):
+                  support: float = 0.0, p_chisqr=None, out=None):
         """callConsensus (assembly.c:1499) over the template nodes of the device matrix. caller: 0 baseCaller, 1 orgBaseCaller
         (-bcg), 2 refCaller, 3 nanoCaller (-bcNano), 4 refNanoCaller; significance: 0 significantNuc, 1 significantAnd90Nuc
         (-bc90), 2 significantAndSupport (-bc support). p_chisqr: C function pointer of the reference's p_chisqr (None: the
         closed form with the host libm). -> (t, s, q uint8 rows, stats structured array, kernel ms); template = 0: all
-        templates concatenated, stats indexed by template id."""
+        templates concatenated, stats indexed by template id. out: (t, s, q, stats) buffers to fill instead of fresh arrays
+        (pinned uint8 tensors / arrays of at least the row length; stats of DB_size * CONSENSUS_STATS.itemsize bytes): a
+        pipeline that calls this every batch downloads at the link's speed instead of through pageable staging."""
         x0 = lib().kmagpu_chi2_threshold(float(evalue), p_chisqr)
         if x0 < 0:
             raise KmaGpuError(lib().kmagpu_last_error().decode())
         cp = ConsensusParams(int(bcd), int(caller), int(significance), 0, float(support), x0)
         info = self.info
         n = int(self.lengths[template]) if template else int(np.sum(self.lengths[1:], dtype=np.int64))
-        t, s, q = (np.empty(n, dtype=np.uint8) for _ in range(3))
-        st = np.zeros(1 if template else info.DB_size, dtype=CONSENSUS_STATS)
+        nst = 1 if template else info.DB_size
+        if out is None:
+            t, s, q = (np.empty(n, dtype=np.uint8) for _ in range(3))
+            st = np.zeros(nst, dtype=CONSENSUS_STATS)
+        else:
+            rows = [o.numpy() if hasattr(o, "numpy") else o for o in out]
+            if any(len(r) < n for r in rows[:3]) or rows[3].nbytes < nst * CONSENSUS_STATS.itemsize:
+                raise KmaGpuError("consensus: the out buffers are shorter than the rows")
+            t, s, q = (r[:n] for r in rows[:3])
+            st = rows[3].view(np.uint8)[:nst * CONSENSUS_STATS.itemsize].view(CONSENSUS_STATS)
         ms = C.c_float()
         _check(lib().kmagpu_consensus(self._h, int(template), C.byref(cp), t.ctypes.data, s.ctypes.data, q.ctypes.data, n,
                                       st.ctypes.data, C.byref(ms)))

@@ -258,7 +258,7 @@ extern "C" int kmagpu_consensus(kmagpu_db *db, int32_t tmpl, const kmagpu_consen
 	}
 	const size_t n = (size_t)(p1 - p0);
 	if ((t || s || q) && n > cap) { kmagpu_set_error("consensus rows need %zu bytes each, caller gave %zu", n, cap); return -1; }
-	KgBuf rows, dstat;
+	KgBuf &rows = db->d_cons_rows, &dstat = db->d_cons_stat;
 	if (rows.reserve(3 * n + 64) || dstat.reserve(sizeof(CsStat) * (size_t)DB)) return -1;
 	cudaStream_t st = db->stream;
 	KG_CUDA(cudaMemsetAsync(dstat.p, 0, sizeof(CsStat) * (size_t)DB, st));
@@ -291,7 +291,6 @@ extern "C" int kmagpu_consensus(kmagpu_db *db, int32_t tmpl, const kmagpu_consen
 	}
 	cudaError_t e = cudaStreamSynchronize(st);
 	if (e == cudaSuccess) e = cudaGetLastError();
-	rows.release(); dstat.release();
 	if (e != cudaSuccess) { kmagpu_set_error("consensus: %s", cudaGetErrorString(e)); return -1; }
 	if (stats) {   // aligned_assem->len = asm_len (assembly.c:1625)
 		if (tmpl) stats[0].len = (uint32_t)db->lengths[tmpl];

@@ -210,6 +210,7 @@ extern "C" void kmagpu_db_close(kmagpu_db *db) {
 	kg_stage1_free(db);
 	kg_memscore_free(db);
 	kg_align_free(db);
+	db->d_cons_rows.release(); db->d_cons_stat.release();
 	bool last = true;
 	KgImageRef *img = db->image;
 	if (img) {

@@ -152,6 +152,7 @@ struct kmagpu_db {
 	int32_t *d_tdups = nullptr;
 	KgTIndexView tix{};
 	AlignBatch aln;
+	KgBuf d_cons_rows, d_cons_stat;   // consensus rows / per-template sums of the last kmagpu_consensus call (kept: no allocation per call)
 };
 int kg_scores_accumulate(kmagpu_db *db, const unsigned long long *batch_scores);
 

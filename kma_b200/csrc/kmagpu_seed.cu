@@ -33,6 +33,7 @@
 #ifndef KG_MINB
 #define KG_MINB 8             // CTAs per SM the seeding grid is sized for (24.9 KB of shared memory each: at most 9). The kernel carries no
 #endif                        // minimum-blocks bound: forcing 6 / 8 / 9 measured 41.8 / 38.8 / 41.9 ms against 37.7 ms without (profiles/r01_ab_seed.log)
+#define KG_QCAP 48            // queued segments per warp: at most 16 stay behind a round, a round files at most 32
 #define KG_WORDS 12           // staged u64 words per chunk: (256 + 31 + 31) / 32 + 2
 
 struct SeedRes { int32_t score, ntmpl, flag; uint32_t pool_off; int32_t src, rev; };   // src: record that supplies read + name, rev: emit its reverse complement
@@ -112,9 +113,10 @@ struct WarpStats { unsigned lookups, hits, lists, listids; };
 // without N's -- compiled without the other branches, which keeps its loops short in the instruction cache.
 template <bool DENSE, bool GENERIC>
 __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p, const ReadCtx &rc, int strand,
-                           Store<DENSE> &st, uint32_t *hits, uint64_t *sw, int *nbest, WarpStats &ws,
+                           Store<DENSE> &st, uint32_t *hits, uint64_t *sw, int *sq, int *nbest, WarpStats &ws,
                            int2 *pool2 = nullptr, unsigned long long pool2_cap = 0, unsigned long long *ctr = nullptr,
-                           uint32_t *list_off = nullptr) {
+                           uint32_t *list_off = nullptr, bool pre = false) {
+	// pre: the kernel staged the whole read (one chunk) and ran the quick check for both strands already
 	const unsigned lane = threadIdx.x & 31;
 	const int k = hv.kmersize;
 	const int L = rc.seqlen;
@@ -142,7 +144,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 	};
 
 	// ---- quick check (savekmers.c:2485-2495): every k-th k-mer of each N-free stretch
-	bool any = p.exhaustive != 0;
+	bool any = p.exhaustive != 0 || pre;
 	if (!any) {
 		for (int c0 = 0; c0 < npos && !any; c0 += KG_CHUNK) {
 			int w0 = stage(c0);
@@ -188,38 +190,63 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 	bool overflow = false;
 	int prev_pos = -1;                 // position / list of the last hit so far
 	uint32_t prev_off = KG_MISS;
-	uint32_t seg_off = KG_MISS;        // the open segment: list, first and last hit position, run score
-	int seg_first = 0, seg_last = 0, seg_run = 0;
+	// Closed segments wait in a per-warp queue {list, first and last hit position, run score}; the last entry is the
+	// open segment, which later hits on its list still extend. The queue is applied in PACKED rounds: the (segment,
+	// template) items of consecutive segments fill the 32 lanes (a list of this kind of database names ~7 templates, so
+	// four segments share a round). Items of one round that name the same template are found with match.any: the
+	// lowest of them does the table work (find or insert, first-seen score or gap score from the table's last-seen
+	// position), the others resume from the segment before them in the round -- whose last position is what the table
+	// would hold by then -- and add their part atomically; the highest one leaves its segment's last position behind.
+	uint32_t *q_off = (uint32_t *)sq;
+	int *q_first = sq + KG_QCAP, *q_last = sq + 2 * KG_QCAP, *q_run = sq + 3 * KG_QCAP;
+	int nseg = 0;
 
-	auto apply_segment = [&](uint32_t off, int first, int last, int run) -> bool {
-		// the list's length and its first 32 ids in one round trip (the id load does not wait for the length: the value
-		// array is padded, ids past the list are never looked at)
-		int id0 = 0;
-		if (!GENERIC) id0 = (int)__ldg(hv.values_s + off + 1 + lane);
-		const int nl = GENERIC ? list_len(hv, off) : (int)__ldg(hv.values_s + off);
-		if (!DENSE && st.ncand + nl > KG_FILL) return false;
-		ws.lists++; ws.listids += lane == 0 ? nl : 0;
+	auto drain = [&](int cnt) -> bool {   // applies queue entries [0, cnt), cnt <= 32
+		uint32_t off = 0;
+		int nl = 0;
+		if ((int)lane < cnt) { off = q_off[lane]; nl = GENERIC ? list_len(hv, off) : (int)__ldg(hv.values_s + off); }
+		int incl = nl;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, incl, o); if ((int)lane >= o) incl += y; }
+		const int excl = incl - nl, total = __shfl_sync(full, incl, 31);
+		ws.lists += cnt; ws.listids += total;
 #pragma unroll 1
-		for (int base = 0; base < nl; base += 32) {
-			const int i = base + (int)lane;
+		for (int g0 = 0; g0 < total; g0 += 32) {
+			if (!DENSE && st.ncand + min(32, total - g0) > KG_FILL) return false;
+			const bool act = g0 + (int)lane < total;
+			const int g = act ? g0 + (int)lane : total - 1;
+			int sg = 0;   // the segment of item g: how many segments end at or before it
+#pragma unroll
+			for (int step = 16; step; step >>= 1) { const int v = __shfl_sync(full, incl, sg + step - 1); if (v <= g) sg += step; }
+			const uint32_t soff = __shfl_sync(full, off, sg);
+			const int idx = g - __shfl_sync(full, excl, sg);
+			const int first = q_first[sg], last = q_last[sg], run = q_run[sg];
+			const int T = GENERIC ? list_id(hv, soff, idx) : (int)__ldg(hv.values_s + soff + 1 + idx);
+			const unsigned mm = __match_any_sync(full, act ? T : -1 - (int)lane);
+			const unsigned below = mm & lt;
+			const bool lead = act && !below;
 			bool isnew = false;
 			int sl = 0;
-			if (i < nl) {
-				sl = st.find_or_insert(GENERIC ? list_id(hv, off, i) : (base ? (int)__ldg(hv.values_s + off + 1 + i) : id0), &isnew);
-				if (isnew) st.score[sl] = k * p.M + run;                                              // savekmers.c:2682-2688
-				else st.score[sl] += gap_score(p, k, (first - 1) - st.ext[sl], false) + run;      // savekmers.c:2583-2655, 2575-2582
-				st.ext[sl] = last;
-			}
+			if (lead) sl = st.find_or_insert(T, &isnew);
+			sl = __shfl_sync(full, sl, __ffs(mm) - 1);
+			const int plast = __shfl_sync(full, last, below ? 31 - __clz(below) : 0);
+			int add = run;
+			if (lead && isnew) add += k * p.M;                                                       // savekmers.c:2682-2688
+			else add += gap_score(p, k, (first - 1) - (lead ? st.ext[sl] : plast), false);            // savekmers.c:2583-2655, 2575-2582
+			if (lead && isnew) st.score[sl] = add;
+			__syncwarp();
+			if (act && !(lead && isnew)) atomicAdd(&st.score[sl], add);
+			if (act && (mm >> lane) == 1u) st.ext[sl] = last;
 			const unsigned nm = __ballot_sync(full, isnew);
 			if (isnew) st.cand[st.ncand + __popc(nm & lt)] = sl;
 			st.ncand += __popc(nm);
+			__syncwarp();
 		}
-		__syncwarp();
 		return true;
 	};
 
 	for (int c0 = 0; c0 < npos && !overflow; c0 += KG_CHUNK) {
-		const int w0 = stage(c0);
+		const int w0 = pre ? 0 : stage(c0);
 		const int lim = min(npos, c0 + KG_CHUNK), nround = (lim - c0 + 31) >> 5;
 		// phase 1: gather, four rounds of 32 positions at a time so that 4 independent probes per lane are in flight
 		if (GENERIC && rc.nN) {   // reads with N's (rare): validity per position, one probe at a time; kept off the hot path
@@ -273,52 +300,67 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 		}
 		__syncwarp();
 
-		// phase 2: segments of this chunk, 32 positions per round
+		// phase 2: the segments of this chunk, 32 positions per round, no loop over the segments: every lane that starts
+		// one files it
 #pragma unroll 1
 		for (int u = 0; u < nround && !overflow; ++u) {
 			const uint32_t myoff = hits[u * 32 + lane];
 			const bool hit = myoff != KG_MISS;
 			const unsigned hm = __ballot_sync(full, hit);
-			if (!hm) continue;
-			nhits += __popc(hm);
-			const int base = c0 + u * 32;
-			// the hit before this position: in this round, or the one carried over
-			const unsigned below = hm & lt;
-			const int pl = below ? 31 - __clz(below) : -1;
-			uint32_t poff = __shfl_sync(full, myoff, pl < 0 ? 0 : pl);
-			int ppos = base + pl;
-			if (pl < 0) { poff = prev_off; ppos = prev_pos; }
-			const bool same = hit && poff == myoff;   // continues (gap 0) or resumes the list of the hit before it
-			int ps = same ? gap_score(p, k, base + (int)lane - ppos - 1, true) : 0;   // what this hit adds to its segment's run score
+			if (hm) {
+				nhits += __popc(hm);
+				const int base = c0 + u * 32;
+				// the hit before this position: in this round, or the one carried over
+				const unsigned below = hm & lt;
+				const int pl = below ? 31 - __clz(below) : -1;
+				uint32_t poff = __shfl_sync(full, myoff, pl < 0 ? 0 : pl);
+				int ppos = base + pl;
+				if (pl < 0) { poff = prev_off; ppos = prev_pos; }
+				const bool same = hit && poff == myoff;   // continues (gap 0) or resumes the list of the hit before it
+				int ps = same ? gap_score(p, k, base + (int)lane - ppos - 1, true) : 0;   // what this hit adds to its segment's run score
 #pragma unroll
-			for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, ps, o); if ((int)lane >= o) ps += y; }
-			const unsigned sm = __ballot_sync(full, hit && !same);   // list changes: a new segment starts
-			const int fs = sm ? __ffs(sm) - 1 : 32;
-			const unsigned head = hm & (fs == 32 ? full : ((1u << fs) - 1u));   // hits that still belong to the open segment
-			if (head) {
-				const int hl = 31 - __clz(head);
-				seg_run += __shfl_sync(full, ps, hl);
-				seg_last = base + hl;
+				for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, ps, o); if ((int)lane >= o) ps += y; }
+				const unsigned sm = __ballot_sync(full, hit && !same);   // list changes: a new segment starts
+				const int fs = sm ? __ffs(sm) - 1 : 32;
+				const unsigned head = hm & (fs == 32 ? full : ((1u << fs) - 1u));   // hits that still belong to the open segment
+				if (head) {
+					const int hl = 31 - __clz(head);
+					const int addrun = __shfl_sync(full, ps, hl);
+					if (lane == 0) { q_run[nseg - 1] += addrun; q_last[nseg - 1] = base + hl; }
+				}
+				if (sm) {
+					const bool start = (sm >> lane) & 1u;
+					const unsigned above = sm & ~lt & ~(1u << lane);   // the starts after this lane
+					const unsigned upto = above ? ((1u << (__ffs(above) - 1)) - 1u) : full;
+					const unsigned body = hm & upto & ~lt;              // this segment's hits in the round
+					const int ll = start ? 31 - __clz(body) : (int)lane;
+					const int runv = __shfl_sync(full, ps, ll) - ps;
+					const int qi = nseg + __popc(sm & lt);
+					if (start) { q_off[qi] = myoff; q_first[qi] = base + (int)lane; q_last[qi] = base + ll; q_run[qi] = runv; }
+					nseg += __popc(sm);
+				}
+				const int lh = 31 - __clz(hm);
+				prev_pos = base + lh;
+				prev_off = __shfl_sync(full, myoff, lh);
+				__syncwarp();
 			}
-			unsigned rest = sm;
-			while (rest) {
-				const int b = __ffs(rest) - 1;
-				rest &= rest - 1;
-				if (seg_off != KG_MISS && !apply_segment(seg_off, seg_first, seg_last, seg_run)) { overflow = true; break; }
-				const int e = rest ? __ffs(rest) - 1 : 32;
-				const unsigned body = hm & (e == 32 ? full : ((1u << e) - 1u)) & ~((1u << b) - 1u);   // this segment's hits in the round
-				const int ll = 31 - __clz(body);
-				seg_off = __shfl_sync(full, myoff, b);
-				seg_first = base + b; seg_last = base + ll;
-				seg_run = __shfl_sync(full, ps, ll) - __shfl_sync(full, ps, b);
+			// make room for the next round (all but the open segment, 32 at most per pass); after the strand's last
+			// round everything goes (savekmers.c:2707-2722)
+			const bool fin = u == nround - 1 && c0 + KG_CHUNK >= npos;
+			while (nseg > (fin ? 0 : KG_QCAP - 32)) {
+				const int cnt = min(fin ? nseg : nseg - 1, 32);
+				if (!drain(cnt)) { overflow = true; break; }
+				uint32_t mo = 0; int mf = 0, ml = 0, mr = 0;
+				const bool mv = (int)lane < nseg - cnt;
+				if (mv) { mo = q_off[cnt + lane]; mf = q_first[cnt + lane]; ml = q_last[cnt + lane]; mr = q_run[cnt + lane]; }
+				__syncwarp();
+				if (mv) { q_off[lane] = mo; q_first[lane] = mf; q_last[lane] = ml; q_run[lane] = mr; }
+				nseg -= cnt;
+				__syncwarp();
 			}
-			const int lh = 31 - __clz(hm);
-			prev_pos = base + lh;
-			prev_off = __shfl_sync(full, myoff, lh);
 		}
 		__syncwarp();
 	}
-	if (!overflow && seg_off != KG_MISS && !apply_segment(seg_off, seg_first, seg_last, seg_run)) overflow = true;   // savekmers.c:2707-2722
 	ws.hits += lane == 0 ? nhits : 0;
 
 	if (overflow) {   // hash mode only: wipe and report
@@ -397,12 +439,14 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
                int2 *pool2, unsigned long long pool2_cap, uint32_t *__restrict__ nlist, int from_nlist) {
 	__shared__ uint32_t s_hits[KG_WARPS][KG_CHUNK];
 	__shared__ uint64_t s_words[KG_WARPS][KG_WORDS];
+	__shared__ int s_queue[KG_WARPS][4 * KG_QCAP];
 	__shared__ int s_tab[DENSE ? 1 : KG_WARPS][DENSE ? 1 : 3 * KG_CAP];
 	__shared__ int s_cand[DENSE ? 1 : KG_WARPS][DENSE ? 1 : 2 * KG_CAP];
 
 	const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	uint32_t *hits = s_hits[wid];
 	uint64_t *sw = s_words[wid];
+	int *sq = s_queue[wid];
 	Store<DENSE> st;
 	int *candF, *candR;
 	if (DENSE) {
@@ -448,22 +492,60 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 		// both strands through ONE call site (one inlined copy of the scan: four copies made 200 KB of code). A mate of
 		// a pair keeps every template's score for pair_select_kernel, a single read only its arg-max sets.
 		const bool mate = kinds && kinds[r];
-		int sres[2] = {0, 0}, scnt[2] = {0, 0};
-		uint32_t soff[2] = {0, 0};
+		int sres0 = 0, sres1 = 0, scnt0 = 0, scnt1 = 0;   // per strand: score / hit count, templates kept, their pool offset
+		uint32_t soff0 = 0, soff1 = 0;
 		bool ovf = false;
 		if (rc.seqlen >= k) {
+			// a read of one chunk (every short read): its words are staged once for both strands, and the quick check
+			// (savekmers.c:2485-2495: every k-th k-mer until one is known) probes both strands at once, 16 lanes each
+			const int npos = rc.seqlen - k + 1;
+			const bool pre = npos <= KG_CHUNK && !(GENERIC && rc.nN);
+			unsigned want = 3u;
+			if (pre) {
+				__syncwarp();
+				if ((int)lane <= ((rc.seqlen - 1) >> 5) + 1) sw[lane] = (int)lane < rc.words ? ld_u64u(rc.seq + 8 * (size_t)lane) : 0ull;
+				__syncwarp();
+				if (!p.exhaustive) {
+					want = 0u;
+					unsigned open = 3u;   // strands still probing
+					const int sd = (int)(lane >> 4);
+#pragma unroll 1
+					for (int jb = 0; jb < npos && open; jb += 16 * k) {
+						const int j = jb + (int)(lane & 15u) * k;
+						const bool act = j < npos && ((open >> sd) & 1u);
+						bool hp = false;
+						if (act) {
+							uint64_t km = kmer_from(sw, 0, sd ? rc.seqlen - k - j : j, k);
+							if (sd) km = rev2(~km) >> (64 - 2 * k);
+							hp = hash_lookup(hv, km) != KG_MISS;
+						}
+						const unsigned am = __ballot_sync(0xffffffffu, act), hm = __ballot_sync(0xffffffffu, hp);
+#pragma unroll
+						for (int sx = 0; sx < 2; ++sx) {
+							const unsigned a = (am >> (16 * sx)) & 0xffffu, h = (hm >> (16 * sx)) & 0xffffu;
+							if (!((open >> sx) & 1u)) continue;
+							if (lane == 0) ws.lookups += h ? __ffs(h) : __popc(a);   // algorithmic probe count: the reference stops at the first hit
+							if (h) { want |= 1u << sx; open &= ~(1u << sx); }
+						}
+					}
+				}
+			}
+#pragma unroll 1
 			for (int strand = 0; strand < 2 && !ovf; ++strand) {
+				if (!((want >> strand) & 1u)) continue;
 				st.cand = strand ? candR : candF;
-				sres[strand] = scan_strand<DENSE, GENERIC>(hv, p, rc, strand, st, hits, sw, &scnt[strand], ws, mate ? pool2 : nullptr,
-				                                  pool2_cap, ctr, &soff[strand]);
-				ovf = sres[strand] < 0;
+				int cnt = 0;
+				uint32_t off = 0;
+				const int sr = scan_strand<DENSE, GENERIC>(hv, p, rc, strand, st, hits, sw, sq, &cnt, ws, mate ? pool2 : nullptr, pool2_cap, ctr, &off, pre);
+				if (strand) { sres1 = sr; scnt1 = cnt; soff1 = off; } else { sres0 = sr; scnt0 = cnt; soff0 = off; }
+				ovf = sr < 0;
 			}
 			if (ovf && lane == 0) ovf_list[atomicAdd(&ctr[C_OVF], 1ull)] = (uint32_t)r;   // table overflow: dense pass
 		}
 		if (mate) {
 			MateRes m = {0, 0, 0, 0, 0, 0};
 			if (rc.seqlen >= k && !ovf) {
-				m.off_f = soff[0]; m.off_r = soff[1]; m.n_f = scnt[0]; m.n_r = scnt[1]; m.hits = max(sres[0], sres[1]); m.scanned = 1;
+				m.off_f = soff0; m.off_r = soff1; m.n_f = scnt0; m.n_r = scnt1; m.hits = max(sres0, sres1); m.scanned = 1;
 			}
 			if (lane == 0 && !ovf) mates[r] = m;
 			__syncwarp();
@@ -472,7 +554,7 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 		SeedRes out = {0, 0, 0, 0, r, 0};
 		uint32_t size = 0;
 		if (rc.seqlen >= k) {
-			const int nf = scnt[0], nr = scnt[1], bf = sres[0], br = sres[1];
+			const int nf = scnt0, nr = scnt1, bf = sres0, br = sres1;
 			if (ovf) out.flag = -1;
 			else if ((bf > 0 || br > 0) && (k <= bf || k <= br)) {   // savekmers.c:3039-3061
 				int nt = bf > br ? nf : (bf < br ? nr : nf + nr);

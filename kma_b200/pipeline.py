@@ -176,7 +176,7 @@ class MapPipeline:
             scores[1][:] += u
         return res
 
-    def map_to_consensus(self, text1, text2, frag_outs, params, fastq=True, consensus_args=None, **ingest):
+    def map_to_consensus(self, text1, text2, frag_outs, params, fastq=True, consensus_args=None, trace=None, cons_out=None, **ingest):
         """The whole mapping core on one batch of FASTQ text (pinned uint8 tensors; text2 = the second file of a pair of
         files or None), every stream resident in HBM, what `kma -i / -ipe ... -o out` computes between its input files and
         its writers: record splitter + stage 1 -> stage 2 -> alignment pass | ConClave sums all-reduced over ranks (NCCL
@@ -186,8 +186,15 @@ class MapPipeline:
         points where the workers meet. Down come: per worker its per-template fragment stream into frag_outs[w] (what the
         .frag.gz writer needs), then the consensus rows and per-template sums (what .res / .fsa / .aln are written from).
         Paired files must line up slice by slice (equal-length records), as map_text_device_split requires.
+        cons_out: (t, s, q, stats) pinned buffers for the consensus rows (api.TemplateDB.consensus's out).
+        trace: optional list; (worker, phase, perf_counter seconds) is appended as each worker leaves a phase.
         Returns dict(reads, fragments, consensus=(t, s, q, stats), totals=(w_scores, fragmentCounts, readCounts), frag_bytes)."""
+        import time
         import torch  # noqa: F401  (pinned tensors come from the caller)
+
+        def mark(w, what):
+            if trace is not None:
+                trace.append((w, what, time.perf_counter()))
         L = api.lib()
         W = len(self.dbs)
 
@@ -212,13 +219,17 @@ class MapPipeline:
 
         def exchange_scores():
             try:
+                mark(-1, "all workers at the score exchange")
                 lead.allreduce_scores(download=False)
+                mark(-1, "scores all-reduced")
             except Exception as e:
                 err.append(e)
 
         def exchange_matrix():
             try:
+                mark(-1, "all workers at the matrix exchange")
                 lead.allreduce_matrix()
+                mark(-1, "matrix all-reduced")
             except Exception as e:
                 err.append(e)
         b1 = threading.Barrier(W, action=exchange_scores)
@@ -233,9 +244,12 @@ class MapPipeline:
                     if u1 != c1[w + 1] - c1[w] or (c2 is not None and u2 != c2[w + 1] - c2[w]):
                         raise api.KmaGpuError("the two files' records do not line up slice by slice")
                     res["reads"][w] = cnt
+                    mark(w, "text up + stage 1")
                     db.seed_run(params)
+                    mark(w, "stage 2")
                     db.align_from_seed()
                     db.align_run(params)
+                    mark(w, "alignment pass")
             except Exception as e:
                 err.append(e)
             b1.wait()
@@ -243,8 +257,10 @@ class MapPipeline:
                 if w < nsl and not err:
                     frag, _, _, _, _ = db.conclave_from_align(None, None, out=frag_outs[w], totals=totals[w])
                     res["frag"][w] = frag
+                    mark(w, "ConClave + fragments down")
                     _, nfr, _ = db.trace_from_conclave(p_trace, download=False)
                     res["fragments"][w] = nfr
+                    mark(w, "traceback + base counts")
             except Exception as e:
                 err.append(e)
             b2.wait()
@@ -256,9 +272,12 @@ class MapPipeline:
             t.join()
         if err:
             raise err[0]
+        mark(-1, "workers joined")
         wsc = sum(t[0] for t in totals)
         lead.allreduce_u64(wsc)
-        cons = lead.consensus(0, **(consensus_args or {}))
+        mark(-1, "w_scores all-reduced")
+        cons = lead.consensus(0, out=cons_out, **(consensus_args or {}))
+        mark(-1, "consensus down")
         return {"reads": sum(res["reads"]), "fragments": sum(res["fragments"]), "consensus": cons[:4],
                 "totals": (wsc, sum(t[1] for t in totals), sum(t[2] for t in totals)),
                 "frag_bytes": sum(int(f.numel() if hasattr(f, "numel") else len(f)) for f in res["frag"] if f is not None)}
