@@ -33,6 +33,9 @@
 #define KG_STAGE_INL                // inlined per call site: 50 ms vs 71 ms out of line (arguments by reference go through the stack)
 #endif
 #define AL_BANDW 64           // align.c:511
+#ifndef AL_CLAIM
+#define AL_CLAIM 4            // tasks a warp claims from the work counter at a time
+#endif
 #ifndef AL_MINB
 #define AL_MINB 6             // resident CTAs per SM the pair kernel is compiled for (register cap 65536 / (128 * AL_MINB))
 #endif
@@ -131,7 +134,7 @@ static __global__ void aln_sizes_kernel(const uint8_t *__restrict__ in, const ui
 			if (prev_len < k || R.q_len < k || prev_rc < 0) atomicAdd(&ctr[A_BAD], 1ull);
 			else ts = 2u * (uint32_t)R.nt;
 		} else if (R.kind == 0) ts = R.q_len >= k ? (uint32_t)R.nt : 0u;
-		atomicMax(&ctr[A_MAXQ], (unsigned long long)R.q_len);
+		warp_max_u64(&ctr[A_MAXQ], (unsigned)R.q_len);
 	}
 	reads[r] = R;
 	slab_sz[r] = ss; task_sz[r] = ts;
@@ -685,10 +688,16 @@ __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(const Aln
 	M.cap = lay.mem_cap;
 	WarpCtr wc;
 	memset(&wc, 0, sizeof(wc));
+	unsigned long long tnext = 0;
+	int tleft = 0;   // tasks are claimed AL_CLAIM at a time: one contended atomic per four tasks, and a read's tasks stay on one warp
 	for (;;) {
-		unsigned long long t = 0;
-		if (lane == 0) t = atomicAdd(&ctr[A_WORK], 1ull);
-		t = __shfl_sync(0xffffffffu, t, 0);
+		if (!tleft) {
+			if (lane == 0) tnext = atomicAdd(&ctr[A_WORK], (unsigned long long)AL_CLAIM);
+			tnext = __shfl_sync(0xffffffffu, tnext, 0);
+			tleft = AL_CLAIM;
+		}
+		const unsigned long long t = tnext++;
+		--tleft;
 		if (t >= (unsigned long long)ntasks) break;
 		const int task = task_list ? task_list[t] : (int)t;
 		const int r = task_read[task];
@@ -939,7 +948,7 @@ __global__ void aln_reduce_kernel(AlnParams P, const uint8_t *__restrict__ in, c
 		uint32_t size = 0;
 		if (R.kind == 2 && R.nt > 0 && reads[r - 1].q_len >= P.k && R.q_len >= P.k) {
 			reduce_pair(P, reads[r - 1], R, in + R.rec_off, cand, meta, as, uas, o, size);
-			if (o.nrec) atomicAdd(&ctr[A_FRAGS], (unsigned long long)(o.form == 1 ? 1 : o.nrec));
+			if (o.nrec) warp_add_u64(&ctr[A_FRAGS], (unsigned)(o.form == 1 ? 1 : o.nrec));
 		}
 		recsize[r] = size;
 		res[r] = o;
@@ -988,7 +997,7 @@ __global__ void aln_reduce_kernel(AlnParams P, const uint8_t *__restrict__ in, c
 		if (kept == 1) atomicAdd(&uas[abs(c[0].tmpl)], (unsigned long long)best_read);
 		o.kept = kept; o.best = best_read;
 		size = 20u + (uint32_t)q_len + (uint32_t)R.hl + 12u * (uint32_t)kept;
-		atomicAdd(&ctr[A_FRAGS], 1ull);
+		warp_add_u64(&ctr[A_FRAGS], 1u);
 	}
 	recsize[r] = size;
 	res[r] = o;
@@ -1084,6 +1093,7 @@ __global__ void __launch_bounds__(256) tr_sizes_kernel(const uint8_t *__restrict
 		TrRec *recs, uint32_t *slab_sz, uint32_t *row_sz, unsigned long long *ctr) {
 	const unsigned lane = threadIdx.x & 31;
 	const int warps = (gridDim.x * blockDim.x) >> 5;
+	int maxq = 0;   // one atomic per warp at the end, not one per record
 	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
 		const uint8_t *rec = in + off[r];
 		TrRec R;
@@ -1107,9 +1117,10 @@ __global__ void __launch_bounds__(256) tr_sizes_kernel(const uint8_t *__restrict
 			recs[r] = R;
 			slab_sz[r] = tr_stride(R) * (R.score == 0 ? 2u : 1u);
 			row_sz[r] = (3u * R.row_cap + 7u) >> 3;   // 8-byte units
-			atomicMax(&ctr[A_MAXQ], (unsigned long long)R.q_len);
+			maxq = max(maxq, R.q_len);
 		}
 	}
+	if (lane == 0 && maxq > 0) atomicMax(&ctr[A_MAXQ], (unsigned long long)maxq);
 }
 
 // bytes -> slab (packed words, bytes, N list + sentinel), reverse complement too for reads without a strand
@@ -1187,6 +1198,18 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 	auto nw_rows = [&](int kk, int t_s, int t_e, int q_s, int q_e, int at, NwStat *a) -> int {
 		if (at + (t_e - t_s) + (q_e - q_s) + 8 > row_cap) return ST_ROWS;
 		const int t_l = t_e - t_s, q_l = q_e - q_s;
+		if (t_l == 1 && q_l == 1 && kk == 0) {   // the single mismatch between two MEMs: one cell in closed form, one diagonal column
+			NwStat a1;
+			if (nw_closed_form(*c.pen, c.tseq, c.qb, 0, t_s, t_e, q_s, q_e, a1) && a1.len == 1) {
+				if (lane == 0) {
+					const uint8_t tb = (uint8_t)nw_nuc(c.tseq, t_s), qb = c.qb[q_s];
+					rows.t[at] = tb; rows.s[at] = tb == qb ? '|' : '_'; rows.q[at] = qb;
+				}
+				++c.wc->full_calls; ++c.wc->full_cells;
+				*a = a1;
+				return ST_OK;
+			}
+		}
 		int band = abs(t_l - q_l) + AL_BANDW;
 		if (q_l <= band || t_l <= band) band = 0;
 		NwRows r = {rows.t + at, rows.s + at, rows.q + at};
@@ -1326,13 +1349,53 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 struct TrOut { int32_t h[12]; int32_t status; };
 
 // one warp per fragment record: (anker_rc when the strand is open) -> KMA -> acceptance (assembly.c:1925-1961)
-__global__ void __launch_bounds__(AL_WARPS * 32, AL_MINB) tr_task_kernel(AlnParams P, KgTIndexView ix, const TrRec *__restrict__ recs,
+// anker_rc (align.c:780-991) for a fragment whose strand is open: both strands' MEMs, the better one stays in M.
+// Out of line: fragments that come from the alignment pass carry their strand, so this is off their path.
+struct TrAnker { int strand, nmem, go, st, oriented; };
+__device__ __noinline__ void tr_anker_rc(const AlnParams &P, const KgTIndexView &ix, const KgTMeta &m, const uint64_t *tseq, const uint64_t *slab,
+                                         const TrRec &R, Mems &M, WarpCtr &wc, TrAnker &A) {
+	const int lane = threadIdx.x & 31, k = ix.k, q_len = R.q_len, nN1 = R.nN + 1;
+	const QView qf = tr_view(slab, R, 0), qr = tr_view(slab, R, 1);
+	int sf = 0, sr = 0, nf = 0, ntot, st = ST_OK;
+	A.strand = 0; A.nmem = 0; A.go = 0; A.oriented = 0;
+	// query bounds (chain-mode fragments): a lower bound skips preseed, the reverse strand sees them mirrored (align.c:806-817)
+	const bool pre = R.q_start || P.exhaustive || preseed_hit(ix, m, qf.b, q_len, R.q_end - R.q_start);
+	if (pre) st = scan_mems<1, true>(ix, m, tseq, qf, nN1, q_len, R.q_start, R.q_end, M, nf, sf, wc);
+	ntot = nf;
+	if (!st) st = scan_mems<1, true>(ix, m, tseq, qr, nN1, q_len, q_len - R.q_end, q_len - R.q_start, M, ntot, sr, wc);
+	const int best = max(sf, sr);
+	if (!st) {
+		int turned = 0;
+		if (P.one2one && best < k && best * k < (q_len - k - best)) turned = 1;   // rejected; the read stays turned
+		else if (best == sf) { A.nmem = nf; A.go = best != 0; }
+		else { A.strand = 1; M.shift(nf); A.nmem = ntot - nf; A.go = 1; turned = 1; }
+		if (turned) {   // "oriented": do the bytes differ from what came in? (a palindrome does not)
+			int diff = 0;
+#pragma unroll 1
+			for (int i = lane; i < q_len; i += 32) diff |= qf.b[i] != qr.b[i];
+			A.oriented = __any_sync(0xffffffffu, diff) ? 1 : 0;
+		}
+	}
+	A.st = st;
+}
+
+#ifndef TR_MINB
+#define TR_MINB 8             // resident CTAs per SM the traceback kernel is compiled for (64 registers). C2 traceback stage: 4 -> 32.0 ms, 5 -> 30.1, 6 -> 29.6, 8 -> 28.5 (profiles/r02_trace_kernel.log)
+#endif
+// one warp per fragment record: (anker_rc when the strand is open) -> KMA -> acceptance (assembly.c:1925-1961)
+__global__ void __launch_bounds__(AL_WARPS * 32, TR_MINB) tr_task_kernel(const AlnParams P_, const KgTIndexView ix_, const TrRec *__restrict__ recs,
 		const uint64_t *slab, int n, const int32_t *__restrict__ task_list, TrOut *outs, uint8_t *rowpool, uint8_t *scratch,
 		ScratchLayout lay, unsigned long long *ctr, int32_t *ovf_list) {
-	__shared__ NwPen spen;
+	// the parameter blocks once per CTA in shared memory: the out-of-line stages take them by reference
+	__shared__ AlnParams sP;
+	__shared__ KgTIndexView six;
 	__shared__ NwRow sring[AL_WARPS][NW_RING];
-	if (threadIdx.x < sizeof(NwPen) / 4) ((int *)&spen)[threadIdx.x] = ((const int *)&P.pen)[threadIdx.x];
+	for (int i = threadIdx.x; i < (int)(sizeof(AlnParams) / 4); i += blockDim.x) ((int *)&sP)[i] = ((const int *)&P_)[i];
+	for (int i = threadIdx.x; i < (int)(sizeof(KgTIndexView) / 4); i += blockDim.x) ((int *)&six)[i] = ((const int *)&ix_)[i];
 	__syncthreads();
+	const AlnParams &P = sP;
+	const KgTIndexView &ix = six;
+	NwPen &spen = sP.pen;
 	const int lane = threadIdx.x & 31;
 	const size_t wid = (size_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
 	uint8_t *sp = scratch + wid * lay.stride;
@@ -1349,53 +1412,51 @@ __global__ void __launch_bounds__(AL_WARPS * 32, AL_MINB) tr_task_kernel(AlnPara
 	nws.rowbuf = (NwRow *)sp; nws.e_cap = lay.e_cap; nws.q_cap = lay.q_cap; nws.finish();
 	WarpCtr wc;
 	memset(&wc, 0, sizeof(wc));
+	unsigned long long tnext = 0;
+	int tleft = 0;
 	for (;;) {
-		unsigned long long t = 0;
-		if (lane == 0) t = atomicAdd(&ctr[A_WORK], 1ull);
-		t = __shfl_sync(0xffffffffu, t, 0);
+		if (!tleft) {   // AL_CLAIM fragments per claim
+			if (lane == 0) tnext = atomicAdd(&ctr[A_WORK], (unsigned long long)AL_CLAIM);
+			tnext = __shfl_sync(0xffffffffu, tnext, 0);
+			tleft = AL_CLAIM;
+		}
+		const unsigned long long t = tnext++;
+		--tleft;
 		if (t >= (unsigned long long)n) break;
 		const int r = task_list ? task_list[t] : (int)t;
 		const TrRec R = recs[r];
 		const KgTMeta m = ix.meta[R.tmpl];
-		const int k = ix.k, q_len = R.q_len, nN1 = R.nN + 1, t_len = m.len;
+		const int q_len = R.q_len, nN1 = R.nN + 1, t_len = m.len;
 		Mems M = M0;
 		TaskCtx c;
 		c.pen = &spen; c.tseq = ix.seq + m.seq_off; c.nw = nws; c.wc = &wc;
-		TrOut o;
-		memset(&o, 0, sizeof(o));
-		int strand = 0, nmem = 0, st = ST_OK;
+		int strand = 0, nmem = 0, st = ST_OK, oriented = 0;
 		bool go = R.score != 0;
-		if (!go) {   // anker_rc (align.c:780-991)
-			const QView qf = tr_view(slab, R, 0), qr = tr_view(slab, R, 1);
-			int sf = 0, sr = 0, nf = 0, ntot;
-			// query bounds (chain-mode fragments): a lower bound skips preseed, the reverse strand sees them mirrored (align.c:806-817)
-			const bool pre = R.q_start || P.exhaustive || preseed_hit(ix, m, qf.b, q_len, R.q_end - R.q_start);
-			if (pre) st = scan_mems<1, true>(ix, m, c.tseq, qf, nN1, q_len, R.q_start, R.q_end, M, nf, sf, wc);
-			ntot = nf;
-			if (!st) st = scan_mems<1, true>(ix, m, c.tseq, qr, nN1, q_len, q_len - R.q_end, q_len - R.q_start, M, ntot, sr, wc);
-			const int best = max(sf, sr);
-			if (!st) {
-				int turned = 0;
-				if (P.one2one && best < k && best * k < (q_len - k - best)) turned = 1;   // rejected; the read stays turned
-				else if (best == sf) { nmem = nf; go = best != 0; }
-				else { strand = 1; M.shift(nf); nmem = ntot - nf; go = true; turned = 1; }
-				if (turned) {   // "oriented": do the bytes differ from what came in? (a palindrome does not)
-					int diff = 0;
-#pragma unroll 1
-					for (int i = lane; i < q_len; i += 32) diff |= qf.b[i] != qr.b[i];
-					o.h[10] = __any_sync(0xffffffffu, diff) ? 1 : 0;
-				}
-			}
+		if (!go) {
+			TrAnker A;
+			tr_anker_rc(P, ix, m, c.tseq, slab, R, M, wc, A);
+			strand = A.strand; nmem = A.nmem; go = A.go != 0; st = A.st; oriented = A.oriented;
 		}
+		NwStat a = {0, 0, 0, 0, 0, 0};
+		int ncol = 0;
+		bool done = false;
 		if (go && !st) {
 			const QView q = tr_view(slab, R, strand);
 			c.qb = q.b;
 			NwRows rows;
 			rows.t = rowpool + R.row_off; rows.s = rows.t + R.row_cap; rows.q = rows.s + R.row_cap;
-			NwStat a = {0, 0, 0, 0, 0, 0};
-			int ncol = 0;
 			st = kma_trace_warp(P, c, ix, m, q, nN1, q_len, R.q_start, R.q_end, M, nmem, &a, rows, (int)R.row_cap, &ncol);
-			if (!st) {
+			done = !st;
+		}
+		__syncwarp();
+		if (st == ST_OVERFLOW && lane == 0) { const unsigned long long x = atomicAdd(&ctr[A_OVF], 1ull); ovf_list[x] = r; }
+		if (st == ST_ROWS && lane == 0) atomicAdd(&ctr[A_BAD], 1ull);
+		if (lane == 0) {   // the acceptance test of assemble_KMA (assembly.c:1925-1961) and the header the host needs
+			TrOut o;
+#pragma unroll
+			for (int i = 0; i < 12; ++i) o.h[i] = 0;
+			o.h[10] = oriented;
+			if (done) {
 				const int aln_len = a.len, start = a.pos;
 				int end = start + aln_len - a.tGaps, read_score = a.score;
 				double score;
@@ -1409,12 +1470,9 @@ __global__ void __launch_bounds__(AL_WARPS * 32, AL_MINB) tr_task_kernel(AlnPara
 				o.h[4] = a.score; o.h[5] = a.len; o.h[6] = a.pos; o.h[7] = a.match; o.h[8] = a.tGaps; o.h[9] = a.qGaps;
 				o.h[11] = ncol;
 			}
+			o.status = st;
+			outs[r] = o;
 		}
-		__syncwarp();
-		o.status = st;
-		if (st == ST_OVERFLOW && lane == 0) { const unsigned long long x = atomicAdd(&ctr[A_OVF], 1ull); ovf_list[x] = r; }
-		if (st == ST_ROWS && lane == 0) atomicAdd(&ctr[A_BAD], 1ull);
-		if (lane == 0) outs[r] = o;
 	}
 	if (lane == 0) {
 		if (wc.mems) atomicAdd(&ctr[A_MEMS], wc.mems);
@@ -2036,7 +2094,7 @@ static int trace_core(kmagpu_db *db, const kmagpu_params *prm, const uint8_t *di
 	const size_t e_cap = std::min<size_t>(std::max<size_t>(2 * (size_t)maxq * (size_t)maxq + 65536, 65536), 4u << 20);
 	ScratchLayout lay = make_layout(2048, q_cap, e_cap);
 	AlignBatch &b = db->aln;   // the per-warp scratch is shared with the alignment pass
-	int grid = db->sm_count * AL_MINB;
+	int grid = db->sm_count * TR_MINB;
 	size_t freeb = 0, totalb = 0;
 	if (lay.stride * (size_t)grid * AL_WARPS > b.d_scratch.cap) {
 		cudaMemGetInfo(&freeb, &totalb);

@@ -29,6 +29,9 @@
 #endif
 #define KG_CAP (1 << KG_CAP_LOG)          // shared hash slots per warp
 #define KG_FILL (3 * KG_CAP / 4)          // distinct templates a read may see before it goes to the dense path
+#ifndef KG_CLAIM
+#define KG_CLAIM 4            // reads a warp claims from the work counter at a time
+#endif
 #define KG_WARPS 4            // warps per CTA
 #ifndef KG_MINB
 #define KG_MINB 8             // CTAs per SM the seeding grid is sized for (24.9 KB of shared memory each: at most 9). The kernel carries no
@@ -468,10 +471,16 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 	// whose template table overflowed (DENSE)
 	const int total = DENSE ? (int)ctr[C_OVF] : (from_nlist ? (int)ctr[C_NLIST] : nreads);
 
+	unsigned long long wnext = 0;
+	int wleft = 0;   // reads are claimed KG_CLAIM at a time: one contended atomic per four reads
 	for (;;) {
-		unsigned long long w = 0;
-		if (lane == 0) w = atomicAdd(&ctr[DENSE ? C_WORK2 : (from_nlist ? C_WORK3 : C_WORK)], 1ull);
-		w = __shfl_sync(0xffffffffu, w, 0);
+		if (!wleft) {
+			if (lane == 0) wnext = atomicAdd(&ctr[DENSE ? C_WORK2 : (from_nlist ? C_WORK3 : C_WORK)], (unsigned long long)KG_CLAIM);
+			wnext = __shfl_sync(0xffffffffu, wnext, 0);
+			wleft = KG_CLAIM;
+		}
+		const unsigned long long w = wnext++;
+		--wleft;
 		if (w >= (unsigned long long)total) break;
 		const int r = DENSE ? (int)ovf_list[w] : (from_nlist ? (int)nlist[w] : (int)w);
 
