@@ -70,7 +70,7 @@ struct AlnParams {
 
 enum { A_WORK = 0, A_OVF = 1, A_NEED_E = 2, A_NEED_MEM = 3, A_NEED_Q = 4, A_MEMS = 5, A_FULL_CALLS = 6, A_BAND_CALLS = 7,
        A_FULL_CELLS = 8, A_BAND_CELLS = 9, A_STEPS = 10, A_SLAB = 11, A_TASKS = 12, A_OUT = 13, A_FRAGS = 14, A_BAD = 15,
-       A_MAXQ = 16, A_LOOKUPS = 17, A_MEMBASES = 18, A_READBYTES = 19, A_NPROB = 20, A_PCLS = 21 /* .. 23 */, A_N = 32 };
+       A_MAXQ = 16, A_LOOKUPS = 17, A_MEMBASES = 18, A_READBYTES = 19, A_NPROB = 20, A_PCLS = 21 /* .. 24 */, A_N = 32 };
 
 // ---------------------------------------------------------------- slab layout
 
@@ -424,7 +424,8 @@ __device__ int chain_warp(const NwPen &pen, Mems &M, int n, int q_len, int t_len
 // (align.c:92-98, 186-192, 478-484) to a queue; queue kernels then solve the problems -- one THREAD per problem for the
 // small ones (classes 0-3 by size, so that a warp's 32 problems are alike), one WARP per problem for the rest -- and add
 // their AlnScore fields into the task's candidate row (all of them are sums; the lead tail also moves `pos`).
-#define NWQ_CLASSES 3
+#define NWQ_CLASSES 4
+#define NWQ_NARROW 4   // cells per lane of the widest row the narrow warp kernel sweeps
 struct NwProb { int32_t task, tmpl, t_s, t_e, q_s, q_e, kband; uint32_t qoff; };   // kband = (k + 2) | band << 8; query bytes at qbase + (qoff << qshift)
 // order / cells: per class `cap` queue slots and their cell counts in arrival order; the thread classes are then sorted by
 // cells so that the 32 problems of a warp are alike
@@ -436,11 +437,14 @@ struct NwQueue { NwProb *probs; uint32_t *order, *cells; unsigned cap; unsigned 
 // measured at 143 GCUPS against the row sweep's 213 (profiles/r02_ab_column_blocks.log: ~77 instructions per cell as
 // compiled, 168 registers), so the row sweep stays.
 __host__ __device__ __forceinline__ int nwq_class(int t_l, int q_l, int band, int d8) {
-	(void)d8;
-	if (band || q_l > 64 || t_l > 128 || t_l <= 0 || q_l <= 0) return 2;
+	if (band || q_l > 64 || t_l > 128 || t_l <= 0 || q_l <= 0) {
+		// warp per problem; rows of up to NWQ_NARROW * 32 cells (every default band) go to the build of the kernel that
+		// sweeps nothing wider: 166 registers for the 256-cell sweep were 3 resident CTAs per SM for all of them
+		const int W = band ? ((band + 1) | 1) : q_l;   // nw_geo_init: an odd band is widened by one, a row is band + 1 cells
+		return (d8 && W <= 32 * NWQ_NARROW) ? 2 : 3;
+	}
 	return (q_l > 32 || t_l > 64) ? 1 : 0;
 }
-static const int nwq_qmax[2] = {32, 64};        // query columns the thread kernel of a class holds in shared memory
 static const int nwq_cells[2] = {2048, 8192};   // traceback bytes per problem
 
 struct TaskCtx {
@@ -499,12 +503,12 @@ __device__ __forceinline__ void nw_enqueue(const TaskCtx &c, int k, int t_s, int
 			*(int4 *)&Q.probs[slot] = *(const int4 *)&p;
 			*((int4 *)&Q.probs[slot] + 1) = *((const int4 *)&p + 1);
 			Q.order[(size_t)cls * Q.cap + ci] = (uint32_t)slot;
-			if (cls != 2) Q.cells[(size_t)cls * Q.cap + ci] = (uint32_t)(t_l * q_l);
+			if (cls < 2) Q.cells[(size_t)cls * Q.cap + ci] = (uint32_t)(t_l * q_l);
 		}
 	}
-	if (cls == 2) {   // the warp-per-problem kernel sizes its scratch from the largest problem
+	if (cls >= 2) {   // the warp-per-problem kernels size their scratch from the largest problem
 		NwGeo g;
-		if (nw_geo_init(g, *c.pen, t_l, q_l, k, band, true)) {
+		if (nw_geo_init(g, *c.pen, t_l, q_l, k, band, NW_RS_MAXC)) {
 			c.wc->need_e = max(c.wc->need_e, (unsigned)min((size_t)0xF0000000u, g.ebytes() + 4096));
 			c.wc->need_q = max(c.wc->need_q, (unsigned)q_l + 64u);
 		}
@@ -689,12 +693,14 @@ __global__ void __launch_bounds__(AL_WARPS * 32, MINB) aln_pair_kernel(const Aln
 	WarpCtr wc;
 	memset(&wc, 0, sizeof(wc));
 	unsigned long long tnext = 0;
-	int tleft = 0;   // tasks are claimed AL_CLAIM at a time: one contended atomic per four tasks, and a read's tasks stay on one warp
+	int tleft = 0;   // tasks are claimed AL_CLAIM at a time: one contended atomic per four tasks, and a read's tasks stay on one warp;
+	                 // one at a time when the batch has few (long) tasks per warp: there the balance is what counts
+	const int claim = (long long)ntasks >= 64ll * gridDim.x * AL_WARPS ? AL_CLAIM : 1;
 	for (;;) {
 		if (!tleft) {
-			if (lane == 0) tnext = atomicAdd(&ctr[A_WORK], (unsigned long long)AL_CLAIM);
+			if (lane == 0) tnext = atomicAdd(&ctr[A_WORK], (unsigned long long)claim);
 			tnext = __shfl_sync(0xffffffffu, tnext, 0);
-			tleft = AL_CLAIM;
+			tleft = claim;
 		}
 		const unsigned long long t = tnext++;
 		--tleft;
@@ -1214,10 +1220,10 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 		if (q_l <= band || t_l <= band) band = 0;
 		NwRows r = {rows.t + at, rows.s + at, rows.q + at};
 		unsigned long long cells = 0;
-		const int st = nw_warp<false>(*c.pen, c.tseq, c.qb, kk, t_s, t_e, q_s, q_e, band, c.nw, a, &cells, &r);
+		const int st = nw_warp<0>(*c.pen, c.tseq, c.qb, kk, t_s, t_e, q_s, q_e, band, c.nw, a, &cells, &r);
 		if (st != NW_OK) {
 			NwGeo g;
-			nw_geo_init(g, *c.pen, t_l, q_l, kk, band, false);
+			nw_geo_init(g, *c.pen, t_l, q_l, kk, band, 0);
 			c.wc->need_e = max(c.wc->need_e, (unsigned)min((size_t)0xF0000000u, g.ebytes() + 4096));
 			c.wc->need_q = max(c.wc->need_q, (unsigned)q_l + 64u);
 			return ST_OVERFLOW;
@@ -1414,11 +1420,12 @@ __global__ void __launch_bounds__(AL_WARPS * 32, TR_MINB) tr_task_kernel(const A
 	memset(&wc, 0, sizeof(wc));
 	unsigned long long tnext = 0;
 	int tleft = 0;
+	const int claim = (long long)n >= 64ll * gridDim.x * AL_WARPS ? AL_CLAIM : 1;   // as in the pair kernel
 	for (;;) {
-		if (!tleft) {   // AL_CLAIM fragments per claim
-			if (lane == 0) tnext = atomicAdd(&ctr[A_WORK], (unsigned long long)AL_CLAIM);
+		if (!tleft) {
+			if (lane == 0) tnext = atomicAdd(&ctr[A_WORK], (unsigned long long)claim);
 			tnext = __shfl_sync(0xffffffffu, tnext, 0);
-			tleft = AL_CLAIM;
+			tleft = claim;
 		}
 		const unsigned long long t = tnext++;
 		--tleft;
@@ -1726,8 +1733,12 @@ __global__ void __launch_bounds__(128) nw_thread_kernel(const NwPen pen, const K
 	if ((threadIdx.x & 31) == 0 && calls) { atomicAdd(&ctr[A_FULL_CELLS], cells); atomicAdd(&ctr[A_FULL_CALLS], (unsigned long long)calls); }
 }
 
-// class 2: one warp per problem (nw_warp: row sweep for rows of up to 256 cells, the continuous wavefront beyond)
-__global__ void __launch_bounds__(AL_WARPS * 32) nw_warp_kernel(const NwPen pen, const KgTIndexView ix, const NwProb *__restrict__ probs,
+// classes 2-3: one warp per problem (nw_warp: row sweep for rows of up to 32 * RSMAX cells, the continuous wavefront beyond)
+#ifndef NW_NARROW_MINB
+#define NW_NARROW_MINB 6   // resident CTAs per SM the narrow build is compiled for
+#endif
+template <int RSMAX>
+__global__ void __launch_bounds__(AL_WARPS * 32, RSMAX <= NWQ_NARROW ? NW_NARROW_MINB : 1) nw_warp_kernel(const NwPen pen, const KgTIndexView ix, const NwProb *__restrict__ probs,
 		const uint32_t *__restrict__ order, int n, const uint8_t *qbase, int qshift, int32_t *res, int32_t *status_out,
 		uint8_t *scratch, ScratchLayout lay, unsigned long long *ctr) {
 	__shared__ NwPen spen;
@@ -1752,12 +1763,12 @@ __global__ void __launch_bounds__(AL_WARPS * 32) nw_warp_kernel(const NwPen pen,
 		const KgTMeta m = ix.meta[p.tmpl];
 		NwStat a = {0, 0, 0, 0, 0, 0};
 		unsigned long long cells = 0;
-		const int st = nw_warp<true>(spen, ix.seq + m.seq_off, qbase + ((size_t)p.qoff << qshift), k, p.t_s, p.t_e, p.q_s, p.q_e, band, nws, &a, &cells);
+		const int st = nw_warp<RSMAX>(spen, ix.seq + m.seq_off, qbase + ((size_t)p.qoff << qshift), k, p.t_s, p.t_e, p.q_s, p.q_e, band, nws, &a, &cells);
 		if (st == NW_OK) {
 			if (lane == 0) nwq_apply(row, a, k, status);
 			if (cells) {
 				NwGeo g;
-				nw_geo_init(g, spen, p.t_e - p.t_s, p.q_e - p.q_s, k, band, true);
+				nw_geo_init(g, spen, p.t_e - p.t_s, p.q_e - p.q_s, k, band, RSMAX);
 				steps += g.C ? (unsigned long long)g.t_len * g.C : (unsigned long long)g.Tmax;
 				if (band) { bcells += cells; ++bcalls; } else { fcells += cells; ++fcalls; }
 			}
@@ -1799,7 +1810,7 @@ static int nw_queue_run(kmagpu_db *db, const AlnParams &P, const NwProb *probs, 
 		const int n = (int)counts[c];
 		if (!n) continue;
 		const uint32_t *ord = order + (size_t)c * cap;
-		if (cells && c != 2) {   // largest problems first, neighbours alike: what a warp works on together finishes together
+		if (cells && c < 2) {   // largest problems first, neighbours alike: what a warp works on together finishes together
 			uint32_t *ks = sorted, *vs = ks + cap;
 			size_t tmp_bytes = 0;
 			const int bits = 14;   // at most 128 x 64 cells
@@ -1818,7 +1829,10 @@ static int nw_queue_run(kmagpu_db *db, const AlnParams &P, const NwProb *probs, 
 			ScratchLayout lay;
 			lay.mem_cap = 0; lay.q_cap = std::max(need_q, 256); lay.e_cap = (std::max<size_t>(need_e, 65536) + 255) & ~(size_t)255;
 			lay.stride = ((size_t)lay.q_cap * 12 + lay.e_cap + 255) & ~(size_t)255;
-			int grid = (int)std::min<size_t>((size_t)db->sm_count * 8, ((size_t)n + AL_WARPS - 1) / AL_WARPS);
+			int per_sm = 0;   // what the build's registers allow (narrow: NW_NARROW_MINB, wide: 3)
+			if (c == 2) KG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_warp_kernel<NWQ_NARROW>, AL_WARPS * 32, 0));
+			else KG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_warp_kernel<NW_RS_MAXC>, AL_WARPS * 32, 0));
+			int grid = (int)std::min<size_t>((size_t)db->sm_count * (size_t)std::max(per_sm, 1), ((size_t)n + AL_WARPS - 1) / AL_WARPS);
 			if (lay.stride * (size_t)grid * AL_WARPS > scr.cap) {
 				size_t freeb = 0, totalb = 0;
 				cudaMemGetInfo(&freeb, &totalb);
@@ -1826,7 +1840,8 @@ static int nw_queue_run(kmagpu_db *db, const AlnParams &P, const NwProb *probs, 
 			}
 			if (scr.reserve(lay.stride * (size_t)grid * AL_WARPS)) return -1;
 			KG_CUDA(cudaMemsetAsync(ctr + A_WORK, 0, 8, st));
-			nw_warp_kernel<<<grid, AL_WARPS * 32, 0, st>>>(P.pen, db->tix, probs, ord, n, qbase, qshift, res, status_out, (uint8_t *)scr.p, lay, ctr);
+			if (c == 2) nw_warp_kernel<NWQ_NARROW><<<grid, AL_WARPS * 32, 0, st>>>(P.pen, db->tix, probs, ord, n, qbase, qshift, res, status_out, (uint8_t *)scr.p, lay, ctr);
+			else nw_warp_kernel<NW_RS_MAXC><<<grid, AL_WARPS * 32, 0, st>>>(P.pen, db->tix, probs, ord, n, qbase, qshift, res, status_out, (uint8_t *)scr.p, lay, ctr);
 		}
 		if (rc) return -1;
 		++*launches;
@@ -2294,7 +2309,7 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 	const AlnParams P = make_params(db, p);
 	std::vector<NwProb> hp(n);
 	std::vector<uint32_t> horder(NWQ_CLASSES * n);
-	unsigned long long counts[NWQ_CLASSES] = {0, 0, 0};
+	unsigned long long counts[NWQ_CLASSES] = {0, 0, 0, 0};
 	for (size_t i = 0; i < n; ++i) {
 		const int32_t *pr = prob + 8 * i;
 		if (pr[0] <= 0 || pr[0] >= db->info.DB_size || pr[1] < 0 || pr[2] < pr[1] || pr[2] > db->lengths[pr[0]] || pr[4] < 0 ||
@@ -2305,7 +2320,7 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 		const int t_l = pr[2] - pr[1], q_l = pr[5] - pr[4];
 		NwGeo g;
 		const int cls = nwq_class(t_l, q_l, pr[7], P.pen.d8);
-		if (cls == 2 && t_l > 0 && q_l > 0 && nw_geo_init(g, P.pen, t_l, q_l, pr[6], pr[7], true)) {
+		if (cls >= 2 && t_l > 0 && q_l > 0 && nw_geo_init(g, P.pen, t_l, q_l, pr[6], pr[7], NW_RS_MAXC)) {
 			need_e = std::max(need_e, g.ebytes() + 256);
 			need_q = std::max(need_q, q_l + 64);
 		}
@@ -2315,7 +2330,7 @@ extern "C" int kmagpu_nw_batch(kmagpu_db *db, const kmagpu_params *p, size_t n, 
 		horder[(size_t)cls * n + counts[cls]++] = (uint32_t)i;
 	}
 	for (int c = 0; c < NWQ_CLASSES; ++c)   // sorted by cells, largest first (the alignment pass sorts on the device)
-		if (c != 2) std::stable_sort(horder.begin() + (size_t)c * n, horder.begin() + (size_t)c * n + counts[c], [&](uint32_t x, uint32_t y) {
+		if (c < 2) std::stable_sort(horder.begin() + (size_t)c * n, horder.begin() + (size_t)c * n + counts[c], [&](uint32_t x, uint32_t y) {
 			const long long bx = hp[x].kband >> 8, by = hp[y].kband >> 8;
 			return (long long)(hp[x].t_e - hp[x].t_s) * (bx ? bx + 2 : hp[x].q_e - hp[x].q_s) > (long long)(hp[y].t_e - hp[y].t_s) * (by ? by + 2 : hp[y].q_e - hp[y].q_s); });
 	uint8_t *dq = nullptr;

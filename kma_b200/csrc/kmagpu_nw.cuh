@@ -64,10 +64,10 @@ struct NwGeo {
 #ifndef NW_RS_BAND
 #define NW_RS_BAND 1   // row sweep for bands
 #endif
-// rs: the caller's kernel sweeps narrow rows (the stand-alone NW batch kernel). Inside the alignment kernels every
+// rs: the widest row (in cells per lane, at most NW_RS_MAXC) the caller's kernel sweeps row by row; 0: none. Inside the alignment kernels every
 // variant of the row sweep measured slower than the wavefront (profiles/r01_ab_rowsweep.log: those kernels stall on
 // instruction fetch, and the sweep adds a dozen more loops to them), so they pass false.
-NW_HD bool nw_geo_init(NwGeo &g, const NwPen &pen, int t_len, int q_len, int k, int band, bool rs) {
+NW_HD bool nw_geo_init(NwGeo &g, const NwPen &pen, int t_len, int q_len, int k, int band, int rs) {
 	g.t_len = t_len; g.q_len = q_len; g.k = k; g.banded = band != 0;
 	g.W1 = pen.W1; g.U = pen.U;
 	if (band & 1) ++band;   // nw.c:374-376
@@ -91,7 +91,7 @@ NW_HD bool nw_geo_init(NwGeo &g, const NwPen &pen, int t_len, int q_len, int k, 
 	g.NEG = (t_len + q_len) * (pen.MM + pen.U + pen.W1);
 	// rows of up to 32 * NW_RS_MAXC cells are swept row by row (nw_rs_*), wider ones run as the wavefront
 	g.C = 0;
-	if (rs && pen.d8 && g.W <= 32 * NW_RS_MAXC && (g.banded ? NW_RS_BAND : NW_RS_FULL)) {
+	if (rs && pen.d8 && g.W <= 32 * (rs < NW_RS_MAXC ? rs : NW_RS_MAXC) && (g.banded ? NW_RS_BAND : NW_RS_FULL)) {
 		int c = (g.W + 31) >> 5;
 		if (c == 5) c = 6;
 		if (c == 7) c = 8;
@@ -387,6 +387,75 @@ NW_HD void nw_rs_rowend(const NwGeo &g, NwRsLane<C> &L, int lane, const NwRsRow 
 	}
 }
 
+// ---- interior rows of a band: a + i >= 1 and a + i + band <= q_len - 2. Such a row starts at in-row offset 0 away from the
+// matrix border, ends at offset `band` (the edge cell, always the same lane and cell) and does not reach the query
+// start: no border values, no partial rows, no start-cell tracking. Nearly every row of a long banded problem is one
+// (all but ~band / 2 at either end), and what is left of the passes is about half the instructions of the general ones.
+NW_HD void nw_rs_interior(const NwGeo &g, int *i1, int *i2) {
+	int lo = 1 - g.a, hi = g.q_len - 1 - g.band - g.a;   // rows [lo, hi)
+	if (lo < 0) lo = 0;
+	if (hi > g.t_len) hi = g.t_len;
+	if (!g.banded || hi < lo) hi = lo;
+	*i1 = lo; *i2 = hi;
+}
+
+// ubc: which of the lane's cells is the row's edge cell (-1: none); lane0: the lane holds the row's first cell
+template <int C>
+NW_HD int nw_rs_pass1i(const NwGeo &g, NwRsLane<C> &L, bool lane0, int ubc, unsigned lo, unsigned hi, int nbD, int nbP, int Ue, int Qstart, int *fP) {
+	int r = lane0 ? Qstart : NW_NINF;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int c = 0; c < C; ++c) {
+		const int upD = c + 1 < C ? L.pD[c + 1 < C ? c + 1 : c] : nbD, upP = c + 1 < C ? L.pP[c + 1 < C ? c + 1 : c] : nbP;
+		const int dg = L.pD[c] + (int)(signed char)nw_fsr(lo, hi, (unsigned)L.qs[c]);
+		const int Po = upD + g.W1, Pe = upP + g.U;
+		const bool edge = c == ubc;   // no vertical move into the band's last cell (nw.c:1076-1102)
+		fP[c] = (!edge && Po >= Pe) ? 1 : 0;
+		const int P = edge ? g.NEG : nw_max(Po, Pe);
+		L.pD[c] = dg; L.pP[c] = P;
+		r = nw_max(nw_max(P, dg) + g.W1, r + Ue);
+	}
+	return r;
+}
+
+template <int C>
+NW_HD void nw_rs_pass2i(const NwGeo &g, NwRsLane<C> &L, bool lane0, int ubc, int Qfirst, int Qstart, const int *fP, int *e, int *Dlast, int *Qlast) {
+	int Dl = 0, Ql = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int c = 0; c < C; ++c) {
+		int Q, cq, fq;
+		if (c == 0) { Q = lane0 ? Qstart : Qfirst; cq = 3; fq = 0; }
+		else {
+			const int Qo = Dl + g.W1, Qe = Ql + g.U;
+			const bool o = Qo >= Qe;
+			Q = o ? Qo : Qe; cq = o ? 2 : 3; fq = o ? 16 : 0;
+		}
+		const int P = L.pP[c], dg = L.pD[c];
+		const bool pw = c != ubc && P >= Q + fP[c];
+		const int D1 = pw ? P : Q;
+		int ec = pw ? 5 - fP[c] : cq;
+		if (D1 <= dg) ec = 1;
+		e[c] = ec + fq + (fP[c] << 5);
+		const int D = nw_max(D1, dg);
+		L.pD[c] = D;
+		Dl = D; Ql = Q;
+	}
+	*Dlast = Dl; *Qlast = Ql;
+}
+
+// the first cell's Q-opened flag; the row's first cell has nothing but the band's outside to its left
+NW_HD int nw_rs_fix0i(const NwGeo &g, bool lane0, int e0, int Dl, int Ql) {
+	if (lane0) { Dl = g.NEG; Ql = g.NEG; }
+	if (Dl + g.W1 >= Ql + g.U) {
+		if ((e0 & 7) == 3) e0 = (e0 & ~7) | 2;
+		e0 |= 16;
+	}
+	return e0;
+}
+
 // the last row's D by query column (what nw_start_cell reads)
 template <int C, bool BANDED> NW_HD void nw_rs_lastrow(const NwGeo &g, const NwRsLane<C> &L, int lane, int *lastD) {
 	const int i = g.t_len - 1, off = g.off(i), ua = g.jlo(i) - off, ub = g.jhi(i) - off;
@@ -648,7 +717,47 @@ __device__ __noinline__ void nw_rs_fill(const NwGeo &gin, const uint64_t *__rest
 	const int Ue = g.W1 > g.U ? g.W1 : g.U, lstep = lane * C * Ue;
 	uint8_t *Erow = E + lane * C;
 	int tpos = t_s + g.t_len - 1;
+	int i1 = 0, i2 = 0;   // the band's interior rows
+	if (BANDED) nw_rs_interior(g, &i1, &i2);
+	const bool lane0 = lane == 0;
+	const int ubc = (g.band >= lane * C && g.band < lane * C + C) ? g.band - lane * C : -1;
+	const int Qs_in = nw_max(g.NEG + g.W1, g.NEG + g.U);
+	auto store_row = [&](const int *e) {
+		if (C == 1) Erow[0] = (uint8_t)e[0];
+		else if (C == 2) *(uint16_t *)Erow = (uint16_t)(e[0] | e[1 % C] << 8);
+		else if (C == 3) { Erow[0] = (uint8_t)e[0]; Erow[1] = (uint8_t)e[1 % C]; Erow[2] = (uint8_t)e[2 % C]; }
+		else if (C == 4) *(uint32_t *)Erow = (uint32_t)(e[0] | e[1 % C] << 8 | e[2 % C] << 16 | e[3 % C] << 24);
+		else if (C == 6) {
+			((uint16_t *)Erow)[0] = (uint16_t)(e[0] | e[1 % C] << 8);
+			((uint16_t *)Erow)[1] = (uint16_t)(e[2 % C] | e[3 % C] << 8);
+			((uint16_t *)Erow)[2] = (uint16_t)(e[4 % C] | e[5 % C] << 8);
+		} else {
+			uint2 w;
+			w.x = (uint32_t)(e[0] | e[1 % C] << 8 | e[2 % C] << 16 | e[3 % C] << 24);
+			w.y = (uint32_t)(e[4 % C] | e[5 % C] << 8 | e[6 % C] << 16 | e[7 % C] << 24);
+			*(uint2 *)Erow = w;
+		}
+	};
 	for (int i = 0; i < g.t_len; ++i, Erow += 32 * C, --tpos) {
+		if (BANDED && i >= i1 && i < i2) {   // interior row: the lean passes
+			const unsigned long long tr = tab[nw_nuc(tseq, tpos)];
+			const int q8n = nw_rs_q8<true>(g, i + 1, lane * C + C - 1, qlast);
+			const int nbD = __shfl_down_sync(full, L.pD[0], 1), nbP = __shfl_down_sync(full, L.pP[0], 1);
+			int fP[C];
+			int B = nw_rs_pass1i<C>(g, L, lane0, ubc, (unsigned)tr, (unsigned)(tr >> 32), nbD, nbP, Ue, Qs_in, fP) - lstep;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) B = max(B, __shfl_up_sync(full, B, o));
+			const int Qf = __shfl_up_sync(full, B + lstep, 1);
+			int e[C], Dlast, Qlast;
+			nw_rs_pass2i<C>(g, L, lane0, ubc, Qf, Qs_in, fP, e, &Dlast, &Qlast);
+			const int Dl = __shfl_up_sync(full, Dlast, 1), Ql = __shfl_up_sync(full, Qlast, 1);
+			e[0] = nw_rs_fix0i(g, lane0, e[0], Dl, Ql);
+			store_row(e);
+#pragma unroll
+			for (int c = 0; c + 1 < C; ++c) L.qs[c] = L.qs[c + 1];
+			L.qs[C - 1] = q8n;
+			continue;
+		}
 		NwRsRow R;
 		nw_rs_row(g, R, i, tab[nw_nuc(tseq, tpos)]);
 		int q8n = 0;
@@ -666,48 +775,24 @@ __device__ __noinline__ void nw_rs_fill(const NwGeo &gin, const uint64_t *__rest
 		nw_rs_pass2<C, BANDED>(g, L, lane, R, Qf, fP, e, &Dlast, &Qlast);
 		const int Dl = __shfl_up_sync(full, Dlast, 1), Ql = __shfl_up_sync(full, Qlast, 1);
 		e[0] = nw_rs_fix0<C>(g, lane, R, e[0], Dl, Ql);
-		if (C == 1) Erow[0] = (uint8_t)e[0];
-		else if (C == 2) *(uint16_t *)Erow = (uint16_t)(e[0] | e[1] << 8);
-		else if (C == 3) { Erow[0] = (uint8_t)e[0]; Erow[1] = (uint8_t)e[1]; Erow[2] = (uint8_t)e[2]; }
-		else if (C == 4) *(uint32_t *)Erow = (uint32_t)(e[0] | e[1] << 8 | e[2] << 16 | e[3] << 24);
-		else if (C == 6) {
-			((uint16_t *)Erow)[0] = (uint16_t)(e[0] | e[1] << 8);
-			((uint16_t *)Erow)[1] = (uint16_t)(e[2 % C] | e[3 % C] << 8);
-			((uint16_t *)Erow)[2] = (uint16_t)(e[4 % C] | e[5 % C] << 8);
-		} else {
-			uint2 w;
-			w.x = (uint32_t)(e[0] | e[1 % C] << 8 | e[2 % C] << 16 | e[3 % C] << 24);
-			w.y = (uint32_t)(e[4 % C] | e[5 % C] << 8 | e[6 % C] << 16 | e[7 % C] << 24);
-			*(uint2 *)Erow = w;
-		}
+		store_row(e);
 		nw_rs_rowend<C, BANDED>(g, L, lane, R, i, q8n);
 	}
 	nw_rs_lastrow<C, BANDED>(g, L, lane, lastD);
 	*cbo = L.colBest; *cio = L.colBestI;
 }
 
-template <bool BANDED>
+template <bool BANDED, int MAXC>
 __device__ __forceinline__ void nw_rs_dispatch(const NwGeo &g, const uint64_t *__restrict__ tseq, int t_s, const uint8_t *q,
                                                const unsigned long long *tab, uint8_t *E, int *lastD, int *cb, int *ci) {
 	if (BANDED ? !NW_RS_BAND : !NW_RS_FULL) return;
-	switch (g.C) {
-	case 1: nw_rs_fill<1, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci); break;
-#if NW_RS_MAXC >= 2
-	case 2: nw_rs_fill<2, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci); break;
-#endif
-#if NW_RS_MAXC >= 3
-	case 3: nw_rs_fill<3, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci); break;
-#endif
-#if NW_RS_MAXC >= 4
-	case 4: nw_rs_fill<4, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci); break;
-#endif
-#if NW_RS_MAXC >= 6
-	case 6: nw_rs_fill<6, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci); break;
-#endif
-#if NW_RS_MAXC >= 8
-	default: nw_rs_fill<8, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci); break;
-#endif
-	}
+	// only the widths the kernel was built for are reachable from it: its register count is the widest sweep's
+	if (g.C == 1) nw_rs_fill<1, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci);
+	if constexpr (MAXC >= 2) if (g.C == 2) nw_rs_fill<2, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci);
+	if constexpr (MAXC >= 3) if (g.C == 3) nw_rs_fill<3, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci);
+	if constexpr (MAXC >= 4) if (g.C == 4) nw_rs_fill<4, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci);
+	if constexpr (MAXC >= 6) if (g.C == 6) nw_rs_fill<6, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci);
+	if constexpr (MAXC >= 8) if (g.C == 8) nw_rs_fill<8, BANDED>(g, tseq, t_s, q, tab, E, lastD, cb, ci);
 }
 
 // How the out-of-line nw_warp takes the scratch descriptor: by reference it lives in the caller's local memory, by value
@@ -719,9 +804,9 @@ typedef const NwScratch NwScratchArg;
 typedef const NwScratch &NwScratchArg;
 #endif
 
-// All 32 lanes call with identical arguments; every lane returns the same result. RS: rows of up to 32 * NW_RS_MAXC
-// cells run as the row sweep.
-template <bool RS>
+// All 32 lanes call with identical arguments; every lane returns the same result. RS: rows of up to 32 * RS cells run
+// as the row sweep (0: none).
+template <int RS>
 __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict__ tseq, const uint8_t *query, int k, int t_s,
                                     int t_e, int q_s, int q_e, int band, NwScratchArg ws, NwStat *out,
                                     unsigned long long *cells, const NwRows *rows = nullptr) {
@@ -774,8 +859,8 @@ __device__ __noinline__ int nw_warp(const NwPen &pen, const uint64_t *__restrict
 		if (lane < 5) tab[lane] = nw_rs_tab(pen, lane);
 		__syncwarp();
 		uint8_t *E8 = (uint8_t *)(((uintptr_t)ws.E() + 7) & ~(uintptr_t)7);
-		if (g.banded) nw_rs_dispatch<true>(g, tseq, t_s, q, tab, E8, ws.lastD(), &cb, &ci);
-		else nw_rs_dispatch<false>(g, tseq, t_s, q, tab, E8, ws.lastD(), &cb, &ci);
+		if (g.banded) nw_rs_dispatch<true, RS>(g, tseq, t_s, q, tab, E8, ws.lastD(), &cb, &ci);
+		else nw_rs_dispatch<false, RS>(g, tseq, t_s, q, tab, E8, ws.lastD(), &cb, &ci);
 		E = E8;
 	} else {
 		NwRow *hand = g.rmask == NW_RING - 1 ? ws.ring : ws.rowbuf;

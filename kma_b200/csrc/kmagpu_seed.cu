@@ -472,12 +472,14 @@ seed_se_kernel(KgHashView hv, SeedParams p, const uint8_t *__restrict__ in, cons
 	const int total = DENSE ? (int)ctr[C_OVF] : (from_nlist ? (int)ctr[C_NLIST] : nreads);
 
 	unsigned long long wnext = 0;
-	int wleft = 0;   // reads are claimed KG_CLAIM at a time: one contended atomic per four reads
+	int wleft = 0;   // reads are claimed KG_CLAIM at a time: one contended atomic per four reads. A batch of few (long) reads is
+	                 // claimed read by read: there the balance over the warps is what counts
+	const int claim = (long long)total >= 64ll * gridDim.x * KG_WARPS ? KG_CLAIM : 1;
 	for (;;) {
 		if (!wleft) {
-			if (lane == 0) wnext = atomicAdd(&ctr[DENSE ? C_WORK2 : (from_nlist ? C_WORK3 : C_WORK)], (unsigned long long)KG_CLAIM);
+			if (lane == 0) wnext = atomicAdd(&ctr[DENSE ? C_WORK2 : (from_nlist ? C_WORK3 : C_WORK)], (unsigned long long)claim);
 			wnext = __shfl_sync(0xffffffffu, wnext, 0);
-			wleft = KG_CLAIM;
+			wleft = claim;
 		}
 		const unsigned long long w = wnext++;
 		--wleft;

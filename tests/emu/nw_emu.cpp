@@ -18,10 +18,39 @@ static int emu_rs_fill(const NwGeo &g, const NwPen &pen, const uint64_t *tseq, i
 	for (int l = 0; l < 32; ++l) nw_rs_init<C, BANDED>(g, L[l], l, qlast);
 	const int Ue = g.W1 > g.U ? g.W1 : g.U, step = C * Ue;
 	int bad = 0;
+	int i1 = 0, i2 = 0;
+	if (BANDED) nw_rs_interior(g, &i1, &i2);
+	const int Qs_in = nw_max(g.NEG + g.W1, g.NEG + g.U);
 	for (int i = 0; i < g.t_len; ++i) {
+		int nbD[32], nbP[32], B[32], old[32], Qf[32], e[32][C], Dlast[32], Qlast[32], fP[32][C];
+		if (BANDED && i >= i1 && i < i2) {   // the interior rows of a band: the lean passes of the kernel
+			const unsigned long long tr = tab[nw_nuc(tseq, t_s + g.t_len - 1 - i)];
+			for (int l = 0; l < 32; ++l) { const int s = l < 31 ? l + 1 : 31; nbD[l] = L[s].pD[0]; nbP[l] = L[s].pP[0]; }
+			for (int l = 0; l < 32; ++l) {
+				const int ubc = (g.band >= l * C && g.band < l * C + C) ? g.band - l * C : -1;
+				B[l] = nw_rs_pass1i<C>(g, L[l], l == 0, ubc, (unsigned)tr, (unsigned)(tr >> 32), nbD[l], nbP[l], Ue, Qs_in, fP[l]) - l * step;
+			}
+			for (int o = 1; o < 32; o <<= 1) {
+				memcpy(old, B, sizeof(B));
+				for (int l = o; l < 32; ++l) if (old[l - o] > B[l]) B[l] = old[l - o];
+			}
+			for (int l = 0; l < 32; ++l) Qf[l] = l ? B[l - 1] + (l - 1) * step : NW_NINF;
+			for (int l = 0; l < 32; ++l) {
+				const int ubc = (g.band >= l * C && g.band < l * C + C) ? g.band - l * C : -1;
+				nw_rs_pass2i<C>(g, L[l], l == 0, ubc, Qf[l], Qs_in, fP[l], e[l], &Dlast[l], &Qlast[l]);
+			}
+			for (int l = 0; l < 32; ++l) { const int s = l ? l - 1 : 0; e[l][0] = nw_rs_fix0i(g, l == 0, e[l][0], Dlast[s], Qlast[s]); }
+			for (int l = 0; l < 32; ++l)
+				for (int c = 0; c < C; ++c) E[(size_t)i * (32 * C) + l * C + c] = (uint8_t)e[l][c];
+			for (int l = 0; l < 32; ++l) {
+				const int q8n = nw_rs_q8<BANDED>(g, i + 1, l * C + C - 1, qlast);
+				for (int c = 0; c + 1 < C; ++c) L[l].qs[c] = L[l].qs[c + 1];
+				L[l].qs[C - 1] = q8n;
+			}
+			continue;
+		}
 		NwRsRow R;
 		nw_rs_row(g, R, i, tab[nw_nuc(tseq, t_s + g.t_len - 1 - i)]);
-		int nbD[32], nbP[32], B[32], old[32], Qf[32], e[32][C], Dlast[32], Qlast[32], fP[32][C];
 		for (int l = 0; l < 32; ++l) {
 			if (BANDED) { const int s = l < 31 ? l + 1 : 31; nbD[l] = L[s].pD[0]; nbP[l] = L[s].pP[0]; }
 			else { const int s = l ? l - 1 : 0; nbD[l] = L[s].pD[C - 1]; nbP[l] = 0; }
@@ -80,7 +109,7 @@ extern "C" int emu_nw2(const int *pen29, const uint64_t *tseq, const uint8_t *qu
 	NwStat s;
 	if (nw_trivial(pen, t_len, q_len, s)) { memcpy(out6, &s, 24); return 0; }
 	NwGeo g;
-	if (!nw_geo_init(g, pen, t_len, q_len, k, band, rs != 0)) return 2;
+	if (!nw_geo_init(g, pen, t_len, q_len, k, band, rs ? NW_RS_MAXC : 0)) return 2;
 	std::vector<uint8_t> E(g.ebytes(), 0xEE);
 	std::vector<NwRow> rowbuf(q_len + NW_RING + 1, NwRow{0x3fffffff, 0x3fffffff});
 	std::vector<int> lastD(q_len + 1, 0x3fffffff);
