@@ -33,6 +33,7 @@ def main():
     rows = list(csv.reader(raw.splitlines()))
     h, units = rows[0], rows[1]
     traffic = json.load(open(tj)) if tj and os.path.exists(tj) else {}
+    seen = {}
     with open(out, "w") as f:
         f.write(f"# ncu --set full --clock-control none, report {os.path.basename(rep)} (per launch, cold cache, serialised)\n")
         for r in rows[2:]:
@@ -46,8 +47,12 @@ def main():
             wr = float(r[h.index("dram__bytes_write.sum")]) * SCALE[units[h.index("dram__bytes_write.sum")]]
             f.write(f"{'dram traffic (read+write)':88s} {rd + wr:18.0f} byte\n")
             if rd + wr == rd + wr:   # a capture whose DRAM counters came back as NaN keeps the older entry
-                traffic[base.split("<")[0].split("::")[-1]] = {"dram_bytes": rd + wr, "report": os.path.basename(rep),
-                                                               "grid": r[h.index("launch__grid_size")], "pairs": pairs}
+                key = base.split("<")[0].split("::")[-1]
+                dur = float(r[h.index("gpu__time_duration.sum")])
+                if key not in seen or dur > seen[key]:   # several builds / launches of one kernel in a report: the longest one counts
+                    seen[key] = dur
+                    traffic[key] = {"dram_bytes": rd + wr, "report": os.path.basename(rep), "kernel": base,
+                                    "grid": r[h.index("launch__grid_size")], "pairs": pairs}
     if tj:
         json.dump(traffic, open(tj, "w"), indent=1)
 

@@ -34,4 +34,14 @@ tail -1 gpurun_out/ncu_full_${tag}_c5.log | cut -c1-200 >> $L
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"nw_warp_kernel" --launch-skip 2 -c 1 \
     -f -o gpurun_out/prof_${tag}_nw python tools/nw_perf.py 24000 > gpurun_out/ncu_full_${tag}_nw.log 2>&1
 tail -1 gpurun_out/ncu_full_${tag}_nw.log | cut -c1-200 >> $L
+# the reports stay on the box (together they exceed what comes back): text summaries, per-launch DRAM traffic and the
+# per-instruction tables of the two big C2 kernels come back instead
+for x in c2 c3 c5 nw; do
+  units=2000000; [ $x = c3 ] && units=20000; [ $x = c5 ] && units=4000000; [ $x = nw ] && units=24000
+  python tools/ncu_summary.py gpurun_out/prof_${tag}_$x.ncu-rep gpurun_out/ncu_${tag}_$x.txt gpurun_out/traffic_${tag}_$x.json $units >> $L 2>&1
+done
+ncu -i gpurun_out/prof_${tag}_c2.ncu-rep --page source --csv --print-source sass 2>/dev/null | gzip -9 > gpurun_out/sass_${tag}_c2.csv.gz
+ncu -i gpurun_out/prof_${tag}_c3.ncu-rep --page source --csv --print-source sass 2>/dev/null | gzip -9 > gpurun_out/sass_${tag}_c3.csv.gz
+rm -f gpurun_out/prof_${tag}_*.ncu-rep
+du -sh gpurun_out >> $L
 cat $L
