@@ -148,7 +148,10 @@ __device__ __forceinline__ int warp_min_i(int v) {
 	return v;
 }
 
-static __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__restrict__ in, int n, AlnRead *reads,
+#ifndef ST_MINB
+#define ST_MINB 8   // resident CTAs per SM the record-streaming kernels (prep / emit) are compiled for: latency-bound, 32 registers and all 64 warps (C2: 9.5 -> 8.45 ms, profiles/r02_stream_kernels.log)
+#endif
+static __global__ void __launch_bounds__(256, ST_MINB) aln_prep_kernel(const uint8_t *__restrict__ in, int n, AlnRead *reads,
 		const uint32_t *__restrict__ slab_off, const uint32_t *__restrict__ task_off, uint64_t *slab, int32_t *task_read, int k) {
 	const unsigned lane = threadIdx.x & 31;
 	const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -163,8 +166,12 @@ static __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__r
 			uint64_t *base = slab + R.slab_off + (strand ? slab_stride(R) : 0);
 			uint8_t *b = (uint8_t *)(base + slab_W(words));
 			int32_t *N = (int32_t *)(base + slab_W(words) + slab_B(L));
-#pragma unroll 1
-			for (int w = lane; w < words + 2; w += 32) {
+			// one round per packed word: every lane reads the word (one broadcast load from the read-only record), lane 0
+			// stores it, lane i takes base 32 w + i of it as a byte 0-3 (unCompDNA, compdna.c:178). The rounds are
+			// independent: unrolled, their loads are in flight together
+			const int nbytes = (int)(slab_B(L) << 3);
+#pragma unroll 4
+			for (int w = 0; w < words + 2; ++w) {
 				uint64_t x = 0;
 				if (w < words) {
 					if (!strand) x = ld_u64u(seq + 8 * (size_t)w);
@@ -174,13 +181,10 @@ static __global__ void __launch_bounds__(256) aln_prep_kernel(const uint8_t *__r
 						if (c < 32) x = c > 0 ? x & (~0ull << (64 - 2 * c)) : 0ull;
 					}
 				}
-				base[w] = x;
+				if (lane == 0) base[w] = x;
+				const int i = 32 * w + (int)lane;
+				if (i < nbytes) b[i] = i < L ? (uint8_t)((x << (lane << 1)) >> 62) : (uint8_t)0;
 			}
-			__syncwarp();
-			// bytes 0-3 from the words just written, then N -> 4 (unCompDNA, compdna.c:178)
-#pragma unroll 1
-			for (int i = lane; i < (int)(slab_B(L) << 3); i += 32)
-				b[i] = i < L ? (uint8_t)((base[i >> 5] << ((i & 31) << 1)) >> 62) : (uint8_t)0;
 			__syncwarp();
 #pragma unroll 1
 			for (int i = lane; i <= nN; i += 32) {
@@ -1010,7 +1014,7 @@ __global__ void aln_reduce_kernel(AlnParams P, const uint8_t *__restrict__ in, c
 }
 
 // frag_raw record (updatescores.c:284-295): int32[5]{q_len, hits, score, hdrlen, flag} read(0-4) header start[] end[] template[]
-__global__ void __launch_bounds__(256) aln_emit_kernel(const uint8_t *__restrict__ in, const AlnRead *__restrict__ reads, int n,
+__global__ void __launch_bounds__(256, ST_MINB) aln_emit_kernel(const uint8_t *__restrict__ in, const AlnRead *__restrict__ reads, int n,
 		const uint64_t *__restrict__ slab, const AlnCand *__restrict__ cand, const AlnRes *__restrict__ res,
 		const uint32_t *__restrict__ out_off, uint8_t *__restrict__ out) {
 	const unsigned lane = threadIdx.x & 31;
@@ -1130,7 +1134,7 @@ __global__ void __launch_bounds__(256) tr_sizes_kernel(const uint8_t *__restrict
 }
 
 // bytes -> slab (packed words, bytes, N list + sentinel), reverse complement too for reads without a strand
-__global__ void __launch_bounds__(256) tr_prep_kernel(const uint8_t *__restrict__ in, int n, TrRec *recs, const uint32_t *__restrict__ slab_off,
+__global__ void __launch_bounds__(256, ST_MINB) tr_prep_kernel(const uint8_t *__restrict__ in, int n, TrRec *recs, const uint32_t *__restrict__ slab_off,
 		const uint32_t *__restrict__ row_off, uint64_t *slab) {
 	const unsigned lane = threadIdx.x & 31;
 	const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -1144,24 +1148,22 @@ __global__ void __launch_bounds__(256) tr_prep_kernel(const uint8_t *__restrict_
 			uint64_t *base = slab + R.slab_off + (strand ? tr_stride(R) : 0);
 			uint8_t *b = (uint8_t *)(base + slab_W(R.words));
 			int32_t *N = (int32_t *)(base + slab_W(R.words) + slab_B(L));
-#pragma unroll 1
-			for (int i = lane; i < (int)(slab_B(L) << 3); i += 32) {
-				uint8_t v = 0;
-				if (i < L) { v = strand ? src[L - 1 - i] : src[i]; if (strand && v < 4) v = 3 - v; }
-				b[i] = v;
-			}
-			__syncwarp();
-#pragma unroll 1
-			for (int w = lane; w < R.words + 2; w += 32) {
-				uint64_t x = 0;
-				if (w < R.words) for (int i = 0; i < 32 && 32 * w + i < L; ++i) x |= (uint64_t)(b[32 * w + i] & 3 & (b[32 * w + i] < 4 ? 3 : 0)) << (62 - 2 * i);
-				base[w] = x;
-			}
-			// N positions in ascending order: ranks by ballot
+			// one round per 32 bases: the byte (complemented and mirrored for the reverse strand), its 2-bit code OR-reduced
+			// over the warp into the packed word (compDNA's `(word << 2) | base` is the OR of `base << (62 - 2 lane)`), and
+			// the N positions in ascending order by ballot rank
+			const int nbytes = (int)(slab_B(L) << 3);
 			int cnt = 0;
-			for (int i0 = 0; i0 < L; i0 += 32) {
-				const int i = i0 + (int)lane;
-				const bool isn = i < L && b[i] == 4;
+#pragma unroll 2
+			for (int w = 0; w < R.words + 2; ++w) {
+				const int i = 32 * w + (int)lane;
+				uint8_t v = 0;
+				if (i < L) { v = strand ? __ldg(src + L - 1 - i) : __ldg(src + i); if (strand && v < 4) v = 3 - v; }
+				if (i < nbytes) b[i] = v;
+				const uint32_t c = v < 4 ? v : 0u;
+				const uint32_t hi = __reduce_or_sync(0xffffffffu, lane < 16 ? c << (30 - 2 * lane) : 0u);
+				const uint32_t lo = __reduce_or_sync(0xffffffffu, lane >= 16 ? c << (62 - 2 * lane) : 0u);
+				if (lane == 0) base[w] = ((uint64_t)hi << 32) | lo;
+				const bool isn = i < L && v == 4;
 				const unsigned mk = __ballot_sync(0xffffffffu, isn);
 				if (isn) N[cnt + __popc(mk & ((1u << lane) - 1))] = i;
 				cnt += __popc(mk);
@@ -1806,8 +1808,17 @@ static int nw_queue_run(kmagpu_db *db, const AlnParams &P, const NwProb *probs, 
                         int32_t *res, int32_t *status_out, unsigned long long *ctr, int *launches) {
 	cudaStream_t st = db->stream;
 	KgBuf &scr = db->aln.d_scratch;
+	unsigned long long cnt[NWQ_CLASSES];
+	for (int c = 0; c < NWQ_CLASSES; ++c) cnt[c] = counts[c];
+	// a thread class with too few problems to fill the machine (C2: 2400 problems of up to 64 x 128 cells = 19 CTAs, 0.75 ms
+	// of one long thread each) goes to the narrow warp kernel instead: a warp sweeps such a problem in ~20 us
+	for (int c = 0; c < 2; ++c)
+		if (cnt[c] && cnt[c] < 32ull * (unsigned long long)db->sm_count && cnt[2] + cnt[c] <= cap) {
+			KG_CUDA(cudaMemcpyAsync(const_cast<uint32_t *>(order) + 2 * cap + cnt[2], order + (size_t)c * cap, 4 * (size_t)cnt[c], cudaMemcpyDeviceToDevice, st));
+			cnt[2] += cnt[c]; cnt[c] = 0;
+		}
 	for (int c = 0; c < NWQ_CLASSES; ++c) {
-		const int n = (int)counts[c];
+		const int n = (int)cnt[c];
 		if (!n) continue;
 		const uint32_t *ord = order + (size_t)c * cap;
 		if (cells && c < 2) {   // largest problems first, neighbours alike: what a warp works on together finishes together
@@ -1895,7 +1906,7 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 	if (b.d_slab.reserve(8 * (slab_units + 4)) || b.d_taskread.reserve(4 * ((size_t)ntasks + 1)) ||
 	    b.d_cand.reserve(sizeof(AlnCand) * ((size_t)ntasks + 1)) || b.d_ovf.reserve(4 * ((size_t)ntasks + 1))) return -1;
 	KG_CUDA(cudaMemcpyAsync(task_off + n, &ntasks, 4, cudaMemcpyHostToDevice, st));   // the prep kernel reads off[r + 1]
-	aln_prep_kernel<<<db->sm_count * 8, 256, 0, st>>>(b.in, n, reads, slab_off, task_off, (uint64_t *)b.d_slab.p, (int32_t *)b.d_taskread.p, P.k);
+	aln_prep_kernel<<<kg_wave_grid(aln_prep_kernel, 256, db->sm_count), 256, 0, st>>>(b.in, n, reads, slab_off, task_off, (uint64_t *)b.d_slab.p, (int32_t *)b.d_taskread.p, P.k);
 	++launches;
 	KG_CUDA(cudaEventRecord(db->ev[3], st));
 	KG_CUDA(cudaEventRecord(db->ev[4], st));
@@ -2009,7 +2020,7 @@ extern "C" int kmagpu_align_run(kmagpu_db *db, const kmagpu_params *prm, int wan
 	KG_SCAN_FITS(h3[A_OUT], "the frag_raw stream");   // reads travel at 1 byte per base here, 4x their stage-2 size
 	b.out_bytes = (size_t)h3[A_OUT];
 	if (b.d_out.reserve(b.out_bytes + 64)) return -1;
-	aln_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>(b.in, reads, n, (const uint64_t *)b.d_slab.p, (const AlnCand *)b.d_cand.p,
+	aln_emit_kernel<<<kg_wave_grid(aln_emit_kernel, 256, db->sm_count), 256, 0, st>>>(b.in, reads, n, (const uint64_t *)b.d_slab.p, (const AlnCand *)b.d_cand.p,
 		(const AlnRes *)b.d_res.p, recoff, (uint8_t *)b.d_out.p);
 	++launches;
 	KG_CUDA(cudaEventRecord(db->ev[7], st));
@@ -2090,7 +2101,7 @@ static int trace_core(kmagpu_db *db, const kmagpu_params *prm, const uint8_t *di
 	int launches = 0;
 	KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * A_N, st));
 	KG_CUDA(cudaEventRecord(db->ev[2], st));
-	tr_sizes_kernel<<<db->sm_count * 8, 256, 0, st>>>(din, doff, n, db->info.DB_size,
+	tr_sizes_kernel<<<kg_wave_grid(tr_sizes_kernel, 256, db->sm_count), 256, 0, st>>>(din, doff, n, db->info.DB_size,
 		(TrRec *)d_recs.p, slab_sz, row_sz, ctr);
 	kg_exscan(slab_sz, n, slab_off, (uint32_t *)d_partial.p, ctr + A_SLAB, st);
 	kg_exscan(row_sz, n, row_off, (uint32_t *)d_partial.p, ctr + A_TASKS, st);
@@ -2103,7 +2114,7 @@ static int trace_core(kmagpu_db *db, const kmagpu_params *prm, const uint8_t *di
 	KG_SCAN_FITS(h[A_SLAB], "the unpacked fragments");
 	KG_SCAN_FITS(h[A_TASKS], "the alignment row pool");
 	if (d_slab.reserve(8 * ((size_t)h[A_SLAB] + 4)) || d_rows.reserve(8 * ((size_t)h[A_TASKS] + 4))) return -1;
-	tr_prep_kernel<<<db->sm_count * 8, 256, 0, st>>>(din, n, (TrRec *)d_recs.p, slab_off, row_off, (uint64_t *)d_slab.p);
+	tr_prep_kernel<<<kg_wave_grid(tr_prep_kernel, 256, db->sm_count), 256, 0, st>>>(din, n, (TrRec *)d_recs.p, slab_off, row_off, (uint64_t *)d_slab.p);
 	++launches;
 	const int q_cap = std::min(std::max(maxq + 64, 256), 1 << 20);
 	const size_t e_cap = std::min<size_t>(std::max<size_t>(2 * (size_t)maxq * (size_t)maxq + 65536, 65536), 4u << 20);
@@ -2151,7 +2162,7 @@ static int trace_core(kmagpu_db *db, const kmagpu_params *prm, const uint8_t *di
 	if (prm->matrix) {   // alnToMatPtr (assembly.c:1968) on every accepted alignment
 		if (prm->matrix != 1 && prm->matrix != 2) { kmagpu_set_error("matrix mode %d: 1 = alnToMat (template nodes), 2 = alnToMatDense", prm->matrix); return -1; }
 		if (!db->image->d_mat && kmagpu_matrix_reset(db)) return -1;
-		tr_matrix_kernel<<<db->sm_count * 8, 256, 0, st>>>((const TrRec *)d_recs.p, (const TrOut *)d_outs.p, n, (const uint8_t *)d_rows.p,
+		tr_matrix_kernel<<<kg_wave_grid(tr_matrix_kernel, 256, db->sm_count), 256, 0, st>>>((const TrRec *)d_recs.p, (const TrOut *)d_outs.p, n, (const uint8_t *)d_rows.p,
 			db->tix.meta, db->image->d_mat_off, prm->matrix == 2, db->image->d_mat, ctr);
 		++launches;
 	}
@@ -2167,7 +2178,7 @@ static int trace_core(kmagpu_db *db, const kmagpu_params *prm, const uint8_t *di
 		if (out_bytes) *out_bytes = ob;
 		if (ob > out_cap) { kmagpu_set_error("trace output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
 		if (d_out.reserve(ob + 64)) return -1;
-		tr_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>((const TrRec *)d_recs.p, (const TrOut *)d_outs.p, n, (const uint8_t *)d_rows.p, ooff,
+		tr_emit_kernel<<<kg_wave_grid(tr_emit_kernel, 256, db->sm_count), 256, 0, st>>>((const TrRec *)d_recs.p, (const TrOut *)d_outs.p, n, (const uint8_t *)d_rows.p, ooff,
 			(uint8_t *)d_out.p);
 		++launches;
 		KG_CUDA(cudaEventRecord(db->ev[7], st));

@@ -968,7 +968,7 @@ int kg_chain_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *sta
 			if (total >= (1ull << 32)) { kmagpu_set_error("chain mode output of %llu bytes exceeds 4 GiB per call; split the batch", total); return -1; }
 			b.out_bytes = (size_t)total;
 			if (b.d_out.reserve(b.out_bytes + 64)) return -1;
-			chain_emit_kernel<<<db->sm_count * 8, 256, 0, db->stream>>>((const uint8_t *)b.d_in.p, (const uint32_t *)b.d_off.p,
+			chain_emit_kernel<<<kg_wave_grid(chain_emit_kernel, 256, db->sm_count), 256, 0, db->stream>>>((const uint8_t *)b.d_in.p, (const uint32_t *)b.d_off.p,
 				(const Region *)b.d_regs.p, (int)NR, roff, (const int32_t *)b.d_pool.p, (uint8_t *)b.d_out.p);
 			launches += 5;
 			b.out_recoff = roff;

@@ -218,7 +218,7 @@ static int conclave_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff
 	if (out_bytes) *out_bytes = ob;
 	if (frags_out && ob > out_cap) { kmagpu_set_error("fragment output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
 	if (d_out.reserve(ob + 64)) return -1;
-	cc_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>(din, keys2, vals2, (const CcItem *)d_items.p, ni, ooff,
+	cc_emit_kernel<<<kg_wave_grid(cc_emit_kernel, 256, db->sm_count), 256, 0, st>>>(din, keys2, vals2, (const CcItem *)d_items.p, ni, ooff,
 		(uint8_t *)d_out.p);
 	cc_tail_kernel<<<1, 1, 0, st>>>((uint8_t *)d_out.p, ctr + 2);
 	KG_CUDA(cudaMemsetAsync((uint8_t *)d_out.p + ob, 0, 64, st));

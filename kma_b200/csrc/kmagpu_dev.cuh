@@ -75,6 +75,14 @@ __device__ __forceinline__ void warp_max_u64(unsigned long long *p, unsigned v) 
 	if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1) && s) atomicMax(p, (unsigned long long)s);
 }
 
+// grid of a persistent (grid-stride) kernel: exactly one wave of resident CTAs. A fixed "8 per SM" ran in two waves when
+// the kernel's registers allowed 6 (aln_emit_kernel: 28 % of the warp slots active).
+template <typename K> static inline int kg_wave_grid(K kernel, int block, int sm_count) {
+	int per_sm = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+	return sm_count * per_sm;
+}
+
 // ---------------------------------------------------------------- exclusive scan (u32 sizes -> u32 offsets)
 
 #define SCAN_THREADS 256

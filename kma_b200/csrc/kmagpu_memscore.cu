@@ -136,7 +136,7 @@ static int memscore_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff
 	if (out_bytes) *out_bytes = ob;
 	if (frag_out && ob > out_cap) { kmagpu_set_error("frag_raw output needs %zu bytes, caller gave %zu", ob, out_cap); return -1; }
 	if (w.d_out.reserve(ob + 64)) return -1;
-	ms_emit_kernel<<<db->sm_count * 8, 256, 0, st>>>(din, (const MsRec *)w.d_recs.p, n, size, ooff, db->d_lengths, (uint8_t *)w.d_out.p);
+	ms_emit_kernel<<<kg_wave_grid(ms_emit_kernel, 256, db->sm_count), 256, 0, st>>>(din, (const MsRec *)w.d_recs.p, n, size, ooff, db->d_lengths, (uint8_t *)w.d_out.p);
 	const uint32_t total = (uint32_t)ob;
 	KG_CUDA(cudaMemcpyAsync(ooff + n, &total, 4, cudaMemcpyHostToDevice, st));   // closing offset for the next stage
 	KG_CUDA(cudaMemsetAsync((uint8_t *)w.d_out.p + ob, 0, 64, st));

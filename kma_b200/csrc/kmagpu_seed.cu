@@ -1048,7 +1048,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 		b.out_bytes = (size_t)h[C_TOTAL];
 		b.out_nrec = n; b.out_recoff = recoff;
 		if (b.d_out.reserve(b.out_bytes + 64)) return -1;
-		emit_records_kernel<<<db->sm_count * 8, 256, 0, db->stream>>>((const uint8_t *)b.d_in.p, (const uint32_t *)b.d_off.p,
+		emit_records_kernel<<<kg_wave_grid(emit_records_kernel, 256, db->sm_count), 256, 0, db->stream>>>((const uint8_t *)b.d_in.p, (const uint32_t *)b.d_off.p,
 			n, (const SeedRes *)b.d_res.p, recoff, (const int32_t *)b.d_pool.p, (uint8_t *)b.d_out.p);
 		KG_CUDA(cudaEventRecord(db->ev[4], db->stream));
 		KG_CUDA(cudaStreamSynchronize(db->stream));
