@@ -176,7 +176,7 @@ class MapPipeline:
             scores[1][:] += u
         return res
 
-    def map_to_consensus(self, text1, text2, frag_outs, params, fastq=True, consensus_args=None, trace=None, cons_out=None, **ingest):
+    def map_to_consensus(self, text1, text2, frag_outs, params, fastq=True, consensus_args=None, trace=None, cons_out=None, slice_weights=None, **ingest):
         """The whole mapping core on one batch of FASTQ text (pinned uint8 tensors; text2 = the second file of a pair of
         files or None), every stream resident in HBM, what `kma -i / -ipe ... -o out` computes between its input files and
         its writers: record splitter + stage 1 -> stage 2 -> alignment pass | ConClave sums all-reduced over ranks (NCCL
@@ -186,6 +186,8 @@ class MapPipeline:
         points where the workers meet. Down come: per worker its per-template fragment stream into frag_outs[w] (what the
         .frag.gz writer needs), then the consensus rows and per-template sums (what .res / .fsa / .aln are written from).
         Paired files must line up slice by slice (equal-length records), as map_text_device_split requires.
+        slice_weights: relative sizes of the workers' slices (default equal). A small first slice lets the kernels start
+        while the rest of the text is still crossing PCIe.
         cons_out: (t, s, q, stats) pinned buffers for the consensus rows (api.TemplateDB.consensus's out).
         trace: optional list; (worker, phase, perf_counter seconds) is appended as each worker leaves a phase.
         Returns dict(reads, fragments, consensus=(t, s, q, stats), totals=(w_scores, fragmentCounts, readCounts), frag_bytes)."""
@@ -198,10 +200,15 @@ class MapPipeline:
         L = api.lib()
         W = len(self.dbs)
 
+        wts = list(slice_weights) if slice_weights else [1.0] * W
+        if len(wts) != W or min(wts) <= 0:
+            raise api.KmaGpuError("slice_weights: one positive weight per worker")
+        fracs = [sum(wts[:i]) / sum(wts) for i in range(W)]
+
         def cuts(t):
             a = t.numpy() if hasattr(t, "numpy") else t
             nb = len(a)
-            return sorted({L.kmagpu_fastx_sync(a.ctypes.data, nb, int(fastq), (nb * i) // W) for i in range(W)} | {nb})
+            return sorted({L.kmagpu_fastx_sync(a.ctypes.data, nb, int(fastq), int(nb * f)) for f in fracs} | {nb})
         c1 = cuts(text1)
         c2 = cuts(text2) if text2 is not None else None
         if c2 is not None and len(c2) != len(c1):

@@ -21,6 +21,7 @@ def main():
     import torch.distributed as dist
     pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
     W = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    wts = [float(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else None
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -48,8 +49,8 @@ def main():
         t = torch.empty(len(a), dtype=torch.uint8, pin_memory=True)
         t.numpy()[:] = a
         txt.append(t)
-    frag_cap = (2 * pairs * 260) // W * 5 // 4 + (1 << 20)
-    frag_outs = [torch.empty(frag_cap, dtype=torch.uint8, pin_memory=True) for _ in range(W)]
+    fr = [w / sum(wts) for w in wts] if wts else [1.0 / W] * W
+    frag_outs = [torch.empty(int(2 * pairs * 260 * f * 5 / 4) + (1 << 20), dtype=torch.uint8, pin_memory=True) for f in fr]
     info = pipe.dbs[0].info
     cons_out = [torch.empty(int(info.seq_bases), dtype=torch.uint8, pin_memory=True) for _ in range(3)] + \
                [torch.empty(info.DB_size * api.CONSENSUS_STATS.itemsize, dtype=torch.uint8, pin_memory=True)]
@@ -63,7 +64,7 @@ def main():
         sync()
         tr = []
         t0 = time.perf_counter()
-        pipe.map_to_consensus(txt[0], txt[1], frag_outs, params, trace=tr, cons_out=cons_out)
+        pipe.map_to_consensus(txt[0], txt[1], frag_outs, params, trace=tr, cons_out=cons_out, slice_weights=wts)
         t1 = time.perf_counter()
         if step >= 3 and rank == 0:
             rows = {}
