@@ -157,7 +157,7 @@ int __wrap_save_kmers_batch(char *templatefilename, char *exePrev, unsigned shm,
 	if (kmerScan == &save_kmers) prm.kmerscan = 0;
 	else if (kmerScan == &save_kmers_chain) prm.kmerscan = 1;
 	else shim_unsupported("this k-mer scan (-hmm / -Sparse / count modes)");
-	if (prm.kmerscan == 1 && kmerAnkerScore != &ankerScore) shim_unsupported("-lc with the chain scan (length-corrected anker selection; -lc -1t1 is covered)");
+	prm.lc = kmerAnkerScore != &ankerScore;   /* -lc (kma.c:694-700) */
 	if (save_kmers_pair == &save_kmers_unionPair) prm.apm = 1;
 	else if (save_kmers_pair == &save_kmers_penaltyPair) prm.apm = 0;
 	else shim_unsupported("-apm f");

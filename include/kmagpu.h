@@ -41,7 +41,9 @@ typedef struct kmagpu_params {
 	int32_t counters;                 /* alignment pass: collect the in-kernel statistic counters (kmagpu_align_stats mems, index_probes,
 	                                     mem_bases, read_bytes, nw_*): measurement only, ~10 % of the pair kernel; kmagpu_default_params sets 1 */
 	int32_t ts;                       /* -ts  seed trim of the traceback alignment (trimSeeds chain.c:496, called by KMA align.c:413); default 0 */
-	int32_t reserved0;
+	int32_t lc;                       /* -lc (kma.c:694-700): save_kmers_chain selects its ankers by the length-corrected score (ankerScoreLen,
+	                                     testExtensionScoreLen, proxiTestBestScoreLen, getBestAnkerScoreLen kmeranker.c:432, getTieAnkerScoreLen :496);
+	                                     the ConClave side of -lc is the `lc` argument of kmagpu_conclave_* */
 	double scoreT;                    /* -mrs (alnfrags.c:1168; also `mrs` of save_kmers_chain, kmers.c:51) */
 	double minFrac;                   /* -mf  (updatescores.c:217-268) */
 	double mrc;                       /* -mrc (alnfrags.h:38 mrcheck) */

@@ -22,7 +22,7 @@ class Params(C.Structure):
     _fields_ = [("M", C.c_int32), ("MM", C.c_int32), ("U", C.c_int32), ("W1", C.c_int32), ("Wl", C.c_int32),
                 ("Mn", C.c_int32), ("PE", C.c_int32), ("d", C.c_int32 * 25), ("exhaustive", C.c_int32),
                 ("mq", C.c_int32), ("one2one", C.c_int32), ("minlen", C.c_int32), ("kmerscan", C.c_int32), ("matrix", C.c_int32), ("apm", C.c_int32), ("counters", C.c_int32),
-                ("ts", C.c_int32), ("reserved0", C.c_int32), ("scoreT", C.c_double), ("minFrac", C.c_double), ("mrc", C.c_double), ("coverT", C.c_double)]
+                ("ts", C.c_int32), ("lc", C.c_int32), ("scoreT", C.c_double), ("minFrac", C.c_double), ("mrc", C.c_double), ("coverT", C.c_double)]
 
 
 class DbInfo(C.Structure):

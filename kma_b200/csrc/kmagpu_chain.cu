@@ -38,13 +38,14 @@
 enum { C_REGS = 12, C_EWALK = 13, C_ETREE = 14, C_BYTES = 15 };
 
 struct ChainParams {
-	int32_t M, MM, U, W1, Wl, exhaustive, minlen, pad;
+	int32_t M, MM, U, W1, Wl, exhaustive, minlen;
+	int32_t lc;   // -lc (kma.c:694-700): length-corrected anker selection (ankerScoreLen, testExtensionScoreLen, ...)
 	double mrs, coverT, mrc;
 };
 struct ChainRes { uint32_t reg_off; int32_t nreg; };
 struct Region { int32_t read, score, ntmpl, rev, b0, b1; uint32_t pool_off, size; };   // 32 bytes
 
-struct Ank { int *start, *end, *weight, *score; uint32_t *vals; };   // ankers of one strand (SoA, per-warp scratch)
+struct Ank { int *start, *end, *weight, *score; uint32_t *vals; int *slen, *llen; };   // ankers of one strand (SoA, per-warp scratch); score_len / len_len kept under -lc only
 
 struct STree { unsigned start[KC_ST + 2], end[KC_ST + 2], cov[KC_ST + 2]; int b0[KC_ST + 2], b1[KC_ST + 2]; int n, err; };
 struct SFrame { int root, state; unsigned pos, right; };
@@ -335,6 +336,8 @@ struct WarpCtx {
 	int *bt[2];
 	int cnt[2];
 	int k;
+	int seqlen;               // of the read at hand
+	const int32_t *lengths;   // template lengths
 };
 
 // Walk back from anker `src` of strand s, re-scoring its templates anker by anker until one of them reproduces src's
@@ -361,7 +364,11 @@ __device__ __noinline__ int chain_templates(const KgHashView &hv, const ChainPar
 	}
 	more = __any_sync(FULL, more);
 	__syncwarp();
-	const int bestScore = V.score[src];
+	// kmerAnkerScore: the anker's score, under -lc the score of its length-corrected best template (ankerScoreLen), which then
+	// has to be reproduced by a template of that corrected length (testExtensionScoreLen, kmeranker.c:45)
+	const bool lc = p.lc != 0;
+	const int bestScore = lc ? V.slen[src] : V.score[src];
+	const int target = lc ? V.llen[src] : 1;
 	int prev = src;
 	for (int node = src; more; --node) {
 		if (node < 0) { *err = 1; break; }
@@ -380,7 +387,7 @@ __device__ __noinline__ int chain_templates(const KgHashView &hv, const ChainPar
 			if (bestScore <= score) {
 				int open = score;
 				if (start) { const int g = p.W1 + (start - 1) * p.U; open = score + (p.Wl < g ? g : p.Wl); }
-				if (open == bestScore) { score = bestScore; done = true; }
+				if (open == bestScore && (!lc || min(W.seqlen, __ldg(W.lengths + t)) == target)) { score = bestScore; done = true; }
 			}
 			x.x = score; x.y = start;
 			W.st[t] = x;
@@ -400,6 +407,8 @@ __device__ __noinline__ int chain_templates(const KgHashView &hv, const ChainPar
 			t = dst[1 + i];
 			const int4 x = W.st[t];
 			keep = x.z == 1 && bestScore <= x.x;
+			if (lc && x.z == 1 && !keep)   // proxiTestBestScoreLen (kmeranker.c:53), proxi == 1.0
+				keep = __dmul_rn(__ddiv_rn((double)bestScore, (double)target), (double)min(W.seqlen, __ldg(W.lengths + t))) <= (double)x.x;
 			W.st[t] = make_int4(0, 0, 0, 0);
 		}
 		const unsigned m = __ballot_sync(FULL, keep);
@@ -436,8 +445,43 @@ __device__ __noinline__ int best_anker(const Ank &V, int cnt, unsigned *ties) {
 	return idx;
 }
 
-// getTieAnkerScore (kmeranker.c:480): nearest anker before src that starts behind `stop` and scores like best
-__device__ __noinline__ int tie_anker(const Ank &V, int stop, int src, int bestScore) {
+// getBestAnkerScoreLen (kmeranker.c:432, -lc): the fold rescales every anker to the length of the best one so far, so it
+// is evaluated in array order over the ankers still in play (a ballot finds them, every lane runs the same fold)
+__device__ __noinline__ int best_anker_len(const Ank &V, int cnt, unsigned *ties) {
+	const unsigned lane = threadIdx.x & 31;
+	int best = -1, bS = 0, bL = 1;
+	unsigned t = 0;
+#pragma unroll 1
+	for (int base = 0; base < cnt; base += 32) {
+		const int a = base + (int)lane;
+		const int sc = a < cnt ? V.score[a] : 0;
+		const int sl = sc ? V.slen[a] : 0, ll = sc ? V.llen[a] : 1;
+		unsigned m = __ballot_sync(FULL, sc != 0);
+		while (m) {
+			const int l = __ffs(m) - 1;
+			m &= m - 1;
+			const int nsl = __shfl_sync(FULL, sl, l), nll = __shfl_sync(FULL, ll, l);
+			bool take = false;
+			if (best < 0) take = true;
+			else {
+				double x = (double)nsl;
+				if (nll != bL) x = __dmul_rn(__ddiv_rn(x, (double)nll), (double)bL);
+				if ((double)bS < x) { take = true; t = 0; }
+				else if ((double)bS == x) {
+					if (bS < nsl) { take = true; t = 0; }
+					else if (bS == nsl) { take = true; ++t; }
+				}
+			}
+			if (take) { best = base + l; bS = nsl; bL = nll; }
+		}
+	}
+	*ties = t;
+	return best;
+}
+
+// getTieAnkerScore (kmeranker.c:480): nearest anker before src that starts behind `stop` and scores like best;
+// getTieAnkerScoreLen (:496, lc): ... whose corrected score and length equal the best one's
+__device__ __noinline__ int tie_anker(const Ank &V, int stop, int src, int bestScore, bool lc, int bestLen) {
 	const unsigned lane = threadIdx.x & 31;
 	if (src < 0 || V.start[src] <= stop) return -1;
 	for (int hi = src - 1; hi >= 0; hi -= 32) {
@@ -445,7 +489,7 @@ __device__ __noinline__ int tie_anker(const Ank &V, int stop, int src, int bestS
 		const bool in = a >= 0;
 		const int st = in ? V.start[a] : 0;
 		const bool out = !in || st <= stop;
-		const bool match = !out && V.score[a] == bestScore;
+		const bool match = !out && (lc ? (V.slen[a] == bestScore && V.llen[a] == bestLen) : V.score[a] == bestScore);
 		const unsigned om = __ballot_sync(FULL, out), mm = __ballot_sync(FULL, match);
 		const int fo = om ? __ffs(om) - 1 : 32, fm = mm ? __ffs(mm) - 1 : 32;
 		if (fm < fo) return hi - fm;
@@ -505,12 +549,15 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 		for (int s = 0; s < 2; ++s) { W.bt[s] = (int *)base; base += 4 * (2 * lay.D + 4); }
 		regs = (Region *)base; base += sizeof(Region) * lay.regcap;
 		for (int s = 0; s < 2; ++s) {
-			int *a = (int *)base; base += 20 * lay.cap;
+			int *a = (int *)base; base += 28 * lay.cap;
 			W.V[s].start = a; W.V[s].end = a + lay.cap; W.V[s].weight = a + 2 * lay.cap; W.V[s].score = a + 3 * lay.cap;
 			W.V[s].vals = (uint32_t *)(a + 4 * lay.cap);
+			W.V[s].slen = a + 5 * lay.cap; W.V[s].llen = a + 6 * lay.cap;
 		}
 		W.k = k;
+		W.lengths = lengths;
 	}
+	const bool lc = p.lc != 0;
 	ChainStats ws = {0, 0, 0, 0};
 	unsigned mapped = 0, words_seen = 0, e_walk = 0, e_tree = 0;
 
@@ -531,6 +578,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 		rc.N = rc.seq + 8 * (size_t)rc.words;
 		words_seen += rc.words;
 		const int seqlen = rc.seqlen;
+		W.seqlen = seqlen;
 		const uint32_t base_size = 28u + 8u * rc.words + 4u * rc.nN + (uint32_t)rc.hdrlen + 9u;
 
 		int nreg = 0;
@@ -547,14 +595,15 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 			if (!W.cnt[0] && !W.cnt[1]) break;
 
 			// ---- chaining DP over the ankers of each strand (savekmers.c:5457-5640)
-			unsigned ties = 0;
-			int bIdx[2] = {0, 0};
+			unsigned ties = 0, ties_len = 0;
+			int bIdx[2] = {0, 0}, blIdx[2] = {0, 0};
 			int btN[2] = {0, 0};
 #pragma unroll 1
 			for (int s = 0; s < 2; ++s) {
 				const Ank &V = W.V[s];
 				int *bests = W.bt[s];
 				int nb = 0, bi = 0, bScore = 0, bSL = 0;
+				int bl = 0, blS = 0, blL = 1;   // -lc: the last best length-corrected anker, its score_len / len_len
 				for (int a = 0; a < W.cnt[s]; ++a) {
 					const int start = V.start[a], end = V.end[a], weight = V.weight[a];
 					const uint32_t off = V.vals[a];
@@ -610,6 +659,19 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 						}
 					}
 					if (lane == 0) V.score[a] = nscore;
+					if (lc) {   // savekmers.c:5590-5609; the first anker of a strand is compared with itself
+						if (lane == 0) { V.slen[a] = nsl; V.llen[a] = nll; }
+						if (a == 0) { blS = nsl; blL = nll; }
+						double x = (double)nscore;
+						if (nll != blL) x = __dmul_rn(__ddiv_rn(x, (double)nll), (double)blL);
+						bool take = false;
+						if ((double)blS < x) { take = true; ties_len = 0; }
+						else if ((double)blS == x) {
+							if (blS < nsl) { take = true; ties_len = 0; }
+							else if (blS == nsl) { take = true; ++ties_len; }
+						}
+						if (take) { bl = a; blS = nsl; blL = nll; }
+					}
 					if (a == 0) { ++ties; bi = 0; bScore = nscore; bSL = nsl; }   // the first anker ties with itself
 					else if (bScore < nscore) { bi = a; bScore = nscore; bSL = nsl; ties = 0; }
 					else if (bScore == nscore) {
@@ -622,9 +684,11 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 				for (int i = lane; i < nb; i += 32) W.st[bests[1 + i]] = make_int4(0, 0, 0, 0);
 				__syncwarp();
 				bIdx[s] = bi;
+				blIdx[s] = bl;
 			}
 			int scF = W.V[0].score[bIdx[0]], scR = W.V[1].score[bIdx[1]];
 			if (scF < k && scR < k) break;
+			const int lcF = W.V[0].score[blIdx[0]], lcR = W.V[1].score[blIdx[1]];
 
 			const int V_start[2] = {W.V[0].start[0], W.V[1].start[0]};
 			// pruneAnkers (kmeranker.c:372): ankers scoring below k leave the list for good
@@ -635,6 +699,18 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 			__syncwarp();
 			if (scF < k) scF = 0;
 			if (scR < k) scR = 0;
+			if (lc) {
+				// savekmers.c:5657-5664: the length-corrected bests take over. pruneAnkers only unlinks an anker, so the new
+				// best keeps its score even below k -- unless it is the plain best of a strand without any anker >= k, whose
+				// score was zeroed (:5645-5650)
+				const int nF = (!scF && blIdx[0] == bIdx[0]) ? 0 : lcF, nR = (!scR && blIdx[1] == bIdx[1]) ? 0 : lcR;
+				__syncwarp();
+				if (lane == 0) { W.V[0].score[blIdx[0]] = nF; W.V[1].score[blIdx[1]] = nR; }
+				__syncwarp();
+				scF = nF; scR = nR;
+				bIdx[0] = blIdx[0]; bIdx[1] = blIdx[1];
+				ties = ties_len;
+			}
 
 			int cs[2] = {-1, -1}, start = 0, len = 0, rcm = 0, tmp;
 			if (!scF || !scR) {
@@ -661,10 +737,10 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 						if (!(rcm & (s + 1))) continue;
 						int *bl = W.bt[s];
 						const Ank &V = W.V[s];
-						const int bsScore = V.score[bIdx[s]];
+						const int bsScore = lc ? V.slen[bIdx[s]] : V.score[bIdx[s]], bsLen = lc ? V.llen[bIdx[s]] : 0;
 						const int stop = start < V_start[s] ? V_start[s] : start;
 						int v = bIdx[s];
-						while ((v = tie_anker(V, stop, v, bsScore)) >= 0) {
+						while ((v = tie_anker(V, stop, v, bsScore, lc, bsLen)) >= 0) {
 							if ((double)((unsigned)V.end[v] - (unsigned)start) < __dmul_rn(p.coverT, (double)len)) break;
 #pragma unroll 1
 							for (int i = lane; i < btN[s]; i += 32) W.st[bl[1 + i]] = make_int4(0, 0, 1, 0);
@@ -749,7 +825,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 						int b = bIdx[s];
 						if (!first) {
 							if (!(b >= 0 && V.score[b] == 0)) break;
-							bIdx[s] = b = best_anker(V, W.cnt[s], &ties);
+							bIdx[s] = b = lc ? best_anker_len(V, W.cnt[s], &ties) : best_anker(V, W.cnt[s], &ties);
 							if (b < 0) break;
 						}
 						const int bsc = V.score[b];
@@ -894,6 +970,7 @@ int kg_chain_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *sta
 	memset(&cp, 0, sizeof(cp));
 	cp.M = prm->M; cp.MM = prm->MM; cp.U = prm->U; cp.W1 = prm->W1; cp.Wl = prm->Wl; cp.exhaustive = prm->exhaustive;
 	cp.minlen = prm->minlen; cp.mrs = prm->scoreT; cp.coverT = prm->coverT; cp.mrc = prm->mrc;
+	cp.lc = prm->lc != 0;
 
 	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	if (b.d_res.reserve(sizeof(ChainRes) * (size_t)n) || b.d_recoff.reserve(4 * (size_t)(2 * n + 2)) ||
@@ -904,7 +981,7 @@ int kg_chain_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *sta
 	lay.D = (size_t)db->info.DB_size + 1;
 	lay.cap = (((size_t)std::max(b.max_seqlen, 64) + 8) + 3) & ~(size_t)3;
 	lay.regcap = lay.cap / 8 + 64;
-	lay.stride = (16 * lay.D + 2 * 4 * (2 * lay.D + 4) + sizeof(Region) * lay.regcap + 2 * 20 * lay.cap + 255) & ~(size_t)255;
+	lay.stride = (16 * lay.D + 2 * 4 * (2 * lay.D + 4) + sizeof(Region) * lay.regcap + 2 * 28 * lay.cap + 255) & ~(size_t)255;
 	int grid = db->sm_count * 5;
 	const size_t budget = (size_t)12 << 30;
 	while (grid > db->sm_count && lay.stride * (size_t)grid * KC_WARPS > budget) grid -= db->sm_count;

@@ -3,7 +3,9 @@
  * A plain-C restatement of what the reference computes per read when no -1t1 is given
  * (reference: savekmers.c:5127-5944 `save_kmers_chain`; kmeranker.c:83 `getBestChainTemplates`, :372 `pruneAnkers`,
  * :398 `getBestAnkerScore`, :480 `getTieAnkerScore`, :512 `chooseChain`, :57 `mrchain`; seqmenttree.c:107-232;
- * qseqs.c:41 `insertKmerBound`). Default selection functions only (no -lc, no -proxi): kmeranker.c:25-30.
+ * qseqs.c:41 `insertKmerBound`). Default selection functions (kmeranker.c:25-30) and, after orc_chain_set_lc(1), the
+ * length-corrected ones -lc binds (kma.c:694-700: ankerScoreLen, testExtensionScoreLen, proxiTestBestScoreLen,
+ * getBestAnkerScoreLen kmeranker.c:432, getTieAnkerScoreLen :496, and the swap of savekmers.c:5657-5664); no -proxi.
  *
  * It exists only so that tests can compare the CUDA chain kernel with something that is pinned byte for byte to the
  * unmodified reference (`kma -s2` without -1t1, tests/test_oracle_chain.py). Nothing outside tests/, smoke() and
@@ -27,6 +29,9 @@
 #include <string.h>
 
 typedef struct { int score, weight, score_len, len_len, start, end; int64_t vals; int next; } ank_t;
+
+static int g_lc = 0;
+void orc_chain_set_lc(int lc) { g_lc = lc; }   /* -lc (kma.c:694): length-corrected anker selection */
 
 typedef struct {
 	const orc_db *db; const orc_params *p;
@@ -132,7 +137,9 @@ static ank_t *chain_templates(cctx *c, ank_t *src, ank_t *lo, int *bests, int *e
 		bests[i] = t;
 		if (++c->incl[t] == 1) more = 1;
 	}
-	const int bestScore = src->score;
+	const int bestScore = g_lc ? src->score_len : src->score;   /* kmerAnkerScore */
+	const int target_len = src->len_len, q_len = c->seqlen;
+	const int32_t *lengths = db->lengths;
 	ank_t *prev = src;
 	for (ank_t *node = src; more; --node) {
 		if (node < lo) { *err = -2; break; }
@@ -154,7 +161,8 @@ static ank_t *chain_templates(cctx *c, ank_t *src, ank_t *lo, int *bests, int *e
 					int g = p->W1 + (node->start - 1) * p->U;
 					open = score + (p->Wl < g ? g : p->Wl);
 				}
-				if (open == bestScore) { score = bestScore; more = 0; prev = node; }
+				/* testExtension: under -lc only a template of the anker's own corrected length closes the chain */
+				if (open == bestScore && (!g_lc || (q_len < lengths[t] ? q_len : lengths[t]) == target_len)) { score = bestScore; more = 0; prev = node; }
 			}
 			c->ext[t] = start;
 			c->score[t] = score;
@@ -163,7 +171,9 @@ static ank_t *chain_templates(cctx *c, ank_t *src, ank_t *lo, int *bests, int *e
 	int j = 0;
 	for (int i = 1; i <= bests[0]; ++i) {
 		const int t = bests[i];
-		if (c->incl[t] == 1 && bestScore <= c->score[t]) bests[++j] = t;
+		int ok = bestScore <= c->score[t];   /* proxiTestBest, proxi == 1.0 */
+		if (g_lc && !ok) ok = (double)bestScore / target_len * (q_len < lengths[t] ? q_len : lengths[t]) <= c->score[t];
+		if (c->incl[t] == 1 && ok) bests[++j] = t;
 		c->score[t] = 0; c->incl[t] = 0; c->ext[t] = 0;
 	}
 	bests[0] = j;
@@ -199,9 +209,34 @@ static ank_t *best_anker(ank_t *A, int *head, unsigned *ties) {   /* getBestAnke
 	return A + best;
 }
 
-static ank_t *tie_anker(int stop, ank_t *src, const ank_t *best) {   /* getTieAnkerScore (kmeranker.c:480) */
+static ank_t *best_anker_len(ank_t *A, int *head, unsigned *ties) {   /* getBestAnkerScoreLen (kmeranker.c:432) */
+	*ties = 0;
+	int prev = *head;
+	while (prev >= 0 && A[prev].score == 0) prev = A[prev].next;
+	*head = prev;
+	if (prev < 0) return 0;
+	int best = prev, node = A[prev].next;
+	while (node >= 0) {
+		if (A[node].score) {
+			double sl = A[node].score_len;
+			if (A[node].len_len != A[best].len_len) { sl /= A[node].len_len; sl *= A[best].len_len; }
+			if (A[best].score_len < sl) { best = node; *ties = 0; }
+			else if (A[best].score_len == sl) {
+				if (A[best].score_len < A[node].score_len) { best = node; *ties = 0; }
+				else if (A[best].score_len == A[node].score_len) { best = node; ++*ties; }
+			}
+			A[prev].next = node; prev = node;
+		}
+		node = A[node].next;
+	}
+	A[prev].next = -1;
+	return A + best;
+}
+
+static ank_t *tie_anker(int stop, ank_t *src, const ank_t *best) {   /* getTieAnkerScore (kmeranker.c:480), ...ScoreLen (:496) */
 	if (!src || src->start <= stop) return 0;
-	while (stop < (--src)->start) if (src->score == best->score) return src;
+	while (stop < (--src)->start)
+		if (g_lc ? (src->score_len == best->score_len && src->len_len == best->len_len) : src->score == best->score) return src;
 	return 0;
 }
 
@@ -347,15 +382,15 @@ static int64_t chain_read(chain_ws *W, int seqlen, int nN, const uint8_t *hdr, i
 	if (!nF && !nR) return 0;
 
 	/* chaining DP over the ankers of each strand (savekmers.c:5457-5640) */
-	ank_t *best = 0, *best_r = VF;
-	unsigned ties = 0;
+	ank_t *best = 0, *best_r = VF, *best_len = 0, *best_len_r = VF;
+	unsigned ties = 0, ties_len = 0;
 	VF[0].score = 0;
 	bt[0] = 0; bt_r[0] = 0;
 	for (int pass = 0; pass < 2; ++pass) {
 		ank_t *V = pass ? VR : VF;
 		int *bests = pass ? bt_r : bt;
 		const unsigned cnt = pass ? nR : nF;
-		if (pass) { V[0].score = 0; V[0].score_len = 0; V[0].len_len = 1; best = best_r; best_r = V; }
+		if (pass) { V[0].score = 0; V[0].score_len = 0; V[0].len_len = 1; best = best_r; best_r = V; best_len = best_len_r; best_len_r = V; }
 		bests[0] = 0;
 		for (unsigned a = 0; a < cnt; ++a) {
 			ank_t *node = V + a;
@@ -390,6 +425,15 @@ static int64_t chain_read(chain_ws *W, int seqlen, int nN, const uint8_t *hdr, i
 				c->score[t] = score;
 				c->ext[t] = end;
 			}
+			{   /* last best length-corrected anker (savekmers.c:5590-5609) */
+				double sl = node->score;
+				if (node->len_len != best_len_r->len_len) { sl /= node->len_len; sl *= best_len_r->len_len; }
+				if (best_len_r->score_len < sl) { best_len_r = node; ties_len = 0; }
+				else if (best_len_r->score_len == sl) {
+					if (best_len_r->score_len < node->score_len) { best_len_r = node; ties_len = 0; }
+					else if (best_len_r->score_len == node->score_len) { best_len_r = node; ++ties_len; }
+				}
+			}
 			if (best_r->score < node->score) { best_r = node; ties = 0; }
 			else if (best_r->score == node->score) {
 				if (best_r->score_len < node->score_len) { best_r = node; ties = 0; }
@@ -405,6 +449,7 @@ static int64_t chain_read(chain_ws *W, int seqlen, int nN, const uint8_t *hdr, i
 	if (headF < 0) best->score = 0;
 	if (headR < 0) best_r->score = 0;
 	bt[0] = 0; bt_r[0] = 0;
+	if (g_lc) { ties = ties_len; best = best_len; best_r = best_len_r; }   /* savekmers.c:5657-5664 */
 
 	int cs = -1, cs_r = -1, start, len, rc;
 	ank_t *tmp;
@@ -488,7 +533,7 @@ static int64_t chain_read(chain_ws *W, int seqlen, int nN, const uint8_t *hdr, i
 				ank_t *b = *bp;
 				if (!first) {
 					if (!(b && b->score == 0)) break;
-					*bp = b = best_anker(V, head, &ties);
+					*bp = b = g_lc ? best_anker_len(V, head, &ties) : best_anker(V, head, &ties);
 					if (!b) break;
 				}
 				const int ok_score = first ? b->score != 0 : k < b->score;

@@ -58,6 +58,7 @@ int kmagpu_seed_batch(kmagpu_db *db, const kmagpu_params *p, const void *stage1,
 	(void)stats;
 	to_orc(p, &o);
 	memset(&st, 0, sizeof(st));
+	orc_chain_set_lc(p->lc);
 	/* save_kmers_chain only sees single reads, pairs always go through save_kmers_pair (savekmers.c:196-199) */
 	n = (p->kmerscan && nbytes >= 16 && ((const int *)stage1)[3] >= 0) ? orc_chain_stream(db->o, &o, stage1, nbytes, p->minlen, p->scoreT, p->coverT, p->mrc, out, cap, &st)
 	                : orc_seed_stream(db->o, &o, stage1, nbytes, out, cap, &st);

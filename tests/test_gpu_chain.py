@@ -5,15 +5,16 @@ import pytest
 
 from kma_b200 import api, synth, records
 from tests import util
-from tests.test_oracle_chain import chain_case, tie_case, recombinant_case, overlap_case
+from tests.test_oracle_chain import chain_case, tie_case, recombinant_case, overlap_case, lc_case
 
 pytestmark = pytest.mark.gpu
 
 
-def _gpu_chain(prefix, s1, exhaustive=0, minlen=16, mrs=0.5, coverT=0.1, mrc=0.0):
+def _gpu_chain(prefix, s1, exhaustive=0, minlen=16, mrs=0.5, coverT=0.1, mrc=0.0, lc=0):
     db = api.TemplateDB(prefix, device=0)
     p = api.default_params()
     p.kmerscan = 1
+    p.lc = lc
     p.exhaustive = exhaustive
     p.minlen = minlen
     p.scoreT = mrs
@@ -73,6 +74,39 @@ def test_chain_ties_and_both_strands(tmp_path, seed):
 def test_chain_recombinant_reads(tmp_path):
     prefix, s1, s2 = recombinant_case(tmp_path, 77)
     got, _ = _gpu_chain(prefix, s1)
+    assert got == s2, _first_diff(got, s2)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", [51, 52, 53])
+def test_chain_length_corrected(tmp_path, seed):
+    """-lc (kma.c:694-700): ankerScoreLen / testExtensionScoreLen / proxiTestBestScoreLen / getBestAnkerScoreLen /
+    getTieAnkerScoreLen and the swap of savekmers.c:5657 vs `kma -s2 -lc`"""
+    prefix, s1, s2, s2_plain = lc_case(tmp_path, seed)
+    got, _ = _gpu_chain(prefix, s1, lc=1)
+    assert got == s2, _first_diff(got, s2)
+    got, _ = _gpu_chain(prefix, s1)
+    assert got == s2_plain, _first_diff(got, s2_plain)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("shape", ["chain", "recombinant", "overlap", "tie"])
+def test_chain_length_corrected_other_shapes(tmp_path, shape):
+    if shape == "chain":
+        prefix, s1, _ = chain_case(tmp_path, 13, 120, 1000, 6000, 0.10, 0.002)
+        kw, extra = {}, []
+    elif shape == "recombinant":
+        prefix, s1, _ = recombinant_case(tmp_path, 77, 3000)
+        kw, extra = {}, []
+    elif shape == "overlap":
+        prefix, s1, _ = overlap_case(tmp_path, 42, 0.5)
+        kw, extra = {"coverT": 0.5}, ["-mct", "0.5"]
+    else:
+        prefix, s1, _ = tie_case(tmp_path, 31)
+        kw, extra = {}, []
+    s2 = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-s2", "-lc"] + extra, cwd=tmp_path)
+    assert util.oracle_chain_stream(prefix, s1, lc=1, **kw).tobytes() == s2
+    got, _ = _gpu_chain(prefix, s1, lc=1, **kw)
     assert got == s2, _first_diff(got, s2)
 
 

@@ -97,8 +97,11 @@ CASES = {
     "c4_genome_mem": dict(reads="genome", n=3000, args=["-mem_mode", "-1t1", "-matrix"]),
     # seed trimming of the traceback alignment (-ts, bound by the -ont / -ill presets)
     "c1_se_ts2": dict(reads="se", n=800, args=["-1t1", "-ts", "2", "-matrix"]),
-    # -lc with -1t1: runConClave_lc (the anker selection of -lc only exists in the chain scan, which the shim refuses)
+    # -lc with -1t1: runConClave_lc alone (the anker selection of -lc only exists in the chain scan)
     "c1_se_lc_1t1": dict(reads="se", n=800, args=["-1t1", "-lc", "-matrix"]),
+    # -lc with the chain scan: length-corrected anker selection (kma.c:694-700) + runConClave_lc, short and long reads
+    "c1_se_lc_chain": dict(reads="se", n=800, args=["-lc", "-matrix"], n_rate=0.005),
+    "c3_long_lc": dict(reads="long", n=40, args=["-lc", "-bcNano", "-bc", "0.7"]),
 }
 
 
@@ -146,10 +149,8 @@ def test_shim_refuses_what_the_gpu_path_does_not_cover(tmp_path):
     args = _make_case(tmp_path, "c1_se_1t1")
     r = subprocess.run([os.path.join(REF, "kma_gpu_mock")] + args + ["-o", "x", "-sam"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0 and b"no CPU fallback" in r.stderr
-    # -lc without -1t1 binds the length-corrected anker selection of save_kmers_chain: not built, refused
-    chain_args = [a for a in args if a != "-1t1"] + ["-lc"]
-    r = subprocess.run([os.path.join(REF, "kma_gpu_mock")] + chain_args + ["-o", "y"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-    assert r.returncode != 0 and b"-lc" in r.stderr
+    r = subprocess.run([os.path.join(REF, "kma_gpu_mock")] + args + ["-o", "y", "-ca"], cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0 and b"no CPU fallback" in r.stderr
 
 
 @pytest.mark.gpu

@@ -164,3 +164,46 @@ def test_chain_oracle_overlapping_regions(tmp_path, seed, mct):
     prefix, s1, s2 = overlap_case(tmp_path, seed, mct)
     got = util.oracle_chain_stream(prefix, s1, coverT=mct)
     assert got.tobytes() == s2
+
+
+def lc_case(tmp_path, seed):
+    """-lc (kma.c:694-700): families whose variants differ in length (truncated and extended copies) so that the
+    length-corrected anker score picks other ankers / templates than the plain one, plus the tie and recombinant shapes."""
+    rng = np.random.default_rng(seed)
+    names, seqs = synth.gene_db(seed, n_families=10, n_variants=5, len_lo=300, len_hi=1200)
+    for i in range(len(seqs)):
+        s = seqs[i]
+        r = rng.random()
+        if r < 0.3:
+            names.append(names[i] + "_cut"); seqs.append(s[int(rng.integers(0, 80)): len(s) - int(rng.integers(0, 200))].copy())
+        elif r < 0.6:
+            names.append(names[i] + "_ext")
+            seqs.append(np.concatenate([rng.integers(0, 4, size=int(rng.integers(20, 300))).astype(np.uint8), s,
+                                        rng.integers(0, 4, size=int(rng.integers(20, 300))).astype(np.uint8)]))
+    synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+    util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+    reads = synth.long_reads(seed + 2, seqs, 150, len_lo=200, len_hi=3000, err=0.05)
+    reads += list(synth.short_reads(seed + 3, seqs, 300, L=150, sub=0.01, junk_frac=0.05))
+    for _ in range(150):
+        t = seqs[int(rng.integers(0, len(seqs)))]
+        parts = []
+        for r in range(int(rng.integers(1, 4))):
+            parts.append(t if rng.random() < 0.7 else synth.mutate_subs(rng, t, 0.01))
+            parts.append(rng.integers(0, 4, size=int(rng.integers(0, 120))).astype(np.uint8))
+        s = np.concatenate(parts)
+        reads.append(synth.revcomp(s) if rng.random() < 0.5 else s)
+    synth.write_fastq(tmp_path / "r.fq", reads, qual="5")
+    s1 = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-s1", "-lc"], cwd=tmp_path)
+    s2 = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-s2", "-lc"], cwd=tmp_path)
+    s2_plain = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-s2"], cwd=tmp_path)
+    return str(tmp_path / "db"), np.frombuffer(s1, dtype=np.uint8), s2, s2_plain
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", [51, 52, 53])
+def test_chain_oracle_length_corrected(tmp_path, seed):
+    prefix, s1, s2, s2_plain = lc_case(tmp_path, seed)
+    assert s2 != s2_plain, "the case is meant to make -lc choose differently"
+    got = util.oracle_chain_stream(prefix, s1, lc=1)
+    assert got.tobytes() == s2
+    assert util.oracle_chain_stream(prefix, s1).tobytes() == s2_plain

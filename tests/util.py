@@ -64,9 +64,10 @@ def oracle_seed_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, stats=None,
     return out[:n].copy()
 
 
-def oracle_chain_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, minlen=16, mrs=0.5, coverT=0.1, mrc=0.0, stats=None) -> np.ndarray:
-    """Stage 2 in chain mode (save_kmers_chain, the default without -1t1); CLI defaults kma.c:309-320."""
+def oracle_chain_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, minlen=16, mrs=0.5, coverT=0.1, mrc=0.0, stats=None, lc=0) -> np.ndarray:
+    """Stage 2 in chain mode (save_kmers_chain, the default without -1t1); CLI defaults kma.c:309-320. lc = -lc (kma.c:694)."""
     L = orc()
+    L.orc_chain_set_lc(int(lc))
     db = L.orc_db_open(os.fsencode(db_prefix))
     assert db, f"oracle cannot open {db_prefix}"
     cap = 8 * len(s1) + 4096
