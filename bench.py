@@ -482,14 +482,14 @@ def c4_files(api, workdir, device, cores, genome_bases, n):
                 what="kma -mem_mode -1t1 -matrix vs the same host on libkmagpu.so")
 
 
-C5_FAMILIES, C5_TLEN = 1250, 10000
+C5_FAMILIES, C5_TLEN = 5000, 10000
 
 
 def c5_db(workdir):
-    """BASELINE.json configs[4] at a quarter of its size (12.5k templates in 1250 families, ~125 Mb, ~29 M distinct 16-mers):
-    the largest database `kma index` builds in about a minute, and already one whose k-mer table (128 MB of buckets +
-    230 MB of keys) and position index (GBs) cannot sit in the 126 MB L2 -- the HBM-resident gather. Built once per box with
-    the reference's own indexer, cached in the work directory."""
+    """BASELINE.json configs[4] at its full size (50k templates in 5000 families of 10 variants, ~500 Mb, ~113 M distinct
+    16-mers): a k-mer table of 1.5 GB and a position index of ~13 GB, two orders of magnitude beyond the 126 MB L2 -- the
+    HBM-resident gather. Built once per box with the reference's own indexer (about two minutes), cached in the work
+    directory; --c5-families scales it down."""
     wd = os.path.join(workdir, f"c5_{C5_FAMILIES}_{C5_TLEN}")
     os.makedirs(wd, exist_ok=True)
     prefix = os.path.join(wd, "db")
@@ -552,7 +552,7 @@ def c5_leg(api, workdir, rank, world, device, cores, pk, dist, n=4_000_000, ref_
     # 32-byte sectors the gather needs at the least: one per bucket probe, one per key / value-offset pair, the lists
     sectors = st.lookups + st.hits + st.list_fetches + (vw * st.list_ids + 31) // 32 + (8 * st.read_words + 31) // 32
     ach = alg / (st.ms_seed * 1e-3) / 1e9
-    out = {"workload": f"C5 (quarter scale): {info.DB_size - 1} templates / {info.seq_bases / 1e6:.0f} Mb redundant DB ({C5_FAMILIES} families x 10), "
+    out = {"workload": f"C5 ({'full' if C5_FAMILIES >= 5000 else 'reduced'} scale): {info.DB_size - 1} templates / {info.seq_bases / 1e6:.0f} Mb redundant DB ({C5_FAMILIES} families x 10), "
                        f"{n} synthetic 150 bp single-end reads per GPU, -1t1: stage 2 + alignment pass resident in HBM",
            "db": {"templates": info.DB_size - 1, "bases": int(info.seq_bases), "kmers": int(info.n), "hash_slots": int(info.size),
                   "device_bytes": int(info.device_bytes), "built": how, "open_s": round(t_open, 1)},
@@ -595,9 +595,11 @@ def main():
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 (one genome, -mem_mode, consensus; resident flow) side measurement")
     ap.add_argument("--no-c5", action="store_true", help="skip the C5 (large redundant DB: k-mer table out of L2) side measurement")
     ap.add_argument("--c5-reads", type=int, default=4_000_000)
+    ap.add_argument("--c5-families", type=int, default=C5_FAMILIES, help="families of 10 templates of ~10 kb in the C5 database (5000 = BASELINE.json configs[4])")
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads / library handles (clones of one database image) of the end-to-end pipelines")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks the batch is cut into for the hot-path-only end-to-end pipeline")
     args = ap.parse_args()
+    globals()["C5_FAMILIES"] = args.c5_families
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -1022,14 +1022,17 @@ __global__ void __launch_bounds__(256, ST_MINB) aln_emit_kernel(const uint8_t *_
 	for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
 		const AlnRes rs = res[r];
 		if (rs.nrec) {   // pair: update_Scores_pe (one record + mate block) or update_Scores_se records (updatescores.c:300-488)
-			const AlnRead RB = reads[r], RA = reads[r - 1];
-			const int32_t *pbase = (const int32_t *)(cand + RB.task0);
+			const int32_t *pbase = (const int32_t *)(cand + reads[r].task0);
+			const int cap = reads[r].nt;
 			uint8_t *o = out + out_off[r];
-			for (int x = 0; x < rs.nrec; ++x) {
-				const AlnRead &Rm = rs.rmate[x] ? RB : RA;
+#pragma unroll
+			for (int x = 0; x < 2; ++x) {   // unrolled: rs stays in registers (indexed by x it lived in local memory)
+				if (x >= rs.nrec) break;
+				const AlnRead Rm = reads[r - 1 + rs.rmate[x]];
 				const QView q = read_view(slab, Rm, rs.rorient[x]);
 				const uint8_t *hdr = in + Rm.rec_off + 28 + 8 * (size_t)Rm.words + 4 * (size_t)Rm.nN + 4 * (size_t)Rm.nt;
-				if (rs.form == 1 && x == 1) {   // mate block: int32[3]{q_len, hdrlen, flag} read header
+				const bool mate_block = rs.form == 1 && x == 1;   // int32[3]{q_len, hdrlen, flag} read header
+				if (mate_block) {
 					if (lane < 3) st_u32b(o + 4 * lane, (uint32_t)(lane == 0 ? Rm.q_len : lane == 1 ? Rm.hl : rs.rflag[x]));
 					o += 12;
 				} else {
@@ -1043,9 +1046,9 @@ __global__ void __launch_bounds__(256, ST_MINB) aln_emit_kernel(const uint8_t *_
 				o += Rm.q_len;
 				warp_copy(o, hdr, Rm.hl, lane);
 				o += Rm.hl;
-				if (!(rs.form == 1 && x == 1)) {
+				if (!mate_block) {
 					const int32_t *arr = pbase + rs.roff[x];
-					const int kept = rs.rkept[x], cap = RB.nt;
+					const int kept = rs.rkept[x];
 					warp_store_u32(o, 3 * kept, lane, [&](int i) { const int a = i / kept; return arr[a * cap + (i - a * kept)]; });
 					o += 12 * (size_t)kept;
 				}

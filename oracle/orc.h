@@ -39,6 +39,8 @@ int64_t orc_seed_stream(const orc_db *db, const orc_params *p, const uint8_t *in
 void orc_default_params(orc_params *p);
 int64_t orc_chain_stream(const orc_db *db, const orc_params *p, const uint8_t *in, size_t in_bytes, int minlen,
                          double mrs, double coverT, double mrc, uint8_t *out, size_t cap, orc_stats *st);
+void orc_set_proxi(double minFrac); /* -proxi (kma.c:702-718) of stage 2: getProxiMatch, getSecondProxiPen, getF_Proxi / getR_Proxi, getProxiChainTemplates, chooseChain; 1.0 = off */
+double orc_get_proxi(void);
 void orc_chain_set_lc(int lc);    /* -lc (kma.c:694-700): length-corrected anker selection of save_kmers_chain, default 0 */
 int orc_db_load_seq(orc_db *db, const char *prefix);
 int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const uint8_t *in, size_t in_bytes,

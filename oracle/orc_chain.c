@@ -180,6 +180,62 @@ static ank_t *chain_templates(cctx *c, ank_t *src, ank_t *lo, int *bests, int *e
 	return j ? prev : 0;
 }
 
+/* getProxiChainTemplates (kmeranker.c:235-370, bound by -proxi): the walk back scores EVERY template it meets on the way
+ * (not only those of src's own list), stops where one of them reproduces src's score at a chain start, and keeps the
+ * templates within minFrac of that score that are not marked in include[] (the marks of the tie path). A template met
+ * on an anker that starts at query position 0 keeps extendScore == 0 and is listed again when it is met again. */
+static ank_t *chain_templates_proxi(cctx *c, ank_t *src, ank_t *lo, int *bests, int *err) {
+	const orc_db *db = c->db; const orc_params *p = c->p;
+	const int k = c->k;
+	if (!src) return 0;
+	bests[0] = 0;
+	const int bestScore = g_lc ? src->score_len : src->score;
+	const double proxiScore = orc_get_proxi() * bestScore;
+	const int target_len = src->len_len, q_len = c->seqlen;
+	const int32_t *lengths = db->lengths;
+	ank_t *prev = src;
+	int more = 1;
+	for (ank_t *node = src; more; --node) {
+		if (node < lo) { *err = -2; break; }
+		const int nl = list_n(db, node->vals);
+		const int start = node->start, end = node->end;
+		for (int i = nl - 1; i >= 0; --i) {
+			const int t = list_at(db, node->vals, i);
+			int score = c->score[t];
+			const int pos = c->ext[t];
+			if (pos == 0) { score = node->weight; bests[++bests[0]] = t; }
+			else {
+				score += link_score(p, k, pos - end, node->weight);
+				node->score = 0;
+			}
+			if (bestScore <= score) {
+				int open = score;
+				if (node->start) {
+					int g = p->W1 + (node->start - 1) * p->U;
+					open = score + (p->Wl < g ? g : p->Wl);
+				}
+				if (open == bestScore && (!g_lc || (q_len < lengths[t] ? q_len : lengths[t]) == target_len)) { score = bestScore; more = 0; prev = node; }
+			}
+			c->ext[t] = start;
+			c->score[t] = score;
+		}
+	}
+	int j = 0;
+	for (int i = 1; i <= bests[0]; ++i) {
+		const int t = bests[i];
+		int ok = proxiScore <= c->score[t];   /* proxiTestBest */
+		if (g_lc && !ok) ok = proxiScore / target_len * (q_len < lengths[t] ? q_len : lengths[t]) <= c->score[t];
+		if (!c->incl[t] && ok) bests[++j] = t;
+		c->score[t] = 0; c->ext[t] = 0; c->incl[t] = 0;
+	}
+	bests[0] = j;
+	return prev;
+}
+
+static ank_t *get_chain_templates(cctx *c, ank_t *src, ank_t *lo, int *bests, int *err) {   /* getChainTemplates */
+	return orc_get_proxi() != 1.0 ? chain_templates_proxi(c, src, lo, bests, err) : chain_templates(c, src, lo, bests, err);
+}
+
 static int prune(ank_t *A, int k) {   /* pruneAnkers (kmeranker.c:372): unlink ankers scoring below k; head or -1 */
 	int i = 0;
 	while (A[i].score < k && (i = A[i].next) >= 0);
@@ -240,9 +296,13 @@ static ank_t *tie_anker(int stop, ank_t *src, const ank_t *best) {   /* getTieAn
 	return 0;
 }
 
-/* chooseChain (kmeranker.c:512-592), proxi == 1.0 */
+/* chooseChain (kmeranker.c:512-592) */
 static int choose_chain(const ank_t *f, const ank_t *r, int cs, int cs_r, double coverT, int *Start, int *Len) {
-	int rc = r->score < f->score ? 1 : f->score < r->score ? 2 : 3, start, end;
+	const double proxi = orc_get_proxi();
+	int rc, start, end;
+	if (proxi == 1.0) rc = r->score < f->score ? 1 : f->score < r->score ? 2 : 3;
+	else if (r->score <= f->score) rc = (proxi * f->score <= r->score) ? 3 : 1;   /* the other strand within the proximity */
+	else rc = (proxi * r->score <= f->score) ? 3 : 2;
 	if (rc == 1) { start = cs; end = f->end; }
 	else if (rc == 2) { start = cs_r; end = r->end; }
 	else if (f->end < cs_r) { start = cs; end = f->end; rc = 1; }
@@ -455,18 +515,18 @@ static int64_t chain_read(chain_ws *W, int seqlen, int nN, const uint8_t *hdr, i
 	ank_t *tmp;
 	if (!best->score || !best_r->score) {
 		if (best->score) {
-			tmp = chain_templates(c, best, VF, bt, &err);
+			tmp = get_chain_templates(c, best, VF, bt, &err);
 			if (err) return err;
 			cs = tmp->start; start = cs; len = best->end - start; rc = 1;
 		} else {
-			tmp = chain_templates(c, best_r, VR, bt_r, &err);
+			tmp = get_chain_templates(c, best_r, VR, bt_r, &err);
 			if (err) return err;
 			cs_r = tmp->start; start = cs_r; len = best_r->end - start; rc = 2;
 		}
 	} else {
-		tmp = chain_templates(c, best, VF, bt, &err); if (err) return err;
+		tmp = get_chain_templates(c, best, VF, bt, &err); if (err) return err;
 		cs = tmp->start;
-		tmp = chain_templates(c, best_r, VR, bt_r, &err); if (err) return err;
+		tmp = get_chain_templates(c, best_r, VR, bt_r, &err); if (err) return err;
 		cs_r = tmp->start;
 		rc = choose_chain(best, best_r, cs, cs_r, W->coverT, &start, &len);
 	}
@@ -489,7 +549,7 @@ static int64_t chain_read(chain_ws *W, int seqlen, int nN, const uint8_t *hdr, i
 						int *tail = bl + bl[0];   /* the new set is collected behind the current one */
 						const int keep = *tail;
 						*tail = 0;
-						chain_templates(c, V, lo, tail, &err);
+						get_chain_templates(c, V, lo, tail, &err);
 						if (err) return err;
 						bl[0] += *tail;
 						*tail = keep;
@@ -538,7 +598,7 @@ static int64_t chain_read(chain_ws *W, int seqlen, int nN, const uint8_t *hdr, i
 				}
 				const int ok_score = first ? b->score != 0 : k < b->score;
 				first = 0;
-				if (ok_score && (tmp = chain_templates(c, b, V, bl, &err))) {
+				if (ok_score && (tmp = get_chain_templates(c, b, V, bl, &err))) {
 					if (err) return err;
 					*csp = tmp->start;
 					const unsigned cover = T.n ? st_query(&T, 0, (unsigned)*csp, (unsigned)b->end) : 0;

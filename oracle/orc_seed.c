@@ -35,6 +35,11 @@
 
 /* ------------------------------------------------------------------ .comp.b ---------- */
 
+/* -proxi (kma.c:702-718): |minFrac| as save_kmers_batch hands it to the get*Proxi* functions (kmers.c:133-150); 1.0 = off */
+static double g_proxi = 1.0;
+void orc_set_proxi(double f) { g_proxi = f < 0 ? -f : f; }
+double orc_get_proxi(void) { return g_proxi; }
+
 static int rd(FILE *f, void *dst, size_t n) { return fread(dst, 1, n, f) == n ? 0 : -1; }
 
 orc_db *orc_db_open(const char *prefix) {
@@ -283,6 +288,18 @@ static int scan_strand(const orc_db *db, const orc_params *p, const uint64_t *se
 		}
 		return nhits;
 	}
+	if (g_proxi != 1.0) {   /* getProxiMatch (savekmers.c:296-340): every template within minFrac of the best score, raw scores */
+		int best = 0, nb = 0;
+		for (int i = 1; i <= cand[0]; ++i) if (best < S->score[cand[i]]) best = S->score[cand[i]];
+		const int proxi = (int)(g_proxi * best);
+		for (int i = 1; i <= cand[0]; ++i) {
+			int t = cand[i];
+			if (proxi <= S->score[t]) cand[++nb] = t;
+			S->score[t] = 0; S->ext[t] = 0; S->incl[t] = 0;
+		}
+		cand[0] = nhits ? nb : 0;
+		return nhits ? best : 0;
+	}
 	/* arg-max set, first-seen order; scratch returned to zero (getBestMatch, savekmers.c:273) */
 	int best = 0, nb = 0;
 	for (int i = 1; i <= cand[0]; ++i) {
@@ -451,6 +468,101 @@ static int r_best(pair_ws *ws) {
 	return best_r;
 }
 
+/* getSecondProxiPen (savekmers.c:1514-1646): as getSecondBestPen, but a union within minFrac of the best union survives,
+ * and without a union every template within minFrac of a mate's own best */
+static int second_proxi_pen(pair_ws *ws, int bestScore, int PE) {
+	int best_r = 0, n;
+	for (int i = 1; i <= ws->bt[0]; ++i) if (best_r < ws->Score[ws->bt[i]]) best_r = ws->Score[ws->bt[i]];
+	n = ws->bt[0];
+	for (int i = 1; i <= ws->bt_r[0]; ++i) {
+		if (best_r < ws->Score_r[ws->bt_r[i]]) best_r = ws->Score_r[ws->bt_r[i]];
+		ws->bt[++n] = -ws->bt_r[i];
+	}
+	ws->bt[0] = n;
+	int hits = 0;
+	if (best_r) {
+		int comp = 0;
+		for (int i = 1; i <= ws->rt[0]; ++i) {
+			int t = ws->rt[i], sc = 0 < t ? ws->Score_r[t] : ws->Score[-t];
+			if (0 < sc) { sc += ws->rs[i]; if (comp < sc) comp = sc; }
+		}
+		if ((bestScore + best_r - PE) <= comp) {
+			const int proxi = (int)(g_proxi * comp);
+			for (int i = 1; i <= ws->rt[0]; ++i) {
+				int t = ws->rt[i], sc = 0 < t ? ws->Score_r[t] : ws->Score[-t];
+				if (0 < sc) { sc += ws->rs[i]; if (proxi <= sc) ws->rt[++hits] = t; }
+			}
+		}
+	}
+	if (hits) {
+		ws->rt[0] = -hits;
+		for (int i = ws->bt[0]; i != 0; --i) { if (0 < ws->bt[i]) ws->Score[ws->bt[i]] = 0; else ws->Score_r[-ws->bt[i]] = 0; }
+	} else {
+		int proxi = (int)(g_proxi * bestScore);
+		for (int i = 1; i <= ws->rt[0]; ++i) if (proxi <= ws->rs[i]) ws->rt[++hits] = ws->rt[i];
+		ws->rt[0] = hits;
+		hits = 0;
+		proxi = (int)(g_proxi * best_r);
+		for (int i = 1; i <= ws->bt[0]; ++i) {
+			int t = ws->bt[i];
+			if (0 < t) { if (proxi <= ws->Score[t]) ws->bt[++hits] = t; ws->Score[t] = 0; }
+			else { if (proxi <= ws->Score_r[-t]) ws->bt[++hits] = t; ws->Score_r[-t] = 0; }
+		}
+		ws->bt[0] = hits;
+	}
+	return best_r;
+}
+
+/* getF_Proxi (savekmers.c:1764) */
+static int f_proxi(pair_ws *ws) {
+	int best = 0, hits = 0;
+	for (int i = 1; i <= ws->bt[0]; ++i) if (best < ws->Score[ws->bt[i]]) best = ws->Score[ws->bt[i]];
+	for (int i = 1; i <= ws->bt_r[0]; ++i) if (best < ws->Score_r[ws->bt_r[i]]) best = ws->Score_r[ws->bt_r[i]];
+	const int proxi = (int)(g_proxi * best);
+	for (int i = 1; i <= ws->bt[0]; ++i) {
+		int t = ws->bt[i];
+		if (proxi <= ws->Score[t]) ws->rt[++hits] = t;
+		ws->Score[t] = 0;
+	}
+	for (int i = 1; i <= ws->bt_r[0]; ++i) {
+		int t = ws->bt_r[i];
+		if (proxi <= ws->Score_r[t]) ws->rt[++hits] = -t;
+		ws->Score_r[t] = 0;
+	}
+	ws->rt[0] = hits;
+	return best;
+}
+
+/* getR_Proxi (savekmers.c:1825): the templates of the first mate's set that are within the second mate's proximity on
+ * the opposite strand (they alone still carry a score) are swapped to the front of rt */
+static int r_proxi(pair_ws *ws) {
+	int best = 0, hits = 0;
+	const int nf = ws->bt[0];
+	for (int i = 1; i <= nf; ++i) if (best < ws->Score[ws->bt[i]]) best = ws->Score[ws->bt[i]];
+	for (int i = 1; i <= ws->bt_r[0]; ++i) if (best < ws->Score_r[ws->bt_r[i]]) best = ws->Score_r[ws->bt_r[i]];
+	const int proxi = (int)(g_proxi * best);
+	for (int i = 1; i <= nf; ++i) {
+		int t = ws->bt[i];
+		if (proxi <= ws->Score[t]) ws->bt[++hits] = t; else ws->Score[t] = 0;
+	}
+	for (int i = 1; i <= ws->bt_r[0]; ++i) {
+		int t = ws->bt_r[i];
+		if (proxi <= ws->Score_r[t]) ws->bt[++hits] = -t; else ws->Score_r[t] = 0;
+	}
+	ws->bt[0] = hits;
+	hits = 0;
+	for (int i = 1; i <= ws->rt[0]; ++i) {
+		const int t = ws->rt[i];
+		if (0 < t ? ws->Score_r[t] : ws->Score[-t]) {
+			++hits;
+			const int tmp = ws->rt[hits]; ws->rt[hits] = ws->rt[i]; ws->rt[i] = tmp;
+		}
+	}
+	if (hits) ws->rt[0] = -hits;
+	for (int i = ws->bt[0]; i != 0; --i) { if (0 < ws->bt[i]) ws->Score[ws->bt[i]] = 0; else ws->Score_r[-ws->bt[i]] = 0; }
+	return best;
+}
+
 /* save_kmers_unionPair (savekmers.c:3367-3570, the default pairing) with getF = getF_Best, getR = getR_Best, rev = 1 */
 static size_t seed_pair_union(const orc_db *db, const orc_params *p, mate_t *m1, mate_t *m2, pair_ws *ws, uint8_t *out, orc_stats *st) {
 	const int k = db->kmersize;
@@ -458,11 +570,11 @@ static size_t seed_pair_union(const orc_db *db, const orc_params *p, mate_t *m1,
 	int best = 0, best_r = 0, flag = 65, flag_r = 129;
 	int *rt = ws->rt, *bt = ws->bt;
 	if (pair_kmers(db, p, m1, ws, st)) {
-		best = f_best(ws);
+		best = g_proxi != 1.0 ? f_proxi(ws) : f_best(ws);
 		if (k < best && best * k < (m1->seqlen - best)) best = 0;
 	}
 	if (pair_kmers(db, p, m2, ws, st)) {
-		best_r = best ? r_best(ws) : f_best(ws);
+		best_r = g_proxi != 1.0 ? (best ? r_proxi(ws) : f_proxi(ws)) : (best ? r_best(ws) : f_best(ws));
 		if (k < best_r && best_r * k < (m2->seqlen - best_r)) { best_r = 0; rt[0] = abs(rt[0]); }
 	} else {   /* the lists are emptied: a first mate that kept its score still has its set in rt */
 		bt[0] = 0; ws->bt_r[0] = 0;
@@ -514,7 +626,10 @@ static size_t seed_pair(const orc_db *db, const orc_params *p, mate_t *m1, mate_
 	size_t op = 0;
 	int hc, hc_r, best = 0, best_r = 0, flag = 65, flag_r = 129;
 	if ((hc = pair_kmers(db, p, m1, ws, st))) best = first_pen(ws);
-	if ((hc_r = pair_kmers(db, p, m2, ws, st))) best_r = 0 < best ? second_pen(ws, best, p->PE) : f_best(ws);
+	if ((hc_r = pair_kmers(db, p, m2, ws, st))) {
+		if (g_proxi != 1.0) best_r = 0 < best ? second_proxi_pen(ws, best, p->PE) : f_proxi(ws);
+		else best_r = 0 < best ? second_pen(ws, best, p->PE) : f_best(ws);
+	}
 	int *rt = ws->rt, *bt = ws->bt;
 	if (0 < best && 0 < best_r) {
 		if (rt[0] < 0) {   /* proper pair */

@@ -1,7 +1,7 @@
 """Exploratory run of a scaled C5 (BASELINE.json configs[4]: large highly redundant DB, short reads, -1t1): a database
 whose k-mer table no longer fits the 126 MB L2, so that seeding is the HBM random-sector gather SURVEY 8d describes.
 usage: c5_perf.py [families=1250] [template_len=10000] [reads=4000000] [check=2000]
-Builds the DB with kma_b200.dbbuild (reference format), maps `reads` 150 bp single-end reads (stage 2 + alignment
+Uses the database of bench.py's C5 leg (built with the reference's `kma index`, cached per box), maps `reads` 150 bp single-end reads (stage 2 + alignment
 pass, resident), checks the first `check` reads against the oracle and prints the stage timings and the seeding
 roofline fraction."""
 import os, sys, time, tempfile, json
@@ -17,12 +17,12 @@ def main():
     tl = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
     nreads = int(sys.argv[3]) if len(sys.argv) > 3 else 4_000_000
     check = int(sys.argv[4]) if len(sys.argv) > 4 else 2000
-    wd = os.path.join(tempfile.gettempdir(), f"kma_b200_c5_{fam}_{tl}"); os.makedirs(wd, exist_ok=True)
-    prefix = os.path.join(wd, "db")
+    # the database of bench.py's C5 leg (same cache directory: built once per box, by the reference's indexer when it is there)
+    import bench
+    bench.C5_FAMILIES, bench.C5_TLEN = fam, tl
+    workdir = os.path.join(tempfile.gettempdir(), "kma_b200_bench"); os.makedirs(workdir, exist_ok=True)
     t0 = time.time()
-    names, seqs = synth.gene_db(55, n_families=fam, n_variants=10, len_lo=tl * 3 // 4, len_hi=tl * 5 // 4)
-    if not os.path.exists(prefix + ".comp.b"):
-        dbbuild.build_db(prefix, names, seqs)
+    prefix, seqs, how = bench.c5_db(workdir)
     t1 = time.time()
     db = api.TemplateDB(prefix)
     t2 = time.time()
