@@ -148,12 +148,13 @@ int __wrap_save_kmers_batch(char *templatefilename, char *exePrev, unsigned shm,
 	if (deConPrintPtr == &deConPrint) shim_unsupported("-decon");
 	if (printPtr != &print_ankers) shim_unsupported("sparse / split databases");
 	if (sam == 1 && out != stdout) shim_unsupported("SAM output of unmapped reads");
-	if (minFrac < 1.0) shim_unsupported("-proxi");
+	if (minFrac < 0) shim_unsupported("soft proximity with -mem_mode (the softProxi sums of kmers.c:133-153)");
 	g_coverT = coverT;
 	SHIM_TRACE("checks done");
 	shim_params(&prm, rewards);
 	SHIM_TRACE("params done");
 	prm.exhaustive = exhaustive; prm.minlen = minlen; prm.scoreT = mrs; prm.coverT = coverT;
+	prm.minFrac = minFrac;   /* -proxi (kma.c:702-718): stage 2 is handed |minFrac| (kma.c:1605) */
 	if (kmerScan == &save_kmers) prm.kmerscan = 0;
 	else if (kmerScan == &save_kmers_chain) prm.kmerscan = 1;
 	else shim_unsupported("this k-mer scan (-hmm / -Sparse / count modes)");

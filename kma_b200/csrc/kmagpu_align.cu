@@ -1197,11 +1197,15 @@ __device__ int kma_trace_warp(const AlnParams &P, const TaskCtx &c, const KgTInd
 	if (P.ts) {   // trimSeeds (chain.c:496-538): the first ts bases of every seed of the chain go back to the DP
 		__syncwarp();
 		if (lane == 0) {
+			// MEM 0 is a valid chain start: only next == 0 ends the walk (the reference's do ... while, chain.c:509-524)
 			int cidx = start;
-			if (!M.qS(cidx)) cidx = M.nx(cidx);
-			for (; cidx; cidx = M.nx(cidx)) {
+			bool go = true;
+			if (!M.qS(cidx)) { cidx = M.nx(cidx); go = cidx != 0; }
+			while (go) {
 				const int len = M.qE(cidx) - M.qS(cidx), cut = len < P.ts ? len - 1 : P.ts;
 				M.tS(cidx) += cut; M.qS(cidx) += cut;
+				cidx = M.nx(cidx);
+				go = cidx != 0;
 			}
 		}
 		__syncwarp();

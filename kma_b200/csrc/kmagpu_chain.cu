@@ -40,6 +40,8 @@ enum { C_REGS = 12, C_EWALK = 13, C_ETREE = 14, C_BYTES = 15 };
 struct ChainParams {
 	int32_t M, MM, U, W1, Wl, exhaustive, minlen;
 	int32_t lc;   // -lc (kma.c:694-700): length-corrected anker selection (ankerScoreLen, testExtensionScoreLen, ...)
+	int32_t use_proxi, pad;   // -proxi (kma.c:702-718): getChainTemplates = getProxiChainTemplates, chooseChain's proximity test
+	double proxi;             // |minFrac|
 	double mrs, coverT, mrc;
 };
 struct ChainRes { uint32_t reg_off; int32_t nreg; };
@@ -340,11 +342,15 @@ struct WarpCtx {
 	const int32_t *lengths;   // template lengths
 };
 
+__device__ __noinline__ int chain_templates_proxi(const KgHashView &hv, const ChainParams &p, WarpCtx &W, const int s, const int src, int *dst,
+                               int *count, int *err);
+
 // Walk back from anker `src` of strand s, re-scoring its templates anker by anker until one of them reproduces src's
 // score at a chain start. dst[1 .. *count] receives the templates that reach it. Marks walked ankers as used.
 // Returns the anker the chain starts at, -1 if no template is left. *err is set when the walk leaves the array.
 __device__ __noinline__ int chain_templates(const KgHashView &hv, const ChainParams &p, WarpCtx &W, const int s, const int src, int *dst,
                                int *count, int *err) {
+	if (p.use_proxi) return chain_templates_proxi(hv, p, W, s, src, dst, count, err);
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned lt = (1u << lane) - 1;
 	const Ank &V = W.V[s];
@@ -419,6 +425,81 @@ __device__ __noinline__ int chain_templates(const KgHashView &hv, const ChainPar
 	}
 	*count = j;
 	return j ? prev : -1;
+}
+
+// getProxiChainTemplates (kmeranker.c:235-370, bound by -proxi): the walk back scores EVERY template it meets (not only
+// those of src's list), in the reference's order -- anker by anker, each list from its end --, stops where one of them
+// reproduces src's score at a chain start, and keeps the templates within minFrac of that score that carry no mark of
+// the tie path (include[]). Always returns the anker the walk stopped at.
+__device__ __noinline__ int chain_templates_proxi(const KgHashView &hv, const ChainParams &p, WarpCtx &W, const int s, const int src, int *dst,
+                               int *count, int *err) {
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1;
+	const Ank &V = W.V[s];
+	const int k = W.k;
+	__syncwarp();
+	const bool lc = p.lc != 0;
+	const int bestScore = lc ? V.slen[src] : V.score[src];
+	const int target = lc ? V.llen[src] : 1;
+	const double proxiScore = __dmul_rn(p.proxi, (double)bestScore);
+	int prev = src, n = 0;
+	bool more = true;
+	for (int node = src; more; --node) {
+		if (node < 0) { *err = 1; break; }
+		const uint32_t off = V.vals[node];
+		const int nl = list_len(hv, off);
+		const int start = V.start[node], end = V.end[node], weight = V.weight[node];
+		bool used = false, done = false;
+#pragma unroll 1
+		for (int base = nl - 1; base >= 0; base -= 32) {   // lane l takes list entry base - l: the reference's order
+			const int i = base - (int)lane;
+			bool isnew = false;
+			int t = 0;
+			if (i >= 0) {
+				t = list_id(hv, off, i);
+				int4 x = W.st[t];
+				int score = x.x;
+				if (x.y == 0) { score = weight; isnew = true; }
+				else { score += link_score(p, k, x.y - end, weight); used = true; }
+				if (bestScore <= score) {
+					int open = score;
+					if (start) { const int g = p.W1 + (start - 1) * p.U; open = score + (p.Wl < g ? g : p.Wl); }
+					if (open == bestScore && (!lc || min(W.seqlen, __ldg(W.lengths + t)) == target)) { score = bestScore; done = true; }
+				}
+				x.x = score; x.y = start;
+				W.st[t] = x;
+			}
+			const unsigned nm = __ballot_sync(FULL, isnew);
+			if (isnew) dst[1 + n + __popc(nm & lt)] = t;
+			n += __popc(nm);
+		}
+		used = __any_sync(FULL, used);
+		done = __any_sync(FULL, done);
+		if (used && lane == 0) V.score[node] = 0;
+		if (done) { more = false; prev = node; }
+		__syncwarp();
+	}
+	int j = 0;
+	for (int base = 0; base < n; base += 32) {
+		const int i = base + (int)lane;
+		bool keep = false;
+		int t = 0;
+		if (i < n) {
+			t = dst[1 + i];
+			const int4 x = W.st[t];
+			bool ok = proxiScore <= (double)x.x;   // proxiTestBestScore / ...ScoreLen (kmeranker.c:49-55)
+			if (lc && !ok) ok = __dmul_rn(__ddiv_rn(proxiScore, (double)target), (double)min(W.seqlen, __ldg(W.lengths + t))) <= (double)x.x;
+			keep = x.z == 0 && ok;
+			W.st[t] = make_int4(0, 0, 0, 0);
+		}
+		const unsigned m = __ballot_sync(FULL, keep);
+		__syncwarp();
+		if (keep) dst[1 + j + __popc(m & lt)] = t;
+		j += __popc(m);
+		__syncwarp();
+	}
+	*count = j;
+	return prev;
 }
 
 // getBestAnkerScore (kmeranker.c:398) as an array reduction: the LAST anker with the largest non-zero score,
@@ -498,9 +579,12 @@ __device__ __noinline__ int tie_anker(const Ank &V, int stop, int src, int bestS
 	return -1;
 }
 
-// chooseChain (kmeranker.c:512-592), proxi == 1.0
-__device__ __noinline__ int choose_chain(int fscore, int fend, int rscore, int rend, int cs, int cs_r, double coverT, int *Start, int *Len) {
-	int rc = rscore < fscore ? 1 : fscore < rscore ? 2 : 3, start, end;
+// chooseChain (kmeranker.c:512-592); proxi == 1.0: off
+__device__ __noinline__ int choose_chain(int fscore, int fend, int rscore, int rend, int cs, int cs_r, double coverT, double proxi, int *Start, int *Len) {
+	int rc, start, end;
+	if (proxi == 1.0) rc = rscore < fscore ? 1 : fscore < rscore ? 2 : 3;
+	else if (rscore <= fscore) rc = (__dmul_rn(proxi, (double)fscore) <= (double)rscore) ? 3 : 1;   // the other strand within the proximity
+	else rc = (__dmul_rn(proxi, (double)rscore) <= (double)fscore) ? 3 : 2;
 	if (rc == 1) { start = cs; end = fend; }
 	else if (rc == 2) { start = cs_r; end = rend; }
 	else if (fend < cs_r) { start = cs; end = fend; rc = 1; }
@@ -724,7 +808,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 				cs[0] = W.V[0].start[max(tmp, 0)];
 				tmp = chain_templates(hv, p, W, 1, bIdx[1], W.bt[1], &btN[1], &err); if (err) break;
 				cs[1] = W.V[1].start[max(tmp, 0)];
-				rcm = choose_chain(scF, W.V[0].end[bIdx[0]], scR, W.V[1].end[bIdx[1]], cs[0], cs[1], p.coverT, &start, &len);
+				rcm = choose_chain(scF, W.V[0].end[bIdx[0]], scR, W.V[1].end[bIdx[1]], cs[0], cs[1], p.coverT, p.proxi, &start, &len);
 			}
 			if (len < p.minlen || max(scF, scR) < k) break;
 
@@ -851,7 +935,7 @@ chain_kernel(KgHashView hv, ChainParams p, const int32_t *__restrict__ lengths, 
 				if (bIdx[0] < 0 && bIdx[1] < 0) break;
 				if (bIdx[0] >= 0 && bIdx[1] >= 0)
 					rcm = choose_chain(W.V[0].score[bIdx[0]], W.V[0].end[bIdx[0]], W.V[1].score[bIdx[1]], W.V[1].end[bIdx[1]],
-					                   cs[0], cs[1], p.coverT, &start, &len);
+					                   cs[0], cs[1], p.coverT, p.proxi, &start, &len);
 				else if (bIdx[0] >= 0) { rcm = 1; start = cs[0]; len = W.V[0].end[bIdx[0]] - start; }
 				else { rcm = 2; start = cs[1]; len = W.V[1].end[bIdx[1]] - start; }
 			}
@@ -971,6 +1055,8 @@ int kg_chain_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *sta
 	cp.M = prm->M; cp.MM = prm->MM; cp.U = prm->U; cp.W1 = prm->W1; cp.Wl = prm->Wl; cp.exhaustive = prm->exhaustive;
 	cp.minlen = prm->minlen; cp.mrs = prm->scoreT; cp.coverT = prm->coverT; cp.mrc = prm->mrc;
 	cp.lc = prm->lc != 0;
+	cp.proxi = fabs(prm->minFrac);   // stage 2 sees |minFrac| (kma.c:1605)
+	cp.use_proxi = cp.proxi != 1.0;
 
 	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	if (b.d_res.reserve(sizeof(ChainRes) * (size_t)n) || b.d_recoff.reserve(4 * (size_t)(2 * n + 2)) ||

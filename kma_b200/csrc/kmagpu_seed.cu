@@ -47,7 +47,12 @@ struct MateRes { uint32_t off_f, off_r; int32_t n_f, n_r, hits, scanned; };
 
 struct SeedParams {
 	int32_t M, MM, U, W1, exhaustive;
+	int32_t use_proxi;   // -proxi (kma.c:702-718): getMatch = getProxiMatch (savekmers.c:296) instead of getBestMatch
+	double proxi;        // |minFrac| as save_kmers_batch hands it on (kmers.c:133-141)
 };
+
+// proxiScore = minFrac * bestScore, truncated into an int as the reference's assignment does
+__device__ __forceinline__ int proxi_of(double f, int best) { return __double2int_rz(__dmul_rn(f, (double)best)); }
 
 // score of a hit that resumes template bookkeeping after `gaps` missed k-mer positions.
 // run == true : contribution to the run score of an unchanged template list (savekmers.c:2529-2569)
@@ -395,12 +400,14 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 		*list_off = (uint32_t)po;
 		return nhits;
 	}
-	// arg-max set in first-seen order (getBestMatch, savekmers.c:273-294), negatives clamp to 0
+	// arg-max set in first-seen order (getBestMatch, savekmers.c:273-294), negatives clamp to 0; under -proxi every
+	// template whose raw score reaches minFrac * best (getProxiMatch, savekmers.c:296-340)
 	int best = 0;
 #pragma unroll 1
 	for (int i = lane; i < st.ncand; i += 32) best = max(best, st.score[st.cand[i]]);
 #pragma unroll
 	for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+	const int thr = p.use_proxi ? proxi_of(p.proxi, best) : 0;
 	int nb = 0;
 #pragma unroll 1
 	for (int base = 0; base < st.ncand; base += 32) {
@@ -409,7 +416,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 		int t = 0;
 		if (i < st.ncand) {
 			int s = st.cand[i];
-			ok = max(st.score[s], 0) == best;
+			ok = p.use_proxi ? thr <= st.score[s] : max(st.score[s], 0) == best;
 			t = st.tmpl_of(s);
 			if (DENSE) { st.score[s] = 0; st.ext[s] = 0; st.incl[s] = 0; }
 		}
@@ -622,7 +629,8 @@ __device__ __forceinline__ int list_score(const int2 *L, int n, int t) {   // Sc
 // printPair's record order (ankers.c:150). Slot r / r+1 of res + recsize describe the first / second record emitted.
 __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ rec_off, int nrec,
 		const uint8_t *__restrict__ kinds, const MateRes *__restrict__ mates, const int2 *__restrict__ pool2, int32_t *pool,
-		unsigned long long pool_cap, unsigned long long *ctr, SeedRes *res, uint32_t *recsize, int k, int PE, int apm) {
+		unsigned long long pool_cap, unsigned long long *ctr, SeedRes *res, uint32_t *recsize, int k, int PE, int apm,
+		int use_proxi, double pf) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= nrec || kinds[r] != 1) return;
 	// a strand list that did not fit the pool was never written and its offset points past the allocation: the host
@@ -645,8 +653,21 @@ __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_
 		// save_kmers_unionPair (savekmers.c:3367-3570, the default pairing) with getF_Best (:1648) / getR_Best (:1682):
 		// each mate keeps its arg-max set; the pair is proper when a template of the first mate's set is also among
 		// the second mate's best on the opposite strand
+		// getF_Best / getR_Best keep the arg-max set; getF_Proxi (:1764) / getR_Proxi (:1825) every template within minFrac of it
+		int thr2 = 0;   // the second mate's proximity score (the union test needs it)
 		auto argmax = [&](const int2 *F, int nf, const int2 *R, int nr, int32_t *dst, int *cnt) {
 			int b = 0, h = 0;
+			if (use_proxi) {
+				for (int i = 0; i < nf + nr; ++i) b = max(b, i < nf ? F[i].y : R[i - nf].y);
+				const int thr = proxi_of(pf, b);
+				for (int i = 0; i < nf + nr; ++i) {
+					const int t = i < nf ? F[i].x : -R[i - nf].x, sc = i < nf ? F[i].y : R[i - nf].y;
+					if (thr <= sc) dst[h++] = t;
+				}
+				thr2 = thr;
+				*cnt = h;
+				return b;
+			}
 			for (int i = 0; i < nf + nr; ++i) {
 				const int t = i < nf ? F[i].x : -R[i - nf].x, sc = i < nf ? F[i].y : R[i - nf].y;
 				if (b < sc) { b = sc; h = 1; dst[0] = t; }
@@ -663,7 +684,16 @@ __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_
 			if (best) {
 				best_r = argmax(F2, B.n_f, R2, B.n_r, bt, &nbt);
 				int hits = 0;
-				if (best_r) {
+				if (use_proxi) {   // getR_Proxi's union: templates of the first set the second mate keeps (with a score) on the opposite strand
+					for (int i = 0; i < nrt; ++i) {
+						const int t = rt[i];
+						const int sc = 0 < t ? list_score(R2, B.n_r, t) : list_score(F2, B.n_f, -t);
+						if (sc && thr2 <= sc) {
+							const int tmp = rt[hits]; rt[hits] = rt[i]; rt[i] = tmp;
+							++hits;
+						}
+					}
+				} else if (best_r) {
 					for (int i = 0; i < nrt; ++i) {
 						const int t = rt[i];
 						if ((0 < t ? list_score(R2, B.n_r, t) : list_score(F2, B.n_f, -t)) == best_r) {
@@ -730,6 +760,34 @@ __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_
 			for (int i = 0; i < B.n_f; ++i) { bt[nbt++] = F2[i].x; best_r = max(best_r, F2[i].y); }
 			for (int i = 0; i < B.n_r; ++i) { bt[nbt++] = -R2[i].x; best_r = max(best_r, R2[i].y); }
 			int hits = 0;
+			if (use_proxi) {   // getSecondProxiPen (savekmers.c:1514-1646)
+				if (best_r) {
+					int comp = 0;
+					for (int i = 0; i < nrt; ++i) {
+						const int t = rt[i];
+						int sc = 0 < t ? list_score(R2, B.n_r, t) : list_score(F2, B.n_f, -t);
+						if (0 < sc) { sc += i < A.n_f ? F1[i].y : R1[i - A.n_f].y; comp = max(comp, sc); }
+					}
+					if (best + best_r - PE <= comp) {
+						const int thr = proxi_of(pf, comp);
+						for (int i = 0; i < nrt; ++i) {
+							const int t = rt[i];
+							int sc = 0 < t ? list_score(R2, B.n_r, t) : list_score(F2, B.n_f, -t);
+							if (0 < sc) { sc += i < A.n_f ? F1[i].y : R1[i - A.n_f].y; if (thr <= sc) rt[hits++] = t; }
+						}
+					}
+				}
+				if (hits) { proper = true; nrt = hits; }
+				else {
+					int thr = proxi_of(pf, best);
+					for (int i = 0; i < nrt; ++i) if (thr <= (i < A.n_f ? F1[i].y : R1[i - A.n_f].y)) rt[hits++] = rt[i];
+					nrt = hits;
+					hits = 0;
+					thr = proxi_of(pf, best_r);
+					for (int i = 0; i < nbt; ++i) if (thr <= (i < B.n_f ? F2[i].y : R2[i - B.n_f].y)) bt[hits++] = bt[i];
+					nbt = hits;
+				}
+			} else {
 			if (best_r) {
 				int comp = max(0, best + best_r - PE);
 				for (int i = 0; i < nrt; ++i) {
@@ -753,6 +811,15 @@ __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_
 					else if (best_r <= R2[i - B.n_f].y) bt[hits++] = t;
 				}
 				nbt = hits;
+			}
+			}
+		} else if (use_proxi) {   // getF_Proxi on the second mate alone
+			nrt = 0;
+			for (int i = 0; i < n2; ++i) best_r = max(best_r, i < B.n_f ? F2[i].y : R2[i - B.n_f].y);
+			const int thr = proxi_of(pf, best_r);
+			for (int i = 0; i < n2; ++i) {
+				const int t = i < B.n_f ? F2[i].x : -R2[i - B.n_f].x, sc = i < B.n_f ? F2[i].y : R2[i - B.n_f].y;
+				if (thr <= sc) rt[nrt++] = t;
 			}
 		} else {          // getF_Best: arg-max set of the second mate alone (written where regionTemplates is expected)
 			nrt = 0;
@@ -975,7 +1042,9 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 	}
 	if (prm->kmerscan == 1 && !all_pairs) return kg_chain_run(db, prm, stats);
 	if (prm->kmerscan != 0 && prm->kmerscan != 1) { kmagpu_set_error("kmerscan %d: only save_kmers (0) and save_kmers_chain (1) are built", prm->kmerscan); return -1; }
-	SeedParams sp = {prm->M, prm->MM, prm->U, prm->W1, prm->exhaustive};
+	SeedParams sp = {prm->M, prm->MM, prm->U, prm->W1, prm->exhaustive, 0, 1.0};
+	sp.proxi = fabs(prm->minFrac);       // stage 2 sees |minFrac| (kma.c:1605, kmers.c:133-141); the sign is stage 3's (soft proximity)
+	sp.use_proxi = sp.proxi != 1.0;
 	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	if (b.pool_cap < (size_t)n * 16 + 1024) b.pool_cap = (size_t)n * 16 + 1024;
 	if (b.d_res.reserve(sizeof(SeedRes) * (size_t)n) || b.d_recoff.reserve(4 * (size_t)(2 * n + 2)) ||
@@ -1028,7 +1097,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 		if (pe) {
 			pair_select_kernel<<<(n + 127) / 128, 128, 0, db->stream>>>((const uint8_t *)b.d_in.p, (const uint32_t *)b.d_off.p, n, kinds,
 				(const MateRes *)b.d_mates.p, (const int2 *)b.d_pool2.p, (int32_t *)b.d_pool.p, (unsigned long long)b.pool_cap, ctr,
-				(SeedRes *)b.d_res.p, recsize, db->hv.kmersize, prm->PE, prm->apm);
+				(SeedRes *)b.d_res.p, recsize, db->hv.kmersize, prm->PE, prm->apm, sp.use_proxi, sp.proxi);
 			++launches;
 		}
 		KG_CUDA(cudaEventRecord(db->ev[3], db->stream));

@@ -49,6 +49,7 @@ int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const 
                      int32_t **cand_out, size_t *cand_rows, int64_t *nw_cells);
 int orc_trace_stream(orc_db *db, const char *prefix, const orc_params *p, const uint8_t *in, size_t in_bytes, int one2one,
                      double scoreT, int mq, int minlen, double mrc, uint8_t **out, size_t *out_bytes);
+void orc_align_set_minfrac(double minFrac);   /* -proxi as stage 3 sees it (update_Scores*, alnFrags*PE), default 1.0 */
 void orc_trace_set_ts(int ts);   /* -ts of the traceback pass (trimSeeds, chain.c:496), default 0 */
 int orc_matrix_stream(const int32_t *lengths, int DB_size, const uint8_t *frags, size_t fb, const uint8_t *trace, size_t tb,
                       int dense, uint16_t *counts);

@@ -865,6 +865,9 @@ static aln_t nw_auto_str(const orc_params *p, nw_ws *w, const uint64_t *tseq, co
 
 /* KMA (align.c:214-507): seed, chain, stitch -- with the aligned rows. tb->a receives t/s/q, tb->len columns. */
 /* -ts (trimSeeds, chain.c:496-538; called by KMA only, align.c:413) */
+static double g_min_frac = 1.0;
+void orc_align_set_minfrac(double f) { g_min_frac = f; }   /* minFrac of -proxi as runKMA hands it to the alignment threads (kma.c:1622, runkma.c:351) */
+
 static int g_trim_seeds = 0;
 void orc_trace_set_ts(int ts) { g_trim_seeds = ts; }
 
@@ -883,13 +886,14 @@ static aln_t kma_trace(const orc_params *p, nw_ws *w, const tindex *ix, const ui
 	/* trimSeeds (chain.c:496-538): the first ts bases of every seed of the chain go back to the DP (all but one base of a
 	 * seed shorter than ts); the first seed keeps its start when it begins at the query start */
 	if (g_trim_seeds) {
-		int c = start;
-		if (!pt->qStart[c]) c = pt->next[c];
-		for (; c; c = pt->next[c]) {
+		int c = start, go = 1;   /* MEM 0 is a valid chain start: only next[] == 0 ends the walk (do ... while, chain.c:509-524) */
+		if (!pt->qStart[c]) { c = pt->next[c]; go = c != 0; }
+		while (go) {
 			int len = pt->qEnd[c] - pt->qStart[c];
 			const int cut = len < g_trim_seeds ? len - 1 : g_trim_seeds;
 			pt->tStart[c] += cut; pt->qStart[c] += cut;
-			if (!pt->next[c]) break;
+			c = pt->next[c];
+			go = c != 0;
 		}
 	}
 
@@ -1114,7 +1118,7 @@ int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const 
 			if (rc_flag < 0) { fprintf(stderr, "orc_align_stream: strand-undecided pairs are not produced by -apm p\n"); return -2; }
 			if (k <= m1.q_len && k <= m2.q_len) {
 				int *bT = calloc((size_t)nt2 + 2, 4), *bTr = calloc((size_t)nt2 + 2, 4), *bS2 = calloc((size_t)nt2 + 2, 4), *bE2 = calloc((size_t)nt2 + 2, 4);
-				align_pe(p, &ws, &pt, tix, db, k, &m1, &m2, mt, nt2, scoreT, mq, minlen, mrc, 1.0, bT, bTr, bS2, bE2, &frag, as, uas,
+				align_pe(p, &ws, &pt, tix, db, k, &m1, &m2, mt, nt2, scoreT, mq, minlen, mrc, g_min_frac, bT, bTr, bS2, bE2, &frag, as, uas,
 				         cand_out ? &cand : 0, ridx);
 				free(bT); free(bTr); free(bS2); free(bE2);
 			}
@@ -1162,13 +1166,17 @@ int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const 
 			}
 		}
 		/* note: a reverse-strand record (rc_flag < 0 path absent) aligns the strand stage 2 wrote: qf */
-		if (best_read > k) {   /* update_Scores, minFrac == 1.0 */
+		if (best_read > k) {   /* update_Scores (updatescores.c:203-298), its three minFrac branches */
 			int kept = 0;
+			const double mf = g_min_frac < 0 ? -g_min_frac : g_min_frac;
+			const double minScoreP = mf * bestScore, minFracP = mf * best_read;
 			for (int i = 0; i < hits; ++i) {
-				double minScore = Sc[i] / Ln[i];
-				if (minScore == bestScore || Sc[i] == best_read) {
+				int keep;
+				if (g_min_frac == 1.0) { double minScore = Sc[i] / Ln[i]; keep = minScore == bestScore || Sc[i] == best_read; }
+				else keep = (Ln[i] * minScoreP <= Sc[i]) || minFracP <= Sc[i];
+				if (keep) {
 					bT[kept] = bT[i]; bS[kept] = bS[i]; bE[kept] = bE[i]; ++kept;
-					as[abs(bT[kept - 1])] += Sc[i];
+					as[abs(bT[kept - 1])] += (g_min_frac == 1.0 || g_min_frac < 0) ? Sc[i] : best_read;
 				}
 			}
 			if (kept == 1) uas[abs(bT[0])] += best_read;

@@ -349,11 +349,13 @@ int main(int argc, char **argv) {
 	int one2one = 0, exhaustive = 0, ts = 0;
 	const char *cand_path = 0;
 	int nthreads = 1;
+	double min_frac = 1.0;
 	for (int a = 5; a < argc; ++a) {
 		if (!strcmp(argv[a], "-1t1")) one2one = 1;
 		else if (!strcmp(argv[a], "-apm-p")) alnFragsPE = &alnFragsPenaltyPE;   /* kma.c:458: -apm p */
 		else if (!strcmp(argv[a], "-apm-u")) alnFragsPE = &alnFragsUnionPE;     /* kma.c:460: -apm u (the default) */
 		else if (!strcmp(argv[a], "-t") && a + 1 < argc) nthreads = atoi(argv[++a]);
+		else if (!strcmp(argv[a], "-mf") && a + 1 < argc) min_frac = strtod(argv[++a], 0);   /* minFrac of -proxi as runKMA gets it (kma.c:1622) */
 		else cand_path = argv[a];
 	}
 	if (nthreads < 1) nthreads = 1;
@@ -418,7 +420,7 @@ int main(int argc, char **argv) {
 				} else { t->qseq_comp = qc; t->qseq_r_comp = qrc; t->NWmatrices = NWm; t->points = points; }
 				t->qseq = setQseqs(1024); t->qseq_r = setQseqs(1024); t->header = setQseqs(256); t->header_r = setQseqs(256);
 				t->kmersize = kmersize; t->minlen = 16; t->mq = 0; t->sam = 0;
-				t->scoreT = 0.5; t->mrc = 0.0; t->minFrac = 1.0;
+				t->scoreT = 0.5; t->mrc = 0.0; t->minFrac = min_frac;
 				t->template_lengths = template_lengths; t->templates_index = templates_index;
 				if (ti) pthread_create(&tid[ti], 0, &alnFrags_threaded, t); else first = t;
 			}

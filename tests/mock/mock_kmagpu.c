@@ -59,6 +59,7 @@ int kmagpu_seed_batch(kmagpu_db *db, const kmagpu_params *p, const void *stage1,
 	to_orc(p, &o);
 	memset(&st, 0, sizeof(st));
 	orc_chain_set_lc(p->lc);
+	orc_set_proxi(p->minFrac);
 	/* save_kmers_chain only sees single reads, pairs always go through save_kmers_pair (savekmers.c:196-199) */
 	n = (p->kmerscan && nbytes >= 16 && ((const int *)stage1)[3] >= 0) ? orc_chain_stream(db->o, &o, stage1, nbytes, p->minlen, p->scoreT, p->coverT, p->mrc, out, cap, &st)
 	                : orc_seed_stream(db->o, &o, stage1, nbytes, out, cap, &st);
@@ -85,6 +86,7 @@ int kmagpu_align_batch(kmagpu_db *db, const kmagpu_params *p, const void *stage2
 	int i;
 	(void)cand_out; (void)cand_cap; (void)cand_rows; (void)stats;
 	to_orc(p, &o);
+	orc_align_set_minfrac(p->minFrac);
 	if (orc_align_stream(db->o, db->prefix, &o, stage2, nbytes, p->one2one, p->scoreT, p->mq, p->minlen, p->mrc, &fo, &fb, a, u, 0, 0, 0)) {
 		snprintf(g_err, sizeof(g_err), "oracle alignment pass failed"); return -1;
 	}

@@ -235,6 +235,23 @@ def test_traceback_alignment_vs_oracle(tmp_path, seed, L, sub, indel):
 
 
 @pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed,L,sub,indel,ts", [(32, 150, 0.03, 0.01, 2), (33, 400, 0.05, 0.02, 2), (34, 1000, 0.04, 0.03, 3), (35, 3000, 0.08, 0.06, 2)])
+def test_traceback_alignment_with_seed_trimming(tmp_path, seed, L, sub, indel, ts):
+    """-ts (trimSeeds, chain.c:496-538; the -ont / -ill / -asm presets set 2) vs the reference's own KMA: a chain that starts
+    at MEM 0 is trimmed like any other (only next == 0 ends the walk)"""
+    from tests.test_oracle_trace import make_frags
+    prefix, frags = make_frags(tmp_path, seed, L, sub, indel)
+    want = util.ref_trace(prefix, frags, str(tmp_path), ts=ts)
+    assert util.oracle_trace(prefix, frags, ts=ts) == want and want != util.ref_trace(prefix, frags, str(tmp_path))
+    db = api.TemplateDB(prefix)
+    p = api.default_params()
+    p.ts = ts
+    got, n, st = db.assemble_align_batch(frags, p)
+    db.close()
+    assert got.tobytes() == want
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref not built")
 def test_chunked_pipeline_equals_single_call(tmp_path):
     """MapPipeline (host threads, one library handle + stream each, chunks in turn) == one resident call; pairs are
     never split across chunks"""

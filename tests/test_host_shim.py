@@ -102,6 +102,18 @@ CASES = {
     # -lc with the chain scan: length-corrected anker selection (kma.c:694-700) + runConClave_lc, short and long reads
     "c1_se_lc_chain": dict(reads="se", n=800, args=["-lc", "-matrix"], n_rate=0.005),
     "c3_long_lc": dict(reads="long", n=40, args=["-lc", "-bcNano", "-bc", "0.7"]),
+    # -proxi: proximity scoring in stage 2 (getProxiMatch / getSecondProxiPen / getF_Proxi / getR_Proxi /
+    # getProxiChainTemplates) and the minFrac branches of update_Scores* in stage 3
+    "c1_se_proxi": dict(reads="se", n=800, args=["-1t1", "-proxi", "0.9", "-matrix"]),
+    "c2_pe_proxi_p": dict(reads="pe", n=600, args=["-apm", "p", "-proxi", "-0.9"]),
+    "c2_pe_proxi_u": dict(reads="pe", n=600, args=["-proxi", "0.8", "-1t1"]),
+    "c3_long_proxi": dict(reads="long", n=40, args=["-proxi", "0.9"]),
+    # the reference's presets (kma.c:1100-1240): -ont = chain scan, -lc, -proxi -0.9, -ts 2, -eq 10, -mrs 0.25, -mrc 0.7, -bcNano -bc 0.7;
+    # -ill = -1t1, -lc, -proxi -0.98, -mrc 0.1, -bc 0.9 -bcd 10; -asm = -lc, -proxi -0.9, -ts 2, -bc 0.5, -mrs 0.25, -mrc 0.7
+    "preset_ont": dict(reads="long", n=40, args=["-ont", "-matrix"]),
+    "preset_ill_se": dict(reads="se", n=800, args=["-ill", "-matrix"]),
+    "preset_ill_pe": dict(reads="pe", n=600, args=["-ill"]),
+    "preset_asm": dict(reads="long", n=30, args=["-asm"]),
 }
 
 

@@ -40,6 +40,16 @@ def test_trace_vs_reference(tmp_path, seed, L, sub, indel):
         assert any(b"_" in rows[1] for _, rows in recs)
 
 
+@pytest.mark.parametrize("seed,L,sub,indel,ts", [(32, 150, 0.03, 0.01, 2), (33, 400, 0.05, 0.02, 2), (34, 1000, 0.04, 0.03, 3), (35, 3000, 0.08, 0.06, 2),
+                                                  (36, 600, 0.06, 0.04, 40)])
+def test_trace_with_seed_trimming_vs_reference(tmp_path, seed, L, sub, indel, ts):
+    """-ts: trimSeeds (chain.c:496-538) through the reference's own KMA (ref_harness -trace -ts); seeds shorter than ts keep one base"""
+    prefix, frags = make_frags(tmp_path, seed, L, sub, indel)
+    want = util.ref_trace(prefix, frags, str(tmp_path), ts=ts)
+    assert want != util.ref_trace(prefix, frags, str(tmp_path))
+    assert util.oracle_trace(prefix, frags, ts=ts) == want
+
+
 @pytest.mark.parametrize("seed,L,sub,indel,mode", [(41, 150, 0.02, 0.02, "sparse"), (42, 150, 0.02, 0.02, "dense"),
                                                     (43, 1000, 0.04, 0.04, "sparse"), (44, 1000, 0.04, 0.04, "dense")])
 def test_matrix_counts_vs_reference(tmp_path, seed, L, sub, indel, mode):

@@ -45,8 +45,10 @@ def oracle_params(exhaustive=0, apm=0):
     return p
 
 
-def oracle_seed_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, stats=None, apm=0) -> np.ndarray:
+def oracle_seed_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, stats=None, apm=0, proxi=1.0) -> np.ndarray:
     L = orc()
+    L.orc_set_proxi.argtypes = [C.c_double]
+    L.orc_set_proxi(float(proxi))   # -proxi (kma.c:702-718); 1.0 = off
     db = L.orc_db_open(os.fsencode(db_prefix))
     assert db, f"oracle cannot open {db_prefix}"
     cap = 3 * len(s1) + 4096
@@ -64,9 +66,11 @@ def oracle_seed_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, stats=None,
     return out[:n].copy()
 
 
-def oracle_chain_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, minlen=16, mrs=0.5, coverT=0.1, mrc=0.0, stats=None, lc=0) -> np.ndarray:
+def oracle_chain_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, minlen=16, mrs=0.5, coverT=0.1, mrc=0.0, stats=None, lc=0, proxi=1.0) -> np.ndarray:
     """Stage 2 in chain mode (save_kmers_chain, the default without -1t1); CLI defaults kma.c:309-320. lc = -lc (kma.c:694)."""
     L = orc()
+    L.orc_set_proxi.argtypes = [C.c_double]
+    L.orc_set_proxi(float(proxi))
     L.orc_chain_set_lc(int(lc))
     db = L.orc_db_open(os.fsencode(db_prefix))
     assert db, f"oracle cannot open {db_prefix}"
@@ -121,7 +125,7 @@ def golden_dir():
 REF_ALN = os.path.join(ROOT, "oracle", "_ref", "ref_aln")
 
 
-def ref_align(db_prefix: str, s2: bytes, tmp: str, one2one=True, cand=True, pe=False):
+def ref_align(db_prefix: str, s2: bytes, tmp: str, one2one=True, cand=True, pe=False, min_frac=1.0):
     """Ground truth of the alignment pass from the unmodified reference (oracle/ref_harness.c):
     (frag_raw bytes, alignment_scores, uniq_alignment_scores, cand rows [n, 8] or None)."""
     p = os.path.join(tmp, "s2.bin")
@@ -134,6 +138,8 @@ def ref_align(db_prefix: str, s2: bytes, tmp: str, one2one=True, cand=True, pe=F
         args.append("-1t1")
     if pe:
         args.append("-apm-u" if pe == "u" else "-apm-p")
+    if min_frac != 1.0:
+        args += ["-mf", repr(float(min_frac))]
     r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     frag = open(os.path.join(tmp, "fr.out"), "rb").read()
@@ -144,9 +150,11 @@ def ref_align(db_prefix: str, s2: bytes, tmp: str, one2one=True, cand=True, pe=F
     return frag, arr[:n].copy(), arr[n:2 * n].copy(), c
 
 
-def oracle_align_stream(db_prefix: str, s2: np.ndarray, one2one=True, want_cand=True, apm=0, mq=0):
+def oracle_align_stream(db_prefix: str, s2: np.ndarray, one2one=True, want_cand=True, apm=0, mq=0, min_frac=1.0):
     """(frag_raw bytes, alignment_scores, uniq_alignment_scores, cand rows, nw cells) from the C oracle."""
     L = orc()
+    L.orc_align_set_minfrac.argtypes = [C.c_double]
+    L.orc_align_set_minfrac(float(min_frac))
     L.orc_align_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_int,
                                    C.c_int, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int64)]
@@ -217,13 +225,15 @@ def assembly_records(frag_raw: bytes, zero_every=5, max_hits=2) -> np.ndarray:
     return np.frombuffer(bytes(out), dtype=np.uint8)
 
 
-def ref_trace(db_prefix: str, frags: np.ndarray, tmp: str, one2one=True, matrix=None):
+def ref_trace(db_prefix: str, frags: np.ndarray, tmp: str, one2one=True, matrix=None, ts=0):
     """ground truth of the traceback alignment (assemble_KMA's anker_rc + KMA) from the unmodified reference.
     matrix = "sparse" | "dense": also run the reference's alnToMat / alnToMatDense on every accepted alignment and
     return (trace bytes, {template: uint16 counts[t_len, 6] of the template nodes}, {template: total nodes})."""
     p = os.path.join(tmp, "frags.bin")
     frags.tofile(p)
     args = [REF_ALN, "-trace", db_prefix, p, os.path.join(tmp, "trace.out")] + (["-1t1"] if one2one else [])
+    if ts:
+        args += ["-ts", str(int(ts))]   # trimSeeds (chain.c:496), kma.c:571
     if matrix:
         args += ["-mat", os.path.join(tmp, "mat.out")] + (["-dense"] if matrix == "dense" else [])
     r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
@@ -267,8 +277,9 @@ def oracle_matrix(db_prefix: str, frags: np.ndarray, trace: bytes, dense=False, 
     return counts
 
 
-def oracle_trace(db_prefix: str, frags: np.ndarray, one2one=True) -> bytes:
+def oracle_trace(db_prefix: str, frags: np.ndarray, one2one=True, ts=0) -> bytes:
     L = orc()
+    L.orc_trace_set_ts(int(ts))
     L.orc_trace_stream.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_int,
                                    C.c_int, C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.orc_free.argtypes = [C.c_void_p]
