@@ -41,6 +41,8 @@ int64_t orc_chain_stream(const orc_db *db, const orc_params *p, const uint8_t *i
                          double mrs, double coverT, double mrc, uint8_t *out, size_t cap, orc_stats *st);
 void orc_set_proxi(double minFrac); /* -proxi (kma.c:702-718) of stage 2: getProxiMatch, getSecondProxiPen, getF_Proxi / getR_Proxi, getProxiChainTemplates, chooseChain; 1.0 = off */
 double orc_get_proxi(void);
+void orc_set_soft_proxi(uint64_t *sums);   /* soft proximity sums (kmers.c:133-153, -proxi < 0 with -mem_mode), [DB_size]; NULL = off */
+uint64_t *orc_get_soft_proxi(void);
 void orc_chain_set_lc(int lc);    /* -lc (kma.c:694-700): length-corrected anker selection of save_kmers_chain, default 0 */
 int orc_db_load_seq(orc_db *db, const char *prefix);
 int orc_align_stream(orc_db *db, const char *prefix, const orc_params *p, const uint8_t *in, size_t in_bytes,

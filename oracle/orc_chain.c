@@ -225,7 +225,7 @@ static ank_t *chain_templates_proxi(cctx *c, ank_t *src, ank_t *lo, int *bests, 
 		const int t = bests[i];
 		int ok = proxiScore <= c->score[t];   /* proxiTestBest */
 		if (g_lc && !ok) ok = proxiScore / target_len * (q_len < lengths[t] ? q_len : lengths[t]) <= c->score[t];
-		if (!c->incl[t] && ok) bests[++j] = t;
+		if (!c->incl[t] && ok) { bests[++j] = t; if (orc_get_soft_proxi()) orc_get_soft_proxi()[t] += c->score[t]; }
 		c->score[t] = 0; c->ext[t] = 0; c->incl[t] = 0;
 	}
 	bests[0] = j;

@@ -39,6 +39,12 @@
 static double g_proxi = 1.0;
 void orc_set_proxi(double f) { g_proxi = f < 0 ? -f : f; }
 double orc_get_proxi(void) { return g_proxi; }
+/* soft proximity (-proxi < 0 together with -mem_mode, kmers.c:133-153): every template a get*Proxi* function keeps adds
+ * its score to softProxi[]; save_kmers_batch appends the sums to the stream (6 ints = the first 24 bytes, then DB_size
+ * unsigned longs) and runKMA_MEM takes them for alignment_scores (runkma.c:1153-1156). NULL = off. */
+static uint64_t *g_soft = 0;
+void orc_set_soft_proxi(uint64_t *sums) { g_soft = sums; }
+uint64_t *orc_get_soft_proxi(void) { return g_soft; }
 
 static int rd(FILE *f, void *dst, size_t n) { return fread(dst, 1, n, f) == n ? 0 : -1; }
 
@@ -294,7 +300,7 @@ static int scan_strand(const orc_db *db, const orc_params *p, const uint64_t *se
 		const int proxi = (int)(g_proxi * best);
 		for (int i = 1; i <= cand[0]; ++i) {
 			int t = cand[i];
-			if (proxi <= S->score[t]) cand[++nb] = t;
+			if (proxi <= S->score[t]) { cand[++nb] = t; if (g_soft) g_soft[t] += S->score[t]; }
 			S->score[t] = 0; S->ext[t] = 0; S->incl[t] = 0;
 		}
 		cand[0] = nhits ? nb : 0;
@@ -490,7 +496,7 @@ static int second_proxi_pen(pair_ws *ws, int bestScore, int PE) {
 			const int proxi = (int)(g_proxi * comp);
 			for (int i = 1; i <= ws->rt[0]; ++i) {
 				int t = ws->rt[i], sc = 0 < t ? ws->Score_r[t] : ws->Score[-t];
-				if (0 < sc) { sc += ws->rs[i]; if (proxi <= sc) ws->rt[++hits] = t; }
+				if (0 < sc) { sc += ws->rs[i]; if (proxi <= sc) { ws->rt[++hits] = t; if (g_soft) g_soft[abs(t)] += sc; } }
 			}
 		}
 	}
@@ -505,8 +511,8 @@ static int second_proxi_pen(pair_ws *ws, int bestScore, int PE) {
 		proxi = (int)(g_proxi * best_r);
 		for (int i = 1; i <= ws->bt[0]; ++i) {
 			int t = ws->bt[i];
-			if (0 < t) { if (proxi <= ws->Score[t]) ws->bt[++hits] = t; ws->Score[t] = 0; }
-			else { if (proxi <= ws->Score_r[-t]) ws->bt[++hits] = t; ws->Score_r[-t] = 0; }
+			if (0 < t) { if (proxi <= ws->Score[t]) { ws->bt[++hits] = t; if (g_soft) g_soft[t] += ws->Score[t]; } ws->Score[t] = 0; }
+			else { if (proxi <= ws->Score_r[-t]) { ws->bt[++hits] = t; if (g_soft) g_soft[-t] += ws->Score_r[-t]; } ws->Score_r[-t] = 0; }
 		}
 		ws->bt[0] = hits;
 	}
@@ -521,12 +527,12 @@ static int f_proxi(pair_ws *ws) {
 	const int proxi = (int)(g_proxi * best);
 	for (int i = 1; i <= ws->bt[0]; ++i) {
 		int t = ws->bt[i];
-		if (proxi <= ws->Score[t]) ws->rt[++hits] = t;
+		if (proxi <= ws->Score[t]) { ws->rt[++hits] = t; if (g_soft) g_soft[t] += ws->Score[t]; }
 		ws->Score[t] = 0;
 	}
 	for (int i = 1; i <= ws->bt_r[0]; ++i) {
 		int t = ws->bt_r[i];
-		if (proxi <= ws->Score_r[t]) ws->rt[++hits] = -t;
+		if (proxi <= ws->Score_r[t]) { ws->rt[++hits] = -t; if (g_soft) g_soft[t] += ws->Score_r[t]; }
 		ws->Score_r[t] = 0;
 	}
 	ws->rt[0] = hits;
@@ -543,11 +549,11 @@ static int r_proxi(pair_ws *ws) {
 	const int proxi = (int)(g_proxi * best);
 	for (int i = 1; i <= nf; ++i) {
 		int t = ws->bt[i];
-		if (proxi <= ws->Score[t]) ws->bt[++hits] = t; else ws->Score[t] = 0;
+		if (proxi <= ws->Score[t]) { ws->bt[++hits] = t; if (g_soft) g_soft[t] += ws->Score[t]; } else ws->Score[t] = 0;
 	}
 	for (int i = 1; i <= ws->bt_r[0]; ++i) {
 		int t = ws->bt_r[i];
-		if (proxi <= ws->Score_r[t]) ws->bt[++hits] = -t; else ws->Score_r[t] = 0;
+		if (proxi <= ws->Score_r[t]) { ws->bt[++hits] = -t; if (g_soft) g_soft[t] += ws->Score_r[t]; } else ws->Score_r[t] = 0;
 	}
 	ws->bt[0] = hits;
 	hits = 0;

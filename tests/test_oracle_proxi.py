@@ -95,3 +95,30 @@ def test_proxi_alignment_pass_read_pairs(tmp_path, seed, apm, proxi):
                                                    apm=1 if apm == "u" else 0, min_frac=proxi)
     assert ofrag == frag
     assert np.array_equal(oa, a) and np.array_equal(ou, u)
+
+
+@pytest.mark.parametrize("kind", ["se", "pe_p", "pe_u", "chain", "chain_lc"])
+def test_soft_proximity_sums_of_mem_mode(tmp_path, kind):
+    """-proxi < 0 with -mem_mode: stage 2 gets the negative value (kma.c:1605), every template a get*Proxi* function keeps
+    adds its score to softProxi[], and the sums travel behind the stream (kmers.c:133-153) to become runKMA_MEM's
+    alignment_scores (runkma.c:1153)"""
+    extra = ["-mem_mode", "-proxi", "-0.9", "-s2"]
+    if kind == "se":
+        prefix, s1, _, _ = se_case(tmp_path, 71, 0.9, n=1500)
+        s2 = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-1t1"] + extra, cwd=tmp_path)
+        with util.soft_proxi(prefix) as sp:
+            got = util.oracle_seed_stream(prefix, s1, proxi=0.9).tobytes() + sp.trailer()
+    elif kind in ("pe_p", "pe_u"):
+        apm = kind[-1]
+        prefix, s1, _ = make_pairs(tmp_path, 82, apm=apm)
+        s2 = util.ref_kma(["-ipe", "r1.fq", "r2.fq", "-o", "o", "-t_db", "db", "-apm", apm] + extra, cwd=tmp_path)
+        with util.soft_proxi(prefix) as sp:
+            got = util.oracle_seed_stream(prefix, s1, apm=1 if apm == "u" else 0, proxi=0.9).tobytes() + sp.trailer()
+    else:
+        lc = kind == "chain_lc"
+        prefix, s1, _ = chain_case(tmp_path, 12, 120, 1000, 6000, 0.03, 0.0)
+        s2 = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db"] + extra + (["-lc"] if lc else []), cwd=tmp_path)
+        with util.soft_proxi(prefix) as sp:
+            got = util.oracle_chain_stream(prefix, s1, proxi=0.9, lc=int(lc)).tobytes() + sp.trailer()
+    assert sp.sums.sum() > 0
+    assert got == s2

@@ -90,6 +90,25 @@ def oracle_chain_stream(db_prefix: str, s1: np.ndarray, exhaustive=0, minlen=16,
     return out[:n].copy()
 
 
+class soft_proxi:
+    """context: the oracle's stage 2 adds the soft proximity sums (kmers.c:133-153) into .sums [DB_size] while it is open"""
+    def __init__(self, db_prefix):
+        self.sums = np.zeros(int(np.fromfile(db_prefix + ".length.b", dtype=np.int32, count=1)[0]), dtype=np.uint64)
+
+    def __enter__(self):
+        orc().orc_set_soft_proxi.argtypes = [C.c_void_p]
+        orc().orc_set_soft_proxi(self.sums.ctypes.data)
+        return self
+
+    def __exit__(self, *a):
+        orc().orc_set_soft_proxi(None)
+
+    def trailer(self) -> bytes:
+        """what save_kmers_batch appends to the stream: the first 24 bytes of the sums, then all of them (kmers.c:151-153)"""
+        b = self.sums.tobytes()
+        return b[:24] + b
+
+
 def have_ref() -> bool:
     return os.path.exists(REF_KMA)
 

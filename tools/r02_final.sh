@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU-box call with the round's evidence: every GPU parity test, smoke, both bench arms, the ncu launch list of the bench step,
 # ncu --set full of the dominant kernels of C2 / C3 / C5 / stand-alone NW. usage: bash tools/r02_final.sh <tag>
-tag=${1:-r02_v2}
+tag=${1:-r02_v3}
 mkdir -p gpurun_out
 L=gpurun_out/final_$tag.log; : > $L
 timeout 1500 python -m pytest tests -m gpu -q --timeout 180 2>&1 | tail -3 >> $L
@@ -29,7 +29,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"aln
     -f -o gpurun_out/prof_${tag}_c3 env KG_COUNTERS=0 python tools/c3_perf.py 20000 0 > gpurun_out/ncu_full_${tag}_c3.log 2>&1
 tail -1 gpurun_out/ncu_full_${tag}_c3.log | cut -c1-200 >> $L
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"seed_se_kernel" --launch-skip 2 -c 1 \
-    -f -o gpurun_out/prof_${tag}_c5 python tools/c5_perf.py 1250 10000 4000000 0 > gpurun_out/ncu_full_${tag}_c5.log 2>&1
+    -f -o gpurun_out/prof_${tag}_c5 python tools/c5_perf.py 5000 10000 4000000 0 > gpurun_out/ncu_full_${tag}_c5.log 2>&1
 tail -1 gpurun_out/ncu_full_${tag}_c5.log | cut -c1-200 >> $L
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"nw_warp_kernel" --launch-skip 2 -c 1 \
     -f -o gpurun_out/prof_${tag}_nw python tools/nw_perf.py 24000 > gpurun_out/ncu_full_${tag}_nw.log 2>&1
@@ -42,6 +42,7 @@ for x in c2 c3 c5 nw; do
 done
 ncu -i gpurun_out/prof_${tag}_c2.ncu-rep --page source --csv --print-source sass 2>/dev/null | gzip -9 > gpurun_out/sass_${tag}_c2.csv.gz
 ncu -i gpurun_out/prof_${tag}_c3.ncu-rep --page source --csv --print-source sass 2>/dev/null | gzip -9 > gpurun_out/sass_${tag}_c3.csv.gz
+python tools/merge_traffic.py $tag >> $L 2>&1
 rm -f gpurun_out/prof_${tag}_*.ncu-rep
 du -sh gpurun_out >> $L
 cat $L
