@@ -258,8 +258,12 @@ typedef struct kmagpu_ingest_params {
 	int32_t phred_scale;  /* what getPhredFileBuff (seqparse.c:551) found: 33 or 64 */
 	int32_t minlen;       /* -ml (kma.c:309, default 16) */
 	int32_t maxlen;       /* -xl (kma.c:310, default 2147483647) */
-	int32_t reserved[2];
+	int32_t min_q;        /* -eq (kma.c:617): phredStat's bidirectional trim until the mean error probability is below 10^(-eq/10)
+	                         (runinput.c:196-296); also raises min_phred to it (runinput.c:380). 0 = off */
+	int32_t hardmask_q;   /* -mi (kma.c:608): bases whose RAW quality byte is below it become N (runinput.c:183). 0 = off */
 	uint8_t trans[256];   /* byte -> 0-3 base, 4 N, 8 other, 16 newline */
+	double prob[256];     /* prob[q] = 10^(-q/10), the table the CLI hands to run_input (kma.c:219); read only when min_q or
+	                         hardmask_q is set */
 } kmagpu_ingest_params;
 
 /* Host only: the line structure of a chunk of 4-line FASTQ (fastq != 0) or 2-line FASTA text. fields[i][5] = {header

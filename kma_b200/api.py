@@ -55,7 +55,17 @@ class AlignStats(C.Structure):
 
 class IngestParams(C.Structure):
     _fields_ = [("fastq", C.c_int32), ("paired", C.c_int32), ("min_phred", C.c_int32), ("phred_scale", C.c_int32),
-                ("minlen", C.c_int32), ("maxlen", C.c_int32), ("reserved", C.c_int32 * 2), ("trans", C.c_uint8 * 256)]
+                ("minlen", C.c_int32), ("maxlen", C.c_int32), ("min_q", C.c_int32), ("hardmask_q", C.c_int32), ("trans", C.c_uint8 * 256),
+                ("prob", C.c_double * 256)]
+
+
+def quality_prob() -> np.ndarray:
+    """prob[q], the error probability of phred score q, as the CLI's table holds it (kma.c:219): pow(10, -0.1 * q) written
+    with 32 decimal places and read back (entries below 1e-15 keep fewer than 17 significant digits, and -0.1 * q is not
+    -q / 10: a third of the entries sit one ulp off the correctly rounded value). tests/test_oracle_stage1.py compares
+    the result with the reference's literals. Host glue like to2bit(): the reference passes its own table."""
+    import math
+    return np.array([float("%.32f" % math.pow(10, -0.1 * q)) for q in range(256)], dtype=np.float64)
 
 
 def to2bit() -> np.ndarray:
@@ -289,7 +299,7 @@ class TemplateDB:
 
     # --- stage 1 -----------------------------------------------------------------------------
     def run_input_batch(self, text, fields: np.ndarray, fastq=True, paired=False, min_phred=20, phred_scale=33, minlen=16,
-                        maxlen=2147483647, trans: np.ndarray | None = None, download=True, text2=None):
+                        maxlen=2147483647, trans: np.ndarray | None = None, download=True, text2=None, min_q=0, hardmask_q=0):
         """FASTQ / FASTA text + its line structure (fastx_split) -> stage-1 records (run_input / run_input_PE per read:
         translation, end trim, -ml / -xl, pairing rule, compDNA, printFsa). The stream stays on the device as the input
         of seed_run(); download=False skips the copy back. text2: the second file's chunk of a pair of files (its fields
@@ -297,6 +307,9 @@ class TemplateDB:
         ip = IngestParams()
         ip.fastq, ip.paired, ip.min_phred, ip.phred_scale, ip.minlen, ip.maxlen = int(fastq), int(paired), min_phred, phred_scale, minlen, maxlen
         C.memmove(ip.trans, (to2bit() if trans is None else trans).ctypes.data, 256)
+        ip.min_q, ip.hardmask_q = int(min_q), int(hardmask_q)   # -eq / -mi (phredStat, runinput.c:168-313)
+        if min_q or hardmask_q:
+            C.memmove(ip.prob, quality_prob().ctypes.data, 2048)
         buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
         fields = np.ascontiguousarray(fields, dtype=np.uint32)
         nbytes = int(buf.numel() if hasattr(buf, "numel") else buf.size)
@@ -310,13 +323,16 @@ class TemplateDB:
         return (out[: ob.value] if download else None), cnt.value, ms.value
 
     def run_input_text(self, text, text2=None, fastq=True, min_phred=20, phred_scale=33, minlen=16, maxlen=2147483647,
-                       trans: np.ndarray | None = None, download=True, eof=True):
+                       trans: np.ndarray | None = None, download=True, eof=True, min_q=0, hardmask_q=0):
         """run_input / run_input_PE on chunks of file text with the record splitter on the device as well
         (kmagpu_stage1_text). text2: the second file's chunk (pairs by record index). -> (stage-1 bytes | None, count,
         kernel ms, bytes used of text, bytes used of text2)"""
         ip = IngestParams()
         ip.fastq, ip.paired, ip.min_phred, ip.phred_scale, ip.minlen, ip.maxlen = int(fastq), int(text2 is not None), min_phred, phred_scale, minlen, maxlen
         C.memmove(ip.trans, (to2bit() if trans is None else trans).ctypes.data, 256)
+        ip.min_q, ip.hardmask_q = int(min_q), int(hardmask_q)   # -eq / -mi (phredStat, runinput.c:168-313)
+        if min_q or hardmask_q:
+            C.memmove(ip.prob, quality_prob().ctypes.data, 2048)
         buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
         buf2 = np.frombuffer(text2, dtype=np.uint8) if isinstance(text2, (bytes, bytearray)) else text2
         nb = int(buf.numel() if hasattr(buf, "numel") else buf.size)

@@ -68,6 +68,7 @@ struct SeedBatch {
 struct Stage1Batch {
 	KgBuf d_text, d_fields, d_win, d_u32, d_kind, d_partial, d_ctr, h_ctr;
 	KgBuf d_cnt1, d_cnt2, d_lines1, d_lines2;   // device record splitter: newline counts + offsets per 64-byte block, line ends
+	KgBuf d_prob, h_prob;                       // -eq / -mi: prob[] shifted by the phred scale + 10^(-eq/10) (device, pinned staging)
 };
 
 // working buffers of the traceback pass (kmagpu_trace_batch / kmagpu_trace_from_conclave), kept across calls

@@ -1,7 +1,8 @@
 // Stage 1 on the device: what run_input / run_input_PE (runinput.c:370-560) do per read between the record splitter
 // (FileBuffgetFq seqparse.c:241 / FileBuffgetFsa) and the stage-1 pipe -- base translation through the caller's `trans`
-// table (to2Bit, kma.c:1439-1482), phredStat's end trim in its default branch (runinput.c:127-167, -mp) or fsastat's
-// N trim (runinput.c:315-368), the -ml / -xl filters, the pairing rule of run_input_PE (runinput.c:528-539), compDNA
+// table (to2Bit, kma.c:1439-1482), phredStat (runinput.c:127-313: the -mp end trim; with -eq / -mi also the hard mask and
+// the bidirectional quality trim, a sequential walk with double sums that one lane runs per read) or fsastat's N trim
+// (runinput.c:315-368), the -ml / -xl filters, the pairing rule of run_input_PE (runinput.c:528-539), compDNA
 // (compdna.c:99-127) and the records of printFsa / printFsa_pair (runinput.c:765-825).
 //
 // The host keeps the one sequential step, finding the line ends (kmagpu_fastx_split, memchr speed); the raw text goes
@@ -22,7 +23,7 @@ struct S1Tab { uint8_t t[256]; };
 
 // fields[r] = {header offset, header length, sequence offset, sequence length, quality offset}
 __global__ void __launch_bounds__(256) s1_window_kernel(const uint8_t *__restrict__ text, const uint32_t *__restrict__ fields, int n, S1Tab tab,
-		int fastq, int thr, int maxlen, S1Win *win) {
+		int fastq, int thr, int maxlen, S1Win *win, int minQ, int maskQ, int minlen, const double *__restrict__ probtab) {
 	__shared__ uint8_t tr[256];
 	tr[threadIdx.x] = tab.t[threadIdx.x];
 	__syncthreads();
@@ -54,7 +55,43 @@ __global__ void __launch_bounds__(256) s1_window_kernel(const uint8_t *__restric
 				nN += __popc(__ballot_sync(0xffffffffu, i < end && tr[seq[i]] == 4));
 			}
 		}
-		if (lane == 0) { S1Win w = {start, end, nN, fastq ? end - start : end - start - nN}; win[r] = w; }
+		int klen = fastq ? end - start : end - start - nN;
+		if (fastq && (minQ | maskQ) && len <= maxlen) {
+			// the -mi / -eq part of phredStat (runinput.c:168-313) on the end-trimmed window: sums of doubles in the reference's
+			// order, so one lane walks it (a rare option; the warp's other lanes wait)
+			if (lane == 0) {
+				const double *prob = probtab;   // already shifted by the phred scale
+#define S1_ISN(i) (tr[seq[i]] == 4 || (int)qual[i] < maskQ)
+				int s = start, e = end, L = e - s, ns = 0;
+				double sp = 0;
+				for (int i = s; i < e; ++i) { sp = __dadd_rn(sp, prob[qual[i]]); ns += S1_ISN(i); }
+				const double minP = prob[256];   // pow(10, -0.1 * minQ) from the host's libm
+				if (minlen <= L - ns && __dmul_rn(minP, (double)L) < sp) {
+					int ns5 = 0, ns3 = 0, l5 = 0, l3 = 0, p5 = s, p3 = e - 1;
+					double sp5 = 0, sp3 = 0;
+					while (l3 < L && thr <= (int)qual[p3]) { sp3 = __dadd_rn(sp3, prob[qual[p3]]); ++l3; ns3 += S1_ISN(p3); --p3; }
+					while (l3 < L && (int)qual[p3] < thr) { sp3 = __dadd_rn(sp3, prob[qual[p3]]); ++l3; ns3 += S1_ISN(p3); --p3; }
+					while (minlen <= L - ns && __dmul_rn(minP, (double)L) < sp) {
+						if (__dmul_rn(sp5, (double)l3) < __dmul_rn(sp3, (double)l5)) {
+							e -= l3; ns -= ns3; L -= l3; sp = __dsub_rn(sp, sp3);
+							ns3 = 0; l3 = 0; sp3 = 0;
+							while (l3 < L && thr <= (int)qual[p3]) { sp3 = __dadd_rn(sp3, prob[qual[p3]]); ++l3; ns3 += S1_ISN(p3); --p3; }
+							while (l3 < L && (int)qual[p3] < thr) { sp3 = __dadd_rn(sp3, prob[qual[p3]]); ++l3; ns3 += S1_ISN(p3); --p3; }
+						} else {
+							s += l5; L -= l5; ns -= ns5; sp = __dsub_rn(sp, sp5);
+							ns5 = 0; l5 = 0; sp5 = 0;
+							while (l5 < L && thr <= (int)qual[p5]) { sp5 = __dadd_rn(sp5, prob[qual[p5]]); ++l5; ns5 += S1_ISN(p5); ++p5; }
+							while (l5 < L && (int)qual[p5] < thr) { sp5 = __dadd_rn(sp5, prob[qual[p5]]); ++l5; ns5 += S1_ISN(p5); ++p5; }
+						}
+					}
+				}
+#undef S1_ISN
+				start = s; end = e; nN = ns; klen = L - ns;
+			}
+			start = __shfl_sync(0xffffffffu, start, 0); end = __shfl_sync(0xffffffffu, end, 0);
+			nN = __shfl_sync(0xffffffffu, nN, 0); klen = __shfl_sync(0xffffffffu, klen, 0);
+		}
+		if (lane == 0) { S1Win w = {start, end, nN, klen}; win[r] = w; }
 	}
 }
 
@@ -94,7 +131,7 @@ __device__ __forceinline__ void s1_store_u64(uint8_t *p, unsigned long long v) {
 // one warp per kept read: compDNA + printFsa
 __global__ void __launch_bounds__(256) s1_emit_kernel(const uint8_t *__restrict__ text, const uint32_t *__restrict__ fields, const S1Win *__restrict__ win,
 		int n, S1Tab tab, const uint32_t *__restrict__ size, const uint32_t *__restrict__ boff, const uint32_t *__restrict__ ridx,
-		const uint8_t *__restrict__ kind, uint8_t *out, uint32_t *rec_off, uint8_t *rec_kind) {
+		const uint8_t *__restrict__ kind, uint8_t *out, uint32_t *rec_off, uint8_t *rec_kind, int maskQ) {
 	__shared__ uint8_t tr[256];
 	tr[threadIdx.x] = tab.t[threadIdx.x];
 	__syncthreads();
@@ -105,6 +142,7 @@ __global__ void __launch_bounds__(256) s1_emit_kernel(const uint8_t *__restrict_
 		const uint32_t *f = fields + 5 * (size_t)r;
 		const S1Win w = win[r];
 		const uint8_t *seq = text + f[2] + w.start, *hdr = text + f[0];
+		const uint8_t *qual = text + f[4] + w.start;   // read only under -mi (FASTQ)
 		const int L = w.end - w.start, words = (L + 31) >> 5, hl = (int)f[1] + 1;
 		uint8_t *o = out + boff[r];
 		if (lane == 0) {
@@ -117,7 +155,7 @@ __global__ void __launch_bounds__(256) s1_emit_kernel(const uint8_t *__restrict_
 		for (int wd = 0; wd < words; ++wd) {
 			const int i = 32 * wd + (int)lane;
 			const unsigned c = i < L ? tr[seq[i]] : 0u;
-			const bool isN = c == 4u;
+			const bool isN = c == 4u || (maskQ && i < L && (int)qual[i] < maskQ);   // hard mask: runinput.c:183
 			// (word << 2) | base for 32 bases = the OR of base << (62 - 2 * lane); an N shifts in zero (compdna.c:113-121)
 			const unsigned long long x = isN ? 0ull : (unsigned long long)c << (62 - 2 * (int)lane);
 			const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(x >> 32)), lo = __reduce_or_sync(0xffffffffu, (unsigned)x);
@@ -211,7 +249,7 @@ extern "C" size_t kmagpu_fastx_sync(const void *text_, size_t nbytes, int fastq,
 int kg_stage1_free(kmagpu_db *db) {
 	Stage1Batch &w = db->s1;
 	KgBuf *all[] = {&w.d_text, &w.d_fields, &w.d_win, &w.d_u32, &w.d_kind, &w.d_partial, &w.d_ctr, &w.h_ctr, &w.d_cnt1, &w.d_cnt2, &w.d_lines1,
-	                &w.d_lines2};
+	                &w.d_lines2, &w.d_prob, &w.h_prob};
 	for (KgBuf *x : all) x->release();
 	return 0;
 }
@@ -230,8 +268,23 @@ static int s1_core(kmagpu_db *db, const kmagpu_ingest_params *ip, int n, void *s
 	S1Tab tab;
 	memcpy(tab.t, ip->trans, 256);
 	const int grid = db->sm_count * 8;
-	s1_window_kernel<<<grid, 256, 0, st>>>((const uint8_t *)w.d_text.p, (const uint32_t *)w.d_fields.p, n, tab, ip->fastq, ip->phred_scale + ip->min_phred,
-		ip->maxlen, (S1Win *)w.d_win.p);
+	// -eq / -mi: phredStat's quality trim needs prob[] shifted by the phred scale (runinput.c:410 passes prob - phredScale)
+	// and 10^(-0.1 * minQ) from the host's libm
+	const bool quality = ip->fastq && (ip->min_q || ip->hardmask_q);
+	const int min_phred = quality && ip->min_phred < ip->min_q ? ip->min_q : ip->min_phred;   // runinput.c:380
+	const double *d_prob = nullptr;
+	if (quality) {
+		if (ip->phred_scale < 0 || ip->phred_scale > 128) { kmagpu_set_error("phred scale %d", ip->phred_scale); return -1; }
+		w.h_prob.pinned = true;
+		if (w.d_prob.reserve(8 * 260) || w.h_prob.reserve(8 * 260)) return -1;
+		double *hp = (double *)w.h_prob.p;
+		for (int q = 0; q < 256; ++q) hp[q] = q >= ip->phred_scale ? ip->prob[q - ip->phred_scale] : 1.0;   // below the scale the reference reads before its table
+		hp[256] = pow(10, (-0.1) * ip->min_q);
+		KG_CUDA(cudaMemcpyAsync(w.d_prob.p, hp, 8 * 257, cudaMemcpyHostToDevice, st));
+		d_prob = (const double *)w.d_prob.p;
+	}
+	s1_window_kernel<<<grid, 256, 0, st>>>((const uint8_t *)w.d_text.p, (const uint32_t *)w.d_fields.p, n, tab, ip->fastq, ip->phred_scale + min_phred,
+		ip->maxlen, (S1Win *)w.d_win.p, quality ? ip->min_q : 0, quality ? ip->hardmask_q : 0, ip->minlen, d_prob);
 	const int units = ip->paired ? n / 2 : n;
 	s1_decide_kernel<<<(units + 255) / 256, 256, 0, st>>>((const uint32_t *)w.d_fields.p, (const S1Win *)w.d_win.p, n, ip->paired, ip->minlen, size, keep,
 		(uint8_t *)w.d_kind.p, ctr);
@@ -245,7 +298,7 @@ static int s1_core(kmagpu_db *db, const kmagpu_ingest_params *ip, int n, void *s
 	if (ob >= (1ull << 31)) { kmagpu_set_error("stage-1 stream of %zu bytes exceeds the 2 GiB per-call limit of stage 2; split the text", ob); return -1; }
 	if (b.d_in.reserve(ob + 64) || b.d_off.reserve(4 * (nrec + 1)) || b.d_kinds.reserve(nrec + 1)) return -1;
 	s1_emit_kernel<<<grid, 256, 0, st>>>((const uint8_t *)w.d_text.p, (const uint32_t *)w.d_fields.p, (const S1Win *)w.d_win.p, n, tab, size, boff, ridx,
-		(const uint8_t *)w.d_kind.p, (uint8_t *)b.d_in.p, (uint32_t *)b.d_off.p, (uint8_t *)b.d_kinds.p);
+		(const uint8_t *)w.d_kind.p, (uint8_t *)b.d_in.p, (uint32_t *)b.d_off.p, (uint8_t *)b.d_kinds.p, quality ? ip->hardmask_q : 0);
 	h[7] = (unsigned long long)ob;   // the closing offset, from pinned memory
 	KG_CUDA(cudaMemcpyAsync((uint32_t *)b.d_off.p + nrec, &h[7], 4, cudaMemcpyHostToDevice, st));
 	KG_CUDA(cudaMemsetAsync((uint8_t *)b.d_kinds.p + nrec, 0, 1, st));

@@ -136,6 +136,40 @@ def test_text_to_stage2_in_hbm(tmp_path):
 
 
 @gpu
+@pytest.mark.parametrize("seed,kw", [(31, {"min_q": 20}), (32, {"min_q": 25, "min_phred": 10}), (33, {"hardmask_q": 30, "min_phred": 30}),
+                                     (34, {"min_q": 18, "hardmask_q": 28, "min_phred": 28, "minlen": 40}), (35, {"min_q": 30, "min_phred": 35}),
+                                     (36, {"min_q": 12, "min_phred": 0})])
+def test_quality_trim_and_hard_mask(tmp_path, seed, kw):
+    """-eq / -mi: phredStat's bidirectional quality trim and hard mask (runinput.c:168-313) on the device, vs the oracle that
+    tests/test_oracle_stage1.py pins to `kma -s1 -eq / -mi`; single reads through both entry points and read pairs"""
+    rng, names, seqs, reads = _reads(seed, n=900)
+    quals = util.random_quals(rng, reads)
+    for i in range(0, len(reads), 3):
+        L = len(reads[i])
+        if L < 4:
+            continue
+        ramp = np.linspace(40, 2, L) if i % 2 else np.concatenate([np.linspace(3, 40, L // 2), np.linspace(40, 3, L - L // 2)])
+        quals[i] = np.clip(ramp + rng.integers(-6, 7, size=L), 0, 41).astype(np.uint8) + 33
+    text = util.fastq_text(reads, quals)
+    want, wcnt = util.oracle_stage1(text, **kw)
+    plain, _ = util.oracle_stage1(text, **{k: v for k, v in kw.items() if k not in ("min_q", "hardmask_q")})
+    assert want != plain or "min_q" not in kw
+    prefix = util.build_db(tmp_path, names, seqs)
+    db = api.TemplateDB(prefix, device=0)
+    f, _ = api.fastx_split(text)
+    got, cnt, _ = db.run_input_batch(text, f, **kw)
+    assert got.tobytes() == want and cnt == wcnt
+    got, cnt, _, _, _ = db.run_input_text(text, **kw)
+    assert got.tobytes() == want and cnt == wcnt
+    _, _, _, r2 = _reads(seed + 100, n=900)
+    t2 = util.fastq_text(r2, util.random_quals(rng, r2))
+    wpe, cpe = util.oracle_stage1(text, t2, **kw)
+    gpe, gcpe, _, _, _ = db.run_input_text(text, text2=t2, **kw)
+    db.close()
+    assert gpe.tobytes() == wpe and gcpe == cpe
+
+
+@gpu
 @pytest.mark.parametrize("crlf", [False, True])
 def test_device_splitter_vs_oracle(tmp_path, crlf):
     """kmagpu_stage1_text: the record splitter on the device too -- single end, FASTA, pairs, a chunk cut inside a record,

@@ -114,6 +114,12 @@ CASES = {
     "preset_ill_se": dict(reads="se", n=800, args=["-ill", "-matrix"]),
     "preset_ill_pe": dict(reads="pe", n=600, args=["-ill"]),
     "preset_asm": dict(reads="long", n=30, args=["-asm"]),
+    # options that stay in the reference's own host code around the device calls: ConClave version 2 (runConClave2,
+    # conclave.c:386), dense base counts, reference-guided consensus, stage-1 quality filters (-eq / -mi / -mp / -5p)
+    "c1_se_conclave2": dict(reads="se", n=800, args=["-1t1", "-ConClave", "2", "-matrix"]),
+    "c3_long_conclave2_lc": dict(reads="long", n=40, args=["-ConClave", "2", "-lc"]),
+    "c1_se_dense_reffsa": dict(reads="se", n=800, args=["-1t1", "-dense", "-ref_fsa", "-matrix"]),
+    "c1_se_quality_filters": dict(reads="se", n=800, args=["-1t1", "-eq", "15", "-mp", "25", "-mi", "40", "-5p", "3"], n_rate=0.01),
 }
 
 

@@ -67,3 +67,49 @@ def test_paired_end(tmp_path, seed, extra, kw):
     assert got == want
     h = np.frombuffer(want[:16], dtype=np.int32)
     assert cnt > 300 and (np.frombuffer(want, dtype=np.uint8).size > 0) and h[0] > 0
+
+
+def test_quality_table_equals_the_reference_literals():
+    """prob[q] = 10^(-q/10): kma.c:219 holds the table as 32-digit literals, kma_b200.api.quality_prob() computes it"""
+    import os, re
+    from kma_b200 import api
+    src = "/root/reference/kma.c"
+    if not os.path.exists(src):
+        pytest.skip("reference sources not here")
+    m = re.search(r"static const double prob\[256\] = \{([^}]*)\}", open(src).read())
+    lit = np.array([float(x) for x in m.group(1).replace("\n", " ").split(",")], dtype=np.float64)
+    assert len(lit) == 256 and np.array_equal(lit, api.quality_prob())
+
+
+@pytest.mark.parametrize("seed,extra,kw", [(31, ["-eq", "20"], {"min_q": 20}), (32, ["-eq", "25", "-mp", "10"], {"min_q": 25, "min_phred": 10}),
+                                            (33, ["-mi", "30"], {"hardmask_q": 30, "min_phred": 30}),
+                                            (34, ["-eq", "18", "-mi", "28", "-ml", "40"], {"min_q": 18, "hardmask_q": 28, "min_phred": 28, "minlen": 40}),
+                                            (35, ["-eq", "30", "-mp", "35"], {"min_q": 30, "min_phred": 35})])
+def test_quality_trim_and_hard_mask(tmp_path, seed, extra, kw):
+    """-eq (phredStat's bidirectional trim, runinput.c:196-296) and -mi (hard mask on the raw quality byte, :183; the CLI
+    also raises -mp to it, kma.c:1554, which is all it ever does: a byte that survives the end trim is above it)"""
+    rng, reads = make(tmp_path, seed, n=800)
+    quals = util.random_quals(rng, reads)
+    for i in range(0, len(reads), 3):   # reads whose quality decays towards one or both ends: the segment-wise trim has work to do
+        L = len(reads[i])
+        ramp = np.linspace(40, 2, L) if i % 2 else np.concatenate([np.linspace(3, 40, L // 2), np.linspace(40, 3, L - L // 2)])
+        quals[i] = np.clip(ramp + rng.integers(-6, 7, size=L), 0, 41).astype(np.uint8) + 33
+    text = util.fastq_text(reads, quals)
+    (tmp_path / "r.fq").write_bytes(text)
+    want = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-s1"] + extra, cwd=tmp_path)
+    plain = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-s1"], cwd=tmp_path)
+    got, cnt = util.oracle_stage1(text, **kw)
+    assert want != plain
+    assert got == want
+
+
+def test_quality_trim_paired(tmp_path):
+    rng, r1 = make(tmp_path, 41, n=400)
+    _, r2 = make(tmp_path, 141, n=400)
+    q1, q2 = util.random_quals(rng, r1), util.random_quals(rng, r2)
+    t1, t2 = util.fastq_text(r1, q1), util.fastq_text(r2, q2)
+    (tmp_path / "r1.fq").write_bytes(t1)
+    (tmp_path / "r2.fq").write_bytes(t2)
+    want = util.ref_kma(["-ipe", "r1.fq", "r2.fq", "-o", "o", "-t_db", "db", "-s1", "-eq", "22", "-mi", "25"], cwd=tmp_path)
+    got, _ = util.oracle_stage1(t1, t2, min_q=22, hardmask_q=25, min_phred=25)
+    assert got == want

@@ -531,8 +531,13 @@ def random_quals(rng, reads, scale=33):
     return out
 
 
-def oracle_stage1(text1: bytes, text2: bytes | None = None, fastq=True, min_phred=20, phred_scale=33, minlen=16, maxlen=2147483647):
+def oracle_stage1(text1: bytes, text2: bytes | None = None, fastq=True, min_phred=20, phred_scale=33, minlen=16, maxlen=2147483647,
+                  min_q=0, hardmask_q=0):
     L = orc()
+    from kma_b200 import api as _api
+    prob = _api.quality_prob()
+    L.orc_stage1_set_quality.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    L.orc_stage1_set_quality(int(min_q), int(hardmask_q), prob.ctypes.data)   # -eq / -mi; prob must outlive the call below
     L.orc_stage1.restype = C.c_size_t
     L.orc_stage1.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                              C.c_size_t, C.POINTER(C.c_int64)]
