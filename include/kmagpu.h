@@ -272,6 +272,13 @@ typedef struct kmagpu_ingest_params {
  * (fields = NULL only counts); -1 on malformed input. */
 int64_t kmagpu_fastx_split(const void *text, size_t nbytes, int fastq, const uint8_t *trans, uint32_t *fields, size_t cap, size_t *used);
 
+/* Host only: multi-line FASTA -> the 2-line form kmagpu_fastx_split / kmagpu_stage1_text take. What FileBuffgetFsa
+ * (seqparse.c:66-160) keeps of a record: the header line, and between it and the next '>' every byte `trans` maps below 8
+ * (line ends, '\r' and blanks drop out wherever they stand) as ONE sequence line. Whole records only: *used = the input
+ * bytes consumed (without eof the last record stays, its end is not known yet). Returns the bytes written (out_cap >=
+ * nbytes + 1), -1 on error. */
+int64_t kmagpu_fasta_unwrap(const void *text, size_t nbytes, const uint8_t *trans, int eof, void *out, size_t out_cap, size_t *used);
+
 /* Host only: the start of the first record at or after byte `from` (FASTQ: a line starting with '@' whose second-next
  * line starts with '+'), so that several host threads can run kmagpu_fastx_split on byte ranges of one chunk.
  * Returns nbytes when there is none. */

@@ -79,6 +79,21 @@ def to2bit() -> np.ndarray:
     return t
 
 
+def fasta_unwrap(text, trans: np.ndarray | None = None, eof: bool = True):
+    """host only: multi-line FASTA -> 2-line FASTA as FileBuffgetFsa reads it (seqparse.c:66-160) -> (bytes, input bytes used)"""
+    trans = to2bit() if trans is None else trans
+    buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
+    out = np.empty(len(buf) + 1, dtype=np.uint8)
+    used = C.c_size_t()
+    L = lib()
+    L.kmagpu_fasta_unwrap.restype = C.c_int64
+    L.kmagpu_fasta_unwrap.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    n = L.kmagpu_fasta_unwrap(buf.ctypes.data, len(buf), trans.ctypes.data, int(eof), out.ctypes.data, len(out), C.byref(used))
+    if n < 0:
+        raise KmaGpuError(L.kmagpu_last_error().decode())
+    return out[:n].tobytes(), used.value
+
+
 def fastx_split(text, fastq: bool = True, trans: np.ndarray | None = None):
     """host only: line structure of a FASTQ / FASTA chunk -> (uint32 fields[n, 5], bytes used)"""
     trans = to2bit() if trans is None else trans
@@ -306,10 +321,12 @@ class TemplateDB:
         count their offsets from len(text) on). -> (stage-1 bytes | None, count, kernel ms)"""
         ip = IngestParams()
         ip.fastq, ip.paired, ip.min_phred, ip.phred_scale, ip.minlen, ip.maxlen = int(fastq), int(paired), min_phred, phred_scale, minlen, maxlen
-        C.memmove(ip.trans, (to2bit() if trans is None else trans).ctypes.data, 256)
+        tab = to2bit() if trans is None else np.ascontiguousarray(trans, dtype=np.uint8)   # held in a name while memmove reads it
+        C.memmove(ip.trans, tab.ctypes.data, 256)
         ip.min_q, ip.hardmask_q = int(min_q), int(hardmask_q)   # -eq / -mi (phredStat, runinput.c:168-313)
         if min_q or hardmask_q:
-            C.memmove(ip.prob, quality_prob().ctypes.data, 2048)
+            prob = quality_prob()   # held in a name: the temporary would be gone before memmove reads it
+            C.memmove(ip.prob, prob.ctypes.data, 2048)
         buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
         fields = np.ascontiguousarray(fields, dtype=np.uint32)
         nbytes = int(buf.numel() if hasattr(buf, "numel") else buf.size)
@@ -329,10 +346,12 @@ class TemplateDB:
         kernel ms, bytes used of text, bytes used of text2)"""
         ip = IngestParams()
         ip.fastq, ip.paired, ip.min_phred, ip.phred_scale, ip.minlen, ip.maxlen = int(fastq), int(text2 is not None), min_phred, phred_scale, minlen, maxlen
-        C.memmove(ip.trans, (to2bit() if trans is None else trans).ctypes.data, 256)
+        tab = to2bit() if trans is None else np.ascontiguousarray(trans, dtype=np.uint8)   # held in a name while memmove reads it
+        C.memmove(ip.trans, tab.ctypes.data, 256)
         ip.min_q, ip.hardmask_q = int(min_q), int(hardmask_q)   # -eq / -mi (phredStat, runinput.c:168-313)
         if min_q or hardmask_q:
-            C.memmove(ip.prob, quality_prob().ctypes.data, 2048)
+            prob = quality_prob()   # held in a name: the temporary would be gone before memmove reads it
+            C.memmove(ip.prob, prob.ctypes.data, 2048)
         buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
         buf2 = np.frombuffer(text2, dtype=np.uint8) if isinstance(text2, (bytes, bytearray)) else text2
         nb = int(buf.numel() if hasattr(buf, "numel") else buf.size)

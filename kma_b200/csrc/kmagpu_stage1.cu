@@ -246,6 +246,37 @@ extern "C" size_t kmagpu_fastx_sync(const void *text_, size_t nbytes, int fastq,
 	return nbytes;
 }
 
+// Host only: multi-line FASTA -> the 2-line form the splitters and kernels take. FileBuffgetFsa (seqparse.c:66-160) keeps,
+// between a header line and the next '>', every byte `trans` maps below 8 -- line ends, '\r', blanks and anything else
+// drop out wherever they stand -- so a record becomes its header line as it is plus ONE sequence line of the kept bytes.
+// Whole records only: *used = the bytes consumed (up to the start of the last record unless eof: its end is only known
+// when the next '>' or the end of the file is seen). Returns the bytes written to out (cap >= nbytes + 1), -1 on error.
+extern "C" int64_t kmagpu_fasta_unwrap(const void *text_, size_t nbytes, const uint8_t *trans, int eof, void *out_, size_t cap, size_t *used) {
+	const uint8_t *text = (const uint8_t *)text_;
+	uint8_t *out = (uint8_t *)out_;
+	if (!text || !trans || !out) { kmagpu_set_error("null argument"); return -1; }
+	if (cap < nbytes + 1) { kmagpu_set_error("kmagpu_fasta_unwrap needs %zu output bytes, caller gave %zu", nbytes + 1, cap); return -1; }
+	size_t p = 0, o = 0, done_in = 0, done_out = 0;
+	while (p < nbytes) {
+		if (text[p] != '>') { kmagpu_set_error("malformed FASTA at byte %zu", p); return -1; }
+		const uint8_t *e = (const uint8_t *)memchr(text + p, '\n', nbytes - p);
+		if (!e) break;   // header line not complete
+		const size_t hend = (size_t)(e - text) + 1;
+		memcpy(out + o, text + p, hend - p);
+		o += hend - p;
+		// sequence: up to the next '>' (anywhere, like the reference's byte loop) or the end of the chunk
+		const uint8_t *nx = (const uint8_t *)memchr(text + hend, '>', nbytes - hend);
+		const size_t send = nx ? (size_t)(nx - text) : nbytes;
+		if (!nx && !eof) { o = done_out; break; }   // the record may continue in the next chunk
+		for (size_t i = hend; i < send; ++i) { const uint8_t c = text[i]; if (trans[c] < 8) out[o++] = c; }
+		out[o++] = '\n';
+		p = send;
+		done_in = p; done_out = o;
+	}
+	if (used) *used = done_in;
+	return (int64_t)done_out;
+}
+
 int kg_stage1_free(kmagpu_db *db) {
 	Stage1Batch &w = db->s1;
 	KgBuf *all[] = {&w.d_text, &w.d_fields, &w.d_win, &w.d_u32, &w.d_kind, &w.d_partial, &w.d_ctr, &w.h_ctr, &w.d_cnt1, &w.d_cnt2, &w.d_lines1,

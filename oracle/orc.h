@@ -39,6 +39,7 @@ int64_t orc_seed_stream(const orc_db *db, const orc_params *p, const uint8_t *in
 void orc_default_params(orc_params *p);
 int64_t orc_chain_stream(const orc_db *db, const orc_params *p, const uint8_t *in, size_t in_bytes, int minlen,
                          double mrs, double coverT, double mrc, uint8_t *out, size_t cap, orc_stats *st);
+size_t orc_fasta_unwrap(const uint8_t *text, size_t n, uint8_t *out);   /* multi-line FASTA -> 2-line FASTA as FileBuffgetFsa reads it */
 void orc_stage1_set_quality(int minQ, int hardmaskQ, const double *prob);   /* -eq, -mi and prob[256] = 10^(-q/10) (kma.c:219) of phredStat; 0, 0: off */
 void orc_set_proxi(double minFrac); /* -proxi (kma.c:702-718) of stage 2: getProxiMatch, getSecondProxiPen, getF_Proxi / getR_Proxi, getProxiChainTemplates, chooseChain; 1.0 = off */
 double orc_get_proxi(void);

@@ -140,6 +140,23 @@ static size_t s1_emit(const s1_rec *r, const uint8_t *trans, int start, int end,
 #undef ISN
 }
 
+/* FileBuffgetFsa (seqparse.c:66-160) on multi-line FASTA, restated as a rewrite into 2-line FASTA: the header line as it
+ * is, then every byte up to the next '>' (or the end of the text) that trans maps below 8, as one line. Returns the bytes
+ * written (out holds at least n + 1). */
+size_t orc_fasta_unwrap(const uint8_t *text, size_t n, uint8_t *out) {
+	uint8_t trans[256];
+	orc_to2bit(trans);
+	size_t p = 0, o = 0;
+	while (p < n && text[p] == '>') {
+		while (p < n && text[p] != '\n') out[o++] = text[p++];
+		if (p >= n) break;
+		out[o++] = text[p++];
+		while (p < n && text[p] != '>') { if (trans[text[p]] < 8) out[o++] = text[p]; ++p; }
+		out[o++] = '\n';
+	}
+	return o;
+}
+
 /* text2 != NULL: run_input_PE over the two files in lockstep. Returns the bytes of the stream (if > cap: needed). */
 size_t orc_stage1(const uint8_t *text1, size_t n1, const uint8_t *text2, size_t n2, int fastq, int min_phred, int phred_scale,
                   int minlen, int maxlen, uint8_t *out, size_t cap, int64_t *count) {

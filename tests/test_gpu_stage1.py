@@ -135,6 +135,35 @@ def test_text_to_stage2_in_hbm(tmp_path):
     assert gotpe.tobytes() + api.stream_terminator(cntpe) == wantpe.tobytes()
 
 
+def _first_record_diff(a: bytes, b: bytes) -> str:
+    """first stage-1 record in which two streams differ (for assertion messages)"""
+    pa = pb = i = 0
+    while pa + 16 <= len(a) and pb + 16 <= len(b):
+        ha, hb = np.frombuffer(a, np.int32, 4, pa), np.frombuffer(b, np.int32, 4, pb)
+        sa, sb = 16 + 8 * int(ha[1]) + 4 * int(ha[2]) + abs(int(ha[3])), 16 + 8 * int(hb[1]) + 4 * int(hb[2]) + abs(int(hb[3]))
+        if a[pa:pa + sa] != b[pb:pb + sb]:
+            return f"record {i}: got {ha.tolist()} {a[pa + sa - abs(int(ha[3])):pa + sa]!r} want {hb.tolist()} {b[pb + sb - abs(int(hb[3])):pb + sb]!r}"
+        pa += sa; pb += sb; i += 1
+    return f"lengths {len(a)} vs {len(b)} after {i} equal records"
+
+
+@gpu
+def test_multi_line_fasta_on_the_device(tmp_path):
+    """multi-line FASTA: the host unwrap (kmagpu_fasta_unwrap) + the device's 2-line path vs the oracle that
+    tests/test_oracle_stage1.py pins to `kma -s1` on the wrapped file"""
+    from tests.test_oracle_stage1 import _wrap_fasta
+    rng, names, seqs, reads = _reads(51, n=400, L=400, n_rate=0.02)
+    text = _wrap_fasta(rng, reads, crlf=True)
+    flat, used = api.fasta_unwrap(text)
+    assert used == len(text) and flat == util.oracle_fasta_unwrap(text)
+    want, wcnt = util.oracle_stage1(flat, fastq=False, minlen=40)
+    prefix = util.build_db(tmp_path, names, seqs)
+    db = api.TemplateDB(prefix, device=0)
+    got, cnt, _, _, _ = db.run_input_text(flat, fastq=False, minlen=40)
+    db.close()
+    assert got.tobytes() == want and cnt == wcnt and cnt > 300
+
+
 @gpu
 @pytest.mark.parametrize("seed,kw", [(31, {"min_q": 20}), (32, {"min_q": 25, "min_phred": 10}), (33, {"hardmask_q": 30, "min_phred": 30}),
                                      (34, {"min_q": 18, "hardmask_q": 28, "min_phred": 28, "minlen": 40}), (35, {"min_q": 30, "min_phred": 35}),
@@ -158,7 +187,8 @@ def test_quality_trim_and_hard_mask(tmp_path, seed, kw):
     db = api.TemplateDB(prefix, device=0)
     f, _ = api.fastx_split(text)
     got, cnt, _ = db.run_input_batch(text, f, **kw)
-    assert got.tobytes() == want and cnt == wcnt
+    assert cnt == wcnt, (cnt, wcnt)
+    assert got.tobytes() == want, _first_record_diff(got.tobytes(), want)
     got, cnt, _, _, _ = db.run_input_text(text, **kw)
     assert got.tobytes() == want and cnt == wcnt
     _, _, _, r2 = _reads(seed + 100, n=900)

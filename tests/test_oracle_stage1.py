@@ -113,3 +113,47 @@ def test_quality_trim_paired(tmp_path):
     want = util.ref_kma(["-ipe", "r1.fq", "r2.fq", "-o", "o", "-t_db", "db", "-s1", "-eq", "22", "-mi", "25"], cwd=tmp_path)
     got, _ = util.oracle_stage1(t1, t2, min_q=22, hardmask_q=25, min_phred=25)
     assert got == want
+
+
+def _wrap_fasta(rng, reads, crlf=False):
+    """multi-line FASTA: lines of 60, a few 70, blank lines, lower case, blanks inside lines"""
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    nl = b"\r\n" if crlf else b"\n"
+    out = []
+    for i, r in enumerate(reads):
+        s = lut[r].tobytes()
+        if i % 5 == 0:
+            s = s.lower()
+        w = 70 if i % 4 == 0 else 60
+        lines = [s[j:j + w] for j in range(0, len(s), w)] or [b""]
+        if i % 7 == 0 and len(lines) > 1:
+            lines.insert(1, b"")
+        if i % 9 == 0:
+            lines[0] = lines[0][:10] + b" " + lines[0][10:]
+        out.append(b">r%d some description" % i + (b"  " if i % 3 == 0 else b"") + nl + nl.join(lines) + nl)
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("crlf", [False, True])
+def test_multi_line_fasta(tmp_path, crlf):
+    """FileBuffgetFsa (seqparse.c:66-160) keeps every byte that translates below 8 between a header line and the next '>':
+    the oracle's unwrap + its 2-line path == `kma -s1` on the wrapped file; the library's host function gives the same bytes,
+    whole and in chunks"""
+    from kma_b200 import api
+    rng, reads = make(tmp_path, 51, n=300, L=400, n_rate=0.02)
+    text = _wrap_fasta(rng, reads, crlf)
+    (tmp_path / "r.fa").write_bytes(text)
+    want = util.ref_kma(["-i", "r.fa", "-o", "o", "-t_db", "db", "-s1", "-ml", "40"], cwd=tmp_path)
+    flat = util.oracle_fasta_unwrap(text)
+    got, _ = util.oracle_stage1(flat, fastq=False, minlen=40)
+    assert got == want and len(want) > 10000
+    lib_flat, used = api.fasta_unwrap(text)
+    assert lib_flat == flat and used == len(text)
+    # chunks: a cut inside a record leaves that record (and the bytes after it) for the next call
+    cut = len(text) // 2
+    a, ua = api.fasta_unwrap(text[:cut], eof=False)
+    assert 0 < ua <= cut and text[ua:ua + 1] == b">"
+    b, ub = api.fasta_unwrap(text[ua:])
+    assert a + b == flat and ua + ub == len(text)
+    with pytest.raises(api.KmaGpuError):
+        api.fasta_unwrap(b"ACGT\n>r1\nACGT\n")

@@ -550,6 +550,14 @@ def oracle_stage1(text1: bytes, text2: bytes | None = None, fastq=True, min_phre
     return out[:n].tobytes(), cnt.value
 
 
+def oracle_fasta_unwrap(text: bytes) -> bytes:
+    L = orc()
+    L.orc_fasta_unwrap.restype = C.c_size_t
+    L.orc_fasta_unwrap.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
+    out = np.empty(len(text) + 1, dtype=np.uint8)
+    return out[: L.orc_fasta_unwrap(text, len(text), out.ctypes.data)].tobytes()
+
+
 def build_db(tmp_path, names, seqs) -> str:
     """a database in the reference's format made by kma_b200.dbbuild (no reference binary needed)"""
     from kma_b200 import dbbuild
