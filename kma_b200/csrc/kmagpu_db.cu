@@ -9,6 +9,8 @@
 #include <string.h>
 #include <stdlib.h>
 #include <mutex>
+#include <thread>
+#include <algorithm>
 
 static std::mutex g_image_mutex;
 
@@ -108,9 +110,11 @@ extern "C" int kmagpu_db_open(const char *prefix, int device, kmagpu_db **out) {
 
 	auto fail = [&](const char *what) { kmagpu_db_close(db); if (what) kmagpu_set_error("%s", what); return -1; };
 	size_t dev_bytes = 0;
-	if (cudaMalloc(&db->d_exist, size * 4) != cudaSuccess) return fail("cudaMalloc exist");
-	if (cudaMemcpy(db->d_exist, exist.data(), size * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail("H2D exist");
-	dev_bytes += size * 4;
+	if (mega) {
+		if (cudaMalloc(&db->d_exist, size * 4) != cudaSuccess) return fail("cudaMalloc exist");
+		if (cudaMemcpy(db->d_exist, exist.data(), size * 4, cudaMemcpyHostToDevice) != cudaSuccess) return fail("H2D exist");
+		dev_bytes += size * 4;
+	}
 	if (cudaMalloc(&db->d_values, values.size() + 64) != cudaSuccess) return fail("cudaMalloc values");
 	if (cudaMemcpy(db->d_values, values.data(), values.size(), cudaMemcpyHostToDevice) != cudaSuccess) return fail("H2D values");
 	dev_bytes += values.size();
@@ -121,8 +125,35 @@ extern "C" int kmagpu_db_open(const char *prefix, int device, kmagpu_db **out) {
 		if (cudaMalloc(&db->d_kv, (n + 1) * 8) != cudaSuccess) return fail("cudaMalloc kv");
 		if (cudaMemcpy(db->d_kv, kv.data(), (n + 1) * 8, cudaMemcpyHostToDevice) != cudaSuccess) return fail("H2D kv");
 		dev_bytes += (n + 1) * 8;
+		// bucket entries {key0, value0, pos, cnt}: the reference's lookup (hashmapkma.c:149-178) reads exist[bucket], then the
+		// keys from there on while they mismatch, stay in the bucket and lie below n. cnt = how many entries such a scan examines
+		// when every key mismatches, so a device lookup that examines entries pos .. pos + cnt - 1 in order returns what it returns.
+		// The first entry sits in the bucket itself: a probe of an empty or single-key bucket and a hit on a first key cost one
+		// 16-byte load instead of two dependent ones. (d_exist holds this array for hashed tables.)
+		std::vector<uint4> bk(size);
+		const uint32_t hm = (uint32_t)(size - 1);
+		auto fill = [&](uint64_t b0, uint64_t b1) {
+			for (uint64_t b = b0; b < b1; ++b) {
+				const uint32_t pos = exist[b];
+				if (pos == (uint32_t)null_index || pos > n) { bk[b] = make_uint4(0, 0, 0, 0); continue; }
+				uint32_t p = pos, cnt = 1;
+				while ((kv[p].x & hm) == (uint32_t)b && p < n) { ++p; ++cnt; }
+				bk[b] = make_uint4(kv[pos].x, kv[pos].y, pos, cnt);
+			}
+		};
+		{
+			const unsigned nth = size >= (1u << 22) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+			std::vector<std::thread> th;
+			for (unsigned t = 1; t < nth; ++t) th.emplace_back(fill, size * t / nth, size * (t + 1) / nth);
+			fill(0, size / nth);
+			for (auto &x : th) x.join();
+		}
+		if (cudaMalloc(&db->d_exist, size * 16) != cudaSuccess) return fail("cudaMalloc buckets");
+		if (cudaMemcpy(db->d_exist, bk.data(), size * 16, cudaMemcpyHostToDevice) != cudaSuccess) return fail("H2D buckets");
+		dev_bytes += size * 16;
 	}
-	db->hv.exist = (const uint32_t *)db->d_exist;
+	db->hv.exist = mega ? (const uint32_t *)db->d_exist : nullptr;
+	db->hv.bk = mega ? nullptr : (const uint4 *)db->d_exist;
 	db->hv.kv = (const uint2 *)db->d_kv;
 	db->hv.values_s = vshort ? (const uint16_t *)db->d_values : nullptr;
 	db->hv.values_w = vshort ? nullptr : (const uint32_t *)db->d_values;

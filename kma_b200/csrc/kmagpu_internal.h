@@ -22,8 +22,11 @@ void kmagpu_set_error(const char *fmt, ...);
 
 // Device view of the template k-mer hash (.comp.b re-laid for one-sector lookups).
 struct KgHashView {
-	const uint32_t *exist;   // [size]   bucket -> first slot in kv, or null_index   (mega: value offset, 1 = null)
-	const uint2 *kv;         // [n + 1]  {key, value offset}: key_index and value_index fused (8 B, one sector)
+	const uint32_t *exist;   // mega (direct-addressed) tables only: [size] value offset, 1 = null
+	const uint4 *bk;         // hashed tables: [size] bucket -> {key0, value0, pos, cnt}: the first {key, value offset} of the bucket's
+	                         // run in kv inline, where the run starts and how many entries a failing scan examines (0: empty).
+	                         // One 16-byte load answers every miss in an empty or single-key bucket and every hit on a first key
+	const uint2 *kv;         // [n + 1]  {key, value offset}: key_index and value_index fused; read only behind a first-key mismatch
 	const uint16_t *values_s;  // template lists, u16 when DB_size < 65535 ...
 	const uint32_t *values_w;  // ... else u32
 	uint64_t hmask;          // size - 1

@@ -270,37 +270,29 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 #pragma unroll 1
 			for (int ug = 0; ug < nround; ug += 4) {
 				uint32_t e1[4];
-				uint64_t km[4];
-#pragma unroll
-				for (int u = 0; u < 4; ++u) {
-					const int j = c0 + (ug + u) * 32 + (int)lane;
-					const bool ok = j < lim;
-					km[u] = ok ? kmer_of(w0, j) : 0ull;
-					e1[u] = KG_MISS;
-					if (ok) {
-						if (GENERIC && hv.mega) { uint32_t v = __ldg(hv.exist + km[u]); e1[u] = v != 1u ? v : KG_MISS; }
-						else { uint32_t q = __ldg(hv.exist + (uint32_t)(km[u] & hv.hmask)); e1[u] = q != hv.null_index ? q : KG_MISS; }
-						ws.lookups++;
-					}
-				}
-				if (!GENERIC || !hv.mega) {
-					uint2 e2[4];
-#pragma unroll
-					for (int u = 0; u < 4; ++u) e2[u] = e1[u] != KG_MISS ? __ldg(hv.kv + e1[u]) : make_uint2(0, 0);
+				if (GENERIC && hv.mega) {
 #pragma unroll
 					for (int u = 0; u < 4; ++u) {
-						if (e1[u] == KG_MISS) continue;
-						const uint32_t key = (uint32_t)km[u], bucket = key & (uint32_t)hv.hmask;
-						uint32_t pos = e1[u];
-						uint2 e = e2[u];
-						uint32_t v = KG_MISS;
-						for (;;) {
-							if (e.x == key) { v = e.y; break; }
-							if ((e.x & (uint32_t)hv.hmask) != bucket || pos >= hv.n) break;
-							e = __ldg(hv.kv + ++pos);
-						}
-						e1[u] = v;
+						const int j = c0 + (ug + u) * 32 + (int)lane;
+						e1[u] = KG_MISS;
+						if (j < lim) { const uint32_t v = __ldg(hv.exist + kmer_of(w0, j)); e1[u] = v != 1u ? v : KG_MISS; ws.lookups++; }
 					}
+				} else {
+					// four independent 16-byte bucket loads in flight per lane; a bucket entry answers the probe by itself unless its
+					// first key differs and the bucket holds more (then the run in kv is read: one more dependent sector)
+					uint32_t key[4];
+					uint4 b4[4];
+#pragma unroll
+					for (int u = 0; u < 4; ++u) {
+						const int j = c0 + (ug + u) * 32 + (int)lane;
+						const bool ok = j < lim;
+						const uint64_t km = ok ? kmer_of(w0, j) : 0ull;
+						key[u] = (uint32_t)km;
+						b4[u] = make_uint4(0, 0, 0, 0);
+						if (ok) { b4[u] = __ldg(hv.bk + (uint32_t)(km & hv.hmask)); ws.lookups++; }
+					}
+#pragma unroll
+					for (int u = 0; u < 4; ++u) e1[u] = hash_resolve(hv, b4[u], key[u]);
 				}
 #pragma unroll
 				for (int u = 0; u < 4; ++u) hits[(ug + u) * 32 + lane] = e1[u];

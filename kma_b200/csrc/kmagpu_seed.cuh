@@ -12,20 +12,29 @@ enum { C_WORK = 0, C_POOL = 1, C_OVF = 2, C_WORK2 = 3, C_POOLFAIL = 4, C_LOOKUPS
 
 // ---------------------------------------------------------------- small device helpers
 
+// the rest of a bucket's run after its first key did not match: entries pos + 1 .. pos + cnt - 1 are the ones the
+// reference's scan (hashmapkma.c:149-178: same bucket, below n) would still examine
+__device__ __forceinline__ uint32_t hash_chain(const KgHashView &hv, const uint4 b, uint32_t key) {
+	for (uint32_t i = 1; i < b.w; ++i) {
+		const uint2 e = __ldg(hv.kv + b.z + i);
+		if (e.x == key) return e.y;
+	}
+	return KG_MISS;
+}
+
+// one bucket entry resolved against a key
+__device__ __forceinline__ uint32_t hash_resolve(const KgHashView &hv, const uint4 b, uint32_t key) {
+	if (b.w == 0) return KG_MISS;
+	if (b.x == key) return b.y;
+	return b.w == 1 ? KG_MISS : hash_chain(hv, b, key);
+}
+
 __device__ __forceinline__ uint32_t hash_lookup(const KgHashView &hv, uint64_t key) {
 	if (hv.mega) {
 		uint32_t v = __ldg(hv.exist + key);
 		return v != 1u ? v : KG_MISS;
 	}
-	const uint32_t bucket = (uint32_t)(key & hv.hmask);
-	uint32_t pos = __ldg(hv.exist + bucket);
-	if (pos == hv.null_index) return KG_MISS;
-	uint2 e = __ldg(hv.kv + pos);
-	while (e.x != (uint32_t)key) {
-		if ((e.x & (uint32_t)hv.hmask) != bucket || pos >= hv.n) return KG_MISS;
-		e = __ldg(hv.kv + ++pos);
-	}
-	return e.y;
+	return hash_resolve(hv, __ldg(hv.bk + (uint32_t)(key & hv.hmask)), (uint32_t)key);
 }
 
 __device__ __forceinline__ int list_len(const KgHashView &hv, uint32_t off) {
