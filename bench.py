@@ -549,8 +549,8 @@ def c5_leg(api, workdir, rank, world, device, cores, pk, dist, n=4_000_000, ref_
     info = db.info
     vw = 2 if info.DB_size < 65535 else 4
     alg = algorithmic_bytes(st, vw)
-    # 32-byte sectors the gather needs at the least: one per bucket probe, one per key / value-offset pair, the lists
-    sectors = st.lookups + st.hits + st.list_fetches + (vw * st.list_ids + 31) // 32 + (8 * st.read_words + 31) // 32
+    # 32-byte sectors the gather needs at the least: one per bucket probe (the bucket entry carries its first key and value), the lists
+    sectors = st.lookups + st.list_fetches + (vw * st.list_ids + 31) // 32 + (8 * st.read_words + 31) // 32
     ach = alg / (st.ms_seed * 1e-3) / 1e9
     out = {"workload": f"C5 ({'full' if C5_FAMILIES >= 5000 else 'reduced'} scale): {info.DB_size - 1} templates / {info.seq_bases / 1e6:.0f} Mb redundant DB ({C5_FAMILIES} families x 10), "
                        f"{n} synthetic 150 bp single-end reads per GPU, -1t1: stage 2 + alignment pass resident in HBM",
@@ -563,7 +563,12 @@ def c5_leg(api, workdir, rank, world, device, cores, pk, dist, n=4_000_000, ref_
                         "algorithmic_bytes_per_launch": int(alg), "kernel_ms": st.ms_seed, "traffic": ncu_traffic("c5:seed_se_kernel", n),
                         "sector_bytes_per_launch": int(32 * sectors), "sector_GBs": 32 * sectors / (st.ms_seed * 1e-3) / 1e9,
                         "sector_frac": 32 * sectors / (st.ms_seed * 1e-3) / 1e9 / pk["hbm_gbs"],
-                        "note": "k-mer table out of L2: every bucket / key probe is a 32-byte HBM sector"}}
+                        "note": "k-mer table out of L2: every bucket probe is a 32-byte HBM sector (16-byte bucket entries {key0, value0, pos, cnt}: "
+                                "one sector per lookup unless the first key of a multi-key bucket differs)"}}
+    tr = out["roofline"]["traffic"]
+    if tr:   # DRAM bytes of the ncu capture over this run's kernel time: what the random gather costs the memory system
+        out["roofline"]["dram_GBs"] = tr / (st.ms_seed * 1e-3) / 1e9
+        out["roofline"]["dram_frac"] = out["roofline"]["dram_GBs"] / pk["hbm_gbs"]
     if rank == 0 and os.path.exists(os.path.join(REF, "kma")) and os.path.exists(os.path.join(REF, "ref_aln")):
         fq = os.path.join(workdir, f"c5_{ref_n}.fq")
         open(fq, "wb").write(synth.fastq_fixed(np.asarray(reads[:ref_n])).tobytes())
