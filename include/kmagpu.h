@@ -184,6 +184,16 @@ int kmagpu_conclave_batch(kmagpu_db *db, const void *frag_raw, size_t nbytes, co
  * default), 1 = runConClave_lc (conclave.c:215-384, bound by -lc: score per template base before the total). */
 int kmagpu_conclave_mode(kmagpu_db *db, int length_corrected);
 
+/* -ConClave 2 (runkma.c:591: ConClave2Ptr = runConClave2 / runConClave2_lc, conclave.c:386 / 749): the ConClave entry points
+ * then make a provisional choice, drop the templates whose provisional sum is not significant (the chi-square test of
+ * conclave.c:467-491 in the reference's long double arithmetic over the caller's p_chisqr, stdstat.c:136; or / and the
+ * depth test `w >= scoreT * t_len` with cmp_or / cmp_and, kma.c:916), let reads with exactly one significant candidate add
+ * to its unique score, and draw the final template with probability proportional to the unique scores (4-key order as the
+ * fallback). The batch of such a call has to be the whole run. scoreT / evalue as runKMA passes them. version 1 = runConClave.
+ * kmagpu_conclave_uniq_scores: the unique scores as the last ConClave call left them (runConClave2 updates them in place). */
+int kmagpu_conclave_version(kmagpu_db *db, int version, double scoreT, double evalue, int and_mode, double (*p_chisqr)(long double));
+int kmagpu_conclave_uniq_scores(kmagpu_db *db, uint64_t *uniq_alignment_scores);
+
 /* kmagpu_conclave_batch on the frag_raw stream the last score collection (kmagpu_memscore_batch / _from_seed) of this
  * handle left in HBM; with kmagpu_trace_from_conclave the whole -mem_mode flow (stage 1 text -> stage 2 -> score
  * collection -> ConClave -> traceback + base counts -> consensus) runs without a record leaving the device. */

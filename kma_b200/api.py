@@ -484,6 +484,22 @@ class TemplateDB:
         """ConClavePtr: False = runConClave, True = runConClave_lc (-lc)"""
         _check(lib().kmagpu_conclave_mode(self._h, int(length_corrected)))
 
+    def conclave_version(self, version: int, p_chisqr=None, scoreT: float = 0.5, evalue: float = 0.05, and_mode: bool = False):
+        """-ConClave 2: the ConClave calls run runConClave2 / runConClave2_lc (conclave.c:386 / 749) over the batch they get (the
+        whole run). p_chisqr: the caller's chi-square tail function as a C pointer double (*)(long double) (stdstat.c:136).
+        version 1 restores runConClave."""
+        L = lib()
+        L.kmagpu_conclave_version.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p]
+        _check(L.kmagpu_conclave_version(self._h, int(version), float(scoreT), float(evalue), int(and_mode), p_chisqr))
+
+    def conclave_uniq_scores(self) -> np.ndarray:
+        """the unique scores as the last ConClave call left them (runConClave2 adds to them, conclave.c:519)"""
+        u = np.zeros(self.info.DB_size, dtype=np.uint64)
+        L = lib()
+        L.kmagpu_conclave_uniq_scores.argtypes = [C.c_void_p, C.c_void_p]
+        _check(L.kmagpu_conclave_uniq_scores(self._h, u.ctypes.data))
+        return u
+
     def memscore_from_seed(self, scores=None, download=True, cap=None):
         """memscore_batch on the stage-2 stream the last seed_run left in HBM; the frag_raw stream stays resident for
         conclave_resident. -> (frag_raw bytes | None, alignment_scores, uniq_alignment_scores, nrecords)"""

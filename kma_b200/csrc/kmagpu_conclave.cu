@@ -23,53 +23,91 @@ struct CcItem {
 	int32_t q_len, hl, tmpl, bestHits, score, start, end, flag, rc, has_bound, b0, b1;
 };
 
+// the 4-key order over a record's candidates (conclave.c:66-113; runConClave_lc :238-285 with lc): returns the winning
+// candidate's index (-1: none) with the reference's int truncations (best_read_score / bestNum are ints compared with the
+// 64-bit sums). first = the value bestTemplate starts from: -1 in runConClave, 0 in runConClave2's fallback (conclave.c:598),
+// which only matters to the last tie rule (the smaller template id wins against abs(first)).
+__device__ int cc_four_keys(const uint8_t *T, int bestHits, const unsigned long long *__restrict__ as, const unsigned long long *__restrict__ uas,
+		const int32_t *__restrict__ lengths, int DB_size, int lc, int first, unsigned long long *ctr) {
+	double bestScore = 0;
+	int best_read_score = 0, bestNum = 0, bestTemplate = first, besti = -1;
+	for (int i = 0; i < bestHits; ++i) {
+		const int tt = (int)ld_u32u(T + 4 * (size_t)i);
+		const int t = tt < 0 ? -tt : tt;
+		if (t <= 0 || t >= DB_size) { atomicAdd(&ctr[1], 1ull); continue; }
+		const unsigned long long a = as[t], u = uas[t];
+		const double tmp_score = __ddiv_rn(1.0 * (double)a, (double)__ldg(lengths + t));
+		// the reference compares the 64-bit sums with ints: the ints are converted (sign-extended) to unsigned long
+		const unsigned long long brs = (unsigned long long)(long long)best_read_score, bn = (unsigned long long)(long long)bestNum;
+		bool take = false;
+		if (lc) {   // runConClave_lc (conclave.c:215-384, -lc): score per template base first, then the total
+			if (tmp_score > bestScore) take = true;
+			else if (tmp_score == bestScore) {
+				if (a > brs) take = true;
+				else if (a == brs) {
+					if (u > bn) take = true;
+					else if (u == bn && t < abs(bestTemplate)) take = true;
+				}
+			}
+		} else if (a > brs) take = true;
+		else if (a == brs) {
+			if (tmp_score > bestScore) take = true;
+			else if (tmp_score == bestScore) {
+				if (u > bn) take = true;
+				else if (u == bn && t < abs(bestTemplate)) take = true;
+			}
+		}
+		if (take) { bestTemplate = tt; best_read_score = (int)a; bestScore = tmp_score; bestNum = (int)u; besti = i; }
+	}
+	return besti;
+}
+
+// the final choice of runConClave2 for a record with bestHits != 1 (conclave.c:547-655): a candidate drawn with probability
+// proportional to the (updated) unique scores -- Lehmer generator 16807 seeded from the read's first and last 7 bases --
+// else the 4-key order; -1: no candidate (the record is skipped)
+__device__ int cc2_choice(const uint8_t *q, int q_len, const uint8_t *T, int bestHits, const unsigned long long *__restrict__ as,
+		const unsigned long long *__restrict__ uas, const int32_t *__restrict__ lengths, int DB_size, int lc, unsigned long long *ctr) {
+	int tot = 0;
+	for (int i = bestHits; i--;) {
+		const int t = abs((int)ld_u32u(T + 4 * (size_t)i));
+		if (t > 0 && t < DB_size) tot = (int)((long long)tot + (long long)uas[t]);   // int += unsigned long: the low 32 bits
+	}
+	if (tot && 16 <= q_len) {
+		int rnd = q[0], i = -1, j = q_len;
+		while (++i < 7) rnd = (((rnd << 2) | q[i]) << 2) | q[--j];
+		rnd = 16807 * (rnd % 127773) - 2836 * (rnd / 127773);   // minimal standard
+		if (rnd <= 0) rnd += 0x7fffffff;
+		const double tmp_score = __ddiv_rn((double)rnd, 2147483647.0);
+		const unsigned randScore = __double2uint_rz(__dmul_rn(tmp_score, (double)tot));
+		unsigned long long score = 0;
+		for (i = 0; i != bestHits; ++i) {
+			const int tt = (int)ld_u32u(T + 4 * (size_t)i), t = abs(tt);
+			if (t <= 0 || t >= DB_size) continue;
+			score += uas[t];
+			if ((unsigned long long)randScore < score) return tt ? i : -1;
+		}
+	}
+	return cc_four_keys(T, bestHits, as, uas, lengths, DB_size, lc, 0, ctr);
+}
+
 // one frag_raw record at byte `pos`: the choice among its candidates, the item(s) it contributes (idx, and idx + 1 for
 // the mate block of a pair record); returns the bytes the record spans
 __device__ uint32_t cc_record(const uint8_t *__restrict__ in, uint32_t pos, int idx, const unsigned long long *__restrict__ as,
 		const unsigned long long *__restrict__ uas, const int32_t *__restrict__ lengths, int DB_size, CcItem *items, unsigned long long *keys,
-		unsigned long long *w, unsigned int *fc, unsigned int *rcn, unsigned long long *ctr, bool *has_mate, int lc) {
+		unsigned long long *w, unsigned int *fc, unsigned int *rcn, unsigned long long *ctr, bool *has_mate, int lc, int version) {
 	const uint8_t *rec = in + pos;
 	const int q_len = (int)ld_u32u(rec), sparse = (int)ld_u32u(rec + 4), sc = (int)ld_u32u(rec + 8), hl = (int)ld_u32u(rec + 12);
 	int flag = (int)ld_u32u(rec + 16);
 	const int bestHits = abs(sparse), read_score = abs(sc);
 	const uint8_t *S = rec + 20 + (size_t)q_len + (size_t)hl, *E = S + 4 * (size_t)bestHits, *T = E + 4 * (size_t)bestHits;
-	int bestTemplate, start, end;
-	if (bestHits > 1) {
-		double bestScore = 0;
-		int best_read_score = 0, bestNum = 0;
-		bestTemplate = -1; start = 0; end = 0;
-		for (int i = 0; i < bestHits; ++i) {
-			const int tt = (int)ld_u32u(T + 4 * (size_t)i);
-			const int t = tt < 0 ? -tt : tt;
-			if (t <= 0 || t >= DB_size) { atomicAdd(&ctr[1], 1ull); continue; }
-			const unsigned long long a = as[t], u = uas[t];
-			const double tmp_score = __ddiv_rn(1.0 * (double)a, (double)__ldg(lengths + t));
-			// the reference compares the 64-bit sums with ints: the ints are converted (sign-extended) to unsigned long
-			const unsigned long long brs = (unsigned long long)(long long)best_read_score, bn = (unsigned long long)(long long)bestNum;
-			bool take = false;
-			if (lc) {   // runConClave_lc (conclave.c:215-384, -lc): score per template base first, then the total
-				if (tmp_score > bestScore) take = true;
-				else if (tmp_score == bestScore) {
-					if (a > brs) take = true;
-					else if (a == brs) {
-						if (u > bn) take = true;
-						else if (u == bn && t < abs(bestTemplate)) take = true;
-					}
-				}
-			} else if (a > brs) take = true;
-			else if (a == brs) {
-				if (tmp_score > bestScore) take = true;
-				else if (tmp_score == bestScore) {
-					if (u > bn) take = true;
-					else if (u == bn && t < abs(bestTemplate)) take = true;
-				}
-			}
-			if (take) {
-				bestTemplate = tt; best_read_score = (int)a; bestScore = tmp_score; bestNum = (int)u;
-				start = (int)ld_u32u(S + 4 * (size_t)i); end = (int)ld_u32u(E + 4 * (size_t)i);
-			}
-		}
+	int bestTemplate = 0, start = 0, end = 0;
+	if (version == 2 ? bestHits != 1 : bestHits > 1) {
+		const int bi = version == 2 ? cc2_choice(rec + 20, q_len, T, bestHits, as, uas, lengths, DB_size, lc, ctr)
+		                            : cc_four_keys(T, bestHits, as, uas, lengths, DB_size, lc, -1, ctr);
+		if (bi >= 0) { bestTemplate = (int)ld_u32u(T + 4 * (size_t)bi); start = (int)ld_u32u(S + 4 * (size_t)bi); end = (int)ld_u32u(E + 4 * (size_t)bi); }
+		else bestTemplate = version == 2 ? 0 : -1;
 	} else { bestTemplate = (int)ld_u32u(T); start = (int)ld_u32u(S); end = (int)ld_u32u(E); }
+	const bool skipped = version == 2 && bestTemplate == 0;   // runConClave2 without a candidate: the record leaves no fragment (conclave.c:722)
 	CcItem a;
 	a.q_off = pos + 20u; a.hdr_off = a.q_off + (uint32_t)q_len; a.q_len = q_len; a.hl = hl;
 	a.rc = 0; a.has_bound = 0; a.b0 = a.b1 = 0;
@@ -83,7 +121,7 @@ __device__ uint32_t cc_record(const uint8_t *__restrict__ in, uint32_t pos, int 
 		}
 	}
 	const bool ok = bestTemplate > 0 && bestTemplate < DB_size;
-	if (!ok) atomicAdd(&ctr[1], 1ull);
+	if (!ok && !skipped) atomicAdd(&ctr[1], 1ull);
 	a.tmpl = bestTemplate; a.bestHits = bestHits; a.score = sparse < 0 ? 0 : read_score; a.start = start; a.end = end; a.flag = flag;
 	const bool mate = sc < 0;
 	if (ok) {
@@ -115,7 +153,7 @@ __device__ uint32_t cc_record(const uint8_t *__restrict__ in, uint32_t pos, int 
 __global__ void __launch_bounds__(256) cc_choose_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ off, int n,
 		const unsigned long long *__restrict__ as, const unsigned long long *__restrict__ uas, const int32_t *__restrict__ lengths,
 		int DB_size, CcItem *items, unsigned long long *keys, uint32_t *vals, unsigned long long *w, unsigned int *fc, unsigned int *rcn,
-		unsigned long long *ctr, int lc) {
+		unsigned long long *ctr, int lc, int version) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n) return;
 	keys[2 * r] = ~0ull; keys[2 * r + 1] = ~0ull; vals[2 * r] = 2u * (unsigned)r; vals[2 * r + 1] = 2u * (unsigned)r + 1u;
@@ -123,10 +161,46 @@ __global__ void __launch_bounds__(256) cc_choose_kernel(const uint8_t *__restric
 	const uint32_t end = off[r + 1];
 	for (int idx = 2 * r; idx < 2 * r + 2 && end - pos >= 20u && pos < end;) {
 		bool mate = false;
-		pos += cc_record(in, pos, idx, as, uas, lengths, DB_size, items, keys, w, fc, rcn, ctr, &mate, lc);
+		pos += cc_record(in, pos, idx, as, uas, lengths, DB_size, items, keys, w, fc, rcn, ctr, &mate, lc, version);
 		idx += mate ? 2 : 1;
 	}
 	if (pos != end && end - off[r] >= 20u) atomicAdd(&ctr[3], 1ull);   // the slot's bytes are not a whole number of records
+}
+
+// runConClave2's two passes before the final choice, one thread per slot like cc_choose_kernel:
+// pass 0 (conclave.c:405-465): the provisional choice (4-key order) adds the read score to w[template];
+// pass 1 (:493-530): a read with several candidates of which exactly ONE kept its (significant) w adds its score to that
+// template's unique score.
+__global__ void __launch_bounds__(256) cc2_pre_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ off, int n,
+		const unsigned long long *__restrict__ as, unsigned long long *uas, const int32_t *__restrict__ lengths, int DB_size,
+		unsigned long long *w, unsigned long long *ctr, int lc, int pass) {
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n) return;
+	uint32_t pos = off[r];
+	const uint32_t end = off[r + 1];
+	for (int k = 0; k < 2 && end - pos >= 20u && pos < end; ++k) {
+		const uint8_t *rec = in + pos;
+		const int q_len = (int)ld_u32u(rec), bestHits = abs((int)ld_u32u(rec + 4)), sc = (int)ld_u32u(rec + 8), hl = (int)ld_u32u(rec + 12);
+		const int read_score = abs(sc);
+		const uint8_t *T = rec + 20 + (size_t)q_len + (size_t)hl + 8 * (size_t)bestHits;
+		if (pass == 0) {
+			int best = 0;
+			if (bestHits > 1) { const int bi = cc_four_keys(T, bestHits, as, uas, lengths, DB_size, lc, -1, ctr); best = bi >= 0 ? (int)ld_u32u(T + 4 * (size_t)bi) : -1; }
+			else best = (int)ld_u32u(T);
+			const int t = abs(best);
+			if (t > 0 && t < DB_size) atomicAdd(&w[t], (unsigned long long)read_score);
+			else atomicAdd(&ctr[1], 1ull);
+		} else if (bestHits != 1) {
+			int best = 0;
+			for (int i = bestHits; i--;) {
+				const int t = abs((int)ld_u32u(T + 4 * (size_t)i));
+				if (t > 0 && t < DB_size && w[t]) { if (best) { best = 0; break; } else best = t; }
+			}
+			if (best) atomicAdd(&uas[best], (unsigned long long)read_score);
+		}
+		pos += 20u + (uint32_t)q_len + (uint32_t)hl + 12u * (uint32_t)bestHits;
+		if (sc < 0) { const uint8_t *m = in + pos; pos += 12u + ld_u32u(m) + ld_u32u(m + 4); k = 2; }   // the mate block closes the slot
+	}
 }
 
 __global__ void __launch_bounds__(256) cc_sizes_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals,
@@ -199,8 +273,40 @@ static int conclave_core(kmagpu_db *db, const uint8_t *din, const uint32_t *doff
 	}
 	KG_CUDA(cudaMemsetAsync(ctr, 0, 64, st));
 	KG_CUDA(cudaMemsetAsync(d_acc.p, 0, 16 * (size_t)DB, st));
+	const int version = db->cc2.version == 2 ? 2 : 1;
+	if (version == 2) {
+		// runConClave2 (conclave.c:386-747): provisional sums -> significance on the host (long double arithmetic and the caller's
+		// p_chisqr, exactly as conclave.c:467-491) -> unique-score update -> the sums start again for the final choice
+		if (!db->cc2.p_chisqr) { kmagpu_set_error("ConClave 2 needs the caller's p_chisqr (kmagpu_conclave_version)"); return -1; }
+		cc2_pre_kernel<<<(n + 255) / 256, 256, 0, st>>>(din, doff, n, as, uas, db->d_lengths, DB, w, ctr, db->conclave_lc, 0);
+		std::vector<unsigned long> hw((size_t)DB);
+		KG_CUDA(cudaMemcpyAsync(hw.data(), w, 8 * (size_t)DB, cudaMemcpyDeviceToHost, st));
+		KG_CUDA(cudaStreamSynchronize(st));
+		KG_CUDA(cudaGetLastError());
+		unsigned long Nhits = 0, template_tot_ulen = 0;
+		for (int t = 1; t < DB; ++t) { Nhits += hw[t]; template_tot_ulen += (unsigned long)db->lengths[t]; }
+		for (int t = DB; --t;) {
+			int read_score;
+			if ((read_score = (int)hw[t])) {
+				const int t_len = db->lengths[t];
+				long double expected = t_len, q_value;
+				expected /= (1 < (template_tot_ulen - t_len) ? (template_tot_ulen - t_len) : 1);
+				expected *= (Nhits - read_score);
+				q_value = read_score - expected;
+				q_value /= (expected + read_score);
+				q_value *= read_score - expected;
+				const double p_value = db->cc2.p_chisqr(q_value);
+				const int a = (p_value <= db->cc2.evalue && read_score > expected), b = (read_score >= db->cc2.scoreT * t_len);
+				if ((db->cc2.and_mode ? (a && b) : (a || b)) == 0) hw[t] = 0;
+			}
+		}
+		KG_CUDA(cudaMemcpyAsync(w, hw.data(), 8 * (size_t)DB, cudaMemcpyHostToDevice, st));
+		cc2_pre_kernel<<<(n + 255) / 256, 256, 0, st>>>(din, doff, n, as, uas, db->d_lengths, DB, w, ctr, db->conclave_lc, 1);
+		KG_CUDA(cudaMemsetAsync(d_acc.p, 0, 16 * (size_t)DB, st));
+		KG_CUDA(cudaStreamSynchronize(st));   // hw is a host vector: the upload must be done before it goes
+	}
 	cc_choose_kernel<<<(n + 255) / 256, 256, 0, st>>>(din, doff, n, as, uas, db->d_lengths, DB,
-		(CcItem *)d_items.p, keys, vals, w, fc, rcn, ctr, db->conclave_lc);
+		(CcItem *)d_items.p, keys, vals, w, fc, rcn, ctr, db->conclave_lc, version);
 	size_t tmp_bytes = 0;
 	cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, ni, 0, 64, st);
 	if (d_tmp.reserve(tmp_bytes + 64)) return -1;
@@ -327,6 +433,26 @@ extern "C" int kmagpu_conclave_from_align(kmagpu_db *db, const uint64_t *alignme
 	KG_CUDA(cudaStreamSynchronize(db->stream));
 	return conclave_core(db, (const uint8_t *)b.d_out.p, recoff, n, alignment_scores, uniq_alignment_scores, frags_out, out_cap, out_bytes,
 	                     w_scores, fragmentCounts, readCounts);
+}
+
+// -ConClave 2 (runkma.c:591): the ConClave entry points run runConClave2 / runConClave2_lc (conclave.c:386 / 749) over the
+// batch they are given, which then has to be the whole run (its significance filter sums over every read). scoreT / evalue as
+// runKMA passes them, and_mode = cmp_and (kma.c:916), p_chisqr = the caller's (stdstat.c:136). version 1 restores runConClave.
+extern "C" int kmagpu_conclave_version(kmagpu_db *db, int version, double scoreT, double evalue, int and_mode, double (*p_chisqr)(long double)) {
+	if (!db || (version != 1 && version != 2)) { kmagpu_set_error("ConClave version %d: 1 or 2", version); return -1; }
+	db->cc2.version = version; db->cc2.scoreT = scoreT; db->cc2.evalue = evalue; db->cc2.and_mode = and_mode != 0; db->cc2.p_chisqr = p_chisqr;
+	return 0;
+}
+
+// the unique scores as the last ConClave call of this handle left them (runConClave2 adds to them, conclave.c:519)
+extern "C" int kmagpu_conclave_uniq_scores(kmagpu_db *db, uint64_t *uniq_alignment_scores) {
+	if (!db || !uniq_alignment_scores) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->frg.d_sc.p) { kmagpu_set_error("kmagpu_conclave_uniq_scores before a ConClave call on this handle"); return -1; }
+	const size_t DB = (size_t)db->info.DB_size;
+	KG_CUDA(cudaSetDevice(db->device));
+	KG_CUDA(cudaMemcpyAsync(uniq_alignment_scores, (const unsigned long long *)db->frg.d_sc.p + DB, 8 * DB, cudaMemcpyDeviceToHost, db->stream));
+	KG_CUDA(cudaStreamSynchronize(db->stream));
+	return 0;
 }
 
 // which ConClavePtr the three ConClave entry points stand for: 0 = runConClave (conclave.c:43), 1 = runConClave_lc (:215, -lc)

@@ -151,6 +151,7 @@ struct kmagpu_db {
 	FragBatch frg;
 	RawBatch raw;
 	int conclave_lc = 0;   // 1: runConClave_lc
+	struct { int version = 1; double scoreT = 0.5, evalue = 0.05; bool and_mode = false; double (*p_chisqr)(long double) = nullptr; } cc2;   // -ConClave 2
 	// per-template alignment index (kmagpu_tindex.cu)
 	void *d_tmeta = nullptr, *d_tslots = nullptr;
 	int32_t *d_tdups = nullptr;

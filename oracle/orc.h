@@ -60,6 +60,10 @@ int orc_matrix_stream(const int32_t *lengths, int DB_size, const uint8_t *frags,
 int64_t orc_conclave_stream(const int32_t *template_lengths, int DB_size, const uint8_t *frag, size_t fb,
                             const uint64_t *alignment_scores, const uint64_t *uniq_alignment_scores,
                             uint8_t *out, size_t cap, uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts);
+int64_t orc_conclave2_stream(const int32_t *template_lengths, int DB_size, const uint8_t *frag, size_t fb,
+                             const uint64_t *alignment_scores, uint64_t *uniq_alignment_scores,
+                             uint8_t *out, size_t cap, uint64_t *w_scores, uint32_t *fragmentCounts, uint32_t *readCounts,
+                             double scoreT, double evalue, int and_mode, double (*p_chisqr)(long double));   /* runConClave2(_lc), -ConClave 2 */
 int orc_memscore_stream(const int32_t *lengths, int DB_size, const uint8_t *in, size_t in_bytes, uint8_t **frag_out, size_t *frag_bytes,
                         uint64_t *as, uint64_t *uas);
 int orc_consensus(const uint16_t *counts, const uint64_t *seq, int t_len, int bcd, int caller, int sig, double support, double evalue,

@@ -37,6 +37,7 @@
 #include "penalties.h"
 #include "qseqs.h"
 #include "runkma.h"
+#include "stdstat.h"
 #ifndef MAX
 #define MAX(X, Y) ((X) < (Y) ? (Y) : (X))
 #endif
@@ -186,8 +187,13 @@ static int conclave_main(int argc, char **argv) {
 	int *template_lengths; long unsigned *as, *uas;
 	char *p2 = malloc(strlen(argv[2]) + 64); strcpy(p2, argv[2]);
 	int DB_size = load_DBs_KMA(p2, &as, &uas, &template_lengths, 0);
-	int maxFrag = argc > 6 && strcmp(argv[6], "-lc") ? atoi(argv[6]) : 1048576;
+	int maxFrag = argc > 6 && argv[6][0] != '-' ? atoi(argv[6]) : 1048576;
 	const int lc = !strcmp(argv[argc - 1], "-lc");   /* runConClave_lc (kma.c:700: -lc) */
+	int version = 1; double c2_scoreT = 0.5, c2_evalue = 0.05;   /* -c2 scoreT evalue [-and]: runConClave2 (-ConClave 2, runkma.c:591) */
+	for (int a = 6; a < argc; ++a) {
+		if (!strcmp(argv[a], "-c2") && a + 2 < argc) { version = 2; c2_scoreT = strtod(argv[a + 1], 0); c2_evalue = strtod(argv[a + 2], 0); }
+		else if (!strcmp(argv[a], "-and")) cmp = &cmp_and;   /* kma.c:916 */
+	}
 	FILE *sc = fopen(argv[4], "rb");
 	int n = 0;
 	if (!sc || fread(&n, 4, 1, sc) != 1 || n != DB_size) { fprintf(stderr, "scores file does not match the database\n"); return 1; }
@@ -208,7 +214,13 @@ static int conclave_main(int argc, char **argv) {
 	Frag **alignFrags = calloc(DB_size, sizeof(Frag *));
 	long unsigned *w_scores = calloc(DB_size, sizeof(long unsigned));
 	unsigned *fragmentCounts = calloc(DB_size, sizeof(unsigned)), *readCounts = calloc(DB_size, sizeof(unsigned));
-	int files = (lc ? runConClave_lc : runConClave)(tmp, &template_fragments, DB_size, maxFrag, w_scores, fragmentCounts, readCounts, as, uas, template_lengths,
+	int files;
+	if (version == 2) {
+		long unsigned template_tot_ulen = 0;
+		for (int i = 1; i < DB_size; ++i) template_tot_ulen += template_lengths[i];   /* runkma.c:581-585 */
+		files = (lc ? runConClave2_lc : runConClave2)(tmp, &template_fragments, DB_size, maxFrag, w_scores, fragmentCounts, readCounts, as, uas,
+		                        template_lengths, header, qseq, bestTemplates, bs, be, alignFrags, template_tot_ulen, c2_scoreT, c2_evalue);
+	} else files = (lc ? runConClave_lc : runConClave)(tmp, &template_fragments, DB_size, maxFrag, w_scores, fragmentCounts, readCounts, as, uas, template_lengths,
 	                        header, qseq, bestTemplates, bs, be, alignFrags);
 	FILE *out = fopen(argv[5], "wb");
 	fwrite(&files, 4, 1, out);
@@ -221,6 +233,7 @@ static int conclave_main(int argc, char **argv) {
 		while ((got = fread(buf, 1, sizeof(buf), tf))) fwrite(buf, 1, got, out);
 	}
 	fwrite(w_scores, 8, DB_size, out); fwrite(fragmentCounts, 4, DB_size, out); fwrite(readCounts, 4, DB_size, out);
+	if (version == 2) fwrite(uas, 8, DB_size, out);   /* runConClave2 updates the unique scores (conclave.c:519) */
 	fclose(out);
 	return 0;
 }

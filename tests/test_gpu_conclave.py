@@ -212,3 +212,27 @@ def test_mem_mode_flow_on_one_genome(tmp_path):
     assert np.array_equal(mat, omat) and mat.shape == (200_000, 6)
     depth = mat[:, :4].sum(axis=1)
     assert depth.mean() > 1.5     # 3000 x 150 bp over 200 kb
+
+
+@pytest.mark.parametrize("seed,kind,scoreT,evalue,lc,and_mode", [(81, "se", 0.5, 0.05, False, False), (82, "chain", 0.25, 0.05, False, False),
+                                                                 (83, "pe", 0.5, 0.05, False, False), (84, "se", 0.5, 1e-6, True, False),
+                                                                 (85, "se", 2.0, 0.05, False, True), (86, "chain", 0.5, 0.5, True, True)])
+def test_conclave_version_2(tmp_path, seed, kind, scoreT, evalue, lc, and_mode):
+    """-ConClave 2 (runConClave2 / _lc, conclave.c:386-1110) on the device: provisional sums, the host's significance filter over
+    the reference's p_chisqr, unique-score update, weighted random draw with the 4-key fallback -- fragments, sums, counts and
+    the updated unique scores vs the oracle that tests/test_oracle_conclave.py pins to the reference's own functions"""
+    from tests.test_oracle_conclave import _cc2_case
+    prefix, frag, a, u = _cc2_case(tmp_path, seed, kind)
+    want, ow, ofc, orc_, ou = util.oracle_conclave2(prefix, frag, a, u, scoreT=scoreT, evalue=evalue, lc=lc, and_mode=and_mode)
+    db = api.TemplateDB(prefix, device=0)
+    db.conclave_mode(lc)
+    db.conclave_version(2, util.ref_p_chisqr(), scoreT=scoreT, evalue=evalue, and_mode=and_mode)
+    got, w, fc, rc, n = db.conclave_batch(frag, a, u)
+    gu = db.conclave_uniq_scores()
+    assert got.tobytes() == want
+    assert np.array_equal(w, ow) and np.array_equal(fc, ofc) and np.array_equal(rc, orc_) and np.array_equal(gu, ou)
+    db.conclave_version(1)   # back to runConClave
+    want1, ow1, _, _ = util.oracle_conclave(prefix, frag, a, u, lc=lc)
+    got1, w1, _, _, _ = db.conclave_batch(frag, a, u)
+    db.close()
+    assert got1.tobytes() == want1 and np.array_equal(w1, ow1) and got1.tobytes() != got.tobytes()

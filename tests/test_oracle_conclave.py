@@ -103,3 +103,33 @@ def test_conclave_length_corrected(tmp_path, seed, chain):
         got3, ow3, _, _ = util.oracle_conclave(prefix, rec, a3, u3, lc=lc)
         assert got3 == files3[0] and np.array_equal(ow3, w3)
         assert int(np.frombuffer(got3[:4], dtype=np.int32)[0]) == want_t
+
+
+def _cc2_case(tmp_path, seed, kind):
+    if kind == "pe":
+        names, seqs = synth.gene_db(seed, n_families=10, n_variants=8, len_lo=500, len_hi=1500)
+        synth.write_fasta(tmp_path / "db.fsa", names, seqs)
+        util.ref_kma(["index", "-i", "db.fsa", "-o", "db"], cwd=tmp_path)
+        r1, r2 = synth.paired_reads(seed + 1, seqs, 1500, sub=0.01)
+        synth.write_fastq(tmp_path / "a.fq", r1)
+        synth.write_fastq(tmp_path / "b.fq", r2)
+        s2 = util.ref_kma(["-ipe", "a.fq", "b.fq", "-o", "o", "-t_db", "db", "-apm", "p", "-s2"], cwd=tmp_path)
+        prefix = str(tmp_path / "db")
+        frag, a, u, _ = util.ref_align(prefix, s2, str(tmp_path), one2one=False, cand=False, pe=True)
+        return prefix, frag, a, u
+    return se_case(tmp_path, seed, n=2500, chain=kind == "chain")
+
+
+@pytest.mark.parametrize("seed,kind,scoreT,evalue,lc,and_mode", [(81, "se", 0.5, 0.05, False, False), (82, "chain", 0.25, 0.05, False, False),
+                                                                 (83, "pe", 0.5, 0.05, False, False), (84, "se", 0.5, 1e-6, True, False),
+                                                                 (85, "se", 2.0, 0.05, False, True), (86, "chain", 0.5, 0.5, True, True)])
+def test_conclave_version_2(tmp_path, seed, kind, scoreT, evalue, lc, and_mode):
+    """-ConClave 2 (runConClave2 / _lc, conclave.c:386-1110): provisional sums, significance filter, unique-score update,
+    weighted random draw with the 4-key fallback -- fragments, sums, counts and the updated unique scores vs the reference"""
+    prefix, frag, a, u = _cc2_case(tmp_path, seed, kind)
+    files, w, fc, rc, u2 = util.ref_conclave(prefix, frag, a, u, str(tmp_path), lc=lc, c2=(scoreT, evalue), and_mode=and_mode)
+    got, ow, ofc, orc_, ou = util.oracle_conclave2(prefix, frag, a, u, scoreT=scoreT, evalue=evalue, lc=lc, and_mode=and_mode)
+    one, _, _, _ = util.oracle_conclave(prefix, frag, a, u, lc=lc)
+    assert len(files) == 1 and got == files[0]
+    assert np.array_equal(ow, w) and np.array_equal(ofc, fc) and np.array_equal(orc_, rc) and np.array_equal(ou, u2)
+    assert got != one, "the case is meant to make version 2 choose differently from version 1"

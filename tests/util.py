@@ -327,14 +327,17 @@ def parse_trace(buf: bytes):
     return out
 
 
-def ref_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarray, tmp: str, max_frag=None, lc=False):
+def ref_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarray, tmp: str, max_frag=None, lc=False, c2=None, and_mode=False):
     """ground truth of ConClave's choice pass + printFrags from the unmodified reference (ref_harness -conclave):
     (list of per-file byte strings, w_scores u64[DB], fragmentCounts u32[DB], readCounts u32[DB])"""
     fp, sp, op = os.path.join(tmp, "cc_frag.bin"), os.path.join(tmp, "cc_sc.bin"), os.path.join(tmp, "cc_out.bin")
     open(fp, "wb").write(frag_raw)
     with open(sp, "wb") as f:
         f.write(np.array([len(a)], dtype=np.int32).tobytes() + a.astype(np.uint64).tobytes() + u.astype(np.uint64).tobytes())
-    args = [REF_ALN, "-conclave", db_prefix, fp, sp, op] + ([str(max_frag)] if max_frag else []) + (["-lc"] if lc else [])
+    args = [REF_ALN, "-conclave", db_prefix, fp, sp, op] + ([str(max_frag)] if max_frag else [])
+    if c2:   # (scoreT, evalue): runConClave2 (-ConClave 2); the unique scores it updates come back as a fifth value
+        args += ["-c2", repr(float(c2[0])), repr(float(c2[1]))] + (["-and"] if and_mode else [])
+    args += ["-lc"] if lc else []
     r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     buf = open(op, "rb").read()
@@ -347,7 +350,9 @@ def ref_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarray, 
     DB = len(a)
     w = np.frombuffer(buf, dtype=np.uint64, count=DB, offset=o).copy(); o += 8 * DB
     fc = np.frombuffer(buf, dtype=np.uint32, count=DB, offset=o).copy(); o += 4 * DB
-    rc = np.frombuffer(buf, dtype=np.uint32, count=DB, offset=o).copy()
+    rc = np.frombuffer(buf, dtype=np.uint32, count=DB, offset=o).copy(); o += 4 * DB
+    if c2:
+        return files, w, fc, rc, np.frombuffer(buf, dtype=np.uint64, count=DB, offset=o).copy()
     return files, w, fc, rc
 
 
@@ -369,6 +374,33 @@ def oracle_conclave(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarra
     L.orc_conclave_set_lc(0)
     assert n >= 0, f"oracle conclave error {n}"
     return out[:n].tobytes(), w, fc, rc
+
+
+def ref_p_chisqr():
+    """the reference's own p_chisqr (stdstat.c:136) as a C function pointer: double (*)(long double)"""
+    ref = C.CDLL(REF_SO)
+    return C.cast(ref.p_chisqr, C.c_void_p)
+
+
+def oracle_conclave2(db_prefix: str, frag_raw: bytes, a: np.ndarray, u: np.ndarray, scoreT=0.5, evalue=0.05, lc=False, and_mode=False):
+    """runConClave2 (-ConClave 2) from the C oracle over the reference's p_chisqr:
+    (fragment records of the one file, w_scores, fragmentCounts, readCounts, updated unique scores)"""
+    L = orc()
+    raw = np.fromfile(db_prefix + ".length.b", dtype=np.int32)
+    DB, lengths = int(raw[0]), np.ascontiguousarray(raw[1:])
+    fr = np.frombuffer(frag_raw, dtype=np.uint8)
+    out = np.zeros(2 * len(fr) + 4096, dtype=np.uint8)
+    w, fc, rc = np.zeros(DB, np.uint64), np.zeros(DB, np.uint32), np.zeros(DB, np.uint32)
+    a, u = np.ascontiguousarray(a, dtype=np.uint64), np.array(u, dtype=np.uint64)
+    L.orc_conclave2_stream.restype = C.c_int64
+    L.orc_conclave2_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]
+    L.orc_conclave_set_lc(int(lc))
+    n = L.orc_conclave2_stream(lengths.ctypes.data, DB, fr.ctypes.data, len(fr), a.ctypes.data, u.ctypes.data, out.ctypes.data, len(out),
+                               w.ctypes.data, fc.ctypes.data, rc.ctypes.data, float(scoreT), float(evalue), int(and_mode), ref_p_chisqr())
+    L.orc_conclave_set_lc(0)
+    assert n >= 0, f"oracle conclave2 error {n}"
+    return out[:n].tobytes(), w, fc, rc, u
 
 
 def ref_memscore(db_prefix: str, s2: bytes, tmp: str):
