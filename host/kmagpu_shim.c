@@ -148,7 +148,6 @@ int __wrap_save_kmers_batch(char *templatefilename, char *exePrev, unsigned shm,
 	if (deConPrintPtr == &deConPrint) shim_unsupported("-decon");
 	if (printPtr != &print_ankers) shim_unsupported("sparse / split databases");
 	if (sam == 1 && out != stdout) shim_unsupported("SAM output of unmapped reads");
-	if (minFrac < 0) shim_unsupported("soft proximity with -mem_mode (the softProxi sums of kmers.c:133-153)");
 	g_coverT = coverT;
 	SHIM_TRACE("checks done");
 	shim_params(&prm, rewards);
@@ -165,6 +164,8 @@ int __wrap_save_kmers_batch(char *templatefilename, char *exePrev, unsigned shm,
 	if (get_kmers_for_pair_ptr != &get_kmers_for_pair) shim_unsupported("this pair scan");
 	SHIM_TRACE("stage 2: kmerscan %d apm %d", prm.kmerscan, prm.apm);
 	db = shim_db(templatefilename, 2);
+	/* soft proximity (kmers.c:133-153): a negative minFrac reaches this function only in -mem_mode (kma.c:1605) */
+	if (minFrac < 0 && minFrac != -1.0 && kmagpu_softproxi_reset(db)) shim_die("kmagpu_softproxi_reset");
 	fprintf(stderr, "# Finding k-mer ankers (GPU)\n");
 
 	while (!eof || fill || have_hdr) {
@@ -198,6 +199,17 @@ int __wrap_save_kmers_batch(char *templatefilename, char *exePrev, unsigned shm,
 	}
 	/* number of fragments, negated: the terminating record (kmers.c:257) */
 	sfwrite(&(int){-(int)total}, sizeof(int), 1, out);
+	if (minFrac < 0 && minFrac != -1.0) {   /* the sums travel behind the stream: their first 6 ints, then all of them (kmers.c:151-153) */
+		kmagpu_db_info info;
+		long unsigned *soft;
+		if (kmagpu_db_get_info(db, &info)) shim_die("kmagpu_db_get_info");
+		soft = calloc((size_t)info.DB_size + 3, sizeof(long unsigned));
+		if (!soft) { ERROR(); }
+		if (kmagpu_softproxi_download(db, (uint64_t *)soft)) shim_die("kmagpu_softproxi_download");
+		sfwrite(soft, sizeof(int), 6, out);
+		sfwrite(soft, sizeof(long unsigned), info.DB_size, out);
+		free(soft);
+	}
 	kmaPipe(0, 0, in, &status);
 	fprintf(stderr, "# Query ankered\n#\n");
 	free(buf); free(obuf);

@@ -345,6 +345,14 @@ int kmagpu_comm_unique_id(void *id128, size_t cap);
 int kmagpu_comm_init(kmagpu_db *db, const void *id128, int rank, int world);
 void kmagpu_comm_destroy(kmagpu_db *db);
 int kmagpu_scores_reset(kmagpu_db *db);
+/* Soft proximity (-proxi < 0 together with -mem_mode: the only case in which stage 2 is handed a negative minFrac, kma.c:1605):
+ * every template a get*Proxi* function keeps adds its score to softProxi[] (savekmers.c:330, 1577, 1636, 1803, 1868;
+ * kmeranker.c:357), save_kmers_batch appends the sums to the stage-2 stream (6 ints = their first 24 bytes, then DB_size
+ * unsigned longs, kmers.c:151-153) and runKMA_MEM takes them for alignment_scores (runkma.c:1153). kmagpu_softproxi_reset starts
+ * the sums of this handle's database image; every kmagpu_seed_run with params.minFrac < 0 then adds its batch;
+ * kmagpu_softproxi_download copies them out ([DB_size]; sum them over ranks with kmagpu_allreduce_u64). */
+int kmagpu_softproxi_reset(kmagpu_db *db);
+int kmagpu_softproxi_download(kmagpu_db *db, uint64_t *sums);
 int kmagpu_allreduce_scores(kmagpu_db *db, uint64_t *alignment_scores, uint64_t *uniq_alignment_scores, float *ms);
 int kmagpu_allreduce_matrix(kmagpu_db *db, float *ms);
 int kmagpu_allreduce_u64(kmagpu_db *db, uint64_t *buf, size_t n);

@@ -484,6 +484,17 @@ class TemplateDB:
         """ConClavePtr: False = runConClave, True = runConClave_lc (-lc)"""
         _check(lib().kmagpu_conclave_mode(self._h, int(length_corrected)))
 
+    def softproxi_reset(self):
+        """start the soft proximity sums of this database image (kmers.c:133-153); every seed_run with params.minFrac < 0 adds to them"""
+        _check(lib().kmagpu_softproxi_reset(self._h))
+
+    def softproxi_download(self) -> np.ndarray:
+        s = np.zeros(self.info.DB_size, dtype=np.uint64)
+        L = lib()
+        L.kmagpu_softproxi_download.argtypes = [C.c_void_p, C.c_void_p]
+        _check(L.kmagpu_softproxi_download(self._h, s.ctypes.data))
+        return s
+
     def conclave_version(self, version: int, p_chisqr=None, scoreT: float = 0.5, evalue: float = 0.05, and_mode: bool = False):
         """-ConClave 2: the ConClave calls run runConClave2 / runConClave2_lc (conclave.c:386 / 749) over the batch they get (the
         whole run). p_chisqr: the caller's chi-square tail function as a C pointer double (*)(long double) (stdstat.c:136).

@@ -42,6 +42,7 @@ struct ChainParams {
 	int32_t lc;   // -lc (kma.c:694-700): length-corrected anker selection (ankerScoreLen, testExtensionScoreLen, ...)
 	int32_t use_proxi, pad;   // -proxi (kma.c:702-718): getChainTemplates = getProxiChainTemplates, chooseChain's proximity test
 	double proxi;             // |minFrac|
+	unsigned long long *soft; // soft proximity sums of the batch (kmers.c:133-153), NULL = off
 	double mrs, coverT, mrc;
 };
 struct ChainRes { uint32_t reg_off; int32_t nreg; };
@@ -496,6 +497,7 @@ __device__ __noinline__ int chain_templates_proxi(const KgHashView &hv, const Ch
 			bool ok = proxiScore <= (double)x.x;   // proxiTestBestScore / ...ScoreLen (kmeranker.c:49-55)
 			if (lc && !ok) ok = __dmul_rn(__ddiv_rn(proxiScore, (double)target), (double)min(W.seqlen, __ldg(W.lengths + t))) <= (double)x.x;
 			keep = x.z == 0 && ok;
+			if (keep && p.soft) atomicAdd(p.soft + t, (unsigned long long)x.x);   // kmeranker.c:357-359
 			W.st[t] = make_int4(0, 0, 0, 0);
 		}
 		const unsigned m = __ballot_sync(FULL, keep);
@@ -1063,6 +1065,12 @@ int kg_chain_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *sta
 	cp.lc = prm->lc != 0;
 	cp.proxi = fabs(prm->minFrac);   // stage 2 sees |minFrac| (kma.c:1605)
 	cp.use_proxi = cp.proxi != 1.0;
+	const bool soft = prm->minFrac < 0 && cp.use_proxi && db->image->d_soft;
+	if (prm->minFrac < 0 && cp.use_proxi && !soft) { kmagpu_set_error("soft proximity (minFrac < 0 in stage 2) needs kmagpu_softproxi_reset first"); return -1; }
+	if (soft) {
+		if (b.d_soft.reserve(8 * (size_t)db->info.DB_size)) return -1;
+		cp.soft = (unsigned long long *)b.d_soft.p;
+	}
 
 	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	if (b.d_res.reserve(sizeof(ChainRes) * (size_t)n) || b.d_recoff.reserve(4 * (size_t)(2 * n + 2)) ||
@@ -1097,6 +1105,7 @@ int kg_chain_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *sta
 	for (int attempt = 0;; ++attempt) {
 		if (b.d_pool.reserve(4 * b.pool_cap) || b.d_regpool.reserve(sizeof(Region) * b.reg_cap)) return -1;
 		KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * C_N, db->stream));
+		if (soft) KG_CUDA(cudaMemsetAsync(b.d_soft.p, 0, 8 * (size_t)db->info.DB_size, db->stream));   // per attempt: a pool overflow redoes the batch
 		KG_CUDA(cudaEventRecord(db->ev[2], db->stream));
 		chain_kernel<<<grid, KC_WARPS * 32, 0, db->stream>>>(db->hv, cp, db->d_lengths, (const uint8_t *)b.d_in.p,
 			(const uint32_t *)b.d_off.p, n, (ChainRes *)b.d_res.p, nregs, (int32_t *)b.d_pool.p, (unsigned long long)b.pool_cap,
@@ -1120,6 +1129,7 @@ int kg_chain_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *sta
 			b.reg_cap = std::max(b.reg_cap, (size_t)h[C_REGS] + 1024);
 			continue;
 		}
+		if (soft) kg_softproxi_accumulate(db, (const unsigned long long *)b.d_soft.p);
 		const size_t NR = (size_t)h[C_TOTAL];
 		const int rtiles = (int)((NR + SCAN_TILE - 1) / SCAN_TILE);
 		b.out_nrec = (int64_t)NR;

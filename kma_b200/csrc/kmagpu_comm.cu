@@ -110,6 +110,38 @@ int kg_scores_accumulate(kmagpu_db *db, const unsigned long long *batch_scores) 
 	return 0;
 }
 
+// soft proximity sums of the run (kmers.c:133-153): one array per database image, every handle's batches join it
+extern "C" int kmagpu_softproxi_reset(kmagpu_db *db) {
+	if (!db) { kmagpu_set_error("null argument"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	KgImageRef *img = db->image;
+	const size_t bytes = 8 * (size_t)db->info.DB_size;
+	if (!img->d_soft) {
+		unsigned long long *p = nullptr;
+		KG_CUDA(cudaMalloc(&p, bytes));
+		img->d_soft = p;
+	}
+	KG_CUDA(cudaMemsetAsync(img->d_soft, 0, bytes, db->stream));
+	KG_CUDA(cudaStreamSynchronize(db->stream));
+	return 0;
+}
+
+int kg_softproxi_accumulate(kmagpu_db *db, const unsigned long long *batch_sums) {
+	if (!db->image->d_soft) return 0;
+	const size_t n = (size_t)db->info.DB_size;
+	add_u64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, db->stream>>>(db->image->d_soft, batch_sums, n);
+	return 0;
+}
+
+extern "C" int kmagpu_softproxi_download(kmagpu_db *db, uint64_t *sums) {
+	if (!db || !sums) { kmagpu_set_error("null argument"); return -1; }
+	if (!db->image->d_soft) { kmagpu_set_error("kmagpu_softproxi_download before kmagpu_softproxi_reset"); return -1; }
+	KG_CUDA(cudaSetDevice(db->device));
+	KG_CUDA(cudaMemcpyAsync(sums, db->image->d_soft, 8 * (size_t)db->info.DB_size, cudaMemcpyDeviceToHost, db->stream));
+	KG_CUDA(cudaStreamSynchronize(db->stream));
+	return 0;
+}
+
 extern "C" int kmagpu_allreduce_scores(kmagpu_db *db, uint64_t *alignment_scores, uint64_t *uniq_alignment_scores, float *ms) {
 	if (!db) { kmagpu_set_error("null argument"); return -1; }
 	KgImageRef *img = db->image;

@@ -254,7 +254,7 @@ extern "C" void kmagpu_db_close(kmagpu_db *db) {
 		cudaFree(db->d_seq); cudaFree(db->d_lengths); cudaFree(db->d_seq_off);
 		if (img) {
 			kmagpu_comm_destroy(db);
-			cudaFree(img->d_mat); cudaFree(img->d_mat_off); cudaFree(img->d_run_scores);
+			cudaFree(img->d_mat); cudaFree(img->d_mat_off); cudaFree(img->d_run_scores); cudaFree(img->d_soft);
 			delete img;
 		}
 	}

@@ -48,6 +48,7 @@ struct KgBuf {
 
 struct SeedBatch {
 	KgBuf d_in, d_off, d_res, d_pool, d_recoff, d_out, d_ctr, d_partial, d_dense;
+	KgBuf d_soft;   // soft proximity sums of the batch at hand ([DB_size] u64; joins KgImageRef::d_soft when the batch is through)
 	KgBuf d_kinds, d_mates, d_pool2;   // paired end: record kinds (0 single, 1/2 mates), per-mate strand lists
 	KgBuf h_kinds;                     // pinned staging of the record kinds
 	KgBuf d_chain, d_regpool, d_regs, d_rsize, d_partial2;   // chain mode: per-warp scratch, regions (as found / in read order), sizes
@@ -125,6 +126,7 @@ struct KgImageRef {
 	int64_t *d_mat_off = nullptr;
 	size_t mat_entries = 0;
 	unsigned long long *d_run_scores = nullptr;   // [alignment_scores[DB_size], uniq_alignment_scores[DB_size]]
+	unsigned long long *d_soft = nullptr;         // soft proximity sums of the run (kmers.c:133-153), [DB_size]; NULL until kmagpu_softproxi_reset
 	void *comm = nullptr;
 	int comm_rank = 0, comm_world = 1;
 };
@@ -160,6 +162,7 @@ struct kmagpu_db {
 	KgBuf d_cons_rows, d_cons_stat;   // consensus rows / per-template sums of the last kmagpu_consensus call (kept: no allocation per call)
 };
 int kg_scores_accumulate(kmagpu_db *db, const unsigned long long *batch_scores);
+int kg_softproxi_accumulate(kmagpu_db *db, const unsigned long long *batch_sums);
 
 int kg_tindex_build(kmagpu_db *db);
 int kg_check_record(const uint8_t *rec, int stage, int DB_size, size_t at);

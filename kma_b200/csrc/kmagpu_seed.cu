@@ -49,6 +49,8 @@ struct SeedParams {
 	int32_t M, MM, U, W1, exhaustive;
 	int32_t use_proxi;   // -proxi (kma.c:702-718): getMatch = getProxiMatch (savekmers.c:296) instead of getBestMatch
 	double proxi;        // |minFrac| as save_kmers_batch hands it on (kmers.c:133-141)
+	unsigned long long *soft;   // soft proximity (-proxi < 0 with -mem_mode, kmers.c:133-153): softProxi[template] += score for every
+	                            // template a get*Proxi* function keeps; NULL = off. Only the dense pass runs then (no second try per read)
 };
 
 // proxiScore = minFrac * bestScore, truncated into an int as the reference's assignment does
@@ -410,6 +412,7 @@ __device__ KG_SCAN_INL int scan_strand(const KgHashView &hv, const SeedParams &p
 			int s = st.cand[i];
 			ok = p.use_proxi ? thr <= st.score[s] : max(st.score[s], 0) == best;
 			t = st.tmpl_of(s);
+			if (ok && p.soft) atomicAdd(p.soft + t, (unsigned long long)st.score[s]);   // getProxiMatch (savekmers.c:330-332)
 			if (DENSE) { st.score[s] = 0; st.ext[s] = 0; st.incl[s] = 0; }
 		}
 		unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -622,7 +625,7 @@ __device__ __forceinline__ int list_score(const int2 *L, int n, int t) {   // Sc
 __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ rec_off, int nrec,
 		const uint8_t *__restrict__ kinds, const MateRes *__restrict__ mates, const int2 *__restrict__ pool2, int32_t *pool,
 		unsigned long long pool_cap, unsigned long long *ctr, SeedRes *res, uint32_t *recsize, int k, int PE, int apm,
-		int use_proxi, double pf) {
+		int use_proxi, double pf, unsigned long long *soft) {
 	const int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= nrec || kinds[r] != 1) return;
 	// a strand list that did not fit the pool was never written and its offset points past the allocation: the host
@@ -654,7 +657,7 @@ __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_
 				const int thr = proxi_of(pf, b);
 				for (int i = 0; i < nf + nr; ++i) {
 					const int t = i < nf ? F[i].x : -R[i - nf].x, sc = i < nf ? F[i].y : R[i - nf].y;
-					if (thr <= sc) dst[h++] = t;
+					if (thr <= sc) { dst[h++] = t; if (soft) atomicAdd(soft + abs(t), (unsigned long long)sc); }   // getF_Proxi / getR_Proxi
 				}
 				thr2 = thr;
 				*cnt = h;
@@ -765,7 +768,10 @@ __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_
 						for (int i = 0; i < nrt; ++i) {
 							const int t = rt[i];
 							int sc = 0 < t ? list_score(R2, B.n_r, t) : list_score(F2, B.n_f, -t);
-							if (0 < sc) { sc += i < A.n_f ? F1[i].y : R1[i - A.n_f].y; if (thr <= sc) rt[hits++] = t; }
+							if (0 < sc) {
+								sc += i < A.n_f ? F1[i].y : R1[i - A.n_f].y;
+								if (thr <= sc) { rt[hits++] = t; if (soft) atomicAdd(soft + abs(t), (unsigned long long)sc); }
+							}
 						}
 					}
 				}
@@ -776,7 +782,10 @@ __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_
 					nrt = hits;
 					hits = 0;
 					thr = proxi_of(pf, best_r);
-					for (int i = 0; i < nbt; ++i) if (thr <= (i < B.n_f ? F2[i].y : R2[i - B.n_f].y)) bt[hits++] = bt[i];
+					for (int i = 0; i < nbt; ++i) {
+						const int sc = i < B.n_f ? F2[i].y : R2[i - B.n_f].y;
+						if (thr <= sc) { if (soft) atomicAdd(soft + abs(bt[i]), (unsigned long long)sc); bt[hits++] = bt[i]; }
+					}
 					nbt = hits;
 				}
 			} else {
@@ -811,7 +820,7 @@ __global__ void pair_select_kernel(const uint8_t *__restrict__ in, const uint32_
 			const int thr = proxi_of(pf, best_r);
 			for (int i = 0; i < n2; ++i) {
 				const int t = i < B.n_f ? F2[i].x : -R2[i - B.n_f].x, sc = i < B.n_f ? F2[i].y : R2[i - B.n_f].y;
-				if (thr <= sc) rt[nrt++] = t;
+				if (thr <= sc) { rt[nrt++] = t; if (soft) atomicAdd(soft + abs(t), (unsigned long long)sc); }
 			}
 		} else {          // getF_Best: arg-max set of the second mate alone (written where regionTemplates is expected)
 			nrt = 0;
@@ -945,7 +954,7 @@ __global__ void lookup_kernel(KgHashView hv, const uint64_t *kmers, size_t n, in
 
 int kg_seed_free(kmagpu_db *db) {
 	SeedBatch &b = db->seed;
-	KgBuf *all[] = {&b.d_in, &b.d_off, &b.d_res, &b.d_pool, &b.d_recoff, &b.d_out, &b.d_ctr, &b.d_partial, &b.d_dense, &b.d_kinds, &b.d_mates, &b.d_pool2,
+	KgBuf *all[] = {&b.d_in, &b.d_off, &b.d_res, &b.d_pool, &b.d_recoff, &b.d_out, &b.d_ctr, &b.d_partial, &b.d_dense, &b.d_soft, &b.d_kinds, &b.d_mates, &b.d_pool2,
 	                &b.h_off, &b.h_in, &b.h_out, &b.h_kinds, &b.d_chain, &b.d_regpool, &b.d_regs, &b.d_rsize, &b.d_partial2};
 	for (KgBuf *x : all) x->release();
 	return 0;
@@ -1016,6 +1025,13 @@ extern "C" int kmagpu_seed_upload(kmagpu_db *db, const void *stage1, size_t nbyt
 	return 0;
 }
 
+// soft proximity: the overflow list = every read, so that the dense pass alone maps the batch
+static __global__ void seed_all_dense_kernel(uint32_t *ovf_list, int n, unsigned long long *ctr) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) ovf_list[i] = (uint32_t)i;
+	if (i == 0) ctr[C_OVF] = (unsigned long long)n;
+}
+
 extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_seed_stats *stats) {
 	if (!db || !prm) { kmagpu_set_error("null argument"); return -1; }
 	KG_CUDA(cudaSetDevice(db->device));
@@ -1034,9 +1050,17 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 	}
 	if (prm->kmerscan == 1 && !all_pairs) return kg_chain_run(db, prm, stats);
 	if (prm->kmerscan != 0 && prm->kmerscan != 1) { kmagpu_set_error("kmerscan %d: only save_kmers (0) and save_kmers_chain (1) are built", prm->kmerscan); return -1; }
-	SeedParams sp = {prm->M, prm->MM, prm->U, prm->W1, prm->exhaustive, 0, 1.0};
+	SeedParams sp = {prm->M, prm->MM, prm->U, prm->W1, prm->exhaustive, 0, 1.0, nullptr};
 	sp.proxi = fabs(prm->minFrac);       // stage 2 sees |minFrac| (kma.c:1605, kmers.c:133-141); the sign is stage 3's (soft proximity)
 	sp.use_proxi = sp.proxi != 1.0;
+	// soft proximity: a negative minFrac reaches stage 2 only in -mem_mode (kma.c:1605); the sums of this batch are collected in a
+	// scratch array per attempt (a pool overflow redoes the batch) and join the image's sums once the batch is through
+	const bool soft = prm->minFrac < 0 && sp.use_proxi && db->image->d_soft;
+	if (prm->minFrac < 0 && sp.use_proxi && !soft) { kmagpu_set_error("soft proximity (minFrac < 0 in stage 2) needs kmagpu_softproxi_reset first"); return -1; }
+	if (soft) {
+		if (b.d_soft.reserve(8 * (size_t)db->info.DB_size)) return -1;
+		sp.soft = (unsigned long long *)b.d_soft.p;
+	}
 	const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	if (b.pool_cap < (size_t)n * 16 + 1024) b.pool_cap = (size_t)n * 16 + 1024;
 	if (b.d_res.reserve(sizeof(SeedRes) * (size_t)n) || b.d_recoff.reserve(4 * (size_t)(2 * n + 2)) ||
@@ -1069,10 +1093,15 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 		if (b.d_pool.reserve(4 * b.pool_cap)) return -1;
 		if (pe && b.d_pool2.reserve(8 * b.pool2_cap)) return -1;
 		KG_CUDA(cudaMemsetAsync(ctr, 0, 8 * C_N, db->stream));
+		if (soft) KG_CUDA(cudaMemsetAsync(b.d_soft.p, 0, 8 * (size_t)db->info.DB_size, db->stream));
 		KG_CUDA(cudaEventRecord(db->ev[2], db->stream));
 		// the common shape (hashed table, 16-bit lists) runs the specialised kernel and sets reads with N's aside for the
 		// generic one; any other database runs the generic kernel on every read
 		const bool common = !db->hv.mega && db->hv.values_s;
+		if (soft) {
+			// every read takes the dense pass: it cannot overflow, so no read is scanned twice and its kept templates add once
+			seed_all_dense_kernel<<<(n + 255) / 256, 256, 0, db->stream>>>(ovf, n, ctr);
+		} else {
 		if (common)
 			seed_se_kernel<false, false><<<grid, KG_WARPS * 32, 0, db->stream>>>(db->hv, sp, (const uint8_t *)b.d_in.p,
 				(const uint32_t *)b.d_off.p, n, (SeedRes *)b.d_res.p, recsize, (int32_t *)b.d_pool.p,
@@ -1082,6 +1111,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 			(const uint32_t *)b.d_off.p, n, (SeedRes *)b.d_res.p, recsize, (int32_t *)b.d_pool.p,
 			(unsigned long long)b.pool_cap, ctr, ovf, nullptr, 0, kinds, (MateRes *)b.d_mates.p, (int2 *)b.d_pool2.p,
 			(unsigned long long)b.pool2_cap, nlist, common ? 1 : 0);
+		}
 		seed_se_kernel<true, true><<<dense_grid, KG_WARPS * 32, 0, db->stream>>>(db->hv, sp, (const uint8_t *)b.d_in.p,
 			(const uint32_t *)b.d_off.p, n, (SeedRes *)b.d_res.p, recsize, (int32_t *)b.d_pool.p,
 			(unsigned long long)b.pool_cap, ctr, ovf, (uint8_t *)b.d_dense.p, dense_stride, kinds, (MateRes *)b.d_mates.p,
@@ -1089,7 +1119,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 		if (pe) {
 			pair_select_kernel<<<(n + 127) / 128, 128, 0, db->stream>>>((const uint8_t *)b.d_in.p, (const uint32_t *)b.d_off.p, n, kinds,
 				(const MateRes *)b.d_mates.p, (const int2 *)b.d_pool2.p, (int32_t *)b.d_pool.p, (unsigned long long)b.pool_cap, ctr,
-				(SeedRes *)b.d_res.p, recsize, db->hv.kmersize, prm->PE, prm->apm, sp.use_proxi, sp.proxi);
+				(SeedRes *)b.d_res.p, recsize, db->hv.kmersize, prm->PE, prm->apm, sp.use_proxi, sp.proxi, sp.soft);
 			++launches;
 		}
 		KG_CUDA(cudaEventRecord(db->ev[3], db->stream));
@@ -1106,6 +1136,7 @@ extern "C" int kmagpu_seed_run(kmagpu_db *db, const kmagpu_params *prm, kmagpu_s
 			continue;
 		}
 		KG_SCAN_FITS(h[C_TOTAL], "the stage-2 stream");
+		if (soft) kg_softproxi_accumulate(db, (const unsigned long long *)b.d_soft.p);
 		b.out_bytes = (size_t)h[C_TOTAL];
 		b.out_nrec = n; b.out_recoff = recoff;
 		if (b.d_out.reserve(b.out_bytes + 64)) return -1;

@@ -43,6 +43,19 @@ int kmagpu_db_get_info(const kmagpu_db *db, kmagpu_db_info *info) {
 	return 0;
 }
 
+/* soft proximity sums of the run (one mock process = one run) */
+static uint64_t *g_soft = 0;
+int kmagpu_softproxi_reset(kmagpu_db *db) {
+	free(g_soft);
+	g_soft = calloc((size_t)db->o->DB_size + 3, sizeof(uint64_t));
+	return g_soft ? 0 : -1;
+}
+int kmagpu_softproxi_download(kmagpu_db *db, uint64_t *sums) {
+	if (!g_soft) { snprintf(g_err, sizeof(g_err), "kmagpu_softproxi_download before kmagpu_softproxi_reset"); return -1; }
+	memcpy(sums, g_soft, sizeof(uint64_t) * (size_t)db->o->DB_size);
+	return 0;
+}
+
 static void to_orc(const kmagpu_params *p, orc_params *o) {
 	orc_default_params(o);
 	o->M = p->M; o->MM = p->MM; o->U = p->U; o->W1 = p->W1; o->Wl = p->Wl; o->Mn = p->Mn; o->PE = p->PE;
@@ -60,11 +73,12 @@ int kmagpu_seed_batch(kmagpu_db *db, const kmagpu_params *p, const void *stage1,
 	memset(&st, 0, sizeof(st));
 	orc_chain_set_lc(p->lc);
 	orc_set_proxi(p->minFrac);
+	orc_set_soft_proxi(p->minFrac < 0 && p->minFrac != -1.0 ? g_soft : 0);
 	/* save_kmers_chain only sees single reads, pairs always go through save_kmers_pair (savekmers.c:196-199) */
 	n = (p->kmerscan && nbytes >= 16 && ((const int *)stage1)[3] >= 0) ? orc_chain_stream(db->o, &o, stage1, nbytes, p->minlen, p->scoreT, p->coverT, p->mrc, out, cap, &st)
 	                : orc_seed_stream(db->o, &o, stage1, nbytes, out, cap, &st);
 	if (n < 0) { snprintf(g_err, sizeof(g_err), "oracle stage 2 failed (%lld)", (long long)n); return -1; }
-	*out_bytes = (size_t)n;
+	*out_bytes = (size_t)n - 4;   /* the oracle's streams end with the terminator int; kmagpu_seed_batch leaves it to the caller (kmers.c:257) */
 	if (nreads) {   /* one per single read, one per pair (savekmers.c:183) */
 		const unsigned char *b = stage1;
 		size_t ip = 0; int64_t cnt = 0; int mate = 0;

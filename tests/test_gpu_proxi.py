@@ -58,3 +58,45 @@ def test_proxi_chain_mode(tmp_path, shape, proxi, lc):
     prefix, s1, s2, kw = chain_with(tmp_path, shape, proxi, lc)
     got = _stage2(prefix, s1, kmerscan=1, lc=lc, minFrac=abs(proxi), coverT=kw.get("coverT", 0.1))
     assert got == s2
+
+
+@pytest.mark.parametrize("kind", ["se", "pe_p", "pe_u", "chain", "chain_lc"])
+def test_soft_proximity_sums(tmp_path, kind):
+    """-proxi < 0 with -mem_mode: every template a get*Proxi* function keeps adds its score to softProxi[] (kmers.c:133-153).
+    Stream and sums vs `kma -mem_mode -proxi -0.9 -s2` (the sums travel behind the stream); two batches add up"""
+    from tests.test_oracle_pair import make_pairs
+    from tests.test_oracle_chain import chain_case
+    extra = ["-mem_mode", "-proxi", "-0.9", "-s2"]
+    kw = {}
+    if kind == "se":
+        prefix, s1, _, _ = se_case(tmp_path, 71, 0.9, n=1500)
+        s2 = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db", "-1t1"] + extra, cwd=tmp_path)
+        kw = dict(one2one=1)
+    elif kind in ("pe_p", "pe_u"):
+        apm = kind[-1]
+        prefix, s1, _ = make_pairs(tmp_path, 82, apm=apm)
+        s2 = util.ref_kma(["-ipe", "r1.fq", "r2.fq", "-o", "o", "-t_db", "db", "-apm", apm] + extra, cwd=tmp_path)
+        kw = dict(apm=1 if apm == "u" else 0)
+    else:
+        lc = kind == "chain_lc"
+        prefix, s1, _ = chain_case(tmp_path, 12, 120, 1000, 6000, 0.03, 0.0)
+        s2 = util.ref_kma(["-i", "r.fq", "-o", "o", "-t_db", "db"] + extra + (["-lc"] if lc else []), cwd=tmp_path)
+        kw = dict(kmerscan=1, lc=int(lc))
+    db = api.TemplateDB(prefix, device=0)
+    DB = db.info.DB_size
+    p = api.default_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    p.minFrac = -0.9
+    with pytest.raises(api.KmaGpuError):
+        db.save_kmers_batch(s1, p)          # the sums have to be started first
+    db.softproxi_reset()
+    out, n, _ = db.save_kmers_batch(s1, p)
+    sums = db.softproxi_download()
+    stream = out.tobytes() + api.stream_terminator(n)
+    trailer = sums.tobytes()[:24] + sums.tobytes()
+    assert len(s2) == len(stream) + 24 + 8 * DB and sums.sum() > 0
+    assert stream + trailer == s2
+    db.save_kmers_batch(s1, p)              # a second batch joins the same sums
+    assert np.array_equal(db.softproxi_download(), 2 * sums)
+    db.close()

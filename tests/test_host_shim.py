@@ -116,6 +116,14 @@ CASES = {
     "preset_asm": dict(reads="long", n=30, args=["-asm"]),
     # options that stay in the reference's own host code around the device calls: ConClave version 2 (runConClave2,
     # conclave.c:386), dense base counts, reference-guided consensus, stage-1 quality filters (-eq / -mi / -mp / -5p)
+    # soft proximity together with -mem_mode: stage 2 collects the softProxi sums (kmers.c:133-153), they travel behind the
+    # stream and become runKMA_MEM's alignment_scores (runkma.c:1153) -- the -ill and -ont presets on a genome in -mem_mode
+    "c4_genome_mem_ill": dict(reads="genome", n=3000, args=["-mem_mode", "-ill", "-matrix"]),
+    "c4_genome_mem_soft_chain": dict(reads="genome", n=2000, args=["-mem_mode", "-proxi", "-0.9"]),
+    "c1_se_mem_soft": dict(reads="se", n=800, args=["-mem_mode", "-1t1", "-proxi", "-0.9", "-matrix"]),
+    "c2_pe_mem_soft_u": dict(reads="pe", n=600, args=["-mem_mode", "-proxi", "-0.8"]),
+    "c2_pe_mem_soft_p": dict(reads="pe", n=600, args=["-mem_mode", "-apm", "p", "-proxi", "-0.9"]),
+    "c3_long_mem_ont": dict(reads="long", n=40, args=["-mem_mode", "-ont"]),
     "c1_se_conclave2": dict(reads="se", n=800, args=["-1t1", "-ConClave", "2", "-matrix"]),
     "c3_long_conclave2_lc": dict(reads="long", n=40, args=["-ConClave", "2", "-lc"]),
     "c1_se_dense_reffsa": dict(reads="se", n=800, args=["-1t1", "-dense", "-ref_fsa", "-matrix"]),
