@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU-box call with the round's evidence: every GPU parity test, smoke, both bench arms, the ncu launch list of the bench step,
 # ncu --set full of the dominant kernels of C2 / C3 / C5 / stand-alone NW. usage: bash tools/r02_final.sh <tag>
-tag=${1:-r02_v4}
+tag=${1:-r02_v5}
 mkdir -p gpurun_out
 L=gpurun_out/final_$tag.log; : > $L
 timeout 1500 python -m pytest tests -m gpu -q --timeout 180 2>&1 | tail -3 >> $L
@@ -23,7 +23,7 @@ PY
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$tag.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-c3 --no-c4 --no-c5 --no-parity > gpurun_out/ncu_launch_$tag.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"aln_pair_kernel|seed_se_kernel|nw_thread_kernel" --launch-skip 12 -c 7 \
-    -f -o gpurun_out/prof_${tag}_c2 python tools/pe_perf.py 2000000 2 > gpurun_out/ncu_full_${tag}_c2.log 2>&1
+    -f -o gpurun_out/prof_${tag}_c2 python tools/pe_perf.py 2000000 5 > gpurun_out/ncu_full_${tag}_c2.log 2>&1
 tail -1 gpurun_out/ncu_full_${tag}_c2.log >> $L
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"aln_pair_kernel|chain_kernel|nw_warp_kernel|nw_thread_kernel" --launch-skip 12 -c 6 \
     -f -o gpurun_out/prof_${tag}_c3 env KG_COUNTERS=0 python tools/c3_perf.py 20000 0 > gpurun_out/ncu_full_${tag}_c3.log 2>&1
