@@ -227,6 +227,33 @@ def default_params() -> Params:
     return p
 
 
+def preset(name: str) -> dict:
+    """What the reference's presets bind (kma.c:1100-1240), as arguments for this package's calls. Host glue like
+    default_params(): `params` for the stage-2 / stage-3 / traceback calls, `ingest` for run_input_text / run_input_batch,
+    `consensus` for TemplateDB.consensus, `conclave_lc` for conclave_mode.
+      ont: chain scan, -lc, -proxi -0.9, -ts 2, -eq 10, -mrs 0.25, -mrc 0.7, -mct 0.1, -bcNano, -bc 0.7, -bcd 10
+      ill: -1t1, -lc, -proxi -0.98, -mrc 0.1, -bc 0.9, -bcd 10
+      asm: chain scan, -lc, -proxi -0.9, -ts 2, -mrs 0.25, -mrc 0.7, -mct 0.1, -bc 0.5, -p 0.5, -bcd 1"""
+    p = default_params()
+    p.kmerscan, p.one2one = 1, 0   # the CLI's default scan is save_kmers_chain (savekmers.c:40)
+    p.apm = 1                      # -apm u, the default pairing
+    ingest, cons = {}, dict(bcd=1, evalue=0.05, caller=0, significance=0, support=0.0)
+    if name == "ont":
+        p.lc, p.minFrac, p.ts, p.scoreT, p.mrc, p.coverT = 1, -0.9, 2, 0.25, 0.7, 0.1
+        ingest = dict(min_q=10)
+        cons.update(bcd=10, caller=3, significance=2, support=0.7)
+    elif name == "ill":
+        p.kmerscan, p.one2one = 0, 1
+        p.lc, p.minFrac, p.mrc = 1, -0.98, 0.1
+        cons.update(bcd=10, significance=2, support=0.9)
+    elif name == "asm":
+        p.lc, p.minFrac, p.ts, p.scoreT, p.mrc, p.coverT = 1, -0.9, 2, 0.25, 0.7, 0.1
+        cons.update(bcd=1, evalue=0.5, significance=2, support=0.5)
+    else:
+        raise ValueError(f"preset {name!r}: ont, ill or asm")
+    return dict(params=p, ingest=ingest, consensus=cons, conclave_lc=True)
+
+
 def _ptr(a):
     """address of a numpy array or torch tensor's storage"""
     if hasattr(a, "data_ptr"):

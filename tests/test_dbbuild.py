@@ -29,3 +29,16 @@ def test_reference_maps_identically_with_our_db(tmp_path):
     # the oracle reads it too
     s1 = np.frombuffer(util.ref_kma(["-i", "r.fq", "-o", "a", "-t_db", "ref", "-1t1", "-s1"], cwd=tmp_path), dtype=np.uint8)
     assert util.oracle_seed_stream(str(tmp_path / "mine"), s1).tobytes() == a
+
+
+def test_presets_mirror_the_cli():
+    """api.preset(): the option bundles of kma.c:1100-1240 (behaviour checked at file level by tests/test_host_shim.py's preset cases)"""
+    from kma_b200 import api
+    ont, ill, asm = api.preset("ont"), api.preset("ill"), api.preset("asm")
+    assert (ont["params"].kmerscan, ont["params"].lc, ont["params"].ts, ont["params"].minFrac, ont["ingest"]["min_q"]) == (1, 1, 2, -0.9, 10)
+    assert (ont["consensus"]["caller"], ont["consensus"]["support"], ont["params"].scoreT, ont["params"].mrc) == (3, 0.7, 0.25, 0.7)
+    assert (ill["params"].kmerscan, ill["params"].one2one, ill["params"].minFrac, ill["params"].mrc, ill["consensus"]["support"]) == (0, 1, -0.98, 0.1, 0.9)
+    assert (asm["params"].ts, asm["consensus"]["evalue"], asm["consensus"]["bcd"], asm["params"].coverT) == (2, 0.5, 1, 0.1)
+    import pytest
+    with pytest.raises(ValueError):
+        api.preset("x")
