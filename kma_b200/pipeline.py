@@ -13,6 +13,57 @@ import numpy as np
 from . import api
 
 
+def phred_scale(text, chunk: int = 1048576) -> int:
+    """getPhredFileBuff (seqparse.c:551-589) on the first buffer of a FASTQ file (CHUNK = 1 MiB, filebuff.h:36): 33 as soon as a
+    quality byte lies in 54..58, 64 if one above 94 was seen, 0 for a byte below 33; reads longer than 301 count as 33"""
+    buf = memoryview(text)[:chunk].tobytes()
+    scale, maxlen, pos, n = 33, 0, 0, len(buf)
+    while pos < n:
+        for _ in range(3):                       # the three lines before the quality line (the scan starts behind its first byte)
+            nl = buf.find(b"\n", pos + 1)
+            if nl < 0:
+                return scale if maxlen <= 301 else 33
+            pos = nl
+        end = buf.find(b"\n", pos + 1)
+        line = buf[pos + 1:end if end >= 0 else n]
+        for c in line:                           # in file order: the first decisive byte wins (a '\r' counts as below 33)
+            if c < 33:
+                return 0
+            if 53 < c < 59:
+                return 33
+            if c > 94:
+                scale = 64
+        maxlen = max(maxlen, len(line))
+        if end < 0:
+            break
+        pos = end
+    return scale if maxlen <= 301 else 33
+
+
+def read_reads(path: str):
+    """Host I/O in front of stage 1, what openAndDetermine + the FileBuff readers do (filebuff.c, seqparse.c): the file as plain
+    text -- gzip members inflated with zlib like the reference's BuffgzFileBuff (filebuff.c:29-74) --, FASTA unwrapped to
+    one sequence line per record (kmagpu_fasta_unwrap = FileBuffgetFsa's view of it). -> (text bytes, fastq?, phred scale).
+    The decompression is sequential per file (that is DEFLATE); pair files can be read by two threads."""
+    import zlib
+    raw = open(path, "rb").read()
+    if raw[:2] == b"\x1f\x8b":
+        parts, data = [], raw
+        while data:                              # concatenated members (bgzip, cat a.gz b.gz)
+            d = zlib.decompressobj(31)
+            parts.append(d.decompress(data))
+            data = d.unused_data
+        raw = b"".join(parts)
+    if not raw:
+        return raw, True, 33
+    if raw[:1] == b">":
+        flat, used = api.fasta_unwrap(raw)
+        return flat, False, 33
+    if raw[:1] != b"@":
+        raise api.KmaGpuError(f"{path}: neither FASTQ nor FASTA")
+    return raw, True, phred_scale(raw)
+
+
 class MapPipeline:
     def __init__(self, prefix: str, device: int = 0, workers: int = 2, params=None):
         first = api.TemplateDB(prefix, device)

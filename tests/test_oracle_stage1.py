@@ -157,3 +157,29 @@ def test_multi_line_fasta(tmp_path, crlf):
     assert a + b == flat and ua + ub == len(text)
     with pytest.raises(api.KmaGpuError):
         api.fasta_unwrap(b"ACGT\n>r1\nACGT\n")
+
+
+def test_host_reader_gz_fasta_and_phred_scale(tmp_path):
+    """kma_b200.pipeline.read_reads / phred_scale: gzip input (one and several members), multi-line FASTA, and the phred scale
+    getPhredFileBuff (seqparse.c:551) reports -- the text they hand to stage 1 gives the reference's stage-1 stream"""
+    import gzip, re
+    from kma_b200 import pipeline
+    rng, reads = make(tmp_path, 61, n=300)
+    for scale, mp in ((33, "20"), (64, "20")):
+        quals = util.random_quals(rng, reads, scale=scale)
+        if scale == 64:
+            quals = [np.maximum(q, 95) for q in quals]
+        text = util.fastq_text(reads, quals)
+        half = text.index(b"\n@r150") + 1
+        (tmp_path / "r.fq.gz").write_bytes(gzip.compress(text[:half]) + gzip.compress(text[half:]))   # two members
+        got, fastq, ps = pipeline.read_reads(str(tmp_path / "r.fq.gz"))
+        r = __import__("subprocess").run([util.REF_KMA, "-i", "r.fq.gz", "-o", "o", "-t_db", "db", "-s1", "-mp", mp], cwd=tmp_path,
+                                          stdout=__import__("subprocess").PIPE, stderr=__import__("subprocess").PIPE)
+        ref_scale = int(re.search(rb"Phred scale:\s*(\d+)", r.stderr).group(1))
+        assert got == text and fastq and ps == ref_scale == scale
+        assert util.oracle_stage1(got, min_phred=int(mp), phred_scale=ps)[0] == r.stdout
+    fa = _wrap_fasta(rng, reads)
+    (tmp_path / "r.fa.gz").write_bytes(gzip.compress(fa))
+    got, fastq, _ = pipeline.read_reads(str(tmp_path / "r.fa.gz"))
+    want = util.ref_kma(["-i", "r.fa.gz", "-o", "o", "-t_db", "db", "-s1"], cwd=tmp_path)
+    assert not fastq and util.oracle_stage1(got, fastq=False)[0] == want
