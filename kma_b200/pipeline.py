@@ -6,6 +6,7 @@ back over PCIe, the next chunk's records are being walked / uploaded and a third
 behind the compute instead of adding to it. Output order is chunk order = input order."""
 from __future__ import annotations
 
+import os
 import threading
 
 import numpy as np
@@ -292,13 +293,22 @@ class MapPipeline:
                 err.append(e)
         b1 = threading.Barrier(W, action=exchange_scores)
         b2 = threading.Barrier(W, action=exchange_matrix)
+        # the slices go up one after the other, in order: four uploads issued at once share the link, and the first slice -- the
+        # one the kernels wait for -- arrived after 17 ms instead of the 8 ms it takes alone (profiles/r02_e2e_phases_v5.log)
+        up_done = [threading.Event() for _ in range(W)]
+        in_order = os.environ.get("KMA_B200_E2E_UPLOAD_ORDER", "1") != "0"
 
         def work(w):
             db = self.dbs[w]
             try:
                 if w < nsl:
                     t2 = None if c2 is None else text2[c2[w]:c2[w + 1]]
-                    _, cnt, _, u1, u2 = db.run_input_text(text1[c1[w]:c1[w + 1]], text2=t2, fastq=fastq, download=False, **ingest)
+                    if in_order and w:
+                        up_done[w - 1].wait()
+                    try:
+                        _, cnt, _, u1, u2 = db.run_input_text(text1[c1[w]:c1[w + 1]], text2=t2, fastq=fastq, download=False, **ingest)
+                    finally:
+                        up_done[w].set()
                     if u1 != c1[w + 1] - c1[w] or (c2 is not None and u2 != c2[w + 1] - c2[w]):
                         raise api.KmaGpuError("the two files' records do not line up slice by slice")
                     res["reads"][w] = cnt
@@ -310,6 +320,7 @@ class MapPipeline:
                     mark(w, "alignment pass")
             except Exception as e:
                 err.append(e)
+            up_done[w].set()   # a worker without a slice (or one that failed earlier) must not hold up the next one
             b1.wait()
             try:
                 if w < nsl and not err:
