@@ -796,7 +796,7 @@ def main():
                "per_read": {"alignments": sa.tasks / sa.reads, "index_probes": sa.index_probes / sa.reads, "mems": sa.mems / sa.reads, "nw_cells": cells / sa.reads, "bytes": alg_pair / sa.reads}}
     rf_seed = {"kernel": "seed_se_kernel<hash, common shape>", "bound": "hbm", "achieved": ach_seed, "peak": pk["hbm_gbs"], "unit": "GB/s",
                "frac": ach_seed / pk["hbm_gbs"], "peak_kind": pk_kind, "traffic": ncu_traffic("seed_se_kernel", args.pairs), "algorithmic_bytes_per_launch": alg_seed, "kernel_ms": ms_seed,
-               "note": "the C2 database image (20 MB table) is L2 resident: the gather never reaches HBM here; c5.roofline is the same kernel with the table out of L2",
+               "note": "the C2 k-mer table (32 MB of bucket entries + lists) is L2 resident: the gather never reaches HBM here; c5.roofline is the same kernel with the table out of L2",
                "per_read": {"lookups": st.lookups / st.reads, "hits": st.hits / st.reads,
                             "list_fetches": st.list_fetches / st.reads, "bytes": alg_seed / st.reads}}
     line = {
