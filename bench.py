@@ -637,8 +637,10 @@ def main():
                 "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * statistics.mean(dt for _, dt in vals), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "pairs_per_step": sample, "reads_per_step": 2 * sample},
-                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores if have_ref else 1, "kind": "reference" if have_ref else "port", "sample": what},
+                # the named workload, under the keys of the GPU arm's line; each step of this arm is a bounded sample of it
+                "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": args.pairs, "reads_per_gpu_per_step": 2 * args.pairs, "read_len": 150},
+                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores if have_ref else 1, "kind": "reference" if have_ref else "port", "sample": what,
+                                 "sample_pairs_per_step": sample},
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
