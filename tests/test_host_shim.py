@@ -57,7 +57,7 @@ def _same_res(a: bytes, b: bytes):
                 assert abs(du - dv) <= 1e-9 * max(abs(du), abs(dv)), (x, y)
 
 
-def _compare(cwd, want="ref", got="gpu", exts=("res", "fsa", "aln", "frag.gz", "mat.gz"), sort_frag=False):
+def _compare(cwd, want="ref", got="gpu", exts=("res", "fsa", "aln", "frag.gz", "mat.gz"), sort_frag=False, at_least=3):
     n = 0
     for e in exts:
         pw, pg = os.path.join(cwd, f"{want}.{e}"), os.path.join(cwd, f"{got}.{e}")
@@ -72,7 +72,7 @@ def _compare(cwd, want="ref", got="gpu", exts=("res", "fsa", "aln", "frag.gz", "
         else:
             assert a == b, f".{e} differs ({len(a)} vs {len(b)} bytes)"
         n += len(a) > 0
-    assert n >= 3, "nothing to compare"
+    assert n >= at_least, "nothing to compare"
 
 
 def _gene_case(tmp, seed=5, fam=12, var=5):
@@ -131,8 +131,20 @@ CASES = {
 }
 
 
+# more of the reference's options around the device calls, over the mock ABI only (CPU suite): other penalties (-cge sets
+# MM -3, W1 -5, PE 17), base callers and significance tests, -and, output switches
+CASES_HOST = {
+    "c1_se_cge": dict(reads="se", n=600, args=["-1t1", "-cge", "-matrix"]),
+    "c2_pe_cge": dict(reads="pe", n=500, args=["-cge", "-apm", "p"]),
+    "c1_se_bc90_and": dict(reads="se", n=600, args=["-1t1", "-bc90", "-and", "-mrs", "0.3"]),
+    "c1_se_bcg_nc_nf": dict(reads="se", n=600, args=["-1t1", "-bcg", "-nc", "-nf"]),
+    "c3_long_mrc_mct": dict(reads="long", n=30, args=["-mrc", "0.5", "-mct", "0.3", "-ml", "60"]),
+    "c1_se_exhaustive": dict(reads="se", n=600, args=["-1t1", "-ex_mode", "-matrix"], n_rate=0.01),
+}
+
+
 def _make_case(tmp, name):
-    c = CASES[name]
+    c = CASES.get(name) or CASES_HOST[name]
     if c["reads"] == "genome":
         names, seqs = synth.genome_db(4, length=60000)
         synth.write_fasta(tmp / "db.fsa", names, seqs)
@@ -166,6 +178,20 @@ def test_shim_host_logic_with_the_oracle_behind_the_abi(tmp_path, name):
     _run("kma", args + ["-o", "ref", "-t", "1"], tmp_path)
     _run("kma_gpu_mock", args + ["-o", "gpu", "-t", "1"], tmp_path)
     _compare(tmp_path)
+
+
+@pytest.mark.parametrize("name", list(CASES_HOST))
+def test_shim_host_logic_more_options(tmp_path, name):
+    if not os.path.isdir("/root/reference") and not os.path.exists(os.path.join(REF, "kma_gpu_mock")):
+        pytest.skip("reference host not built in this environment")
+    _build_host()
+    args = _make_case(tmp_path, name)
+    _run("kma", args + ["-o", "ref", "-t", "1"], tmp_path)
+    _run("kma_gpu_mock", args + ["-o", "gpu", "-t", "1"], tmp_path)
+    exts = ("res", "fsa", "aln", "frag.gz", "mat.gz")
+    if "-nc" in args or "-nf" in args:
+        exts = tuple(e for e in exts if not (e in ("fsa", "aln") and "-nc" in args) and not (e == "frag.gz" and "-nf" in args))
+    _compare(tmp_path, exts=exts, at_least=min(3, len(exts) - 1))
 
 
 def test_shim_refuses_what_the_gpu_path_does_not_cover(tmp_path):
