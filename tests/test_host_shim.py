@@ -217,6 +217,21 @@ def test_output_files_equal_the_reference(tmp_path, name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES_HOST))
+def test_output_files_more_options(tmp_path, name):
+    """other penalties (-cge), base callers / significance tests, -and, -nc / -nf, -ex_mode through the device (checked by
+    tools/host_options_gpu.py as well)"""
+    assert os.path.exists(os.path.join(REF, "kma_gpu")), "oracle/_ref/kma_gpu missing: run __graft_entry__.build() where /root/reference exists"
+    args = _make_case(tmp_path, name)
+    _run("kma", args + ["-o", "ref", "-t", "1"], tmp_path)
+    _run("kma_gpu", args + ["-o", "gpu", "-t", "1"], tmp_path)
+    exts = ("res", "fsa", "aln", "frag.gz", "mat.gz")
+    if "-nc" in args or "-nf" in args:
+        exts = tuple(e for e in exts if not (e in ("fsa", "aln") and "-nc" in args) and not (e == "frag.gz" and "-nf" in args))
+    _compare(tmp_path, exts=exts, at_least=min(3, len(exts) - 1))
+
+
+@pytest.mark.gpu
 def test_output_files_with_host_threads(tmp_path):
     """-t 3: the reference's assembly threads pull the device results out of order; only the order of .frag.gz lines may differ"""
     args = _make_case(tmp_path, "c1_se_1t1")
