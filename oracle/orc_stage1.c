@@ -148,8 +148,9 @@ size_t orc_fasta_unwrap(const uint8_t *text, size_t n, uint8_t *out) {
 	orc_to2bit(trans);
 	size_t p = 0, o = 0;
 	while (p < n && text[p] == '>') {
+		const size_t o0 = o;
 		while (p < n && text[p] != '\n') out[o++] = text[p++];
-		if (p >= n) break;
+		if (p >= n) { o = o0; break; }   /* a header line cut off by the end of the file is no record (seqparse.c:85-91) */
 		out[o++] = text[p++];
 		while (p < n && text[p] != '>') { if (trans[text[p]] < 8) out[o++] = text[p]; ++p; }
 		out[o++] = '\n';

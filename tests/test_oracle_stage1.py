@@ -183,3 +183,29 @@ def test_host_reader_gz_fasta_and_phred_scale(tmp_path):
     got, fastq, _ = pipeline.read_reads(str(tmp_path / "r.fa.gz"))
     want = util.ref_kma(["-i", "r.fa.gz", "-o", "o", "-t_db", "db", "-s1"], cwd=tmp_path)
     assert not fastq and util.oracle_stage1(got, fastq=False)[0] == want
+
+
+def test_fasta_unwrap_fuzz():
+    """kmagpu_fasta_unwrap == the oracle's restatement on random texts: odd bytes, blank lines, '>' right after a header, records
+    without sequence, missing final newline, and every cut position of a small text in the chunked mode"""
+    from kma_b200 import api
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTNacgtnRYKMxX*- \t\r\n\n\n", dtype=np.uint8)
+    for it in range(200):
+        recs = []
+        for r in range(int(rng.integers(1, 6))):
+            hdr = b">h%d" % r + (b" d e" if rng.random() < 0.5 else b"") + (b"\r" if rng.random() < 0.2 else b"")
+            body = alphabet[rng.integers(0, len(alphabet), size=int(rng.integers(0, 80)))].tobytes().replace(b">", b"")
+            recs.append(hdr + b"\n" + body + (b"\n" if rng.random() < 0.8 else b""))
+        text = b"".join(recs)
+        want = util.oracle_fasta_unwrap(text)
+        got, used = api.fasta_unwrap(text)
+        assert got == want and used == len(text), (it, text)
+        if it % 10 == 0:   # a header line cut off by the end of the file is no record
+            t2 = text + b">last one"
+            assert api.fasta_unwrap(t2)[0] == util.oracle_fasta_unwrap(t2) == want
+        if it < 20:   # chunked: any cut, the rest carried over
+            for cut in range(1, len(text)):
+                a, ua = api.fasta_unwrap(text[:cut], eof=False)
+                b, ub = api.fasta_unwrap(text[ua:])
+                assert a + b == want and ua + ub == len(text), (it, cut, text)
